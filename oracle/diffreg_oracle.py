@@ -1,0 +1,440 @@
+"""CPU oracle for the Diff-Reg denoising hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a CPU restatement (torch CPU ops, fp32 unless the reference itself
+promotes to fp64) of the reference's coarse matching-matrix update.  It exists
+so that the CUDA path in ``diff-reg_b200/`` can be checked on a box that has no
+copy of the reference.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it; the
+product path never does (it raises when the CUDA library is missing).
+
+Parity pinning.  The reference ships NO golden vectors, known-answer tests or
+fixtures for this path, so the reference's own tests pin
+nothing: "parity unpinned" by the reference's tests.  What pins this oracle
+instead is the reference code itself, imported unmodified from /root/reference
+in the build container by ``tests/golden/make_golden.py``; the inputs and the
+reference's outputs are committed as ``tests/golden/*.npz`` and
+``tests/test_oracle_golden.py`` checks every function here against them.
+
+Reference files restated (paths relative to the reference checkout):
+  4d  = Diff-Reg-4dmatch/   3d = Diff-Reg-3dmatch/
+  2d3d = Diff-Reg-2d3d/experiments/2d3dmatr.rgbdv2.stage4.level3.stage1/
+
+The arithmetic deliberately follows the reference's operation ORDER (cat-built
+score matrix, ``logsumexp`` of a materialised sum, full descending sort, fp64
+SVD on the host) because the oracle doubles as the CPU timing baseline ("port")
+and must pay for the same passes the reference pays for.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+NEG_INF = float("-inf")
+
+
+# --------------------------------------------------------------------------------------
+# Sinkhorn (a4)
+# --------------------------------------------------------------------------------------
+def log_optimal_transport(scores, alpha, iters, src_mask, tgt_mask):
+    """Log-domain Sinkhorn with one dustbin row and one dustbin column.
+
+    Follows 4d/models/matching.py:6-38 (byte-identical copies at
+    3d/models/matching.py:61-93 and 2d3d/matching.py:6-38).
+
+    scores : [B, N, M]   may contain -inf (padding) and may be fp64 (quirk Q4)
+    alpha  : 0-dim tensor, the shared dustbin score
+    masks  : [B, N] / [B, M] bool; only their COUNTS are used here (Q1: padded
+             rows/columns keep marginal mass ``norm`` and drain into the dustbin)
+    returns: [B, N+1, M+1] log-assignment  (Z + u + v - norm)
+    """
+    B, N, M = scores.shape
+    n_src = src_mask.sum(dim=1, keepdim=True)          # :14  int64 [B,1]
+    n_tgt = tgt_mask.sum(dim=1, keepdim=True)          # :15
+    a = alpha                                          # cat() promotes fp32 alpha with fp64 scores (Q4)
+
+    # :17-22  augmented score matrix, dustbins hold alpha
+    top = torch.cat((scores, a.expand(B, N, 1)), dim=2)
+    bottom = a.expand(B, 1, M + 1)
+    Z = torch.cat((top, bottom), dim=1)
+
+    norm = -(n_src + n_tgt).log()                      # :24  fp32 [B,1]
+    log_mu = torch.cat((norm.expand(B, N), n_tgt.log() + norm), dim=1)   # :26
+    log_nu = torch.cat((norm.expand(B, M), n_src.log() + norm), dim=1)   # :27
+
+    u = torch.zeros_like(log_mu)
+    v = torch.zeros_like(log_nu)
+    for _ in range(int(iters)):                        # :30-32
+        u = log_mu - torch.logsumexp(Z + v[:, None, :], dim=2)
+        v = log_nu - torch.logsumexp(Z + u[:, :, None], dim=1)
+    out = Z + u[:, :, None] + v[:, None, :]            # :34
+    return out - norm.view(-1, 1, 1)                   # :36
+
+
+def sinkhorn_potentials(scores, alpha, iters, src_mask, tgt_mask):
+    """Same recursion as ``log_optimal_transport`` but returns (u, v, norm).
+
+    Not a reference function: it exposes the dual potentials the CUDA library
+    also returns, so that they can be checked directly.
+    """
+    B, N, M = scores.shape
+    n_src = src_mask.sum(dim=1, keepdim=True)
+    n_tgt = tgt_mask.sum(dim=1, keepdim=True)
+    Z = torch.cat((torch.cat((scores, alpha.expand(B, N, 1)), dim=2), alpha.expand(B, 1, M + 1)), dim=1)
+    norm = -(n_src + n_tgt).log()
+    log_mu = torch.cat((norm.expand(B, N), n_tgt.log() + norm), dim=1)
+    log_nu = torch.cat((norm.expand(B, M), n_src.log() + norm), dim=1)
+    u = torch.zeros_like(log_mu)
+    v = torch.zeros_like(log_nu)
+    for _ in range(int(iters)):
+        u = log_mu - torch.logsumexp(Z + v[:, None, :], dim=2)
+        v = log_nu - torch.logsumexp(Z + u[:, :, None], dim=1)
+    return u, v, norm
+
+
+def pair_mask(src_mask, tgt_mask):
+    """[B,N,M] validity mask, as built at 4d/models/matching.py:163-165."""
+    return (src_mask[..., None] * tgt_mask[:, None]).bool()
+
+
+# --------------------------------------------------------------------------------------
+# rotary embedding (a11)
+# --------------------------------------------------------------------------------------
+def embed_rotary(x, cos, sin):
+    """4d/models/position_encoding.py:26-35: rotate feature pairs (x0,x1)->(-x1,x0)."""
+    rot = torch.empty_like(x)
+    rot[..., 0::2] = -x[..., 1::2]
+    rot[..., 1::2] = x[..., 0::2]
+    return x * cos + rot * sin
+
+
+# --------------------------------------------------------------------------------------
+# correspondence extraction (a5, a6)
+# --------------------------------------------------------------------------------------
+def get_match(conf, thr=0.0, mutual=True):
+    """4d/models/matching.py:71-88.  Returns (index [K,3] int64, mconf [K], mask)."""
+    keep = conf > thr
+    if mutual:
+        row_best = conf.max(dim=2, keepdim=True)[0]
+        col_best = conf.max(dim=1, keepdim=True)[0]
+        keep = keep & (conf == row_best) & (conf == col_best)
+    index = keep.nonzero()
+    mconf = conf[index[:, 0], index[:, 1], index[:, 2]]
+    return index, mconf, keep
+
+
+def mutual_topk_select(score_mat, k, largest=True, threshold=None, mutual=True, reduce_result=True):
+    """2d3d vision3d/ops/mutual_topk_select.py:7-60 (copies 3d/models/matching.py:6-59,
+    3d/models/pipeline.py:12-65), with the hard-coded ``.cuda()`` of :34,:39 replaced by
+    the score matrix's own device so it runs on CPU."""
+    n_rows, n_cols = score_mat.shape
+    dev = score_mat.device
+    row_pick = score_mat.topk(k=k, largest=largest, dim=1)[1]            # [N,k]
+    row_hit = torch.zeros_like(score_mat, dtype=torch.bool)
+    row_hit[torch.arange(n_rows, device=dev)[:, None].expand(-1, k), row_pick] = True
+    col_pick = score_mat.topk(k=k, largest=largest, dim=0)[1]            # [k,M]
+    col_hit = torch.zeros_like(score_mat, dtype=torch.bool)
+    col_hit[col_pick, torch.arange(n_cols, device=dev)[None, :].expand(k, -1)] = True
+    corr = (row_hit & col_hit) if mutual else (row_hit | col_hit)
+    if threshold is not None:
+        corr = corr & ((score_mat > threshold) if largest else (score_mat < threshold))
+    if not reduce_result:
+        return corr
+    r, c = torch.nonzero(corr, as_tuple=True)
+    return r, c, score_mat[r, c]
+
+
+# --------------------------------------------------------------------------------------
+# matching head (a1, a1', a1'', a2, a3)
+# --------------------------------------------------------------------------------------
+@dataclass
+class MatchingParams:
+    """The learnable state of the reference ``Matching`` module (matching.py:43-68)."""
+    src_proj_weight: torch.Tensor            # [C,C]; applied to BOTH sides (:127-128)
+    bin_score: Optional[torch.Tensor] = None  # 0-dim, sinkhorn only
+    match_type: str = "sinkhorn"
+    skh_iters: int = 3
+    temperature: float = 0.1
+    confidence_threshold: float = 0.2
+    entangled: bool = True
+
+
+def similarity(p: MatchingParams, src_feats, tgt_feats, src_pe=None, tgt_pe=None):
+    """Projection, optional rotary PE, 1/sqrt(C) scaling and the contraction.
+
+    4d/models/matching.py:127-128,135-137,144-145,161.  Returns (sim, fs, ft, fs_nopos,
+    ft_nopos) where fs/ft are what the reference stores in ``data`` (:131-141).
+    """
+    W = p.src_proj_weight
+    fs_nopos = src_feats @ W.t()
+    ft_nopos = tgt_feats @ W.t()
+    fs, ft = fs_nopos, ft_nopos
+    if not p.entangled:
+        fs = embed_rotary(fs, src_pe[..., 0], src_pe[..., 1])
+        ft = embed_rotary(ft, tgt_pe[..., 0], tgt_pe[..., 1])
+    C = fs.shape[-1]
+    a = fs / C ** 0.5
+    b = ft / C ** 0.5
+    sim = torch.einsum("bsc,btc->bst", a, b)
+    return sim, fs, ft, fs_nopos, ft_nopos
+
+
+def confidence_from_similarity(p: MatchingParams, sim, src_mask, tgt_mask):
+    """Branches :147-157 (dual softmax) and :159-170 (sinkhorn) of 4d/models/matching.py."""
+    if p.match_type == "dual_softmax":
+        s = sim / p.temperature
+        s_rows = s.masked_fill(~src_mask[:, :, None], NEG_INF)   # invalid src rows
+        s_cols = s.masked_fill(~tgt_mask[:, None, :], NEG_INF)   # invalid tgt cols
+        return torch.softmax(s_rows, dim=1) * torch.softmax(s_cols, dim=2)
+    s = sim.masked_fill(~pair_mask(src_mask, tgt_mask), NEG_INF)
+    log_assign = log_optimal_transport(s, p.bin_score, p.skh_iters, src_mask, tgt_mask)
+    return log_assign.exp()[:, :-1, :-1].contiguous()
+
+
+def matching_forward_3d(p: MatchingParams, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask):
+    """``Matching.forward`` of the 3D flavour, 4d/models/matching.py:118-173.
+    Returns (conf [B,N,M], coarse_match [K,3] int64)."""
+    sim, *_ = similarity(p, src_feats, tgt_feats, src_pe, tgt_pe)
+    conf = confidence_from_similarity(p, sim, src_mask, tgt_mask)
+    idx, _, _ = get_match(conf, p.confidence_threshold)
+    return conf, idx
+
+
+def matching_forward_2d3d(p: MatchingParams, src_feats, tgt_feats, src_mask, tgt_mask, mutual=True):
+    """``Matching.forward`` of the 2D-3D flavour, 2d3d/matching.py:91-147.
+    Returns (conf [1,N,M], src_idx [K], tgt_idx [K], weights [K])."""
+    sim, *_ = similarity(p, src_feats, tgt_feats)
+    conf = confidence_from_similarity(p, sim, src_mask, tgt_mask)
+    r, c, w = mutual_topk_select(conf.squeeze(0), 1, largest=True, threshold=None, mutual=mutual)
+    return conf, r, c, w
+
+
+def matching_forward1_3d(p: MatchingParams, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, mutual=False):
+    """``Matching.forward1``, 3d/models/matching.py:221-283: top-1 row/col union as [K,3]."""
+    sim, *_ = similarity(p, src_feats, tgt_feats, src_pe, tgt_pe)
+    conf = confidence_from_similarity(p, sim, src_mask, tgt_mask)
+    r, c, _ = mutual_topk_select(conf.squeeze(0), 1, largest=True, threshold=None, mutual=mutual)
+    return conf, torch.stack((torch.zeros_like(r), r, c), dim=-1)
+
+
+# --------------------------------------------------------------------------------------
+# SoftProcrustes (a7, a8)
+# --------------------------------------------------------------------------------------
+def batch_weighted_procrustes(X, Y, w, eps=1e-4):
+    """Weighted Kabsch, 4d/models/procrustes.py:18-44.
+
+    X, Y: [B,K,3]; w: [B,K,1].  Returns (R [B,3,3] fp32, t [B,3,1], condition [B] fp64).
+    Note w is normalised by (sum|w| + eps), so the normalised weights sum to slightly
+    less than one and the centroids are slightly shrunk (:27-30)."""
+    B = X.shape[0]
+    total = w.abs().sum(dim=1, keepdim=True)
+    wn = w / (total + eps)
+    cx = (wn * X).sum(dim=1, keepdim=True)
+    cy = (wn * Y).sum(dim=1, keepdim=True)
+    S = (Y - cy).transpose(1, 2) @ (wn * (X - cx))                      # :34
+    U, D, V = torch.linalg.svd(S.double().cpu(), full_matrices=False)  # :35-36 (Vh here)
+    V = V.transpose(1, 2)
+    cond = D.max(dim=1)[0] / D.min(dim=1)[0]
+    fix = torch.eye(3, dtype=torch.float64).repeat(B, 1, 1)
+    fix[:, 2, 2] = torch.linalg.det(U) * torch.linalg.det(V)           # reflection fix :38-40
+    R = (U @ fix @ V.transpose(1, 2)).float().to(X.device)
+    t = cy.transpose(1, 2) - R @ cx.transpose(1, 2)
+    return R, t, cond
+
+
+def soft_procrustes(conf, src_pcd, tgt_pcd, src_mask, tgt_mask, sample_rate=1.0,
+                    max_condition_num=40.0, padded_lengths=False):
+    """``SoftProcrustesLayer.forward``, 4d/models/procrustes.py:48-93.
+
+    ``padded_lengths=True`` selects the 3d variant (3d/models/procrustes.py:61-62) that
+    uses the padded sizes instead of the mask sums.  Returns the reference's 6-tuple
+    (R, t, R_forwd, t_forwd, condition, solution_mask)."""
+    B, N, M = conf.shape
+    if padded_lengths:
+        src_len = torch.tensor([float(N)])
+        tgt_len = torch.tensor([float(M)])
+    else:
+        src_len = src_mask.sum(dim=1)
+        tgt_len = tgt_mask.sum(dim=1)
+    cap = (torch.maximum(src_len, tgt_len) * sample_rate).int()          # :63-64
+    K = int(cap.float().mean().int())                                    # :65
+    vals, flat = conf.reshape(B, -1).sort(descending=True, dim=1)        # :66 full sort
+    w = vals[:, :K].clone()
+    flat = flat[:, :K]
+    i_src = flat // M
+    i_tgt = flat % M
+    bidx = torch.arange(B)[:, None].expand(B, K)
+    P = src_pcd[bidx, i_src]
+    Q = tgt_pcd[bidx, i_tgt]
+    w[torch.arange(K)[None, :].expand(B, K) >= cap[:, None]] = 0.0       # :74-76
+    R, t, cond = batch_weighted_procrustes(P, Q, w[..., None])
+    ok = cond < max_condition_num                                        # :87
+    R_f, t_f = R.clone(), t.clone()
+    R_f[~ok] = torch.eye(3, dtype=R.dtype)
+    t_f[~ok] = torch.zeros(3, 1, dtype=R.dtype)
+    return R, t, R_f, t_f, cond, ok
+
+
+def warp_points(R, t, pts):
+    """(R p + t) for row-vector point sets, 4d/models/pipeline.py:220."""
+    return (R.float() @ pts.transpose(1, 2) + t.float()).transpose(1, 2)
+
+
+# --------------------------------------------------------------------------------------
+# diffusion schedule and DDIM update (a10)
+# --------------------------------------------------------------------------------------
+def alphas_cumprod(timesteps=1000, s=0.008):
+    """Cosine schedule, 4d/models/pipeline.py:24-34,97-99 (fp64 throughout)."""
+    x = torch.linspace(0, timesteps, timesteps + 1, dtype=torch.float64)
+    f = torch.cos(((x / timesteps) + s) / (1 + s) * math.pi * 0.5) ** 2
+    f = f / f[0]
+    betas = torch.clip(1 - (f[1:] / f[:-1]), 0, 0.999)
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+def time_pairs(sampling_steps, timesteps=1000):
+    """4d/models/pipeline.py:166-169: [(999,949),...,(49,0)] for 20 steps."""
+    ts = torch.linspace(0, timesteps - 1, steps=sampling_steps + 1)
+    ts = list(reversed(ts.int().tolist()))
+    return list(zip(ts[:-1], ts[1:]))
+
+
+def ddim_coefficients(ac, t, t_next, eta=1.0):
+    """Scalars of one reverse step as fp64 Python floats.
+
+    Returns (sqrt_recip, sqrt_recipm1, sqrt_alpha_next, c, sigma), see
+    4d/models/pipeline.py:101-104,182-186."""
+    a, an = ac[t], ac[t_next]
+    sigma = eta * ((1 - a / an) * (1 - an) / (1 - a)).sqrt()
+    c = (1 - an - sigma ** 2).sqrt()
+    return (float(torch.sqrt(1.0 / a)), float(torch.sqrt(1.0 / a - 1)), float(an.sqrt()),
+            float(c), float(sigma))
+
+
+def ddim_update(x_t, x0, ac, t, t_next, noise=None, eta=1.0):
+    """pred_noise (:201-205) and the x update (:190 with noise; 3d :256 / 2d3d :678 without).
+
+    Reproduces the fp64 promotion (Q4): the schedule buffers are fp64 so the result is
+    fp64 whatever the input dtype."""
+    r = torch.sqrt(1.0 / ac[t]).reshape(1, 1, 1)
+    rm1 = torch.sqrt(1.0 / ac[t] - 1).reshape(1, 1, 1)
+    pred = (r * x_t - x0) / rm1
+    a, an = ac[t], ac[t_next]
+    sigma = eta * ((1 - a / an) * (1 - an) / (1 - a)).sqrt()
+    c = (1 - an - sigma ** 2).sqrt()
+    out = x0 * an.sqrt() + c * pred
+    if noise is not None:
+        out = out + sigma * noise
+    return out
+
+
+def noisy_matching_to_pose(x, alpha, iters, s_pcd, t_pcd, src_mask, tgt_mask,
+                           sample_rate=1.0, max_condition_num=40.0, padded_lengths=False):
+    """``get_warped_from_noising_matching`` 4d/models/pipeline.py:207-223 (3d :293-309,
+    2d3d model.py:830-846).  Mutates ``x`` in place (Q7).  Returns (src_warped, conf, pose6)."""
+    x.masked_fill_(~pair_mask(src_mask, tgt_mask), NEG_INF)
+    conf = log_optimal_transport(x, alpha, iters, src_mask, tgt_mask).exp()[:, :-1, :-1].contiguous().float()
+    pose = soft_procrustes(conf, s_pcd, t_pcd, src_mask, tgt_mask, sample_rate, max_condition_num, padded_lengths)
+    return warp_points(pose[2], pose[3], s_pcd), conf, pose
+
+
+def sampler(flavour, p: MatchingParams, src_feats, tgt_feats, s_pcd, t_pcd, src_mask, tgt_mask,
+            x_T, steps, noises=None, sample_rate=1.0, max_condition_num=40.0,
+            tgt_mask_pose=None, t_pcd_pose=None, state_dtype=None, trace=None):
+    """Reverse-diffusion loop with the denoising transformer replaced by FIXED features.
+
+    flavour '4d'  : 4d/models/pipeline.py:171-192   (sigma*noise term, final sigmoid)
+    flavour '3d'  : 3d/models/pipeline.py:235-278   (x -= x.min() first, no noise, final
+                                                    Sinkhorn + top-1 row/col union)
+    flavour '2d3d': 2d3d/model.py:651-694           (no noise, final Sinkhorn + top-1 union;
+                                                    pose step matches against t_pcd_pose with
+                                                    tgt_mask_pose)
+    ``state_dtype=torch.float32`` casts the state back to fp32 after every update (what the
+    CUDA path does); ``None`` keeps the reference's fp64 creep (Q4).
+    Returns a dict with the final matrix, matches and the last pose.
+    """
+    ac = alphas_cumprod()
+    x = x_T.clone()
+    out = {}
+    pose_mask = tgt_mask if tgt_mask_pose is None else tgt_mask_pose
+    pose_pcd = t_pcd if t_pcd_pose is None else t_pcd_pose
+    for k, (t, t_next) in enumerate(time_pairs(steps)):
+        if flavour == "3d":
+            x = x - x.min()
+        warped, conf_d, pose = noisy_matching_to_pose(
+            x, p.bin_score, p.skh_iters, s_pcd, pose_pcd, src_mask, pose_mask,
+            sample_rate, max_condition_num, padded_lengths=(flavour == "3d"))
+        sim, *_ = similarity(p, src_feats, tgt_feats)
+        x0 = confidence_from_similarity(p, sim, src_mask, tgt_mask)
+        if flavour != "2d3d":
+            get_match(x0, p.confidence_threshold)       # computed and discarded (:172 / :178)
+        else:
+            mutual_topk_select(x0.squeeze(0), 1, True, None, True)
+        noise = noises[k] if (flavour == "4d" and noises is not None) else None
+        x_prev = x
+        x = ddim_update(x, x0, ac, t, t_next, noise)
+        if state_dtype is not None:
+            x = x.to(state_dtype)
+        if trace is not None:
+            trace.append({"x_in": x_prev, "conf_d": conf_d, "pose": pose, "warped": warped,
+                          "x0": x0, "x_out": x})
+        out["pose"] = pose
+    if flavour == "4d":
+        out["conf_matrix_pred"] = torch.sigmoid(x)
+    else:
+        s = x - x.min() if flavour == "3d" else x
+        s = s.masked_fill(~pair_mask(src_mask, tgt_mask), NEG_INF)
+        conf = log_optimal_transport(s, p.bin_score, p.skh_iters, src_mask, tgt_mask).exp()[:, :-1, :-1].contiguous()
+        r, c, w = mutual_topk_select(conf.squeeze(0), 1, True, None, False)
+        out["conf_matrix_pred"] = conf
+        out["match_pred"] = torch.stack((torch.zeros_like(r), r, c), dim=-1)
+        out["match_weights"] = w
+    out["x_final"] = x
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# synthetic inputs shared by tests, smoke() and bench.py
+# --------------------------------------------------------------------------------------
+def random_rotation(gen):
+    q = torch.randn(4, generator=gen)
+    q = q / q.norm()
+    w, x, y, z = q.tolist()
+    return torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def make_problem(seed, B, N, M, C=256, prefix_valid=None, arbitrary_invalid=0.0):
+    """Seeded synthetic pair(s): unit-normal features, nn.Linear-style projection weight,
+    points related by a random rigid motion plus 1 % noise, masks (all true / prefix /
+    arbitrary)."""
+    g = torch.Generator().manual_seed(seed)
+    src_feats = torch.randn(B, N, C, generator=g)
+    tgt_feats = torch.randn(B, M, C, generator=g)
+    bound = 1.0 / math.sqrt(C)
+    W = (torch.rand(C, C, generator=g) * 2 - 1) * bound
+    s_pcd = torch.randn(B, N, 3, generator=g)
+    t_pcd = torch.empty(B, M, 3)
+    for b in range(B):
+        R = random_rotation(g)
+        t = torch.randn(3, generator=g)
+        perm = torch.randint(0, N, (M,), generator=g)
+        t_pcd[b] = s_pcd[b, perm] @ R.t() + t + 0.01 * torch.randn(M, 3, generator=g)
+    src_mask = torch.ones(B, N, dtype=torch.bool)
+    tgt_mask = torch.ones(B, M, dtype=torch.bool)
+    if prefix_valid is not None:
+        for b, (ns, nt) in enumerate(prefix_valid):
+            src_mask[b, ns:] = False
+            tgt_mask[b, nt:] = False
+            src_feats[b, ns:] = 0
+            tgt_feats[b, nt:] = 0
+            s_pcd[b, ns:] = 0
+            t_pcd[b, nt:] = 0
+    if arbitrary_invalid > 0:
+        src_mask &= torch.rand(B, N, generator=g) >= arbitrary_invalid
+        tgt_mask &= torch.rand(B, M, generator=g) >= arbitrary_invalid
+    return dict(src_feats=src_feats, tgt_feats=tgt_feats, W=W, s_pcd=s_pcd, t_pcd=t_pcd,
+                src_mask=src_mask, tgt_mask=tgt_mask)
