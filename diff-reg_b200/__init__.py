@@ -1,0 +1,32 @@
+"""diffreg_b200 -- B200 (sm_100a) kernels for Diff-Reg's per-step coarse matching-matrix
+update, behind the reference's own PyTorch module API.
+
+Public surface (mirrors the reference):
+    Matching, log_optimal_transport, mutual_topk_select      (matching.py)
+    Matching2D3D                                             (2D-3D flavour head)
+    SoftProcrustesLayer                                      (procrustes.py)
+    DenoisingSampler                                         (fused per-step driver)
+Everything computes through libdiffreg_b200.so (C ABI, include/diffreg_b200.h).  There is
+no CPU or eager-PyTorch fallback: a missing library or a non-CUDA tensor raises.
+"""
+from . import _lib  # noqa: F401
+from ._lib import library_path, load_library, launch_count  # noqa: F401
+
+__all__ = ["library_path", "load_library", "launch_count"]
+
+
+def __getattr__(name):
+    # lazy: the modules below import torch
+    if name in ("Matching", "Matching2D3D", "log_optimal_transport", "mutual_topk_select"):
+        from . import matching
+        return getattr(matching, name)
+    if name == "SoftProcrustesLayer":
+        from . import procrustes
+        return procrustes.SoftProcrustesLayer
+    if name in ("DenoisingSampler",):
+        from . import sampler
+        return getattr(sampler, name)
+    if name == "ops":
+        import importlib
+        return importlib.import_module(__name__ + ".ops")
+    raise AttributeError(name)

@@ -1,0 +1,66 @@
+"""ctypes binding of libdiffreg_b200.so (the C ABI in include/diffreg_b200.h)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libdiffreg_b200.so")
+_lib = None
+
+DRG_OUT_LOG_FULL, DRG_OUT_CONF, DRG_OUT_DDIM, DRG_OUT_NONE = 0, 1, 2, 3
+
+c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+
+class SinkhornArgs(ctypes.Structure):
+    """struct drg_sinkhorn_args"""
+    _fields_ = [
+        ("scores", c_void_p), ("src_mask", c_void_p), ("tgt_mask", c_void_p), ("alpha", c_void_p), ("shift", c_void_p),
+        ("B", c_int), ("N", c_int), ("M", c_int), ("iters", c_int), ("apply_mask", c_int),
+        ("out_mode", c_int), ("out", c_void_p), ("u", c_void_p), ("v", c_void_p),
+        ("x_t", c_void_p), ("noise", c_void_p), ("conf", c_void_p),
+        ("k_x0", c_float), ("k_xt", c_float), ("sigma", c_float), ("x_min", c_void_p),
+    ]
+
+
+class DiffRegLibraryError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def _declare(lib):
+    lib.drg_version.restype = c_int
+    lib.drg_last_error.restype = ctypes.c_char_p
+    lib.drg_launch_count.restype = ctypes.c_ulonglong
+    lib.drg_sinkhorn_workspace_bytes.restype = c_size_t
+    lib.drg_sinkhorn_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.drg_sinkhorn.restype = c_int
+    lib.drg_sinkhorn.argtypes = [ctypes.POINTER(SinkhornArgs), c_void_p, c_size_t, c_void_p]
+    lib.drg_dual_softmax.restype = c_int
+    lib.drg_dual_softmax.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                     c_size_t, c_void_p]
+    return lib
+
+
+def load_library():
+    """Load the CUDA library.  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise DiffRegLibraryError(
+                f"{_LIB_PATH} not found: build it with `python diff-reg_b200/build.py` "
+                "(or __graft_entry__.build()); diffreg_b200 has no CPU / eager fallback")
+        _lib = _declare(ctypes.CDLL(_LIB_PATH))
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = load_library().drg_last_error().decode()
+        raise DiffRegLibraryError(f"diffreg_b200 error {status}: {msg}")
+
+
+def launch_count():
+    return int(load_library().drg_launch_count())

@@ -1,0 +1,846 @@
+// Fused log-domain Sinkhorn (dustbin row/column, masked padding), dual-softmax statistics
+// and the final exp / DDIM pass.  sm_100a.
+//
+// Replaces log_optimal_transport (Diff-Reg-4dmatch/models/matching.py:6-38) and its
+// consumers; see include/diffreg_b200.h.
+//
+// Layout in HBM: scores [B,N,M] fp32 row-major, never copied into an (N+1)x(M+1) matrix --
+// the dustbin row and column are the constant alpha and are handled analytically.
+//
+// One Sinkhorn iteration = ONE read of the score matrix:
+//   skh_iter_kernel   persistent CTAs, each owns a contiguous range of R-row slabs.  A slab
+//                     (R x M fp32, one contiguous chunk) is brought into shared memory by a
+//                     single TMA bulk copy (cp.async.bulk + mbarrier, 2-3 stages in flight).
+//                     From shared memory the CTA computes (a) the row log-sum-exp of
+//                     Z + v  ->  u_i, and then, with the fresh u_i, (b) this slab's
+//                     contribution to every column's log-sum-exp of Z + u, kept as
+//                     per-thread (max, sum) register accumulators over all the CTA's slabs.
+//   skh_col_kernel    merges the G per-CTA column partials (+ the dustbin row term) into v.
+// All log-sum-exps are carried in the log2 domain so that each element costs one FFMA
+// and one MUFU.EX2 per direction.
+#include "common.cuh"
+
+namespace drg {
+
+constexpr int SKH_THREADS = 512;
+constexpr int SKH_WARPS = SKH_THREADS / 32;
+constexpr int SKH_STAGE_FLOATS = 16384;  // R * M <= 16384 floats (64 KB) per stage
+constexpr int SKH_MAX_M = 16384;
+constexpr size_t SKH_SMEM_LIMIT = 227 * 1024;
+
+struct SkhConst {  // per batch element, written by skh_prep_kernel
+  float norm;        // -log(ms + ns)
+  float log_mu_bin;  // log(ns) + norm
+  float log_nu_bin;  // log(ms) + norm
+  float pad;
+};
+
+struct SkhParams {
+  const float* scores;
+  const uint8_t* src_mask;
+  const uint8_t* tgt_mask;
+  const float* alpha;
+  const float* shift;
+  float* u;         // [B, N+1]
+  float* v;         // [B, M+1]
+  float2* colpart;  // [B, G, M]   (max, sum) in the log2 domain
+  float2* upart;    // [B, G]
+  const SkhConst* bc;
+  int B, N, M, G;
+  int ldu, ldv;  // row pitch of u / v (multiples of 4 floats)
+  int apply_mask;
+  int dual;       // 1: dual-softmax statistics (no dustbins, no potentials)
+  float zscale2;  // log2(e) (Sinkhorn) or log2(e)/temperature (dual softmax)
+  int nstage;
+};
+
+// ---------------------------------------------------------------------------------------
+// prep: mask counts -> constants; v = 0
+// ---------------------------------------------------------------------------------------
+__global__ void skh_prep_kernel(const uint8_t* __restrict__ src_mask, const uint8_t* __restrict__ tgt_mask, int N, int M,
+                                SkhConst* __restrict__ bc, float* __restrict__ v, float* __restrict__ u, int ldu, int ldv) {
+  const int b = blockIdx.x;
+  __shared__ int cnt[2];
+  if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int cs = 0, ct = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) cs += src_mask[(size_t)b * N + i] ? 1 : 0;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) ct += tgt_mask[(size_t)b * M + j] ? 1 : 0;
+  cs = __reduce_add_sync(0xffffffffu, cs);
+  ct = __reduce_add_sync(0xffffffffu, ct);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&cnt[0], cs);
+    atomicAdd(&cnt[1], ct);
+  }
+  for (int j = threadIdx.x; j <= M; j += blockDim.x) v[(size_t)b * ldv + j] = 0.f;
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) u[(size_t)b * ldu + i] = 0.f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // reference: norm = -(ms+ns).log() on int64 -> fp32 (matching.py:24); ns.log() + norm (:26-27)
+    float ms = (float)cnt[0], ns = (float)cnt[1];
+    float norm = -logf(ms + ns);
+    SkhConst c;
+    c.norm = norm;
+    c.log_mu_bin = logf(ns) + norm;
+    c.log_nu_bin = logf(ms) + norm;
+    c.pad = 0.f;
+    bc[b] = c;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// one Sinkhorn iteration over the score matrix
+// ---------------------------------------------------------------------------------------
+template <int R, int KQ, bool VEC>
+__global__ void __launch_bounds__(SKH_THREADS, 1) skh_iter_kernel(const SkhParams p) {
+  constexpr int SEG = SKH_WARPS / R;  // warps cooperating on one row
+  static_assert(SEG >= 1 && SEG * R == SKH_WARPS, "R must divide the warp count");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+
+  const int N = p.N, M = p.M;
+  const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  const int nslab = (N + R - 1) / R;
+  const int s_begin = (int)(((long long)nslab * g) / G);
+  const int s_end = (int)(((long long)nslab * (g + 1)) / G);
+  const int nstage = p.nstage;
+
+  // ---- shared memory carve-up
+  const int Mv = (M + 1 + 3) & ~3;            // v2 vector, index M = dustbin column term
+  const int stage_floats = ((R * M) + 3) & ~3;
+  float* v2_s = reinterpret_cast<float*>(smem_raw);
+  float* stage0 = v2_s + Mv;
+  float* after = stage0 + (size_t)nstage * stage_floats;
+  float2* rowpart = reinterpret_cast<float2*>(after);  // [R][SEG]
+  float* u2_s = reinterpret_cast<float*>(rowpart + R * SEG);  // [R]
+  float* red_s = u2_s + R;                                      // [2*SKH_WARPS] scratch
+  uint64_t* full = reinterpret_cast<uint64_t*>(red_s + 2 * SKH_WARPS + ((R & 1) ? 1 : 0));  // 8-byte aligned
+
+  const float* sc_b = p.scores + (size_t)b * N * M;
+  const SkhConst bc = p.bc[b];
+  const float zs = p.zscale2;
+  const float shift = p.shift ? *p.shift : 0.f;
+
+  if (tid == 0) {
+    for (int s = 0; s < nstage; ++s) mbar_init(&full[s], VEC ? 1u : (uint32_t)SKH_THREADS);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // ---- producer: bring slab `s` into stage `st`
+  auto issue_slab = [&](int s, int st) {
+    const int i0 = s * R;
+    const int rows = min(R, N - i0);
+    const float* src = sc_b + (size_t)i0 * M;
+    float* dst = stage0 + (size_t)st * stage_floats;
+    if constexpr (VEC) {
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)M * 4u;
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&full[st], bytes);
+        tma_bulk_g2s(dst, src, bytes, &full[st]);
+      }
+    } else {
+      const int n = rows * M;
+      for (int e = tid; e < n; e += SKH_THREADS) cp_async_4(dst + e, src + e);
+      cp_async_mbar_arrive_noinc(&full[st]);
+    }
+  };
+  for (int k = 0; k < nstage; ++k)
+    if (s_begin + k < s_end) issue_slab(s_begin + k, k);
+
+  // ---- prologue: column potentials into shared memory (log2 domain), dustbin-row potential
+  float uN = 0.f;       // u of the dustbin row for this iteration
+  float uN2 = NEG_BIG;  // its log2-domain value used in the dustbin-column partial
+  if (!p.dual) {
+    const float* v_b = p.v + (size_t)b * p.ldv;
+    const float alpha = *p.alpha;
+    // LSE over v[0..M] (block reduction), needed for the dustbin row: r_N = alpha + LSE(v)
+    float mloc = NEG_BIG;
+    for (int j = tid; j <= M; j += SKH_THREADS) mloc = fmaxf(mloc, v_b[j] * LOG2E);
+    mloc = warp_max(mloc);
+    if (lane == 0) red_s[warp] = mloc;
+    __syncthreads();
+    float mall = red_s[0];
+#pragma unroll
+    for (int w = 1; w < SKH_WARPS; ++w) mall = fmaxf(mall, red_s[w]);
+    float sloc = 0.f;
+    for (int j = tid; j <= M; j += SKH_THREADS) {
+      const float vj = v_b[j];
+      sloc += ex2(vj * LOG2E - mall);
+      float v2;
+      if (j < M) {
+        v2 = (vj - shift) * LOG2E;
+        if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
+      } else {
+        v2 = (alpha + vj) * LOG2E;  // dustbin column entry of every real row: alpha + v_M
+      }
+      v2_s[j] = v2;
+    }
+    sloc = warp_sum(sloc);
+    if (lane == 0) red_s[SKH_WARPS + warp] = sloc;
+    __syncthreads();
+    float sall = 0.f;
+#pragma unroll
+    for (int w = 0; w < SKH_WARPS; ++w) sall += red_s[SKH_WARPS + w];
+    const float vlse = (mall + lg2(sall)) * LN2;
+    uN = bc.log_mu_bin - (alpha + vlse);
+    uN2 = uN * LOG2E;
+    if (g == 0 && tid == 0) p.u[(size_t)b * p.ldu + N] = uN;
+  } else {
+    for (int j = tid; j < M; j += SKH_THREADS)
+      v2_s[j] = (p.tgt_mask[(size_t)b * M + j]) ? 0.f : -INFINITY;
+    if (tid == 0) v2_s[M] = -INFINITY;
+  }
+  for (int j = M + 1 + tid; j < Mv; j += SKH_THREADS) v2_s[j] = -INFINITY;
+  __syncthreads();
+
+  // ---- per-thread column accumulators (log2 domain)
+  float cm[KQ * 4], cs[KQ * 4];
+#pragma unroll
+  for (int e = 0; e < KQ * 4; ++e) {
+    cm[e] = NEG_BIG;
+    cs[e] = 0.f;
+  }
+  LseAcc uacc = lse_empty();  // threads < R: running LSE of the u_i they produced (dustbin column)
+
+  const int seg_len = VEC ? ((((M + SEG - 1) / SEG) + 127) & ~127) : ((((M + SEG - 1) / SEG) + 31) & ~31);
+
+  for (int s = s_begin; s < s_end; ++s) {
+    const int it = s - s_begin;
+    const int st = it % nstage;
+    const uint32_t parity = (uint32_t)((it / nstage) & 1);
+    const float* slab = stage0 + (size_t)st * stage_floats;
+    const int i0 = s * R;
+    const int rows = min(R, N - i0);
+
+    mbar_wait(&full[st], parity);
+
+    // ---- (a) row pass: warp -> (row r, segment seg)
+    {
+      const int r = warp / SEG, seg = warp % SEG;
+      // with the fused mask a padded src row holds only its dustbin entry
+      const bool row_live = (r < rows) && !(p.apply_mask && !p.dual && !p.src_mask[(size_t)b * N + i0 + r]);
+      if (r < rows && !row_live) {
+        if (lane == 0) rowpart[r * SEG + seg] = make_float2(NEG_BIG, 0.f);
+      } else if (r < rows) {
+        const float* row = slab + (size_t)r * M;
+        const int c0 = seg * seg_len;
+        const int c1 = min(M, c0 + seg_len);
+        float xs[32];
+        float m = NEG_BIG;
+        if constexpr (VEC) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = c0 + 4 * lane + 128 * k;
+            if (c < c1) {
+              const float4 z = *reinterpret_cast<const float4*>(row + c);
+              const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+              xs[4 * k + 0] = fmaf(z.x, zs, vv.x);
+              xs[4 * k + 1] = fmaf(z.y, zs, vv.y);
+              xs[4 * k + 2] = fmaf(z.z, zs, vv.z);
+              xs[4 * k + 3] = fmaf(z.w, zs, vv.w);
+              m = fmaxf(m, fmaxf(fmaxf(xs[4 * k], xs[4 * k + 1]), fmaxf(xs[4 * k + 2], xs[4 * k + 3])));
+            } else {
+              xs[4 * k + 0] = xs[4 * k + 1] = xs[4 * k + 2] = xs[4 * k + 3] = -INFINITY;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const int c = c0 + lane + 32 * k;
+            if (c < c1) {
+              xs[k] = fmaf(row[c], zs, v2_s[c]);
+              m = fmaxf(m, xs[k]);
+            } else {
+              xs[k] = -INFINITY;
+            }
+          }
+        }
+        m = warp_max(m);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) sum += ex2(xs[k] - m);
+        sum = warp_sum(sum);
+        if (lane == 0) rowpart[r * SEG + seg] = make_float2(m, sum);
+      }
+    }
+    __syncthreads();
+
+    // ---- (b) one thread per row merges the segments (+ dustbin column entry) -> u_i
+    if (tid < R) {
+      const int r = tid;
+      float u2 = -INFINITY;
+      if (r < rows) {
+        const int i = i0 + r;
+        LseAcc a = lse_empty();
+#pragma unroll
+        for (int sg = 0; sg < SEG; ++sg) {
+          const float2 ps = rowpart[r * SEG + sg];
+          lse_merge(a, ps.x, ps.y);
+        }
+        float ui;
+        if (!p.dual) {
+          lse_add_value(a, v2_s[M]);  // alpha + v_M
+          ui = bc.norm - lse_value(a) * LN2;
+        } else {
+          ui = -lse_value(a) * LN2;  // -(row log-sum-exp), natural log
+        }
+        p.u[(size_t)b * p.ldu + i] = ui;
+        const bool src_ok = (!p.apply_mask && !p.dual) || p.src_mask[(size_t)b * N + i];
+        if (!p.dual) {
+          lse_add_value(uacc, ui * LOG2E);
+          u2 = src_ok ? (ui - shift) * LOG2E : -INFINITY;  // column pass sees (S - shift) + u
+        } else {
+          u2 = src_ok ? 0.f : -INFINITY;
+        }
+      }
+      u2_s[r] = u2;
+    }
+    __syncthreads();
+
+    // ---- (c) column pass: thread -> KQ column quads, all R rows of the slab
+    {
+      float u2r[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) u2r[r] = u2_s[r];  // rows beyond `rows` hold -inf
+#pragma unroll
+      for (int k = 0; k < KQ; ++k) {
+        if constexpr (VEC) {
+          const int c = 4 * (tid + SKH_THREADS * k);
+          if (c < M) {
+            float x[R][4];
+            float mx[4] = {NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG};
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              if (r < rows) {
+                const float4 z = *reinterpret_cast<const float4*>(slab + (size_t)r * M + c);
+                x[r][0] = fmaf(z.x, zs, u2r[r]);
+                x[r][1] = fmaf(z.y, zs, u2r[r]);
+                x[r][2] = fmaf(z.z, zs, u2r[r]);
+                x[r][3] = fmaf(z.w, zs, u2r[r]);
+              } else {
+                x[r][0] = x[r][1] = x[r][2] = x[r][3] = -INFINITY;
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) mx[e] = fmaxf(mx[e], x[r][e]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float& am = cm[4 * k + e];
+              float& as = cs[4 * k + e];
+              if (mx[e] > am + 32.f) {  // lazy re-reference: rare after the first slab
+                as *= ex2(am - mx[e]);
+                am = mx[e];
+              }
+              float acc = 0.f;
+#pragma unroll
+              for (int r = 0; r < R; ++r) acc += ex2(x[r][e] - am);
+              as += acc;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = tid + SKH_THREADS * (4 * k + e);
+            if (c < M) {
+              float x[R];
+              float mx = NEG_BIG;
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                x[r] = (r < rows) ? fmaf(slab[(size_t)r * M + c], zs, u2r[r]) : -INFINITY;
+                mx = fmaxf(mx, x[r]);
+              }
+              float& am = cm[4 * k + e];
+              float& as = cs[4 * k + e];
+              if (mx > am + 32.f) {
+                as *= ex2(am - mx);
+                am = mx;
+              }
+              float acc = 0.f;
+#pragma unroll
+              for (int r = 0; r < R; ++r) acc += ex2(x[r] - am);
+              as += acc;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with stage `st`
+    if (s + nstage < s_end) issue_slab(s + nstage, st);
+  }
+
+  // ---- write this CTA's column partials
+  float2* cp = p.colpart + ((size_t)b * G + g) * M;
+#pragma unroll
+  for (int k = 0; k < KQ; ++k) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = VEC ? (4 * (tid + SKH_THREADS * k) + e) : (tid + SKH_THREADS * (4 * k + e));
+      if (c < M) cp[c] = make_float2(cm[4 * k + e], cs[4 * k + e]);
+    }
+  }
+  // dustbin-column partial: LSE of this CTA's u_i (threads < R hold disjoint rows)
+  if (!p.dual) {
+    __syncthreads();
+    if (tid < R) rowpart[tid] = make_float2(uacc.m, uacc.s);
+    __syncthreads();
+    if (tid == 0) {
+      LseAcc a = lse_empty();
+      for (int r = 0; r < R; ++r) lse_merge(a, rowpart[r].x, rowpart[r].y);
+      p.upart[(size_t)b * G + g] = make_float2(a.m, a.s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// merge the per-CTA column partials into v (and the dustbin column entry v_M)
+//   block = 32 columns x 8 slices of the G partials; every thread first pulls its <= 19
+//   partials into registers (all loads in flight at once), reduces them with one ex2 each,
+//   then the 8 slices are merged through shared memory.
+// ---------------------------------------------------------------------------------------
+constexpr int COL_SLICES = 8;
+constexpr int COL_MAXG = (NUM_SMS + COL_SLICES - 1) / COL_SLICES;  // 19
+
+__global__ void __launch_bounds__(256) skh_col_kernel(const SkhParams p) {
+  const int b = blockIdx.y;
+  const int jj = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jj;
+  const int M = p.M, N = p.N, G = p.G;
+  __shared__ float2 part_s[COL_SLICES][32];
+
+  LseAcc a = lse_empty();
+  const bool in_range = (j <= M) && !(p.dual && j == M);
+  if (in_range) {
+    const bool is_bin = (j == M);
+    const bool col_ok = is_bin || p.dual || !p.apply_mask || p.tgt_mask[(size_t)b * M + j];
+    if (col_ok) {
+      const float2* src = is_bin ? (p.upart + (size_t)b * G) : (p.colpart + (size_t)b * G * M + j);
+      const size_t gstride = is_bin ? 1 : (size_t)M;
+      float2 q[COL_MAXG];
+      float m = NEG_BIG;
+#pragma unroll
+      for (int k = 0; k < COL_MAXG; ++k) {
+        const int g = sl + COL_SLICES * k;
+        q[k] = (g < G) ? src[(size_t)g * gstride] : make_float2(NEG_BIG, 0.f);
+        m = fmaxf(m, q[k].x);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < COL_MAXG; ++k) sum += q[k].y * ex2(q[k].x - m);
+      a.m = m;
+      a.s = sum;
+    }
+  }
+  part_s[sl][jj] = make_float2(a.m, a.s);
+  __syncthreads();
+  if (sl != 0 || !in_range) return;
+
+  float m = part_s[0][jj].x;
+#pragma unroll
+  for (int k = 1; k < COL_SLICES; ++k) m = fmaxf(m, part_s[k][jj].x);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < COL_SLICES; ++k) sum += part_s[k][jj].y * ex2(part_s[k][jj].x - m);
+  a.m = m;
+  a.s = sum;
+
+  float* v_b = p.v + (size_t)b * p.ldv;
+  if (p.dual) {
+    v_b[j] = -lse_value(a) * LN2;
+    return;
+  }
+  const SkhConst bc = p.bc[b];
+  const float alpha = *p.alpha;
+  const float uN = p.u[(size_t)b * p.ldu + N];
+  if (j < M) {
+    lse_add_value(a, (alpha + uN) * LOG2E);  // dustbin row entry
+    v_b[j] = bc.norm - lse_value(a) * LN2;
+  } else {
+    lse_add_value(a, uN * LOG2E);  // c_M = alpha + LSE(u[0..N])
+    v_b[M] = bc.log_nu_bin - (alpha + lse_value(a) * LN2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// final pass
+// ---------------------------------------------------------------------------------------
+struct SkhFinalParams {
+  const float* scores;
+  const uint8_t* src_mask;
+  const uint8_t* tgt_mask;
+  const float* alpha;
+  const float* shift;
+  const float* u;
+  const float* v;
+  const SkhConst* bc;
+  int B, N, M;
+  int ldu, ldv;
+  int apply_mask;
+  int mode;  // DRG_OUT_* ; 100 = dual softmax product
+  float* out;
+  const float* x_t;
+  const float* noise;
+  float* conf;
+  float k_x0, k_xt, sigma;
+  float* x_min;
+  float inv_temp;  // dual softmax
+};
+
+__device__ __forceinline__ void atomic_min_float(float* addr, float value) {
+  if (value >= 0.f)
+    atomicMin(reinterpret_cast<int*>(addr), __float_as_int(value));
+  else
+    atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(value));
+}
+
+// full (N+1)x(M+1) log-assignment (API parity with log_optimal_transport); odd row pitch -> scalar IO
+__global__ void __launch_bounds__(256) skh_final_full_kernel(const SkhFinalParams p) {
+  const int b = blockIdx.y;
+  const int N = p.N, M = p.M;
+  const SkhConst bc = p.bc[b];
+  const float alpha = *p.alpha;
+  const float shift = p.shift ? *p.shift : 0.f;
+  const float* u_b = p.u + (size_t)b * p.ldu;
+  const float* v_b = p.v + (size_t)b * p.ldv;
+  for (int i = blockIdx.x; i <= N; i += gridDim.x) {
+    const float ui = u_b[i];
+    const bool row_ok = (i < N) && (!p.apply_mask || p.src_mask[(size_t)b * N + i]);
+    const float* z = p.scores + ((size_t)b * N + i) * M;
+    float* o = p.out + ((size_t)b * (N + 1) + i) * (M + 1);
+    for (int j = threadIdx.x; j <= M; j += blockDim.x) {
+      float zz;
+      if (i < N && j < M) {
+        zz = z[j] - shift;
+        if (p.apply_mask && !(row_ok && p.tgt_mask[(size_t)b * M + j])) zz = -INFINITY;
+      } else {
+        zz = alpha;
+      }
+      o[j] = ((zz + ui) + v_b[j]) - bc.norm;  // same association as matching.py:34-36
+    }
+  }
+}
+
+// N x M outputs: conf / DDIM / dual-softmax product.  VEC: M % 4 == 0 and 16-byte aligned bases.
+template <bool VEC>
+__global__ void __launch_bounds__(256) skh_final_kernel(const SkhFinalParams p) {
+  const int b = blockIdx.y;
+  const int N = p.N, M = p.M;
+  const SkhConst bc = p.bc[b];
+  const float shift = p.shift ? *p.shift : 0.f;
+  const float* u_b = p.u + (size_t)b * p.ldu;
+  const float* v_b = p.v + (size_t)b * p.ldv;
+  const bool dual = (p.mode == 100);
+  const bool ddim = (p.mode == DRG_OUT_DDIM);
+  float local_min = INFINITY;
+
+  auto one = [&](float z, float ui, float vj, bool ok, float xt, float nz, float& conf_out) -> float {
+    float conf;
+    if (dual) {
+      conf = ok ? ex2((2.f * z * p.inv_temp + ui + vj) * LOG2E) : 0.f;
+      conf_out = conf;
+      return conf;
+    }
+    const float zz = ok ? (z - shift) : -INFINITY;
+    const float la = ((zz + ui) + vj) - bc.norm;
+    conf = ex2(la * LOG2E);
+    conf_out = conf;
+    if (!ddim) return conf;
+    float xn = ok ? fmaf(p.k_x0, conf, fmaf(p.k_xt, xt - shift, p.sigma * nz)) : -INFINITY;
+    if (ok && xn > -INFINITY) local_min = fminf(local_min, xn);
+    return xn;
+  };
+
+  for (int i = blockIdx.x; i < N; i += gridDim.x) {
+    const float ui = u_b[i];
+    const bool row_ok = (!p.apply_mask && !dual) || p.src_mask[(size_t)b * N + i];
+    const size_t base = ((size_t)b * N + i) * M;
+    if constexpr (VEC) {
+      for (int j = 4 * threadIdx.x; j < M; j += 4 * blockDim.x) {
+        const float4 z = *reinterpret_cast<const float4*>(p.scores + base + j);
+        const float4 vj = *reinterpret_cast<const float4*>(v_b + j);
+        bool ok[4] = {row_ok, row_ok, row_ok, row_ok};
+        if (p.apply_mask || dual) {
+          const uchar4 tm = *reinterpret_cast<const uchar4*>(p.tgt_mask + (size_t)b * M + j);
+          ok[0] = row_ok && tm.x;
+          ok[1] = row_ok && tm.y;
+          ok[2] = row_ok && tm.z;
+          ok[3] = row_ok && tm.w;
+        }
+        float4 xt = make_float4(0.f, 0.f, 0.f, 0.f), nz = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ddim) {
+          xt = *reinterpret_cast<const float4*>(p.x_t + base + j);
+          if (p.noise) nz = *reinterpret_cast<const float4*>(p.noise + base + j);
+        }
+        float4 o, c;
+        o.x = one(z.x, ui, vj.x, ok[0], xt.x, nz.x, c.x);
+        o.y = one(z.y, ui, vj.y, ok[1], xt.y, nz.y, c.y);
+        o.z = one(z.z, ui, vj.z, ok[2], xt.z, nz.z, c.z);
+        o.w = one(z.w, ui, vj.w, ok[3], xt.w, nz.w, c.w);
+        *reinterpret_cast<float4*>(p.out + base + j) = o;
+        if (ddim && p.conf) *reinterpret_cast<float4*>(p.conf + base + j) = c;
+      }
+    } else {
+      for (int j = threadIdx.x; j < M; j += blockDim.x) {
+        bool ok = row_ok;
+        if (p.apply_mask || dual) ok = row_ok && p.tgt_mask[(size_t)b * M + j];
+        const float xt = ddim ? p.x_t[base + j] : 0.f;
+        const float nz = (ddim && p.noise) ? p.noise[base + j] : 0.f;
+        float c;
+        p.out[base + j] = one(p.scores[base + j], ui, v_b[j], ok, xt, nz, c);
+        if (ddim && p.conf) p.conf[base + j] = c;
+      }
+    }
+  }
+  if (ddim && p.x_min) {
+    local_min = warp_min(local_min);
+    if ((threadIdx.x & 31) == 0 && local_min < INFINITY) atomic_min_float(p.x_min, local_min);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct SkhPlan {
+  int R, KQ, nstage, G;
+  size_t smem;
+  bool ok;
+};
+
+static SkhPlan make_plan(int B, int N, int M) {
+  SkhPlan pl{};
+  pl.ok = false;
+  if (M < 1 || M > SKH_MAX_M || N < 1) return pl;
+  int R = 16;
+  while (R > 1 && (long long)R * M > SKH_STAGE_FLOATS) R >>= 1;
+  pl.R = R;
+  pl.KQ = (M <= 2048) ? 1 : (M <= 4096) ? 2 : (M <= 8192) ? 4 : 8;
+  const size_t Mv = (size_t)((M + 1 + 3) & ~3);
+  const size_t stage_floats = (size_t)(((R * M) + 3) & ~3);
+  const int SEG = SKH_WARPS / R;
+  const size_t fixed = Mv * 4 + (size_t)R * SEG * 8 + (size_t)R * 4 + 2 * SKH_WARPS * 4 + 8 /*align*/ + 4 * 8 /*bars*/ + 64;
+  int nstage = (int)((SKH_SMEM_LIMIT - fixed) / (stage_floats * 4));
+  if (nstage > 4) nstage = 4;
+  if (nstage < 1) return pl;
+  pl.nstage = nstage;
+  pl.smem = fixed + (size_t)nstage * stage_floats * 4;
+  const int nslab = (N + R - 1) / R;
+  int G = NUM_SMS / (B < 1 ? 1 : B);
+  if (G < 1) G = 1;
+  if (G > nslab) G = nslab;
+  pl.G = G;
+  pl.ok = true;
+  return pl;
+}
+
+struct SkhWorkspace {
+  SkhConst* bc;
+  float* u;
+  float* v;
+  float2* colpart;
+  float2* upart;
+  size_t total;
+};
+
+static inline int pitch4(int n) { return (n + 3) & ~3; }
+
+static SkhWorkspace carve(void* ws, int B, int N, int M, int G) {
+  SkhWorkspace w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* ptr = ws ? (void*)((char*)ws + off) : nullptr;
+    off += align_up(bytes, 256);
+    return ptr;
+  };
+  w.bc = (SkhConst*)take(sizeof(SkhConst) * B);
+  w.u = (float*)take(sizeof(float) * (size_t)B * pitch4(N + 1));
+  w.v = (float*)take(sizeof(float) * (size_t)B * pitch4(M + 1));
+  w.colpart = (float2*)take(sizeof(float2) * (size_t)B * G * M);
+  w.upart = (float2*)take(sizeof(float2) * (size_t)B * G);
+  w.total = off;
+  return w;
+}
+
+template <int R, int KQ>
+static cudaError_t launch_iter_rk(const SkhParams& p, const SkhPlan& pl, bool vec, cudaStream_t st) {
+  dim3 grid(pl.G, p.B);
+  cudaError_t e;
+  if (vec) {
+    e = cudaFuncSetAttribute(skh_iter_kernel<R, KQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return e;
+    skh_iter_kernel<R, KQ, true><<<grid, SKH_THREADS, pl.smem, st>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(skh_iter_kernel<R, KQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return e;
+    skh_iter_kernel<R, KQ, false><<<grid, SKH_THREADS, pl.smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_iter(const SkhParams& p, const SkhPlan& pl, bool vec, cudaStream_t st) {
+  switch (pl.R) {
+    case 16: return launch_iter_rk<16, 1>(p, pl, vec, st);
+    case 8: return launch_iter_rk<8, 1>(p, pl, vec, st);
+    case 4: return launch_iter_rk<4, 2>(p, pl, vec, st);
+    case 2: return launch_iter_rk<2, 4>(p, pl, vec, st);
+    default: return launch_iter_rk<1, 8>(p, pl, vec, st);
+  }
+}
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+}  // namespace drg
+
+using namespace drg;
+
+extern "C" size_t drg_sinkhorn_workspace_bytes(int B, int N, int M) {
+  if (B < 1 || N < 1 || M < 1) return 0;
+  SkhPlan pl = make_plan(B, N, M);
+  if (!pl.ok) return 0;
+  return carve(nullptr, B, N, M, pl.G).total;
+}
+
+static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = a->B, N = a->N, M = a->M;
+  SkhPlan pl = make_plan(B, N, M);
+  if (!pl.ok) {
+    set_error("sinkhorn: unsupported shape B=%d N=%d M=%d (need 1 <= M <= %d)", B, N, M, SKH_MAX_M);
+    return DRG_ERR_UNSUPPORTED;
+  }
+  // with R rows per stage the column accumulators need KQ*2048 >= M
+  if (pl.KQ * 2048 < M) {
+    set_error("sinkhorn: internal plan error");
+    return DRG_ERR_UNSUPPORTED;
+  }
+  SkhWorkspace w = carve(workspace, B, N, M, pl.G);
+  if (workspace == nullptr || workspace_bytes < w.total) {
+    set_error("sinkhorn: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    return DRG_ERR_WORKSPACE;
+  }
+  if (((uintptr_t)workspace & 255u) != 0) {
+    set_error("sinkhorn: workspace must be 256-byte aligned");
+    return DRG_ERR_INVALID;
+  }
+  const bool vec = (M % 4 == 0) && aligned16(a->scores);
+
+  skh_prep_kernel<<<B, 256, 0, st>>>(a->src_mask, a->tgt_mask, N, M, w.bc, w.v, w.u, pitch4(N + 1), pitch4(M + 1));
+  DRG_LAUNCH_CHECK();
+
+  SkhParams p{};
+  p.scores = a->scores;
+  p.src_mask = a->src_mask;
+  p.tgt_mask = a->tgt_mask;
+  p.alpha = a->alpha;
+  p.shift = a->shift;
+  p.u = w.u;
+  p.v = w.v;
+  p.colpart = w.colpart;
+  p.upart = w.upart;
+  p.bc = w.bc;
+  p.B = B;
+  p.N = N;
+  p.M = M;
+  p.G = pl.G;
+  p.ldu = pitch4(N + 1);
+  p.ldv = pitch4(M + 1);
+  p.apply_mask = a->apply_mask;
+  p.dual = dual ? 1 : 0;
+  p.zscale2 = dual ? LOG2E / temperature : LOG2E;
+  p.nstage = pl.nstage;
+
+  const int iters = dual ? 1 : a->iters;
+  dim3 cgrid((M + 1 + 31) / 32, B);
+  for (int k = 0; k < iters; ++k) {
+    cudaError_t e = launch_iter(p, pl, vec, st);
+    if (e != cudaSuccess) {
+      set_error("sinkhorn iteration launch failed: %s (smem=%zu)", cudaGetErrorString(e), pl.smem);
+      return DRG_ERR_CUDA;
+    }
+    count_launch();
+    skh_col_kernel<<<cgrid, 256, 0, st>>>(p);
+    DRG_LAUNCH_CHECK();
+  }
+
+  if (a->out_mode != DRG_OUT_NONE || dual) {
+    SkhFinalParams f{};
+    f.scores = a->scores;
+    f.src_mask = a->src_mask;
+    f.tgt_mask = a->tgt_mask;
+    f.alpha = a->alpha;
+    f.shift = a->shift;
+    f.u = w.u;
+    f.v = w.v;
+    f.bc = w.bc;
+    f.B = B;
+    f.N = N;
+    f.M = M;
+    f.ldu = pitch4(N + 1);
+    f.ldv = pitch4(M + 1);
+    f.apply_mask = a->apply_mask;
+    f.mode = dual ? 100 : a->out_mode;
+    f.out = a->out;
+    f.x_t = a->x_t;
+    f.noise = a->noise;
+    f.conf = a->conf;
+    f.k_x0 = a->k_x0;
+    f.k_xt = a->k_xt;
+    f.sigma = a->sigma;
+    f.x_min = a->x_min;
+    f.inv_temp = dual ? 1.f / temperature : 0.f;
+    int gx = (NUM_SMS * 8) / B;
+    if (gx < 1) gx = 1;
+    if (!dual && a->out_mode == DRG_OUT_LOG_FULL) {
+      if (gx > N + 1) gx = N + 1;
+      skh_final_full_kernel<<<dim3(gx, B), 256, 0, st>>>(f);
+    } else {
+      if (gx > N) gx = N;
+      bool fvec = vec && aligned16(a->out) && (!f.x_t || aligned16(f.x_t)) && (!f.noise || aligned16(f.noise)) &&
+                  (!f.conf || aligned16(f.conf)) && (((uintptr_t)a->tgt_mask & 3u) == 0);
+      if (fvec)
+        skh_final_kernel<true><<<dim3(gx, B), 256, 0, st>>>(f);
+      else
+        skh_final_kernel<false><<<dim3(gx, B), 256, 0, st>>>(f);
+    }
+    DRG_LAUNCH_CHECK();
+  }
+  if (a->u)
+    DRG_CUDA(cudaMemcpy2DAsync(a->u, sizeof(float) * (N + 1), w.u, sizeof(float) * pitch4(N + 1), sizeof(float) * (N + 1), B,
+                               cudaMemcpyDeviceToDevice, st));
+  if (a->v)
+    DRG_CUDA(cudaMemcpy2DAsync(a->v, sizeof(float) * (M + 1), w.v, sizeof(float) * pitch4(M + 1), sizeof(float) * (M + 1), B,
+                               cudaMemcpyDeviceToDevice, st));
+  return DRG_OK;
+}
+
+extern "C" int drg_sinkhorn(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  DRG_CHECK_ARG(a != nullptr, "args is null");
+  DRG_CHECK_ARG(a->scores && a->src_mask && a->tgt_mask && a->alpha, "scores/src_mask/tgt_mask/alpha must be non-null");
+  DRG_CHECK_ARG(a->B >= 1 && a->N >= 1 && a->M >= 1, "B, N, M must be >= 1");
+  DRG_CHECK_ARG(a->iters >= 0, "iters must be >= 0");
+  DRG_CHECK_ARG(a->out_mode >= DRG_OUT_LOG_FULL && a->out_mode <= DRG_OUT_NONE, "unknown out_mode");
+  DRG_CHECK_ARG(a->out_mode == DRG_OUT_NONE || a->out != nullptr, "out is null");
+  DRG_CHECK_ARG(a->out_mode != DRG_OUT_DDIM || a->x_t != nullptr, "DDIM mode needs x_t");
+  return run_sinkhorn(a, false, 1.f, workspace, workspace_bytes, stream);
+}
+
+extern "C" int drg_dual_softmax(const float* sim, const uint8_t* src_mask, const uint8_t* tgt_mask, int B, int N, int M,
+                                float temperature, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  DRG_CHECK_ARG(sim && src_mask && tgt_mask && out, "sim/src_mask/tgt_mask/out must be non-null");
+  DRG_CHECK_ARG(B >= 1 && N >= 1 && M >= 1, "B, N, M must be >= 1");
+  DRG_CHECK_ARG(temperature > 0.f, "temperature must be > 0");
+  drg_sinkhorn_args a{};
+  a.scores = sim;
+  a.src_mask = src_mask;
+  a.tgt_mask = tgt_mask;
+  a.B = B;
+  a.N = N;
+  a.M = M;
+  a.iters = 1;
+  a.apply_mask = 1;
+  a.out_mode = DRG_OUT_CONF;
+  a.out = out;
+  return run_sinkhorn(&a, true, temperature, workspace, workspace_bytes, stream);
+}
