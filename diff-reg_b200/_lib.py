@@ -17,8 +17,20 @@ class SinkhornArgs(ctypes.Structure):
         ("scores", c_void_p), ("src_mask", c_void_p), ("tgt_mask", c_void_p), ("alpha", c_void_p), ("shift", c_void_p),
         ("B", c_int), ("N", c_int), ("M", c_int), ("iters", c_int), ("apply_mask", c_int),
         ("out_mode", c_int), ("out", c_void_p), ("u", c_void_p), ("v", c_void_p),
-        ("x_t", c_void_p), ("noise", c_void_p), ("conf", c_void_p),
+        ("x_t", c_void_p), ("xt_shift", c_void_p), ("noise", c_void_p), ("conf", c_void_p),
         ("k_x0", c_float), ("k_xt", c_float), ("sigma", c_float), ("x_min", c_void_p),
+    ]
+
+
+class ProcrustesArgs(ctypes.Structure):
+    """struct drg_procrustes_args"""
+    _fields_ = [
+        ("conf", c_void_p), ("src_pcd", c_void_p), ("tgt_pcd", c_void_p), ("src_mask", c_void_p), ("tgt_mask", c_void_p),
+        ("B", c_int), ("N", c_int), ("M", c_int), ("sample_rate", c_float), ("max_condition_num", c_float),
+        ("padded_lengths", c_int),
+        ("R", c_void_p), ("t", c_void_p), ("R_forwd", c_void_p), ("t_forwd", c_void_p), ("condition", c_void_p),
+        ("solution_mask", c_void_p), ("src_warped", c_void_p),
+        ("K_max", c_int), ("sel_w", c_void_p), ("sel_src", c_void_p), ("sel_tgt", c_void_p),
     ]
 
 
@@ -41,6 +53,30 @@ def _declare(lib):
     lib.drg_dual_softmax.restype = c_int
     lib.drg_dual_softmax.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                      c_size_t, c_void_p]
+    c_ll = ctypes.c_longlong
+    lib.drg_gemm_nt_tf32.restype = c_int
+    lib.drg_gemm_nt_tf32.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
+    lib.drg_prep_operand.restype = c_int
+    lib.drg_prep_operand.argtypes = [c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.drg_match_workspace_bytes.restype = c_size_t
+    lib.drg_match_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.drg_match_count.restype = c_int
+    lib.drg_match_count.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t,
+                                    c_void_p, c_void_p]
+    lib.drg_match_write.restype = c_int
+    lib.drg_match_write.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t,
+                                    c_void_p, c_void_p, c_ll, c_void_p, c_void_p]
+    lib.drg_soft_procrustes_workspace_bytes.restype = c_size_t
+    lib.drg_soft_procrustes_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.drg_soft_procrustes.restype = c_int
+    lib.drg_soft_procrustes.argtypes = [ctypes.POINTER(ProcrustesArgs), c_void_p, c_size_t, c_void_p]
+    lib.drg_weighted_procrustes.restype = c_int
+    lib.drg_weighted_procrustes.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                            c_void_p]
+    lib.drg_sigmoid.restype = c_int
+    lib.drg_sigmoid.argtypes = [c_void_p, c_void_p, c_ll, c_void_p]
+    lib.drg_min_value.restype = c_int
+    lib.drg_min_value.argtypes = [c_void_p, c_ll, c_void_p, c_void_p, c_void_p]
     return lib
 
 

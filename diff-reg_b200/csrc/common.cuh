@@ -53,12 +53,12 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 #ifdef __CUDACC__
 __device__ __forceinline__ float ex2(float x) {
   float y;
-  asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float lg2(float x) {
   float y;
-  asm("lg2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -1,0 +1,160 @@
+// Operand preparation for the similarity GEMM: positional embedding, 1/sqrt(C) scaling and the
+// hi/lo split that turns the tf32 tensor-core GEMM into an fp32-accurate "3xTF32" product.
+//
+// Replaces the elementwise lines of Matching.forward between the projection and the einsum:
+//   VolPE.embed_pos / embed_rotary   Diff-Reg-4dmatch/models/position_encoding.py:26-46
+//   feat / feat.shape[-1] ** .5      Diff-Reg-4dmatch/models/matching.py:144-145
+//
+// Layout: in [rows, K] fp32 row-major.  out [rows, 3K] (split) or [rows, K] (plain):
+//   pattern 0 (left operand):  [ lo | hi | hi ]
+//   pattern 1 (right operand): [ hi | lo | hi ]
+// so that  A'.B'^T = lo.hi + hi.lo + hi.hi  with hi = rna_tf32(x), lo = rna_tf32(x - hi).
+#include "common.cuh"
+
+namespace drg {
+
+__device__ __forceinline__ float to_tf32_rna(float x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+  return __uint_as_float(y);
+}
+
+struct PrepParams {
+  const float* in;   // [rows, K]
+  const float* pe;   // rotary: [rows, K, 2] (cos, sin); sinusoidal: [rows, K]; or NULL
+  float* embedded;   // optional [rows, K]: features after the positional embedding, before scaling
+  float* out;        // [rows, 3K] or [rows, K]
+  long long rows;
+  int K;
+  int pe_type;       // 0 none, 1 rotary, 2 sinusoidal (additive)
+  int split;         // 1: 3xTF32 layout, 0: plain scaled copy
+  int pattern;       // 0: hi,hi,lo   1: hi,lo,hi
+  float scale;
+};
+
+__global__ void __launch_bounds__(256) prep_operand_kernel(const PrepParams p) {
+  const int K4 = p.K >> 2;
+  const long long total = p.rows * K4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / K4;
+    const int k = (int)(idx - row * K4) << 2;
+    float4 x = *reinterpret_cast<const float4*>(p.in + row * p.K + k);
+    if (p.pe_type == 1) {
+      // x*cos + rot(x)*sin with rot(x)[2i] = -x[2i+1], rot(x)[2i+1] = x[2i]; same op order as the reference
+      const float4 cs0 = *reinterpret_cast<const float4*>(p.pe + (row * p.K + k) * 2);      // cos0 sin0 cos1 sin1
+      const float4 cs1 = *reinterpret_cast<const float4*>(p.pe + (row * p.K + k) * 2 + 4);  // cos2 sin2 cos3 sin3
+      float4 y;
+      y.x = __fadd_rn(__fmul_rn(x.x, cs0.x), __fmul_rn(-x.y, cs0.y));
+      y.y = __fadd_rn(__fmul_rn(x.y, cs0.z), __fmul_rn(x.x, cs0.w));
+      y.z = __fadd_rn(__fmul_rn(x.z, cs1.x), __fmul_rn(-x.w, cs1.y));
+      y.w = __fadd_rn(__fmul_rn(x.w, cs1.z), __fmul_rn(x.z, cs1.w));
+      x = y;
+    } else if (p.pe_type == 2) {
+      const float4 pe = *reinterpret_cast<const float4*>(p.pe + row * p.K + k);
+      x.x += pe.x;
+      x.y += pe.y;
+      x.z += pe.z;
+      x.w += pe.w;
+    }
+    if (p.embedded) *reinterpret_cast<float4*>(p.embedded + row * p.K + k) = x;
+    x.x *= p.scale;
+    x.y *= p.scale;
+    x.z *= p.scale;
+    x.w *= p.scale;
+    if (!p.split) {
+      *reinterpret_cast<float4*>(p.out + row * p.K + k) = x;
+      continue;
+    }
+    float4 hi, lo;
+    hi.x = to_tf32_rna(x.x);
+    hi.y = to_tf32_rna(x.y);
+    hi.z = to_tf32_rna(x.z);
+    hi.w = to_tf32_rna(x.w);
+    // lo is rounded to tf32 here (round-to-nearest) so that the tensor core's own truncation is a no-op
+    lo.x = to_tf32_rna(x.x - hi.x);
+    lo.y = to_tf32_rna(x.y - hi.y);
+    lo.z = to_tf32_rna(x.z - hi.z);
+    lo.w = to_tf32_rna(x.w - hi.w);
+    float* o = p.out + row * 3 * p.K + k;
+    // The correction terms come FIRST along K: the tensor core truncates its fp32 accumulator at every
+    // K=8 step (~2^-24 |acc| each, measured), so the small terms are added while the accumulator is small.
+    *reinterpret_cast<float4*>(o) = p.pattern == 0 ? lo : hi;
+    *reinterpret_cast<float4*>(o + p.K) = p.pattern == 0 ? hi : lo;
+    *reinterpret_cast<float4*>(o + 2 * p.K) = hi;
+  }
+}
+
+}  // namespace drg
+
+using namespace drg;
+
+extern "C" int drg_prep_operand(const float* in, const float* pe, int pe_type, long long rows, int K, float scale, int split,
+                                int pattern, float* embedded, float* out, void* stream) {
+  DRG_CHECK_ARG(in && out, "in/out must be non-null");
+  DRG_CHECK_ARG(rows >= 1 && K >= 4, "rows >= 1 and K >= 4 required");
+  DRG_CHECK_ARG(pe_type >= 0 && pe_type <= 2, "pe_type must be 0 (none), 1 (rotary) or 2 (sinusoidal)");
+  DRG_CHECK_ARG(pe_type == 0 || pe != nullptr, "pe is null");
+  if (K % 4 != 0 || ((uintptr_t)in & 15u) || ((uintptr_t)out & 15u) || (pe && ((uintptr_t)pe & 15u)) ||
+      (embedded && ((uintptr_t)embedded & 15u))) {
+    set_error("prep_operand: K must be a multiple of 4 and all pointers 16-byte aligned (K=%d)", K);
+    return DRG_ERR_UNSUPPORTED;
+  }
+  PrepParams p{};
+  p.in = in;
+  p.pe = pe;
+  p.embedded = embedded;
+  p.out = out;
+  p.rows = rows;
+  p.K = K;
+  p.pe_type = pe_type;
+  p.split = split;
+  p.pattern = pattern;
+  p.scale = scale;
+  const long long total = rows * (K / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
+  prep_operand_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+// ---- small elementwise / reduction helpers of the sampler -----------------------------------
+namespace drg {
+// conf_matrix_pred = sigmoid(x)                     Diff-Reg-4dmatch/models/pipeline.py:192
+__global__ void __launch_bounds__(256) sigmoid_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = 1.f / (1.f + expf(-x[i]));
+}
+// global minimum (x.min() of the 3DMatch sampler)   Diff-Reg-3dmatch/models/pipeline.py:239,264
+__global__ void __launch_bounds__(256) min_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ out_ordered) {
+  float m = INFINITY;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fminf(m, x[i]);
+  m = warp_min(m);
+  if ((threadIdx.x & 31) == 0) atomicMin(out_ordered, float_to_ordered(m));
+}
+__global__ void min_init_kernel(unsigned int* o) { *o = 0xFFFFFFFFu; }
+__global__ void min_finish_kernel(const unsigned int* o, float* out) { *out = ordered_to_float(*o); }
+}  // namespace drg
+
+extern "C" int drg_sigmoid(const float* x, float* y, long long n, void* stream) {
+  DRG_CHECK_ARG(x && y && n >= 1, "x/y must be non-null and n >= 1");
+  long long blocks = (n + 255) / 256;
+  if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+  sigmoid_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, (size_t)n);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+extern "C" int drg_min_value(const float* x, long long n, float* out, unsigned int* scratch, void* stream) {
+  DRG_CHECK_ARG(x && out && scratch && n >= 1, "x/out/scratch must be non-null and n >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  min_init_kernel<<<1, 1, 0, st>>>(scratch);
+  DRG_LAUNCH_CHECK();
+  long long blocks = (n + 255) / 256;
+  if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
+  min_kernel<<<(int)blocks, 256, 0, st>>>(x, (size_t)n, scratch);
+  DRG_LAUNCH_CHECK();
+  min_finish_kernel<<<1, 1, 0, st>>>(scratch, out);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}

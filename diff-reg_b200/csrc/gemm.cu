@@ -1,0 +1,405 @@
+// Feature-similarity contraction  C[b] = alpha * A[b] . B[b]^T  on the 5th-gen tensor cores.  sm_100a.
+//
+// Replaces torch.einsum("bsc,btc->bst", src_feats, tgt_feats) (Diff-Reg-4dmatch/models/matching.py:149,161;
+// Diff-Reg-2d3d/experiments/<exp>/matching.py:110,122) and the nn.Linear projections in front of it
+// (matching.py:127-128).  See include/diffreg_b200.h.
+//
+// Both operands are K-major fp32 ([rows, K], K contiguous).  The kernel is a persistent,
+// warp-specialised tcgen05 pipeline:
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of a 128 x 32 A block and a
+//               BN x 32 B block per k-step into a ring of shared-memory stages (mbarrier full/empty)
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8),
+//               four per k-step, accumulating in TMEM; tcgen05.commit releases the smem stage and,
+//               after the last k-step, publishes the accumulator to the epilogue
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), scale, swizzled st.shared,
+//               TMA tensor store of 32 x 32 boxes (clipped at the matrix edge by the TMA unit)
+// Two TMEM accumulator stages (2 x BN columns) let the MMA of tile t+1 overlap the epilogue of t.
+//
+// fp32 parity: kind::tf32 keeps 10 mantissa bits of each operand.  The host side (features.cu)
+// can hand this kernel "3xTF32" operands -- A' = [A_lo | A_hi | A_hi], B' = [B_hi | B_lo | B_hi]
+// concatenated along K -- so that the same kernel returns an fp32-accurate product (the
+// dropped term is A_lo.B_lo ~ 2^-22 relative).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace drg {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 32;  // fp32 elements per k-step: 128 bytes = one swizzle-atom row
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 4;  // 16 KB
+constexpr int GEMM_OUT_BOX_BYTES = 32 * 32 * 4;            // one epilogue box: 32 rows x 32 columns
+constexpr int GEMM_MAX_STAGES = 8;
+
+// ---- PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :: "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all tcgen05.mma issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = lane = accumulator row)
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows are 128 B apart, groups of
+// 8 rows (one 1024-byte swizzle atom) are `stride byte offset` = 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // [0,14)  start address >> 4
+  d |= (uint64_t)0 << 16;                        // [16,30) leading byte offset (unused: one atom along K)
+  d |= (uint64_t)(1024u >> 4) << 32;             // [32,46) stride byte offset >> 4
+  d |= (uint64_t)1 << 46;                        // [46,48) descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                        // [61,64) SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, M x N tile
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4)                      // [4,6)   D format  = F32
+         | (2u << 7)                    // [7,10)  A format  = TF32
+         | (2u << 10)                   // [10,13) B format  = TF32
+         | (0u << 15) | (0u << 16)      // A, B K-major
+         | ((uint32_t)(N >> 3) << 17)   // [17,23) N >> 3
+         | ((uint32_t)(M >> 4) << 24);  // [24,29) M >> 4
+}
+
+struct GemmShape {
+  int N, M, K, batch;
+  float alpha;
+  int nstage;
+  int direct_store;  // 1: C row pitch not TMA-storable (M % 4 != 0) -> coalesced st.global from the staging tile
+  float* C;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const GemmShape s) {
+  constexpr int B_STAGE_BYTES = BN * GEMM_BK * 4;
+  constexpr int TMEM_COLS = 2 * BN;  // 128, 256 or 512: a power of two >= 32
+  static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[GEMM_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nstage = s.nstage;
+  // 1024-byte aligned carve-up (swizzle atoms)
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  uint8_t* aligned = smem_dyn + (base - smem_u32(smem_dyn));
+  uint8_t* sA = aligned;
+  uint8_t* sB = sA + (size_t)nstage * GEMM_A_STAGE_BYTES;
+  uint8_t* sOut = sB + (size_t)nstage * B_STAGE_BYTES;  // [4 warps][2][4 KB]
+
+  const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_n = (s.M + BN - 1) / BN;
+  const int tiles = s.batch * tiles_m * tiles_n;
+  const int kblocks = (s.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (!s.direct_store) prefetch_tmap(&tmC);
+    for (int i = 0; i < nstage; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int b = tile / (tiles_m * tiles_n);
+        const int rem = tile - b * tiles_m * tiles_n;
+        const int mb = rem / tiles_n, nb = rem - mb * tiles_n;
+        for (int k = 0; k < kblocks; ++k) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(GEMM_A_STAGE_BYTES + B_STAGE_BYTES));
+          tma_load_3d(sA + (size_t)stage * GEMM_A_STAGE_BYTES, &tmA, k * GEMM_BK, mb * GEMM_BM, b, &full_bar[stage]);
+          tma_load_3d(sB + (size_t)stage * B_STAGE_BYTES, &tmB, k * GEMM_BK, nb * BN, b, &full_bar[stage]);
+          if (++stage == nstage) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int k = 0; k < kblocks; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + (size_t)stage * GEMM_A_STAGE_BYTES));
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sB + (size_t)stage * B_STAGE_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < GEMM_BK / 8; ++kk) {
+            // advance 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_tf32(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (uint32_t)((k | kk) != 0));
+          }
+          umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs have read it
+          if (++stage == nstage) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full_bar[as]);  // accumulator complete
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read: lanes 32q .. 32q+31
+    uint8_t* stg = sOut + (size_t)q * 2 * GEMM_OUT_BOX_BYTES;
+    int as = 0;
+    uint32_t aphase = 0;
+    int buf = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int b = tile / (tiles_m * tiles_n);
+      const int rem = tile - b * tiles_m * tiles_n;
+      const int mb = rem / tiles_n, nb = rem - mb * tiles_n;
+      const int row0 = mb * GEMM_BM + q * 32;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = nb * BN + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
+        tmem_wait_ld();
+        if (row0 >= s.N || col0 >= s.M) continue;  // whole box outside the matrix (warp-uniform)
+        uint8_t* box = stg + (size_t)buf * GEMM_OUT_BOX_BYTES;
+        if (!s.direct_store) {
+          // the TMA store issued two boxes ago from this buffer must have finished READING it
+          if (lane == 0) bulk_wait_group_read<1>();
+          __syncwarp();
+        }
+        // 128B-swizzled staging: row = lane, 16-byte chunk j lands at chunk j ^ (lane & 7)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          o.x = __uint_as_float(r[4 * j + 0]) * s.alpha;
+          o.y = __uint_as_float(r[4 * j + 1]) * s.alpha;
+          o.z = __uint_as_float(r[4 * j + 2]) * s.alpha;
+          o.w = __uint_as_float(r[4 * j + 3]) * s.alpha;
+          *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+        }
+        if (!s.direct_store) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmC, box, col0, row0, b);
+            bulk_commit_group();
+          }
+        } else {
+          __syncwarp();
+          // coalesced scalar stores: lane = column, loop over the 32 rows of the box
+          const int col = col0 + lane;
+          float* Cb = s.C + (size_t)b * s.N * s.M;
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = row0 + rr;
+            if (row < s.N && col < s.M) {
+              const float val = *reinterpret_cast<const float*>(box + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
+              Cb[(size_t)row * s.M + col] = val;
+            }
+          }
+          __syncwarp();
+        }
+        buf ^= 1;
+      }
+      // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+    if (!s.direct_store && lane == 0) bulk_wait_group<0>();  // smem must outlive the last stores
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---- host side --------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (PFN_encodeTiled)p;
+  return fn;
+}
+
+// [batch, rows, cols] fp32 row-major -> rank-3 tensor map with box {box_cols, box_rows, 1}, 128B swizzle
+static bool make_tmap(CUtensorMap* tm, const void* ptr, int batch, int rows, int cols, int box_rows, int box_cols) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return false;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 4ull, (cuuint64_t)rows * (cuuint64_t)cols * 4ull};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d] box [%d,%d]", (int)r, batch, rows, cols, box_rows, box_cols);
+    return false;
+  }
+  return true;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, GemmShape s, cudaStream_t st) {
+  constexpr int B_STAGE_BYTES = BN * GEMM_BK * 4;
+  const size_t out_bytes = 4 * 2 * GEMM_OUT_BOX_BYTES;
+  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - out_bytes - 256 /*static*/;
+  int nstage = (int)(budget / (GEMM_A_STAGE_BYTES + B_STAGE_BYTES));
+  if (nstage > GEMM_MAX_STAGES) nstage = GEMM_MAX_STAGES;
+  const int kblocks = (s.K + GEMM_BK - 1) / GEMM_BK;
+  if (nstage > 2 * kblocks) nstage = 2 * kblocks;  // no point in more stages than two tiles of k-steps
+  if (nstage < 2) nstage = 2;
+  s.nstage = nstage;
+  const size_t smem = 1024 + (size_t)nstage * (GEMM_A_STAGE_BYTES + B_STAGE_BYTES) + out_bytes;
+  DRG_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM, tiles_n = (s.M + BN - 1) / BN;
+  const long long tiles = (long long)s.batch * tiles_m * tiles_n;
+  const int grid = (int)(tiles < NUM_SMS ? tiles : NUM_SMS);
+  gemm_tf32_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, s);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+}  // namespace drg
+
+using namespace drg;
+
+extern "C" int drg_gemm_nt_tf32(const float* A, const float* B, float* C, int batch, int N, int M, int K, float alpha,
+                                void* stream) {
+  DRG_CHECK_ARG(A && B && C, "A/B/C must be non-null");
+  DRG_CHECK_ARG(batch >= 1 && N >= 1 && M >= 1 && K >= 1, "batch, N, M, K must be >= 1");
+  if (K % 4 != 0 || ((uintptr_t)A & 15u) || ((uintptr_t)B & 15u)) {
+    set_error("gemm: K must be a multiple of 4 and A, B 16-byte aligned (TMA row pitch); got K=%d", K);
+    return DRG_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // tile width: the widest N-tile that still gives every SM work
+  const long long t256 = (long long)batch * ((N + 127) / 128) * ((M + 255) / 256);
+  const long long t128 = (long long)batch * ((N + 127) / 128) * ((M + 127) / 128);
+  const int BN = (t256 >= 2 * NUM_SMS) ? 256 : (t128 >= NUM_SMS ? 128 : 64);
+  GemmShape s{};
+  s.N = N;
+  s.M = M;
+  s.K = K;
+  s.batch = batch;
+  s.alpha = alpha;
+  s.C = C;
+  s.direct_store = (M % 4 != 0 || ((uintptr_t)C & 15u)) ? 1 : 0;
+  CUtensorMap tA, tB, tC;
+  if (!make_tmap(&tA, A, batch, N, K, GEMM_BM, GEMM_BK)) return DRG_ERR_CUDA;
+  if (!make_tmap(&tB, B, batch, M, K, BN, GEMM_BK)) return DRG_ERR_CUDA;
+  if (!s.direct_store) {
+    if (!make_tmap(&tC, C, batch, N, M, 32, 32)) return DRG_ERR_CUDA;
+  } else {
+    tC = tA;  // unused
+  }
+  switch (BN) {
+    case 256: return launch_gemm<256>(tA, tB, tC, s, st);
+    case 128: return launch_gemm<128>(tA, tB, tC, s, st);
+    default: return launch_gemm<64>(tA, tB, tC, s, st);
+  }
+}

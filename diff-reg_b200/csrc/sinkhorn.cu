@@ -481,6 +481,7 @@ struct SkhFinalParams {
   int mode;  // DRG_OUT_* ; 100 = dual softmax product
   float* out;
   const float* x_t;
+  const float* xt_shift;
   const float* noise;
   float* conf;
   float k_x0, k_xt, sigma;
@@ -533,6 +534,7 @@ __global__ void __launch_bounds__(256) skh_final_kernel(const SkhFinalParams p) 
   const float* v_b = p.v + (size_t)b * p.ldv;
   const bool dual = (p.mode == 100);
   const bool ddim = (p.mode == DRG_OUT_DDIM);
+  const float xt_shift = p.xt_shift ? *p.xt_shift : 0.f;
   float local_min = INFINITY;
 
   auto one = [&](float z, float ui, float vj, bool ok, float xt, float nz, float& conf_out) -> float {
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(256) skh_final_kernel(const SkhFinalParams p) 
     conf = ex2(la * LOG2E);
     conf_out = conf;
     if (!ddim) return conf;
-    float xn = ok ? fmaf(p.k_x0, conf, fmaf(p.k_xt, xt - shift, p.sigma * nz)) : -INFINITY;
+    float xn = ok ? fmaf(p.k_x0, conf, fmaf(p.k_xt, xt - xt_shift, p.sigma * nz)) : -INFINITY;
     if (ok && xn > -INFINITY) local_min = fminf(local_min, xn);
     return xn;
   };
@@ -783,6 +785,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     f.mode = dual ? 100 : a->out_mode;
     f.out = a->out;
     f.x_t = a->x_t;
+    f.xt_shift = a->xt_shift;
     f.noise = a->noise;
     f.conf = a->conf;
     f.k_x0 = a->k_x0;

@@ -1,0 +1,173 @@
+"""Drop-in replacements for the reference's matching modules, computing through libdiffreg_b200.so.
+
+Mirrors (same names, arguments, return structure, state_dict keys):
+    log_optimal_transport          Diff-Reg-4dmatch/models/matching.py:6-38
+    mutual_topk_select             Diff-Reg-2d3d/vision3d/ops/mutual_topk_select.py:7-60
+    Matching (3D flavour)          Diff-Reg-4dmatch/models/matching.py:41-173, Diff-Reg-3dmatch/models/matching.py:96-283
+    Matching2D3D (2D-3D flavour)   Diff-Reg-2d3d/experiments/<exp>/matching.py:41-147
+
+Forward only: the kernels have no backward, so calls with autograd-tracked inputs raise instead of
+silently detaching.  There is no CPU path: CPU tensors raise.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import DiffRegLibraryError
+
+
+def _no_grad_inputs(*tensors):
+    if torch.is_grad_enabled():
+        for t in tensors:
+            if t is not None and t.requires_grad:
+                raise DiffRegLibraryError(
+                    "diffreg_b200 kernels are forward-only: call under torch.no_grad() (training keeps the reference modules)")
+
+
+def log_optimal_transport(scores, alpha, iters, src_mask, tgt_mask):
+    """[B,N,M] scores -> [B,N+1,M+1] log-assignment (Z + u + v - norm).
+
+    Computed in fp32; an fp64 `scores` (the reference's fp64 sampler state) gives an
+    fp64 result holding the fp32-accurate values."""
+    _no_grad_inputs(scores, alpha)
+    out = ops.sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full")
+    return out.to(scores.dtype) if scores.dtype == torch.float64 else out
+
+
+def mutual_topk_select(score_mat, k, largest=True, threshold=None, mutual=True, reduce_result=True):
+    """Top-1 row/column selection.  Only k = 1 exists on the Diff-Reg path (3d pipeline.py:275-277,
+    2d3d model.py:692-694, matching.py:134-136); other k raise."""
+    if k != 1:
+        raise NotImplementedError("diffreg_b200.mutual_topk_select implements k = 1 (the only value the sampler uses)")
+    r, c, s = ops.top1_select(score_mat, largest, threshold, mutual)
+    if reduce_result:
+        return r, c, s
+    corr = torch.zeros_like(score_mat, dtype=torch.bool)
+    corr[r, c] = True
+    return corr
+
+
+class Matching(nn.Module):
+    """3D flavour.  `precision`: '3xtf32' (default; fp32-accurate tensor-core GEMM) or 'tf32'."""
+
+    def __init__(self, config, precision="3xtf32"):
+        super().__init__()
+        self.match_type = config['match_type']
+        self.confidence_threshold = config['confidence_threshold']
+        d_model = config['feature_dim']
+        self.src_proj = nn.Linear(d_model, d_model, bias=False)
+        self.tgt_proj = nn.Linear(d_model, d_model, bias=False)   # unused by forward, kept for checkpoints (matching.py:53)
+        self.entangled = config['entangled']
+        if self.match_type == "dual_softmax":
+            self.temperature = config['dsmax_temperature']
+        elif self.match_type == 'sinkhorn':
+            self.skh_init_bin_score = config['skh_init_bin_score']
+            self.skh_iters = config['skh_iters']
+            self.skh_prefilter = config['skh_prefilter']
+            self.bin_score = nn.Parameter(torch.tensor(self.skh_init_bin_score, requires_grad=True))
+        else:
+            raise NotImplementedError()
+        if precision not in ("3xtf32", "tf32"):
+            raise ValueError(precision)
+        self.precision = precision
+        self._w_cache = None
+
+    # ---- correspondence extraction (static, like the reference) ----
+    @staticmethod
+    @torch.no_grad()
+    def get_match(conf_matrix, thr, mutual=True):
+        index, mconf, mask = ops.get_match(conf_matrix, thr, mutual, want_mask=True)
+        return index, mconf, mask
+
+    @staticmethod
+    @torch.no_grad()
+    def get_topk_match(conf_matrix, thr, mutual=True):
+        return Matching.get_match(conf_matrix, thr, mutual)
+
+    # ---- similarity ----
+    def _weight_operand(self):
+        w = self.src_proj.weight
+        key = (w.data_ptr(), w._version, self.precision, w.device)
+        if self._w_cache is None or self._w_cache[0] != key:
+            split = self.precision == "3xtf32"
+            self._w_cache = (key, ops.prep_operand(w.detach(), 1.0, split, 1))
+        return self._w_cache[1]
+
+    def project(self, feats):
+        """src_proj applied through the tensor-core GEMM: [B,L,C] -> [B,L,C]."""
+        B, L, C = feats.shape
+        split = self.precision == "3xtf32"
+        a = ops.prep_operand(feats, 1.0, split, 0)
+        out = ops.gemm_nt(a.reshape(B * L, a.shape[-1]), self._weight_operand())
+        return out.view(B, L, C)
+
+    def similarity(self, src_feats, tgt_feats, src_pe=None, tgt_pe=None, pe_type="rotary", data=None):
+        """Projection (same weight on both sides, matching.py:127-128), optional positional embedding,
+        1/sqrt(C) scaling and the N x M contraction.  Returns sim [B,N,M]."""
+        fs = self.project(src_feats)
+        ft = self.project(tgt_feats)
+        C = fs.shape[-1]
+        split = self.precision == "3xtf32"
+        scale = 1.0 / (C ** .5)
+        use_pe = (not self.entangled) and src_pe is not None
+        want = data is not None and use_pe
+        a = ops.prep_operand(fs, scale, split, 0, pe=src_pe if use_pe else None, pe_type=pe_type if use_pe else None,
+                             want_embedded=want)
+        b = ops.prep_operand(ft, scale, split, 1, pe=tgt_pe if use_pe else None, pe_type=pe_type if use_pe else None,
+                             want_embedded=want)
+        if data is not None:
+            data["src_feats_nopos"] = fs
+            data["tgt_feats_nopos"] = ft
+            data["src_feats"] = a[1] if want else fs
+            data["tgt_feats"] = b[1] if want else ft
+        if want:
+            a, b = a[0], b[0]
+        return ops.gemm_nt(a, b)
+
+    def confidence(self, sim, src_mask, tgt_mask):
+        B, N, M = sim.shape
+        if src_mask is None:
+            src_mask = torch.ones(B, N, dtype=torch.bool, device=sim.device)
+            tgt_mask = torch.ones(B, M, dtype=torch.bool, device=sim.device)
+        if self.match_type == "dual_softmax":
+            return ops.dual_softmax(sim, src_mask, tgt_mask, self.temperature)
+        return ops.sinkhorn(sim, self.bin_score, self.skh_iters, src_mask, tgt_mask, out_mode="conf", apply_mask=True)
+
+    @torch.no_grad()
+    def forward(self, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type="rotary"):
+        """-> (conf_matrix [B,N,M], coarse_match [K,3] int64); writes the four feature tensors into `data`."""
+        _no_grad_inputs(src_feats, tgt_feats)
+        sim = self.similarity(src_feats, tgt_feats, src_pe, tgt_pe, pe_type, data)
+        conf_matrix = self.confidence(sim, src_mask, tgt_mask)
+        coarse_match, _, _ = ops.get_match(conf_matrix, self.confidence_threshold, True, want_mask=False)
+        return conf_matrix, coarse_match
+
+    @torch.no_grad()
+    def forward1(self, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type="rotary", mutual=False):
+        """3DMatch variant (3d matching.py:221-283): top-1 row/column matches as [K,3] with a zero batch column."""
+        _no_grad_inputs(src_feats, tgt_feats)
+        sim = self.similarity(src_feats, tgt_feats, src_pe, tgt_pe, pe_type, data)
+        conf_matrix = self.confidence(sim, src_mask, tgt_mask)
+        r, c, _ = ops.top1_select(conf_matrix.squeeze(0), True, None, mutual)
+        coarse_match = torch.cat([torch.zeros_like(r).unsqueeze(-1), r.unsqueeze(-1), c.unsqueeze(-1)], dim=-1)
+        return conf_matrix, coarse_match
+
+
+class Matching2D3D(Matching):
+    """2D-3D flavour: no positional arguments, no `data`; returns top-1 selected correspondences."""
+
+    def __init__(self, config, mutual=True, precision="3xtf32"):
+        super().__init__(config, precision)
+        self.mutual = mutual
+
+    @torch.no_grad()
+    def forward(self, src_feats, tgt_feats, src_mask, tgt_mask, mutual=True):
+        """-> (conf_matrix [1,N,M], src_indices [K], tgt_indices [K], weights [K])"""
+        _no_grad_inputs(src_feats, tgt_feats)
+        sim = self.similarity(src_feats, tgt_feats)
+        conf_matrix = self.confidence(sim, src_mask, tgt_mask)
+        if self.match_type != "sinkhorn":
+            # the reference only defines the selection inside its sinkhorn branch (matching.py:134-136)
+            raise NotImplementedError("the 2D-3D head selects correspondences in the sinkhorn branch only")
+        src_indices, tgt_indices, weights = ops.top1_select(conf_matrix.squeeze(0), True, None, mutual)
+        return conf_matrix, src_indices, tgt_indices, weights

@@ -45,13 +45,14 @@ def _f32c(t):
 
 
 def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", apply_mask=False, shift=None,
-             x_t=None, noise=None, k_x0=0.0, k_xt=0.0, sigma=0.0, want_conf=False, x_min=None, return_potentials=False):
+             x_t=None, noise=None, k_x0=0.0, k_xt=0.0, sigma=0.0, want_conf=False, x_min=None, return_potentials=False,
+             xt_shift=None):
     """Log-domain Sinkhorn with dustbins (drg_sinkhorn).
 
     out_mode: 'log_full' -> [B,N+1,M+1] log-assignment; 'conf' -> [B,N,M] exp()[:, :-1, :-1];
               'ddim' -> x_next [B,N,M] (and conf if want_conf); 'none' -> potentials only.
     """
-    _require_cuda(scores, alpha, src_mask, tgt_mask, shift, x_t, noise, x_min)
+    _require_cuda(scores, alpha, src_mask, tgt_mask, shift, x_t, noise, x_min, xt_shift)
     lib = load_library()
     scores = _f32c(scores)
     B, N, M = scores.shape
@@ -79,7 +80,7 @@ def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", appl
     ws = workspace(nbytes, dev, "sinkhorn")
     a = SinkhornArgs(scores=_ptr(scores), src_mask=_ptr(src_mask), tgt_mask=_ptr(tgt_mask), alpha=_ptr(alpha),
                      shift=_ptr(shift), B=B, N=N, M=M, iters=int(iters), apply_mask=int(bool(apply_mask)),
-                     out_mode=mode, out=_ptr(out), u=_ptr(u), v=_ptr(v), x_t=_ptr(x_t), noise=_ptr(noise),
+                     out_mode=mode, out=_ptr(out), u=_ptr(u), v=_ptr(v), x_t=_ptr(x_t), xt_shift=_ptr(xt_shift), noise=_ptr(noise),
                      conf=_ptr(conf), k_x0=float(k_x0), k_xt=float(k_xt), sigma=float(sigma), x_min=_ptr(x_min))
     check(lib.drg_sinkhorn(a, ws.data_ptr(), ws.numel(), _stream()))
     res = [out]
@@ -105,4 +106,154 @@ def dual_softmax(sim, src_mask, tgt_mask, temperature):
     ws = workspace(nbytes, sim.device, "sinkhorn")
     check(lib.drg_dual_softmax(sim.data_ptr(), src_mask.data_ptr(), tgt_mask.data_ptr(), B, N, M, float(temperature),
                                out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
+def gemm_nt(A, B, alpha=1.0, out=None):
+    """C[b] = alpha * A[b] @ B[b]^T on the tensor cores (drg_gemm_nt_tf32).  A [batch,N,K] or [N,K]; B likewise."""
+    _require_cuda(A, B)
+    lib = load_library()
+    A = _f32c(A)
+    B = _f32c(B)
+    squeeze = A.dim() == 2
+    if squeeze:
+        A = A.unsqueeze(0)
+        B = B.unsqueeze(0)
+    batch, N, K = A.shape
+    M = B.shape[1]
+    if B.shape[0] != batch or B.shape[2] != K:
+        raise ValueError(f"gemm_nt: incompatible shapes {tuple(A.shape)} x {tuple(B.shape)}")
+    if out is None:
+        out = torch.empty(batch, N, M, dtype=torch.float32, device=A.device)
+    check(lib.drg_gemm_nt_tf32(A.data_ptr(), B.data_ptr(), out.data_ptr(), batch, N, M, K, float(alpha), _stream()))
+    return out.squeeze(0) if squeeze else out
+
+
+def prep_operand(x, scale=1.0, split=True, pattern=0, pe=None, pe_type=None, want_embedded=False):
+    """Positional embedding + scaling + hi/lo split of a [..., K] feature tensor (drg_prep_operand).
+    Returns out ([..., 3K] if split else [..., K]) and, if want_embedded, the embedded features."""
+    _require_cuda(x, pe)
+    lib = load_library()
+    x = _f32c(x)
+    K = x.shape[-1]
+    rows = x.numel() // K
+    code = 0
+    if pe is not None:
+        code = {"rotary": 1, "sinusoidal": 2}[pe_type]
+        pe = _f32c(pe)
+        want = (*x.shape, 2) if code == 1 else tuple(x.shape)
+        if tuple(pe.shape) != want:
+            raise ValueError(f"prep_operand: position code shape {tuple(pe.shape)} != {want}")
+    out = torch.empty(*x.shape[:-1], 3 * K if split else K, dtype=torch.float32, device=x.device)
+    emb = torch.empty_like(x) if want_embedded else None
+    check(lib.drg_prep_operand(x.data_ptr(), _ptr(pe), code, rows, K, float(scale), int(bool(split)), int(pattern),
+                               _ptr(emb), out.data_ptr(), _stream()))
+    return (out, emb) if want_embedded else out
+
+
+def _match(x, mode, mutual, threshold, largest, want_mask, capacity=None):
+    """capacity=None: read the match count on the host (as torch.nonzero() does) and return exact-size outputs.
+    capacity=int: sync-free; returns (index [capacity,3], vals [capacity], mask, count) with the count on the device."""
+    _require_cuda(x)
+    lib = load_library()
+    x = _f32c(x)
+    B, N, M = x.shape
+    dev = x.device
+    nbytes = lib.drg_match_workspace_bytes(B, N, M)
+    ws = workspace(nbytes, dev, "match")
+    total = torch.empty(1, dtype=torch.int32, device=dev)
+    has_thr = threshold is not None
+    thr = float(threshold) if has_thr else 0.0
+    args = (x.data_ptr(), B, N, M, int(mode), int(bool(mutual)), int(has_thr), thr, int(bool(largest)), ws.data_ptr(), ws.numel())
+    check(lib.drg_match_count(*args, total.data_ptr(), _stream()))
+    k = int(total.item()) if capacity is None else int(capacity)
+    index = torch.empty(max(k, 1), 3, dtype=torch.int64, device=dev)
+    vals = torch.empty(max(k, 1), dtype=torch.float32, device=dev)
+    mask = torch.empty(B, N, M, dtype=torch.bool, device=dev) if want_mask else None
+    check(lib.drg_match_write(*args, index.data_ptr(), vals.data_ptr(), max(k, 1), _ptr(mask), _stream()))
+    if capacity is None:
+        return index[:k], vals[:k], mask
+    return index, vals, mask, total
+
+
+def get_match(conf, thr, mutual=True, want_mask=True):
+    """(index [K,3] int64, mconf [K], mask [B,N,M] bool) -- Matching.get_match."""
+    return _match(conf, 0, mutual, thr, True, want_mask)
+
+
+def top1_select(score_mat, largest=True, threshold=None, mutual=True):
+    """mutual_topk_select with k = 1 on a 2-D score matrix: (row_idx [K], col_idx [K], scores [K])."""
+    index, vals, _ = _match(score_mat.unsqueeze(0), 1, mutual, threshold, largest, False)
+    return index[:, 1].contiguous(), index[:, 2].contiguous(), vals
+
+
+def soft_procrustes(conf, src_pcd, tgt_pcd, src_mask, tgt_mask, sample_rate, max_condition_num, padded_lengths=False,
+                    want_warped=False, want_selection=False):
+    """SoftProcrustesLayer.forward on the device (drg_soft_procrustes).
+    Returns dict(R, t, R_forwd, t_forwd, condition, solution_mask[, src_warped][, sel_w, sel_src, sel_tgt])."""
+    _require_cuda(conf, src_pcd, tgt_pcd, src_mask, tgt_mask)
+    lib = load_library()
+    conf = _f32c(conf)
+    src_pcd = _f32c(src_pcd)
+    tgt_pcd = _f32c(tgt_pcd)
+    B, N, M = conf.shape
+    dev = conf.device
+    sm = _as_mask(src_mask) if src_mask is not None else None
+    tm = _as_mask(tgt_mask) if tgt_mask is not None else None
+    out = dict(R=torch.empty(B, 3, 3, dtype=torch.float32, device=dev), t=torch.empty(B, 3, 1, dtype=torch.float32, device=dev),
+               R_forwd=torch.empty(B, 3, 3, dtype=torch.float32, device=dev),
+               t_forwd=torch.empty(B, 3, 1, dtype=torch.float32, device=dev),
+               condition=torch.empty(B, dtype=torch.float64, device=dev),
+               solution_mask=torch.empty(B, dtype=torch.bool, device=dev))
+    if want_warped:
+        out["src_warped"] = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+    k_max = min(int(max(N, M) * float(sample_rate)) + 1, N * M)
+    if want_selection:
+        out["sel_w"] = torch.empty(B, k_max, dtype=torch.float32, device=dev)
+        out["sel_src"] = torch.empty(B, k_max, dtype=torch.int32, device=dev)
+        out["sel_tgt"] = torch.empty(B, k_max, dtype=torch.int32, device=dev)
+    nbytes = lib.drg_soft_procrustes_workspace_bytes(B, N, M)
+    ws = workspace(nbytes, dev, "procrustes")
+    a = _lib.ProcrustesArgs(conf=_ptr(conf), src_pcd=_ptr(src_pcd), tgt_pcd=_ptr(tgt_pcd), src_mask=_ptr(sm), tgt_mask=_ptr(tm),
+                            B=B, N=N, M=M, sample_rate=float(sample_rate), max_condition_num=float(max_condition_num),
+                            padded_lengths=int(bool(padded_lengths)), R=_ptr(out["R"]), t=_ptr(out["t"]),
+                            R_forwd=_ptr(out["R_forwd"]), t_forwd=_ptr(out["t_forwd"]), condition=_ptr(out["condition"]),
+                            solution_mask=_ptr(out["solution_mask"]), src_warped=_ptr(out.get("src_warped")), K_max=k_max,
+                            sel_w=_ptr(out.get("sel_w")), sel_src=_ptr(out.get("sel_src")), sel_tgt=_ptr(out.get("sel_tgt")))
+    check(lib.drg_soft_procrustes(a, ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
+def weighted_procrustes(X, Y, w, eps=1e-4):
+    """batch_weighted_procrustes on the device: X, Y [B,K,3], w [B,K,1] -> (R [B,3,3], t [B,3,1], condition [B] fp64)."""
+    _require_cuda(X, Y, w)
+    lib = load_library()
+    X = _f32c(X)
+    Y = _f32c(Y)
+    w = _f32c(w).reshape(X.shape[0], X.shape[1])
+    B, K, _ = X.shape
+    dev = X.device
+    R = torch.empty(B, 3, 3, dtype=torch.float32, device=dev)
+    t = torch.empty(B, 3, 1, dtype=torch.float32, device=dev)
+    cond = torch.empty(B, dtype=torch.float64, device=dev)
+    check(lib.drg_weighted_procrustes(X.data_ptr(), Y.data_ptr(), w.data_ptr(), B, K, float(eps), R.data_ptr(), t.data_ptr(),
+                                      cond.data_ptr(), _stream()))
+    return R, t, cond
+
+
+def sigmoid(x):
+    _require_cuda(x)
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    check(load_library().drg_sigmoid(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
+    return y
+
+
+def min_value(x):
+    """Global minimum as a 1-element device tensor (no host read)."""
+    _require_cuda(x)
+    x = _f32c(x)
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(1, dtype=torch.int32, device=x.device)
+    check(load_library().drg_min_value(x.data_ptr(), x.numel(), out.data_ptr(), scratch.data_ptr(), _stream()))
     return out

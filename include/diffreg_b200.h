@@ -78,7 +78,9 @@ typedef struct drg_sinkhorn_args {
   float* u;                /* [B,N+1] row potentials (optional, NULL = keep in workspace)        */
   float* v;                /* [B,M+1] column potentials (optional)                               */
   /* DRG_OUT_DDIM only */
-  const float* x_t;        /* [B,N,M] current sampler state (read as x_t - *shift)               */
+  const float* x_t;        /* [B,N,M] current sampler state (read as x_t - *xt_shift)            */
+  const float* xt_shift;   /* device scalar or NULL: the 3DMatch sampler's x.min() for x_t; `shift`
+                              above applies to `scores` only                                     */
   const float* noise;      /* [B,N,M] N(0,1) draws or NULL (no noise term)                       */
   float* conf;             /* optional [B,N,M]: also store x0 = conf                             */
   float k_x0, k_xt, sigma; /* x_next = k_x0*conf + k_xt*x_t + sigma*noise                        */
@@ -94,6 +96,93 @@ int drg_sinkhorn(const drg_sinkhorn_args* args, void* workspace, size_t workspac
  *   the temperature is applied here).  out[B,N,M]. */
 int drg_dual_softmax(const float* sim, const uint8_t* src_mask, const uint8_t* tgt_mask, int B, int N, int M,
                      float temperature, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Feature-similarity contraction on the tensor cores (tcgen05 / TMEM / TMA)
+ *   C[b] = alpha * A[b] . B[b]^T,  A [batch,N,K], B [batch,M,K], C [batch,N,M], all fp32 row-major.
+ *   replaces torch.einsum("bsc,btc->bst", src, tgt)   Diff-Reg-4dmatch/models/matching.py:149,161
+ *            (= Diff-Reg-3dmatch/models/matching.py:195,207; Diff-Reg-2d3d/experiments/<exp>/matching.py:110,122)
+ *   and, with B = the weight [C_out, C_in], the nn.Linear projections  matching.py:127-128.
+ *   Arithmetic: tcgen05.mma kind::tf32 with fp32 accumulation.  Feed operands produced by
+ *   drg_prep_operand(split=1) (K -> 3K) for an fp32-accurate ("3xTF32") product.
+ *   Requires K % 4 == 0 and 16-byte aligned A, B.  No workspace.
+ * ------------------------------------------------------------------------------------ */
+int drg_gemm_nt_tf32(const float* A, const float* B, float* C, int batch, int N, int M, int K, float alpha, void* stream);
+
+/* Operand preparation: positional embedding + scaling + optional hi/lo split.
+ *   replaces VolPE.embed_pos / embed_rotary   Diff-Reg-4dmatch/models/position_encoding.py:26-46
+ *   and       feat / feat.shape[-1] ** .5     Diff-Reg-4dmatch/models/matching.py:144-145
+ *   in [rows,K]; pe: rotary [rows,K,2] (cos,sin) for pe_type 1, additive [rows,K] for pe_type 2, NULL for 0;
+ *   embedded (optional) [rows,K] receives the features after the embedding and before scaling (data["src_feats"]);
+ *   out: split=0 -> [rows,K] = scale*x;  split=1 -> [rows,3K] = [lo|hi|hi] (pattern 0) or [hi|lo|hi] (pattern 1). */
+int drg_prep_operand(const float* in, const float* pe, int pe_type, long long rows, int K, float scale, int split, int pattern,
+                     float* embedded, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Correspondence extraction
+ *   mode 0: Matching.get_match(conf, thr, mutual)       Diff-Reg-4dmatch/models/matching.py:71-88 (= get_topk_match :90-107)
+ *           hit = conf > thr [and conf == row max and conf == column max]
+ *   mode 1: mutual_topk_select(score, k=1, largest, threshold, mutual)
+ *                                                       Diff-Reg-2d3d/vision3d/ops/mutual_topk_select.py:7-60
+ *           hit = (top-1 of its row) AND/OR (top-1 of its column) [and score > threshold]
+ *   Two calls because the number of matches is data dependent (the reference's nonzero() synchronises too):
+ *   drg_match_count leaves the total in *total_out (device int); the caller reads it, allocates
+ *   index_out [total,3] int64 (b, row, col; row-major order like nonzero()) and val_out [total], and calls
+ *   drg_match_write with the SAME arguments and workspace.  `capacity` is the number of slots in index_out / val_out
+ *   (hits beyond it are dropped, so a caller that sizes the outputs by an upper bound never needs the host read).
+ *   mask_out (optional, mode 0) is the [B,N,M] bool mask.
+ * ------------------------------------------------------------------------------------ */
+size_t drg_match_workspace_bytes(int B, int N, int M);
+int drg_match_count(const float* x, int B, int N, int M, int mode, int mutual, int has_thr, float thr, int largest, void* workspace,
+                    size_t workspace_bytes, int* total_out, void* stream);
+int drg_match_write(const float* x, int B, int N, int M, int mode, int mutual, int has_thr, float thr, int largest, void* workspace,
+                    size_t workspace_bytes, long long* index_out, float* val_out, long long capacity, unsigned char* mask_out,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * SoftProcrustes
+ *   replaces SoftProcrustesLayer.forward(conf, src_pcd, tgt_pcd, src_mask, tgt_mask)
+ *            Diff-Reg-4dmatch/models/procrustes.py:48-93 (3DMatch: Diff-Reg-3dmatch/models/procrustes.py:61-62)
+ *   and the warp of the source points by the gated pose, Diff-Reg-4dmatch/models/pipeline.py:220.
+ * ------------------------------------------------------------------------------------ */
+typedef struct drg_procrustes_args {
+  const float* conf;             /* [B,N,M]                                                          */
+  const float* src_pcd;          /* [B,N,3]                                                          */
+  const float* tgt_pcd;          /* [B,M,3]                                                          */
+  const uint8_t* src_mask;       /* [B,N] bool                                                       */
+  const uint8_t* tgt_mask;       /* [B,M] bool                                                       */
+  int B, N, M;
+  float sample_rate;             /* config.sample_rate                                               */
+  float max_condition_num;       /* config.max_condition_num                                         */
+  int padded_lengths;            /* 1: 3DMatch variant, lengths are N and M whatever the masks say   */
+  float* R;                      /* [B,3,3]                                                          */
+  float* t;                      /* [B,3,1]                                                          */
+  float* R_forwd;                /* [B,3,3] identity where the condition gate fails                  */
+  float* t_forwd;                /* [B,3,1] zero where the condition gate fails                      */
+  double* condition;             /* [B] fp64 (the reference returns it on the CPU; here on the device) */
+  uint8_t* solution_mask;        /* [B] bool                                                         */
+  float* src_warped;             /* optional [B,N,3]: R_forwd s + t_forwd                            */
+  int K_max;                     /* slots per batch element in sel_* (>= max(N,M)*sample_rate)       */
+  float* sel_w;                  /* optional [B,K_max]: weights of the selected correspondences      */
+  int* sel_src;                  /* optional [B,K_max]: their src indices                            */
+  int* sel_tgt;                  /* optional [B,K_max]: their tgt indices                            */
+} drg_procrustes_args;
+
+size_t drg_soft_procrustes_workspace_bytes(int B, int N, int M);
+int drg_soft_procrustes(const drg_procrustes_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Weighted Kabsch on given correspondences.
+ *   replaces SoftProcrustesLayer.batch_weighted_procrustes(X, Y, w, eps)  Diff-Reg-4dmatch/models/procrustes.py:18-44
+ *   X, Y [B,K,3], w [B,K] -> R [B,3,3], t [B,3,1], condition [B] fp64 */
+int drg_weighted_procrustes(const float* X, const float* Y, const float* w, int B, int K, float eps, float* R, float* t,
+                            double* condition, void* stream);
+
+/* Elementwise tail / head of the samplers.
+ *   drg_sigmoid:   conf_matrix_pred = sigmoid(x)        Diff-Reg-4dmatch/models/pipeline.py:192
+ *   drg_min_value: x.min() of the 3DMatch sampler       Diff-Reg-3dmatch/models/pipeline.py:239,264
+ *                  (scratch: one device uint32; *out receives the minimum) */
+int drg_sigmoid(const float* x, float* y, long long n, void* stream);
+int drg_min_value(const float* x, long long n, float* out, unsigned int* scratch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,3 +46,41 @@ def finite_close(a, b, tol):
     m = torch.isfinite(a) & torch.isfinite(b)
     err = (a[m] - b[m]).abs().max().item() if m.any() else 0.0
     return bool(same_inf) and err <= tol, err
+
+
+def check_top1_pairs(conf_ref, rows, cols, mutual, margin=MARGIN):
+    """Top-1 row/column selection against a reference confidence matrix [N,M], honouring the north_star rule:
+    indices must be identical wherever the reference's top-1 margin exceeds `margin`; inside the margin (ties,
+    e.g. all-zero padded rows where torch.topk's pick is implementation defined) any near-maximal entry is allowed.
+    Returns (ok, message)."""
+    conf_ref = conf_ref.double()
+    N, M = conf_ref.shape
+    got = set(zip(rows.tolist(), cols.tolist()))
+    rmax, rarg = conf_ref.max(dim=1)
+    cmax, carg = conf_ref.max(dim=0)
+    r2 = conf_ref.topk(min(2, M), dim=1)[0]
+    c2 = conf_ref.topk(min(2, N), dim=0)[0]
+    r_clear = (r2[:, 0] - r2[:, -1] > margin) if M > 1 else torch.ones(N, dtype=torch.bool)
+    c_clear = (c2[0] - c2[-1] > margin) if N > 1 else torch.ones(M, dtype=torch.bool)
+    near_row = conf_ref >= (rmax[:, None] - margin)
+    near_col = conf_ref >= (cmax[None, :] - margin)
+    row_hit = torch.zeros_like(near_row)
+    row_hit[torch.arange(N), rarg] = True
+    col_hit = torch.zeros_like(near_col)
+    col_hit[carg, torch.arange(M)] = True
+    if mutual:
+        required = row_hit & col_hit & r_clear[:, None] & c_clear[None, :]
+        allowed = near_row & near_col
+    else:
+        required = (row_hit & r_clear[:, None]) | (col_hit & c_clear[None, :])
+        allowed = near_row | near_col
+    req = set(map(tuple, required.nonzero().tolist()))
+    alw = set(map(tuple, allowed.nonzero().tolist()))
+    if not req <= got:
+        return False, f"missing required pairs {sorted(req - got)[:5]}"
+    if not got <= alw:
+        return False, f"pairs outside the margin {sorted(got - alw)[:5]}"
+    order = sorted(got)
+    if order != list(zip(rows.tolist(), cols.tolist())):
+        return False, "pairs are not in row-major order"
+    return True, ""

@@ -1,0 +1,73 @@
+"""Correspondence extraction (drg_match_count / drg_match_write) against the reference's golden
+vectors and the oracle.  Index work: bit-exact."""
+import pytest
+import torch
+
+from oracle import diffreg_oracle as O
+from helpers import load, names
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import diffreg_b200
+    return diffreg_b200.ops
+
+
+@pytest.mark.parametrize("name", names("getmatch_"))
+def test_get_match_golden(name):
+    g = load(name)
+    idx, mconf, mask = _ops().get_match(g["conf"].cuda(), float(g["thr"]), bool(g["mutual"]))
+    assert torch.equal(idx.cpu(), g["index"]) and torch.equal(mconf.cpu(), g["mconf"]) and torch.equal(mask.cpu(), g["mask"])
+
+
+@pytest.mark.parametrize("name", names("mts_"))
+def test_top1_select_golden(name):
+    g = load(name)
+    thr = float(g["threshold"]) if bool(g["has_threshold"]) else None
+    r, c, s = _ops().top1_select(g["score"].cuda(), True, thr, bool(g["mutual"]))
+    assert torch.equal(r.cpu(), g["rows"]) and torch.equal(c.cpu(), g["cols"]) and torch.equal(s.cpu(), g["scores"])
+
+
+@pytest.mark.parametrize("B,N,M", [(1, 1, 1), (2, 33, 65), (1, 257, 1030), (3, 128, 1024), (1, 1000, 37), (1, 2048, 2050)])
+@pytest.mark.parametrize("mutual", [True, False])
+def test_get_match_vs_oracle(B, N, M, mutual):
+    g = torch.Generator().manual_seed(N + M)
+    conf = torch.rand(B, N, M, generator=g)
+    conf[:, N // 2] = 0.0                      # an all-zero row (padded rows look like this)
+    if N > 2 and M > 2:
+        conf[0, 1, 1] = conf[0, 1, 2] = 2.0    # a tie for the row maximum
+    thr = 0.2 if mutual else 0.97
+    ref_idx, ref_conf, ref_mask = O.get_match(conf, thr, mutual)
+    idx, mconf, mask = _ops().get_match(conf.cuda(), thr, mutual)
+    assert torch.equal(idx.cpu(), ref_idx) and torch.equal(mconf.cpu(), ref_conf) and torch.equal(mask.cpu(), ref_mask)
+
+
+@pytest.mark.parametrize("N,M", [(1, 1), (40, 70), (513, 1025), (1200, 300), (2048, 2048)])
+@pytest.mark.parametrize("mutual", [True, False])
+@pytest.mark.parametrize("thr", [None, 0.999])
+def test_top1_select_vs_oracle(N, M, mutual, thr):
+    g = torch.Generator().manual_seed(N * 3 + M)
+    s = torch.rand(N, M, generator=g)
+    r0, c0, v0 = O.mutual_topk_select(s, 1, True, thr, mutual)
+    r, c, v = _ops().top1_select(s.cuda(), True, thr, mutual)
+    assert torch.equal(r.cpu(), r0) and torch.equal(c.cpu(), c0) and torch.equal(v.cpu(), v0)
+
+
+def test_top1_select_smallest():
+    g = torch.Generator().manual_seed(4)
+    s = torch.rand(90, 50, generator=g)
+    r0, c0, v0 = O.mutual_topk_select(s, 1, False, 0.5, True)
+    r, c, v = _ops().top1_select(s.cuda(), False, 0.5, True)
+    assert torch.equal(r.cpu(), r0) and torch.equal(c.cpu(), c0) and torch.equal(v.cpu(), v0)
+
+
+def test_full_size_mutual_property():
+    """4096 x 4096: every mutual match is the arg-max of its row and of its column; count matches torch."""
+    conf = torch.rand(1, 4096, 4096, generator=torch.Generator(device="cuda").manual_seed(1), device="cuda")
+    idx, mconf, _ = _ops().get_match(conf, 0.2, True, want_mask=False)
+    rows, cols = idx[:, 1], idx[:, 2]
+    assert torch.equal(conf[0].max(dim=1)[0][rows], mconf) and torch.equal(conf[0].max(dim=0)[0][cols], mconf)
+    assert torch.equal(conf[0, rows, cols], mconf) and bool((mconf > 0.2).all())
+    ref = O.get_match(conf, 0.2, True)[0]
+    assert torch.equal(idx, ref)

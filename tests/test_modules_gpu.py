@@ -1,0 +1,193 @@
+"""The drop-in modules (Matching, Matching2D3D, SoftProcrustesLayer, DenoisingSampler, module-level functions)
+against the reference's golden outputs.  Tolerances from BASELINE.json north_star: 1e-4 abs on confidences and
+the log matrix, 1e-5 rad / 1e-5 m on the pose, indices bit-exact where the reference's top-1 margin > 1e-5."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from helpers import MARGIN, TOL_LOG, TOL_ROT, TOL_TRANS, check_top1_pairs, finite_close, load, names, rot_angle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _cfg(C, match_type="sinkhorn", entangled=True):
+    return dict(match_type=match_type, confidence_threshold=0.2, feature_dim=C, entangled=entangled, dsmax_temperature=0.1,
+                skh_init_bin_score=1.0, skh_iters=3, skh_prefilter=False)
+
+
+def _head(cls, g, match_type="sinkhorn", entangled=True, **kw):
+    import diffreg_b200
+    C = g["W"].shape[0]
+    m = getattr(diffreg_b200, cls)(_cfg(C, match_type, entangled), **kw).to(DEV).eval()
+    with torch.no_grad():
+        m.src_proj.weight.copy_(g["W"].to(DEV))
+    return m
+
+
+def _cu(t):
+    return None if t is None else t.to(DEV)
+
+
+def _same_matches_where_margin(conf_ref, got, ref):
+    """Indices must be identical unless the reference's decision hangs on a margin below 1e-5."""
+    if torch.equal(got.cpu(), ref):
+        return True
+    top2 = conf_ref.topk(2, dim=-1)[0]
+    return bool(((top2[..., 0] - top2[..., 1]) < MARGIN).any())
+
+
+@pytest.mark.parametrize("name,mt,ent", [("match4d_sinkhorn", "sinkhorn", True), ("match4d_sinkhorn_prefix_b2", "sinkhorn", True),
+                                         ("match4d_dualsoftmax_b3", "dual_softmax", True), ("match4d_sinkhorn_rotary", "sinkhorn", False)])
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
+def test_matching_forward_3d(name, mt, ent, precision):
+    g = load(name)
+    m = _head("Matching", g, mt, ent, precision=precision)
+    data = {}
+    conf, match = m(_cu(g["src_feats"]), _cu(g["tgt_feats"]), _cu(g.get("src_pe")), _cu(g.get("tgt_pe")), _cu(g["src_mask"]),
+                    _cu(g["tgt_mask"]), data)
+    tol = TOL_LOG if precision == "3xtf32" else 2e-3
+    assert (conf.cpu() - g["conf"]).abs().max() <= tol
+    if precision == "3xtf32":
+        assert match.dtype == torch.int64 and _same_matches_where_margin(g["conf"], match, g["match"])
+        for k in ("src_feats", "tgt_feats", "src_feats_nopos", "tgt_feats_nopos"):
+            assert (data[k].cpu() - g["data_" + k]).abs().max() <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["match2d3d_mutual1", "match2d3d_mutual0"])
+def test_matching_forward_2d3d(name):
+    g = load(name)
+    m = _head("Matching2D3D", g)
+    conf, r, c, w = m(_cu(g["src_feats"]), _cu(g["tgt_feats"]), _cu(g["src_mask"]), _cu(g["tgt_mask"]), bool(g["mutual"]))
+    assert (conf.cpu() - g["conf"]).abs().max() <= TOL_LOG
+    ok, msg = check_top1_pairs(g["conf"][0], r.cpu(), c.cpu(), bool(g["mutual"]))
+    assert ok, msg
+    assert (w.cpu() - g["conf"][0][r.cpu(), c.cpu()]).abs().max() <= TOL_LOG
+    if bool(g["mutual"]):        # no padded-row ties can survive the mutual test: bit-exact
+        assert torch.equal(r.cpu(), g["src_indices"]) and torch.equal(c.cpu(), g["tgt_indices"])
+
+
+def test_matching_forward1_3d():
+    g = load("match3d_forward1")
+    m = _head("Matching", g)
+    conf, match = m.forward1(_cu(g["src_feats"]), _cu(g["tgt_feats"]), None, None, _cu(g["src_mask"]), _cu(g["tgt_mask"]), {},
+                             mutual=False)
+    assert (conf.cpu() - g["conf"]).abs().max() <= TOL_LOG
+    assert torch.equal(match.cpu(), g["match"])
+
+
+def test_state_dict_keys_match_reference():
+    import diffreg_b200
+    m = diffreg_b200.Matching(_cfg(32))
+    assert set(m.state_dict().keys()) == {"src_proj.weight", "tgt_proj.weight", "bin_score"}
+    m = diffreg_b200.Matching(_cfg(32, "dual_softmax"))
+    assert set(m.state_dict().keys()) == {"src_proj.weight", "tgt_proj.weight"}
+
+
+@pytest.mark.parametrize("name", [n for n in names("lot_")])
+def test_log_optimal_transport_function(name):
+    import diffreg_b200
+    g = load(name)
+    out = diffreg_b200.log_optimal_transport(_cu(g["scores"]), torch.tensor(float(g["alpha"]), device=DEV), int(g["iters"]),
+                                             _cu(g["src_mask"]), _cu(g["tgt_mask"]))
+    assert out.dtype == g["out"].dtype
+    tol = TOL_LOG if name != "lot_iters100" else 2e-4
+    ok, err = finite_close(out.cpu(), g["out"], tol)
+    assert ok, err
+
+
+@pytest.mark.parametrize("name", names("mts_"))
+def test_mutual_topk_select_function(name):
+    import diffreg_b200
+    g = load(name)
+    thr = float(g["threshold"]) if bool(g["has_threshold"]) else None
+    r, c, s = diffreg_b200.mutual_topk_select(_cu(g["score"]), 1, largest=True, threshold=thr, mutual=bool(g["mutual"]))
+    assert torch.equal(r.cpu(), g["rows"]) and torch.equal(c.cpu(), g["cols"]) and torch.equal(s.cpu(), g["scores"])
+    corr = diffreg_b200.mutual_topk_select(_cu(g["score"]), 1, threshold=thr, mutual=bool(g["mutual"]), reduce_result=False)
+    assert corr.dtype == torch.bool and int(corr.sum()) == len(g["rows"])
+    with pytest.raises(NotImplementedError):
+        diffreg_b200.mutual_topk_select(_cu(g["score"]), 2)
+
+
+@pytest.mark.parametrize("name", names("procrustes"))
+def test_soft_procrustes_layer(name):
+    import diffreg_b200
+    from diffreg_b200.procrustes import SoftProcrustesLayer3DMatch
+    g = load(name)
+    cls = SoftProcrustesLayer3DMatch if name.startswith("procrustes3d") else diffreg_b200.SoftProcrustesLayer
+    layer = cls(SimpleNamespace(sample_rate=float(g["sample_rate"]), max_condition_num=float(g["max_condition_num"])))
+    R, t, Rf, tf, cond, ok = layer(_cu(g["conf"]), _cu(g["s_pcd"]), _cu(g["t_pcd"]), _cu(g["src_mask"]), _cu(g["tgt_mask"]))
+    assert R.shape == g["R"].shape and t.shape == g["t"].shape and cond.dtype == torch.float64 and ok.dtype == torch.bool
+    assert torch.equal(ok.cpu(), g["solution_mask"])
+    assert rot_angle(Rf.cpu(), g["R_forwd"]).max() <= TOL_ROT and (tf.cpu() - g["t_forwd"]).abs().max() <= TOL_TRANS
+    good = torch.isfinite(g["condition"]) & (g["condition"] < 1e4)
+    if good.any():
+        assert rot_angle(R.cpu()[good], g["R"][good]).max() <= TOL_ROT and (t.cpu()[good] - g["t"][good]).abs().max() <= TOL_TRANS
+
+
+def test_forward_only_guard():
+    import diffreg_b200
+    m = diffreg_b200.Matching(_cfg(32)).to(DEV)
+    x = torch.randn(1, 8, 32, device=DEV, requires_grad=True)
+    ones = torch.ones(1, 8, dtype=torch.bool, device=DEV)
+    with pytest.raises(diffreg_b200._lib.DiffRegLibraryError):
+        diffreg_b200.log_optimal_transport(torch.randn(1, 4, 4, device=DEV, requires_grad=True), torch.tensor(1.0, device=DEV), 3,
+                                           ones[:, :4], ones[:, :4])
+    # CPU tensors have no path at all
+    with pytest.raises(diffreg_b200._lib.DiffRegLibraryError):
+        diffreg_b200.log_optimal_transport(torch.randn(1, 4, 4), torch.tensor(1.0), 3, ones[:, :4].cpu(), ones[:, :4].cpu())
+    del m, x
+
+
+@pytest.mark.parametrize("name", ["sampler4d_3steps", "sampler3d_3steps", "sampler2d3d_3steps"])
+def test_sampler_against_reference_trace(name):
+    import diffreg_b200
+    from diffreg_b200.procrustes import SoftProcrustesLayer3DMatch
+    g = load(name)
+    flavour, steps = str(g["flavour"]), int(g["steps"])
+    head = _head("Matching2D3D" if flavour == "2d3d" else "Matching", g)
+    pcls = SoftProcrustesLayer3DMatch if flavour == "3d" else diffreg_b200.SoftProcrustesLayer
+    proc = pcls(SimpleNamespace(sample_rate=1.0, max_condition_num=float(g["max_condition_num"])))
+    smp = diffreg_b200.DenoisingSampler(flavour, head, proc, steps)
+    trace = []
+    out = smp.sample(_cu(g["x_T"]), _cu(g["src_feats"]), _cu(g["tgt_feats"]), _cu(g["s_pcd"]), _cu(g["t_pcd"]), _cu(g["src_mask"]),
+                     _cu(g["tgt_mask"]), noises=[_cu(n) for n in g["noises"]], trace=trace)
+    for k in range(steps):
+        assert (trace[k]["x0"].cpu() - g[f"x0_{k}"]).abs().max() <= TOL_LOG
+        assert (trace[k]["pose"]["src_warped"].cpu() - g[f"warped_{k}"]).abs().max() <= 5e-5
+        ok, err = finite_close(trace[k]["x_out"].cpu(), g[f"x_out_{k}"].float(), TOL_LOG)
+        assert ok, (k, err)
+    ok, err = finite_close(out["conf_matrix_pred"].cpu(), g["conf_matrix_pred"].float(), TOL_LOG)
+    assert ok, err
+    if flavour != "4d":
+        mp = out["match_pred"].cpu()
+        ok, msg = check_top1_pairs(g["conf_matrix_pred"][0], mp[:, 1], mp[:, 2], False)
+        assert ok, msg
+
+
+def test_sampler_step_is_graph_capturable():
+    """No host read inside a step: capture one 4d step in a CUDA graph and replay it."""
+    import diffreg_b200
+    from oracle import diffreg_oracle as O
+    N = M = 256
+    pb = O.make_problem(5, 1, N, M, 64)
+    head = diffreg_b200.Matching(_cfg(64)).to(DEV).eval()
+    proc = diffreg_b200.SoftProcrustesLayer(SimpleNamespace(sample_rate=1.0, max_condition_num=40.0))
+    smp = diffreg_b200.DenoisingSampler("4d", head, proc, 20)
+    args = [pb[k].to(DEV) for k in ("src_feats", "tgt_feats", "s_pcd", "t_pcd", "src_mask", "tgt_mask")]
+    x = torch.randn(1, N, M, device=DEV)
+    noise = torch.randn(1, N, M, device=DEV)
+    eager, _, _ = smp.step(0, x, None, *args, noise=noise)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        smp.step(0, x, None, *args, noise=noise)          # warm-up on the capture stream (workspaces)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        captured, _, _ = smp.step(0, x, None, *args, noise=noise)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager)
