@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""Benchmark of the Diff-Reg denoising hot path on B200 (BASELINE.json metric: denoising steps/sec at
+N=M=4096, d=256; Sinkhorn HBM GB/s vs peak).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port) on the host
+
+One "step" is one reverse-diffusion step of one 4DMatch-shaped sample (BASELINE.json configs[2]: N=M=4096,
+d=256, Sinkhorn iters 3, eta=1 with noise), transformer excluded (features held fixed):
+    mask + Sinkhorn(x_t) + exp -> top-K + SoftProcrustes + warp -> projection + similarity GEMM
+    -> mask + Sinkhorn(sim) + exp -> mutual-NN matches at thr 0.2 -> DDIM update with fresh N(0,1) noise.
+Each GPU runs its own independent sample (weak scaling, no collective on the data path).
+
+Printed JSON line (rank 0): value = steps/s with inputs resident in HBM (CUDA-graph replay of the 20 step
+graphs); e2e = the same step driven through the public modules with HOST (pinned) inputs copied in and the
+step's results (pose, match count, matches) copied out every step; roofline = the fused Sinkhorn/DDIM call
+timed with CUDA events inside an eager pass over the same steps; cpu_baseline = the oracle port on the host.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_PTS = 4096
+FEAT_DIM = 256
+SAMPLER_STEPS = 20
+SKH_ITERS = 3
+METRIC = "denoising steps/sec at N=M=4096,d=256"
+UNIT = "steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_PTS, help="N = M (default: the headline 4096)")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32"])
+    return ap.parse_args()
+
+
+def workload_config(n, extra=None):
+    cfg = {"workload": f"4DMatch diffusion sampler (BASELINE.json configs[2]): B=1 per GPU, N=M={n}, d={FEAT_DIM}, "
+                       f"sampler steps={SAMPLER_STEPS}, sinkhorn iters={SKH_ITERS}, eta=1 with noise, thr=0.2",
+           "N": n, "M": n, "d": FEAT_DIM, "sampler_steps": SAMPLER_STEPS, "skh_iters": SKH_ITERS}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic inputs: unit-normal features, nn.Linear-style weight, rigidly related points
+# --------------------------------------------------------------------------------------------
+def make_inputs(seed, n, c):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    src_feats = torch.randn(1, n, c, generator=g)
+    tgt_feats = torch.randn(1, n, c, generator=g)
+    bound = 1.0 / math.sqrt(c)
+    W = (torch.rand(c, c, generator=g) * 2 - 1) * bound
+    s_pcd = torch.randn(1, n, 3, generator=g)
+    q = torch.randn(4, generator=g)
+    q = q / q.norm()
+    w, x, y, z = q.tolist()
+    R = torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    t = torch.randn(3, generator=g)
+    perm = torch.randint(0, n, (n,), generator=g)
+    t_pcd = (s_pcd[0, perm] @ R.t() + t + 0.01 * torch.randn(n, 3, generator=g))[None]
+    ones = torch.ones(1, n, dtype=torch.bool)
+    x_T = torch.randn(1, n, n, generator=g)
+    return dict(src_feats=src_feats, tgt_feats=tgt_feats, W=W, s_pcd=s_pcd, t_pcd=t_pcd, src_mask=ones, tgt_mask=ones.clone(),
+                x_T=x_T)
+
+
+MATCH_CFG = dict(match_type="sinkhorn", confidence_threshold=0.2, feature_dim=FEAT_DIM, entangled=True, dsmax_temperature=0.1,
+                 skh_init_bin_score=1.0, skh_iters=SKH_ITERS, skh_prefilter=False)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks during the timed region
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU leg: the oracle port (restatement of the reference's PyTorch code) on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_step_runner(n, seed=3000):
+    """Returns (run_one_step, cores).  The oracle is the checker / CPU baseline only (oracle/ header)."""
+    import torch
+    from oracle import diffreg_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    inp = make_inputs(seed, n, FEAT_DIM)
+    p = O.MatchingParams(src_proj_weight=inp["W"], bin_score=torch.tensor(1.0), skh_iters=SKH_ITERS)
+    ac = O.alphas_cumprod()
+    pairs = O.time_pairs(SAMPLER_STEPS)
+    state = {"x": inp["x_T"].clone(), "k": 0}
+    g = torch.Generator().manual_seed(seed + 1)
+
+    def one_step():
+        with torch.no_grad():
+            t, tn = pairs[state["k"] % SAMPLER_STEPS]
+            x = state["x"]
+            O.noisy_matching_to_pose(x, p.bin_score, p.skh_iters, inp["s_pcd"], inp["t_pcd"], inp["src_mask"], inp["tgt_mask"],
+                                     1.0, 40.0)
+            sim, *_ = O.similarity(p, inp["src_feats"], inp["tgt_feats"])
+            x0 = O.confidence_from_similarity(p, sim, inp["src_mask"], inp["tgt_mask"])
+            O.get_match(x0, p.confidence_threshold)
+            noise = torch.randn(x.shape, generator=g)
+            state["x"] = O.ddim_update(x, x0, ac, t, tn, noise).float()
+            state["k"] += 1
+
+    return one_step, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    one_step, cores = cpu_step_runner(args.n)
+    for _ in range(args.warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    sample = f"{args.steps} full denoising steps at N=M={args.n} on {cores} host threads (torch CPU, fp32; oracle port of the reference)"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference", "config": workload_config(args.n),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# this framework
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from types import SimpleNamespace
+    import diffreg_b200
+    from diffreg_b200 import ops, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (diffreg_b200 has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n, c = args.n, FEAT_DIM
+    host = make_inputs(3000 + rank, n, c)
+    pinned = {k: host[k].pin_memory() for k in ("src_feats", "tgt_feats", "s_pcd", "t_pcd", "src_mask", "tgt_mask")}
+    d = {k: v.to(dev) for k, v in host.items()}
+    head = diffreg_b200.Matching(MATCH_CFG, precision=args.precision).to(dev).eval()
+    with torch.no_grad():
+        head.src_proj.weight.copy_(d["W"])
+    proc = diffreg_b200.SoftProcrustesLayer(SimpleNamespace(sample_rate=1.0, max_condition_num=40.0))
+    smp = diffreg_b200.DenoisingSampler("4d", head, proc, SAMPLER_STEPS, noise_seed=1234 + rank)
+    feats = [d[k] for k in ("src_feats", "tgt_feats", "s_pcd", "t_pcd", "src_mask", "tgt_mask")]
+    bufs = [d["x_T"].clone(), torch.empty_like(d["x_T"])]
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def eager_step(i):
+        k = i % SAMPLER_STEPS
+        return smp.step(k, bufs[i % 2], None, *feats, x_out=bufs[(i + 1) % 2], noise_counter=counter)
+
+    # ---- warm-up (eager) and graph capture of the 20 distinct steps
+    for i in range(max(args.warmup, 3)):
+        eager_step(i)
+    torch.cuda.synchronize()
+    graphs = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                eager_step(0)
+                eager_step(1)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graphs = []
+            pool = None
+            for k in range(SAMPLER_STEPS):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, pool=pool):
+                    eager_step(k)
+                pool = gph.pool()
+                graphs.append(gph)
+        except Exception as e:  # noqa: BLE001 -- report and fall back to eager timing
+            print(f"[bench] CUDA graph capture failed ({e}); timing eager launches", file=sys.stderr)
+            graphs = None
+    bufs[0].copy_(d["x_T"])
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % SAMPLER_STEPS].replay()
+        else:
+            eager_step(i)
+
+    # kernels per step (counted once, eagerly)
+    torch.cuda.synchronize()
+    c0 = diffreg_b200.launch_count()
+    eager_step(0)
+    torch.cuda.synchronize()
+    launches_per_step = diffreg_b200.launch_count() - c0
+    bufs[0].copy_(d["x_T"])
+
+    # ---- timed region 1: inputs resident in HBM
+    for i in range(args.warmup):
+        run_step(i)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run_step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clock_info = clocks.stop() if rank == 0 else None
+    if dist is not None:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- timed region 2 (e2e): host inputs in, step results out, every step, through the public modules
+    dev_in = {k: torch.empty_like(v, device=dev) for k, v in pinned.items()}
+    cap = n
+    host_out = {"R": torch.empty(1, 3, 3).pin_memory(), "t": torch.empty(1, 3, 1).pin_memory(),
+                "cond": torch.empty(1, dtype=torch.float64).pin_memory(), "count": torch.empty(1, dtype=torch.int32).pin_memory(),
+                "index": torch.empty(cap, 3, dtype=torch.int64).pin_memory(), "mconf": torch.empty(cap).pin_memory()}
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+
+    def e2e_step(i):
+        for k2, v in pinned.items():
+            dev_in[k2].copy_(v, non_blocking=True)
+        k = i % SAMPLER_STEPS
+        _, _, aux = smp.step(k, bufs[i % 2], None, dev_in["src_feats"], dev_in["tgt_feats"], dev_in["s_pcd"], dev_in["t_pcd"],
+                             dev_in["src_mask"], dev_in["tgt_mask"], x_out=bufs[(i + 1) % 2], noise_counter=counter)
+        index, mconf, _, count = aux["match"]
+        host_out["R"].copy_(aux["pose"]["R_forwd"], non_blocking=True)
+        host_out["t"].copy_(aux["pose"]["t_forwd"], non_blocking=True)
+        host_out["cond"].copy_(aux["pose"]["condition"], non_blocking=True)
+        host_out["count"].copy_(count, non_blocking=True)
+        host_out["index"].copy_(index, non_blocking=True)
+        host_out["mconf"].copy_(mconf, non_blocking=True)
+        torch.cuda.synchronize()          # the caller consumes the step's result on the host
+        return int(host_out["count"][0])
+
+    bufs[0].copy_(d["x_T"])
+    for i in range(max(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    l0 = diffreg_b200.launch_count()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(args.warmup + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = diffreg_b200.launch_count() - l0
+    barrier()
+    if dist is not None:
+        tt = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = world * args.steps / e2e_s
+
+    # ---- roofline leg: eager pass over the same steps with the library's per-kernel CUDA-event hooks
+    roofline = None
+    kernel_ms = None
+    if rank == 0:
+        bufs[0].copy_(d["x_T"])
+        for i in range(3):
+            eager_step(i)
+        torch.cuda.synchronize()
+        _lib.profile_enable(True)
+        ev = []
+        for i in range(args.steps):
+            eager_step(3 + i)
+        torch.cuda.synchronize()
+        prof = _lib.profile_read()
+        _lib.profile_enable(False)
+        kernel_ms = {k: round(v[0] / max(args.steps, 1), 5) for k, v in prof.items()}
+        # dominant kernel: the Sinkhorn iteration (row + column log-sum-exp in one read of the matrix)
+        it_ms, it_n = prof["skh_iter"]
+        E = 4.0 * (n + 1) * (n + 1)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        if it_n:
+            per_launch_s = it_ms * 1e-3 / it_n
+            achieved = 2.0 * E / per_launch_s / 1e9          # one iteration = 1 row-LSE read + 1 column-LSE read (algorithmic)
+            roofline = {"bound": "hbm", "kernel": "skh_iter_kernel (one Sinkhorn iteration: row and column log-sum-exp)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "algorithmic_bytes_per_launch": 2.0 * E, "us_per_launch": per_launch_s * 1e6, "launches": it_n,
+                        "peak_source": peak_src}
+        # the fused Sinkhorn call as a whole (BASELINE.json: "(2I+2)E" per log_optimal_transport)
+        skh_ms = sum(prof[k][0] for k in ("skh_prep", "skh_iter", "skh_col", "skh_final"))
+        calls = 2 * args.steps
+        if roofline is not None and calls:
+            roofline["sinkhorn_call"] = {"algorithmic_bytes": (2 * SKH_ITERS + 2) * E, "us_per_call": skh_ms * 1e3 / calls,
+                                         "achieved": (2 * SKH_ITERS + 2) * E / (skh_ms * 1e-3 / calls) / 1e9,
+                                         "frac": (2 * SKH_ITERS + 2) * E / (skh_ms * 1e-3 / calls) / 1e9 / peak}
+
+    # ---- CPU baseline (rank 0, single-GPU runs only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        one_step, cores = cpu_step_runner(n)
+        one_step()
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 12):
+            one_step()
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{reps} full denoising steps at N=M={n} (oracle port of the reference's PyTorch path, torch CPU fp32, "
+                         f"after 1 warm-up step)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (tf32x3 tensor-core GEMM, fp32 accumulate)" if args.precision == "3xtf32" else "tf32",
+                "data": "synthetic",
+                "config": workload_config(n, {"timing": "cuda_graph_replay" if graphs is not None else "eager",
+                                              "l2": "no explicit flush: each step streams five distinct 64 MiB fp32 matrices "
+                                                    "(x_t, conf_d, sim, x0, x_next) > 126 MB L2",
+                                              "precision": args.precision, "noise": "in-kernel Philox4x32-10"}),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(e2e_launches * world), "launches_per_step": int(launches_per_step),
+                "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "kernel_ms_per_step": kernel_ms}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,8 @@ class SinkhornArgs(ctypes.Structure):
         ("out_mode", c_int), ("out", c_void_p), ("u", c_void_p), ("v", c_void_p),
         ("x_t", c_void_p), ("xt_shift", c_void_p), ("noise", c_void_p), ("conf", c_void_p),
         ("k_x0", c_float), ("k_xt", c_float), ("sigma", c_float), ("x_min", c_void_p),
+        ("gen_noise", c_int), ("noise_seed", ctypes.c_ulonglong), ("noise_offset", ctypes.c_ulonglong),
+        ("noise_offset_dev", c_void_p),
     ]
 
 
@@ -73,6 +75,14 @@ def _declare(lib):
     lib.drg_weighted_procrustes.restype = c_int
     lib.drg_weighted_procrustes.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                             c_void_p]
+    lib.drg_profile_enable.restype = None
+    lib.drg_profile_enable.argtypes = [c_int]
+    lib.drg_profile_reset.restype = None
+    lib.drg_profile_read.restype = c_int
+    lib.drg_profile_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
+    lib.drg_profile_slots.restype = c_int
+    lib.drg_counter_add.restype = c_int
+    lib.drg_counter_add.argtypes = [c_void_p, ctypes.c_ulonglong, c_void_p]
     lib.drg_sigmoid.restype = c_int
     lib.drg_sigmoid.argtypes = [c_void_p, c_void_p, c_ll, c_void_p]
     lib.drg_min_value.restype = c_int
@@ -100,3 +110,24 @@ def check(status):
 
 def launch_count():
     return int(load_library().drg_launch_count())
+
+
+PROFILE_SLOTS = ["skh_iter", "skh_col", "skh_final", "skh_prep", "gemm", "prep_operand", "rowcol_best", "match_rows",
+                 "topk_collect", "procr_solve", "topk_threshold"]
+
+
+def profile_enable(on=True):
+    lib = load_library()
+    lib.drg_profile_reset()
+    lib.drg_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{slot name: (total_ms, launches)} for the launches recorded since profile_enable()."""
+    lib = load_library()
+    out = {}
+    for k, name in enumerate(PROFILE_SLOTS):
+        ms, n = ctypes.c_double(0.0), ctypes.c_longlong(0)
+        check(lib.drg_profile_read(k, ctypes.byref(ms), ctypes.byref(n)))
+        out[name] = (ms.value, n.value)
+    return out

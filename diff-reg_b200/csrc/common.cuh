@@ -49,6 +49,38 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- optional per-kernel timing (bench.py's roofline leg) ---------------------------------
+// When enabled through drg_profile_enable(1), every launch of a slotted kernel is bracketed by two
+// CUDA events on the launching stream; drg_profile_read() sums the elapsed times.  Disabled: no cost.
+enum ProfSlot {
+  PROF_SKH_ITER = 0,
+  PROF_SKH_COL,
+  PROF_SKH_FINAL,
+  PROF_SKH_PREP,
+  PROF_GEMM,
+  PROF_PREP_OPERAND,
+  PROF_ROWCOL_BEST,
+  PROF_MATCH_ROWS,
+  PROF_TOPK_COLLECT,
+  PROF_PROCR_SOLVE,
+  PROF_TOPK_THRESHOLD,
+  PROF_NSLOTS
+};
+extern std::atomic<int> g_prof_enabled;
+void prof_begin(int slot, cudaStream_t st);
+void prof_end(int slot, cudaStream_t st);
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  bool on;
+  ProfScope(int s, cudaStream_t stream) : slot(s), st(stream), on(g_prof_enabled.load(std::memory_order_relaxed) != 0) {
+    if (on) prof_begin(slot, st);
+  }
+  ~ProfScope() {
+    if (on) prof_end(slot, st);
+  }
+};
+
 // ---- device helpers -------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ float ex2(float x) {

@@ -113,7 +113,10 @@ extern "C" int drg_prep_operand(const float* in, const float* pe, int pe_type, l
   const long long total = rows * (K / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
-  prep_operand_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  {
+    ProfScope prof_scope(PROF_PREP_OPERAND, (cudaStream_t)stream);
+    prep_operand_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }
@@ -135,6 +138,16 @@ __global__ void __launch_bounds__(256) min_kernel(const float* __restrict__ x, s
 __global__ void min_init_kernel(unsigned int* o) { *o = 0xFFFFFFFFu; }
 __global__ void min_finish_kernel(const unsigned int* o, float* out) { *out = ordered_to_float(*o); }
 }  // namespace drg
+
+namespace drg {
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+}  // namespace drg
+extern "C" int drg_counter_add(unsigned long long* counter, unsigned long long inc, void* stream) {
+  DRG_CHECK_ARG(counter != nullptr, "counter is null");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
 
 extern "C" int drg_sigmoid(const float* x, float* y, long long n, void* stream) {
   DRG_CHECK_ARG(x && y && n >= 1, "x/y must be non-null and n >= 1");

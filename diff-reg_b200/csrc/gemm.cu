@@ -359,7 +359,10 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM, tiles_n = (s.M + BN - 1) / BN;
   const long long tiles = (long long)s.batch * tiles_m * tiles_n;
   const int grid = (int)(tiles < NUM_SMS ? tiles : NUM_SMS);
-  gemm_tf32_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, s);
+  {
+    ProfScope prof_scope(PROF_GEMM, st);
+    gemm_tf32_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, s);
+  }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }

@@ -300,14 +300,23 @@ extern "C" int drg_match_count(const float* x, int B, int N, int M, int mode, in
     dim3 grid((M + MT_STRIP - 1) / MT_STRIP, (N + MT_BAND - 1) / MT_BAND, B);
     const bool vec = (M % 4 == 0) && (((uintptr_t)x & 15u) == 0);
     if (vec)
-      rowcol_best_kernel<true><<<grid, MT_THREADS, 0, st>>>(x, N, M, largest, w.rowbest, w.colbest);
+      {
+        ProfScope prof_scope(PROF_ROWCOL_BEST, st);
+        rowcol_best_kernel<true><<<grid, MT_THREADS, 0, st>>>(x, N, M, largest, w.rowbest, w.colbest);
+      }
     else
-      rowcol_best_kernel<false><<<grid, MT_THREADS, 0, st>>>(x, N, M, largest, w.rowbest, w.colbest);
+      {
+        ProfScope prof_scope(PROF_ROWCOL_BEST, st);
+        rowcol_best_kernel<false><<<grid, MT_THREADS, 0, st>>>(x, N, M, largest, w.rowbest, w.colbest);
+      }
     DRG_LAUNCH_CHECK();
   }
   MatchParams p = match_params(x, B, N, M, mode, mutual, has_thr, thr, largest, w);
   const int nrows = B * N;
-  match_rows_kernel<false><<<(nrows + 7) / 8, 256, 0, st>>>(p);
+  {
+    ProfScope prof_scope(PROF_MATCH_ROWS, st);
+    match_rows_kernel<false><<<(nrows + 7) / 8, 256, 0, st>>>(p);
+  }
   DRG_LAUNCH_CHECK();
   scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, nrows, w.offsets, total_out);
   DRG_LAUNCH_CHECK();

@@ -9,33 +9,32 @@
 //
 // The reference sorts all N*M confidences to use the best K = max(|src|,|tgt|)*rate of them and
 // ships a 3x3 matrix to the host for a LAPACK SVD.  Here:
-//   1. procr_setup_kernel     mask counts -> per-batch K_b (all on the device)
-//   2. topk_sample_kernel     histogram (top 11 bits of the order-preserving key) of a hashed
-//                             sample of the matrix
-//   3. topk_pick_kernel       choose a lower bound L with ~3x K_b expected entries above it
-//   4. topk_collect_kernel    ONE pass over the matrix: entries >= L are appended to a candidate
+//   1. topk_threshold_kernel  one CTA per batch element: mask counts -> K_b; 32768 hashed samples of the
+//                             matrix into shared memory; EXACT radix select of the t-th largest sample
+//                             (64-bit key = ordered value << 32 | ~flat index, so ties are ordered too),
+//                             t ~ 2x the expected number of top-K_b entries in the sample -> lower bound L
+//   2. topk_collect_kernel    ONE pass over the matrix: entries with key >= L are appended to a candidate
 //                             list (warp-aggregated atomics); everything else is never touched again
-//   5. procr_solve_kernel     one CTA per batch element: exact radix select of the K_b largest
-//                             candidates (64-bit key = value | ~flat index, so there are no ties),
-//                             fp64 weighted moments, closed-form 3x3 SVD (one-sided Jacobi, fp64),
-//                             reflection fix, condition-number gate, and the src-point warp.
-// If the sample misleads (fewer than K_b candidates) the solve kernel falls back to collecting the
-// whole matrix itself: slow, but exact.
+//   3. procr_solve_kernel     one CTA per batch element: exact radix select of the K_b largest
+//                             candidates, fp64 weighted moments, closed-form 3x3 SVD (one-sided Jacobi,
+//                             fp64), reflection fix, condition-number gate, and the src-point warp.
+// Because L is an order statistic of the sample (not a histogram bin edge) the candidate list holds
+// ~2 K_b + 32 N M / 32768 entries whatever the value distribution (flat, tied or all-zero matrices
+// included).  If the sample still misleads (fewer than K_b candidates) the solve kernel falls back to
+// collecting the whole matrix itself: slow, but exact.
 #include "common.cuh"
 
 namespace drg {
 
 constexpr int TK_BINS = 2048;
-constexpr int TK_SAMPLE_CTAS = 64;
-constexpr int TK_SAMPLE_THREADS = 256;
-constexpr int TK_SAMPLE_PER_THREAD = 4;  // float4 each -> 64*256*4*4 = 262144 sampled entries per batch element
+constexpr int TS_THREADS = 512;
+constexpr int TS_SAMPLES = 32768;  // sample keys held in shared memory (128 KB)
 constexpr int SOLVE_THREADS = 1024;
 
 struct ProcrState {  // per batch element
-  int Kb;                    // number of correspondences to use
-  unsigned int lower_key;    // candidates have ordered key >= lower_key
-  unsigned int n_cand;       // candidates appended so far
-  int sample_all;            // the "sample" covered the whole matrix
+  int Kb;                         // number of correspondences to use
+  unsigned int n_cand;            // candidates appended so far
+  unsigned long long lower_key;   // candidates have 64-bit key >= lower_key
 };
 
 struct ProcrParams {
@@ -50,7 +49,6 @@ struct ProcrParams {
   int padded_lengths;            // 3DMatch variant: lengths are N, M whatever the masks say
   // workspace
   ProcrState* state;             // [B]
-  unsigned int* hist;            // [B, TK_BINS]
   unsigned int* cand_key;        // [B, N*M]
   unsigned int* cand_idx;        // [B, N*M]
   // outputs
@@ -77,108 +75,149 @@ __device__ __forceinline__ unsigned int hash_u32(unsigned int x) {
   return x;
 }
 
-// ---- 1. setup -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) procr_setup_kernel(const ProcrParams p) {
-  __shared__ int red[2];
-  __shared__ float cap_sum;
-  __shared__ int caps[1024];
-  if (threadIdx.x == 0) cap_sum = 0.f;
-  for (int b = 0; b < p.B; ++b) {
-    if (threadIdx.x < 2) red[threadIdx.x] = 0;
+__device__ __forceinline__ unsigned long long make_key64(unsigned int ordered_value, unsigned int flat_index) {
+  return ((unsigned long long)ordered_value << 32) | (unsigned long long)(0xFFFFFFFFu - flat_index);
+}
+
+// Exact selection of the k-th largest of n distinct 64-bit keys by one CTA (1 <= k <= n).
+// key_at(e) returns the key of element e.  Six radix levels (11,11,10,11,11,10 bits, MSB first); stops
+// early once the remaining bucket is wanted whole.  Returns T such that exactly k keys are >= T.
+// scratch: hist[TK_BINS] plus three words of shared memory.
+struct SelectScratch {
+  unsigned int hist[TK_BINS];
+  unsigned long long prefix;
+  int krem;
+  int done;
+};
+
+template <int NT, class KeyAt>
+__device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, SelectScratch& sc) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    sc.prefix = 0ull;
+    sc.krem = k;
+    sc.done = 0;
+  }
+  __syncthreads();
+  int shift = 64;
+  const int widths[6] = {11, 11, 10, 11, 11, 10};
+  for (int level = 0; level < 6; ++level) {
+    const int wbits = widths[level];
+    shift -= wbits;
+    for (int q = tid; q < TK_BINS; q += NT) sc.hist[q] = 0u;
     __syncthreads();
-    int cs = 0, ct = 0;
-    if (!p.padded_lengths) {
-      for (int i = threadIdx.x; i < p.N; i += blockDim.x) cs += p.src_mask[(size_t)b * p.N + i] ? 1 : 0;
-      for (int j = threadIdx.x; j < p.M; j += blockDim.x) ct += p.tgt_mask[(size_t)b * p.M + j] ? 1 : 0;
-      cs = __reduce_add_sync(0xffffffffu, cs);
-      ct = __reduce_add_sync(0xffffffffu, ct);
-      if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&red[0], cs);
-        atomicAdd(&red[1], ct);
+    const unsigned long long prefix = sc.prefix;
+    const int hi_shift = shift + wbits;  // bits above the current digit
+    for (size_t e = tid; e < n; e += NT) {
+      const unsigned long long key = key_at(e);
+      const bool match = (hi_shift >= 64) ? true : ((key >> hi_shift) == prefix);
+      if (match) atomicAdd(&sc.hist[(unsigned int)((key >> shift) & ((1u << wbits) - 1u))], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // warp 0 walks the histogram from the top: lane l owns the l-th chunk of bins (descending)
+      const int nb = 1 << wbits, chunk = nb >> 5;
+      const int hi = nb - 1 - chunk * tid;  // highest bin of this lane's chunk
+      unsigned int local = 0u;
+      for (int d = hi; d > hi - chunk; --d) local += sc.hist[d];
+      unsigned int incl = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int tmp = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += tmp;
+      }
+      const unsigned int krem = (unsigned int)sc.krem;
+      const unsigned int crossing = __ballot_sync(0xffffffffu, incl >= krem);
+      const int owner = crossing ? (__ffs(crossing) - 1) : 31;
+      if (tid == owner) {
+        unsigned int cum = incl - local;
+        int d = hi;
+        for (; d > hi - chunk + 1; --d) {
+          if (cum + sc.hist[d] >= krem) break;
+          cum += sc.hist[d];
+        }
+        sc.prefix = (prefix << wbits) | (unsigned long long)d;
+        sc.krem = (int)(krem - cum);
+        if (sc.hist[d] == krem - cum) sc.done = 1;  // the whole bucket is wanted
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      const int ns = p.padded_lengths ? p.N : red[0];
-      const int nt = p.padded_lengths ? p.M : red[1];
-      // (max(len) * sample_rate).int()   procrustes.py:63-64 (fp32 product, truncation)
-      const int cap = (int)((float)max(ns, nt) * p.sample_rate);
-      caps[b & 1023] = cap;
-      cap_sum += (float)cap;
-    }
-    __syncthreads();
+    if (sc.done) break;
   }
-  if (threadIdx.x == 0) {
-    // sample_n_points = entry_max.float().mean().int()   procrustes.py:65
-    const int K = (int)(cap_sum / (float)p.B);
-    for (int b = 0; b < p.B; ++b) {
-      ProcrState s;
-      s.Kb = min(min(K, caps[b & 1023]), p.K_max);
-      s.lower_key = 0u;
-      s.n_cand = 0u;
-      s.sample_all = 0;
-      p.state[b] = s;
-    }
-  }
-  for (int k = threadIdx.x; k < p.B * TK_BINS; k += blockDim.x) p.hist[k] = 0u;
+  const unsigned long long T = sc.prefix << shift;
+  __syncthreads();
+  return T;
 }
 
-// ---- 2. sample histogram --------------------------------------------------------------------
-__global__ void __launch_bounds__(TK_SAMPLE_THREADS) topk_sample_kernel(const ProcrParams p) {
-  __shared__ unsigned int h[TK_BINS];
-  const int b = blockIdx.y;
-  for (int k = threadIdx.x; k < TK_BINS; k += blockDim.x) h[k] = 0u;
-  __syncthreads();
+// ---- 1. K_b and the sample-based lower bound ---------------------------------------------------
+__global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrParams p) {
+  extern __shared__ unsigned int sample_key[];  // [TS_SAMPLES]
+  __shared__ SelectScratch sc;
+  __shared__ unsigned long long cnt_s;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  // ---- mask counts of every batch element (K is a mean over the batch)      procrustes.py:61-65
+  float cap_sum = 0.f;
+  int my_cap = 0;
+  for (int bb = 0; bb < p.B; ++bb) {
+    int ns = p.N, nt = p.M;
+    if (!p.padded_lengths) {
+      if (tid == 0) cnt_s = 0ull;
+      __syncthreads();
+      unsigned long long c = 0ull;
+      for (int i = tid; i < p.N; i += TS_THREADS) c += p.src_mask[(size_t)bb * p.N + i] ? (1ull << 32) : 0ull;
+      for (int j = tid; j < p.M; j += TS_THREADS) c += p.tgt_mask[(size_t)bb * p.M + j] ? 1ull : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if ((tid & 31) == 0) atomicAdd(&cnt_s, c);
+      __syncthreads();
+      ns = (int)(cnt_s >> 32);
+      nt = (int)(cnt_s & 0xFFFFFFFFull);
+      __syncthreads();
+    }
+    // (max(len) * sample_rate).int()   procrustes.py:63-64 (fp32 product, truncation)
+    const int cap = (int)((float)max(ns, nt) * p.sample_rate);
+    cap_sum += (float)cap;
+    if (bb == b) my_cap = cap;
+  }
+  // sample_n_points = entry_max.float().mean().int()   procrustes.py:65
+  const int K = (int)(cap_sum / (float)p.B);
+  const int Kb = min(min(K, my_cap), p.K_max);
+
+  // ---- sample the matrix
   const size_t total = (size_t)p.N * p.M;
   const float* x = p.conf + (size_t)b * total;
-  const size_t n_sample = (size_t)TK_SAMPLE_CTAS * TK_SAMPLE_THREADS * TK_SAMPLE_PER_THREAD * 4;
-  const unsigned int t = blockIdx.x * TK_SAMPLE_THREADS + threadIdx.x;
-  if (total <= n_sample || (total & 3) != 0 || (((uintptr_t)x) & 15u) != 0) {
-    // small (or unaligned) matrix: histogram all of it
-    for (size_t e = t; e < total; e += (size_t)TK_SAMPLE_CTAS * TK_SAMPLE_THREADS)
-      atomicAdd(&h[float_to_ordered(x[e]) >> 21], 1u);
-    if (t == 0) p.state[b].sample_all = 1;
-  } else {
-    const unsigned int n4 = (unsigned int)(total >> 2);
-#pragma unroll
-    for (int s = 0; s < TK_SAMPLE_PER_THREAD; ++s) {
-      const unsigned int q = hash_u32(t * TK_SAMPLE_PER_THREAD + s + 0x9e3779b9u * (unsigned int)(b + 1)) % n4;
-      const float4 v = *reinterpret_cast<const float4*>(x + (size_t)q * 4);
-      atomicAdd(&h[float_to_ordered(v.x) >> 21], 1u);
-      atomicAdd(&h[float_to_ordered(v.y) >> 21], 1u);
-      atomicAdd(&h[float_to_ordered(v.z) >> 21], 1u);
-      atomicAdd(&h[float_to_ordered(v.w) >> 21], 1u);
+  const bool all = total <= (size_t)TS_SAMPLES;
+  const unsigned int n_s = all ? (unsigned int)total : (unsigned int)TS_SAMPLES;
+  const unsigned int salt = 0x9e3779b9u * (unsigned int)(b + 1);
+  auto sample_pos = [&](unsigned int q) -> unsigned int {
+    return all ? q : (unsigned int)(((unsigned long long)hash_u32(q + salt) * (unsigned long long)total) >> 32);
+  };
+  for (unsigned int q = tid; q < n_s; q += TS_THREADS) sample_key[q] = float_to_ordered(x[sample_pos(q)]);
+  __syncthreads();
+
+  // ---- the t-th largest sample key is the lower bound
+  unsigned long long lower = 0ull;
+  if (Kb > 0) {
+    long long target;
+    if (all) {
+      target = Kb;  // the sample IS the matrix: the bound is the exact K_b-th largest
+    } else {
+      // twice the expected number of top-K_b entries inside the sample, plus slack for small counts
+      const double expect = (double)Kb * ((double)n_s / (double)total);
+      target = (long long)(2.0 * expect + 32.0);
+    }
+    if (target < (long long)n_s) {
+      lower = block_select_kth<TS_THREADS>(
+          [&](size_t e) { return make_key64(sample_key[e], sample_pos((unsigned int)e)); }, (size_t)n_s, (int)target, sc);
     }
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < TK_BINS; k += blockDim.x)
-    if (h[k]) atomicAdd(&p.hist[(size_t)b * TK_BINS + k], h[k]);
-}
-
-// ---- 3. pick the lower bound ----------------------------------------------------------------
-__global__ void __launch_bounds__(32) topk_pick_kernel(const ProcrParams p) {
-  const int b = blockIdx.x;
-  if (threadIdx.x != 0) return;
-  ProcrState s = p.state[b];
-  const double total = (double)p.N * p.M;
-  const double n_sample = (double)TK_SAMPLE_CTAS * TK_SAMPLE_THREADS * TK_SAMPLE_PER_THREAD * 4;
-  unsigned int target;
-  if (s.sample_all) {
-    target = (unsigned int)s.Kb;
-  } else {
-    // expected number of the K_b best inside the sample, times 3, plus slack for small counts
-    const double expect = (double)s.Kb * (n_sample / total);
-    target = (unsigned int)(3.0 * expect + 64.0);
+  if (tid == 0) {
+    ProcrState s;
+    s.Kb = Kb;
+    s.n_cand = 0u;
+    s.lower_key = lower;
+    p.state[b] = s;
   }
-  const unsigned int* h = p.hist + (size_t)b * TK_BINS;
-  unsigned int cum = 0;
-  int d = TK_BINS - 1;
-  for (; d > 0; --d) {
-    cum += h[d];
-    if (cum >= target) break;
-  }
-  s.lower_key = (unsigned int)d << 21;
-  p.state[b].lower_key = s.lower_key;
 }
 
 // ---- 4. collect candidates ------------------------------------------------------------------
@@ -214,7 +253,7 @@ __global__ void __launch_bounds__(256) topk_collect_kernel(const ProcrParams p) 
   const int b = blockIdx.y;
   const size_t total = (size_t)p.N * p.M;
   const float* x = p.conf + (size_t)b * total;
-  const unsigned int lower = p.state[b].lower_key;
+  const unsigned long long lower = p.state[b].lower_key;
   const bool vec = ((total & 3) == 0) && ((((uintptr_t)x) & 15u) == 0);
   const size_t n4 = vec ? (total >> 2) : ((total + 3) >> 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -236,7 +275,7 @@ __global__ void __launch_bounds__(256) topk_collect_kernel(const ProcrParams p) 
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         key[e] = float_to_ordered(v[e]);
-        take[e] = (q * 4 + e < total) && key[e] >= lower;
+        take[e] = (q * 4 + e < total) && make_key64(key[e], (unsigned int)(q * 4 + e)) >= lower;
       }
     }
     append_candidates(p, b, total, take, key, (unsigned int)(q * 4));
@@ -395,13 +434,10 @@ __device__ void finish_pose(const ProcrParams& p, int b, const float R[9], const
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrParams p) {
-  __shared__ unsigned int hist[TK_BINS];
+  __shared__ SelectScratch sc;
   __shared__ double red[32];
-  __shared__ unsigned long long prefix_s;
-  __shared__ int krem_s, done_s;
   __shared__ unsigned int n_emit;
   __shared__ float pose_s[12];
-  __shared__ int ok_s;
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const size_t total = (size_t)p.N * p.M;
@@ -423,61 +459,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
 
   // ---- exact radix select of the Kb largest 64-bit keys (value << 32 | ~index): no ties
   unsigned long long T = 0ull;  // select keys >= T
-  if (Kb > 0 && (size_t)Kb < n) {
-    if (tid == 0) {
-      prefix_s = 0ull;
-      krem_s = Kb;
-      done_s = 0;
-    }
-    __syncthreads();
-    int shift = 64;
-    const int widths[6] = {11, 11, 10, 11, 11, 10};
-    for (int level = 0; level < 6; ++level) {
-      const int wbits = widths[level];
-      shift -= wbits;
-      for (int k = tid; k < TK_BINS; k += SOLVE_THREADS) hist[k] = 0u;
-      __syncthreads();
-      const unsigned long long prefix = prefix_s;
-      const int hi_shift = shift + wbits;  // bits above the current digit
-      for (size_t e = tid; e < n; e += SOLVE_THREADS) {
-        const unsigned long long key = ((unsigned long long)ckey[e] << 32) | (unsigned long long)(0xFFFFFFFFu - cidx[e]);
-        const bool match = (hi_shift >= 64) ? true : ((key >> hi_shift) == prefix);
-        if (match) atomicAdd(&hist[(unsigned int)((key >> shift) & ((1u << wbits) - 1u))], 1u);
-      }
-      __syncthreads();
-      if (tid < 32) {
-        // warp 0 walks the histogram from the top: lane l owns the l-th chunk of bins (descending)
-        const int nb = 1 << wbits, chunk = nb >> 5;
-        const int hi = nb - 1 - chunk * tid;  // highest bin of this lane's chunk
-        unsigned int local = 0u;
-        for (int d = hi; d > hi - chunk; --d) local += hist[d];
-        unsigned int incl = local;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const unsigned int tmp = __shfl_up_sync(0xffffffffu, incl, o);
-          if (tid >= o) incl += tmp;
-        }
-        const unsigned int krem = (unsigned int)krem_s;
-        const unsigned int crossing = __ballot_sync(0xffffffffu, incl >= krem);
-        const int owner = crossing ? (__ffs(crossing) - 1) : 31;
-        if (tid == owner) {
-          unsigned int cum = incl - local;
-          int d = hi;
-          for (; d > hi - chunk + 1; --d) {
-            if (cum + hist[d] >= krem) break;
-            cum += hist[d];
-          }
-          prefix_s = (prefix << wbits) | (unsigned long long)d;
-          krem_s = (int)(krem - cum);
-          // the whole bin is wanted: every key with this prefix qualifies
-          if (hist[d] == krem - cum) done_s = 1;
-        }
-      }
-      __syncthreads();
-      if (done_s) break;
-    }
-    T = prefix_s << shift;
-  }
+  if (Kb > 0 && (size_t)Kb < n)
+    T = block_select_kth<SOLVE_THREADS>([&](size_t e) { return make_key64(ckey[e], cidx[e]); }, n, Kb, sc);
 
   // ---- emit the selection and accumulate the weighted moments in fp64
   if (tid == 0) n_emit = 0u;
@@ -488,8 +471,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
   if (Kb > 0) {
     for (size_t e = tid; e < n; e += SOLVE_THREADS) {
       const unsigned int k32 = ckey[e], fi = cidx[e];
-      const unsigned long long key = ((unsigned long long)k32 << 32) | (unsigned long long)(0xFFFFFFFFu - fi);
-      if (key >= T) {
+      if (make_key64(k32, fi) >= T) {
         const float wf = ordered_to_float(k32);
         const int i = (int)(fi / (unsigned int)p.M), j = (int)(fi - (unsigned int)i * (unsigned int)p.M);
         if (p.sel_w) {
@@ -535,7 +517,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
     finish_pose(p, b, R, t, cond);
     for (int k = 0; k < 9; ++k) pose_s[k] = p.R_forwd[b * 9 + k];
     for (int k = 0; k < 3; ++k) pose_s[9 + k] = p.t_forwd[b * 3 + k];
-    ok_s = 1;
   }
   __syncthreads();
   // ---- warp the source points with the gated pose:  (R_forwd s + t_forwd)     pipeline.py:220
@@ -603,7 +584,6 @@ __global__ void __launch_bounds__(256) kabsch_kernel(const KabschParams p) {
 
 struct ProcrWorkspace {
   ProcrState* state;
-  unsigned int* hist;
   unsigned int* cand_key;
   unsigned int* cand_idx;
   size_t total;
@@ -618,7 +598,6 @@ static ProcrWorkspace procr_carve(void* ws, int B, int N, int M) {
     return ptr;
   };
   w.state = (ProcrState*)take(sizeof(ProcrState) * B);
-  w.hist = (unsigned int*)take(4ull * B * TK_BINS);
   w.cand_key = (unsigned int*)take(4ull * B * N * M);
   w.cand_idx = (unsigned int*)take(4ull * B * N * M);
   w.total = off;
@@ -664,7 +643,6 @@ extern "C" int drg_soft_procrustes(const drg_procrustes_args* a, void* workspace
   p.max_condition_num = a->max_condition_num;
   p.padded_lengths = a->padded_lengths;
   p.state = w.state;
-  p.hist = w.hist;
   p.cand_key = w.cand_key;
   p.cand_idx = w.cand_idx;
   p.R = a->R;
@@ -682,19 +660,29 @@ extern "C" int drg_soft_procrustes(const drg_procrustes_args* a, void* workspace
   p.sel_src = a->sel_src;
   p.sel_tgt = a->sel_tgt;
 
-  procr_setup_kernel<<<1, 256, 0, st>>>(p);
-  DRG_LAUNCH_CHECK();
-  topk_sample_kernel<<<dim3(TK_SAMPLE_CTAS, B), TK_SAMPLE_THREADS, 0, st>>>(p);
-  DRG_LAUNCH_CHECK();
-  topk_pick_kernel<<<B, 32, 0, st>>>(p);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DRG_CUDA(cudaFuncSetAttribute(topk_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SAMPLES * 4));
+    attr_set = true;
+  }
+  {
+    ProfScope prof_scope(PROF_TOPK_THRESHOLD, st);
+    topk_threshold_kernel<<<B, TS_THREADS, TS_SAMPLES * 4, st>>>(p);
+  }
   DRG_LAUNCH_CHECK();
   int gx = (NUM_SMS * 8) / B;
   if (gx < 1) gx = 1;
   const long long n4 = ((long long)N * M + 3) / 4;
   if ((long long)gx * 256 > n4) gx = (int)((n4 + 255) / 256);
-  topk_collect_kernel<<<dim3(gx, B), 256, 0, st>>>(p);
+  {
+    ProfScope prof_scope(PROF_TOPK_COLLECT, st);
+    topk_collect_kernel<<<dim3(gx, B), 256, 0, st>>>(p);
+  }
   DRG_LAUNCH_CHECK();
-  procr_solve_kernel<<<B, SOLVE_THREADS, 0, st>>>(p);
+  {
+    ProfScope prof_scope(PROF_PROCR_SOLVE, st);
+    procr_solve_kernel<<<B, SOLVE_THREADS, 0, st>>>(p);
+  }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }

@@ -487,7 +487,39 @@ struct SkhFinalParams {
   float k_x0, k_xt, sigma;
   float* x_min;
   float inv_temp;  // dual softmax
+  int gen_noise;   // 1: N(0,1) draws come from the in-kernel Philox stream (noise == NULL)
+  unsigned long long noise_seed, noise_offset;
+  const unsigned long long* noise_offset_dev;
 };
+
+// Philox4x32-10 counter-based generator (Salmon et al., SC'11) + Box-Muller: four N(0,1) draws per counter.
+// Counter = (quad index of the element, noise_offset); key = noise_seed.  Replaces torch.randn_like(x)
+// (Diff-Reg-4dmatch/models/pipeline.py:188) in throughput mode; parity tests pass the noise tensor instead.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const unsigned int hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+__device__ __forceinline__ float4 philox_normal4(unsigned long long quad, unsigned long long offset, unsigned long long seed) {
+  const uint4 r = philox4x32_10(make_uint4((unsigned int)quad, (unsigned int)(quad >> 32), (unsigned int)offset,
+                                           (unsigned int)(offset >> 32)),
+                                make_uint2((unsigned int)seed, (unsigned int)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = fmaf((float)r.x, k, 0.5f * k), u1 = (float)r.y * k;
+  const float u2 = fmaf((float)r.z, k, 0.5f * k), u3 = (float)r.w * k;
+  const float ra = sqrtf(-2.f * __logf(u0)), rb = sqrtf(-2.f * __logf(u2));
+  float sa, ca, sb, cb;
+  __sincosf(6.283185307179586f * u1, &sa, &ca);
+  __sincosf(6.283185307179586f * u3, &sb, &cb);
+  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
 
 __device__ __forceinline__ void atomic_min_float(float* addr, float value) {
   if (value >= 0.f)
@@ -535,6 +567,7 @@ __global__ void __launch_bounds__(256) skh_final_kernel(const SkhFinalParams p) 
   const bool dual = (p.mode == 100);
   const bool ddim = (p.mode == DRG_OUT_DDIM);
   const float xt_shift = p.xt_shift ? *p.xt_shift : 0.f;
+  const unsigned long long noise_offset = p.noise_offset + (p.noise_offset_dev ? *p.noise_offset_dev : 0ull);
   float local_min = INFINITY;
 
   auto one = [&](float z, float ui, float vj, bool ok, float xt, float nz, float& conf_out) -> float {
@@ -574,6 +607,7 @@ __global__ void __launch_bounds__(256) skh_final_kernel(const SkhFinalParams p) 
         if (ddim) {
           xt = *reinterpret_cast<const float4*>(p.x_t + base + j);
           if (p.noise) nz = *reinterpret_cast<const float4*>(p.noise + base + j);
+          else if (p.gen_noise) nz = philox_normal4((unsigned long long)((base + j) >> 2), noise_offset, p.noise_seed);
         }
         float4 o, c;
         o.x = one(z.x, ui, vj.x, ok[0], xt.x, nz.x, c.x);
@@ -588,7 +622,8 @@ __global__ void __launch_bounds__(256) skh_final_kernel(const SkhFinalParams p) 
         bool ok = row_ok;
         if (p.apply_mask || dual) ok = row_ok && p.tgt_mask[(size_t)b * M + j];
         const float xt = ddim ? p.x_t[base + j] : 0.f;
-        const float nz = (ddim && p.noise) ? p.noise[base + j] : 0.f;
+        float nz = (ddim && p.noise) ? p.noise[base + j] : 0.f;
+        if (ddim && !p.noise && p.gen_noise) nz = philox_normal4((unsigned long long)(base + j), noise_offset, p.noise_seed).x;
         float c;
         p.out[base + j] = one(p.scores[base + j], ui, v_b[j], ok, xt, nz, c);
         if (ddim && p.conf) p.conf[base + j] = c;
@@ -728,7 +763,10 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   }
   const bool vec = (M % 4 == 0) && aligned16(a->scores);
 
-  skh_prep_kernel<<<B, 256, 0, st>>>(a->src_mask, a->tgt_mask, N, M, w.bc, w.v, w.u, pitch4(N + 1), pitch4(M + 1));
+  {
+    ProfScope prof_scope(PROF_SKH_PREP, st);
+    skh_prep_kernel<<<B, 256, 0, st>>>(a->src_mask, a->tgt_mask, N, M, w.bc, w.v, w.u, pitch4(N + 1), pitch4(M + 1));
+  }
   DRG_LAUNCH_CHECK();
 
   SkhParams p{};
@@ -756,13 +794,20 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   const int iters = dual ? 1 : a->iters;
   dim3 cgrid((M + 1 + 31) / 32, B);
   for (int k = 0; k < iters; ++k) {
-    cudaError_t e = launch_iter(p, pl, vec, st);
+    cudaError_t e;
+    {
+      ProfScope prof_scope(PROF_SKH_ITER, st);
+      e = launch_iter(p, pl, vec, st);
+    }
     if (e != cudaSuccess) {
       set_error("sinkhorn iteration launch failed: %s (smem=%zu)", cudaGetErrorString(e), pl.smem);
       return DRG_ERR_CUDA;
     }
     count_launch();
-    skh_col_kernel<<<cgrid, 256, 0, st>>>(p);
+    {
+      ProfScope prof_scope(PROF_SKH_COL, st);
+      skh_col_kernel<<<cgrid, 256, 0, st>>>(p);
+    }
     DRG_LAUNCH_CHECK();
   }
 
@@ -792,20 +837,33 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     f.k_xt = a->k_xt;
     f.sigma = a->sigma;
     f.x_min = a->x_min;
+    f.gen_noise = (a->noise == nullptr && a->gen_noise) ? 1 : 0;
+    f.noise_seed = a->noise_seed;
+    f.noise_offset = a->noise_offset;
+    f.noise_offset_dev = a->noise_offset_dev;
     f.inv_temp = dual ? 1.f / temperature : 0.f;
     int gx = (NUM_SMS * 8) / B;
     if (gx < 1) gx = 1;
     if (!dual && a->out_mode == DRG_OUT_LOG_FULL) {
       if (gx > N + 1) gx = N + 1;
-      skh_final_full_kernel<<<dim3(gx, B), 256, 0, st>>>(f);
+      {
+        ProfScope prof_scope(PROF_SKH_FINAL, st);
+        skh_final_full_kernel<<<dim3(gx, B), 256, 0, st>>>(f);
+      }
     } else {
       if (gx > N) gx = N;
       bool fvec = vec && aligned16(a->out) && (!f.x_t || aligned16(f.x_t)) && (!f.noise || aligned16(f.noise)) &&
                   (!f.conf || aligned16(f.conf)) && (((uintptr_t)a->tgt_mask & 3u) == 0);
       if (fvec)
-        skh_final_kernel<true><<<dim3(gx, B), 256, 0, st>>>(f);
+        {
+          ProfScope prof_scope(PROF_SKH_FINAL, st);
+          skh_final_kernel<true><<<dim3(gx, B), 256, 0, st>>>(f);
+        }
       else
-        skh_final_kernel<false><<<dim3(gx, B), 256, 0, st>>>(f);
+        {
+          ProfScope prof_scope(PROF_SKH_FINAL, st);
+          skh_final_kernel<false><<<dim3(gx, B), 256, 0, st>>>(f);
+        }
     }
     DRG_LAUNCH_CHECK();
   }

@@ -46,7 +46,7 @@ def _f32c(t):
 
 def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", apply_mask=False, shift=None,
              x_t=None, noise=None, k_x0=0.0, k_xt=0.0, sigma=0.0, want_conf=False, x_min=None, return_potentials=False,
-             xt_shift=None):
+             xt_shift=None, noise_seed=None, noise_offset=0, noise_offset_dev=None, out=None):
     """Log-domain Sinkhorn with dustbins (drg_sinkhorn).
 
     out_mode: 'log_full' -> [B,N+1,M+1] log-assignment; 'conf' -> [B,N,M] exp()[:, :-1, :-1];
@@ -62,11 +62,13 @@ def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", appl
     alpha = _f32c(alpha.detach().reshape(()))
     mode = {"log_full": _lib.DRG_OUT_LOG_FULL, "conf": _lib.DRG_OUT_CONF, "ddim": _lib.DRG_OUT_DDIM,
             "none": _lib.DRG_OUT_NONE}[out_mode]
-    out = None
-    if mode == _lib.DRG_OUT_LOG_FULL:
-        out = torch.empty(B, N + 1, M + 1, dtype=torch.float32, device=dev)
-    elif mode in (_lib.DRG_OUT_CONF, _lib.DRG_OUT_DDIM):
-        out = torch.empty(B, N, M, dtype=torch.float32, device=dev)
+    want_shape = {_lib.DRG_OUT_LOG_FULL: (B, N + 1, M + 1), _lib.DRG_OUT_CONF: (B, N, M), _lib.DRG_OUT_DDIM: (B, N, M)}.get(mode)
+    if want_shape is None:
+        out = None
+    elif out is None:
+        out = torch.empty(*want_shape, dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != want_shape or out.dtype != torch.float32 or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError(f"sinkhorn: out must be a contiguous CUDA fp32 tensor of shape {want_shape}")
     conf = torch.empty(B, N, M, dtype=torch.float32, device=dev) if (mode == _lib.DRG_OUT_DDIM and want_conf) else None
     u = torch.empty(B, N + 1, dtype=torch.float32, device=dev) if return_potentials else None
     v = torch.empty(B, M + 1, dtype=torch.float32, device=dev) if return_potentials else None
@@ -81,7 +83,9 @@ def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", appl
     a = SinkhornArgs(scores=_ptr(scores), src_mask=_ptr(src_mask), tgt_mask=_ptr(tgt_mask), alpha=_ptr(alpha),
                      shift=_ptr(shift), B=B, N=N, M=M, iters=int(iters), apply_mask=int(bool(apply_mask)),
                      out_mode=mode, out=_ptr(out), u=_ptr(u), v=_ptr(v), x_t=_ptr(x_t), xt_shift=_ptr(xt_shift), noise=_ptr(noise),
-                     conf=_ptr(conf), k_x0=float(k_x0), k_xt=float(k_xt), sigma=float(sigma), x_min=_ptr(x_min))
+                     conf=_ptr(conf), k_x0=float(k_x0), k_xt=float(k_xt), sigma=float(sigma), x_min=_ptr(x_min),
+                     gen_noise=int(noise_seed is not None and noise is None), noise_seed=int(noise_seed or 0),
+                     noise_offset=int(noise_offset), noise_offset_dev=_ptr(noise_offset_dev))
     check(lib.drg_sinkhorn(a, ws.data_ptr(), ws.numel(), _stream()))
     res = [out]
     if conf is not None:
@@ -257,3 +261,9 @@ def min_value(x):
     scratch = torch.empty(1, dtype=torch.int32, device=x.device)
     check(load_library().drg_min_value(x.data_ptr(), x.numel(), out.data_ptr(), scratch.data_ptr(), _stream()))
     return out
+
+
+def counter_add(counter, inc=1):
+    """counter (1-element int64 CUDA tensor) += inc, on the stream."""
+    _require_cuda(counter)
+    check(load_library().drg_counter_add(counter.data_ptr(), int(inc), _stream()))

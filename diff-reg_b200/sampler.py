@@ -53,7 +53,7 @@ def ddim_coefficients(ac, t, t_next, eta=1.0):
 
 class DenoisingSampler:
     def __init__(self, flavour, matching, procrustes, steps, denoising_matching=None, eta=1.0, timesteps=1000,
-                 extract_matches=True):
+                 extract_matches=True, noise_seed=0):
         """matching: the head producing x0 each step (Matching / Matching2D3D); denoising_matching: the module whose
         bin_score / skh_iters drive the Sinkhorn on the noisy state (defaults to `matching`, as in the reference where
         both are `denoising_coarse_matching`)."""
@@ -66,12 +66,16 @@ class DenoisingSampler:
         self.eta = eta
         self.ac = cosine_alphas_cumprod(timesteps)
         self.pairs = time_pairs(steps, timesteps)
+        self.noise_calls = 0
         self.extract_matches = extract_matches
+        self.noise_seed = noise_seed      # key of the in-kernel Philox stream used when no noise tensor is passed
 
     @torch.no_grad()
     def step(self, k, x, shift, src_feats, tgt_feats, s_pcd, t_pcd, src_mask, tgt_mask, noise=None,
-             pose_tgt_pcd=None, pose_tgt_mask=None, feature_fn=None):
+             pose_tgt_pcd=None, pose_tgt_mask=None, feature_fn=None, x_out=None, noise_counter=None):
         """One reverse step.  x: [1,N,M] state (as stored: for the 3d flavour the true state is x - shift).
+        x_out: optional preallocated [1,N,M] buffer for x_next; noise_counter: optional 1-element int64 device
+        counter used as the Philox offset (and incremented) instead of the host-side call count.
         Returns (x_next, shift_next, aux)."""
         t, t_next = self.pairs[k]
         k_x0, k_xt, sigma = ddim_coefficients(self.ac, t, t_next, self.eta)
@@ -87,13 +91,20 @@ class DenoisingSampler:
         # x0 from the matching head, fused with the DDIM update
         m = self.matching
         sim = m.similarity(src_feats, tgt_feats)
-        use_noise = self.flavour == "4d" and noise is not None
+        gen = self.flavour == "4d" and noise is None      # throughput mode: draw the noise inside the final pass
+        use_noise = self.flavour == "4d"
         x_min = None
         if self.flavour == "3d":
             x_min = torch.full((1,), float("inf"), dtype=torch.float32, device=x.device)
         x_next, x0 = ops.sinkhorn(sim, m.bin_score, m.skh_iters, src_mask, tgt_mask, out_mode="ddim", apply_mask=True,
                                   x_t=x, xt_shift=shift, noise=noise if use_noise else None, k_x0=k_x0, k_xt=k_xt,
-                                  sigma=sigma if use_noise else 0.0, want_conf=True, x_min=x_min)
+                                  sigma=sigma if use_noise else 0.0, want_conf=True, x_min=x_min,
+                                  noise_seed=self.noise_seed if gen else None,
+                                  noise_offset=0 if noise_counter is not None else self.noise_calls,
+                                  noise_offset_dev=noise_counter, out=x_out)
+        if noise_counter is not None:
+            ops.counter_add(noise_counter, 1)       # device-side Philox offset: graph replays draw fresh noise
+        self.noise_calls += 1
         aux = {"pose": pose, "x0": x0, "conf_d": conf_d}
         if self.extract_matches:
             B, N, M = x0.shape

@@ -41,6 +41,14 @@ const char* drg_last_error(void);
 /* Number of kernels this library has launched since load (all streams); bench.py reports
  * the difference over the timed region as "gpu_launches". */
 unsigned long long drg_launch_count(void);
+/* Optional per-kernel timing used by bench.py's roofline leg: when enabled every launch of a slotted kernel is
+ * bracketed by CUDA events on its stream.  Slots: 0 sinkhorn iteration, 1 column merge, 2 sinkhorn final/DDIM pass,
+ * 3 sinkhorn prep, 4 similarity GEMM, 5 operand prep, 6 row/column best, 7 match rows, 8 top-K collect,
+ * 9 Procrustes solve, 10 top-K threshold.  drg_profile_read synchronises on the recorded events. */
+void drg_profile_enable(int on);
+void drg_profile_reset(void);
+int drg_profile_read(int slot, double* total_ms, long long* count);
+int drg_profile_slots(void);
 
 /* ------------------------------------------------------------------------------------
  * Log-domain Sinkhorn with dustbin row/column
@@ -86,6 +94,12 @@ typedef struct drg_sinkhorn_args {
   float k_x0, k_xt, sigma; /* x_next = k_x0*conf + k_xt*x_t + sigma*noise                        */
   float* x_min;            /* optional device scalar: min over valid entries of x_next is folded
                               in with atomicMin (caller initialises to +inf)                     */
+  int gen_noise;           /* 1 and noise == NULL: draw the N(0,1) noise in the kernel (Philox4x32-10
+                              + Box-Muller), replacing torch.randn_like(x) of pipeline.py:188    */
+  unsigned long long noise_seed;   /* Philox key                                                  */
+  unsigned long long noise_offset; /* high half of the Philox counter: use a new value per step   */
+  const unsigned long long* noise_offset_dev; /* optional device counter added to noise_offset, so a
+                              CUDA-graph replay of the same step draws fresh noise (drg_counter_add) */
 } drg_sinkhorn_args;
 
 size_t drg_sinkhorn_workspace_bytes(int B, int N, int M);
@@ -182,6 +196,8 @@ int drg_weighted_procrustes(const float* X, const float* Y, const float* w, int 
  *   drg_min_value: x.min() of the 3DMatch sampler       Diff-Reg-3dmatch/models/pipeline.py:239,264
  *                  (scratch: one device uint32; *out receives the minimum) */
 int drg_sigmoid(const float* x, float* y, long long n, void* stream);
+/* *counter += inc on the stream (the Philox offset of a graph-captured sampler step). */
+int drg_counter_add(unsigned long long* counter, unsigned long long inc, void* stream);
 int drg_min_value(const float* x, long long n, float* out, unsigned int* scratch, void* stream);
 
 #ifdef __cplusplus
