@@ -34,11 +34,36 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _obj_path(src):
+    return os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+
+
+def _compile_one(args):
+    nvcc, src, verbose = args
+    obj = _obj_path(src)
+    deps = [src] + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    if os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
+        return obj
+    cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", src, "-o", obj]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return obj
+
+
 def build(force=False, verbose=True):
+    """One nvcc -c per source file (in parallel), then one link into the shared library."""
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources() + ["-lcuda"]
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    if force:
+        for o in glob.glob(os.path.join(HERE, "build", "*.o")):
+            os.remove(o)
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(_compile_one, [(nvcc, src, verbose) for src in sources()]))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

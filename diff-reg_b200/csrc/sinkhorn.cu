@@ -18,6 +18,8 @@
 //   skh_col_kernel    merges the G per-CTA column partials (+ the dustbin row term) into v.
 // All log-sum-exps are carried in the log2 domain so that each element costs one FFMA
 // and one MUFU.EX2 per direction.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace drg {
@@ -52,28 +54,51 @@ struct SkhParams {
   int dual;       // 1: dual-softmax statistics (no dustbins, no potentials)
   float zscale2;  // log2(e) (Sinkhorn) or log2(e)/temperature (dual softmax)
   int nstage;
+  int keep_slabs;  // >= 0: the first keep_slabs slabs of every CTA are loaded L2::evict_last, the rest evict_first
 };
 
 // ---------------------------------------------------------------------------------------
 // prep: mask counts -> constants; v = 0
 // ---------------------------------------------------------------------------------------
-__global__ void skh_prep_kernel(const uint8_t* __restrict__ src_mask, const uint8_t* __restrict__ tgt_mask, int N, int M,
-                                SkhConst* __restrict__ bc, float* __restrict__ v, float* __restrict__ u, int ldu, int ldv) {
+// 16 mask bytes per load when the row of masks is 16-byte aligned, else byte loads
+__device__ __forceinline__ int count_mask_bytes(const uint8_t* __restrict__ m, int n, int tid, int nthreads) {
+  int c = 0;
+  if ((((uintptr_t)m) & 15u) == 0) {
+    const int n16 = n >> 4;
+    const uint4* m4 = reinterpret_cast<const uint4*>(m);
+    for (int i = tid; i < n16; i += nthreads) {
+      const uint4 q = m4[i];
+      // bools are 0 / 1 bytes: the popcount of the low bit of every byte
+      c += __popc(q.x & 0x01010101u) + __popc(q.y & 0x01010101u) + __popc(q.z & 0x01010101u) + __popc(q.w & 0x01010101u);
+    }
+    for (int i = (n16 << 4) + tid; i < n; i += nthreads) c += m[i] ? 1 : 0;
+  } else {
+    for (int i = tid; i < n; i += nthreads) c += m[i] ? 1 : 0;
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(1024) skh_prep_kernel(const uint8_t* __restrict__ src_mask, const uint8_t* __restrict__ tgt_mask,
+                                                        int N, int M, SkhConst* __restrict__ bc, float* __restrict__ v,
+                                                        float* __restrict__ u, int ldu, int ldv) {
   const int b = blockIdx.x;
   __shared__ int cnt[2];
   if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
   __syncthreads();
-  int cs = 0, ct = 0;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) cs += src_mask[(size_t)b * N + i] ? 1 : 0;
-  for (int j = threadIdx.x; j < M; j += blockDim.x) ct += tgt_mask[(size_t)b * M + j] ? 1 : 0;
+  int cs = count_mask_bytes(src_mask + (size_t)b * N, N, threadIdx.x, blockDim.x);
+  int ct = count_mask_bytes(tgt_mask + (size_t)b * M, M, threadIdx.x, blockDim.x);
   cs = __reduce_add_sync(0xffffffffu, cs);
   ct = __reduce_add_sync(0xffffffffu, ct);
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&cnt[0], cs);
-    atomicAdd(&cnt[1], ct);
+    if (cs) atomicAdd(&cnt[0], cs);
+    if (ct) atomicAdd(&cnt[1], ct);
   }
-  for (int j = threadIdx.x; j <= M; j += blockDim.x) v[(size_t)b * ldv + j] = 0.f;
-  for (int i = threadIdx.x; i <= N; i += blockDim.x) u[(size_t)b * ldu + i] = 0.f;
+  // u, v rows are padded to multiples of 4 floats and 16-byte aligned
+  float4* v4 = reinterpret_cast<float4*>(v + (size_t)b * ldv);
+  float4* u4 = reinterpret_cast<float4*>(u + (size_t)b * ldu);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = threadIdx.x; j < (ldv >> 2); j += blockDim.x) v4[j] = z4;
+  for (int i = threadIdx.x; i < (ldu >> 2); i += blockDim.x) u4[i] = z4;
   __syncthreads();
   if (threadIdx.x == 0) {
     // reference: norm = -(ms+ns).log() on int64 -> fp32 (matching.py:24); ns.log() + norm (:26-27)
@@ -391,6 +416,306 @@ __global__ void __launch_bounds__(SKH_THREADS, 1) skh_iter_kernel(const SkhParam
       for (int r = 0; r < R; ++r) lse_merge(a, rowpart[r].x, rowpart[r].y);
       p.upart[(size_t)b * G + g] = make_float2(a.m, a.s);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// one Sinkhorn iteration, software-pipelined (16-byte aligned rows: M % 4 == 0)
+//   Same data flow as skh_iter_kernel but ONE block barrier per slab: in loop step k every warp
+//   first produces its row-segment partial of slab k+1, then merges the partials of slab k (lanes
+//   < R of every warp, redundantly -- a handful of instructions -- so no serial phase and no extra
+//   barrier) and runs the column pass of slab k.  The column potentials of the warp's row segment
+//   live in registers for the whole kernel (KQ <= 2).  FULL = no bounds checks (M == SEG*128*NCH,
+//   and M == 2048*KQ for the column pass).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+template <int R, int KQ, int NCH, bool FULL>
+__global__ void __launch_bounds__(SKH_THREADS, 1) skh_iter2_kernel(const SkhParams p) {
+  constexpr int SEG = SKH_WARPS / R;  // warps cooperating on one row
+  constexpr bool V2REG = (KQ <= 2);
+  static_assert(SEG >= 1 && SEG * R == SKH_WARPS, "R must divide the warp count");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+
+  const int N = p.N, M = p.M;
+  const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  const int nslab = (N + R - 1) / R;
+  const int s_begin = (int)(((long long)nslab * g) / G);
+  const int s_end = (int)(((long long)nslab * (g + 1)) / G);
+  const int nstage = p.nstage;
+
+  // ---- shared memory carve-up
+  const int Mv = (M + 1 + 3) & ~3;  // v2 vector, index M = dustbin column term
+  const int stage_floats = R * M;   // M % 4 == 0
+  float* v2_s = reinterpret_cast<float*>(smem_raw);
+  float* stage0 = v2_s + Mv;
+  float2* rowpart = reinterpret_cast<float2*>(stage0 + (size_t)nstage * stage_floats);  // [2][R*SEG]
+  float* red_s = reinterpret_cast<float*>(rowpart + 2 * SKH_WARPS);                      // [2*SKH_WARPS]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red_s + 2 * SKH_WARPS);
+
+  const float* sc_b = p.scores + (size_t)b * N * M;
+  const SkhConst bc = p.bc[b];
+  const float zs = p.zscale2;
+  const float shift = p.shift ? *p.shift : 0.f;
+
+  uint64_t pol_keep = 0, pol_stream = 0;
+  if (tid == 0) {
+    for (int s = 0; s < nstage; ++s) mbar_init(&full[s], 1u);
+    fence_mbar_init();
+    if (p.keep_slabs >= 0) {
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    }
+  }
+  __syncthreads();
+
+  // ---- producer (thread 0): bring slab `s` into stage `st`
+  auto issue_slab = [&](int s, int st) {
+    const int i0 = s * R;
+    const int rows = min(R, N - i0);
+    const float* src = sc_b + (size_t)i0 * M;
+    float* dst = stage0 + (size_t)st * stage_floats;
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)M * 4u;
+    fence_proxy_async();
+    mbar_arrive_expect_tx(&full[st], bytes);
+    if (p.keep_slabs >= 0)
+      tma_bulk_g2s_hint(dst, src, bytes, &full[st], (s - s_begin) < p.keep_slabs ? pol_keep : pol_stream);
+    else
+      tma_bulk_g2s(dst, src, bytes, &full[st]);
+  };
+  if (tid == 0)
+    for (int k = 0; k < nstage; ++k)
+      if (s_begin + k < s_end) issue_slab(s_begin + k, k);
+
+  // ---- prologue: column potentials into shared memory (log2 domain), dustbin-row potential
+  float uN = 0.f;
+  if (!p.dual) {
+    const float* v_b = p.v + (size_t)b * p.ldv;
+    const float alpha = *p.alpha;
+    float mloc = NEG_BIG;
+    for (int j = tid; j <= M; j += SKH_THREADS) mloc = fmaxf(mloc, v_b[j] * LOG2E);
+    mloc = warp_max(mloc);
+    if (lane == 0) red_s[warp] = mloc;
+    __syncthreads();
+    float mall = red_s[0];
+#pragma unroll
+    for (int w = 1; w < SKH_WARPS; ++w) mall = fmaxf(mall, red_s[w]);
+    float sloc = 0.f;
+    for (int j = tid; j <= M; j += SKH_THREADS) {
+      const float vj = v_b[j];
+      sloc += ex2(vj * LOG2E - mall);
+      float v2;
+      if (j < M) {
+        v2 = (vj - shift) * LOG2E;
+        if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
+      } else {
+        v2 = (alpha + vj) * LOG2E;  // dustbin column entry of every real row: alpha + v_M
+      }
+      v2_s[j] = v2;
+    }
+    sloc = warp_sum(sloc);
+    if (lane == 0) red_s[SKH_WARPS + warp] = sloc;
+    __syncthreads();
+    float sall = 0.f;
+#pragma unroll
+    for (int w = 0; w < SKH_WARPS; ++w) sall += red_s[SKH_WARPS + w];
+    const float vlse = (mall + lg2(sall)) * LN2;
+    uN = bc.log_mu_bin - (alpha + vlse);
+    if (g == 0 && tid == 0) p.u[(size_t)b * p.ldu + N] = uN;
+  } else {
+    for (int j = tid; j < M; j += SKH_THREADS) v2_s[j] = (p.tgt_mask[(size_t)b * M + j]) ? 0.f : -INFINITY;
+    if (tid == 0) v2_s[M] = -INFINITY;
+  }
+  for (int j = M + 1 + tid; j < Mv; j += SKH_THREADS) v2_s[j] = -INFINITY;
+  __syncthreads();
+
+  // ---- this warp's row segment
+  const int wr = warp / SEG, wseg = warp % SEG;
+  const int seg_len = FULL ? NCH * 128 : ((((M + SEG - 1) / SEG) + 127) & ~127);
+  const int c0 = wseg * seg_len;
+  const int c1 = min(M, c0 + seg_len);
+  const float dust2 = v2_s[M];
+  float4 v2r[V2REG ? NCH : 1];
+  if constexpr (V2REG) {
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = c0 + 4 * lane + 128 * k;
+      v2r[k] = (FULL || c < c1) ? *reinterpret_cast<const float4*>(v2_s + c) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+  }
+
+  // ---- per-thread column accumulators (log2 domain)
+  float cm[KQ * 4], cs[KQ * 4];
+#pragma unroll
+  for (int e = 0; e < KQ * 4; ++e) {
+    cm[e] = NEG_BIG;
+    cs[e] = 0.f;
+  }
+  LseAcc uacc = lse_empty();  // warp 0, lanes < R: running LSE of the u_i they produced (dustbin column)
+
+  // ---- (a) row-segment partial of slab s (stage st) -> rowpart[buf]
+  auto row_partial = [&](int s, int st, int buf) {
+    const int i0 = s * R;
+    const int rows = min(R, N - i0);
+    if (wr >= rows) return;
+    const bool row_live = !(p.apply_mask && !p.dual && !p.src_mask[(size_t)b * N + i0 + wr]);
+    if (!row_live) {  // with the fused mask a padded src row holds only its dustbin entry
+      if (lane == 0) rowpart[buf * SKH_WARPS + warp] = make_float2(NEG_BIG, 0.f);
+      return;
+    }
+    const float* row = stage0 + (size_t)st * stage_floats + (size_t)wr * M;
+    float xs[4 * NCH];
+    float m = NEG_BIG;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = c0 + 4 * lane + 128 * k;
+      if (FULL || c < c1) {
+        const float4 z = *reinterpret_cast<const float4*>(row + c);
+        float4 vv;
+        if constexpr (V2REG)
+          vv = v2r[k];
+        else
+          vv = *reinterpret_cast<const float4*>(v2_s + c);
+        xs[4 * k + 0] = fmaf(z.x, zs, vv.x);
+        xs[4 * k + 1] = fmaf(z.y, zs, vv.y);
+        xs[4 * k + 2] = fmaf(z.z, zs, vv.z);
+        xs[4 * k + 3] = fmaf(z.w, zs, vv.w);
+        m = fmaxf(m, fmaxf(fmaxf(xs[4 * k], xs[4 * k + 1]), fmaxf(xs[4 * k + 2], xs[4 * k + 3])));
+      } else {
+        xs[4 * k + 0] = xs[4 * k + 1] = xs[4 * k + 2] = xs[4 * k + 3] = -INFINITY;
+      }
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4 * NCH; ++k) sum += ex2(xs[k] - m);
+    sum = warp_sum(sum);
+    if (lane == 0) rowpart[buf * SKH_WARPS + warp] = make_float2(m, sum);
+  };
+
+  // ---- (b)+(c) merge the partials of slab s into u_i, then the column pass over the slab
+  auto col_pass = [&](int s, int st, int buf) {
+    const int i0 = s * R;
+    const int rows = min(R, N - i0);
+    const float* slab = stage0 + (size_t)st * stage_floats;
+    float u2 = -INFINITY;
+    if (lane < R && lane < rows) {
+      const int r = lane, i = i0 + r;
+      LseAcc a = lse_empty();
+#pragma unroll
+      for (int sg = 0; sg < SEG; ++sg) {
+        const float2 ps = rowpart[buf * SKH_WARPS + r * SEG + sg];
+        lse_merge(a, ps.x, ps.y);
+      }
+      float ui;
+      if (!p.dual) {
+        lse_add_value(a, dust2);  // alpha + v_M
+        ui = bc.norm - lse_value(a) * LN2;
+      } else {
+        ui = -lse_value(a) * LN2;  // -(row log-sum-exp), natural log
+      }
+      const bool src_ok = (!p.apply_mask && !p.dual) || p.src_mask[(size_t)b * N + i];
+      if (warp == 0) {
+        p.u[(size_t)b * p.ldu + i] = ui;
+        if (!p.dual) lse_add_value(uacc, ui * LOG2E);
+      }
+      if (!p.dual)
+        u2 = src_ok ? (ui - shift) * LOG2E : -INFINITY;  // column pass sees (S - shift) + u
+      else
+        u2 = src_ok ? 0.f : -INFINITY;
+    }
+    float u2r[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) u2r[r] = __shfl_sync(0xffffffffu, u2, r);  // rows beyond `rows` hold -inf
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+      const int c = 4 * (tid + SKH_THREADS * k);
+      if (FULL || c < M) {
+        float x[R][4];
+        float mx[4] = {NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r < rows) {
+            const float4 z = *reinterpret_cast<const float4*>(slab + (size_t)r * M + c);
+            x[r][0] = fmaf(z.x, zs, u2r[r]);
+            x[r][1] = fmaf(z.y, zs, u2r[r]);
+            x[r][2] = fmaf(z.z, zs, u2r[r]);
+            x[r][3] = fmaf(z.w, zs, u2r[r]);
+          } else {
+            x[r][0] = x[r][1] = x[r][2] = x[r][3] = -INFINITY;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mx[e] = fmaxf(mx[e], x[r][e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float& am = cm[4 * k + e];
+          float& as = cs[4 * k + e];
+          if (mx[e] > am + 32.f) {  // lazy re-reference: rare after the first slab
+            as *= ex2(am - mx[e]);
+            am = mx[e];
+          }
+          float acc = 0.f;
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc += ex2(x[r][e] - am);
+          as += acc;
+        }
+      }
+    }
+  };
+
+  // ---- main loop
+  if (s_begin < s_end) {
+    mbar_wait(&full[0], 0u);
+    row_partial(s_begin, 0, 0);
+  }
+  __syncthreads();
+  for (int s = s_begin; s < s_end; ++s) {
+    const int it = s - s_begin;
+    const int st = it % nstage;
+    const int buf = it & 1;
+    if (s + 1 < s_end) {
+      const int it1 = it + 1;
+      mbar_wait(&full[it1 % nstage], (uint32_t)((it1 / nstage) & 1));
+      row_partial(s + 1, it1 % nstage, buf ^ 1);
+    }
+    col_pass(s, st, buf);
+    __syncthreads();  // every warp is done with stage `st`, and rowpart[buf ^ 1] is complete
+    if (tid == 0 && s + nstage < s_end) issue_slab(s + nstage, st);
+  }
+
+  // ---- write this CTA's column partials
+  float2* cp = p.colpart + ((size_t)b * G + g) * M;
+#pragma unroll
+  for (int k = 0; k < KQ; ++k) {
+    const int c = 4 * (tid + SKH_THREADS * k);
+    if (FULL || c < M) {
+      *reinterpret_cast<float4*>(cp + c) = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
+      *reinterpret_cast<float4*>(cp + c + 2) = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
+    }
+  }
+  // dustbin-column partial: LSE of this CTA's u_i (warp 0, lanes < R hold disjoint rows)
+  if (!p.dual && warp == 0) {
+    float am = uacc.m, as = uacc.s;
+#pragma unroll
+    for (int o = 1; o < R; o <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, am, o);
+      const float s2 = __shfl_xor_sync(0xffffffffu, as, o);
+      LseAcc a{am, as};
+      lse_merge(a, m2, s2);
+      am = a.m;
+      as = a.s;
+    }
+    if (lane == 0) p.upart[(size_t)b * G + g] = make_float2(am, as);
   }
 }
 
@@ -715,14 +1040,115 @@ static cudaError_t launch_iter_rk(const SkhParams& p, const SkhPlan& pl, bool ve
   return cudaGetLastError();
 }
 
-static cudaError_t launch_iter(const SkhParams& p, const SkhPlan& pl, bool vec, cudaStream_t st) {
+static cudaError_t launch_iter(const SkhParams& p, const SkhPlan& pl, cudaStream_t st) {
+  // unaligned rows (M % 4 != 0): the scalar cp.async variant
   switch (pl.R) {
-    case 16: return launch_iter_rk<16, 1>(p, pl, vec, st);
-    case 8: return launch_iter_rk<8, 1>(p, pl, vec, st);
-    case 4: return launch_iter_rk<4, 2>(p, pl, vec, st);
-    case 2: return launch_iter_rk<2, 4>(p, pl, vec, st);
-    default: return launch_iter_rk<1, 8>(p, pl, vec, st);
+    case 16: return launch_iter_rk<16, 1>(p, pl, false, st);
+    case 8: return launch_iter_rk<8, 1>(p, pl, false, st);
+    case 4: return launch_iter_rk<4, 2>(p, pl, false, st);
+    case 2: return launch_iter_rk<2, 4>(p, pl, false, st);
+    default: return launch_iter_rk<1, 8>(p, pl, false, st);
   }
+}
+
+// ---- plan / launch of the software-pipelined kernel (aligned rows)
+struct SkhPlan2 {
+  int R, KQ, NCH, nstage, G;
+  bool full;
+  size_t smem;
+  bool ok;
+};
+
+static int skh_stage_floats_target() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DRG_SKH_STAGE_FLOATS");
+    v = e ? atoi(e) : 16384;
+    if (v != 4096 && v != 8192 && v != 16384) v = 16384;
+  }
+  return v;
+}
+static float skh_keep_fraction() {
+  static float v = -2.f;
+  if (v < -1.5f) {
+    const char* e = getenv("DRG_SKH_L2_KEEP");
+    v = e ? (float)atof(e) : -1.f;  // < 0: no cache hints
+  }
+  return v;
+}
+
+static SkhPlan2 make_plan2(int B, int N, int M) {
+  SkhPlan2 pl{};
+  pl.ok = false;
+  if (M < 4 || M > SKH_MAX_M || N < 1 || (M % 4) != 0) return pl;
+  const int target = skh_stage_floats_target();
+  int R = 16;
+  while (R > 1 && (long long)R * M > target) R >>= 1;
+  pl.R = R;
+  pl.KQ = (M <= 2048) ? 1 : (M <= 4096) ? 2 : (M <= 8192) ? 4 : 8;
+  const int SEG = SKH_WARPS / R;
+  pl.full = false;
+  pl.NCH = 8;
+  if (M >= 2048 && (M & (M - 1)) == 0 && M % (SEG * 128) == 0) {
+    const int nch = M / (SEG * 128);
+    if (nch == 1 || nch == 2 || nch == 4 || nch == 8) {
+      pl.full = true;
+      pl.NCH = nch;
+    }
+  }
+  if ((long long)SEG * 1024 < M) return pl;  // a warp segment holds at most 1024 columns
+  const size_t Mv = (size_t)((M + 1 + 3) & ~3);
+  const size_t stage_bytes = (size_t)R * M * 4;
+  const size_t fixed = Mv * 4 + 2 * SKH_WARPS * 8 + 2 * SKH_WARPS * 4 + 8 * 8 + 64;
+  int nstage = (int)((SKH_SMEM_LIMIT - fixed) / stage_bytes);
+  if (nstage > 8) nstage = 8;
+  if (nstage < 2) return pl;
+  pl.nstage = nstage;
+  pl.smem = fixed + (size_t)nstage * stage_bytes;
+  const int nslab = (N + R - 1) / R;
+  int G = NUM_SMS / (B < 1 ? 1 : B);
+  if (G < 1) G = 1;
+  if (G > nslab) G = nslab;
+  pl.G = G;
+  pl.ok = true;
+  return pl;
+}
+
+template <int R, int KQ, int NCH, bool FULL>
+static cudaError_t launch_iter2_t(const SkhParams& p, const SkhPlan2& pl, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(skh_iter2_kernel<R, KQ, NCH, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  if (e != cudaSuccess) return e;
+  skh_iter2_kernel<R, KQ, NCH, FULL><<<dim3(pl.G, p.B), SKH_THREADS, pl.smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_iter2(const SkhParams& p, const SkhPlan2& pl, cudaStream_t st) {
+#define DRG_SKH_CASE(r, kq, nch, fl) \
+  if (pl.R == r && pl.KQ == kq && pl.NCH == nch && pl.full == fl) return launch_iter2_t<r, kq, nch, fl>(p, pl, st);
+  // power-of-two widths: no bounds checks
+  DRG_SKH_CASE(8, 1, 8, true)   // M = 2048, 64 KB stages
+  DRG_SKH_CASE(4, 1, 4, true)   // M = 2048, 32 KB stages
+  DRG_SKH_CASE(2, 1, 2, true)   // M = 2048, 16 KB stages
+  DRG_SKH_CASE(4, 2, 8, true)   // M = 4096, 64 KB stages
+  DRG_SKH_CASE(2, 2, 4, true)   // M = 4096, 32 KB stages
+  DRG_SKH_CASE(1, 2, 2, true)   // M = 4096, 16 KB stages
+  DRG_SKH_CASE(2, 4, 8, true)   // M = 8192, 64 KB stages
+  DRG_SKH_CASE(1, 4, 4, true)   // M = 8192, 32 KB stages
+  DRG_SKH_CASE(1, 8, 8, true)   // M = 16384
+  // everything else: guarded
+  DRG_SKH_CASE(16, 1, 8, false)
+  DRG_SKH_CASE(8, 1, 8, false)
+  DRG_SKH_CASE(4, 1, 8, false)
+  DRG_SKH_CASE(2, 1, 8, false)
+  DRG_SKH_CASE(1, 1, 8, false)
+  DRG_SKH_CASE(4, 2, 8, false)
+  DRG_SKH_CASE(2, 2, 8, false)
+  DRG_SKH_CASE(1, 2, 8, false)
+  DRG_SKH_CASE(2, 4, 8, false)
+  DRG_SKH_CASE(1, 4, 8, false)
+  DRG_SKH_CASE(1, 8, 8, false)
+#undef DRG_SKH_CASE
+  return cudaErrorInvalidConfiguration;
 }
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
@@ -731,11 +1157,16 @@ static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; 
 
 using namespace drg;
 
+static int skh_max_g(int B) {
+  int G = NUM_SMS / (B < 1 ? 1 : B);
+  return G < 1 ? 1 : G;
+}
+
 extern "C" size_t drg_sinkhorn_workspace_bytes(int B, int N, int M) {
   if (B < 1 || N < 1 || M < 1) return 0;
   SkhPlan pl = make_plan(B, N, M);
   if (!pl.ok) return 0;
-  return carve(nullptr, B, N, M, pl.G).total;
+  return carve(nullptr, B, N, M, skh_max_g(B)).total;
 }
 
 static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature, void* workspace, size_t workspace_bytes,
@@ -752,7 +1183,10 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     set_error("sinkhorn: internal plan error");
     return DRG_ERR_UNSUPPORTED;
   }
-  SkhWorkspace w = carve(workspace, B, N, M, pl.G);
+  const bool vec = (M % 4 == 0) && aligned16(a->scores);
+  SkhPlan2 pl2 = vec ? make_plan2(B, N, M) : SkhPlan2{};
+  const bool use2 = vec && pl2.ok;
+  SkhWorkspace w = carve(workspace, B, N, M, skh_max_g(B));
   if (workspace == nullptr || workspace_bytes < w.total) {
     set_error("sinkhorn: workspace too small (%zu < %zu)", workspace_bytes, w.total);
     return DRG_ERR_WORKSPACE;
@@ -761,11 +1195,9 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     set_error("sinkhorn: workspace must be 256-byte aligned");
     return DRG_ERR_INVALID;
   }
-  const bool vec = (M % 4 == 0) && aligned16(a->scores);
-
   {
     ProfScope prof_scope(PROF_SKH_PREP, st);
-    skh_prep_kernel<<<B, 256, 0, st>>>(a->src_mask, a->tgt_mask, N, M, w.bc, w.v, w.u, pitch4(N + 1), pitch4(M + 1));
+    skh_prep_kernel<<<B, 1024, 0, st>>>(a->src_mask, a->tgt_mask, N, M, w.bc, w.v, w.u, pitch4(N + 1), pitch4(M + 1));
   }
   DRG_LAUNCH_CHECK();
 
@@ -783,13 +1215,18 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   p.B = B;
   p.N = N;
   p.M = M;
-  p.G = pl.G;
+  p.G = use2 ? pl2.G : pl.G;
   p.ldu = pitch4(N + 1);
   p.ldv = pitch4(M + 1);
   p.apply_mask = a->apply_mask;
   p.dual = dual ? 1 : 0;
   p.zscale2 = dual ? LOG2E / temperature : LOG2E;
-  p.nstage = pl.nstage;
+  p.nstage = use2 ? pl2.nstage : pl.nstage;
+  p.keep_slabs = -1;
+  if (use2 && skh_keep_fraction() >= 0.f) {
+    const int nslab = (N + pl2.R - 1) / pl2.R;
+    p.keep_slabs = (int)(skh_keep_fraction() * (float)((nslab + pl2.G - 1) / pl2.G) + 0.5f);
+  }
 
   const int iters = dual ? 1 : a->iters;
   dim3 cgrid((M + 1 + 31) / 32, B);
@@ -797,10 +1234,10 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     cudaError_t e;
     {
       ProfScope prof_scope(PROF_SKH_ITER, st);
-      e = launch_iter(p, pl, vec, st);
+      e = use2 ? launch_iter2(p, pl2, st) : launch_iter(p, pl, st);
     }
     if (e != cudaSuccess) {
-      set_error("sinkhorn iteration launch failed: %s (smem=%zu)", cudaGetErrorString(e), pl.smem);
+      set_error("sinkhorn iteration launch failed: %s (smem=%zu)", cudaGetErrorString(e), use2 ? pl2.smem : pl.smem);
       return DRG_ERR_CUDA;
     }
     count_launch();

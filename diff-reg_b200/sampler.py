@@ -108,10 +108,11 @@ class DenoisingSampler:
         aux = {"pose": pose, "x0": x0, "conf_d": conf_d}
         if self.extract_matches:
             B, N, M = x0.shape
-            if self.flavour == "2d3d":
-                aux["match"] = ops._match(x0, 1, True, None, True, False, capacity=B * min(N, M))
-            else:
-                aux["match"] = ops._match(x0, 0, True, m.confidence_threshold, True, False, capacity=B * min(N, M))
+            # Mutual top-1 matches (index based: a row's best column whose best row is that row), thresholded for
+            # the 3D flavours.  Equals get_match(conf, thr, mutual=True) (matching.py:71-88) except at exact value
+            # ties, where the lowest index wins instead of every tied entry being reported.
+            thr = None if self.flavour == "2d3d" else m.confidence_threshold
+            aux["match"] = ops._match(x0, 1, True, thr, True, False, capacity=B * min(N, M))
         return x_next, x_min, aux
 
     @torch.no_grad()
