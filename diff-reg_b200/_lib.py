@@ -52,6 +52,14 @@ def _declare(lib):
     lib.drg_sinkhorn_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.drg_sinkhorn.restype = c_int
     lib.drg_sinkhorn.argtypes = [ctypes.POINTER(SinkhornArgs), c_void_p, c_size_t, c_void_p]
+    for name, extra in (("drg_sinkhorn_shard_begin", [c_void_p]), ("drg_sinkhorn_shard_local", None), ("drg_sinkhorn_shard_update", None),
+                        ("drg_sinkhorn_shard_final", None)):
+        fn = getattr(lib, name)
+        fn.restype = c_int
+    lib.drg_sinkhorn_shard_begin.argtypes = [ctypes.POINTER(SinkhornArgs), c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.drg_sinkhorn_shard_local.argtypes = [ctypes.POINTER(SinkhornArgs), c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.drg_sinkhorn_shard_update.argtypes = [ctypes.POINTER(SinkhornArgs), c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.drg_sinkhorn_shard_final.argtypes = [ctypes.POINTER(SinkhornArgs), c_void_p, c_size_t, c_void_p]
     lib.drg_dual_softmax.restype = c_int
     lib.drg_dual_softmax.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                      c_size_t, c_void_p]

@@ -48,12 +48,15 @@ struct SkhParams {
   float2* colpart;  // [B, G, M]   (max, sum) in the log2 domain
   float2* upart;    // [B, G]
   const SkhConst* bc;
+  SkhConst* bc_out;  // persistent kernel: writes the constants it computes
+  float2* shard_partial;  // row-sharded mode: the column merge writes (max, sum) per column here instead of updating v
   int B, N, M, G;
   int ldu, ldv;  // row pitch of u / v (multiples of 4 floats)
   int apply_mask;
   int dual;       // 1: dual-softmax statistics (no dustbins, no potentials)
   float zscale2;  // log2(e) (Sinkhorn) or log2(e)/temperature (dual softmax)
   int nstage;
+  int dbg;         // tuning experiments only (DRG_SKH_DBG): 1 skip row math, 2 skip column math, 4 skip prologue reductions
   int keep_slabs;  // >= 0: the first keep_slabs slabs of every CTA are loaded L2::evict_last, the rest evict_first
 };
 
@@ -720,6 +723,668 @@ __global__ void __launch_bounds__(SKH_THREADS, 1) skh_iter2_kernel(const SkhPara
 }
 
 // ---------------------------------------------------------------------------------------
+// one Sinkhorn iteration, warp-specialised (M % 4 == 0, M <= 4096): 1024 threads per CTA
+//   warps 0..14   ROW warps: each owns whole rows (row q of the CTA's range goes to warp q % 15):
+//                 per-lane online log-sum-exp over the row, ONE warp reduction per row, then
+//                 u_i -> shared memory + global; arrives on u_ready[stage] and stage_free[stage]
+//   warp 15       producer: one thread issues the TMA bulk copy of the next slab as soon as its
+//                 stage is free
+//   warps 16..31  COLUMN warps: thread -> KQ column quads; wait for u_ready[stage], accumulate the
+//                 slab's contribution to the column log-sum-exps, arrive on stage_free[stage]
+//   The two groups are coupled only through mbarriers, so row work on slab k+1.. overlaps the
+//   column work on slab k and nobody waits at a block barrier inside the loop.
+// ---------------------------------------------------------------------------------------
+constexpr int WS_THREADS = 1024;
+constexpr int WS_ROW_WARPS = 15;
+constexpr int WS_COL_THREADS = 512;
+constexpr int WS_MAX_STAGES = 8;
+
+template <int R, int KQ, bool ROWFULL, bool COLFULL>
+__global__ void __launch_bounds__(WS_THREADS, 1) skh_iter_ws_kernel(const SkhParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int N = p.N, M = p.M;
+  const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nslab = (N + R - 1) / R;
+  const int s_begin = (int)(((long long)nslab * g) / G);
+  const int s_end = (int)(((long long)nslab * (g + 1)) / G);
+  const int nstage = p.nstage;
+
+  // ---- shared memory carve-up
+  const int Mv = (M + 1 + 3) & ~3;
+  const int stage_floats = R * M;
+  float* v2_s = reinterpret_cast<float*>(smem_raw);
+  float* stage0 = v2_s + Mv;
+  float* u2_s = stage0 + (size_t)nstage * stage_floats;             // [WS_MAX_STAGES][16]
+  float* red_s = u2_s + WS_MAX_STAGES * 16;                          // [64]
+  float2* upart_s = reinterpret_cast<float2*>(red_s + 64);           // [16]
+  uint64_t* full = reinterpret_cast<uint64_t*>(upart_s + 16);        // [WS_MAX_STAGES]
+  uint64_t* u_ready = full + WS_MAX_STAGES;
+  uint64_t* stage_free = u_ready + WS_MAX_STAGES;
+
+  const float* sc_b = p.scores + (size_t)b * N * M;
+  const SkhConst bc = p.bc[b];
+  const float zs = p.zscale2;
+  const float shift = p.shift ? *p.shift : 0.f;
+
+  if (tid == 0) {
+    for (int s = 0; s < nstage; ++s) {
+      mbar_init(&full[s], 1u);
+      mbar_init(&u_ready[s], (uint32_t)R);
+      mbar_init(&stage_free[s], (uint32_t)(R + WS_COL_THREADS / 32));
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue_slab = [&](int s, int st) {
+    const int i0 = s * R;
+    const int rows = min(R, N - i0);
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)M * 4u;
+    fence_proxy_async();
+    mbar_arrive_expect_tx(&full[st], bytes);
+    tma_bulk_g2s(stage0 + (size_t)st * stage_floats, sc_b + (size_t)i0 * M, bytes, &full[st]);
+  };
+  // the first loads go out before the prologue so that they overlap it
+  if (warp == WS_ROW_WARPS && lane == 0)
+    for (int k = 0; k < nstage; ++k)
+      if (s_begin + k < s_end) issue_slab(s_begin + k, k);
+
+  // ---- prologue (all threads): column potentials into shared memory (log2 domain), dustbin-row potential
+  if (p.dbg & 4) {
+    for (int j = tid; j <= M; j += WS_THREADS) v2_s[j] = 0.f;
+  } else if (!p.dual) {
+    const float* v_b = p.v + (size_t)b * p.ldv;
+    const float alpha = *p.alpha;
+    float mloc = NEG_BIG;
+    for (int j = tid; j <= M; j += WS_THREADS) mloc = fmaxf(mloc, v_b[j] * LOG2E);
+    mloc = warp_max(mloc);
+    if (lane == 0) red_s[warp] = mloc;
+    __syncthreads();
+    float mall = red_s[0];
+#pragma unroll
+    for (int w = 1; w < WS_THREADS / 32; ++w) mall = fmaxf(mall, red_s[w]);
+    float sloc = 0.f;
+    for (int j = tid; j <= M; j += WS_THREADS) {
+      const float vj = v_b[j];
+      sloc += ex2(vj * LOG2E - mall);
+      float v2;
+      if (j < M) {
+        v2 = (vj - shift) * LOG2E;
+        if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
+      } else {
+        v2 = (alpha + vj) * LOG2E;  // dustbin column entry of every real row: alpha + v_M
+      }
+      v2_s[j] = v2;
+    }
+    sloc = warp_sum(sloc);
+    if (lane == 0) red_s[32 + warp] = sloc;
+    __syncthreads();
+    if (g == 0 && tid == 0) {
+      float sall = 0.f;
+      for (int w = 0; w < WS_THREADS / 32; ++w) sall += red_s[32 + w];
+      const float vlse = (mall + lg2(sall)) * LN2;
+      p.u[(size_t)b * p.ldu + N] = bc.log_mu_bin - (alpha + vlse);  // dustbin row potential
+    }
+  } else {
+    for (int j = tid; j < M; j += WS_THREADS) v2_s[j] = (p.tgt_mask[(size_t)b * M + j]) ? 0.f : -INFINITY;
+    if (tid == 0) v2_s[M] = -INFINITY;
+  }
+  for (int j = M + 1 + tid; j < Mv; j += WS_THREADS) v2_s[j] = -INFINITY;
+  __syncthreads();
+
+  if (warp < WS_ROW_WARPS) {
+    // =========================== ROW warps ===========================
+    const float dust2 = v2_s[M];
+    LseAcc uacc = lse_empty();  // lane 0: running LSE of the u_i this warp produced (dustbin column)
+    const int nq = (s_end - s_begin) * R;  // padded row slots of this CTA
+    const float* v2_lane = v2_s + 4 * lane;
+    // Every row warp observes the `full` barrier of EVERY slab in order (a parity wait is only meaningful for a
+    // waiter that has seen the previous phase of the same barrier), but computes only the rows assigned to it.
+    int st = 0;
+    uint32_t ph = 0;
+    for (int q0 = 0; q0 < nq; q0 += R) {
+      mbar_wait_sleep(&full[st], ph, 200u);
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+      const int q = q0 + r;
+      if (q % WS_ROW_WARPS != warp) continue;
+      const int i = s_begin * R + q;
+      float u2 = -INFINITY;
+      if (i < N) {
+        const bool row_live = !(p.apply_mask && !p.dual && !p.src_mask[(size_t)b * N + i]);
+        float m_l = NEG_BIG, s_l = 0.f;
+        if (row_live && !(p.dbg & 1)) {
+          const float* row_lane = stage0 + (size_t)st * stage_floats + (size_t)r * M + 4 * lane;
+          for (int cb = 0; cb < M; cb += 1024) {
+            float xs[32];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (ROWFULL || cb + 4 * lane + 128 * k < M) {
+                const float4 z = *reinterpret_cast<const float4*>(row_lane + cb + 128 * k);
+                const float4 vv = *reinterpret_cast<const float4*>(v2_lane + cb + 128 * k);
+                xs[4 * k + 0] = fmaf(z.x, zs, vv.x);
+                xs[4 * k + 1] = fmaf(z.y, zs, vv.y);
+                xs[4 * k + 2] = fmaf(z.z, zs, vv.z);
+                xs[4 * k + 3] = fmaf(z.w, zs, vv.w);
+              } else {
+                xs[4 * k + 0] = xs[4 * k + 1] = xs[4 * k + 2] = xs[4 * k + 3] = -INFINITY;
+              }
+            }
+            float cmax = NEG_BIG;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) cmax = fmaxf(cmax, xs[k]);
+            if (cmax > m_l) {  // per-lane online rescale (at most once per 32 elements)
+              s_l *= ex2(m_l - cmax);
+              m_l = cmax;
+            }
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              a0 += ex2(xs[4 * k + 0] - m_l);
+              a1 += ex2(xs[4 * k + 1] - m_l);
+              a2 += ex2(xs[4 * k + 2] - m_l);
+              a3 += ex2(xs[4 * k + 3] - m_l);
+            }
+            s_l += (a0 + a1) + (a2 + a3);
+          }
+        }
+        // one warp reduction per row
+        const float mrow = warp_max(m_l);
+        float srow = warp_sum(s_l * ex2(m_l - mrow));
+        float ui;
+        if (!p.dual) {
+          const float mm = fmaxf(mrow, dust2);
+          srow = srow * ex2(mrow - mm) + ex2(dust2 - mm);  // + dustbin column entry alpha + v_M
+          ui = bc.norm - (mm + lg2(srow)) * LN2;
+        } else {
+          ui = -(mrow + lg2(srow)) * LN2;  // -(row log-sum-exp), natural log
+        }
+        const bool src_ok = (!p.apply_mask && !p.dual) || p.src_mask[(size_t)b * N + i];
+        if (!p.dual)
+          u2 = src_ok ? (ui - shift) * LOG2E : -INFINITY;  // column pass sees (S - shift) + u
+        else
+          u2 = src_ok ? 0.f : -INFINITY;
+        if (lane == 0) {
+          p.u[(size_t)b * p.ldu + i] = ui;
+          if (!p.dual) lse_add_value(uacc, ui * LOG2E);
+        }
+      }
+      if (lane == 0) {
+        u2_s[st * 16 + r] = u2;
+        mbar_arrive(&u_ready[st]);     // release: u2 is visible to the column warps that acquire the barrier
+        mbar_arrive(&stage_free[st]);  // this warp no longer reads the stage
+      }
+      __syncwarp();
+      }
+      if (++st == nstage) {
+        st = 0;
+        ph ^= 1u;
+      }
+    }
+    if (lane == 0) upart_s[warp] = make_float2(uacc.m, uacc.s);
+  } else if (warp == WS_ROW_WARPS) {
+    // =========================== producer ===========================
+    if (lane == 0) {
+      for (int s = s_begin + nstage; s < s_end; ++s) {
+        const int sl = s - s_begin;
+        const int st = sl % nstage;
+        mbar_wait_sleep(&stage_free[st], (uint32_t)(((sl / nstage) - 1) & 1), 200u);
+        issue_slab(s, st);
+      }
+      upart_s[WS_ROW_WARPS] = make_float2(NEG_BIG, 0.f);
+    }
+  } else {
+    // =========================== COLUMN warps ===========================
+    const int ct = tid - WS_COL_THREADS;  // 0..511
+    float cm[KQ * 4], cs[KQ * 4];
+#pragma unroll
+    for (int e = 0; e < KQ * 4; ++e) {
+      cm[e] = NEG_BIG;
+      cs[e] = 0.f;
+    }
+    for (int s = s_begin; s < s_end; ++s) {
+      const int sl = s - s_begin;
+      const int st = sl % nstage;
+      const int i0 = s * R;
+      const int rows = min(R, N - i0);
+      const float* slab = stage0 + (size_t)st * stage_floats;
+      mbar_wait_sleep(&u_ready[st], (uint32_t)((sl / nstage) & 1), 500u);
+      float u2r[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) u2r[r] = u2_s[st * 16 + r];  // rows beyond `rows` hold -inf
+#pragma unroll
+      for (int k = 0; k < KQ; ++k) {
+        const int c = 4 * (ct + WS_COL_THREADS * k);
+        if ((COLFULL || c < M) && !(p.dbg & 2)) {
+          float x[R][4];
+          float mx[4] = {NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG};
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (r < rows) {
+              const float4 z = *reinterpret_cast<const float4*>(slab + (size_t)r * M + c);
+              x[r][0] = fmaf(z.x, zs, u2r[r]);
+              x[r][1] = fmaf(z.y, zs, u2r[r]);
+              x[r][2] = fmaf(z.z, zs, u2r[r]);
+              x[r][3] = fmaf(z.w, zs, u2r[r]);
+            } else {
+              x[r][0] = x[r][1] = x[r][2] = x[r][3] = -INFINITY;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) mx[e] = fmaxf(mx[e], x[r][e]);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float& am = cm[4 * k + e];
+            float& as = cs[4 * k + e];
+            if (mx[e] > am + 32.f) {  // lazy re-reference: rare after the first slab
+              as *= ex2(am - mx[e]);
+              am = mx[e];
+            }
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc += ex2(x[r][e] - am);
+            as += acc;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stage_free[st]);
+    }
+    float2* cp = p.colpart + ((size_t)b * G + g) * M;
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+      const int c = 4 * (ct + WS_COL_THREADS * k);
+      if (COLFULL || c < M) {
+        *reinterpret_cast<float4*>(cp + c) = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
+        *reinterpret_cast<float4*>(cp + c + 2) = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
+      }
+    }
+  }
+  // ---- dustbin-column partial: LSE of this CTA's u_i
+  __syncthreads();
+  if (!p.dual && tid == 0) {
+    LseAcc a = lse_empty();
+    for (int w = 0; w < WS_ROW_WARPS; ++w) lse_merge(a, upart_s[w].x, upart_s[w].y);
+    p.upart[(size_t)b * G + g] = make_float2(a.m, a.s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// ALL Sinkhorn iterations in one persistent cooperative kernel (M % 4 == 0, M <= 4096, G*B <= #SMs)
+//   Same warp roles as skh_iter_ws_kernel.  Per iteration: prologue (v -> shared memory), the fused
+//   row/column pass over the CTA's rows, a grid-wide barrier, the merge of the per-CTA column partials
+//   (every warp of every CTA merges one column at a time), another grid-wide barrier.  The TMA ring
+//   never drains: the scores do not change, so the producer keeps prefetching the next iteration's
+//   slabs while the CTAs sit in the barriers.  Mask counts / normalisation constants are computed in
+//   the kernel, so one launch replaces 1 + 2*iters launches.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// barrier over the CTAs of one batch element; `counter` counts arrivals since the launch
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (ld_acquire_u32(counter) < target) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int R, int KQ, bool ROWFULL, bool COLFULL>
+__global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhParams p, const int iters, unsigned int* gsync) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int N = p.N, M = p.M;
+  const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nslab = (N + R - 1) / R;
+  const int s_begin = (int)(((long long)nslab * g) / G);
+  const int s_end = (int)(((long long)nslab * (g + 1)) / G);
+  const int nsl = s_end - s_begin;
+  const int nstage = p.nstage;
+
+  // ---- shared memory carve-up
+  const int Mv = (M + 1 + 3) & ~3;
+  const int stage_floats = R * M;
+  float* v2_s = reinterpret_cast<float*>(smem_raw);
+  float* stage0 = v2_s + Mv;
+  float* u2_s = stage0 + (size_t)nstage * stage_floats;             // [WS_MAX_STAGES][16]
+  float* red_s = u2_s + WS_MAX_STAGES * 16;                          // [64]
+  float2* upart_s = reinterpret_cast<float2*>(red_s + 64);           // [16]
+  uint64_t* full = reinterpret_cast<uint64_t*>(upart_s + 16);        // [WS_MAX_STAGES]
+  uint64_t* u_ready = full + WS_MAX_STAGES;
+  uint64_t* stage_free = u_ready + WS_MAX_STAGES;
+  __shared__ int cnt_s[2];
+
+  const float* sc_b = p.scores + (size_t)b * N * M;
+  const float zs = p.zscale2;
+  const float shift = p.shift ? *p.shift : 0.f;
+  const float alpha = *p.alpha;
+  unsigned int* gcount = gsync + b;
+
+  if (tid == 0) {
+    for (int s = 0; s < nstage; ++s) {
+      mbar_init(&full[s], 1u);
+      mbar_init(&u_ready[s], (uint32_t)R);
+      mbar_init(&stage_free[s], (uint32_t)(R + WS_COL_THREADS / 32));
+    }
+    fence_mbar_init();
+    cnt_s[0] = cnt_s[1] = 0;
+  }
+  __syncthreads();
+
+  const long long total_slabs = (long long)iters * nsl;  // the producer's stream: the CTA's slabs, once per iteration
+  auto issue_slab = [&](long long t) {                    // t-th slab of the stream -> stage t % nstage
+    const int s = s_begin + (int)(t % nsl);
+    const int st = (int)(t % nstage);
+    const int i0 = s * R;
+    const int rows = min(R, N - i0);
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)M * 4u;
+    fence_proxy_async();
+    mbar_arrive_expect_tx(&full[st], bytes);
+    tma_bulk_g2s(stage0 + (size_t)st * stage_floats, sc_b + (size_t)i0 * M, bytes, &full[st]);
+  };
+  if (warp == WS_ROW_WARPS && lane == 0)
+    for (int k = 0; k < nstage; ++k)
+      if (k < total_slabs) issue_slab(k);
+
+  // ---- mask counts -> normalisation constants (matching.py:14-15, 24-27)
+  {
+    int cs = count_mask_bytes(p.src_mask + (size_t)b * N, N, tid, WS_THREADS);
+    int ct = count_mask_bytes(p.tgt_mask + (size_t)b * M, M, tid, WS_THREADS);
+    cs = __reduce_add_sync(0xffffffffu, cs);
+    ct = __reduce_add_sync(0xffffffffu, ct);
+    if (lane == 0) {
+      if (cs) atomicAdd(&cnt_s[0], cs);
+      if (ct) atomicAdd(&cnt_s[1], ct);
+    }
+  }
+  __syncthreads();
+  SkhConst bc;
+  {
+    const float ms = (float)cnt_s[0], ns = (float)cnt_s[1];
+    bc.norm = -logf(ms + ns);
+    bc.log_mu_bin = logf(ns) + bc.norm;
+    bc.log_nu_bin = logf(ms) + bc.norm;
+    bc.pad = 0.f;
+    if (g == 0 && tid == 0) p.bc_out[b] = bc;
+  }
+
+  // persistent pipeline state of each role
+  int r_st = 0;          // row warps: stage / phase of the next slab to observe
+  uint32_t r_ph = 0;
+  int c_st = 0;          // column warps
+  uint32_t c_ph = 0;
+  long long p_next = nstage;  // producer: next slab of the stream to issue
+  int p_st = 0;
+  uint32_t p_ph = 0;
+  unsigned int barriers_done = 0;
+
+  for (int it = 0; it < iters; ++it) {
+    // ---- prologue: column potentials into shared memory (log2 domain), dustbin-row potential
+    float uN;
+    if (it == 0) {
+      // v = 0: LSE over M+1 zeros = log(M+1)
+      for (int j = tid; j <= M; j += WS_THREADS) {
+        float v2;
+        if (j < M) {
+          v2 = (0.f - shift) * LOG2E;
+          if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
+        } else {
+          v2 = alpha * LOG2E;
+        }
+        v2_s[j] = v2;
+      }
+      uN = bc.log_mu_bin - (alpha + logf((float)(M + 1)));
+    } else {
+      const float* v_b = p.v + (size_t)b * p.ldv;
+      float mloc = NEG_BIG;
+      for (int j = tid; j <= M; j += WS_THREADS) mloc = fmaxf(mloc, __ldcg(v_b + j) * LOG2E);  // written by other SMs: L2 only
+      mloc = warp_max(mloc);
+      if (lane == 0) red_s[warp] = mloc;
+      __syncthreads();
+      float mall = red_s[0];
+#pragma unroll
+      for (int w = 1; w < WS_THREADS / 32; ++w) mall = fmaxf(mall, red_s[w]);
+      float sloc = 0.f;
+      for (int j = tid; j <= M; j += WS_THREADS) {
+        const float vj = __ldcg(v_b + j);
+        sloc += ex2(vj * LOG2E - mall);
+        float v2;
+        if (j < M) {
+          v2 = (vj - shift) * LOG2E;
+          if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
+        } else {
+          v2 = (alpha + vj) * LOG2E;  // dustbin column entry of every real row: alpha + v_M
+        }
+        v2_s[j] = v2;
+      }
+      sloc = warp_sum(sloc);
+      if (lane == 0) red_s[32 + warp] = sloc;
+      __syncthreads();
+      float sall = 0.f;
+#pragma unroll
+      for (int w = 0; w < WS_THREADS / 32; ++w) sall += red_s[32 + w];
+      uN = bc.log_mu_bin - (alpha + (mall + lg2(sall)) * LN2);
+    }
+    if (g == 0 && tid == 0) p.u[(size_t)b * p.ldu + N] = uN;
+    for (int j = M + 1 + tid; j < Mv; j += WS_THREADS) v2_s[j] = -INFINITY;
+    __syncthreads();
+
+    if (warp < WS_ROW_WARPS) {
+      // =========================== ROW warps ===========================
+      const float dust2 = v2_s[M];
+      LseAcc uacc = lse_empty();
+      const int nq = nsl * R;
+      const float* v2_lane = v2_s + 4 * lane;
+      for (int q0 = 0; q0 < nq; q0 += R) {
+        mbar_wait_sleep(&full[r_st], r_ph, 200u);
+#pragma unroll 1
+        for (int r = 0; r < R; ++r) {
+          const int q = q0 + r;
+          if (q % WS_ROW_WARPS != warp) continue;
+          const int i = s_begin * R + q;
+          float u2 = -INFINITY;
+          if (i < N) {
+            const bool row_live = !(p.apply_mask && !p.src_mask[(size_t)b * N + i]);
+            float m_l = NEG_BIG, s_l = 0.f;
+            if (row_live) {
+              const float* row_lane = stage0 + (size_t)r_st * stage_floats + (size_t)r * M + 4 * lane;
+              for (int cb = 0; cb < M; cb += 1024) {
+                float xs[32];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  if (ROWFULL || cb + 4 * lane + 128 * k < M) {
+                    const float4 z = *reinterpret_cast<const float4*>(row_lane + cb + 128 * k);
+                    const float4 vv = *reinterpret_cast<const float4*>(v2_lane + cb + 128 * k);
+                    xs[4 * k + 0] = fmaf(z.x, zs, vv.x);
+                    xs[4 * k + 1] = fmaf(z.y, zs, vv.y);
+                    xs[4 * k + 2] = fmaf(z.z, zs, vv.z);
+                    xs[4 * k + 3] = fmaf(z.w, zs, vv.w);
+                  } else {
+                    xs[4 * k + 0] = xs[4 * k + 1] = xs[4 * k + 2] = xs[4 * k + 3] = -INFINITY;
+                  }
+                }
+                float cmax = NEG_BIG;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) cmax = fmaxf(cmax, xs[k]);
+                if (cmax > m_l) {  // per-lane online rescale (at most once per 32 elements)
+                  s_l *= ex2(m_l - cmax);
+                  m_l = cmax;
+                }
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  a0 += ex2(xs[4 * k + 0] - m_l);
+                  a1 += ex2(xs[4 * k + 1] - m_l);
+                  a2 += ex2(xs[4 * k + 2] - m_l);
+                  a3 += ex2(xs[4 * k + 3] - m_l);
+                }
+                s_l += (a0 + a1) + (a2 + a3);
+              }
+            }
+            const float mrow = warp_max(m_l);
+            float srow = warp_sum(s_l * ex2(m_l - mrow));
+            const float mm = fmaxf(mrow, dust2);
+            srow = srow * ex2(mrow - mm) + ex2(dust2 - mm);  // + dustbin column entry alpha + v_M
+            const float ui = bc.norm - (mm + lg2(srow)) * LN2;
+            const bool src_ok = !p.apply_mask || p.src_mask[(size_t)b * N + i];
+            u2 = src_ok ? (ui - shift) * LOG2E : -INFINITY;  // column pass sees (S - shift) + u
+            if (lane == 0) {
+              p.u[(size_t)b * p.ldu + i] = ui;
+              lse_add_value(uacc, ui * LOG2E);
+            }
+          }
+          if (lane == 0) {
+            u2_s[r_st * 16 + r] = u2;
+            mbar_arrive(&u_ready[r_st]);
+            mbar_arrive(&stage_free[r_st]);
+          }
+          __syncwarp();
+        }
+        if (++r_st == nstage) {
+          r_st = 0;
+          r_ph ^= 1u;
+        }
+      }
+      if (lane == 0) upart_s[warp] = make_float2(uacc.m, uacc.s);
+    } else if (warp == WS_ROW_WARPS) {
+      // =========================== producer ===========================
+      // issue everything this iteration's consumers will need plus the prefetch of the next iteration
+      if (lane == 0) {
+        const long long upto = min(total_slabs, (long long)(it + 1) * nsl + nstage);
+        for (; p_next < upto; ++p_next) {
+          mbar_wait_sleep(&stage_free[p_st], p_ph, 200u);
+          issue_slab(p_next);
+          if (++p_st == nstage) {
+            p_st = 0;
+            p_ph ^= 1u;
+          }
+        }
+        upart_s[WS_ROW_WARPS] = make_float2(NEG_BIG, 0.f);
+      }
+    } else {
+      // =========================== COLUMN warps ===========================
+      const int ct = tid - WS_COL_THREADS;  // 0..511
+      float cm[KQ * 4], cs[KQ * 4];
+#pragma unroll
+      for (int e = 0; e < KQ * 4; ++e) {
+        cm[e] = NEG_BIG;
+        cs[e] = 0.f;
+      }
+      for (int sl = 0; sl < nsl; ++sl) {
+        const int i0 = (s_begin + sl) * R;
+        const int rows = min(R, N - i0);
+        const float* slab = stage0 + (size_t)c_st * stage_floats;
+        mbar_wait_sleep(&u_ready[c_st], c_ph, 500u);
+        float u2r[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) u2r[r] = u2_s[c_st * 16 + r];  // rows beyond `rows` hold -inf
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (ct + WS_COL_THREADS * k);
+          if (COLFULL || c < M) {
+            float x[R][4];
+            float mx[4] = {NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG};
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              if (r < rows) {
+                const float4 z = *reinterpret_cast<const float4*>(slab + (size_t)r * M + c);
+                x[r][0] = fmaf(z.x, zs, u2r[r]);
+                x[r][1] = fmaf(z.y, zs, u2r[r]);
+                x[r][2] = fmaf(z.z, zs, u2r[r]);
+                x[r][3] = fmaf(z.w, zs, u2r[r]);
+              } else {
+                x[r][0] = x[r][1] = x[r][2] = x[r][3] = -INFINITY;
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) mx[e] = fmaxf(mx[e], x[r][e]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float& am = cm[4 * k + e];
+              float& as = cs[4 * k + e];
+              if (mx[e] > am + 32.f) {  // lazy re-reference: rare after the first slab
+                as *= ex2(am - mx[e]);
+                am = mx[e];
+              }
+              float acc = 0.f;
+#pragma unroll
+              for (int r = 0; r < R; ++r) acc += ex2(x[r][e] - am);
+              as += acc;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stage_free[c_st]);
+        if (++c_st == nstage) {
+          c_st = 0;
+          c_ph ^= 1u;
+        }
+      }
+      float2* cp = p.colpart + ((size_t)b * G + g) * M;
+#pragma unroll
+      for (int k = 0; k < KQ; ++k) {
+        const int c = 4 * (ct + WS_COL_THREADS * k);
+        if (COLFULL || c < M) {
+          *reinterpret_cast<float4*>(cp + c) = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
+          *reinterpret_cast<float4*>(cp + c + 2) = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
+        }
+      }
+    }
+    // ---- dustbin-column partial of this CTA, then wait for every CTA's partials
+    __syncthreads();
+    if (tid == 0) {
+      LseAcc a = lse_empty();
+      for (int w = 0; w < WS_ROW_WARPS; ++w) lse_merge(a, upart_s[w].x, upart_s[w].y);
+      p.upart[(size_t)b * G + g] = make_float2(a.m, a.s);
+    }
+    grid_barrier(gcount, (unsigned int)G * (++barriers_done));
+
+    // ---- merge: one column per warp at a time, lanes split the G partials            (skh_col_kernel)
+    {
+      float* v_b = p.v + (size_t)b * p.ldv;
+      for (int j = g * (WS_THREADS / 32) + warp; j <= M; j += G * (WS_THREADS / 32)) {
+        const bool is_bin = (j == M);
+        const bool col_ok = is_bin || !p.apply_mask || p.tgt_mask[(size_t)b * M + j];
+        float m = NEG_BIG, sum = 0.f;
+        if (col_ok) {
+          const float2* src = is_bin ? (p.upart + (size_t)b * G) : (p.colpart + (size_t)b * G * M + j);
+          const size_t gstride = is_bin ? 1 : (size_t)M;
+          float2 q[(NUM_SMS + 31) / 32];
+#pragma unroll
+          for (int k = 0; k < (NUM_SMS + 31) / 32; ++k) {
+            const int gg = lane + 32 * k;
+            q[k] = (gg < G) ? __ldcg(src + (size_t)gg * gstride) : make_float2(NEG_BIG, 0.f);
+            m = fmaxf(m, q[k].x);
+          }
+          m = warp_max(m);
+#pragma unroll
+          for (int k = 0; k < (NUM_SMS + 31) / 32; ++k) sum += q[k].y * ex2(q[k].x - m);
+          sum = warp_sum(sum);
+        }
+        if (lane == 0) {
+          LseAcc a{m, sum};
+          if (!is_bin) {
+            lse_add_value(a, (alpha + uN) * LOG2E);  // dustbin row entry
+            v_b[j] = bc.norm - lse_value(a) * LN2;
+          } else {
+            lse_add_value(a, uN * LOG2E);  // c_M = alpha + LSE(u[0..N])
+            v_b[M] = bc.log_nu_bin - (alpha + lse_value(a) * LN2);
+          }
+        }
+      }
+    }
+    if (it + 1 < iters) grid_barrier(gcount, (unsigned int)G * (++barriers_done));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // merge the per-CTA column partials into v (and the dustbin column entry v_M)
 //   block = 32 columns x 8 slices of the G partials; every thread first pulls its <= 19
 //   partials into registers (all loads in flight at once), reduces them with one ex2 each,
@@ -771,6 +1436,10 @@ __global__ void __launch_bounds__(256) skh_col_kernel(const SkhParams p) {
   a.m = m;
   a.s = sum;
 
+  if (p.shard_partial) {  // row-sharded Sinkhorn: the ranks all-reduce these before any of them updates v
+    p.shard_partial[(size_t)b * (M + 1) + j] = make_float2(a.m, a.s);
+    return;
+  }
   float* v_b = p.v + (size_t)b * p.ldv;
   if (p.dual) {
     v_b[j] = -lse_value(a) * LN2;
@@ -784,6 +1453,52 @@ __global__ void __launch_bounds__(256) skh_col_kernel(const SkhParams p) {
     v_b[j] = bc.norm - lse_value(a) * LN2;
   } else {
     lse_add_value(a, uN * LOG2E);  // c_M = alpha + LSE(u[0..N])
+    v_b[M] = bc.log_nu_bin - (alpha + lse_value(a) * LN2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// row-sharded Sinkhorn (rows of one matrix spread over several GPUs, BASELINE.json configs[4])
+//   begin : constants from the GLOBAL valid counts, u = v = 0
+//   local : skh_iter*_kernel + skh_col_kernel(shard_partial) -> this rank's (max, sum) per column
+//   [caller: all-reduce the partials over the ranks -- log-sum-exp is associative]
+//   update: v from the reduced partials + the dustbin row term (identical on every rank)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) skh_shard_begin_kernel(const int* __restrict__ global_counts, SkhConst* __restrict__ bc,
+                                                               float* __restrict__ v, float* __restrict__ u, int ldu, int ldv) {
+  const int b = blockIdx.x;
+  float4* v4 = reinterpret_cast<float4*>(v + (size_t)b * ldv);
+  float4* u4 = reinterpret_cast<float4*>(u + (size_t)b * ldu);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = threadIdx.x; j < (ldv >> 2); j += blockDim.x) v4[j] = z4;
+  for (int i = threadIdx.x; i < (ldu >> 2); i += blockDim.x) u4[i] = z4;
+  if (threadIdx.x == 0) {
+    const float ms = (float)global_counts[2 * b], ns = (float)global_counts[2 * b + 1];
+    SkhConst c;
+    c.norm = -logf(ms + ns);
+    c.log_mu_bin = logf(ns) + c.norm;
+    c.log_nu_bin = logf(ms) + c.norm;
+    c.pad = 0.f;
+    bc[b] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256) skh_shard_update_kernel(const SkhParams p, const float2* __restrict__ reduced) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int M = p.M, N = p.N;
+  if (j > M) return;
+  const float2 r = reduced[(size_t)b * (M + 1) + j];
+  LseAcc a{r.x, r.y};
+  const SkhConst bc = p.bc[b];
+  const float alpha = *p.alpha;
+  const float uN = p.u[(size_t)b * p.ldu + N];
+  float* v_b = p.v + (size_t)b * p.ldv;
+  if (j < M) {
+    lse_add_value(a, (alpha + uN) * LOG2E);  // dustbin row entry (the dustbin row exists once, on every rank alike)
+    v_b[j] = bc.norm - lse_value(a) * LN2;
+  } else {
+    lse_add_value(a, uN * LOG2E);
     v_b[M] = bc.log_nu_bin - (alpha + lse_value(a) * LN2);
   }
 }
@@ -1002,6 +1717,7 @@ struct SkhWorkspace {
   float* v;
   float2* colpart;
   float2* upart;
+  unsigned int* gsync;  // [B] grid-barrier counters of the persistent kernel
   size_t total;
 };
 
@@ -1020,6 +1736,7 @@ static SkhWorkspace carve(void* ws, int B, int N, int M, int G) {
   w.v = (float*)take(sizeof(float) * (size_t)B * pitch4(M + 1));
   w.colpart = (float2*)take(sizeof(float2) * (size_t)B * G * M);
   w.upart = (float2*)take(sizeof(float2) * (size_t)B * G);
+  w.gsync = (unsigned int*)take(sizeof(unsigned int) * (size_t)B);
   w.total = off;
   return w;
 }
@@ -1151,6 +1868,116 @@ static cudaError_t launch_iter2(const SkhParams& p, const SkhPlan2& pl, cudaStre
   return cudaErrorInvalidConfiguration;
 }
 
+struct SkhPlanWS {
+  int R, KQ, nstage, G;
+  size_t smem;
+  bool ok;
+};
+
+static int skh_ws_rows() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DRG_SKH_WS_ROWS");
+    v = e ? atoi(e) : 4;
+    if (v != 1 && v != 2 && v != 4 && v != 8) v = 4;
+  }
+  return v;
+}
+static int skh_ws_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DRG_SKH_WS");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+static SkhPlanWS make_plan_ws(int B, int N, int M) {
+  SkhPlanWS pl{};
+  pl.ok = false;
+  if (!skh_ws_enabled() || M < 4 || M > 4096 || N < 1 || (M % 4) != 0) return pl;
+  int R = skh_ws_rows();
+  while (R > 1 && (size_t)R * M * 4 * 2 > SKH_SMEM_LIMIT - 32 * 1024) R >>= 1;
+  // small matrices: wider slabs keep the per-slab synchronisation negligible
+  while (R < 8 && (long long)R * M < 8192) R <<= 1;
+  pl.R = R;
+  pl.KQ = (M <= 2048) ? 1 : 2;
+  const size_t Mv = (size_t)((M + 1 + 3) & ~3);
+  const size_t stage_bytes = (size_t)R * M * 4;
+  const size_t fixed = Mv * 4 + WS_MAX_STAGES * 16 * 4 + 64 * 4 + 16 * 8 + 3 * WS_MAX_STAGES * 8 + 128;
+  int nstage = (int)((SKH_SMEM_LIMIT - fixed) / stage_bytes);
+  if (nstage > WS_MAX_STAGES) nstage = WS_MAX_STAGES;
+  if (nstage < 2) return pl;
+  pl.nstage = nstage;
+  pl.smem = fixed + (size_t)nstage * stage_bytes;
+  const int nslab = (N + R - 1) / R;
+  int G = NUM_SMS / (B < 1 ? 1 : B);
+  if (G < 1) G = 1;
+  if (G > nslab) G = nslab;
+  pl.G = G;
+  pl.ok = true;
+  return pl;
+}
+
+template <int R, int KQ, bool ROWFULL, bool COLFULL>
+static cudaError_t launch_iter_ws_t(const SkhParams& p, const SkhPlanWS& pl, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(skh_iter_ws_kernel<R, KQ, ROWFULL, COLFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)pl.smem);
+  if (e != cudaSuccess) return e;
+  skh_iter_ws_kernel<R, KQ, ROWFULL, COLFULL><<<dim3(pl.G, p.B), WS_THREADS, pl.smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_iter_ws(const SkhParams& p, const SkhPlanWS& pl, cudaStream_t st) {
+  const bool rowfull = (p.M % 1024) == 0;
+  const bool colfull = p.M == 2048 * pl.KQ;
+#define DRG_WS_CASE(r, kq)                                                                 \
+  if (pl.R == r && pl.KQ == kq) {                                                          \
+    if (rowfull && colfull) return launch_iter_ws_t<r, kq, true, true>(p, pl, st);         \
+    if (rowfull) return launch_iter_ws_t<r, kq, true, false>(p, pl, st);                   \
+    return launch_iter_ws_t<r, kq, false, false>(p, pl, st);                               \
+  }
+  DRG_WS_CASE(1, 1) DRG_WS_CASE(2, 1) DRG_WS_CASE(4, 1) DRG_WS_CASE(8, 1)
+  DRG_WS_CASE(1, 2) DRG_WS_CASE(2, 2) DRG_WS_CASE(4, 2) DRG_WS_CASE(8, 2)
+#undef DRG_WS_CASE
+  return cudaErrorInvalidConfiguration;
+}
+
+static int skh_persist_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DRG_SKH_PERSIST");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+template <int R, int KQ, bool ROWFULL, bool COLFULL>
+static cudaError_t launch_persist_t(const SkhParams& p, const SkhPlanWS& pl, int iters, unsigned int* gsync, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(skh_persist_kernel<R, KQ, ROWFULL, COLFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)pl.smem);
+  if (e != cudaSuccess) return e;
+  SkhParams pp = p;
+  void* args[] = {(void*)&pp, (void*)&iters, (void*)&gsync};
+  return cudaLaunchCooperativeKernel((const void*)skh_persist_kernel<R, KQ, ROWFULL, COLFULL>, dim3(pl.G, p.B), dim3(WS_THREADS), args,
+                                     pl.smem, st);
+}
+
+static cudaError_t launch_persist(const SkhParams& p, const SkhPlanWS& pl, int iters, unsigned int* gsync, cudaStream_t st) {
+  const bool rowfull = (p.M % 1024) == 0;
+  const bool colfull = p.M == 2048 * pl.KQ;
+#define DRG_PS_CASE(r, kq)                                                                            \
+  if (pl.R == r && pl.KQ == kq) {                                                                     \
+    if (rowfull && colfull) return launch_persist_t<r, kq, true, true>(p, pl, iters, gsync, st);      \
+    if (rowfull) return launch_persist_t<r, kq, true, false>(p, pl, iters, gsync, st);                \
+    return launch_persist_t<r, kq, false, false>(p, pl, iters, gsync, st);                            \
+  }
+  DRG_PS_CASE(1, 1) DRG_PS_CASE(2, 1) DRG_PS_CASE(4, 1) DRG_PS_CASE(8, 1)
+  DRG_PS_CASE(1, 2) DRG_PS_CASE(2, 2) DRG_PS_CASE(4, 2)
+#undef DRG_PS_CASE
+  return cudaErrorInvalidConfiguration;
+}
+
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 }  // namespace drg
@@ -1169,8 +1996,10 @@ extern "C" size_t drg_sinkhorn_workspace_bytes(int B, int N, int M) {
   return carve(nullptr, B, N, M, skh_max_g(B)).total;
 }
 
+enum SkhRun { SKH_RUN_ALL = 0, SKH_SHARD_BEGIN, SKH_SHARD_LOCAL, SKH_SHARD_UPDATE, SKH_SHARD_FINAL };
+
 static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature, void* workspace, size_t workspace_bytes,
-                        void* stream) {
+                        void* stream, SkhRun run = SKH_RUN_ALL, const int* global_counts = nullptr, float2* shard_partial = nullptr) {
   cudaStream_t st = (cudaStream_t)stream;
   const int B = a->B, N = a->N, M = a->M;
   SkhPlan pl = make_plan(B, N, M);
@@ -1186,6 +2015,8 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   const bool vec = (M % 4 == 0) && aligned16(a->scores);
   SkhPlan2 pl2 = vec ? make_plan2(B, N, M) : SkhPlan2{};
   const bool use2 = vec && pl2.ok;
+  SkhPlanWS plw = vec ? make_plan_ws(B, N, M) : SkhPlanWS{};
+  const bool usew = vec && plw.ok;
   SkhWorkspace w = carve(workspace, B, N, M, skh_max_g(B));
   if (workspace == nullptr || workspace_bytes < w.total) {
     set_error("sinkhorn: workspace too small (%zu < %zu)", workspace_bytes, w.total);
@@ -1195,11 +2026,17 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     set_error("sinkhorn: workspace must be 256-byte aligned");
     return DRG_ERR_INVALID;
   }
-  {
+  const bool persist = run == SKH_RUN_ALL && usew && !dual && a->iters >= 1 && skh_persist_enabled() && (long long)plw.G * B <= NUM_SMS;
+  if (run == SKH_SHARD_BEGIN) {
+    skh_shard_begin_kernel<<<B, 1024, 0, st>>>(global_counts, w.bc, w.v, w.u, pitch4(N + 1), pitch4(M + 1));
+    DRG_LAUNCH_CHECK();
+    return DRG_OK;
+  }
+  if (!persist && run == SKH_RUN_ALL) {
     ProfScope prof_scope(PROF_SKH_PREP, st);
     skh_prep_kernel<<<B, 1024, 0, st>>>(a->src_mask, a->tgt_mask, N, M, w.bc, w.v, w.u, pitch4(N + 1), pitch4(M + 1));
+    DRG_LAUNCH_CHECK();
   }
-  DRG_LAUNCH_CHECK();
 
   SkhParams p{};
   p.scores = a->scores;
@@ -1212,29 +2049,57 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   p.colpart = w.colpart;
   p.upart = w.upart;
   p.bc = w.bc;
+  p.bc_out = w.bc;
+  p.shard_partial = (run == SKH_SHARD_LOCAL) ? shard_partial : nullptr;
   p.B = B;
   p.N = N;
   p.M = M;
-  p.G = use2 ? pl2.G : pl.G;
+  p.G = usew ? plw.G : use2 ? pl2.G : pl.G;
   p.ldu = pitch4(N + 1);
   p.ldv = pitch4(M + 1);
   p.apply_mask = a->apply_mask;
   p.dual = dual ? 1 : 0;
   p.zscale2 = dual ? LOG2E / temperature : LOG2E;
-  p.nstage = use2 ? pl2.nstage : pl.nstage;
+  p.nstage = usew ? plw.nstage : use2 ? pl2.nstage : pl.nstage;
   p.keep_slabs = -1;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("DRG_SKH_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.dbg = dbg;
+  }
   if (use2 && skh_keep_fraction() >= 0.f) {
     const int nslab = (N + pl2.R - 1) / pl2.R;
     p.keep_slabs = (int)(skh_keep_fraction() * (float)((nslab + pl2.G - 1) / pl2.G) + 0.5f);
   }
 
-  const int iters = dual ? 1 : a->iters;
+  if (run == SKH_SHARD_UPDATE) {
+    skh_shard_update_kernel<<<dim3((M + 1 + 255) / 256, B), 256, 0, st>>>(p, shard_partial);
+    DRG_LAUNCH_CHECK();
+    return DRG_OK;
+  }
+  const int iters = run == SKH_SHARD_LOCAL ? 1 : run == SKH_SHARD_FINAL ? 0 : dual ? 1 : a->iters;
   dim3 cgrid((M + 1 + 31) / 32, B);
-  for (int k = 0; k < iters; ++k) {
+  if (persist) {
+    DRG_CUDA(cudaMemsetAsync(w.gsync, 0, sizeof(unsigned int) * B, st));
     cudaError_t e;
     {
       ProfScope prof_scope(PROF_SKH_ITER, st);
-      e = use2 ? launch_iter2(p, pl2, st) : launch_iter(p, pl, st);
+      e = launch_persist(p, plw, iters, w.gsync, st);
+    }
+    if (e != cudaSuccess) {
+      set_error("persistent sinkhorn launch failed: %s (smem=%zu, grid %d x %d)", cudaGetErrorString(e), plw.smem, plw.G, B);
+      return DRG_ERR_CUDA;
+    }
+    count_launch();
+  }
+  for (int k = 0; k < (persist ? 0 : iters); ++k) {
+    cudaError_t e;
+    {
+      ProfScope prof_scope(PROF_SKH_ITER, st);
+      e = usew ? launch_iter_ws(p, plw, st) : use2 ? launch_iter2(p, pl2, st) : launch_iter(p, pl, st);
     }
     if (e != cudaSuccess) {
       set_error("sinkhorn iteration launch failed: %s (smem=%zu)", cudaGetErrorString(e), use2 ? pl2.smem : pl.smem);
@@ -1248,6 +2113,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     DRG_LAUNCH_CHECK();
   }
 
+  if (run == SKH_SHARD_LOCAL) return DRG_OK;
   if (a->out_mode != DRG_OUT_NONE || dual) {
     SkhFinalParams f{};
     f.scores = a->scores;
@@ -1341,4 +2207,41 @@ extern "C" int drg_dual_softmax(const float* sim, const uint8_t* src_mask, const
   a.out_mode = DRG_OUT_CONF;
   a.out = out;
   return run_sinkhorn(&a, true, temperature, workspace, workspace_bytes, stream);
+}
+
+/* ---- row-sharded Sinkhorn: see include/diffreg_b200.h ---- */
+static int shard_check(const drg_sinkhorn_args* a) {
+  DRG_CHECK_ARG(a != nullptr, "args is null");
+  DRG_CHECK_ARG(a->scores && a->src_mask && a->tgt_mask && a->alpha, "scores/src_mask/tgt_mask/alpha must be non-null");
+  DRG_CHECK_ARG(a->B >= 1 && a->N >= 1 && a->M >= 1, "B, N (local rows), M must be >= 1");
+  return DRG_OK;
+}
+extern "C" int drg_sinkhorn_shard_begin(const drg_sinkhorn_args* a, const int* global_counts, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  int rc = shard_check(a);
+  if (rc != DRG_OK) return rc;
+  DRG_CHECK_ARG(global_counts != nullptr, "global_counts is null");
+  return run_sinkhorn(a, false, 1.f, workspace, workspace_bytes, stream, SKH_SHARD_BEGIN, global_counts, nullptr);
+}
+extern "C" int drg_sinkhorn_shard_local(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, float* partial,
+                                        void* stream) {
+  int rc = shard_check(a);
+  if (rc != DRG_OK) return rc;
+  DRG_CHECK_ARG(partial != nullptr && (((uintptr_t)partial) & 7u) == 0, "partial must be a non-null 8-byte aligned [B, M+1, 2] buffer");
+  return run_sinkhorn(a, false, 1.f, workspace, workspace_bytes, stream, SKH_SHARD_LOCAL, nullptr, reinterpret_cast<float2*>(partial));
+}
+extern "C" int drg_sinkhorn_shard_update(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, const float* reduced,
+                                         void* stream) {
+  int rc = shard_check(a);
+  if (rc != DRG_OK) return rc;
+  DRG_CHECK_ARG(reduced != nullptr && (((uintptr_t)reduced) & 7u) == 0, "reduced must be a non-null 8-byte aligned [B, M+1, 2] buffer");
+  return run_sinkhorn(a, false, 1.f, workspace, workspace_bytes, stream, SKH_SHARD_UPDATE, nullptr,
+                      const_cast<float2*>(reinterpret_cast<const float2*>(reduced)));
+}
+extern "C" int drg_sinkhorn_shard_final(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = shard_check(a);
+  if (rc != DRG_OK) return rc;
+  DRG_CHECK_ARG(a->out_mode >= DRG_OUT_LOG_FULL && a->out_mode <= DRG_OUT_NONE, "unknown out_mode");
+  DRG_CHECK_ARG(a->out_mode == DRG_OUT_NONE || a->out != nullptr, "out is null");
+  return run_sinkhorn(a, false, 1.f, workspace, workspace_bytes, stream, SKH_SHARD_FINAL, nullptr, nullptr);
 }

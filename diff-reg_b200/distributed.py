@@ -1,0 +1,100 @@
+"""Multi-GPU paths of the hot path.
+
+(i)  Independent units -- registration pairs / diffusion samples -- are sharded over the ranks with NO collective:
+     `shard_units` is the partition (unit index mod world size); bench.py runs one sample per GPU this way.
+(ii) One very large Sinkhorn (BASELINE.json configs[4]: N = M = 16384, 100 iterations) is ROW-SHARDED: rank r owns a
+     contiguous block of rows, `v` is replicated, and the ranks all-reduce the per-column log-sum-exp partials once per
+     iteration.  The reference has no counterpart (its matrix always lives on one GPU).
+
+The collective is log-sum-exp, which NCCL does not offer: `lse_allreduce` does MAX on the maxima, rescales the sums and
+does SUM (two small all-reduces), or -- once a per-column reference is known -- a single SUM of sums rescaled to that
+reference (the previous iteration's column log-sum-exp, which the iteration converges to).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def shard_units(n_units, world_size, rank):
+    """Indices of the independent units (pairs / samples) this rank processes."""
+    return list(range(rank, n_units, world_size))
+
+
+def shard_rows(n_rows, world_size, rank):
+    """Contiguous-equal row block [start, stop) of rank `rank` (the first n_rows % world_size ranks get one extra row)."""
+    base, extra = divmod(n_rows, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def lse_combine(partials):
+    """Reference combine of a list of [.., 2] (max, sum) log2-domain partials (single process; used by tests and by the
+    one-process emulation of the sharded path)."""
+    m = torch.stack([p[..., 0] for p in partials]).max(dim=0)[0]
+    s = sum(p[..., 1] * torch.exp2(p[..., 0] - m) for p in partials)
+    return torch.stack((m, s), dim=-1)
+
+
+def lse_allreduce(partial, group=None, ref=None):
+    """All-reduce [.., 2] (max, sum) log2-domain partials over the process group.
+    ref=None: exact two-step (MAX, then SUM of rescaled sums).  ref=[..] tensor: one SUM with every rank's sum rescaled
+    to the shared reference (valid while |max - ref| stays far below the fp32 exponent range)."""
+    m_loc, s_loc = partial[..., 0], partial[..., 1]
+    if ref is None:
+        m = m_loc.clone()
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    else:
+        m = ref
+    s = s_loc * torch.exp2(torch.clamp(m_loc - m, max=120.0))
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    return torch.stack((m, s), dim=-1)
+
+
+class RowShardedSinkhorn:
+    """log_optimal_transport over a row-sharded score matrix.  Call on every rank with its local rows."""
+
+    def __init__(self, group=None, single_allreduce_after=2):
+        self.group = group
+        self.single_after = single_allreduce_after
+
+    @torch.no_grad()
+    def __call__(self, scores_local, alpha, iters, src_mask_local, tgt_mask, out_mode="conf", apply_mask=False):
+        st = ops.ShardedSinkhornState(scores_local, alpha, src_mask_local, tgt_mask, apply_mask)
+        counts = st.local_counts()
+        src_total = counts[:, 0].clone()
+        dist.all_reduce(src_total, op=dist.ReduceOp.SUM, group=self.group)
+        counts[:, 0] = src_total
+        st.begin(counts)
+        ref = None
+        for it in range(int(iters)):
+            partial = st.local()
+            reduced = lse_allreduce(partial, self.group, ref if it >= self.single_after else None)
+            st.update(reduced)
+            # the column log-sum-exp this iteration found is the next iteration's rescaling reference
+            ref = reduced[..., 0] + torch.log2(reduced[..., 1].clamp_min(1e-38))
+        return st.final(out_mode)
+
+
+class EmulatedRowShards:
+    """The same algorithm with all P shards living in ONE process on one GPU (no process group): validates the sharded
+    kernels against the unsharded result where only one GPU is available."""
+
+    def __init__(self, n_shards):
+        self.P = n_shards
+
+    @torch.no_grad()
+    def __call__(self, scores, alpha, iters, src_mask, tgt_mask, out_mode="conf", apply_mask=False):
+        B, N, M = scores.shape
+        bounds = [shard_rows(N, self.P, r) for r in range(self.P)]
+        states = [ops.ShardedSinkhornState(scores[:, a:b].contiguous(), alpha, src_mask[:, a:b].contiguous(), tgt_mask, apply_mask)
+                  for a, b in bounds]
+        counts = states[0].local_counts()
+        counts[:, 0] = sum(s.local_counts()[:, 0] for s in states)
+        for s in states:
+            s.begin(counts)
+        for _ in range(int(iters)):
+            reduced = lse_combine([s.local().clone() for s in states])
+            for s in states:
+                s.update(reduced)
+        return torch.cat([s.final(out_mode)[:, : (b - a)] for s, (a, b) in zip(states, bounds)], dim=1)

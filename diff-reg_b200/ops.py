@@ -267,3 +267,53 @@ def counter_add(counter, inc=1):
     """counter (1-element int64 CUDA tensor) += inc, on the stream."""
     _require_cuda(counter)
     check(load_library().drg_counter_add(counter.data_ptr(), int(inc), _stream()))
+
+
+class ShardedSinkhornState:
+    """The rank-local state of a row-sharded Sinkhorn (drg_sinkhorn_shard_*): local rows of the scores, local src mask,
+    replicated tgt mask, and a private workspace holding u (local rows), v (replicated) and the constants."""
+
+    def __init__(self, scores_local, alpha, src_mask_local, tgt_mask, apply_mask=False, shift=None):
+        _require_cuda(scores_local, alpha, src_mask_local, tgt_mask, shift)
+        self.lib = load_library()
+        self.scores = _f32c(scores_local)
+        self.B, self.N, self.M = self.scores.shape
+        self.src_mask = _as_mask(src_mask_local)
+        self.tgt_mask = _as_mask(tgt_mask)
+        self.alpha = _f32c(alpha.detach().reshape(()))
+        self.shift = shift
+        self.apply_mask = bool(apply_mask)
+        nbytes = self.lib.drg_sinkhorn_workspace_bytes(self.B, self.N, self.M)
+        if nbytes == 0:
+            raise _lib.DiffRegLibraryError(f"sharded sinkhorn: unsupported local shape {tuple(self.scores.shape)}")
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.scores.device)   # private: potentials live here
+        self.partial = torch.empty(self.B, self.M + 1, 2, dtype=torch.float32, device=self.scores.device)
+
+    def _args(self, out_mode=_lib.DRG_OUT_NONE, out=None):
+        return SinkhornArgs(scores=_ptr(self.scores), src_mask=_ptr(self.src_mask), tgt_mask=_ptr(self.tgt_mask), alpha=_ptr(self.alpha),
+                            shift=_ptr(self.shift), B=self.B, N=self.N, M=self.M, iters=1, apply_mask=int(self.apply_mask),
+                            out_mode=out_mode, out=_ptr(out))
+
+    def local_counts(self):
+        """[B,2] int32: (valid src rows of THIS rank, valid tgt columns); sum column 0 over the ranks before begin()."""
+        return torch.stack((self.src_mask.sum(dim=1), self.tgt_mask.sum(dim=1)), dim=1).to(torch.int32)
+
+    def begin(self, global_counts):
+        gc = global_counts.to(torch.int32).contiguous()
+        check(self.lib.drg_sinkhorn_shard_begin(self._args(), gc.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream()))
+
+    def local(self):
+        """Row pass over the local rows with the current v; returns this rank's column partials [B, M+1, 2]."""
+        check(self.lib.drg_sinkhorn_shard_local(self._args(), self.ws.data_ptr(), self.ws.numel(), self.partial.data_ptr(), _stream()))
+        return self.partial
+
+    def update(self, reduced):
+        reduced = _f32c(reduced)
+        check(self.lib.drg_sinkhorn_shard_update(self._args(), self.ws.data_ptr(), self.ws.numel(), reduced.data_ptr(), _stream()))
+
+    def final(self, out_mode="conf"):
+        mode = {"log_full": _lib.DRG_OUT_LOG_FULL, "conf": _lib.DRG_OUT_CONF}[out_mode]
+        shape = (self.B, self.N + 1, self.M + 1) if mode == _lib.DRG_OUT_LOG_FULL else (self.B, self.N, self.M)
+        out = torch.empty(*shape, dtype=torch.float32, device=self.scores.device)
+        check(self.lib.drg_sinkhorn_shard_final(self._args(mode, out), self.ws.data_ptr(), self.ws.numel(), _stream()))
+        return out

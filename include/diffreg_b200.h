@@ -105,6 +105,26 @@ typedef struct drg_sinkhorn_args {
 size_t drg_sinkhorn_workspace_bytes(int B, int N, int M);
 int drg_sinkhorn(const drg_sinkhorn_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Row-sharded Sinkhorn: ONE matrix whose rows are spread over several GPUs (BASELINE.json configs[4]).
+ *   The reference has no counterpart (its matrix always lives on one GPU); the arithmetic is
+ *   log_optimal_transport's (Diff-Reg-4dmatch/models/matching.py:6-38) with the column log-sum-exp split as
+ *   LSE_i = LSE over ranks of (LSE over the rank's rows).
+ *   Every call takes the rank's LOCAL problem in drg_sinkhorn_args (scores [B,Nloc,M], src_mask [B,Nloc], N = Nloc)
+ *   and the same workspace (drg_sinkhorn_workspace_bytes(B, Nloc, M)).  Per iteration:
+ *     drg_sinkhorn_shard_local   row pass + this rank's column partials -> partial [B, M+1, 2] = (max, sum) in the log2 domain
+ *     (caller)                   all-reduce the partials over the ranks: MAX on max, SUM on sum * 2^(max_local - max_global)
+ *     drg_sinkhorn_shard_update  v from the reduced partials (+ the dustbin row, identical on every rank)
+ *   drg_sinkhorn_shard_begin sets the normalisation constants from global_counts [B,2] = (valid src rows over ALL ranks,
+ *   valid tgt columns) and zeroes the potentials; drg_sinkhorn_shard_final writes the rank's rows of the output (out_mode).
+ * ------------------------------------------------------------------------------------ */
+int drg_sinkhorn_shard_begin(const drg_sinkhorn_args* args, const int* global_counts, void* workspace, size_t workspace_bytes,
+                             void* stream);
+int drg_sinkhorn_shard_local(const drg_sinkhorn_args* args, void* workspace, size_t workspace_bytes, float* partial, void* stream);
+int drg_sinkhorn_shard_update(const drg_sinkhorn_args* args, void* workspace, size_t workspace_bytes, const float* reduced,
+                              void* stream);
+int drg_sinkhorn_shard_final(const drg_sinkhorn_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Dual-softmax confidence: conf = softmax_src(sim/T | src mask) * softmax_tgt(sim/T | tgt mask)
  *   replaces Diff-Reg-4dmatch/models/matching.py:147-157 (sim already divided by nothing:
  *   the temperature is applied here).  out[B,N,M]. */

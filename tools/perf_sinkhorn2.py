@@ -24,8 +24,7 @@ for (B, N, M, I) in shapes:
     prof = _lib.profile_read(); _lib.profile_enable(False)
     E = 4.0 * B * (N + 1) * (M + 1)
     us = e0.elapsed_time(e1) * 1e3 / reps
-    print(json.dumps(dict(env=dict(stage=os.environ.get("DRG_SKH_STAGE_FLOATS"), keep=os.environ.get("DRG_SKH_L2_KEEP")), B=B, N=N, M=M, us_call=round(us, 1),
-                          algo_GBps=round((2 * I + 2) * E / us / 1e3), iter_us=round(prof["skh_iter"][0] * 1e3 / prof["skh_iter"][1], 2),
-                          col_us=round(prof["skh_col"][0] * 1e3 / prof["skh_col"][1], 2), final_us=round(prof["skh_final"][0] * 1e3 / prof["skh_final"][1], 2),
-                          prep_us=round(prof["skh_prep"][0] * 1e3 / prof["skh_prep"][1], 2))), flush=True)
+    per = lambda k: round(prof[k][0] * 1e3 / prof[k][1], 2) if prof[k][1] else None
+    print(json.dumps(dict(B=B, N=N, M=M, us_call=round(us, 1), algo_GBps=round((2 * I + 2) * E / us / 1e3), iter_us=per("skh_iter"),
+                          col_us=per("skh_col"), final_us=per("skh_final"), prep_us=per("skh_prep"))), flush=True)
     del s
