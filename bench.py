@@ -362,28 +362,31 @@ def run_ours(args):
         prof = _lib.profile_read()
         _lib.profile_enable(False)
         kernel_ms = {k: round(v[0] / max(args.steps, 1), 5) for k, v in prof.items()}
-        # dominant kernel: the Sinkhorn iteration (row + column log-sum-exp in one read of the matrix)
-        it_ms, it_n = prof["skh_iter"]
+        # dominant kernels: the fused Sinkhorn call = skh_persist_kernel (all iterations: one read of the matrix per
+        # iteration, row and column log-sum-exp) + skh_final_kernel (exp / DDIM update).  Algorithmic bytes per call
+        # are SURVEY.md section 8d's (2I+2) * E with E = 4 (N+1)(M+1).
         E = 4.0 * (n + 1) * (n + 1)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        if it_n:
-            per_launch_s = it_ms * 1e-3 / it_n
-            achieved = 2.0 * E / per_launch_s / 1e9          # one iteration = 1 row-LSE read + 1 column-LSE read (algorithmic)
-            roofline = {"bound": "hbm", "kernel": "skh_iter_kernel (one Sinkhorn iteration: row and column log-sum-exp)",
-                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                        "algorithmic_bytes_per_launch": 2.0 * E, "us_per_launch": per_launch_s * 1e6, "launches": it_n,
-                        "peak_source": peak_src}
-        # the fused Sinkhorn call as a whole (BASELINE.json: "(2I+2)E" per log_optimal_transport)
+        it_ms, it_n = prof["skh_iter"]
+        persistent = prof["skh_col"][1] == 0          # one launch runs all iterations
         skh_ms = sum(prof[k][0] for k in ("skh_prep", "skh_iter", "skh_col", "skh_final"))
         calls = 2 * args.steps
-        if roofline is not None and calls:
-            roofline["sinkhorn_call"] = {"algorithmic_bytes": (2 * SKH_ITERS + 2) * E, "us_per_call": skh_ms * 1e3 / calls,
-                                         "achieved": (2 * SKH_ITERS + 2) * E / (skh_ms * 1e-3 / calls) / 1e9,
-                                         "frac": (2 * SKH_ITERS + 2) * E / (skh_ms * 1e-3 / calls) / 1e9 / peak}
+        if it_n and calls:
+            per_call_s = skh_ms * 1e-3 / calls
+            alg = (2 * SKH_ITERS + 2) * E
+            roofline = {"bound": "hbm",
+                        "kernel": ("skh_persist_kernel + skh_final_kernel" if persistent else "skh_iter*_kernel x I + skh_col_kernel x I + "
+                                   "skh_final_kernel") + " = one fused log-Sinkhorn call (I=3 iterations + exp/DDIM pass)",
+                        "achieved": alg / per_call_s / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / per_call_s / 1e9 / peak,
+                        "traffic": None, "algorithmic_bytes_per_launch": alg, "us_per_launch": per_call_s * 1e6, "launches": calls,
+                        "peak_source": peak_src,
+                        "iterations_kernel": {"us_per_launch": it_ms * 1e3 / it_n, "launches": it_n,
+                                              "algorithmic_bytes": (2 * SKH_ITERS * E) if persistent else 2 * E,
+                                              "achieved": ((2 * SKH_ITERS * E) if persistent else 2 * E) / (it_ms * 1e-3 / it_n) / 1e9}}
 
     # ---- CPU baseline (rank 0, single-GPU runs only)
     cpu = None

@@ -126,18 +126,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // try_wait with a suspend-time hint: the hardware parks the thread for up to `ns` instead of re-issuing the probe
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
-  uint32_t ok = 0;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-        : "memory");
-  } while (!ok);
+  // probe; if the phase is not complete, back off with nanosleep so that waiting warps do not take issue slots
+  // from the warps that are computing on the same scheduler
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier.
 // dst, src and bytes must be multiples of 16.

@@ -56,6 +56,7 @@ struct SkhParams {
   int dual;       // 1: dual-softmax statistics (no dustbins, no potentials)
   float zscale2;  // log2(e) (Sinkhorn) or log2(e)/temperature (dual softmax)
   int nstage;
+  long long* dbg_times;  // tuning only: CTA 0 writes clock64() stamps here (NULL = off)
   int dbg;         // tuning experiments only (DRG_SKH_DBG): 1 skip row math, 2 skip column math, 4 skip prologue reductions
   int keep_slabs;  // >= 0: the first keep_slabs slabs of every CTA are loaded L2::evict_last, the rest evict_first
 };
@@ -1060,13 +1061,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
   uint64_t* u_ready = full + WS_MAX_STAGES;
   uint64_t* stage_free = u_ready + WS_MAX_STAGES;
   __shared__ int cnt_s[2];
+  __shared__ float2 comb[(WS_THREADS / 32) * 32];  // merge scratch: [32 warps][32 columns]
 
+#define DRG_STAMP(slot) do { if (p.dbg_times && g == 0 && b == 0) p.dbg_times[(slot)] = clock64(); } while (0)
   const float* sc_b = p.scores + (size_t)b * N * M;
   const float zs = p.zscale2;
   const float shift = p.shift ? *p.shift : 0.f;
   const float alpha = *p.alpha;
   unsigned int* gcount = gsync + b;
 
+  if (tid == 0) DRG_STAMP(0);
   if (tid == 0) {
     for (int s = 0; s < nstage; ++s) {
       mbar_init(&full[s], 1u);
@@ -1125,7 +1129,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
   uint32_t p_ph = 0;
   unsigned int barriers_done = 0;
 
+  if (tid == 0) DRG_STAMP(1);
   for (int it = 0; it < iters; ++it) {
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 0);
     // ---- prologue: column potentials into shared memory (log2 domain), dustbin-row potential
     float uN;
     if (it == 0) {
@@ -1143,8 +1149,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
       uN = bc.log_mu_bin - (alpha + logf((float)(M + 1)));
     } else {
       const float* v_b = p.v + (size_t)b * p.ldv;
+      // one read of v (written by other SMs in the merge: L2 only), kept in registers for both passes
+      constexpr int VPT = (4096 + 1 + WS_THREADS - 1) / WS_THREADS;  // M <= 4096
+      float vr[VPT];
       float mloc = NEG_BIG;
-      for (int j = tid; j <= M; j += WS_THREADS) mloc = fmaxf(mloc, __ldcg(v_b + j) * LOG2E);  // written by other SMs: L2 only
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) {
+        const int j = tid + k * WS_THREADS;
+        vr[k] = (j <= M) ? __ldcg(v_b + j) : -INFINITY;
+        mloc = fmaxf(mloc, vr[k] * LOG2E);
+      }
       mloc = warp_max(mloc);
       if (lane == 0) red_s[warp] = mloc;
       __syncthreads();
@@ -1152,17 +1166,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
 #pragma unroll
       for (int w = 1; w < WS_THREADS / 32; ++w) mall = fmaxf(mall, red_s[w]);
       float sloc = 0.f;
-      for (int j = tid; j <= M; j += WS_THREADS) {
-        const float vj = __ldcg(v_b + j);
-        sloc += ex2(vj * LOG2E - mall);
-        float v2;
-        if (j < M) {
-          v2 = (vj - shift) * LOG2E;
-          if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
-        } else {
-          v2 = (alpha + vj) * LOG2E;  // dustbin column entry of every real row: alpha + v_M
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) {
+        const int j = tid + k * WS_THREADS;
+        if (j <= M) {
+          const float vj = vr[k];
+          sloc += ex2(vj * LOG2E - mall);
+          float v2;
+          if (j < M) {
+            v2 = (vj - shift) * LOG2E;
+            if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
+          } else {
+            v2 = (alpha + vj) * LOG2E;  // dustbin column entry of every real row: alpha + v_M
+          }
+          v2_s[j] = v2;
         }
-        v2_s[j] = v2;
       }
       sloc = warp_sum(sloc);
       if (lane == 0) red_s[32 + warp] = sloc;
@@ -1175,6 +1193,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
     if (g == 0 && tid == 0) p.u[(size_t)b * p.ldu + N] = uN;
     for (int j = M + 1 + tid; j < Mv; j += WS_THREADS) v2_s[j] = -INFINITY;
     __syncthreads();
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 1);
 
     if (warp < WS_ROW_WARPS) {
       // =========================== ROW warps ===========================
@@ -1184,6 +1203,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
       const float* v2_lane = v2_s + 4 * lane;
       for (int q0 = 0; q0 < nq; q0 += R) {
         mbar_wait_sleep(&full[r_st], r_ph, 200u);
+        if (warp == 0 && lane == 0) DRG_STAMP(10 + it * 100 + 20 + q0 / R);
 #pragma unroll 1
         for (int r = 0; r < R; ++r) {
           const int q = q0 + r;
@@ -1195,10 +1215,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
             float m_l = NEG_BIG, s_l = 0.f;
             if (row_live) {
               const float* row_lane = stage0 + (size_t)r_st * stage_floats + (size_t)r * M + 4 * lane;
-              for (int cb = 0; cb < M; cb += 1024) {
-                float xs[32];
+              for (int cb = 0; cb < M; cb += 512) {
+                float xs[16];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 4; ++k) {
                   if (ROWFULL || cb + 4 * lane + 128 * k < M) {
                     const float4 z = *reinterpret_cast<const float4*>(row_lane + cb + 128 * k);
                     const float4 vv = *reinterpret_cast<const float4*>(v2_lane + cb + 128 * k);
@@ -1212,14 +1232,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
                 }
                 float cmax = NEG_BIG;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) cmax = fmaxf(cmax, xs[k]);
-                if (cmax > m_l) {  // per-lane online rescale (at most once per 32 elements)
+                for (int k = 0; k < 16; ++k) cmax = fmaxf(cmax, xs[k]);
+                if (cmax > m_l) {  // per-lane online rescale (at most once per 16 elements)
                   s_l *= ex2(m_l - cmax);
                   m_l = cmax;
                 }
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 4; ++k) {
                   a0 += ex2(xs[4 * k + 0] - m_l);
                   a1 += ex2(xs[4 * k + 1] - m_l);
                   a2 += ex2(xs[4 * k + 2] - m_l);
@@ -1252,6 +1272,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
           r_ph ^= 1u;
         }
       }
+      if (warp == 0 && lane == 0) DRG_STAMP(10 + it * 100 + 2);
       if (lane == 0) upart_s[warp] = make_float2(uacc.m, uacc.s);
     } else if (warp == WS_ROW_WARPS) {
       // =========================== producer ===========================
@@ -1282,6 +1303,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
         const int rows = min(R, N - i0);
         const float* slab = stage0 + (size_t)c_st * stage_floats;
         mbar_wait_sleep(&u_ready[c_st], c_ph, 500u);
+        if (tid == WS_COL_THREADS) DRG_STAMP(10 + it * 100 + 40 + sl);
         float u2r[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) u2r[r] = u2_s[c_st * 16 + r];  // rows beyond `rows` hold -inf
@@ -1321,6 +1343,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
           }
         }
         __syncwarp();
+        if (tid == WS_COL_THREADS) DRG_STAMP(10 + it * 100 + 60 + sl);
         if (lane == 0) mbar_arrive(&stage_free[c_st]);
         if (++c_st == nstage) {
           c_st = 0;
@@ -1339,19 +1362,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
     }
     // ---- dustbin-column partial of this CTA, then wait for every CTA's partials
     __syncthreads();
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 3);
     if (tid == 0) {
       LseAcc a = lse_empty();
       for (int w = 0; w < WS_ROW_WARPS; ++w) lse_merge(a, upart_s[w].x, upart_s[w].y);
       p.upart[(size_t)b * G + g] = make_float2(a.m, a.s);
     }
     grid_barrier(gcount, (unsigned int)G * (++barriers_done));
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 4);
 
-    // ---- merge: one column per warp at a time, lanes split the G partials            (skh_col_kernel)
+    // ---- merge: a CTA takes 32 consecutive columns at a time (lane = column: coalesced 256-byte loads), its 32 warps
+    //      split the G partials, and warp 0 combines the 32 per-warp results through shared memory        (skh_col_kernel)
     {
       float* v_b = p.v + (size_t)b * p.ldv;
-      for (int j = g * (WS_THREADS / 32) + warp; j <= M; j += G * (WS_THREADS / 32)) {
+      for (int j0 = g * 32; j0 <= M; j0 += G * 32) {
+        const int j = j0 + lane;
+        const bool in_range = j <= M;
         const bool is_bin = (j == M);
-        const bool col_ok = is_bin || !p.apply_mask || p.tgt_mask[(size_t)b * M + j];
+        const bool col_ok = in_range && (is_bin || !p.apply_mask || p.tgt_mask[(size_t)b * M + j]);
         float m = NEG_BIG, sum = 0.f;
         if (col_ok) {
           const float2* src = is_bin ? (p.upart + (size_t)b * G) : (p.colpart + (size_t)b * G * M + j);
@@ -1359,17 +1387,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
           float2 q[(NUM_SMS + 31) / 32];
 #pragma unroll
           for (int k = 0; k < (NUM_SMS + 31) / 32; ++k) {
-            const int gg = lane + 32 * k;
+            const int gg = warp + 32 * k;
             q[k] = (gg < G) ? __ldcg(src + (size_t)gg * gstride) : make_float2(NEG_BIG, 0.f);
             m = fmaxf(m, q[k].x);
           }
-          m = warp_max(m);
 #pragma unroll
           for (int k = 0; k < (NUM_SMS + 31) / 32; ++k) sum += q[k].y * ex2(q[k].x - m);
-          sum = warp_sum(sum);
         }
-        if (lane == 0) {
-          LseAcc a{m, sum};
+        comb[warp * 32 + lane] = make_float2(m, sum);
+        __syncthreads();
+        if (warp == 0 && in_range) {
+          float mm = NEG_BIG;
+#pragma unroll
+          for (int w = 0; w < WS_THREADS / 32; ++w) mm = fmaxf(mm, comb[w * 32 + lane].x);
+          float ss = 0.f;
+#pragma unroll
+          for (int w = 0; w < WS_THREADS / 32; ++w) {
+            const float2 c2 = comb[w * 32 + lane];
+            ss += c2.y * ex2(c2.x - mm);
+          }
+          LseAcc a{mm, ss};
           if (!is_bin) {
             lse_add_value(a, (alpha + uN) * LOG2E);  // dustbin row entry
             v_b[j] = bc.norm - lse_value(a) * LN2;
@@ -1378,10 +1415,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
             v_b[M] = bc.log_nu_bin - (alpha + lse_value(a) * LN2);
           }
         }
+        __syncthreads();
       }
     }
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 5);
     if (it + 1 < iters) grid_barrier(gcount, (unsigned int)G * (++barriers_done));
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 6);
   }
+#undef DRG_STAMP
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1878,8 +1919,8 @@ static int skh_ws_rows() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DRG_SKH_WS_ROWS");
-    v = e ? atoi(e) : 4;
-    if (v != 1 && v != 2 && v != 4 && v != 8) v = 4;
+    v = e ? atoi(e) : 2;
+    if (v != 1 && v != 2 && v != 4 && v != 8) v = 2;
   }
   return v;
 }
@@ -1904,7 +1945,7 @@ static SkhPlanWS make_plan_ws(int B, int N, int M) {
   pl.KQ = (M <= 2048) ? 1 : 2;
   const size_t Mv = (size_t)((M + 1 + 3) & ~3);
   const size_t stage_bytes = (size_t)R * M * 4;
-  const size_t fixed = Mv * 4 + WS_MAX_STAGES * 16 * 4 + 64 * 4 + 16 * 8 + 3 * WS_MAX_STAGES * 8 + 128;
+  const size_t fixed = Mv * 4 + WS_MAX_STAGES * 16 * 4 + 64 * 4 + 16 * 8 + 3 * WS_MAX_STAGES * 8 + 128 + 8192 + 64 /* static: merge scratch */;
   int nstage = (int)((SKH_SMEM_LIMIT - fixed) / stage_bytes);
   if (nstage > WS_MAX_STAGES) nstage = WS_MAX_STAGES;
   if (nstage < 2) return pl;
@@ -1996,6 +2037,8 @@ extern "C" size_t drg_sinkhorn_workspace_bytes(int B, int N, int M) {
   return carve(nullptr, B, N, M, skh_max_g(B)).total;
 }
 
+static long long* g_skh_times = nullptr;  // tuning only (DRG_SKH_TIMES=1)
+
 enum SkhRun { SKH_RUN_ALL = 0, SKH_SHARD_BEGIN, SKH_SHARD_LOCAL, SKH_SHARD_UPDATE, SKH_SHARD_FINAL };
 
 static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature, void* workspace, size_t workspace_bytes,
@@ -2062,6 +2105,18 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   p.zscale2 = dual ? LOG2E / temperature : LOG2E;
   p.nstage = usew ? plw.nstage : use2 ? pl2.nstage : pl.nstage;
   p.keep_slabs = -1;
+  p.dbg_times = nullptr;
+  {
+    static int want = -1;
+    if (want < 0) want = getenv("DRG_SKH_TIMES") ? 1 : 0;
+    if (want) {
+      if (!g_skh_times) {
+        cudaMalloc(&g_skh_times, 512 * sizeof(long long));
+        cudaMemset(g_skh_times, 0, 512 * sizeof(long long));
+      }
+      p.dbg_times = g_skh_times;
+    }
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -2244,4 +2299,11 @@ extern "C" int drg_sinkhorn_shard_final(const drg_sinkhorn_args* a, void* worksp
   DRG_CHECK_ARG(a->out_mode >= DRG_OUT_LOG_FULL && a->out_mode <= DRG_OUT_NONE, "unknown out_mode");
   DRG_CHECK_ARG(a->out_mode == DRG_OUT_NONE || a->out != nullptr, "out is null");
   return run_sinkhorn(a, false, 1.f, workspace, workspace_bytes, stream, SKH_SHARD_FINAL, nullptr, nullptr);
+}
+
+extern "C" int drg_debug_read_times(long long* host_out, int n) {
+  // tuning only: copies the clock64() stamps of the last persistent Sinkhorn launch (DRG_SKH_TIMES=1)
+  if (!g_skh_times || n > 512) return DRG_ERR_UNSUPPORTED;
+  DRG_CUDA(cudaMemcpy(host_out, g_skh_times, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+  return DRG_OK;
 }
