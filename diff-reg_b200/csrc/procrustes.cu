@@ -19,9 +19,11 @@
 //                             candidates, fp64 weighted moments, closed-form 3x3 SVD (one-sided Jacobi,
 //                             fp64), reflection fix, condition-number gate, and the src-point warp.
 // Because L is an order statistic of the sample (not a histogram bin edge) the candidate list holds
-// ~2 K_b + 32 N M / 32768 entries whatever the value distribution (flat, tied or all-zero matrices
+// ~2 K_b + 16 N M / 32768 entries whatever the value distribution (flat, tied or all-zero matrices
 // included).  If the sample still misleads (fewer than K_b candidates) the solve kernel falls back to
 // collecting the whole matrix itself: slow, but exact.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace drg {
@@ -30,6 +32,7 @@ constexpr int TK_BINS = 2048;
 constexpr int TS_THREADS = 512;
 constexpr int TS_SAMPLES = 32768;  // sample keys held in shared memory (128 KB)
 constexpr int SOLVE_THREADS = 1024;
+constexpr int SOLVE_SMEM_CAND = 24576;  // candidates staged in shared memory by the solve kernel (192 KB)
 
 struct ProcrState {  // per batch element
   int Kb;                         // number of correspondences to use
@@ -51,6 +54,8 @@ struct ProcrParams {
   ProcrState* state;             // [B]
   unsigned int* cand_key;        // [B, N*M]
   unsigned int* cand_idx;        // [B, N*M]
+  unsigned int* sample_buf;      // [B, TS_SAMPLES]
+  unsigned int* sample_arrive;   // [B] arrival counters of the sampling CTAs (zero between calls)
   // outputs
   float* R;                      // [B,3,3]
   float* t;                      // [B,3]
@@ -64,6 +69,7 @@ struct ProcrParams {
   float* sel_w;                  // [B,K_max] or NULL
   int* sel_src;                  // [B,K_max] or NULL
   int* sel_tgt;                  // [B,K_max] or NULL
+  long long* dbg_times;          // tuning only (DRG_PROCR_TIMES=1): clock64 stamps of batch element 0
 };
 
 __device__ __forceinline__ unsigned int hash_u32(unsigned int x) {
@@ -75,6 +81,23 @@ __device__ __forceinline__ unsigned int hash_u32(unsigned int x) {
   return x;
 }
 
+// number of non-zero bytes among m[tid], m[tid + nthreads], ... (16 bytes per load when aligned; bools are 0 / 1)
+__device__ __forceinline__ unsigned int count_bytes16(const unsigned char* __restrict__ m, int n, int tid, int nthreads) {
+  unsigned int c = 0;
+  if ((((uintptr_t)m) & 15u) == 0) {
+    const int n16 = n >> 4;
+    const uint4* m4 = reinterpret_cast<const uint4*>(m);
+    for (int i = tid; i < n16; i += nthreads) {
+      const uint4 q = m4[i];
+      c += __popc(q.x & 0x01010101u) + __popc(q.y & 0x01010101u) + __popc(q.z & 0x01010101u) + __popc(q.w & 0x01010101u);
+    }
+    for (int i = (n16 << 4) + tid; i < n; i += nthreads) c += m[i] ? 1u : 0u;
+  } else {
+    for (int i = tid; i < n; i += nthreads) c += m[i] ? 1u : 0u;
+  }
+  return c;
+}
+
 __device__ __forceinline__ unsigned long long make_key64(unsigned int ordered_value, unsigned int flat_index) {
   return ((unsigned long long)ordered_value << 32) | (unsigned long long)(0xFFFFFFFFu - flat_index);
 }
@@ -82,8 +105,9 @@ __device__ __forceinline__ unsigned long long make_key64(unsigned int ordered_va
 // Exact selection of the k-th largest of n distinct 64-bit keys by one CTA (1 <= k <= n).
 // key_at(e) returns the key of element e.  Six radix levels (11,11,10,11,11,10 bits, MSB first); stops
 // early once the remaining bucket is wanted whole.  Returns T such that exactly k keys are >= T.
-// scratch: hist[TK_BINS] plus three words of shared memory.
-struct SelectScratch {
+// (Measured alternatives that were slower on B200: warp-aggregated histogram updates via match.any, and
+// normalising the keys to their common range first.)
+struct __align__(16) SelectScratch {
   unsigned int hist[TK_BINS];
   unsigned long long prefix;
   int krem;
@@ -115,11 +139,22 @@ __device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, Se
     }
     __syncthreads();
     if (tid < 32) {
-      // warp 0 walks the histogram from the top: lane l owns the l-th chunk of bins (descending)
-      const int nb = 1 << wbits, chunk = nb >> 5;
-      const int hi = nb - 1 - chunk * tid;  // highest bin of this lane's chunk
+      // warp 0 walks the histogram from the top: lane l owns the l-th chunk of bins (descending), pulled into
+      // registers with 128-bit loads (bins beyond 2^wbits stay zero)
+      constexpr int chunk = TK_BINS / 32;                    // 64 bins per lane
+      const int lo = TK_BINS - chunk * (tid + 1);            // lowest bin of this lane's chunk
+      unsigned int hreg[chunk];
+      const uint4* h4 = reinterpret_cast<const uint4*>(&sc.hist[lo]);
       unsigned int local = 0u;
-      for (int d = hi; d > hi - chunk; --d) local += sc.hist[d];
+#pragma unroll
+      for (int q = 0; q < chunk / 4; ++q) {
+        const uint4 v4 = h4[q];
+        hreg[4 * q + 0] = v4.x;
+        hreg[4 * q + 1] = v4.y;
+        hreg[4 * q + 2] = v4.z;
+        hreg[4 * q + 3] = v4.w;
+        local += v4.x + v4.y + v4.z + v4.w;
+      }
       unsigned int incl = local;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -131,14 +166,24 @@ __device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, Se
       const int owner = crossing ? (__ffs(crossing) - 1) : 31;
       if (tid == owner) {
         unsigned int cum = incl - local;
-        int d = hi;
-        for (; d > hi - chunk + 1; --d) {
-          if (cum + sc.hist[d] >= krem) break;
-          cum += sc.hist[d];
+        int dsel = 0;
+        unsigned int hsel = hreg[0];
+        bool found = false;
+#pragma unroll
+        for (int t = chunk - 1; t >= 0; --t) {
+          if (!found) {
+            if (cum + hreg[t] >= krem || t == 0) {
+              found = true;
+              dsel = t;
+              hsel = hreg[t];
+            } else {
+              cum += hreg[t];
+            }
+          }
         }
-        sc.prefix = (prefix << wbits) | (unsigned long long)d;
+        sc.prefix = (prefix << wbits) | (unsigned long long)(lo + dsel);
         sc.krem = (int)(krem - cum);
-        if (sc.hist[d] == krem - cum) sc.done = 1;  // the whole bucket is wanted
+        if (hsel == krem - cum) sc.done = 1;  // the whole bucket is wanted
       }
     }
     __syncthreads();
@@ -154,7 +199,49 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
   extern __shared__ unsigned int sample_key[];  // [TS_SAMPLES]
   __shared__ SelectScratch sc;
   __shared__ unsigned long long cnt_s;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.y, tid = threadIdx.x;
+#define TSTAMP(k) do { if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[(k)] = clock64(); } while (0)
+  TSTAMP(20);
+  TSTAMP(21);
+  // ---- sample the matrix: every CTA of the batch element fetches its share of the hashed positions (scattered
+  //      4-byte reads: spread over TS_CTAS CTAs so that they are all in flight at once) into a global buffer; the
+  //      last CTA to arrive pulls the whole sample into shared memory and carries on alone.
+  const size_t total = (size_t)p.N * p.M;
+  const float* x = p.conf + (size_t)b * total;
+  const bool all = total <= (size_t)TS_SAMPLES;
+  const unsigned int n_s = all ? (unsigned int)total : (unsigned int)TS_SAMPLES;
+  const unsigned int salt = 0x9e3779b9u * (unsigned int)(b + 1);
+  auto sample_pos = [&](unsigned int q) -> unsigned int {
+    return all ? q : (unsigned int)(((unsigned long long)hash_u32(q + salt) * (unsigned long long)total) >> 32);
+  };
+  unsigned int* sbuf = p.sample_buf + (size_t)b * TS_SAMPLES;
+  {
+    const unsigned int per_cta = (n_s + gridDim.x - 1) / gridDim.x;
+    const unsigned int q_lo = blockIdx.x * per_cta, q_hi = min(n_s, q_lo + per_cta);
+    for (unsigned int q0 = q_lo + tid; q0 < q_hi; q0 += TS_THREADS * 4) {
+      float val[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned int q = q0 + k * TS_THREADS;
+        val[k] = (q < q_hi) ? x[sample_pos(q)] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned int q = q0 + k * TS_THREADS;
+        if (q < q_hi) sbuf[q] = float_to_ordered(val[k]);
+      }
+    }
+  }
+  __shared__ unsigned int ticket_s;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket_s = atomicAdd(&p.sample_arrive[b], 1u);
+  __syncthreads();
+  if (ticket_s != gridDim.x - 1) return;   // not the last CTA of this batch element
+  if (tid == 0) p.sample_arrive[b] = 0u;   // self-reset for the next call
+  __threadfence();
+  for (unsigned int q = tid; q < n_s; q += TS_THREADS) sample_key[q] = __ldcg(sbuf + q);
+  __syncthreads();
   // ---- mask counts of every batch element (K is a mean over the batch)      procrustes.py:61-65
   float cap_sum = 0.f;
   int my_cap = 0;
@@ -163,9 +250,8 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
     if (!p.padded_lengths) {
       if (tid == 0) cnt_s = 0ull;
       __syncthreads();
-      unsigned long long c = 0ull;
-      for (int i = tid; i < p.N; i += TS_THREADS) c += p.src_mask[(size_t)bb * p.N + i] ? (1ull << 32) : 0ull;
-      for (int j = tid; j < p.M; j += TS_THREADS) c += p.tgt_mask[(size_t)bb * p.M + j] ? 1ull : 0ull;
+      unsigned long long c = ((unsigned long long)count_bytes16(p.src_mask + (size_t)bb * p.N, p.N, tid, TS_THREADS) << 32) |
+                             (unsigned long long)count_bytes16(p.tgt_mask + (size_t)bb * p.M, p.M, tid, TS_THREADS);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
       if ((tid & 31) == 0) atomicAdd(&cnt_s, c);
@@ -182,19 +268,7 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
   // sample_n_points = entry_max.float().mean().int()   procrustes.py:65
   const int K = (int)(cap_sum / (float)p.B);
   const int Kb = min(min(K, my_cap), p.K_max);
-
-  // ---- sample the matrix
-  const size_t total = (size_t)p.N * p.M;
-  const float* x = p.conf + (size_t)b * total;
-  const bool all = total <= (size_t)TS_SAMPLES;
-  const unsigned int n_s = all ? (unsigned int)total : (unsigned int)TS_SAMPLES;
-  const unsigned int salt = 0x9e3779b9u * (unsigned int)(b + 1);
-  auto sample_pos = [&](unsigned int q) -> unsigned int {
-    return all ? q : (unsigned int)(((unsigned long long)hash_u32(q + salt) * (unsigned long long)total) >> 32);
-  };
-  for (unsigned int q = tid; q < n_s; q += TS_THREADS) sample_key[q] = float_to_ordered(x[sample_pos(q)]);
-  __syncthreads();
-
+  TSTAMP(22);
   // ---- the t-th largest sample key is the lower bound
   unsigned long long lower = 0ull;
   if (Kb > 0) {
@@ -204,13 +278,15 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
     } else {
       // twice the expected number of top-K_b entries inside the sample, plus slack for small counts
       const double expect = (double)Kb * ((double)n_s / (double)total);
-      target = (long long)(2.0 * expect + 32.0);
+      target = (long long)(2.0 * expect + 16.0);
     }
     if (target < (long long)n_s) {
       lower = block_select_kth<TS_THREADS>(
           [&](size_t e) { return make_key64(sample_key[e], sample_pos((unsigned int)e)); }, (size_t)n_s, (int)target, sc);
     }
   }
+  TSTAMP(23);
+#undef TSTAMP
   if (tid == 0) {
     ProcrState s;
     s.Kb = Kb;
@@ -283,17 +359,35 @@ __global__ void __launch_bounds__(256) topk_collect_kernel(const ProcrParams p) 
 }
 
 // ---- 5. select + Kabsch + warp ----------------------------------------------------------------
-__device__ __forceinline__ double block_sum(double v, double* red /*[32]*/) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+// Block-wide sums of K fp32 per-thread partials: fp32 warp shuffles (pairwise), then the per-warp partials are added
+// in fp64 in a fixed order (bitwise reproducible) and everybody reads the totals.  fp64 vector math is slow on this
+// part, so it is kept to this last step and to the 3x3 solve.
+struct MomentScratch {
+  float part[32][12];
+  double total[12];
+};
+template <int K>
+__device__ __forceinline__ void block_sum_f32(const float (&v)[K], double (&out)[K], MomentScratch& ms) {
+  static_assert(K <= 12, "MomentScratch holds 12 values");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  double s = 0.0;
   const int nw = (blockDim.x + 31) >> 5;
-  for (int w = 0; w < nw; ++w) s += red[w];  // same order in every thread: bitwise identical
-  return s;
+  __syncthreads();  // scratch reuse
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) ms.part[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += (double)ms.part[w][threadIdx.x];
+    ms.total[threadIdx.x] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = ms.total[k];
 }
 
 // One-sided Jacobi SVD of a 3x3 matrix (fp64): A = U diag(s) V^T, singular values descending.
@@ -381,22 +475,10 @@ __device__ __forceinline__ double det3(const double A[3][3]) {
          A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
 }
 
-// From the weighted raw moments to (R, t, condition); thread 0 only.
-//   sw = sum |w|, sx = sum w x, sy = sum w y, sxy[a][c] = sum w y_a x_c  (all fp64)
-__device__ void kabsch_from_moments(double sw_abs, double sw, const double sx[3], const double sy[3], const double syx[3][3],
-                                    double eps, float R_out[9], float t_out[3], double* cond_out) {
-  // w_norm = w / (sum|w| + eps): the normalised weights sum to slightly less than one  (procrustes.py:29-30)
-  const double inv = 1.0 / (sw_abs + eps);
-  const double sn = sw * inv;
-  double mx[3], my[3];
-  for (int a = 0; a < 3; ++a) {
-    mx[a] = sx[a] * inv;
-    my[a] = sy[a] * inv;
-  }
-  // Sxy = sum w_norm (y - my)(x - mx)^T = sum w_norm y x^T - (2 - sn) my mx^T      (procrustes.py:34)
-  double S[3][3];
-  for (int a = 0; a < 3; ++a)
-    for (int c = 0; c < 3; ++c) S[a][c] = syx[a][c] * inv - (2.0 - sn) * my[a] * mx[c];
+// From the centred weighted covariance S = sum w_norm (y - my)(x - mx)^T and the (shrunk) weighted means to
+// (R, t, condition); one thread.                                                 procrustes.py:35-43
+__device__ void kabsch_solve(const double S[3][3], const double mx[3], const double my[3], float R_out[9], float t_out[3],
+                             double* cond_out) {
   double U[3][3], sv[3], V[3][3];
   svd3x3(S, U, sv, V);
   *cond_out = sv[0] / sv[2];  // D.max / D.min   (inf or nan for rank-deficient input, as in the reference)
@@ -435,17 +517,21 @@ __device__ void finish_pose(const ProcrParams& p, int b, const float R[9], const
 
 __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrParams p) {
   __shared__ SelectScratch sc;
-  __shared__ double red[32];
-  __shared__ unsigned int n_emit;
+  __shared__ MomentScratch ms;
+  __shared__ unsigned int warp_cnt[SOLVE_THREADS / 32];
+  __shared__ double mean_s[6], cov_s[9];
   __shared__ float pose_s[12];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
+#define PSTAMP(k) do { if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[(k)] = clock64(); } while (0)
+  PSTAMP(0);
   const size_t total = (size_t)p.N * p.M;
   const ProcrState st = p.state[b];
   const int Kb = st.Kb;
   unsigned int* ckey = p.cand_key + (size_t)b * total;
   unsigned int* cidx = p.cand_idx + (size_t)b * total;
   size_t n = st.n_cand;
+  extern __shared__ unsigned int cand_s[];  // [2][SOLVE_SMEM_CAND]: keys, indices
   if (n < (size_t)Kb) {
     // fallback: the sample-based bound left too few candidates; take the whole matrix
     const float* x = p.conf + (size_t)b * total;
@@ -457,63 +543,116 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
     __syncthreads();
   }
 
+  // The candidate list normally fits in shared memory: stage it once (coalesced, many loads in flight) so that the
+  // radix levels and the emission below do not pay a global-memory round trip per 1024 candidates.
+  const bool in_smem = n <= (size_t)SOLVE_SMEM_CAND;
+  if (in_smem) {
+#pragma unroll 4
+    for (size_t e = tid; e < n; e += SOLVE_THREADS) {
+      cand_s[e] = ckey[e];
+      cand_s[SOLVE_SMEM_CAND + e] = cidx[e];
+    }
+    __syncthreads();
+  }
+  PSTAMP(1);
+  const unsigned int* kp = in_smem ? cand_s : ckey;
+  const unsigned int* ip = in_smem ? cand_s + SOLVE_SMEM_CAND : cidx;
+
   // ---- exact radix select of the Kb largest 64-bit keys (value << 32 | ~index): no ties
   unsigned long long T = 0ull;  // select keys >= T
   if (Kb > 0 && (size_t)Kb < n)
-    T = block_select_kth<SOLVE_THREADS>([&](size_t e) { return make_key64(ckey[e], cidx[e]); }, n, Kb, sc);
+    T = block_select_kth<SOLVE_THREADS>([&](size_t e) { return make_key64(kp[e], ip[e]); }, n, Kb, sc);
 
-  // ---- emit the selection and accumulate the weighted moments in fp64
-  if (tid == 0) n_emit = 0u;
-  __syncthreads();
+  PSTAMP(2);
+  if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[10] = (long long)n;
+  // ---- two fp32 passes over the candidates (shared memory), skipping the unselected ones: weighted means, then the
+  //      centred covariance -- the reference's own order of operations (procrustes.py:29-34).
+  //      (Measured: compacting the selection first and fp64 moments were both slower on B200.)
   const float* sp = p.src_pcd + (size_t)b * p.N * 3;
   const float* tp = p.tgt_pcd + (size_t)b * p.M * 3;
-  double a_w = 0.0, a_wabs = 0.0, a_x[3] = {0, 0, 0}, a_y[3] = {0, 0, 0}, a_yx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  unsigned int ne = 0;
+  if (tid == 0) warp_cnt[0] = 0u;
+  __syncthreads();
   if (Kb > 0) {
+    float m1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // sum w, sum |w|, sum w x (3), sum w y (3)
     for (size_t e = tid; e < n; e += SOLVE_THREADS) {
-      const unsigned int k32 = ckey[e], fi = cidx[e];
+      const unsigned int k32 = kp[e], fi = ip[e];
       if (make_key64(k32, fi) >= T) {
         const float wf = ordered_to_float(k32);
         const int i = (int)(fi / (unsigned int)p.M), j = (int)(fi - (unsigned int)i * (unsigned int)p.M);
         if (p.sel_w) {
-          const unsigned int pos = atomicAdd(&n_emit, 1u);
+          const unsigned int pos = atomicAdd(&warp_cnt[0], 1u);
           if (pos < (unsigned int)p.K_max) {
             p.sel_w[(size_t)b * p.K_max + pos] = wf;
             p.sel_src[(size_t)b * p.K_max + pos] = i;
             p.sel_tgt[(size_t)b * p.K_max + pos] = j;
           }
         }
-        const double w = (double)wf;
-        const double x[3] = {(double)sp[i * 3 + 0], (double)sp[i * 3 + 1], (double)sp[i * 3 + 2]};
-        const double y[3] = {(double)tp[j * 3 + 0], (double)tp[j * 3 + 1], (double)tp[j * 3 + 2]};
-        a_w += w;
-        a_wabs += fabs(w);
+        m1[0] += wf;
+        m1[1] += fabsf(wf);
+#pragma unroll
         for (int a = 0; a < 3; ++a) {
-          a_x[a] += w * x[a];
-          a_y[a] += w * y[a];
-          for (int c = 0; c < 3; ++c) a_yx[a][c] += w * y[a] * x[c];
+          m1[2 + a] = fmaf(wf, sp[i * 3 + a], m1[2 + a]);
+          m1[5 + a] = fmaf(wf, tp[j * 3 + a], m1[5 + a]);
         }
       }
     }
-  }
-  double m_w = block_sum(a_w, red), m_wabs = block_sum(a_wabs, red);
-  double m_x[3], m_y[3], m_yx[3][3];
-  for (int a = 0; a < 3; ++a) {
-    m_x[a] = block_sum(a_x[a], red);
-    m_y[a] = block_sum(a_y[a], red);
-    for (int c = 0; c < 3; ++c) m_yx[a][c] = block_sum(a_yx[a][c], red);
+    double s1[8];
+    block_sum_f32<8>(m1, s1, ms);
+    PSTAMP(7);
+    // w_norm = w / (sum|w| + eps): the normalised weights sum to slightly less than one  (procrustes.py:29-30)
+    const double inv = 1.0 / (s1[1] + 1e-4);
+    const float invf = (float)inv;
+    const float mxf[3] = {(float)(s1[2] * inv), (float)(s1[3] * inv), (float)(s1[4] * inv)};
+    const float myf[3] = {(float)(s1[5] * inv), (float)(s1[6] * inv), (float)(s1[7] * inv)};
+    float m2[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (size_t e = tid; e < n; e += SOLVE_THREADS) {
+      const unsigned int k32 = kp[e], fi = ip[e];
+      if (make_key64(k32, fi) >= T) {
+        const float wn = ordered_to_float(k32) * invf;
+        const int i = (int)(fi / (unsigned int)p.M), j = (int)(fi - (unsigned int)i * (unsigned int)p.M);
+        const float xc[3] = {sp[i * 3 + 0] - mxf[0], sp[i * 3 + 1] - mxf[1], sp[i * 3 + 2] - mxf[2]};
+        const float yc[3] = {tp[j * 3 + 0] - myf[0], tp[j * 3 + 1] - myf[1], tp[j * 3 + 2] - myf[2]};
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) m2[a * 3 + c] = fmaf(wn * yc[a], xc[c], m2[a * 3 + c]);
+      }
+    }
+    double s2[9];
+    block_sum_f32<9>(m2, s2, ms);
+    PSTAMP(3);
+    if (tid == 0) {
+      for (int a = 0; a < 3; ++a) {
+        mean_s[a] = (double)mxf[a];
+        mean_s[3 + a] = (double)myf[a];
+        for (int c = 0; c < 3; ++c) cov_s[a * 3 + c] = s2[a * 3 + c];
+      }
+    }
+    ne = warp_cnt[0];
+  } else if (tid == 0) {
+    for (int k = 0; k < 6; ++k) mean_s[k] = 0.0;
+    for (int k = 0; k < 9; ++k) cov_s[k] = 0.0;
   }
   if (p.sel_w) {
     __syncthreads();
-    for (int k = (int)n_emit + tid; k < p.K_max; k += SOLVE_THREADS) {
+    ne = warp_cnt[0];
+    for (int k = (int)ne + tid; k < p.K_max; k += SOLVE_THREADS) {
       p.sel_w[(size_t)b * p.K_max + k] = 0.f;
       p.sel_src[(size_t)b * p.K_max + k] = 0;
       p.sel_tgt[(size_t)b * p.K_max + k] = 0;
     }
   }
+  __syncthreads();
+  PSTAMP(4);
   if (tid == 0) {
     float R[9], t[3];
     double cond;
-    kabsch_from_moments(m_wabs, m_w, m_x, m_y, m_yx, 1e-4, R, t, &cond);
+    double S[3][3];
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) S[a][c] = cov_s[a * 3 + c];
+    kabsch_solve(S, mean_s, mean_s + 3, R, t, &cond);
+    PSTAMP(5);
     finish_pose(p, b, R, t, cond);
     for (int k = 0; k < 9; ++k) pose_s[k] = p.R_forwd[b * 9 + k];
     for (int k = 0; k < 3; ++k) pose_s[9 + k] = p.t_forwd[b * 3 + k];
@@ -533,6 +672,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
       }
     }
   }
+  PSTAMP(6);
+#undef PSTAMP
 }
 
 // standalone weighted Kabsch on given correspondences: X, Y [B,K,3], w [B,K]
@@ -548,44 +689,62 @@ struct KabschParams {
 };
 
 __global__ void __launch_bounds__(256) kabsch_kernel(const KabschParams p) {
-  __shared__ double red[32];
+  __shared__ MomentScratch ms;
   const int b = blockIdx.x;
   const float* X = p.X + (size_t)b * p.K * 3;
   const float* Y = p.Y + (size_t)b * p.K * 3;
   const float* w = p.w + (size_t)b * p.K;
-  double a_w = 0.0, a_wabs = 0.0, a_x[3] = {0, 0, 0}, a_y[3] = {0, 0, 0}, a_yx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  float m1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
-    const double wk = (double)w[k];
-    a_w += wk;
-    a_wabs += fabs(wk);
+    const float wk = w[k];
+    m1[0] += wk;
+    m1[1] += fabsf(wk);
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const double xa = (double)X[k * 3 + a], ya = (double)Y[k * 3 + a];
-      a_x[a] += wk * xa;
-      a_y[a] += wk * ya;
-      for (int c = 0; c < 3; ++c) a_yx[a][c] += wk * ya * (double)X[k * 3 + c];
+      m1[2 + a] = fmaf(wk, X[k * 3 + a], m1[2 + a]);
+      m1[5 + a] = fmaf(wk, Y[k * 3 + a], m1[5 + a]);
     }
   }
-  double m_w = block_sum(a_w, red), m_wabs = block_sum(a_wabs, red);
-  double m_x[3], m_y[3], m_yx[3][3];
-  for (int a = 0; a < 3; ++a) {
-    m_x[a] = block_sum(a_x[a], red);
-    m_y[a] = block_sum(a_y[a], red);
-    for (int c = 0; c < 3; ++c) m_yx[a][c] = block_sum(a_yx[a][c], red);
+  double s1[8];
+  block_sum_f32<8>(m1, s1, ms);
+  const double inv = 1.0 / (s1[1] + (double)p.eps);
+  const float invf = (float)inv;
+  const float mxf[3] = {(float)(s1[2] * inv), (float)(s1[3] * inv), (float)(s1[4] * inv)};
+  const float myf[3] = {(float)(s1[5] * inv), (float)(s1[6] * inv), (float)(s1[7] * inv)};
+  float m2[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
+    const float wn = w[k] * invf;
+    const float xc[3] = {X[k * 3 + 0] - mxf[0], X[k * 3 + 1] - mxf[1], X[k * 3 + 2] - mxf[2]};
+    const float yc[3] = {Y[k * 3 + 0] - myf[0], Y[k * 3 + 1] - myf[1], Y[k * 3 + 2] - myf[2]};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) m2[a * 3 + c] = fmaf(wn * yc[a], xc[c], m2[a * 3 + c]);
   }
+  double s2[9];
+  block_sum_f32<9>(m2, s2, ms);
   if (threadIdx.x == 0) {
     float R[9], t[3];
     double cond;
-    kabsch_from_moments(m_wabs, m_w, m_x, m_y, m_yx, (double)p.eps, R, t, &cond);
+    double S[3][3];
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) S[a][c] = s2[a * 3 + c];
+    const double mx[3] = {(double)mxf[0], (double)mxf[1], (double)mxf[2]}, my[3] = {(double)myf[0], (double)myf[1], (double)myf[2]};
+    kabsch_solve(S, mx, my, R, t, &cond);
     for (int k = 0; k < 9; ++k) p.R[b * 9 + k] = R[k];
     for (int k = 0; k < 3; ++k) p.t[b * 3 + k] = t[k];
     p.condition[b] = cond;
   }
 }
 
+static long long* g_procr_times = nullptr;  // tuning only
+
 struct ProcrWorkspace {
   ProcrState* state;
   unsigned int* cand_key;
   unsigned int* cand_idx;
+  unsigned int* sample_buf;
+  unsigned int* sample_arrive;
   size_t total;
 };
 
@@ -600,6 +759,8 @@ static ProcrWorkspace procr_carve(void* ws, int B, int N, int M) {
   w.state = (ProcrState*)take(sizeof(ProcrState) * B);
   w.cand_key = (unsigned int*)take(4ull * B * N * M);
   w.cand_idx = (unsigned int*)take(4ull * B * N * M);
+  w.sample_buf = (unsigned int*)take(4ull * B * TS_SAMPLES);
+  w.sample_arrive = (unsigned int*)take(4ull * B);
   w.total = off;
   return w;
 }
@@ -645,6 +806,8 @@ extern "C" int drg_soft_procrustes(const drg_procrustes_args* a, void* workspace
   p.state = w.state;
   p.cand_key = w.cand_key;
   p.cand_idx = w.cand_idx;
+  p.sample_buf = w.sample_buf;
+  p.sample_arrive = w.sample_arrive;
   p.R = a->R;
   p.t = a->t;
   p.R_forwd = a->R_forwd;
@@ -659,15 +822,31 @@ extern "C" int drg_soft_procrustes(const drg_procrustes_args* a, void* workspace
   p.sel_w = a->sel_w;
   p.sel_src = a->sel_src;
   p.sel_tgt = a->sel_tgt;
+  {
+    static long long* tbuf = nullptr;
+    static int want = -1;
+    if (want < 0) want = getenv("DRG_PROCR_TIMES") ? 1 : 0;
+    if (want && !tbuf) {
+      cudaMalloc(&tbuf, 64 * sizeof(long long));
+      cudaMemset(tbuf, 0, 64 * sizeof(long long));
+      g_procr_times = tbuf;
+    }
+    p.dbg_times = want ? tbuf : nullptr;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
     DRG_CUDA(cudaFuncSetAttribute(topk_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SAMPLES * 4));
     attr_set = true;
   }
+  // the arrival counters must be zero on entry (the workspace is caller memory of unknown content)
+  DRG_CUDA(cudaMemsetAsync(w.sample_arrive, 0, 4ull * B, st));
+  int ts_ctas = NUM_SMS / (2 * B);
+  if (ts_ctas > 32) ts_ctas = 32;
+  if (ts_ctas < 1) ts_ctas = 1;
   {
     ProfScope prof_scope(PROF_TOPK_THRESHOLD, st);
-    topk_threshold_kernel<<<B, TS_THREADS, TS_SAMPLES * 4, st>>>(p);
+    topk_threshold_kernel<<<dim3(ts_ctas, B), TS_THREADS, TS_SAMPLES * 4, st>>>(p);
   }
   DRG_LAUNCH_CHECK();
   int gx = (NUM_SMS * 8) / B;
@@ -680,8 +859,13 @@ extern "C" int drg_soft_procrustes(const drg_procrustes_args* a, void* workspace
   }
   DRG_LAUNCH_CHECK();
   {
+    static bool solve_attr_set = false;
+    if (!solve_attr_set) {
+      DRG_CUDA(cudaFuncSetAttribute(procr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_SMEM_CAND * 8));
+      solve_attr_set = true;
+    }
     ProfScope prof_scope(PROF_PROCR_SOLVE, st);
-    procr_solve_kernel<<<B, SOLVE_THREADS, 0, st>>>(p);
+    procr_solve_kernel<<<B, SOLVE_THREADS, SOLVE_SMEM_CAND * 8, st>>>(p);
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
@@ -694,5 +878,11 @@ extern "C" int drg_weighted_procrustes(const float* X, const float* Y, const flo
   KabschParams p{X, Y, w, B, K, eps, R, t, condition};
   kabsch_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(p);
   DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+extern "C" int drg_debug_read_procr_times(long long* host_out, int n) {
+  if (!g_procr_times || n > 64) return DRG_ERR_UNSUPPORTED;
+  DRG_CUDA(cudaMemcpy(host_out, g_procr_times, sizeof(long long) * n, cudaMemcpyDeviceToHost));
   return DRG_OK;
 }
