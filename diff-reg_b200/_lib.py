@@ -20,7 +20,7 @@ class SinkhornArgs(ctypes.Structure):
         ("x_t", c_void_p), ("xt_shift", c_void_p), ("noise", c_void_p), ("conf", c_void_p),
         ("k_x0", c_float), ("k_xt", c_float), ("sigma", c_float), ("x_min", c_void_p),
         ("gen_noise", c_int), ("noise_seed", ctypes.c_ulonglong), ("noise_offset", ctypes.c_ulonglong),
-        ("noise_offset_dev", c_void_p),
+        ("noise_offset_dev", c_void_p), ("rowbest", c_void_p), ("colbest", c_void_p),
     ]
 
 
@@ -76,6 +76,9 @@ def _declare(lib):
     lib.drg_match_write.restype = c_int
     lib.drg_match_write.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t,
                                     c_void_p, c_void_p, c_ll, c_void_p, c_void_p]
+    lib.drg_match_from_best.restype = c_int
+    lib.drg_match_from_best.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_ll, c_void_p,
+                                        c_void_p]
     lib.drg_soft_procrustes_workspace_bytes.restype = c_size_t
     lib.drg_soft_procrustes_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.drg_soft_procrustes.restype = c_int

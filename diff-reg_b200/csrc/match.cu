@@ -220,6 +220,64 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int* __restrict
   }
 }
 
+// mutual top-1 matches from packed bests: one CTA, ordered compaction over the B*N rows
+__global__ void __launch_bounds__(1024) match_from_best_kernel(const unsigned long long* __restrict__ rowbest,
+                                                               const unsigned long long* __restrict__ colbest, int B, int N, int M,
+                                                               int has_thr, float thr, long long* __restrict__ index_out,
+                                                               float* __restrict__ val_out, long long capacity,
+                                                               int* __restrict__ total_out) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  const int nrows = B * N;
+  for (int base = 0; base < nrows; base += 1024) {
+    const int r = base + tid;
+    bool hit = false;
+    int b = 0, i = 0, j = 0;
+    float v = 0.f;
+    if (r < nrows) {
+      b = r / N;
+      i = r - b * N;
+      const unsigned long long rk = rowbest[r];
+      if (rk != 0ull) {
+        j = (int)key_index(rk);
+        v = key_value(rk, true);
+        const unsigned long long ck = colbest[(size_t)b * M + j];
+        hit = (ck != 0ull) && (key_index(ck) == (unsigned int)i) && (!has_thr || v > thr);
+      }
+    }
+    const unsigned int bal = __ballot_sync(0xffffffffu, hit);
+    const int wcount = __popc(bal);
+    if (lane == 0) warp_sums[warp] = wcount;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_sums[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (hit) {
+      const long long pos = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + __popc(bal & ((1u << lane) - 1u));
+      if (pos < capacity) {
+        long long* o = index_out + pos * 3;
+        o[0] = b; o[1] = i; o[2] = j;
+        val_out[pos] = v;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) carry_s = carry + warp_sums[31];
+    __syncthreads();
+  }
+  if (tid == 0) *total_out = carry_s;
+}
+
 struct MatchWorkspace {
   unsigned long long* rowbest;
   unsigned long long* colbest;
@@ -338,6 +396,21 @@ extern "C" int drg_match_write(const float* x, int B, int N, int M, int mode, in
   p.capacity = capacity;
   const int nrows = B * N;
   match_rows_kernel<true><<<(nrows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+extern "C" int drg_match_from_best(const unsigned long long* rowbest, const unsigned long long* colbest, int B, int N, int M,
+                                   int has_thr, float thr, long long* index_out, float* val_out, long long capacity, int* total_out,
+                                   void* stream) {
+  DRG_CHECK_ARG(rowbest && colbest && index_out && val_out && total_out, "rowbest/colbest/index_out/val_out/total_out must be non-null");
+  DRG_CHECK_ARG(B >= 1 && N >= 1 && M >= 1 && capacity >= 1, "B, N, M, capacity must be >= 1");
+  DRG_CHECK_ARG((long long)B * N < (1ll << 31), "too many rows");
+  {
+    ProfScope prof_scope(PROF_MATCH_ROWS, (cudaStream_t)stream);
+    match_from_best_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rowbest, colbest, B, N, M, has_thr, thr, index_out, val_out, capacity,
+                                                                 total_out);
+  }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }

@@ -1571,6 +1571,8 @@ struct SkhFinalParams {
   int gen_noise;   // 1: N(0,1) draws come from the in-kernel Philox stream (noise == NULL)
   unsigned long long noise_seed, noise_offset;
   const unsigned long long* noise_offset_dev;
+  unsigned long long* rowbest;  // optional [B,N]: packed (ordered(conf) << 32 | ~column) of every row's best entry
+  unsigned long long* colbest;  // optional [B,M]: packed (ordered(conf) << 32 | ~row) of every column's best entry
 };
 
 // Philox4x32-10 counter-based generator (Salmon et al., SC'11) + Box-Muller: four N(0,1) draws per counter.
@@ -1714,6 +1716,121 @@ __global__ void __launch_bounds__(256) skh_final_kernel(const SkhFinalParams p) 
   if (ddim && p.x_min) {
     local_min = warp_min(local_min);
     if ((threadIdx.x & 31) == 0 && local_min < INFINITY) atomic_min_float(p.x_min, local_min);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// tiled final pass (rows 16-byte aligned): CTA = 32 rows x 1024 columns, thread = one column quad.
+//   v, the target mask and the column bests of the quad stay in registers down the band of rows; the row best is a
+//   warp max + ballot per row.  Writes conf and / or the DDIM update like skh_final_kernel and, when asked, the
+//   packed row / column arg-max keys that the correspondence extraction needs (so that x0 = conf never has to be
+//   re-read -- or even stored -- to find the mutual matches; Matching.get_match, matching.py:71-88).
+// ---------------------------------------------------------------------------------------
+constexpr int FT_THREADS = 256;
+constexpr int FT_ROWS = 32;
+
+__global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFinalParams p) {
+  const int b = blockIdx.z;
+  const int N = p.N, M = p.M;
+  const int c = blockIdx.x * (FT_THREADS * 4) + 4 * (int)threadIdx.x;
+  const bool active = c < M;
+  const int lane = threadIdx.x & 31;
+  const int i0 = blockIdx.y * FT_ROWS, i1 = min(N, i0 + FT_ROWS);
+  const SkhConst bc = p.bc[b];
+  const float shift = p.shift ? *p.shift : 0.f;
+  const float xt_shift = p.xt_shift ? *p.xt_shift : 0.f;
+  const bool ddim = (p.mode == DRG_OUT_DDIM);
+  const unsigned long long noise_offset = p.noise_offset + (p.noise_offset_dev ? *p.noise_offset_dev : 0ull);
+  const float* u_b = p.u + (size_t)b * p.ldu;
+  float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool tm[4] = {true, true, true, true};
+  if (active) {
+    v4 = *reinterpret_cast<const float4*>(p.v + (size_t)b * p.ldv + c);
+    if (p.apply_mask) {
+      const uchar4 t4 = *reinterpret_cast<const uchar4*>(p.tgt_mask + (size_t)b * M + c);
+      tm[0] = t4.x; tm[1] = t4.y; tm[2] = t4.z; tm[3] = t4.w;
+    }
+  }
+  const float vj[4] = {v4.x, v4.y, v4.z, v4.w};
+  float cbv[4] = {-1.f, -1.f, -1.f, -1.f};
+  int cbi[4] = {0, 0, 0, 0};
+  float local_min = INFINITY;
+  const bool track = p.rowbest != nullptr;
+  for (int i = i0; i < i1; ++i) {
+    const float ui = u_b[i];
+    const bool row_ok = !p.apply_mask || p.src_mask[(size_t)b * N + i];
+    float cf[4] = {-1.f, -1.f, -1.f, -1.f};
+    if (active) {
+      const size_t base = ((size_t)b * N + i) * M + c;
+      const float4 z4 = *reinterpret_cast<const float4*>(p.scores + base);
+      const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+      float xt[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ddim) {
+        const float4 t4 = *reinterpret_cast<const float4*>(p.x_t + base);
+        xt[0] = t4.x; xt[1] = t4.y; xt[2] = t4.z; xt[3] = t4.w;
+        if (p.noise) {
+          const float4 n4 = *reinterpret_cast<const float4*>(p.noise + base);
+          nz[0] = n4.x; nz[1] = n4.y; nz[2] = n4.z; nz[3] = n4.w;
+        } else if (p.gen_noise) {
+          const float4 n4 = philox_normal4((unsigned long long)(base >> 2), noise_offset, p.noise_seed);
+          nz[0] = n4.x; nz[1] = n4.y; nz[2] = n4.z; nz[3] = n4.w;
+        }
+      }
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = row_ok && tm[e];
+        const float zz = ok ? (z[e] - shift) : -INFINITY;
+        const float la = ((zz + ui) + vj[e]) - bc.norm;  // same association as matching.py:34-36
+        cf[e] = ex2(la * LOG2E);
+        if (ddim) {
+          const float xn = ok ? fmaf(p.k_x0, cf[e], fmaf(p.k_xt, xt[e] - xt_shift, p.sigma * nz[e])) : -INFINITY;
+          if (ok && xn > -INFINITY) local_min = fminf(local_min, xn);
+          o[e] = xn;
+        } else {
+          o[e] = cf[e];
+        }
+      }
+      *reinterpret_cast<float4*>(p.out + base) = make_float4(o[0], o[1], o[2], o[3]);
+      if (ddim && p.conf) *reinterpret_cast<float4*>(p.conf + base) = make_float4(cf[0], cf[1], cf[2], cf[3]);
+    }
+    if (track) {
+      // column bests (rows ascend, strict > keeps the lowest row on ties)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (cf[e] > cbv[e]) {
+          cbv[e] = cf[e];
+          cbi[e] = i;
+        }
+      // row best of this warp's 128 columns: value by shuffle max, owner by ballot (lowest lane, lowest column)
+      float rv = cf[0];
+      int re = 0;
+#pragma unroll
+      for (int e = 1; e < 4; ++e)
+        if (cf[e] > rv) {
+          rv = cf[e];
+          re = e;
+        }
+      const float wv = warp_max(rv);
+      const unsigned int owners = __ballot_sync(0xffffffffu, active && rv == wv);
+      if (owners && lane == __ffs(owners) - 1) {
+        const unsigned long long key =
+            ((unsigned long long)float_to_ordered(rv) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)(c + re));
+        atomicMax(&p.rowbest[(size_t)b * N + i], key);
+      }
+    }
+  }
+  if (track && active && i1 > i0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned long long key =
+          ((unsigned long long)float_to_ordered(cbv[e]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)cbi[e]);
+      atomicMax(&p.colbest[(size_t)b * M + c + e], key);
+    }
+  }
+  if (ddim && p.x_min) {
+    local_min = warp_min(local_min);
+    if (lane == 0 && local_min < INFINITY) atomic_min_float(p.x_min, local_min);
   }
 }
 
@@ -2199,6 +2316,8 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     f.noise_seed = a->noise_seed;
     f.noise_offset = a->noise_offset;
     f.noise_offset_dev = a->noise_offset_dev;
+    f.rowbest = (a->rowbest && a->colbest) ? a->rowbest : nullptr;
+    f.colbest = f.rowbest ? a->colbest : nullptr;
     f.inv_temp = dual ? 1.f / temperature : 0.f;
     int gx = (NUM_SMS * 8) / B;
     if (gx < 1) gx = 1;
@@ -2210,12 +2329,20 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
       }
     } else {
       if (gx > N) gx = N;
-      bool fvec = vec && aligned16(a->out) && (!f.x_t || aligned16(f.x_t)) && (!f.noise || aligned16(f.noise)) &&
+      if (f.rowbest && !(vec && !dual && (a->out_mode == DRG_OUT_CONF || a->out_mode == DRG_OUT_DDIM))) {
+        set_error("sinkhorn: rowbest/colbest need M % 4 == 0 and out_mode CONF or DDIM");
+        return DRG_ERR_UNSUPPORTED;
+      }
+      bool fvec = vec && !dual && aligned16(a->out) && (!f.x_t || aligned16(f.x_t)) && (!f.noise || aligned16(f.noise)) &&
                   (!f.conf || aligned16(f.conf)) && (((uintptr_t)a->tgt_mask & 3u) == 0);
       if (fvec)
         {
+          if (f.rowbest) {
+            DRG_CUDA(cudaMemsetAsync(f.rowbest, 0, sizeof(unsigned long long) * (size_t)B * N, st));
+            DRG_CUDA(cudaMemsetAsync(f.colbest, 0, sizeof(unsigned long long) * (size_t)B * M, st));
+          }
           ProfScope prof_scope(PROF_SKH_FINAL, st);
-          skh_final_kernel<true><<<dim3(gx, B), 256, 0, st>>>(f);
+          skh_final_tile_kernel<<<dim3((M + FT_THREADS * 4 - 1) / (FT_THREADS * 4), (N + FT_ROWS - 1) / FT_ROWS, B), FT_THREADS, 0, st>>>(f);
         }
       else
         {

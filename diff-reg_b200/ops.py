@@ -46,7 +46,7 @@ def _f32c(t):
 
 def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", apply_mask=False, shift=None,
              x_t=None, noise=None, k_x0=0.0, k_xt=0.0, sigma=0.0, want_conf=False, x_min=None, return_potentials=False,
-             xt_shift=None, noise_seed=None, noise_offset=0, noise_offset_dev=None, out=None):
+             xt_shift=None, noise_seed=None, noise_offset=0, noise_offset_dev=None, out=None, want_best=False):
     """Log-domain Sinkhorn with dustbins (drg_sinkhorn).
 
     out_mode: 'log_full' -> [B,N+1,M+1] log-assignment; 'conf' -> [B,N,M] exp()[:, :-1, :-1];
@@ -76,6 +76,8 @@ def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", appl
         x_t = _f32c(x_t)
     if noise is not None:
         noise = _f32c(noise)
+    rowbest = torch.empty(B, N, dtype=torch.int64, device=dev) if want_best else None
+    colbest = torch.empty(B, M, dtype=torch.int64, device=dev) if want_best else None
     nbytes = lib.drg_sinkhorn_workspace_bytes(B, N, M)
     if nbytes == 0:
         raise _lib.DiffRegLibraryError(f"sinkhorn: unsupported shape B={B} N={N} M={M}")
@@ -85,13 +87,16 @@ def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", appl
                      out_mode=mode, out=_ptr(out), u=_ptr(u), v=_ptr(v), x_t=_ptr(x_t), xt_shift=_ptr(xt_shift), noise=_ptr(noise),
                      conf=_ptr(conf), k_x0=float(k_x0), k_xt=float(k_xt), sigma=float(sigma), x_min=_ptr(x_min),
                      gen_noise=int(noise_seed is not None and noise is None), noise_seed=int(noise_seed or 0),
-                     noise_offset=int(noise_offset), noise_offset_dev=_ptr(noise_offset_dev))
+                     noise_offset=int(noise_offset), noise_offset_dev=_ptr(noise_offset_dev), rowbest=_ptr(rowbest),
+                     colbest=_ptr(colbest))
     check(lib.drg_sinkhorn(a, ws.data_ptr(), ws.numel(), _stream()))
     res = [out]
     if conf is not None:
         res.append(conf)
     if return_potentials:
         res += [u, v]
+    if want_best:
+        res += [rowbest, colbest]
     return res[0] if len(res) == 1 else tuple(res)
 
 
@@ -317,3 +322,24 @@ class ShardedSinkhornState:
         out = torch.empty(*shape, dtype=torch.float32, device=self.scores.device)
         check(self.lib.drg_sinkhorn_shard_final(self._args(mode, out), self.ws.data_ptr(), self.ws.numel(), _stream()))
         return out
+
+
+def match_from_best(rowbest, colbest, M, threshold=None, capacity=None):
+    """Mutual top-1 matches from the packed bests of sinkhorn(..., want_best=True) (drg_match_from_best).
+    capacity=None reads the count on the host and returns exact-size (index [K,3], vals [K]); otherwise returns
+    (index [capacity,3], vals [capacity], count) with the count on the device."""
+    _require_cuda(rowbest, colbest)
+    lib = load_library()
+    B, N = rowbest.shape
+    dev = rowbest.device
+    cap = int(capacity) if capacity is not None else B * min(N, M)
+    index = torch.empty(max(cap, 1), 3, dtype=torch.int64, device=dev)
+    vals = torch.empty(max(cap, 1), dtype=torch.float32, device=dev)
+    total = torch.empty(1, dtype=torch.int32, device=dev)
+    has_thr = threshold is not None
+    check(lib.drg_match_from_best(rowbest.data_ptr(), colbest.data_ptr(), B, N, M, int(has_thr), float(threshold) if has_thr else 0.0,
+                                  index.data_ptr(), vals.data_ptr(), max(cap, 1), total.data_ptr(), _stream()))
+    if capacity is None:
+        k = int(total.item())
+        return index[:k], vals[:k]
+    return index, vals, total

@@ -72,7 +72,7 @@ class DenoisingSampler:
 
     @torch.no_grad()
     def step(self, k, x, shift, src_feats, tgt_feats, s_pcd, t_pcd, src_mask, tgt_mask, noise=None,
-             pose_tgt_pcd=None, pose_tgt_mask=None, feature_fn=None, x_out=None, noise_counter=None):
+             pose_tgt_pcd=None, pose_tgt_mask=None, feature_fn=None, x_out=None, noise_counter=None, want_x0=False):
         """One reverse step.  x: [1,N,M] state (as stored: for the 3d flavour the true state is x - shift).
         x_out: optional preallocated [1,N,M] buffer for x_next; noise_counter: optional 1-element int64 device
         counter used as the Philox offset (and incremented) instead of the host-side call count.
@@ -96,23 +96,33 @@ class DenoisingSampler:
         x_min = None
         if self.flavour == "3d":
             x_min = torch.full((1,), float("inf"), dtype=torch.float32, device=x.device)
-        x_next, x0 = ops.sinkhorn(sim, m.bin_score, m.skh_iters, src_mask, tgt_mask, out_mode="ddim", apply_mask=True,
-                                  x_t=x, xt_shift=shift, noise=noise if use_noise else None, k_x0=k_x0, k_xt=k_xt,
-                                  sigma=sigma if use_noise else 0.0, want_conf=True, x_min=x_min,
-                                  noise_seed=self.noise_seed if gen else None,
-                                  noise_offset=0 if noise_counter is not None else self.noise_calls,
-                                  noise_offset_dev=noise_counter, out=x_out)
+        B, N, M = sim.shape
+        fused_match = self.extract_matches and M % 4 == 0
+        res = ops.sinkhorn(sim, m.bin_score, m.skh_iters, src_mask, tgt_mask, out_mode="ddim", apply_mask=True,
+                           x_t=x, xt_shift=shift, noise=noise if use_noise else None, k_x0=k_x0, k_xt=k_xt,
+                           sigma=sigma if use_noise else 0.0, want_conf=want_x0 or (self.extract_matches and not fused_match),
+                           x_min=x_min, noise_seed=self.noise_seed if gen else None,
+                           noise_offset=0 if noise_counter is not None else self.noise_calls,
+                           noise_offset_dev=noise_counter, out=x_out, want_best=fused_match)
+        res = list(res) if isinstance(res, tuple) else [res]
+        x_next = res.pop(0)
+        x0 = res.pop(0) if (want_x0 or (self.extract_matches and not fused_match)) else None
         if noise_counter is not None:
             ops.counter_add(noise_counter, 1)       # device-side Philox offset: graph replays draw fresh noise
         self.noise_calls += 1
         aux = {"pose": pose, "x0": x0, "conf_d": conf_d}
         if self.extract_matches:
-            B, N, M = x0.shape
             # Mutual top-1 matches (index based: a row's best column whose best row is that row), thresholded for
             # the 3D flavours.  Equals get_match(conf, thr, mutual=True) (matching.py:71-88) except at exact value
-            # ties, where the lowest index wins instead of every tied entry being reported.
+            # ties, where the lowest index wins instead of every tied entry being reported.  With aligned rows the
+            # row / column bests come out of the DDIM pass itself and x0 is neither stored nor re-read.
             thr = None if self.flavour == "2d3d" else m.confidence_threshold
-            aux["match"] = ops._match(x0, 1, True, thr, True, False, capacity=B * min(N, M))
+            if fused_match:
+                rowbest, colbest = res
+                aux["match"] = ops.match_from_best(rowbest, colbest, M, thr, capacity=B * min(N, M))
+                aux["match"] = (aux["match"][0], aux["match"][1], None, aux["match"][2])
+            else:
+                aux["match"] = ops._match(x0, 1, True, thr, True, False, capacity=B * min(N, M))
         return x_next, x_min, aux
 
     @torch.no_grad()
@@ -125,7 +135,7 @@ class DenoisingSampler:
             noise = noises[k] if (noises is not None and self.flavour == "4d") else None
             x_in = x
             x, shift, aux = self.step(k, x, shift, src_feats, tgt_feats, s_pcd, t_pcd, src_mask, tgt_mask, noise,
-                                      pose_tgt_pcd, pose_tgt_mask, feature_fn)
+                                      pose_tgt_pcd, pose_tgt_mask, feature_fn, want_x0=trace is not None)
             if trace is not None:
                 trace.append({"x_in": x_in, "x_out": x, **aux})
         out = {"x_final": x, "pose": aux["pose"] if aux else None}

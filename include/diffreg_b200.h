@@ -100,6 +100,10 @@ typedef struct drg_sinkhorn_args {
   unsigned long long noise_offset; /* high half of the Philox counter: use a new value per step   */
   const unsigned long long* noise_offset_dev; /* optional device counter added to noise_offset, so a
                               CUDA-graph replay of the same step draws fresh noise (drg_counter_add) */
+  unsigned long long* rowbest; /* optional [B,N] (with colbest [B,M]; out_mode CONF or DDIM, M % 4 == 0): the final pass
+                              also leaves every row's / column's best confidence and its lowest index as packed keys
+                              (order-preserving float bits << 32 | ~index) for drg_match_from_best               */
+  unsigned long long* colbest;
 } drg_sinkhorn_args;
 
 size_t drg_sinkhorn_workspace_bytes(int B, int N, int M);
@@ -172,6 +176,14 @@ int drg_match_count(const float* x, int B, int N, int M, int mode, int mutual, i
 int drg_match_write(const float* x, int B, int N, int M, int mode, int mutual, int has_thr, float thr, int largest, void* workspace,
                     size_t workspace_bytes, long long* index_out, float* val_out, long long capacity, unsigned char* mask_out,
                     void* stream);
+
+/* Mutual top-1 matches from the packed row / column bests written by drg_sinkhorn (rowbest / colbest): row i matches its
+ * best column j iff j's best row is i [and conf > thr].  Same hits as Matching.get_match(conf, thr, mutual=True)
+ * (Diff-Reg-4dmatch/models/matching.py:71-88) and mutual_topk_select(k=1, mutual=True) except at exact value ties, where
+ * the lowest index wins.  O(B*N) work: the confidence matrix is not read.  index_out [capacity,3] int64 in row-major order,
+ * val_out [capacity], *total_out = number of matches (device int). */
+int drg_match_from_best(const unsigned long long* rowbest, const unsigned long long* colbest, int B, int N, int M, int has_thr,
+                        float thr, long long* index_out, float* val_out, long long capacity, int* total_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * SoftProcrustes

@@ -71,3 +71,37 @@ def test_full_size_mutual_property():
     assert torch.equal(conf[0, rows, cols], mconf) and bool((mconf > 0.2).all())
     ref = O.get_match(conf, 0.2, True)[0]
     assert torch.equal(idx, ref)
+
+
+@pytest.mark.parametrize("B,N,M,kind", [(1, 64, 48, "full"), (2, 130, 260, "prefix"), (1, 1000, 1024, "arbitrary"), (1, 300, 4096, "full")])
+def test_fused_bests_of_the_final_pass(B, N, M, kind):
+    """The row / column bests written by the Sinkhorn final pass (DDIM and CONF modes) give the same mutual top-1
+    matches as the stand-alone extraction on the stored confidence matrix."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(N + 3 * M)
+    s = torch.randn(B, N, M, generator=gen) * 3.0
+    sm = torch.ones(B, N, dtype=torch.bool)
+    tm = torch.ones(B, M, dtype=torch.bool)
+    if kind == "prefix":
+        sm[:, N - 7:] = False
+        tm[:, M - 20:] = False
+    elif kind == "arbitrary":
+        sm = torch.rand(B, N, generator=gen) > 0.1
+        tm = torch.rand(B, M, generator=gen) > 0.1
+    alpha = torch.tensor(1.0)
+    x_t = torch.randn(B, N, M, generator=gen)
+    args = (s.cuda(), alpha.cuda(), 3, sm.cuda(), tm.cuda())
+    conf, rb, cb = ops.sinkhorn(*args, out_mode="conf", apply_mask=True, want_best=True)
+    xn, conf2, rb2, cb2 = ops.sinkhorn(*args, out_mode="ddim", apply_mask=True, x_t=x_t.cuda(), k_x0=0.7, k_xt=0.1, sigma=0.0,
+                                       want_conf=True, want_best=True)
+    assert torch.equal(conf, conf2) and torch.equal(rb, rb2) and torch.equal(cb, cb2)
+    for thr in (None, 0.05):
+        idx, vals = ops.match_from_best(rb, cb, M, thr)
+        ref_idx, ref_vals, _ = ops._match(conf, 1, True, thr, True, False)
+        assert torch.equal(idx, ref_idx) and torch.equal(vals, ref_vals)
+    # and against the oracle's get_match on the oracle's own confidence matrix (no exact ties in random data)
+    filled = s.masked_fill(~O.pair_mask(sm, tm), float("-inf"))
+    ref_conf = O.log_optimal_transport(filled, alpha, 3, sm, tm).exp()[:, :-1, :-1]
+    o_idx, _, _ = O.get_match(ref_conf, 0.05, True)
+    idx, _ = ops.match_from_best(rb, cb, M, 0.05)
+    assert torch.equal(idx.cpu(), o_idx)
