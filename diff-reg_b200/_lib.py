@@ -83,6 +83,9 @@ def _declare(lib):
     lib.drg_soft_procrustes_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.drg_soft_procrustes.restype = c_int
     lib.drg_soft_procrustes.argtypes = [ctypes.POINTER(ProcrustesArgs), c_void_p, c_size_t, c_void_p]
+    lib.drg_sinkhorn_soft_procrustes.restype = c_int
+    lib.drg_sinkhorn_soft_procrustes.argtypes = [ctypes.POINTER(SinkhornArgs), ctypes.POINTER(ProcrustesArgs), c_void_p, c_size_t,
+                                                 c_void_p, c_size_t, c_void_p]
     lib.drg_weighted_procrustes.restype = c_int
     lib.drg_weighted_procrustes.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                             c_void_p]

@@ -49,6 +49,23 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- shared between sinkhorn.cu and procrustes.cu ------------------------------------------
+struct SkhConst {  // per batch element normalisation constants of the Sinkhorn (matching.py:24-27)
+  float norm;        // -log(ms + ns)
+  float log_mu_bin;  // log(ns) + norm
+  float log_nu_bin;  // log(ms) + norm
+  float pad;
+};
+// where a finished Sinkhorn left its potentials inside its workspace
+struct SkhViews {
+  const float* u;       // [B, ldu]
+  const float* v;       // [B, ldv]
+  const SkhConst* bc;   // [B]
+  int ldu, ldv;
+};
+// runs drg_sinkhorn (out_mode NONE allowed) and reports the views (sinkhorn.cu)
+int skh_run_with_views(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* stream, SkhViews* views);
+
 // ---- optional per-kernel timing (bench.py's roofline leg) ---------------------------------
 // When enabled through drg_profile_enable(1), every launch of a slotted kernel is bracketed by two
 // CUDA events on the launching stream; drg_profile_read() sums the elapsed times.  Disabled: no cost.

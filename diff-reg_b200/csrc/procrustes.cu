@@ -41,7 +41,13 @@ struct ProcrState {  // per batch element
 };
 
 struct ProcrParams {
-  const float* conf;             // [B,N,M]
+  const float* conf;             // [B,N,M], or NULL: potentials mode, conf = exp((scores - shift | mask) + u + v - norm)
+  const float* scores;           // potentials mode: [B,N,M]
+  const float* pu;               // [B, ldu]
+  const float* pv;               // [B, ldv]
+  const SkhConst* pbc;           // [B]
+  const float* pshift;           // device scalar or NULL
+  int ldu, ldv, apply_mask;
   const float* src_pcd;          // [B,N,3]
   const float* tgt_pcd;          // [B,M,3]
   const unsigned char* src_mask; // [B,N]
@@ -96,6 +102,19 @@ __device__ __forceinline__ unsigned int count_bytes16(const unsigned char* __res
     for (int i = tid; i < n; i += nthreads) c += m[i] ? 1u : 0u;
   }
   return c;
+}
+
+// the confidence at flat position `pos` of batch element b: stored, or recomputed from the Sinkhorn potentials with
+// the arithmetic of skh_final_tile_kernel (so that the matrix never has to be materialised for the pose step)
+__device__ __forceinline__ float conf_at(const ProcrParams& p, int b, size_t pos) {
+  const size_t total = (size_t)p.N * p.M;
+  if (p.conf) return p.conf[(size_t)b * total + pos];
+  const int i = (int)(pos / (size_t)p.M), j = (int)(pos - (size_t)i * p.M);
+  const bool ok = !p.apply_mask || (p.src_mask[(size_t)b * p.N + i] && p.tgt_mask[(size_t)b * p.M + j]);
+  const float shift = p.pshift ? *p.pshift : 0.f;
+  const float zz = ok ? (p.scores[(size_t)b * total + pos] - shift) : -INFINITY;
+  const float la = ((zz + p.pu[(size_t)b * p.ldu + i]) + p.pv[(size_t)b * p.ldv + j]) - p.pbc[b].norm;
+  return ex2(la * LOG2E);
 }
 
 __device__ __forceinline__ unsigned long long make_key64(unsigned int ordered_value, unsigned int flat_index) {
@@ -207,7 +226,6 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
   //      4-byte reads: spread over TS_CTAS CTAs so that they are all in flight at once) into a global buffer; the
   //      last CTA to arrive pulls the whole sample into shared memory and carries on alone.
   const size_t total = (size_t)p.N * p.M;
-  const float* x = p.conf + (size_t)b * total;
   const bool all = total <= (size_t)TS_SAMPLES;
   const unsigned int n_s = all ? (unsigned int)total : (unsigned int)TS_SAMPLES;
   const unsigned int salt = 0x9e3779b9u * (unsigned int)(b + 1);
@@ -223,7 +241,7 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const unsigned int q = q0 + k * TS_THREADS;
-        val[k] = (q < q_hi) ? x[sample_pos(q)] : 0.f;
+        val[k] = (q < q_hi) ? conf_at(p, b, sample_pos(q)) : 0.f;
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -328,11 +346,14 @@ __device__ __forceinline__ void append_candidates(const ProcrParams& p, int b, s
 __global__ void __launch_bounds__(256) topk_collect_kernel(const ProcrParams p) {
   const int b = blockIdx.y;
   const size_t total = (size_t)p.N * p.M;
-  const float* x = p.conf + (size_t)b * total;
+  const float* x = (p.conf ? p.conf : p.scores) + (size_t)b * total;
   const unsigned long long lower = p.state[b].lower_key;
-  const bool vec = ((total & 3) == 0) && ((((uintptr_t)x) & 15u) == 0);
+  // vector path: quads never straddle a row in potentials mode (M % 4 == 0)
+  const bool vec = ((total & 3) == 0) && ((((uintptr_t)x) & 15u) == 0) && (p.conf || (p.M & 3) == 0);
   const size_t n4 = vec ? (total >> 2) : ((total + 3) >> 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const float shift = (!p.conf && p.pshift) ? *p.pshift : 0.f;
+  const float norm = p.conf ? 0.f : p.pbc[b].norm;
   // all lanes of a warp iterate the same number of times (warp-collective append)
   const size_t iters = (n4 + stride - 1) / stride;
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,9 +365,26 @@ __global__ void __launch_bounds__(256) topk_collect_kernel(const ProcrParams p) 
       if (vec) {
         const float4 t = *reinterpret_cast<const float4*>(x + q * 4);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        if (!p.conf) {
+          const int i = (int)((q * 4) / (size_t)p.M), j = (int)(q * 4 - (size_t)i * p.M);
+          const float ui = p.pu[(size_t)b * p.ldu + i];
+          const float4 vj = *reinterpret_cast<const float4*>(p.pv + (size_t)b * p.ldv + j);
+          bool ok[4] = {true, true, true, true};
+          if (p.apply_mask) {
+            const bool row_ok = p.src_mask[(size_t)b * p.N + i];
+            const uchar4 tm = *reinterpret_cast<const uchar4*>(p.tgt_mask + (size_t)b * p.M + j);
+            ok[0] = row_ok && tm.x; ok[1] = row_ok && tm.y; ok[2] = row_ok && tm.z; ok[3] = row_ok && tm.w;
+          }
+          const float vv[4] = {vj.x, vj.y, vj.z, vj.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float zz = ok[e] ? (v[e] - shift) : -INFINITY;
+            v[e] = ex2((((zz + ui) + vv[e]) - norm) * LOG2E);
+          }
+        }
       } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = (q * 4 + e < total) ? x[q * 4 + e] : -INFINITY;
+        for (int e = 0; e < 4; ++e) v[e] = (q * 4 + e < total) ? conf_at(p, b, q * 4 + e) : -INFINITY;
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -534,9 +572,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
   extern __shared__ unsigned int cand_s[];  // [2][SOLVE_SMEM_CAND]: keys, indices
   if (n < (size_t)Kb) {
     // fallback: the sample-based bound left too few candidates; take the whole matrix
-    const float* x = p.conf + (size_t)b * total;
     for (size_t e = tid; e < total; e += SOLVE_THREADS) {
-      ckey[e] = float_to_ordered(x[e]);
+      ckey[e] = float_to_ordered(conf_at(p, b, e));
       cidx[e] = (unsigned int)e;
     }
     n = total;
@@ -774,9 +811,16 @@ extern "C" size_t drg_soft_procrustes_workspace_bytes(int B, int N, int M) {
   return procr_carve(nullptr, B, N, M).total;
 }
 
-extern "C" int drg_soft_procrustes(const drg_procrustes_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+struct ProcrSource {  // potentials mode inputs (conf == NULL)
+  const float* scores;
+  const float* shift;
+  int apply_mask;
+  SkhViews views;
+};
+
+static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void* workspace, size_t workspace_bytes, void* stream) {
   DRG_CHECK_ARG(a != nullptr, "args is null");
-  DRG_CHECK_ARG(a->conf && a->src_pcd && a->tgt_pcd, "conf/src_pcd/tgt_pcd must be non-null");
+  DRG_CHECK_ARG((a->conf != nullptr || src != nullptr) && a->src_pcd && a->tgt_pcd, "conf/src_pcd/tgt_pcd must be non-null");
   DRG_CHECK_ARG(a->padded_lengths || (a->src_mask && a->tgt_mask), "masks must be non-null unless padded_lengths is set");
   DRG_CHECK_ARG(a->B >= 1 && a->B <= 1024 && a->N >= 1 && a->M >= 1, "need 1 <= B <= 1024 and N, M >= 1");
   DRG_CHECK_ARG((long long)a->N * a->M < (1ll << 32), "N*M must fit in 32 bits");
@@ -792,7 +836,17 @@ extern "C" int drg_soft_procrustes(const drg_procrustes_args* a, void* workspace
   }
   cudaStream_t st = (cudaStream_t)stream;
   ProcrParams p{};
-  p.conf = a->conf;
+  p.conf = src ? nullptr : a->conf;
+  if (src) {
+    p.scores = src->scores;
+    p.pu = src->views.u;
+    p.pv = src->views.v;
+    p.pbc = src->views.bc;
+    p.pshift = src->shift;
+    p.ldu = src->views.ldu;
+    p.ldv = src->views.ldv;
+    p.apply_mask = src->apply_mask;
+  }
   p.src_pcd = a->src_pcd;
   p.tgt_pcd = a->tgt_pcd;
   p.src_mask = a->src_mask;
@@ -869,6 +923,27 @@ extern "C" int drg_soft_procrustes(const drg_procrustes_args* a, void* workspace
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
+}
+
+extern "C" int drg_soft_procrustes(const drg_procrustes_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  DRG_CHECK_ARG(a != nullptr && a->conf != nullptr, "args / conf is null");
+  return procr_run(a, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int drg_sinkhorn_soft_procrustes(const drg_sinkhorn_args* s, const drg_procrustes_args* a, void* skh_workspace,
+                                            size_t skh_workspace_bytes, void* procr_workspace, size_t procr_workspace_bytes,
+                                            void* stream) {
+  DRG_CHECK_ARG(s != nullptr && a != nullptr, "args are null");
+  DRG_CHECK_ARG(s->out_mode == DRG_OUT_NONE, "the fused call takes out_mode DRG_OUT_NONE: the confidence matrix is never written");
+  DRG_CHECK_ARG(s->B == a->B && s->N == a->N && s->M == a->M, "sinkhorn and procrustes shapes differ");
+  DRG_CHECK_ARG(a->src_mask == s->src_mask && a->tgt_mask == s->tgt_mask, "the fused call uses one pair of masks");
+  ProcrSource src{};
+  int rc = skh_run_with_views(s, skh_workspace, skh_workspace_bytes, stream, &src.views);
+  if (rc != DRG_OK) return rc;
+  src.scores = s->scores;
+  src.shift = s->shift;
+  src.apply_mask = s->apply_mask;
+  return procr_run(a, &src, procr_workspace, procr_workspace_bytes, stream);
 }
 
 extern "C" int drg_weighted_procrustes(const float* X, const float* Y, const float* w, int B, int K, float eps, float* R, float* t,

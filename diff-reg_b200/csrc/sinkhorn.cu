@@ -30,13 +30,6 @@ constexpr int SKH_STAGE_FLOATS = 16384;  // R * M <= 16384 floats (64 KB) per st
 constexpr int SKH_MAX_M = 16384;
 constexpr size_t SKH_SMEM_LIMIT = 227 * 1024;
 
-struct SkhConst {  // per batch element, written by skh_prep_kernel
-  float norm;        // -log(ms + ns)
-  float log_mu_bin;  // log(ns) + norm
-  float log_nu_bin;  // log(ms) + norm
-  float pad;
-};
-
 struct SkhParams {
   const float* scores;
   const uint8_t* src_mask;
@@ -2434,3 +2427,17 @@ extern "C" int drg_debug_read_times(long long* host_out, int n) {
   DRG_CUDA(cudaMemcpy(host_out, g_skh_times, sizeof(long long) * n, cudaMemcpyDeviceToHost));
   return DRG_OK;
 }
+
+namespace drg {
+int skh_run_with_views(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* stream, SkhViews* views) {
+  int rc = drg_sinkhorn(a, workspace, workspace_bytes, stream);
+  if (rc != DRG_OK) return rc;
+  SkhWorkspace w = carve(workspace, a->B, a->N, a->M, skh_max_g(a->B));
+  views->u = w.u;
+  views->v = w.v;
+  views->bc = w.bc;
+  views->ldu = pitch4(a->N + 1);
+  views->ldv = pitch4(a->M + 1);
+  return DRG_OK;
+}
+}  // namespace drg

@@ -343,3 +343,42 @@ def match_from_best(rowbest, colbest, M, threshold=None, capacity=None):
         k = int(total.item())
         return index[:k], vals[:k]
     return index, vals, total
+
+
+def sinkhorn_soft_procrustes(scores, alpha, iters, src_mask, tgt_mask, src_pcd, tgt_pcd, sample_rate, max_condition_num,
+                             padded_lengths=False, apply_mask=True, shift=None, want_warped=True):
+    """get_warped_from_noising_matching in one call (drg_sinkhorn_soft_procrustes): Sinkhorn on the sampler state, then
+    SoftProcrustes + warp straight from the potentials -- the confidence matrix is never written.
+    Returns the same dict as soft_procrustes()."""
+    _require_cuda(scores, alpha, src_mask, tgt_mask, src_pcd, tgt_pcd, shift)
+    lib = load_library()
+    scores = _f32c(scores)
+    src_pcd = _f32c(src_pcd)
+    tgt_pcd = _f32c(tgt_pcd)
+    B, N, M = scores.shape
+    dev = scores.device
+    sm = _as_mask(src_mask)
+    tm = _as_mask(tgt_mask)
+    alpha = _f32c(alpha.detach().reshape(()))
+    out = dict(R=torch.empty(B, 3, 3, dtype=torch.float32, device=dev), t=torch.empty(B, 3, 1, dtype=torch.float32, device=dev),
+               R_forwd=torch.empty(B, 3, 3, dtype=torch.float32, device=dev),
+               t_forwd=torch.empty(B, 3, 1, dtype=torch.float32, device=dev),
+               condition=torch.empty(B, dtype=torch.float64, device=dev),
+               solution_mask=torch.empty(B, dtype=torch.bool, device=dev))
+    if want_warped:
+        out["src_warped"] = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+    n_s = lib.drg_sinkhorn_workspace_bytes(B, N, M)
+    if n_s == 0:
+        raise _lib.DiffRegLibraryError(f"sinkhorn: unsupported shape B={B} N={N} M={M}")
+    ws_s = workspace(n_s, dev, "sinkhorn")
+    ws_p = workspace(lib.drg_soft_procrustes_workspace_bytes(B, N, M), dev, "procrustes")
+    s = SinkhornArgs(scores=_ptr(scores), src_mask=_ptr(sm), tgt_mask=_ptr(tm), alpha=_ptr(alpha), shift=_ptr(shift), B=B, N=N, M=M,
+                     iters=int(iters), apply_mask=int(bool(apply_mask)), out_mode=_lib.DRG_OUT_NONE)
+    k_max = min(int(max(N, M) * float(sample_rate)) + 1, N * M)
+    a = _lib.ProcrustesArgs(conf=None, src_pcd=_ptr(src_pcd), tgt_pcd=_ptr(tgt_pcd), src_mask=_ptr(sm), tgt_mask=_ptr(tm), B=B, N=N,
+                            M=M, sample_rate=float(sample_rate), max_condition_num=float(max_condition_num),
+                            padded_lengths=int(bool(padded_lengths)), R=_ptr(out["R"]), t=_ptr(out["t"]),
+                            R_forwd=_ptr(out["R_forwd"]), t_forwd=_ptr(out["t_forwd"]), condition=_ptr(out["condition"]),
+                            solution_mask=_ptr(out["solution_mask"]), src_warped=_ptr(out.get("src_warped")), K_max=k_max)
+    check(lib.drg_sinkhorn_soft_procrustes(s, a, ws_s.data_ptr(), ws_s.numel(), ws_p.data_ptr(), ws_p.numel(), _stream()))
+    return out

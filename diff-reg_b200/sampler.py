@@ -83,9 +83,15 @@ class DenoisingSampler:
         p_pcd = t_pcd if pose_tgt_pcd is None else pose_tgt_pcd
         p_mask = tgt_mask if pose_tgt_mask is None else pose_tgt_mask
         # noisy matching -> pose -> warped source points        get_warped_from_noising_matching
-        conf_d = ops.sinkhorn(x, sm.bin_score, sm.skh_iters, src_mask, p_mask, out_mode="conf", apply_mask=True, shift=shift)
-        pose = ops.soft_procrustes(conf_d, s_pcd, p_pcd, src_mask, p_mask, pm.sample_rate, pm.max_condition_num,
-                                   padded_lengths=pm.padded_lengths, want_warped=True)
+        if want_x0:      # tracing: also return the intermediate confidence matrix
+            conf_d = ops.sinkhorn(x, sm.bin_score, sm.skh_iters, src_mask, p_mask, out_mode="conf", apply_mask=True, shift=shift)
+            pose = ops.soft_procrustes(conf_d, s_pcd, p_pcd, src_mask, p_mask, pm.sample_rate, pm.max_condition_num,
+                                       padded_lengths=pm.padded_lengths, want_warped=True)
+        else:            # one call, no confidence matrix in HBM
+            conf_d = None
+            pose = ops.sinkhorn_soft_procrustes(x, sm.bin_score, sm.skh_iters, src_mask, p_mask, s_pcd, p_pcd, pm.sample_rate,
+                                                pm.max_condition_num, padded_lengths=pm.padded_lengths, apply_mask=True,
+                                                shift=shift, want_warped=True)
         if feature_fn is not None:
             src_feats, tgt_feats = feature_fn(pose["src_warped"], t_pcd, src_feats, tgt_feats)
         # x0 from the matching head, fused with the DDIM update

@@ -217,6 +217,14 @@ typedef struct drg_procrustes_args {
 size_t drg_soft_procrustes_workspace_bytes(int B, int N, int M);
 int drg_soft_procrustes(const drg_procrustes_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Noisy matching -> pose in one call: log-Sinkhorn on the sampler state followed by SoftProcrustes + warp, WITHOUT
+ * materialising the confidence matrix (the top-K search recomputes exp(Z+u+v-norm) from the potentials).
+ *   replaces get_warped_from_noising_matching   Diff-Reg-4dmatch/models/pipeline.py:207-223 (3d :293-309,
+ *            2d3d get_warped_from_noising_matching3D3D model.py:830-846)
+ *   s: the Sinkhorn problem with out_mode DRG_OUT_NONE; a: the Procrustes problem with conf = NULL and the same masks. */
+int drg_sinkhorn_soft_procrustes(const drg_sinkhorn_args* s, const drg_procrustes_args* a, void* skh_workspace,
+                                 size_t skh_workspace_bytes, void* procr_workspace, size_t procr_workspace_bytes, void* stream);
+
 /* Weighted Kabsch on given correspondences.
  *   replaces SoftProcrustesLayer.batch_weighted_procrustes(X, Y, w, eps)  Diff-Reg-4dmatch/models/procrustes.py:18-44
  *   X, Y [B,K,3], w [B,K] -> R [B,3,3], t [B,3,1], condition [B] fp64 */

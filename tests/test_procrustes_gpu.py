@@ -101,3 +101,23 @@ def test_degenerate_inputs_gate_to_identity():
     out = ops.soft_procrustes(conf.cuda(), pts.cuda(), torch.zeros(1, M, 3).cuda(), ones_s.cuda(), ones_t.cuda(), 1.0, 40.0)
     assert not bool(out["solution_mask"][0])
     assert torch.equal(out["R_forwd"].cpu()[0], torch.eye(3)) and torch.equal(out["t_forwd"].cpu()[0], torch.zeros(3, 1))
+
+
+@pytest.mark.parametrize("B,N,M,kind", [(1, 64, 48, "full"), (2, 200, 260, "prefix"), (1, 1024, 1024, "arbitrary"), (1, 37, 1530, "arbitrary")])
+def test_fused_sinkhorn_procrustes_matches_two_calls(B, N, M, kind):
+    """drg_sinkhorn_soft_procrustes (no confidence matrix in memory) == drg_sinkhorn(conf) + drg_soft_procrustes."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(B + N + M)
+    pv = [(N - 5 - b, M - 9 - b) for b in range(B)] if kind == "prefix" else None
+    pb = O.make_problem(5 + N, B, N, M, C=8, prefix_valid=pv, arbitrary_invalid=0.1 if kind == "arbitrary" else 0.0)
+    x = torch.randn(B, N, M, generator=gen) * 2.0
+    alpha = torch.tensor(1.0).cuda()
+    args = (x.cuda(), alpha, 3, pb["src_mask"].cuda(), pb["tgt_mask"].cuda())
+    conf = ops.sinkhorn(*args, out_mode="conf", apply_mask=True)
+    two = ops.soft_procrustes(conf, pb["s_pcd"].cuda(), pb["t_pcd"].cuda(), pb["src_mask"].cuda(), pb["tgt_mask"].cuda(), 1.0, 1e9,
+                              want_warped=True)
+    one = ops.sinkhorn_soft_procrustes(*args, pb["s_pcd"].cuda(), pb["t_pcd"].cuda(), 1.0, 1e9, apply_mask=True, want_warped=True)
+    assert rot_angle(one["R"].cpu(), two["R"].cpu()).max() <= TOL_ROT
+    assert (one["t"] - two["t"]).abs().max() <= TOL_TRANS
+    assert (one["src_warped"] - two["src_warped"]).abs().max() <= 5e-5
+    assert torch.equal(one["solution_mask"], two["solution_mask"])
