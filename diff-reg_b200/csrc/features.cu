@@ -21,6 +21,9 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
 
 struct PrepParams {
   const float* in;   // [rows, K]
+  const float* in2;  // optional second source: rows >= rows1 come from in2[row - rows1] (two tensors, one launch)
+  long long rows1;
+  int pattern2;      // split pattern of the rows taken from in2
   const float* pe;   // rotary: [rows, K, 2] (cos, sin); sinusoidal: [rows, K]; or NULL
   float* embedded;   // optional [rows, K]: features after the positional embedding, before scaling
   float* out;        // [rows, 3K] or [rows, K]
@@ -38,7 +41,9 @@ __global__ void __launch_bounds__(256) prep_operand_kernel(const PrepParams p) {
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long row = idx / K4;
     const int k = (int)(idx - row * K4) << 2;
-    float4 x = *reinterpret_cast<const float4*>(p.in + row * p.K + k);
+    const bool second = p.in2 != nullptr && row >= p.rows1;
+    float4 x = second ? *reinterpret_cast<const float4*>(p.in2 + (row - p.rows1) * p.K + k)
+                      : *reinterpret_cast<const float4*>(p.in + row * p.K + k);
     if (p.pe_type == 1) {
       // x*cos + rot(x)*sin with rot(x)[2i] = -x[2i+1], rot(x)[2i+1] = x[2i]; same op order as the reference
       const float4 cs0 = *reinterpret_cast<const float4*>(p.pe + (row * p.K + k) * 2);      // cos0 sin0 cos1 sin1
@@ -78,8 +83,9 @@ __global__ void __launch_bounds__(256) prep_operand_kernel(const PrepParams p) {
     float* o = p.out + row * 3 * p.K + k;
     // The correction terms come FIRST along K: the tensor core truncates its fp32 accumulator at every
     // K=8 step (~2^-24 |acc| each, measured), so the small terms are added while the accumulator is small.
-    *reinterpret_cast<float4*>(o) = p.pattern == 0 ? lo : hi;
-    *reinterpret_cast<float4*>(o + p.K) = p.pattern == 0 ? hi : lo;
+    const int pat = second ? p.pattern2 : p.pattern;
+    *reinterpret_cast<float4*>(o) = pat == 0 ? lo : hi;
+    *reinterpret_cast<float4*>(o + p.K) = pat == 0 ? hi : lo;
     *reinterpret_cast<float4*>(o + 2 * p.K) = hi;
   }
 }
@@ -88,8 +94,8 @@ __global__ void __launch_bounds__(256) prep_operand_kernel(const PrepParams p) {
 
 using namespace drg;
 
-extern "C" int drg_prep_operand(const float* in, const float* pe, int pe_type, long long rows, int K, float scale, int split,
-                                int pattern, float* embedded, float* out, void* stream) {
+static int prep_run(const float* in, const float* in2, long long rows1, const float* pe, int pe_type, long long rows, int K,
+                    float scale, int split, int pattern, int pattern2, float* embedded, float* out, void* stream) {
   DRG_CHECK_ARG(in && out, "in/out must be non-null");
   DRG_CHECK_ARG(rows >= 1 && K >= 4, "rows >= 1 and K >= 4 required");
   DRG_CHECK_ARG(pe_type >= 0 && pe_type <= 2, "pe_type must be 0 (none), 1 (rotary) or 2 (sinusoidal)");
@@ -101,6 +107,9 @@ extern "C" int drg_prep_operand(const float* in, const float* pe, int pe_type, l
   }
   PrepParams p{};
   p.in = in;
+  p.in2 = in2;
+  p.rows1 = rows1;
+  p.pattern2 = pattern2;
   p.pe = pe;
   p.embedded = embedded;
   p.out = out;
@@ -119,6 +128,17 @@ extern "C" int drg_prep_operand(const float* in, const float* pe, int pe_type, l
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
+}
+
+extern "C" int drg_prep_operand(const float* in, const float* pe, int pe_type, long long rows, int K, float scale, int split,
+                                int pattern, float* embedded, float* out, void* stream) {
+  return prep_run(in, nullptr, rows, pe, pe_type, rows, K, scale, split, pattern, pattern, embedded, out, stream);
+}
+
+extern "C" int drg_prep_operand_pair(const float* in_a, long long rows_a, int pattern_a, const float* in_b, long long rows_b,
+                                     int pattern_b, int K, float scale, int split, float* out, void* stream) {
+  DRG_CHECK_ARG(in_b != nullptr && rows_b >= 1 && (((uintptr_t)in_b) & 15u) == 0, "second input must be non-null, non-empty, 16-byte aligned");
+  return prep_run(in_a, in_b, rows_a, nullptr, 0, rows_a + rows_b, K, scale, split, pattern_a, pattern_b, nullptr, out, stream);
 }
 
 // ---- small elementwise / reduction helpers of the sampler -----------------------------------

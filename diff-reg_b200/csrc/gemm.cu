@@ -119,12 +119,23 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);  // [24,29) M >> 4
 }
 
+__device__ __forceinline__ float gemm_to_tf32_rna(float x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+  return __uint_as_float(y);
+}
+
 struct GemmShape {
   int N, M, K, batch;
   float alpha;
   int nstage;
   int direct_store;  // 1: C row pitch not TMA-storable (M % 4 != 0) -> coalesced st.global from the staging tile
-  float* C;
+  float* C;          // may be NULL when only the split output is wanted
+  // optional fused operand preparation of the NEXT GEMM (projection -> similarity): split_out [N, 3M] receives
+  // scale*alpha*acc as [lo|hi|hi] for rows < split_rows0 (left operand) and [hi|lo|hi] for the others (right operand)
+  float* split_out;
+  int split_rows0;
+  float split_scale;
 };
 
 template <int BN>
@@ -250,6 +261,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
         tmem_wait_ld();
         if (row0 >= s.N || col0 >= s.M) continue;  // whole box outside the matrix (warp-uniform)
+        if (s.split_out) {
+          // fused drg_prep_operand(split=1) of the projected features: lane = row, 32 consecutive columns
+          const int row = row0 + lane;
+          if (row < s.N) {
+            const bool left = row < s.split_rows0;
+            float* o = s.split_out + (size_t)row * 3 * s.M + col0;
+            const float sc = s.alpha * s.split_scale;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (col0 + 4 * j < s.M) {  // M % 4 == 0 in this mode
+                float4 hi, lo;
+                const float x0 = __uint_as_float(r[4 * j + 0]) * sc, x1 = __uint_as_float(r[4 * j + 1]) * sc;
+                const float x2 = __uint_as_float(r[4 * j + 2]) * sc, x3 = __uint_as_float(r[4 * j + 3]) * sc;
+                hi.x = gemm_to_tf32_rna(x0); hi.y = gemm_to_tf32_rna(x1); hi.z = gemm_to_tf32_rna(x2); hi.w = gemm_to_tf32_rna(x3);
+                lo.x = gemm_to_tf32_rna(x0 - hi.x); lo.y = gemm_to_tf32_rna(x1 - hi.y);
+                lo.z = gemm_to_tf32_rna(x2 - hi.z); lo.w = gemm_to_tf32_rna(x3 - hi.w);
+                *reinterpret_cast<float4*>(o + 4 * j) = left ? lo : hi;
+                *reinterpret_cast<float4*>(o + s.M + 4 * j) = left ? hi : lo;
+                *reinterpret_cast<float4*>(o + 2 * s.M + 4 * j) = hi;
+              }
+            }
+          }
+          if (s.C == nullptr) continue;
+        }
         uint8_t* box = stg + (size_t)buf * GEMM_OUT_BOX_BYTES;
         if (!s.direct_store) {
           // the TMA store issued two boxes ago from this buffer must have finished READING it
@@ -371,12 +406,16 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
 
 using namespace drg;
 
-extern "C" int drg_gemm_nt_tf32(const float* A, const float* B, float* C, int batch, int N, int M, int K, float alpha,
-                                void* stream) {
-  DRG_CHECK_ARG(A && B && C, "A/B/C must be non-null");
+static int gemm_run(const float* A, const float* B, float* C, int batch, int N, int M, int K, float alpha, float* split_out,
+                    int split_rows0, float split_scale, void* stream) {
+  DRG_CHECK_ARG(A && B && (C || split_out), "A/B and an output must be non-null");
   DRG_CHECK_ARG(batch >= 1 && N >= 1 && M >= 1 && K >= 1, "batch, N, M, K must be >= 1");
   if (K % 4 != 0 || ((uintptr_t)A & 15u) || ((uintptr_t)B & 15u)) {
     set_error("gemm: K must be a multiple of 4 and A, B 16-byte aligned (TMA row pitch); got K=%d", K);
+    return DRG_ERR_UNSUPPORTED;
+  }
+  if (split_out && (M % 4 != 0 || batch != 1 || ((uintptr_t)split_out & 15u))) {
+    set_error("gemm: the split epilogue needs batch == 1, M %% 4 == 0 and a 16-byte aligned output");
     return DRG_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -391,7 +430,10 @@ extern "C" int drg_gemm_nt_tf32(const float* A, const float* B, float* C, int ba
   s.batch = batch;
   s.alpha = alpha;
   s.C = C;
-  s.direct_store = (M % 4 != 0 || ((uintptr_t)C & 15u)) ? 1 : 0;
+  s.split_out = split_out;
+  s.split_rows0 = split_rows0;
+  s.split_scale = split_scale;
+  s.direct_store = (C == nullptr || M % 4 != 0 || ((uintptr_t)C & 15u)) ? 1 : 0;
   CUtensorMap tA, tB, tC;
   if (!make_tmap(&tA, A, batch, N, K, GEMM_BM, GEMM_BK)) return DRG_ERR_CUDA;
   if (!make_tmap(&tB, B, batch, M, K, BN, GEMM_BK)) return DRG_ERR_CUDA;
@@ -405,4 +447,17 @@ extern "C" int drg_gemm_nt_tf32(const float* A, const float* B, float* C, int ba
     case 128: return launch_gemm<128>(tA, tB, tC, s, st);
     default: return launch_gemm<64>(tA, tB, tC, s, st);
   }
+}
+
+extern "C" int drg_gemm_nt_tf32(const float* A, const float* B, float* C, int batch, int N, int M, int K, float alpha,
+                                void* stream) {
+  DRG_CHECK_ARG(C != nullptr, "C is null");
+  return gemm_run(A, B, C, batch, N, M, K, alpha, nullptr, 0, 1.f, stream);
+}
+
+extern "C" int drg_project_split(const float* A, const float* W, int rows, int rows_left, int C_out, int K, float scale,
+                                 float* plain_out, float* split_out, void* stream) {
+  DRG_CHECK_ARG(split_out != nullptr, "split_out is null");
+  DRG_CHECK_ARG(rows_left >= 0 && rows_left <= rows, "rows_left out of range");
+  return gemm_run(A, W, plain_out, 1, rows, C_out, K, 1.f, split_out, rows_left, scale, stream);
 }

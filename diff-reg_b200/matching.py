@@ -104,12 +104,24 @@ class Matching(nn.Module):
     def similarity(self, src_feats, tgt_feats, src_pe=None, tgt_pe=None, pe_type="rotary", data=None):
         """Projection (same weight on both sides, matching.py:127-128), optional positional embedding,
         1/sqrt(C) scaling and the N x M contraction.  Returns sim [B,N,M]."""
-        fs = self.project(src_feats)
-        ft = self.project(tgt_feats)
-        C = fs.shape[-1]
+        C = self.src_proj.weight.shape[0]
         split = self.precision == "3xtf32"
         scale = 1.0 / (C ** .5)
         use_pe = (not self.entangled) and src_pe is not None
+        if split and not use_pe:
+            # fast path: one split launch for both feature sets, one projection GEMM whose epilogue already writes the
+            # scaled, split operands of the similarity GEMM (3 launches in all)
+            B, N, _ = src_feats.shape
+            a, b, plain = ops.project_pair_split(src_feats, tgt_feats, self._weight_operand(), C, scale, want_plain=data is not None)
+            if data is not None:
+                fs, ft = plain[:B * N].view(B, N, C), plain[B * N:].view(B, tgt_feats.shape[1], C)
+                data["src_feats_nopos"] = fs
+                data["tgt_feats_nopos"] = ft
+                data["src_feats"] = fs
+                data["tgt_feats"] = ft
+            return ops.gemm_nt(a, b)
+        fs = self.project(src_feats)
+        ft = self.project(tgt_feats)
         want = data is not None and use_pe
         a = ops.prep_operand(fs, scale, split, 0, pe=src_pe if use_pe else None, pe_type=pe_type if use_pe else None,
                              want_embedded=want)

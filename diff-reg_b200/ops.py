@@ -382,3 +382,26 @@ def sinkhorn_soft_procrustes(scores, alpha, iters, src_mask, tgt_mask, src_pcd, 
                             solution_mask=_ptr(out["solution_mask"]), src_warped=_ptr(out.get("src_warped")), K_max=k_max)
     check(lib.drg_sinkhorn_soft_procrustes(s, a, ws_s.data_ptr(), ws_s.numel(), ws_p.data_ptr(), ws_p.numel(), _stream()))
     return out
+
+
+def project_pair_split(src_feats, tgt_feats, w_operand, out_dim, scale, want_plain=False):
+    """Both projections of Matching.forward and the operand preparation of the similarity GEMM in two launches:
+    drg_prep_operand_pair (hi/lo split of src | tgt features) + drg_project_split (tensor-core GEMM against the prepared
+    weight, epilogue writes scale * (x W^T) already split: src rows as the left operand, tgt rows as the right one).
+    src_feats [B,N,C], tgt_feats [B,M,C], w_operand = prep_operand(W, split=True, pattern=1) [C_out, 3C].
+    Returns (src_operand [B,N,3*C_out], tgt_operand [B,M,3*C_out], plain [B*(N+M), C_out] or None)."""
+    _require_cuda(src_feats, tgt_feats, w_operand)
+    lib = load_library()
+    src_feats = _f32c(src_feats)
+    tgt_feats = _f32c(tgt_feats)
+    B, N, C = src_feats.shape
+    M = tgt_feats.shape[1]
+    dev = src_feats.device
+    rows_a, rows_b = B * N, B * M
+    a3 = torch.empty(rows_a + rows_b, 3 * C, dtype=torch.float32, device=dev)
+    check(lib.drg_prep_operand_pair(src_feats.data_ptr(), rows_a, 0, tgt_feats.data_ptr(), rows_b, 0, C, 1.0, 1, a3.data_ptr(), _stream()))
+    split = torch.empty(rows_a + rows_b, 3 * out_dim, dtype=torch.float32, device=dev)
+    plain = torch.empty(rows_a + rows_b, out_dim, dtype=torch.float32, device=dev) if want_plain else None
+    check(lib.drg_project_split(a3.data_ptr(), w_operand.data_ptr(), rows_a + rows_b, rows_a, out_dim, 3 * C, float(scale), _ptr(plain),
+                                split.data_ptr(), _stream()))
+    return split[:rows_a].view(B, N, 3 * out_dim), split[rows_a:].view(B, M, 3 * out_dim), plain

@@ -147,6 +147,17 @@ int drg_dual_softmax(const float* sim, const uint8_t* src_mask, const uint8_t* t
  * ------------------------------------------------------------------------------------ */
 int drg_gemm_nt_tf32(const float* A, const float* B, float* C, int batch, int N, int M, int K, float alpha, void* stream);
 
+/* Projection with the operand preparation of the similarity GEMM fused into its epilogue:
+ *   split_out[rows, 3*C_out] = split(scale * A . W^T), rows < rows_left as the left operand [lo|hi|hi], the others as the
+ *   right operand [hi|lo|hi]; plain_out (optional) [rows, C_out] = A . W^T (what the reference stores in data[...]).
+ *   replaces src_proj on both feature sets + the 1/sqrt(C) scaling  Diff-Reg-4dmatch/models/matching.py:127-128,144-145
+ *   A [rows, K], W [C_out, K] (both already split with drg_prep_operand / drg_prep_operand_pair when K = 3*C_in). */
+int drg_project_split(const float* A, const float* W, int rows, int rows_left, int C_out, int K, float scale, float* plain_out,
+                      float* split_out, void* stream);
+/* drg_prep_operand over two source tensors in one launch: out rows [0, rows_a) from in_a (pattern_a), then rows_b rows from in_b. */
+int drg_prep_operand_pair(const float* in_a, long long rows_a, int pattern_a, const float* in_b, long long rows_b, int pattern_b,
+                          int K, float scale, int split, float* out, void* stream);
+
 /* Operand preparation: positional embedding + scaling + optional hi/lo split.
  *   replaces VolPE.embed_pos / embed_rotary   Diff-Reg-4dmatch/models/position_encoding.py:26-46
  *   and       feat / feat.shape[-1] ** .5     Diff-Reg-4dmatch/models/matching.py:144-145
