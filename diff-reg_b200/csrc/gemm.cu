@@ -419,10 +419,28 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
     return DRG_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  // tile width: the widest N-tile that still gives every SM work
-  const long long t256 = (long long)batch * ((N + 127) / 128) * ((M + 255) / 256);
-  const long long t128 = (long long)batch * ((N + 127) / 128) * ((M + 127) / 128);
-  const int BN = (t256 >= 2 * NUM_SMS) ? 256 : (t128 >= NUM_SMS ? 128 : 64);
+  // Tile width by a two-term cost model (cycles): the MMA time of the busiest SM, and the operand traffic through L2
+  // (every tile re-reads its A and B k-blocks; measured on B200 the fabric delivers ~6.5 KB/clk to the SMs, which is
+  // what bounds both the 4096^2 similarity GEMM and the skinny projection GEMM -- profiles/r1_gemm_ncu.txt).
+  int BN = 64;
+  {
+    const double kblocks = (double)((K + GEMM_BK - 1) / GEMM_BK);
+    double best = 1e300;
+    for (int bn : {64, 128, 256}) {
+      const double tiles = (double)batch * ((N + 127) / 128) * ((M + bn - 1) / bn);
+      const double rounds = (double)((long long)((tiles + NUM_SMS - 1) / NUM_SMS));
+      const double t_mma = rounds * kblocks * 4.0 * (bn / 2.0);                    // 128 x bn x 8 tf32 MMA = bn/2 clk
+      const double t_l2 = tiles * kblocks * (double)((128 + bn) * GEMM_BK * 4) / 6500.0;
+      const double t = (t_mma > t_l2 ? t_mma : t_l2) + rounds * 1500.0;            // + per-tile epilogue exposure
+      if (t < best) {
+        best = t;
+        BN = bn;
+      }
+    }
+    // the split epilogue stores 3x the output with row-strided 16-byte stores from four warps only: it wants many
+    // small tiles in flight rather than few wide ones (measured: BN=256 was 10 us slower on the 8192 x 256 projection)
+    if (split_out) BN = 64;
+  }
   GemmShape s{};
   s.N = N;
   s.M = M;
