@@ -396,6 +396,49 @@ __global__ void __launch_bounds__(256) topk_collect_kernel(const ProcrParams p) 
   }
 }
 
+// potentials mode, aligned rows (M % 4 == 0): CTAs stride over rows, threads over column quads -- no index division,
+// u_i once per row, v and the target mask as 16-byte loads
+__global__ void __launch_bounds__(256) topk_collect_rows_kernel(const ProcrParams p) {
+  const int b = blockIdx.y;
+  const int N = p.N, M = p.M;
+  const size_t total = (size_t)N * M;
+  const float* x = p.scores + (size_t)b * total;
+  const unsigned long long lower = p.state[b].lower_key;
+  const float shift = p.pshift ? *p.pshift : 0.f;
+  const float norm = p.pbc[b].norm;
+  const float* u_b = p.pu + (size_t)b * p.ldu;
+  const float* v_b = p.pv + (size_t)b * p.ldv;
+  const int ncol_iters = (M + 1023) / 1024;  // all lanes iterate alike (warp-collective append)
+  for (int i = blockIdx.x; i < N; i += gridDim.x) {
+    const float ui = u_b[i];
+    const bool row_ok = !p.apply_mask || p.src_mask[(size_t)b * N + i];
+    for (int k = 0; k < ncol_iters; ++k) {
+      const int j = 4 * (int)threadIdx.x + 1024 * k;
+      bool take[4] = {false, false, false, false};
+      unsigned int key[4] = {0u, 0u, 0u, 0u};
+      const unsigned int flat0 = (unsigned int)((size_t)i * M + j);
+      if (j < M) {
+        const float4 z = *reinterpret_cast<const float4*>(x + (size_t)i * M + j);
+        const float4 vj = *reinterpret_cast<const float4*>(v_b + j);
+        bool ok[4] = {row_ok, row_ok, row_ok, row_ok};
+        if (p.apply_mask) {
+          const uchar4 tm = *reinterpret_cast<const uchar4*>(p.tgt_mask + (size_t)b * M + j);
+          ok[0] = row_ok && tm.x; ok[1] = row_ok && tm.y; ok[2] = row_ok && tm.z; ok[3] = row_ok && tm.w;
+        }
+        const float zz[4] = {z.x, z.y, z.z, z.w}, vv[4] = {vj.x, vj.y, vj.z, vj.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float zs = ok[e] ? (zz[e] - shift) : -INFINITY;
+          const float c = ex2((((zs + ui) + vv[e]) - norm) * LOG2E);
+          key[e] = float_to_ordered(c);
+          take[e] = make_key64(key[e], flat0 + e) >= lower;
+        }
+      }
+      append_candidates(p, b, total, take, key, flat0);
+    }
+  }
+}
+
 // ---- 5. select + Kabsch + warp ----------------------------------------------------------------
 // Block-wide sums of K fp32 per-thread partials: fp32 warp shuffles (pairwise), then the per-warp partials are added
 // in fp64 in a fixed order (bitwise reproducible) and everybody reads the totals.  fp64 vector math is slow on this
@@ -909,7 +952,15 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
   if ((long long)gx * 256 > n4) gx = (int)((n4 + 255) / 256);
   {
     ProfScope prof_scope(PROF_TOPK_COLLECT, st);
+    if (!p.conf && (M % 4) == 0 && ((((uintptr_t)p.scores) | ((uintptr_t)p.pv) | ((uintptr_t)p.tgt_mask)) & 15u) == 0 &&
+      ((p.ldv & 3) == 0)) {
+    int gr = (NUM_SMS * 8) / B;
+    if (gr < 1) gr = 1;
+    if (gr > N) gr = N;
+    topk_collect_rows_kernel<<<dim3(gr, B), 256, 0, st>>>(p);
+  } else {
     topk_collect_kernel<<<dim3(gx, B), 256, 0, st>>>(p);
+  }
   }
   DRG_LAUNCH_CHECK();
   {
