@@ -94,7 +94,7 @@ typedef struct drg_sinkhorn_args {
   float k_x0, k_xt, sigma; /* x_next = k_x0*conf + k_xt*x_t + sigma*noise                        */
   float* x_min;            /* optional device scalar: min over valid entries of x_next is folded
                               in with atomicMin (caller initialises to +inf)                     */
-  int gen_noise;           /* 1 and noise == NULL: draw the N(0,1) noise in the kernel (Philox4x32-10
+  int gen_noise;           /* 1 and noise == NULL: draw the N(0,1) noise in the kernel (Philox4x32-7
                               + Box-Muller), replacing torch.randn_like(x) of pipeline.py:188    */
   unsigned long long noise_seed;   /* Philox key                                                  */
   unsigned long long noise_offset; /* high half of the Philox counter: use a new value per step   */
