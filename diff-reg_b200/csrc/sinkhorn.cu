@@ -1030,8 +1030,14 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
+// 768 threads: 15 ROW warps + 1 producer warp + 8 COLUMN warps (thread -> KQ column quads, KQ = M / 1024 rounded up), so that
+// every thread may use 85 registers: with 1024 threads the 64-register cap put spills inside the row loop.
+constexpr int PS_THREADS = 768;
+constexpr int PS_COL_BEGIN = 512;
+constexpr int PS_COL_NTHREADS = PS_THREADS - PS_COL_BEGIN;
+
 template <int R, int KQ, bool ROWFULL, bool COLFULL>
-__global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhParams p, const int iters, unsigned int* gsync) {
+__global__ void __launch_bounds__(PS_THREADS, 1) skh_persist_kernel(const SkhParams p, const int iters, unsigned int* gsync) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = p.N, M = p.M;
   const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x;
@@ -1054,7 +1060,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
   uint64_t* u_ready = full + WS_MAX_STAGES;
   uint64_t* stage_free = u_ready + WS_MAX_STAGES;
   __shared__ int cnt_s[2];
-  __shared__ float2 comb[(WS_THREADS / 32) * 32];  // merge scratch: [32 warps][32 columns]
+  __shared__ float2 comb[(PS_THREADS / 32) * 32];  // merge scratch: [32 warps][32 columns]
+  __shared__ float lse_prev_s[1024];               // log2-domain row log-sum-exp of the previous iteration, per row slot
 
 #define DRG_STAMP(slot) do { if (p.dbg_times && g == 0 && b == 0) p.dbg_times[(slot)] = clock64(); } while (0)
   const float* sc_b = p.scores + (size_t)b * N * M;
@@ -1062,13 +1069,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
   const float shift = p.shift ? *p.shift : 0.f;
   const float alpha = *p.alpha;
   unsigned int* gcount = gsync + b;
+  unsigned int* dv_slots = gsync + gridDim.y + 2 * b;  // max |v_new - v_old| * log2(e) of the last two merges (float bits)
 
   if (tid == 0) DRG_STAMP(0);
   if (tid == 0) {
     for (int s = 0; s < nstage; ++s) {
       mbar_init(&full[s], 1u);
       mbar_init(&u_ready[s], (uint32_t)R);
-      mbar_init(&stage_free[s], (uint32_t)(R + WS_COL_THREADS / 32));
+      mbar_init(&stage_free[s], (uint32_t)(R + PS_COL_NTHREADS / 32));
     }
     fence_mbar_init();
     cnt_s[0] = cnt_s[1] = 0;
@@ -1092,8 +1100,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
 
   // ---- mask counts -> normalisation constants (matching.py:14-15, 24-27)
   {
-    int cs = count_mask_bytes(p.src_mask + (size_t)b * N, N, tid, WS_THREADS);
-    int ct = count_mask_bytes(p.tgt_mask + (size_t)b * M, M, tid, WS_THREADS);
+    int cs = count_mask_bytes(p.src_mask + (size_t)b * N, N, tid, PS_THREADS);
+    int ct = count_mask_bytes(p.tgt_mask + (size_t)b * M, M, tid, PS_THREADS);
     cs = __reduce_add_sync(0xffffffffu, cs);
     ct = __reduce_add_sync(0xffffffffu, ct);
     if (lane == 0) {
@@ -1125,11 +1133,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
   if (tid == 0) DRG_STAMP(1);
   for (int it = 0; it < iters; ++it) {
     if (tid == 0) DRG_STAMP(10 + it * 100 + 0);
+    // Scaled ("fast") pass: once a row's log-sum-exp of the previous iteration is known it is used as the reference of
+    // this iteration's exponentials, e_ij = 2^(x_ij - ref_i): no running maximum, and the column pass reuses e_ij
+    // (written back over the slab) with one FMA per element instead of a second exponential.  Exactly as accurate as
+    // the log-domain pass while the reference is within ~2^50 of the new value, which is guaranteed when the column
+    // potentials moved by less than 50 (log2 units) in the last merge -- checked here, identically on every CTA;
+    // otherwise (and in the first iteration) the log-domain pass below runs.
+    bool fast = false;
+    if (it >= 1 && nsl * R <= 1024 && alpha >= -20.f && !(p.dbg & 8)) {
+      const float dv = __uint_as_float(ld_acquire_u32(dv_slots + ((it - 1) & 1)));
+      fast = dv <= 50.f;
+    }
+    if (p.dbg_times && g == 0 && b == 0 && tid == 0) {
+      p.dbg_times[400 + it] = fast ? 1 : 0;
+      p.dbg_times[410 + it] = (it >= 1) ? (long long)ld_acquire_u32(dv_slots + ((it - 1) & 1)) : -1;
+    }
+    const float norm2 = bc.norm * LOG2E;
     // ---- prologue: column potentials into shared memory (log2 domain), dustbin-row potential
     float uN;
     if (it == 0) {
       // v = 0: LSE over M+1 zeros = log(M+1)
-      for (int j = tid; j <= M; j += WS_THREADS) {
+      for (int j = tid; j <= M; j += PS_THREADS) {
         float v2;
         if (j < M) {
           v2 = (0.f - shift) * LOG2E;
@@ -1143,12 +1167,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
     } else {
       const float* v_b = p.v + (size_t)b * p.ldv;
       // one read of v (written by other SMs in the merge: L2 only), kept in registers for both passes
-      constexpr int VPT = (4096 + 1 + WS_THREADS - 1) / WS_THREADS;  // M <= 4096
+      constexpr int VPT = (4096 + 1 + PS_THREADS - 1) / PS_THREADS;  // M <= 4096
       float vr[VPT];
       float mloc = NEG_BIG;
 #pragma unroll
       for (int k = 0; k < VPT; ++k) {
-        const int j = tid + k * WS_THREADS;
+        const int j = tid + k * PS_THREADS;
         vr[k] = (j <= M) ? __ldcg(v_b + j) : -INFINITY;
         mloc = fmaxf(mloc, vr[k] * LOG2E);
       }
@@ -1157,11 +1181,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
       __syncthreads();
       float mall = red_s[0];
 #pragma unroll
-      for (int w = 1; w < WS_THREADS / 32; ++w) mall = fmaxf(mall, red_s[w]);
+      for (int w = 1; w < PS_THREADS / 32; ++w) mall = fmaxf(mall, red_s[w]);
       float sloc = 0.f;
 #pragma unroll
       for (int k = 0; k < VPT; ++k) {
-        const int j = tid + k * WS_THREADS;
+        const int j = tid + k * PS_THREADS;
         if (j <= M) {
           const float vj = vr[k];
           sloc += ex2(vj * LOG2E - mall);
@@ -1180,11 +1204,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
       __syncthreads();
       float sall = 0.f;
 #pragma unroll
-      for (int w = 0; w < WS_THREADS / 32; ++w) sall += red_s[32 + w];
+      for (int w = 0; w < PS_THREADS / 32; ++w) sall += red_s[32 + w];
       uN = bc.log_mu_bin - (alpha + (mall + lg2(sall)) * LN2);
     }
     if (g == 0 && tid == 0) p.u[(size_t)b * p.ldu + N] = uN;
-    for (int j = M + 1 + tid; j < Mv; j += WS_THREADS) v2_s[j] = -INFINITY;
+    for (int j = M + 1 + tid; j < Mv; j += PS_THREADS) v2_s[j] = -INFINITY;
     __syncthreads();
     if (tid == 0) DRG_STAMP(10 + it * 100 + 1);
 
@@ -1205,6 +1229,40 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
           float u2 = -INFINITY;
           if (i < N) {
             const bool row_live = !(p.apply_mask && !p.src_mask[(size_t)b * N + i]);
+            const bool src_ok = !p.apply_mask || p.src_mask[(size_t)b * N + i];
+            float rowlse2, ui;
+            if (fast) {
+              float* row_lane = stage0 + (size_t)r_st * stage_floats + (size_t)r * M + 4 * lane;
+              const float mhat = lse_prev_s[q];
+              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+              if (row_live) {
+                for (int cb = 0; cb < M; cb += 512) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    if (ROWFULL || cb + 4 * lane + 128 * k < M) {
+                      const float4 z = *reinterpret_cast<const float4*>(row_lane + cb + 128 * k);
+                      const float4 vv = *reinterpret_cast<const float4*>(v2_lane + cb + 128 * k);
+                      float4 e;
+                      e.x = ex2(fmaf(z.x, zs, vv.x) - mhat);
+                      e.y = ex2(fmaf(z.y, zs, vv.y) - mhat);
+                      e.z = ex2(fmaf(z.z, zs, vv.z) - mhat);
+                      e.w = ex2(fmaf(z.w, zs, vv.w) - mhat);
+                      *reinterpret_cast<float4*>(row_lane + cb + 128 * k) = e;  // the column pass reads e, not z
+                      a0 += e.x;
+                      a1 += e.y;
+                      a2 += e.z;
+                      a3 += e.w;
+                    }
+                  }
+                }
+              } else {
+                for (int cb = 4 * lane; cb < M; cb += 128) *reinterpret_cast<float4*>(row_lane - 4 * lane + cb) = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              const float srow = warp_sum((a0 + a1) + (a2 + a3)) + ex2(dust2 - mhat);  // + dustbin column entry
+              rowlse2 = mhat + lg2(srow);
+              ui = bc.norm - rowlse2 * LN2;
+              u2 = src_ok ? 1.f / srow : 0.f;  // the column pass multiplies by w_i = 2^(ref_i + u_i log2e - norm2) = 1 / srow
+            } else {
             float m_l = NEG_BIG, s_l = 0.f;
             if (row_live) {
               const float* row_lane = stage0 + (size_t)r_st * stage_floats + (size_t)r * M + 4 * lane;
@@ -1245,13 +1303,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
             float srow = warp_sum(s_l * ex2(m_l - mrow));
             const float mm = fmaxf(mrow, dust2);
             srow = srow * ex2(mrow - mm) + ex2(dust2 - mm);  // + dustbin column entry alpha + v_M
-            const float ui = bc.norm - (mm + lg2(srow)) * LN2;
-            const bool src_ok = !p.apply_mask || p.src_mask[(size_t)b * N + i];
+            rowlse2 = mm + lg2(srow);
+            ui = bc.norm - rowlse2 * LN2;
             u2 = src_ok ? (ui - shift) * LOG2E : -INFINITY;  // column pass sees (S - shift) + u
+            }
             if (lane == 0) {
               p.u[(size_t)b * p.ldu + i] = ui;
               lse_add_value(uacc, ui * LOG2E);
+              if (q < 1024) lse_prev_s[q] = rowlse2;
             }
+          } else if (fast) {
+            u2 = 0.f;  // padded row slot: weight zero
           }
           if (lane == 0) {
             u2_s[r_st * 16 + r] = u2;
@@ -1284,7 +1346,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
       }
     } else {
       // =========================== COLUMN warps ===========================
-      const int ct = tid - WS_COL_THREADS;  // 0..511
+      const int ct = tid - PS_COL_BEGIN;  // 0..511
       float cm[KQ * 4], cs[KQ * 4];
 #pragma unroll
       for (int e = 0; e < KQ * 4; ++e) {
@@ -1296,13 +1358,31 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
         const int rows = min(R, N - i0);
         const float* slab = stage0 + (size_t)c_st * stage_floats;
         mbar_wait_sleep(&u_ready[c_st], c_ph, 500u);
-        if (tid == WS_COL_THREADS) DRG_STAMP(10 + it * 100 + 40 + sl);
+        if (tid == PS_COL_BEGIN) DRG_STAMP(10 + it * 100 + 40 + sl);
         float u2r[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) u2r[r] = u2_s[c_st * 16 + r];  // rows beyond `rows` hold -inf
+        for (int r = 0; r < R; ++r) u2r[r] = u2_s[c_st * 16 + r];  // rows beyond `rows` hold -inf (0 in the scaled pass)
+        if (fast) {
+#pragma unroll
+          for (int k = 0; k < KQ; ++k) {
+            const int c = 4 * (ct + PS_COL_NTHREADS * k);
+            if (COLFULL || c < M) {
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                if (r < rows) {
+                  const float4 e = *reinterpret_cast<const float4*>(slab + (size_t)r * M + c);
+                  cs[4 * k + 0] = fmaf(e.x, u2r[r], cs[4 * k + 0]);
+                  cs[4 * k + 1] = fmaf(e.y, u2r[r], cs[4 * k + 1]);
+                  cs[4 * k + 2] = fmaf(e.z, u2r[r], cs[4 * k + 2]);
+                  cs[4 * k + 3] = fmaf(e.w, u2r[r], cs[4 * k + 3]);
+                }
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int k = 0; k < KQ; ++k) {
-          const int c = 4 * (ct + WS_COL_THREADS * k);
+          const int c = 4 * (ct + PS_COL_NTHREADS * k);
           if (COLFULL || c < M) {
             float x[R][4];
             float mx[4] = {NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG};
@@ -1335,18 +1415,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
             }
           }
         }
+        }
         __syncwarp();
-        if (tid == WS_COL_THREADS) DRG_STAMP(10 + it * 100 + 60 + sl);
+        if (tid == PS_COL_BEGIN) DRG_STAMP(10 + it * 100 + 60 + sl);
         if (lane == 0) mbar_arrive(&stage_free[c_st]);
         if (++c_st == nstage) {
           c_st = 0;
           c_ph ^= 1u;
         }
       }
+      if (fast) {
+        // sum_i 2^(x_ij + u_i log2e) = 2^(norm2 - v_j log2e) * sum_i e_ij w_i   (v2_s holds (v_j - shift) log2e)
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (ct + PS_COL_NTHREADS * k);
+          if (COLFULL || c < M) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float v2j = v2_s[c + e];
+              cm[4 * k + e] = (v2j > -INFINITY) ? (norm2 - v2j - shift * LOG2E) : NEG_BIG;
+              if (!(v2j > -INFINITY)) cs[4 * k + e] = 0.f;
+            }
+          }
+        }
+      }
       float2* cp = p.colpart + ((size_t)b * G + g) * M;
 #pragma unroll
       for (int k = 0; k < KQ; ++k) {
-        const int c = 4 * (ct + WS_COL_THREADS * k);
+        const int c = 4 * (ct + PS_COL_NTHREADS * k);
         if (COLFULL || c < M) {
           *reinterpret_cast<float4*>(cp + c) = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
           *reinterpret_cast<float4*>(cp + c + 2) = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
@@ -1368,6 +1464,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
     //      split the G partials, and warp 0 combines the 32 per-warp results through shared memory        (skh_col_kernel)
     {
       float* v_b = p.v + (size_t)b * p.ldv;
+      if (g == 0 && tid == 0) dv_slots[(it + 1) & 1] = 0u;  // nobody reads or writes that slot during this merge
+      float dv_loc = 0.f;
       for (int j0 = g * 32; j0 <= M; j0 += G * 32) {
         const int j = j0 + lane;
         const bool in_range = j <= M;
@@ -1377,38 +1475,49 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skh_persist_kernel(const SkhPar
         if (col_ok) {
           const float2* src = is_bin ? (p.upart + (size_t)b * G) : (p.colpart + (size_t)b * G * M + j);
           const size_t gstride = is_bin ? 1 : (size_t)M;
-          float2 q[(NUM_SMS + 31) / 32];
+          constexpr int NW = PS_THREADS / 32;               // the warps of the CTA split the G partials
+          constexpr int PER_WARP = (NUM_SMS + NW - 1) / NW;
+          float2 q[PER_WARP];
 #pragma unroll
-          for (int k = 0; k < (NUM_SMS + 31) / 32; ++k) {
-            const int gg = warp + 32 * k;
+          for (int k = 0; k < PER_WARP; ++k) {
+            const int gg = warp + NW * k;
             q[k] = (gg < G) ? __ldcg(src + (size_t)gg * gstride) : make_float2(NEG_BIG, 0.f);
             m = fmaxf(m, q[k].x);
           }
 #pragma unroll
-          for (int k = 0; k < (NUM_SMS + 31) / 32; ++k) sum += q[k].y * ex2(q[k].x - m);
+          for (int k = 0; k < PER_WARP; ++k) sum += q[k].y * ex2(q[k].x - m);
         }
         comb[warp * 32 + lane] = make_float2(m, sum);
         __syncthreads();
         if (warp == 0 && in_range) {
           float mm = NEG_BIG;
 #pragma unroll
-          for (int w = 0; w < WS_THREADS / 32; ++w) mm = fmaxf(mm, comb[w * 32 + lane].x);
+          for (int w = 0; w < PS_THREADS / 32; ++w) mm = fmaxf(mm, comb[w * 32 + lane].x);
           float ss = 0.f;
 #pragma unroll
-          for (int w = 0; w < WS_THREADS / 32; ++w) {
+          for (int w = 0; w < PS_THREADS / 32; ++w) {
             const float2 c2 = comb[w * 32 + lane];
             ss += c2.y * ex2(c2.x - mm);
           }
           LseAcc a{mm, ss};
+          const float v_old = (it == 0) ? 0.f : __ldcg(v_b + j);
+          float v_new;
           if (!is_bin) {
             lse_add_value(a, (alpha + uN) * LOG2E);  // dustbin row entry
-            v_b[j] = bc.norm - lse_value(a) * LN2;
+            v_new = bc.norm - lse_value(a) * LN2;
           } else {
             lse_add_value(a, uN * LOG2E);  // c_M = alpha + LSE(u[0..N])
-            v_b[M] = bc.log_nu_bin - (alpha + lse_value(a) * LN2);
+            v_new = bc.log_nu_bin - (alpha + lse_value(a) * LN2);
           }
+          v_b[j] = v_new;
+          const float d = fabsf(v_new - v_old) * LOG2E;
+          dv_loc = fmaxf(dv_loc, (d == d) ? d : INFINITY);  // NaN counts as unbounded
         }
         __syncthreads();
+      }
+      if (warp == 0) {
+        dv_loc = warp_max(dv_loc);
+        if (lane == 0 && dv_loc > 0.f) atomicMax(dv_slots + (it & 1), __float_as_uint(dv_loc));
       }
     }
     if (tid == 0) DRG_STAMP(10 + it * 100 + 5);
@@ -1890,7 +1999,7 @@ static SkhWorkspace carve(void* ws, int B, int N, int M, int G) {
   w.v = (float*)take(sizeof(float) * (size_t)B * pitch4(M + 1));
   w.colpart = (float2*)take(sizeof(float2) * (size_t)B * G * M);
   w.upart = (float2*)take(sizeof(float2) * (size_t)B * G);
-  w.gsync = (unsigned int*)take(sizeof(unsigned int) * (size_t)B);
+  w.gsync = (unsigned int*)take(sizeof(unsigned int) * (size_t)B * 3);  // [B] barrier counters + [B][2] dv slots
   w.total = off;
   return w;
 }
@@ -2058,8 +2167,9 @@ static SkhPlanWS make_plan_ws(int B, int N, int M) {
   pl.KQ = (M <= 2048) ? 1 : 2;
   const size_t Mv = (size_t)((M + 1 + 3) & ~3);
   const size_t stage_bytes = (size_t)R * M * 4;
-  const size_t fixed = Mv * 4 + WS_MAX_STAGES * 16 * 4 + 64 * 4 + 16 * 8 + 3 * WS_MAX_STAGES * 8 + 128 + 8192 + 64 /* static: merge scratch */;
-  int nstage = (int)((SKH_SMEM_LIMIT - fixed) / stage_bytes);
+  const size_t fixed = Mv * 4 + WS_MAX_STAGES * 16 * 4 + 64 * 4 + 16 * 8 + 3 * WS_MAX_STAGES * 8 + 128;  // dynamic, besides the ring
+  const size_t static_smem = 8192 + 4096 + 512;  // __shared__ arrays of skh_persist_kernel: merge scratch, row references, counters
+  int nstage = (int)((SKH_SMEM_LIMIT - fixed - static_smem) / stage_bytes);
   if (nstage > WS_MAX_STAGES) nstage = WS_MAX_STAGES;
   if (nstage < 2) return pl;
   pl.nstage = nstage;
@@ -2113,21 +2223,23 @@ static cudaError_t launch_persist_t(const SkhParams& p, const SkhPlanWS& pl, int
   if (e != cudaSuccess) return e;
   SkhParams pp = p;
   void* args[] = {(void*)&pp, (void*)&iters, (void*)&gsync};
-  return cudaLaunchCooperativeKernel((const void*)skh_persist_kernel<R, KQ, ROWFULL, COLFULL>, dim3(pl.G, p.B), dim3(WS_THREADS), args,
+  return cudaLaunchCooperativeKernel((const void*)skh_persist_kernel<R, KQ, ROWFULL, COLFULL>, dim3(pl.G, p.B), dim3(PS_THREADS), args,
                                      pl.smem, st);
 }
 
 static cudaError_t launch_persist(const SkhParams& p, const SkhPlanWS& pl, int iters, unsigned int* gsync, cudaStream_t st) {
   const bool rowfull = (p.M % 1024) == 0;
-  const bool colfull = p.M == 2048 * pl.KQ;
-#define DRG_PS_CASE(r, kq)                                                                            \
-  if (pl.R == r && pl.KQ == kq) {                                                                     \
-    if (rowfull && colfull) return launch_persist_t<r, kq, true, true>(p, pl, iters, gsync, st);      \
-    if (rowfull) return launch_persist_t<r, kq, true, false>(p, pl, iters, gsync, st);                \
-    return launch_persist_t<r, kq, false, false>(p, pl, iters, gsync, st);                            \
+  const int kq = (p.M <= 1024) ? 1 : (p.M <= 2048) ? 2 : 4;  // column quads per column thread (256 column threads)
+  const bool colfull = p.M == 1024 * kq;
+#define DRG_PS_CASE(r, q)                                                                            \
+  if (pl.R == r && kq == q) {                                                                        \
+    if (rowfull && colfull) return launch_persist_t<r, q, true, true>(p, pl, iters, gsync, st);      \
+    if (rowfull) return launch_persist_t<r, q, true, false>(p, pl, iters, gsync, st);                \
+    return launch_persist_t<r, q, false, false>(p, pl, iters, gsync, st);                            \
   }
   DRG_PS_CASE(1, 1) DRG_PS_CASE(2, 1) DRG_PS_CASE(4, 1) DRG_PS_CASE(8, 1)
-  DRG_PS_CASE(1, 2) DRG_PS_CASE(2, 2) DRG_PS_CASE(4, 2)
+  DRG_PS_CASE(1, 2) DRG_PS_CASE(2, 2) DRG_PS_CASE(4, 2) DRG_PS_CASE(8, 2)
+  DRG_PS_CASE(1, 4) DRG_PS_CASE(2, 4) DRG_PS_CASE(4, 4)
 #undef DRG_PS_CASE
   return cudaErrorInvalidConfiguration;
 }
@@ -2251,7 +2363,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   const int iters = run == SKH_SHARD_LOCAL ? 1 : run == SKH_SHARD_FINAL ? 0 : dual ? 1 : a->iters;
   dim3 cgrid((M + 1 + 31) / 32, B);
   if (persist) {
-    DRG_CUDA(cudaMemsetAsync(w.gsync, 0, sizeof(unsigned int) * B, st));
+    DRG_CUDA(cudaMemsetAsync(w.gsync, 0, sizeof(unsigned int) * B * 3, st));
     cudaError_t e;
     {
       ProfScope prof_scope(PROF_SKH_ITER, st);

@@ -28,3 +28,6 @@ for it in range(3):
     print(" row warp0: full-wait passed per slab:", [rel(base + 20 + k) for k in range(8)])
     print(" col warp16: u_ready passed per slab: ", [rel(base + 40 + k) for k in range(8)])
     print(" col warp16: slab done:               ", [rel(base + 60 + k) for k in range(8)])
+
+import struct
+print("fast flags:", t[400:403], "dv bits:", [hex(x & 0xffffffff) for x in t[410:413]], [struct.unpack("f", struct.pack("I", x & 0xffffffff))[0] if x >= 0 else None for x in t[410:413]])
