@@ -1528,6 +1528,507 @@ __global__ void __launch_bounds__(PS_THREADS, 1) skh_persist_kernel(const SkhPar
 }
 
 // ---------------------------------------------------------------------------------------
+// Register-slab persistent Sinkhorn (M % 4 == 0, M <= 4096, G*B <= #SMs)
+//   skh_persist_kernel above hands every element from the row warps to the column warps through shared memory and
+//   is bound by shared-memory bandwidth (TMA write + row read + potentials read + e write + column read: 16-20 bytes
+//   per element against 128 B/clk/SM).  Here shared memory is only the landing zone of the TMA ring (4 B written +
+//   4 B read per element): a CTA is two row groups of 256 threads, a thread owns KQ column quads (columns
+//   4*(ct + 256k) .. +3) and pulls RR rows x KQ quads of a mini-slab into registers, where BOTH directions are
+//   computed.  Row log-sum-exps are reduced across the 256 threads of the group (warp shuffles + 8 partials through
+//   shared memory + ONE named barrier per mini-slab); the column log-sum-exp partials stay in the thread's registers
+//   for the whole pass.  The ring holds up to ~190 KB of loads in flight per SM (deep enough for the L2 / HBM
+//   latency; loading straight into registers one mini-slab ahead was latency-bound at 5.6 TB/s); a stage is re-armed
+//   by the group that consumed it right after its barrier, so no "empty" barriers are needed.
+//   Scaled pass (iterations >= 1, see skh_persist_kernel): e_ij = 2^(x_ij - ref_i) is computed once and used for both
+//   directions -- 1 MUFU, 2 FFMA, 2 FADD per element.
+//   Iteration structure (prologue, grid barrier, merge of the per-CTA column partials, grid barrier) as above.
+// ---------------------------------------------------------------------------------------
+constexpr int P2_THREADS = 512;
+constexpr int P2_TPR = 256;            // threads per row group
+constexpr int P2_GW = P2_TPR / 32;     // warps per row group
+constexpr int P2_MAX_STAGES = 8;
+
+__device__ __forceinline__ float4 ldg_stream4(const float* ptr) {
+  float4 r;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr));
+  return r;
+}
+__device__ __forceinline__ void group_barrier(int rg) { asm volatile("bar.sync %0, %1;" ::"r"(rg + 1), "r"(P2_TPR) : "memory"); }
+
+template <int KQ, int RR, bool FULL>
+__global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhParams p, const int iters, unsigned int* gsync) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = p.N, M = p.M;
+  const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rg = tid >> 8, ct = tid & (P2_TPR - 1), wg = warp & (P2_GW - 1);
+  const int row0 = (int)(((long long)N * g) / G), row1 = (int)(((long long)N * (g + 1)) / G);
+  const int nrows = row1 - row0;              // <= 1024 (host check)
+  const int ns = (nrows + RR - 1) / RR;       // mini-slabs of this CTA; row group rg takes s = rg, rg + 2, ...
+
+  const int Mv = (M + 1 + 3) & ~3;
+  float* v2_s = reinterpret_cast<float*>(smem_raw);             // [Mv]  column potentials, log2 domain, minus the shift
+  float* lse_prev_s = v2_s + Mv;                                // [1024] row log-sum-exp (log2) of the previous iteration
+  float* red_part = lse_prev_s + 1024;                          // [2 buffers][2 groups][8 rows][8 warps]
+  float* red_s = red_part + 256;                                // [64]
+  float2* upart_s = reinterpret_cast<float2*>(red_s + 64);      // [2] (+2 pad)
+  float2* comb = upart_s + 4;                                   // [16 warps][32] merge scratch
+  uint64_t* full = reinterpret_cast<uint64_t*>(comb + (P2_THREADS / 32) * 32);  // [P2_MAX_STAGES]
+  float* ring = reinterpret_cast<float*>(full + P2_MAX_STAGES);  // [D][RR * M] TMA landing zone, shared by the two row groups
+  float2* xcomb = reinterpret_cast<float2*>(ring);              // [KQ*4][256] column partials of row group 1 (pass is over: ring idle)
+  const int D = p.nstage;
+  const int stage_floats = RR * M;
+  __shared__ int cnt_s[2];
+
+#define DRG_STAMP(slot) do { if (p.dbg_times && g == 0 && b == 0) p.dbg_times[(slot)] = clock64(); } while (0)
+  const float* sc_b = p.scores + (size_t)b * N * M;
+  const float zs = p.zscale2;
+  const float shift = p.shift ? *p.shift : 0.f;
+  const float shift2 = shift * LOG2E;
+  const float alpha = *p.alpha;
+  unsigned int* gcount = gsync + b;
+  unsigned int* dv_slots = gsync + gridDim.y + 2 * b;
+
+  // stream of mini-slabs: element T = it * ns + s lands in stage T % D; row group (s & 1) consumes it
+  auto issue_slab = [&](int it_, int s_) {
+    const int T = it_ * ns + s_;
+    const int stg = T % D;
+    const int i0 = row0 + s_ * RR;
+    const uint32_t bytes = (uint32_t)min(RR, row1 - i0) * (uint32_t)M * 4u;
+    fence_proxy_async();
+    mbar_arrive_expect_tx(&full[stg], bytes);
+    tma_bulk_g2s(ring + (size_t)stg * stage_floats, sc_b + (size_t)i0 * M, bytes, &full[stg]);
+  };
+  if (tid == 0) {
+    DRG_STAMP(0);
+    cnt_s[0] = cnt_s[1] = 0;
+    for (int s = 0; s < D; ++s) mbar_init(&full[s], 1u);
+    fence_mbar_init();
+    if (iters > 0)
+      for (int s = 0; s < D && s < ns; ++s) issue_slab(0, s);
+  }
+  __syncthreads();
+  {
+    int cs = count_mask_bytes(p.src_mask + (size_t)b * N, N, tid, P2_THREADS);
+    int ctg = count_mask_bytes(p.tgt_mask + (size_t)b * M, M, tid, P2_THREADS);
+    cs = __reduce_add_sync(0xffffffffu, cs);
+    ctg = __reduce_add_sync(0xffffffffu, ctg);
+    if (lane == 0) {
+      if (cs) atomicAdd(&cnt_s[0], cs);
+      if (ctg) atomicAdd(&cnt_s[1], ctg);
+    }
+  }
+  __syncthreads();
+  SkhConst bc;
+  {
+    const float ms = (float)cnt_s[0], nsv = (float)cnt_s[1];
+    bc.norm = -logf(ms + nsv);
+    bc.log_mu_bin = logf(nsv) + bc.norm;
+    bc.log_nu_bin = logf(ms) + bc.norm;
+    bc.pad = 0.f;
+    if (g == 0 && tid == 0) p.bc_out[b] = bc;
+  }
+  const float norm2 = bc.norm * LOG2E;
+  unsigned int barriers_done = 0;
+  const uint8_t* smask = p.src_mask + (size_t)b * N;
+
+  if (tid == 0) DRG_STAMP(1);
+  for (int it = 0; it < iters; ++it) {
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 0);
+    bool fast = false;
+    if (it >= 1 && alpha >= -20.f && !(p.dbg & 8)) {
+      const float dv = __uint_as_float(ld_acquire_u32(dv_slots + ((it - 1) & 1)));
+      fast = dv <= 50.f;
+    }
+    if (p.dbg_times && g == 0 && b == 0 && tid == 0) p.dbg_times[400 + it] = fast ? 1 : 0;
+
+    // ---- prologue: column potentials into shared memory (log2 domain), dustbin-row potential
+    float uN;
+    if (it == 0) {
+      for (int j = tid; j <= M; j += P2_THREADS) {
+        float v2;
+        if (j < M) {
+          v2 = -shift2;
+          if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
+        } else {
+          v2 = alpha * LOG2E;
+        }
+        v2_s[j] = v2;
+      }
+      uN = bc.log_mu_bin - (alpha + logf((float)(M + 1)));
+    } else {
+      const float* v_b = p.v + (size_t)b * p.ldv;
+      constexpr int VPT = (4096 + 1 + P2_THREADS - 1) / P2_THREADS;  // M <= 4096
+      float vr[VPT];
+      float mloc = NEG_BIG;
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) {
+        const int j = tid + k * P2_THREADS;
+        vr[k] = (j <= M) ? __ldcg(v_b + j) : -INFINITY;
+        mloc = fmaxf(mloc, vr[k] * LOG2E);
+      }
+      mloc = warp_max(mloc);
+      if (lane == 0) red_s[warp] = mloc;
+      __syncthreads();
+      float mall = red_s[0];
+#pragma unroll
+      for (int w = 1; w < P2_THREADS / 32; ++w) mall = fmaxf(mall, red_s[w]);
+      float sloc = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) {
+        const int j = tid + k * P2_THREADS;
+        if (j <= M) {
+          const float vj = vr[k];
+          sloc += ex2(vj * LOG2E - mall);
+          float v2;
+          if (j < M) {
+            v2 = (vj - shift) * LOG2E;
+            if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
+          } else {
+            v2 = (alpha + vj) * LOG2E;
+          }
+          v2_s[j] = v2;
+        }
+      }
+      sloc = warp_sum(sloc);
+      if (lane == 0) red_s[32 + warp] = sloc;
+      __syncthreads();
+      float sall = 0.f;
+#pragma unroll
+      for (int w = 0; w < P2_THREADS / 32; ++w) sall += red_s[32 + w];
+      uN = bc.log_mu_bin - (alpha + (mall + lg2(sall)) * LN2);
+    }
+    if (g == 0 && tid == 0) p.u[(size_t)b * p.ldu + N] = uN;
+    for (int j = M + 1 + tid; j < Mv; j += P2_THREADS) v2_s[j] = -INFINITY;
+    __syncthreads();
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 1);
+
+    // ---- the pass over this CTA's rows
+    const float dust2 = v2_s[M];
+    float cs[KQ * 4], cm[KQ * 4];
+#pragma unroll
+    for (int e = 0; e < KQ * 4; ++e) {
+      cs[e] = 0.f;
+      cm[e] = NEG_BIG;
+    }
+    LseAcc uacc = lse_empty();
+    int buf = 0;
+    for (int s = rg; s < ns; s += 2) {
+      const int T = it * ns + s;
+      const int stg = T % D;
+      const float* slab = ring + (size_t)stg * stage_floats;
+      mbar_wait(&full[stg], (uint32_t)((T / D) & 1));
+      float4 z[RR][KQ];
+#pragma unroll
+      for (int r = 0; r < RR; ++r) {
+        const bool row_in = row0 + s * RR + r < row1;  // rows past the CTA's range were not copied: stale shared memory
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (ct + P2_TPR * k);
+          z[r][k] = (row_in && (FULL || c < M)) ? *reinterpret_cast<const float4*>(slab + (size_t)r * M + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+
+      bool live[RR];
+#pragma unroll
+      for (int r = 0; r < RR; ++r) {
+        const int i = row0 + s * RR + r;
+        live[r] = (i < row1) && !(p.apply_mask && !smask[i < N ? i : 0]);
+      }
+      float* part = red_part + ((buf * 2 + rg) * 8) * 8;
+      if (fast) {
+        float mh[RR], rs[RR];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+          const int q = s * RR + r;
+          mh[r] = lse_prev_s[q < 1024 ? q : 1023];
+          rs[r] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (ct + P2_TPR * k);
+          if (FULL || c < M) {
+            const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+              const float ref = live[r] ? mh[r] : 1.0e30f;  // dead rows: every e is 0
+              float4 e;
+              e.x = ex2(fmaf(z[r][k].x, zs, vv.x) - ref);
+              e.y = ex2(fmaf(z[r][k].y, zs, vv.y) - ref);
+              e.z = ex2(fmaf(z[r][k].z, zs, vv.z) - ref);
+              e.w = ex2(fmaf(z[r][k].w, zs, vv.w) - ref);
+              z[r][k] = e;
+              rs[r] += (e.x + e.y) + (e.z + e.w);
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < RR; ++r) z[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < RR; ++r) rs[r] = warp_sum(rs[r]);
+        if (lane == 0) {
+#pragma unroll
+          for (int r = 0; r < RR; ++r) part[r * 8 + wg] = rs[r];
+        }
+        group_barrier(rg);
+        if (ct == 0 && s + D < ns) issue_slab(it, s + D);  // every thread of the group has its registers: re-arm the stage
+        float w[RR];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(part + r * 8);
+          const float4 c4 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
+          const float tot = ((a.x + a.y) + (a.z + a.w)) + ((c4.x + c4.y) + (c4.z + c4.w));
+          const float srow = tot + ex2(dust2 - mh[r]);  // + dustbin column entry
+          w[r] = live[r] ? 1.f / srow : 0.f;            // = 2^(ref_i + u_i log2e - norm2)
+          const int i = row0 + s * RR + r;
+          if (ct == 0 && i < row1) {
+            const float rowlse2 = mh[r] + lg2(srow);
+            const float ui = bc.norm - rowlse2 * LN2;
+            p.u[(size_t)b * p.ldu + i] = ui;
+            lse_add_value(uacc, ui * LOG2E);
+            lse_prev_s[s * RR + r] = rowlse2;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+#pragma unroll
+          for (int r = 0; r < RR; ++r) {
+            cs[4 * k + 0] = fmaf(z[r][k].x, w[r], cs[4 * k + 0]);
+            cs[4 * k + 1] = fmaf(z[r][k].y, w[r], cs[4 * k + 1]);
+            cs[4 * k + 2] = fmaf(z[r][k].z, w[r], cs[4 * k + 2]);
+            cs[4 * k + 3] = fmaf(z[r][k].w, w[r], cs[4 * k + 3]);
+          }
+        }
+        buf ^= 1;
+      } else {
+        // log-domain pass: exact row maximum first, then the exponential sum, then an online column log-sum-exp
+        float tm[RR];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) tm[r] = NEG_BIG;
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (ct + P2_TPR * k);
+          if (FULL || c < M) {
+            const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+              const float t = fmaxf(fmaxf(fmaf(z[r][k].x, zs, vv.x), fmaf(z[r][k].y, zs, vv.y)),
+                                    fmaxf(fmaf(z[r][k].z, zs, vv.z), fmaf(z[r][k].w, zs, vv.w)));
+              if (live[r]) tm[r] = fmaxf(tm[r], t);
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < RR; ++r) tm[r] = warp_max(tm[r]);
+        if (lane == 0) {
+#pragma unroll
+          for (int r = 0; r < RR; ++r) part[r * 8 + wg] = tm[r];
+        }
+        group_barrier(rg);
+        if (ct == 0 && s + D < ns) issue_slab(it, s + D);  // every thread of the group has its registers: re-arm the stage
+        float mrow[RR], rs[RR];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(part + r * 8);
+          const float4 c4 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
+          mrow[r] = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w)));
+          mrow[r] = fmaxf(mrow[r], dust2);  // the dustbin column entry is always finite
+          rs[r] = 0.f;
+        }
+        buf ^= 1;
+        part = red_part + ((buf * 2 + rg) * 8) * 8;
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (ct + P2_TPR * k);
+          if (FULL || c < M) {
+            const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+              if (live[r]) {
+                rs[r] += (ex2(fmaf(z[r][k].x, zs, vv.x) - mrow[r]) + ex2(fmaf(z[r][k].y, zs, vv.y) - mrow[r])) +
+                         (ex2(fmaf(z[r][k].z, zs, vv.z) - mrow[r]) + ex2(fmaf(z[r][k].w, zs, vv.w) - mrow[r]));
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < RR; ++r) rs[r] = warp_sum(rs[r]);
+        if (lane == 0) {
+#pragma unroll
+          for (int r = 0; r < RR; ++r) part[r * 8 + wg] = rs[r];
+        }
+        group_barrier(rg);
+        float u2[RR];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(part + r * 8);
+          const float4 c4 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
+          const float tot = ((a.x + a.y) + (a.z + a.w)) + ((c4.x + c4.y) + (c4.z + c4.w));
+          const float srow = tot + ex2(dust2 - mrow[r]);
+          const float rowlse2 = mrow[r] + lg2(srow);
+          const float ui = bc.norm - rowlse2 * LN2;
+          u2[r] = live[r] ? (ui - shift) * LOG2E : -INFINITY;  // column pass sees (S - shift) + u
+          const int i = row0 + s * RR + r;
+          if (ct == 0 && i < row1) {
+            p.u[(size_t)b * p.ldu + i] = ui;
+            lse_add_value(uacc, ui * LOG2E);
+            lse_prev_s[s * RR + r] = rowlse2;
+          }
+        }
+        buf ^= 1;
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (ct + P2_TPR * k);
+          if (FULL || c < M) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float y[RR];
+              float mx = NEG_BIG;
+#pragma unroll
+              for (int r = 0; r < RR; ++r) {
+                const float zz = (e == 0) ? z[r][k].x : (e == 1) ? z[r][k].y : (e == 2) ? z[r][k].z : z[r][k].w;
+                y[r] = fmaf(zz, zs, u2[r]);
+                mx = fmaxf(mx, y[r]);
+              }
+              float& am = cm[4 * k + e];
+              float& as = cs[4 * k + e];
+              if (mx > am + 32.f) {  // lazy re-reference
+                as *= ex2(am - mx);
+                am = mx;
+              }
+              float acc = 0.f;
+#pragma unroll
+              for (int r = 0; r < RR; ++r) acc += ex2(y[r] - am);
+              as += acc;
+            }
+          }
+        }
+      }
+    }
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 2);
+    if (fast) {
+      // sum_i 2^(x_ij + u_i log2e) = 2^(norm2 - v_j log2e) * sum_i e_ij w_i   (v2_s holds (v_j - shift) log2e)
+#pragma unroll
+      for (int k = 0; k < KQ; ++k) {
+        const int c = 4 * (ct + P2_TPR * k);
+        if (FULL || c < M) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v2j = v2_s[c + e];
+            const bool okc = v2j > -INFINITY;
+            cm[4 * k + e] = okc ? (norm2 - v2j - shift2) : NEG_BIG;
+            if (!okc) cs[4 * k + e] = 0.f;
+          }
+        }
+      }
+    }
+    // ---- the two row groups combine their column partials; row group 0 writes them
+    __syncthreads();  // the ring is idle from here until the next iteration's first slabs are requested below
+    if (rg == 1) {
+#pragma unroll
+      for (int e = 0; e < KQ * 4; ++e) xcomb[e * P2_TPR + ct] = make_float2(cm[e], cs[e]);
+    }
+    if (ct == 0) upart_s[rg] = make_float2(uacc.m, uacc.s);
+    __syncthreads();
+    if (rg == 0) {
+#pragma unroll
+      for (int e = 0; e < KQ * 4; ++e) {
+        const float2 o = xcomb[e * P2_TPR + ct];
+        LseAcc a{cm[e], cs[e]};
+        lse_merge(a, o.x, o.y);
+        cm[e] = a.m;
+        cs[e] = a.s;
+      }
+      float2* cp = p.colpart + ((size_t)b * G + g) * M;
+#pragma unroll
+      for (int k = 0; k < KQ; ++k) {
+        const int c = 4 * (ct + P2_TPR * k);
+        if (FULL || c < M) {
+          *reinterpret_cast<float4*>(cp + c) = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
+          *reinterpret_cast<float4*>(cp + c + 2) = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
+        }
+      }
+      group_barrier(0);  // xcomb (aliased on the ring) has been read
+      if (tid == 0 && it + 1 < iters)
+        for (int s = 0; s < D && s < ns; ++s) issue_slab(it + 1, s);  // the scores do not change: prefetch across the barriers
+    }
+    if (tid == 0) {
+      LseAcc a{upart_s[0].x, upart_s[0].y};
+      lse_merge(a, upart_s[1].x, upart_s[1].y);
+      p.upart[(size_t)b * G + g] = make_float2(a.m, a.s);
+      DRG_STAMP(10 + it * 100 + 3);
+    }
+    grid_barrier(gcount, (unsigned int)G * (++barriers_done));
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 4);
+
+    // ---- merge: a CTA takes 32 consecutive columns at a time (lane = column), its 16 warps split the G partials
+    {
+      float* v_b = p.v + (size_t)b * p.ldv;
+      if (g == 0 && tid == 0) dv_slots[(it + 1) & 1] = 0u;
+      float dv_loc = 0.f;
+      for (int j0 = g * 32; j0 <= M; j0 += G * 32) {
+        const int j = j0 + lane;
+        const bool in_range = j <= M;
+        const bool is_bin = (j == M);
+        const bool col_ok = in_range && (is_bin || !p.apply_mask || p.tgt_mask[(size_t)b * M + j]);
+        float m = NEG_BIG, sum = 0.f;
+        if (col_ok) {
+          const float2* src = is_bin ? (p.upart + (size_t)b * G) : (p.colpart + (size_t)b * G * M + j);
+          const size_t gstride = is_bin ? 1 : (size_t)M;
+          constexpr int NW = P2_THREADS / 32;
+          constexpr int PER_WARP = (NUM_SMS + NW - 1) / NW;
+          float2 q[PER_WARP];
+#pragma unroll
+          for (int k = 0; k < PER_WARP; ++k) {
+            const int gg = warp + NW * k;
+            q[k] = (gg < G) ? __ldcg(src + (size_t)gg * gstride) : make_float2(NEG_BIG, 0.f);
+            m = fmaxf(m, q[k].x);
+          }
+#pragma unroll
+          for (int k = 0; k < PER_WARP; ++k) sum += q[k].y * ex2(q[k].x - m);
+        }
+        comb[warp * 32 + lane] = make_float2(m, sum);
+        __syncthreads();
+        if (warp == 0 && in_range) {
+          float mm = NEG_BIG;
+#pragma unroll
+          for (int w = 0; w < P2_THREADS / 32; ++w) mm = fmaxf(mm, comb[w * 32 + lane].x);
+          float ss = 0.f;
+#pragma unroll
+          for (int w = 0; w < P2_THREADS / 32; ++w) {
+            const float2 c2 = comb[w * 32 + lane];
+            ss += c2.y * ex2(c2.x - mm);
+          }
+          LseAcc a{mm, ss};
+          const float v_old = (it == 0) ? 0.f : __ldcg(v_b + j);
+          float v_new;
+          if (!is_bin) {
+            lse_add_value(a, (alpha + uN) * LOG2E);  // dustbin row entry
+            v_new = bc.norm - lse_value(a) * LN2;
+          } else {
+            lse_add_value(a, uN * LOG2E);  // c_M = alpha + LSE(u[0..N])
+            v_new = bc.log_nu_bin - (alpha + lse_value(a) * LN2);
+          }
+          v_b[j] = v_new;
+          const float d = fabsf(v_new - v_old) * LOG2E;
+          dv_loc = fmaxf(dv_loc, (d == d) ? d : INFINITY);
+        }
+        __syncthreads();
+      }
+      if (warp == 0) {
+        dv_loc = warp_max(dv_loc);
+        if (lane == 0 && dv_loc > 0.f) atomicMax(dv_slots + (it & 1), __float_as_uint(dv_loc));
+      }
+    }
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 5);
+    if (it + 1 < iters) grid_barrier(gcount, (unsigned int)G * (++barriers_done));
+    if (tid == 0) DRG_STAMP(10 + it * 100 + 6);
+  }
+#undef DRG_STAMP
+}
+
+// ---------------------------------------------------------------------------------------
 // merge the per-CTA column partials into v (and the dustbin column entry v_M)
 //   block = 32 columns x 8 slices of the G partials; every thread first pulls its <= 19
 //   partials into registers (all loads in flight at once), reduces them with one ex2 each,
@@ -2211,7 +2712,7 @@ static int skh_persist_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DRG_SKH_PERSIST");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 2;
   }
   return v;
 }
@@ -2241,6 +2742,63 @@ static cudaError_t launch_persist(const SkhParams& p, const SkhPlanWS& pl, int i
   DRG_PS_CASE(1, 2) DRG_PS_CASE(2, 2) DRG_PS_CASE(4, 2) DRG_PS_CASE(8, 2)
   DRG_PS_CASE(1, 4) DRG_PS_CASE(2, 4) DRG_PS_CASE(4, 4)
 #undef DRG_PS_CASE
+  return cudaErrorInvalidConfiguration;
+}
+
+// ---- register-slab persistent kernel: plan and launch
+struct SkhPlanP2 {
+  int KQ, RR, G, nstage;
+  bool full, ok;
+  size_t smem;
+};
+
+static SkhPlanP2 make_plan_p2(int B, int N, int M) {
+  SkhPlanP2 pl{};
+  pl.ok = false;
+  if (M < 4 || M > 4096 || (M % 4) != 0 || N < 1 || B < 1 || B > NUM_SMS) return pl;
+  pl.KQ = (M <= 1024) ? 1 : (M <= 2048) ? 2 : 4;
+  pl.full = (M == 1024 * pl.KQ);
+  const int gmax = NUM_SMS / B;
+  const int rr_max = 8 / pl.KQ;
+  const int rr_min = (pl.KQ == 1) ? 2 : 1;
+  pl.RR = ((long long)2 * rr_max * gmax <= N) ? rr_max : rr_min;
+  int G = (N + 2 * pl.RR - 1) / (2 * pl.RR);  // at least one mini-slab per row group
+  if (G > gmax) G = gmax;
+  if (G < 1) G = 1;
+  pl.G = G;
+  if ((N + G - 1) / G > 1024) return pl;  // row references of a CTA live in a 1024-entry shared array
+  const size_t Mv = (size_t)((M + 1 + 3) & ~3);
+  const size_t fixed = (Mv + 1024 + 256 + 64 + 8 + (P2_THREADS / 32) * 32 * 2) * 4 + P2_MAX_STAGES * 8;
+  const size_t stage_bytes = (size_t)pl.RR * M * 4;
+  const size_t xcomb_bytes = (size_t)P2_TPR * pl.KQ * 4 * 8;
+  int nstage = (int)((SKH_SMEM_LIMIT - 256 - fixed) / stage_bytes);
+  if (nstage > P2_MAX_STAGES) nstage = P2_MAX_STAGES;
+  if (nstage < 2) return pl;
+  pl.nstage = nstage;
+  const size_t ring_bytes = (size_t)nstage * stage_bytes;
+  pl.smem = fixed + (ring_bytes > xcomb_bytes ? ring_bytes : xcomb_bytes);
+  pl.ok = true;
+  return pl;
+}
+
+template <int KQ, int RR, bool FULL>
+static cudaError_t launch_persist2_t(const SkhParams& p, const SkhPlanP2& pl, int iters, unsigned int* gsync, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(skh_persist2_kernel<KQ, RR, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  if (e != cudaSuccess) return e;
+  SkhParams pp = p;
+  pp.nstage = pl.nstage;
+  void* args[] = {(void*)&pp, (void*)&iters, (void*)&gsync};
+  return cudaLaunchCooperativeKernel((const void*)skh_persist2_kernel<KQ, RR, FULL>, dim3(pl.G, p.B), dim3(P2_THREADS), args, pl.smem, st);
+}
+
+static cudaError_t launch_persist2(const SkhParams& p, const SkhPlanP2& pl, int iters, unsigned int* gsync, cudaStream_t st) {
+#define DRG_P2_CASE(kq, rr)                                                                  \
+  if (pl.KQ == kq && pl.RR == rr) {                                                          \
+    if (pl.full) return launch_persist2_t<kq, rr, true>(p, pl, iters, gsync, st);            \
+    return launch_persist2_t<kq, rr, false>(p, pl, iters, gsync, st);                        \
+  }
+  DRG_P2_CASE(4, 2) DRG_P2_CASE(4, 1) DRG_P2_CASE(2, 4) DRG_P2_CASE(2, 1) DRG_P2_CASE(1, 8) DRG_P2_CASE(1, 2)
+#undef DRG_P2_CASE
   return cudaErrorInvalidConfiguration;
 }
 
@@ -2295,6 +2853,9 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     return DRG_ERR_INVALID;
   }
   const bool persist = run == SKH_RUN_ALL && usew && !dual && a->iters >= 1 && skh_persist_enabled() && (long long)plw.G * B <= NUM_SMS;
+  // DRG_SKH_PERSIST: 0 = one launch per iteration, 1 = shared-memory slab kernel, 2 (default) = register-slab kernel
+  SkhPlanP2 plp = (persist && skh_persist_enabled() >= 2) ? make_plan_p2(B, N, M) : SkhPlanP2{};
+  const bool persist2 = persist && plp.ok;
   if (run == SKH_SHARD_BEGIN) {
     skh_shard_begin_kernel<<<B, 1024, 0, st>>>(global_counts, w.bc, w.v, w.u, pitch4(N + 1), pitch4(M + 1));
     DRG_LAUNCH_CHECK();
@@ -2322,7 +2883,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   p.B = B;
   p.N = N;
   p.M = M;
-  p.G = usew ? plw.G : use2 ? pl2.G : pl.G;
+  p.G = persist2 ? plp.G : usew ? plw.G : use2 ? pl2.G : pl.G;
   p.ldu = pitch4(N + 1);
   p.ldv = pitch4(M + 1);
   p.apply_mask = a->apply_mask;
@@ -2367,10 +2928,11 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     cudaError_t e;
     {
       ProfScope prof_scope(PROF_SKH_ITER, st);
-      e = launch_persist(p, plw, iters, w.gsync, st);
+      e = persist2 ? launch_persist2(p, plp, iters, w.gsync, st) : launch_persist(p, plw, iters, w.gsync, st);
     }
     if (e != cudaSuccess) {
-      set_error("persistent sinkhorn launch failed: %s (smem=%zu, grid %d x %d)", cudaGetErrorString(e), plw.smem, plw.G, B);
+      set_error("persistent sinkhorn launch failed: %s (smem=%zu, grid %d x %d)", cudaGetErrorString(e), persist2 ? plp.smem : plw.smem,
+                persist2 ? plp.G : plw.G, B);
       return DRG_ERR_CUDA;
     }
     count_launch();
