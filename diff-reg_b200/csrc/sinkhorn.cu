@@ -1555,6 +1555,17 @@ __device__ __forceinline__ float4 ldg_stream4(const float* ptr) {
 }
 __device__ __forceinline__ void group_barrier(int rg) { asm volatile("bar.sync %0, %1;" ::"r"(rg + 1), "r"(P2_TPR) : "memory"); }
 
+// grid barrier with a release add / acquire poll by one thread per CTA (the block barriers make it cumulative)
+__device__ __forceinline__ void grid_barrier_ra(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    while (ld_acquire_u32(counter) < target) {
+    }
+  }
+  __syncthreads();
+}
+
 template <int KQ, int RR, bool FULL>
 __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhParams p, const int iters, unsigned int* gsync) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1590,9 +1601,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
   unsigned int* dv_slots = gsync + gridDim.y + 2 * b;
 
   // stream of mini-slabs: element T = it * ns + s lands in stage T % D; row group (s & 1) consumes it
-  auto issue_slab = [&](int it_, int s_) {
-    const int T = it_ * ns + s_;
-    const int stg = T % D;
+  auto issue_slab_to = [&](int stg, int s_) {
     const int i0 = row0 + s_ * RR;
     const uint32_t bytes = (uint32_t)min(RR, row1 - i0) * (uint32_t)M * 4u;
     fence_proxy_async();
@@ -1605,7 +1614,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     for (int s = 0; s < D; ++s) mbar_init(&full[s], 1u);
     fence_mbar_init();
     if (iters > 0)
-      for (int s = 0; s < D && s < ns; ++s) issue_slab(0, s);
+      for (int s = 0; s < D && s < ns; ++s) issue_slab_to(s, s);
   }
   __syncthreads();
   {
@@ -1631,6 +1640,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
   const float norm2 = bc.norm * LOG2E;
   unsigned int barriers_done = 0;
   const uint8_t* smask = p.src_mask + (size_t)b * N;
+  // row slots: log2-domain row log-sum-exp of the previous iteration; >= 1e30 marks a row without real entries
+  // (masked source row: 1e30, written by the log-domain pass; slot past the CTA's rows: 2e30)
+  for (int q = nrows + tid; q < 1024; q += P2_THREADS) lse_prev_s[q] = 2.0e30f;
 
   if (tid == 0) DRG_STAMP(1);
   for (int it = 0; it < iters; ++it) {
@@ -1713,35 +1725,43 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     }
     LseAcc uacc = lse_empty();
     int buf = 0;
+    int stg = (it * ns + rg) % D;                         // stream element T = it * ns + s lands in stage T % D ...
+    uint32_t ph = (uint32_t)(((it * ns + rg) / D) & 1);   // ... on its (T / D)-th use
+    const bool ragged = (nrows % RR) != 0;
     for (int s = rg; s < ns; s += 2) {
-      const int T = it * ns + s;
-      const int stg = T % D;
       const float* slab = ring + (size_t)stg * stage_floats;
-      mbar_wait(&full[stg], (uint32_t)((T / D) & 1));
+      mbar_wait(&full[stg], ph);
       float4 z[RR][KQ];
-#pragma unroll
-      for (int r = 0; r < RR; ++r) {
-        const bool row_in = row0 + s * RR + r < row1;  // rows past the CTA's range were not copied: stale shared memory
-#pragma unroll
-        for (int k = 0; k < KQ; ++k) {
-          const int c = 4 * (ct + P2_TPR * k);
-          z[r][k] = (row_in && (FULL || c < M)) ? *reinterpret_cast<const float4*>(slab + (size_t)r * M + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-
       bool live[RR];
+      if (fast) {
 #pragma unroll
-      for (int r = 0; r < RR; ++r) {
-        const int i = row0 + s * RR + r;
-        live[r] = (i < row1) && !(p.apply_mask && !smask[i < N ? i : 0]);
+        for (int r = 0; r < RR; ++r) {
+          live[r] = true;
+#pragma unroll
+          for (int k = 0; k < KQ; ++k) {
+            const int c = 4 * (ct + P2_TPR * k);
+            if (FULL || c < M) z[r][k] = *reinterpret_cast<const float4*>(slab + (size_t)r * M + c);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+          const int i = row0 + s * RR + r;
+          const bool row_in = i < row1;  // rows past the CTA's range were not copied: stale shared memory
+          live[r] = row_in && !(p.apply_mask && !smask[i < N ? i : 0]);
+#pragma unroll
+          for (int k = 0; k < KQ; ++k) {
+            const int c = 4 * (ct + P2_TPR * k);
+            z[r][k] = (row_in && (FULL || c < M)) ? *reinterpret_cast<const float4*>(slab + (size_t)r * M + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
       }
       float* part = red_part + ((buf * 2 + rg) * 8) * 8;
       if (fast) {
         float mh[RR], rs[RR];
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
-          const int q = s * RR + r;
-          mh[r] = lse_prev_s[q < 1024 ? q : 1023];
+          mh[r] = lse_prev_s[s * RR + r];  // >= 1e30: a row without real entries (masked, or past the CTA's range): every e is 0
           rs[r] = 0.f;
         }
 #pragma unroll
@@ -1751,18 +1771,27 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
             const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
 #pragma unroll
             for (int r = 0; r < RR; ++r) {
-              const float ref = live[r] ? mh[r] : 1.0e30f;  // dead rows: every e is 0
               float4 e;
-              e.x = ex2(fmaf(z[r][k].x, zs, vv.x) - ref);
-              e.y = ex2(fmaf(z[r][k].y, zs, vv.y) - ref);
-              e.z = ex2(fmaf(z[r][k].z, zs, vv.z) - ref);
-              e.w = ex2(fmaf(z[r][k].w, zs, vv.w) - ref);
+              e.x = ex2(fmaf(z[r][k].x, zs, vv.x) - mh[r]);
+              e.y = ex2(fmaf(z[r][k].y, zs, vv.y) - mh[r]);
+              e.z = ex2(fmaf(z[r][k].z, zs, vv.z) - mh[r]);
+              e.w = ex2(fmaf(z[r][k].w, zs, vv.w) - mh[r]);
               z[r][k] = e;
               rs[r] += (e.x + e.y) + (e.z + e.w);
             }
           } else {
 #pragma unroll
             for (int r = 0; r < RR; ++r) z[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (ragged && s == ns - 1) {  // rows past the CTA's range were not copied: stale shared memory, possibly NaN
+#pragma unroll
+          for (int r = 0; r < RR; ++r) {
+            if (s * RR + r >= nrows) {
+              rs[r] = 0.f;
+#pragma unroll
+              for (int k = 0; k < KQ; ++k) z[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
 #pragma unroll
@@ -1772,22 +1801,22 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           for (int r = 0; r < RR; ++r) part[r * 8 + wg] = rs[r];
         }
         group_barrier(rg);
-        if (ct == 0 && s + D < ns) issue_slab(it, s + D);  // every thread of the group has its registers: re-arm the stage
+        if (ct == 0 && s + D < ns) issue_slab_to(stg, s + D);  // every thread of the group has its registers: re-arm the stage
         float w[RR];
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
           const float4 a = *reinterpret_cast<const float4*>(part + r * 8);
           const float4 c4 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
           const float tot = ((a.x + a.y) + (a.z + a.w)) + ((c4.x + c4.y) + (c4.z + c4.w));
+          const bool dead = mh[r] > 1.0e29f;
           const float srow = tot + ex2(dust2 - mh[r]);  // + dustbin column entry
-          w[r] = live[r] ? 1.f / srow : 0.f;            // = 2^(ref_i + u_i log2e - norm2)
-          const int i = row0 + s * RR + r;
-          if (ct == 0 && i < row1) {
-            const float rowlse2 = mh[r] + lg2(srow);
+          w[r] = dead ? 0.f : 1.f / srow;               // = 2^(ref_i + u_i log2e - norm2)
+          if (ct == 0 && s * RR + r < nrows) {
+            const float rowlse2 = dead ? dust2 : mh[r] + lg2(srow);  // a masked row holds the dustbin entry only
             const float ui = bc.norm - rowlse2 * LN2;
-            p.u[(size_t)b * p.ldu + i] = ui;
+            p.u[(size_t)b * p.ldu + row0 + s * RR + r] = ui;
             lse_add_value(uacc, ui * LOG2E);
-            lse_prev_s[s * RR + r] = rowlse2;
+            if (!dead) lse_prev_s[s * RR + r] = rowlse2;
           }
         }
 #pragma unroll
@@ -1826,7 +1855,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           for (int r = 0; r < RR; ++r) part[r * 8 + wg] = tm[r];
         }
         group_barrier(rg);
-        if (ct == 0 && s + D < ns) issue_slab(it, s + D);  // every thread of the group has its registers: re-arm the stage
+        if (ct == 0 && s + D < ns) issue_slab_to(stg, s + D);  // every thread of the group has its registers: re-arm the stage
         float mrow[RR], rs[RR];
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
@@ -1873,7 +1902,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           if (ct == 0 && i < row1) {
             p.u[(size_t)b * p.ldu + i] = ui;
             lse_add_value(uacc, ui * LOG2E);
-            lse_prev_s[s * RR + r] = rowlse2;
+            lse_prev_s[s * RR + r] = live[r] ? rowlse2 : 1.0e30f;
           }
         }
         buf ^= 1;
@@ -1904,6 +1933,11 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
             }
           }
         }
+      }
+      stg += 2;
+      if (stg >= D) {
+        stg -= D;
+        ph ^= 1u;
       }
     }
     if (tid == 0) DRG_STAMP(10 + it * 100 + 2);
@@ -1951,7 +1985,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
       }
       group_barrier(0);  // xcomb (aliased on the ring) has been read
       if (tid == 0 && it + 1 < iters)
-        for (int s = 0; s < D && s < ns; ++s) issue_slab(it + 1, s);  // the scores do not change: prefetch across the barriers
+        for (int s = 0; s < D && s < ns; ++s) issue_slab_to(((it + 1) * ns + s) % D, s);  // the scores do not change: prefetch across the barriers
     }
     if (tid == 0) {
       LseAcc a{upart_s[0].x, upart_s[0].y};
@@ -1959,7 +1993,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
       p.upart[(size_t)b * G + g] = make_float2(a.m, a.s);
       DRG_STAMP(10 + it * 100 + 3);
     }
-    grid_barrier(gcount, (unsigned int)G * (++barriers_done));
+    grid_barrier_ra(gcount, (unsigned int)G * (++barriers_done));
     if (tid == 0) DRG_STAMP(10 + it * 100 + 4);
 
     // ---- merge: a CTA takes 32 consecutive columns at a time (lane = column), its 16 warps split the G partials
@@ -2022,7 +2056,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
       }
     }
     if (tid == 0) DRG_STAMP(10 + it * 100 + 5);
-    if (it + 1 < iters) grid_barrier(gcount, (unsigned int)G * (++barriers_done));
+    if (it + 1 < iters) grid_barrier_ra(gcount, (unsigned int)G * (++barriers_done));
     if (tid == 0) DRG_STAMP(10 + it * 100 + 6);
   }
 #undef DRG_STAMP
