@@ -6,6 +6,7 @@ Public surface (mirrors the reference):
     Matching2D3D                                             (2D-3D flavour head)
     SoftProcrustesLayer                                      (procrustes.py)
     DenoisingSampler                                         (fused per-step driver)
+    HostStepPipeline                                         (host buffers in / results out, copies overlapped, graph replay)
     RowShardedSinkhorn, shard_rows, shard_units              (multi-GPU paths, distributed.py)
 Everything computes through libdiffreg_b200.so (C ABI, include/diffreg_b200.h).  There is
 no CPU or eager-PyTorch fallback: a missing library or a non-CUDA tensor raises.
@@ -27,6 +28,9 @@ def __getattr__(name):
     if name in ("DenoisingSampler",):
         from . import sampler
         return getattr(sampler, name)
+    if name == "HostStepPipeline":
+        from . import hostpipe
+        return hostpipe.HostStepPipeline
     if name in ("RowShardedSinkhorn", "EmulatedRowShards", "shard_rows", "shard_units", "lse_allreduce", "lse_combine"):
         from . import distributed
         return getattr(distributed, name)

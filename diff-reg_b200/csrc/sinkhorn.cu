@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(1024) skh_prep_kernel(const uint8_t* __restric
     c.norm = norm;
     c.log_mu_bin = logf(ns) + norm;
     c.log_nu_bin = logf(ms) + norm;
-    c.pad = 0.f;
+    c.pad = (cnt[0] == N && cnt[1] == M) ? 1.f : 0.f;  // 1: no padded row or column (the final pass skips its mask logic)
     bc[b] = c;
   }
 }
@@ -1116,7 +1116,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) skh_persist_kernel(const SkhPar
     bc.norm = -logf(ms + ns);
     bc.log_mu_bin = logf(ns) + bc.norm;
     bc.log_nu_bin = logf(ms) + bc.norm;
-    bc.pad = 0.f;
+    bc.pad = (cnt_s[0] == N && cnt_s[1] == M) ? 1.f : 0.f;  // 1: no padded row or column
     if (g == 0 && tid == 0) p.bc_out[b] = bc;
   }
 
@@ -1634,7 +1634,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     bc.norm = -logf(ms + nsv);
     bc.log_mu_bin = logf(nsv) + bc.norm;
     bc.log_nu_bin = logf(ms) + bc.norm;
-    bc.pad = 0.f;
+    bc.pad = (cnt_s[0] == N && cnt_s[1] == M) ? 1.f : 0.f;  // 1: no padded row or column
     if (g == 0 && tid == 0) p.bc_out[b] = bc;
   }
   const float norm2 = bc.norm * LOG2E;
@@ -1969,10 +1969,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
 #pragma unroll
       for (int e = 0; e < KQ * 4; ++e) {
         const float2 o = xcomb[e * P2_TPR + ct];
-        LseAcc a{cm[e], cs[e]};
-        lse_merge(a, o.x, o.y);
-        cm[e] = a.m;
-        cs[e] = a.s;
+        if (fast) {  // both groups carry the same reference
+          cs[e] += o.y;
+        } else {
+          LseAcc a{cm[e], cs[e]};
+          lse_merge(a, o.x, o.y);
+          cm[e] = a.m;
+          cs[e] = a.s;
+        }
       }
       float2* cp = p.colpart + ((size_t)b * G + g) * M;
 #pragma unroll
@@ -2220,8 +2224,9 @@ __device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) {
   const unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 7; ++r) {
-    const unsigned int hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-    const unsigned int hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    const unsigned long long p0 = (unsigned long long)M0 * c.x, p1 = (unsigned long long)M1 * c.z;  // one IMAD.WIDE each
+    const unsigned int hi0 = (unsigned int)(p0 >> 32), lo0 = (unsigned int)p0;
+    const unsigned int hi1 = (unsigned int)(p1 >> 32), lo1 = (unsigned int)p1;
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
     k.x += W0;
     k.y += W1;
@@ -2369,7 +2374,8 @@ __global__ void __launch_bounds__(256) skh_final_kernel(const SkhFinalParams p) 
 constexpr int FT_THREADS = 256;
 constexpr int FT_ROWS = 16;  // 1024 CTAs at 4096^2: ~7 resident per SM to cover the load latency
 
-__global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFinalParams p) {
+template <bool MASKED, bool TRACK, bool WANT_MIN>
+__device__ __forceinline__ void final_tile_body(const SkhFinalParams& p) {
   const int b = blockIdx.z;
   const int N = p.N, M = p.M;
   const int c = blockIdx.x * (FT_THREADS * 4) + 4 * (int)threadIdx.x;
@@ -2386,7 +2392,7 @@ __global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFin
   bool tm[4] = {true, true, true, true};
   if (active) {
     v4 = *reinterpret_cast<const float4*>(p.v + (size_t)b * p.ldv + c);
-    if (p.apply_mask) {
+    if (MASKED) {
       const uchar4 t4 = *reinterpret_cast<const uchar4*>(p.tgt_mask + (size_t)b * M + c);
       tm[0] = t4.x; tm[1] = t4.y; tm[2] = t4.z; tm[3] = t4.w;
     }
@@ -2395,10 +2401,9 @@ __global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFin
   float cbv[4] = {-1.f, -1.f, -1.f, -1.f};
   int cbi[4] = {0, 0, 0, 0};
   float local_min = INFINITY;
-  const bool track = p.rowbest != nullptr;
   for (int i = i0; i < i1; ++i) {
     const float ui = u_b[i];
-    const bool row_ok = !p.apply_mask || p.src_mask[(size_t)b * N + i];
+    const bool row_ok = !MASKED || p.src_mask[(size_t)b * N + i];
     float cf[4] = {-1.f, -1.f, -1.f, -1.f};
     if (active) {
       const size_t base = ((size_t)b * N + i) * M + c;
@@ -2419,13 +2424,13 @@ __global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFin
       float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const bool ok = row_ok && tm[e];
+        const bool ok = !MASKED || (row_ok && tm[e]);
         const float zz = ok ? (z[e] - shift) : -INFINITY;
         const float la = ((zz + ui) + vj[e]) - bc.norm;  // same association as matching.py:34-36
         cf[e] = ex2(la * LOG2E);
         if (ddim) {
           const float xn = ok ? fmaf(p.k_x0, cf[e], fmaf(p.k_xt, xt[e] - xt_shift, p.sigma * nz[e])) : -INFINITY;
-          if (ok && xn > -INFINITY) local_min = fminf(local_min, xn);
+          if (WANT_MIN && ok && xn > -INFINITY) local_min = fminf(local_min, xn);
           o[e] = xn;
         } else {
           o[e] = cf[e];
@@ -2434,7 +2439,7 @@ __global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFin
       *reinterpret_cast<float4*>(p.out + base) = make_float4(o[0], o[1], o[2], o[3]);
       if (ddim && p.conf) *reinterpret_cast<float4*>(p.conf + base) = make_float4(cf[0], cf[1], cf[2], cf[3]);
     }
-    if (track) {
+    if (TRACK) {
       // column bests (rows ascend, strict > keeps the lowest row on ties)
 #pragma unroll
       for (int e = 0; e < 4; ++e)
@@ -2442,7 +2447,8 @@ __global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFin
           cbv[e] = cf[e];
           cbi[e] = i;
         }
-      // row best of this warp's 128 columns: value by shuffle max, owner by ballot (lowest lane, lowest column)
+      // row best of this warp's 128 columns: confidences are >= 0, so their bit patterns order like unsigned integers
+      // and ONE redux.sync finds the warp maximum; the owner is the lowest lane holding it (lowest column)
       float rv = cf[0];
       int re = 0;
 #pragma unroll
@@ -2451,8 +2457,9 @@ __global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFin
           rv = cf[e];
           re = e;
         }
-      const float wv = warp_max(rv);
-      const unsigned int owners = __ballot_sync(0xffffffffu, active && rv == wv);
+      const unsigned int rbits = (active && rv >= 0.f) ? __float_as_uint(rv) : 0u;  // NaN / inactive lanes never win
+      const unsigned int wbits = __reduce_max_sync(0xffffffffu, rbits);
+      const unsigned int owners = __ballot_sync(0xffffffffu, active && rbits == wbits);
       if (owners && lane == __ffs(owners) - 1) {
         const unsigned long long key =
             ((unsigned long long)float_to_ordered(rv) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)(c + re));
@@ -2460,7 +2467,7 @@ __global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFin
       }
     }
   }
-  if (track && active && i1 > i0) {
+  if (TRACK && active && i1 > i0) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const unsigned long long key =
@@ -2468,9 +2475,34 @@ __global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFin
       atomicMax(&p.colbest[(size_t)b * M + c + e], key);
     }
   }
-  if (ddim && p.x_min) {
+  if (WANT_MIN && ddim) {
     local_min = warp_min(local_min);
     if (lane == 0 && local_min < INFINITY) atomic_min_float(p.x_min, local_min);
+  }
+}
+
+// The mask predicates, the arg-max tracking and the running minimum are compiled out when not needed: the pass is
+// issue-bound (in-kernel Philox + Box-Muller), not bandwidth-bound, so every instruction per element counts.
+__global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFinalParams p) {
+  const bool masked = p.apply_mask && p.bc[blockIdx.z].pad != 1.f;  // pad == 1: the Sinkhorn saw no padded row / column
+  const bool track = p.rowbest != nullptr;
+  const bool want_min = p.x_min != nullptr;
+  if (masked) {
+    if (track) {
+      if (want_min) final_tile_body<true, true, true>(p);
+      else final_tile_body<true, true, false>(p);
+    } else {
+      if (want_min) final_tile_body<true, false, true>(p);
+      else final_tile_body<true, false, false>(p);
+    }
+  } else {
+    if (track) {
+      if (want_min) final_tile_body<false, true, true>(p);
+      else final_tile_body<false, true, false>(p);
+    } else {
+      if (want_min) final_tile_body<false, false, true>(p);
+      else final_tile_body<false, false, false>(p);
+    }
   }
 }
 
