@@ -1652,7 +1652,12 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
       const float dv = __uint_as_float(ld_acquire_u32(dv_slots + ((it - 1) & 1)));
       fast = dv <= 50.f;
     }
-    if (p.dbg_times && g == 0 && b == 0 && tid == 0) p.dbg_times[400 + it] = fast ? 1 : 0;
+    // First iteration: same arithmetic, but the row reference is this pass's exact row maximum (one more reduction per
+    // mini-slab).  Flushing e_ij / srow_i < 2^-126 cannot hurt the column sums there: with v = 0 the dustbin-row entry of
+    // every column is ~2^norm2, 2^126 / N times larger than anything that can be flushed.
+    const bool semi = (it == 0) && alpha >= -20.f && !(p.dbg & 8);
+    const bool scaled = fast || semi;
+    if (p.dbg_times && g == 0 && b == 0 && tid == 0) p.dbg_times[400 + it] = fast ? 1 : semi ? 2 : 0;
 
     // ---- prologue: column potentials into shared memory (log2 domain), dustbin-row potential
     float uN;
@@ -1757,12 +1762,48 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
         }
       }
       float* part = red_part + ((buf * 2 + rg) * 8) * 8;
-      if (fast) {
+      if (scaled) {
         float mh[RR], rs[RR];
+        if (semi) {
+          // exact row maxima of x = z * zs + v2 (and the dustbin column entry) as the references
+          float tm[RR];
 #pragma unroll
-        for (int r = 0; r < RR; ++r) {
-          mh[r] = lse_prev_s[s * RR + r];  // >= 1e30: a row without real entries (masked, or past the CTA's range): every e is 0
-          rs[r] = 0.f;
+          for (int r = 0; r < RR; ++r) tm[r] = NEG_BIG;
+#pragma unroll
+          for (int k = 0; k < KQ; ++k) {
+            const int c = 4 * (ct + P2_TPR * k);
+            if (FULL || c < M) {
+              const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+#pragma unroll
+              for (int r = 0; r < RR; ++r)
+                tm[r] = fmaxf(tm[r], fmaxf(fmaxf(fmaf(z[r][k].x, zs, vv.x), fmaf(z[r][k].y, zs, vv.y)),
+                                           fmaxf(fmaf(z[r][k].z, zs, vv.z), fmaf(z[r][k].w, zs, vv.w))));
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < RR; ++r) tm[r] = warp_max(tm[r]);
+          if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < RR; ++r) part[r * 8 + wg] = tm[r];
+          }
+          group_barrier(rg);
+          if (ct == 0 && s + D < ns) issue_slab_to(stg, s + D);  // every thread of the group has its registers: re-arm the stage
+#pragma unroll
+          for (int r = 0; r < RR; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(part + r * 8);
+            const float4 c4 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
+            const float m8 = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w)));
+            mh[r] = live[r] ? fmaxf(m8, dust2) : 1.0e30f;  // masked / out-of-range row: every e is 0
+            rs[r] = 0.f;
+          }
+          buf ^= 1;
+          part = red_part + ((buf * 2 + rg) * 8) * 8;
+        } else {
+#pragma unroll
+          for (int r = 0; r < RR; ++r) {
+            mh[r] = lse_prev_s[s * RR + r];  // >= 1e30: a row without real entries (masked, or past the CTA's range): every e is 0
+            rs[r] = 0.f;
+          }
         }
 #pragma unroll
         for (int k = 0; k < KQ; ++k) {
@@ -1784,7 +1825,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
             for (int r = 0; r < RR; ++r) z[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        if (ragged && s == ns - 1) {  // rows past the CTA's range were not copied: stale shared memory, possibly NaN
+        if (!semi && ragged && s == ns - 1) {  // rows past the CTA's range were not copied: stale shared memory, possibly NaN
 #pragma unroll
           for (int r = 0; r < RR; ++r) {
             if (s * RR + r >= nrows) {
@@ -1801,7 +1842,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           for (int r = 0; r < RR; ++r) part[r * 8 + wg] = rs[r];
         }
         group_barrier(rg);
-        if (ct == 0 && s + D < ns) issue_slab_to(stg, s + D);  // every thread of the group has its registers: re-arm the stage
+        if (!semi && ct == 0 && s + D < ns) issue_slab_to(stg, s + D);  // every thread of the group has its registers: re-arm the stage
         float w[RR];
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
@@ -1816,7 +1857,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
             const float ui = bc.norm - rowlse2 * LN2;
             p.u[(size_t)b * p.ldu + row0 + s * RR + r] = ui;
             lse_add_value(uacc, ui * LOG2E);
-            if (!dead) lse_prev_s[s * RR + r] = rowlse2;
+            lse_prev_s[s * RR + r] = dead ? 1.0e30f : rowlse2;
           }
         }
 #pragma unroll
@@ -1941,7 +1982,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
       }
     }
     if (tid == 0) DRG_STAMP(10 + it * 100 + 2);
-    if (fast) {
+    if (scaled) {
       // sum_i 2^(x_ij + u_i log2e) = 2^(norm2 - v_j log2e) * sum_i e_ij w_i   (v2_s holds (v_j - shift) log2e)
 #pragma unroll
       for (int k = 0; k < KQ; ++k) {
@@ -1969,7 +2010,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
 #pragma unroll
       for (int e = 0; e < KQ * 4; ++e) {
         const float2 o = xcomb[e * P2_TPR + ct];
-        if (fast) {  // both groups carry the same reference
+        if (scaled) {  // both groups carry the same reference
           cs[e] += o.y;
         } else {
           LseAcc a{cm[e], cs[e]};
