@@ -343,6 +343,36 @@ __device__ __forceinline__ void append_candidates(const ProcrParams& p, int b, s
   }
 }
 
+// CTA-local variant: candidates go to a shared-memory list first; the CTA reserves its slice of the global list with
+// ONE atomic per flush (the single global counter was the bottleneck: ~19 k dependent same-address atomics).
+constexpr int COLLECT_CAP = 5120;  // shared-memory candidate list of a CTA; flushed when a worst-case chunk (4096) might not fit
+__device__ __forceinline__ void append_candidates_smem(unsigned int* s_key, unsigned int* s_idx, unsigned int* s_n,
+                                                       const bool (&take)[4], const unsigned int (&key)[4], unsigned int flat0) {
+  const int lane = threadIdx.x & 31;
+  int mine = (int)take[0] + (int)take[1] + (int)take[2] + (int)take[3];
+  const unsigned int any = __ballot_sync(0xffffffffu, mine > 0);
+  if (any == 0u) return;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int tmp = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += tmp;
+  }
+  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned int base = 0;
+  if (lane == 0) base = atomicAdd(s_n, (unsigned int)warp_total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  unsigned int pos = base + (unsigned int)(incl - mine);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (take[e]) {
+      s_key[pos] = key[e];
+      s_idx[pos] = flat0 + e;
+      ++pos;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) topk_collect_kernel(const ProcrParams p) {
   const int b = blockIdx.y;
   const size_t total = (size_t)p.N * p.M;
@@ -405,38 +435,117 @@ __global__ void __launch_bounds__(256) topk_collect_rows_kernel(const ProcrParam
   const float* x = p.scores + (size_t)b * total;
   const unsigned long long lower = p.state[b].lower_key;
   const float shift = p.pshift ? *p.pshift : 0.f;
-  const float norm = p.pbc[b].norm;
+  const SkhConst bc = p.pbc[b];
+  const float norm = bc.norm;
+  const bool masked = p.apply_mask && bc.pad != 1.f;  // pad == 1: the Sinkhorn saw no padded row / column
   const float* u_b = p.pu + (size_t)b * p.ldu;
   const float* v_b = p.pv + (size_t)b * p.ldv;
-  const int ncol_iters = (M + 1023) / 1024;  // all lanes iterate alike (warp-collective append)
-  for (int i = blockIdx.x; i < N; i += gridDim.x) {
-    const float ui = u_b[i];
-    const bool row_ok = !p.apply_mask || p.src_mask[(size_t)b * N + i];
-    for (int k = 0; k < ncol_iters; ++k) {
-      const int j = 4 * (int)threadIdx.x + 1024 * k;
-      bool take[4] = {false, false, false, false};
-      unsigned int key[4] = {0u, 0u, 0u, 0u};
-      const unsigned int flat0 = (unsigned int)((size_t)i * M + j);
-      if (j < M) {
-        const float4 z = *reinterpret_cast<const float4*>(x + (size_t)i * M + j);
-        const float4 vj = *reinterpret_cast<const float4*>(v_b + j);
-        bool ok[4] = {row_ok, row_ok, row_ok, row_ok};
-        if (p.apply_mask) {
-          const uchar4 tm = *reinterpret_cast<const uchar4*>(p.tgt_mask + (size_t)b * M + j);
-          ok[0] = row_ok && tm.x; ok[1] = row_ok && tm.y; ok[2] = row_ok && tm.z; ok[3] = row_ok && tm.w;
-        }
-        const float zz[4] = {z.x, z.y, z.z, z.w}, vv[4] = {vj.x, vj.y, vj.z, vj.w};
+  // Pre-filter in the log2 domain: conf = 2^(la2) >= L  <=>  la2 >= log2 L up to rounding (~1e-5 here, the pre-filter
+  // folds the constants differently from the exact expression); the 1e-3 margin only lets a few extra quads through to
+  // the exact 64-bit key comparison.  Almost every quad stops after 1 FADD + 1 FFMA + 1 compare per element and one
+  // warp vote -- the pass was issue-bound, not bandwidth-bound, with the exponential and the key compare on every element.
+  const float lower_val = ordered_to_float((unsigned int)(lower >> 32));
+  const float thr2 = (lower_val > 0.f) ? (log2f(lower_val) - 1.0e-3f) : -INFINITY;
+  const int ncol_iters = (M + 1023) / 1024;  // all lanes iterate alike (warp-collective vote / append)
+  constexpr int CU = 4;                      // column chunks loaded together: 4 x 16 bytes in flight per thread
+  __shared__ unsigned int s_key[COLLECT_CAP], s_idx[COLLECT_CAP];
+  __shared__ unsigned int s_n, s_base;
+  if (threadIdx.x == 0) s_n = 0u;
+  __syncthreads();
+  float cterm[CU][4];  // (v_j - norm - shift) * log2e of this thread's columns; -inf: masked or out of range
+  auto load_cterm = [&](int k0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float zs = ok[e] ? (zz[e] - shift) : -INFINITY;
-          const float c = ex2((((zs + ui) + vv[e]) - norm) * LOG2E);
-          key[e] = float_to_ordered(c);
-          take[e] = make_key64(key[e], flat0 + e) >= lower;
+    for (int q = 0; q < CU; ++q) {
+      const int j = 4 * (int)threadIdx.x + 1024 * (k0 + q);
+      float4 vj = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      bool okc[4] = {true, true, true, true};
+      if (k0 + q < ncol_iters && j < M) {
+        vj = *reinterpret_cast<const float4*>(v_b + j);
+        if (masked) {
+          const uchar4 tm = *reinterpret_cast<const uchar4*>(p.tgt_mask + (size_t)b * M + j);
+          okc[0] = tm.x; okc[1] = tm.y; okc[2] = tm.z; okc[3] = tm.w;
         }
       }
-      append_candidates(p, b, total, take, key, flat0);
+      const float vv[4] = {vj.x, vj.y, vj.z, vj.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cterm[q][e] = okc[e] ? ((vv[e] - norm) - shift) * LOG2E : -INFINITY;
+    }
+  };
+  if (ncol_iters <= CU) load_cterm(0);
+  auto flush = [&]() {  // CTA-wide: reserve a slice of the global list with one atomic, copy, reset
+    __syncthreads();
+    const unsigned int cnt = s_n;
+    if (cnt) {
+      if (threadIdx.x == 0) s_base = atomicAdd(&p.state[b].n_cand, cnt);
+      __syncthreads();
+      const unsigned int base = s_base;
+      for (unsigned int e = threadIdx.x; e < cnt; e += blockDim.x) {
+        p.cand_key[(size_t)b * total + base + e] = s_key[e];
+        p.cand_idx[(size_t)b * total + base + e] = s_idx[e];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) s_n = 0u;
+      __syncthreads();
+    }
+  };
+  auto load_row = [&](float4(&dst)[CU], int i, int k0) {
+#pragma unroll
+    for (int q = 0; q < CU; ++q) {
+      const int j = 4 * (int)threadIdx.x + 1024 * (k0 + q);
+      dst[q] = (i < N && k0 + q < ncol_iters && j < M) ? __ldcs(reinterpret_cast<const float4*>(x + (size_t)i * M + j))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  // the next chunk (normally: the next row) is requested before this one is examined
+  float4 zn[CU];
+  load_row(zn, blockIdx.x, 0);
+  for (int i = blockIdx.x; i < N; i += gridDim.x) {
+    const float ui = u_b[i];
+    const bool row_ok = !masked || p.src_mask[(size_t)b * N + i];
+    const float ui2 = row_ok ? ui * LOG2E : -INFINITY;
+    for (int k0 = 0; k0 < ncol_iters; k0 += CU) {
+      if (ncol_iters > CU) load_cterm(k0);
+      float4 zq[CU];
+#pragma unroll
+      for (int q = 0; q < CU; ++q) zq[q] = zn[q];
+      if (k0 + CU < ncol_iters) load_row(zn, i, k0 + CU);
+      else load_row(zn, i + (int)gridDim.x, 0);
+      // room for a worst-case chunk (every element a candidate)?  Block-uniform: s_n is read between barriers.
+      __syncthreads();
+      if (s_n > (unsigned int)(COLLECT_CAP - CU * 1024)) flush();
+#pragma unroll
+      for (int q = 0; q < CU; ++q) {
+        if (k0 + q >= ncol_iters) break;  // uniform
+        const float zz[4] = {zq[q].x, zq[q].y, zq[q].z, zq[q].w};
+        bool maybe = false;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) maybe = maybe || !(fmaf(zz[e], LOG2E, ui2 + cterm[q][e]) < thr2);  // NaN passes too
+        if (!__any_sync(0xffffffffu, maybe)) continue;
+        // exact path (rare): the expression and association of skh_final_tile_kernel, ordered key, 64-bit compare
+        const int j = 4 * (int)threadIdx.x + 1024 * (k0 + q);
+        bool take[4] = {false, false, false, false};
+        unsigned int key[4] = {0u, 0u, 0u, 0u};
+        const unsigned int flat0 = (unsigned int)((size_t)i * M + j);
+        if (maybe && j < M) {
+          const float4 vj = *reinterpret_cast<const float4*>(v_b + j);
+          bool ok[4] = {row_ok, row_ok, row_ok, row_ok};
+          if (masked) {
+            const uchar4 tm = *reinterpret_cast<const uchar4*>(p.tgt_mask + (size_t)b * M + j);
+            ok[0] = row_ok && tm.x; ok[1] = row_ok && tm.y; ok[2] = row_ok && tm.z; ok[3] = row_ok && tm.w;
+          }
+          const float vv[4] = {vj.x, vj.y, vj.z, vj.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float zs = ok[e] ? (zz[e] - shift) : -INFINITY;
+            key[e] = float_to_ordered(ex2((((zs + ui) + vv[e]) - norm) * LOG2E));
+            take[e] = make_key64(key[e], flat0 + e) >= lower;
+          }
+        }
+        append_candidates_smem(s_key, s_idx, &s_n, take, key, flat0);
+      }
     }
   }
+  flush();
 }
 
 // ---- 5. select + Kabsch + warp ----------------------------------------------------------------
@@ -954,7 +1063,7 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
     ProfScope prof_scope(PROF_TOPK_COLLECT, st);
     if (!p.conf && (M % 4) == 0 && ((((uintptr_t)p.scores) | ((uintptr_t)p.pv) | ((uintptr_t)p.tgt_mask)) & 15u) == 0 &&
       ((p.ldv & 3) == 0)) {
-    int gr = (NUM_SMS * 8) / B;
+    int gr = (NUM_SMS * 5) / B;  // one wave: 40 KB of shared memory per CTA -> 5 CTAs per SM
     if (gr < 1) gr = 1;
     if (gr > N) gr = N;
     topk_collect_rows_kernel<<<dim3(gr, B), 256, 0, st>>>(p);
