@@ -62,6 +62,7 @@ struct ProcrParams {
   unsigned int* cand_idx;        // [B, N*M]
   unsigned int* sample_buf;      // [B, TS_SAMPLES]
   unsigned int* sample_arrive;   // [B] arrival counters of the sampling CTAs (zero between calls)
+  float4* pcd4;                  // [B][N + M] the points padded to 16 bytes (src, then tgt): one gather per point in the solve kernel
   // outputs
   float* R;                      // [B,3,3]
   float* t;                      // [B,3]
@@ -373,8 +374,19 @@ __device__ __forceinline__ void append_candidates_smem(unsigned int* s_key, unsi
   }
 }
 
+// [N,3] / [M,3] points -> 16-byte records (the solve kernel then needs one gather per point instead of three; its two
+// moment passes are bound by the L1 wavefronts of those scattered loads)
+__device__ __forceinline__ void pad_points(const ProcrParams& p, int b) {
+  const int L = p.N + p.M;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < L; q += gridDim.x * blockDim.x) {
+    const float* src = (q < p.N) ? (p.src_pcd + ((size_t)b * p.N + q) * 3) : (p.tgt_pcd + ((size_t)b * p.M + (q - p.N)) * 3);
+    p.pcd4[(size_t)b * L + q] = make_float4(src[0], src[1], src[2], 0.f);
+  }
+}
+
 __global__ void __launch_bounds__(256) topk_collect_kernel(const ProcrParams p) {
   const int b = blockIdx.y;
+  pad_points(p, b);
   const size_t total = (size_t)p.N * p.M;
   const float* x = (p.conf ? p.conf : p.scores) + (size_t)b * total;
   const unsigned long long lower = p.state[b].lower_key;
@@ -430,6 +442,7 @@ __global__ void __launch_bounds__(256) topk_collect_kernel(const ProcrParams p) 
 // u_i once per row, v and the target mask as 16-byte loads
 __global__ void __launch_bounds__(256) topk_collect_rows_kernel(const ProcrParams p) {
   const int b = blockIdx.y;
+  pad_points(p, b);
   const int N = p.N, M = p.M;
   const size_t total = (size_t)N * M;
   const float* x = p.scores + (size_t)b * total;
@@ -588,8 +601,11 @@ __device__ void svd3x3(const double A[3][3], double U[3][3], double s[3], double
       W[i][j] = A[i][j];
       V[i][j] = (i == j) ? 1.0 : 0.0;
     }
+  // fp64 divisions and square roots are ~100-cycle software sequences and this runs on ONE thread: a rotation uses one
+  // sqrt, one division and one rsqrt (t = 2g sign(d) / (|d| + sqrt(d^2 + 4 g^2)) with d = beta - alpha is the same
+  // tangent as sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = d / 2g), and convergence is tested on squares.
   for (int sweep = 0; sweep < 30; ++sweep) {
-    double off = 0.0;
+    bool rotated = false;
     for (int pcol = 0; pcol < 2; ++pcol) {
       for (int qcol = pcol + 1; qcol < 3; ++qcol) {
         double alpha = 0.0, beta = 0.0, gamma = 0.0;
@@ -599,10 +615,10 @@ __device__ void svd3x3(const double A[3][3], double U[3][3], double s[3], double
           gamma += W[i][pcol] * W[i][qcol];
         }
         if (gamma == 0.0) continue;
-        off = fmax(off, fabs(gamma) / sqrt(fmax(alpha * beta, 1e-300)));
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + tt * tt), sn = c * tt;
+        if (gamma * gamma > 1e-30 * fmax(alpha * beta, 1e-300)) rotated = true;  // |gamma| / sqrt(alpha beta) > 1e-15
+        const double d = beta - alpha;
+        const double tt = (d >= 0.0 ? 2.0 : -2.0) * gamma / (fabs(d) + sqrt(d * d + 4.0 * gamma * gamma));
+        const double c = rsqrt(1.0 + tt * tt), sn = c * tt;
         for (int i = 0; i < 3; ++i) {
           const double wp = W[i][pcol], wq = W[i][qcol];
           W[i][pcol] = c * wp - sn * wq;
@@ -613,7 +629,7 @@ __device__ void svd3x3(const double A[3][3], double U[3][3], double s[3], double
         }
       }
     }
-    if (off < 1e-15) break;
+    if (!rotated) break;
   }
   for (int j = 0; j < 3; ++j) s[j] = sqrt(W[0][j] * W[0][j] + W[1][j] * W[1][j] + W[2][j] * W[2][j]);
   // sort descending (columns of W and V move together)
@@ -758,7 +774,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
   //      centred covariance -- the reference's own order of operations (procrustes.py:29-34).
   //      (Measured: compacting the selection first and fp64 moments were both slower on B200.)
   const float* sp = p.src_pcd + (size_t)b * p.N * 3;
-  const float* tp = p.tgt_pcd + (size_t)b * p.M * 3;
+  const float4* sp4 = p.pcd4 + (size_t)b * (p.N + p.M);  // written by the collect kernel
+  const float4* tp4 = sp4 + p.N;
   unsigned int ne = 0;
   if (tid == 0) warp_cnt[0] = 0u;
   __syncthreads();
@@ -777,12 +794,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
             p.sel_tgt[(size_t)b * p.K_max + pos] = j;
           }
         }
+        const float4 x4 = sp4[i], y4 = tp4[j];
+        const float xs[3] = {x4.x, x4.y, x4.z}, ys[3] = {y4.x, y4.y, y4.z};
         m1[0] += wf;
         m1[1] += fabsf(wf);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          m1[2 + a] = fmaf(wf, sp[i * 3 + a], m1[2 + a]);
-          m1[5 + a] = fmaf(wf, tp[j * 3 + a], m1[5 + a]);
+          m1[2 + a] = fmaf(wf, xs[a], m1[2 + a]);
+          m1[5 + a] = fmaf(wf, ys[a], m1[5 + a]);
         }
       }
     }
@@ -800,8 +819,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
       if (make_key64(k32, fi) >= T) {
         const float wn = ordered_to_float(k32) * invf;
         const int i = (int)(fi / (unsigned int)p.M), j = (int)(fi - (unsigned int)i * (unsigned int)p.M);
-        const float xc[3] = {sp[i * 3 + 0] - mxf[0], sp[i * 3 + 1] - mxf[1], sp[i * 3 + 2] - mxf[2]};
-        const float yc[3] = {tp[j * 3 + 0] - myf[0], tp[j * 3 + 1] - myf[1], tp[j * 3 + 2] - myf[2]};
+        const float4 x4 = sp4[i], y4 = tp4[j];
+        const float xc[3] = {x4.x - mxf[0], x4.y - mxf[1], x4.z - mxf[2]};
+        const float yc[3] = {y4.x - myf[0], y4.y - myf[1], y4.z - myf[2]};
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -934,6 +954,7 @@ struct ProcrWorkspace {
   unsigned int* cand_idx;
   unsigned int* sample_buf;
   unsigned int* sample_arrive;
+  float4* pcd4;
   size_t total;
 };
 
@@ -950,6 +971,7 @@ static ProcrWorkspace procr_carve(void* ws, int B, int N, int M) {
   w.cand_idx = (unsigned int*)take(4ull * B * N * M);
   w.sample_buf = (unsigned int*)take(4ull * B * TS_SAMPLES);
   w.sample_arrive = (unsigned int*)take(4ull * B);
+  w.pcd4 = (float4*)take(16ull * B * ((size_t)N + M));
   w.total = off;
   return w;
 }
@@ -1014,6 +1036,7 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
   p.cand_idx = w.cand_idx;
   p.sample_buf = w.sample_buf;
   p.sample_arrive = w.sample_arrive;
+  p.pcd4 = w.pcd4;
   p.R = a->R;
   p.t = a->t;
   p.R_forwd = a->R_forwd;
