@@ -316,6 +316,8 @@ def run_ours(args):
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
 
     def e2e_run(first, count):
+        # (measured, tools/perf_e2e.py: launching step i + 1 before reading step i's results is SLOWER on this box --
+        # 1930 vs 2250 steps/s -- the 8.5 MB input copy then always competes with the kernels and becomes the bound)
         pipe.prefetch(first, pinned)
         last = None
         for i in range(first, first + count):

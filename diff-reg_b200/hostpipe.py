@@ -9,9 +9,12 @@ number, match count, matches) are copied back into pinned host buffers before `f
     pipe.reset(x_T)
     pipe.prefetch(0, inputs)                   # inputs: dict of pinned host tensors (src_feats, tgt_feats, s_pcd, ...)
     for i in range(steps):
-        pipe.launch(i)                         # graph replay on the compute stream
-        if i + 1 < steps: pipe.prefetch(i + 1, inputs)
-        out = pipe.finish(i)                   # dict of pinned host tensors, valid until the next finish()
+        pipe.launch(i)                         # graph replay + result copies on the compute stream
+        pipe.prefetch(i + 1, inputs)           # overlaps step i
+        out = pipe.finish(i)                   # waits for step i only; pinned host tensors, valid until launch(i + 2)
+
+(launch(i + 1) may also be issued before finish(i); on the B200 boxes measured here that was slower, the input copy
+then competes with the kernels all the time -- tools/perf_e2e.py.)
 
 The step index selects the DDIM time pair (i mod sampler.steps); consecutive steps alternate between the two
 input sets and between the two state buffers, which is why sampler.steps must be even when graphs are used.
@@ -40,20 +43,20 @@ class HostStepPipeline:
         self.x = [torch.zeros(1, n, m, device=self.dev), torch.zeros(1, n, m, device=self.dev)]
         self.counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
         cap = min(n, m)
-        self.host_out = {"R": torch.empty(1, 3, 3).pin_memory(), "t": torch.empty(1, 3, 1).pin_memory(),
-                         "condition": torch.empty(1, dtype=torch.float64).pin_memory(),
-                         "count": torch.empty(1, dtype=torch.int32).pin_memory(),
-                         "index": torch.empty(cap, 3, dtype=torch.int64).pin_memory(),
-                         "mconf": torch.empty(cap).pin_memory()}
+        self.host_out = [{"R": torch.empty(1, 3, 3).pin_memory(), "t": torch.empty(1, 3, 1).pin_memory(),
+                          "condition": torch.empty(1, dtype=torch.float64).pin_memory(),
+                          "count": torch.empty(1, dtype=torch.int32).pin_memory(),
+                          "index": torch.empty(cap, 3, dtype=torch.int64).pin_memory(),
+                          "mconf": torch.empty(cap).pin_memory()} for _ in range(2)]
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.sets[0].values())
-        self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.host_out.values())
+        self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.host_out[0].values())
         self.compute = torch.cuda.Stream(device=self.dev)
         self.copy = torch.cuda.Stream(device=self.dev)
         self.ev_in = [torch.cuda.Event(), torch.cuda.Event()]
         self.ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ev_out = [torch.cuda.Event(), torch.cuda.Event()]
         self.graphs = None
         self.aux = [None] * sampler.steps
-        self._eager_aux = None
         if use_graphs:
             self._capture()
 
@@ -98,30 +101,29 @@ class HostStepPipeline:
             self.ev_in[i % 2].record(self.copy)
 
     def launch(self, i):
-        """Run step i on the compute stream (asynchronous)."""
+        """Run step i on the compute stream and enqueue the copy of its results to the host (all asynchronous)."""
         with torch.cuda.stream(self.compute):
             self.compute.wait_event(self.ev_in[i % 2])
             if self.graphs is not None:
                 self.graphs[i % self.smp.steps].replay()
-                self._eager_aux = self.aux[i % self.smp.steps]
+                aux = self.aux[i % self.smp.steps]
             else:
-                self._eager_aux = self._eager(i)
+                aux = self._eager(i)
             self.ev_free[i % 2].record(self.compute)
-
-    def finish(self, i):
-        """Copy step i's results to the host and wait for them."""
-        aux = self._eager_aux
-        index, mconf, _, count = aux["match"]
-        ho = self.host_out
-        with torch.cuda.stream(self.compute):
+            index, mconf, _, count = aux["match"]
+            ho = self.host_out[i % 2]
             ho["R"].copy_(aux["pose"]["R_forwd"], non_blocking=True)
             ho["t"].copy_(aux["pose"]["t_forwd"], non_blocking=True)
             ho["condition"].copy_(aux["pose"]["condition"], non_blocking=True)
             ho["count"].copy_(count, non_blocking=True)
             ho["index"].copy_(index, non_blocking=True)
             ho["mconf"].copy_(mconf, non_blocking=True)
-        self.compute.synchronize()
-        return ho
+            self.ev_out[i % 2].record(self.compute)
+
+    def finish(self, i):
+        """Wait for step i's results; returns a dict of pinned host tensors (valid until launch(i + 2))."""
+        self.ev_out[i % 2].synchronize()
+        return self.host_out[i % 2]
 
     def state(self, i):
         """The device state x after step i-1 (input of step i)."""
