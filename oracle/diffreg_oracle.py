@@ -241,7 +241,7 @@ def batch_weighted_procrustes(X, Y, w, eps=1e-4):
     fix[:, 2, 2] = torch.linalg.det(U) * torch.linalg.det(V)           # reflection fix :38-40
     R = (U @ fix @ V.transpose(1, 2)).float().to(X.device)
     t = cy.transpose(1, 2) - R @ cx.transpose(1, 2)
-    return R, t, cond
+    return R, t, cond                                                   # cond stays on the CPU, as in the reference
 
 
 def soft_procrustes(conf, src_pcd, tgt_pcd, src_mask, tgt_mask, sample_rate=1.0,
@@ -253,8 +253,8 @@ def soft_procrustes(conf, src_pcd, tgt_pcd, src_mask, tgt_mask, sample_rate=1.0,
     (R, t, R_forwd, t_forwd, condition, solution_mask)."""
     B, N, M = conf.shape
     if padded_lengths:
-        src_len = torch.tensor([float(N)])
-        tgt_len = torch.tensor([float(M)])
+        src_len = torch.tensor([float(N)], device=conf.device)
+        tgt_len = torch.tensor([float(M)], device=conf.device)
     else:
         src_len = src_mask.sum(dim=1)
         tgt_len = tgt_mask.sum(dim=1)
@@ -265,15 +265,16 @@ def soft_procrustes(conf, src_pcd, tgt_pcd, src_mask, tgt_mask, sample_rate=1.0,
     flat = flat[:, :K]
     i_src = flat // M
     i_tgt = flat % M
-    bidx = torch.arange(B)[:, None].expand(B, K)
+    bidx = torch.arange(B, device=conf.device)[:, None].expand(B, K)
     P = src_pcd[bidx, i_src]
     Q = tgt_pcd[bidx, i_tgt]
-    w[torch.arange(K)[None, :].expand(B, K) >= cap[:, None]] = 0.0       # :74-76
+    w[torch.arange(K, device=conf.device)[None, :].expand(B, K) >= cap[:, None]] = 0.0       # :74-76
     R, t, cond = batch_weighted_procrustes(P, Q, w[..., None])
-    ok = cond < max_condition_num                                        # :87
+    ok = cond < max_condition_num                                        # :87 (CPU tensors, like cond)
     R_f, t_f = R.clone(), t.clone()
-    R_f[~ok] = torch.eye(3, dtype=R.dtype)
-    t_f[~ok] = torch.zeros(3, 1, dtype=R.dtype)
+    okd = ok.to(R.device)
+    R_f[~okd] = torch.eye(3, dtype=R.dtype, device=R.device)
+    t_f[~okd] = torch.zeros(3, 1, dtype=R.dtype, device=R.device)
     return R, t, R_f, t_f, cond, ok
 
 
@@ -318,6 +319,7 @@ def ddim_update(x_t, x0, ac, t, t_next, noise=None, eta=1.0):
 
     Reproduces the fp64 promotion (Q4): the schedule buffers are fp64 so the result is
     fp64 whatever the input dtype."""
+    ac = ac.to(x_t.device)
     r = torch.sqrt(1.0 / ac[t]).reshape(1, 1, 1)
     rm1 = torch.sqrt(1.0 / ac[t] - 1).reshape(1, 1, 1)
     pred = (r * x_t - x0) / rm1
