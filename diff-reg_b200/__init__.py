@@ -31,7 +31,7 @@ def __getattr__(name):
     if name == "HostStepPipeline":
         from . import hostpipe
         return hostpipe.HostStepPipeline
-    if name in ("RowShardedSinkhorn", "EmulatedRowShards", "shard_rows", "shard_units", "lse_allreduce", "lse_combine"):
+    if name in ("RowShardedSinkhorn", "EmulatedRowShards", "P2PComm", "shard_rows", "shard_units", "lse_allreduce", "lse_combine"):
         from . import distributed
         return getattr(distributed, name)
     if name == "ops":

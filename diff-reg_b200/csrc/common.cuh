@@ -66,6 +66,45 @@ struct SkhViews {
 // runs drg_sinkhorn (out_mode NONE allowed) and reports the views (sinkhorn.cu)
 int skh_run_with_views(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* stream, SkhViews* views);
 
+// ---- peer-to-peer exchange over NVLink (row-sharded Sinkhorn, p2p.cu / sinkhorn.cu) ---------------------
+constexpr int P2P_MAX_RANKS = 8;
+// One allocation per rank, exported to the peers with CUDA IPC:
+//   inbox [2 slots][world senders][slot_elems] float2, flags [2 slots][nflags] u32, status (1 = a wait timed out)
+struct P2PComm {
+  int rank, world;
+  size_t slot_elems;
+  int nflags;
+  void* base;                     // this rank's allocation
+  void* peer_base[P2P_MAX_RANKS]; // every rank's allocation as mapped into this process (own: base)
+  bool peer_open[P2P_MAX_RANKS];
+  unsigned int epoch;             // exchanges performed so far (identical on every rank)
+  size_t bytes;
+};
+struct P2PView {  // what an exchange kernel needs, by value
+  float2* inbox[P2P_MAX_RANKS];
+  unsigned int* flags[P2P_MAX_RANKS];
+  int* status;
+  size_t slot_elems;
+  int world, rank, slot, nflags;
+  unsigned int target;            // arrivals expected on a flag of this slot once every rank has sent
+};
+inline size_t p2p_inbox_bytes(const P2PComm& c) { return 2 * (size_t)c.world * c.slot_elems * sizeof(float2); }
+inline P2PView p2p_view(P2PComm& c) {
+  P2PView v{};
+  for (int r = 0; r < c.world; ++r) {
+    v.inbox[r] = reinterpret_cast<float2*>(c.peer_base[r]);
+    v.flags[r] = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(c.peer_base[r]) + p2p_inbox_bytes(c));
+  }
+  v.status = reinterpret_cast<int*>(reinterpret_cast<char*>(c.base) + p2p_inbox_bytes(c) + 2 * (size_t)c.nflags * sizeof(unsigned int));
+  v.slot_elems = c.slot_elems;
+  v.world = c.world;
+  v.rank = c.rank;
+  v.slot = (int)(c.epoch & 1u);
+  v.nflags = c.nflags;
+  v.target = (unsigned int)c.world * (c.epoch / 2u + 1u);
+  return v;
+}
+
 // ---- optional per-kernel timing (bench.py's roofline leg) ---------------------------------
 // When enabled through drg_profile_enable(1), every launch of a slotted kernel is bracketed by two
 // CUDA events on the launching stream; drg_profile_read() sums the elapsed times.  Disabled: no cost.

@@ -1568,7 +1568,7 @@ __device__ __forceinline__ void grid_barrier_ra(unsigned int* counter, unsigned 
 
 template <int KQ, int RR, bool FULL>
 __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhParams p, const int iters, unsigned int* gsync) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = p.N, M = p.M;
   const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -2223,6 +2223,100 @@ __global__ void __launch_bounds__(256) skh_shard_update_kernel(const SkhParams p
   } else {
     lse_add_value(a, uN * LOG2E);
     v_b[M] = bc.log_nu_bin - (alpha + lse_value(a) * LN2);
+  }
+}
+
+// Fused column merge + peer-to-peer all-reduce + potential update of the row-sharded path: ONE kernel per iteration
+// instead of skh_col_kernel -> NCCL all-reduce (MAX, SUM) -> skh_shard_update_kernel.  A CTA owns 32 columns: it
+// merges this rank's G per-CTA partials, stores the (max, sum) pair straight into every rank's inbox over NVLink
+// (peer mappings from CUDA IPC), publishes them with a system-scope release on one flag per (rank, column chunk), waits
+// until all ranks have published the same chunk, combines the P partials from its own inbox in rank order (every
+// rank computes bit-identical potentials) and writes v.  CTAs depend only on the same-index CTA of the peers.
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void __launch_bounds__(256) skh_shard_exchange_kernel(const SkhParams p, const P2PView c) {
+  const int b = blockIdx.y;
+  const int jj = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jj;
+  const int M = p.M, N = p.N, G = p.G;
+  __shared__ float2 part_s[COL_SLICES][32];
+
+  LseAcc a = lse_empty();
+  const bool in_range = (j <= M);
+  if (in_range) {
+    const bool is_bin = (j == M);
+    const bool col_ok = is_bin || !p.apply_mask || p.tgt_mask[(size_t)b * M + j];
+    if (col_ok) {
+      const float2* src = is_bin ? (p.upart + (size_t)b * G) : (p.colpart + (size_t)b * G * M + j);
+      const size_t gstride = is_bin ? 1 : (size_t)M;
+      float2 q[COL_MAXG];
+      float m = NEG_BIG;
+#pragma unroll
+      for (int k = 0; k < COL_MAXG; ++k) {
+        const int g = sl + COL_SLICES * k;
+        q[k] = (g < G) ? src[(size_t)g * gstride] : make_float2(NEG_BIG, 0.f);
+        m = fmaxf(m, q[k].x);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < COL_MAXG; ++k) sum += q[k].y * ex2(q[k].x - m);
+      a.m = m;
+      a.s = sum;
+    }
+  }
+  part_s[sl][jj] = make_float2(a.m, a.s);
+  __syncthreads();
+  const size_t eoff = (size_t)b * (M + 1) + j;
+  if (sl == 0 && in_range) {
+    float m = part_s[0][jj].x;
+#pragma unroll
+    for (int k = 1; k < COL_SLICES; ++k) m = fmaxf(m, part_s[k][jj].x);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < COL_SLICES; ++k) sum += part_s[k][jj].y * ex2(part_s[k][jj].x - m);
+    const float2 mine = make_float2(m, sum);
+    for (int r = 0; r < c.world; ++r)  // this rank's slot in every inbox (its own included)
+      c.inbox[r][((size_t)c.slot * c.world + c.rank) * c.slot_elems + eoff] = mine;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // the stores above (ordered before this thread by the barrier) become visible to the peers first
+    const size_t fidx = (size_t)c.slot * c.nflags + (size_t)b * gridDim.x + blockIdx.x;
+    for (int r = 0; r < c.world; ++r) atomicAdd_system(c.flags[r] + fidx, 1u);
+    const unsigned int* mine = c.flags[c.rank] + fidx;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys_u32(mine) < c.target) {
+      if (global_timer_ns() - t0 > 4000000000ull) {  // a peer never arrived: report instead of hanging the GPU
+        *c.status = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (sl != 0 || !in_range) return;
+  LseAcc tot = lse_empty();
+  for (int r = 0; r < c.world; ++r) {
+    const float2 q = __ldcg(c.inbox[c.rank] + ((size_t)c.slot * c.world + r) * c.slot_elems + eoff);  // written by peers: L2
+    lse_merge(tot, q.x, q.y);
+  }
+  const SkhConst bc = p.bc[b];
+  const float alpha = *p.alpha;
+  const float uN = p.u[(size_t)b * p.ldu + N];
+  float* v_b = p.v + (size_t)b * p.ldv;
+  if (j < M) {
+    lse_add_value(tot, (alpha + uN) * LOG2E);  // dustbin row entry (the dustbin row exists once, on every rank alike)
+    v_b[j] = bc.norm - lse_value(tot) * LN2;
+  } else {
+    lse_add_value(tot, uN * LOG2E);
+    v_b[M] = bc.log_nu_bin - (alpha + lse_value(tot) * LN2);
   }
 }
 
@@ -2929,10 +3023,11 @@ extern "C" size_t drg_sinkhorn_workspace_bytes(int B, int N, int M) {
 
 static long long* g_skh_times = nullptr;  // tuning only (DRG_SKH_TIMES=1)
 
-enum SkhRun { SKH_RUN_ALL = 0, SKH_SHARD_BEGIN, SKH_SHARD_LOCAL, SKH_SHARD_UPDATE, SKH_SHARD_FINAL };
+enum SkhRun { SKH_RUN_ALL = 0, SKH_SHARD_BEGIN, SKH_SHARD_LOCAL, SKH_SHARD_UPDATE, SKH_SHARD_FINAL, SKH_SHARD_LOCAL_X };
 
 static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature, void* workspace, size_t workspace_bytes,
-                        void* stream, SkhRun run = SKH_RUN_ALL, const int* global_counts = nullptr, float2* shard_partial = nullptr) {
+                        void* stream, SkhRun run = SKH_RUN_ALL, const int* global_counts = nullptr, float2* shard_partial = nullptr,
+                        const P2PView* xview = nullptr) {
   cudaStream_t st = (cudaStream_t)stream;
   const int B = a->B, N = a->N, M = a->M;
   SkhPlan pl = make_plan(B, N, M);
@@ -3028,7 +3123,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     DRG_LAUNCH_CHECK();
     return DRG_OK;
   }
-  const int iters = run == SKH_SHARD_LOCAL ? 1 : run == SKH_SHARD_FINAL ? 0 : dual ? 1 : a->iters;
+  const int iters = (run == SKH_SHARD_LOCAL || run == SKH_SHARD_LOCAL_X) ? 1 : run == SKH_SHARD_FINAL ? 0 : dual ? 1 : a->iters;
   dim3 cgrid((M + 1 + 31) / 32, B);
   if (persist) {
     DRG_CUDA(cudaMemsetAsync(w.gsync, 0, sizeof(unsigned int) * B * 3, st));
@@ -3057,12 +3152,13 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     count_launch();
     {
       ProfScope prof_scope(PROF_SKH_COL, st);
-      skh_col_kernel<<<cgrid, 256, 0, st>>>(p);
+      if (run == SKH_SHARD_LOCAL_X) skh_shard_exchange_kernel<<<cgrid, 256, 0, st>>>(p, *xview);
+      else skh_col_kernel<<<cgrid, 256, 0, st>>>(p);
     }
     DRG_LAUNCH_CHECK();
   }
 
-  if (run == SKH_SHARD_LOCAL) return DRG_OK;
+  if (run == SKH_SHARD_LOCAL || run == SKH_SHARD_LOCAL_X) return DRG_OK;
   if (a->out_mode != DRG_OUT_NONE || dual) {
     SkhFinalParams f{};
     f.scores = a->scores;
@@ -3188,6 +3284,21 @@ extern "C" int drg_sinkhorn_shard_local(const drg_sinkhorn_args* a, void* worksp
   if (rc != DRG_OK) return rc;
   DRG_CHECK_ARG(partial != nullptr && (((uintptr_t)partial) & 7u) == 0, "partial must be a non-null 8-byte aligned [B, M+1, 2] buffer");
   return run_sinkhorn(a, false, 1.f, workspace, workspace_bytes, stream, SKH_SHARD_LOCAL, nullptr, reinterpret_cast<float2*>(partial));
+}
+extern "C" int drg_sinkhorn_shard_local_exchange(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* comm,
+                                                 void* stream) {
+  int rc = shard_check(a);
+  if (rc != DRG_OK) return rc;
+  DRG_CHECK_ARG(comm != nullptr, "comm is null");
+  P2PComm* c = reinterpret_cast<P2PComm*>(comm);
+  const int nchunk = (a->M + 1 + 31) / 32;
+  DRG_CHECK_ARG((size_t)a->B * (a->M + 1) <= c->slot_elems && (long long)a->B * nchunk <= c->nflags,
+                "p2p comm too small for this shape (drg_p2p_create capacity)");
+  for (int r = 0; r < c->world; ++r) DRG_CHECK_ARG(c->peer_base[r] != nullptr, "p2p comm is not connected (drg_p2p_connect)");
+  const P2PView view = p2p_view(*c);
+  rc = run_sinkhorn(a, false, 1.f, workspace, workspace_bytes, stream, SKH_SHARD_LOCAL_X, nullptr, nullptr, &view);
+  if (rc == DRG_OK) c->epoch += 1u;
+  return rc;
 }
 extern "C" int drg_sinkhorn_shard_update(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, const float* reduced,
                                          void* stream) {

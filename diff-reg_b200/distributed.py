@@ -51,12 +51,74 @@ def lse_allreduce(partial, group=None, ref=None):
     return torch.stack((m, s), dim=-1)
 
 
-class RowShardedSinkhorn:
-    """log_optimal_transport over a row-sharded score matrix.  Call on every rank with its local rows."""
+class P2PComm:
+    """Peer-mapped exchange buffers of the ranks of one node (drg_p2p_*): every rank allocates an inbox, the CUDA IPC
+    handles are all-gathered over the process group, and every rank maps every inbox.  Kernels then store into the
+    peers' inboxes directly over NVLink / NVSwitch -- the all-reduce of the row-sharded Sinkhorn happens inside its own
+    kernel instead of two NCCL calls per iteration.  One process per GPU, all on the same node, world size <= 8."""
 
-    def __init__(self, group=None, single_allreduce_after=2):
+    def __init__(self, slot_elems, nflags, group=None, device=None):
+        import ctypes
+        from . import _lib
+        self.lib = _lib.load_library()
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.slot_elems, self.nflags = int(slot_elems), int(nflags)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        hb = int(self.lib.drg_p2p_handle_bytes())
+        mine = (ctypes.c_ubyte * hb)()
+        comm = ctypes.c_void_p()
+        _lib.check(self.lib.drg_p2p_create(self.rank, self.world, self.slot_elems, self.nflags, ctypes.byref(comm), mine))
+        self.handle = comm
+        # all-gather the handles through device tensors: works with the NCCL backend (and with gloo via a CPU copy)
+        backend = dist.get_backend(group)
+        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=dev if backend == "nccl" else "cpu")
+        allh = torch.empty(self.world * hb, dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(allh, t, group=group)
+        raw = bytes(allh.cpu().tolist())
+        buf = (ctypes.c_ubyte * len(raw)).from_buffer_copy(raw)
+        _lib.check(self.lib.drg_p2p_connect(self.handle, buf))
+        dist.barrier(group=group)          # nobody sends before everybody has mapped everybody
+
+    def fits(self, B, M):
+        return B * (M + 1) <= self.slot_elems and B * ((M + 1 + 31) // 32) <= self.nflags
+
+    def status(self):
+        return int(self.lib.drg_p2p_status(self.handle))
+
+    def close(self):
+        if self.handle is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            self.lib.drg_p2p_destroy(self.handle)
+            self.handle = None
+
+
+class RowShardedSinkhorn:
+    """log_optimal_transport over a row-sharded score matrix.  Call on every rank with its local rows.
+
+    exchange="p2p" (default when the backend is NCCL): the per-iteration all-reduce of the column partials runs inside
+    the kernel over peer-mapped memory (P2PComm).  exchange="nccl": two (later one) NCCL all-reduces per iteration
+    between the local pass and the update -- the portable path, also used under gloo in the CPU tests' logic."""
+
+    def __init__(self, group=None, single_allreduce_after=2, exchange=None):
         self.group = group
         self.single_after = single_allreduce_after
+        self.exchange = exchange
+        self.comm = None
+
+    def _p2p(self, B, M):
+        mode = self.exchange
+        if mode is None:
+            mode = "p2p" if dist.get_backend(self.group) == "nccl" else "nccl"
+        if mode != "p2p":
+            return None
+        if self.comm is None or not self.comm.fits(B, M):
+            if self.comm is not None:
+                self.comm.close()
+            self.comm = P2PComm(B * (M + 1), B * ((M + 1 + 31) // 32), self.group)
+        return self.comm
 
     @torch.no_grad()
     def __call__(self, scores_local, alpha, iters, src_mask_local, tgt_mask, out_mode="conf", apply_mask=False):
@@ -66,6 +128,11 @@ class RowShardedSinkhorn:
         dist.all_reduce(src_total, op=dist.ReduceOp.SUM, group=self.group)
         counts[:, 0] = src_total
         st.begin(counts)
+        comm = self._p2p(st.B, st.M)
+        if comm is not None:
+            for it in range(int(iters)):
+                st.local_exchange(comm.handle)
+            return st.final(out_mode)
         ref = None
         for it in range(int(iters)):
             partial = st.local()

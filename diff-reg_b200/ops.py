@@ -312,6 +312,11 @@ class ShardedSinkhornState:
         check(self.lib.drg_sinkhorn_shard_local(self._args(), self.ws.data_ptr(), self.ws.numel(), self.partial.data_ptr(), _stream()))
         return self.partial
 
+    def local_exchange(self, comm):
+        """Row pass + in-kernel peer-to-peer all-reduce of the column partials + update of v (one call per iteration;
+        `comm` is distributed.P2PComm.handle)."""
+        check(self.lib.drg_sinkhorn_shard_local_exchange(self._args(), self.ws.data_ptr(), self.ws.numel(), comm, _stream()))
+
     def update(self, reduced):
         reduced = _f32c(reduced)
         check(self.lib.drg_sinkhorn_shard_update(self._args(), self.ws.data_ptr(), self.ws.numel(), reduced.data_ptr(), _stream()))

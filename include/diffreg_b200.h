@@ -129,6 +129,25 @@ int drg_sinkhorn_shard_update(const drg_sinkhorn_args* args, void* workspace, si
                               void* stream);
 int drg_sinkhorn_shard_final(const drg_sinkhorn_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same iteration with the all-reduce INSIDE the kernel (one process per GPU on one NVLink / NVSwitch node):
+ *   drg_p2p_create     allocates this rank's exchange buffer (inboxes for `slot_elems` (max, sum) pairs per sender --
+ *                      at least B * (M + 1) -- and `nflags` >= B * ceil((M + 1) / 32) flags), returns an opaque comm and
+ *                      its CUDA IPC handle (drg_p2p_handle_bytes() bytes) for the other ranks
+ *   drg_p2p_connect    maps every rank's buffer: `handles` = the world handles, rank-major (exchange them with any
+ *                      host-side all-gather)
+ *   drg_sinkhorn_shard_local_exchange   = shard_local + all-reduce + shard_update: after the row pass one kernel merges
+ *                      this rank's column partials, stores them into every rank's inbox over NVLink, waits for the
+ *                      peers' partials of the same columns and updates v (bit-identical on every rank).  Every rank must
+ *                      issue the same sequence of calls on a comm.
+ *   drg_p2p_status     0, or 1 if a wait ever timed out (a peer never arrived; that call's result is invalid)      */
+size_t drg_p2p_handle_bytes(void);
+int drg_p2p_create(int rank, int world, size_t slot_elems, int nflags, void** comm_out, void* handle_out);
+int drg_p2p_connect(void* comm, const void* handles);
+int drg_p2p_status(void* comm);
+int drg_p2p_destroy(void* comm);
+int drg_sinkhorn_shard_local_exchange(const drg_sinkhorn_args* args, void* workspace, size_t workspace_bytes, void* comm,
+                                      void* stream);
+
 /* Dual-softmax confidence: conf = softmax_src(sim/T | src mask) * softmax_tgt(sim/T | tgt mask)
  *   replaces Diff-Reg-4dmatch/models/matching.py:147-157 (sim already divided by nothing:
  *   the temperature is applied here).  out[B,N,M]. */

@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=16384)
 ap.add_argument("--iters", type=int, default=100)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
 args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -38,7 +39,7 @@ for r0 in range(a, b, blk):
 src_mask = torch.ones(1, b - a, dtype=torch.bool, device=dev)
 tgt_mask = torch.ones(1, M, dtype=torch.bool, device=dev)
 alpha = torch.tensor(1.0, device=dev)
-op = D.RowShardedSinkhorn()
+op = D.RowShardedSinkhorn(exchange=args.exchange)
 out = op(scores, alpha, args.iters, src_mask, tgt_mask, out_mode="conf")
 torch.cuda.synchronize(); dist.barrier()
 times = []
@@ -52,6 +53,14 @@ for _ in range(args.reps):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     times.append(float(t.item()))
 ms = sorted(times)[len(times) // 2]
+# the two exchange paths must agree (same arithmetic up to the order of the P-way combine)
+other = D.RowShardedSinkhorn(exchange="nccl" if args.exchange == "p2p" else "p2p")
+ref = other(scores, alpha, min(args.iters, 10), src_mask, tgt_mask, out_mode="conf")
+mine = op(scores, alpha, min(args.iters, 10), src_mask, tgt_mask, out_mode="conf")
+diff = (ref - mine).abs().max()
+dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+if other.comm is not None:
+    other.comm.close()
 # size-independent property: every real column of the full plan sums to 1 minus its dustbin-row entry; check the global column sums
 col = out.double().sum(dim=1)
 dist.all_reduce(col, op=dist.ReduceOp.SUM)
@@ -59,5 +68,8 @@ E = 4.0 * (N + 1) * (M + 1)
 if rank == 0:
     print(json.dumps({"workload": f"row-sharded log-Sinkhorn N=M={N}, iters={args.iters}", "n_gpus": world, "ms_per_call": ms,
                       "algorithmic_GBps_whole_job": (2 * args.iters + 2) * E / (ms * 1e-3) / 1e9,
-                      "ms_per_iteration": ms / args.iters, "col_sum_min": float(col.min()), "col_sum_max": float(col.max())}), flush=True)
+                      "ms_per_iteration": ms / args.iters, "col_sum_min": float(col.min()), "col_sum_max": float(col.max()),
+                      "exchange": args.exchange, "max_abs_diff_vs_other_exchange_10_iters": float(diff), "p2p_status": (op.comm.status() if op.comm is not None else None)}), flush=True)
+if op.comm is not None:
+    op.comm.close()
 dist.destroy_process_group()
