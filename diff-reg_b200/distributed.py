@@ -107,6 +107,7 @@ class RowShardedSinkhorn:
         self.single_after = single_allreduce_after
         self.exchange = exchange
         self.comm = None
+        self._shape = None
 
     def _p2p(self, B, M):
         mode = self.exchange
@@ -114,10 +115,11 @@ class RowShardedSinkhorn:
             mode = "p2p" if dist.get_backend(self.group) == "nccl" else "nccl"
         if mode != "p2p":
             return None
-        if self.comm is None or not self.comm.fits(B, M):
+        if self.comm is None or self._shape != (B, M):   # the flag <-> column-chunk mapping is per shape
             if self.comm is not None:
                 self.comm.close()
             self.comm = P2PComm(B * (M + 1), B * ((M + 1 + 31) // 32), self.group)
+            self._shape = (B, M)
         return self.comm
 
     @torch.no_grad()
