@@ -160,3 +160,24 @@ def test_unsupported_and_errors():
         z = torch.zeros(1, 2, 20000, device="cuda")
         ops.sinkhorn(z, torch.tensor(1.0, device="cuda"), 3, torch.ones(1, 2, dtype=torch.bool, device="cuda"),
                      torch.ones(1, 20000, dtype=torch.bool, device="cuda"))
+
+
+@pytest.mark.parametrize("scale,alpha_v,iters", [(60.0, 1.0, 4), (3.0, -30.0, 3), (25.0, 2.0, 20), (3.0, 1.0, 40)])
+def test_persistent_kernel_fallback_paths(scale, alpha_v, iters):
+    """The register-slab kernel leaves its scaled arithmetic when the potentials move by more than 2^50 between
+    iterations (huge dynamic range of the scores) or when the dustbin score is very negative, and runs the classical
+    log-domain pass instead; many iterations exercise the grid-barrier counters.  Same tolerance as everywhere."""
+    B, N, M = 2, 300, 1024
+    gen = torch.Generator().manual_seed(int(scale * 10) + iters)
+    sm, tm = _masks(B, N, M, "arbitrary", gen)
+    s = torch.randn(B, N, M, generator=gen) * scale
+    filled = s.masked_fill(~O.pair_mask(sm, tm), float("-inf"))
+    alpha = torch.tensor(alpha_v)
+    ref = O.log_optimal_transport(filled, alpha, iters, sm, tm)
+    out = _ops().sinkhorn(s.cuda(), alpha.cuda(), iters, sm.cuda(), tm.cuda(), out_mode="log_full", apply_mask=True)
+    # the log matrix reaches magnitudes of several hundred here: 1e-4 absolute below 100, relative 2e-6 above
+    a, b = out.cpu().double(), ref.double()
+    fin = torch.isfinite(b)
+    assert torch.equal(torch.isfinite(a), fin)
+    err = ((a[fin] - b[fin]).abs() / b[fin].abs().clamp_min(50.0)).max().item()
+    assert err <= 2e-6, err
