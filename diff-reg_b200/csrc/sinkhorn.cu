@@ -1543,8 +1543,9 @@ __global__ void __launch_bounds__(PS_THREADS, 1) skh_persist_kernel(const SkhPar
 //   directions -- 1 MUFU, 2 FFMA, 2 FADD per element.
 //   Iteration structure (prologue, grid barrier, merge of the per-CTA column partials, grid barrier) as above.
 // ---------------------------------------------------------------------------------------
-constexpr int P2_THREADS = 512;
+constexpr int P2_GROUPS = 2;           // row groups per CTA (each consumes every P2_GROUPS-th mini-slab); 3 measured slower (82 vs 73 us)
 constexpr int P2_TPR = 256;            // threads per row group
+constexpr int P2_THREADS = P2_GROUPS * P2_TPR;
 constexpr int P2_GW = P2_TPR / 32;     // warps per row group
 constexpr int P2_MAX_STAGES = 8;
 
@@ -1580,8 +1581,8 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
   const int Mv = (M + 1 + 3) & ~3;
   float* v2_s = reinterpret_cast<float*>(smem_raw);             // [Mv]  column potentials, log2 domain, minus the shift
   float* lse_prev_s = v2_s + Mv;                                // [1024] row log-sum-exp (log2) of the previous iteration
-  float* red_part = lse_prev_s + 1024;                          // [2 buffers][2 groups][8 rows][8 warps]
-  float* red_s = red_part + 256;                                // [64]
+  float* red_part = lse_prev_s + 1024;                          // [2 buffers][P2_GROUPS][8 rows][8 warps]
+  float* red_s = red_part + 2 * P2_GROUPS * 64;                                // [64]
   float2* upart_s = reinterpret_cast<float2*>(red_s + 64);      // [2] (+2 pad)
   float2* comb = upart_s + 4;                                   // [16 warps][32] merge scratch
   uint64_t* full = reinterpret_cast<uint64_t*>(comb + (P2_THREADS / 32) * 32);  // [P2_MAX_STAGES]
@@ -1733,7 +1734,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     int stg = (it * ns + rg) % D;                         // stream element T = it * ns + s lands in stage T % D ...
     uint32_t ph = (uint32_t)(((it * ns + rg) / D) & 1);   // ... on its (T / D)-th use
     const bool ragged = (nrows % RR) != 0;
-    for (int s = rg; s < ns; s += 2) {
+    for (int s = rg; s < ns; s += P2_GROUPS) {
       const float* slab = ring + (size_t)stg * stage_floats;
       mbar_wait(&full[stg], ph);
       float4 z[RR][KQ];
@@ -1761,7 +1762,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           }
         }
       }
-      float* part = red_part + ((buf * 2 + rg) * 8) * 8;
+      float* part = red_part + ((buf * P2_GROUPS + rg) * 8) * 8;
       if (scaled) {
         float mh[RR], rs[RR];
         if (semi) {
@@ -1797,7 +1798,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
             rs[r] = 0.f;
           }
           buf ^= 1;
-          part = red_part + ((buf * 2 + rg) * 8) * 8;
+          part = red_part + ((buf * P2_GROUPS + rg) * 8) * 8;
         } else {
 #pragma unroll
           for (int r = 0; r < RR; ++r) {
@@ -1907,7 +1908,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           rs[r] = 0.f;
         }
         buf ^= 1;
-        part = red_part + ((buf * 2 + rg) * 8) * 8;
+        part = red_part + ((buf * P2_GROUPS + rg) * 8) * 8;
 #pragma unroll
         for (int k = 0; k < KQ; ++k) {
           const int c = 4 * (ct + P2_TPR * k);
@@ -1975,8 +1976,8 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           }
         }
       }
-      stg += 2;
-      if (stg >= D) {
+      stg += P2_GROUPS;
+      while (stg >= D) {
         stg -= D;
         ph ^= 1u;
       }
@@ -2000,23 +2001,26 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     }
     // ---- the two row groups combine their column partials; row group 0 writes them
     __syncthreads();  // the ring is idle from here until the next iteration's first slabs are requested below
-    if (rg == 1) {
+    if (rg >= 1) {
 #pragma unroll
-      for (int e = 0; e < KQ * 4; ++e) xcomb[e * P2_TPR + ct] = make_float2(cm[e], cs[e]);
+      for (int e = 0; e < KQ * 4; ++e) xcomb[((rg - 1) * KQ * 4 + e) * P2_TPR + ct] = make_float2(cm[e], cs[e]);
     }
     if (ct == 0) upart_s[rg] = make_float2(uacc.m, uacc.s);
     __syncthreads();
     if (rg == 0) {
 #pragma unroll
       for (int e = 0; e < KQ * 4; ++e) {
-        const float2 o = xcomb[e * P2_TPR + ct];
-        if (scaled) {  // both groups carry the same reference
-          cs[e] += o.y;
-        } else {
-          LseAcc a{cm[e], cs[e]};
-          lse_merge(a, o.x, o.y);
-          cm[e] = a.m;
-          cs[e] = a.s;
+#pragma unroll
+        for (int og = 0; og < P2_GROUPS - 1; ++og) {
+          const float2 o = xcomb[(og * KQ * 4 + e) * P2_TPR + ct];
+          if (scaled) {  // all groups carry the same reference
+            cs[e] += o.y;
+          } else {
+            LseAcc a{cm[e], cs[e]};
+            lse_merge(a, o.x, o.y);
+            cm[e] = a.m;
+            cs[e] = a.s;
+          }
         }
       }
       float2* cp = p.colpart + ((size_t)b * G + g) * M;
@@ -2034,7 +2038,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     }
     if (tid == 0) {
       LseAcc a{upart_s[0].x, upart_s[0].y};
-      lse_merge(a, upart_s[1].x, upart_s[1].y);
+      for (int og = 1; og < P2_GROUPS; ++og) lse_merge(a, upart_s[og].x, upart_s[og].y);
       p.upart[(size_t)b * G + g] = make_float2(a.m, a.s);
       DRG_STAMP(10 + it * 100 + 3);
     }
@@ -2962,16 +2966,16 @@ static SkhPlanP2 make_plan_p2(int B, int N, int M) {
   const int gmax = NUM_SMS / B;
   const int rr_max = 8 / pl.KQ;
   const int rr_min = (pl.KQ == 1) ? 2 : 1;
-  pl.RR = ((long long)2 * rr_max * gmax <= N) ? rr_max : rr_min;
-  int G = (N + 2 * pl.RR - 1) / (2 * pl.RR);  // at least one mini-slab per row group
+  pl.RR = ((long long)P2_GROUPS * rr_max * gmax <= N) ? rr_max : rr_min;
+  int G = (N + P2_GROUPS * pl.RR - 1) / (P2_GROUPS * pl.RR);  // at least one mini-slab per row group
   if (G > gmax) G = gmax;
   if (G < 1) G = 1;
   pl.G = G;
   if ((N + G - 1) / G > 1024) return pl;  // row references of a CTA live in a 1024-entry shared array
   const size_t Mv = (size_t)((M + 1 + 3) & ~3);
-  const size_t fixed = (Mv + 1024 + 256 + 64 + 8 + (P2_THREADS / 32) * 32 * 2) * 4 + P2_MAX_STAGES * 8;
+  const size_t fixed = (Mv + 1024 + 2 * P2_GROUPS * 64 + 64 + 8 + (P2_THREADS / 32) * 32 * 2) * 4 + P2_MAX_STAGES * 8;
   const size_t stage_bytes = (size_t)pl.RR * M * 4;
-  const size_t xcomb_bytes = (size_t)P2_TPR * pl.KQ * 4 * 8;
+  const size_t xcomb_bytes = (size_t)(P2_GROUPS - 1) * P2_TPR * pl.KQ * 4 * 8;
   int nstage = (int)((SKH_SMEM_LIMIT - 256 - fixed) / stage_bytes);
   if (nstage > P2_MAX_STAGES) nstage = P2_MAX_STAGES;
   if (nstage < 2) return pl;
