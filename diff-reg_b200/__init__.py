@@ -5,6 +5,7 @@ Public surface (mirrors the reference):
     Matching, log_optimal_transport, mutual_topk_select      (matching.py)
     Matching2D3D                                             (2D-3D flavour head)
     SoftProcrustesLayer                                      (procrustes.py)
+    VolumetricPositionEncoding                               (position_encoding.py; next-row widening)
     DenoisingSampler                                         (fused per-step driver)
     HostStepPipeline                                         (host buffers in / results out, copies overlapped, graph replay)
     RowShardedSinkhorn, shard_rows, shard_units              (multi-GPU paths, distributed.py)
@@ -28,6 +29,9 @@ def __getattr__(name):
     if name in ("DenoisingSampler",):
         from . import sampler
         return getattr(sampler, name)
+    if name == "VolumetricPositionEncoding":
+        from . import position_encoding
+        return position_encoding.VolumetricPositionEncoding
     if name == "HostStepPipeline":
         from . import hostpipe
         return hostpipe.HostStepPipeline

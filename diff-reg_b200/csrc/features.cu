@@ -162,6 +162,59 @@ __global__ void min_finish_kernel(const unsigned int* o, float* out) { *out = or
 namespace drg {
 __global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
 }  // namespace drg
+// ---- volumetric position code
+//   VolumetricPositionEncoding.forward  Diff-Reg-4dmatch/models/position_encoding.py:49-87: vox = (xyz - origin) / voxel_size
+//   (:16-24), angle = vox[axis] * div_term[k]; rotary: [P, d, 2] = (cos, sin) with every angle duplicated over a feature
+//   pair, axes x | y | z over thirds of d; sinusoidal: [P, d] = cat(sinx, cosx, siny, cosy, sinz, cosz).
+//   div_term is passed in (d/6 values computed once by the host module exactly as the reference does) so that the
+//   angles are bit-identical; sinf / cosf are the accurate library versions (the build does not use fast-math).
+__global__ void __launch_bounds__(256) position_code_kernel(const float* __restrict__ xyz, const float* __restrict__ div_term,
+                                                            long long points, int d, float ox, float oy, float oz, float voxel,
+                                                            int pe_type, float* __restrict__ out) {
+  const long long total = points * d;
+  const int d6 = d / 6, d3 = d / 3;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long pt = e / d;
+    const int c = (int)(e - pt * d);
+    int axis, k;
+    bool want_cos = false;
+    if (pe_type == 1) {  // rotary
+      axis = c / d3;
+      k = (c - axis * d3) >> 1;
+    } else {             // sinusoidal
+      const int seg = c / d6;
+      axis = seg >> 1;
+      want_cos = (seg & 1) != 0;
+      k = c - seg * d6;
+    }
+    const float origin = axis == 0 ? ox : axis == 1 ? oy : oz;
+    const float vox = (xyz[pt * 3 + axis] - origin) / voxel;
+    const float ang = vox * div_term[k];
+    if (pe_type == 1) {
+      reinterpret_cast<float2*>(out)[e] = make_float2(cosf(ang), sinf(ang));
+    } else {
+      out[e] = want_cos ? cosf(ang) : sinf(ang);
+    }
+  }
+}
+
+extern "C" int drg_position_code(const float* xyz, const float* div_term, long long points, int feature_dim, const float* origin3,
+                                 float voxel_size, int pe_type, float* out, void* stream) {
+  DRG_CHECK_ARG(xyz && div_term && origin3 && out, "xyz / div_term / origin / out must be non-null");
+  DRG_CHECK_ARG(points >= 1 && feature_dim >= 6 && feature_dim % 6 == 0, "points >= 1 and feature_dim a positive multiple of 6");
+  DRG_CHECK_ARG(pe_type == 1 || pe_type == 2, "pe_type must be 1 (rotary) or 2 (sinusoidal)");
+  DRG_CHECK_ARG(voxel_size != 0.f, "voxel_size must be non-zero");
+  DRG_CHECK_ARG(pe_type != 1 || (((uintptr_t)out) & 7u) == 0, "rotary output must be 8-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = points * feature_dim;
+  long long blocks = (total + 255) / 256;
+  if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+  position_code_kernel<<<(int)blocks, 256, 0, st>>>(xyz, div_term, points, feature_dim, origin3[0], origin3[1], origin3[2],
+                                                     voxel_size, pe_type, out);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
 extern "C" int drg_counter_add(unsigned long long* counter, unsigned long long inc, void* stream) {
   DRG_CHECK_ARG(counter != nullptr, "counter is null");
   counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);

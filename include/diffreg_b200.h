@@ -177,6 +177,14 @@ int drg_project_split(const float* A, const float* W, int rows, int rows_left, i
 int drg_prep_operand_pair(const float* in_a, long long rows_a, int pattern_a, const float* in_b, long long rows_b, int pattern_b,
                           int K, float scale, int split, float* out, void* stream);
 
+/* Volumetric position code from point coordinates (next-row widening)
+ *   replaces VolumetricPositionEncoding.forward / voxelize   Diff-Reg-4dmatch/models/position_encoding.py:16-24,49-87
+ *   xyz [points,3] (device), div_term [feature_dim/6] (device; exp(arange(0, d/3, 2) * -ln(1e4) / (d/3)) as the reference
+ *   computes it), origin3 = vol_bnds[0] (HOST pointer to 3 floats), pe_type 1 rotary -> out [points, d, 2] (cos, sin),
+ *   2 sinusoidal -> out [points, d].  feature_dim must be a multiple of 6 (as in the reference). */
+int drg_position_code(const float* xyz, const float* div_term, long long points, int feature_dim, const float* origin3,
+                      float voxel_size, int pe_type, float* out, void* stream);
+
 /* Operand preparation: positional embedding + scaling + optional hi/lo split.
  *   replaces VolPE.embed_pos / embed_rotary   Diff-Reg-4dmatch/models/position_encoding.py:26-46
  *   and       feat / feat.shape[-1] ** .5     Diff-Reg-4dmatch/models/matching.py:144-145

@@ -110,6 +110,38 @@ def embed_rotary(x, cos, sin):
     return x * cos + rot * sin
 
 
+def volumetric_position_code(xyz, feature_dim, vol_origin, voxel_size, pe_type="rotary"):
+    """``VolumetricPositionEncoding.forward`` 4d/models/position_encoding.py:49-87.
+    xyz [B,N,3] -> rotary: [B,N,d,2] = (cos, sin) with every angle duplicated over a feature pair;
+    sinusoidal: [B,N,d] = cat(sinx, cosx, siny, cosy, sinz, cosz).  d must be a multiple of 6."""
+    B, N, _ = xyz.shape
+    origin = torch.as_tensor(vol_origin, dtype=torch.float32, device=xyz.device).view(1, 1, -1)
+    vox = (xyz - origin) / voxel_size                                                   # voxelize :16-24
+    d3 = feature_dim // 3
+    div = torch.exp(torch.arange(0, d3, 2, dtype=torch.float, device=xyz.device) * (-math.log(10000.0) / d3)).view(1, 1, -1)
+    parts = []
+    for a in range(3):
+        ang = vox[..., a:a + 1] * div
+        parts.append((torch.sin(ang), torch.cos(ang)))
+    if pe_type == "sinusoidal":
+        return torch.cat([t for sc in parts for t in sc], dim=-1)
+    if pe_type != "rotary":
+        raise KeyError(pe_type)
+    dup = lambda f: torch.stack([f, f], dim=-1).view(B, N, -1)                          # noqa: E731  theta_k, theta_k
+    sin_pos = torch.cat([dup(s_) for s_, _ in parts], dim=-1)
+    cos_pos = torch.cat([dup(c_) for _, c_ in parts], dim=-1)
+    return torch.stack([cos_pos, sin_pos], dim=-1)
+
+
+def embed_pos(pe_type, x, pe):
+    """``VolumetricPositionEncoding.embed_pos`` 4d/models/position_encoding.py:37-46."""
+    if pe_type == "rotary":
+        return embed_rotary(x, pe[..., 0], pe[..., 1])
+    if pe_type == "sinusoidal":
+        return x + pe
+    raise KeyError(pe_type)
+
+
 # --------------------------------------------------------------------------------------
 # correspondence extraction (a5, a6)
 # --------------------------------------------------------------------------------------

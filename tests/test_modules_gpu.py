@@ -239,3 +239,23 @@ def test_host_step_pipeline_matches_direct_steps():
         assert torch.equal(out["index"][:n], idx) and torch.equal(out["mconf"][:n], mconf)
     assert torch.equal(pipe.state(STEPS), x_direct)
     assert pipe.h2d_bytes == sum(v.numel() * v.element_size() for v in pinned.values())
+
+
+@pytest.mark.parametrize("name", ["pe_rotary_528", "pe_sinusoidal_432", "pe_rotary_36_b2"])
+def test_volumetric_position_encoding(name):
+    """VolumetricPositionEncoding.forward / embed_pos against the reference's outputs."""
+    import diffreg_b200
+    g = load(name)
+    cfg = SimpleNamespace(feature_dim=int(g["feature_dim"]), vol_bnds=[g["vol_origin"].tolist(), [1.093, 0.78, 2.92]],
+                          voxel_size=float(g["voxel_size"]), pe_type=str(g["pe_type"]))
+    vol = diffreg_b200.VolumetricPositionEncoding(cfg).to(DEV)
+    code = vol(_cu(g["xyz"]))
+    assert code.shape == g["code"].shape
+    assert (code.cpu() - g["code"]).abs().max() <= 1e-6
+    emb = vol.embed_pos(cfg.pe_type, _cu(g["x"]), _cu(g["code"]))
+    assert (emb.cpu() - g["embedded"]).abs().max() <= 1e-6
+    if cfg.pe_type == "rotary":
+        emb2 = vol.embed_rotary(_cu(g["x"]), _cu(g["code"][..., 0].contiguous()), _cu(g["code"][..., 1].contiguous()))
+        assert torch.equal(emb2, emb)
+    with pytest.raises(diffreg_b200._lib.DiffRegLibraryError):
+        vol(g["xyz"])                       # CPU tensors have no path
