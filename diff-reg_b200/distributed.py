@@ -51,6 +51,10 @@ def lse_allreduce(partial, group=None, ref=None):
     return torch.stack((m, s), dim=-1)
 
 
+class P2PUnavailable(RuntimeError):
+    """CUDA IPC / peer access is not available between the ranks (raised on every rank of the group together)."""
+
+
 class P2PComm:
     """Peer-mapped exchange buffers of the ranks of one node (drg_p2p_*): every rank allocates an inbox, the CUDA IPC
     handles are all-gathered over the process group, and every rank maps every inbox.  Kernels then store into the
@@ -69,17 +73,36 @@ class P2PComm:
         hb = int(self.lib.drg_p2p_handle_bytes())
         mine = (ctypes.c_ubyte * hb)()
         comm = ctypes.c_void_p()
-        _lib.check(self.lib.drg_p2p_create(self.rank, self.world, self.slot_elems, self.nflags, ctypes.byref(comm), mine))
-        self.handle = comm
-        # all-gather the handles through device tensors: works with the NCCL backend (and with gloo via a CPU copy)
         backend = dist.get_backend(group)
-        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=dev if backend == "nccl" else "cpu")
-        allh = torch.empty(self.world * hb, dtype=torch.uint8, device=t.device)
+        cdev = dev if backend == "nccl" else torch.device("cpu")
+
+        def all_ok(rc):        # every rank learns whether every rank succeeded, so that they fail (or go on) together
+            flag = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=cdev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            return int(flag.item()) == 1
+
+        rc = self.lib.drg_p2p_create(self.rank, self.world, self.slot_elems, self.nflags, ctypes.byref(comm), mine)
+        self.handle = comm if rc == 0 else None
+        if not all_ok(rc):
+            msg = self.lib.drg_last_error().decode() if rc else "another rank failed"
+            self._abort()
+            raise P2PUnavailable(f"drg_p2p_create: {msg}")
+        # all-gather the handles through tensors of the group's backend
+        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=cdev)
+        allh = torch.empty(self.world * hb, dtype=torch.uint8, device=cdev)
         dist.all_gather_into_tensor(allh, t, group=group)
         raw = bytes(allh.cpu().tolist())
         buf = (ctypes.c_ubyte * len(raw)).from_buffer_copy(raw)
-        _lib.check(self.lib.drg_p2p_connect(self.handle, buf))
-        dist.barrier(group=group)          # nobody sends before everybody has mapped everybody
+        rc = self.lib.drg_p2p_connect(self.handle, buf)
+        if not all_ok(rc):                 # also the barrier: nobody sends before everybody has mapped everybody
+            msg = self.lib.drg_last_error().decode() if rc else "another rank failed"
+            self._abort()
+            raise P2PUnavailable(f"drg_p2p_connect: {msg}")
+
+    def _abort(self):
+        if self.handle is not None:
+            self.lib.drg_p2p_destroy(self.handle)
+            self.handle = None
 
     def fits(self, B, M):
         return B * (M + 1) <= self.slot_elems and B * ((M + 1 + 31) // 32) <= self.nflags
@@ -108,6 +131,7 @@ class RowShardedSinkhorn:
         self.exchange = exchange
         self.comm = None
         self._shape = None
+        self._p2p_failed = False
 
     def _p2p(self, B, M):
         mode = self.exchange
@@ -115,11 +139,22 @@ class RowShardedSinkhorn:
             mode = "p2p" if dist.get_backend(self.group) == "nccl" else "nccl"
         if mode != "p2p":
             return None
+        if self._p2p_failed:
+            return None
         if self.comm is None or self._shape != (B, M):   # the flag <-> column-chunk mapping is per shape
             if self.comm is not None:
                 self.comm.close()
-            self.comm = P2PComm(B * (M + 1), B * ((M + 1 + 31) // 32), self.group)
-            self._shape = (B, M)
+                self.comm = None
+            try:
+                self.comm = P2PComm(B * (M + 1), B * ((M + 1 + 31) // 32), self.group)
+                self._shape = (B, M)
+            except P2PUnavailable as e:       # raised on EVERY rank together (the ranks agree before connecting)
+                if self.exchange == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"RowShardedSinkhorn: peer-to-peer exchange unavailable ({e}); using NCCL all-reduces")
+                self._p2p_failed = True
+                return None
         return self.comm
 
     @torch.no_grad()

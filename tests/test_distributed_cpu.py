@@ -87,3 +87,41 @@ def test_lse_allreduce_two_gloo_ranks():
         assert p.exitcode == 0
     for _, err1, err2 in res:
         assert err1 < 1e-5 and err2 < 1e-5
+
+
+def _p2p_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # No GPU here: drg_p2p_create cannot allocate.  The point of the test is the protocol -- every rank must learn
+        # that the exchange is unavailable and raise TOGETHER (a rank that went on alone would hang its peers).
+        try:
+            D.P2PComm(128, 8, device="cpu")
+            q.put((rank, "created"))
+        except D.P2PUnavailable as e:
+            q.put((rank, "unavailable:" + str(e)[:40]))
+        # the sharded driver then falls back to the NCCL / gloo all-reduce path instead of raising ...
+        op = D.RowShardedSinkhorn(exchange=None)
+        op._p2p_failed = False
+        q.put((rank, "fallback" if (dist.get_backend() != "nccl" and op._p2p(1, 31) is None) else "p2p"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_p2p_comm_fails_on_all_ranks_together_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU (the working exchange is covered by tools/bench_rowshard.py on 2 GPUs)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_p2p_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(4)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    states = sorted(res)
+    assert all(s.startswith("unavailable") or s == "fallback" for _, s in states), states
+    assert sum(s == "fallback" for _, s in states) == 2
