@@ -77,6 +77,10 @@ def _declare(lib):
     c_ll = ctypes.c_longlong
     lib.drg_gemm_nt_tf32.restype = c_int
     lib.drg_gemm_nt_tf32.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
+    lib.drg_gemm_nt_3xtf32.restype = c_int
+    lib.drg_gemm_nt_3xtf32.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
+    lib.drg_project_split3.restype = c_int
+    lib.drg_project_split3.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
     lib.drg_prep_operand.restype = c_int
     lib.drg_prep_operand.argtypes = [c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.drg_position_code.restype = c_int

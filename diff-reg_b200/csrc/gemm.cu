@@ -130,6 +130,7 @@ struct GemmShape {
   float alpha;
   int nstage;
   int direct_store;  // 1: C row pitch not TMA-storable (M % 4 != 0) -> coalesced st.global from the staging tile
+  int kc;            // SPLIT3 kernels: columns of ONE operand segment (K = 3 * kc), a multiple of GEMM_BK
   float* C;          // may be NULL when only the split output is wanted
   // optional fused operand preparation of the NEXT GEMM (projection -> similarity): split_out [N, 3M] receives
   // scale*alpha*acc as [lo|hi|hi] for rows < split_rows0 (left operand) and [hi|lo|hi] for the others (right operand)
@@ -138,11 +139,18 @@ struct GemmShape {
   float split_scale;
 };
 
-template <int BN>
+// SPLIT3: the operands are the 3xTF32 concatenations A' = [A_lo | A_hi | A_hi], B' = [B_hi | B_lo | B_hi] (each segment kc
+// columns).  Instead of streaming 3 * kc columns of both (the third segments are copies), a stage holds the four DISTINCT
+// 32-column tiles A_lo, A_hi, B_hi, B_lo of one k-chunk and the MMA warp issues lo.hi, hi.lo, hi.hi from them: the same
+// 12 MMAs per chunk with one third less operand traffic from L2 -- which is what bounds this kernel (fp32 operands want
+// ~90 B/clk/SM, the fabric delivers ~44).
+template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const GemmShape s) {
-  constexpr int B_STAGE_BYTES = BN * GEMM_BK * 4;
+  constexpr int B_TILE_BYTES = BN * GEMM_BK * 4;
+  constexpr int A_STAGE_BYTES = (SPLIT3 ? 2 : 1) * GEMM_A_STAGE_BYTES;
+  constexpr int B_STAGE_BYTES = (SPLIT3 ? 2 : 1) * B_TILE_BYTES;
   constexpr int TMEM_COLS = 2 * BN;  // 128, 256 or 512: a power of two >= 32
   static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
   extern __shared__ uint8_t smem_dyn[];
@@ -158,13 +166,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* aligned = smem_dyn + (base - smem_u32(smem_dyn));
   uint8_t* sA = aligned;
-  uint8_t* sB = sA + (size_t)nstage * GEMM_A_STAGE_BYTES;
+  uint8_t* sB = sA + (size_t)nstage * A_STAGE_BYTES;
   uint8_t* sOut = sB + (size_t)nstage * B_STAGE_BYTES;  // [4 warps][2][4 KB]
 
   const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM;
   const int tiles_n = (s.M + BN - 1) / BN;
   const int tiles = s.batch * tiles_m * tiles_n;
-  const int kblocks = (s.K + GEMM_BK - 1) / GEMM_BK;
+  const int kblocks = SPLIT3 ? s.kc / GEMM_BK : (s.K + GEMM_BK - 1) / GEMM_BK;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -197,9 +205,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int mb = rem / tiles_n, nb = rem - mb * tiles_n;
         for (int k = 0; k < kblocks; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(GEMM_A_STAGE_BYTES + B_STAGE_BYTES));
-          tma_load_3d(sA + (size_t)stage * GEMM_A_STAGE_BYTES, &tmA, k * GEMM_BK, mb * GEMM_BM, b, &full_bar[stage]);
-          tma_load_3d(sB + (size_t)stage * B_STAGE_BYTES, &tmB, k * GEMM_BK, nb * BN, b, &full_bar[stage]);
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(A_STAGE_BYTES + B_STAGE_BYTES));
+          uint8_t* a_dst = sA + (size_t)stage * A_STAGE_BYTES;
+          uint8_t* b_dst = sB + (size_t)stage * B_STAGE_BYTES;
+          tma_load_3d(a_dst, &tmA, k * GEMM_BK, mb * GEMM_BM, b, &full_bar[stage]);   // SPLIT3: A_lo
+          tma_load_3d(b_dst, &tmB, k * GEMM_BK, nb * BN, b, &full_bar[stage]);        // SPLIT3: B_hi
+          if (SPLIT3) {
+            tma_load_3d(a_dst + GEMM_A_STAGE_BYTES, &tmA, s.kc + k * GEMM_BK, mb * GEMM_BM, b, &full_bar[stage]);  // A_hi
+            tma_load_3d(b_dst + B_TILE_BYTES, &tmB, s.kc + k * GEMM_BK, nb * BN, b, &full_bar[stage]);             // B_lo
+          }
           if (++stage == nstage) {
             stage = 0;
             phase ^= 1u;
@@ -222,12 +236,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (int k = 0; k < kblocks; ++k) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + (size_t)stage * GEMM_A_STAGE_BYTES));
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + (size_t)stage * A_STAGE_BYTES));
           const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sB + (size_t)stage * B_STAGE_BYTES));
+          if (SPLIT3) {
+            const uint64_t ah_desc = make_smem_desc_sw128(smem_u32(sA + (size_t)stage * A_STAGE_BYTES + GEMM_A_STAGE_BYTES));
+            const uint64_t bl_desc = make_smem_desc_sw128(smem_u32(sB + (size_t)stage * B_STAGE_BYTES + B_TILE_BYTES));
 #pragma unroll
-          for (int kk = 0; kk < GEMM_BK / 8; ++kk) {
-            // advance 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_tf32(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (uint32_t)((k | kk) != 0));
+            for (int kk = 0; kk < GEMM_BK / 8; ++kk) {
+              const uint64_t o = (uint64_t)(2 * kk);
+              umma_tf32(d_tmem, a_desc + o, b_desc + o, idesc, (uint32_t)((k | kk) != 0));  // lo . hi
+              umma_tf32(d_tmem, ah_desc + o, bl_desc + o, idesc, 1u);                        // hi . lo
+              umma_tf32(d_tmem, ah_desc + o, b_desc + o, idesc, 1u);                         // hi . hi
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < GEMM_BK / 8; ++kk) {
+              // advance 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+              umma_tf32(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (uint32_t)((k | kk) != 0));
+            }
           }
           umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs have read it
           if (++stage == nstage) {
@@ -378,25 +404,25 @@ static bool make_tmap(CUtensorMap* tm, const void* ptr, int batch, int rows, int
   return true;
 }
 
-template <int BN>
+template <int BN, bool SPLIT3>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, GemmShape s, cudaStream_t st) {
-  constexpr int B_STAGE_BYTES = BN * GEMM_BK * 4;
+  constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (GEMM_A_STAGE_BYTES + BN * GEMM_BK * 4);
   const size_t out_bytes = 4 * 2 * GEMM_OUT_BOX_BYTES;
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - out_bytes - 256 /*static*/;
-  int nstage = (int)(budget / (GEMM_A_STAGE_BYTES + B_STAGE_BYTES));
+  int nstage = (int)(budget / STAGE_BYTES);
   if (nstage > GEMM_MAX_STAGES) nstage = GEMM_MAX_STAGES;
-  const int kblocks = (s.K + GEMM_BK - 1) / GEMM_BK;
+  const int kblocks = SPLIT3 ? s.kc / GEMM_BK : (s.K + GEMM_BK - 1) / GEMM_BK;
   if (nstage > 2 * kblocks) nstage = 2 * kblocks;  // no point in more stages than two tiles of k-steps
   if (nstage < 2) nstage = 2;
   s.nstage = nstage;
-  const size_t smem = 1024 + (size_t)nstage * (GEMM_A_STAGE_BYTES + B_STAGE_BYTES) + out_bytes;
-  DRG_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = 1024 + (size_t)nstage * STAGE_BYTES + out_bytes;
+  DRG_CUDA((cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM, tiles_n = (s.M + BN - 1) / BN;
   const long long tiles = (long long)s.batch * tiles_m * tiles_n;
   const int grid = (int)(tiles < NUM_SMS ? tiles : NUM_SMS);
   {
     ProfScope prof_scope(PROF_GEMM, st);
-    gemm_tf32_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, s);
+    gemm_tf32_kernel<BN, SPLIT3><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, s);
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
@@ -407,7 +433,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
 using namespace drg;
 
 static int gemm_run(const float* A, const float* B, float* C, int batch, int N, int M, int K, float alpha, float* split_out,
-                    int split_rows0, float split_scale, void* stream) {
+                    int split_rows0, float split_scale, void* stream, bool split3 = false) {
   DRG_CHECK_ARG(A && B && (C || split_out), "A/B and an output must be non-null");
   DRG_CHECK_ARG(batch >= 1 && N >= 1 && M >= 1 && K >= 1, "batch, N, M, K must be >= 1");
   if (K % 4 != 0 || ((uintptr_t)A & 15u) || ((uintptr_t)B & 15u)) {
@@ -418,6 +444,7 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
     set_error("gemm: the split epilogue needs batch == 1, M %% 4 == 0 and a 16-byte aligned output");
     return DRG_ERR_UNSUPPORTED;
   }
+  if (split3 && (K % 3 != 0 || (K / 3) % GEMM_BK != 0)) split3 = false;  // segments must be whole k-chunks: generic path
   cudaStream_t st = (cudaStream_t)stream;
   // Tile width by a two-term cost model (cycles): the MMA time of the busiest SM, and the operand traffic through L2
   // (every tile re-reads its A and B k-blocks; measured on B200 the fabric delivers ~6.5 KB/clk to the SMs, which is
@@ -430,7 +457,7 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
       const double tiles = (double)batch * ((N + 127) / 128) * ((M + bn - 1) / bn);
       const double rounds = (double)((long long)((tiles + NUM_SMS - 1) / NUM_SMS));
       const double t_mma = rounds * kblocks * 4.0 * (bn / 2.0);                    // 128 x bn x 8 tf32 MMA = bn/2 clk
-      const double t_l2 = tiles * kblocks * (double)((128 + bn) * GEMM_BK * 4) / 6500.0;
+      const double t_l2 = tiles * kblocks * (double)((128 + bn) * GEMM_BK * 4) / 6500.0 * (split3 ? 2.0 / 3.0 : 1.0);
       const double t = (t_mma > t_l2 ? t_mma : t_l2) + rounds * 1500.0;            // + per-tile epilogue exposure
       if (t < best) {
         best = t;
@@ -452,6 +479,7 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
   s.split_rows0 = split_rows0;
   s.split_scale = split_scale;
   s.direct_store = (C == nullptr || M % 4 != 0 || ((uintptr_t)C & 15u)) ? 1 : 0;
+  s.kc = split3 ? K / 3 : 0;
   CUtensorMap tA, tB, tC;
   if (!make_tmap(&tA, A, batch, N, K, GEMM_BM, GEMM_BK)) return DRG_ERR_CUDA;
   if (!make_tmap(&tB, B, batch, M, K, BN, GEMM_BK)) return DRG_ERR_CUDA;
@@ -460,10 +488,17 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
   } else {
     tC = tA;  // unused
   }
+  if (split3) {
+    switch (BN) {
+      case 256: return launch_gemm<256, true>(tA, tB, tC, s, st);
+      case 128: return launch_gemm<128, true>(tA, tB, tC, s, st);
+      default: return launch_gemm<64, true>(tA, tB, tC, s, st);
+    }
+  }
   switch (BN) {
-    case 256: return launch_gemm<256>(tA, tB, tC, s, st);
-    case 128: return launch_gemm<128>(tA, tB, tC, s, st);
-    default: return launch_gemm<64>(tA, tB, tC, s, st);
+    case 256: return launch_gemm<256, false>(tA, tB, tC, s, st);
+    case 128: return launch_gemm<128, false>(tA, tB, tC, s, st);
+    default: return launch_gemm<64, false>(tA, tB, tC, s, st);
   }
 }
 
@@ -471,6 +506,23 @@ extern "C" int drg_gemm_nt_tf32(const float* A, const float* B, float* C, int ba
                                 void* stream) {
   DRG_CHECK_ARG(C != nullptr, "C is null");
   return gemm_run(A, B, C, batch, N, M, K, alpha, nullptr, 0, 1.f, stream);
+}
+
+// A' = [A_lo | A_hi | A_hi], B' = [B_hi | B_lo | B_hi] (drg_prep_operand split = 1, patterns 0 / 1), K3 = 3 * K: same result as
+// drg_gemm_nt_tf32 on the same operands up to the order of the fp32 accumulation, with one third less operand traffic.
+extern "C" int drg_gemm_nt_3xtf32(const float* A, const float* B, float* C, int batch, int N, int M, int K3, float alpha,
+                                  void* stream) {
+  DRG_CHECK_ARG(C != nullptr, "C is null");
+  DRG_CHECK_ARG(K3 % 3 == 0, "K3 must be 3 * K");
+  return gemm_run(A, B, C, batch, N, M, K3, alpha, nullptr, 0, 1.f, stream, true);
+}
+
+extern "C" int drg_project_split3(const float* A, const float* W, int rows, int rows_left, int C_out, int K3, float scale,
+                                  float* plain_out, float* split_out, void* stream) {
+  DRG_CHECK_ARG(split_out != nullptr, "split_out is null");
+  DRG_CHECK_ARG(rows_left >= 0 && rows_left <= rows, "rows_left out of range");
+  DRG_CHECK_ARG(K3 % 3 == 0, "K3 must be 3 * K");
+  return gemm_run(A, W, plain_out, 1, rows, C_out, K3, 1.f, split_out, rows_left, scale, stream, true);
 }
 
 extern "C" int drg_project_split(const float* A, const float* W, int rows, int rows_left, int C_out, int K, float scale,

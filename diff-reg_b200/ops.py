@@ -118,8 +118,11 @@ def dual_softmax(sim, src_mask, tgt_mask, temperature):
     return out
 
 
-def gemm_nt(A, B, alpha=1.0, out=None):
-    """C[b] = alpha * A[b] @ B[b]^T on the tensor cores (drg_gemm_nt_tf32).  A [batch,N,K] or [N,K]; B likewise."""
+def gemm_nt(A, B, alpha=1.0, out=None, split3=False):
+    """C[b] = alpha * A[b] @ B[b]^T on the tensor cores (drg_gemm_nt_tf32).  A [batch,N,K] or [N,K]; B likewise.
+    split3=True: A, B are prep_operand(split=True) outputs (patterns 0 / 1); drg_gemm_nt_3xtf32 then fetches each distinct
+    operand tile once (same product, one third less operand traffic from L2 -- measured: no faster on B200, the kernel is
+    not bound by operand traffic; kept as an option, not the default)."""
     _require_cuda(A, B)
     lib = load_library()
     A = _f32c(A)
@@ -134,7 +137,8 @@ def gemm_nt(A, B, alpha=1.0, out=None):
         raise ValueError(f"gemm_nt: incompatible shapes {tuple(A.shape)} x {tuple(B.shape)}")
     if out is None:
         out = torch.empty(batch, N, M, dtype=torch.float32, device=A.device)
-    check(lib.drg_gemm_nt_tf32(A.data_ptr(), B.data_ptr(), out.data_ptr(), batch, N, M, K, float(alpha), _stream()))
+    fn = lib.drg_gemm_nt_3xtf32 if (split3 and K % 3 == 0) else lib.drg_gemm_nt_tf32
+    check(fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), batch, N, M, K, float(alpha), _stream()))
     return out.squeeze(0) if squeeze else out
 
 

@@ -166,6 +166,15 @@ int drg_dual_softmax(const float* sim, const uint8_t* src_mask, const uint8_t* t
  * ------------------------------------------------------------------------------------ */
 int drg_gemm_nt_tf32(const float* A, const float* B, float* C, int batch, int N, int M, int K, float alpha, void* stream);
 
+/* The same product for operands in the 3xTF32 layout of drg_prep_operand(split = 1): A' = [A_lo | A_hi | A_hi] (pattern 0),
+ *   B' = [B_hi | B_lo | B_hi] (pattern 1), K3 = 3 * K.  The kernel fetches the four distinct tiles of a k-chunk once and
+ *   issues lo.hi + hi.lo + hi.hi from them (one third less operand traffic than drg_gemm_nt_tf32 on the same arrays; equal
+ *   up to the order of the fp32 accumulation).  Falls back to the generic kernel when K is not a multiple of 32.
+ *   drg_project_split3 is drg_project_split for operands in that layout. */
+int drg_gemm_nt_3xtf32(const float* A, const float* B, float* C, int batch, int N, int M, int K3, float alpha, void* stream);
+int drg_project_split3(const float* A, const float* W, int rows, int rows_left, int C_out, int K3, float scale, float* plain_out,
+                       float* split_out, void* stream);
+
 /* Projection with the operand preparation of the similarity GEMM fused into its epilogue:
  *   split_out[rows, 3*C_out] = split(scale * A . W^T), rows < rows_left as the left operand [lo|hi|hi], the others as the
  *   right operand [hi|lo|hi]; plain_out (optional) [rows, C_out] = A . W^T (what the reference stores in data[...]).

@@ -37,6 +37,10 @@ def test_gemm_tf32_and_3xtf32(b, n, m, k):
     C3 = ops.gemm_nt(A3, B3, alpha=0.25).cpu()
     # the tensor core truncates its fp32 accumulator once per K=8 step: |err| <= steps * 2^-24 * max|C|
     assert (C3.double() - ref).abs().max().item() <= (3 * k / 8 + 8) * 2.0 ** -24 * ref.abs().max().item() + 1e-7
+    # shared-tile kernel on the same operands (falls back to the generic one when k is not a multiple of 32)
+    C3s = ops.gemm_nt(A3, B3, alpha=0.25, split3=True).cpu()
+    assert (C3s.double() - ref).abs().max().item() <= (3 * k / 8 + 8) * 2.0 ** -24 * ref.abs().max().item() + 1e-7
+    assert (C3s - C3).abs().max().item() <= 4 * (3 * k / 8 + 8) * 2.0 ** -24 * ref.abs().max().item() + 1e-7
 
 
 def test_gemm_full_size_property():
