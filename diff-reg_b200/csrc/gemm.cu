@@ -20,6 +20,7 @@
 // concatenated along K -- so that the same kernel returns an fp32-accurate product (the
 // dropped term is A_lo.B_lo ~ 2^-22 relative).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -129,6 +130,7 @@ struct GemmShape {
   int N, M, K, batch;
   float alpha;
   int nstage;
+  int split_tma;     // 1: the split epilogue stages hi / lo boxes in shared memory and writes them with TMA stores (tmS)
   int direct_store;  // 1: C row pitch not TMA-storable (M % 4 != 0) -> coalesced st.global from the staging tile
   int kc;            // SPLIT3 kernels: columns of ONE operand segment (K = 3 * kc), a multiple of GEMM_BK
   float* C;          // may be NULL when only the split output is wanted
@@ -147,7 +149,7 @@ struct GemmShape {
 template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmC, const GemmShape s) {
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS, const GemmShape s) {
   constexpr int B_TILE_BYTES = BN * GEMM_BK * 4;
   constexpr int A_STAGE_BYTES = (SPLIT3 ? 2 : 1) * GEMM_A_STAGE_BYTES;
   constexpr int B_STAGE_BYTES = (SPLIT3 ? 2 : 1) * B_TILE_BYTES;
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     if (!s.direct_store) prefetch_tmap(&tmC);
+    if (s.split_tma) prefetch_tmap(&tmS);
     for (int i = 0; i < nstage; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -287,6 +290,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
         tmem_wait_ld();
         if (row0 >= s.N || col0 >= s.M) continue;  // whole box outside the matrix (warp-uniform)
+        if (s.split_out && s.split_tma) {
+          // fused drg_prep_operand(split=1) of the projected features, coalesced: the hi and lo boxes are staged (128B-swizzled)
+          // in this warp's two buffers and leave as three TMA tensor stores into the [rows, 3M] operand
+          // (the row-strided 16-byte stores of the path below were what bounded the projection GEMM)
+          const float sc = s.alpha * s.split_scale;
+          uint8_t* hi_box = stg;
+          uint8_t* lo_box = stg + GEMM_OUT_BOX_BYTES;
+          if (lane == 0) bulk_wait_group_read<0>();  // the previous chunk's stores have finished reading both buffers
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 hi, lo;
+            const float x0 = __uint_as_float(r[4 * j + 0]) * sc, x1 = __uint_as_float(r[4 * j + 1]) * sc;
+            const float x2 = __uint_as_float(r[4 * j + 2]) * sc, x3 = __uint_as_float(r[4 * j + 3]) * sc;
+            hi.x = gemm_to_tf32_rna(x0); hi.y = gemm_to_tf32_rna(x1); hi.z = gemm_to_tf32_rna(x2); hi.w = gemm_to_tf32_rna(x3);
+            lo.x = gemm_to_tf32_rna(x0 - hi.x); lo.y = gemm_to_tf32_rna(x1 - hi.y);
+            lo.z = gemm_to_tf32_rna(x2 - hi.z); lo.w = gemm_to_tf32_rna(x3 - hi.w);
+            *reinterpret_cast<float4*>(hi_box + lane * 128 + ((j ^ (lane & 7)) << 4)) = hi;
+            *reinterpret_cast<float4*>(lo_box + lane * 128 + ((j ^ (lane & 7)) << 4)) = lo;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            const bool left = row0 < s.split_rows0;  // split_rows0 % 32 == 0 in this mode: a box never straddles the boundary
+            tma_store_3d(&tmS, left ? lo_box : hi_box, col0, row0, 0);
+            tma_store_3d(&tmS, left ? hi_box : lo_box, s.M + col0, row0, 0);
+            tma_store_3d(&tmS, hi_box, 2 * s.M + col0, row0, 0);
+            bulk_commit_group();
+          }
+          continue;
+        }
         if (s.split_out) {
           // fused drg_prep_operand(split=1) of the projected features: lane = row, 32 consecutive columns
           const int row = row0 + lane;
@@ -357,7 +391,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
-    if (!s.direct_store && lane == 0) bulk_wait_group<0>();  // smem must outlive the last stores
+    if ((!s.direct_store || s.split_tma) && lane == 0) bulk_wait_group<0>();  // smem must outlive the last stores
   }
 
   tcgen05_fence_before();
@@ -405,7 +439,8 @@ static bool make_tmap(CUtensorMap* tm, const void* ptr, int batch, int rows, int
 }
 
 template <int BN, bool SPLIT3>
-static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, GemmShape s, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tS, GemmShape s,
+                       cudaStream_t st) {
   constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (GEMM_A_STAGE_BYTES + BN * GEMM_BK * 4);
   const size_t out_bytes = 4 * 2 * GEMM_OUT_BOX_BYTES;
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - out_bytes - 256 /*static*/;
@@ -422,7 +457,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   const int grid = (int)(tiles < NUM_SMS ? tiles : NUM_SMS);
   {
     ProfScope prof_scope(PROF_GEMM, st);
-    gemm_tf32_kernel<BN, SPLIT3><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, s);
+    gemm_tf32_kernel<BN, SPLIT3><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tS, s);
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
@@ -466,7 +501,20 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
     }
     // the split epilogue stores 3x the output with row-strided 16-byte stores from four warps only: it wants many
     // small tiles in flight rather than few wide ones (measured: BN=256 was 10 us slower on the 8192 x 256 projection)
-    if (split_out) BN = 64;
+    const bool split_tma_early = split_out != nullptr && C == nullptr && (split_rows0 % 32) == 0;
+    if (split_out && !split_tma_early) BN = 64;
+    static int force_bn_split = -1;  // tuning only: DRG_GEMM_BN_SPLIT for the projection with the TMA split epilogue
+    if (force_bn_split < 0) {
+      const char* e = getenv("DRG_GEMM_BN_SPLIT");
+      force_bn_split = e ? atoi(e) : 0;
+    }
+    if (split_tma_early && (force_bn_split == 64 || force_bn_split == 128 || force_bn_split == 256)) BN = force_bn_split;
+    static int force_bn = -1;  // tuning only: DRG_GEMM_BN=64|128|256 overrides the model for the plain (non-split) GEMM
+    if (force_bn < 0) {
+      const char* e = getenv("DRG_GEMM_BN");
+      force_bn = e ? atoi(e) : 0;
+    }
+    if (!split_out && (force_bn == 64 || force_bn == 128 || force_bn == 256)) BN = force_bn;
   }
   GemmShape s{};
   s.N = N;
@@ -480,7 +528,9 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
   s.split_scale = split_scale;
   s.direct_store = (C == nullptr || M % 4 != 0 || ((uintptr_t)C & 15u)) ? 1 : 0;
   s.kc = split3 ? K / 3 : 0;
-  CUtensorMap tA, tB, tC;
+  // split epilogue through TMA stores when only the split operand is wanted and the left / right boundary is box-aligned
+  s.split_tma = (split_out != nullptr && C == nullptr && (split_rows0 % 32) == 0) ? 1 : 0;
+  CUtensorMap tA, tB, tC, tS;
   if (!make_tmap(&tA, A, batch, N, K, GEMM_BM, GEMM_BK)) return DRG_ERR_CUDA;
   if (!make_tmap(&tB, B, batch, M, K, BN, GEMM_BK)) return DRG_ERR_CUDA;
   if (!s.direct_store) {
@@ -488,17 +538,22 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
   } else {
     tC = tA;  // unused
   }
+  if (s.split_tma) {
+    if (!make_tmap(&tS, split_out, 1, N, 3 * M, 32, 32)) return DRG_ERR_CUDA;
+  } else {
+    tS = tA;  // unused
+  }
   if (split3) {
     switch (BN) {
-      case 256: return launch_gemm<256, true>(tA, tB, tC, s, st);
-      case 128: return launch_gemm<128, true>(tA, tB, tC, s, st);
-      default: return launch_gemm<64, true>(tA, tB, tC, s, st);
+      case 256: return launch_gemm<256, true>(tA, tB, tC, tS, s, st);
+      case 128: return launch_gemm<128, true>(tA, tB, tC, tS, s, st);
+      default: return launch_gemm<64, true>(tA, tB, tC, tS, s, st);
     }
   }
   switch (BN) {
-    case 256: return launch_gemm<256, false>(tA, tB, tC, s, st);
-    case 128: return launch_gemm<128, false>(tA, tB, tC, s, st);
-    default: return launch_gemm<64, false>(tA, tB, tC, s, st);
+    case 256: return launch_gemm<256, false>(tA, tB, tC, tS, s, st);
+    case 128: return launch_gemm<128, false>(tA, tB, tC, tS, s, st);
+    default: return launch_gemm<64, false>(tA, tB, tC, tS, s, st);
   }
 }
 

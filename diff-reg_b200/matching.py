@@ -98,7 +98,7 @@ class Matching(nn.Module):
         B, L, C = feats.shape
         split = self.precision == "3xtf32"
         a = ops.prep_operand(feats, 1.0, split, 0)
-        out = ops.gemm_nt(a.reshape(B * L, a.shape[-1]), self._weight_operand())
+        out = ops.gemm_nt(a.reshape(B * L, a.shape[-1]), self._weight_operand(), split3=split)
         return out.view(B, L, C)
 
     def similarity(self, src_feats, tgt_feats, src_pe=None, tgt_pe=None, pe_type="rotary", data=None):
@@ -119,7 +119,7 @@ class Matching(nn.Module):
                 data["tgt_feats_nopos"] = ft
                 data["src_feats"] = fs
                 data["tgt_feats"] = ft
-            return ops.gemm_nt(a, b)
+            return ops.gemm_nt(a, b, split3=True)
         fs = self.project(src_feats)
         ft = self.project(tgt_feats)
         want = data is not None and use_pe
@@ -134,7 +134,7 @@ class Matching(nn.Module):
             data["tgt_feats"] = b[1] if want else ft
         if want:
             a, b = a[0], b[0]
-        return ops.gemm_nt(a, b)
+        return ops.gemm_nt(a, b, split3=split)
 
     def confidence(self, sim, src_mask, tgt_mask):
         B, N, M = sim.shape
