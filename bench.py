@@ -198,7 +198,7 @@ def run_reference_arm(args):
             "dtype": "f32", "data": "synthetic", "impl": "reference", "config": workload_config(args.n),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -426,13 +426,32 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(e2e_launches * world), "launches_per_step": int(launches_per_step),
                 "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "kernel_ms_per_step": kernel_ms}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _emit(line):
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse_args()
+    # Libraries write to stdout behind our back (NCCL prints its version line there on communicator creation): keep the
+    # original stdout for the JSON line only and send everything else to stderr.
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
