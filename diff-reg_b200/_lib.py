@@ -148,7 +148,7 @@ def launch_count():
 
 
 PROFILE_SLOTS = ["skh_iter", "skh_col", "skh_final", "skh_prep", "gemm", "prep_operand", "rowcol_best", "match_rows",
-                 "topk_collect", "procr_solve", "topk_threshold"]
+                 "topk_collect", "procr_solve", "topk_threshold", "procr_select"]
 
 
 def profile_enable(on=True):

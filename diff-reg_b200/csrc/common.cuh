@@ -120,6 +120,7 @@ enum ProfSlot {
   PROF_TOPK_COLLECT,
   PROF_PROCR_SOLVE,
   PROF_TOPK_THRESHOLD,
+  PROF_PROCR_SELECT,
   PROF_NSLOTS
 };
 extern std::atomic<int> g_prof_enabled;

@@ -31,14 +31,32 @@ namespace drg {
 constexpr int TK_BINS = 2048;
 constexpr int TS_THREADS = 512;
 constexpr int TS_SAMPLES = 32768;  // sample keys held in shared memory (128 KB)
+constexpr int TS_FAST_TARGET = 128;  // order statistics up to this rank use the thread-maxima short cut of the bound select
+constexpr int TS_FAST_LIST = 256;    // capacity of its short list (TS_THREADS threads rank it)
 constexpr int SOLVE_THREADS = 1024;
 constexpr int SOLVE_SMEM_CAND = 24576;  // candidates staged in shared memory by the solve kernel (192 KB)
+
+constexpr int PM_THREADS = 256;   // multi-CTA moments kernel
+constexpr int PM_MAX_G = 64;      // its CTAs per batch element (at most)
+constexpr int PM_PART = 24;       // doubles per CTA partial: W, W_abs, cx[3], cy[3], D[3], E[3], C[9]
+constexpr int SEL_THREADS = 1024; // select kernel
+constexpr int SEL_LIST = 256;     // short list of the select kernel (candidates of the crossing histogram bin)
 
 struct ProcrState {  // per batch element
   int Kb;                         // number of correspondences to use
   unsigned int n_cand;            // candidates appended so far
   unsigned long long lower_key;   // candidates have 64-bit key >= lower_key
+  unsigned long long T;           // written by the select kernel: the Kb best candidates are those with key >= T
+  unsigned int hist_kmin;         // candidate histogram (filled by the collect kernels): bin = ((value key - kmin) << sh) >> 21,
+  int hist_sh;                    //   clamped to the top bin -- monotone in the key, ~2048 bins over [bound, 2 x sample range]
+  unsigned int sel_count;         // selected correspondences written to sel_* so far
+  unsigned int pad_;
 };
+
+__device__ __forceinline__ unsigned int cand_bin(unsigned int k32, unsigned int kmin, int sh) {
+  const unsigned long long d = ((unsigned long long)(k32 - kmin) << sh) >> 21;  // k32 >= kmin for every candidate
+  return d > (unsigned long long)(TK_BINS - 1) ? (unsigned int)(TK_BINS - 1) : (unsigned int)d;
+}
 
 struct ProcrParams {
   const float* conf;             // [B,N,M], or NULL: potentials mode, conf = exp((scores - shift | mask) + u + v - norm)
@@ -62,6 +80,9 @@ struct ProcrParams {
   unsigned int* cand_idx;        // [B, N*M]
   unsigned int* sample_buf;      // [B, TS_SAMPLES]
   unsigned int* sample_arrive;   // [B] arrival counters of the sampling CTAs (zero between calls)
+  unsigned int* moments_arrive;  // [B] arrival counters of the moments CTAs (zero between calls)
+  unsigned int* cand_hist;       // [B, TK_BINS] histogram of the candidates' value keys (zeroed by the threshold kernel)
+  double* partials;              // [B, PM_MAX_G, PM_PART] per-CTA moment partials
   float4* pcd4;                  // [B][N + M] the points padded to 16 bytes (src, then tgt): one gather per point in the solve kernel
   // outputs
   float* R;                      // [B,3,3]
@@ -134,6 +155,54 @@ struct __align__(16) SelectScratch {
   int done;
 };
 
+// One warp walks a TK_BINS-bin histogram (shared memory) from the top and finds the bin where the running count reaches
+// krem: `bin`, the count `cum` in the bins above it and its own count `hsel`, returned to all lanes.  Two steps, nothing
+// kept in registers and no serial scan (an earlier version held a lane's 64 bins in registers -- spilled at 64 registers
+// per thread -- and let the owning lane step through them one by one).  Step 1: lane l sums the l-th chunk of 64 bins
+// (descending); a warp scan finds the chunk of the crossing.  Step 2: the 32 lanes split that chunk two bins each and
+// scan again.  If krem exceeds the total count the lowest bin is returned.
+__device__ __forceinline__ void warp_walk_hist(const unsigned int* hist, unsigned int krem, int& bin, unsigned int& cum,
+                                               unsigned int& hsel) {
+  const int lane = threadIdx.x & 31;
+  constexpr int chunk = TK_BINS / 32;                    // 64 bins per lane
+  const int lo = TK_BINS - chunk * (lane + 1);           // lowest bin of this lane's chunk
+  const uint4* h4 = reinterpret_cast<const uint4*>(&hist[lo]);
+  unsigned int local = 0u;
+#pragma unroll
+  for (int q = 0; q < chunk / 4; ++q) {
+    const uint4 v4 = h4[q];
+    local += v4.x + v4.y + v4.z + v4.w;
+  }
+  unsigned int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int tmp = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += tmp;
+  }
+  const unsigned int crossing = __ballot_sync(0xffffffffu, incl >= krem);
+  const int owner = crossing ? (__ffs(crossing) - 1) : 31;
+  const unsigned int before = __shfl_sync(0xffffffffu, incl - local, owner);  // keys in the chunks above the owner's
+  const int top = TK_BINS - chunk * owner - 1;           // highest bin of the owner's chunk
+  const unsigned int h0 = hist[top - 2 * lane], h1 = hist[top - 2 * lane - 1];
+  const unsigned int pair = h0 + h1;
+  unsigned int incl2 = pair;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int tmp = __shfl_up_sync(0xffffffffu, incl2, o);
+    if (lane >= o) incl2 += tmp;
+  }
+  const unsigned int crossing2 = __ballot_sync(0xffffffffu, before + incl2 >= krem);
+  const int lane2 = crossing2 ? (__ffs(crossing2) - 1) : 31;  // no crossing (krem beyond the count): the lowest bins
+  const unsigned int c0 = before + incl2 - pair;
+  const bool first = crossing2 != 0u && c0 + h0 >= krem;
+  const int my_bin = first ? (top - 2 * lane) : (top - 2 * lane - 1);
+  const unsigned int my_cum = first ? c0 : (c0 + h0);
+  const unsigned int my_h = first ? h0 : h1;
+  bin = __shfl_sync(0xffffffffu, my_bin, lane2);
+  cum = __shfl_sync(0xffffffffu, my_cum, lane2);
+  hsel = __shfl_sync(0xffffffffu, my_h, lane2);
+}
+
 template <int NT, class KeyAt>
 __device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, SelectScratch& sc) {
   const int tid = threadIdx.x;
@@ -159,49 +228,12 @@ __device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, Se
     }
     __syncthreads();
     if (tid < 32) {
-      // warp 0 walks the histogram from the top: lane l owns the l-th chunk of bins (descending), pulled into
-      // registers with 128-bit loads (bins beyond 2^wbits stay zero)
-      constexpr int chunk = TK_BINS / 32;                    // 64 bins per lane
-      const int lo = TK_BINS - chunk * (tid + 1);            // lowest bin of this lane's chunk
-      unsigned int hreg[chunk];
-      const uint4* h4 = reinterpret_cast<const uint4*>(&sc.hist[lo]);
-      unsigned int local = 0u;
-#pragma unroll
-      for (int q = 0; q < chunk / 4; ++q) {
-        const uint4 v4 = h4[q];
-        hreg[4 * q + 0] = v4.x;
-        hreg[4 * q + 1] = v4.y;
-        hreg[4 * q + 2] = v4.z;
-        hreg[4 * q + 3] = v4.w;
-        local += v4.x + v4.y + v4.z + v4.w;
-      }
-      unsigned int incl = local;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int tmp = __shfl_up_sync(0xffffffffu, incl, o);
-        if (tid >= o) incl += tmp;
-      }
+      int dbin;
+      unsigned int cum, hsel;
       const unsigned int krem = (unsigned int)sc.krem;
-      const unsigned int crossing = __ballot_sync(0xffffffffu, incl >= krem);
-      const int owner = crossing ? (__ffs(crossing) - 1) : 31;
-      if (tid == owner) {
-        unsigned int cum = incl - local;
-        int dsel = 0;
-        unsigned int hsel = hreg[0];
-        bool found = false;
-#pragma unroll
-        for (int t = chunk - 1; t >= 0; --t) {
-          if (!found) {
-            if (cum + hreg[t] >= krem || t == 0) {
-              found = true;
-              dsel = t;
-              hsel = hreg[t];
-            } else {
-              cum += hreg[t];
-            }
-          }
-        }
-        sc.prefix = (prefix << wbits) | (unsigned long long)(lo + dsel);
+      warp_walk_hist(sc.hist, krem, dbin, cum, hsel);
+      if (tid == 0) {
+        sc.prefix = (prefix << wbits) | (unsigned long long)dbin;
         sc.krem = (int)(krem - cum);
         if (hsel == krem - cum) sc.done = 1;  // the whole bucket is wanted
       }
@@ -259,8 +291,22 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
   if (ticket_s != gridDim.x - 1) return;   // not the last CTA of this batch element
   if (tid == 0) p.sample_arrive[b] = 0u;   // self-reset for the next call
   __threadfence();
-  for (unsigned int q = tid; q < n_s; q += TS_THREADS) sample_key[q] = __ldcg(sbuf + q);
+  for (int q = tid; q < TK_BINS; q += TS_THREADS) p.cand_hist[(size_t)b * TK_BINS + q] = 0u;  // filled by the collect kernel
+  __shared__ unsigned int smax_s;
+  if (tid == 0) smax_s = 0u;
+  // the staging loop also tracks this thread's largest sample value (fast path of the select below)
+  unsigned int tmax = 0u;
+#pragma unroll 8
+  for (unsigned int q = tid; q < n_s; q += TS_THREADS) {
+    const unsigned int v = __ldcg(sbuf + q);
+    sample_key[q] = v;
+    tmax = max(tmax, v);
+  }
   __syncthreads();
+  {
+    const unsigned int wm = __reduce_max_sync(0xffffffffu, tmax);
+    if ((tid & 31) == 0) atomicMax(&smax_s, wm);
+  }
   // ---- mask counts of every batch element (K is a mean over the batch)      procrustes.py:61-65
   float cap_sum = 0.f;
   int my_cap = 0;
@@ -300,8 +346,60 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
       target = (long long)(2.0 * expect + 16.0);
     }
     if (target < (long long)n_s) {
-      lower = block_select_kth<TS_THREADS>(
-          [&](size_t e) { return make_key64(sample_key[e], sample_pos((unsigned int)e)); }, (size_t)n_s, (int)target, sc);
+      // Fast path (the normal case: the 32nd largest of 32768 samples).  A radix select over the whole sample spends
+      // its levels on ~32 k shared-memory atomics into the few bins the exponents of the confidences occupy.  Instead:
+      // the target-th largest of the 512 per-thread maxima is a value b0 that at least `target` samples reach, and
+      // hardly more than `target` do (the top samples are spread over the threads at random); those few go to a short
+      // list whose target-th largest 64-bit key, found by rank counting, is exactly the key the full select returns.
+      bool found = false;
+      if (target <= (long long)TS_FAST_TARGET) {
+        __shared__ unsigned int tmax_s[TS_THREADS];
+        __shared__ unsigned long long list_s[TS_FAST_LIST];
+        __shared__ unsigned int list_n, b0_s;
+        __shared__ unsigned long long lower_s;
+        tmax_s[tid] = tmax;
+        if (tid == 0) {
+          list_n = 0u;
+          b0_s = 0xFFFFFFFFu;
+          lower_s = 0ull;
+        }
+        __syncthreads();
+        const unsigned long long tb = block_select_kth<TS_THREADS>(
+            [&](size_t e) { return make_key64(tmax_s[e], (unsigned int)e); }, (size_t)TS_THREADS, (int)target, sc);
+        // the select may stop at a bucket edge: the exact bound is the smallest selected maximum
+        unsigned int mine = (make_key64(tmax, (unsigned int)tid) >= tb) ? tmax : 0xFFFFFFFFu;
+        mine = __reduce_min_sync(0xffffffffu, mine);
+        if ((tid & 31) == 0) atomicMin(&b0_s, mine);
+        __syncthreads();
+        const unsigned int b0 = b0_s;
+        for (unsigned int q = tid; q < n_s; q += TS_THREADS) {
+          const unsigned int v = sample_key[q];
+          if (v >= b0) {
+            const unsigned int pos = atomicAdd(&list_n, 1u);
+            if (pos < (unsigned int)TS_FAST_LIST) list_s[pos] = make_key64(v, sample_pos(q));
+          }
+        }
+        __syncthreads();
+        const unsigned int L = list_n;
+        if (L <= (unsigned int)TS_FAST_LIST && (long long)L >= target) {
+          if ((unsigned int)tid < L) {
+            const unsigned long long my = list_s[tid];
+            unsigned int rank = 0u;
+            for (unsigned int q = 0; q < L; ++q) {
+              const unsigned long long o = list_s[q];
+              rank += (o > my || (o == my && q < (unsigned int)tid)) ? 1u : 0u;  // duplicates (hash collisions) ranked by position
+            }
+            if (rank == (unsigned int)(target - 1)) lower_s = my;
+          }
+          __syncthreads();
+          lower = lower_s;
+          found = true;
+        }
+      }
+      if (!found) {
+        lower = block_select_kth<TS_THREADS>(
+            [&](size_t e) { return make_key64(sample_key[e], sample_pos((unsigned int)e)); }, (size_t)n_s, (int)target, sc);
+      }
     }
   }
   TSTAMP(23);
@@ -311,6 +409,19 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
     s.Kb = Kb;
     s.n_cand = 0u;
     s.lower_key = lower;
+    s.T = 0ull;
+    // histogram range: from the bound to twice the distance of the largest sample (larger keys share the top bin)
+    const unsigned int kmin = (unsigned int)(lower >> 32);
+    const unsigned int smax = smax_s;
+    unsigned int range = 0xFFFFFFFFu - kmin;
+    if (lower != 0ull && smax > kmin) {
+      const unsigned long long r2 = 2ull * (unsigned long long)(smax - kmin) + 1ull;
+      if (r2 < (unsigned long long)range) range = (unsigned int)r2;
+    }
+    s.hist_kmin = kmin;
+    s.hist_sh = range ? __clz((int)range) : 32;
+    s.sel_count = 0u;
+    s.pad_ = 0u;
     p.state[b] = s;
   }
 }
@@ -334,11 +445,14 @@ __device__ __forceinline__ void append_candidates(const ProcrParams& p, int b, s
   if (lane == 0) base = atomicAdd(&p.state[b].n_cand, (unsigned int)warp_total);
   base = __shfl_sync(0xffffffffu, base, 0);
   unsigned int pos = base + (unsigned int)(incl - mine);
+  const unsigned int hk = p.state[b].hist_kmin;
+  const int hs = p.state[b].hist_sh;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     if (take[e]) {
       p.cand_key[(size_t)b * total + pos] = key[e];
       p.cand_idx[(size_t)b * total + pos] = flat0 + e;
+      atomicAdd(&p.cand_hist[(size_t)b * TK_BINS + cand_bin(key[e], hk, hs)], 1u);
       ++pos;
     }
   }
@@ -447,6 +561,8 @@ __global__ void __launch_bounds__(256) topk_collect_rows_kernel(const ProcrParam
   const size_t total = (size_t)N * M;
   const float* x = p.scores + (size_t)b * total;
   const unsigned long long lower = p.state[b].lower_key;
+  const unsigned int hist_kmin = p.state[b].hist_kmin;
+  const int hist_sh = p.state[b].hist_sh;
   const float shift = p.pshift ? *p.pshift : 0.f;
   const SkhConst bc = p.pbc[b];
   const float norm = bc.norm;
@@ -493,8 +609,10 @@ __global__ void __launch_bounds__(256) topk_collect_rows_kernel(const ProcrParam
       __syncthreads();
       const unsigned int base = s_base;
       for (unsigned int e = threadIdx.x; e < cnt; e += blockDim.x) {
-        p.cand_key[(size_t)b * total + base + e] = s_key[e];
+        const unsigned int k32 = s_key[e];
+        p.cand_key[(size_t)b * total + base + e] = k32;
         p.cand_idx[(size_t)b * total + base + e] = s_idx[e];
+        atomicAdd(&p.cand_hist[(size_t)b * TK_BINS + cand_bin(k32, hist_kmin, hist_sh)], 1u);  // level 1 of the select, for free
       }
       __syncthreads();
       if (threadIdx.x == 0) s_n = 0u;
@@ -566,12 +684,12 @@ __global__ void __launch_bounds__(256) topk_collect_rows_kernel(const ProcrParam
 // in fp64 in a fixed order (bitwise reproducible) and everybody reads the totals.  fp64 vector math is slow on this
 // part, so it is kept to this last step and to the 3x3 solve.
 struct MomentScratch {
-  float part[32][12];
-  double total[12];
+  float part[32][16];
+  double total[16];
 };
 template <int K>
 __device__ __forceinline__ void block_sum_f32(const float (&v)[K], double (&out)[K], MomentScratch& ms) {
-  static_assert(K <= 12, "MomentScratch holds 12 values");
+  static_assert(K <= 16, "MomentScratch holds 16 values");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nw = (blockDim.x + 31) >> 5;
   __syncthreads();  // scratch reuse
@@ -727,8 +845,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
   __shared__ unsigned int warp_cnt[SOLVE_THREADS / 32];
   __shared__ double mean_s[6], cov_s[9];
   __shared__ float pose_s[12];
+  __shared__ unsigned int range_s[2];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
+  if (tid == 0) {
+    range_s[0] = 0xFFFFFFFFu;
+    range_s[1] = 0u;
+  }
+  __syncthreads();
 #define PSTAMP(k) do { if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[(k)] = clock64(); } while (0)
   PSTAMP(0);
   const size_t total = (size_t)p.N * p.M;
@@ -748,63 +872,139 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
     __syncthreads();
   }
 
-  // The candidate list normally fits in shared memory: stage it once (coalesced, many loads in flight) so that the
-  // radix levels and the emission below do not pay a global-memory round trip per 1024 candidates.
+  // The candidate list normally fits in shared memory: stage it once (coalesced, 16 loads in flight per thread) so that
+  // the radix levels and the emission below do not pay a global-memory round trip per 1024 candidates.  The staging
+  // pass also finds the range [kmin, kmax] of the 32-bit value keys: the select then runs on keys normalised to that
+  // range (value - kmin, left-aligned), so its first level spreads the candidates over all 2048 bins instead of the
+  // handful of bins that share the confidences' exponent (19 k atomics into ~4 addresses), and two levels normally do.
+  constexpr int QMAX = SOLVE_SMEM_CAND / SOLVE_THREADS;
   const bool in_smem = n <= (size_t)SOLVE_SMEM_CAND;
+  unsigned int kmin = 0u;
+  int nsh = 0;
   if (in_smem) {
-#pragma unroll 4
-    for (size_t e = tid; e < n; e += SOLVE_THREADS) {
-      cand_s[e] = ckey[e];
-      cand_s[SOLVE_SMEM_CAND + e] = cidx[e];
+    unsigned int lo = 0xFFFFFFFFu, hi = 0u;
+    for (int q0 = 0; q0 < QMAX; q0 += 8) {
+      if ((size_t)q0 * SOLVE_THREADS >= n) break;  // uniform
+      unsigned int kk[8], ii[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const size_t e = (size_t)tid + (size_t)(q0 + u) * SOLVE_THREADS;
+        const bool in = e < n;
+        kk[u] = in ? ckey[e] : 0u;
+        ii[u] = in ? cidx[e] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const size_t e = (size_t)tid + (size_t)(q0 + u) * SOLVE_THREADS;
+        if (e < n) {
+          cand_s[e] = kk[u];
+          cand_s[SOLVE_SMEM_CAND + e] = ii[u];
+          lo = min(lo, kk[u]);
+          hi = max(hi, kk[u]);
+        }
+      }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((tid & 31) == 0) {
+      atomicMin(&range_s[0], lo);
+      atomicMax(&range_s[1], hi);
     }
     __syncthreads();
+    kmin = range_s[0];
+    const unsigned int kmax = range_s[1];
+    nsh = (kmax > kmin) ? __clz((int)(kmax - kmin)) : 32;
   }
   PSTAMP(1);
   const unsigned int* kp = in_smem ? cand_s : ckey;
   const unsigned int* ip = in_smem ? cand_s + SOLVE_SMEM_CAND : cidx;
+  // order-preserving on the candidates (all values >= kmin, value range below 2^(32 - nsh)); identity when not staged
+  auto nkey = [&](unsigned int k32, unsigned int fi) -> unsigned long long { return make_key64(k32 - kmin, fi) << nsh; };
 
   // ---- exact radix select of the Kb largest 64-bit keys (value << 32 | ~index): no ties
   unsigned long long T = 0ull;  // select keys >= T
   if (Kb > 0 && (size_t)Kb < n)
-    T = block_select_kth<SOLVE_THREADS>([&](size_t e) { return make_key64(kp[e], ip[e]); }, n, Kb, sc);
+    T = block_select_kth<SOLVE_THREADS>([&](size_t e) { return nkey(kp[e], ip[e]); }, n, Kb, sc);
 
   PSTAMP(2);
   if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[10] = (long long)n;
-  // ---- two fp32 passes over the candidates (shared memory), skipping the unselected ones: weighted means, then the
-  //      centred covariance -- the reference's own order of operations (procrustes.py:29-34).
+  // ---- two fp32 passes over the selected candidates: weighted means, then the centred covariance -- the reference's
+  //      own order of operations (procrustes.py:29-34).  A thread first marks which of its (at most QMAX) staged
+  //      candidates are selected, then visits them four at a time so that the eight point gathers of a batch are in
+  //      flight together (one L2 round trip per selected candidate was what bounded these passes).
   //      (Measured: compacting the selection first and fp64 moments were both slower on B200.)
   const float* sp = p.src_pcd + (size_t)b * p.N * 3;
   const float4* sp4 = p.pcd4 + (size_t)b * (p.N + p.M);  // written by the collect kernel
   const float4* tp4 = sp4 + p.N;
+  unsigned int selmask = 0u;
+  if (in_smem && Kb > 0) {
+#pragma unroll
+    for (int q = 0; q < QMAX; ++q) {
+      const size_t e = (size_t)tid + (size_t)q * SOLVE_THREADS;
+      if (e < n && nkey(kp[e], ip[e]) >= T) selmask |= 1u << q;
+    }
+  }
+  auto visit_selected = [&](auto&& f) {
+    if (in_smem) {
+      unsigned int m = selmask;
+      while (m) {
+        unsigned int kk[4];
+        int ii[4], jj[4];
+        float4 xx[4], yy[4];
+        bool on[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          on[u] = m != 0u;
+          if (on[u]) {
+            const int q = __ffs((int)m) - 1;
+            m &= m - 1u;
+            const size_t e = (size_t)tid + (size_t)q * SOLVE_THREADS;
+            kk[u] = kp[e];
+            const unsigned int fi = ip[e];
+            ii[u] = (int)(fi / (unsigned int)p.M);
+            jj[u] = (int)(fi - (unsigned int)ii[u] * (unsigned int)p.M);
+            xx[u] = sp4[ii[u]];
+            yy[u] = tp4[jj[u]];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (on[u]) f(kk[u], ii[u], jj[u], xx[u], yy[u]);
+      }
+    } else {
+      for (size_t e = tid; e < n; e += SOLVE_THREADS) {
+        const unsigned int k32 = kp[e], fi = ip[e];
+        if (nkey(k32, fi) >= T) {
+          const int i = (int)(fi / (unsigned int)p.M), j = (int)(fi - (unsigned int)i * (unsigned int)p.M);
+          f(k32, i, j, sp4[i], tp4[j]);
+        }
+      }
+    }
+  };
   unsigned int ne = 0;
   if (tid == 0) warp_cnt[0] = 0u;
   __syncthreads();
   if (Kb > 0) {
     float m1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // sum w, sum |w|, sum w x (3), sum w y (3)
-    for (size_t e = tid; e < n; e += SOLVE_THREADS) {
-      const unsigned int k32 = kp[e], fi = ip[e];
-      if (make_key64(k32, fi) >= T) {
-        const float wf = ordered_to_float(k32);
-        const int i = (int)(fi / (unsigned int)p.M), j = (int)(fi - (unsigned int)i * (unsigned int)p.M);
-        if (p.sel_w) {
-          const unsigned int pos = atomicAdd(&warp_cnt[0], 1u);
-          if (pos < (unsigned int)p.K_max) {
-            p.sel_w[(size_t)b * p.K_max + pos] = wf;
-            p.sel_src[(size_t)b * p.K_max + pos] = i;
-            p.sel_tgt[(size_t)b * p.K_max + pos] = j;
-          }
-        }
-        const float4 x4 = sp4[i], y4 = tp4[j];
-        const float xs[3] = {x4.x, x4.y, x4.z}, ys[3] = {y4.x, y4.y, y4.z};
-        m1[0] += wf;
-        m1[1] += fabsf(wf);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          m1[2 + a] = fmaf(wf, xs[a], m1[2 + a]);
-          m1[5 + a] = fmaf(wf, ys[a], m1[5 + a]);
+    visit_selected([&](unsigned int k32, int i, int j, const float4& x4, const float4& y4) {
+      const float wf = ordered_to_float(k32);
+      if (p.sel_w) {
+        const unsigned int pos = atomicAdd(&warp_cnt[0], 1u);
+        if (pos < (unsigned int)p.K_max) {
+          p.sel_w[(size_t)b * p.K_max + pos] = wf;
+          p.sel_src[(size_t)b * p.K_max + pos] = i;
+          p.sel_tgt[(size_t)b * p.K_max + pos] = j;
         }
       }
-    }
+      const float xs[3] = {x4.x, x4.y, x4.z}, ys[3] = {y4.x, y4.y, y4.z};
+      m1[0] += wf;
+      m1[1] += fabsf(wf);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        m1[2 + a] = fmaf(wf, xs[a], m1[2 + a]);
+        m1[5 + a] = fmaf(wf, ys[a], m1[5 + a]);
+      }
+    });
     double s1[8];
     block_sum_f32<8>(m1, s1, ms);
     PSTAMP(7);
@@ -814,20 +1014,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
     const float mxf[3] = {(float)(s1[2] * inv), (float)(s1[3] * inv), (float)(s1[4] * inv)};
     const float myf[3] = {(float)(s1[5] * inv), (float)(s1[6] * inv), (float)(s1[7] * inv)};
     float m2[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (size_t e = tid; e < n; e += SOLVE_THREADS) {
-      const unsigned int k32 = kp[e], fi = ip[e];
-      if (make_key64(k32, fi) >= T) {
-        const float wn = ordered_to_float(k32) * invf;
-        const int i = (int)(fi / (unsigned int)p.M), j = (int)(fi - (unsigned int)i * (unsigned int)p.M);
-        const float4 x4 = sp4[i], y4 = tp4[j];
-        const float xc[3] = {x4.x - mxf[0], x4.y - mxf[1], x4.z - mxf[2]};
-        const float yc[3] = {y4.x - myf[0], y4.y - myf[1], y4.z - myf[2]};
+    visit_selected([&](unsigned int k32, int, int, const float4& x4, const float4& y4) {
+      const float wn = ordered_to_float(k32) * invf;
+      const float xc[3] = {x4.x - mxf[0], x4.y - mxf[1], x4.z - mxf[2]};
+      const float yc[3] = {y4.x - myf[0], y4.y - myf[1], y4.z - myf[2]};
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
+      for (int a = 0; a < 3; ++a)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) m2[a * 3 + c] = fmaf(wn * yc[a], xc[c], m2[a * 3 + c]);
-      }
-    }
+        for (int c = 0; c < 3; ++c) m2[a * 3 + c] = fmaf(wn * yc[a], xc[c], m2[a * 3 + c]);
+    });
     double s2[9];
     block_sum_f32<9>(m2, s2, ms);
     PSTAMP(3);
@@ -883,6 +1078,328 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
   }
   PSTAMP(6);
 #undef PSTAMP
+}
+
+// ---- 5b. the pose step spread over several CTAs (the default) -----------------------------------------------
+// The single-CTA kernel above is bound by things one SM does badly: ~19 k shared-memory atomics for the first radix
+// level of the select (~10 k cycles) and ~8 k scattered 16-byte point gathers per moment pass, which one SM issues at
+// well under one request per clock (~20 k cycles per pass) -- 75-80 k cycles in all.  Here instead:
+//   * the collect kernels build the first-level histogram of the candidates as they append them (global atomics spread
+//     over the whole GPU);
+//   * procr_select_kernel (one CTA per batch element) walks that histogram, reads the candidate keys once, puts the
+//     few candidates of the crossing bin on a short list and finds the exact K_b-th largest key T by rank counting;
+//   * procr_moments_kernel (up to 64 CTAs per batch element) splits the candidates: every CTA gathers the points of its
+//     selected candidates and reduces them to weighted moments about ITS OWN weighted mean (two passes, as the
+//     reference centres before it multiplies); the last CTA to arrive combines the partials exactly (parallel-axis
+//     terms in fp64), solves the 3x3 problem, applies the condition gate and warps the source points.
+__global__ void __launch_bounds__(SEL_THREADS) procr_select_kernel(const ProcrParams p) {
+  __shared__ SelectScratch sc;
+  __shared__ unsigned long long list_s[SEL_LIST];
+  __shared__ unsigned int list_n;
+  __shared__ int bin_s;
+  __shared__ unsigned int cum_s, hsel_s;
+  __shared__ unsigned long long T_s;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const size_t total = (size_t)p.N * p.M;
+  const ProcrState st = p.state[b];
+  const int Kb = st.Kb;
+  unsigned int* ckey = p.cand_key + (size_t)b * total;
+  unsigned int* cidx = p.cand_idx + (size_t)b * total;
+  size_t n = st.n_cand;
+  bool slow = false;
+  if (n < (size_t)Kb) {
+    // fallback: the sample-based bound left too few candidates; take the whole matrix
+    for (size_t e = tid; e < total; e += SEL_THREADS) {
+      ckey[e] = float_to_ordered(conf_at(p, b, e));
+      cidx[e] = (unsigned int)e;
+    }
+    n = total;
+    slow = true;
+    __syncthreads();
+  }
+  unsigned long long T = 0ull;  // Kb >= n: every candidate is used
+  if (Kb > 0 && (size_t)Kb < n) {
+    if (!slow) {
+      for (int q = tid; q < TK_BINS; q += SEL_THREADS) sc.hist[q] = __ldcg(p.cand_hist + (size_t)b * TK_BINS + q);
+      if (tid == 0) {
+        list_n = 0u;
+        T_s = 0ull;
+      }
+      __syncthreads();
+      if (tid < 32) {
+        int bin;
+        unsigned int cum, hsel;
+        warp_walk_hist(sc.hist, (unsigned int)Kb, bin, cum, hsel);
+        if (tid == 0) {
+          bin_s = bin;
+          cum_s = cum;
+          hsel_s = hsel;
+        }
+      }
+      __syncthreads();
+      const int bin = bin_s;
+      const unsigned int want = (unsigned int)Kb - cum_s;  // how many of the crossing bin's candidates are selected
+      const unsigned int hsel = hsel_s;
+      if (hsel > (unsigned int)SEL_LIST || want < 1u || want > hsel) {
+        slow = true;  // heavily tied values (or an inconsistent histogram): the general select
+      } else {
+        // one pass over the candidate keys: those of the crossing bin go to the short list
+        for (size_t e0 = 0; e0 < n; e0 += (size_t)SEL_THREADS * 8) {
+          unsigned int kk[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const size_t e = e0 + (size_t)u * SEL_THREADS + tid;
+            kk[u] = e < n ? ckey[e] : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const size_t e = e0 + (size_t)u * SEL_THREADS + tid;
+            if (e < n && (int)cand_bin(kk[u], st.hist_kmin, st.hist_sh) == bin) {
+              const unsigned int pos = atomicAdd(&list_n, 1u);
+              if (pos < (unsigned int)SEL_LIST) list_s[pos] = make_key64(kk[u], cidx[e]);
+            }
+          }
+        }
+        __syncthreads();
+        const unsigned int L = list_n;
+        if (L != hsel) {
+          slow = true;  // cannot happen unless the histogram and the list disagree; stay exact
+        } else {
+          if ((unsigned int)tid < L) {
+            const unsigned long long my = list_s[tid];
+            unsigned int rank = 0u;
+            for (unsigned int q = 0; q < L; ++q) rank += (list_s[q] > my) ? 1u : 0u;  // keys are distinct (distinct indices)
+            if (rank == want - 1u) T_s = my;
+          }
+          __syncthreads();
+          T = T_s;
+        }
+      }
+    }
+    if (slow) T = block_select_kth<SEL_THREADS>([&](size_t e) { return make_key64(ckey[e], cidx[e]); }, n, Kb, sc);
+  }
+  if (tid == 0) {
+    p.state[b].T = T;
+    p.state[b].n_cand = (unsigned int)n;
+    p.state[b].pad_ = (slow ? 0x80000000u : 0u) | (unsigned int)(Kb > 0 && (size_t)Kb < n ? hsel_s & 0x7FFFFFFFu : 0u);  // diagnostics
+  }
+}
+
+__global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrParams p) {
+  __shared__ MomentScratch ms;
+  __shared__ unsigned int ticket_s;
+  __shared__ double comb_s[16];
+  __shared__ double mean_s[6], cov_s[9];
+  __shared__ float pose_s[12];
+  const int b = blockIdx.y;
+  const int G = gridDim.x;
+  const int tid = threadIdx.x;
+  const size_t total = (size_t)p.N * p.M;
+  const ProcrState st = p.state[b];
+  const int Kb = st.Kb;
+  const unsigned long long T = st.T;
+  const size_t n = st.n_cand;
+  const unsigned int* ckey = p.cand_key + (size_t)b * total;
+  const unsigned int* cidx = p.cand_idx + (size_t)b * total;
+  const float4* sp4 = p.pcd4 + (size_t)b * (p.N + p.M);  // written by the collect kernel
+  const float4* tp4 = sp4 + p.N;
+  // this CTA's slice of the candidate list
+  const size_t per = (n + G - 1) / G;
+  const size_t e_lo = min(n, per * blockIdx.x), e_hi = min(n, e_lo + per);
+  // visit the selected candidates of the slice, two per thread at a time (four gathers in flight)
+  auto visit_selected = [&](auto&& f) {
+    if (Kb <= 0) return;
+    for (size_t e0 = e_lo; e0 < e_hi; e0 += (size_t)PM_THREADS * 2) {
+      unsigned int kk[2], fi[2];
+      int ii[2], jj[2];
+      float4 xx[2], yy[2];
+      bool on[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const size_t e = e0 + (size_t)u * PM_THREADS + tid;
+        on[u] = e < e_hi;
+        kk[u] = on[u] ? ckey[e] : 0u;
+        fi[u] = on[u] ? cidx[e] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        on[u] = on[u] && make_key64(kk[u], fi[u]) >= T;
+        if (on[u]) {
+          ii[u] = (int)(fi[u] / (unsigned int)p.M);
+          jj[u] = (int)(fi[u] - (unsigned int)ii[u] * (unsigned int)p.M);
+          xx[u] = sp4[ii[u]];
+          yy[u] = tp4[jj[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (on[u]) f(kk[u], ii[u], jj[u], xx[u], yy[u]);
+    }
+  };
+  // pass A: sum w, sum |w|, sum w x, sum w y  ->  this CTA's centre (its weighted mean)
+  float m1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  visit_selected([&](unsigned int k32, int i, int j, const float4& x4, const float4& y4) {
+    const float wf = ordered_to_float(k32);
+    if (p.sel_w) {
+      const unsigned int pos = atomicAdd(&p.state[b].sel_count, 1u);
+      if (pos < (unsigned int)p.K_max) {
+        p.sel_w[(size_t)b * p.K_max + pos] = wf;
+        p.sel_src[(size_t)b * p.K_max + pos] = i;
+        p.sel_tgt[(size_t)b * p.K_max + pos] = j;
+      }
+    }
+    const float xs[3] = {x4.x, x4.y, x4.z}, ys[3] = {y4.x, y4.y, y4.z};
+    m1[0] += wf;
+    m1[1] += fabsf(wf);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      m1[2 + a] = fmaf(wf, xs[a], m1[2 + a]);
+      m1[5 + a] = fmaf(wf, ys[a], m1[5 + a]);
+    }
+  });
+  double s1[8];
+  block_sum_f32<8>(m1, s1, ms);
+  float cxf[3] = {0.f, 0.f, 0.f}, cyf[3] = {0.f, 0.f, 0.f};
+  if (s1[0] != 0.0 && s1[1] > 0.0) {
+    const double iw = 1.0 / s1[0];
+    for (int a = 0; a < 3; ++a) {
+      cxf[a] = (float)(s1[2 + a] * iw);
+      cyf[a] = (float)(s1[5 + a] * iw);
+      if (!(fabsf(cxf[a]) < INFINITY)) cxf[a] = 0.f;  // any finite centre is valid
+      if (!(fabsf(cyf[a]) < INFINITY)) cyf[a] = 0.f;
+    }
+  }
+  // pass B: moments about the centre: D = sum w (x - cx), E = sum w (y - cy), C = sum w (y - cy)(x - cx)^T
+  float m2[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) m2[k] = 0.f;
+  visit_selected([&](unsigned int k32, int, int, const float4& x4, const float4& y4) {
+    const float wf = ordered_to_float(k32);
+    const float xc[3] = {x4.x - cxf[0], x4.y - cxf[1], x4.z - cxf[2]};
+    const float yc[3] = {y4.x - cyf[0], y4.y - cyf[1], y4.z - cyf[2]};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      m2[a] = fmaf(wf, xc[a], m2[a]);
+      m2[3 + a] = fmaf(wf, yc[a], m2[3 + a]);
+      const float wy = wf * yc[a];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) m2[6 + a * 3 + c] = fmaf(wy, xc[c], m2[6 + a * 3 + c]);
+    }
+  });
+  double s2[15];
+  block_sum_f32<15>(m2, s2, ms);
+  double* part = p.partials + ((size_t)b * PM_MAX_G + blockIdx.x) * PM_PART;
+  if (tid == 0) {
+    part[0] = s1[0];
+    part[1] = s1[1];
+    for (int a = 0; a < 3; ++a) {
+      part[2 + a] = (double)cxf[a];
+      part[5 + a] = (double)cyf[a];
+    }
+    for (int k = 0; k < 15; ++k) part[8 + k] = s2[k];
+    __threadfence();
+    ticket_s = atomicAdd(&p.moments_arrive[b], 1u);
+  }
+  __syncthreads();
+  if (ticket_s != (unsigned int)(G - 1)) return;  // not the last CTA of this batch element
+  if (tid == 0) p.moments_arrive[b] = 0u;         // self-reset for the next call
+  __threadfence();
+  // ---- combine (fixed order over the CTAs: reproducible).  With centres c_g:
+  //   sum w x = sum_g (D_g + W_g cx_g),   S = inv * sum_g [ C_g + E_g (cx_g - mx)^T + (cy_g - my) D_g^T + W_g (cy_g - my)(cx_g - mx)^T ]
+  // all partials into shared memory with one round trip (a thread walking them in global memory pays an L2 latency
+  // per CTA: 64 x ~700 cycles)
+  __shared__ double part_s[PM_MAX_G * PM_PART];
+  {
+    const double* pg = p.partials + (size_t)b * PM_MAX_G * PM_PART;
+    for (int q = tid; q < G * PM_PART; q += PM_THREADS) part_s[q] = __ldcg(pg + q);
+  }
+  __syncthreads();
+  const double* pb = part_s;
+  if (tid < 7) {
+    double acc = 0.0;
+    for (int g = 0; g < G; ++g) {
+      const double* q = pb + (size_t)g * PM_PART;
+      if (tid == 0) acc += q[1];
+      else if (tid < 4) acc += q[8 + (tid - 1)] + q[0] * q[2 + (tid - 1)];
+      else acc += q[11 + (tid - 4)] + q[0] * q[5 + (tid - 4)];
+    }
+    comb_s[tid] = acc;
+  }
+  __syncthreads();
+  // w_norm = w / (sum|w| + eps): the normalised weights sum to slightly less than one  (procrustes.py:29-30)
+  const double inv = 1.0 / (comb_s[0] + 1e-4);
+  const float invf = (float)inv;
+  double mx[3], my[3];
+  for (int a = 0; a < 3; ++a) {
+    mx[a] = (double)(float)(comb_s[1 + a] * inv);  // the means are fp32 values, as in the reference
+    my[a] = (double)(float)(comb_s[4 + a] * inv);
+  }
+  if (tid < 9) {
+    const int a = tid / 3, c = tid - 3 * a;
+    double acc = 0.0;
+    for (int g = 0; g < G; ++g) {
+      const double* q = pb + (size_t)g * PM_PART;
+      const double W = q[0], dx = q[2 + c] - mx[c], dy = q[5 + a] - my[a];
+      acc += q[14 + a * 3 + c] + q[11 + a] * dx + dy * q[8 + c] + W * dy * dx;
+    }
+    cov_s[tid] = (Kb > 0) ? acc * (double)invf : 0.0;
+  }
+  if (tid == 0) {
+    for (int a = 0; a < 3; ++a) {
+      mean_s[a] = (Kb > 0) ? mx[a] : 0.0;
+      mean_s[3 + a] = (Kb > 0) ? my[a] : 0.0;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float R[9], t[3];
+    double cond;
+    double S[3][3];
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) S[a][c] = cov_s[a * 3 + c];
+    kabsch_solve(S, mean_s, mean_s + 3, R, t, &cond);
+    finish_pose(p, b, R, t, cond);
+    for (int k = 0; k < 9; ++k) pose_s[k] = p.R_forwd[b * 9 + k];
+    for (int k = 0; k < 3; ++k) pose_s[9 + k] = p.t_forwd[b * 3 + k];
+  }
+  if (p.sel_w) {
+    const unsigned int ne = min(__ldcg(&p.state[b].sel_count), (unsigned int)p.K_max);
+    for (int k = (int)ne + tid; k < p.K_max; k += PM_THREADS) {
+      p.sel_w[(size_t)b * p.K_max + k] = 0.f;
+      p.sel_src[(size_t)b * p.K_max + k] = 0;
+      p.sel_tgt[(size_t)b * p.K_max + k] = 0;
+    }
+  }
+  __syncthreads();
+  // ---- warp the source points with the gated pose:  (R_forwd s + t_forwd)     pipeline.py:220
+  if (p.src_warped) {
+    const float* sp = p.src_pcd + (size_t)b * p.N * 3;
+    float* o = p.src_warped + (size_t)b * p.N * 3;
+    for (int i0 = 0; i0 < p.N; i0 += PM_THREADS * 4) {
+      float xin[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * PM_THREADS + tid;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) xin[u][a] = i < p.N ? sp[i * 3 + a] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * PM_THREADS + tid;
+        if (i < p.N) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            // same association as a 3-term dot product followed by the translation add
+            float acc = pose_s[a * 3 + 0] * xin[u][0];
+            acc = fmaf(pose_s[a * 3 + 1], xin[u][1], acc);
+            acc = fmaf(pose_s[a * 3 + 2], xin[u][2], acc);
+            o[i * 3 + a] = acc + pose_s[9 + a];
+          }
+        }
+      }
+    }
+  }
 }
 
 // standalone weighted Kabsch on given correspondences: X, Y [B,K,3], w [B,K]
@@ -954,6 +1471,9 @@ struct ProcrWorkspace {
   unsigned int* cand_idx;
   unsigned int* sample_buf;
   unsigned int* sample_arrive;
+  unsigned int* moments_arrive;
+  unsigned int* cand_hist;
+  double* partials;
   float4* pcd4;
   size_t total;
 };
@@ -970,7 +1490,10 @@ static ProcrWorkspace procr_carve(void* ws, int B, int N, int M) {
   w.cand_key = (unsigned int*)take(4ull * B * N * M);
   w.cand_idx = (unsigned int*)take(4ull * B * N * M);
   w.sample_buf = (unsigned int*)take(4ull * B * TS_SAMPLES);
-  w.sample_arrive = (unsigned int*)take(4ull * B);
+  w.sample_arrive = (unsigned int*)take(4ull * 2 * B);  // sampling CTAs, then moments CTAs
+  w.moments_arrive = w.sample_arrive ? w.sample_arrive + B : nullptr;
+  w.cand_hist = (unsigned int*)take(4ull * B * TK_BINS);
+  w.partials = (double*)take(8ull * B * PM_MAX_G * PM_PART);
   w.pcd4 = (float4*)take(16ull * B * ((size_t)N + M));
   w.total = off;
   return w;
@@ -1036,6 +1559,9 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
   p.cand_idx = w.cand_idx;
   p.sample_buf = w.sample_buf;
   p.sample_arrive = w.sample_arrive;
+  p.moments_arrive = w.moments_arrive;
+  p.cand_hist = w.cand_hist;
+  p.partials = w.partials;
   p.pcd4 = w.pcd4;
   p.R = a->R;
   p.t = a->t;
@@ -1069,7 +1595,7 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
     attr_set = true;
   }
   // the arrival counters must be zero on entry (the workspace is caller memory of unknown content)
-  DRG_CUDA(cudaMemsetAsync(w.sample_arrive, 0, 4ull * B, st));
+  DRG_CUDA(cudaMemsetAsync(w.sample_arrive, 0, 4ull * 2 * B, st));
   int ts_ctas = NUM_SMS / (2 * B);
   if (ts_ctas > 32) ts_ctas = 32;
   if (ts_ctas < 1) ts_ctas = 1;
@@ -1095,7 +1621,9 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
   }
   }
   DRG_LAUNCH_CHECK();
-  {
+  static int single_cta = -1;  // DRG_PROCR_SINGLE=1: the single-CTA solve kernel (A/B comparisons)
+  if (single_cta < 0) single_cta = getenv("DRG_PROCR_SINGLE") ? 1 : 0;
+  if (single_cta) {
     static bool solve_attr_set = false;
     if (!solve_attr_set) {
       DRG_CUDA(cudaFuncSetAttribute(procr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_SMEM_CAND * 8));
@@ -1103,6 +1631,17 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
     }
     ProfScope prof_scope(PROF_PROCR_SOLVE, st);
     procr_solve_kernel<<<B, SOLVE_THREADS, SOLVE_SMEM_CAND * 8, st>>>(p);
+  } else {
+    int G = NUM_SMS / B;
+    if (G > PM_MAX_G) G = PM_MAX_G;
+    if (G < 4) G = 4;
+    {
+      ProfScope prof_scope(PROF_PROCR_SELECT, st);
+      procr_select_kernel<<<B, SEL_THREADS, 0, st>>>(p);
+    }
+    DRG_LAUNCH_CHECK();
+    ProfScope prof_scope(PROF_PROCR_SOLVE, st);
+    procr_moments_kernel<<<dim3(G, B), PM_THREADS, 0, st>>>(p);
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
