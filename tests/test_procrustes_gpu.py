@@ -72,6 +72,41 @@ def test_soft_procrustes_vs_oracle(B, N, M, rate, prefix):
     assert (out["t"].cpu() - ref[1]).abs().max() <= TOL_TRANS
 
 
+@pytest.mark.parametrize("kind", ["tied", "sparse"])
+def test_soft_procrustes_ties_take_the_general_select(kind):
+    """Heavily tied confidences put every candidate into one histogram bin: the select kernel must leave its short-list
+    path for the general radix select and still return exactly K entries whose values are the K largest (ties are
+    ordered by lowest flat index on the GPU; the reference's sort order among equal values is unspecified, so the pose is
+    only checked for being a finite rotation)."""
+    B, N, M = 1, 700, 600
+    gen = torch.Generator().manual_seed(77)
+    pb = O.make_problem(99, B, N, M, C=8)
+    if kind == "tied":
+        conf = torch.floor(torch.rand(B, N, M, generator=gen) * 8.0) / 8.0        # 8 distinct values, ~52 k entries each
+    else:
+        conf = torch.zeros(B, N, M)
+        idx = torch.randperm(N * M, generator=gen)[:300]                            # fewer positive entries than K
+        conf.view(-1)[idx] = 0.2 + 0.7 * torch.rand(300, generator=gen)
+    out = _ops().soft_procrustes(conf.cuda(), pb["s_pcd"].cuda(), pb["t_pcd"].cuda(), pb["src_mask"].cuda(), pb["tgt_mask"].cuda(),
+                                 1.0, 1e9, want_selection=True)
+    kb = max(N, M)
+    w = out["sel_w"][0].cpu()
+    src, tgt = out["sel_src"][0].cpu().long(), out["sel_tgt"][0].cpu().long()
+    top = conf[0].reshape(-1).sort(descending=True)[0][:kb]
+    assert torch.equal(w.sort(descending=True)[0][:kb], top)
+    flat = (src * M + tgt)[:kb]
+    assert flat.unique().numel() == kb                                              # K distinct entries
+    assert torch.equal(conf[0].reshape(-1)[flat], w[:kb])                           # the weights are the entries' values
+    if kind == "tied":
+        # among the entries tied with the K-th value the lowest flat indices win
+        kth = top[-1]
+        tied_sel = flat[w[:kb] == kth].sort()[0]
+        tied_all = (conf[0].reshape(-1) == kth).nonzero().flatten()
+        assert torch.equal(tied_sel, tied_all[: tied_sel.numel()])
+    R = out["R"].cpu()[0]
+    assert torch.isfinite(R).all() and (R @ R.t() - torch.eye(3)).abs().max() <= 1e-4
+
+
 def test_soft_procrustes_full_size_recovers_motion():
     """4096 x 4096 with a planted permutation: the recovered pose is the planted rigid motion."""
     N = M = 4096

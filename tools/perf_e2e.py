@@ -30,6 +30,17 @@ def run_nocopy(first, count):
     for i in range(first, first + count):
         pipe.graphs[i % 20].replay()
     torch.cuda.synchronize()
+# host time spent inside each call (perf_counter), per loop order
+import collections
+_acc = collections.defaultdict(float)
+def _timed(name, fn):
+    def w(*a, **k):
+        t = time.perf_counter()
+        r = fn(*a, **k)
+        _acc[name] += time.perf_counter() - t
+        return r
+    return w
+pipe.launch = _timed("launch", pipe.launch); pipe.prefetch = _timed("prefetch", pipe.prefetch); pipe.finish = _timed("finish", pipe.finish)
 K = 200
 pos = 0
 for name, fn in (("plain", run_plain), ("ahead", run_ahead), ("plain", run_plain), ("ahead", run_ahead)):
@@ -37,7 +48,9 @@ for name, fn in (("plain", run_plain), ("ahead", run_ahead), ("plain", run_plain
     torch.cuda.synchronize(); t0 = time.perf_counter()
     fn(pos, K); pos += K
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print(name, round(K / dt, 1), "steps/s", round(1e6 * dt / K, 1), "us/step", flush=True)
+    print(name, round(K / dt, 1), "steps/s", round(1e6 * dt / K, 1), "us/step",
+          {k: round(1e6 * v / (K + 20), 1) for k, v in _acc.items()}, "host us/step", flush=True)
+    _acc.clear()
 with torch.cuda.stream(pipe.compute):
     run_nocopy(0, 20)
     torch.cuda.synchronize(); t0 = time.perf_counter()
