@@ -9,18 +9,22 @@
 //
 // The reference sorts all N*M confidences to use the best K = max(|src|,|tgt|)*rate of them and
 // ships a 3x3 matrix to the host for a LAPACK SVD.  Here:
-//   1. topk_threshold_kernel  one CTA per batch element: mask counts -> K_b; 32768 hashed samples of the
-//                             matrix into shared memory; EXACT radix select of the t-th largest sample
-//                             (64-bit key = ordered value << 32 | ~flat index, so ties are ordered too),
-//                             t ~ 2x the expected number of top-K_b entries in the sample -> lower bound L
-//   2. topk_collect_kernel    ONE pass over the matrix: entries with key >= L are appended to a candidate
-//                             list (warp-aggregated atomics); everything else is never touched again
-//   3. procr_solve_kernel     one CTA per batch element: exact radix select of the K_b largest
-//                             candidates, fp64 weighted moments, closed-form 3x3 SVD (one-sided Jacobi,
-//                             fp64), reflection fix, condition-number gate, and the src-point warp.
+//   1. topk_threshold_kernel  mask counts -> K_b; 32768 hashed samples of the matrix (32 CTAs fetch, the last one
+//                             carries on); the EXACT t-th largest sample (64-bit key = ordered value << 32 |
+//                             ~flat index, so ties are ordered too), t ~ 2x the expected number of top-K_b
+//                             entries in the sample -> lower bound L; range of the candidate histogram
+//   2. topk_collect_*_kernel  ONE pass over the matrix: entries with key >= L are appended to a candidate
+//                             list (CTA-local lists, one global atomic per flush) and counted in a 2048-bin
+//                             histogram of their values; everything else is never touched again
+//   3. procr_select_kernel    one CTA per batch element: histogram walk, short list of the crossing bin, the
+//                             exact K_b-th largest key T by rank counting (general radix select for ties)
+//   4. procr_moments_kernel   up to 64 CTAs per batch element: fp32 moments of the selected candidates about
+//                             per-CTA centres, exact fp64 combination in the last CTA, closed-form 3x3 SVD
+//                             (one-sided Jacobi, fp64), reflection fix, condition-number gate, src-point warp
+//      (procr_solve_kernel: the earlier single-CTA version of 3 + 4, DRG_PROCR_SINGLE=1)
 // Because L is an order statistic of the sample (not a histogram bin edge) the candidate list holds
 // ~2 K_b + 16 N M / 32768 entries whatever the value distribution (flat, tied or all-zero matrices
-// included).  If the sample still misleads (fewer than K_b candidates) the solve kernel falls back to
+// included).  If the sample still misleads (fewer than K_b candidates) the select kernel falls back to
 // collecting the whole matrix itself: slow, but exact.
 #include <stdlib.h>
 

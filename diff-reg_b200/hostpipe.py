@@ -2,7 +2,7 @@
 
 Per step the caller's (pinned) inputs are copied into one of two device input sets on a copy stream -- the
 copy of step i+1 overlaps the kernels of step i -- the step itself runs as ONE CUDA-graph replay of
-DenoisingSampler.step (11 kernels, no host round trip inside), and the step's results (gated pose, condition
+DenoisingSampler.step (12 kernels, no host round trip inside), and the step's results (gated pose, condition
 number, match count, matches) are copied back into pinned host buffers before `finish` returns.
 
     pipe = HostStepPipeline(sampler, n, m, c, device)
