@@ -21,6 +21,7 @@ class SinkhornArgs(ctypes.Structure):
         ("k_x0", c_float), ("k_xt", c_float), ("sigma", c_float), ("x_min", c_void_p),
         ("gen_noise", c_int), ("noise_seed", ctypes.c_ulonglong), ("noise_offset", ctypes.c_ulonglong),
         ("noise_offset_dev", c_void_p), ("rowbest", c_void_p), ("colbest", c_void_p),
+        ("has_best_floor", c_int), ("best_floor", c_float),
     ]
 
 

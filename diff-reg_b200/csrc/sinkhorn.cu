@@ -2353,6 +2353,8 @@ struct SkhFinalParams {
   const unsigned long long* noise_offset_dev;
   unsigned long long* rowbest;  // optional [B,N]: packed (ordered(conf) << 32 | ~column) of every row's best entry
   unsigned long long* colbest;  // optional [B,M]: packed (ordered(conf) << 32 | ~row) of every column's best entry
+  int tile_rows;                // rows per CTA of skh_final_tile_kernel (chosen by the host: one full wave of CTAs)
+  float best_floor;             // only confidences > best_floor enter rowbest / colbest (-1: all of them)
 };
 
 // Philox4x32-7 counter-based generator (Salmon et al., SC'11: 7 rounds is the fewest that passes BigCrush; 10 is the
@@ -2372,19 +2374,32 @@ __device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) {
   }
   return c;
 }
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float4 philox_normal4(unsigned long long quad, unsigned long long offset, unsigned long long seed) {
   const uint4 r = philox4x32_7(make_uint4((unsigned int)quad, (unsigned int)(quad >> 32), (unsigned int)offset,
                                            (unsigned int)(offset >> 32)),
                                 make_uint2((unsigned int)seed, (unsigned int)(seed >> 32)));
   const float k = 2.3283064365386963e-10f;  // 2^-32
-  const float u0 = fmaf((float)r.x, k, 0.5f * k), u1 = (float)r.y * k;
-  const float u2 = fmaf((float)r.z, k, 0.5f * k), u3 = (float)r.w * k;
+  const float u0 = fmaf((float)r.x, k, 0.5f * k);   // in [2^-33, 1]: never denormal
+  const float u2 = fmaf((float)r.z, k, 0.5f * k);
+  // The pass is issue-bound, so the flush-to-zero forms are used: the default lg2 / rsqrt carry a denormal guard
+  // (compare, two predicated multiplies / adds each) that these arguments can never need.
   // sqrt(x) = x * rsqrt(x): two instructions, ~1 ulp -- irrelevant for noise draws
-  const float xa = -2.f * __logf(u0), xb = -2.f * __logf(u2);
-  const float ra = xa * rsqrtf(fmaxf(xa, 1e-30f)), rb = xb * rsqrtf(fmaxf(xb, 1e-30f));
+  const float xa = -1.3862943611198906f * lg2_ftz(u0), xb = -1.3862943611198906f * lg2_ftz(u2);  // -2 ln u
+  const float ra = xa * rsqrt_ftz(fmaxf(xa, 1e-30f)), rb = xb * rsqrt_ftz(fmaxf(xb, 1e-30f));
   float sa, ca, sb, cb;
-  __sincosf(6.283185307179586f * u1, &sa, &ca);
-  __sincosf(6.283185307179586f * u3, &sb, &cb);
+  const float k2pi = 1.4629180792671596e-09f;  // 2 pi 2^-32: the angle in one multiply
+  __sincosf((float)r.y * k2pi, &sa, &ca);
+  __sincosf((float)r.w * k2pi, &sb, &cb);
   return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
 }
 
@@ -2511,7 +2526,26 @@ __global__ void __launch_bounds__(256) skh_final_kernel(const SkhFinalParams p) 
 //   re-read -- or even stored -- to find the mutual matches; Matching.get_match, matching.py:71-88).
 // ---------------------------------------------------------------------------------------
 constexpr int FT_THREADS = 256;
-constexpr int FT_ROWS = 16;  // 1024 CTAs at 4096^2: ~7 resident per SM to cover the load latency
+constexpr int FT_CTAS_PER_SM = 4;  // 256 threads x <= 64 registers
+// Rows per CTA: the grid is ONE full wave of resident CTAs (588 of 592 at 4096^2: 28 rows each) -- with 16 rows per
+// CTA the 1024 CTAs ran as 1.73 waves -- and every thread requests the next row's scores / x_t before it works on the
+// current one: the pass was bound by the latency of those loads (one 32-byte request per thread in flight, ncu:
+// long-scoreboard 49 %, issue slots 61 %), not by instruction issue.
+static int final_tile_rows(int B, int N, int M) {
+  static int forced = -1;  // tuning only: DRG_FT_ROWS
+  if (forced < 0) {
+    const char* e = getenv("DRG_FT_ROWS");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0) return forced;
+  const int ctas_x = (M + FT_THREADS * 4 - 1) / (FT_THREADS * 4);
+  int slots = (NUM_SMS * FT_CTAS_PER_SM) / (ctas_x * (B < 1 ? 1 : B));
+  if (slots < 1) slots = 1;
+  int rows = (N + slots - 1) / slots;
+  if (rows < 8) rows = 8;
+  if (rows > 64) rows = 64;
+  return rows;
+}
 
 template <bool MASKED, bool TRACK, bool WANT_MIN>
 __device__ __forceinline__ void final_tile_body(const SkhFinalParams& p) {
@@ -2520,7 +2554,7 @@ __device__ __forceinline__ void final_tile_body(const SkhFinalParams& p) {
   const int c = blockIdx.x * (FT_THREADS * 4) + 4 * (int)threadIdx.x;
   const bool active = c < M;
   const int lane = threadIdx.x & 31;
-  const int i0 = blockIdx.y * FT_ROWS, i1 = min(N, i0 + FT_ROWS);
+  const int i0 = blockIdx.y * p.tile_rows, i1 = min(N, i0 + p.tile_rows);
   const SkhConst bc = p.bc[b];
   const float shift = p.shift ? *p.shift : 0.f;
   const float xt_shift = p.xt_shift ? *p.xt_shift : 0.f;
@@ -2537,20 +2571,36 @@ __device__ __forceinline__ void final_tile_body(const SkhFinalParams& p) {
     }
   }
   const float vj[4] = {v4.x, v4.y, v4.z, v4.w};
-  float cbv[4] = {-1.f, -1.f, -1.f, -1.f};
+  // column bests start at the floor: only entries above it are ever recorded (floor -1: every entry, confidences are >= 0)
+  const float floor_v = p.best_floor;
+  float cbv[4] = {floor_v, floor_v, floor_v, floor_v};
   int cbi[4] = {0, 0, 0, 0};
   float local_min = INFINITY;
+  // software prefetch: the next row's operands are requested before the current row is processed
+  float4 z_nx = make_float4(0.f, 0.f, 0.f, 0.f), t_nx = make_float4(0.f, 0.f, 0.f, 0.f);
+  float u_nx = 0.f;
+  auto fetch_row = [&](int i) {
+    if (i < i1) {
+      u_nx = u_b[i];
+      if (active) {
+        const size_t base = ((size_t)b * N + i) * M + c;
+        z_nx = __ldcs(reinterpret_cast<const float4*>(p.scores + base));
+        if (ddim) t_nx = __ldcs(reinterpret_cast<const float4*>(p.x_t + base));
+      }
+    }
+  };
+  fetch_row(i0);
   for (int i = i0; i < i1; ++i) {
-    const float ui = u_b[i];
+    const float ui = u_nx;
+    const float4 z4 = z_nx, t4 = t_nx;
+    fetch_row(i + 1);
     const bool row_ok = !MASKED || p.src_mask[(size_t)b * N + i];
     float cf[4] = {-1.f, -1.f, -1.f, -1.f};
     if (active) {
       const size_t base = ((size_t)b * N + i) * M + c;
-      const float4 z4 = *reinterpret_cast<const float4*>(p.scores + base);
       const float z[4] = {z4.x, z4.y, z4.z, z4.w};
       float xt[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
       if (ddim) {
-        const float4 t4 = *reinterpret_cast<const float4*>(p.x_t + base);
         xt[0] = t4.x; xt[1] = t4.y; xt[2] = t4.z; xt[3] = t4.w;
         if (p.noise) {
           const float4 n4 = *reinterpret_cast<const float4*>(p.noise + base);
@@ -2578,7 +2628,10 @@ __device__ __forceinline__ void final_tile_body(const SkhFinalParams& p) {
       *reinterpret_cast<float4*>(p.out + base) = make_float4(o[0], o[1], o[2], o[3]);
       if (ddim && p.conf) *reinterpret_cast<float4*>(p.conf + base) = make_float4(cf[0], cf[1], cf[2], cf[3]);
     }
-    if (TRACK) {
+    // The arg-max bookkeeping below (~47 instructions per quad) only matters for entries above the floor; with the
+    // matcher's confidence threshold as the floor at most a handful of the 32 warps of a row hold one (a row of the
+    // transport plan sums to <= 1), so one 4-way max, one compare and one vote skip it for almost every warp-row.
+    if (TRACK && __any_sync(0xffffffffu, fmaxf(fmaxf(cf[0], cf[1]), fmaxf(cf[2], cf[3])) > floor_v)) {
       // column bests (rows ascend, strict > keeps the lowest row on ties)
 #pragma unroll
       for (int e = 0; e < 4; ++e)
@@ -2596,7 +2649,7 @@ __device__ __forceinline__ void final_tile_body(const SkhFinalParams& p) {
           rv = cf[e];
           re = e;
         }
-      const unsigned int rbits = (active && rv >= 0.f) ? __float_as_uint(rv) : 0u;  // NaN / inactive lanes never win
+      const unsigned int rbits = (active && rv >= 0.f && rv > floor_v) ? __float_as_uint(rv) : 0u;  // NaN / inactive lanes never win
       const unsigned int wbits = __reduce_max_sync(0xffffffffu, rbits);
       const unsigned int owners = __ballot_sync(0xffffffffu, active && rbits == wbits);
       if (owners && lane == __ffs(owners) - 1) {
@@ -2609,6 +2662,7 @@ __device__ __forceinline__ void final_tile_body(const SkhFinalParams& p) {
   if (TRACK && active && i1 > i0) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
+      if (!(cbv[e] > floor_v)) continue;  // nothing above the floor in this column band: the key stays 0
       const unsigned long long key =
           ((unsigned long long)float_to_ordered(cbv[e]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)cbi[e]);
       atomicMax(&p.colbest[(size_t)b * M + c + e], key);
@@ -2622,7 +2676,7 @@ __device__ __forceinline__ void final_tile_body(const SkhFinalParams& p) {
 
 // The mask predicates, the arg-max tracking and the running minimum are compiled out when not needed: the pass is
 // issue-bound (in-kernel Philox + Box-Muller), not bandwidth-bound, so every instruction per element counts.
-__global__ void __launch_bounds__(FT_THREADS) skh_final_tile_kernel(const SkhFinalParams p) {
+__global__ void __launch_bounds__(FT_THREADS, FT_CTAS_PER_SM) skh_final_tile_kernel(const SkhFinalParams p) {
   const bool masked = p.apply_mask && p.bc[blockIdx.z].pad != 1.f;  // pad == 1: the Sinkhorn saw no padded row / column
   const bool track = p.rowbest != nullptr;
   const bool want_min = p.x_min != nullptr;
@@ -3195,6 +3249,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     f.noise_offset_dev = a->noise_offset_dev;
     f.rowbest = (a->rowbest && a->colbest) ? a->rowbest : nullptr;
     f.colbest = f.rowbest ? a->colbest : nullptr;
+    f.best_floor = a->has_best_floor ? a->best_floor : -1.f;
     f.inv_temp = dual ? 1.f / temperature : 0.f;
     int gx = (NUM_SMS * 8) / B;
     if (gx < 1) gx = 1;
@@ -3219,7 +3274,17 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
             DRG_CUDA(cudaMemsetAsync(f.colbest, 0, sizeof(unsigned long long) * (size_t)B * M, st));
           }
           ProfScope prof_scope(PROF_SKH_FINAL, st);
-          skh_final_tile_kernel<<<dim3((M + FT_THREADS * 4 - 1) / (FT_THREADS * 4), (N + FT_ROWS - 1) / FT_ROWS, B), FT_THREADS, 0, st>>>(f);
+          f.tile_rows = final_tile_rows(B, N, M);
+          {
+            static int dbg = -1;  // tuning only: DRG_FT_DEBUG bit 0 = no arg-max tracking, bit 1 = no noise draws (wrong results, timing only)
+            if (dbg < 0) {
+              const char* e = getenv("DRG_FT_DEBUG");
+              dbg = e ? atoi(e) : 0;
+            }
+            if (dbg & 1) f.rowbest = nullptr;
+            if (dbg & 2) f.gen_noise = 0;
+          }
+          skh_final_tile_kernel<<<dim3((M + FT_THREADS * 4 - 1) / (FT_THREADS * 4), (N + f.tile_rows - 1) / f.tile_rows, B), FT_THREADS, 0, st>>>(f);
         }
       else
         {

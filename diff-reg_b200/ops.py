@@ -46,8 +46,10 @@ def _f32c(t):
 
 def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", apply_mask=False, shift=None,
              x_t=None, noise=None, k_x0=0.0, k_xt=0.0, sigma=0.0, want_conf=False, x_min=None, return_potentials=False,
-             xt_shift=None, noise_seed=None, noise_offset=0, noise_offset_dev=None, out=None, want_best=False):
+             xt_shift=None, noise_seed=None, noise_offset=0, noise_offset_dev=None, out=None, want_best=False, best_floor=None):
     """Log-domain Sinkhorn with dustbins (drg_sinkhorn).
+    want_best: also return the packed row / column bests for match_from_best; best_floor: only confidences above it are
+    tracked (pass the matcher's threshold: exact for match_from_best with a threshold >= best_floor, and much cheaper).
 
     out_mode: 'log_full' -> [B,N+1,M+1] log-assignment; 'conf' -> [B,N,M] exp()[:, :-1, :-1];
               'ddim' -> x_next [B,N,M] (and conf if want_conf); 'none' -> potentials only.
@@ -88,7 +90,8 @@ def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", appl
                      conf=_ptr(conf), k_x0=float(k_x0), k_xt=float(k_xt), sigma=float(sigma), x_min=_ptr(x_min),
                      gen_noise=int(noise_seed is not None and noise is None), noise_seed=int(noise_seed or 0),
                      noise_offset=int(noise_offset), noise_offset_dev=_ptr(noise_offset_dev), rowbest=_ptr(rowbest),
-                     colbest=_ptr(colbest))
+                     colbest=_ptr(colbest), has_best_floor=int(best_floor is not None),
+                     best_floor=float(best_floor) if best_floor is not None else 0.0)
     check(lib.drg_sinkhorn(a, ws.data_ptr(), ws.numel(), _stream()))
     res = [out]
     if conf is not None:

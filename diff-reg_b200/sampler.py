@@ -109,7 +109,8 @@ class DenoisingSampler:
                            sigma=sigma if use_noise else 0.0, want_conf=want_x0 or (self.extract_matches and not fused_match),
                            x_min=x_min, noise_seed=self.noise_seed if gen else None,
                            noise_offset=0 if noise_counter is not None else self.noise_calls,
-                           noise_offset_dev=noise_counter, out=x_out, want_best=fused_match)
+                           noise_offset_dev=noise_counter, out=x_out, want_best=fused_match,
+                           best_floor=(None if self.flavour == "2d3d" else m.confidence_threshold) if fused_match else None)
         res = list(res) if isinstance(res, tuple) else [res]
         x_next = res.pop(0)
         x0 = res.pop(0) if (want_x0 or (self.extract_matches and not fused_match)) else None

@@ -104,6 +104,12 @@ typedef struct drg_sinkhorn_args {
                               also leaves every row's / column's best confidence and its lowest index as packed keys
                               (order-preserving float bits << 32 | ~index) for drg_match_from_best               */
   unsigned long long* colbest;
+  int has_best_floor;      /* 1: only entries with confidence > best_floor are tracked in rowbest / colbest; rows / columns
+                              without such an entry keep key 0 ("no best").  Exact for drg_match_from_best with a threshold
+                              >= best_floor (Matching.get_match, matching.py:71-88: a match must exceed the threshold, and
+                              whatever beats it in its row / column does too) and lets the pass skip the arg-max
+                              bookkeeping for the ~97 % of warp-rows that hold no such entry.  0: track everything        */
+  float best_floor;
 } drg_sinkhorn_args;
 
 size_t drg_sinkhorn_workspace_bytes(int B, int N, int M);

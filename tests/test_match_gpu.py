@@ -99,6 +99,18 @@ def test_fused_bests_of_the_final_pass(B, N, M, kind):
         idx, vals = ops.match_from_best(rb, cb, M, thr)
         ref_idx, ref_vals, _ = ops._match(conf, 1, True, thr, True, False)
         assert torch.equal(idx, ref_idx) and torch.equal(vals, ref_vals)
+    # with the matcher's threshold as the tracking floor the pass skips the arg-max bookkeeping almost everywhere and the
+    # matches at that (or any higher) threshold are unchanged; rows / columns without an entry above the floor keep key 0
+    for floor in (0.05, 0.2):
+        _, rbf, cbf = ops.sinkhorn(*args, out_mode="conf", apply_mask=True, want_best=True, best_floor=floor)
+        for thr in (floor, 0.5):
+            idx_f, vals_f = ops.match_from_best(rbf, cbf, M, thr)
+            idx_a, vals_a = ops.match_from_best(rb, cb, M, thr)
+            assert torch.equal(idx_f, idx_a) and torch.equal(vals_f, vals_a)
+        row_has = (conf > floor).any(dim=2)
+        col_has = (conf > floor).any(dim=1)
+        assert torch.equal(rbf != 0, row_has) and torch.equal(cbf != 0, col_has)
+        assert torch.equal(rbf[row_has], rb[row_has]) and torch.equal(cbf[col_has], cb[col_has])
     # and against the oracle's get_match on the oracle's own confidence matrix (no exact ties in random data)
     filled = s.masked_fill(~O.pair_mask(sm, tm), float("-inf"))
     ref_conf = O.log_optimal_transport(filled, alpha, 3, sm, tm).exp()[:, :-1, :-1]
