@@ -2527,10 +2527,9 @@ __global__ void __launch_bounds__(256) skh_final_kernel(const SkhFinalParams p) 
 // ---------------------------------------------------------------------------------------
 constexpr int FT_THREADS = 256;
 constexpr int FT_CTAS_PER_SM = 4;  // 256 threads x <= 64 registers
-// Rows per CTA: the grid is ONE full wave of resident CTAs (588 of 592 at 4096^2: 28 rows each) -- with 16 rows per
-// CTA the 1024 CTAs ran as 1.73 waves -- and every thread requests the next row's scores / x_t before it works on the
-// current one: the pass was bound by the latency of those loads (one 32-byte request per thread in flight, ncu:
-// long-scoreboard 49 %, issue slots 61 %), not by instruction issue.
+// Rows per CTA.  Measured at 4096^2 (tools/perf_final.py, DRG_FT_ROWS): 8 and 16 rows 49 us, 24 rows 54 us, 28 rows (one
+// full wave of 588 resident CTAs) 52 us, 32+ rows 65 us -- many small CTAs balance better than one exact wave.  Every
+// thread requests the next row's scores / x_t before it works on the current one.
 static int final_tile_rows(int B, int N, int M) {
   static int forced = -1;  // tuning only: DRG_FT_ROWS
   if (forced < 0) {
@@ -2538,13 +2537,10 @@ static int final_tile_rows(int B, int N, int M) {
     forced = e ? atoi(e) : 0;
   }
   if (forced > 0) return forced;
-  const int ctas_x = (M + FT_THREADS * 4 - 1) / (FT_THREADS * 4);
-  int slots = (NUM_SMS * FT_CTAS_PER_SM) / (ctas_x * (B < 1 ? 1 : B));
-  if (slots < 1) slots = 1;
-  int rows = (N + slots - 1) / slots;
-  if (rows < 8) rows = 8;
-  if (rows > 64) rows = 64;
-  return rows;
+  (void)B;
+  (void)N;
+  (void)M;
+  return 16;
 }
 
 template <bool MASKED, bool TRACK, bool WANT_MIN>
