@@ -252,7 +252,7 @@ __device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, Se
 
 // ---- 1. K_b and the sample-based lower bound ---------------------------------------------------
 __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrParams p) {
-  extern __shared__ unsigned int sample_key[];  // [TS_SAMPLES]
+  extern __shared__ __align__(16) unsigned int sample_key[];  // [TS_SAMPLES]
   __shared__ SelectScratch sc;
   __shared__ unsigned long long cnt_s;
   const int b = blockIdx.y, tid = threadIdx.x;
@@ -299,12 +299,33 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
   __shared__ unsigned int smax_s;
   if (tid == 0) smax_s = 0u;
   // the staging loop also tracks this thread's largest sample value (fast path of the select below)
+  // (16-byte loads, eight in flight per thread: the 128 KB come in two round trips instead of eight)
   unsigned int tmax = 0u;
-#pragma unroll 8
-  for (unsigned int q = tid; q < n_s; q += TS_THREADS) {
-    const unsigned int v = __ldcg(sbuf + q);
-    sample_key[q] = v;
-    tmax = max(tmax, v);
+  {
+    const unsigned int n4 = n_s >> 2;
+    const uint4* s4 = reinterpret_cast<const uint4*>(sbuf);  // sbuf is 256-byte aligned (workspace carve)
+    uint4* d4 = reinterpret_cast<uint4*>(sample_key);
+    for (unsigned int q0 = 0; q0 < n4; q0 += TS_THREADS * 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const unsigned int q = q0 + k * TS_THREADS + tid;
+        v[k] = q < n4 ? __ldcg(s4 + q) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const unsigned int q = q0 + k * TS_THREADS + tid;
+        if (q < n4) {
+          d4[q] = v[k];
+          tmax = max(max(tmax, max(v[k].x, v[k].y)), max(v[k].z, v[k].w));
+        }
+      }
+    }
+    for (unsigned int q = (n4 << 2) + tid; q < n_s; q += TS_THREADS) {
+      const unsigned int v = __ldcg(sbuf + q);
+      sample_key[q] = v;
+      tmax = max(tmax, v);
+    }
   }
   __syncthreads();
   {
@@ -1149,20 +1170,37 @@ __global__ void __launch_bounds__(SEL_THREADS) procr_select_kernel(const ProcrPa
         slow = true;  // heavily tied values (or an inconsistent histogram): the general select
       } else {
         // one pass over the candidate keys: those of the crossing bin go to the short list
-        for (size_t e0 = 0; e0 < n; e0 += (size_t)SEL_THREADS * 8) {
-          unsigned int kk[8];
+        // (16-byte loads, up to eight in flight per thread: ~19 k keys arrive in one round trip; ckey is 256-byte aligned)
+        // (a batch element's list starts at b * N * M keys: 16-byte aligned unless N * M is odd-ish -- then no vector part)
+        const bool vec4 = (((uintptr_t)ckey) & 15u) == 0;
+        const size_t n4 = vec4 ? ((n + 3) >> 2) : 0;   // reading up to 3 keys past n stays inside the (padded) workspace
+        const uint4* k4 = reinterpret_cast<const uint4*>(ckey);
+        for (size_t q0 = 0; q0 < n4; q0 += (size_t)SEL_THREADS * 8) {
+          uint4 kk[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const size_t e = e0 + (size_t)u * SEL_THREADS + tid;
-            kk[u] = e < n ? ckey[e] : 0u;
+            const size_t q = q0 + (size_t)u * SEL_THREADS + tid;
+            kk[u] = q < n4 ? k4[q] : make_uint4(0u, 0u, 0u, 0u);
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const size_t e = e0 + (size_t)u * SEL_THREADS + tid;
-            if (e < n && (int)cand_bin(kk[u], st.hist_kmin, st.hist_sh) == bin) {
-              const unsigned int pos = atomicAdd(&list_n, 1u);
-              if (pos < (unsigned int)SEL_LIST) list_s[pos] = make_key64(kk[u], cidx[e]);
+            const size_t q = q0 + (size_t)u * SEL_THREADS + tid;
+            const unsigned int k1[4] = {kk[u].x, kk[u].y, kk[u].z, kk[u].w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const size_t e = (q << 2) + w;
+              if (q < n4 && e < n && (int)cand_bin(k1[w], st.hist_kmin, st.hist_sh) == bin) {
+                const unsigned int pos = atomicAdd(&list_n, 1u);
+                if (pos < (unsigned int)SEL_LIST) list_s[pos] = make_key64(k1[w], cidx[e]);
+              }
             }
+          }
+        }
+        for (size_t e = (n4 << 2) + tid; e < n; e += SEL_THREADS) {  // unaligned list: scalar loads
+          const unsigned int k32 = ckey[e];
+          if ((int)cand_bin(k32, st.hist_kmin, st.hist_sh) == bin) {
+            const unsigned int pos = atomicAdd(&list_n, 1u);
+            if (pos < (unsigned int)SEL_LIST) list_s[pos] = make_key64(k32, cidx[e]);
           }
         }
         __syncthreads();
