@@ -83,5 +83,7 @@ extern "C" int drg_profile_read(int slot, double* total_ms, long long* count) {
   return DRG_OK;
 }
 extern "C" int drg_profile_slots(void) { return drg::PROF_NSLOTS; }
+extern "C" size_t drg_sizeof_sinkhorn_args(void) { return sizeof(drg_sinkhorn_args); }
+extern "C" size_t drg_sizeof_procrustes_args(void) { return sizeof(drg_procrustes_args); }
 extern "C" const char* drg_last_error(void) { return drg::g_err; }
 extern "C" unsigned long long drg_launch_count(void) { return drg::g_launches.load(); }

@@ -44,11 +44,15 @@ unsigned long long drg_launch_count(void);
 /* Optional per-kernel timing used by bench.py's roofline leg: when enabled every launch of a slotted kernel is
  * bracketed by CUDA events on its stream.  Slots: 0 sinkhorn iteration, 1 column merge, 2 sinkhorn final/DDIM pass,
  * 3 sinkhorn prep, 4 similarity GEMM, 5 operand prep, 6 row/column best, 7 match rows, 8 top-K collect,
- * 9 Procrustes solve, 10 top-K threshold.  drg_profile_read synchronises on the recorded events. */
+ * 9 Procrustes moments / solve, 10 top-K threshold, 11 Procrustes select.  drg_profile_read synchronises on the recorded events. */
 void drg_profile_enable(int on);
 void drg_profile_reset(void);
 int drg_profile_read(int slot, double* total_ms, long long* count);
 int drg_profile_slots(void);
+/* sizeof(drg_sinkhorn_args) / sizeof(drg_procrustes_args) as this library was compiled: a binding checks its own mirror of
+ * the argument structs against these before the first call (a shorter mirror would make the library read past its end). */
+size_t drg_sizeof_sinkhorn_args(void);
+size_t drg_sizeof_procrustes_args(void);
 
 /* ------------------------------------------------------------------------------------
  * Log-domain Sinkhorn with dustbin row/column

@@ -42,6 +42,23 @@ def test_workspace_queries_need_no_gpu():
     assert lib.drg_soft_procrustes_workspace_bytes(1, 64, 64) >= 2 * 4 * 64 * 64
 
 
+def test_ctypes_mirrors_match_the_compiled_structs():
+    """The ctypes mirrors of the argument structs (diffreg_b200/_lib.py, and the stub shown in INTEGRATION.md) have the size
+    the library was compiled with: a shorter mirror would make the library read past its end."""
+    import diffreg_b200
+    from diffreg_b200 import _lib
+    lib = diffreg_b200.load_library()
+    lib.drg_sizeof_sinkhorn_args.restype = ctypes.c_size_t
+    lib.drg_sizeof_procrustes_args.restype = ctypes.c_size_t
+    assert ctypes.sizeof(_lib.SinkhornArgs) == lib.drg_sizeof_sinkhorn_args()
+    assert ctypes.sizeof(_lib.ProcrustesArgs) == lib.drg_sizeof_procrustes_args()
+    # the stub in INTEGRATION.md lists the same fields in the same order
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = text[text.index("class SinkhornArgs(ctypes.Structure)"):]
+    stub = stub[:stub.index("lib.drg_sinkhorn_workspace_bytes")]
+    assert re.findall(r'\("([a-z_0-9A-Z]+)", ctypes', stub) == [f[0] for f in _lib.SinkhornArgs._fields_]
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour on a box without a GPU")
 def test_no_cpu_fallback():
     import diffreg_b200
