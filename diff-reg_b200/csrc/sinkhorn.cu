@@ -3271,15 +3271,6 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
           }
           ProfScope prof_scope(PROF_SKH_FINAL, st);
           f.tile_rows = final_tile_rows(B, N, M);
-          {
-            static int dbg = -1;  // tuning only: DRG_FT_DEBUG bit 0 = no arg-max tracking, bit 1 = no noise draws (wrong results, timing only)
-            if (dbg < 0) {
-              const char* e = getenv("DRG_FT_DEBUG");
-              dbg = e ? atoi(e) : 0;
-            }
-            if (dbg & 1) f.rowbest = nullptr;
-            if (dbg & 2) f.gen_noise = 0;
-          }
           skh_final_tile_kernel<<<dim3((M + FT_THREADS * 4 - 1) / (FT_THREADS * 4), (N + f.tile_rows - 1) / f.tile_rows, B), FT_THREADS, 0, st>>>(f);
         }
       else
