@@ -1117,6 +1117,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrP
 //     selected candidates and reduces them to weighted moments about ITS OWN weighted mean (two passes, as the
 //     reference centres before it multiplies); the last CTA to arrive combines the partials exactly (parallel-axis
 //     terms in fp64), solves the 3x3 problem, applies the condition gate and warps the source points.
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __global__ void __launch_bounds__(SEL_THREADS) procr_select_kernel(const ProcrParams p) {
   __shared__ SelectScratch sc;
   __shared__ unsigned long long list_s[SEL_LIST];
@@ -1126,6 +1131,10 @@ __global__ void __launch_bounds__(SEL_THREADS) procr_select_kernel(const ProcrPa
   __shared__ unsigned long long T_s;
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
+#define SSTAMP(k) do { if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[(k)] = global_ns(); } while (0)
+  SSTAMP(30);
+  // the histogram is requested before anything else (it does not depend on the state record read next)
+  for (int q = tid; q < TK_BINS; q += SEL_THREADS) sc.hist[q] = __ldcg(p.cand_hist + (size_t)b * TK_BINS + q);
   const size_t total = (size_t)p.N * p.M;
   const ProcrState st = p.state[b];
   const int Kb = st.Kb;
@@ -1146,7 +1155,6 @@ __global__ void __launch_bounds__(SEL_THREADS) procr_select_kernel(const ProcrPa
   unsigned long long T = 0ull;  // Kb >= n: every candidate is used
   if (Kb > 0 && (size_t)Kb < n) {
     if (!slow) {
-      for (int q = tid; q < TK_BINS; q += SEL_THREADS) sc.hist[q] = __ldcg(p.cand_hist + (size_t)b * TK_BINS + q);
       if (tid == 0) {
         list_n = 0u;
         T_s = 0ull;
@@ -1163,6 +1171,7 @@ __global__ void __launch_bounds__(SEL_THREADS) procr_select_kernel(const ProcrPa
         }
       }
       __syncthreads();
+      SSTAMP(31);
       const int bin = bin_s;
       const unsigned int want = (unsigned int)Kb - cum_s;  // how many of the crossing bin's candidates are selected
       const unsigned int hsel = hsel_s;
@@ -1191,7 +1200,7 @@ __global__ void __launch_bounds__(SEL_THREADS) procr_select_kernel(const ProcrPa
               const size_t e = (q << 2) + w;
               if (q < n4 && e < n && (int)cand_bin(k1[w], st.hist_kmin, st.hist_sh) == bin) {
                 const unsigned int pos = atomicAdd(&list_n, 1u);
-                if (pos < (unsigned int)SEL_LIST) list_s[pos] = make_key64(k1[w], cidx[e]);
+                if (pos < (unsigned int)SEL_LIST) list_s[pos] = make_key64(k1[w], cidx[e]);  // (fetching all indices with the keys: slower)
               }
             }
           }
@@ -1204,6 +1213,7 @@ __global__ void __launch_bounds__(SEL_THREADS) procr_select_kernel(const ProcrPa
           }
         }
         __syncthreads();
+        SSTAMP(32);
         const unsigned int L = list_n;
         if (L != hsel) {
           slow = true;  // cannot happen unless the histogram and the list disagree; stay exact
@@ -1221,6 +1231,8 @@ __global__ void __launch_bounds__(SEL_THREADS) procr_select_kernel(const ProcrPa
     }
     if (slow) T = block_select_kth<SEL_THREADS>([&](size_t e) { return make_key64(ckey[e], cidx[e]); }, n, Kb, sc);
   }
+  SSTAMP(33);
+#undef SSTAMP
   if (tid == 0) {
     p.state[b].T = T;
     p.state[b].n_cand = (unsigned int)n;
@@ -1237,6 +1249,9 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
   const int b = blockIdx.y;
   const int G = gridDim.x;
   const int tid = threadIdx.x;
+#define MSTAMP0(k) do { if (p.dbg_times && b == 0 && blockIdx.x == 0 && tid == 0) p.dbg_times[(k)] = global_ns(); } while (0)
+#define MSTAMPL(k) do { if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[(k)] = global_ns(); } while (0)
+  MSTAMP0(40);
   const size_t total = (size_t)p.N * p.M;
   const ProcrState st = p.state[b];
   const int Kb = st.Kb;
@@ -1302,6 +1317,7 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
   });
   double s1[8];
   block_sum_f32<8>(m1, s1, ms);
+  MSTAMP0(41);
   float cxf[3] = {0.f, 0.f, 0.f}, cyf[3] = {0.f, 0.f, 0.f};
   if (s1[0] != 0.0 && s1[1] > 0.0) {
     const double iw = 1.0 / s1[0];
@@ -1331,6 +1347,7 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
   });
   double s2[15];
   block_sum_f32<15>(m2, s2, ms);
+  MSTAMP0(42);
   double* part = p.partials + ((size_t)b * PM_MAX_G + blockIdx.x) * PM_PART;
   if (tid == 0) {
     part[0] = s1[0];
@@ -1344,7 +1361,9 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
     ticket_s = atomicAdd(&p.moments_arrive[b], 1u);
   }
   __syncthreads();
+  MSTAMP0(43);
   if (ticket_s != (unsigned int)(G - 1)) return;  // not the last CTA of this batch element
+  MSTAMPL(44);
   if (tid == 0) p.moments_arrive[b] = 0u;         // self-reset for the next call
   __threadfence();
   // ---- combine (fixed order over the CTAs: reproducible).  With centres c_g:
@@ -1358,15 +1377,24 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
   }
   __syncthreads();
   const double* pb = part_s;
-  if (tid < 7) {
+  // one warp per output value: lane l takes CTAs l and l + 32, then a fixed shuffle tree adds the lanes (a single thread
+  // walking the 64 partials in fp64 cost ~3 us per phase: a dependent chain of ~100 cycles per CTA)
+  const int lane = tid & 31, warp = tid >> 5;
+  auto warp_sum_f64 = [&](double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+  };
+  for (int out = warp; out < 7; out += PM_THREADS / 32) {
     double acc = 0.0;
-    for (int g = 0; g < G; ++g) {
+    for (int g = lane; g < G; g += 32) {
       const double* q = pb + (size_t)g * PM_PART;
-      if (tid == 0) acc += q[1];
-      else if (tid < 4) acc += q[8 + (tid - 1)] + q[0] * q[2 + (tid - 1)];
-      else acc += q[11 + (tid - 4)] + q[0] * q[5 + (tid - 4)];
+      if (out == 0) acc += q[1];
+      else if (out < 4) acc += q[8 + (out - 1)] + q[0] * q[2 + (out - 1)];
+      else acc += q[11 + (out - 4)] + q[0] * q[5 + (out - 4)];
     }
-    comb_s[tid] = acc;
+    acc = warp_sum_f64(acc);
+    if (lane == 0) comb_s[out] = acc;
   }
   __syncthreads();
   // w_norm = w / (sum|w| + eps): the normalised weights sum to slightly less than one  (procrustes.py:29-30)
@@ -1377,15 +1405,16 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
     mx[a] = (double)(float)(comb_s[1 + a] * inv);  // the means are fp32 values, as in the reference
     my[a] = (double)(float)(comb_s[4 + a] * inv);
   }
-  if (tid < 9) {
-    const int a = tid / 3, c = tid - 3 * a;
+  for (int out = warp; out < 9; out += PM_THREADS / 32) {
+    const int a = out / 3, c = out - 3 * a;
     double acc = 0.0;
-    for (int g = 0; g < G; ++g) {
+    for (int g = lane; g < G; g += 32) {
       const double* q = pb + (size_t)g * PM_PART;
       const double W = q[0], dx = q[2 + c] - mx[c], dy = q[5 + a] - my[a];
       acc += q[14 + a * 3 + c] + q[11 + a] * dx + dy * q[8 + c] + W * dy * dx;
     }
-    cov_s[tid] = (Kb > 0) ? acc * (double)invf : 0.0;
+    acc = warp_sum_f64(acc);
+    if (lane == 0) cov_s[out] = (Kb > 0) ? acc * (double)invf : 0.0;
   }
   if (tid == 0) {
     for (int a = 0; a < 3; ++a) {
@@ -1394,6 +1423,7 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
     }
   }
   __syncthreads();
+  MSTAMPL(45);
   if (tid == 0) {
     float R[9], t[3];
     double cond;
@@ -1401,6 +1431,7 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
     for (int a = 0; a < 3; ++a)
       for (int c = 0; c < 3; ++c) S[a][c] = cov_s[a * 3 + c];
     kabsch_solve(S, mean_s, mean_s + 3, R, t, &cond);
+    MSTAMPL(46);
     finish_pose(p, b, R, t, cond);
     for (int k = 0; k < 9; ++k) pose_s[k] = p.R_forwd[b * 9 + k];
     for (int k = 0; k < 3; ++k) pose_s[9 + k] = p.t_forwd[b * 3 + k];
@@ -1418,16 +1449,16 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
   if (p.src_warped) {
     const float* sp = p.src_pcd + (size_t)b * p.N * 3;
     float* o = p.src_warped + (size_t)b * p.N * 3;
-    for (int i0 = 0; i0 < p.N; i0 += PM_THREADS * 4) {
-      float xin[4][3];
+    for (int i0 = 0; i0 < p.N; i0 += PM_THREADS * 8) {  // eight points per thread and batch: 24 loads in flight
+      float xin[8][3];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int i = i0 + u * PM_THREADS + tid;
 #pragma unroll
         for (int a = 0; a < 3; ++a) xin[u][a] = i < p.N ? sp[i * 3 + a] : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int i = i0 + u * PM_THREADS + tid;
         if (i < p.N) {
 #pragma unroll
@@ -1442,6 +1473,9 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
       }
     }
   }
+  MSTAMPL(47);
+#undef MSTAMP0
+#undef MSTAMPL
 }
 
 // standalone weighted Kabsch on given correspondences: X, Y [B,K,3], w [B,K]
