@@ -52,6 +52,9 @@ struct SkhParams {
   long long* dbg_times;  // tuning only: CTA 0 writes clock64() stamps here (NULL = off)
   int dbg;         // tuning experiments only (DRG_SKH_DBG): 1 skip row math, 2 skip column math, 4 skip prologue reductions
   int keep_slabs;  // >= 0: the first keep_slabs slabs of every CTA are loaded L2::evict_last, the rest evict_first
+  unsigned long long* zero_a;  // optional: arrays the persistent kernel clears on its way in (rowbest / colbest of the
+  unsigned long long* zero_b;  //   final pass of the same call: two memset nodes less per step)
+  size_t zero_a_n, zero_b_n;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -1577,6 +1580,12 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
   const int row0 = (int)(((long long)N * g) / G), row1 = (int)(((long long)N * (g + 1)) / G);
   const int nrows = row1 - row0;              // <= 1024 (host check)
   const int ns = (nrows + RR - 1) / RR;       // mini-slabs of this CTA; row group rg takes s = rg, rg + 2, ...
+  if (p.zero_a) {
+    const size_t nthr = (size_t)gridDim.x * gridDim.y * P2_THREADS;
+    const size_t me = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * P2_THREADS + tid;
+    for (size_t i = me; i < p.zero_a_n; i += nthr) p.zero_a[i] = 0ull;
+    for (size_t i = me; i < p.zero_b_n; i += nthr) p.zero_b[i] = 0ull;
+  }
 
   const int Mv = (M + 1 + 3) & ~3;
   float* v2_s = reinterpret_cast<float*>(smem_raw);             // [Mv]  column potentials, log2 domain, minus the shift
@@ -3179,7 +3188,15 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   }
   const int iters = (run == SKH_SHARD_LOCAL || run == SKH_SHARD_LOCAL_X) ? 1 : run == SKH_SHARD_FINAL ? 0 : dual ? 1 : a->iters;
   dim3 cgrid((M + 1 + 31) / 32, B);
+  bool bests_cleared = false;
   if (persist) {
+    if (persist2 && run == SKH_RUN_ALL && !dual && a->rowbest && a->colbest) {
+      p.zero_a = a->rowbest;
+      p.zero_a_n = (size_t)B * N;
+      p.zero_b = a->colbest;
+      p.zero_b_n = (size_t)B * M;
+      bests_cleared = true;
+    }
     DRG_CUDA(cudaMemsetAsync(w.gsync, 0, sizeof(unsigned int) * B * 3, st));
     cudaError_t e;
     {
@@ -3265,7 +3282,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
                   (!f.conf || aligned16(f.conf)) && (((uintptr_t)a->tgt_mask & 3u) == 0);
       if (fvec)
         {
-          if (f.rowbest) {
+          if (f.rowbest && !bests_cleared) {
             DRG_CUDA(cudaMemsetAsync(f.rowbest, 0, sizeof(unsigned long long) * (size_t)B * N, st));
             DRG_CUDA(cudaMemsetAsync(f.colbest, 0, sizeof(unsigned long long) * (size_t)B * M, st));
           }
