@@ -1688,7 +1688,16 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
     ProfScope prof_scope(PROF_TOPK_COLLECT, st);
     if (!p.conf && (M % 4) == 0 && ((((uintptr_t)p.scores) | ((uintptr_t)p.pv) | ((uintptr_t)p.tgt_mask)) & 15u) == 0 &&
       ((p.ldv & 3) == 0)) {
-    int gr = (NUM_SMS * 5) / B;  // one wave: 40 KB of shared memory per CTA -> 5 CTAs per SM
+    static int per_sm = -1;  // tuning only: DRG_COLLECT_PER_SM
+    if (per_sm < 0) {
+      const char* e = getenv("DRG_COLLECT_PER_SM");
+      per_sm = e ? atoi(e) : 2;
+      if (per_sm < 1 || per_sm > 16) per_sm = 2;
+    }
+    // CTAs per SM.  80 registers x 256 threads allow three resident CTAs per SM; measured at 4096^2 inside the step
+    // (tools/collect_sweep.sh): 1 -> 43.7 us, 2 -> 28.9 us, 3 -> 35.1 us, 4 -> 30.6 us, 5 -> 34.1 us (2960 / 2991 / 3005
+    // steps/s for 5 / 4 / 2): one resident wave of 296 CTAs with ~14 rows each beats more, shorter CTAs.
+    int gr = (NUM_SMS * per_sm) / B;
     if (gr < 1) gr = 1;
     if (gr > N) gr = N;
     topk_collect_rows_kernel<<<dim3(gr, B), 256, 0, st>>>(p);
