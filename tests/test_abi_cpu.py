@@ -42,6 +42,12 @@ def test_workspace_queries_need_no_gpu():
     assert lib.drg_soft_procrustes_workspace_bytes(1, 64, 64) >= 2 * 4 * 64 * 64
 
 
+def test_profile_slot_table_matches_the_library():
+    import diffreg_b200
+    from diffreg_b200 import _lib
+    assert diffreg_b200.load_library().drg_profile_slots() == len(_lib.PROFILE_SLOTS)
+
+
 def test_ctypes_mirrors_match_the_compiled_structs():
     """The ctypes mirrors of the argument structs (diffreg_b200/_lib.py, and the stub shown in INTEGRATION.md) have the size
     the library was compiled with: a shorter mirror would make the library read past its end."""
