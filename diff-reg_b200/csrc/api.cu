@@ -56,7 +56,17 @@ void prof_end(int slot, cudaStream_t st) {
 }
 }  // namespace drg
 
-extern "C" int drg_version(void) { return 100; }
+namespace drg {
+long long* g_tuning_stamps = nullptr;
+}
+/* Tuning hook (tools/pose_timeline.py, tools/skh_timeline.py): a caller-owned device buffer of >= 1024 int64 in which CTA 0 of
+ * the persistent Sinkhorn (clock64) and the pose kernel (globaltimer ns, slots 800+) leave stamps of their phases; NULL
+ * switches the stamps off.  The library itself never allocates. */
+extern "C" int drg_tuning_set_stamp_buffer(long long* device_buffer) {
+  drg::g_tuning_stamps = device_buffer;
+  return DRG_OK;
+}
+extern "C" int drg_version(void) { return 200; }
 extern "C" void drg_profile_enable(int on) { drg::g_prof_enabled.store(on ? 1 : 0); }
 extern "C" void drg_profile_reset(void) {
   std::lock_guard<std::mutex> lk(drg::g_prof_mu);

@@ -63,8 +63,41 @@ struct SkhViews {
   const SkhConst* bc;   // [B]
   int ldu, ldv;
 };
-// runs drg_sinkhorn (out_mode NONE allowed) and reports the views (sinkhorn.cu)
-int skh_run_with_views(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* stream, SkhViews* views);
+
+// ---- top-K candidate search shared by the Sinkhorn tail (sinkhorn.cu) and the SoftProcrustes kernels (procrustes.cu) ----
+constexpr int TK_BINS = 2048;
+struct ProcrState {  // per batch element
+  int Kb;                         // number of correspondences to use
+  unsigned int n_cand;            // candidates appended so far
+  unsigned long long lower_key;   // stand-alone path: candidates have 64-bit key >= lower_key
+  unsigned long long T;           // written by the pose kernel: the Kb best candidates are those with key >= T
+  unsigned int hist_kmin;         // candidate histogram (filled by the collect pass): bin = ((value key - kmin) << sh) >> 21,
+  int hist_sh;                    //   clamped to [0, TK_BINS) -- monotone in the key, ~2048 bins over [bound, 2 x sample range]
+  unsigned int sel_count;         // selected correspondences written to sel_* so far
+  unsigned int pad_;
+  int seg_G;                      // > 0: the list was written by seg_G producer CTAs, producer g owning the rows
+                                  //   [N g / seg_G, N (g + 1) / seg_G) and ONE contiguous segment of the list (cand_seg)
+  unsigned int seg_broken;        // != 0: some producer also appended outside its segment (its shared list was full)
+};
+// What the persistent Sinkhorn needs to run the candidate search of SoftProcrustes as its own last phase (the pose step
+// of get_warped_from_noising_matching, Diff-Reg-4dmatch/models/pipeline.py:207-223): the score slab is still L2-resident
+// and the potentials are final, so neither a sampling kernel nor a separate pass over the matrix is needed.
+struct SkhCollect {
+  ProcrState* state;              // [B]
+  unsigned int* cand_key;         // [B, N*M] order-preserving bits of the candidates' confidences
+  unsigned int* cand_idx;         // [B, N*M] their flat indices
+  unsigned int* cand_hist;        // [B, TK_BINS]
+  unsigned int* sample_hist;      // [B, TK_BINS] histogram of the sampled log2 confidences (SH_PER_OCTAVE bins per octave)
+  uint2* cand_seg;                // [B, NUM_SMS] (offset, count) of every producer CTA's segment of the candidate list
+  float sample_rate;              // SoftProcrustesLayer.sample_rate
+  int padded_lengths;             // 3DMatch variant: lengths are N, M whatever the masks say
+  int K_max;                      // K_b is clamped to this
+};
+// runs drg_sinkhorn (out_mode NONE allowed) and reports the views (sinkhorn.cu).  collect != NULL: if the persistent
+// kernel handles the shape it also leaves the top-K candidate list / histogram / state for procr_pose_kernel and sets
+// *collected; otherwise *collected = false and the caller runs the stand-alone threshold + collect kernels.
+int skh_run_with_views(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* stream, SkhViews* views,
+                       const SkhCollect* collect = nullptr, bool* collected = nullptr);
 
 // ---- peer-to-peer exchange over NVLink (row-sharded Sinkhorn, p2p.cu / sinkhorn.cu) ---------------------
 constexpr int P2P_MAX_RANKS = 8;
@@ -124,6 +157,8 @@ enum ProfSlot {
   PROF_NSLOTS
 };
 extern std::atomic<int> g_prof_enabled;
+// tuning only: caller-owned device buffer (>= 1024 int64) for in-kernel phase stamps, NULL = off (drg_tuning_set_stamp_buffer)
+extern long long* g_tuning_stamps;
 void prof_begin(int slot, cudaStream_t st);
 void prof_end(int slot, cudaStream_t st);
 struct ProfScope {
@@ -244,6 +279,78 @@ __device__ __forceinline__ unsigned int float_to_ordered(float f) {
 }
 __device__ __forceinline__ float ordered_to_float(unsigned int u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// bin of a candidate's value key in the candidate histogram (monotone in the key)
+__device__ __forceinline__ unsigned int cand_bin(unsigned int k32, unsigned int kmin, int sh) {
+  if (k32 < kmin) return 0u;
+  const unsigned long long d = ((unsigned long long)(k32 - kmin) << sh) >> 21;
+  return d > (unsigned long long)(TK_BINS - 1) ? (unsigned int)(TK_BINS - 1) : (unsigned int)d;
+}
+// range of the candidate histogram: from the bound (key kmin) to twice the distance of the largest sample (key smax);
+// larger keys share the top bin
+__device__ __forceinline__ int cand_hist_shift(unsigned int kmin, unsigned int smax, bool have_bound) {
+  unsigned int range = 0xFFFFFFFFu - kmin;
+  if (have_bound && smax > kmin) {
+    const unsigned long long r2 = 2ull * (unsigned long long)(smax - kmin) + 1ull;
+    if (r2 < (unsigned long long)range) range = (unsigned int)r2;
+  }
+  return range ? __clz((int)range) : 32;
+}
+__device__ __forceinline__ unsigned int hash_u32(unsigned int x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+
+// One warp walks a TK_BINS-bin histogram (shared memory) from the top and finds the bin where the running count reaches
+// krem: `bin`, the count `cum` in the bins above it and its own count `hsel`, returned to all lanes.  Two steps, nothing
+// kept in registers and no serial scan.  Step 1: lane l sums the l-th chunk of 64 bins (descending); a warp scan finds
+// the chunk of the crossing.  Step 2: the 32 lanes split that chunk two bins each and scan again.  If krem exceeds the
+// total count the lowest bin is returned.
+__device__ __forceinline__ void warp_walk_hist(const unsigned int* hist, unsigned int krem, int& bin, unsigned int& cum,
+                                               unsigned int& hsel) {
+  const int lane = threadIdx.x & 31;
+  constexpr int chunk = TK_BINS / 32;                    // 64 bins per lane
+  const int lo = TK_BINS - chunk * (lane + 1);           // lowest bin of this lane's chunk
+  const uint4* h4 = reinterpret_cast<const uint4*>(&hist[lo]);
+  unsigned int local = 0u;
+#pragma unroll
+  for (int q = 0; q < chunk / 4; ++q) {
+    const uint4 v4 = h4[q];
+    local += v4.x + v4.y + v4.z + v4.w;
+  }
+  unsigned int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int tmp = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += tmp;
+  }
+  const unsigned int crossing = __ballot_sync(0xffffffffu, incl >= krem);
+  const int owner = crossing ? (__ffs(crossing) - 1) : 31;
+  const unsigned int before = __shfl_sync(0xffffffffu, incl - local, owner);  // keys in the chunks above the owner's
+  const int top = TK_BINS - chunk * owner - 1;           // highest bin of the owner's chunk
+  const unsigned int h0 = hist[top - 2 * lane], h1 = hist[top - 2 * lane - 1];
+  const unsigned int pair = h0 + h1;
+  unsigned int incl2 = pair;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int tmp = __shfl_up_sync(0xffffffffu, incl2, o);
+    if (lane >= o) incl2 += tmp;
+  }
+  const unsigned int crossing2 = __ballot_sync(0xffffffffu, before + incl2 >= krem);
+  const int lane2 = crossing2 ? (__ffs(crossing2) - 1) : 31;  // no crossing (krem beyond the count): the lowest bins
+  const unsigned int c0 = before + incl2 - pair;
+  const bool first = crossing2 != 0u && c0 + h0 >= krem;
+  const int my_bin = first ? (top - 2 * lane) : (top - 2 * lane - 1);
+  const unsigned int my_cum = first ? c0 : (c0 + h0);
+  const unsigned int my_h = first ? h0 : h1;
+  bin = __shfl_sync(0xffffffffu, my_bin, lane2);
+  cum = __shfl_sync(0xffffffffu, my_cum, lane2);
+  hsel = __shfl_sync(0xffffffffu, my_h, lane2);
 }
 #endif  // __CUDACC__
 

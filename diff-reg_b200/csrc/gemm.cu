@@ -20,7 +20,6 @@
 // concatenated along K -- so that the same kernel returns an fp32-accurate product (the
 // dropped term is A_lo.B_lo ~ 2^-22 relative).
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -503,18 +502,6 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
     // small tiles in flight rather than few wide ones (measured: BN=256 was 10 us slower on the 8192 x 256 projection)
     const bool split_tma_early = split_out != nullptr && C == nullptr && (split_rows0 % 32) == 0;
     if (split_out && !split_tma_early) BN = 64;
-    static int force_bn_split = -1;  // tuning only: DRG_GEMM_BN_SPLIT for the projection with the TMA split epilogue
-    if (force_bn_split < 0) {
-      const char* e = getenv("DRG_GEMM_BN_SPLIT");
-      force_bn_split = e ? atoi(e) : 0;
-    }
-    if (split_tma_early && (force_bn_split == 64 || force_bn_split == 128 || force_bn_split == 256)) BN = force_bn_split;
-    static int force_bn = -1;  // tuning only: DRG_GEMM_BN=64|128|256 overrides the model for the plain (non-split) GEMM
-    if (force_bn < 0) {
-      const char* e = getenv("DRG_GEMM_BN");
-      force_bn = e ? atoi(e) : 0;
-    }
-    if (!split_out && (force_bn == 64 || force_bn == 128 || force_bn == 256)) BN = force_bn;
   }
   GemmShape s{};
   s.N = N;

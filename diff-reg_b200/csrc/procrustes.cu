@@ -32,35 +32,10 @@
 
 namespace drg {
 
-constexpr int TK_BINS = 2048;
 constexpr int TS_THREADS = 512;
 constexpr int TS_SAMPLES = 32768;  // sample keys held in shared memory (128 KB)
 constexpr int TS_FAST_TARGET = 128;  // order statistics up to this rank use the thread-maxima short cut of the bound select
 constexpr int TS_FAST_LIST = 256;    // capacity of its short list (TS_THREADS threads rank it)
-constexpr int SOLVE_THREADS = 1024;
-constexpr int SOLVE_SMEM_CAND = 24576;  // candidates staged in shared memory by the solve kernel (192 KB)
-
-constexpr int PM_THREADS = 256;   // multi-CTA moments kernel
-constexpr int PM_MAX_G = 64;      // its CTAs per batch element (at most)
-constexpr int PM_PART = 24;       // doubles per CTA partial: W, W_abs, cx[3], cy[3], D[3], E[3], C[9]
-constexpr int SEL_THREADS = 1024; // select kernel
-constexpr int SEL_LIST = 256;     // short list of the select kernel (candidates of the crossing histogram bin)
-
-struct ProcrState {  // per batch element
-  int Kb;                         // number of correspondences to use
-  unsigned int n_cand;            // candidates appended so far
-  unsigned long long lower_key;   // candidates have 64-bit key >= lower_key
-  unsigned long long T;           // written by the select kernel: the Kb best candidates are those with key >= T
-  unsigned int hist_kmin;         // candidate histogram (filled by the collect kernels): bin = ((value key - kmin) << sh) >> 21,
-  int hist_sh;                    //   clamped to the top bin -- monotone in the key, ~2048 bins over [bound, 2 x sample range]
-  unsigned int sel_count;         // selected correspondences written to sel_* so far
-  unsigned int pad_;
-};
-
-__device__ __forceinline__ unsigned int cand_bin(unsigned int k32, unsigned int kmin, int sh) {
-  const unsigned long long d = ((unsigned long long)(k32 - kmin) << sh) >> 21;  // k32 >= kmin for every candidate
-  return d > (unsigned long long)(TK_BINS - 1) ? (unsigned int)(TK_BINS - 1) : (unsigned int)d;
-}
 
 struct ProcrParams {
   const float* conf;             // [B,N,M], or NULL: potentials mode, conf = exp((scores - shift | mask) + u + v - norm)
@@ -83,11 +58,14 @@ struct ProcrParams {
   unsigned int* cand_key;        // [B, N*M]
   unsigned int* cand_idx;        // [B, N*M]
   unsigned int* sample_buf;      // [B, TS_SAMPLES]
-  unsigned int* sample_arrive;   // [B] arrival counters of the sampling CTAs (zero between calls)
-  unsigned int* moments_arrive;  // [B] arrival counters of the moments CTAs (zero between calls)
+  unsigned int* sample_arrive;   // [B] arrival counters of the sampling CTAs (zero on entry)
+  const uint2* cand_seg;         // [B, NUM_SMS] producer segments of the candidate list (state.seg_G > 0)
+  unsigned int* pose_sync;       // [B][4] pose kernel: fallback barrier, T-ready flag, moments arrivals (zero on entry)
+  long long* stamps;             // tuning only (drg_tuning_set_stamp_buffer): globaltimer stamps of batch element 0, slots 800+
+  int surv_cap;                  // pose kernel: entries of the survivor list (positions of the candidates in the crossing bin or above)
+  int mine_cap;                  // pose kernel: entries of its dynamic shared-memory list (>= K_max + SEL_LIST, power of two)
   unsigned int* cand_hist;       // [B, TK_BINS] histogram of the candidates' value keys (zeroed by the threshold kernel)
-  double* partials;              // [B, PM_MAX_G, PM_PART] per-CTA moment partials
-  float4* pcd4;                  // [B][N + M] the points padded to 16 bytes (src, then tgt): one gather per point in the solve kernel
+  double* partials;              // [B, PP_MAX_G, PM_PART] per-CTA moment partials
   // outputs
   float* R;                      // [B,3,3]
   float* t;                      // [B,3]
@@ -101,17 +79,7 @@ struct ProcrParams {
   float* sel_w;                  // [B,K_max] or NULL
   int* sel_src;                  // [B,K_max] or NULL
   int* sel_tgt;                  // [B,K_max] or NULL
-  long long* dbg_times;          // tuning only (DRG_PROCR_TIMES=1): clock64 stamps of batch element 0
 };
-
-__device__ __forceinline__ unsigned int hash_u32(unsigned int x) {
-  x ^= x >> 16;
-  x *= 0x7feb352du;
-  x ^= x >> 15;
-  x *= 0x846ca68bu;
-  x ^= x >> 16;
-  return x;
-}
 
 // number of non-zero bytes among m[tid], m[tid + nthreads], ... (16 bytes per load when aligned; bools are 0 / 1)
 __device__ __forceinline__ unsigned int count_bytes16(const unsigned char* __restrict__ m, int n, int tid, int nthreads) {
@@ -158,54 +126,6 @@ struct __align__(16) SelectScratch {
   int krem;
   int done;
 };
-
-// One warp walks a TK_BINS-bin histogram (shared memory) from the top and finds the bin where the running count reaches
-// krem: `bin`, the count `cum` in the bins above it and its own count `hsel`, returned to all lanes.  Two steps, nothing
-// kept in registers and no serial scan (an earlier version held a lane's 64 bins in registers -- spilled at 64 registers
-// per thread -- and let the owning lane step through them one by one).  Step 1: lane l sums the l-th chunk of 64 bins
-// (descending); a warp scan finds the chunk of the crossing.  Step 2: the 32 lanes split that chunk two bins each and
-// scan again.  If krem exceeds the total count the lowest bin is returned.
-__device__ __forceinline__ void warp_walk_hist(const unsigned int* hist, unsigned int krem, int& bin, unsigned int& cum,
-                                               unsigned int& hsel) {
-  const int lane = threadIdx.x & 31;
-  constexpr int chunk = TK_BINS / 32;                    // 64 bins per lane
-  const int lo = TK_BINS - chunk * (lane + 1);           // lowest bin of this lane's chunk
-  const uint4* h4 = reinterpret_cast<const uint4*>(&hist[lo]);
-  unsigned int local = 0u;
-#pragma unroll
-  for (int q = 0; q < chunk / 4; ++q) {
-    const uint4 v4 = h4[q];
-    local += v4.x + v4.y + v4.z + v4.w;
-  }
-  unsigned int incl = local;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int tmp = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += tmp;
-  }
-  const unsigned int crossing = __ballot_sync(0xffffffffu, incl >= krem);
-  const int owner = crossing ? (__ffs(crossing) - 1) : 31;
-  const unsigned int before = __shfl_sync(0xffffffffu, incl - local, owner);  // keys in the chunks above the owner's
-  const int top = TK_BINS - chunk * owner - 1;           // highest bin of the owner's chunk
-  const unsigned int h0 = hist[top - 2 * lane], h1 = hist[top - 2 * lane - 1];
-  const unsigned int pair = h0 + h1;
-  unsigned int incl2 = pair;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int tmp = __shfl_up_sync(0xffffffffu, incl2, o);
-    if (lane >= o) incl2 += tmp;
-  }
-  const unsigned int crossing2 = __ballot_sync(0xffffffffu, before + incl2 >= krem);
-  const int lane2 = crossing2 ? (__ffs(crossing2) - 1) : 31;  // no crossing (krem beyond the count): the lowest bins
-  const unsigned int c0 = before + incl2 - pair;
-  const bool first = crossing2 != 0u && c0 + h0 >= krem;
-  const int my_bin = first ? (top - 2 * lane) : (top - 2 * lane - 1);
-  const unsigned int my_cum = first ? c0 : (c0 + h0);
-  const unsigned int my_h = first ? h0 : h1;
-  bin = __shfl_sync(0xffffffffu, my_bin, lane2);
-  cum = __shfl_sync(0xffffffffu, my_cum, lane2);
-  hsel = __shfl_sync(0xffffffffu, my_h, lane2);
-}
 
 template <int NT, class KeyAt>
 __device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, SelectScratch& sc) {
@@ -256,9 +176,6 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
   __shared__ SelectScratch sc;
   __shared__ unsigned long long cnt_s;
   const int b = blockIdx.y, tid = threadIdx.x;
-#define TSTAMP(k) do { if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[(k)] = clock64(); } while (0)
-  TSTAMP(20);
-  TSTAMP(21);
   // ---- sample the matrix: every CTA of the batch element fetches its share of the hashed positions (scattered
   //      4-byte reads: spread over TS_CTAS CTAs so that they are all in flight at once) into a global buffer; the
   //      last CTA to arrive pulls the whole sample into shared memory and carries on alone.
@@ -358,7 +275,6 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
   // sample_n_points = entry_max.float().mean().int()   procrustes.py:65
   const int K = (int)(cap_sum / (float)p.B);
   const int Kb = min(min(K, my_cap), p.K_max);
-  TSTAMP(22);
   // ---- the t-th largest sample key is the lower bound
   unsigned long long lower = 0ull;
   if (Kb > 0) {
@@ -427,8 +343,6 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
       }
     }
   }
-  TSTAMP(23);
-#undef TSTAMP
   if (tid == 0) {
     ProcrState s;
     s.Kb = Kb;
@@ -447,6 +361,8 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
     s.hist_sh = range ? __clz((int)range) : 32;
     s.sel_count = 0u;
     s.pad_ = 0u;
+    s.seg_G = 0;          // the stand-alone collect kernels stride over the rows: no per-producer segments
+    s.seg_broken = 0u;
     p.state[b] = s;
   }
 }
@@ -513,19 +429,8 @@ __device__ __forceinline__ void append_candidates_smem(unsigned int* s_key, unsi
   }
 }
 
-// [N,3] / [M,3] points -> 16-byte records (the solve kernel then needs one gather per point instead of three; its two
-// moment passes are bound by the L1 wavefronts of those scattered loads)
-__device__ __forceinline__ void pad_points(const ProcrParams& p, int b) {
-  const int L = p.N + p.M;
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < L; q += gridDim.x * blockDim.x) {
-    const float* src = (q < p.N) ? (p.src_pcd + ((size_t)b * p.N + q) * 3) : (p.tgt_pcd + ((size_t)b * p.M + (q - p.N)) * 3);
-    p.pcd4[(size_t)b * L + q] = make_float4(src[0], src[1], src[2], 0.f);
-  }
-}
-
 __global__ void __launch_bounds__(256) topk_collect_kernel(const ProcrParams p) {
   const int b = blockIdx.y;
-  pad_points(p, b);
   const size_t total = (size_t)p.N * p.M;
   const float* x = (p.conf ? p.conf : p.scores) + (size_t)b * total;
   const unsigned long long lower = p.state[b].lower_key;
@@ -581,7 +486,6 @@ __global__ void __launch_bounds__(256) topk_collect_kernel(const ProcrParams p) 
 // u_i once per row, v and the target mask as 16-byte loads
 __global__ void __launch_bounds__(256) topk_collect_rows_kernel(const ProcrParams p) {
   const int b = blockIdx.y;
-  pad_points(p, b);
   const int N = p.N, M = p.M;
   const size_t total = (size_t)N * M;
   const float* x = p.scores + (size_t)b * total;
@@ -864,440 +768,406 @@ __device__ void finish_pose(const ProcrParams& p, int b, const float R[9], const
   p.solution_mask[b] = ok ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(SOLVE_THREADS) procr_solve_kernel(const ProcrParams p) {
-  __shared__ SelectScratch sc;
-  __shared__ MomentScratch ms;
-  __shared__ unsigned int warp_cnt[SOLVE_THREADS / 32];
-  __shared__ double mean_s[6], cov_s[9];
-  __shared__ float pose_s[12];
-  __shared__ unsigned int range_s[2];
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    range_s[0] = 0xFFFFFFFFu;
-    range_s[1] = 0u;
-  }
-  __syncthreads();
-#define PSTAMP(k) do { if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[(k)] = clock64(); } while (0)
-  PSTAMP(0);
-  const size_t total = (size_t)p.N * p.M;
-  const ProcrState st = p.state[b];
-  const int Kb = st.Kb;
-  unsigned int* ckey = p.cand_key + (size_t)b * total;
-  unsigned int* cidx = p.cand_idx + (size_t)b * total;
-  size_t n = st.n_cand;
-  extern __shared__ unsigned int cand_s[];  // [2][SOLVE_SMEM_CAND]: keys, indices
-  if (n < (size_t)Kb) {
-    // fallback: the sample-based bound left too few candidates; take the whole matrix
-    for (size_t e = tid; e < total; e += SOLVE_THREADS) {
-      ckey[e] = float_to_ordered(conf_at(p, b, e));
-      cidx[e] = (unsigned int)e;
-    }
-    n = total;
-    __syncthreads();
-  }
+// ---- 3. select + moments + Kabsch + warp: ONE cooperative kernel ---------------------------------------------------
+// G CTAs per batch element.  Every CTA walks the candidate histogram and scans the candidate keys itself (the list is
+// ~16-25 k keys, L2-resident), so every CTA knows the exact K_b-th largest key T without a kernel boundary or a broadcast:
+//   * the candidates of the histogram bin where the count crosses K_b (10-70 of them) go to a short list that is ranked
+//     by counting -- 64-bit keys (value, ~index) are distinct, so T is exact and identical on every CTA;
+//   * heavily tied values (crossing bin > SEL_LIST entries) take the general six-level radix select on CTA 0, the other
+//     CTAs wait for its T (release / acquire flag; the launch is cooperative, so they are co-resident);
+//   * fewer candidates than K_b (the bound misled): all CTAs rebuild the candidate list from the whole matrix, one
+//     grid barrier, then the general select -- slow, exact, practically never taken.
+// In the same scan a CTA keeps the selected candidates of ITS rows (source index in [g N / G, (g + 1) N / G)), sorts
+// them by flat index (bitonic, shared memory) and reduces them in that order: thread t takes sorted entries t, t + 256, ...
+// and the partial sums meet in fixed shuffle / warp order, so the fp32 moments -- and the pose -- are bit-reproducible
+// from run to run although the candidate list is appended with atomics.  As in the reference (procrustes.py:30-35) the
+// points are centred before they are multiplied: each CTA centres on its own weighted mean, the last CTA to arrive
+// combines the partials exactly in fp64 (fixed order over the CTAs), solves the 3x3 problem and warps the source points.
+constexpr int PP_THREADS = 512;    // (one CTA per SM: the more warps, the better the L2 latency of the list scan is hidden)
+constexpr int PP_MAX_G = 64;       // CTAs per batch element (at most)
+constexpr int PM_SUMS = 17;        // W, W_abs, sum w x [3], sum w y [3], sum w y x^T [9]
+constexpr int PM_PART = 24;        // doubles per CTA partial (PM_SUMS, padded)
+constexpr int PP_RANK_SORT = 1024; // up to this many entries a CTA's list is sorted by rank counting, beyond by a bitonic sort
+constexpr int SEL_LIST = 256;      // short list of the crossing histogram bin
+constexpr unsigned long long PP_SENTINEL = 0xFFFFFFFFFFFFFFFFull;
 
-  // The candidate list normally fits in shared memory: stage it once (coalesced, 16 loads in flight per thread) so that
-  // the radix levels and the emission below do not pay a global-memory round trip per 1024 candidates.  The staging
-  // pass also finds the range [kmin, kmax] of the 32-bit value keys: the select then runs on keys normalised to that
-  // range (value - kmin, left-aligned), so its first level spreads the candidates over all 2048 bins instead of the
-  // handful of bins that share the confidences' exponent (19 k atomics into ~4 addresses), and two levels normally do.
-  constexpr int QMAX = SOLVE_SMEM_CAND / SOLVE_THREADS;
-  const bool in_smem = n <= (size_t)SOLVE_SMEM_CAND;
-  unsigned int kmin = 0u;
-  int nsh = 0;
-  if (in_smem) {
-    unsigned int lo = 0xFFFFFFFFu, hi = 0u;
-    for (int q0 = 0; q0 < QMAX; q0 += 8) {
-      if ((size_t)q0 * SOLVE_THREADS >= n) break;  // uniform
-      unsigned int kk[8], ii[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const size_t e = (size_t)tid + (size_t)(q0 + u) * SOLVE_THREADS;
-        const bool in = e < n;
-        kk[u] = in ? ckey[e] : 0u;
-        ii[u] = in ? cidx[e] : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const size_t e = (size_t)tid + (size_t)(q0 + u) * SOLVE_THREADS;
-        if (e < n) {
-          cand_s[e] = kk[u];
-          cand_s[SOLVE_SMEM_CAND + e] = ii[u];
-          lo = min(lo, kk[u]);
-          hi = max(hi, kk[u]);
-        }
-      }
-    }
-    lo = __reduce_min_sync(0xffffffffu, lo);
-    hi = __reduce_max_sync(0xffffffffu, hi);
-    if ((tid & 31) == 0) {
-      atomicMin(&range_s[0], lo);
-      atomicMax(&range_s[1], hi);
-    }
-    __syncthreads();
-    kmin = range_s[0];
-    const unsigned int kmax = range_s[1];
-    nsh = (kmax > kmin) ? __clz((int)(kmax - kmin)) : 32;
-  }
-  PSTAMP(1);
-  const unsigned int* kp = in_smem ? cand_s : ckey;
-  const unsigned int* ip = in_smem ? cand_s + SOLVE_SMEM_CAND : cidx;
-  // order-preserving on the candidates (all values >= kmin, value range below 2^(32 - nsh)); identity when not staged
-  auto nkey = [&](unsigned int k32, unsigned int fi) -> unsigned long long { return make_key64(k32 - kmin, fi) << nsh; };
-
-  // ---- exact radix select of the Kb largest 64-bit keys (value << 32 | ~index): no ties
-  unsigned long long T = 0ull;  // select keys >= T
-  if (Kb > 0 && (size_t)Kb < n)
-    T = block_select_kth<SOLVE_THREADS>([&](size_t e) { return nkey(kp[e], ip[e]); }, n, Kb, sc);
-
-  PSTAMP(2);
-  if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[10] = (long long)n;
-  // ---- two fp32 passes over the selected candidates: weighted means, then the centred covariance -- the reference's
-  //      own order of operations (procrustes.py:29-34).  A thread first marks which of its (at most QMAX) staged
-  //      candidates are selected, then visits them four at a time so that the eight point gathers of a batch are in
-  //      flight together (one L2 round trip per selected candidate was what bounded these passes).
-  //      (Measured: compacting the selection first and fp64 moments were both slower on B200.)
-  const float* sp = p.src_pcd + (size_t)b * p.N * 3;
-  const float4* sp4 = p.pcd4 + (size_t)b * (p.N + p.M);  // written by the collect kernel
-  const float4* tp4 = sp4 + p.N;
-  unsigned int selmask = 0u;
-  if (in_smem && Kb > 0) {
-#pragma unroll
-    for (int q = 0; q < QMAX; ++q) {
-      const size_t e = (size_t)tid + (size_t)q * SOLVE_THREADS;
-      if (e < n && nkey(kp[e], ip[e]) >= T) selmask |= 1u << q;
-    }
-  }
-  auto visit_selected = [&](auto&& f) {
-    if (in_smem) {
-      unsigned int m = selmask;
-      while (m) {
-        unsigned int kk[4];
-        int ii[4], jj[4];
-        float4 xx[4], yy[4];
-        bool on[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          on[u] = m != 0u;
-          if (on[u]) {
-            const int q = __ffs((int)m) - 1;
-            m &= m - 1u;
-            const size_t e = (size_t)tid + (size_t)q * SOLVE_THREADS;
-            kk[u] = kp[e];
-            const unsigned int fi = ip[e];
-            ii[u] = (int)(fi / (unsigned int)p.M);
-            jj[u] = (int)(fi - (unsigned int)ii[u] * (unsigned int)p.M);
-            xx[u] = sp4[ii[u]];
-            yy[u] = tp4[jj[u]];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (on[u]) f(kk[u], ii[u], jj[u], xx[u], yy[u]);
-      }
-    } else {
-      for (size_t e = tid; e < n; e += SOLVE_THREADS) {
-        const unsigned int k32 = kp[e], fi = ip[e];
-        if (nkey(k32, fi) >= T) {
-          const int i = (int)(fi / (unsigned int)p.M), j = (int)(fi - (unsigned int)i * (unsigned int)p.M);
-          f(k32, i, j, sp4[i], tp4[j]);
-        }
-      }
-    }
-  };
-  unsigned int ne = 0;
-  if (tid == 0) warp_cnt[0] = 0u;
-  __syncthreads();
-  if (Kb > 0) {
-    float m1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // sum w, sum |w|, sum w x (3), sum w y (3)
-    visit_selected([&](unsigned int k32, int i, int j, const float4& x4, const float4& y4) {
-      const float wf = ordered_to_float(k32);
-      if (p.sel_w) {
-        const unsigned int pos = atomicAdd(&warp_cnt[0], 1u);
-        if (pos < (unsigned int)p.K_max) {
-          p.sel_w[(size_t)b * p.K_max + pos] = wf;
-          p.sel_src[(size_t)b * p.K_max + pos] = i;
-          p.sel_tgt[(size_t)b * p.K_max + pos] = j;
-        }
-      }
-      const float xs[3] = {x4.x, x4.y, x4.z}, ys[3] = {y4.x, y4.y, y4.z};
-      m1[0] += wf;
-      m1[1] += fabsf(wf);
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        m1[2 + a] = fmaf(wf, xs[a], m1[2 + a]);
-        m1[5 + a] = fmaf(wf, ys[a], m1[5 + a]);
-      }
-    });
-    double s1[8];
-    block_sum_f32<8>(m1, s1, ms);
-    PSTAMP(7);
-    // w_norm = w / (sum|w| + eps): the normalised weights sum to slightly less than one  (procrustes.py:29-30)
-    const double inv = 1.0 / (s1[1] + 1e-4);
-    const float invf = (float)inv;
-    const float mxf[3] = {(float)(s1[2] * inv), (float)(s1[3] * inv), (float)(s1[4] * inv)};
-    const float myf[3] = {(float)(s1[5] * inv), (float)(s1[6] * inv), (float)(s1[7] * inv)};
-    float m2[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    visit_selected([&](unsigned int k32, int, int, const float4& x4, const float4& y4) {
-      const float wn = ordered_to_float(k32) * invf;
-      const float xc[3] = {x4.x - mxf[0], x4.y - mxf[1], x4.z - mxf[2]};
-      const float yc[3] = {y4.x - myf[0], y4.y - myf[1], y4.z - myf[2]};
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) m2[a * 3 + c] = fmaf(wn * yc[a], xc[c], m2[a * 3 + c]);
-    });
-    double s2[9];
-    block_sum_f32<9>(m2, s2, ms);
-    PSTAMP(3);
-    if (tid == 0) {
-      for (int a = 0; a < 3; ++a) {
-        mean_s[a] = (double)mxf[a];
-        mean_s[3 + a] = (double)myf[a];
-        for (int c = 0; c < 3; ++c) cov_s[a * 3 + c] = s2[a * 3 + c];
-      }
-    }
-    ne = warp_cnt[0];
-  } else if (tid == 0) {
-    for (int k = 0; k < 6; ++k) mean_s[k] = 0.0;
-    for (int k = 0; k < 9; ++k) cov_s[k] = 0.0;
-  }
-  if (p.sel_w) {
-    __syncthreads();
-    ne = warp_cnt[0];
-    for (int k = (int)ne + tid; k < p.K_max; k += SOLVE_THREADS) {
-      p.sel_w[(size_t)b * p.K_max + k] = 0.f;
-      p.sel_src[(size_t)b * p.K_max + k] = 0;
-      p.sel_tgt[(size_t)b * p.K_max + k] = 0;
-    }
-  }
-  __syncthreads();
-  PSTAMP(4);
-  if (tid == 0) {
-    float R[9], t[3];
-    double cond;
-    double S[3][3];
-    for (int a = 0; a < 3; ++a)
-      for (int c = 0; c < 3; ++c) S[a][c] = cov_s[a * 3 + c];
-    kabsch_solve(S, mean_s, mean_s + 3, R, t, &cond);
-    PSTAMP(5);
-    finish_pose(p, b, R, t, cond);
-    for (int k = 0; k < 9; ++k) pose_s[k] = p.R_forwd[b * 9 + k];
-    for (int k = 0; k < 3; ++k) pose_s[9 + k] = p.t_forwd[b * 3 + k];
-  }
-  __syncthreads();
-  // ---- warp the source points with the gated pose:  (R_forwd s + t_forwd)     pipeline.py:220
-  if (p.src_warped) {
-    float* o = p.src_warped + (size_t)b * p.N * 3;
-    for (int i = tid; i < p.N; i += SOLVE_THREADS) {
-      const float x0 = sp[i * 3 + 0], x1 = sp[i * 3 + 1], x2 = sp[i * 3 + 2];
-      for (int a = 0; a < 3; ++a) {
-        // same association as a 3-term dot product followed by the translation add
-        float acc = pose_s[a * 3 + 0] * x0;
-        acc = fmaf(pose_s[a * 3 + 1], x1, acc);
-        acc = fmaf(pose_s[a * 3 + 2], x2, acc);
-        o[i * 3 + a] = acc + pose_s[9 + a];
-      }
-    }
-  }
-  PSTAMP(6);
-#undef PSTAMP
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add_u32(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// ---- 5b. the pose step spread over several CTAs (the default) -----------------------------------------------
-// The single-CTA kernel above is bound by things one SM does badly: ~19 k shared-memory atomics for the first radix
-// level of the select (~10 k cycles) and ~8 k scattered 16-byte point gathers per moment pass, which one SM issues at
-// well under one request per clock (~20 k cycles per pass) -- 75-80 k cycles in all.  Here instead:
-//   * the collect kernels build the first-level histogram of the candidates as they append them (global atomics spread
-//     over the whole GPU);
-//   * procr_select_kernel (one CTA per batch element) walks that histogram, reads the candidate keys once, puts the
-//     few candidates of the crossing bin on a short list and finds the exact K_b-th largest key T by rank counting;
-//   * procr_moments_kernel (up to 64 CTAs per batch element) splits the candidates: every CTA gathers the points of its
-//     selected candidates and reduces them to weighted moments about ITS OWN weighted mean (two passes, as the
-//     reference centres before it multiplies); the last CTA to arrive combines the partials exactly (parallel-axis
-//     terms in fp64), solves the 3x3 problem, applies the condition gate and warps the source points.
 __device__ __forceinline__ long long global_ns() {
   long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__global__ void __launch_bounds__(SEL_THREADS) procr_select_kernel(const ProcrParams p) {
+#define PSTAMP0(k) do { if (p.stamps && b == 0 && g == 0 && tid == 0) p.stamps[(k)] = global_ns(); } while (0)
+#define PSTAMPL(k) do { if (p.stamps && b == 0 && tid == 0) { p.stamps[(k)] = global_ns(); p.stamps[(k) + 100] = clock64(); } } while (0)
+__global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParams p) {
+  extern __shared__ __align__(16) unsigned long long mine_s[];  // [mine_cap] (flat index << 32 | value key) of this CTA's rows
   __shared__ SelectScratch sc;
   __shared__ unsigned long long list_s[SEL_LIST];
-  __shared__ unsigned int list_n;
+  __shared__ unsigned int list_n, mine_n, surv_n, ticket_s;
   __shared__ int bin_s;
   __shared__ unsigned int cum_s, hsel_s;
   __shared__ unsigned long long T_s;
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x;
-#define SSTAMP(k) do { if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[(k)] = global_ns(); } while (0)
-  SSTAMP(30);
-  // the histogram is requested before anything else (it does not depend on the state record read next)
-  for (int q = tid; q < TK_BINS; q += SEL_THREADS) sc.hist[q] = __ldcg(p.cand_hist + (size_t)b * TK_BINS + q);
-  const size_t total = (size_t)p.N * p.M;
-  const ProcrState st = p.state[b];
-  const int Kb = st.Kb;
+  __shared__ double comb_s[PM_SUMS + 1];
+  __shared__ double mean_s[6], cov_s[9];
+  __shared__ float pose_s[12];
+  __shared__ double wsum_s[PP_THREADS / 32][PM_SUMS + 1];
+  const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x - 1;   // (the last CTA of a batch element only warms the code)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N, M = p.M;
+  const size_t total = (size_t)N * M;
   unsigned int* ckey = p.cand_key + (size_t)b * total;
   unsigned int* cidx = p.cand_idx + (size_t)b * total;
+  unsigned int* sync = p.pose_sync + 4 * b;  // [0] fallback barrier arrivals, [1] T-ready flag, [2] moments arrivals (zero on entry)
+  PSTAMP0(800);
+  // The 3x3 solve at the very end runs on ONE thread of the LAST CTA, through fp64 division / square-root subroutines
+  // that are cold in the instruction caches -- and, inside a sampler step that streams hundreds of MB through L2, cold in
+  // L2 too: every first touch of a code line then costs a DRAM round trip on the critical path (measured: 9.8 us cold
+  // against 5.0 us warm).  One extra CTA per batch element runs the same code on a harmless matrix right away, so that
+  // the lines are in L2 when the last CTA needs them ~20 us later.
+  if (g == G) {
+    if (tid == 0) {
+      const double eps = (double)N * 1e-12;
+      const double Sw[3][3] = {{0.9 + eps, 0.2, -0.1}, {0.1, 0.7 - eps, 0.3}, {-0.2, 0.1, 0.5 + eps}};
+      const double mw[3] = {0.1, -0.2 + eps, 0.3};
+      float Rw[9], tw[3];
+      double cw;
+      kabsch_solve(Sw, mw, mw, Rw, tw, &cw);
+      if (cw < 0.0) p.partials[0] = (double)(Rw[0] + tw[0]);   // never true (a condition number is >= 1): keeps the call alive
+    }
+    return;
+  }
+  // the histogram is requested before anything else (it does not depend on the state record read next)
+  for (int q = tid; q < TK_BINS; q += PP_THREADS) sc.hist[q] = __ldcg(p.cand_hist + (size_t)b * TK_BINS + q);
+  const ProcrState st = p.state[b];
+  const int Kb = st.Kb;
   size_t n = st.n_cand;
+  const int row_lo = (int)(((long long)N * g) / G), row_hi = (int)(((long long)N * (g + 1)) / G);
+  if (tid == 0) {
+    list_n = 0u;
+    mine_n = 0u;
+    surv_n = 0u;
+    T_s = 0ull;
+  }
   bool slow = false;
-  if (n < (size_t)Kb) {
-    // fallback: the sample-based bound left too few candidates; take the whole matrix
-    for (size_t e = tid; e < total; e += SEL_THREADS) {
+  if (Kb > 0 && n < (size_t)Kb) {
+    // fallback: the bound left too few candidates; every CTA rebuilds its stripe of the list from the whole matrix
+    for (size_t e = (size_t)g * PP_THREADS + tid; e < total; e += (size_t)G * PP_THREADS) {
       ckey[e] = float_to_ordered(conf_at(p, b, e));
       cidx[e] = (unsigned int)e;
     }
     n = total;
     slow = true;
     __syncthreads();
+    if (tid == 0) {
+      red_release_gpu_add_u32(sync + 0, 1u);
+      while (ld_acquire_gpu_u32(sync + 0) < (unsigned int)G) {
+      }
+    }
   }
-  unsigned long long T = 0ull;  // Kb >= n: every candidate is used
-  if (Kb > 0 && (size_t)Kb < n) {
-    if (!slow) {
+  __syncthreads();
+  const bool select_some = Kb > 0 && (size_t)Kb < n;   // otherwise every candidate is used (T = 0)
+  int bin = 0;
+  unsigned int want = 0u, hsel = 0u;
+  if (select_some && !slow) {
+    if (tid < 32) {
+      int bn;
+      unsigned int cum, hs;
+      warp_walk_hist(sc.hist, (unsigned int)Kb, bn, cum, hs);
       if (tid == 0) {
-        list_n = 0u;
-        T_s = 0ull;
+        bin_s = bn;
+        cum_s = cum;
+        hsel_s = hs;
+      }
+    }
+    __syncthreads();
+    bin = bin_s;
+    want = (unsigned int)Kb - cum_s;  // how many of the crossing bin's candidates are selected
+    hsel = hsel_s;
+    if (hsel > (unsigned int)SEL_LIST || want < 1u || want > hsel) slow = true;  // heavy ties: the general select
+  }
+  PSTAMP0(801);
+  // ---- slow cases first: T from the general select on CTA 0, published through the state record.  `slow` is a function
+  //      of the state and the histogram every CTA reads, so all CTAs of the batch element take this branch together.
+  unsigned long long T = 0ull;
+  if (select_some && slow) {
+    if (g == 0) {
+      T = block_select_kth<PP_THREADS>([&](size_t e) { return make_key64(ckey[e], cidx[e]); }, n, Kb, sc);
+      if (tid == 0) {
+        p.state[b].T = T;
+        __threadfence();
+        red_release_gpu_add_u32(sync + 1, 1u);
+      }
+    } else {
+      if (tid == 0) {
+        while (ld_acquire_gpu_u32(sync + 1) == 0u) {
+        }
+        T_s = *((volatile unsigned long long*)&p.state[b].T);
       }
       __syncthreads();
-      if (tid < 32) {
-        int bin;
-        unsigned int cum, hsel;
-        warp_walk_hist(sc.hist, (unsigned int)Kb, bin, cum, hsel);
-        if (tid == 0) {
-          bin_s = bin;
-          cum_s = cum;
-          hsel_s = hsel;
+      T = T_s;
+    }
+  }
+  // ---- the candidate list (~16-25 k entries, L2-resident): crossing bin's short list + the selected candidates of my rows.
+  //      Pass 1 reads the KEYS only (16-byte loads, eight in flight per thread) and keeps the positions of those in the
+  //      crossing bin or above (one compare each: the bins are intervals of the key) in a shared-memory list, appended per
+  //      warp (ballot + one atomic); pass 2 fetches key and index of those ~K_b survivors, all loads of a thread in flight
+  //      together.  (Fetching an index inside pass 1 is a dependent load per candidate; fetching all of them doubles the bytes.)
+  const unsigned int row_fi_lo = (unsigned int)row_lo * (unsigned int)M;
+  const unsigned long long row_fi_hi = (unsigned long long)row_hi * (unsigned long long)M;
+  if (Kb > 0) {
+    const bool by_bin = select_some && !slow;   // bins above the crossing one are selected whole; T decides inside it
+    auto take = [&](unsigned int k32, unsigned int fi) {
+      if ((unsigned long long)fi >= (unsigned long long)row_fi_lo && (unsigned long long)fi < row_fi_hi) {
+        const unsigned int pos = atomicAdd(&mine_n, 1u);   // <= K_b + SEL_LIST <= mine_cap entries
+        if (pos < (unsigned int)p.mine_cap) mine_s[pos] = ((unsigned long long)fi << 32) | (unsigned long long)k32;
+      }
+    };
+    if (!(select_some && slow)) {
+      // key interval of the crossing bin: bin(k) = ((k - kmin) << sh) >> 21, clamped
+      unsigned long long key_lo = 0ull, key_hi = 1ull << 32;
+      if (by_bin) {
+        const int sh = st.hist_sh;
+        const unsigned long long one = (sh >= 64) ? 0ull : ((1ull << sh) - 1ull);
+        if (bin > 0) key_lo = (unsigned long long)st.hist_kmin + ((((unsigned long long)bin << 21) + one) >> sh);
+        if (bin < TK_BINS - 1) key_hi = (unsigned long long)st.hist_kmin + ((((unsigned long long)(bin + 1) << 21) + one) >> sh);
+      }
+      // The Sinkhorn tail leaves the list as one contiguous segment per producer CTA, each producer owning a row range:
+      // then my rows' candidates sit in the few segments that overlap my rows and pass 1 only has to find the crossing
+      // bin's handful of entries (whose indices the ranking needs).  Otherwise pass 1 keeps everything from the crossing
+      // bin upwards and pass 2 sorts out the rows.
+      const bool segmented = st.seg_G > 0 && st.seg_broken == 0u;
+      const unsigned long long keep_hi = segmented ? key_hi : (1ull << 32);
+      unsigned int* surv_s = reinterpret_cast<unsigned int*>(mine_s + p.mine_cap);  // [surv_cap] positions in the candidate list
+      if (segmented) {
+        const int Gp = st.seg_G;
+        int gp_lo = (int)(((long long)row_lo * Gp) / N) - 1, gp_hi = (int)(((long long)row_hi * Gp) / N) + 1;
+        gp_lo = max(gp_lo, 0);
+        gp_hi = min(gp_hi, Gp - 1);
+        for (int gp = gp_lo; gp <= gp_hi; ++gp) {
+          const int r0 = (int)(((long long)N * gp) / Gp), r1 = (int)(((long long)N * (gp + 1)) / Gp);
+          if (r1 <= row_lo || r0 >= row_hi) continue;   // (block-uniform)
+          const uint2 seg = __ldcg(p.cand_seg + (size_t)b * NUM_SMS + gp);
+          for (unsigned int q = tid; q < seg.y; q += PP_THREADS) {
+            const unsigned int k32 = __ldcg(ckey + seg.x + q);
+            const unsigned int fi = __ldcg(cidx + seg.x + q);
+            if ((unsigned long long)k32 >= key_lo) take(k32, fi);
+          }
         }
       }
-      __syncthreads();
-      SSTAMP(31);
-      const int bin = bin_s;
-      const unsigned int want = (unsigned int)Kb - cum_s;  // how many of the crossing bin's candidates are selected
-      const unsigned int hsel = hsel_s;
-      if (hsel > (unsigned int)SEL_LIST || want < 1u || want > hsel) {
-        slow = true;  // heavily tied values (or an inconsistent histogram): the general select
-      } else {
-        // one pass over the candidate keys: those of the crossing bin go to the short list
-        // (16-byte loads, up to eight in flight per thread: ~19 k keys arrive in one round trip; ckey is 256-byte aligned)
-        // (a batch element's list starts at b * N * M keys: 16-byte aligned unless N * M is odd-ish -- then no vector part)
+      if (by_bin || !segmented) {
+        auto keep = [&](const unsigned int (&k)[32], const unsigned int (&e)[32], int cntv) {
+          // warp-collective append of this thread's passing keys: one scan + one atomic per warp and round
+          unsigned int mask = 0u;
+#pragma unroll
+          for (int u = 0; u < 32; ++u)
+            if (u < cntv && e[u] != 0xFFFFFFFFu && (unsigned long long)k[u] >= key_lo && (unsigned long long)k[u] < keep_hi) mask |= 1u << u;
+          const int mine_c = __popc(mask);
+          int incl = mine_c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int tmp = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += tmp;
+          }
+          const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+          if (wtot == 0) return;
+          unsigned int base = 0u;
+          if (lane == 31) base = atomicAdd(&surv_n, (unsigned int)wtot);
+          base = __shfl_sync(0xffffffffu, base, 31);
+          unsigned int pos = base + (unsigned int)(incl - mine_c);
+#pragma unroll
+          for (int u = 0; u < 32; ++u)
+            if (mask & (1u << u)) {
+              if (pos < (unsigned int)p.surv_cap) surv_s[pos] = e[u];
+              ++pos;
+            }
+        };
         const bool vec4 = (((uintptr_t)ckey) & 15u) == 0;
-        const size_t n4 = vec4 ? ((n + 3) >> 2) : 0;   // reading up to 3 keys past n stays inside the (padded) workspace
+        const size_t n4 = vec4 ? (n >> 2) : 0;
         const uint4* k4 = reinterpret_cast<const uint4*>(ckey);
-        for (size_t q0 = 0; q0 < n4; q0 += (size_t)SEL_THREADS * 8) {
+        for (size_t q0 = 0; q0 < n4; q0 += (size_t)PP_THREADS * 8) {   // (block-uniform trip count: the appends are warp-collective)
           uint4 kk[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const size_t q = q0 + (size_t)u * SEL_THREADS + tid;
-            kk[u] = q < n4 ? k4[q] : make_uint4(0u, 0u, 0u, 0u);
+            const size_t q = q0 + (size_t)u * PP_THREADS + tid;
+            kk[u] = q < n4 ? __ldcg(k4 + q) : make_uint4(0u, 0u, 0u, 0u);
           }
+          unsigned int k[32], e[32];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const size_t q = q0 + (size_t)u * SEL_THREADS + tid;
-            const unsigned int k1[4] = {kk[u].x, kk[u].y, kk[u].z, kk[u].w};
+            const size_t q = q0 + (size_t)u * PP_THREADS + tid;
+            const bool v = q < n4;
+            // (an out-of-range slot gets key 0 with key_lo > 0, or passes harmlessly when everything is kept: guard by e)
+            k[4 * u + 0] = v ? kk[u].x : 0u; k[4 * u + 1] = v ? kk[u].y : 0u; k[4 * u + 2] = v ? kk[u].z : 0u; k[4 * u + 3] = v ? kk[u].w : 0u;
+            e[4 * u + 0] = v ? (unsigned int)(q << 2) + 0u : 0xFFFFFFFFu; e[4 * u + 1] = v ? (unsigned int)(q << 2) + 1u : 0xFFFFFFFFu;
+            e[4 * u + 2] = v ? (unsigned int)(q << 2) + 2u : 0xFFFFFFFFu; e[4 * u + 3] = v ? (unsigned int)(q << 2) + 3u : 0xFFFFFFFFu;
+          }
+          keep(k, e, 32);
+        }
+        for (size_t e0 = (n4 << 2); e0 < n; e0 += PP_THREADS) {
+          const size_t ee = e0 + tid;
+          unsigned int k[32], e[32];
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              const size_t e = (q << 2) + w;
-              if (q < n4 && e < n && (int)cand_bin(k1[w], st.hist_kmin, st.hist_sh) == bin) {
+          for (int u = 0; u < 32; ++u) {
+            k[u] = 0u;
+            e[u] = 0xFFFFFFFFu;
+          }
+          if (ee < n) {
+            k[0] = __ldcg(ckey + ee);
+            e[0] = (unsigned int)ee;
+          }
+          keep(k, e, 1);
+        }
+        __syncthreads();
+        const unsigned int ns = min(surv_n, (unsigned int)p.surv_cap);
+        for (unsigned int q0 = 0; q0 < ns; q0 += PP_THREADS * 4) {
+          unsigned int kk[4], fi[4];
+          bool on[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const unsigned int q = q0 + u * PP_THREADS + tid;
+            const unsigned int e = q < ns ? surv_s[q] : 0xFFFFFFFFu;
+            on[u] = e != 0xFFFFFFFFu;
+            kk[u] = on[u] ? __ldcg(ckey + e) : 0u;
+            fi[u] = on[u] ? __ldcg(cidx + e) : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (on[u]) {
+              if (by_bin && (unsigned long long)kk[u] < key_hi) {   // the crossing bin
                 const unsigned int pos = atomicAdd(&list_n, 1u);
-                if (pos < (unsigned int)SEL_LIST) list_s[pos] = make_key64(k1[w], cidx[e]);  // (fetching all indices with the keys: slower)
+                if (pos < (unsigned int)SEL_LIST) list_s[pos] = make_key64(kk[u], fi[u]);
               }
+              if (!segmented) take(kk[u], fi[u]);
             }
           }
         }
-        for (size_t e = (n4 << 2) + tid; e < n; e += SEL_THREADS) {  // unaligned list: scalar loads
-          const unsigned int k32 = ckey[e];
-          if ((int)cand_bin(k32, st.hist_kmin, st.hist_sh) == bin) {
-            const unsigned int pos = atomicAdd(&list_n, 1u);
-            if (pos < (unsigned int)SEL_LIST) list_s[pos] = make_key64(k32, cidx[e]);
+      }
+    } else {
+      // general-select case: T is known; a candidate's index is needed to compare its 64-bit key (rare and slow anyway)
+      for (size_t e = tid; e < n; e += PP_THREADS) {
+        const unsigned int k32 = __ldcg(ckey + e);
+        if (k32 < (unsigned int)(T >> 32)) continue;
+        const unsigned int fi = __ldcg(cidx + e);
+        if (make_key64(k32, fi) >= T) take(k32, fi);
+      }
+    }
+  }
+  __syncthreads();
+  PSTAMP0(802);
+  // ---- T of the normal case: rank the crossing bin's short list (64-bit keys are distinct: distinct indices)
+  if (select_some && !slow) {
+    const unsigned int L = min(list_n, (unsigned int)SEL_LIST);
+    if ((unsigned int)tid < L) {
+      const unsigned long long my = list_s[tid];
+      unsigned int rank = 0u;
+      for (unsigned int q = 0; q < L; ++q) rank += (list_s[q] > my) ? 1u : 0u;
+      if (rank == want - 1u) T_s = my;
+    }
+    __syncthreads();
+    T = T_s;
+  }
+  if (g == 0 && tid == 0) {
+    p.state[b].T = T;
+    p.state[b].n_cand = (unsigned int)n;
+    p.state[b].pad_ = (slow ? 0x80000000u : 0u) | (hsel & 0x7FFFFFFFu);  // diagnostics
+  }
+  PSTAMP0(803);
+  // ---- my rows' selected candidates in ascending flat-index order (the appends above came in atomic order)
+  const unsigned int cnt_raw = min(mine_n, (unsigned int)p.mine_cap);  // (mine_cap >= K_b + SEL_LIST: no overflow)
+  __syncthreads();
+  if (tid == 0) mine_n = 0u;
+  unsigned long long* sorted_s = mine_s;
+  if (cnt_raw <= (unsigned int)PP_RANK_SORT) {
+    // few entries (the normal case: ~K_b / G): rank every selected entry by counting, scatter into the upper half
+    unsigned long long mv[PP_RANK_SORT / PP_THREADS];
+    unsigned int rk[PP_RANK_SORT / PP_THREADS];
+#pragma unroll
+    for (int u = 0; u < PP_RANK_SORT / PP_THREADS; ++u) {
+      const unsigned int q = tid + u * PP_THREADS;
+      mv[u] = q < cnt_raw ? mine_s[q] : PP_SENTINEL;
+      if (mv[u] != PP_SENTINEL && make_key64((unsigned int)mv[u], (unsigned int)(mv[u] >> 32)) < T) mv[u] = PP_SENTINEL;  // not among the K_b best
+      rk[u] = 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < PP_RANK_SORT / PP_THREADS; ++u) {
+      const unsigned int q = tid + u * PP_THREADS;
+      if (q < cnt_raw) mine_s[q] = mv[u];
+    }
+    __syncthreads();
+    for (unsigned int q = 0; q < cnt_raw; ++q) {
+      const unsigned long long o = mine_s[q];  // broadcast read; sentinels are larger than every real entry
+#pragma unroll
+      for (int u = 0; u < PP_RANK_SORT / PP_THREADS; ++u) rk[u] += (o < mv[u]) ? 1u : 0u;
+    }
+    sorted_s = mine_s + PP_RANK_SORT;   // mine_cap >= 2 * PP_RANK_SORT (host)
+    unsigned int real = 0u;
+#pragma unroll
+    for (int u = 0; u < PP_RANK_SORT / PP_THREADS; ++u) {
+      if (mv[u] != PP_SENTINEL) {
+        sorted_s[rk[u]] = mv[u];   // distinct flat indices: a permutation of 0 .. count-1
+        ++real;
+      }
+    }
+    real = __reduce_add_sync(0xffffffffu, real);
+    if (lane == 0 && real) atomicAdd(&mine_n, real);
+    __syncthreads();
+  } else {
+    // many entries in one CTA's rows (concentrated confidences): bitonic sort in place, sentinels sort to the end
+    unsigned int npow = 32u;
+    while (npow < cnt_raw) npow <<= 1;
+    for (unsigned int q = tid; q < npow; q += PP_THREADS) {
+      unsigned long long v = q < cnt_raw ? mine_s[q] : PP_SENTINEL;
+      if (q < cnt_raw && make_key64((unsigned int)v, (unsigned int)(v >> 32)) < T) v = PP_SENTINEL;
+      mine_s[q] = v;
+    }
+    __syncthreads();
+    for (unsigned int k = 2u; k <= npow; k <<= 1) {
+      for (unsigned int j = k >> 1; j > 0u; j >>= 1) {
+        for (unsigned int q = tid; q < npow; q += PP_THREADS) {
+          const unsigned int partner = q ^ j;
+          if (partner > q) {
+            const unsigned long long a = mine_s[q], c = mine_s[partner];
+            const bool up = (q & k) == 0u;
+            if ((a > c) == up) {
+              mine_s[q] = c;
+              mine_s[partner] = a;
+            }
           }
         }
         __syncthreads();
-        SSTAMP(32);
-        const unsigned int L = list_n;
-        if (L != hsel) {
-          slow = true;  // cannot happen unless the histogram and the list disagree; stay exact
-        } else {
-          if ((unsigned int)tid < L) {
-            const unsigned long long my = list_s[tid];
-            unsigned int rank = 0u;
-            for (unsigned int q = 0; q < L; ++q) rank += (list_s[q] > my) ? 1u : 0u;  // keys are distinct (distinct indices)
-            if (rank == want - 1u) T_s = my;
-          }
-          __syncthreads();
-          T = T_s;
-        }
       }
     }
-    if (slow) T = block_select_kth<SEL_THREADS>([&](size_t e) { return make_key64(ckey[e], cidx[e]); }, n, Kb, sc);
+    unsigned int c = 0u;
+    for (unsigned int q = tid; q < npow; q += PP_THREADS) c += (mine_s[q] != PP_SENTINEL) ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0 && c) atomicAdd(&mine_n, c);
+    __syncthreads();
   }
-  SSTAMP(33);
-#undef SSTAMP
-  if (tid == 0) {
-    p.state[b].T = T;
-    p.state[b].n_cand = (unsigned int)n;
-    p.state[b].pad_ = (slow ? 0x80000000u : 0u) | (unsigned int)(Kb > 0 && (size_t)Kb < n ? hsel_s & 0x7FFFFFFFu : 0u);  // diagnostics
-  }
-}
-
-__global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrParams p) {
-  __shared__ MomentScratch ms;
-  __shared__ unsigned int ticket_s;
-  __shared__ double comb_s[16];
-  __shared__ double mean_s[6], cov_s[9];
-  __shared__ float pose_s[12];
-  const int b = blockIdx.y;
-  const int G = gridDim.x;
-  const int tid = threadIdx.x;
-#define MSTAMP0(k) do { if (p.dbg_times && b == 0 && blockIdx.x == 0 && tid == 0) p.dbg_times[(k)] = global_ns(); } while (0)
-#define MSTAMPL(k) do { if (p.dbg_times && b == 0 && tid == 0) p.dbg_times[(k)] = global_ns(); } while (0)
-  MSTAMP0(40);
-  const size_t total = (size_t)p.N * p.M;
-  const ProcrState st = p.state[b];
-  const int Kb = st.Kb;
-  const unsigned long long T = st.T;
-  const size_t n = st.n_cand;
-  const unsigned int* ckey = p.cand_key + (size_t)b * total;
-  const unsigned int* cidx = p.cand_idx + (size_t)b * total;
-  const float4* sp4 = p.pcd4 + (size_t)b * (p.N + p.M);  // written by the collect kernel
-  const float4* tp4 = sp4 + p.N;
-  // this CTA's slice of the candidate list
-  const size_t per = (n + G - 1) / G;
-  const size_t e_lo = min(n, per * blockIdx.x), e_hi = min(n, e_lo + per);
-  // visit the selected candidates of the slice, two per thread at a time (four gathers in flight)
-  auto visit_selected = [&](auto&& f) {
-    if (Kb <= 0) return;
-    for (size_t e0 = e_lo; e0 < e_hi; e0 += (size_t)PM_THREADS * 2) {
-      unsigned int kk[2], fi[2];
-      int ii[2], jj[2];
-      float4 xx[2], yy[2];
-      bool on[2];
+  const unsigned int cnt = mine_n;
+  PSTAMP0(804);
+  const float* sp = p.src_pcd + (size_t)b * N * 3;
+  const float* tp = p.tgt_pcd + (size_t)b * M * 3;
+  // ---- weighted moments of my entries, ONE pass: sum w, sum |w|, sum w x, sum w y, sum w y x^T in fp64 (products of fp32
+  //      values are exact there, so no centring pass is needed: the covariance about the weighted means is formed from
+  //      these sums at the end).  ~K_b / G entries per CTA: the fp64 work is a few hundred DFMAs per SM.
+  //      Thread t takes sorted entries t, t + 256, ...; lanes, warps and CTAs are added in fixed order: bit-reproducible.
+  double acc[PM_SUMS];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const size_t e = e0 + (size_t)u * PM_THREADS + tid;
-        on[u] = e < e_hi;
-        kk[u] = on[u] ? ckey[e] : 0u;
-        fi[u] = on[u] ? cidx[e] : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        on[u] = on[u] && make_key64(kk[u], fi[u]) >= T;
-        if (on[u]) {
-          ii[u] = (int)(fi[u] / (unsigned int)p.M);
-          jj[u] = (int)(fi[u] - (unsigned int)ii[u] * (unsigned int)p.M);
-          xx[u] = sp4[ii[u]];
-          yy[u] = tp4[jj[u]];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (on[u]) f(kk[u], ii[u], jj[u], xx[u], yy[u]);
-    }
-  };
-  // pass A: sum w, sum |w|, sum w x, sum w y  ->  this CTA's centre (its weighted mean)
-  float m1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  visit_selected([&](unsigned int k32, int i, int j, const float4& x4, const float4& y4) {
-    const float wf = ordered_to_float(k32);
+  for (int k = 0; k < PM_SUMS; ++k) acc[k] = 0.0;
+  for (unsigned int q = tid; q < cnt; q += PP_THREADS) {
+    const unsigned long long v = sorted_s[q];
+    const unsigned int fi = (unsigned int)(v >> 32);
+    const float wf = ordered_to_float((unsigned int)v);
+    const int i = (int)(fi / (unsigned int)M), j = (int)(fi - (unsigned int)i * (unsigned int)M);
     if (p.sel_w) {
       const unsigned int pos = atomicAdd(&p.state[b].sel_count, 1u);
       if (pos < (unsigned int)p.K_max) {
@@ -1306,139 +1176,95 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
         p.sel_tgt[(size_t)b * p.K_max + pos] = j;
       }
     }
-    const float xs[3] = {x4.x, x4.y, x4.z}, ys[3] = {y4.x, y4.y, y4.z};
-    m1[0] += wf;
-    m1[1] += fabsf(wf);
+    const double w = (double)wf;
+    const double xs[3] = {(double)sp[i * 3 + 0], (double)sp[i * 3 + 1], (double)sp[i * 3 + 2]};
+    const double ys[3] = {(double)tp[j * 3 + 0], (double)tp[j * 3 + 1], (double)tp[j * 3 + 2]};
+    acc[0] += w;
+    acc[1] += fabs(w);
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      m1[2 + a] = fmaf(wf, xs[a], m1[2 + a]);
-      m1[5 + a] = fmaf(wf, ys[a], m1[5 + a]);
-    }
-  });
-  double s1[8];
-  block_sum_f32<8>(m1, s1, ms);
-  MSTAMP0(41);
-  float cxf[3] = {0.f, 0.f, 0.f}, cyf[3] = {0.f, 0.f, 0.f};
-  if (s1[0] != 0.0 && s1[1] > 0.0) {
-    const double iw = 1.0 / s1[0];
-    for (int a = 0; a < 3; ++a) {
-      cxf[a] = (float)(s1[2 + a] * iw);
-      cyf[a] = (float)(s1[5 + a] * iw);
-      if (!(fabsf(cxf[a]) < INFINITY)) cxf[a] = 0.f;  // any finite centre is valid
-      if (!(fabsf(cyf[a]) < INFINITY)) cyf[a] = 0.f;
+      acc[2 + a] = fma(w, xs[a], acc[2 + a]);
+      const double wy = w * ys[a];
+      acc[5 + a] += wy;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[8 + a * 3 + c] = fma(wy, xs[c], acc[8 + a * 3 + c]);
     }
   }
-  // pass B: moments about the centre: D = sum w (x - cx), E = sum w (y - cy), C = sum w (y - cy)(x - cx)^T
-  float m2[15];
+  PSTAMP0(805);
+  // lanes (fixed shuffle tree), then warps (fixed order)
 #pragma unroll
-  for (int k = 0; k < 15; ++k) m2[k] = 0.f;
-  visit_selected([&](unsigned int k32, int, int, const float4& x4, const float4& y4) {
-    const float wf = ordered_to_float(k32);
-    const float xc[3] = {x4.x - cxf[0], x4.y - cxf[1], x4.z - cxf[2]};
-    const float yc[3] = {y4.x - cyf[0], y4.y - cyf[1], y4.z - cyf[2]};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      m2[a] = fmaf(wf, xc[a], m2[a]);
-      m2[3 + a] = fmaf(wf, yc[a], m2[3 + a]);
-      const float wy = wf * yc[a];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) m2[6 + a * 3 + c] = fmaf(wy, xc[c], m2[6 + a * 3 + c]);
-    }
-  });
-  double s2[15];
-  block_sum_f32<15>(m2, s2, ms);
-  MSTAMP0(42);
-  double* part = p.partials + ((size_t)b * PM_MAX_G + blockIdx.x) * PM_PART;
-  if (tid == 0) {
-    part[0] = s1[0];
-    part[1] = s1[1];
-    for (int a = 0; a < 3; ++a) {
-      part[2 + a] = (double)cxf[a];
-      part[5 + a] = (double)cyf[a];
-    }
-    for (int k = 0; k < 15; ++k) part[8 + k] = s2[k];
-    __threadfence();
-    ticket_s = atomicAdd(&p.moments_arrive[b], 1u);
-  }
-  __syncthreads();
-  MSTAMP0(43);
-  if (ticket_s != (unsigned int)(G - 1)) return;  // not the last CTA of this batch element
-  MSTAMPL(44);
-  if (tid == 0) p.moments_arrive[b] = 0u;         // self-reset for the next call
-  __threadfence();
-  // ---- combine (fixed order over the CTAs: reproducible).  With centres c_g:
-  //   sum w x = sum_g (D_g + W_g cx_g),   S = inv * sum_g [ C_g + E_g (cx_g - mx)^T + (cy_g - my) D_g^T + W_g (cy_g - my)(cx_g - mx)^T ]
-  // all partials into shared memory with one round trip (a thread walking them in global memory pays an L2 latency
-  // per CTA: 64 x ~700 cycles)
-  __shared__ double part_s[PM_MAX_G * PM_PART];
-  {
-    const double* pg = p.partials + (size_t)b * PM_MAX_G * PM_PART;
-    for (int q = tid; q < G * PM_PART; q += PM_THREADS) part_s[q] = __ldcg(pg + q);
-  }
-  __syncthreads();
-  const double* pb = part_s;
-  // one warp per output value: lane l takes CTAs l and l + 32, then a fixed shuffle tree adds the lanes (a single thread
-  // walking the 64 partials in fp64 cost ~3 us per phase: a dependent chain of ~100 cycles per CTA)
-  const int lane = tid & 31, warp = tid >> 5;
-  auto warp_sum_f64 = [&](double x) {
+  for (int k = 0; k < PM_SUMS; ++k) {
+    double x = acc[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    return x;
-  };
-  for (int out = warp; out < 7; out += PM_THREADS / 32) {
-    double acc = 0.0;
-    for (int g = lane; g < G; g += 32) {
-      const double* q = pb + (size_t)g * PM_PART;
-      if (out == 0) acc += q[1];
-      else if (out < 4) acc += q[8 + (out - 1)] + q[0] * q[2 + (out - 1)];
-      else acc += q[11 + (out - 4)] + q[0] * q[5 + (out - 4)];
-    }
-    acc = warp_sum_f64(acc);
-    if (lane == 0) comb_s[out] = acc;
+    if (lane == 0) wsum_s[warp][k] = x;
   }
   __syncthreads();
-  // w_norm = w / (sum|w| + eps): the normalised weights sum to slightly less than one  (procrustes.py:29-30)
-  const double inv = 1.0 / (comb_s[0] + 1e-4);
-  const float invf = (float)inv;
-  double mx[3], my[3];
-  for (int a = 0; a < 3; ++a) {
-    mx[a] = (double)(float)(comb_s[1 + a] * inv);  // the means are fp32 values, as in the reference
-    my[a] = (double)(float)(comb_s[4 + a] * inv);
+  double* part = p.partials + ((size_t)b * PP_MAX_G + g) * PM_PART;
+  if (tid < PM_SUMS) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < PP_THREADS / 32; ++w) t += wsum_s[w][tid];
+    part[tid] = t;
   }
-  for (int out = warp; out < 9; out += PM_THREADS / 32) {
-    const int a = out / 3, c = out - 3 * a;
-    double acc = 0.0;
-    for (int g = lane; g < G; g += 32) {
-      const double* q = pb + (size_t)g * PM_PART;
-      const double W = q[0], dx = q[2 + c] - mx[c], dy = q[5 + a] - my[a];
-      acc += q[14 + a * 3 + c] + q[11 + a] * dx + dy * q[8 + c] + W * dy * dx;
-    }
-    acc = warp_sum_f64(acc);
-    if (lane == 0) cov_s[out] = (Kb > 0) ? acc * (double)invf : 0.0;
-  }
+  __syncthreads();
   if (tid == 0) {
-    for (int a = 0; a < 3; ++a) {
-      mean_s[a] = (Kb > 0) ? mx[a] : 0.0;
-      mean_s[3 + a] = (Kb > 0) ? my[a] : 0.0;
+    __threadfence();
+    ticket_s = atomicAdd(sync + 2, 1u);
+  }
+  __syncthreads();
+  PSTAMP0(806);
+  if (ticket_s != (unsigned int)(G - 1)) return;  // not the last CTA of this batch element
+  PSTAMPL(807);
+  __threadfence();
+  // ---- combine the CTAs' sums (fixed order: reproducible): all partials into shared memory with one round trip, then
+  //      one warp per value, lane l takes CTAs l and l + 32 and a fixed shuffle tree adds the lanes
+  {
+    double* part_s = reinterpret_cast<double*>(mine_s);   // [G * PM_PART] (the candidate lists are dead)
+    const double* pg = p.partials + (size_t)b * PP_MAX_G * PM_PART;
+    for (int q = tid; q < G * PM_PART; q += PP_THREADS) part_s[q] = __ldcg(pg + q);
+    __syncthreads();
+    for (int k = warp; k < PM_SUMS; k += PP_THREADS / 32) {
+      double x = 0.0;
+      for (int gg = lane; gg < G; gg += 32) x += part_s[gg * PM_PART + k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0) comb_s[k] = x;
     }
   }
   __syncthreads();
-  MSTAMPL(45);
+  if (tid < 9) {
+    // w_norm = w / (sum|w| + eps): the normalised weights sum to slightly less than one  (procrustes.py:29-30);
+    // S = sum w_norm (y - my)(x - mx)^T = inv * [sum w y x^T - (sum w y) mx^T - my (sum w x)^T + W my mx^T]
+    const double inv = 1.0 / (comb_s[1] + 1e-4);
+    const float invf = (float)inv;
+    const int a = tid / 3, c = tid - 3 * a;
+    const double mxc = (double)(float)(comb_s[2 + c] * inv);  // the means are fp32 values, as in the reference
+    const double mya = (double)(float)(comb_s[5 + a] * inv);
+    const double sv = comb_s[8 + a * 3 + c] - comb_s[5 + a] * mxc - mya * comb_s[2 + c] + comb_s[0] * mya * mxc;
+    cov_s[tid] = (Kb > 0) ? sv * (double)invf : 0.0;
+    if (tid < 3) {
+      mean_s[tid] = (Kb > 0) ? (double)(float)(comb_s[2 + tid] * inv) : 0.0;
+      mean_s[3 + tid] = (Kb > 0) ? (double)(float)(comb_s[5 + tid] * inv) : 0.0;
+    }
+  }
+  __syncthreads();
   if (tid == 0) {
     float R[9], t[3];
     double cond;
     double S[3][3];
     for (int a = 0; a < 3; ++a)
       for (int c = 0; c < 3; ++c) S[a][c] = cov_s[a * 3 + c];
+    PSTAMPL(808);
     kabsch_solve(S, mean_s, mean_s + 3, R, t, &cond);
-    MSTAMPL(46);
+    PSTAMPL(809);
     finish_pose(p, b, R, t, cond);
     for (int k = 0; k < 9; ++k) pose_s[k] = p.R_forwd[b * 9 + k];
     for (int k = 0; k < 3; ++k) pose_s[9 + k] = p.t_forwd[b * 3 + k];
   }
   if (p.sel_w) {
     const unsigned int ne = min(__ldcg(&p.state[b].sel_count), (unsigned int)p.K_max);
-    for (int k = (int)ne + tid; k < p.K_max; k += PM_THREADS) {
+    for (int k = (int)ne + tid; k < p.K_max; k += PP_THREADS) {
       p.sel_w[(size_t)b * p.K_max + k] = 0.f;
       p.sel_src[(size_t)b * p.K_max + k] = 0;
       p.sel_tgt[(size_t)b * p.K_max + k] = 0;
@@ -1447,20 +1273,19 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
   __syncthreads();
   // ---- warp the source points with the gated pose:  (R_forwd s + t_forwd)     pipeline.py:220
   if (p.src_warped) {
-    const float* sp = p.src_pcd + (size_t)b * p.N * 3;
-    float* o = p.src_warped + (size_t)b * p.N * 3;
-    for (int i0 = 0; i0 < p.N; i0 += PM_THREADS * 8) {  // eight points per thread and batch: 24 loads in flight
+    float* o = p.src_warped + (size_t)b * N * 3;
+    for (int i0 = 0; i0 < N; i0 += PP_THREADS * 8) {  // eight points per thread and batch: 24 loads in flight
       float xin[8][3];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * PM_THREADS + tid;
+        const int i = i0 + u * PP_THREADS + tid;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) xin[u][a] = i < p.N ? sp[i * 3 + a] : 0.f;
+        for (int a = 0; a < 3; ++a) xin[u][a] = i < N ? sp[i * 3 + a] : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * PM_THREADS + tid;
-        if (i < p.N) {
+        const int i = i0 + u * PP_THREADS + tid;
+        if (i < N) {
 #pragma unroll
           for (int a = 0; a < 3; ++a) {
             // same association as a 3-term dot product followed by the translation add
@@ -1473,10 +1298,10 @@ __global__ void __launch_bounds__(PM_THREADS) procr_moments_kernel(const ProcrPa
       }
     }
   }
-  MSTAMPL(47);
-#undef MSTAMP0
-#undef MSTAMPL
+  PSTAMPL(810);
 }
+#undef PSTAMP0
+#undef PSTAMPL
 
 // standalone weighted Kabsch on given correspondences: X, Y [B,K,3], w [B,K]
 struct KabschParams {
@@ -1539,7 +1364,6 @@ __global__ void __launch_bounds__(256) kabsch_kernel(const KabschParams p) {
   }
 }
 
-static long long* g_procr_times = nullptr;  // tuning only
 
 struct ProcrWorkspace {
   ProcrState* state;
@@ -1547,10 +1371,11 @@ struct ProcrWorkspace {
   unsigned int* cand_idx;
   unsigned int* sample_buf;
   unsigned int* sample_arrive;
-  unsigned int* moments_arrive;
+  unsigned int* pose_sync;
   unsigned int* cand_hist;
+  unsigned int* sample_hist;
+  uint2* cand_seg;
   double* partials;
-  float4* pcd4;
   size_t total;
 };
 
@@ -1566,11 +1391,12 @@ static ProcrWorkspace procr_carve(void* ws, int B, int N, int M) {
   w.cand_key = (unsigned int*)take(4ull * B * N * M);
   w.cand_idx = (unsigned int*)take(4ull * B * N * M);
   w.sample_buf = (unsigned int*)take(4ull * B * TS_SAMPLES);
-  w.sample_arrive = (unsigned int*)take(4ull * 2 * B);  // sampling CTAs, then moments CTAs
-  w.moments_arrive = w.sample_arrive ? w.sample_arrive + B : nullptr;
+  w.sample_arrive = (unsigned int*)take(4ull * 5 * B);  // sampling CTAs [B], then the pose kernel's words [B][4]: one memset
+  w.pose_sync = w.sample_arrive ? w.sample_arrive + B : nullptr;
   w.cand_hist = (unsigned int*)take(4ull * B * TK_BINS);
-  w.partials = (double*)take(8ull * B * PM_MAX_G * PM_PART);
-  w.pcd4 = (float4*)take(16ull * B * ((size_t)N + M));
+  w.sample_hist = (unsigned int*)take(4ull * B * TK_BINS);  // fused Sinkhorn -> collect path: histogram of the sampled log2 confidences
+  w.cand_seg = (uint2*)take(8ull * B * NUM_SMS);
+  w.partials = (double*)take(8ull * B * PP_MAX_G * PM_PART);
   w.total = off;
   return w;
 }
@@ -1591,9 +1417,17 @@ struct ProcrSource {  // potentials mode inputs (conf == NULL)
   SkhViews views;
 };
 
-static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void* workspace, size_t workspace_bytes, void* stream) {
+static int pow2_ceil(int x) {
+  int v = 32;
+  while (v < x) v <<= 1;
+  return v;
+}
+
+// validate the arguments and describe the problem / workspace to the kernels
+static int procr_setup(const drg_procrustes_args* a, bool potentials, void* workspace, size_t workspace_bytes, ProcrParams& p,
+                       ProcrWorkspace& w) {
   DRG_CHECK_ARG(a != nullptr, "args is null");
-  DRG_CHECK_ARG((a->conf != nullptr || src != nullptr) && a->src_pcd && a->tgt_pcd, "conf/src_pcd/tgt_pcd must be non-null");
+  DRG_CHECK_ARG((a->conf != nullptr || potentials) && a->src_pcd && a->tgt_pcd, "conf/src_pcd/tgt_pcd must be non-null");
   DRG_CHECK_ARG(a->padded_lengths || (a->src_mask && a->tgt_mask), "masks must be non-null unless padded_lengths is set");
   DRG_CHECK_ARG(a->B >= 1 && a->B <= 1024 && a->N >= 1 && a->M >= 1, "need 1 <= B <= 1024 and N, M >= 1");
   DRG_CHECK_ARG((long long)a->N * a->M < (1ll << 32), "N*M must fit in 32 bits");
@@ -1602,24 +1436,13 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
   DRG_CHECK_ARG((a->sel_w == nullptr) == (a->sel_src == nullptr) && (a->sel_w == nullptr) == (a->sel_tgt == nullptr),
                 "sel_w/sel_src/sel_tgt must be given together");
   const int B = a->B, N = a->N, M = a->M;
-  ProcrWorkspace w = procr_carve(workspace, B, N, M);
+  w = procr_carve(workspace, B, N, M);
   if (workspace == nullptr || workspace_bytes < w.total || ((uintptr_t)workspace & 255u)) {
     set_error("soft_procrustes: workspace missing, too small (%zu < %zu) or not 256-byte aligned", workspace_bytes, w.total);
     return DRG_ERR_WORKSPACE;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  ProcrParams p{};
-  p.conf = src ? nullptr : a->conf;
-  if (src) {
-    p.scores = src->scores;
-    p.pu = src->views.u;
-    p.pv = src->views.v;
-    p.pbc = src->views.bc;
-    p.pshift = src->shift;
-    p.ldu = src->views.ldu;
-    p.ldv = src->views.ldv;
-    p.apply_mask = src->apply_mask;
-  }
+  p = ProcrParams{};
+  p.conf = potentials ? nullptr : a->conf;
   p.src_pcd = a->src_pcd;
   p.tgt_pcd = a->tgt_pcd;
   p.src_mask = a->src_mask;
@@ -1635,10 +1458,10 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
   p.cand_idx = w.cand_idx;
   p.sample_buf = w.sample_buf;
   p.sample_arrive = w.sample_arrive;
-  p.moments_arrive = w.moments_arrive;
+  p.pose_sync = w.pose_sync;
   p.cand_hist = w.cand_hist;
+  p.cand_seg = w.cand_seg;
   p.partials = w.partials;
-  p.pcd4 = w.pcd4;
   p.R = a->R;
   p.t = a->t;
   p.R_forwd = a->R_forwd;
@@ -1653,25 +1476,23 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
   p.sel_w = a->sel_w;
   p.sel_src = a->sel_src;
   p.sel_tgt = a->sel_tgt;
-  {
-    static long long* tbuf = nullptr;
-    static int want = -1;
-    if (want < 0) want = getenv("DRG_PROCR_TIMES") ? 1 : 0;
-    if (want && !tbuf) {
-      cudaMalloc(&tbuf, 64 * sizeof(long long));
-      cudaMemset(tbuf, 0, 64 * sizeof(long long));
-      g_procr_times = tbuf;
-    }
-    p.dbg_times = want ? tbuf : nullptr;
+  p.stamps = g_tuning_stamps;
+  // the pose kernel keeps a CTA's selected candidates (at most K_b + the crossing bin's short list) in shared memory
+  p.mine_cap = pow2_ceil((int)(kmax_ll < (long long)N * M ? kmax_ll : (long long)N * M) + SEL_LIST);
+  if (p.mine_cap < 2 * PP_RANK_SORT) p.mine_cap = 2 * PP_RANK_SORT;  // the rank sort scatters into the upper half
+  p.surv_cap = (int)(kmax_ll < (long long)N * M ? kmax_ll : (long long)N * M) + SEL_LIST + 64;
+  if ((size_t)p.mine_cap * 8 + (size_t)p.surv_cap * 4 > 220 * 1024) {
+    set_error("soft_procrustes: max(N, M) * sample_rate = %lld correspondences exceed the pose kernel's shared-memory lists (about 16000)",
+              kmax_ll);
+    return DRG_ERR_UNSUPPORTED;
   }
+  return DRG_OK;
+}
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    DRG_CUDA(cudaFuncSetAttribute(topk_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SAMPLES * 4));
-    attr_set = true;
-  }
-  // the arrival counters must be zero on entry (the workspace is caller memory of unknown content)
-  DRG_CUDA(cudaMemsetAsync(w.sample_arrive, 0, 4ull * 2 * B, st));
+// stand-alone candidate search (a stored confidence matrix, or shapes the persistent Sinkhorn does not take)
+static int procr_search(const ProcrParams& p, cudaStream_t st) {
+  const int B = p.B, N = p.N, M = p.M;
+  DRG_CUDA(cudaFuncSetAttribute(topk_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SAMPLES * 4));
   int ts_ctas = NUM_SMS / (2 * B);
   if (ts_ctas > 32) ts_ctas = 32;
   if (ts_ctas < 1) ts_ctas = 1;
@@ -1687,54 +1508,55 @@ static int procr_run(const drg_procrustes_args* a, const ProcrSource* src, void*
   {
     ProfScope prof_scope(PROF_TOPK_COLLECT, st);
     if (!p.conf && (M % 4) == 0 && ((((uintptr_t)p.scores) | ((uintptr_t)p.pv) | ((uintptr_t)p.tgt_mask)) & 15u) == 0 &&
-      ((p.ldv & 3) == 0)) {
-    static int per_sm = -1;  // tuning only: DRG_COLLECT_PER_SM
-    if (per_sm < 0) {
-      const char* e = getenv("DRG_COLLECT_PER_SM");
-      per_sm = e ? atoi(e) : 2;
-      if (per_sm < 1 || per_sm > 16) per_sm = 2;
+        ((p.ldv & 3) == 0)) {
+      // two CTAs per SM: one resident wave with ~14 rows each measured best at 4096^2 (1 -> 43.7 us, 2 -> 28.9 us, 3 -> 35.1 us)
+      int gr = (NUM_SMS * 2) / B;
+      if (gr < 1) gr = 1;
+      if (gr > N) gr = N;
+      topk_collect_rows_kernel<<<dim3(gr, B), 256, 0, st>>>(p);
+    } else {
+      topk_collect_kernel<<<dim3(gx, B), 256, 0, st>>>(p);
     }
-    // CTAs per SM.  80 registers x 256 threads allow three resident CTAs per SM; measured at 4096^2 inside the step
-    // (tools/collect_sweep.sh): 1 -> 43.7 us, 2 -> 28.9 us, 3 -> 35.1 us, 4 -> 30.6 us, 5 -> 34.1 us (2960 / 2991 / 3005
-    // steps/s for 5 / 4 / 2): one resident wave of 296 CTAs with ~14 rows each beats more, shorter CTAs.
-    int gr = (NUM_SMS * per_sm) / B;
-    if (gr < 1) gr = 1;
-    if (gr > N) gr = N;
-    topk_collect_rows_kernel<<<dim3(gr, B), 256, 0, st>>>(p);
-  } else {
-    topk_collect_kernel<<<dim3(gx, B), 256, 0, st>>>(p);
-  }
-  }
-  DRG_LAUNCH_CHECK();
-  static int single_cta = -1;  // DRG_PROCR_SINGLE=1: the single-CTA solve kernel (A/B comparisons)
-  if (single_cta < 0) single_cta = getenv("DRG_PROCR_SINGLE") ? 1 : 0;
-  if (single_cta) {
-    static bool solve_attr_set = false;
-    if (!solve_attr_set) {
-      DRG_CUDA(cudaFuncSetAttribute(procr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_SMEM_CAND * 8));
-      solve_attr_set = true;
-    }
-    ProfScope prof_scope(PROF_PROCR_SOLVE, st);
-    procr_solve_kernel<<<B, SOLVE_THREADS, SOLVE_SMEM_CAND * 8, st>>>(p);
-  } else {
-    int G = NUM_SMS / B;
-    if (G > PM_MAX_G) G = PM_MAX_G;
-    if (G < 4) G = 4;
-    {
-      ProfScope prof_scope(PROF_PROCR_SELECT, st);
-      procr_select_kernel<<<B, SEL_THREADS, 0, st>>>(p);
-    }
-    DRG_LAUNCH_CHECK();
-    ProfScope prof_scope(PROF_PROCR_SOLVE, st);
-    procr_moments_kernel<<<dim3(G, B), PM_THREADS, 0, st>>>(p);
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }
 
+static int procr_pose(const ProcrParams& p, cudaStream_t st) {
+  int G = NUM_SMS / p.B - 1;   // working CTAs per batch element (+ one that only warms the instruction caches)
+  if (G > PP_MAX_G) G = PP_MAX_G;
+  if (G > p.N) G = p.N;
+  if (G < 1) G = 1;
+  const size_t smem = (size_t)p.mine_cap * 8 + (size_t)p.surv_cap * 4;
+  DRG_CUDA(cudaFuncSetAttribute(procr_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof_scope(PROF_PROCR_SOLVE, st);
+  if ((long long)(G + 1) * p.B > NUM_SMS || G == 1) {
+    // one working CTA per batch element never waits for another CTA: an ordinary launch, any batch size
+    procr_pose_kernel<<<dim3(2, p.B), PP_THREADS, smem, st>>>(p);
+    DRG_LAUNCH_CHECK();
+    return DRG_OK;
+  }
+  // several CTAs per batch element wait for each other on the rare paths (general select, whole-matrix fallback): the
+  // cooperative launch guarantees that they are co-resident
+  ProcrParams pp = p;
+  void* args[] = {(void*)&pp};
+  DRG_CUDA(cudaLaunchCooperativeKernel((const void*)procr_pose_kernel, dim3(G + 1, p.B), dim3(PP_THREADS), args, smem, st));
+  count_launch();
+  return DRG_OK;
+}
+
 extern "C" int drg_soft_procrustes(const drg_procrustes_args* a, void* workspace, size_t workspace_bytes, void* stream) {
   DRG_CHECK_ARG(a != nullptr && a->conf != nullptr, "args / conf is null");
-  return procr_run(a, nullptr, workspace, workspace_bytes, stream);
+  ProcrParams p;
+  ProcrWorkspace w;
+  int rc = procr_setup(a, false, workspace, workspace_bytes, p, w);
+  if (rc != DRG_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // the arrival counters / flags must be zero on entry (the workspace is caller memory of unknown content)
+  DRG_CUDA(cudaMemsetAsync(w.sample_arrive, 0, 4ull * 5 * a->B, st));
+  rc = procr_search(p, st);
+  if (rc != DRG_OK) return rc;
+  return procr_pose(p, st);
 }
 
 extern "C" int drg_sinkhorn_soft_procrustes(const drg_sinkhorn_args* s, const drg_procrustes_args* a, void* skh_workspace,
@@ -1744,13 +1566,40 @@ extern "C" int drg_sinkhorn_soft_procrustes(const drg_sinkhorn_args* s, const dr
   DRG_CHECK_ARG(s->out_mode == DRG_OUT_NONE, "the fused call takes out_mode DRG_OUT_NONE: the confidence matrix is never written");
   DRG_CHECK_ARG(s->B == a->B && s->N == a->N && s->M == a->M, "sinkhorn and procrustes shapes differ");
   DRG_CHECK_ARG(a->src_mask == s->src_mask && a->tgt_mask == s->tgt_mask, "the fused call uses one pair of masks");
-  ProcrSource src{};
-  int rc = skh_run_with_views(s, skh_workspace, skh_workspace_bytes, stream, &src.views);
+  ProcrParams p;
+  ProcrWorkspace w;
+  int rc = procr_setup(a, true, procr_workspace, procr_workspace_bytes, p, w);
   if (rc != DRG_OK) return rc;
-  src.scores = s->scores;
-  src.shift = s->shift;
-  src.apply_mask = s->apply_mask;
-  return procr_run(a, &src, procr_workspace, procr_workspace_bytes, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  DRG_CUDA(cudaMemsetAsync(w.sample_arrive, 0, 4ull * 5 * a->B, st));
+  // Sinkhorn; when the persistent kernel takes the shape, the candidate search runs as its last phase
+  SkhCollect col{};
+  col.state = w.state;
+  col.cand_key = w.cand_key;
+  col.cand_idx = w.cand_idx;
+  col.cand_hist = w.cand_hist;
+  col.sample_hist = w.sample_hist;
+  col.cand_seg = w.cand_seg;
+  col.sample_rate = a->sample_rate;
+  col.padded_lengths = a->padded_lengths;
+  col.K_max = p.K_max;
+  bool collected = false;
+  SkhViews views{};
+  rc = skh_run_with_views(s, skh_workspace, skh_workspace_bytes, stream, &views, &col, &collected);
+  if (rc != DRG_OK) return rc;
+  p.scores = s->scores;
+  p.pu = views.u;
+  p.pv = views.v;
+  p.pbc = views.bc;
+  p.pshift = s->shift;
+  p.ldu = views.ldu;
+  p.ldv = views.ldv;
+  p.apply_mask = s->apply_mask;
+  if (!collected) {
+    rc = procr_search(p, st);
+    if (rc != DRG_OK) return rc;
+  }
+  return procr_pose(p, st);
 }
 
 extern "C" int drg_weighted_procrustes(const float* X, const float* Y, const float* w, int B, int K, float eps, float* R, float* t,
@@ -1760,11 +1609,5 @@ extern "C" int drg_weighted_procrustes(const float* X, const float* Y, const flo
   KabschParams p{X, Y, w, B, K, eps, R, t, condition};
   kabsch_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(p);
   DRG_LAUNCH_CHECK();
-  return DRG_OK;
-}
-
-extern "C" int drg_debug_read_procr_times(long long* host_out, int n) {
-  if (!g_procr_times || n > 64) return DRG_ERR_UNSUPPORTED;
-  DRG_CUDA(cudaMemcpy(host_out, g_procr_times, sizeof(long long) * n, cudaMemcpyDeviceToHost));
   return DRG_OK;
 }

@@ -49,12 +49,11 @@ struct SkhParams {
   int dual;       // 1: dual-softmax statistics (no dustbins, no potentials)
   float zscale2;  // log2(e) (Sinkhorn) or log2(e)/temperature (dual softmax)
   int nstage;
-  long long* dbg_times;  // tuning only: CTA 0 writes clock64() stamps here (NULL = off)
-  int dbg;         // tuning experiments only (DRG_SKH_DBG): 1 skip row math, 2 skip column math, 4 skip prologue reductions
-  int keep_slabs;  // >= 0: the first keep_slabs slabs of every CTA are loaded L2::evict_last, the rest evict_first
+  long long* dbg_times;  // tuning only: CTA 0 writes clock64() stamps here (NULL = off; drg_tuning_set_stamp_buffer)
   unsigned long long* zero_a;  // optional: arrays the persistent kernel clears on its way in (rowbest / colbest of the
   unsigned long long* zero_b;  //   final pass of the same call: two memset nodes less per step)
   size_t zero_a_n, zero_b_n;
+  SkhCollect col;  // col.state != NULL: the persistent kernel runs the top-K candidate search of SoftProcrustes as its last phase
 };
 
 // ---------------------------------------------------------------------------------------
@@ -467,14 +466,9 @@ __global__ void __launch_bounds__(SKH_THREADS, 1) skh_iter2_kernel(const SkhPara
   const float zs = p.zscale2;
   const float shift = p.shift ? *p.shift : 0.f;
 
-  uint64_t pol_keep = 0, pol_stream = 0;
   if (tid == 0) {
     for (int s = 0; s < nstage; ++s) mbar_init(&full[s], 1u);
     fence_mbar_init();
-    if (p.keep_slabs >= 0) {
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-    }
   }
   __syncthreads();
 
@@ -487,10 +481,7 @@ __global__ void __launch_bounds__(SKH_THREADS, 1) skh_iter2_kernel(const SkhPara
     const uint32_t bytes = (uint32_t)rows * (uint32_t)M * 4u;
     fence_proxy_async();
     mbar_arrive_expect_tx(&full[st], bytes);
-    if (p.keep_slabs >= 0)
-      tma_bulk_g2s_hint(dst, src, bytes, &full[st], (s - s_begin) < p.keep_slabs ? pol_keep : pol_stream);
-    else
-      tma_bulk_g2s(dst, src, bytes, &full[st]);
+    tma_bulk_g2s(dst, src, bytes, &full[st]);
   };
   if (tid == 0)
     for (int k = 0; k < nstage; ++k)
@@ -719,815 +710,10 @@ __global__ void __launch_bounds__(SKH_THREADS, 1) skh_iter2_kernel(const SkhPara
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// one Sinkhorn iteration, warp-specialised (M % 4 == 0, M <= 4096): 1024 threads per CTA
-//   warps 0..14   ROW warps: each owns whole rows (row q of the CTA's range goes to warp q % 15):
-//                 per-lane online log-sum-exp over the row, ONE warp reduction per row, then
-//                 u_i -> shared memory + global; arrives on u_ready[stage] and stage_free[stage]
-//   warp 15       producer: one thread issues the TMA bulk copy of the next slab as soon as its
-//                 stage is free
-//   warps 16..31  COLUMN warps: thread -> KQ column quads; wait for u_ready[stage], accumulate the
-//                 slab's contribution to the column log-sum-exps, arrive on stage_free[stage]
-//   The two groups are coupled only through mbarriers, so row work on slab k+1.. overlaps the
-//   column work on slab k and nobody waits at a block barrier inside the loop.
-// ---------------------------------------------------------------------------------------
-constexpr int WS_THREADS = 1024;
-constexpr int WS_ROW_WARPS = 15;
-constexpr int WS_COL_THREADS = 512;
-constexpr int WS_MAX_STAGES = 8;
-
-template <int R, int KQ, bool ROWFULL, bool COLFULL>
-__global__ void __launch_bounds__(WS_THREADS, 1) skh_iter_ws_kernel(const SkhParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int N = p.N, M = p.M;
-  const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nslab = (N + R - 1) / R;
-  const int s_begin = (int)(((long long)nslab * g) / G);
-  const int s_end = (int)(((long long)nslab * (g + 1)) / G);
-  const int nstage = p.nstage;
-
-  // ---- shared memory carve-up
-  const int Mv = (M + 1 + 3) & ~3;
-  const int stage_floats = R * M;
-  float* v2_s = reinterpret_cast<float*>(smem_raw);
-  float* stage0 = v2_s + Mv;
-  float* u2_s = stage0 + (size_t)nstage * stage_floats;             // [WS_MAX_STAGES][16]
-  float* red_s = u2_s + WS_MAX_STAGES * 16;                          // [64]
-  float2* upart_s = reinterpret_cast<float2*>(red_s + 64);           // [16]
-  uint64_t* full = reinterpret_cast<uint64_t*>(upart_s + 16);        // [WS_MAX_STAGES]
-  uint64_t* u_ready = full + WS_MAX_STAGES;
-  uint64_t* stage_free = u_ready + WS_MAX_STAGES;
-
-  const float* sc_b = p.scores + (size_t)b * N * M;
-  const SkhConst bc = p.bc[b];
-  const float zs = p.zscale2;
-  const float shift = p.shift ? *p.shift : 0.f;
-
-  if (tid == 0) {
-    for (int s = 0; s < nstage; ++s) {
-      mbar_init(&full[s], 1u);
-      mbar_init(&u_ready[s], (uint32_t)R);
-      mbar_init(&stage_free[s], (uint32_t)(R + WS_COL_THREADS / 32));
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  auto issue_slab = [&](int s, int st) {
-    const int i0 = s * R;
-    const int rows = min(R, N - i0);
-    const uint32_t bytes = (uint32_t)rows * (uint32_t)M * 4u;
-    fence_proxy_async();
-    mbar_arrive_expect_tx(&full[st], bytes);
-    tma_bulk_g2s(stage0 + (size_t)st * stage_floats, sc_b + (size_t)i0 * M, bytes, &full[st]);
-  };
-  // the first loads go out before the prologue so that they overlap it
-  if (warp == WS_ROW_WARPS && lane == 0)
-    for (int k = 0; k < nstage; ++k)
-      if (s_begin + k < s_end) issue_slab(s_begin + k, k);
-
-  // ---- prologue (all threads): column potentials into shared memory (log2 domain), dustbin-row potential
-  if (p.dbg & 4) {
-    for (int j = tid; j <= M; j += WS_THREADS) v2_s[j] = 0.f;
-  } else if (!p.dual) {
-    const float* v_b = p.v + (size_t)b * p.ldv;
-    const float alpha = *p.alpha;
-    float mloc = NEG_BIG;
-    for (int j = tid; j <= M; j += WS_THREADS) mloc = fmaxf(mloc, v_b[j] * LOG2E);
-    mloc = warp_max(mloc);
-    if (lane == 0) red_s[warp] = mloc;
-    __syncthreads();
-    float mall = red_s[0];
-#pragma unroll
-    for (int w = 1; w < WS_THREADS / 32; ++w) mall = fmaxf(mall, red_s[w]);
-    float sloc = 0.f;
-    for (int j = tid; j <= M; j += WS_THREADS) {
-      const float vj = v_b[j];
-      sloc += ex2(vj * LOG2E - mall);
-      float v2;
-      if (j < M) {
-        v2 = (vj - shift) * LOG2E;
-        if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
-      } else {
-        v2 = (alpha + vj) * LOG2E;  // dustbin column entry of every real row: alpha + v_M
-      }
-      v2_s[j] = v2;
-    }
-    sloc = warp_sum(sloc);
-    if (lane == 0) red_s[32 + warp] = sloc;
-    __syncthreads();
-    if (g == 0 && tid == 0) {
-      float sall = 0.f;
-      for (int w = 0; w < WS_THREADS / 32; ++w) sall += red_s[32 + w];
-      const float vlse = (mall + lg2(sall)) * LN2;
-      p.u[(size_t)b * p.ldu + N] = bc.log_mu_bin - (alpha + vlse);  // dustbin row potential
-    }
-  } else {
-    for (int j = tid; j < M; j += WS_THREADS) v2_s[j] = (p.tgt_mask[(size_t)b * M + j]) ? 0.f : -INFINITY;
-    if (tid == 0) v2_s[M] = -INFINITY;
-  }
-  for (int j = M + 1 + tid; j < Mv; j += WS_THREADS) v2_s[j] = -INFINITY;
-  __syncthreads();
-
-  if (warp < WS_ROW_WARPS) {
-    // =========================== ROW warps ===========================
-    const float dust2 = v2_s[M];
-    LseAcc uacc = lse_empty();  // lane 0: running LSE of the u_i this warp produced (dustbin column)
-    const int nq = (s_end - s_begin) * R;  // padded row slots of this CTA
-    const float* v2_lane = v2_s + 4 * lane;
-    // Every row warp observes the `full` barrier of EVERY slab in order (a parity wait is only meaningful for a
-    // waiter that has seen the previous phase of the same barrier), but computes only the rows assigned to it.
-    int st = 0;
-    uint32_t ph = 0;
-    for (int q0 = 0; q0 < nq; q0 += R) {
-      mbar_wait_sleep(&full[st], ph, 200u);
-#pragma unroll 1
-      for (int r = 0; r < R; ++r) {
-      const int q = q0 + r;
-      if (q % WS_ROW_WARPS != warp) continue;
-      const int i = s_begin * R + q;
-      float u2 = -INFINITY;
-      if (i < N) {
-        const bool row_live = !(p.apply_mask && !p.dual && !p.src_mask[(size_t)b * N + i]);
-        float m_l = NEG_BIG, s_l = 0.f;
-        if (row_live && !(p.dbg & 1)) {
-          const float* row_lane = stage0 + (size_t)st * stage_floats + (size_t)r * M + 4 * lane;
-          for (int cb = 0; cb < M; cb += 1024) {
-            float xs[32];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              if (ROWFULL || cb + 4 * lane + 128 * k < M) {
-                const float4 z = *reinterpret_cast<const float4*>(row_lane + cb + 128 * k);
-                const float4 vv = *reinterpret_cast<const float4*>(v2_lane + cb + 128 * k);
-                xs[4 * k + 0] = fmaf(z.x, zs, vv.x);
-                xs[4 * k + 1] = fmaf(z.y, zs, vv.y);
-                xs[4 * k + 2] = fmaf(z.z, zs, vv.z);
-                xs[4 * k + 3] = fmaf(z.w, zs, vv.w);
-              } else {
-                xs[4 * k + 0] = xs[4 * k + 1] = xs[4 * k + 2] = xs[4 * k + 3] = -INFINITY;
-              }
-            }
-            float cmax = NEG_BIG;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) cmax = fmaxf(cmax, xs[k]);
-            if (cmax > m_l) {  // per-lane online rescale (at most once per 32 elements)
-              s_l *= ex2(m_l - cmax);
-              m_l = cmax;
-            }
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              a0 += ex2(xs[4 * k + 0] - m_l);
-              a1 += ex2(xs[4 * k + 1] - m_l);
-              a2 += ex2(xs[4 * k + 2] - m_l);
-              a3 += ex2(xs[4 * k + 3] - m_l);
-            }
-            s_l += (a0 + a1) + (a2 + a3);
-          }
-        }
-        // one warp reduction per row
-        const float mrow = warp_max(m_l);
-        float srow = warp_sum(s_l * ex2(m_l - mrow));
-        float ui;
-        if (!p.dual) {
-          const float mm = fmaxf(mrow, dust2);
-          srow = srow * ex2(mrow - mm) + ex2(dust2 - mm);  // + dustbin column entry alpha + v_M
-          ui = bc.norm - (mm + lg2(srow)) * LN2;
-        } else {
-          ui = -(mrow + lg2(srow)) * LN2;  // -(row log-sum-exp), natural log
-        }
-        const bool src_ok = (!p.apply_mask && !p.dual) || p.src_mask[(size_t)b * N + i];
-        if (!p.dual)
-          u2 = src_ok ? (ui - shift) * LOG2E : -INFINITY;  // column pass sees (S - shift) + u
-        else
-          u2 = src_ok ? 0.f : -INFINITY;
-        if (lane == 0) {
-          p.u[(size_t)b * p.ldu + i] = ui;
-          if (!p.dual) lse_add_value(uacc, ui * LOG2E);
-        }
-      }
-      if (lane == 0) {
-        u2_s[st * 16 + r] = u2;
-        mbar_arrive(&u_ready[st]);     // release: u2 is visible to the column warps that acquire the barrier
-        mbar_arrive(&stage_free[st]);  // this warp no longer reads the stage
-      }
-      __syncwarp();
-      }
-      if (++st == nstage) {
-        st = 0;
-        ph ^= 1u;
-      }
-    }
-    if (lane == 0) upart_s[warp] = make_float2(uacc.m, uacc.s);
-  } else if (warp == WS_ROW_WARPS) {
-    // =========================== producer ===========================
-    if (lane == 0) {
-      for (int s = s_begin + nstage; s < s_end; ++s) {
-        const int sl = s - s_begin;
-        const int st = sl % nstage;
-        mbar_wait_sleep(&stage_free[st], (uint32_t)(((sl / nstage) - 1) & 1), 200u);
-        issue_slab(s, st);
-      }
-      upart_s[WS_ROW_WARPS] = make_float2(NEG_BIG, 0.f);
-    }
-  } else {
-    // =========================== COLUMN warps ===========================
-    const int ct = tid - WS_COL_THREADS;  // 0..511
-    float cm[KQ * 4], cs[KQ * 4];
-#pragma unroll
-    for (int e = 0; e < KQ * 4; ++e) {
-      cm[e] = NEG_BIG;
-      cs[e] = 0.f;
-    }
-    for (int s = s_begin; s < s_end; ++s) {
-      const int sl = s - s_begin;
-      const int st = sl % nstage;
-      const int i0 = s * R;
-      const int rows = min(R, N - i0);
-      const float* slab = stage0 + (size_t)st * stage_floats;
-      mbar_wait_sleep(&u_ready[st], (uint32_t)((sl / nstage) & 1), 500u);
-      float u2r[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) u2r[r] = u2_s[st * 16 + r];  // rows beyond `rows` hold -inf
-#pragma unroll
-      for (int k = 0; k < KQ; ++k) {
-        const int c = 4 * (ct + WS_COL_THREADS * k);
-        if ((COLFULL || c < M) && !(p.dbg & 2)) {
-          float x[R][4];
-          float mx[4] = {NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG};
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            if (r < rows) {
-              const float4 z = *reinterpret_cast<const float4*>(slab + (size_t)r * M + c);
-              x[r][0] = fmaf(z.x, zs, u2r[r]);
-              x[r][1] = fmaf(z.y, zs, u2r[r]);
-              x[r][2] = fmaf(z.z, zs, u2r[r]);
-              x[r][3] = fmaf(z.w, zs, u2r[r]);
-            } else {
-              x[r][0] = x[r][1] = x[r][2] = x[r][3] = -INFINITY;
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) mx[e] = fmaxf(mx[e], x[r][e]);
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float& am = cm[4 * k + e];
-            float& as = cs[4 * k + e];
-            if (mx[e] > am + 32.f) {  // lazy re-reference: rare after the first slab
-              as *= ex2(am - mx[e]);
-              am = mx[e];
-            }
-            float acc = 0.f;
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc += ex2(x[r][e] - am);
-            as += acc;
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&stage_free[st]);
-    }
-    float2* cp = p.colpart + ((size_t)b * G + g) * M;
-#pragma unroll
-    for (int k = 0; k < KQ; ++k) {
-      const int c = 4 * (ct + WS_COL_THREADS * k);
-      if (COLFULL || c < M) {
-        *reinterpret_cast<float4*>(cp + c) = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
-        *reinterpret_cast<float4*>(cp + c + 2) = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
-      }
-    }
-  }
-  // ---- dustbin-column partial: LSE of this CTA's u_i
-  __syncthreads();
-  if (!p.dual && tid == 0) {
-    LseAcc a = lse_empty();
-    for (int w = 0; w < WS_ROW_WARPS; ++w) lse_merge(a, upart_s[w].x, upart_s[w].y);
-    p.upart[(size_t)b * G + g] = make_float2(a.m, a.s);
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// ALL Sinkhorn iterations in one persistent cooperative kernel (M % 4 == 0, M <= 4096, G*B <= #SMs)
-//   Same warp roles as skh_iter_ws_kernel.  Per iteration: prologue (v -> shared memory), the fused
-//   row/column pass over the CTA's rows, a grid-wide barrier, the merge of the per-CTA column partials
-//   (every warp of every CTA merges one column at a time), another grid-wide barrier.  The TMA ring
-//   never drains: the scores do not change, so the producer keeps prefetching the next iteration's
-//   slabs while the CTAs sit in the barriers.  Mask counts / normalisation constants are computed in
-//   the kernel, so one launch replaces 1 + 2*iters launches.
-// ---------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-// barrier over the CTAs of one batch element; `counter` counts arrivals since the launch
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (ld_acquire_u32(counter) < target) __nanosleep(32);
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// 768 threads: 15 ROW warps + 1 producer warp + 8 COLUMN warps (thread -> KQ column quads, KQ = M / 1024 rounded up), so that
-// every thread may use 85 registers: with 1024 threads the 64-register cap put spills inside the row loop.
-constexpr int PS_THREADS = 768;
-constexpr int PS_COL_BEGIN = 512;
-constexpr int PS_COL_NTHREADS = PS_THREADS - PS_COL_BEGIN;
-
-template <int R, int KQ, bool ROWFULL, bool COLFULL>
-__global__ void __launch_bounds__(PS_THREADS, 1) skh_persist_kernel(const SkhParams p, const int iters, unsigned int* gsync) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int N = p.N, M = p.M;
-  const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nslab = (N + R - 1) / R;
-  const int s_begin = (int)(((long long)nslab * g) / G);
-  const int s_end = (int)(((long long)nslab * (g + 1)) / G);
-  const int nsl = s_end - s_begin;
-  const int nstage = p.nstage;
-
-  // ---- shared memory carve-up
-  const int Mv = (M + 1 + 3) & ~3;
-  const int stage_floats = R * M;
-  float* v2_s = reinterpret_cast<float*>(smem_raw);
-  float* stage0 = v2_s + Mv;
-  float* u2_s = stage0 + (size_t)nstage * stage_floats;             // [WS_MAX_STAGES][16]
-  float* red_s = u2_s + WS_MAX_STAGES * 16;                          // [64]
-  float2* upart_s = reinterpret_cast<float2*>(red_s + 64);           // [16]
-  uint64_t* full = reinterpret_cast<uint64_t*>(upart_s + 16);        // [WS_MAX_STAGES]
-  uint64_t* u_ready = full + WS_MAX_STAGES;
-  uint64_t* stage_free = u_ready + WS_MAX_STAGES;
-  __shared__ int cnt_s[2];
-  __shared__ float2 comb[(PS_THREADS / 32) * 32];  // merge scratch: [32 warps][32 columns]
-  __shared__ float lse_prev_s[1024];               // log2-domain row log-sum-exp of the previous iteration, per row slot
-
-#define DRG_STAMP(slot) do { if (p.dbg_times && g == 0 && b == 0) p.dbg_times[(slot)] = clock64(); } while (0)
-  const float* sc_b = p.scores + (size_t)b * N * M;
-  const float zs = p.zscale2;
-  const float shift = p.shift ? *p.shift : 0.f;
-  const float alpha = *p.alpha;
-  unsigned int* gcount = gsync + b;
-  unsigned int* dv_slots = gsync + gridDim.y + 2 * b;  // max |v_new - v_old| * log2(e) of the last two merges (float bits)
-
-  if (tid == 0) DRG_STAMP(0);
-  if (tid == 0) {
-    for (int s = 0; s < nstage; ++s) {
-      mbar_init(&full[s], 1u);
-      mbar_init(&u_ready[s], (uint32_t)R);
-      mbar_init(&stage_free[s], (uint32_t)(R + PS_COL_NTHREADS / 32));
-    }
-    fence_mbar_init();
-    cnt_s[0] = cnt_s[1] = 0;
-  }
-  __syncthreads();
-
-  const long long total_slabs = (long long)iters * nsl;  // the producer's stream: the CTA's slabs, once per iteration
-  auto issue_slab = [&](long long t) {                    // t-th slab of the stream -> stage t % nstage
-    const int s = s_begin + (int)(t % nsl);
-    const int st = (int)(t % nstage);
-    const int i0 = s * R;
-    const int rows = min(R, N - i0);
-    const uint32_t bytes = (uint32_t)rows * (uint32_t)M * 4u;
-    fence_proxy_async();
-    mbar_arrive_expect_tx(&full[st], bytes);
-    tma_bulk_g2s(stage0 + (size_t)st * stage_floats, sc_b + (size_t)i0 * M, bytes, &full[st]);
-  };
-  if (warp == WS_ROW_WARPS && lane == 0)
-    for (int k = 0; k < nstage; ++k)
-      if (k < total_slabs) issue_slab(k);
-
-  // ---- mask counts -> normalisation constants (matching.py:14-15, 24-27)
-  {
-    int cs = count_mask_bytes(p.src_mask + (size_t)b * N, N, tid, PS_THREADS);
-    int ct = count_mask_bytes(p.tgt_mask + (size_t)b * M, M, tid, PS_THREADS);
-    cs = __reduce_add_sync(0xffffffffu, cs);
-    ct = __reduce_add_sync(0xffffffffu, ct);
-    if (lane == 0) {
-      if (cs) atomicAdd(&cnt_s[0], cs);
-      if (ct) atomicAdd(&cnt_s[1], ct);
-    }
-  }
-  __syncthreads();
-  SkhConst bc;
-  {
-    const float ms = (float)cnt_s[0], ns = (float)cnt_s[1];
-    bc.norm = -logf(ms + ns);
-    bc.log_mu_bin = logf(ns) + bc.norm;
-    bc.log_nu_bin = logf(ms) + bc.norm;
-    bc.pad = (cnt_s[0] == N && cnt_s[1] == M) ? 1.f : 0.f;  // 1: no padded row or column
-    if (g == 0 && tid == 0) p.bc_out[b] = bc;
-  }
-
-  // persistent pipeline state of each role
-  int r_st = 0;          // row warps: stage / phase of the next slab to observe
-  uint32_t r_ph = 0;
-  int c_st = 0;          // column warps
-  uint32_t c_ph = 0;
-  long long p_next = nstage;  // producer: next slab of the stream to issue
-  int p_st = 0;
-  uint32_t p_ph = 0;
-  unsigned int barriers_done = 0;
-
-  if (tid == 0) DRG_STAMP(1);
-  for (int it = 0; it < iters; ++it) {
-    if (tid == 0) DRG_STAMP(10 + it * 100 + 0);
-    // Scaled ("fast") pass: once a row's log-sum-exp of the previous iteration is known it is used as the reference of
-    // this iteration's exponentials, e_ij = 2^(x_ij - ref_i): no running maximum, and the column pass reuses e_ij
-    // (written back over the slab) with one FMA per element instead of a second exponential.  Exactly as accurate as
-    // the log-domain pass while the reference is within ~2^50 of the new value, which is guaranteed when the column
-    // potentials moved by less than 50 (log2 units) in the last merge -- checked here, identically on every CTA;
-    // otherwise (and in the first iteration) the log-domain pass below runs.
-    bool fast = false;
-    if (it >= 1 && nsl * R <= 1024 && alpha >= -20.f && !(p.dbg & 8)) {
-      const float dv = __uint_as_float(ld_acquire_u32(dv_slots + ((it - 1) & 1)));
-      fast = dv <= 50.f;
-    }
-    if (p.dbg_times && g == 0 && b == 0 && tid == 0) {
-      p.dbg_times[400 + it] = fast ? 1 : 0;
-      p.dbg_times[410 + it] = (it >= 1) ? (long long)ld_acquire_u32(dv_slots + ((it - 1) & 1)) : -1;
-    }
-    const float norm2 = bc.norm * LOG2E;
-    // ---- prologue: column potentials into shared memory (log2 domain), dustbin-row potential
-    float uN;
-    if (it == 0) {
-      // v = 0: LSE over M+1 zeros = log(M+1)
-      for (int j = tid; j <= M; j += PS_THREADS) {
-        float v2;
-        if (j < M) {
-          v2 = (0.f - shift) * LOG2E;
-          if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
-        } else {
-          v2 = alpha * LOG2E;
-        }
-        v2_s[j] = v2;
-      }
-      uN = bc.log_mu_bin - (alpha + logf((float)(M + 1)));
-    } else {
-      const float* v_b = p.v + (size_t)b * p.ldv;
-      // one read of v (written by other SMs in the merge: L2 only), kept in registers for both passes
-      constexpr int VPT = (4096 + 1 + PS_THREADS - 1) / PS_THREADS;  // M <= 4096
-      float vr[VPT];
-      float mloc = NEG_BIG;
-#pragma unroll
-      for (int k = 0; k < VPT; ++k) {
-        const int j = tid + k * PS_THREADS;
-        vr[k] = (j <= M) ? __ldcg(v_b + j) : -INFINITY;
-        mloc = fmaxf(mloc, vr[k] * LOG2E);
-      }
-      mloc = warp_max(mloc);
-      if (lane == 0) red_s[warp] = mloc;
-      __syncthreads();
-      float mall = red_s[0];
-#pragma unroll
-      for (int w = 1; w < PS_THREADS / 32; ++w) mall = fmaxf(mall, red_s[w]);
-      float sloc = 0.f;
-#pragma unroll
-      for (int k = 0; k < VPT; ++k) {
-        const int j = tid + k * PS_THREADS;
-        if (j <= M) {
-          const float vj = vr[k];
-          sloc += ex2(vj * LOG2E - mall);
-          float v2;
-          if (j < M) {
-            v2 = (vj - shift) * LOG2E;
-            if (p.apply_mask && !p.tgt_mask[(size_t)b * M + j]) v2 = -INFINITY;
-          } else {
-            v2 = (alpha + vj) * LOG2E;  // dustbin column entry of every real row: alpha + v_M
-          }
-          v2_s[j] = v2;
-        }
-      }
-      sloc = warp_sum(sloc);
-      if (lane == 0) red_s[32 + warp] = sloc;
-      __syncthreads();
-      float sall = 0.f;
-#pragma unroll
-      for (int w = 0; w < PS_THREADS / 32; ++w) sall += red_s[32 + w];
-      uN = bc.log_mu_bin - (alpha + (mall + lg2(sall)) * LN2);
-    }
-    if (g == 0 && tid == 0) p.u[(size_t)b * p.ldu + N] = uN;
-    for (int j = M + 1 + tid; j < Mv; j += PS_THREADS) v2_s[j] = -INFINITY;
-    __syncthreads();
-    if (tid == 0) DRG_STAMP(10 + it * 100 + 1);
-
-    if (warp < WS_ROW_WARPS) {
-      // =========================== ROW warps ===========================
-      const float dust2 = v2_s[M];
-      LseAcc uacc = lse_empty();
-      const int nq = nsl * R;
-      const float* v2_lane = v2_s + 4 * lane;
-      for (int q0 = 0; q0 < nq; q0 += R) {
-        mbar_wait_sleep(&full[r_st], r_ph, 200u);
-        if (warp == 0 && lane == 0) DRG_STAMP(10 + it * 100 + 20 + q0 / R);
-#pragma unroll 1
-        for (int r = 0; r < R; ++r) {
-          const int q = q0 + r;
-          if (q % WS_ROW_WARPS != warp) continue;
-          const int i = s_begin * R + q;
-          float u2 = -INFINITY;
-          if (i < N) {
-            const bool row_live = !(p.apply_mask && !p.src_mask[(size_t)b * N + i]);
-            const bool src_ok = !p.apply_mask || p.src_mask[(size_t)b * N + i];
-            float rowlse2, ui;
-            if (fast) {
-              float* row_lane = stage0 + (size_t)r_st * stage_floats + (size_t)r * M + 4 * lane;
-              const float mhat = lse_prev_s[q];
-              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-              if (row_live) {
-                for (int cb = 0; cb < M; cb += 512) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    if (ROWFULL || cb + 4 * lane + 128 * k < M) {
-                      const float4 z = *reinterpret_cast<const float4*>(row_lane + cb + 128 * k);
-                      const float4 vv = *reinterpret_cast<const float4*>(v2_lane + cb + 128 * k);
-                      float4 e;
-                      e.x = ex2(fmaf(z.x, zs, vv.x) - mhat);
-                      e.y = ex2(fmaf(z.y, zs, vv.y) - mhat);
-                      e.z = ex2(fmaf(z.z, zs, vv.z) - mhat);
-                      e.w = ex2(fmaf(z.w, zs, vv.w) - mhat);
-                      *reinterpret_cast<float4*>(row_lane + cb + 128 * k) = e;  // the column pass reads e, not z
-                      a0 += e.x;
-                      a1 += e.y;
-                      a2 += e.z;
-                      a3 += e.w;
-                    }
-                  }
-                }
-              } else {
-                for (int cb = 4 * lane; cb < M; cb += 128) *reinterpret_cast<float4*>(row_lane - 4 * lane + cb) = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-              const float srow = warp_sum((a0 + a1) + (a2 + a3)) + ex2(dust2 - mhat);  // + dustbin column entry
-              rowlse2 = mhat + lg2(srow);
-              ui = bc.norm - rowlse2 * LN2;
-              u2 = src_ok ? 1.f / srow : 0.f;  // the column pass multiplies by w_i = 2^(ref_i + u_i log2e - norm2) = 1 / srow
-            } else {
-            float m_l = NEG_BIG, s_l = 0.f;
-            if (row_live) {
-              const float* row_lane = stage0 + (size_t)r_st * stage_floats + (size_t)r * M + 4 * lane;
-              for (int cb = 0; cb < M; cb += 512) {
-                float xs[16];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (ROWFULL || cb + 4 * lane + 128 * k < M) {
-                    const float4 z = *reinterpret_cast<const float4*>(row_lane + cb + 128 * k);
-                    const float4 vv = *reinterpret_cast<const float4*>(v2_lane + cb + 128 * k);
-                    xs[4 * k + 0] = fmaf(z.x, zs, vv.x);
-                    xs[4 * k + 1] = fmaf(z.y, zs, vv.y);
-                    xs[4 * k + 2] = fmaf(z.z, zs, vv.z);
-                    xs[4 * k + 3] = fmaf(z.w, zs, vv.w);
-                  } else {
-                    xs[4 * k + 0] = xs[4 * k + 1] = xs[4 * k + 2] = xs[4 * k + 3] = -INFINITY;
-                  }
-                }
-                float cmax = NEG_BIG;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) cmax = fmaxf(cmax, xs[k]);
-                if (cmax > m_l) {  // per-lane online rescale (at most once per 16 elements)
-                  s_l *= ex2(m_l - cmax);
-                  m_l = cmax;
-                }
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  a0 += ex2(xs[4 * k + 0] - m_l);
-                  a1 += ex2(xs[4 * k + 1] - m_l);
-                  a2 += ex2(xs[4 * k + 2] - m_l);
-                  a3 += ex2(xs[4 * k + 3] - m_l);
-                }
-                s_l += (a0 + a1) + (a2 + a3);
-              }
-            }
-            const float mrow = warp_max(m_l);
-            float srow = warp_sum(s_l * ex2(m_l - mrow));
-            const float mm = fmaxf(mrow, dust2);
-            srow = srow * ex2(mrow - mm) + ex2(dust2 - mm);  // + dustbin column entry alpha + v_M
-            rowlse2 = mm + lg2(srow);
-            ui = bc.norm - rowlse2 * LN2;
-            u2 = src_ok ? (ui - shift) * LOG2E : -INFINITY;  // column pass sees (S - shift) + u
-            }
-            if (lane == 0) {
-              p.u[(size_t)b * p.ldu + i] = ui;
-              lse_add_value(uacc, ui * LOG2E);
-              if (q < 1024) lse_prev_s[q] = rowlse2;
-            }
-          } else if (fast) {
-            u2 = 0.f;  // padded row slot: weight zero
-          }
-          if (lane == 0) {
-            u2_s[r_st * 16 + r] = u2;
-            mbar_arrive(&u_ready[r_st]);
-            mbar_arrive(&stage_free[r_st]);
-          }
-          __syncwarp();
-        }
-        if (++r_st == nstage) {
-          r_st = 0;
-          r_ph ^= 1u;
-        }
-      }
-      if (warp == 0 && lane == 0) DRG_STAMP(10 + it * 100 + 2);
-      if (lane == 0) upart_s[warp] = make_float2(uacc.m, uacc.s);
-    } else if (warp == WS_ROW_WARPS) {
-      // =========================== producer ===========================
-      // issue everything this iteration's consumers will need plus the prefetch of the next iteration
-      if (lane == 0) {
-        const long long upto = min(total_slabs, (long long)(it + 1) * nsl + nstage);
-        for (; p_next < upto; ++p_next) {
-          mbar_wait_sleep(&stage_free[p_st], p_ph, 200u);
-          issue_slab(p_next);
-          if (++p_st == nstage) {
-            p_st = 0;
-            p_ph ^= 1u;
-          }
-        }
-        upart_s[WS_ROW_WARPS] = make_float2(NEG_BIG, 0.f);
-      }
-    } else {
-      // =========================== COLUMN warps ===========================
-      const int ct = tid - PS_COL_BEGIN;  // 0..511
-      float cm[KQ * 4], cs[KQ * 4];
-#pragma unroll
-      for (int e = 0; e < KQ * 4; ++e) {
-        cm[e] = NEG_BIG;
-        cs[e] = 0.f;
-      }
-      for (int sl = 0; sl < nsl; ++sl) {
-        const int i0 = (s_begin + sl) * R;
-        const int rows = min(R, N - i0);
-        const float* slab = stage0 + (size_t)c_st * stage_floats;
-        mbar_wait_sleep(&u_ready[c_st], c_ph, 500u);
-        if (tid == PS_COL_BEGIN) DRG_STAMP(10 + it * 100 + 40 + sl);
-        float u2r[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) u2r[r] = u2_s[c_st * 16 + r];  // rows beyond `rows` hold -inf (0 in the scaled pass)
-        if (fast) {
-#pragma unroll
-          for (int k = 0; k < KQ; ++k) {
-            const int c = 4 * (ct + PS_COL_NTHREADS * k);
-            if (COLFULL || c < M) {
-#pragma unroll
-              for (int r = 0; r < R; ++r) {
-                if (r < rows) {
-                  const float4 e = *reinterpret_cast<const float4*>(slab + (size_t)r * M + c);
-                  cs[4 * k + 0] = fmaf(e.x, u2r[r], cs[4 * k + 0]);
-                  cs[4 * k + 1] = fmaf(e.y, u2r[r], cs[4 * k + 1]);
-                  cs[4 * k + 2] = fmaf(e.z, u2r[r], cs[4 * k + 2]);
-                  cs[4 * k + 3] = fmaf(e.w, u2r[r], cs[4 * k + 3]);
-                }
-              }
-            }
-          }
-        } else {
-#pragma unroll
-        for (int k = 0; k < KQ; ++k) {
-          const int c = 4 * (ct + PS_COL_NTHREADS * k);
-          if (COLFULL || c < M) {
-            float x[R][4];
-            float mx[4] = {NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG};
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              if (r < rows) {
-                const float4 z = *reinterpret_cast<const float4*>(slab + (size_t)r * M + c);
-                x[r][0] = fmaf(z.x, zs, u2r[r]);
-                x[r][1] = fmaf(z.y, zs, u2r[r]);
-                x[r][2] = fmaf(z.z, zs, u2r[r]);
-                x[r][3] = fmaf(z.w, zs, u2r[r]);
-              } else {
-                x[r][0] = x[r][1] = x[r][2] = x[r][3] = -INFINITY;
-              }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) mx[e] = fmaxf(mx[e], x[r][e]);
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float& am = cm[4 * k + e];
-              float& as = cs[4 * k + e];
-              if (mx[e] > am + 32.f) {  // lazy re-reference: rare after the first slab
-                as *= ex2(am - mx[e]);
-                am = mx[e];
-              }
-              float acc = 0.f;
-#pragma unroll
-              for (int r = 0; r < R; ++r) acc += ex2(x[r][e] - am);
-              as += acc;
-            }
-          }
-        }
-        }
-        __syncwarp();
-        if (tid == PS_COL_BEGIN) DRG_STAMP(10 + it * 100 + 60 + sl);
-        if (lane == 0) mbar_arrive(&stage_free[c_st]);
-        if (++c_st == nstage) {
-          c_st = 0;
-          c_ph ^= 1u;
-        }
-      }
-      if (fast) {
-        // sum_i 2^(x_ij + u_i log2e) = 2^(norm2 - v_j log2e) * sum_i e_ij w_i   (v2_s holds (v_j - shift) log2e)
-#pragma unroll
-        for (int k = 0; k < KQ; ++k) {
-          const int c = 4 * (ct + PS_COL_NTHREADS * k);
-          if (COLFULL || c < M) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float v2j = v2_s[c + e];
-              cm[4 * k + e] = (v2j > -INFINITY) ? (norm2 - v2j - shift * LOG2E) : NEG_BIG;
-              if (!(v2j > -INFINITY)) cs[4 * k + e] = 0.f;
-            }
-          }
-        }
-      }
-      float2* cp = p.colpart + ((size_t)b * G + g) * M;
-#pragma unroll
-      for (int k = 0; k < KQ; ++k) {
-        const int c = 4 * (ct + PS_COL_NTHREADS * k);
-        if (COLFULL || c < M) {
-          *reinterpret_cast<float4*>(cp + c) = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
-          *reinterpret_cast<float4*>(cp + c + 2) = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
-        }
-      }
-    }
-    // ---- dustbin-column partial of this CTA, then wait for every CTA's partials
-    __syncthreads();
-    if (tid == 0) DRG_STAMP(10 + it * 100 + 3);
-    if (tid == 0) {
-      LseAcc a = lse_empty();
-      for (int w = 0; w < WS_ROW_WARPS; ++w) lse_merge(a, upart_s[w].x, upart_s[w].y);
-      p.upart[(size_t)b * G + g] = make_float2(a.m, a.s);
-    }
-    grid_barrier(gcount, (unsigned int)G * (++barriers_done));
-    if (tid == 0) DRG_STAMP(10 + it * 100 + 4);
-
-    // ---- merge: a CTA takes 32 consecutive columns at a time (lane = column: coalesced 256-byte loads), its 32 warps
-    //      split the G partials, and warp 0 combines the 32 per-warp results through shared memory        (skh_col_kernel)
-    {
-      float* v_b = p.v + (size_t)b * p.ldv;
-      if (g == 0 && tid == 0) dv_slots[(it + 1) & 1] = 0u;  // nobody reads or writes that slot during this merge
-      float dv_loc = 0.f;
-      for (int j0 = g * 32; j0 <= M; j0 += G * 32) {
-        const int j = j0 + lane;
-        const bool in_range = j <= M;
-        const bool is_bin = (j == M);
-        const bool col_ok = in_range && (is_bin || !p.apply_mask || p.tgt_mask[(size_t)b * M + j]);
-        float m = NEG_BIG, sum = 0.f;
-        if (col_ok) {
-          const float2* src = is_bin ? (p.upart + (size_t)b * G) : (p.colpart + (size_t)b * G * M + j);
-          const size_t gstride = is_bin ? 1 : (size_t)M;
-          constexpr int NW = PS_THREADS / 32;               // the warps of the CTA split the G partials
-          constexpr int PER_WARP = (NUM_SMS + NW - 1) / NW;
-          float2 q[PER_WARP];
-#pragma unroll
-          for (int k = 0; k < PER_WARP; ++k) {
-            const int gg = warp + NW * k;
-            q[k] = (gg < G) ? __ldcg(src + (size_t)gg * gstride) : make_float2(NEG_BIG, 0.f);
-            m = fmaxf(m, q[k].x);
-          }
-#pragma unroll
-          for (int k = 0; k < PER_WARP; ++k) sum += q[k].y * ex2(q[k].x - m);
-        }
-        comb[warp * 32 + lane] = make_float2(m, sum);
-        __syncthreads();
-        if (warp == 0 && in_range) {
-          float mm = NEG_BIG;
-#pragma unroll
-          for (int w = 0; w < PS_THREADS / 32; ++w) mm = fmaxf(mm, comb[w * 32 + lane].x);
-          float ss = 0.f;
-#pragma unroll
-          for (int w = 0; w < PS_THREADS / 32; ++w) {
-            const float2 c2 = comb[w * 32 + lane];
-            ss += c2.y * ex2(c2.x - mm);
-          }
-          LseAcc a{mm, ss};
-          const float v_old = (it == 0) ? 0.f : __ldcg(v_b + j);
-          float v_new;
-          if (!is_bin) {
-            lse_add_value(a, (alpha + uN) * LOG2E);  // dustbin row entry
-            v_new = bc.norm - lse_value(a) * LN2;
-          } else {
-            lse_add_value(a, uN * LOG2E);  // c_M = alpha + LSE(u[0..N])
-            v_new = bc.log_nu_bin - (alpha + lse_value(a) * LN2);
-          }
-          v_b[j] = v_new;
-          const float d = fabsf(v_new - v_old) * LOG2E;
-          dv_loc = fmaxf(dv_loc, (d == d) ? d : INFINITY);  // NaN counts as unbounded
-        }
-        __syncthreads();
-      }
-      if (warp == 0) {
-        dv_loc = warp_max(dv_loc);
-        if (lane == 0 && dv_loc > 0.f) atomicMax(dv_slots + (it & 1), __float_as_uint(dv_loc));
-      }
-    }
-    if (tid == 0) DRG_STAMP(10 + it * 100 + 5);
-    if (it + 1 < iters) grid_barrier(gcount, (unsigned int)G * (++barriers_done));
-    if (tid == 0) DRG_STAMP(10 + it * 100 + 6);
-  }
-#undef DRG_STAMP
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1551,6 +737,11 @@ constexpr int P2_TPR = 256;            // threads per row group
 constexpr int P2_THREADS = P2_GROUPS * P2_TPR;
 constexpr int P2_GW = P2_TPR / 32;     // warps per row group
 constexpr int P2_MAX_STAGES = 8;
+// candidate-search tail: sampled rows per column, and the histogram of the samples' log2 confidences
+// (SH_PER_OCTAVE bins per octave over [2^-SH_OFFSET, 2^(TK_BINS / SH_PER_OCTAVE - SH_OFFSET)); bin 0 also takes everything below)
+constexpr int SH_ROWS = P2_THREADS / 32;
+constexpr int SH_PER_OCTAVE = 16;
+constexpr float SH_OFFSET = 120.f;
 
 __device__ __forceinline__ float4 ldg_stream4(const float* ptr) {
   float4 r;
@@ -1587,6 +778,18 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     for (size_t i = me; i < p.zero_b_n; i += nthr) p.zero_b[i] = 0ull;
   }
 
+  const bool do_collect = p.col.state != nullptr;
+  if (do_collect) {  // ordered before their first use (the last iteration's merge) by the grid barriers in between
+    for (int q = g * P2_THREADS + tid; q < TK_BINS; q += G * P2_THREADS) {
+      p.col.sample_hist[(size_t)b * TK_BINS + q] = 0u;
+      p.col.cand_hist[(size_t)b * TK_BINS + q] = 0u;
+    }
+    if (g == 0 && tid == 0) {
+      p.col.state[b].n_cand = 0u;
+      p.col.state[b].seg_broken = 0u;
+    }
+  }
+
   const int Mv = (M + 1 + 3) & ~3;
   float* v2_s = reinterpret_cast<float*>(smem_raw);             // [Mv]  column potentials, log2 domain, minus the shift
   float* lse_prev_s = v2_s + Mv;                                // [1024] row log-sum-exp (log2) of the previous iteration
@@ -1594,12 +797,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
   float* red_s = red_part + 2 * P2_GROUPS * 64;                                // [64]
   float2* upart_s = reinterpret_cast<float2*>(red_s + 64);      // [2] (+2 pad)
   float2* comb = upart_s + 4;                                   // [16 warps][32] merge scratch
-  uint64_t* full = reinterpret_cast<uint64_t*>(comb + (P2_THREADS / 32) * 32);  // [P2_MAX_STAGES]
+  unsigned int* tail_s = reinterpret_cast<unsigned int*>(comb + (P2_THREADS / 32) * 32);  // [TK_BINS] candidate-search tail: sample histogram, then the CTA's candidate list
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail_s + TK_BINS);  // [P2_MAX_STAGES]
   float* ring = reinterpret_cast<float*>(full + P2_MAX_STAGES);  // [D][RR * M] TMA landing zone, shared by the two row groups
   float2* xcomb = reinterpret_cast<float2*>(ring);              // [KQ*4][256] column partials of row group 1 (pass is over: ring idle)
   const int D = p.nstage;
   const int stage_floats = RR * M;
-  __shared__ int cnt_s[2];
+  __shared__ int cnt_s[2], cnt2_s[2];
 
 #define DRG_STAMP(slot) do { if (p.dbg_times && g == 0 && b == 0) p.dbg_times[(slot)] = clock64(); } while (0)
   const float* sc_b = p.scores + (size_t)b * N * M;
@@ -1648,6 +852,40 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     if (g == 0 && tid == 0) p.bc_out[b] = bc;
   }
   const float norm2 = bc.norm * LOG2E;
+  // K_b of the candidate search: the mean over the batch of the per-element caps (procrustes.py:61-65), from the masks
+  int Kb = 0;
+  if (do_collect) {
+    float cap_sum = 0.f;
+    int my_cap = 0;
+    for (int bb = 0; bb < (int)gridDim.y; ++bb) {
+      int nsrc = N, ntgt = M;
+      if (!p.col.padded_lengths) {
+        if (bb == b) {
+          nsrc = cnt_s[0];
+          ntgt = cnt_s[1];
+        } else {
+          __syncthreads();
+          if (tid == 0) cnt2_s[0] = cnt2_s[1] = 0;
+          __syncthreads();
+          int cs = count_mask_bytes(p.src_mask + (size_t)bb * N, N, tid, P2_THREADS);
+          int ctg = count_mask_bytes(p.tgt_mask + (size_t)bb * M, M, tid, P2_THREADS);
+          cs = __reduce_add_sync(0xffffffffu, cs);
+          ctg = __reduce_add_sync(0xffffffffu, ctg);
+          if (lane == 0) {
+            if (cs) atomicAdd(&cnt2_s[0], cs);
+            if (ctg) atomicAdd(&cnt2_s[1], ctg);
+          }
+          __syncthreads();
+          nsrc = cnt2_s[0];
+          ntgt = cnt2_s[1];
+        }
+      }
+      const int cap = (int)((float)max(nsrc, ntgt) * p.col.sample_rate);  // (max(len) * sample_rate).int(), fp32 product
+      cap_sum += (float)cap;
+      if (bb == b) my_cap = cap;
+    }
+    Kb = min(min((int)(cap_sum / (float)gridDim.y), my_cap), p.col.K_max);
+  }
   unsigned int barriers_done = 0;
   const uint8_t* smask = p.src_mask + (size_t)b * N;
   // row slots: log2-domain row log-sum-exp of the previous iteration; >= 1e30 marks a row without real entries
@@ -1658,14 +896,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
   for (int it = 0; it < iters; ++it) {
     if (tid == 0) DRG_STAMP(10 + it * 100 + 0);
     bool fast = false;
-    if (it >= 1 && alpha >= -20.f && !(p.dbg & 8)) {
+    if (it >= 1 && alpha >= -20.f) {
       const float dv = __uint_as_float(ld_acquire_u32(dv_slots + ((it - 1) & 1)));
       fast = dv <= 50.f;
     }
     // First iteration: same arithmetic, but the row reference is this pass's exact row maximum (one more reduction per
     // mini-slab).  Flushing e_ij / srow_i < 2^-126 cannot hurt the column sums there: with v = 0 the dustbin-row entry of
     // every column is ~2^norm2, 2^126 / N times larger than anything that can be flushed.
-    const bool semi = (it == 0) && alpha >= -20.f && !(p.dbg & 8);
+    const bool semi = (it == 0) && alpha >= -20.f;
     const bool scaled = fast || semi;
     if (p.dbg_times && g == 0 && b == 0 && tid == 0) p.dbg_times[400 + it] = fast ? 1 : semi ? 2 : 0;
 
@@ -1864,7 +1102,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           w[r] = dead ? 0.f : 1.f / srow;               // = 2^(ref_i + u_i log2e - norm2)
           if (ct == 0 && s * RR + r < nrows) {
             const float rowlse2 = dead ? dust2 : mh[r] + lg2(srow);  // a masked row holds the dustbin entry only
-            const float ui = bc.norm - rowlse2 * LN2;
+            const float ui = fmaf(-rowlse2, LN2, bc.norm);  // (explicit: the candidate-search tail recomputes it bit for bit)
             p.u[(size_t)b * p.ldu + row0 + s * RR + r] = ui;
             lse_add_value(uacc, ui * LOG2E);
             lse_prev_s[s * RR + r] = dead ? 1.0e30f : rowlse2;
@@ -1947,7 +1185,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           const float tot = ((a.x + a.y) + (a.z + a.w)) + ((c4.x + c4.y) + (c4.z + c4.w));
           const float srow = tot + ex2(dust2 - mrow[r]);
           const float rowlse2 = mrow[r] + lg2(srow);
-          const float ui = bc.norm - rowlse2 * LN2;
+          const float ui = fmaf(-rowlse2, LN2, bc.norm);  // (explicit: the candidate-search tail recomputes it bit for bit)
           u2[r] = live[r] ? (ui - shift) * LOG2E : -INFINITY;  // column pass sees (S - shift) + u
           const int i = row0 + s * RR + r;
           if (ct == 0 && i < row1) {
@@ -2042,7 +1280,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
         }
       }
       group_barrier(0);  // xcomb (aliased on the ring) has been read
-      if (tid == 0 && it + 1 < iters)
+      if (tid == 0 && (it + 1 < iters || do_collect))
         for (int s = 0; s < D && s < ns; ++s) issue_slab_to(((it + 1) * ns + s) % D, s);  // the scores do not change: prefetch across the barriers
     }
     if (tid == 0) {
@@ -2059,6 +1297,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
       float* v_b = p.v + (size_t)b * p.ldv;
       if (g == 0 && tid == 0) dv_slots[(it + 1) & 1] = 0u;
       float dv_loc = 0.f;
+      const bool sampling = do_collect && it + 1 == iters;  // the final v of this CTA's columns is known right here
+      if (sampling)
+        for (int q = tid; q < TK_BINS; q += P2_THREADS) tail_s[q] = 0u;
       for (int j0 = g * 32; j0 <= M; j0 += G * 32) {
         const int j = j0 + lane;
         const bool in_range = j <= M;
@@ -2105,8 +1346,36 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           v_b[j] = v_new;
           const float d = fabsf(v_new - v_old) * LOG2E;
           dv_loc = fmaxf(dv_loc, (d == d) ? d : INFINITY);
+          if (sampling) red_s[lane] = (col_ok && !is_bin) ? v_new : -INFINITY;
+        } else if (sampling && warp == 0) {
+          red_s[lane] = -INFINITY;
         }
         __syncthreads();
+        if (sampling) {
+          // SH_ROWS sampled rows per column (warp w takes the w-th), their log2 confidences into the CTA's histogram.
+          // A sample is exp(Z + u + v - norm) at its FINAL potentials: u was final before the grid barrier above.
+          const float vn = red_s[lane];
+          const int jc = j0 + lane;
+          int i = warp;
+          if (N > SH_ROWS) i = (int)(((unsigned long long)hash_u32((unsigned int)(jc * SH_ROWS + warp) + 0x9e3779b9u * (unsigned int)(b + 1)) *
+                                      (unsigned long long)N) >> 32);
+          if (vn > -INFINITY && i < N && !(p.apply_mask && !smask[i])) {
+            const float z = __ldcg(sc_b + (size_t)i * M + jc);
+            const float ui = __ldcg(p.u + (size_t)b * p.ldu + i);
+            const float la2 = ((((z - shift) + ui) + vn) - bc.norm) * LOG2E;
+            if (la2 > -INFINITY) {  // (false for NaN)
+              const float fb = fminf(fmaxf((la2 + SH_OFFSET) * (float)SH_PER_OCTAVE, 0.f), (float)(TK_BINS - 1));
+              atomicAdd(&tail_s[(int)fb], 1u);
+            }
+          }
+        }
+      }
+      if (sampling) {
+        __syncthreads();
+        for (int q = tid; q < TK_BINS; q += P2_THREADS) {
+          const unsigned int c = tail_s[q];
+          if (c) atomicAdd(&p.col.sample_hist[(size_t)b * TK_BINS + q], c);
+        }
       }
       if (warp == 0) {
         dv_loc = warp_max(dv_loc);
@@ -2114,8 +1383,190 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
       }
     }
     if (tid == 0) DRG_STAMP(10 + it * 100 + 5);
-    if (it + 1 < iters) grid_barrier_ra(gcount, (unsigned int)G * (++barriers_done));
+    if (it + 1 < iters || do_collect) grid_barrier_ra(gcount, (unsigned int)G * (++barriers_done));
     if (tid == 0) DRG_STAMP(10 + it * 100 + 6);
+  }
+  if (do_collect) {
+    // =====================================================================================================
+    // Candidate search of SoftProcrustes (procrustes.py:61-76) as a last pass over the L2-resident slab:
+    //   bound   the sampled log2 confidences (SH_ROWS per column, drawn by the CTAs that merged the columns) are in a
+    //           global histogram; every CTA walks it and takes the lower edge of the bin holding the t-th largest
+    //           sample, t ~ twice the expected number of top-K_b entries in the sample (+16) -- a value Lv that
+    //           ~(2 K_b + N M / (SH_ROWS M / 16)) entries of the matrix reach, whatever their distribution;
+    //   pass    1 FFMA + 1 compare per element against thr_i = log2(Lv) + (row log-sum-exp of the last iteration);
+    //           the few that pass are evaluated exactly (the association of the final pass, so that the weights equal
+    //           the confidences a stored matrix would hold) and appended with conf >= Lv;
+    //   the candidates' histogram (first level of the select in procr_pose_kernel) is filled as they are flushed.
+    // =====================================================================================================
+    __shared__ int tail_i[4];     // Kb, crossing bin, top non-empty bin
+    __shared__ float tail_f[2];   // Lv
+    __shared__ unsigned int cand_n_s, cand_base_s;
+    const float* v_b = p.v + (size_t)b * p.ldv;
+    if (tid == 0) DRG_STAMP(700);
+    // this thread's columns: the final v (raw, for the exact expression) and its log2-domain form (for the filter)
+    float vraw[KQ][4], v2c[KQ][4];
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+      const int c = 4 * (ct + P2_TPR * k);
+      float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned char mm[4] = {1, 1, 1, 1};
+      const bool in = FULL || c < M;
+      if (in) {
+        vq = __ldcg(reinterpret_cast<const float4*>(v_b + c));
+        if (p.apply_mask) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mm[e] = p.tgt_mask[(size_t)b * M + c + e];
+        }
+      }
+      const float vr[4] = {vq.x, vq.y, vq.z, vq.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        vraw[k][e] = vr[e];
+        v2c[k][e] = (in && mm[e]) ? (vr[e] - shift) * LOG2E : -INFINITY;
+      }
+    }
+    for (int q = tid; q < TK_BINS; q += P2_THREADS) tail_s[q] = __ldcg(p.col.sample_hist + (size_t)b * TK_BINS + q);
+    __syncthreads();
+    if (warp == 0) {
+      long long target = Kb;  // N <= SH_ROWS: the sample is the whole matrix
+      if (N > SH_ROWS) target = (long long)(2.0 * (double)Kb * (double)SH_ROWS / (double)N + 16.0);
+      int bin = 0;
+      unsigned int cum, hsel;
+      if (target >= 1) warp_walk_hist(tail_s, (unsigned int)min(target, 0x7fffffffll), bin, cum, hsel);
+      // highest non-empty bin (range of the candidate histogram)
+      int top = 0;
+      for (int q = TK_BINS - 1 - lane; q >= 0; q -= 32)
+        if (tail_s[q]) {
+          top = q;
+          break;
+        }
+      top = __reduce_max_sync(0xffffffffu, top);
+      if (lane == 0) {
+        tail_i[0] = Kb;
+        tail_i[1] = bin;
+        tail_i[2] = top;
+        tail_f[0] = bin > 0 ? exp2f((float)bin / (float)SH_PER_OCTAVE - SH_OFFSET) : 0.f;
+      }
+    }
+    __syncthreads();
+    const int bin = tail_i[1];
+    const float Lv = tail_f[0];
+    const float thr2 = bin > 0 ? ((float)bin / (float)SH_PER_OCTAVE - SH_OFFSET) - 1.0e-3f : -INFINITY;  // pre-filter margin
+    const unsigned int kmin = float_to_ordered(Lv);
+    const unsigned int smax = float_to_ordered(exp2f((float)(tail_i[2] + 1) / (float)SH_PER_OCTAVE - SH_OFFSET));
+    const int hist_sh = cand_hist_shift(kmin, smax, bin > 0);
+    if (g == 0 && tid == 0) {
+      ProcrState* sp = p.col.state + b;  // n_cand is being accumulated by the CTAs: field-wise
+      sp->Kb = Kb;
+      sp->lower_key = (unsigned long long)kmin << 32;
+      sp->T = 0ull;
+      sp->hist_kmin = kmin;
+      sp->hist_sh = hist_sh;
+      sp->sel_count = 0u;
+      sp->pad_ = 0u;
+      sp->seg_G = G;
+    }
+    if (tid == 0) cand_n_s = 0u;
+    if (tid == 0) DRG_STAMP(701);
+    __syncthreads();  // tail_s becomes the candidate list: keys [0, CL_CAP), flat indices [CL_CAP, 2 CL_CAP)
+    constexpr int CL_CAP = TK_BINS / 2;
+    unsigned int* gkey = p.col.cand_key + (size_t)b * N * M;
+    unsigned int* gidx = p.col.cand_idx + (size_t)b * N * M;
+    int stg = (iters * ns + rg) % D;
+    uint32_t ph = (uint32_t)(((iters * ns + rg) / D) & 1);
+    if (Kb > 0) {
+      for (int s = rg; s < ns; s += P2_GROUPS) {
+        const float* slab = ring + (size_t)stg * stage_floats;
+        mbar_wait(&full[stg], ph);
+        float4 z[RR][KQ];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+#pragma unroll
+          for (int k = 0; k < KQ; ++k) {
+            const int c = 4 * (ct + P2_TPR * k);
+            if (FULL || c < M) z[r][k] = *reinterpret_cast<const float4*>(slab + (size_t)r * M + c);
+          }
+        }
+        group_barrier(rg);
+        if (ct == 0 && s + D < ns) issue_slab_to(stg, s + D);  // every thread of the group has its registers: re-arm the stage
+        float tr[RR];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+          const float rl = lse_prev_s[s * RR + r];          // >= 1e30: masked row / slot past the CTA's rows (stale data)
+          tr[r] = rl > 1.0e29f ? INFINITY : thr2 + rl;     // conf_ij = 2^(x_ij - rowlse_i)
+        }
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (ct + P2_TPR * k);
+          if (FULL || c < M) {
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+              const bool hit = (fmaf(z[r][k].x, zs, v2c[k][0]) >= tr[r]) | (fmaf(z[r][k].y, zs, v2c[k][1]) >= tr[r]) |
+                               (fmaf(z[r][k].z, zs, v2c[k][2]) >= tr[r]) | (fmaf(z[r][k].w, zs, v2c[k][3]) >= tr[r]);
+              if (hit) {  // rare (~0.1 % of the quads): the exact expression of the final pass, then conf >= Lv; no global load
+                const int i = row0 + s * RR + r;
+                const float ui = fmaf(-lse_prev_s[s * RR + r], LN2, bc.norm);  // = p.u[i], bit for bit (see the passes)
+                const float zq[4] = {z[r][k].x, z[r][k].y, z[r][k].z, z[r][k].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!(v2c[k][e] > -INFINITY)) continue;  // masked column
+                  const float cf = ex2(((((zq[e] - shift) + ui) + vraw[k][e]) - bc.norm) * LOG2E);
+                  if (cf >= Lv) {
+                    const unsigned int key = float_to_ordered(cf);
+                    const unsigned int fi = (unsigned int)((size_t)i * M + c + e);
+                    const unsigned int pos = atomicAdd(&cand_n_s, 1u);
+                    if (pos < (unsigned int)CL_CAP) {
+                      tail_s[pos] = key;
+                      tail_s[CL_CAP + pos] = fi;
+                    } else {  // the CTA's list is full (dense candidates: degenerate inputs): straight to the global list
+                      p.col.state[b].seg_broken = 1u;
+                      const unsigned int gp = atomicAdd(&p.col.state[b].n_cand, 1u);
+                      gkey[gp] = key;
+                      gidx[gp] = fi;
+                      atomicAdd(&p.col.cand_hist[(size_t)b * TK_BINS + cand_bin(key, kmin, hist_sh)], 1u);
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+        stg += P2_GROUPS;
+        while (stg >= D) {
+          stg -= D;
+          ph ^= 1u;
+        }
+      }
+    } else {
+      // nothing to select: drain the prefetched slabs so that no bulk copy is in flight when the CTA exits
+      for (int s = rg; s < ns && s < D; s += P2_GROUPS) {
+        mbar_wait(&full[stg], ph);
+        stg += P2_GROUPS;
+        while (stg >= D) {
+          stg -= D;
+          ph ^= 1u;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) DRG_STAMP(702);
+    const unsigned int cnt = min(cand_n_s, (unsigned int)CL_CAP);
+    if (cnt == 0u && tid == 0) p.col.cand_seg[(size_t)b * NUM_SMS + g] = make_uint2(0u, 0u);
+    if (cnt) {
+      if (tid == 0) {
+        cand_base_s = atomicAdd(&p.col.state[b].n_cand, cnt);
+        p.col.cand_seg[(size_t)b * NUM_SMS + g] = make_uint2(cand_base_s, cnt);  // this CTA's rows, one contiguous segment
+      }
+      __syncthreads();
+      const unsigned int base = cand_base_s;
+      for (unsigned int e = tid; e < cnt; e += P2_THREADS) {
+        const unsigned int k32 = tail_s[e];
+        gkey[base + e] = k32;
+        gidx[base + e] = tail_s[CL_CAP + e];
+        atomicAdd(&p.col.cand_hist[(size_t)b * TK_BINS + cand_bin(k32, kmin, hist_sh)], 1u);
+      }
+    }
+    if (tid == 0) DRG_STAMP(703);
   }
 #undef DRG_STAMP
 }
@@ -2536,21 +1987,10 @@ __global__ void __launch_bounds__(256) skh_final_kernel(const SkhFinalParams p) 
 // ---------------------------------------------------------------------------------------
 constexpr int FT_THREADS = 256;
 constexpr int FT_CTAS_PER_SM = 4;  // 256 threads x <= 64 registers
-// Rows per CTA.  Measured at 4096^2 (tools/perf_final.py, DRG_FT_ROWS): 8 and 16 rows 49 us, 24 rows 54 us, 28 rows (one
+// Rows per CTA.  Measured at 4096^2 (round-1 tuning build): 8 and 16 rows 49 us, 24 rows 54 us, 28 rows (one
 // full wave of 588 resident CTAs) 52 us, 32+ rows 65 us -- many small CTAs balance better than one exact wave.  Every
 // thread requests the next row's scores / x_t before it works on the current one.
-static int final_tile_rows(int B, int N, int M) {
-  static int forced = -1;  // tuning only: DRG_FT_ROWS
-  if (forced < 0) {
-    const char* e = getenv("DRG_FT_ROWS");
-    forced = e ? atoi(e) : 0;
-  }
-  if (forced > 0) return forced;
-  (void)B;
-  (void)N;
-  (void)M;
-  return 16;
-}
+constexpr int FT_ROWS = 16;
 
 template <bool MASKED, bool TRACK, bool WANT_MIN>
 __device__ __forceinline__ void final_tile_body(const SkhFinalParams& p) {
@@ -2804,29 +2244,11 @@ struct SkhPlan2 {
   bool ok;
 };
 
-static int skh_stage_floats_target() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DRG_SKH_STAGE_FLOATS");
-    v = e ? atoi(e) : 16384;
-    if (v != 4096 && v != 8192 && v != 16384) v = 16384;
-  }
-  return v;
-}
-static float skh_keep_fraction() {
-  static float v = -2.f;
-  if (v < -1.5f) {
-    const char* e = getenv("DRG_SKH_L2_KEEP");
-    v = e ? (float)atof(e) : -1.f;  // < 0: no cache hints
-  }
-  return v;
-}
-
 static SkhPlan2 make_plan2(int B, int N, int M) {
   SkhPlan2 pl{};
   pl.ok = false;
   if (M < 4 || M > SKH_MAX_M || N < 1 || (M % 4) != 0) return pl;
-  const int target = skh_stage_floats_target();
+  const int target = SKH_STAGE_FLOATS;
   int R = 16;
   while (R > 1 && (long long)R * M > target) R >>= 1;
   pl.R = R;
@@ -2872,13 +2294,8 @@ static cudaError_t launch_iter2(const SkhParams& p, const SkhPlan2& pl, cudaStre
   if (pl.R == r && pl.KQ == kq && pl.NCH == nch && pl.full == fl) return launch_iter2_t<r, kq, nch, fl>(p, pl, st);
   // power-of-two widths: no bounds checks
   DRG_SKH_CASE(8, 1, 8, true)   // M = 2048, 64 KB stages
-  DRG_SKH_CASE(4, 1, 4, true)   // M = 2048, 32 KB stages
-  DRG_SKH_CASE(2, 1, 2, true)   // M = 2048, 16 KB stages
   DRG_SKH_CASE(4, 2, 8, true)   // M = 4096, 64 KB stages
-  DRG_SKH_CASE(2, 2, 4, true)   // M = 4096, 32 KB stages
-  DRG_SKH_CASE(1, 2, 2, true)   // M = 4096, 16 KB stages
   DRG_SKH_CASE(2, 4, 8, true)   // M = 8192, 64 KB stages
-  DRG_SKH_CASE(1, 4, 4, true)   // M = 8192, 32 KB stages
   DRG_SKH_CASE(1, 8, 8, true)   // M = 16384
   // everything else: guarded
   DRG_SKH_CASE(16, 1, 8, false)
@@ -2893,119 +2310,6 @@ static cudaError_t launch_iter2(const SkhParams& p, const SkhPlan2& pl, cudaStre
   DRG_SKH_CASE(1, 4, 8, false)
   DRG_SKH_CASE(1, 8, 8, false)
 #undef DRG_SKH_CASE
-  return cudaErrorInvalidConfiguration;
-}
-
-struct SkhPlanWS {
-  int R, KQ, nstage, G;
-  size_t smem;
-  bool ok;
-};
-
-static int skh_ws_rows() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DRG_SKH_WS_ROWS");
-    v = e ? atoi(e) : 2;
-    if (v != 1 && v != 2 && v != 4 && v != 8) v = 2;
-  }
-  return v;
-}
-static int skh_ws_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DRG_SKH_WS");
-    v = e ? atoi(e) : 1;
-  }
-  return v;
-}
-
-static SkhPlanWS make_plan_ws(int B, int N, int M) {
-  SkhPlanWS pl{};
-  pl.ok = false;
-  if (!skh_ws_enabled() || M < 4 || M > 4096 || N < 1 || (M % 4) != 0) return pl;
-  int R = skh_ws_rows();
-  while (R > 1 && (size_t)R * M * 4 * 2 > SKH_SMEM_LIMIT - 32 * 1024) R >>= 1;
-  // small matrices: wider slabs keep the per-slab synchronisation negligible
-  while (R < 8 && (long long)R * M < 8192) R <<= 1;
-  pl.R = R;
-  pl.KQ = (M <= 2048) ? 1 : 2;
-  const size_t Mv = (size_t)((M + 1 + 3) & ~3);
-  const size_t stage_bytes = (size_t)R * M * 4;
-  const size_t fixed = Mv * 4 + WS_MAX_STAGES * 16 * 4 + 64 * 4 + 16 * 8 + 3 * WS_MAX_STAGES * 8 + 128;  // dynamic, besides the ring
-  const size_t static_smem = 8192 + 4096 + 512;  // __shared__ arrays of skh_persist_kernel: merge scratch, row references, counters
-  int nstage = (int)((SKH_SMEM_LIMIT - fixed - static_smem) / stage_bytes);
-  if (nstage > WS_MAX_STAGES) nstage = WS_MAX_STAGES;
-  if (nstage < 2) return pl;
-  pl.nstage = nstage;
-  pl.smem = fixed + (size_t)nstage * stage_bytes;
-  const int nslab = (N + R - 1) / R;
-  int G = NUM_SMS / (B < 1 ? 1 : B);
-  if (G < 1) G = 1;
-  if (G > nslab) G = nslab;
-  pl.G = G;
-  pl.ok = true;
-  return pl;
-}
-
-template <int R, int KQ, bool ROWFULL, bool COLFULL>
-static cudaError_t launch_iter_ws_t(const SkhParams& p, const SkhPlanWS& pl, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(skh_iter_ws_kernel<R, KQ, ROWFULL, COLFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)pl.smem);
-  if (e != cudaSuccess) return e;
-  skh_iter_ws_kernel<R, KQ, ROWFULL, COLFULL><<<dim3(pl.G, p.B), WS_THREADS, pl.smem, st>>>(p);
-  return cudaGetLastError();
-}
-
-static cudaError_t launch_iter_ws(const SkhParams& p, const SkhPlanWS& pl, cudaStream_t st) {
-  const bool rowfull = (p.M % 1024) == 0;
-  const bool colfull = p.M == 2048 * pl.KQ;
-#define DRG_WS_CASE(r, kq)                                                                 \
-  if (pl.R == r && pl.KQ == kq) {                                                          \
-    if (rowfull && colfull) return launch_iter_ws_t<r, kq, true, true>(p, pl, st);         \
-    if (rowfull) return launch_iter_ws_t<r, kq, true, false>(p, pl, st);                   \
-    return launch_iter_ws_t<r, kq, false, false>(p, pl, st);                               \
-  }
-  DRG_WS_CASE(1, 1) DRG_WS_CASE(2, 1) DRG_WS_CASE(4, 1) DRG_WS_CASE(8, 1)
-  DRG_WS_CASE(1, 2) DRG_WS_CASE(2, 2) DRG_WS_CASE(4, 2) DRG_WS_CASE(8, 2)
-#undef DRG_WS_CASE
-  return cudaErrorInvalidConfiguration;
-}
-
-static int skh_persist_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DRG_SKH_PERSIST");
-    v = e ? atoi(e) : 2;
-  }
-  return v;
-}
-
-template <int R, int KQ, bool ROWFULL, bool COLFULL>
-static cudaError_t launch_persist_t(const SkhParams& p, const SkhPlanWS& pl, int iters, unsigned int* gsync, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(skh_persist_kernel<R, KQ, ROWFULL, COLFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)pl.smem);
-  if (e != cudaSuccess) return e;
-  SkhParams pp = p;
-  void* args[] = {(void*)&pp, (void*)&iters, (void*)&gsync};
-  return cudaLaunchCooperativeKernel((const void*)skh_persist_kernel<R, KQ, ROWFULL, COLFULL>, dim3(pl.G, p.B), dim3(PS_THREADS), args,
-                                     pl.smem, st);
-}
-
-static cudaError_t launch_persist(const SkhParams& p, const SkhPlanWS& pl, int iters, unsigned int* gsync, cudaStream_t st) {
-  const bool rowfull = (p.M % 1024) == 0;
-  const int kq = (p.M <= 1024) ? 1 : (p.M <= 2048) ? 2 : 4;  // column quads per column thread (256 column threads)
-  const bool colfull = p.M == 1024 * kq;
-#define DRG_PS_CASE(r, q)                                                                            \
-  if (pl.R == r && kq == q) {                                                                        \
-    if (rowfull && colfull) return launch_persist_t<r, q, true, true>(p, pl, iters, gsync, st);      \
-    if (rowfull) return launch_persist_t<r, q, true, false>(p, pl, iters, gsync, st);                \
-    return launch_persist_t<r, q, false, false>(p, pl, iters, gsync, st);                            \
-  }
-  DRG_PS_CASE(1, 1) DRG_PS_CASE(2, 1) DRG_PS_CASE(4, 1) DRG_PS_CASE(8, 1)
-  DRG_PS_CASE(1, 2) DRG_PS_CASE(2, 2) DRG_PS_CASE(4, 2) DRG_PS_CASE(8, 2)
-  DRG_PS_CASE(1, 4) DRG_PS_CASE(2, 4) DRG_PS_CASE(4, 4)
-#undef DRG_PS_CASE
   return cudaErrorInvalidConfiguration;
 }
 
@@ -3032,7 +2336,7 @@ static SkhPlanP2 make_plan_p2(int B, int N, int M) {
   pl.G = G;
   if ((N + G - 1) / G > 1024) return pl;  // row references of a CTA live in a 1024-entry shared array
   const size_t Mv = (size_t)((M + 1 + 3) & ~3);
-  const size_t fixed = (Mv + 1024 + 2 * P2_GROUPS * 64 + 64 + 8 + (P2_THREADS / 32) * 32 * 2) * 4 + P2_MAX_STAGES * 8;
+  const size_t fixed = (Mv + 1024 + 2 * P2_GROUPS * 64 + 64 + 8 + (P2_THREADS / 32) * 32 * 2 + TK_BINS) * 4 + P2_MAX_STAGES * 8;
   const size_t stage_bytes = (size_t)pl.RR * M * 4;
   const size_t xcomb_bytes = (size_t)(P2_GROUPS - 1) * P2_TPR * pl.KQ * 4 * 8;
   int nstage = (int)((SKH_SMEM_LIMIT - 256 - fixed) / stage_bytes);
@@ -3084,13 +2388,12 @@ extern "C" size_t drg_sinkhorn_workspace_bytes(int B, int N, int M) {
   return carve(nullptr, B, N, M, skh_max_g(B)).total;
 }
 
-static long long* g_skh_times = nullptr;  // tuning only (DRG_SKH_TIMES=1)
 
 enum SkhRun { SKH_RUN_ALL = 0, SKH_SHARD_BEGIN, SKH_SHARD_LOCAL, SKH_SHARD_UPDATE, SKH_SHARD_FINAL, SKH_SHARD_LOCAL_X };
 
 static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature, void* workspace, size_t workspace_bytes,
                         void* stream, SkhRun run = SKH_RUN_ALL, const int* global_counts = nullptr, float2* shard_partial = nullptr,
-                        const P2PView* xview = nullptr) {
+                        const P2PView* xview = nullptr, const SkhCollect* collect = nullptr, bool* collected = nullptr) {
   cudaStream_t st = (cudaStream_t)stream;
   const int B = a->B, N = a->N, M = a->M;
   SkhPlan pl = make_plan(B, N, M);
@@ -3106,8 +2409,6 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   const bool vec = (M % 4 == 0) && aligned16(a->scores);
   SkhPlan2 pl2 = vec ? make_plan2(B, N, M) : SkhPlan2{};
   const bool use2 = vec && pl2.ok;
-  SkhPlanWS plw = vec ? make_plan_ws(B, N, M) : SkhPlanWS{};
-  const bool usew = vec && plw.ok;
   SkhWorkspace w = carve(workspace, B, N, M, skh_max_g(B));
   if (workspace == nullptr || workspace_bytes < w.total) {
     set_error("sinkhorn: workspace too small (%zu < %zu)", workspace_bytes, w.total);
@@ -3117,10 +2418,11 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     set_error("sinkhorn: workspace must be 256-byte aligned");
     return DRG_ERR_INVALID;
   }
-  const bool persist = run == SKH_RUN_ALL && usew && !dual && a->iters >= 1 && skh_persist_enabled() && (long long)plw.G * B <= NUM_SMS;
-  // DRG_SKH_PERSIST: 0 = one launch per iteration, 1 = shared-memory slab kernel, 2 (default) = register-slab kernel
-  SkhPlanP2 plp = (persist && skh_persist_enabled() >= 2) ? make_plan_p2(B, N, M) : SkhPlanP2{};
-  const bool persist2 = persist && plp.ok;
+  // all iterations in one cooperative launch (register-slab kernel) whenever the shape allows it; otherwise one launch
+  // per iteration (skh_iter2_kernel for 16-byte aligned rows, skh_iter_kernel for the rest) + the column merge
+  SkhPlanP2 plp = (run == SKH_RUN_ALL && vec && !dual && a->iters >= 1) ? make_plan_p2(B, N, M) : SkhPlanP2{};
+  const bool persist2 = plp.ok;
+  const bool persist = persist2;
   if (run == SKH_SHARD_BEGIN) {
     skh_shard_begin_kernel<<<B, 1024, 0, st>>>(global_counts, w.bc, w.v, w.u, pitch4(N + 1), pitch4(M + 1));
     DRG_LAUNCH_CHECK();
@@ -3148,38 +2450,14 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   p.B = B;
   p.N = N;
   p.M = M;
-  p.G = persist2 ? plp.G : usew ? plw.G : use2 ? pl2.G : pl.G;
+  p.G = persist2 ? plp.G : use2 ? pl2.G : pl.G;
   p.ldu = pitch4(N + 1);
   p.ldv = pitch4(M + 1);
   p.apply_mask = a->apply_mask;
   p.dual = dual ? 1 : 0;
   p.zscale2 = dual ? LOG2E / temperature : LOG2E;
-  p.nstage = usew ? plw.nstage : use2 ? pl2.nstage : pl.nstage;
-  p.keep_slabs = -1;
-  p.dbg_times = nullptr;
-  {
-    static int want = -1;
-    if (want < 0) want = getenv("DRG_SKH_TIMES") ? 1 : 0;
-    if (want) {
-      if (!g_skh_times) {
-        cudaMalloc(&g_skh_times, 512 * sizeof(long long));
-        cudaMemset(g_skh_times, 0, 512 * sizeof(long long));
-      }
-      p.dbg_times = g_skh_times;
-    }
-  }
-  {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("DRG_SKH_DBG");
-      dbg = e ? atoi(e) : 0;
-    }
-    p.dbg = dbg;
-  }
-  if (use2 && skh_keep_fraction() >= 0.f) {
-    const int nslab = (N + pl2.R - 1) / pl2.R;
-    p.keep_slabs = (int)(skh_keep_fraction() * (float)((nslab + pl2.G - 1) / pl2.G) + 0.5f);
-  }
+  p.nstage = use2 ? pl2.nstage : pl.nstage;
+  p.dbg_times = g_tuning_stamps;
 
   if (run == SKH_SHARD_UPDATE) {
     skh_shard_update_kernel<<<dim3((M + 1 + 255) / 256, B), 256, 0, st>>>(p, shard_partial);
@@ -3197,15 +2475,19 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
       p.zero_b_n = (size_t)B * M;
       bests_cleared = true;
     }
+    if (collect && (long long)N * M < (1ll << 32)) {
+      p.col = *collect;
+      if (collected) *collected = true;
+    }
     DRG_CUDA(cudaMemsetAsync(w.gsync, 0, sizeof(unsigned int) * B * 3, st));
     cudaError_t e;
     {
-      ProfScope prof_scope(PROF_SKH_ITER, st);
-      e = persist2 ? launch_persist2(p, plp, iters, w.gsync, st) : launch_persist(p, plw, iters, w.gsync, st);
+      // (slot "skh_col" is free in this mode: it times the launches that carry the candidate-search tail)
+      ProfScope prof_scope(p.col.state ? PROF_SKH_COL : PROF_SKH_ITER, st);
+      e = launch_persist2(p, plp, iters, w.gsync, st);
     }
     if (e != cudaSuccess) {
-      set_error("persistent sinkhorn launch failed: %s (smem=%zu, grid %d x %d)", cudaGetErrorString(e), persist2 ? plp.smem : plw.smem,
-                persist2 ? plp.G : plw.G, B);
+      set_error("persistent sinkhorn launch failed: %s (smem=%zu, grid %d x %d)", cudaGetErrorString(e), plp.smem, plp.G, B);
       return DRG_ERR_CUDA;
     }
     count_launch();
@@ -3214,7 +2496,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
     cudaError_t e;
     {
       ProfScope prof_scope(PROF_SKH_ITER, st);
-      e = usew ? launch_iter_ws(p, plw, st) : use2 ? launch_iter2(p, pl2, st) : launch_iter(p, pl, st);
+      e = use2 ? launch_iter2(p, pl2, st) : launch_iter(p, pl, st);
     }
     if (e != cudaSuccess) {
       set_error("sinkhorn iteration launch failed: %s (smem=%zu)", cudaGetErrorString(e), use2 ? pl2.smem : pl.smem);
@@ -3280,6 +2562,11 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
       }
       bool fvec = vec && !dual && aligned16(a->out) && (!f.x_t || aligned16(f.x_t)) && (!f.noise || aligned16(f.noise)) &&
                   (!f.conf || aligned16(f.conf)) && (((uintptr_t)a->tgt_mask & 3u) == 0);
+      if (f.rowbest && !fvec) {
+        set_error("sinkhorn: rowbest/colbest need 16-byte aligned out / x_t / noise / conf and a 4-byte aligned tgt_mask "
+                  "(only the tiled final pass tracks the bests)");
+        return DRG_ERR_UNSUPPORTED;
+      }
       if (fvec)
         {
           if (f.rowbest && !bests_cleared) {
@@ -3287,7 +2574,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
             DRG_CUDA(cudaMemsetAsync(f.colbest, 0, sizeof(unsigned long long) * (size_t)B * M, st));
           }
           ProfScope prof_scope(PROF_SKH_FINAL, st);
-          f.tile_rows = final_tile_rows(B, N, M);
+          f.tile_rows = FT_ROWS;
           skh_final_tile_kernel<<<dim3((M + FT_THREADS * 4 - 1) / (FT_THREADS * 4), (N + f.tile_rows - 1) / f.tile_rows, B), FT_THREADS, 0, st>>>(f);
         }
       else
@@ -3307,7 +2594,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   return DRG_OK;
 }
 
-extern "C" int drg_sinkhorn(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+static int skh_check_args(const drg_sinkhorn_args* a) {
   DRG_CHECK_ARG(a != nullptr, "args is null");
   DRG_CHECK_ARG(a->scores && a->src_mask && a->tgt_mask && a->alpha, "scores/src_mask/tgt_mask/alpha must be non-null");
   DRG_CHECK_ARG(a->B >= 1 && a->N >= 1 && a->M >= 1, "B, N, M must be >= 1");
@@ -3315,6 +2602,12 @@ extern "C" int drg_sinkhorn(const drg_sinkhorn_args* a, void* workspace, size_t 
   DRG_CHECK_ARG(a->out_mode >= DRG_OUT_LOG_FULL && a->out_mode <= DRG_OUT_NONE, "unknown out_mode");
   DRG_CHECK_ARG(a->out_mode == DRG_OUT_NONE || a->out != nullptr, "out is null");
   DRG_CHECK_ARG(a->out_mode != DRG_OUT_DDIM || a->x_t != nullptr, "DDIM mode needs x_t");
+  return DRG_OK;
+}
+
+extern "C" int drg_sinkhorn(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = skh_check_args(a);
+  if (rc != DRG_OK) return rc;
   return run_sinkhorn(a, false, 1.f, workspace, workspace_bytes, stream);
 }
 
@@ -3389,16 +2682,13 @@ extern "C" int drg_sinkhorn_shard_final(const drg_sinkhorn_args* a, void* worksp
   return run_sinkhorn(a, false, 1.f, workspace, workspace_bytes, stream, SKH_SHARD_FINAL, nullptr, nullptr);
 }
 
-extern "C" int drg_debug_read_times(long long* host_out, int n) {
-  // tuning only: copies the clock64() stamps of the last persistent Sinkhorn launch (DRG_SKH_TIMES=1)
-  if (!g_skh_times || n > 512) return DRG_ERR_UNSUPPORTED;
-  DRG_CUDA(cudaMemcpy(host_out, g_skh_times, sizeof(long long) * n, cudaMemcpyDeviceToHost));
-  return DRG_OK;
-}
-
 namespace drg {
-int skh_run_with_views(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* stream, SkhViews* views) {
-  int rc = drg_sinkhorn(a, workspace, workspace_bytes, stream);
+int skh_run_with_views(const drg_sinkhorn_args* a, void* workspace, size_t workspace_bytes, void* stream, SkhViews* views,
+                       const SkhCollect* collect, bool* collected) {
+  if (collected) *collected = false;
+  int rc = skh_check_args(a);
+  if (rc != DRG_OK) return rc;
+  rc = run_sinkhorn(a, false, 1.f, workspace, workspace_bytes, stream, SKH_RUN_ALL, nullptr, nullptr, nullptr, collect, collected);
   if (rc != DRG_OK) return rc;
   SkhWorkspace w = carve(workspace, a->B, a->N, a->M, skh_max_g(a->B));
   views->u = w.u;

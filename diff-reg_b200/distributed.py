@@ -157,6 +157,19 @@ class RowShardedSinkhorn:
                 return None
         return self.comm
 
+    def _check_exchange(self, comm, device):
+        """A wait inside the exchange kernel that timed out (a peer never arrived) leaves a status word instead of
+        hanging the GPU; the result of that call is then invalid on at least one rank and the cumulative flag counters
+        are out of step.  Every rank learns about it (MAX over the group), the comm is dropped and the call raises."""
+        bad = torch.tensor([comm.status()], dtype=torch.int32, device=device if dist.get_backend(self.group) == "nccl" else "cpu")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.group)
+        if int(bad.item()) != 0:
+            comm._abort()
+            self.comm = None
+            self._shape = None
+            raise RuntimeError("RowShardedSinkhorn: the peer-to-peer exchange timed out on at least one rank; the result is "
+                               "invalid (the exchange buffers were released; the next call reconnects)")
+
     @torch.no_grad()
     def __call__(self, scores_local, alpha, iters, src_mask_local, tgt_mask, out_mode="conf", apply_mask=False):
         st = ops.ShardedSinkhornState(scores_local, alpha, src_mask_local, tgt_mask, apply_mask)
@@ -169,7 +182,9 @@ class RowShardedSinkhorn:
         if comm is not None:
             for it in range(int(iters)):
                 st.local_exchange(comm.handle)
-            return st.final(out_mode)
+            out = st.final(out_mode)
+            self._check_exchange(comm, scores_local.device)
+            return out
         ref = None
         for it in range(int(iters)):
             partial = st.local()

@@ -41,6 +41,9 @@ class HostStepPipeline:
             s["src_mask"].fill_(True)
             s["tgt_mask"].fill_(True)
         self.x = [torch.zeros(1, n, m, device=self.dev), torch.zeros(1, n, m, device=self.dev)]
+        # 3d flavour: the per-step x - x.min() (Diff-Reg-3dmatch pipeline.py:239) as a double-buffered device scalar:
+        # step i reads shift[i % 2] and leaves min(x_next) in shift[(i + 1) % 2]
+        self.shift = [torch.zeros(1, device=self.dev), torch.zeros(1, device=self.dev)] if sampler.flavour == "3d" else None
         self.counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
         cap = min(n, m)
         self.host_out = [{"R": torch.empty(1, 3, 3).pin_memory(), "t": torch.empty(1, 3, 1).pin_memory(),
@@ -64,8 +67,9 @@ class HostStepPipeline:
     def _eager(self, i):
         k = i % self.smp.steps
         s = self.sets[i % 2]
-        _, _, aux = self.smp.step(k, self.x[i % 2], None, *[s[key] for key in _INPUT_KEYS], x_out=self.x[(i + 1) % 2],
-                                  noise_counter=self.counter)
+        shift = self.shift[i % 2] if self.shift is not None else None
+        _, _, aux = self.smp.step(k, self.x[i % 2], shift, *[s[key] for key in _INPUT_KEYS], x_out=self.x[(i + 1) % 2],
+                                  noise_counter=self.counter, x_min_out=self.shift[(i + 1) % 2] if self.shift is not None else None)
         return aux
 
     def _capture(self):
@@ -89,6 +93,8 @@ class HostStepPipeline:
         """Start a new sample from the noise state x_T (device or host tensor)."""
         with torch.cuda.stream(self.compute):
             self.x[0].copy_(x_T, non_blocking=True)
+            if self.shift is not None:
+                self.shift[0].copy_(ops.min_value(self.x[0]))
         self.compute.synchronize()
 
     def prefetch(self, i, inputs):

@@ -16,12 +16,22 @@ from . import ops
 from ._lib import DiffRegLibraryError
 
 
-def _no_grad_inputs(*tensors):
-    if torch.is_grad_enabled():
-        for t in tensors:
-            if t is not None and t.requires_grad:
-                raise DiffRegLibraryError(
-                    "diffreg_b200 kernels are forward-only: call under torch.no_grad() (training keeps the reference modules)")
+_FORWARD_ONLY = ("diffreg_b200 kernels are forward-only: call under torch.no_grad() with the module in eval() mode "
+                 "(training keeps the reference modules)")
+
+
+def _no_grad_inputs(*tensors, module=None):
+    """The autograd rule of SURVEY.md 8b: never detach silently.  Must run BEFORE grad mode is switched off, so the
+    public entry points call it first and only then enter torch.no_grad() (a @torch.no_grad() decorator would make
+    this check dead code).  Raises when autograd is recording and (a) an input requires grad, or (b) the module is in
+    training mode with trainable parameters -- the reference would return a differentiable result in both cases."""
+    if not torch.is_grad_enabled():
+        return
+    for t in tensors:
+        if torch.is_tensor(t) and t.requires_grad:
+            raise DiffRegLibraryError(_FORWARD_ONLY)
+    if module is not None and module.training and any(q.requires_grad for q in module.parameters()):
+        raise DiffRegLibraryError(_FORWARD_ONLY)
 
 
 def log_optimal_transport(scores, alpha, iters, src_mask, tgt_mask):
@@ -30,8 +40,9 @@ def log_optimal_transport(scores, alpha, iters, src_mask, tgt_mask):
     Computed in fp32; an fp64 `scores` (the reference's fp64 sampler state) gives an
     fp64 result holding the fp32-accurate values."""
     _no_grad_inputs(scores, alpha)
-    out = ops.sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full")
-    return out.to(scores.dtype) if scores.dtype == torch.float64 else out
+    with torch.no_grad():
+        out = ops.sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full")
+        return out.to(scores.dtype) if scores.dtype == torch.float64 else out
 
 
 def mutual_topk_select(score_mat, k, largest=True, threshold=None, mutual=True, reduce_result=True):
@@ -74,13 +85,15 @@ class Matching(nn.Module):
 
     # ---- correspondence extraction (static, like the reference) ----
     @staticmethod
-    @torch.no_grad()
-    def get_match(conf_matrix, thr, mutual=True):
-        index, mconf, mask = ops.get_match(conf_matrix, thr, mutual, want_mask=True)
+    def get_match(conf_matrix, thr=0.0, mutual=True):
+        """(index [K,3], mconf [K], mask): the reference's mconf = conf[index] is differentiable, so a tracked
+        conf_matrix raises here too."""
+        _no_grad_inputs(conf_matrix)
+        with torch.no_grad():
+            index, mconf, mask = ops.get_match(conf_matrix, thr, mutual, want_mask=True)
         return index, mconf, mask
 
     @staticmethod
-    @torch.no_grad()
     def get_topk_match(conf_matrix, thr, mutual=True):
         return Matching.get_match(conf_matrix, thr, mutual)
 
@@ -145,23 +158,23 @@ class Matching(nn.Module):
             return ops.dual_softmax(sim, src_mask, tgt_mask, self.temperature)
         return ops.sinkhorn(sim, self.bin_score, self.skh_iters, src_mask, tgt_mask, out_mode="conf", apply_mask=True)
 
-    @torch.no_grad()
     def forward(self, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type="rotary"):
         """-> (conf_matrix [B,N,M], coarse_match [K,3] int64); writes the four feature tensors into `data`."""
-        _no_grad_inputs(src_feats, tgt_feats)
-        sim = self.similarity(src_feats, tgt_feats, src_pe, tgt_pe, pe_type, data)
-        conf_matrix = self.confidence(sim, src_mask, tgt_mask)
-        coarse_match, _, _ = ops.get_match(conf_matrix, self.confidence_threshold, True, want_mask=False)
+        _no_grad_inputs(src_feats, tgt_feats, src_pe, tgt_pe, module=self)
+        with torch.no_grad():
+            sim = self.similarity(src_feats, tgt_feats, src_pe, tgt_pe, pe_type, data)
+            conf_matrix = self.confidence(sim, src_mask, tgt_mask)
+            coarse_match, _, _ = ops.get_match(conf_matrix, self.confidence_threshold, True, want_mask=False)
         return conf_matrix, coarse_match
 
-    @torch.no_grad()
     def forward1(self, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type="rotary", mutual=False):
         """3DMatch variant (3d matching.py:221-283): top-1 row/column matches as [K,3] with a zero batch column."""
-        _no_grad_inputs(src_feats, tgt_feats)
-        sim = self.similarity(src_feats, tgt_feats, src_pe, tgt_pe, pe_type, data)
-        conf_matrix = self.confidence(sim, src_mask, tgt_mask)
-        r, c, _ = ops.top1_select(conf_matrix.squeeze(0), True, None, mutual)
-        coarse_match = torch.cat([torch.zeros_like(r).unsqueeze(-1), r.unsqueeze(-1), c.unsqueeze(-1)], dim=-1)
+        _no_grad_inputs(src_feats, tgt_feats, src_pe, tgt_pe, module=self)
+        with torch.no_grad():
+            sim = self.similarity(src_feats, tgt_feats, src_pe, tgt_pe, pe_type, data)
+            conf_matrix = self.confidence(sim, src_mask, tgt_mask)
+            r, c, _ = ops.top1_select(conf_matrix.squeeze(0), True, None, mutual)
+            coarse_match = torch.cat([torch.zeros_like(r).unsqueeze(-1), r.unsqueeze(-1), c.unsqueeze(-1)], dim=-1)
         return conf_matrix, coarse_match
 
 
@@ -172,14 +185,14 @@ class Matching2D3D(Matching):
         super().__init__(config, precision)
         self.mutual = mutual
 
-    @torch.no_grad()
     def forward(self, src_feats, tgt_feats, src_mask, tgt_mask, mutual=True):
         """-> (conf_matrix [1,N,M], src_indices [K], tgt_indices [K], weights [K])"""
-        _no_grad_inputs(src_feats, tgt_feats)
-        sim = self.similarity(src_feats, tgt_feats)
-        conf_matrix = self.confidence(sim, src_mask, tgt_mask)
-        if self.match_type != "sinkhorn":
-            # the reference only defines the selection inside its sinkhorn branch (matching.py:134-136)
-            raise NotImplementedError("the 2D-3D head selects correspondences in the sinkhorn branch only")
-        src_indices, tgt_indices, weights = ops.top1_select(conf_matrix.squeeze(0), True, None, mutual)
+        _no_grad_inputs(src_feats, tgt_feats, module=self)
+        with torch.no_grad():
+            sim = self.similarity(src_feats, tgt_feats)
+            conf_matrix = self.confidence(sim, src_mask, tgt_mask)
+            if self.match_type != "sinkhorn":
+                # the reference only defines the selection inside its sinkhorn branch (matching.py:134-136)
+                raise NotImplementedError("the 2D-3D head selects correspondences in the sinkhorn branch only")
+            src_indices, tgt_indices, weights = ops.top1_select(conf_matrix.squeeze(0), True, None, mutual)
         return conf_matrix, src_indices, tgt_indices, weights

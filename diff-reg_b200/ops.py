@@ -1,5 +1,7 @@
 """Tensor-level wrappers: torch CUDA tensors in, C-ABI calls out.  torch is used for device
 memory, streams and nothing else."""
+import functools
+
 import torch
 
 from . import _lib
@@ -22,6 +24,21 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_device(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current: the launch, the workspace and the stream
+    handed to the C ABI then belong to the tensors' device even when another device is current in the caller."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if torch.is_tensor(a) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapped
+
+
 def workspace(nbytes, device, tag="default"):
     """Grow-only per-(device, stream, tag) scratch buffer handed to the C ABI."""
     key = (device.index, _stream(), tag)
@@ -32,7 +49,9 @@ def workspace(nbytes, device, tag="default"):
     return buf
 
 
-def _as_mask(m):
+def _as_mask(m, batch=None, length=None, device=None):
+    if m is None:      # the reference accepts src_mask = tgt_mask = None (matching.py:10-12): every entry is valid
+        return torch.ones(batch, length, dtype=torch.bool, device=device)
     if m.dtype != torch.bool:
         m = m != 0
     return m.contiguous()
@@ -44,6 +63,7 @@ def _f32c(t):
     return t.contiguous()
 
 
+@_on_device
 def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", apply_mask=False, shift=None,
              x_t=None, noise=None, k_x0=0.0, k_xt=0.0, sigma=0.0, want_conf=False, x_min=None, return_potentials=False,
              xt_shift=None, noise_seed=None, noise_offset=0, noise_offset_dev=None, out=None, want_best=False, best_floor=None):
@@ -59,8 +79,8 @@ def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", appl
     scores = _f32c(scores)
     B, N, M = scores.shape
     dev = scores.device
-    src_mask = _as_mask(src_mask)
-    tgt_mask = _as_mask(tgt_mask)
+    src_mask = _as_mask(src_mask, B, N, dev)
+    tgt_mask = _as_mask(tgt_mask, B, M, dev)
     alpha = _f32c(alpha.detach().reshape(()))
     mode = {"log_full": _lib.DRG_OUT_LOG_FULL, "conf": _lib.DRG_OUT_CONF, "ddim": _lib.DRG_OUT_DDIM,
             "none": _lib.DRG_OUT_NONE}[out_mode]
@@ -103,6 +123,7 @@ def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", appl
     return res[0] if len(res) == 1 else tuple(res)
 
 
+@_on_device
 def dual_softmax(sim, src_mask, tgt_mask, temperature):
     """conf = softmax over src (masked) * softmax over tgt (masked) of sim / temperature."""
     _require_cuda(sim, src_mask, tgt_mask)
@@ -121,6 +142,7 @@ def dual_softmax(sim, src_mask, tgt_mask, temperature):
     return out
 
 
+@_on_device
 def gemm_nt(A, B, alpha=1.0, out=None, split3=False):
     """C[b] = alpha * A[b] @ B[b]^T on the tensor cores (drg_gemm_nt_tf32).  A [batch,N,K] or [N,K]; B likewise.
     split3=True: A, B are prep_operand(split=True) outputs (patterns 0 / 1); drg_gemm_nt_3xtf32 then fetches each distinct
@@ -145,6 +167,7 @@ def gemm_nt(A, B, alpha=1.0, out=None, split3=False):
     return out.squeeze(0) if squeeze else out
 
 
+@_on_device
 def prep_operand(x, scale=1.0, split=True, pattern=0, pe=None, pe_type=None, want_embedded=False):
     """Positional embedding + scaling + hi/lo split of a [..., K] feature tensor (drg_prep_operand).
     Returns out ([..., 3K] if split else [..., K]) and, if want_embedded, the embedded features."""
@@ -167,6 +190,7 @@ def prep_operand(x, scale=1.0, split=True, pattern=0, pe=None, pe_type=None, wan
     return (out, emb) if want_embedded else out
 
 
+@_on_device
 def _match(x, mode, mutual, threshold, largest, want_mask, capacity=None):
     """capacity=None: read the match count on the host (as torch.nonzero() does) and return exact-size outputs.
     capacity=int: sync-free; returns (index [capacity,3], vals [capacity], mask, count) with the count on the device."""
@@ -192,7 +216,7 @@ def _match(x, mode, mutual, threshold, largest, want_mask, capacity=None):
     return index, vals, mask, total
 
 
-def get_match(conf, thr, mutual=True, want_mask=True):
+def get_match(conf, thr=0.0, mutual=True, want_mask=True):
     """(index [K,3] int64, mconf [K], mask [B,N,M] bool) -- Matching.get_match."""
     return _match(conf, 0, mutual, thr, True, want_mask)
 
@@ -203,6 +227,7 @@ def top1_select(score_mat, largest=True, threshold=None, mutual=True):
     return index[:, 1].contiguous(), index[:, 2].contiguous(), vals
 
 
+@_on_device
 def soft_procrustes(conf, src_pcd, tgt_pcd, src_mask, tgt_mask, sample_rate, max_condition_num, padded_lengths=False,
                     want_warped=False, want_selection=False):
     """SoftProcrustesLayer.forward on the device (drg_soft_procrustes).
@@ -240,6 +265,7 @@ def soft_procrustes(conf, src_pcd, tgt_pcd, src_mask, tgt_mask, sample_rate, max
     return out
 
 
+@_on_device
 def weighted_procrustes(X, Y, w, eps=1e-4):
     """batch_weighted_procrustes on the device: X, Y [B,K,3], w [B,K,1] -> (R [B,3,3], t [B,3,1], condition [B] fp64)."""
     _require_cuda(X, Y, w)
@@ -257,6 +283,7 @@ def weighted_procrustes(X, Y, w, eps=1e-4):
     return R, t, cond
 
 
+@_on_device
 def sigmoid(x):
     _require_cuda(x)
     x = _f32c(x)
@@ -265,6 +292,7 @@ def sigmoid(x):
     return y
 
 
+@_on_device
 def min_value(x):
     """Global minimum as a 1-element device tensor (no host read)."""
     _require_cuda(x)
@@ -275,6 +303,7 @@ def min_value(x):
     return out
 
 
+@_on_device
 def counter_add(counter, inc=1):
     """counter (1-element int64 CUDA tensor) += inc, on the stream."""
     _require_cuda(counter)
@@ -336,6 +365,7 @@ class ShardedSinkhornState:
         return out
 
 
+@_on_device
 def match_from_best(rowbest, colbest, M, threshold=None, capacity=None):
     """Mutual top-1 matches from the packed bests of sinkhorn(..., want_best=True) (drg_match_from_best).
     capacity=None reads the count on the host and returns exact-size (index [K,3], vals [K]); otherwise returns
@@ -357,6 +387,7 @@ def match_from_best(rowbest, colbest, M, threshold=None, capacity=None):
     return index, vals, total
 
 
+@_on_device
 def sinkhorn_soft_procrustes(scores, alpha, iters, src_mask, tgt_mask, src_pcd, tgt_pcd, sample_rate, max_condition_num,
                              padded_lengths=False, apply_mask=True, shift=None, want_warped=True):
     """get_warped_from_noising_matching in one call (drg_sinkhorn_soft_procrustes): Sinkhorn on the sampler state, then
@@ -396,6 +427,7 @@ def sinkhorn_soft_procrustes(scores, alpha, iters, src_mask, tgt_mask, src_pcd, 
     return out
 
 
+@_on_device
 def project_pair_split(src_feats, tgt_feats, w_operand, out_dim, scale, want_plain=False):
     """Both projections of Matching.forward and the operand preparation of the similarity GEMM in two launches:
     drg_prep_operand_pair (hi/lo split of src | tgt features) + drg_project_split (tensor-core GEMM against the prepared

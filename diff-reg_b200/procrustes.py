@@ -25,25 +25,27 @@ class SoftProcrustesLayer(nn.Module):
         self.max_condition_num = config.max_condition_num
 
     @staticmethod
-    @torch.no_grad()
     def batch_weighted_procrustes(X, Y, w, eps=0.0001):
         """X, Y [B,K,3], w [B,K,1] -> (R [B,3,3], t [B,3,1], condition [B] fp64)"""
-        return ops.weighted_procrustes(X, Y, w, eps)
+        _no_grad_inputs(X, Y, w)
+        with torch.no_grad():
+            return ops.weighted_procrustes(X, Y, w, eps)
 
-    @torch.no_grad()
     def forward(self, conf_matrix, src_pcd, tgt_pcd, src_mask, tgt_mask):
         """-> (R, t, R_forwd, t_forwd, condition, solution_mask)"""
         _no_grad_inputs(conf_matrix, src_pcd, tgt_pcd)
-        o = ops.soft_procrustes(conf_matrix, src_pcd, tgt_pcd, src_mask, tgt_mask, self.sample_rate, self.max_condition_num,
-                                padded_lengths=self.padded_lengths)
+        with torch.no_grad():
+            o = ops.soft_procrustes(conf_matrix, src_pcd, tgt_pcd, src_mask, tgt_mask, self.sample_rate, self.max_condition_num,
+                                    padded_lengths=self.padded_lengths)
         return o["R"], o["t"], o["R_forwd"], o["t_forwd"], o["condition"], o["solution_mask"]
 
-    @torch.no_grad()
     def forward_warp(self, conf_matrix, src_pcd, tgt_pcd, src_mask, tgt_mask):
         """forward() plus the source points moved by the gated pose (pipeline.py:218-220) in the same kernel.
         -> (src_pcd_wrapped [B,N,3], pose 6-tuple)"""
-        o = ops.soft_procrustes(conf_matrix, src_pcd, tgt_pcd, src_mask, tgt_mask, self.sample_rate, self.max_condition_num,
-                                padded_lengths=self.padded_lengths, want_warped=True)
+        _no_grad_inputs(conf_matrix, src_pcd, tgt_pcd)
+        with torch.no_grad():
+            o = ops.soft_procrustes(conf_matrix, src_pcd, tgt_pcd, src_mask, tgt_mask, self.sample_rate, self.max_condition_num,
+                                    padded_lengths=self.padded_lengths, want_warped=True)
         return o["src_warped"], (o["R"], o["t"], o["R_forwd"], o["t_forwd"], o["condition"], o["solution_mask"])
 
 

@@ -72,10 +72,16 @@ class DenoisingSampler:
 
     @torch.no_grad()
     def step(self, k, x, shift, src_feats, tgt_feats, s_pcd, t_pcd, src_mask, tgt_mask, noise=None,
-             pose_tgt_pcd=None, pose_tgt_mask=None, feature_fn=None, x_out=None, noise_counter=None, want_x0=False):
+             pose_tgt_pcd=None, pose_tgt_mask=None, feature_fn=None, x_out=None, noise_counter=None, want_x0=False,
+             src_pe=None, tgt_pe=None, pe_type="rotary", x_min_out=None):
         """One reverse step.  x: [1,N,M] state (as stored: for the 3d flavour the true state is x - shift).
         x_out: optional preallocated [1,N,M] buffer for x_next; noise_counter: optional 1-element int64 device
         counter used as the Philox offset (and incremented) instead of the host-side call count.
+        src_pe / tgt_pe / pe_type: position codes handed to the matching head exactly as the reference loop hands the
+        denoising transformer's to `denoising_coarse_matching` (pipeline.py:177-178); with `entangled: False` (every
+        shipped 3DMatch / 4DMatch config) the head applies them after the projection.  `feature_fn` may return
+        (src_feats, tgt_feats) or (src_feats, tgt_feats, src_pe, tgt_pe).
+        x_min_out: optional 1-element fp32 buffer receiving min(x_next) (3d flavour; a fresh tensor otherwise).
         Returns (x_next, shift_next, aux)."""
         t, t_next = self.pairs[k]
         k_x0, k_xt, sigma = ddim_coefficients(self.ac, t, t_next, self.eta)
@@ -93,17 +99,29 @@ class DenoisingSampler:
                                                 pm.max_condition_num, padded_lengths=pm.padded_lengths, apply_mask=True,
                                                 shift=shift, want_warped=True)
         if feature_fn is not None:
-            src_feats, tgt_feats = feature_fn(pose["src_warped"], t_pcd, src_feats, tgt_feats)
+            feats = feature_fn(pose["src_warped"], t_pcd, src_feats, tgt_feats)
+            if len(feats) == 4:
+                src_feats, tgt_feats, src_pe, tgt_pe = feats
+            else:
+                src_feats, tgt_feats = feats
         # x0 from the matching head, fused with the DDIM update
         m = self.matching
-        sim = m.similarity(src_feats, tgt_feats)
+        if self.flavour == "2d3d":        # the 2D-3D head takes no position codes (2d3d matching.py:91)
+            sim = m.similarity(src_feats, tgt_feats)
+        else:
+            sim = m.similarity(src_feats, tgt_feats, src_pe, tgt_pe, pe_type)
         gen = self.flavour == "4d" and noise is None      # throughput mode: draw the noise inside the final pass
         use_noise = self.flavour == "4d"
         x_min = None
         if self.flavour == "3d":
-            x_min = torch.full((1,), float("inf"), dtype=torch.float32, device=x.device)
+            if x_min_out is not None:
+                x_min = x_min_out.fill_(float("inf"))
+            else:
+                x_min = torch.full((1,), float("inf"), dtype=torch.float32, device=x.device)
         B, N, M = sim.shape
-        fused_match = self.extract_matches and M % 4 == 0
+        # the row / column bests come out of the tiled final pass, which needs 16-byte aligned rows and buffers
+        fused_match = (self.extract_matches and M % 4 == 0 and all(t is None or t.data_ptr() % 16 == 0 for t in (x, x_out, noise))
+                       and tgt_mask.data_ptr() % 4 == 0)
         res = ops.sinkhorn(sim, m.bin_score, m.skh_iters, src_mask, tgt_mask, out_mode="ddim", apply_mask=True,
                            x_t=x, xt_shift=shift, noise=noise if use_noise else None, k_x0=k_x0, k_xt=k_xt,
                            sigma=sigma if use_noise else 0.0, want_conf=want_x0 or (self.extract_matches and not fused_match),
@@ -134,7 +152,7 @@ class DenoisingSampler:
 
     @torch.no_grad()
     def sample(self, x_T, src_feats, tgt_feats, s_pcd, t_pcd, src_mask, tgt_mask, noises=None, pose_tgt_pcd=None,
-               pose_tgt_mask=None, feature_fn=None, trace=None):
+               pose_tgt_mask=None, feature_fn=None, trace=None, src_pe=None, tgt_pe=None, pe_type="rotary"):
         x = x_T
         shift = ops.min_value(x) if self.flavour == "3d" else None
         aux = None
@@ -142,7 +160,8 @@ class DenoisingSampler:
             noise = noises[k] if (noises is not None and self.flavour == "4d") else None
             x_in = x
             x, shift, aux = self.step(k, x, shift, src_feats, tgt_feats, s_pcd, t_pcd, src_mask, tgt_mask, noise,
-                                      pose_tgt_pcd, pose_tgt_mask, feature_fn, want_x0=trace is not None)
+                                      pose_tgt_pcd, pose_tgt_mask, feature_fn, want_x0=trace is not None,
+                                      src_pe=src_pe, tgt_pe=tgt_pe, pe_type=pe_type)
             if trace is not None:
                 trace.append({"x_in": x_in, "x_out": x, **aux})
         out = {"x_final": x, "pose": aux["pose"] if aux else None}

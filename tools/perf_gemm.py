@@ -1,4 +1,4 @@
-"""Similarity GEMM timing at the headline shape (tuning: DRG_GEMM_BN)."""
+"""Similarity GEMM timing at the headline shape."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,5 +17,5 @@ for split3 in (False, True):
         ops.gemm_nt(A3, B3, out=out, split3=split3)
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / 20
-    print(json.dumps({"BN": os.environ.get("DRG_GEMM_BN", "model"), "split3": split3, "us": round(us, 1),
+    print(json.dumps({"split3": split3, "us": round(us, 1),
                       "tf32_TFLOPs": round(2 * 3 * k * n * n / us / 1e6, 1)}), flush=True)
