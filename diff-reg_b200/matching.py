@@ -50,7 +50,9 @@ def mutual_topk_select(score_mat, k, largest=True, threshold=None, mutual=True, 
     2d3d model.py:692-694, matching.py:134-136); other k raise."""
     if k != 1:
         raise NotImplementedError("diffreg_b200.mutual_topk_select implements k = 1 (the only value the sampler uses)")
-    r, c, s = ops.top1_select(score_mat, largest, threshold, mutual)
+    _no_grad_inputs(score_mat)          # the reference's gathered scores are differentiable
+    with torch.no_grad():
+        r, c, s = ops.top1_select(score_mat, largest, threshold, mutual)
     if reduce_result:
         return r, c, s
     corr = torch.zeros_like(score_mat, dtype=torch.bool)

@@ -35,10 +35,16 @@ def _params(fn):
 
 
 def _assert_prefix(ref_fn, our_fn, what):
-    """Our callable takes the reference's parameters -- same names, order, kinds and defaults -- and may only ADD
-    keyword parameters with defaults after them."""
+    """Every call the reference accepts is accepted with the same meaning: our callable takes the reference's parameters
+    -- same names, order and kinds; the same default wherever the reference has one (one drop-in function serves copies
+    of the reference that differ only in having defaults: 3d models/matching.py:6 vs vision3d/ops/mutual_topk_select.py:7)
+    -- and may only ADD keyword parameters with defaults after them."""
     r, o = _params(ref_fn), _params(our_fn)
-    assert o[:len(r)] == r, f"{what}: reference {r} vs ours {o}"
+    assert len(o) >= len(r), f"{what}: reference {r} vs ours {o}"
+    for (rn, rk, rd), (on, ok, od) in zip(r, o):
+        assert (rn, rk) == (on, ok), f"{what}: reference {r} vs ours {o}"
+        if rd is not inspect.Parameter.empty:
+            assert od == rd, f"{what}: default of {rn}: reference {rd!r} vs ours {od!r}"
     for name, _, default in o[len(r):]:
         assert default is not inspect.Parameter.empty, f"{what}: extra parameter {name} has no default"
 

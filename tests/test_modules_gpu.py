@@ -127,17 +127,42 @@ def test_soft_procrustes_layer(name):
 
 
 def test_forward_only_guard():
+    """The kernels are forward-only: calls autograd would record raise -- through the MODULE entry points,
+    on CUDA tensors; under torch.no_grad() the same calls run."""
     import diffreg_b200
-    m = diffreg_b200.Matching(_cfg(32)).to(DEV)
+    from diffreg_b200.procrustes import SoftProcrustesLayer
+    Err = diffreg_b200._lib.DiffRegLibraryError
+    m = diffreg_b200.Matching(_cfg(32)).to(DEV).eval()
+    m2 = diffreg_b200.Matching2D3D(_cfg(32)).to(DEV).eval()
+    proc = SoftProcrustesLayer(SimpleNamespace(sample_rate=1.0, max_condition_num=40.0))
     x = torch.randn(1, 8, 32, device=DEV, requires_grad=True)
+    y = torch.randn(1, 8, 32, device=DEV)
     ones = torch.ones(1, 8, dtype=torch.bool, device=DEV)
-    with pytest.raises(diffreg_b200._lib.DiffRegLibraryError):
+    conf = torch.rand(1, 8, 8, device=DEV, requires_grad=True)
+    pts = torch.randn(1, 8, 3, device=DEV)
+    with pytest.raises(Err, match="forward-only"):
+        m(x, y, None, None, ones, ones, {})
+    with pytest.raises(Err, match="forward-only"):
+        m.forward1(x, y, None, None, ones, ones, {})
+    with pytest.raises(Err, match="forward-only"):
+        m2(x, y, ones, ones)
+    with pytest.raises(Err, match="forward-only"):
+        proc(conf, pts, pts, ones, ones)
+    with pytest.raises(Err, match="forward-only"):
+        SoftProcrustesLayer.batch_weighted_procrustes(pts, pts, torch.rand(1, 8, 1, device=DEV, requires_grad=True))
+    with pytest.raises(Err, match="forward-only"):
         diffreg_b200.log_optimal_transport(torch.randn(1, 4, 4, device=DEV, requires_grad=True), torch.tensor(1.0, device=DEV), 3,
                                            ones[:, :4], ones[:, :4])
+    with pytest.raises(Err, match="forward-only"):
+        diffreg_b200.Matching(_cfg(32)).to(DEV)(x.detach(), y, None, None, ones, ones, {})      # training mode, trainable weights
+    # the same calls under no_grad (how the reference's testers call) run
+    with torch.no_grad():
+        c1, _ = m(x, y, None, None, ones, ones, {})
+        R, *_ = proc(conf, pts, pts, ones, ones)
+    assert not c1.requires_grad and not R.requires_grad
     # CPU tensors have no path at all
-    with pytest.raises(diffreg_b200._lib.DiffRegLibraryError):
+    with pytest.raises(Err, match="CUDA tensors only"):
         diffreg_b200.log_optimal_transport(torch.randn(1, 4, 4), torch.tensor(1.0), 3, ones[:, :4].cpu(), ones[:, :4].cpu())
-    del m, x
 
 
 @pytest.mark.parametrize("name", ["sampler4d_3steps", "sampler3d_3steps", "sampler2d3d_3steps"])
