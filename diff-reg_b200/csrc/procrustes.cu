@@ -127,22 +127,25 @@ struct __align__(16) SelectScratch {
   int done;
 };
 
-template <int NT, class KeyAt>
-__device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, SelectScratch& sc) {
+struct SyncAll {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+template <int NT, class KeyAt, class Sync = SyncAll>
+__device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, SelectScratch& sc, Sync sync = Sync()) {
   const int tid = threadIdx.x;
   if (tid == 0) {
     sc.prefix = 0ull;
     sc.krem = k;
     sc.done = 0;
   }
-  __syncthreads();
+  sync();
   int shift = 64;
   const int widths[6] = {11, 11, 10, 11, 11, 10};
   for (int level = 0; level < 6; ++level) {
     const int wbits = widths[level];
     shift -= wbits;
     for (int q = tid; q < TK_BINS; q += NT) sc.hist[q] = 0u;
-    __syncthreads();
+    sync();
     const unsigned long long prefix = sc.prefix;
     const int hi_shift = shift + wbits;  // bits above the current digit
     for (size_t e = tid; e < n; e += NT) {
@@ -150,7 +153,7 @@ __device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, Se
       const bool match = (hi_shift >= 64) ? true : ((key >> hi_shift) == prefix);
       if (match) atomicAdd(&sc.hist[(unsigned int)((key >> shift) & ((1u << wbits) - 1u))], 1u);
     }
-    __syncthreads();
+    sync();
     if (tid < 32) {
       int dbin;
       unsigned int cum, hsel;
@@ -162,11 +165,11 @@ __device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, Se
         if (hsel == krem - cum) sc.done = 1;  // the whole bucket is wanted
       }
     }
-    __syncthreads();
+    sync();
     if (sc.done) break;
   }
   const unsigned long long T = sc.prefix << shift;
-  __syncthreads();
+  sync();
   return T;
 }
 
@@ -730,7 +733,8 @@ __device__ __forceinline__ double det3(const double A[3][3]) {
 
 // From the centred weighted covariance S = sum w_norm (y - my)(x - mx)^T and the (shrunk) weighted means to
 // (R, t, condition); one thread.                                                 procrustes.py:35-43
-__device__ void kabsch_solve(const double S[3][3], const double mx[3], const double my[3], float R_out[9], float t_out[3],
+// (not inlined: the pose kernel calls it twice -- once to warm the caches -- and both calls must run the SAME code)
+__device__ __noinline__ void kabsch_solve(const double S[3][3], const double mx[3], const double my[3], float R_out[9], float t_out[3],
                              double* cond_out) {
   double U[3][3], sv[3], V[3][3];
   svd3x3(S, U, sv, V);
@@ -805,21 +809,24 @@ __device__ __forceinline__ long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#define WSYNC() asm volatile("bar.sync 1, %0;" ::"n"(PP_THREADS) : "memory")
+struct SyncWorkers {
+  __device__ __forceinline__ void operator()() const { WSYNC(); }
+};
+#define PSTAMPF(k) do { if (p.stamps && b == 0 && lane == 0) { p.stamps[(k)] = global_ns(); p.stamps[(k) + 100] = clock64(); } } while (0)
 #define PSTAMP0(k) do { if (p.stamps && b == 0 && g == 0 && tid == 0) p.stamps[(k)] = global_ns(); } while (0)
 #define PSTAMPL(k) do { if (p.stamps && b == 0 && tid == 0) { p.stamps[(k)] = global_ns(); p.stamps[(k) + 100] = clock64(); } } while (0)
-__global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParams p) {
+__global__ void __launch_bounds__(PP_THREADS + 32) procr_pose_kernel(const ProcrParams p) {
   extern __shared__ __align__(16) unsigned long long mine_s[];  // [mine_cap] (flat index << 32 | value key) of this CTA's rows
   __shared__ SelectScratch sc;
   __shared__ unsigned long long list_s[SEL_LIST];
-  __shared__ unsigned int list_n, mine_n, surv_n, ticket_s;
+  __shared__ unsigned int list_n, mine_n, surv_n;
   __shared__ int bin_s;
   __shared__ unsigned int cum_s, hsel_s;
   __shared__ unsigned long long T_s;
-  __shared__ double comb_s[PM_SUMS + 1];
-  __shared__ double mean_s[6], cov_s[9];
   __shared__ float pose_s[12];
   __shared__ double wsum_s[PP_THREADS / 32][PM_SUMS + 1];
-  const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x - 1;   // (the last CTA of a batch element only warms the code)
+  const int b = blockIdx.y, g = blockIdx.x, G = gridDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N, M = p.M;
   const size_t total = (size_t)N * M;
@@ -827,20 +834,82 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
   unsigned int* cidx = p.cand_idx + (size_t)b * total;
   unsigned int* sync = p.pose_sync + 4 * b;  // [0] fallback barrier arrivals, [1] T-ready flag, [2] moments arrivals (zero on entry)
   PSTAMP0(800);
-  // The 3x3 solve at the very end runs on ONE thread of the LAST CTA, through fp64 division / square-root subroutines
-  // that are cold in the instruction caches -- and, inside a sampler step that streams hundreds of MB through L2, cold in
-  // L2 too: every first touch of a code line then costs a DRAM round trip on the critical path (measured: 9.8 us cold
-  // against 5.0 us warm).  One extra CTA per batch element runs the same code on a harmless matrix right away, so that
-  // the lines are in L2 when the last CTA needs them ~20 us later.
-  if (g == G) {
-    if (tid == 0) {
-      const double eps = (double)N * 1e-12;
-      const double Sw[3][3] = {{0.9 + eps, 0.2, -0.1}, {0.1, 0.7 - eps, 0.3}, {-0.2, 0.1, 0.5 + eps}};
-      const double mw[3] = {0.1, -0.2 + eps, 0.3};
-      float Rw[9], tw[3];
-      double cw;
-      kabsch_solve(Sw, mw, mw, Rw, tw, &cw);
-      if (cw < 0.0) p.partials[0] = (double)(Rw[0] + tw[0]);   // never true (a condition number is >= 1): keeps the call alive
+  // ---- the finisher: warp PP_THREADS / 32 of CTA 0 (it exits at once in the other CTAs; the 512 working threads of every
+  //      CTA synchronise among themselves on named barrier 1).  The 3x3 solve runs on ONE thread through fp64 division /
+  //      square-root subroutines; inside a sampler step that streams hundreds of MB through L2 that code is cold in every
+  //      cache and each first touch of a line is a DRAM round trip on the critical path (measured: 9.8 us cold, 5.0 us
+  //      warm).  So this warp first runs the solve on a harmless matrix -- while the working warps scan the candidates --
+  //      then waits for the G partial sums, combines them in fixed order, solves and publishes the pose.
+  if (tid >= PP_THREADS) {
+    if (g != 0) return;
+    const int Kb = __ldcg(&p.state[b].Kb);
+    const double* pg = p.partials + (size_t)b * PP_MAX_G * PM_PART;
+    // Two trips through the SAME code: trip 0 is the warm-up (it combines whatever the partial records hold and solves a
+    // harmless matrix, publishing nothing) while the working warps still scan the candidates; trip 1 waits for the G
+    // arrivals and is the real thing, now with every instruction line in this SM's caches.
+    for (int trip = 0; trip < 2; ++trip) {
+      if (trip == 1) {
+        if (lane == 0) {
+          while (ld_acquire_gpu_u32(sync + 2) < (unsigned int)G) {
+          }
+        }
+        __syncwarp();
+        PSTAMPF(807);
+      }
+      // lane l adds the CTAs l, l + 32 (ascending), a fixed shuffle tree adds the lanes: bit-reproducible
+      double tot[PM_SUMS];
+#pragma unroll
+      for (int k = 0; k < PM_SUMS; ++k) tot[k] = 0.0;
+      for (int gg = lane; gg < G; gg += 32) {
+#pragma unroll
+        for (int k = 0; k < PM_SUMS; ++k) tot[k] += __ldcg(pg + (size_t)gg * PM_PART + k);
+      }
+#pragma unroll
+      for (int k = 0; k < PM_SUMS; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot[k] += __shfl_xor_sync(0xffffffffu, tot[k], o);
+      }
+      if (lane == 0) {
+        if (trip == 0) {   // harmless, well-conditioned stand-in sums (the records may hold anything)
+#pragma unroll
+          for (int k = 0; k < PM_SUMS; ++k) tot[k] = (k == 0 || k == 1) ? 1.0 : ((k == 8 || k == 12 || k == 16) ? 0.7 + 0.1 * k : 0.01 * k);
+        }
+        // w_norm = w / (sum|w| + eps): the normalised weights sum to slightly less than one  (procrustes.py:29-30);
+        // S = sum w_norm (y - my)(x - mx)^T = inv * [sum w y x^T - (sum w y) mx^T - my (sum w x)^T + W my mx^T]
+        const double inv = 1.0 / (tot[1] + 1e-4);
+        const float invf = (float)inv;
+        double mx[3], my[3], S[3][3];
+        for (int a = 0; a < 3; ++a) {
+          mx[a] = (Kb > 0) ? (double)(float)(tot[2 + a] * inv) : 0.0;  // the means are fp32 values, as in the reference
+          my[a] = (Kb > 0) ? (double)(float)(tot[5 + a] * inv) : 0.0;
+        }
+        for (int a = 0; a < 3; ++a)
+          for (int c = 0; c < 3; ++c) {
+            const double sv = tot[8 + a * 3 + c] - tot[5 + a] * mx[c] - my[a] * tot[2 + c] + tot[0] * my[a] * mx[c];
+            S[a][c] = (Kb > 0) ? sv * (double)invf : 0.0;
+          }
+        float R[9], t[3];
+        double cond;
+        if (trip == 1) PSTAMPF(808);
+        kabsch_solve(S, mx, my, R, t, &cond);
+        if (trip == 1) {
+          PSTAMPF(809);
+          finish_pose(p, b, R, t, cond);
+          __threadfence();
+          red_release_gpu_add_u32(sync + 3, 1u);   // the pose is public: every CTA warps its rows now
+        } else if (cond < 0.0) {
+          p.partials[0] = (double)(R[0] + t[0]);   // never true (a condition number is >= 1): keeps the warm-up alive
+        }
+      }
+      __syncwarp();
+    }
+    if (p.sel_w) {   // (tests / diagnostics) unused slots of the selection outputs
+      const unsigned int ne = min(__ldcg(&p.state[b].sel_count), (unsigned int)p.K_max);
+      for (int k = (int)ne + lane; k < p.K_max; k += 32) {
+        p.sel_w[(size_t)b * p.K_max + k] = 0.f;
+        p.sel_src[(size_t)b * p.K_max + k] = 0;
+        p.sel_tgt[(size_t)b * p.K_max + k] = 0;
+      }
     }
     return;
   }
@@ -865,14 +934,14 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
     }
     n = total;
     slow = true;
-    __syncthreads();
+    WSYNC();
     if (tid == 0) {
       red_release_gpu_add_u32(sync + 0, 1u);
       while (ld_acquire_gpu_u32(sync + 0) < (unsigned int)G) {
       }
     }
   }
-  __syncthreads();
+  WSYNC();
   const bool select_some = Kb > 0 && (size_t)Kb < n;   // otherwise every candidate is used (T = 0)
   int bin = 0;
   unsigned int want = 0u, hsel = 0u;
@@ -887,7 +956,7 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
         hsel_s = hs;
       }
     }
-    __syncthreads();
+    WSYNC();
     bin = bin_s;
     want = (unsigned int)Kb - cum_s;  // how many of the crossing bin's candidates are selected
     hsel = hsel_s;
@@ -899,7 +968,7 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
   unsigned long long T = 0ull;
   if (select_some && slow) {
     if (g == 0) {
-      T = block_select_kth<PP_THREADS>([&](size_t e) { return make_key64(ckey[e], cidx[e]); }, n, Kb, sc);
+      T = block_select_kth<PP_THREADS>([&](size_t e) { return make_key64(ckey[e], cidx[e]); }, n, Kb, sc, SyncWorkers());
       if (tid == 0) {
         p.state[b].T = T;
         __threadfence();
@@ -911,7 +980,7 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
         }
         T_s = *((volatile unsigned long long*)&p.state[b].T);
       }
-      __syncthreads();
+      WSYNC();
       T = T_s;
     }
   }
@@ -1025,7 +1094,7 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
           }
           keep(k, e, 1);
         }
-        __syncthreads();
+        WSYNC();
         const unsigned int ns = min(surv_n, (unsigned int)p.surv_cap);
         for (unsigned int q0 = 0; q0 < ns; q0 += PP_THREADS * 4) {
           unsigned int kk[4], fi[4];
@@ -1060,7 +1129,7 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
       }
     }
   }
-  __syncthreads();
+  WSYNC();
   PSTAMP0(802);
   // ---- T of the normal case: rank the crossing bin's short list (64-bit keys are distinct: distinct indices)
   if (select_some && !slow) {
@@ -1071,7 +1140,7 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
       for (unsigned int q = 0; q < L; ++q) rank += (list_s[q] > my) ? 1u : 0u;
       if (rank == want - 1u) T_s = my;
     }
-    __syncthreads();
+    WSYNC();
     T = T_s;
   }
   if (g == 0 && tid == 0) {
@@ -1082,7 +1151,7 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
   PSTAMP0(803);
   // ---- my rows' selected candidates in ascending flat-index order (the appends above came in atomic order)
   const unsigned int cnt_raw = min(mine_n, (unsigned int)p.mine_cap);  // (mine_cap >= K_b + SEL_LIST: no overflow)
-  __syncthreads();
+  WSYNC();
   if (tid == 0) mine_n = 0u;
   unsigned long long* sorted_s = mine_s;
   if (cnt_raw <= (unsigned int)PP_RANK_SORT) {
@@ -1096,13 +1165,13 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
       if (mv[u] != PP_SENTINEL && make_key64((unsigned int)mv[u], (unsigned int)(mv[u] >> 32)) < T) mv[u] = PP_SENTINEL;  // not among the K_b best
       rk[u] = 0u;
     }
-    __syncthreads();
+    WSYNC();
 #pragma unroll
     for (int u = 0; u < PP_RANK_SORT / PP_THREADS; ++u) {
       const unsigned int q = tid + u * PP_THREADS;
       if (q < cnt_raw) mine_s[q] = mv[u];
     }
-    __syncthreads();
+    WSYNC();
     for (unsigned int q = 0; q < cnt_raw; ++q) {
       const unsigned long long o = mine_s[q];  // broadcast read; sentinels are larger than every real entry
 #pragma unroll
@@ -1119,7 +1188,7 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
     }
     real = __reduce_add_sync(0xffffffffu, real);
     if (lane == 0 && real) atomicAdd(&mine_n, real);
-    __syncthreads();
+    WSYNC();
   } else {
     // many entries in one CTA's rows (concentrated confidences): bitonic sort in place, sentinels sort to the end
     unsigned int npow = 32u;
@@ -1129,7 +1198,7 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
       if (q < cnt_raw && make_key64((unsigned int)v, (unsigned int)(v >> 32)) < T) v = PP_SENTINEL;
       mine_s[q] = v;
     }
-    __syncthreads();
+    WSYNC();
     for (unsigned int k = 2u; k <= npow; k <<= 1) {
       for (unsigned int j = k >> 1; j > 0u; j >>= 1) {
         for (unsigned int q = tid; q < npow; q += PP_THREADS) {
@@ -1143,14 +1212,14 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
             }
           }
         }
-        __syncthreads();
+        WSYNC();
       }
     }
     unsigned int c = 0u;
     for (unsigned int q = tid; q < npow; q += PP_THREADS) c += (mine_s[q] != PP_SENTINEL) ? 1u : 0u;
     c = __reduce_add_sync(0xffffffffu, c);
     if (lane == 0 && c) atomicAdd(&mine_n, c);
-    __syncthreads();
+    WSYNC();
   }
   const unsigned int cnt = mine_n;
   PSTAMP0(804);
@@ -1199,7 +1268,7 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     if (lane == 0) wsum_s[warp][k] = x;
   }
-  __syncthreads();
+  WSYNC();
   double* part = p.partials + ((size_t)b * PP_MAX_G + g) * PM_PART;
   if (tid < PM_SUMS) {
     double t = 0.0;
@@ -1207,101 +1276,37 @@ __global__ void __launch_bounds__(PP_THREADS) procr_pose_kernel(const ProcrParam
     for (int w = 0; w < PP_THREADS / 32; ++w) t += wsum_s[w][tid];
     part[tid] = t;
   }
-  __syncthreads();
+  WSYNC();
   if (tid == 0) {
     __threadfence();
-    ticket_s = atomicAdd(sync + 2, 1u);
-  }
-  __syncthreads();
-  PSTAMP0(806);
-  if (ticket_s != (unsigned int)(G - 1)) return;  // not the last CTA of this batch element
-  PSTAMPL(807);
-  __threadfence();
-  // ---- combine the CTAs' sums (fixed order: reproducible): all partials into shared memory with one round trip, then
-  //      one warp per value, lane l takes CTAs l and l + 32 and a fixed shuffle tree adds the lanes
-  {
-    double* part_s = reinterpret_cast<double*>(mine_s);   // [G * PM_PART] (the candidate lists are dead)
-    const double* pg = p.partials + (size_t)b * PP_MAX_G * PM_PART;
-    for (int q = tid; q < G * PM_PART; q += PP_THREADS) part_s[q] = __ldcg(pg + q);
-    __syncthreads();
-    for (int k = warp; k < PM_SUMS; k += PP_THREADS / 32) {
-      double x = 0.0;
-      for (int gg = lane; gg < G; gg += 32) x += part_s[gg * PM_PART + k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-      if (lane == 0) comb_s[k] = x;
+    red_release_gpu_add_u32(sync + 2, 1u);   // this CTA's sums are public (the finisher waits for G arrivals)
+    PSTAMP0(806);
+    while (ld_acquire_gpu_u32(sync + 3) == 0u) {
     }
   }
-  __syncthreads();
-  if (tid < 9) {
-    // w_norm = w / (sum|w| + eps): the normalised weights sum to slightly less than one  (procrustes.py:29-30);
-    // S = sum w_norm (y - my)(x - mx)^T = inv * [sum w y x^T - (sum w y) mx^T - my (sum w x)^T + W my mx^T]
-    const double inv = 1.0 / (comb_s[1] + 1e-4);
-    const float invf = (float)inv;
-    const int a = tid / 3, c = tid - 3 * a;
-    const double mxc = (double)(float)(comb_s[2 + c] * inv);  // the means are fp32 values, as in the reference
-    const double mya = (double)(float)(comb_s[5 + a] * inv);
-    const double sv = comb_s[8 + a * 3 + c] - comb_s[5 + a] * mxc - mya * comb_s[2 + c] + comb_s[0] * mya * mxc;
-    cov_s[tid] = (Kb > 0) ? sv * (double)invf : 0.0;
-    if (tid < 3) {
-      mean_s[tid] = (Kb > 0) ? (double)(float)(comb_s[2 + tid] * inv) : 0.0;
-      mean_s[3 + tid] = (Kb > 0) ? (double)(float)(comb_s[5 + tid] * inv) : 0.0;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    float R[9], t[3];
-    double cond;
-    double S[3][3];
-    for (int a = 0; a < 3; ++a)
-      for (int c = 0; c < 3; ++c) S[a][c] = cov_s[a * 3 + c];
-    PSTAMPL(808);
-    kabsch_solve(S, mean_s, mean_s + 3, R, t, &cond);
-    PSTAMPL(809);
-    finish_pose(p, b, R, t, cond);
-    for (int k = 0; k < 9; ++k) pose_s[k] = p.R_forwd[b * 9 + k];
-    for (int k = 0; k < 3; ++k) pose_s[9 + k] = p.t_forwd[b * 3 + k];
-  }
-  if (p.sel_w) {
-    const unsigned int ne = min(__ldcg(&p.state[b].sel_count), (unsigned int)p.K_max);
-    for (int k = (int)ne + tid; k < p.K_max; k += PP_THREADS) {
-      p.sel_w[(size_t)b * p.K_max + k] = 0.f;
-      p.sel_src[(size_t)b * p.K_max + k] = 0;
-      p.sel_tgt[(size_t)b * p.K_max + k] = 0;
-    }
-  }
-  __syncthreads();
-  // ---- warp the source points with the gated pose:  (R_forwd s + t_forwd)     pipeline.py:220
+  WSYNC();
+  // ---- warp my rows' source points with the gated pose:  (R_forwd s + t_forwd)     pipeline.py:220
   if (p.src_warped) {
+    if (tid < 12) pose_s[tid] = tid < 9 ? __ldcg(p.R_forwd + b * 9 + tid) : __ldcg(p.t_forwd + b * 3 + (tid - 9));
+    WSYNC();
     float* o = p.src_warped + (size_t)b * N * 3;
-    for (int i0 = 0; i0 < N; i0 += PP_THREADS * 8) {  // eight points per thread and batch: 24 loads in flight
-      float xin[8][3];
+    for (int i = row_lo + tid; i < row_hi; i += PP_THREADS) {
+      const float x0 = sp[i * 3 + 0], x1 = sp[i * 3 + 1], x2 = sp[i * 3 + 2];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * PP_THREADS + tid;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) xin[u][a] = i < N ? sp[i * 3 + a] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * PP_THREADS + tid;
-        if (i < N) {
-#pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            // same association as a 3-term dot product followed by the translation add
-            float acc = pose_s[a * 3 + 0] * xin[u][0];
-            acc = fmaf(pose_s[a * 3 + 1], xin[u][1], acc);
-            acc = fmaf(pose_s[a * 3 + 2], xin[u][2], acc);
-            o[i * 3 + a] = acc + pose_s[9 + a];
-          }
-        }
+      for (int a = 0; a < 3; ++a) {
+        // same association as a 3-term dot product followed by the translation add
+        float acc = pose_s[a * 3 + 0] * x0;
+        acc = fmaf(pose_s[a * 3 + 1], x1, acc);
+        acc = fmaf(pose_s[a * 3 + 2], x2, acc);
+        o[i * 3 + a] = acc + pose_s[9 + a];
       }
     }
   }
-  PSTAMPL(810);
+  PSTAMP0(810);
 }
 #undef PSTAMP0
 #undef PSTAMPL
+#undef PSTAMPF
 
 // standalone weighted Kabsch on given correspondences: X, Y [B,K,3], w [B,K]
 struct KabschParams {
@@ -1523,16 +1528,16 @@ static int procr_search(const ProcrParams& p, cudaStream_t st) {
 }
 
 static int procr_pose(const ProcrParams& p, cudaStream_t st) {
-  int G = NUM_SMS / p.B - 1;   // working CTAs per batch element (+ one that only warms the instruction caches)
+  int G = NUM_SMS / p.B;
   if (G > PP_MAX_G) G = PP_MAX_G;
   if (G > p.N) G = p.N;
   if (G < 1) G = 1;
   const size_t smem = (size_t)p.mine_cap * 8 + (size_t)p.surv_cap * 4;
   DRG_CUDA(cudaFuncSetAttribute(procr_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof_scope(PROF_PROCR_SOLVE, st);
-  if ((long long)(G + 1) * p.B > NUM_SMS || G == 1) {
+  if ((long long)G * p.B > NUM_SMS || G == 1) {
     // one working CTA per batch element never waits for another CTA: an ordinary launch, any batch size
-    procr_pose_kernel<<<dim3(2, p.B), PP_THREADS, smem, st>>>(p);
+    procr_pose_kernel<<<dim3(1, p.B), PP_THREADS + 32, smem, st>>>(p);
     DRG_LAUNCH_CHECK();
     return DRG_OK;
   }
@@ -1540,7 +1545,7 @@ static int procr_pose(const ProcrParams& p, cudaStream_t st) {
   // cooperative launch guarantees that they are co-resident
   ProcrParams pp = p;
   void* args[] = {(void*)&pp};
-  DRG_CUDA(cudaLaunchCooperativeKernel((const void*)procr_pose_kernel, dim3(G + 1, p.B), dim3(PP_THREADS), args, smem, st));
+  DRG_CUDA(cudaLaunchCooperativeKernel((const void*)procr_pose_kernel, dim3(G, p.B), dim3(PP_THREADS + 32), args, smem, st));
   count_launch();
   return DRG_OK;
 }

@@ -824,6 +824,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
   };
   if (tid == 0) {
     DRG_STAMP(0);
+    if (do_collect) DRG_STAMP(704);
     cnt_s[0] = cnt_s[1] = 0;
     for (int s = 0; s < D; ++s) mbar_init(&full[s], 1u);
     fence_mbar_init();

@@ -250,20 +250,25 @@ def test_host_step_pipeline_matches_direct_steps():
     pipe = diffreg_b200.HostStepPipeline(smp2, N, M, C, DEV)
     pipe.counter.zero_()                       # the capture / warm-up runs advanced the Philox offset
     pinned = {k: pb[k].pin_memory() for k in keys}
+    for slot in range(2):                      # even steps travel as ONE packed copy out of the pipeline's staging views ...
+        for k in keys:
+            pipe.staging(slot)[k].copy_(pb[k])
     pipe.reset(x_T)
-    pipe.prefetch(0, pinned)
+    pipe.prefetch(0)
     for i in range(STEPS):
         pipe.launch(i)
         if i + 1 < STEPS:
-            pipe.prefetch(i + 1, pinned)
+            pipe.prefetch(i + 1, pinned if (i + 1) % 2 else None)      # ... odd steps tensor by tensor from caller memory
         out = pipe.finish(i)
         R, t, n, idx, mconf = want[i]
         assert int(out["count"][0]) == n
-        # the candidate list of the pose step is appended with atomics: its order, hence the rounding of the moment sums, varies
-        assert torch.allclose(out["R"], R, atol=2e-6, rtol=0) and torch.allclose(out["t"], t, atol=2e-6, rtol=0)
+        # the pose is bit-reproducible: the selected candidates are reduced in index order, whatever order the atomics
+        # appended them in (eager launches there, graph replays here)
+        assert torch.equal(out["R"], R) and torch.equal(out["t"], t)
         assert torch.equal(out["index"][:n], idx) and torch.equal(out["mconf"][:n], mconf)
     assert torch.equal(pipe.state(STEPS), x_direct)
-    assert pipe.h2d_bytes == sum(v.numel() * v.element_size() for v in pinned.values())
+    payload = sum(v.numel() * v.element_size() for v in pinned.values())
+    assert payload <= pipe.h2d_bytes < payload + 6 * 256               # the six tensors + alignment padding, one copy
 
 
 @pytest.mark.parametrize("name", ["pe_rotary_528", "pe_sinusoidal_432", "pe_rotary_36_b2"])

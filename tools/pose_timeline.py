@@ -67,12 +67,12 @@ for it in range(3):
     b0 = 10 + it * 100
     print(f"  it {it}: prologue {us(b0, b0 + 1):.1f}  pass {us(b0 + 1, b0 + 2):.1f}  partials {us(b0 + 2, b0 + 3):.1f}  barrier1 {us(b0 + 3, b0 + 4):.1f}"
           f"  merge {us(b0 + 4, b0 + 5):.1f}  barrier2 {us(b0 + 5, b0 + 6):.1f}")
-print(f"  tail: bound {us(700, 701):.1f}  pass {us(701, 702):.1f}  flush {us(702, 703):.1f}   total kernel {us(0, 703):.1f} us")
+print(f"  tail: bound {us(700, 701):.1f}  pass {us(701, 702):.1f}  flush {us(702, 703):.1f}   total kernel {us(704, 703):.1f} us")
 ns = lambda a, b: (t[b] - t[a]) / 1e3 if t[a] and t[b] else float("nan")
 print(f"pose kernel (CTA 0): hist+state+walk {ns(800, 801):.1f}  scan {ns(801, 802):.1f}  T {ns(802, 803):.1f}  sort {ns(803, 804):.1f}  "
       f"gather+moments {ns(804, 805):.1f}  reduce+ticket {ns(805, 806):.1f}")
-print(f"pose kernel (last CTA): start->last ticket {ns(800, 807):.1f}  combine {ns(807, 808):.1f}  svd {ns(808, 809):.1f}  finish+warp {ns(809, 810):.1f}  "
-      f"total {ns(800, 810):.1f} us")
+print(f"pose kernel (finisher warp of CTA 0): start->all sums arrived {ns(800, 807):.1f}  combine {ns(807, 808):.1f}  svd {ns(808, 809):.1f}  "
+      f"publish + warp of CTA 0's rows {ns(809, 810):.1f}  total {ns(800, 810):.1f} us")
 if t[908] and t[909]:
     print(f"SM clock during the single-thread SVD: {(t[909] - t[908]) / max(t[809] - t[808], 1) * 1e3:.0f} MHz (clock64 / globaltimer)")
 ws = [v for k, v in ops._workspaces.items() if k[2] == "procrustes"][0]
