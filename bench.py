@@ -3,7 +3,9 @@
 N=M=4096, d=256; Sinkhorn HBM GB/s vs peak).
 
     python bench.py --gpus N --steps K --warmup W            # this framework (one process per GPU under torchrun)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port) on the host
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation on the host cores
+                                                             # (oracle/_ref = the unmodified reference modules; the oracle
+                                                             # port when that copy is absent)
 
 One "step" is one reverse-diffusion step of one 4DMatch-shaped sample (BASELINE.json configs[2]: N=M=4096,
 d=256, Sinkhorn iters 3, eta=1 with noise), transformer excluded (features held fixed):
@@ -13,8 +15,10 @@ Each GPU runs its own independent sample (weak scaling, no collective on the dat
 
 Printed JSON line (rank 0): value = steps/s with inputs resident in HBM (CUDA-graph replay of the 20 step
 graphs); e2e = the same step driven through the public modules with HOST (pinned) inputs copied in and the
-step's results (pose, match count, matches) copied out every step; roofline = the fused Sinkhorn/DDIM call
-timed with CUDA events inside an eager pass over the same steps; cpu_baseline = the oracle port on the host.
+step's results (pose, match count, matches) copied out every step; roofline = the dominant kernel (the persistent
+Sinkhorn) timed with CUDA events inside an eager pass over the same steps; cpu_baseline = the reference on the host;
+rowshard = BASELINE.json configs[4] (N=M=16384, 100 iterations; rows sharded over the N ranks); other_configs =
+configs[0], [1], [3] timed once each (N=1 only).  `config` is identical in both arms; how a run was timed is in `run_info`.
 """
 import argparse
 import json
@@ -47,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32"])
+    ap.add_argument("--no-rowshard", action="store_true", help="skip the BASELINE configs[4] line (16384^2 x 100 iterations)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the configs[0] / [1] / [3] lines")
     return ap.parse_args()
 
 
@@ -83,6 +89,35 @@ def make_inputs(seed, n, c):
     x_T = torch.randn(1, n, n, generator=g)
     return dict(src_feats=src_feats, tgt_feats=tgt_feats, W=W, s_pcd=s_pcd, t_pcd=t_pcd, src_mask=ones, tgt_mask=ones.clone(),
                 x_T=x_T)
+
+
+def make_batch(seed, B, N, M, c, valid=None, invalid_fraction=0.0):
+    """Batched synthetic pairs for the non-headline configurations: the inputs of make_inputs per pair, with prefix masks
+    (valid = [(n_src, n_tgt), ...]: padded features / points are zero, as the reference's collate leaves them) or
+    arbitrary masks (invalid_fraction of the entries of each side switched off)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    pb = dict(src_feats=torch.randn(B, N, c, generator=g), tgt_feats=torch.randn(B, M, c, generator=g),
+              W=(torch.rand(c, c, generator=g) * 2 - 1) / math.sqrt(c), s_pcd=torch.randn(B, N, 3, generator=g),
+              t_pcd=torch.empty(B, M, 3), src_mask=torch.ones(B, N, dtype=torch.bool), tgt_mask=torch.ones(B, M, dtype=torch.bool))
+    for b in range(B):
+        q = torch.randn(4, generator=g)
+        w, x, y, z = (q / q.norm()).tolist()
+        R = torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                          [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        perm = torch.randint(0, N, (M,), generator=g)
+        pb["t_pcd"][b] = pb["s_pcd"][b, perm] @ R.t() + torch.randn(3, generator=g) + 0.01 * torch.randn(M, 3, generator=g)
+    if valid is not None:
+        for b, (ns, nt) in enumerate(valid):
+            pb["src_mask"][b, ns:] = False
+            pb["tgt_mask"][b, nt:] = False
+            for k_, cut in (("src_feats", ns), ("s_pcd", ns), ("tgt_feats", nt), ("t_pcd", nt)):
+                pb[k_][b, cut:] = 0
+    if invalid_fraction > 0:
+        pb["src_mask"] &= torch.rand(B, N, generator=g) >= invalid_fraction
+        pb["tgt_mask"] &= torch.rand(B, M, generator=g) >= invalid_fraction
+    return pb
 
 
 MATCH_CFG = dict(match_type="sinkhorn", confidence_threshold=0.2, feature_dim=FEAT_DIM, entangled=True, dsmax_temperature=0.1,
@@ -145,19 +180,58 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU leg: the oracle port (restatement of the reference's PyTorch code) on the host cores
+# CPU leg: the reference's own modules (unmodified, from oracle/_ref or /root/reference) on the host cores; the oracle
+# port (a restatement of the same PyTorch code) only when no copy of the reference is at hand
 # --------------------------------------------------------------------------------------------
 def cpu_step_runner(n, seed=3000):
-    """Returns (run_one_step, cores).  The oracle is the checker / CPU baseline only (oracle/ header)."""
+    """Returns (run_one_step, cores, kind, what).  oracle/ is the checker / CPU baseline only (oracle/ header)."""
     import torch
-    from oracle import diffreg_oracle as O
+    from types import SimpleNamespace
+    from oracle import ref_loader
     torch.set_num_threads(os.cpu_count() or 1)
     inp = make_inputs(seed, n, FEAT_DIM)
+    g = torch.Generator().manual_seed(seed + 1)
+    if ref_loader.available():
+        # the loop body of Diff-Reg-4dmatch/models/pipeline.py:171-190 driven with the reference's own objects (the
+        # denoising transformer is outside the step: features held fixed, SURVEY.md 8d).  Note the reference's state turns
+        # fp64 after the first step (its fp64 schedule buffers promote it, SURVEY.md Q4): that is what it costs on a CPU.
+        ns = ref_loader.load_flavour("4d")
+        P = ns.pipeline
+        with torch.no_grad():
+            head = ns.matching.Matching(MATCH_CFG)
+            head.src_proj.weight.copy_(inp["W"])
+            head.eval()
+        proc = ns.procrustes.SoftProcrustesLayer(SimpleNamespace(sample_rate=1.0, max_condition_num=40.0))
+        ac = torch.cumprod(1.0 - P.cosine_beta_schedule(1000), dim=0)
+        fake = SimpleNamespace(alphas_cumprod=ac, sqrt_recip_alphas_cumprod=torch.sqrt(1.0 / ac),
+                               sqrt_recipm1_alphas_cumprod=torch.sqrt(1.0 / ac - 1), denoising_coarse_matching=head,
+                               denoising_soft_procrustes=proc)
+        times = list(reversed(torch.linspace(0, 999, steps=SAMPLER_STEPS + 1).int().tolist()))
+        pairs = list(zip(times[:-1], times[1:]))
+        state = {"x": inp["x_T"].clone(), "k": 0}
+
+        def one_step():
+            with torch.no_grad():
+                time_, time_next = pairs[state["k"] % SAMPLER_STEPS]
+                if state["k"] % SAMPLER_STEPS == 0:
+                    state["x"] = inp["x_T"].clone()          # a new sample starts in fp32, as in the reference
+                x = state["x"]
+                P.Pipeline.get_warped_from_noising_matching(fake, inp["s_pcd"], inp["t_pcd"], inp["src_mask"], inp["tgt_mask"], x)
+                x_start, _ = head(inp["src_feats"], inp["tgt_feats"], None, None, inp["src_mask"], inp["tgt_mask"], {})
+                pred = P.Pipeline.predict_noise_from_start(fake, x, torch.full((1,), time_, dtype=torch.long), x_start)
+                alpha, alpha_next = ac[time_], ac[time_next]
+                sigma = 1.0 * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+                c = (1 - alpha_next - sigma ** 2).sqrt()
+                state["x"] = x_start * alpha_next.sqrt() + c * pred + sigma * torch.randn(x.shape, generator=g)
+                state["k"] += 1
+
+        root, where = ref_loader.reference_root()
+        return one_step, torch.get_num_threads(), "reference", f"the unmodified reference modules ({where}: Diff-Reg-4dmatch models/matching.py, procrustes.py, pipeline.py), torch CPU"
+    from oracle import diffreg_oracle as O
     p = O.MatchingParams(src_proj_weight=inp["W"], bin_score=torch.tensor(1.0), skh_iters=SKH_ITERS)
     ac = O.alphas_cumprod()
     pairs = O.time_pairs(SAMPLER_STEPS)
     state = {"x": inp["x_T"].clone(), "k": 0}
-    g = torch.Generator().manual_seed(seed + 1)
 
     def one_step():
         with torch.no_grad():
@@ -172,16 +246,16 @@ def cpu_step_runner(n, seed=3000):
             state["x"] = O.ddim_update(x, x0, ac, t, tn, noise).float()
             state["k"] += 1
 
-    return one_step, torch.get_num_threads()
+    return one_step, torch.get_num_threads(), "port", "oracle port of the reference's PyTorch path (oracle/_ref absent), torch CPU fp32"
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    one_step, cores = cpu_step_runner(args.n)
+    one_step, cores, kind, what = cpu_step_runner(args.n)
     # bounded sample: every step is a full denoising step of the workload; at most ~2.5 min of timed CPU work
-    # (about 3 s per step at the headline shape), so K large only raises the cap, not the run time
+    # (seconds per step at the headline shape), so K large only raises the cap, not the run time
     for _ in range(min(args.warmup, 2)):
         one_step()
     t0 = time.perf_counter()
@@ -191,12 +265,12 @@ def run_reference_arm(args):
         done += 1
     dt = time.perf_counter() - t0
     value = done / dt
-    sample = (f"{done} full denoising steps (of K={args.steps} requested; capped at 150 s) at N=M={args.n} on {cores} host threads "
-              f"(torch CPU, fp32; oracle port of the reference's PyTorch path)")
+    sample = (f"{done} full denoising steps (of K={args.steps} requested; capped at 150 s) at N=M={args.n} on {cores} host threads; "
+              f"{what}")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference", "config": workload_config(args.n),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     _emit(line)
 
@@ -341,17 +415,25 @@ def run_ours(args):
     w2 = max(args.warmup, 3)
     e2e_run(0, w2)
     torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(w2, args.steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    # K steps per repetition, E2E_REPS repetitions, the MEDIAN is reported (K = 20 steps are ~7 ms of wall clock: one host
+    # hiccup would move a single measurement by percent); every repetition is bracketed like the timed region above
+    e2e_reps = []
+    pos = w2
+    for _ in range(E2E_REPS):
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(pos, args.steps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        pos += args.steps
+        if dist is not None:
+            tt = torch.tensor([dt], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e_reps.append(dt)
+    e2e_s = sorted(e2e_reps)[len(e2e_reps) // 2]
     e2e_launches = launches_per_step * args.steps      # graph nodes replayed (counted once, eagerly, above)
     barrier()
-    if dist is not None:
-        tt = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
     e2e_value = world * args.steps / e2e_s
 
     # ---- roofline leg: eager pass over the same steps with the library's per-kernel CUDA-event hooks
@@ -363,83 +445,238 @@ def run_ours(args):
             eager_step(i)
         torch.cuda.synchronize()
         _lib.profile_enable(True)
-        ev = []
         for i in range(args.steps):
             eager_step(3 + i)
         torch.cuda.synchronize()
         prof = _lib.profile_read()
         _lib.profile_enable(False)
         kernel_ms = {k: round(v[0] / max(args.steps, 1), 5) for k, v in prof.items()}
-        # dominant kernels: the fused Sinkhorn call = skh_persist_kernel (all iterations: one read of the matrix per
-        # iteration, row and column log-sum-exp) + skh_final_kernel (exp / DDIM update).  Algorithmic bytes per call
-        # are SURVEY.md section 8d's (2I+2) * E with E = 4 (N+1)(M+1).
-        E = 4.0 * (n + 1) * (n + 1)
+        E = 4.0 * (n + 1) * (n + 1)          # one fp32 pass over the padded matrix
+        Ep = 4.0 * n * n
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        it_ms, it_n = prof["skh_iter"]
-        persistent = prof["skh_col"][1] == 0          # one launch runs all iterations
-        skh_ms = sum(prof[k][0] for k in ("skh_prep", "skh_iter", "skh_col", "skh_final"))
-        calls = 2 * args.steps
+        it_ms, it_n = prof["skh_iter"]           # persistent launches WITHOUT the candidate-search tail: Sinkhorn(sim), one per step
+        col_ms, col_n = prof["skh_col"]          # persistent launches WITH the tail: Sinkhorn(x_t) -> top-K candidates, one per step
+        fin_ms, fin_n = prof["skh_final"]        # the DDIM final pass of the Sinkhorn(sim) call
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if persistent and os.path.exists(tpath):      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full)
+        if os.path.exists(tpath):      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full)
             tj = json.load(open(tpath)).get("skh_persist2_kernel")
             if tj:
                 traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
-        if it_n and calls:
-            # Dominant kernel: skh_persist2_kernel = ALL I iterations of one log_optimal_transport call in one launch
-            # (row and column log-sum-exp of every iteration).  Algorithmic bytes per launch are SURVEY.md section 8d's
-            # 2*I*E (I row-LSE reads + I column-LSE reads of the padded matrix, E = 4 (N+1)(M+1)); the final exp / DDIM
-            # pass (the other 2E of the (2I+2)E call) is skh_final_tile_kernel, reported in "sinkhorn_call".
-            # DRAM traffic is far below the algorithmic bytes because the row and column pass of an iteration share
-            # one read and iterations 2..I hit the L2-resident matrix.
+        if it_n:
+            # Dominant kernel: skh_persist2_kernel = ALL I iterations of one log_optimal_transport call in one launch.
+            # Algorithmic bytes per launch are SURVEY.md 8d's 2*I*E (I row-LSE reads + I column-LSE reads of the padded
+            # matrix).  DRAM traffic is far below that: the row and the column pass of an iteration share one read and
+            # iterations 2..I hit the L2-resident matrix.  Timed: the launches of the Sinkhorn(sim) call only (the
+            # Sinkhorn(x_t) launch carries the candidate search of the pose step and is listed separately).
             it_s = it_ms * 1e-3 / it_n
-            alg_it = ((2 * SKH_ITERS) if persistent else 2) * E
-            per_call_s = skh_ms * 1e-3 / calls
-            alg_call = (2 * SKH_ITERS + 2) * E
+            alg_it = 2 * SKH_ITERS * E
             roofline = {"bound": "hbm",
-                        "kernel": "skh_persist2_kernel (register-slab persistent log-domain Sinkhorn, I=3 iterations per launch)"
-                                  if persistent else "skh_iter*_kernel (one Sinkhorn iteration)",
+                        "kernel": "skh_persist2_kernel (register-slab persistent log-domain Sinkhorn, I=3 iterations per launch)",
                         "achieved": alg_it / it_s / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_it / it_s / 1e9 / peak,
                         "traffic": traffic, "algorithmic_bytes_per_launch": alg_it, "us_per_launch": it_s * 1e6,
-                        "launches": it_n, "peak_source": peak_src,
-                        "sinkhorn_call": {"kernels": "skh_persist2_kernel + skh_final_tile_kernel (exp / DDIM + noise + arg-max pass)",
-                                          "algorithmic_bytes": alg_call, "us_per_call": per_call_s * 1e6,
-                                          "achieved": alg_call / per_call_s / 1e9, "frac": alg_call / per_call_s / 1e9 / peak}}
+                        "launches": it_n, "peak_source": peak_src}
+            if fin_n:
+                # the fused Sinkhorn(sim) + DDIM call of a step = ONE persistent launch + ONE final-pass launch.
+                # Two accountings of its algorithmic bytes: SURVEY.md's (2I+2)*E (final read + final write), and the
+                # same plus the read of x_t that the fused DDIM update adds (6E + 3E')
+                call_s = it_s + fin_ms * 1e-3 / fin_n
+                roofline["sinkhorn_ddim_call"] = {
+                    "kernels": "skh_persist2_kernel + skh_final_tile_kernel (exp, DDIM update, in-kernel noise, row/column arg-max)",
+                    "us_per_call": call_s * 1e6, "us_final_pass": fin_ms * 1e3 / fin_n,
+                    "algorithmic_bytes_2I+2": (2 * SKH_ITERS + 2) * E, "frac_2I+2": (2 * SKH_ITERS + 2) * E / call_s / 1e9 / peak,
+                    "algorithmic_bytes_6E+3Ep": 2 * SKH_ITERS * E + 3 * Ep,
+                    "frac_6E+3Ep": (2 * SKH_ITERS * E + 3 * Ep) / call_s / 1e9 / peak,
+                    "final_pass_frac_3Ep": 3 * Ep / (fin_ms * 1e-3 / fin_n) / 1e9 / peak}
+            if col_n:
+                # Sinkhorn(x_t) + candidate search: 2*I*E for the iterations + one more read of the matrix (E') for the search
+                col_s = col_ms * 1e-3 / col_n
+                roofline["sinkhorn_topk_call"] = {
+                    "kernels": "skh_persist2_kernel with the candidate-search tail (sampled bound, L2-hot pass, candidate list)",
+                    "us_per_call": col_s * 1e6, "algorithmic_bytes": alg_it + Ep, "frac": (alg_it + Ep) / col_s / 1e9 / peak,
+                    "pose_kernel_us": prof["procr_solve"][0] * 1e3 / max(prof["procr_solve"][1], 1)}
+
+    # ---- BASELINE.json configs[4]: one 16384 x 16384 log-domain Sinkhorn, 100 iterations, rows sharded over the ranks
+    rowshard = None
+    if not args.no_rowshard:
+        rowshard = bench_rowshard(torch, dist, dev, rank, world)
+
+    # ---- the other configurations, once each (single-GPU runs)
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        other = bench_other_configs(torch, dev)
 
     # ---- CPU baseline (rank 0, single-GPU runs only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        one_step, cores = cpu_step_runner(n)
+        one_step, cores, kind, what = cpu_step_runner(n)
         one_step()
         t0 = time.perf_counter()
         reps = 0
-        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 12):
+        while reps < 3 or (time.perf_counter() - t0 < 12.0 and reps < 12):
             one_step()
             reps += 1
         dt = time.perf_counter() - t0
-        cpu = {"value": reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{reps} full denoising steps at N=M={n} (oracle port of the reference's PyTorch path, torch CPU fp32, "
-                         f"after 1 warm-up step)"}
+        cpu = {"value": reps / dt, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{reps} full denoising steps at N=M={n} after 1 warm-up step; {what}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (tf32x3 tensor-core GEMM, fp32 accumulate)" if args.precision == "3xtf32" else "tf32",
-                "data": "synthetic",
-                "config": workload_config(n, {"timing": "cuda_graph_replay" if graphs is not None else "eager",
-                                              "l2": "no explicit flush: each step streams five distinct 64 MiB fp32 matrices "
-                                                    "(x_t, conf_d, sim, x0, x_next) > 126 MB L2",
-                                              "precision": args.precision, "noise": "in-kernel Philox4x32-7"}),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "data": "synthetic", "config": workload_config(n),
+                "run_info": {"timing": "cuda_graph_replay" if graphs is not None else "eager",
+                             "l2": "no explicit flush: each step streams four distinct 64 MiB fp32 matrices (x_t, sim, x_next "
+                                   "and the previous x_t) > 126 MB L2",
+                             "precision": args.precision, "noise": "in-kernel Philox4x32-7"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "h2d_copies_per_step": 1, "repetitions_s": [round(x, 6) for x in e2e_reps], "statistic": "median of repetitions",
+                        "host_runs_ahead_steps": 1},
                 "gpu_launches": int(e2e_launches * world), "launches_per_step": int(launches_per_step),
-                "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "kernel_ms_per_step": kernel_ms}
+                "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "kernel_ms_per_step": kernel_ms,
+                "rowshard": rowshard, "other_configs": other}
         _emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+E2E_REPS = 5
+
+
+def _event_ms(torch, fn, reps, dist=None, dev=None):
+    """Median CUDA-event time of fn() over `reps` runs (max over ranks per run)."""
+    times = []
+    for _ in range(reps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1)
+        if dist is not None:
+            tt = torch.tensor([t], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        times.append(t)
+    return sorted(times)[len(times) // 2]
+
+
+def bench_rowshard(torch, dist, dev, rank, world, size=16384, iters=100, reps=3):
+    """BASELINE.json configs[4]: log_optimal_transport on one size x size matrix, `iters` iterations.  world == 1: the
+    unsharded kernels; world > 1: rows sharded over the ranks, the column log-sum-exp partials exchanged inside the kernel
+    over peer-mapped memory (NVLink / NVSwitch) every iteration.  Returns the JSON sub-object (rank 0) or None."""
+    from diffreg_b200 import ops, distributed as D
+    import json as _json
+    N = M = size
+    a, b = D.shard_rows(N, world, rank)
+    scores = torch.empty(1, b - a, M, device=dev)
+    blk = 1024
+    for r0 in range(a - a % blk, b, blk):       # the same matrix whatever the world size: one generator per 1024-row block
+        gg = torch.Generator(device=dev).manual_seed(5000 + r0 // blk)
+        full_blk = torch.randn(blk, M, generator=gg, device=dev)
+        lo, hi = max(r0, a), min(r0 + blk, b)
+        if lo < hi:
+            scores[0, lo - a:hi - a] = full_blk[lo - r0:hi - r0]
+    src_mask = torch.ones(1, b - a, dtype=torch.bool, device=dev)
+    tgt_mask = torch.ones(1, M, dtype=torch.bool, device=dev)
+    alpha = torch.tensor(1.0, device=dev)
+    exchange = None
+    if world == 1:
+        call = lambda: ops.sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="conf")
+    else:
+        op = D.RowShardedSinkhorn()
+        call = lambda: op(scores, alpha, iters, src_mask, tgt_mask, out_mode="conf")
+    out = call()                                # warm-up (and the peer-to-peer connection)
+    if world > 1:
+        exchange = "p2p (in-kernel, peer-mapped memory)" if op.comm is not None else "nccl all-reduce"
+    ms = _event_ms(torch, call, reps, dist if world > 1 else None, dev)
+    # size-independent parity property: every real column of the plan, plus its dustbin-row entry, carries mass exp(norm);
+    # here: the global column sums of the N x M block must be in (0, exp(norm)] and identical for any world size
+    col = out.double().sum(dim=1)
+    if world > 1:
+        dist.all_reduce(col, op=dist.ReduceOp.SUM)
+    E = 4.0 * (N + 1) * (M + 1)
+    alg = (2 * iters + 2) * E
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(_json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    res = None
+    if rank == 0:
+        res = {"workload": f"BASELINE.json configs[4]: log-domain Sinkhorn N=M={N}, {iters} iterations, rows sharded over {world} GPU(s)",
+               "ms_per_call": ms, "us_per_iteration": 1e3 * ms / iters, "algorithmic_bytes_per_call": alg,
+               "algorithmic_GBps_whole_job": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak_per_gpu": alg / (ms * 1e-3) / 1e9 / peak / world,
+               "exchange": exchange, "repetitions": reps, "col_sum_checksum": float(col.sum()), "col_sum_max": float(col.max())}
+    if world > 1 and op.comm is not None:
+        op.comm.close()
+    del scores, out
+    return res
+
+
+def bench_other_configs(torch, dev):
+    """BASELINE.json configs[0], [1], [3] once each (CUDA events, median of a few repetitions; parity for these shapes is in
+    tests/test_configs_gpu.py).  They are reported next to the headline, they are not the metric."""
+    from types import SimpleNamespace
+    import diffreg_b200
+    from diffreg_b200.procrustes import SoftProcrustesLayer3DMatch
+    out = {}
+    keys = ("src_feats", "tgt_feats", "s_pcd", "t_pcd", "src_mask", "tgt_mask")
+
+    def head_of(cls, pb, match_type="sinkhorn"):
+        cfg = dict(MATCH_CFG, match_type=match_type)
+        h = getattr(diffreg_b200, cls)(cfg).to(dev).eval()
+        with torch.no_grad():
+            h.src_proj.weight.copy_(pb["W"].to(dev))
+        return h
+
+    # configs[0]: 4DMatch-shaped single pair, N=M=1024, Sinkhorn + SoftProcrustes, one step
+    pb = make_batch(1000, 1, 1024, 1024, FEAT_DIM)
+    dd = [pb[k].to(dev) for k in keys]
+    proc = diffreg_b200.SoftProcrustesLayer(SimpleNamespace(sample_rate=1.0, max_condition_num=40.0))
+    smp = diffreg_b200.DenoisingSampler("4d", head_of("Matching", pb), proc, 1, noise_seed=1)
+    x = torch.randn(1, 1024, 1024, device=dev)
+    fn = lambda: smp.step(0, x, None, *dd)
+    fn()
+    ms = _event_ms(torch, fn, 20)
+    out["config0"] = {"workload": "configs[0]: single pair N=M=1024, d=256, one denoising step (Sinkhorn + SoftProcrustes + GEMM + DDIM), eager launches",
+                      "ms_per_step": ms, "steps_per_s": 1e3 / ms}
+    # configs[1]: 3DMatch-shaped batch of 16 pairs, valid counts in [1792, 2048], dual-softmax matching + Procrustes
+    B, L = 16, 2048
+    g = torch.Generator().manual_seed(2000)
+    valid = [(int(torch.randint(1792, L + 1, (1,), generator=g)), int(torch.randint(1792, L + 1, (1,), generator=g))) for _ in range(B)]
+    valid[0] = (L, L)
+    pb = make_batch(2001, B, L, L, FEAT_DIM, valid=valid)
+    dd = {k: pb[k].to(dev) for k in keys}
+    head = head_of("Matching", pb, "dual_softmax")
+    proc3 = SoftProcrustesLayer3DMatch(SimpleNamespace(sample_rate=1.0, max_condition_num=40.0))
+
+    def fn1():
+        with torch.no_grad():
+            conf, _ = head(dd["src_feats"], dd["tgt_feats"], None, None, dd["src_mask"], dd["tgt_mask"], {}, None)
+            proc3(conf, dd["s_pcd"], dd["t_pcd"], dd["src_mask"], dd["tgt_mask"])
+    fn1()
+    ms = _event_ms(torch, fn1, 5)
+    out["config1"] = {"workload": "configs[1]: 16 pairs, N~M~2048 (prefix masks), dual-softmax Matching.forward (matches extracted, host count "
+                                  "read as in the reference) + SoftProcrustes (3DMatch variant), one step",
+                      "ms_per_batch": ms, "pairs_per_s": 1e3 * B / ms}
+    del dd, pb
+    # configs[3]: 2D-3D flavour, N=4800 x M=2048, arbitrary masks (~5 % invalid), 10 steps, final Sinkhorn + top-1 union
+    pb = make_batch(4000, 1, 4800, 2048, FEAT_DIM, invalid_fraction=0.05)
+    dd = [pb[k].to(dev) for k in keys]
+    smp3 = diffreg_b200.DenoisingSampler("2d3d", head_of("Matching2D3D", pb), proc, 10)
+    x_T = torch.randn(1, 4800, 2048, device=dev)
+    fn3 = lambda: smp3.sample(x_T.clone(), *dd)
+    fn3()
+    ms = _event_ms(torch, fn3, 3)
+    out["config3"] = {"workload": "configs[3]: 2D-3D flavour N=4800 x M=2048, d=256, arbitrary masks, 10 sampler steps + final Sinkhorn + "
+                                  "mutual_topk_select(k=1, mutual=False), eager launches",
+                      "ms_per_sample": ms, "steps_per_s": 1e3 * 10 / ms}
+    return out
 
 
 _JSON_FD = None

@@ -111,68 +111,6 @@ __device__ __forceinline__ float conf_at(const ProcrParams& p, int b, size_t pos
   return ex2(la * LOG2E);
 }
 
-__device__ __forceinline__ unsigned long long make_key64(unsigned int ordered_value, unsigned int flat_index) {
-  return ((unsigned long long)ordered_value << 32) | (unsigned long long)(0xFFFFFFFFu - flat_index);
-}
-
-// Exact selection of the k-th largest of n distinct 64-bit keys by one CTA (1 <= k <= n).
-// key_at(e) returns the key of element e.  Six radix levels (11,11,10,11,11,10 bits, MSB first); stops
-// early once the remaining bucket is wanted whole.  Returns T such that exactly k keys are >= T.
-// (Measured alternatives that were slower on B200: warp-aggregated histogram updates via match.any, and
-// normalising the keys to their common range first.)
-struct __align__(16) SelectScratch {
-  unsigned int hist[TK_BINS];
-  unsigned long long prefix;
-  int krem;
-  int done;
-};
-
-struct SyncAll {
-  __device__ __forceinline__ void operator()() const { __syncthreads(); }
-};
-template <int NT, class KeyAt, class Sync = SyncAll>
-__device__ unsigned long long block_select_kth(KeyAt key_at, size_t n, int k, SelectScratch& sc, Sync sync = Sync()) {
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    sc.prefix = 0ull;
-    sc.krem = k;
-    sc.done = 0;
-  }
-  sync();
-  int shift = 64;
-  const int widths[6] = {11, 11, 10, 11, 11, 10};
-  for (int level = 0; level < 6; ++level) {
-    const int wbits = widths[level];
-    shift -= wbits;
-    for (int q = tid; q < TK_BINS; q += NT) sc.hist[q] = 0u;
-    sync();
-    const unsigned long long prefix = sc.prefix;
-    const int hi_shift = shift + wbits;  // bits above the current digit
-    for (size_t e = tid; e < n; e += NT) {
-      const unsigned long long key = key_at(e);
-      const bool match = (hi_shift >= 64) ? true : ((key >> hi_shift) == prefix);
-      if (match) atomicAdd(&sc.hist[(unsigned int)((key >> shift) & ((1u << wbits) - 1u))], 1u);
-    }
-    sync();
-    if (tid < 32) {
-      int dbin;
-      unsigned int cum, hsel;
-      const unsigned int krem = (unsigned int)sc.krem;
-      warp_walk_hist(sc.hist, krem, dbin, cum, hsel);
-      if (tid == 0) {
-        sc.prefix = (prefix << wbits) | (unsigned long long)dbin;
-        sc.krem = (int)(krem - cum);
-        if (hsel == krem - cum) sc.done = 1;  // the whole bucket is wanted
-      }
-    }
-    sync();
-    if (sc.done) break;
-  }
-  const unsigned long long T = sc.prefix << shift;
-  sync();
-  return T;
-}
-
 // ---- 1. K_b and the sample-based lower bound ---------------------------------------------------
 __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrParams p) {
   extern __shared__ __align__(16) unsigned int sample_key[];  // [TS_SAMPLES]
@@ -308,8 +246,7 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
           lower_s = 0ull;
         }
         __syncthreads();
-        const unsigned long long tb = block_select_kth<TS_THREADS>(
-            [&](size_t e) { return make_key64(tmax_s[e], (unsigned int)e); }, (size_t)TS_THREADS, (int)target, sc);
+        const unsigned long long tb = block_select_kth<TS_THREADS>([&](size_t e) { return make_key64(tmax_s[e], (unsigned int)e); }, (size_t)TS_THREADS, (int)target, sc.hist, sc.ctl);
         // the select may stop at a bucket edge: the exact bound is the smallest selected maximum
         unsigned int mine = (make_key64(tmax, (unsigned int)tid) >= tb) ? tmax : 0xFFFFFFFFu;
         mine = __reduce_min_sync(0xffffffffu, mine);
@@ -341,8 +278,7 @@ __global__ void __launch_bounds__(TS_THREADS) topk_threshold_kernel(const ProcrP
         }
       }
       if (!found) {
-        lower = block_select_kth<TS_THREADS>(
-            [&](size_t e) { return make_key64(sample_key[e], sample_pos((unsigned int)e)); }, (size_t)n_s, (int)target, sc);
+        lower = block_select_kth<TS_THREADS>([&](size_t e) { return make_key64(sample_key[e], sample_pos((unsigned int)e)); }, (size_t)n_s, (int)target, sc.hist, sc.ctl);
       }
     }
   }
@@ -968,7 +904,7 @@ __global__ void __launch_bounds__(PP_THREADS + 32) procr_pose_kernel(const Procr
   unsigned long long T = 0ull;
   if (select_some && slow) {
     if (g == 0) {
-      T = block_select_kth<PP_THREADS>([&](size_t e) { return make_key64(ckey[e], cidx[e]); }, n, Kb, sc, SyncWorkers());
+      T = block_select_kth<PP_THREADS>([&](size_t e) { return make_key64(ckey[e], cidx[e]); }, n, Kb, sc.hist, sc.ctl, SyncWorkers());
       if (tid == 0) {
         p.state[b].T = T;
         __threadfence();
@@ -1380,6 +1316,10 @@ struct ProcrWorkspace {
   unsigned int* cand_hist;
   unsigned int* sample_hist;
   uint2* cand_seg;
+  unsigned int* sample_hist2;
+  float* sample_val;
+  unsigned long long* sample_list;
+  unsigned int* sample_list_n;
   double* partials;
   size_t total;
 };
@@ -1401,6 +1341,10 @@ static ProcrWorkspace procr_carve(void* ws, int B, int N, int M) {
   w.cand_hist = (unsigned int*)take(4ull * B * TK_BINS);
   w.sample_hist = (unsigned int*)take(4ull * B * TK_BINS);  // fused Sinkhorn -> collect path: histogram of the sampled log2 confidences
   w.cand_seg = (uint2*)take(8ull * B * NUM_SMS);
+  w.sample_hist2 = (unsigned int*)take(4ull * B * TK_BINS);
+  w.sample_val = (float*)take(4ull * B * 16 * (((size_t)M + 1 + 3) & ~(size_t)3));   // [B][SH_ROWS = 16][pitch4(M + 1)]
+  w.sample_list = (unsigned long long*)take(8ull * B * 16 * (((size_t)M + 1 + 3) & ~(size_t)3));
+  w.sample_list_n = (unsigned int*)take(4ull * B);
   w.partials = (double*)take(8ull * B * PP_MAX_G * PM_PART);
   w.total = off;
   return w;
@@ -1585,6 +1529,10 @@ extern "C" int drg_sinkhorn_soft_procrustes(const drg_sinkhorn_args* s, const dr
   col.cand_hist = w.cand_hist;
   col.sample_hist = w.sample_hist;
   col.cand_seg = w.cand_seg;
+  col.sample_hist2 = w.sample_hist2;
+  col.sample_val = w.sample_val;
+  col.sample_list = w.sample_list;
+  col.sample_list_n = w.sample_list_n;
   col.sample_rate = a->sample_rate;
   col.padded_lengths = a->padded_lengths;
   col.K_max = p.K_max;

@@ -782,11 +782,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
   if (do_collect) {  // ordered before their first use (the last iteration's merge) by the grid barriers in between
     for (int q = g * P2_THREADS + tid; q < TK_BINS; q += G * P2_THREADS) {
       p.col.sample_hist[(size_t)b * TK_BINS + q] = 0u;
+      p.col.sample_hist2[(size_t)b * TK_BINS + q] = 0u;
       p.col.cand_hist[(size_t)b * TK_BINS + q] = 0u;
     }
     if (g == 0 && tid == 0) {
       p.col.state[b].n_cand = 0u;
       p.col.state[b].seg_broken = 0u;
+      p.col.sample_list_n[b] = 0u;
     }
   }
 
@@ -1360,15 +1362,19 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           int i = warp;
           if (N > SH_ROWS) i = (int)(((unsigned long long)hash_u32((unsigned int)(jc * SH_ROWS + warp) + 0x9e3779b9u * (unsigned int)(b + 1)) *
                                       (unsigned long long)N) >> 32);
+          float la2 = -INFINITY;
           if (vn > -INFINITY && i < N && !(p.apply_mask && !smask[i])) {
             const float z = __ldcg(sc_b + (size_t)i * M + jc);
             const float ui = __ldcg(p.u + (size_t)b * p.ldu + i);
-            const float la2 = ((((z - shift) + ui) + vn) - bc.norm) * LOG2E;
+            la2 = ((((z - shift) + ui) + vn) - bc.norm) * LOG2E;
             if (la2 > -INFINITY) {  // (false for NaN)
               const float fb = fminf(fmaxf((la2 + SH_OFFSET) * (float)SH_PER_OCTAVE, 0.f), (float)(TK_BINS - 1));
               atomicAdd(&tail_s[(int)fb], 1u);
+            } else {
+              la2 = -INFINITY;
             }
           }
+          if (jc <= M) p.col.sample_val[((size_t)b * SH_ROWS + warp) * p.ldv + jc] = la2;  // kept for a second-level binning
         }
       }
       if (sampling) {
@@ -1399,8 +1405,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     //           the confidences a stored matrix would hold) and appended with conf >= Lv;
     //   the candidates' histogram (first level of the select in procr_pose_kernel) is filled as they are flushed.
     // =====================================================================================================
-    __shared__ int tail_i[4];     // Kb, crossing bin, top non-empty bin
-    __shared__ float tail_f[2];   // Lv
+    __shared__ int tail_i[8];     // Kb, crossing bin, top non-empty bin, crowded?, rank wanted inside the crossing bin, sub-bin, rank inside it, target
+    __shared__ unsigned long long tail_k64;   // exact 64-bit key bound (third level); 0: the bound is the value Lv alone
+    __shared__ float tail_f[3];   // Lv, log2 Lv, log2 of (an upper bound of) the largest sample
     __shared__ unsigned int cand_n_s, cand_base_s;
     const float* v_b = p.v + (size_t)b * p.ldv;
     if (tid == 0) DRG_STAMP(700);
@@ -1432,7 +1439,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
       long long target = Kb;  // N <= SH_ROWS: the sample is the whole matrix
       if (N > SH_ROWS) target = (long long)(2.0 * (double)Kb * (double)SH_ROWS / (double)N + 16.0);
       int bin = 0;
-      unsigned int cum, hsel;
+      unsigned int cum = 0u, hsel = 0u;
       if (target >= 1) warp_walk_hist(tail_s, (unsigned int)min(target, 0x7fffffffll), bin, cum, hsel);
       // highest non-empty bin (range of the candidate histogram)
       int top = 0;
@@ -1446,20 +1453,110 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
         tail_i[0] = Kb;
         tail_i[1] = bin;
         tail_i[2] = top;
-        tail_f[0] = bin > 0 ? exp2f((float)bin / (float)SH_PER_OCTAVE - SH_OFFSET) : 0.f;
+        tail_i[3] = (bin > 0 && target >= 1 && (long long)hsel > target) ? 1 : 0;   // crowded: refine
+        tail_i[7] = (int)min(target, 0x7fffffffll);
+        tail_i[4] = (int)min(target - (long long)cum, 0x7fffffffll);                // rank still wanted inside the bin
+        tail_f[1] = (float)bin / (float)SH_PER_OCTAVE - SH_OFFSET;
+        tail_f[0] = bin > 0 ? exp2f(tail_f[1]) : 0.f;
+        tail_f[2] = (float)(top + 1) / (float)SH_PER_OCTAVE - SH_OFFSET;
       }
     }
     __syncthreads();
     const int bin = tail_i[1];
+    // A crowded crossing bin (more samples in it than the whole target: a narrow distribution -- the noise-free 3DMatch /
+    // 2D-3D samplers produce nearly flat plans -- whose bin edge would let a multiple of the wanted candidates through)
+    // is re-binned: every CTA adds ITS samples of that bin to a second-level histogram (TK_BINS sub-bins across the bin),
+    // one more grid barrier, and the bound becomes a sub-bin edge: 1 / (16 * 2048) of an octave.  All CTAs read the same
+    // first-level histogram, so they take this branch together.
+    if (tail_i[3]) {
+      const float edge_lo = (float)bin / (float)SH_PER_OCTAVE - SH_OFFSET;
+      for (int j0 = g * 32; j0 <= M; j0 += G * 32) {
+        const int jc = j0 + lane;
+        if (jc < M) {
+          const float la2 = __ldcg(p.col.sample_val + ((size_t)b * SH_ROWS + warp) * p.ldv + jc);
+          if (la2 > -INFINITY) {
+            const float fb = fminf(fmaxf((la2 + SH_OFFSET) * (float)SH_PER_OCTAVE, 0.f), (float)(TK_BINS - 1));
+            if ((int)fb == bin) {
+              const float fs = fminf(fmaxf((la2 - edge_lo) * (float)(SH_PER_OCTAVE * TK_BINS), 0.f), (float)(TK_BINS - 1));
+              atomicAdd(&p.col.sample_hist2[(size_t)b * TK_BINS + (int)fs], 1u);
+            }
+          }
+        }
+      }
+      grid_barrier_ra(gcount, (unsigned int)G * (++barriers_done));
+      for (int q = tid; q < TK_BINS; q += P2_THREADS) tail_s[q] = __ldcg(p.col.sample_hist2 + (size_t)b * TK_BINS + q);
+      __syncthreads();
+      if (warp == 0) {
+        int sub = 0;
+        unsigned int cum2, hsel2;
+        warp_walk_hist(tail_s, (unsigned int)tail_i[4], sub, cum2, hsel2);   // the remaining rank inside the bin
+        int top2 = 0;
+        for (int q = TK_BINS - 1 - lane; q >= 0; q -= 32)
+          if (tail_s[q]) {
+            top2 = q;
+            break;
+          }
+        top2 = __reduce_max_sync(0xffffffffu, top2);
+        if (lane == 0) {
+          const float thr = edge_lo + (float)sub / (float)(SH_PER_OCTAVE * TK_BINS);
+          tail_f[0] = exp2f(thr);
+          tail_f[1] = thr;
+          // the largest sample: inside this bin (then known to a sub-bin) or in a higher first-level bin
+          tail_f[2] = (tail_i[2] == bin) ? edge_lo + (float)(top2 + 1) / (float)(SH_PER_OCTAVE * TK_BINS) : tail_f[2];
+          tail_i[5] = sub;
+          tail_i[6] = (int)tail_i[4] - (int)cum2;                     // rank still wanted inside the sub-bin
+          tail_i[3] = ((long long)hsel2 > 2ll * tail_i[7] + 64) ? 2 : 1;  // still crowded: values (nearly) tied -> exact keys
+        }
+      }
+      __syncthreads();
+      if (tail_i[3] == 2) {
+        // Third level, exact: the samples of the crowded sub-bin as 64-bit keys (value, ~flat index) in a global list, one
+        // more grid barrier, and every CTA selects the wanted rank among them itself (general radix select: slow, but this
+        // is the path of nearly flat / tied plans).  The bound is then a KEY: ties in value are cut by index, so the
+        // candidate count stays ~2 K_b whatever the distribution.
+        const int sub = tail_i[5];
+        for (int j0 = g * 32; j0 <= M; j0 += G * 32) {
+          const int jc = j0 + lane;
+          if (jc < M) {
+            const float la2 = __ldcg(p.col.sample_val + ((size_t)b * SH_ROWS + warp) * p.ldv + jc);
+            if (la2 > -INFINITY) {
+              const float fb = fminf(fmaxf((la2 + SH_OFFSET) * (float)SH_PER_OCTAVE, 0.f), (float)(TK_BINS - 1));
+              const float fs = fminf(fmaxf((la2 - edge_lo) * (float)(SH_PER_OCTAVE * TK_BINS), 0.f), (float)(TK_BINS - 1));
+              if ((int)fb == bin && (int)fs == sub) {
+                int i = warp;
+                if (N > SH_ROWS) i = (int)(((unsigned long long)hash_u32((unsigned int)(jc * SH_ROWS + warp) + 0x9e3779b9u * (unsigned int)(b + 1)) *
+                                            (unsigned long long)N) >> 32);
+                const unsigned int pos = atomicAdd(&p.col.sample_list_n[b], 1u);
+                p.col.sample_list[(size_t)b * SH_ROWS * p.ldv + pos] = make_key64(float_to_ordered(ex2(la2)), (unsigned int)((size_t)i * M + jc));
+              }
+            }
+          }
+        }
+        grid_barrier_ra(gcount, (unsigned int)G * (++barriers_done));
+        const unsigned int n3 = __ldcg(p.col.sample_list_n + b);
+        const unsigned long long* lst = p.col.sample_list + (size_t)b * SH_ROWS * p.ldv;
+        __shared__ SelectCtl sel_ctl;
+        const int want3 = max(1, min(tail_i[6], (int)n3));
+        const unsigned long long T3 = block_select_kth<P2_THREADS>([&](size_t e) { return __ldcg(lst + e); }, (size_t)n3, want3, tail_s, sel_ctl);
+        if (tid == 0) {
+          tail_k64 = T3;
+          tail_f[0] = ordered_to_float((unsigned int)(T3 >> 32));
+        }
+        __syncthreads();
+      }
+    }
     const float Lv = tail_f[0];
-    const float thr2 = bin > 0 ? ((float)bin / (float)SH_PER_OCTAVE - SH_OFFSET) - 1.0e-3f : -INFINITY;  // pre-filter margin
+    const bool exact_bound = tail_i[3] == 2;
+    // candidates are the entries with 64-bit key (value, ~flat index) >= lower64; without the third level that is conf >= Lv
+    const unsigned long long lower64 = exact_bound ? tail_k64 : ((unsigned long long)float_to_ordered(Lv) << 32);
+    const float thr2 = bin > 0 ? tail_f[1] - 1.0e-3f : -INFINITY;  // pre-filter margin (its arithmetic is folded differently)
     const unsigned int kmin = float_to_ordered(Lv);
-    const unsigned int smax = float_to_ordered(exp2f((float)(tail_i[2] + 1) / (float)SH_PER_OCTAVE - SH_OFFSET));
+    const unsigned int smax = float_to_ordered(exp2f(tail_f[2]));
     const int hist_sh = cand_hist_shift(kmin, smax, bin > 0);
     if (g == 0 && tid == 0) {
       ProcrState* sp = p.col.state + b;  // n_cand is being accumulated by the CTAs: field-wise
       sp->Kb = Kb;
-      sp->lower_key = (unsigned long long)kmin << 32;
+      sp->lower_key = lower64;
       sp->T = 0ull;
       sp->hist_kmin = kmin;
       sp->hist_sh = hist_sh;
@@ -1512,9 +1609,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
                 for (int e = 0; e < 4; ++e) {
                   if (!(v2c[k][e] > -INFINITY)) continue;  // masked column
                   const float cf = ex2(((((zq[e] - shift) + ui) + vraw[k][e]) - bc.norm) * LOG2E);
-                  if (cf >= Lv) {
-                    const unsigned int key = float_to_ordered(cf);
-                    const unsigned int fi = (unsigned int)((size_t)i * M + c + e);
+                  const unsigned int key = float_to_ordered(cf);
+                  const unsigned int fi = (unsigned int)((size_t)i * M + c + e);
+                  if (make_key64(key, fi) >= lower64) {
                     const unsigned int pos = atomicAdd(&cand_n_s, 1u);
                     if (pos < (unsigned int)CL_CAP) {
                       tail_s[pos] = key;
