@@ -63,6 +63,8 @@ def _declare(lib):
     lib.drg_sinkhorn_shard_final.argtypes = [ctypes.POINTER(SinkhornArgs), c_void_p, c_size_t, c_void_p]
     lib.drg_sinkhorn_shard_local_exchange.restype = c_int
     lib.drg_sinkhorn_shard_local_exchange.argtypes = [ctypes.POINTER(SinkhornArgs), c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.drg_sinkhorn_shard_iterate.restype = c_int
+    lib.drg_sinkhorn_shard_iterate.argtypes = [ctypes.POINTER(SinkhornArgs), c_void_p, c_size_t, c_void_p, c_int, c_void_p]
     lib.drg_p2p_handle_bytes.restype = c_size_t
     lib.drg_p2p_create.restype = c_int
     lib.drg_p2p_create.argtypes = [c_int, c_int, c_size_t, c_int, ctypes.POINTER(c_void_p), c_void_p]

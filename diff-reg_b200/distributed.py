@@ -180,8 +180,7 @@ class RowShardedSinkhorn:
         st.begin(counts)
         comm = self._p2p(st.B, st.M)
         if comm is not None:
-            for it in range(int(iters)):
-                st.local_exchange(comm.handle)
+            st.iterate_exchange(comm.handle, int(iters))
             out = st.final(out_mode)
             self._check_exchange(comm, scores_local.device)
             return out

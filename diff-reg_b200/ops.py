@@ -353,6 +353,10 @@ class ShardedSinkhornState:
         `comm` is distributed.P2PComm.handle)."""
         check(self.lib.drg_sinkhorn_shard_local_exchange(self._args(), self.ws.data_ptr(), self.ws.numel(), comm, _stream()))
 
+    def iterate_exchange(self, comm, iters):
+        """`iters` iterations of local_exchange enqueued by ONE library call."""
+        check(self.lib.drg_sinkhorn_shard_iterate(self._args(), self.ws.data_ptr(), self.ws.numel(), comm, int(iters), _stream()))
+
     def update(self, reduced):
         reduced = _f32c(reduced)
         check(self.lib.drg_sinkhorn_shard_update(self._args(), self.ws.data_ptr(), self.ws.numel(), reduced.data_ptr(), _stream()))

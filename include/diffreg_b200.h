@@ -51,6 +51,10 @@ int drg_profile_read(int slot, double* total_ms, long long* count);
 int drg_profile_slots(void);
 /* sizeof(drg_sinkhorn_args) / sizeof(drg_procrustes_args) as this library was compiled: a binding checks its own mirror of
  * the argument structs against these before the first call (a shorter mirror would make the library read past its end). */
+/* Tuning hook: a caller-owned DEVICE buffer of >= 1024 int64 in which CTA 0 of the persistent Sinkhorn (clock64 cycles) and
+ * the pose kernel (globaltimer ns, slots 800+) leave stamps of their phases; NULL switches the stamps off (the default).
+ * Used by tools/pose_timeline.py and tools/skh_timeline.py; the library itself never allocates. */
+int drg_tuning_set_stamp_buffer(long long* device_buffer);
 size_t drg_sizeof_sinkhorn_args(void);
 size_t drg_sizeof_procrustes_args(void);
 
@@ -157,6 +161,10 @@ int drg_p2p_status(void* comm);
 int drg_p2p_destroy(void* comm);
 int drg_sinkhorn_shard_local_exchange(const drg_sinkhorn_args* args, void* workspace, size_t workspace_bytes, void* comm,
                                       void* stream);
+/* `iters` iterations of drg_sinkhorn_shard_local_exchange enqueued back to back (one host call per Sinkhorn instead of one
+ * per iteration: at 8 GPUs an iteration is shorter than a host round trip). */
+int drg_sinkhorn_shard_iterate(const drg_sinkhorn_args* args, void* workspace, size_t workspace_bytes, void* comm, int iters,
+                               void* stream);
 
 /* Dual-softmax confidence: conf = softmax_src(sim/T | src mask) * softmax_tgt(sim/T | tgt mask)
  *   replaces Diff-Reg-4dmatch/models/matching.py:147-157 (sim already divided by nothing:

@@ -20,7 +20,7 @@ def test_header_declares_the_path():
     names = _declared()
     for needed in ("drg_sinkhorn", "drg_dual_softmax", "drg_gemm_nt_tf32", "drg_prep_operand", "drg_match_count", "drg_match_write",
                    "drg_soft_procrustes", "drg_weighted_procrustes", "drg_sinkhorn_shard_local", "drg_sinkhorn_shard_update",
-                   "drg_sinkhorn_shard_local_exchange", "drg_p2p_handle_bytes", "drg_p2p_create", "drg_p2p_connect", "drg_p2p_status",
+                   "drg_sinkhorn_shard_local_exchange", "drg_sinkhorn_shard_iterate", "drg_p2p_handle_bytes", "drg_p2p_create", "drg_p2p_connect", "drg_p2p_status",
                    "drg_p2p_destroy", "drg_position_code", "drg_gemm_nt_3xtf32", "drg_project_split3"):
         assert needed in names
 

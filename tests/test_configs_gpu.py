@@ -207,3 +207,94 @@ def test_config4_sinkhorn_16384_100_iterations_and_row_shards():
     shards = diffreg_b200.EmulatedRowShards(8)(s, alpha, 100, sm, tm, out_mode="conf")
     assert (shards - whole).abs().max().item() <= 2e-6
     assert (whole - out[:, :N, :M].exp()).abs().max().item() <= 1e-6
+
+
+def test_config2_all_20_steps_against_the_fp64_creep_of_the_reference():
+    """the bench runs 20 sampler steps with an fp32 state; the reference's state drifts to fp64 after the
+    first step (its fp64 schedule buffers promote it).  All 20 steps at N = M = 4096 with the noise supplied,
+    against the oracle with state_dtype=None (the reference's dtype behaviour, its Sinkhorn on the state in fp64): the final
+    sigmoid(x) must agree to 1e-4, and the per-step drift of the state is written to gpurun_out/ (copied to profiles/)."""
+    import json
+    import os
+    import diffreg_b200
+    N = M = 4096
+    STEPS = 20
+    pb = O.make_problem(3000, 1, N, M, 256)
+    d = {k: pb[k].to(DEV) for k in KEYS}
+    g = torch.Generator(device=DEV).manual_seed(3003)
+    x_T = torch.randn(1, N, M, generator=g, device=DEV)
+    noises = [torch.randn(1, N, M, generator=g, device=DEV) for _ in range(STEPS)]
+    p = _params(pb, DEV)
+    ac = O.alphas_cumprod()
+    pairs = O.time_pairs(STEPS)
+    head = _head("Matching", pb)
+    proc = diffreg_b200.SoftProcrustesLayer(SimpleNamespace(sample_rate=1.0, max_condition_num=40.0))
+    smp = diffreg_b200.DenoisingSampler("4d", head, proc, STEPS)
+    sim, *_ = O.similarity(p, d["src_feats"], d["tgt_feats"])                    # fixed features: x0 is the same every step
+    x0_ref = O.confidence_from_similarity(p, sim, d["src_mask"], d["tgt_mask"])
+    del sim
+    x = x_T.clone()        # reference state: fp32 at the start, fp64 from the first update on
+    xg = x_T.clone()       # ours: fp32 throughout
+    drift = []
+    for k in range(STEPS):
+        warped, _, pose = O.noisy_matching_to_pose(x, p.bin_score, p.skh_iters, d["s_pcd"], d["t_pcd"], d["src_mask"],
+                                                   d["tgt_mask"], 1.0, 40.0)
+        x = O.ddim_update(x, x0_ref, ac, pairs[k][0], pairs[k][1], noises[k])      # state_dtype=None: stays fp64
+        assert x.dtype == torch.float64
+        xg, _, aux = smp.step(k, xg, None, *[d[kk] for kk in KEYS], noise=noises[k])
+        err = (xg.double() - x).abs().max().item()
+        scale = x.abs().max().item()
+        ang = rot_angle(aux["pose"]["R"].cpu(), pose[0].cpu()).max().item()
+        drift.append({"step": k, "t": pairs[k][0], "max_abs_state_err": err, "state_abs_max": scale,
+                      "pose_angle_err_rad": ang, "pose_t_err": (aux["pose"]["t"].cpu() - pose[1].cpu()).abs().max().item(),
+                      "gate_agrees": bool(torch.equal(aux["pose"]["solution_mask"].cpu().bool(), pose[5].cpu().bool()))})
+        assert err <= TOL_LOG * max(1.0, scale), (k, err, scale)
+        del warped
+    conf_ref = torch.sigmoid(x)
+    conf = diffreg_b200.ops.sigmoid(xg)
+    final_err = (conf.double() - conf_ref).abs().max().item()
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "r2_drift_20steps_4096.json"), "w") as f:
+        json.dump({"workload": "BASELINE configs[2], 20 steps, N=M=4096, noise supplied; ours (fp32 state) vs oracle with the "
+                               "reference's fp64 state creep", "final_sigmoid_max_abs_err": final_err, "steps": drift}, f, indent=1)
+    assert final_err <= TOL_LOG, final_err
+
+
+def test_config1_3dmatch_variant_and_3d_sampler_at_2048():
+    """configs[1] through the 3DMatch SoftProcrustes variant (padded lengths, 3d procrustes.py:61-62),
+    and the '3d' sampler flavour (x -= x.min() first, no noise, max_condition_num = 0 as configs/test/3dmatch.yaml ships it,
+    final Sinkhorn + top-1 union) at 2048 x 2048 against the oracle."""
+    import diffreg_b200
+    from diffreg_b200.procrustes import SoftProcrustesLayer3DMatch
+    B, L = 4, 2048
+    g = torch.Generator().manual_seed(2100)
+    valid = [(int(torch.randint(1792, L + 1, (1,), generator=g)), int(torch.randint(1792, L + 1, (1,), generator=g))) for _ in range(B)]
+    pb = O.make_problem(2101, B, L, L, 256, prefix_valid=valid)
+    d = {k: pb[k].to(DEV) for k in KEYS}
+    p = _params(pb, DEV)
+    p.match_type = "dual_softmax"
+    ref_conf = O.matching_forward_3d(p, d["src_feats"], d["tgt_feats"], None, None, d["src_mask"], d["tgt_mask"])[0]
+    proc3 = SoftProcrustesLayer3DMatch(SimpleNamespace(sample_rate=1.0, max_condition_num=40.0))
+    R, t, Rf, tf, cond, ok_mask = proc3(ref_conf, d["s_pcd"], d["t_pcd"], d["src_mask"], d["tgt_mask"])
+    rR, rt, rRf, rtf, rcond, rok = O.soft_procrustes(ref_conf, d["s_pcd"], d["t_pcd"], d["src_mask"], d["tgt_mask"], 1.0, 40.0,
+                                                     padded_lengths=True)
+    assert rot_angle(R.cpu(), rR.cpu()).max() <= TOL_ROT
+    assert (t.cpu() - rt.cpu()).abs().max() <= TOL_TRANS
+    assert torch.equal(ok_mask.cpu().bool(), rok.cpu().bool())
+    del ref_conf
+    # the 3d sampler flavour, one pair, three steps + the final Sinkhorn / selection
+    # (all-true masks: with padding the reference's own x - x.min() turns the state into inf / nan after the first step,
+    #  because get_warped_from_noising_matching leaves -inf in the caller's x, SURVEY.md Q7; 3DMatch tests run unpadded)
+    pb1 = O.make_problem(2102, 1, L, L, 256)
+    d1 = [pb1[k].to(DEV) for k in KEYS]
+    x_T = torch.randn(1, L, L, generator=torch.Generator().manual_seed(2103)).to(DEV)
+    p1 = _params(pb1, DEV)
+    ref = O.sampler("3d", p1, *d1, x_T, 3, max_condition_num=0.0, state_dtype=torch.float32)
+    head = _head("Matching", pb1)
+    proc = SoftProcrustesLayer3DMatch(SimpleNamespace(sample_rate=1.0, max_condition_num=0.0))
+    out = diffreg_b200.DenoisingSampler("3d", head, proc, 3).sample(x_T, *d1)
+    ok, err = finite_close(out["conf_matrix_pred"].cpu(), ref["conf_matrix_pred"].cpu().float(), TOL_LOG)
+    assert ok, err
+    okp, msg = check_top1_pairs(ref["conf_matrix_pred"][0].cpu(), out["match_pred"][:, 1].cpu(), out["match_pred"][:, 2].cpu(), mutual=False)
+    assert okp, msg

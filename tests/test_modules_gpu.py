@@ -92,7 +92,7 @@ def test_log_optimal_transport_function(name):
     out = diffreg_b200.log_optimal_transport(_cu(g["scores"]), torch.tensor(float(g["alpha"]), device=DEV), int(g["iters"]),
                                              _cu(g["src_mask"]), _cu(g["tgt_mask"]))
     assert out.dtype == g["out"].dtype
-    tol = TOL_LOG if name != "lot_iters100" else 2e-4
+    tol = TOL_LOG          # (also for the 100-iteration fixture: measured 1.6e-6 against an fp64 evaluation, tools/lot_error_probe.py)
     ok, err = finite_close(out.cpu(), g["out"], tol)
     assert ok, err
 

@@ -21,7 +21,7 @@ def test_log_full_against_reference_golden(name):
     dev = "cuda"
     out = _ops().sinkhorn(g["scores"].to(dev), torch.tensor(float(g["alpha"]), device=dev), int(g["iters"]),
                           g["src_mask"].to(dev), g["tgt_mask"].to(dev), out_mode="log_full")
-    tol = TOL_LOG if name != "lot_iters100" else 2e-4
+    tol = TOL_LOG          # (also for the 100-iteration fixture: measured 1.6e-6 against an fp64 evaluation, tools/lot_error_probe.py)
     ok, err = finite_close(out.cpu(), g["out"], tol)
     assert ok, err
 
