@@ -2,7 +2,8 @@
 update, behind the reference's own PyTorch module API.
 
 Public surface (mirrors the reference):
-    Matching, log_optimal_transport, mutual_topk_select      (matching.py)
+    Matching, log_optimal_transport, mutual_topk_select,
+    batch_mutual_topk_select                                 (matching.py)
     Matching2D3D                                             (2D-3D flavour head)
     SoftProcrustesLayer                                      (procrustes.py)
     VolumetricPositionEncoding                               (position_encoding.py; next-row widening)
@@ -20,7 +21,7 @@ __all__ = ["library_path", "load_library", "launch_count"]
 
 def __getattr__(name):
     # lazy: the modules below import torch
-    if name in ("Matching", "Matching2D3D", "log_optimal_transport", "mutual_topk_select"):
+    if name in ("Matching", "Matching2D3D", "log_optimal_transport", "mutual_topk_select", "batch_mutual_topk_select"):
         from . import matching
         return getattr(matching, name)
     if name == "SoftProcrustesLayer":

@@ -100,6 +100,12 @@ def _declare(lib):
     lib.drg_match_write.restype = c_int
     lib.drg_match_write.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t,
                                     c_void_p, c_void_p, c_ll, c_void_p, c_void_p]
+    lib.drg_topk_match_count.restype = c_int
+    lib.drg_topk_match_count.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.drg_topk_match_write.restype = c_int
+    lib.drg_topk_match_write.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_size_t, c_void_p, c_void_p, c_ll, c_void_p, c_void_p]
     lib.drg_match_from_best.restype = c_int
     lib.drg_match_from_best.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_ll, c_void_p,
                                         c_void_p]

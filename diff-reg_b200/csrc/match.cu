@@ -4,6 +4,10 @@
 //   Matching.get_match / get_topk_match       Diff-Reg-4dmatch/models/matching.py:71-107
 //   mutual_topk_select (k = 1)                Diff-Reg-2d3d/vision3d/ops/mutual_topk_select.py:7-60
 //                                             (= Diff-Reg-3dmatch/models/matching.py:6-59)
+//   mutual_topk_select / batch_mutual_topk_select for k > 1 (the 2D-3D fine matching, model.py:738-746: k = 2 on
+//   [B, Kc, Kc] patch similarities)           Diff-Reg-2d3d/vision3d/ops/mutual_topk_select.py:7-133
+//     -> topk_rows_kernel / topk_cols_kernel leave every row's / column's k-th best packed key; an entry is in the top-k
+//        of its row iff its key >= that key (mode 2 of the count / write passes)
 //
 // Pass 1 (rowcol_best_kernel): one read of the matrix gives, for every row and every column, the
 //   best value and the lowest index attaining it, as a packed 64-bit key merged with atomicMax:
@@ -89,10 +93,62 @@ __global__ void __launch_bounds__(MT_THREADS) rowcol_best_kernel(const float* __
     if (cols[e] < M && cbest[e] != 0ull) atomicMax(&colbest[(size_t)b * M + cols[e]], cbest[e]);
 }
 
+// k-th best packed key of every row (one warp per row) / of every column (one warp per column, lanes stride over the
+// rows: uncoalesced, but k > 1 only occurs on the small fine-level patch matrices).  Each lane keeps its own k best keys
+// sorted in registers; k rounds of a warp arg-max then pop the global best k times.  Fewer than k entries: key 0 (every
+// entry is selected, as torch.topk would fail / select all).  k <= TOPK_MAX.
+constexpr int TOPK_MAX = 8;
+template <bool COLS>
+__global__ void __launch_bounds__(256) topk_line_kernel(const float* __restrict__ x, int B, int N, int M, int k, int largest,
+                                                        unsigned long long* __restrict__ kth) {
+  const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  const int nlines = COLS ? B * M : B * N;
+  if (warp >= nlines) return;
+  const int L = COLS ? M : N, len = COLS ? N : M;        // lines per batch element, elements per line
+  const int b = warp / L, l = warp - b * L;
+  const float* base = x + (size_t)b * N * M + (COLS ? (size_t)l : (size_t)l * M);
+  const size_t stride = COLS ? (size_t)M : 1;
+  const bool lg = largest != 0;
+  unsigned long long best[TOPK_MAX];
+#pragma unroll
+  for (int q = 0; q < TOPK_MAX; ++q) best[q] = 0ull;
+  for (int e = lane; e < len; e += 32) {
+    unsigned long long key = pack_key(base[(size_t)e * stride], (unsigned int)e, lg);
+#pragma unroll
+    for (int q = 0; q < TOPK_MAX; ++q) {   // sorted insertion (descending)
+      if (q < k && key > best[q]) {
+        const unsigned long long t = best[q];
+        best[q] = key;
+        key = t;
+      }
+    }
+  }
+  unsigned long long kth_key = 0ull;
+  for (int r = 0; r < k; ++r) {
+    unsigned long long head = best[0], m = head;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
+      m = other > m ? other : m;
+    }
+    kth_key = m;
+    if (m == 0ull) break;                  // fewer than k entries in the line
+    if (head == m) {                       // keys are distinct (distinct indices): exactly one lane pops
+#pragma unroll
+      for (int q = 0; q + 1 < TOPK_MAX; ++q) best[q] = best[q + 1];
+      best[TOPK_MAX - 1] = 0ull;
+    }
+  }
+  if (lane == 0) kth[warp] = (len < k) ? 0ull : kth_key;
+}
+
 struct MatchParams {
   const float* x;
   int B, N, M;
-  int mode;     // 0: get_match (value equality), 1: top-1 select (index based)
+  int mode;     // 0: get_match (value equality), 1: top-1 select (index based), 2: top-k select (rowbest / colbest hold the k-th best keys)
+  const unsigned char* row_mask;  // mode 2, optional [B,N]: hits in masked rows are dropped AFTER the selection
+  const unsigned char* col_mask;  // mode 2, optional [B,M]
   int mutual;
   int has_thr;
   float thr;
@@ -116,6 +172,17 @@ __device__ __forceinline__ bool is_hit(const MatchParams& p, int b, int i, int j
     if (!p.mutual) return true;
     if (v != rowv) return false;
     return v == key_value(p.colbest[(size_t)b * p.M + j], true);
+  }
+  if (p.mode == 2) {
+    // within the top-k of the row / of the column (keys >= the k-th best key), AND / OR, threshold, masks
+    //                                                             mutual_topk_select.py:30-57, 95-127
+    const bool lg = p.largest != 0;
+    const bool row_in = pack_key(v, (unsigned int)j, lg) >= p.rowbest[(size_t)b * p.N + i];
+    const bool col_in = pack_key(v, (unsigned int)i, lg) >= p.colbest[(size_t)b * p.M + j];
+    bool h = (p.mutual ? (row_in && col_in) : (row_in || col_in)) && pass_thr;
+    if (h && p.row_mask) h = p.row_mask[(size_t)b * p.N + i] != 0;
+    if (h && p.col_mask) h = p.col_mask[(size_t)b * p.M + j] != 0;
+    return h;
   }
   // top-1 of the row / of the column, AND (mutual) or OR        mutual_topk_select.py:30-50
   const bool row_hit = ((unsigned int)j == rowj);
@@ -396,6 +463,57 @@ extern "C" int drg_match_write(const float* x, int B, int N, int M, int mode, in
   p.capacity = capacity;
   const int nrows = B * N;
   match_rows_kernel<true><<<(nrows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+/* top-k (k >= 1) selection: see include/diffreg_b200.h */
+static int topk_prepare(const float* x, int B, int N, int M, int k, int largest, const MatchWorkspace& w, cudaStream_t st) {
+  topk_line_kernel<false><<<(B * N + 7) / 8, 256, 0, st>>>(x, B, N, M, k, largest, w.rowbest);
+  DRG_LAUNCH_CHECK();
+  topk_line_kernel<true><<<(B * M + 7) / 8, 256, 0, st>>>(x, B, N, M, k, largest, w.colbest);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+extern "C" int drg_topk_match_count(const float* x, int B, int N, int M, int k, int mutual, int has_thr, float thr, int largest,
+                                    const unsigned char* row_mask, const unsigned char* col_mask, void* ws, size_t ws_bytes,
+                                    int* total_out, void* stream) {
+  int rc = match_check(x, B, N, M, 1, ws, ws_bytes);
+  if (rc != DRG_OK) return rc;
+  DRG_CHECK_ARG(total_out != nullptr, "total_out is null");
+  DRG_CHECK_ARG(k >= 1 && k <= TOPK_MAX, "k must be in 1..8");
+  cudaStream_t st = (cudaStream_t)stream;
+  MatchWorkspace w = match_carve(ws, B, N, M);
+  rc = topk_prepare(x, B, N, M, k, largest, w, st);
+  if (rc != DRG_OK) return rc;
+  MatchParams p = match_params(x, B, N, M, 2, mutual, has_thr, thr, largest, w);
+  p.row_mask = row_mask;
+  p.col_mask = col_mask;
+  const int nrows = B * N;
+  match_rows_kernel<false><<<(nrows + 7) / 8, 256, 0, st>>>(p);
+  DRG_LAUNCH_CHECK();
+  scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, nrows, w.offsets, total_out);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+extern "C" int drg_topk_match_write(const float* x, int B, int N, int M, int k, int mutual, int has_thr, float thr, int largest,
+                                    const unsigned char* row_mask, const unsigned char* col_mask, void* ws, size_t ws_bytes,
+                                    long long* index_out, float* val_out, long long capacity, unsigned char* mask_out, void* stream) {
+  int rc = match_check(x, B, N, M, 1, ws, ws_bytes);
+  if (rc != DRG_OK) return rc;
+  DRG_CHECK_ARG(index_out != nullptr && val_out != nullptr, "index_out/val_out are null (allocate at least one element)");
+  DRG_CHECK_ARG(capacity >= 1 && k >= 1 && k <= TOPK_MAX, "capacity must be >= 1 and k in 1..8");
+  MatchWorkspace w = match_carve(ws, B, N, M);
+  MatchParams p = match_params(x, B, N, M, 2, mutual, has_thr, thr, largest, w);
+  p.row_mask = row_mask;
+  p.col_mask = col_mask;
+  p.index_out = index_out;
+  p.val_out = val_out;
+  p.mask_out = mask_out;
+  p.capacity = capacity;
+  match_rows_kernel<true><<<(B * N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }

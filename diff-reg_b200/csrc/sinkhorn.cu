@@ -898,20 +898,19 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
   if (tid == 0) DRG_STAMP(1);
   for (int it = 0; it < iters; ++it) {
     if (tid == 0) DRG_STAMP(10 + it * 100 + 0);
-    bool fast = false;
-    if (it >= 1 && alpha >= -20.f) {
-      const float dv = __uint_as_float(ld_acquire_u32(dv_slots + ((it - 1) & 1)));
-      fast = dv <= 50.f;
-    }
+    // how far the column potentials moved in the last merge decides between the scaled pass and the log-domain one.
+    // A plain L2 load (the grid barrier already ordered the merge's atomicMax before us): an acquire load here would
+    // hold back the loads of v below by a full round trip.
+    unsigned int dv_bits = 0u;
+    if (it >= 1) dv_bits = __ldcg(dv_slots + ((it - 1) & 1));
     // First iteration: same arithmetic, but the row reference is this pass's exact row maximum (one more reduction per
     // mini-slab).  Flushing e_ij / srow_i < 2^-126 cannot hurt the column sums there: with v = 0 the dustbin-row entry of
     // every column is ~2^norm2, 2^126 / N times larger than anything that can be flushed.
     const bool semi = (it == 0) && alpha >= -20.f;
-    const bool scaled = fast || semi;
-    if (p.dbg_times && g == 0 && b == 0 && tid == 0) p.dbg_times[400 + it] = fast ? 1 : semi ? 2 : 0;
 
-    // ---- prologue: column potentials into shared memory (log2 domain), dustbin-row potential
-    float uN;
+    // ---- prologue: column potentials into shared memory (log2 domain).  The dustbin-row potential u_N needs the
+    //      log-sum-exp of ALL of v; nothing in the pass uses it, so only per-warp (max, sum) partials are formed here (no
+    //      block-wide reduction, no barrier) and they are combined after the pass, where the CTA synchronises anyway.
     if (it == 0) {
       for (int j = tid; j <= M; j += P2_THREADS) {
         float v2;
@@ -923,7 +922,6 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
         }
         v2_s[j] = v2;
       }
-      uN = bc.log_mu_bin - (alpha + logf((float)(M + 1)));
     } else {
       const float* v_b = p.v + (size_t)b * p.ldv;
       constexpr int VPT = (4096 + 1 + P2_THREADS - 1) / P2_THREADS;  // M <= 4096
@@ -935,19 +933,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
         vr[k] = (j <= M) ? __ldcg(v_b + j) : -INFINITY;
         mloc = fmaxf(mloc, vr[k] * LOG2E);
       }
-      mloc = warp_max(mloc);
-      if (lane == 0) red_s[warp] = mloc;
-      __syncthreads();
-      float mall = red_s[0];
-#pragma unroll
-      for (int w = 1; w < P2_THREADS / 32; ++w) mall = fmaxf(mall, red_s[w]);
       float sloc = 0.f;
 #pragma unroll
       for (int k = 0; k < VPT; ++k) {
         const int j = tid + k * P2_THREADS;
         if (j <= M) {
           const float vj = vr[k];
-          sloc += ex2(vj * LOG2E - mall);
+          sloc += ex2(vj * LOG2E - mloc);
           float v2;
           if (j < M) {
             v2 = (vj - shift) * LOG2E;
@@ -958,16 +950,24 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           v2_s[j] = v2;
         }
       }
-      sloc = warp_sum(sloc);
-      if (lane == 0) red_s[32 + warp] = sloc;
-      __syncthreads();
-      float sall = 0.f;
+      // warp-level log-sum-exp of the (max, sum) pairs
 #pragma unroll
-      for (int w = 0; w < P2_THREADS / 32; ++w) sall += red_s[32 + w];
-      uN = bc.log_mu_bin - (alpha + (mall + lg2(sall)) * LN2);
+      for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, mloc, o);
+        const float s2 = __shfl_xor_sync(0xffffffffu, sloc, o);
+        const float mn = fmaxf(mloc, m2);
+        sloc = sloc * ex2(mloc - mn) + s2 * ex2(m2 - mn);
+        mloc = mn;
+      }
+      if (lane == 0) {
+        red_s[warp] = mloc;
+        red_s[32 + warp] = sloc;
+      }
     }
-    if (g == 0 && tid == 0) p.u[(size_t)b * p.ldu + N] = uN;
     for (int j = M + 1 + tid; j < Mv; j += P2_THREADS) v2_s[j] = -INFINITY;
+    const bool fast = it >= 1 && alpha >= -20.f && __uint_as_float(dv_bits) <= 50.f;
+    const bool scaled = fast || semi;
+    if (p.dbg_times && g == 0 && b == 0 && tid == 0) p.dbg_times[400 + it] = fast ? 1 : semi ? 2 : 0;
     __syncthreads();
     if (tid == 0) DRG_STAMP(10 + it * 100 + 1);
 
@@ -1251,6 +1251,20 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     }
     // ---- the two row groups combine their column partials; row group 0 writes them
     __syncthreads();  // the ring is idle from here until the next iteration's first slabs are requested below
+    // the dustbin-row potential from the prologue's per-warp partials (red_s is not touched by the pass)
+    float uN;
+    if (it == 0) {
+      uN = bc.log_mu_bin - (alpha + logf((float)(M + 1)));
+    } else {
+      float mall = red_s[0];
+#pragma unroll
+      for (int w = 1; w < P2_THREADS / 32; ++w) mall = fmaxf(mall, red_s[w]);
+      float sall = 0.f;
+#pragma unroll
+      for (int w = 0; w < P2_THREADS / 32; ++w) sall += red_s[32 + w] * ex2(red_s[w] - mall);
+      uN = bc.log_mu_bin - (alpha + (mall + lg2(sall)) * LN2);
+    }
+    if (g == 0 && tid == 0) p.u[(size_t)b * p.ldu + N] = uN;
     if (rg >= 1) {
 #pragma unroll
       for (int e = 0; e < KQ * 4; ++e) xcomb[((rg - 1) * KQ * 4 + e) * P2_TPR + ct] = make_float2(cm[e], cs[e]);

@@ -46,18 +46,31 @@ def log_optimal_transport(scores, alpha, iters, src_mask, tgt_mask):
 
 
 def mutual_topk_select(score_mat, k, largest=True, threshold=None, mutual=True, reduce_result=True):
-    """Top-1 row/column selection.  Only k = 1 exists on the Diff-Reg path (3d pipeline.py:275-277,
-    2d3d model.py:692-694, matching.py:134-136); other k raise."""
-    if k != 1:
-        raise NotImplementedError("diffreg_b200.mutual_topk_select implements k = 1 (the only value the sampler uses)")
+    """Mutual top-k selection on a 2-D score matrix (vision3d/ops/mutual_topk_select.py:7-60; 3d models/matching.py:6-59).
+    -> (row_indices [K], col_indices [K], scores [K]) in row-major order, or the [N,M] bool matrix if not reduce_result.
+    k = 1 (the sampler's final selection: 3d pipeline.py:275-277, 2d3d model.py:692-694, matching.py:134-136) runs the
+    single-pass arg-max kernels; k > 1 (k <= 8) the general top-k kernels."""
     _no_grad_inputs(score_mat)          # the reference's gathered scores are differentiable
     with torch.no_grad():
-        r, c, s = ops.top1_select(score_mat, largest, threshold, mutual)
-    if reduce_result:
-        return r, c, s
-    corr = torch.zeros_like(score_mat, dtype=torch.bool)
-    corr[r, c] = True
-    return corr
+        if k == 1 and reduce_result:
+            return ops.top1_select(score_mat, largest, threshold, mutual)
+        index, vals, mask = ops.topk_select(score_mat.unsqueeze(0), k, largest, threshold, mutual, want_mask=not reduce_result)
+        if reduce_result:
+            return index[:, 1].contiguous(), index[:, 2].contiguous(), vals
+        return mask.squeeze(0)
+
+
+def batch_mutual_topk_select(score_mat, k, row_masks=None, col_masks=None, largest=True, threshold=None, mutual=True,
+                             reduce_result=True):
+    """Batched mutual top-k selection (vision3d/ops/mutual_topk_select.py:63-133; the 2D-3D fine matching, model.py:738-746).
+    score_mat [B,N,M] -> (batch_indices, row_indices, col_indices, scores), or the [B,N,M] bool matrix."""
+    _no_grad_inputs(score_mat)
+    with torch.no_grad():
+        index, vals, mask = ops.topk_select(score_mat, k, largest, threshold, mutual, row_masks, col_masks,
+                                            want_mask=not reduce_result)
+        if reduce_result:
+            return index[:, 0].contiguous(), index[:, 1].contiguous(), index[:, 2].contiguous(), vals
+        return mask
 
 
 class Matching(nn.Module):

@@ -216,6 +216,31 @@ def _match(x, mode, mutual, threshold, largest, want_mask, capacity=None):
     return index, vals, mask, total
 
 
+@_on_device
+def topk_select(score_mat, k, largest=True, threshold=None, mutual=True, row_masks=None, col_masks=None, want_mask=False):
+    """(batch_)mutual_topk_select for k >= 1 on a [B,N,M] score tensor (drg_topk_match_*).
+    Returns (index [K,3] int64 (b, row, col) in row-major order, scores [K], corr_mat [B,N,M] bool or None)."""
+    _require_cuda(score_mat, row_masks, col_masks)
+    lib = load_library()
+    x = _f32c(score_mat)
+    B, N, M = x.shape
+    dev = x.device
+    rm = _as_mask(row_masks) if row_masks is not None else None
+    cm = _as_mask(col_masks) if col_masks is not None else None
+    ws = workspace(lib.drg_match_workspace_bytes(B, N, M), dev, "match")
+    total = torch.empty(1, dtype=torch.int32, device=dev)
+    has_thr = threshold is not None
+    args = (x.data_ptr(), B, N, M, int(k), int(bool(mutual)), int(has_thr), float(threshold) if has_thr else 0.0, int(bool(largest)),
+            _ptr(rm), _ptr(cm), ws.data_ptr(), ws.numel())
+    check(lib.drg_topk_match_count(*args, total.data_ptr(), _stream()))
+    n = int(total.item())          # as torch.nonzero() in the reference: the number of hits is read on the host
+    index = torch.empty(max(n, 1), 3, dtype=torch.int64, device=dev)
+    vals = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    mask = torch.empty(B, N, M, dtype=torch.bool, device=dev) if want_mask else None
+    check(lib.drg_topk_match_write(*args, index.data_ptr(), vals.data_ptr(), max(n, 1), _ptr(mask), _stream()))
+    return index[:n], vals[:n], mask
+
+
 def get_match(conf, thr=0.0, mutual=True, want_mask=True):
     """(index [K,3] int64, mconf [K], mask [B,N,M] bool) -- Matching.get_match."""
     return _match(conf, 0, mutual, thr, True, want_mask)

@@ -242,6 +242,20 @@ int drg_match_write(const float* x, int B, int N, int M, int mode, int mutual, i
                     size_t workspace_bytes, long long* index_out, float* val_out, long long capacity, unsigned char* mask_out,
                     void* stream);
 
+/* Top-k selection for k >= 1 (k <= 8), batched, with optional row / column masks applied after the selection:
+ *   replaces mutual_topk_select(score_mat, k, ...) and batch_mutual_topk_select(score_mat, k, row_masks, col_masks, ...)
+ *            Diff-Reg-2d3d/vision3d/ops/mutual_topk_select.py:7-60, 63-133 (the 2D-3D fine matching calls it with k = 2,
+ *            threshold 0.75 on [B, Kc, Kc] patch similarities: experiments/<exp>/model.py:738-746)
+ *   hit = (within the top-k of its row) AND/OR (within the top-k of its column) [and score > threshold] [and masks];
+ *   ties are broken towards the lower index.  Same two-call protocol and workspace as drg_match_count / drg_match_write
+ *   (mode 1 shapes: x [B,N,M]); index_out rows are (b, row, col) in row-major order. */
+int drg_topk_match_count(const float* x, int B, int N, int M, int k, int mutual, int has_thr, float thr, int largest,
+                         const unsigned char* row_mask, const unsigned char* col_mask, void* workspace, size_t workspace_bytes,
+                         int* total_out, void* stream);
+int drg_topk_match_write(const float* x, int B, int N, int M, int k, int mutual, int has_thr, float thr, int largest,
+                         const unsigned char* row_mask, const unsigned char* col_mask, void* workspace, size_t workspace_bytes,
+                         long long* index_out, float* val_out, long long capacity, unsigned char* mask_out, void* stream);
+
 /* Mutual top-1 matches from the packed row / column bests written by drg_sinkhorn (rowbest / colbest): row i matches its
  * best column j iff j's best row is i [and conf > thr].  Same hits as Matching.get_match(conf, thr, mutual=True)
  * (Diff-Reg-4dmatch/models/matching.py:71-88) and mutual_topk_select(k=1, mutual=True) except at exact value ties, where

@@ -178,6 +178,32 @@ def mutual_topk_select(score_mat, k, largest=True, threshold=None, mutual=True, 
     return r, c, score_mat[r, c]
 
 
+def batch_mutual_topk_select(score_mat, k, row_masks=None, col_masks=None, largest=True, threshold=None, mutual=True,
+                             reduce_result=True):
+    """2d3d vision3d/ops/mutual_topk_select.py:63-133 (the fine matching of model.py:738-746), ``.cuda()`` replaced by the
+    score tensor's device.  The masks are applied AFTER the top-k selection, as in the reference (:122-125)."""
+    B, n_rows, n_cols = score_mat.shape
+    dev = score_mat.device
+    bi = torch.arange(B, device=dev)
+    row_pick = score_mat.topk(k=k, largest=largest, dim=2)[1]            # [B,N,k]
+    row_hit = torch.zeros_like(score_mat, dtype=torch.bool)
+    row_hit[bi.view(B, 1, 1).expand(-1, n_rows, k), torch.arange(n_rows, device=dev).view(1, n_rows, 1).expand(B, -1, k), row_pick] = True
+    col_pick = score_mat.topk(k=k, largest=largest, dim=1)[1]            # [B,k,M]
+    col_hit = torch.zeros_like(score_mat, dtype=torch.bool)
+    col_hit[bi.view(B, 1, 1).expand(-1, k, n_cols), col_pick, torch.arange(n_cols, device=dev).view(1, 1, n_cols).expand(B, k, -1)] = True
+    corr = (row_hit & col_hit) if mutual else (row_hit | col_hit)
+    if threshold is not None:
+        corr = corr & ((score_mat > threshold) if largest else (score_mat < threshold))
+    if row_masks is not None:
+        corr = corr & row_masks.unsqueeze(2)
+    if col_masks is not None:
+        corr = corr & col_masks.unsqueeze(1)
+    if not reduce_result:
+        return corr
+    b, r, c = torch.nonzero(corr, as_tuple=True)
+    return b, r, c, score_mat[b, r, c]
+
+
 # --------------------------------------------------------------------------------------
 # matching head (a1, a1', a1'', a2, a3)
 # --------------------------------------------------------------------------------------

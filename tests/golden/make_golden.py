@@ -308,6 +308,28 @@ def main():
             npz(f"mts_mutual{int(mutual)}_thr{thr}", score=score, mutual=mutual, threshold=(-1.0 if thr is None else thr),
                 has_threshold=thr is not None, rows=r, cols=c, scores=w)
 
+    # mutual_topk_select / batch_mutual_topk_select for k > 1 (the 2D-3D fine matching: model.py:738-746 uses k = 2, thr 0.75)
+    spec = importlib.util.spec_from_file_location("_ref_mts2", f"{REF}/Diff-Reg-2d3d/vision3d/ops/mutual_topk_select.py")
+    mts2 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mts2)
+    g = torch.Generator().manual_seed(18)
+    score = torch.rand(37, 29, generator=g)
+    for k in (2, 3):
+        for mutual in (True, False):
+            with cpu_cuda():
+                r, c, w = mts2.mutual_topk_select(score, k, largest=True, threshold=0.5, mutual=mutual)
+                cm = mts2.mutual_topk_select(score, k, largest=False, threshold=None, mutual=mutual, reduce_result=False)
+            npz(f"mtsk_k{k}_mutual{int(mutual)}", score=score, k=k, mutual=mutual, threshold=0.5, rows=r, cols=c, scores=w, corr_smallest=cm)
+    bscore = torch.rand(5, 20, 24, generator=g) * 2 - 1
+    rmask = torch.rand(5, 20, generator=g) > 0.15
+    cmask = torch.rand(5, 24, generator=g) > 0.15
+    for mutual in (True, False):
+        with cpu_cuda():
+            bi, ri, ci, w = mts2.batch_mutual_topk_select(bscore, k=2, row_masks=rmask, col_masks=cmask, threshold=0.3, largest=True,
+                                                          mutual=mutual)
+        npz(f"bmts_k2_mutual{int(mutual)}", score=bscore, row_masks=rmask, col_masks=cmask, k=2, mutual=mutual, threshold=0.3,
+            batch=bi, rows=ri, cols=ci, scores=w)
+
     # ---------------------------------------------------------------- forward1 of the 3d flavour (a1'')
     r3 = load_flavour("3d")
     prob = O.make_problem(123, 1, 31, 27, 32)

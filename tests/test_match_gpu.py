@@ -29,6 +29,43 @@ def test_top1_select_golden(name):
     assert torch.equal(r.cpu(), g["rows"]) and torch.equal(c.cpu(), g["cols"]) and torch.equal(s.cpu(), g["scores"])
 
 
+@pytest.mark.parametrize("name", names("mtsk_"))
+def test_mutual_topk_select_k_gt_1_golden(name):
+    """mutual_topk_select with k = 2, 3 against the reference's outputs (largest with a threshold; smallest as a bool matrix)."""
+    import diffreg_b200
+    g = load(name)
+    k, mutual = int(g["k"]), bool(g["mutual"])
+    r, c, s = diffreg_b200.mutual_topk_select(g["score"].cuda(), k, largest=True, threshold=float(g["threshold"]), mutual=mutual)
+    assert torch.equal(r.cpu(), g["rows"]) and torch.equal(c.cpu(), g["cols"]) and torch.equal(s.cpu(), g["scores"])
+    cm = diffreg_b200.mutual_topk_select(g["score"].cuda(), k, largest=False, threshold=None, mutual=mutual, reduce_result=False)
+    assert cm.dtype == torch.bool and torch.equal(cm.cpu(), g["corr_smallest"])
+
+
+@pytest.mark.parametrize("name", names("bmts_"))
+def test_batch_mutual_topk_select_golden(name):
+    """batch_mutual_topk_select (k = 2, masks, threshold: the 2D-3D fine matching's call) against the reference's outputs."""
+    import diffreg_b200
+    g = load(name)
+    b, r, c, s = diffreg_b200.batch_mutual_topk_select(g["score"].cuda(), int(g["k"]), g["row_masks"].cuda(), g["col_masks"].cuda(),
+                                                       largest=True, threshold=float(g["threshold"]), mutual=bool(g["mutual"]))
+    assert torch.equal(b.cpu(), g["batch"]) and torch.equal(r.cpu(), g["rows"]) and torch.equal(c.cpu(), g["cols"])
+    assert torch.equal(s.cpu(), g["scores"])
+
+
+@pytest.mark.parametrize("B,N,M,k", [(1, 64, 64, 2), (7, 33, 65, 3), (2, 300, 17, 8), (1, 5, 900, 4)])
+@pytest.mark.parametrize("mutual", [True, False])
+def test_batch_topk_select_vs_oracle(B, N, M, k, mutual):
+    import diffreg_b200
+    g = torch.Generator().manual_seed(B * 100 + N + M + k)
+    score = torch.rand(B, N, M, generator=g)
+    rm = torch.rand(B, N, generator=g) > 0.2
+    cm = torch.rand(B, M, generator=g) > 0.2
+    want = O.batch_mutual_topk_select(score, k, rm, cm, True, 0.4, mutual)
+    got = diffreg_b200.batch_mutual_topk_select(score.cuda(), k, rm.cuda(), cm.cuda(), True, 0.4, mutual)
+    for a, w_ in zip(got, want):
+        assert torch.equal(a.cpu(), w_)
+
+
 @pytest.mark.parametrize("B,N,M", [(1, 1, 1), (2, 33, 65), (1, 257, 1030), (3, 128, 1024), (1, 1000, 37), (1, 2048, 2050)])
 @pytest.mark.parametrize("mutual", [True, False])
 def test_get_match_vs_oracle(B, N, M, mutual):

@@ -8,6 +8,8 @@ import torch
 
 from helpers import MARGIN, TOL_LOG, TOL_ROT, TOL_TRANS, check_top1_pairs, finite_close, load, names, rot_angle
 
+from oracle.diffreg_oracle import mutual_topk_select as O_mts
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
@@ -106,8 +108,11 @@ def test_mutual_topk_select_function(name):
     assert torch.equal(r.cpu(), g["rows"]) and torch.equal(c.cpu(), g["cols"]) and torch.equal(s.cpu(), g["scores"])
     corr = diffreg_b200.mutual_topk_select(_cu(g["score"]), 1, threshold=thr, mutual=bool(g["mutual"]), reduce_result=False)
     assert corr.dtype == torch.bool and int(corr.sum()) == len(g["rows"])
-    with pytest.raises(NotImplementedError):
-        diffreg_b200.mutual_topk_select(_cu(g["score"]), 2)
+    assert torch.equal(corr.nonzero().cpu(), torch.stack((g["rows"], g["cols"]), dim=1))
+    # k > 1 is implemented too (tests/test_match_gpu.py holds the reference's golden vectors for it)
+    r2, c2, _ = diffreg_b200.mutual_topk_select(_cu(g["score"]), 2, threshold=thr, mutual=bool(g["mutual"]))
+    ref2 = O_mts(g["score"], 2, True, thr, bool(g["mutual"]))
+    assert torch.equal(r2.cpu(), ref2[0]) and torch.equal(c2.cpu(), ref2[1])
 
 
 @pytest.mark.parametrize("name", names("procrustes"))
