@@ -86,6 +86,9 @@ def _declare(lib):
     lib.drg_project_split3.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
     lib.drg_prep_operand.restype = c_int
     lib.drg_prep_operand.argtypes = [c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.drg_prep_operand_xyz.restype = c_int
+    lib.drg_prep_operand_xyz.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), c_float, c_int, c_ll, c_int, c_float,
+                                         c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.drg_position_code.restype = c_int
     lib.drg_position_code.argtypes = [c_void_p, c_void_p, c_ll, c_int, ctypes.POINTER(c_float), c_float, c_int, c_void_p, c_void_p]
     lib.drg_project_split.restype = c_int

@@ -29,7 +29,10 @@ struct PrepParams {
   float* out;        // [rows, 3K] or [rows, K]
   long long rows;
   int K;
-  int pe_type;       // 0 none, 1 rotary, 2 sinusoidal (additive)
+  int pe_type;       // 0 none, 1 rotary, 2 sinusoidal (additive); 3 / 4: the same two, the code computed here from xyz
+  const float* xyz;       // pe_type 3 / 4: [rows, 3] point coordinates (the position code never exists in HBM)
+  const float* div_term;  // [K / 6]
+  float ox, oy, oz, voxel;
   int split;         // 1: 3xTF32 layout, 0: plain scaled copy
   int pattern;       // 0: hi,hi,lo   1: hi,lo,hi
   float scale;
@@ -60,6 +63,38 @@ __global__ void __launch_bounds__(256) prep_operand_kernel(const PrepParams p) {
       x.y += pe.y;
       x.z += pe.z;
       x.w += pe.w;
+    } else if (p.pe_type == 3 || p.pe_type == 4) {
+      // VolumetricPositionEncoding.forward fused into the operand staging (position_encoding.py:49-87 + :26-46): the
+      // angles, sinf / cosf and the embedding arithmetic are those of position_code_kernel + the branches above, so the
+      // result is bit-identical to going through the [rows, K, 2] / [rows, K] code tensor -- which is never written.
+      const int d3 = p.K / 3, d6 = p.K / 6;
+      const float px = p.xyz[row * 3 + 0], py = p.xyz[row * 3 + 1], pz = p.xyz[row * 3 + 2];
+      float xv[4] = {x.x, x.y, x.z, x.w};
+      if (p.pe_type == 3) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {          // the two (even, odd) pairs of the quad share an angle each
+          const int c = k + 2 * h;
+          const int axis = c / d3;
+          const int kk = (c - axis * d3) >> 1;
+          const float vox = ((axis == 0 ? px : axis == 1 ? py : pz) - (axis == 0 ? p.ox : axis == 1 ? p.oy : p.oz)) / p.voxel;
+          const float ang = vox * p.div_term[kk];
+          const float cs = cosf(ang), sn = sinf(ang);
+          const float a = xv[2 * h], b2 = xv[2 * h + 1];
+          xv[2 * h] = __fadd_rn(__fmul_rn(a, cs), __fmul_rn(-b2, sn));
+          xv[2 * h + 1] = __fadd_rn(__fmul_rn(b2, cs), __fmul_rn(a, sn));
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = k + e;
+          const int seg = c / d6;
+          const int axis = seg >> 1;
+          const float vox = ((axis == 0 ? px : axis == 1 ? py : pz) - (axis == 0 ? p.ox : axis == 1 ? p.oy : p.oz)) / p.voxel;
+          const float ang = vox * p.div_term[c - seg * d6];
+          xv[e] += (seg & 1) ? cosf(ang) : sinf(ang);
+        }
+      }
+      x = make_float4(xv[0], xv[1], xv[2], xv[3]);
     }
     if (p.embedded) *reinterpret_cast<float4*>(p.embedded + row * p.K + k) = x;
     x.x *= p.scale;
@@ -95,11 +130,14 @@ __global__ void __launch_bounds__(256) prep_operand_kernel(const PrepParams p) {
 using namespace drg;
 
 static int prep_run(const float* in, const float* in2, long long rows1, const float* pe, int pe_type, long long rows, int K,
-                    float scale, int split, int pattern, int pattern2, float* embedded, float* out, void* stream) {
+                    float scale, int split, int pattern, int pattern2, float* embedded, float* out, void* stream,
+                    const float* xyz = nullptr, const float* div_term = nullptr, const float* origin3 = nullptr, float voxel = 1.f) {
   DRG_CHECK_ARG(in && out, "in/out must be non-null");
   DRG_CHECK_ARG(rows >= 1 && K >= 4, "rows >= 1 and K >= 4 required");
-  DRG_CHECK_ARG(pe_type >= 0 && pe_type <= 2, "pe_type must be 0 (none), 1 (rotary) or 2 (sinusoidal)");
-  DRG_CHECK_ARG(pe_type == 0 || pe != nullptr, "pe is null");
+  DRG_CHECK_ARG(pe_type >= 0 && pe_type <= 4, "pe_type must be 0 (none), 1 (rotary), 2 (sinusoidal), 3 / 4 (the same from xyz)");
+  DRG_CHECK_ARG(pe_type == 0 || pe_type >= 3 || pe != nullptr, "pe is null");
+  DRG_CHECK_ARG(pe_type < 3 || (xyz && div_term && origin3 && voxel != 0.f && K % 6 == 0),
+                "position code from xyz needs xyz / div_term / origin, a non-zero voxel size and K % 6 == 0");
   if (K % 4 != 0 || ((uintptr_t)in & 15u) || ((uintptr_t)out & 15u) || (pe && ((uintptr_t)pe & 15u)) ||
       (embedded && ((uintptr_t)embedded & 15u))) {
     set_error("prep_operand: K must be a multiple of 4 and all pointers 16-byte aligned (K=%d)", K);
@@ -116,6 +154,14 @@ static int prep_run(const float* in, const float* in2, long long rows1, const fl
   p.rows = rows;
   p.K = K;
   p.pe_type = pe_type;
+  p.xyz = xyz;
+  p.div_term = div_term;
+  if (origin3) {
+    p.ox = origin3[0];
+    p.oy = origin3[1];
+    p.oz = origin3[2];
+  }
+  p.voxel = voxel;
   p.split = split;
   p.pattern = pattern;
   p.scale = scale;
@@ -133,6 +179,14 @@ static int prep_run(const float* in, const float* in2, long long rows1, const fl
 extern "C" int drg_prep_operand(const float* in, const float* pe, int pe_type, long long rows, int K, float scale, int split,
                                 int pattern, float* embedded, float* out, void* stream) {
   return prep_run(in, nullptr, rows, pe, pe_type, rows, K, scale, split, pattern, pattern, embedded, out, stream);
+}
+
+extern "C" int drg_prep_operand_xyz(const float* in, const float* xyz, const float* div_term, const float* origin3, float voxel_size,
+                                    int pe_type, long long rows, int K, float scale, int split, int pattern, float* embedded,
+                                    float* out, void* stream) {
+  DRG_CHECK_ARG(pe_type == 1 || pe_type == 2, "pe_type must be 1 (rotary) or 2 (sinusoidal)");
+  return prep_run(in, nullptr, rows, nullptr, pe_type + 2, rows, K, scale, split, pattern, pattern, embedded, out, stream, xyz,
+                  div_term, origin3, voxel_size);
 }
 
 extern "C" int drg_prep_operand_pair(const float* in_a, long long rows_a, int pattern_a, const float* in_b, long long rows_b,

@@ -167,17 +167,40 @@ def gemm_nt(A, B, alpha=1.0, out=None, split3=False):
     return out.squeeze(0) if squeeze else out
 
 
+class LazyPositionCode:
+    """A volumetric position code that is NOT materialised: the points and the encoder's constants.  Handed to
+    prep_operand / Matching.similarity in place of the [B,N,d,2] (rotary) or [B,N,d] (sinusoidal) tensor, it makes the
+    operand staging compute cos / sin from xyz itself (drg_prep_operand_xyz) -- bit-identical, no code tensor in HBM."""
+
+    def __init__(self, xyz, div_term, origin, voxel_size, pe_type, feature_dim):
+        self.xyz = xyz
+        self.div_term = div_term
+        self.origin = tuple(float(v) for v in origin)
+        self.voxel_size = float(voxel_size)
+        self.pe_type = pe_type
+        self.feature_dim = int(feature_dim)
+
+
 @_on_device
 def prep_operand(x, scale=1.0, split=True, pattern=0, pe=None, pe_type=None, want_embedded=False):
     """Positional embedding + scaling + hi/lo split of a [..., K] feature tensor (drg_prep_operand).
+    pe: the position code tensor, or a LazyPositionCode (then the code is computed inside the kernel from the points).
     Returns out ([..., 3K] if split else [..., K]) and, if want_embedded, the embedded features."""
-    _require_cuda(x, pe)
+    lazy = isinstance(pe, LazyPositionCode)
+    _require_cuda(x, None if lazy else pe)
     lib = load_library()
     x = _f32c(x)
     K = x.shape[-1]
     rows = x.numel() // K
     code = 0
-    if pe is not None:
+    if lazy:
+        if pe_type is not None and pe_type != pe.pe_type:
+            raise ValueError(f"prep_operand: pe_type {pe_type!r} does not match the lazy code's {pe.pe_type!r}")
+        code = {"rotary": 1, "sinusoidal": 2}[pe.pe_type]
+        xyz = _f32c(pe.xyz)
+        if xyz.numel() != rows * 3 or pe.feature_dim != K:
+            raise ValueError(f"prep_operand: lazy position code of {xyz.numel() // 3} points x {pe.feature_dim} does not fit {rows} x {K}")
+    elif pe is not None:
         code = {"rotary": 1, "sinusoidal": 2}[pe_type]
         pe = _f32c(pe)
         want = (*x.shape, 2) if code == 1 else tuple(x.shape)
@@ -185,8 +208,15 @@ def prep_operand(x, scale=1.0, split=True, pattern=0, pe=None, pe_type=None, wan
             raise ValueError(f"prep_operand: position code shape {tuple(pe.shape)} != {want}")
     out = torch.empty(*x.shape[:-1], 3 * K if split else K, dtype=torch.float32, device=x.device)
     emb = torch.empty_like(x) if want_embedded else None
-    check(lib.drg_prep_operand(x.data_ptr(), _ptr(pe), code, rows, K, float(scale), int(bool(split)), int(pattern),
-                               _ptr(emb), out.data_ptr(), _stream()))
+    if lazy:
+        import ctypes
+        origin = (ctypes.c_float * 3)(*pe.origin)
+        div = pe.div_term.to(x.device)
+        check(lib.drg_prep_operand_xyz(x.data_ptr(), xyz.data_ptr(), div.data_ptr(), origin, pe.voxel_size, code, rows, K, float(scale),
+                                       int(bool(split)), int(pattern), _ptr(emb), out.data_ptr(), _stream()))
+    else:
+        check(lib.drg_prep_operand(x.data_ptr(), _ptr(pe), code, rows, K, float(scale), int(bool(split)), int(pattern),
+                                   _ptr(emb), out.data_ptr(), _stream()))
     return (out, emb) if want_embedded else out
 
 

@@ -60,6 +60,13 @@ class VolumetricPositionEncoding(nn.Module):
                                     out.data_ptr(), torch.cuda.current_stream().cuda_stream))
         return out
 
+    def lazy(self, XYZ):
+        """The position code of XYZ [B,N,3] WITHOUT materialising it: an ops.LazyPositionCode that Matching.similarity /
+        ops.prep_operand accept in place of forward()'s tensor; the operand staging of the similarity GEMM then computes
+        cos / sin from the points itself (bit-identical to forward() + embed_pos, no [B,N,d,2] tensor in HBM)."""
+        return ops.LazyPositionCode(XYZ.detach().float().contiguous(), self.div_term, self.vol_origin, self.voxel_size, self.pe_type,
+                                    self.feature_dim)
+
     @staticmethod
     def embed_rotary(x, cos, sin):
         """position_encoding.py:26-35."""

@@ -221,6 +221,16 @@ int drg_position_code(const float* xyz, const float* div_term, long long points,
 int drg_prep_operand(const float* in, const float* pe, int pe_type, long long rows, int K, float scale, int split, int pattern,
                      float* embedded, float* out, void* stream);
 
+/* drg_prep_operand with the position code computed inside the kernel from the point coordinates (SURVEY.md 8f rank 1:
+ *   VolumetricPositionEncoding.forward fused into the GEMM operand staging): xyz [rows,3], div_term [K/6] and origin3 (HOST
+ *   pointer) / voxel_size as for drg_position_code; pe_type 1 rotary, 2 sinusoidal.  Bit-identical to
+ *   drg_position_code + drg_prep_operand, without the [rows,K,2] / [rows,K] code tensor in HBM.
+ *   replaces Diff-Reg-4dmatch/models/position_encoding.py:49-87 + :26-46 as called at models/transformer.py:165-166 and
+ *   models/matching.py:135-137 */
+int drg_prep_operand_xyz(const float* in, const float* xyz, const float* div_term, const float* origin3, float voxel_size,
+                         int pe_type, long long rows, int K, float scale, int split, int pattern, float* embedded, float* out,
+                         void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Correspondence extraction
  *   mode 0: Matching.get_match(conf, thr, mutual)       Diff-Reg-4dmatch/models/matching.py:71-88 (= get_topk_match :90-107)

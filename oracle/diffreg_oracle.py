@@ -402,7 +402,7 @@ def noisy_matching_to_pose(x, alpha, iters, s_pcd, t_pcd, src_mask, tgt_mask,
 
 def sampler(flavour, p: MatchingParams, src_feats, tgt_feats, s_pcd, t_pcd, src_mask, tgt_mask,
             x_T, steps, noises=None, sample_rate=1.0, max_condition_num=40.0,
-            tgt_mask_pose=None, t_pcd_pose=None, state_dtype=None, trace=None):
+            tgt_mask_pose=None, t_pcd_pose=None, state_dtype=None, trace=None, pe_fn=None):
     """Reverse-diffusion loop with the denoising transformer replaced by FIXED features.
 
     flavour '4d'  : 4d/models/pipeline.py:171-192   (sigma*noise term, final sigmoid)
@@ -413,6 +413,8 @@ def sampler(flavour, p: MatchingParams, src_feats, tgt_feats, s_pcd, t_pcd, src_
                                                     tgt_mask_pose)
     ``state_dtype=torch.float32`` casts the state back to fp32 after every update (what the
     CUDA path does); ``None`` keeps the reference's fp64 creep (Q4).
+    ``pe_fn(src_warped, t_pcd) -> (src_pe, tgt_pe)``: the position codes the denoising transformer
+    hands to the matching head every step (pipeline.py:177-178; used when ``p.entangled`` is False).
     Returns a dict with the final matrix, matches and the last pose.
     """
     ac = alphas_cumprod()
@@ -426,7 +428,8 @@ def sampler(flavour, p: MatchingParams, src_feats, tgt_feats, s_pcd, t_pcd, src_
         warped, conf_d, pose = noisy_matching_to_pose(
             x, p.bin_score, p.skh_iters, s_pcd, pose_pcd, src_mask, pose_mask,
             sample_rate, max_condition_num, padded_lengths=(flavour == "3d"))
-        sim, *_ = similarity(p, src_feats, tgt_feats)
+        src_pe, tgt_pe = pe_fn(warped, t_pcd) if pe_fn is not None else (None, None)
+        sim, *_ = similarity(p, src_feats, tgt_feats, src_pe, tgt_pe)
         x0 = confidence_from_similarity(p, sim, src_mask, tgt_mask)
         if flavour != "2d3d":
             get_match(x0, p.confidence_threshold)       # computed and discarded (:172 / :178)

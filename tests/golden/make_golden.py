@@ -218,9 +218,15 @@ def main():
                            sqrt_recipm1_alphas_cumprod=torch.sqrt(1.0 / ac - 1))
     npz("schedule", alphas_cumprod=ac)
 
-    def ref_sampler(flavour, tag, N, M, C, steps, arbitrary=0.0, max_cond=40.0):
-        """The reference's loop body driven with fixed features (see module docstring)."""
+    def ref_sampler(flavour, tag, N, M, C, steps, arbitrary=0.0, max_cond=40.0, pe=False):
+        """The reference's loop body driven with fixed features (see module docstring).  pe=True: the head runs with
+        entangled=False and receives, every step, the rotary position codes of the WARPED source points and of the target
+        points -- what the denoising transformer hands to denoising_coarse_matching (pipeline.py:177-178)."""
         prob = O.make_problem(sum(map(ord, tag)), 1, N, M, C, arbitrary_invalid=arbitrary)
+        vol = None
+        if pe:
+            vol = r4.pe.VolumetricPositionEncoding(SimpleNamespace(
+                feature_dim=C, vol_bnds=[[-3.6, -2.4, 1.14], [1.093, 0.78, 2.92]], voxel_size=0.04, pe_type="rotary"))
         g = torch.Generator().manual_seed(99)
         if flavour == "2d3d":
             mods = load_flavour("2d3d")
@@ -230,7 +236,7 @@ def main():
             head = mods.matching.Matching(cfg_match(C))
         else:
             mods = r4
-            head = mods.matching.Matching(cfg_match(C))
+            head = mods.matching.Matching(cfg_match(C, entangled=not pe))
         head.src_proj.weight.copy_(prob["W"])
         head.eval()
         proc = mods.procrustes.SoftProcrustesLayer(SimpleNamespace(sample_rate=1.0, max_condition_num=max_cond))
@@ -252,6 +258,8 @@ def main():
             if flavour == "2d3d":
                 with cpu_cuda():
                     x_start, _, _, _ = head(prob["src_feats"], prob["tgt_feats"], sm, tm, True)
+            elif pe:
+                x_start, _ = head(prob["src_feats"], prob["tgt_feats"], vol(warped), vol(prob["t_pcd"]), sm, tm, {}, pe_type="rotary")
             else:
                 x_start, _ = head(prob["src_feats"], prob["tgt_feats"], None, None, sm, tm, {})
             rec[f"x0_{k}"] = x_start
@@ -285,6 +293,9 @@ def main():
     ref_sampler("4d", "sampler4d_3steps", 28, 24, 32, 3)
     ref_sampler("3d", "sampler3d_3steps", 20, 26, 32, 3, max_cond=0.0)
     ref_sampler("2d3d", "sampler2d3d_3steps", 30, 22, 32, 3, arbitrary=0.1, max_cond=200.0)
+    # every shipped 3DMatch / 4DMatch config has entangled: False with rotary codes (configs/test/4dmatch.yaml:1,46)
+    ref_sampler("4d", "sampler4d_rotary_3steps", 26, 30, 36, 3, max_cond=0.0, pe=True)
+    ref_sampler("4d", "sampler4d_rotary_gate_3steps", 26, 30, 36, 3, max_cond=1e9, pe=True)
 
     # ---------------------------------------------------------------- 2D-3D head (a1') and mutual_topk_select (a6)
     r2 = load_flavour("2d3d")

@@ -196,6 +196,63 @@ def test_sampler_against_reference_trace(name):
         assert ok, msg
 
 
+@pytest.mark.parametrize("name,lazy", [("sampler4d_rotary_3steps", True), ("sampler4d_rotary_3steps", False),
+                                        ("sampler4d_rotary_gate_3steps", True)])
+def test_sampler_with_rotary_codes_against_reference_trace(name, lazy):
+    """every shipped 3DMatch / 4DMatch config has entangled = False, so the head of the sampler loop
+    must receive the position codes of the warped source points and of the target points (pipeline.py:177-178).
+    feature_fn hands them over per step -- as materialised [1,N,C,2] tensors, or as lazy codes that the operand staging of
+    the similarity GEMM evaluates from the points itself (no code tensor in HBM)."""
+    import diffreg_b200
+    g = load(name)
+    steps, C = int(g["steps"]), g["W"].shape[0]
+    head = _head("Matching", g, entangled=False)
+    proc = diffreg_b200.SoftProcrustesLayer(SimpleNamespace(sample_rate=1.0, max_condition_num=float(g["max_condition_num"])))
+    vol = diffreg_b200.VolumetricPositionEncoding(SimpleNamespace(
+        feature_dim=C, vol_bnds=[[-3.6, -2.4, 1.14], [1.093, 0.78, 2.92]], voxel_size=0.04, pe_type="rotary")).to(DEV)
+    code = vol.lazy if lazy else vol
+
+    def feature_fn(src_warped, t_pcd, src_feats, tgt_feats):
+        return src_feats, tgt_feats, code(src_warped), code(t_pcd)
+
+    smp = diffreg_b200.DenoisingSampler("4d", head, proc, steps)
+    trace = []
+    out = smp.sample(_cu(g["x_T"]), _cu(g["src_feats"]), _cu(g["tgt_feats"]), _cu(g["s_pcd"]), _cu(g["t_pcd"]), _cu(g["src_mask"]),
+                     _cu(g["tgt_mask"]), noises=[_cu(n) for n in g["noises"]], trace=trace, feature_fn=feature_fn, pe_type="rotary")
+    # with the condition gate open the warp feeds the codes at 1 / voxel_size = 25 rad per metre: the reference's own fp32
+    # pose (and ours, 1e-6 rad apart) is amplified accordingly, so that fixture is held to 1e-3; gate closed: 1e-4
+    tol = TOL_LOG if float(g["max_condition_num"]) == 0.0 else 1e-3
+    for k in range(steps):
+        assert (trace[k]["pose"]["src_warped"].cpu() - g[f"warped_{k}"]).abs().max() <= 5e-5
+        assert (trace[k]["x0"].cpu() - g[f"x0_{k}"]).abs().max() <= tol, k
+        ok, err = finite_close(trace[k]["x_out"].cpu(), g[f"x_out_{k}"].float(), tol)
+        assert ok, (k, err)
+    ok, err = finite_close(out["conf_matrix_pred"].cpu(), g["conf_matrix_pred"].float(), tol)
+    assert ok, err
+
+
+@pytest.mark.parametrize("C,pe_type", [(36, "rotary"), (528, "rotary"), (432, "sinusoidal")])
+def test_lazy_position_code_is_bit_identical_to_the_materialised_one(C, pe_type):
+    """Matching.forward with lazy codes (cos / sin computed inside drg_prep_operand_xyz) == with VolumetricPositionEncoding's
+    tensors (drg_position_code + drg_prep_operand), bit for bit, at the real feature widths."""
+    import diffreg_b200
+    from oracle import diffreg_oracle as O
+    pb = O.make_problem(C, 2, 70, 55, C, prefix_valid=[(70, 50), (61, 55)])
+    cfg = _cfg(C, entangled=False)
+    head = diffreg_b200.Matching(cfg).to(DEV).eval()
+    vol = diffreg_b200.VolumetricPositionEncoding(SimpleNamespace(
+        feature_dim=C, vol_bnds=[[-3.6, -2.4, 1.14], [1.093, 0.78, 2.92]], voxel_size=0.04, pe_type=pe_type)).to(DEV)
+    d = {k: v.to(DEV) for k, v in pb.items()}
+    data_a, data_b = {}, {}
+    with torch.no_grad():
+        conf_a, match_a = head(d["src_feats"], d["tgt_feats"], vol(d["s_pcd"]), vol(d["t_pcd"]), d["src_mask"], d["tgt_mask"], data_a, pe_type)
+        conf_b, match_b = head(d["src_feats"], d["tgt_feats"], vol.lazy(d["s_pcd"]), vol.lazy(d["t_pcd"]), d["src_mask"], d["tgt_mask"],
+                               data_b, pe_type)
+    assert torch.equal(conf_a, conf_b) and torch.equal(match_a, match_b)
+    for k in ("src_feats", "tgt_feats"):
+        assert torch.equal(data_a[k], data_b[k])
+
+
 def test_sampler_step_is_graph_capturable():
     """No host read inside a step: capture one 4d step in a CUDA graph and replay it."""
     import diffreg_b200
