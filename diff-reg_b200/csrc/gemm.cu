@@ -132,6 +132,9 @@ struct GemmShape {
   int split_tma;     // 1: the split epilogue stages hi / lo boxes in shared memory and writes them with TMA stores (tmS)
   int direct_store;  // 1: C row pitch not TMA-storable (M % 4 != 0) -> coalesced st.global from the staging tile
   int kc;            // SPLIT3 kernels: columns of ONE operand segment (K = 3 * kc), a multiple of GEMM_BK
+  int wide_tiles;    // tail balancing: tiles [0, wide_tiles) are BN wide; the remaining (tiles - wide_tiles) tiles -- the
+                     //   last, partial wave -- are processed as twice as many HALF-width tiles so that one round of the
+                     //   persistent grid finishes them in half a tile time (wide_tiles == tiles: no split)
   float* C;          // may be NULL when only the split output is wanted
   // optional fused operand preparation of the NEXT GEMM (projection -> similarity): split_out [N, 3M] receives
   // scale*alpha*acc as [lo|hi|hi] for rows < split_rows0 (left operand) and [hi|lo|hi] for the others (right operand)
@@ -148,7 +151,8 @@ struct GemmShape {
 template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS, const GemmShape s) {
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS,
+                     const __grid_constant__ CUtensorMap tmBh, const GemmShape s) {
   constexpr int B_TILE_BYTES = BN * GEMM_BK * 4;
   constexpr int A_STAGE_BYTES = (SPLIT3 ? 2 : 1) * GEMM_A_STAGE_BYTES;
   constexpr int B_STAGE_BYTES = (SPLIT3 ? 2 : 1) * B_TILE_BYTES;
@@ -174,10 +178,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int tiles_n = (s.M + BN - 1) / BN;
   const int tiles = s.batch * tiles_m * tiles_n;
   const int kblocks = SPLIT3 ? s.kc / GEMM_BK : (s.K + GEMM_BK - 1) / GEMM_BK;
+  // work units of the persistent loop: the wide tiles, then two half-width units per remaining tile
+  const int units = s.wide_tiles + 2 * (tiles - s.wide_tiles);
+  // unit -> (batch, row block, first column, narrow?)
+  auto decode = [&](int unit, int& b, int& mb, int& n0, bool& narrow) {
+    narrow = unit >= s.wide_tiles;
+    const int tile = narrow ? s.wide_tiles + ((unit - s.wide_tiles) >> 1) : unit;
+    b = tile / (tiles_m * tiles_n);
+    const int rem = tile - b * tiles_m * tiles_n;
+    mb = rem / tiles_n;
+    const int nb = rem - mb * tiles_n;
+    n0 = nb * BN + ((narrow && ((unit - s.wide_tiles) & 1)) ? BN / 2 : 0);
+  };
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (s.wide_tiles < tiles) prefetch_tmap(&tmBh);
     if (!s.direct_store) prefetch_tmap(&tmC);
     if (s.split_tma) prefetch_tmap(&tmS);
     for (int i = 0; i < nstage; ++i) {
@@ -201,20 +218,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int b = tile / (tiles_m * tiles_n);
-        const int rem = tile - b * tiles_m * tiles_n;
-        const int mb = rem / tiles_n, nb = rem - mb * tiles_n;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        int b, mb, n0;
+        bool narrow;
+        decode(unit, b, mb, n0, narrow);
+        const CUtensorMap* tb = narrow ? &tmBh : &tmB;   // half-height boxes for the half-width units
+        const uint32_t bytes = (uint32_t)(A_STAGE_BYTES + (narrow ? B_STAGE_BYTES / 2 : B_STAGE_BYTES));
         for (int k = 0; k < kblocks; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(A_STAGE_BYTES + B_STAGE_BYTES));
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
           uint8_t* a_dst = sA + (size_t)stage * A_STAGE_BYTES;
           uint8_t* b_dst = sB + (size_t)stage * B_STAGE_BYTES;
           tma_load_3d(a_dst, &tmA, k * GEMM_BK, mb * GEMM_BM, b, &full_bar[stage]);   // SPLIT3: A_lo
-          tma_load_3d(b_dst, &tmB, k * GEMM_BK, nb * BN, b, &full_bar[stage]);        // SPLIT3: B_hi
+          tma_load_3d(b_dst, tb, k * GEMM_BK, n0, b, &full_bar[stage]);               // SPLIT3: B_hi
           if (SPLIT3) {
             tma_load_3d(a_dst + GEMM_A_STAGE_BYTES, &tmA, s.kc + k * GEMM_BK, mb * GEMM_BM, b, &full_bar[stage]);  // A_hi
-            tma_load_3d(b_dst + B_TILE_BYTES, &tmB, s.kc + k * GEMM_BK, nb * BN, b, &full_bar[stage]);             // B_lo
+            tma_load_3d(b_dst + B_TILE_BYTES, tb, s.kc + k * GEMM_BK, n0, b, &full_bar[stage]);                    // B_lo
           }
           if (++stage == nstage) {
             stage = 0;
@@ -226,12 +245,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(GEMM_BM, BN);
+      constexpr uint32_t idesc_wide = make_idesc_tf32(GEMM_BM, BN);
+      constexpr uint32_t idesc_half = make_idesc_tf32(GEMM_BM, BN / 2);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const uint32_t idesc = unit >= s.wide_tiles ? idesc_half : idesc_wide;
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -275,16 +296,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     int as = 0;
     uint32_t aphase = 0;
     int buf = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int b = tile / (tiles_m * tiles_n);
-      const int rem = tile - b * tiles_m * tiles_n;
-      const int mb = rem / tiles_n, nb = rem - mb * tiles_n;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      int b, mb, n0;
+      bool narrow;
+      decode(unit, b, mb, n0, narrow);
       const int row0 = mb * GEMM_BM + q * 32;
+      const int nchunks = narrow ? BN / 64 : BN / 32;
       mbar_wait(&tmem_full_bar[as], aphase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = nb * BN + c * 32;
+      for (int c = 0; c < nchunks; ++c) {
+        const int col0 = n0 + c * 32;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
         tmem_wait_ld();
@@ -438,8 +460,8 @@ static bool make_tmap(CUtensorMap* tm, const void* ptr, int batch, int rows, int
 }
 
 template <int BN, bool SPLIT3>
-static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tS, GemmShape s,
-                       cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tS,
+                       const CUtensorMap& tBh, GemmShape s, cudaStream_t st) {
   constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (GEMM_A_STAGE_BYTES + BN * GEMM_BK * 4);
   const size_t out_bytes = 4 * 2 * GEMM_OUT_BOX_BYTES;
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - out_bytes - 256 /*static*/;
@@ -454,9 +476,15 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM, tiles_n = (s.M + BN - 1) / BN;
   const long long tiles = (long long)s.batch * tiles_m * tiles_n;
   const int grid = (int)(tiles < NUM_SMS ? tiles : NUM_SMS);
+  // Tail balancing: with `rem` tiles left for the last, partial wave of the persistent grid, the wave costs a full tile
+  // time although only rem of the grid's CTAs work (4096^2 with 128 x 256 tiles: 512 tiles = 3.46 waves of 148).  When
+  // twice as many half-width tiles still fit into one wave, they finish it in half the time instead.
+  const int rem = (int)(tiles % grid);
+  s.wide_tiles = (int)tiles;
+  if (BN >= 128 && tiles > grid && rem > 0 && 2 * rem <= grid) s.wide_tiles = (int)tiles - rem;
   {
     ProfScope prof_scope(PROF_GEMM, st);
-    gemm_tf32_kernel<BN, SPLIT3><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tS, s);
+    gemm_tf32_kernel<BN, SPLIT3><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tS, tBh, s);
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
@@ -517,9 +545,14 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
   s.kc = split3 ? K / 3 : 0;
   // split epilogue through TMA stores when only the split operand is wanted and the left / right boundary is box-aligned
   s.split_tma = (split_out != nullptr && C == nullptr && (split_rows0 % 32) == 0) ? 1 : 0;
-  CUtensorMap tA, tB, tC, tS;
+  CUtensorMap tA, tB, tC, tS, tBh;
   if (!make_tmap(&tA, A, batch, N, K, GEMM_BM, GEMM_BK)) return DRG_ERR_CUDA;
   if (!make_tmap(&tB, B, batch, M, K, BN, GEMM_BK)) return DRG_ERR_CUDA;
+  if (BN >= 128) {
+    if (!make_tmap(&tBh, B, batch, M, K, BN / 2, GEMM_BK)) return DRG_ERR_CUDA;   // half-width units of the tail wave
+  } else {
+    tBh = tB;
+  }
   if (!s.direct_store) {
     if (!make_tmap(&tC, C, batch, N, M, 32, 32)) return DRG_ERR_CUDA;
   } else {
@@ -532,15 +565,15 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
   }
   if (split3) {
     switch (BN) {
-      case 256: return launch_gemm<256, true>(tA, tB, tC, tS, s, st);
-      case 128: return launch_gemm<128, true>(tA, tB, tC, tS, s, st);
-      default: return launch_gemm<64, true>(tA, tB, tC, tS, s, st);
+      case 256: return launch_gemm<256, true>(tA, tB, tC, tS, tBh, s, st);
+      case 128: return launch_gemm<128, true>(tA, tB, tC, tS, tBh, s, st);
+      default: return launch_gemm<64, true>(tA, tB, tC, tS, tBh, s, st);
     }
   }
   switch (BN) {
-    case 256: return launch_gemm<256, false>(tA, tB, tC, tS, s, st);
-    case 128: return launch_gemm<128, false>(tA, tB, tC, tS, s, st);
-    default: return launch_gemm<64, false>(tA, tB, tC, tS, s, st);
+    case 256: return launch_gemm<256, false>(tA, tB, tC, tS, tBh, s, st);
+    case 128: return launch_gemm<128, false>(tA, tB, tC, tS, tBh, s, st);
+    default: return launch_gemm<64, false>(tA, tB, tC, tS, tBh, s, st);
   }
 }
 

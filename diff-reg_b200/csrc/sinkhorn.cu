@@ -1014,94 +1014,124 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
       }
       float* part = red_part + ((buf * P2_GROUPS + rg) * 8) * 8;
       if (scaled) {
-        float mh[RR], rs[RR];
-        if (semi) {
-          // exact row maxima of x = z * zs + v2 (and the dustbin column entry) as the references
-          float tm[RR];
+        float mh[RR], rs[RR], tot[RR];
 #pragma unroll
-          for (int r = 0; r < RR; ++r) tm[r] = NEG_BIG;
+        for (int r = 0; r < RR; ++r) {
+          // row reference (log2 domain).  Later iterations: the row's log-sum-exp of the previous iteration.  First
+          // iteration: the dustbin-column entry, which every row holds -- the row sum is then >= 1 (no underflow), and
+          // whenever the row maximum lies within ~2^100 of it nothing overflows either; rows outside that range are
+          // caught below and redone with their exact maximum.  >= 1e30: a row without real entries (masked, or past the
+          // CTA's range): every e is 0.
+          mh[r] = semi ? (live[r] ? dust2 : 1.0e30f) : lse_prev_s[s * RR + r];
+        }
+        // e_ij = 2^(x_ij - ref_i) in place of z, row sums reduced over the group (ONE named barrier)
+        auto exp_and_row_sums = [&]() {
+#pragma unroll
+          for (int r = 0; r < RR; ++r) rs[r] = 0.f;
 #pragma unroll
           for (int k = 0; k < KQ; ++k) {
             const int c = 4 * (ct + P2_TPR * k);
             if (FULL || c < M) {
               const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
 #pragma unroll
-              for (int r = 0; r < RR; ++r)
-                tm[r] = fmaxf(tm[r], fmaxf(fmaxf(fmaf(z[r][k].x, zs, vv.x), fmaf(z[r][k].y, zs, vv.y)),
-                                           fmaxf(fmaf(z[r][k].z, zs, vv.z), fmaf(z[r][k].w, zs, vv.w))));
+              for (int r = 0; r < RR; ++r) {
+                float4 e;
+                e.x = ex2(fmaf(z[r][k].x, zs, vv.x) - mh[r]);
+                e.y = ex2(fmaf(z[r][k].y, zs, vv.y) - mh[r]);
+                e.z = ex2(fmaf(z[r][k].z, zs, vv.z) - mh[r]);
+                e.w = ex2(fmaf(z[r][k].w, zs, vv.w) - mh[r]);
+                z[r][k] = e;
+                rs[r] += (e.x + e.y) + (e.z + e.w);
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < RR; ++r) z[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          if (!semi && ragged && s == ns - 1) {  // rows past the CTA's range were not copied: stale shared memory, possibly NaN
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+              if (s * RR + r >= nrows) {
+                rs[r] = 0.f;
+#pragma unroll
+                for (int k = 0; k < KQ; ++k) z[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
             }
           }
 #pragma unroll
-          for (int r = 0; r < RR; ++r) tm[r] = warp_max(tm[r]);
+          for (int r = 0; r < RR; ++r) rs[r] = warp_sum(rs[r]);
           if (lane == 0) {
 #pragma unroll
-            for (int r = 0; r < RR; ++r) part[r * 8 + wg] = tm[r];
+            for (int r = 0; r < RR; ++r) part[r * 8 + wg] = rs[r];
           }
           group_barrier(rg);
-          if (ct == 0 && s + D < ns) issue_slab_to(stg, s + D);  // every thread of the group has its registers: re-arm the stage
 #pragma unroll
           for (int r = 0; r < RR; ++r) {
             const float4 a = *reinterpret_cast<const float4*>(part + r * 8);
             const float4 c4 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
-            const float m8 = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w)));
-            mh[r] = live[r] ? fmaxf(m8, dust2) : 1.0e30f;  // masked / out-of-range row: every e is 0
-            rs[r] = 0.f;
+            tot[r] = ((a.x + a.y) + (a.z + a.w)) + ((c4.x + c4.y) + (c4.z + c4.w));
           }
           buf ^= 1;
           part = red_part + ((buf * P2_GROUPS + rg) * 8) * 8;
-        } else {
+        };
+        exp_and_row_sums();
+        if (semi) {
+          // every thread of the group sees the same totals: a uniform decision
+          bool bad = false;
 #pragma unroll
-          for (int r = 0; r < RR; ++r) {
-            mh[r] = lse_prev_s[s * RR + r];  // >= 1e30: a row without real entries (masked, or past the CTA's range): every e is 0
-            rs[r] = 0.f;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < KQ; ++k) {
-          const int c = 4 * (ct + P2_TPR * k);
-          if (FULL || c < M) {
-            const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+          for (int r = 0; r < RR; ++r)
+            if (live[r] && !(tot[r] + 1.f < 1.2676506e30f)) bad = true;   // overflow / NaN: the row maximum is > 2^100 above the dustbin entry
+          if (bad) {
+            // rare (scores with a huge dynamic range): the slab is still in shared memory -- redo with exact row maxima
 #pragma unroll
             for (int r = 0; r < RR; ++r) {
-              float4 e;
-              e.x = ex2(fmaf(z[r][k].x, zs, vv.x) - mh[r]);
-              e.y = ex2(fmaf(z[r][k].y, zs, vv.y) - mh[r]);
-              e.z = ex2(fmaf(z[r][k].z, zs, vv.z) - mh[r]);
-              e.w = ex2(fmaf(z[r][k].w, zs, vv.w) - mh[r]);
-              z[r][k] = e;
-              rs[r] += (e.x + e.y) + (e.z + e.w);
-            }
-          } else {
+              const int i = row0 + s * RR + r;
+              const bool row_in = i < row1;
 #pragma unroll
-            for (int r = 0; r < RR; ++r) z[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int k = 0; k < KQ; ++k) {
+                const int c = 4 * (ct + P2_TPR * k);
+                z[r][k] = (row_in && (FULL || c < M)) ? *reinterpret_cast<const float4*>(slab + (size_t)r * M + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+            float tm[RR];
+#pragma unroll
+            for (int r = 0; r < RR; ++r) tm[r] = NEG_BIG;
+#pragma unroll
+            for (int k = 0; k < KQ; ++k) {
+              const int c = 4 * (ct + P2_TPR * k);
+              if (FULL || c < M) {
+                const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+#pragma unroll
+                for (int r = 0; r < RR; ++r)
+                  tm[r] = fmaxf(tm[r], fmaxf(fmaxf(fmaf(z[r][k].x, zs, vv.x), fmaf(z[r][k].y, zs, vv.y)),
+                                             fmaxf(fmaf(z[r][k].z, zs, vv.z), fmaf(z[r][k].w, zs, vv.w))));
+              }
+            }
+#pragma unroll
+            for (int r = 0; r < RR; ++r) tm[r] = warp_max(tm[r]);
+            if (lane == 0) {
+#pragma unroll
+              for (int r = 0; r < RR; ++r) part[r * 8 + wg] = tm[r];
+            }
+            group_barrier(rg);
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+              const float4 a = *reinterpret_cast<const float4*>(part + r * 8);
+              const float4 c4 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
+              const float m8 = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w)));
+              mh[r] = live[r] ? fmaxf(m8, dust2) : 1.0e30f;
+            }
+            buf ^= 1;
+            part = red_part + ((buf * P2_GROUPS + rg) * 8) * 8;
+            exp_and_row_sums();
           }
         }
-        if (!semi && ragged && s == ns - 1) {  // rows past the CTA's range were not copied: stale shared memory, possibly NaN
-#pragma unroll
-          for (int r = 0; r < RR; ++r) {
-            if (s * RR + r >= nrows) {
-              rs[r] = 0.f;
-#pragma unroll
-              for (int k = 0; k < KQ; ++k) z[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < RR; ++r) rs[r] = warp_sum(rs[r]);
-        if (lane == 0) {
-#pragma unroll
-          for (int r = 0; r < RR; ++r) part[r * 8 + wg] = rs[r];
-        }
-        group_barrier(rg);
-        if (!semi && ct == 0 && s + D < ns) issue_slab_to(stg, s + D);  // every thread of the group has its registers: re-arm the stage
+        if (ct == 0 && s + D < ns) issue_slab_to(stg, s + D);  // every thread of the group has its registers: re-arm the stage
         float w[RR];
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
-          const float4 a = *reinterpret_cast<const float4*>(part + r * 8);
-          const float4 c4 = *reinterpret_cast<const float4*>(part + r * 8 + 4);
-          const float tot = ((a.x + a.y) + (a.z + a.w)) + ((c4.x + c4.y) + (c4.z + c4.w));
           const bool dead = mh[r] > 1.0e29f;
-          const float srow = tot + ex2(dust2 - mh[r]);  // + dustbin column entry
+          const float srow = tot[r] + ex2(dust2 - mh[r]);  // + dustbin column entry
           w[r] = dead ? 0.f : 1.f / srow;               // = 2^(ref_i + u_i log2e - norm2)
           if (ct == 0 && s * RR + r < nrows) {
             const float rowlse2 = dead ? dust2 : mh[r] + lg2(srow);  // a masked row holds the dustbin entry only
@@ -1121,7 +1151,6 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
             cs[4 * k + 3] = fmaf(z[r][k].w, w[r], cs[4 * k + 3]);
           }
         }
-        buf ^= 1;
       } else {
         // log-domain pass: exact row maximum first, then the exponential sum, then an online column log-sum-exp
         float tm[RR];
