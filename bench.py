@@ -458,21 +458,36 @@ def run_ours(args):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        it_ms, it_n = prof["skh_iter"]           # persistent launches WITHOUT the candidate-search tail: Sinkhorn(sim), one per step
-        col_ms, col_n = prof["skh_col"]          # persistent launches WITH the tail: Sinkhorn(x_t) -> top-K candidates, one per step
-        fin_ms, fin_n = prof["skh_final"]        # the DDIM final pass of the Sinkhorn(sim) call
+        it_ms, it_n = prof["skh_iter"]           # persistent launches without any tail (none in a sampler step since round 2)
+        col_ms, col_n = prof["skh_col"]          # persistent launches WITH the candidate-search tail: Sinkhorn(x_t) -> top-K candidates, one per step
+        fin_ms, fin_n = prof["skh_final"]        # stand-alone final-pass launches (none in a sampler step since round 2)
+        fus_ms, fus_n = prof["skh_fused"]        # persistent launches WITH the final pass inside: Sinkhorn(sim) + DDIM update, one per step
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full)
-            tj = json.load(open(tpath)).get("skh_persist2_kernel")
+            tj = json.load(open(tpath)).get("skh_persist2_kernel_fused" if fus_n else "skh_persist2_kernel")
             if tj:
                 traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
-        if it_n:
-            # Dominant kernel: skh_persist2_kernel = ALL I iterations of one log_optimal_transport call in one launch.
-            # Algorithmic bytes per launch are SURVEY.md 8d's 2*I*E (I row-LSE reads + I column-LSE reads of the padded
-            # matrix).  DRAM traffic is far below that: the row and the column pass of an iteration share one read and
-            # iterations 2..I hit the L2-resident matrix.  Timed: the launches of the Sinkhorn(sim) call only (the
-            # Sinkhorn(x_t) launch carries the candidate search of the pose step and is listed separately).
+        if fus_n:
+            # Dominant kernel: skh_persist2_kernel = the whole log_optimal_transport call of the matching head -- ALL I
+            # iterations AND the final pass (exp, DDIM update with in-kernel noise, arg-max keys) in ONE launch.
+            # Algorithmic bytes per launch: SURVEY.md 8d's (2I+2)*E for the Sinkhorn call (I row-LSE reads + I column-LSE
+            # reads of the padded matrix, one final read, one write), plus the read of x_t the fused DDIM update adds:
+            # 2*I*E + 3*E' ("6E + 3E'").  Both accountings are reported; `achieved` uses 6E + 3E'.  DRAM traffic is far
+            # below either: the row and the column pass of an iteration share one read and iterations 2..I and the final
+            # pass hit the L2-resident matrix.
+            fus_s = fus_ms * 1e-3 / fus_n
+            alg = 2 * SKH_ITERS * E + 3 * Ep
+            roofline = {"bound": "hbm",
+                        "kernel": "skh_persist2_kernel (register-slab persistent log-domain Sinkhorn: I=3 iterations + the final pass "
+                                  "(exp, DDIM update, in-kernel Philox noise, arg-max keys) in one cooperative launch)",
+                        "achieved": alg / fus_s / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / fus_s / 1e9 / peak,
+                        "traffic": traffic, "algorithmic_bytes_per_launch": alg, "accounting": "2*I*E + 3*E' (iterations: 2 reads each; "
+                        "final pass: scores + x_t read, x_next written)", "us_per_launch": fus_s * 1e6, "launches": fus_n,
+                        "peak_source": peak_src,
+                        "survey_accounting": {"algorithmic_bytes_2I+2": (2 * SKH_ITERS + 2) * E,
+                                              "frac_2I+2": (2 * SKH_ITERS + 2) * E / fus_s / 1e9 / peak}}
+        elif it_n:
             it_s = it_ms * 1e-3 / it_n
             alg_it = 2 * SKH_ITERS * E
             roofline = {"bound": "hbm",
@@ -481,24 +496,20 @@ def run_ours(args):
                         "traffic": traffic, "algorithmic_bytes_per_launch": alg_it, "us_per_launch": it_s * 1e6,
                         "launches": it_n, "peak_source": peak_src}
             if fin_n:
-                # the fused Sinkhorn(sim) + DDIM call of a step = ONE persistent launch + ONE final-pass launch.
-                # Two accountings of its algorithmic bytes: SURVEY.md's (2I+2)*E (final read + final write), and the
-                # same plus the read of x_t that the fused DDIM update adds (6E + 3E')
                 call_s = it_s + fin_ms * 1e-3 / fin_n
                 roofline["sinkhorn_ddim_call"] = {
-                    "kernels": "skh_persist2_kernel + skh_final_tile_kernel (exp, DDIM update, in-kernel noise, row/column arg-max)",
+                    "kernels": "skh_persist2_kernel + skh_final_tile_kernel",
                     "us_per_call": call_s * 1e6, "us_final_pass": fin_ms * 1e3 / fin_n,
-                    "algorithmic_bytes_2I+2": (2 * SKH_ITERS + 2) * E, "frac_2I+2": (2 * SKH_ITERS + 2) * E / call_s / 1e9 / peak,
                     "algorithmic_bytes_6E+3Ep": 2 * SKH_ITERS * E + 3 * Ep,
-                    "frac_6E+3Ep": (2 * SKH_ITERS * E + 3 * Ep) / call_s / 1e9 / peak,
-                    "final_pass_frac_3Ep": 3 * Ep / (fin_ms * 1e-3 / fin_n) / 1e9 / peak}
-            if col_n:
-                # Sinkhorn(x_t) + candidate search: 2*I*E for the iterations + one more read of the matrix (E') for the search
-                col_s = col_ms * 1e-3 / col_n
-                roofline["sinkhorn_topk_call"] = {
-                    "kernels": "skh_persist2_kernel with the candidate-search tail (sampled bound, L2-hot pass, candidate list)",
-                    "us_per_call": col_s * 1e6, "algorithmic_bytes": alg_it + Ep, "frac": (alg_it + Ep) / col_s / 1e9 / peak,
-                    "pose_kernel_us": prof["procr_solve"][0] * 1e3 / max(prof["procr_solve"][1], 1)}
+                    "frac_6E+3Ep": (2 * SKH_ITERS * E + 3 * Ep) / call_s / 1e9 / peak}
+        if roofline is not None and col_n:
+            # Sinkhorn(x_t) + candidate search: 2*I*E for the iterations + one more read of the matrix (E') for the search
+            col_s = col_ms * 1e-3 / col_n
+            roofline["sinkhorn_topk_call"] = {
+                "kernels": "skh_persist2_kernel with the candidate-search tail (sampled bound, L2-hot pass, candidate list)",
+                "us_per_call": col_s * 1e6, "algorithmic_bytes": 2 * SKH_ITERS * E + Ep,
+                "frac": (2 * SKH_ITERS * E + Ep) / col_s / 1e9 / peak,
+                "pose_kernel_us": prof["procr_solve"][0] * 1e3 / max(prof["procr_solve"][1], 1)}
 
     # ---- BASELINE.json configs[4]: one 16384 x 16384 log-domain Sinkhorn, 100 iterations, rows sharded over the ranks
     rowshard = None
@@ -527,7 +538,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (tf32x3 tensor-core GEMM, fp32 accumulate)" if args.precision == "3xtf32" else "tf32",
+                "dtype": "f32 (GEMM: fp16 hi/lo split operands, three kind::f16 tensor-core terms, fp32 accumulate)" if args.precision == "3xtf32" else "tf32",
                 "data": "synthetic", "config": workload_config(n),
                 "run_info": {"timing": "cuda_graph_replay" if graphs is not None else "eager",
                              "l2": "no explicit flush: each step streams four distinct 64 MiB fp32 matrices (x_t, sim, x_next "

@@ -80,10 +80,10 @@ def _declare(lib):
     c_ll = ctypes.c_longlong
     lib.drg_gemm_nt_tf32.restype = c_int
     lib.drg_gemm_nt_tf32.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
-    lib.drg_gemm_nt_3xtf32.restype = c_int
-    lib.drg_gemm_nt_3xtf32.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
-    lib.drg_project_split3.restype = c_int
-    lib.drg_project_split3.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
+    lib.drg_gemm_nt_split16.restype = c_int
+    lib.drg_gemm_nt_split16.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
+    lib.drg_project_split16.restype = c_int
+    lib.drg_project_split16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
     lib.drg_prep_operand.restype = c_int
     lib.drg_prep_operand.argtypes = [c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.drg_prep_operand_xyz.restype = c_int
@@ -91,8 +91,6 @@ def _declare(lib):
                                          c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.drg_position_code.restype = c_int
     lib.drg_position_code.argtypes = [c_void_p, c_void_p, c_ll, c_int, ctypes.POINTER(c_float), c_float, c_int, c_void_p, c_void_p]
-    lib.drg_project_split.restype = c_int
-    lib.drg_project_split.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
     lib.drg_prep_operand_pair.restype = c_int
     lib.drg_prep_operand_pair.argtypes = [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_float, c_int, c_void_p, c_void_p]
     lib.drg_match_workspace_bytes.restype = c_size_t
@@ -160,7 +158,7 @@ def launch_count():
 
 
 PROFILE_SLOTS = ["skh_iter", "skh_col", "skh_final", "skh_prep", "gemm", "prep_operand", "rowcol_best", "match_rows",
-                 "topk_collect", "procr_solve", "topk_threshold", "procr_select"]
+                 "topk_collect", "procr_solve", "topk_threshold", "procr_select", "skh_fused"]
 
 
 def profile_enable(on=True):

@@ -14,6 +14,10 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float NEG_BIG = -1.0e30f;  // finite stand-in for -inf in running maxima (avoids inf-inf)
 constexpr int NUM_SMS = 148;
+// 16-bit split GEMM operands (features.cu / gemm.cu): a row holds two segments of kc = K rounded up to 64 columns (hi and lo
+// halves of the row-scaled values) and an 8-column tail with the row's (1 / scale, Euclidean norm) as floats
+__host__ __device__ inline int split16_kc(int K) { return (K + 63) & ~63; }
+__host__ __device__ inline int split16_pitch(int K) { return 2 * split16_kc(K) + 8; }
 
 // ---- error plumbing -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
@@ -158,6 +162,7 @@ enum ProfSlot {
   PROF_PROCR_SOLVE,
   PROF_TOPK_THRESHOLD,
   PROF_PROCR_SELECT,
+  PROF_SKH_FUSED,   // persistent Sinkhorn launches that carry the final pass (exp / DDIM) as their last phase
   PROF_NSLOTS
 };
 extern std::atomic<int> g_prof_enabled;

@@ -15,10 +15,16 @@
 //               TMA tensor store of 32 x 32 boxes (clipped at the matrix edge by the TMA unit)
 // Two TMEM accumulator stages (2 x BN columns) let the MMA of tile t+1 overlap the epilogue of t.
 //
-// fp32 parity: kind::tf32 keeps 10 mantissa bits of each operand.  The host side (features.cu)
-// can hand this kernel "3xTF32" operands -- A' = [A_lo | A_hi | A_hi], B' = [B_hi | B_lo | B_hi]
-// concatenated along K -- so that the same kernel returns an fp32-accurate product (the
-// dropped term is A_lo.B_lo ~ 2^-22 relative).
+// fp32 parity: kind::tf32 keeps 10 mantissa bits of each operand.  The fp32-accurate mode of this kernel (SPLIT) takes
+// 16-bit SPLIT operands instead (features.cu): every row is scaled by a power of two 2^e that puts its maximum into
+// [2^14, 2^15), then x 2^e = hi + lo with hi = fp16(x 2^e) (11 significant bits, as many as tf32 keeps) and
+// lo = fp16(x 2^e - hi); the kernel accumulates
+//     A_lo.B_hi + A_hi.B_lo + A_hi.B_hi          (kind::f16, fp32 accumulation in TMEM; dropped: A_lo.B_lo ~ 2^-22)
+// and the epilogue multiplies the row and column scales back (exact: powers of two).  fp16 x bf16 products (a bf16 lo would
+// need no scaling) are not an option: kind::f16 wants ONE format for A and B -- mixed descriptors raise an illegal-instruction
+// fault (measured, tools/probes/umma_fmt_probe.cu).  Against round 1's 3xTF32 (the same three terms on fp32 operands with
+// kind::tf32) every operand byte and every MMA covers twice as many columns: the operand traffic from L2 -- what bounds this
+// kernel -- and the tensor-pipe time are halved, at the same accuracy (measured against fp64 in tests/test_gemm_gpu.py).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -79,6 +85,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem] . B[smem]^T, 16-bit inputs (fp16 / bf16 per the instruction descriptor), fp32 accumulate, K = 16
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier once all tcgen05.mma issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -119,6 +136,26 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);  // [24,29) M >> 4
 }
 
+// kind::f16 instruction descriptor: D fp32, A / B format 0 = fp16, 1 = bf16 (independent), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+constexpr uint32_t FMT_F16 = 0u;   // (1 = bf16; A and B must share the format)
+
+// x = hi + lo, both fp16 (x is already row-scaled into fp16's range): hi = fp16(x), lo = fp16(x - hi)
+__device__ __forceinline__ void split16(float x, unsigned short& hi_bits, unsigned short& lo_bits) {
+  unsigned short h;
+  asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  float hf;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
+  unsigned short l;
+  asm("cvt.rn.f16.f32 %0, %1;" : "=h"(l) : "f"(x - hf));
+  hi_bits = h;
+  lo_bits = l;
+}
+
+__device__ __forceinline__ uint32_t pack16(unsigned short a, unsigned short b) { return (uint32_t)a | ((uint32_t)b << 16); }
+
 __device__ __forceinline__ float gemm_to_tf32_rna(float x) {
   uint32_t y;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
@@ -131,23 +168,28 @@ struct GemmShape {
   int nstage;
   int split_tma;     // 1: the split epilogue stages hi / lo boxes in shared memory and writes them with TMA stores (tmS)
   int direct_store;  // 1: C row pitch not TMA-storable (M % 4 != 0) -> coalesced st.global from the staging tile
-  int kc;            // SPLIT3 kernels: columns of ONE operand segment (K = 3 * kc), a multiple of GEMM_BK
+  int kc;            // SPLIT kernels: 16-bit columns of ONE operand segment (the operand rows are [seg0 | seg1 | tail], pitch
+                     //   2 * kc + 8; kc = K rounded up to 64, the padding holds zeros), a multiple of 64 = one 128-byte k-step
+  const unsigned short* A16;  // SPLIT kernels: the operands themselves, for the row tails (1 / scale, norm) the epilogue reads
+  const unsigned short* B16;
   int wide_tiles;    // tail balancing: tiles [0, wide_tiles) are BN wide; the remaining (tiles - wide_tiles) tiles -- the
                      //   last, partial wave -- are processed as twice as many HALF-width tiles so that one round of the
                      //   persistent grid finishes them in half a tile time (wide_tiles == tiles: no split)
   float* C;          // may be NULL when only the split output is wanted
-  // optional fused operand preparation of the NEXT GEMM (projection -> similarity): split_out [N, 3M] receives
-  // scale*alpha*acc as [lo|hi|hi] for rows < split_rows0 (left operand) and [hi|lo|hi] for the others (right operand)
-  float* split_out;
+  // optional fused operand preparation of the NEXT GEMM (projection -> similarity): split_out [N, 2 * split_kc + 8] (16-bit)
+  // receives scale*alpha*acc as a split operand: [lo | hi | tail] for rows < split_rows0 (left operand), [hi | lo | tail] for the
+  // others (right operand); columns [M, split_kc) of each segment are the caller's zero padding.  The row scale of an output
+  // row comes from a bound instead of its maximum (a row is spread over several tiles): |y_ij| <= ||x_i|| max_j ||W_j||.
+  unsigned short* split_out;
+  int split_kc;
   int split_rows0;
   float split_scale;
 };
 
-// SPLIT3: the operands are the 3xTF32 concatenations A' = [A_lo | A_hi | A_hi], B' = [B_hi | B_lo | B_hi] (each segment kc
-// columns).  Instead of streaming 3 * kc columns of both (the third segments are copies), a stage holds the four DISTINCT
-// 32-column tiles A_lo, A_hi, B_hi, B_lo of one k-chunk and the MMA warp issues lo.hi, hi.lo, hi.hi from them: the same
-// 12 MMAs per chunk with one third less operand traffic from L2 -- which is what bounds this kernel (fp32 operands want
-// ~90 B/clk/SM, the fabric delivers ~44).
+// SPLIT3 (the 16-bit split mode): the operands are A' = [A_lo | A_hi | tail], B' = [B_hi | B_lo | tail] (fp16), each segment
+// kc 16-bit columns.  A stage holds the four tiles A_lo, A_hi, B_hi, B_lo of one 64-column k-step (128-byte rows, the same
+// tile geometry and swizzle as the fp32 mode) and the MMA warp issues lo.hi, hi.lo, hi.hi (kind::f16, K = 16, four each
+// per k-step) from them.
 template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -177,7 +219,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM;
   const int tiles_n = (s.M + BN - 1) / BN;
   const int tiles = s.batch * tiles_m * tiles_n;
-  const int kblocks = SPLIT3 ? s.kc / GEMM_BK : (s.K + GEMM_BK - 1) / GEMM_BK;
+  constexpr int KSTEP = SPLIT3 ? 64 : GEMM_BK;   // operand columns per k-step: 128 bytes either way
+  const int kblocks = SPLIT3 ? s.kc / KSTEP : (s.K + GEMM_BK - 1) / GEMM_BK;
   // work units of the persistent loop: the wide tiles, then two half-width units per remaining tile
   const int units = s.wide_tiles + 2 * (tiles - s.wide_tiles);
   // unit -> (batch, row block, first column, narrow?)
@@ -229,11 +272,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           mbar_arrive_expect_tx(&full_bar[stage], bytes);
           uint8_t* a_dst = sA + (size_t)stage * A_STAGE_BYTES;
           uint8_t* b_dst = sB + (size_t)stage * B_STAGE_BYTES;
-          tma_load_3d(a_dst, &tmA, k * GEMM_BK, mb * GEMM_BM, b, &full_bar[stage]);   // SPLIT3: A_lo
-          tma_load_3d(b_dst, tb, k * GEMM_BK, n0, b, &full_bar[stage]);               // SPLIT3: B_hi
+          tma_load_3d(a_dst, &tmA, k * KSTEP, mb * GEMM_BM, b, &full_bar[stage]);   // SPLIT3: A_lo
+          tma_load_3d(b_dst, tb, k * KSTEP, n0, b, &full_bar[stage]);               // SPLIT3: B_hi
           if (SPLIT3) {
-            tma_load_3d(a_dst + GEMM_A_STAGE_BYTES, &tmA, s.kc + k * GEMM_BK, mb * GEMM_BM, b, &full_bar[stage]);  // A_hi
-            tma_load_3d(b_dst + B_TILE_BYTES, tb, s.kc + k * GEMM_BK, n0, b, &full_bar[stage]);                    // B_lo
+            tma_load_3d(a_dst + GEMM_A_STAGE_BYTES, &tmA, s.kc + k * KSTEP, mb * GEMM_BM, b, &full_bar[stage]);  // A_hi
+            tma_load_3d(b_dst + B_TILE_BYTES, tb, s.kc + k * KSTEP, n0, b, &full_bar[stage]);                    // B_lo
           }
           if (++stage == nstage) {
             stage = 0;
@@ -247,12 +290,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (lane == 0) {
       constexpr uint32_t idesc_wide = make_idesc_tf32(GEMM_BM, BN);
       constexpr uint32_t idesc_half = make_idesc_tf32(GEMM_BM, BN / 2);
+      // 16-bit split mode: fp16 x fp16 for all three terms
+      constexpr uint32_t id16[2] = {make_idesc_f16(GEMM_BM, BN, FMT_F16, FMT_F16), make_idesc_f16(GEMM_BM, BN / 2, FMT_F16, FMT_F16)};
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-        const uint32_t idesc = unit >= s.wide_tiles ? idesc_half : idesc_wide;
+        const int nw = unit >= s.wide_tiles ? 1 : 0;
+        const uint32_t idesc = nw ? idesc_half : idesc_wide;
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -264,12 +310,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (SPLIT3) {
             const uint64_t ah_desc = make_smem_desc_sw128(smem_u32(sA + (size_t)stage * A_STAGE_BYTES + GEMM_A_STAGE_BYTES));
             const uint64_t bl_desc = make_smem_desc_sw128(smem_u32(sB + (size_t)stage * B_STAGE_BYTES + B_TILE_BYTES));
+            // (the small correction terms first: the accumulator is rounded at every step, so they are added while it is small)
 #pragma unroll
-            for (int kk = 0; kk < GEMM_BK / 8; ++kk) {
+            for (int kk = 0; kk < 4; ++kk) {     // 4 x 16 columns; +32 bytes along K inside the swizzle atom = +2 in (addr >> 4)
               const uint64_t o = (uint64_t)(2 * kk);
-              umma_tf32(d_tmem, a_desc + o, b_desc + o, idesc, (uint32_t)((k | kk) != 0));  // lo . hi
-              umma_tf32(d_tmem, ah_desc + o, bl_desc + o, idesc, 1u);                        // hi . lo
-              umma_tf32(d_tmem, ah_desc + o, b_desc + o, idesc, 1u);                         // hi . hi
+              umma_f16(d_tmem, a_desc + o, b_desc + o, id16[nw], (uint32_t)((k | kk) != 0));  // lo . hi
+              umma_f16(d_tmem, ah_desc + o, bl_desc + o, id16[nw], 1u);                        // hi . lo
+              umma_f16(d_tmem, ah_desc + o, b_desc + o, id16[nw], 1u);                         // hi . hi
             }
           } else {
 #pragma unroll
@@ -296,12 +343,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     int as = 0;
     uint32_t aphase = 0;
     int buf = 0;
+    // SPLIT3: the operands' row tails.  op_pitch in 16-bit units; tail floats: [0] = 1 / row scale, [1] = row norm
+    const int op_pitch = 2 * s.kc + 8;
+    auto tail_of = [&](const unsigned short* op, size_t row) { return reinterpret_cast<const float*>(op + row * op_pitch + 2 * s.kc); };
+    float wmax = 0.f;   // split epilogue: the largest row norm of the right operand (the weight)
+    if (SPLIT3 && s.split_out) {
+      for (int j = lane; j < s.M; j += 32) wmax = fmaxf(wmax, tail_of(s.B16, (size_t)j)[1]);
+      wmax = warp_max(wmax);
+    }
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
       int b, mb, n0;
       bool narrow;
       decode(unit, b, mb, n0, narrow);
       const int row0 = mb * GEMM_BM + q * 32;
       const int nchunks = narrow ? BN / 64 : BN / 32;
+      // this lane's accumulator row: 1 / scale of the left operand's row (and, for the split epilogue, its norm)
+      float rs_a = 1.f, nx_a = 0.f;
+      if (SPLIT3 && row0 + lane < s.N) {
+        const float* t = tail_of(s.A16, (size_t)b * s.N + row0 + lane);
+        rs_a = t[0];
+        nx_a = t[1];
+      }
+      // 1 / scale of the right operand's rows = this tile's output columns (lane = column of every 32-column chunk), fetched
+      // while the MMA warp still works on the tile: a dependent global load per box would sit on the epilogue's critical path
+      float cscale[BN / 32];
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col = n0 + c * 32 + lane;
+        cscale[c] = (SPLIT3 && c < nchunks && col < s.M) ? tail_of(s.B16, (size_t)b * s.M + col)[0] : 1.f;
+      }
       mbar_wait(&tmem_full_bar[as], aphase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -309,58 +379,71 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int col0 = n0 + c * 32;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
+        float rs_b = cscale[0];   // 1 / scale of output column col0 + lane (register select: the chunk loop is not unrolled)
+#pragma unroll
+        for (int t = 1; t < BN / 32; ++t) rs_b = (c == t) ? cscale[t] : rs_b;
         tmem_wait_ld();
         if (row0 >= s.N || col0 >= s.M) continue;  // whole box outside the matrix (warp-uniform)
+        if (SPLIT3) {
+          // undo the operands' power-of-two row scales (exact): acc_ij / (scale_i scale_j)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * __shfl_sync(0xffffffffu, rs_b, j));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * rs_a);
+        }
+        // split epilogue: this row's output scale 2^e from the bound |alpha scale| ||x_i|| max_j ||W_j|| (one octave of margin)
+        float sc_out = 1.f;
+        if (SPLIT3 && s.split_out) {
+          const float bound = fabsf(s.alpha * s.split_scale) * nx_a * wmax;
+          int e = 0;
+          if (bound > 0.f && bound <= 3.0e38f) e = min(max(13 - ilogbf(bound), -126), 126);
+          sc_out = __int_as_float((e + 127) << 23);
+          if (col0 == 0 && row0 + lane < s.N)
+            *reinterpret_cast<float4*>(s.split_out + (size_t)(row0 + lane) * (2 * s.split_kc + 8) + 2 * s.split_kc) =
+                make_float4(__int_as_float((127 - e) << 23), 0.f, 0.f, 0.f);
+        }
         if (s.split_out && s.split_tma) {
-          // fused drg_prep_operand(split=1) of the projected features, coalesced: the hi and lo boxes are staged (128B-swizzled)
-          // in this warp's two buffers and leave as three TMA tensor stores into the [rows, 3M] operand
-          // (the row-strided 16-byte stores of the path below were what bounded the projection GEMM)
-          const float sc = s.alpha * s.split_scale;
+          // fused drg_prep_operand(split=1) of the projected features: the fp16 hi and lo boxes (32 x 32 x 2 bytes, plain
+          // row-major) are staged in this warp's two buffers and leave as two TMA tensor stores into the split operand
+          const float sc = s.alpha * s.split_scale * sc_out;
           uint8_t* hi_box = stg;
           uint8_t* lo_box = stg + GEMM_OUT_BOX_BYTES;
           if (lane == 0) bulk_wait_group_read<0>();  // the previous chunk's stores have finished reading both buffers
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 hi, lo;
-            const float x0 = __uint_as_float(r[4 * j + 0]) * sc, x1 = __uint_as_float(r[4 * j + 1]) * sc;
-            const float x2 = __uint_as_float(r[4 * j + 2]) * sc, x3 = __uint_as_float(r[4 * j + 3]) * sc;
-            hi.x = gemm_to_tf32_rna(x0); hi.y = gemm_to_tf32_rna(x1); hi.z = gemm_to_tf32_rna(x2); hi.w = gemm_to_tf32_rna(x3);
-            lo.x = gemm_to_tf32_rna(x0 - hi.x); lo.y = gemm_to_tf32_rna(x1 - hi.y);
-            lo.z = gemm_to_tf32_rna(x2 - hi.z); lo.w = gemm_to_tf32_rna(x3 - hi.w);
-            *reinterpret_cast<float4*>(hi_box + lane * 128 + ((j ^ (lane & 7)) << 4)) = hi;
-            *reinterpret_cast<float4*>(lo_box + lane * 128 + ((j ^ (lane & 7)) << 4)) = lo;
+          for (int j = 0; j < 4; ++j) {              // lane = row: 32 columns = 4 chunks of 8 values (16 bytes of 16-bit)
+            unsigned short h[8], l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split16(__uint_as_float(r[8 * j + e]) * sc, h[e], l[e]);
+            *reinterpret_cast<uint4*>(hi_box + lane * 64 + j * 16) = make_uint4(pack16(h[0], h[1]), pack16(h[2], h[3]), pack16(h[4], h[5]), pack16(h[6], h[7]));
+            *reinterpret_cast<uint4*>(lo_box + lane * 64 + j * 16) = make_uint4(pack16(l[0], l[1]), pack16(l[2], l[3]), pack16(l[4], l[5]), pack16(l[6], l[7]));
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
             const bool left = row0 < s.split_rows0;  // split_rows0 % 32 == 0 in this mode: a box never straddles the boundary
             tma_store_3d(&tmS, left ? lo_box : hi_box, col0, row0, 0);
-            tma_store_3d(&tmS, left ? hi_box : lo_box, s.M + col0, row0, 0);
-            tma_store_3d(&tmS, hi_box, 2 * s.M + col0, row0, 0);
+            tma_store_3d(&tmS, left ? hi_box : lo_box, s.split_kc + col0, row0, 0);
             bulk_commit_group();
           }
           continue;
         }
         if (s.split_out) {
-          // fused drg_prep_operand(split=1) of the projected features: lane = row, 32 consecutive columns
+          // the same without TMA (left / right boundary not box-aligned): lane = row, 32 consecutive columns
           const int row = row0 + lane;
           if (row < s.N) {
             const bool left = row < s.split_rows0;
-            float* o = s.split_out + (size_t)row * 3 * s.M + col0;
-            const float sc = s.alpha * s.split_scale;
+            unsigned short* o = s.split_out + (size_t)row * (2 * s.split_kc + 8) + col0;
+            const float sc = s.alpha * s.split_scale * sc_out;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (col0 + 4 * j < s.M) {  // M % 4 == 0 in this mode
-                float4 hi, lo;
-                const float x0 = __uint_as_float(r[4 * j + 0]) * sc, x1 = __uint_as_float(r[4 * j + 1]) * sc;
-                const float x2 = __uint_as_float(r[4 * j + 2]) * sc, x3 = __uint_as_float(r[4 * j + 3]) * sc;
-                hi.x = gemm_to_tf32_rna(x0); hi.y = gemm_to_tf32_rna(x1); hi.z = gemm_to_tf32_rna(x2); hi.w = gemm_to_tf32_rna(x3);
-                lo.x = gemm_to_tf32_rna(x0 - hi.x); lo.y = gemm_to_tf32_rna(x1 - hi.y);
-                lo.z = gemm_to_tf32_rna(x2 - hi.z); lo.w = gemm_to_tf32_rna(x3 - hi.w);
-                *reinterpret_cast<float4*>(o + 4 * j) = left ? lo : hi;
-                *reinterpret_cast<float4*>(o + s.M + 4 * j) = left ? hi : lo;
-                *reinterpret_cast<float4*>(o + 2 * s.M + 4 * j) = hi;
+                unsigned short h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split16(__uint_as_float(r[4 * j + e]) * sc, h[e], l[e]);
+                const uint2 hv = make_uint2(pack16(h[0], h[1]), pack16(h[2], h[3])), lv = make_uint2(pack16(l[0], l[1]), pack16(l[2], l[3]));
+                *reinterpret_cast<uint2*>(o + 4 * j) = left ? lv : hv;
+                *reinterpret_cast<uint2*>(o + s.split_kc + 4 * j) = left ? hv : lv;
               }
             }
           }
@@ -439,19 +522,22 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // [batch, rows, cols] fp32 row-major -> rank-3 tensor map with box {box_cols, box_rows, 1}, 128B swizzle
-static bool make_tmap(CUtensorMap* tm, const void* ptr, int batch, int rows, int cols, int box_rows, int box_cols) {
+// elem_bytes 4: fp32, 128-byte swizzle (operands, fp32 output boxes); 2: 16-bit (the type tag is irrelevant to a copy; fp16 and
+// bf16 segments share one map), 128-byte swizzle when `swizzle`, plain rows otherwise (the split epilogue's store boxes)
+static bool make_tmap(CUtensorMap* tm, const void* ptr, int batch, int rows, int cols, int box_rows, int box_cols, int elem_bytes = 4,
+                      bool swizzle = true) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return false;
   }
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
-  cuuint64_t strides[2] = {(cuuint64_t)cols * 4ull, (cuuint64_t)rows * (cuuint64_t)cols * 4ull};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * (cuuint64_t)elem_bytes, (cuuint64_t)rows * (cuuint64_t)cols * (cuuint64_t)elem_bytes};
   cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d] box [%d,%d]", (int)r, batch, rows, cols, box_rows, box_cols);
     return false;
@@ -467,7 +553,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - out_bytes - 256 /*static*/;
   int nstage = (int)(budget / STAGE_BYTES);
   if (nstage > GEMM_MAX_STAGES) nstage = GEMM_MAX_STAGES;
-  const int kblocks = SPLIT3 ? s.kc / GEMM_BK : (s.K + GEMM_BK - 1) / GEMM_BK;
+  const int kblocks = SPLIT3 ? s.kc / 64 : (s.K + GEMM_BK - 1) / GEMM_BK;
   if (nstage > 2 * kblocks) nstage = 2 * kblocks;  // no point in more stages than two tiles of k-steps
   if (nstage < 2) nstage = 2;
   s.nstage = nstage;
@@ -494,40 +580,45 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
 
 using namespace drg;
 
-static int gemm_run(const float* A, const float* B, float* C, int batch, int N, int M, int K, float alpha, float* split_out,
-                    int split_rows0, float split_scale, void* stream, bool split3 = false) {
+// A, B: fp32 [batch, rows, K] (split16 == false) or 16-bit split operands [batch, rows, 2 * kc] with kc = K rounded up to 64
+// (split16 == true; drg_prep_operand(split = 1) / the split epilogue write them).  split_out (optional, batch == 1): the 16-bit
+// split operand [N, 2 * split_kc] of the next GEMM, split_kc = M rounded up to 64 (its padding columns must be zero already).
+static int gemm_run(const void* A, const void* B, float* C, int batch, int N, int M, int K, float alpha, unsigned short* split_out,
+                    int split_rows0, float split_scale, void* stream, bool split16 = false) {
   DRG_CHECK_ARG(A && B && (C || split_out), "A/B and an output must be non-null");
   DRG_CHECK_ARG(batch >= 1 && N >= 1 && M >= 1 && K >= 1, "batch, N, M, K must be >= 1");
-  if (K % 4 != 0 || ((uintptr_t)A & 15u) || ((uintptr_t)B & 15u)) {
+  if ((!split16 && K % 4 != 0) || ((uintptr_t)A & 15u) || ((uintptr_t)B & 15u)) {
     set_error("gemm: K must be a multiple of 4 and A, B 16-byte aligned (TMA row pitch); got K=%d", K);
     return DRG_ERR_UNSUPPORTED;
   }
-  if (split_out && (M % 4 != 0 || batch != 1 || ((uintptr_t)split_out & 15u))) {
-    set_error("gemm: the split epilogue needs batch == 1, M %% 4 == 0 and a 16-byte aligned output");
+  if (split_out && (M % 4 != 0 || batch != 1 || ((uintptr_t)split_out & 15u) || !split16)) {
+    set_error("gemm: the split epilogue needs split operands, batch == 1, M %% 4 == 0 and a 16-byte aligned output");
     return DRG_ERR_UNSUPPORTED;
   }
-  if (split3 && (K % 3 != 0 || (K / 3) % GEMM_BK != 0)) split3 = false;  // segments must be whole k-chunks: generic path
+  const int kc = (K + 63) & ~63;                 // 16-bit columns per operand segment (split mode)
   cudaStream_t st = (cudaStream_t)stream;
   // Tile width by a two-term cost model (cycles): the MMA time of the busiest SM, and the operand traffic through L2
   // (every tile re-reads its A and B k-blocks; measured on B200 the fabric delivers ~6.5 KB/clk to the SMs, which is
   // what bounds both the 4096^2 similarity GEMM and the skinny projection GEMM -- profiles/r1_gemm_ncu.txt).
   int BN = 64;
   {
-    const double kblocks = (double)((K + GEMM_BK - 1) / GEMM_BK);
+    // k-steps of 128-byte operand rows: 32 fp32 columns, or 64 16-bit columns of each of the two segments
+    const double kblocks = split16 ? (double)(kc / 64) : (double)((K + GEMM_BK - 1) / GEMM_BK);
+    const double terms = split16 ? 3.0 : 1.0, tiles_per_step = split16 ? 2.0 : 1.0;
     double best = 1e300;
     for (int bn : {64, 128, 256}) {
       const double tiles = (double)batch * ((N + 127) / 128) * ((M + bn - 1) / bn);
       const double rounds = (double)((long long)((tiles + NUM_SMS - 1) / NUM_SMS));
-      const double t_mma = rounds * kblocks * 4.0 * (bn / 2.0);                    // 128 x bn x 8 tf32 MMA = bn/2 clk
-      const double t_l2 = tiles * kblocks * (double)((128 + bn) * GEMM_BK * 4) / 6500.0 * (split3 ? 2.0 / 3.0 : 1.0);
+      const double t_mma = rounds * kblocks * terms * 4.0 * (bn / 2.0);            // one 128 x bn MMA (K = 8 tf32 / 16 f16) = bn/2 clk
+      const double t_l2 = tiles * kblocks * tiles_per_step * (double)((128 + bn) * 128) / 6500.0;
       const double t = (t_mma > t_l2 ? t_mma : t_l2) + rounds * 1500.0;            // + per-tile epilogue exposure
       if (t < best) {
         best = t;
         BN = bn;
       }
     }
-    // the split epilogue stores 3x the output with row-strided 16-byte stores from four warps only: it wants many
-    // small tiles in flight rather than few wide ones (measured: BN=256 was 10 us slower on the 8192 x 256 projection)
+    // the split epilogue without TMA stores (left / right boundary not box-aligned) writes row-strided 8-byte pieces from
+    // four warps only: it wants many small tiles in flight rather than few wide ones
     const bool split_tma_early = split_out != nullptr && C == nullptr && (split_rows0 % 32) == 0;
     if (split_out && !split_tma_early) BN = 64;
   }
@@ -539,17 +630,21 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
   s.alpha = alpha;
   s.C = C;
   s.split_out = split_out;
+  s.split_kc = (M + 63) & ~63;
   s.split_rows0 = split_rows0;
   s.split_scale = split_scale;
   s.direct_store = (C == nullptr || M % 4 != 0 || ((uintptr_t)C & 15u)) ? 1 : 0;
-  s.kc = split3 ? K / 3 : 0;
+  s.kc = split16 ? kc : 0;
+  s.A16 = split16 ? reinterpret_cast<const unsigned short*>(A) : nullptr;
+  s.B16 = split16 ? reinterpret_cast<const unsigned short*>(B) : nullptr;
   // split epilogue through TMA stores when only the split operand is wanted and the left / right boundary is box-aligned
   s.split_tma = (split_out != nullptr && C == nullptr && (split_rows0 % 32) == 0) ? 1 : 0;
   CUtensorMap tA, tB, tC, tS, tBh;
-  if (!make_tmap(&tA, A, batch, N, K, GEMM_BM, GEMM_BK)) return DRG_ERR_CUDA;
-  if (!make_tmap(&tB, B, batch, M, K, BN, GEMM_BK)) return DRG_ERR_CUDA;
+  const int eb = split16 ? 2 : 4, kcols = split16 ? 2 * kc + 8 : K, kbox = split16 ? 64 : GEMM_BK;   // (+8: the row tail)
+  if (!make_tmap(&tA, A, batch, N, kcols, GEMM_BM, kbox, eb)) return DRG_ERR_CUDA;
+  if (!make_tmap(&tB, B, batch, M, kcols, BN, kbox, eb)) return DRG_ERR_CUDA;
   if (BN >= 128) {
-    if (!make_tmap(&tBh, B, batch, M, K, BN / 2, GEMM_BK)) return DRG_ERR_CUDA;   // half-width units of the tail wave
+    if (!make_tmap(&tBh, B, batch, M, kcols, BN / 2, kbox, eb)) return DRG_ERR_CUDA;   // half-width units of the tail wave
   } else {
     tBh = tB;
   }
@@ -559,11 +654,11 @@ static int gemm_run(const float* A, const float* B, float* C, int batch, int N, 
     tC = tA;  // unused
   }
   if (s.split_tma) {
-    if (!make_tmap(&tS, split_out, 1, N, 3 * M, 32, 32)) return DRG_ERR_CUDA;
+    if (!make_tmap(&tS, split_out, 1, N, 2 * s.split_kc + 8, 32, 32, 2, false)) return DRG_ERR_CUDA;
   } else {
     tS = tA;  // unused
   }
-  if (split3) {
+  if (split16) {
     switch (BN) {
       case 256: return launch_gemm<256, true>(tA, tB, tC, tS, tBh, s, st);
       case 128: return launch_gemm<128, true>(tA, tB, tC, tS, tBh, s, st);
@@ -583,26 +678,18 @@ extern "C" int drg_gemm_nt_tf32(const float* A, const float* B, float* C, int ba
   return gemm_run(A, B, C, batch, N, M, K, alpha, nullptr, 0, 1.f, stream);
 }
 
-// A' = [A_lo | A_hi | A_hi], B' = [B_hi | B_lo | B_hi] (drg_prep_operand split = 1, patterns 0 / 1), K3 = 3 * K: same result as
-// drg_gemm_nt_tf32 on the same operands up to the order of the fp32 accumulation, with one third less operand traffic.
-extern "C" int drg_gemm_nt_3xtf32(const float* A, const float* B, float* C, int batch, int N, int M, int K3, float alpha,
-                                  void* stream) {
+// fp32-accurate product from 16-bit split operands (drg_prep_operand(split = 1), patterns 0 / 1): A16 [batch, N, 2 kc],
+// B16 [batch, M, 2 kc], kc = K rounded up to 64.
+extern "C" int drg_gemm_nt_split16(const void* A16, const void* B16, float* C, int batch, int N, int M, int K, float alpha,
+                                   void* stream) {
   DRG_CHECK_ARG(C != nullptr, "C is null");
-  DRG_CHECK_ARG(K3 % 3 == 0, "K3 must be 3 * K");
-  return gemm_run(A, B, C, batch, N, M, K3, alpha, nullptr, 0, 1.f, stream, true);
+  return gemm_run(A16, B16, C, batch, N, M, K, alpha, nullptr, 0, 1.f, stream, true);
 }
 
-extern "C" int drg_project_split3(const float* A, const float* W, int rows, int rows_left, int C_out, int K3, float scale,
-                                  float* plain_out, float* split_out, void* stream) {
-  DRG_CHECK_ARG(split_out != nullptr, "split_out is null");
+extern "C" int drg_project_split16(const void* A16, const void* W16, int rows, int rows_left, int C_out, int K, float scale,
+                                   float* plain_out, void* split_out16, void* stream) {
+  DRG_CHECK_ARG(split_out16 != nullptr, "split_out is null");
   DRG_CHECK_ARG(rows_left >= 0 && rows_left <= rows, "rows_left out of range");
-  DRG_CHECK_ARG(K3 % 3 == 0, "K3 must be 3 * K");
-  return gemm_run(A, W, plain_out, 1, rows, C_out, K3, 1.f, split_out, rows_left, scale, stream, true);
-}
-
-extern "C" int drg_project_split(const float* A, const float* W, int rows, int rows_left, int C_out, int K, float scale,
-                                 float* plain_out, float* split_out, void* stream) {
-  DRG_CHECK_ARG(split_out != nullptr, "split_out is null");
-  DRG_CHECK_ARG(rows_left >= 0 && rows_left <= rows, "rows_left out of range");
-  return gemm_run(A, W, plain_out, 1, rows, C_out, K, 1.f, split_out, rows_left, scale, stream);
+  return gemm_run(A16, W16, plain_out, 1, rows, C_out, K, 1.f, reinterpret_cast<unsigned short*>(split_out16), rows_left, scale, stream,
+                  true);
 }

@@ -20,6 +20,8 @@
 // and one MUFU.EX2 per direction.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace drg {
@@ -29,6 +31,24 @@ constexpr int SKH_WARPS = SKH_THREADS / 32;
 constexpr int SKH_STAGE_FLOATS = 16384;  // R * M <= 16384 floats (64 KB) per stage
 constexpr int SKH_MAX_M = 16384;
 constexpr size_t SKH_SMEM_LIMIT = 227 * 1024;
+
+// The final pass (exp / DDIM update / in-kernel noise / arg-max keys) as the LAST PHASE of the persistent kernel: the score
+// slab is L2-hot right after the iterations and the potentials are final, so the pass costs one read of x_t and one write of
+// the output in DRAM instead of three matrices, and one launch boundary less.  out == NULL: the stand-alone final kernels run.
+struct SkhFused {
+  float* out;                 // [B,N,M] conf (ddim == 0) or x_next (ddim == 1)
+  const float* x_t;           // ddim: [B,N,M]
+  const float* xt_shift;      // device scalar or NULL
+  const float* noise;         // [B,N,M] caller-supplied N(0,1) draws or NULL
+  float* conf;                // ddim: optional x0 = conf
+  unsigned long long* rowbest;  // optional packed arg-max keys (entries above best_floor only)
+  unsigned long long* colbest;
+  float k_x0, k_xt, sigma, best_floor;
+  int ddim, gen_noise;
+  unsigned long long noise_offset;
+  const unsigned long long* noise_offset_dev;
+  unsigned int rk[14];        // Philox round keys (seed_lo + r W0, seed_hi + r W1), r = 0..6, precomputed on the host
+};
 
 struct SkhParams {
   const float* scores;
@@ -54,6 +74,7 @@ struct SkhParams {
   unsigned long long* zero_b;  //   final pass of the same call: two memset nodes less per step)
   size_t zero_a_n, zero_b_n;
   SkhCollect col;  // col.state != NULL: the persistent kernel runs the top-K candidate search of SoftProcrustes as its last phase
+  SkhFused fin;    // fin.out != NULL: the persistent kernel runs the final pass as its last phase
 };
 
 // ---------------------------------------------------------------------------------------
@@ -716,6 +737,87 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
+// Philox4x32-7 counter-based generator (Salmon et al., SC'11: 7 rounds is the fewest that passes BigCrush; 10 is the
+// library default with extra margin) + Box-Muller: four N(0,1) draws per counter.
+// Counter = (quad index of the element, noise_offset); key = noise_seed.  Replaces torch.randn_like(x)
+// (Diff-Reg-4dmatch/models/pipeline.py:188) in throughput mode; parity tests pass the noise tensor instead.
+__device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) {
+  const unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const unsigned long long p0 = (unsigned long long)M0 * c.x, p1 = (unsigned long long)M1 * c.z;  // one IMAD.WIDE each
+    const unsigned int hi0 = (unsigned int)(p0 >> 32), lo0 = (unsigned int)p0;
+    const unsigned int hi1 = (unsigned int)(p1 >> 32), lo1 = (unsigned int)p1;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+// the same generator with the round keys precomputed (kernel parameters: constant-bank operands, no key schedule in the loop)
+__device__ __forceinline__ uint4 philox4x32_7_rk(uint4 c, const unsigned int (&rk)[14]) {
+  const unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const unsigned long long p0 = (unsigned long long)M0 * c.x, p1 = (unsigned long long)M1 * c.z;
+    const unsigned int hi0 = (unsigned int)(p0 >> 32), lo0 = (unsigned int)p0;
+    const unsigned int hi1 = (unsigned int)(p1 >> 32), lo1 = (unsigned int)p1;
+    c = make_uint4(hi1 ^ c.y ^ rk[2 * r], lo1, hi0 ^ c.w ^ rk[2 * r + 1], lo0);
+  }
+  return c;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float4 philox_normal4(unsigned long long quad, unsigned long long offset, unsigned long long seed) {
+  const uint4 r = philox4x32_7(make_uint4((unsigned int)quad, (unsigned int)(quad >> 32), (unsigned int)offset,
+                                           (unsigned int)(offset >> 32)),
+                                make_uint2((unsigned int)seed, (unsigned int)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = fmaf((float)r.x, k, 0.5f * k);   // in [2^-33, 1]: never denormal
+  const float u2 = fmaf((float)r.z, k, 0.5f * k);
+  // The pass is issue-bound, so the flush-to-zero forms are used: the default lg2 / rsqrt carry a denormal guard
+  // (compare, two predicated multiplies / adds each) that these arguments can never need.
+  // sqrt(x) = x * rsqrt(x): two instructions, ~1 ulp -- irrelevant for noise draws
+  const float xa = -1.3862943611198906f * lg2_ftz(u0), xb = -1.3862943611198906f * lg2_ftz(u2);  // -2 ln u
+  const float ra = xa * rsqrt_ftz(fmaxf(xa, 1e-30f)), rb = xb * rsqrt_ftz(fmaxf(xb, 1e-30f));
+  float sa, ca, sb, cb;
+  const float k2pi = 1.4629180792671596e-09f;  // 2 pi 2^-32: the angle in one multiply
+  __sincosf((float)r.y * k2pi, &sa, &ca);
+  __sincosf((float)r.w * k2pi, &sb, &cb);
+  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
+
+// philox_normal4 with precomputed round keys and the counter words given separately (identical draws)
+__device__ __forceinline__ float4 philox_normal4_rk(unsigned int quad_lo, unsigned int quad_hi, unsigned int off_lo, unsigned int off_hi,
+                                                    const unsigned int (&rk)[14]) {
+  const uint4 r = philox4x32_7_rk(make_uint4(quad_lo, quad_hi, off_lo, off_hi), rk);
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = fmaf((float)r.x, k, 0.5f * k);
+  const float u2 = fmaf((float)r.z, k, 0.5f * k);
+  const float xa = -1.3862943611198906f * lg2_ftz(u0), xb = -1.3862943611198906f * lg2_ftz(u2);  // -2 ln u
+  const float ra = xa * rsqrt_ftz(fmaxf(xa, 1e-30f)), rb = xb * rsqrt_ftz(fmaxf(xb, 1e-30f));
+  float sa, ca, sb, cb;
+  const float k2pi = 1.4629180792671596e-09f;  // 2 pi 2^-32
+  __sincosf((float)r.y * k2pi, &sa, &ca);
+  __sincosf((float)r.w * k2pi, &sb, &cb);
+  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
+
+__device__ __forceinline__ void atomic_min_float(float* addr, float value) {
+  if (value >= 0.f)
+    atomicMin(reinterpret_cast<int*>(addr), __float_as_int(value));
+  else
+    atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(value));
+}
+
 // ---------------------------------------------------------------------------------------
 // Register-slab persistent Sinkhorn (M % 4 == 0, M <= 4096, G*B <= #SMs)
 //   skh_persist_kernel above hands every element from the row warps to the column warps through shared memory and
@@ -823,6 +925,23 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     fence_proxy_async();
     mbar_arrive_expect_tx(&full[stg], bytes);
     tma_bulk_g2s(ring + (size_t)stg * stage_floats, sc_b + (size_t)i0 * M, bytes, &full[stg]);
+  };
+  // final phase (fin.out != NULL): its stream interleaves the score slab and (DDIM) the x_t slab of every mini-slab: element
+  // q = NWf * s + w (w = 0 scores, 1 x_t) lands in stage q % Df (Df even in DDIM mode, so that a mini-slab's two stages are
+  // re-armed for the same later mini-slab)
+  const bool do_final = p.fin.out != nullptr;
+  const bool f_ddim = do_final && p.fin.ddim != 0;
+  const int NWf = f_ddim ? 2 : 1;
+  const int Df = f_ddim ? (D & ~1) : D;
+  const float* xt_b = f_ddim ? p.fin.x_t + (size_t)b * N * M : nullptr;
+  auto issue_final = [&](int q) {
+    const int s_ = q / NWf, wsrc = q - s_ * NWf;
+    const int i0 = row0 + s_ * RR;
+    const int stg_ = q % Df;
+    const uint32_t bytes = (uint32_t)min(RR, row1 - i0) * (uint32_t)M * 4u;
+    fence_proxy_async();
+    mbar_arrive_expect_tx(&full[stg_], bytes);
+    tma_bulk_g2s(ring + (size_t)stg_ * stage_floats, (wsrc ? xt_b : sc_b) + (size_t)i0 * M, bytes, &full[stg_]);
   };
   if (tid == 0) {
     DRG_STAMP(0);
@@ -1328,6 +1447,8 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
       group_barrier(0);  // xcomb (aliased on the ring) has been read
       if (tid == 0 && (it + 1 < iters || do_collect))
         for (int s = 0; s < D && s < ns; ++s) issue_slab_to(((it + 1) * ns + s) % D, s);  // the scores do not change: prefetch across the barriers
+      if (tid == 0 && it + 1 == iters && do_final)
+        for (int q = 0; q < Df && q < NWf * ns; ++q) issue_final(q);   // neither do the final phase's inputs
     }
     if (tid == 0) {
       LseAcc a{upart_s[0].x, upart_s[0].y};
@@ -1433,8 +1554,139 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
       }
     }
     if (tid == 0) DRG_STAMP(10 + it * 100 + 5);
-    if (it + 1 < iters || do_collect) grid_barrier_ra(gcount, (unsigned int)G * (++barriers_done));
+    if (it + 1 < iters || do_collect || do_final) grid_barrier_ra(gcount, (unsigned int)G * (++barriers_done));
     if (tid == 0) DRG_STAMP(10 + it * 100 + 6);
+  }
+  if (do_final) {
+    // =====================================================================================================
+    // Final pass over this CTA's rows (exp(Z + u + v - norm)[:-1, :-1], matching.py:169-170, or the DDIM update
+    // pipeline.py:180-190 with the noise drawn here), the arithmetic of skh_final_tile_kernel element for element (the two
+    // paths agree bit for bit).  The score slab comes out of L2 through the same ring, x_t out of DRAM through the other
+    // half of it.  The pass is ISSUE-bound (Philox + Box-Muller + exp per element on 16 warps per SM): the Philox round keys
+    // come precomputed from the host (constant-bank operands) and the running minimum of the 3DMatch flavour is not
+    // offered here (those calls take the stand-alone kernel).
+    // =====================================================================================================
+    if (tid == 0) DRG_STAMP(750);
+    const SkhFused& f = p.fin;
+    const float* v_b = p.v + (size_t)b * p.ldv;
+    const float* u_b = p.u + (size_t)b * p.ldu;
+    const bool masked = p.apply_mask && bc.pad != 1.f;
+    const bool track = f.rowbest != nullptr;
+    const float floor_v = f.best_floor;
+    const float xt_shift = f.xt_shift ? *f.xt_shift : 0.f;
+    const unsigned long long noise_offset = f.noise_offset + (f.noise_offset_dev ? *f.noise_offset_dev : 0ull);
+    const unsigned int off_lo = (unsigned int)noise_offset, off_hi = (unsigned int)(noise_offset >> 32);
+    float vj[KQ][4];
+    unsigned int tmbits = 0xffffffffu;   // bit 4 k + e: target column valid
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+      const int c = 4 * (ct + P2_TPR * k);
+      float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (FULL || c < M) {
+        vq = __ldcg(reinterpret_cast<const float4*>(v_b + c));
+        if (masked) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (!p.tgt_mask[(size_t)b * M + c + e]) tmbits &= ~(1u << (4 * k + e));
+        }
+      }
+      vj[k][0] = vq.x; vj[k][1] = vq.y; vj[k][2] = vq.z; vj[k][3] = vq.w;
+    }
+    // mbarrier phase of every stage after the iteration passes: stage k has completed ceil((Ttot - k) / D) uses
+    const int Ttot = iters * ns;
+    auto base_parity = [&](int k) -> uint32_t { return (uint32_t)((Ttot > k ? (Ttot - k + D - 1) / D : 0) & 1); };
+    float* out_b = f.out + (size_t)b * N * M;
+    float* conf_b = f.conf ? f.conf + (size_t)b * N * M : nullptr;
+    const float* noise_b = f.noise ? f.noise + (size_t)b * N * M : nullptr;
+    const unsigned long long quad_base = ((unsigned long long)b * N * M) >> 2;   // Philox counter = global quad index
+    auto body = [&](auto masked_c, auto ddim_c) {
+      constexpr bool MASKED = decltype(masked_c)::value;
+      constexpr bool DDIM = decltype(ddim_c)::value;
+      for (int s = rg; s < ns; s += P2_GROUPS) {
+        const int q0 = NWf * s;
+        const int stg_z = q0 % Df;
+        mbar_wait(&full[stg_z], (base_parity(stg_z) + (uint32_t)(q0 / Df)) & 1u);
+        const float* slab_z = ring + (size_t)stg_z * stage_floats;
+        const float* slab_x = slab_z;
+        if (DDIM) {
+          const int stg_x = (q0 + 1) % Df;
+          mbar_wait(&full[stg_x], (base_parity(stg_x) + (uint32_t)((q0 + 1) / Df)) & 1u);
+          slab_x = ring + (size_t)stg_x * stage_floats;
+        }
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+          const int i = row0 + s * RR + r;
+          if (i < row1) {   // rows past the CTA's range were not copied
+            const float ui = __ldcg(u_b + i);
+            const bool row_ok = !MASKED || smask[i];
+            const size_t row_off = (size_t)i * M + 4 * ct;
+            float* out_r = out_b + row_off;
+#pragma unroll
+            for (int k = 0; k < KQ; ++k) {
+              const int c = 4 * (ct + P2_TPR * k);
+              if (FULL || c < M) {
+                const float4 z4 = *reinterpret_cast<const float4*>(slab_z + (size_t)r * M + c);
+                float nz[4] = {0.f, 0.f, 0.f, 0.f};
+                float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (DDIM) {
+                  t4 = *reinterpret_cast<const float4*>(slab_x + (size_t)r * M + c);
+                  if (noise_b) {
+                    const float4 n4 = ldg_stream4(noise_b + row_off + 4 * P2_TPR * k);
+                    nz[0] = n4.x; nz[1] = n4.y; nz[2] = n4.z; nz[3] = n4.w;
+                  } else if (f.gen_noise) {
+                    const unsigned long long quad = quad_base + ((row_off + 4 * P2_TPR * k) >> 2);
+                    const float4 n4 = philox_normal4_rk((unsigned int)quad, (unsigned int)(quad >> 32), off_lo, off_hi, f.rk);
+                    nz[0] = n4.x; nz[1] = n4.y; nz[2] = n4.z; nz[3] = n4.w;
+                  }
+                }
+                const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+                const float xt[4] = {t4.x, t4.y, t4.z, t4.w};
+                float cf[4], o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const bool ok = !MASKED || (row_ok && ((tmbits >> (4 * k + e)) & 1u));
+                  const float zz = ok ? (z[e] - shift) : -INFINITY;
+                  const float la = ((zz + ui) + vj[k][e]) - bc.norm;  // same association as matching.py:34-36
+                  cf[e] = ex2(la * LOG2E);
+                  if (DDIM) o[e] = ok ? fmaf(f.k_x0, cf[e], fmaf(f.k_xt, xt[e] - xt_shift, f.sigma * nz[e])) : -INFINITY;
+                  else o[e] = cf[e];
+                }
+                *reinterpret_cast<float4*>(out_r + 4 * P2_TPR * k) = make_float4(o[0], o[1], o[2], o[3]);
+                if (DDIM && conf_b) *reinterpret_cast<float4*>(conf_b + row_off + 4 * P2_TPR * k) = make_float4(cf[0], cf[1], cf[2], cf[3]);
+                // arg-max keys: only entries above the floor (a row of the plan sums to <= 1: a handful per row) -- straight
+                // to the packed 64-bit keys with atomicMax (largest value, then lowest index)
+                if (track && fmaxf(fmaxf(cf[0], cf[1]), fmaxf(cf[2], cf[3])) > floor_v) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    if (cf[e] > floor_v) {
+                      const unsigned long long hi = (unsigned long long)float_to_ordered(cf[e]) << 32;
+                      atomicMax(&f.rowbest[(size_t)b * N + i], hi | (unsigned long long)(0xFFFFFFFFu - (unsigned int)(c + e)));
+                      atomicMax(&f.colbest[(size_t)b * M + c + e], hi | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i));
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+        group_barrier(rg);   // every thread of the group is done with the two stages: re-arm them for mini-slab s + Df / NWf
+        if (ct == 0) {
+          const int s2 = s + Df / NWf;
+          if (s2 < ns) {
+            issue_final(NWf * s2);
+            if (DDIM) issue_final(NWf * s2 + 1);
+          }
+        }
+      }
+    };
+    if (masked) {
+      if (f_ddim) body(std::true_type{}, std::true_type{});
+      else body(std::true_type{}, std::false_type{});
+    } else {
+      if (f_ddim) body(std::false_type{}, std::true_type{});
+      else body(std::false_type{}, std::false_type{});
+    }
+    if (tid == 0) DRG_STAMP(751);
   }
   if (do_collect) {
     // =====================================================================================================
@@ -1957,59 +2209,6 @@ struct SkhFinalParams {
   int tile_rows;                // rows per CTA of skh_final_tile_kernel (chosen by the host: one full wave of CTAs)
   float best_floor;             // only confidences > best_floor enter rowbest / colbest (-1: all of them)
 };
-
-// Philox4x32-7 counter-based generator (Salmon et al., SC'11: 7 rounds is the fewest that passes BigCrush; 10 is the
-// library default with extra margin) + Box-Muller: four N(0,1) draws per counter.
-// Counter = (quad index of the element, noise_offset); key = noise_seed.  Replaces torch.randn_like(x)
-// (Diff-Reg-4dmatch/models/pipeline.py:188) in throughput mode; parity tests pass the noise tensor instead.
-__device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) {
-  const unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 7; ++r) {
-    const unsigned long long p0 = (unsigned long long)M0 * c.x, p1 = (unsigned long long)M1 * c.z;  // one IMAD.WIDE each
-    const unsigned int hi0 = (unsigned int)(p0 >> 32), lo0 = (unsigned int)p0;
-    const unsigned int hi1 = (unsigned int)(p1 >> 32), lo1 = (unsigned int)p1;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += W0;
-    k.y += W1;
-  }
-  return c;
-}
-__device__ __forceinline__ float lg2_ftz(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rsqrt_ftz(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float4 philox_normal4(unsigned long long quad, unsigned long long offset, unsigned long long seed) {
-  const uint4 r = philox4x32_7(make_uint4((unsigned int)quad, (unsigned int)(quad >> 32), (unsigned int)offset,
-                                           (unsigned int)(offset >> 32)),
-                                make_uint2((unsigned int)seed, (unsigned int)(seed >> 32)));
-  const float k = 2.3283064365386963e-10f;  // 2^-32
-  const float u0 = fmaf((float)r.x, k, 0.5f * k);   // in [2^-33, 1]: never denormal
-  const float u2 = fmaf((float)r.z, k, 0.5f * k);
-  // The pass is issue-bound, so the flush-to-zero forms are used: the default lg2 / rsqrt carry a denormal guard
-  // (compare, two predicated multiplies / adds each) that these arguments can never need.
-  // sqrt(x) = x * rsqrt(x): two instructions, ~1 ulp -- irrelevant for noise draws
-  const float xa = -1.3862943611198906f * lg2_ftz(u0), xb = -1.3862943611198906f * lg2_ftz(u2);  // -2 ln u
-  const float ra = xa * rsqrt_ftz(fmaxf(xa, 1e-30f)), rb = xb * rsqrt_ftz(fmaxf(xb, 1e-30f));
-  float sa, ca, sb, cb;
-  const float k2pi = 1.4629180792671596e-09f;  // 2 pi 2^-32: the angle in one multiply
-  __sincosf((float)r.y * k2pi, &sa, &ca);
-  __sincosf((float)r.w * k2pi, &sb, &cb);
-  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
-}
-
-__device__ __forceinline__ void atomic_min_float(float* addr, float value) {
-  if (value >= 0.f)
-    atomicMin(reinterpret_cast<int*>(addr), __float_as_int(value));
-  else
-    atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(value));
-}
 
 // full (N+1)x(M+1) log-assignment (API parity with log_optimal_transport); odd row pitch -> scalar IO
 __global__ void __launch_bounds__(256) skh_final_full_kernel(const SkhFinalParams p) {
@@ -2608,6 +2807,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   const int iters = (run == SKH_SHARD_LOCAL || run == SKH_SHARD_LOCAL_X) ? 1 : run == SKH_SHARD_FINAL ? 0 : dual ? 1 : a->iters;
   dim3 cgrid((M + 1 + 31) / 32, B);
   bool bests_cleared = false;
+  bool final_fused = false;
   if (persist) {
     if (persist2 && run == SKH_RUN_ALL && !dual && a->rowbest && a->colbest) {
       p.zero_a = a->rowbest;
@@ -2620,11 +2820,44 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
       p.col = *collect;
       if (collected) *collected = true;
     }
+    // The final pass as the last phase of the same launch (conf / DDIM outputs on 16-byte aligned buffers).  The in-kernel
+    // arg-max keys go straight to rowbest / colbest with atomics, which is only cheap when a floor keeps them rare (a row of
+    // the plan sums to <= 1: at most 1 / floor entries per row exceed it); without a floor the tiled final kernel runs.
+    {
+      const bool want_best = a->rowbest && a->colbest;
+      const bool fuse = persist2 && run == SKH_RUN_ALL && !dual && !p.col.state &&
+                        (a->out_mode == DRG_OUT_CONF || a->out_mode == DRG_OUT_DDIM) && aligned16(a->out) &&
+                        (a->out_mode != DRG_OUT_DDIM || aligned16(a->x_t)) && (!a->noise || aligned16(a->noise)) &&
+                        (!a->conf || aligned16(a->conf)) && (!want_best || (a->has_best_floor && a->best_floor >= 0.01f)) &&
+                        a->x_min == nullptr;   // (the running minimum of the 3DMatch flavour stays with the stand-alone kernel)
+      if (fuse) {
+        p.fin.out = a->out;
+        p.fin.ddim = a->out_mode == DRG_OUT_DDIM ? 1 : 0;
+        p.fin.x_t = a->x_t;
+        p.fin.xt_shift = a->xt_shift;
+        p.fin.noise = p.fin.ddim ? a->noise : nullptr;
+        p.fin.conf = p.fin.ddim ? a->conf : nullptr;
+        p.fin.rowbest = want_best ? a->rowbest : nullptr;
+        p.fin.colbest = want_best ? a->colbest : nullptr;
+        p.fin.k_x0 = a->k_x0;
+        p.fin.k_xt = a->k_xt;
+        p.fin.sigma = a->sigma;
+        p.fin.best_floor = a->best_floor;
+        p.fin.gen_noise = (a->noise == nullptr && a->gen_noise) ? 1 : 0;
+        for (int r = 0; r < 7; ++r) {
+          p.fin.rk[2 * r] = (unsigned int)a->noise_seed + (unsigned int)r * 0x9E3779B9u;
+          p.fin.rk[2 * r + 1] = (unsigned int)(a->noise_seed >> 32) + (unsigned int)r * 0xBB67AE85u;
+        }
+        p.fin.noise_offset = a->noise_offset;
+        p.fin.noise_offset_dev = a->noise_offset_dev;
+        final_fused = true;
+      }
+    }
     DRG_CUDA(cudaMemsetAsync(w.gsync, 0, sizeof(unsigned int) * B * 3, st));
     cudaError_t e;
     {
       // (slot "skh_col" is free in this mode: it times the launches that carry the candidate-search tail)
-      ProfScope prof_scope(p.col.state ? PROF_SKH_COL : PROF_SKH_ITER, st);
+      ProfScope prof_scope(p.col.state ? PROF_SKH_COL : final_fused ? PROF_SKH_FUSED : PROF_SKH_ITER, st);
       e = launch_persist2(p, plp, iters, w.gsync, st);
     }
     if (e != cudaSuccess) {
@@ -2653,7 +2886,7 @@ static int run_sinkhorn(const drg_sinkhorn_args* a, bool dual, float temperature
   }
 
   if (run == SKH_SHARD_LOCAL || run == SKH_SHARD_LOCAL_X) return DRG_OK;
-  if (a->out_mode != DRG_OUT_NONE || dual) {
+  if ((a->out_mode != DRG_OUT_NONE || dual) && !final_fused) {
     SkhFinalParams f{};
     f.scores = a->scores;
     f.src_mask = a->src_mask;

@@ -74,7 +74,8 @@ def batch_mutual_topk_select(score_mat, k, row_masks=None, col_masks=None, large
 
 
 class Matching(nn.Module):
-    """3D flavour.  `precision`: '3xtf32' (default; fp32-accurate tensor-core GEMM) or 'tf32'."""
+    """3D flavour.  `precision`: '3xtf32' (default; the fp32-accurate tensor-core GEMM: three-term hi/lo split products --
+    since round 2 on row-scaled fp16 split operands instead of tf32 ones, same accuracy) or 'tf32' (one kind::tf32 pass)."""
 
     def __init__(self, config, precision="3xtf32"):
         super().__init__()
@@ -126,8 +127,8 @@ class Matching(nn.Module):
         B, L, C = feats.shape
         split = self.precision == "3xtf32"
         a = ops.prep_operand(feats, 1.0, split, 0)
-        out = ops.gemm_nt(a.reshape(B * L, a.shape[-1]), self._weight_operand(), split3=split)
-        return out.view(B, L, C)
+        out = ops.gemm_nt(a.reshape(B * L, a.shape[-1]), self._weight_operand(), split3=split, K=feats.shape[-1])
+        return out.view(B, L, self.src_proj.weight.shape[0])
 
     def similarity(self, src_feats, tgt_feats, src_pe=None, tgt_pe=None, pe_type="rotary", data=None):
         """Projection (same weight on both sides, matching.py:127-128), optional positional embedding,
@@ -147,7 +148,7 @@ class Matching(nn.Module):
                 data["tgt_feats_nopos"] = ft
                 data["src_feats"] = fs
                 data["tgt_feats"] = ft
-            return ops.gemm_nt(a, b, split3=True)
+            return ops.gemm_nt(a, b, split3=True, K=C)
         fs = self.project(src_feats)
         ft = self.project(tgt_feats)
         want = data is not None and use_pe
@@ -162,7 +163,7 @@ class Matching(nn.Module):
             data["tgt_feats"] = b[1] if want else ft
         if want:
             a, b = a[0], b[0]
-        return ops.gemm_nt(a, b, split3=split)
+        return ops.gemm_nt(a, b, split3=split, K=C)
 
     def confidence(self, sim, src_mask, tgt_mask):
         B, N, M = sim.shape

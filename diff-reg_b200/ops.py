@@ -142,28 +142,53 @@ def dual_softmax(sim, src_mask, tgt_mask, temperature):
     return out
 
 
+def split_cols(K):
+    """16-bit columns of ONE segment of a split operand of a [.., K] tensor (K rounded up to whole 64-column k-steps)."""
+    return (int(K) + 63) // 64 * 64
+
+
+SPLIT_TAIL = 8   # 16-bit columns behind the two segments of a split operand row: four floats (1 / row scale, row norm, 0, 0)
+
+
+def split_pitch(K):
+    """Row length (16-bit columns) of a split operand of a [.., K] tensor: [seg0 | seg1 | tail]."""
+    return 2 * split_cols(K) + SPLIT_TAIL
+
+
 @_on_device
-def gemm_nt(A, B, alpha=1.0, out=None, split3=False):
-    """C[b] = alpha * A[b] @ B[b]^T on the tensor cores (drg_gemm_nt_tf32).  A [batch,N,K] or [N,K]; B likewise.
-    split3=True: A, B are prep_operand(split=True) outputs (patterns 0 / 1); drg_gemm_nt_3xtf32 then fetches each distinct
-    operand tile once (same product, one third less operand traffic from L2: 45.5 vs 47.8 us at 4096^2 x 256 with
-    256-wide tiles, 64 vs 102 us with 64-wide tiles -- tools/perf_gemm.py)."""
+def gemm_nt(A, B, alpha=1.0, out=None, split3=False, K=None):
+    """C[b] = alpha * A[b] @ B[b]^T on the tensor cores.  A [batch,N,K] or [N,K]; B likewise.
+    split3=False: fp32 operands, one tcgen05 kind::tf32 pass (drg_gemm_nt_tf32; 10 mantissa bits of the operands).
+    split3=True: A, B are the 16-bit split operands of prep_operand(split=True) (patterns 0 / 1, torch.int16 [.., split_pitch(K)]);
+    the product is fp32-accurate (drg_gemm_nt_split16: lo.hi + hi.lo + hi.hi in kind::f16 with fp32 accumulation, the operands'
+    power-of-two row scales undone in the epilogue).  K: the column count of the original operands (default: the padded segment
+    width)."""
     _require_cuda(A, B)
     lib = load_library()
-    A = _f32c(A)
-    B = _f32c(B)
+    if split3:
+        if A.dtype != torch.int16 or B.dtype != torch.int16:
+            raise ValueError("gemm_nt(split3=True) takes the int16 split operands of prep_operand(split=True)")
+        A, B = A.contiguous(), B.contiguous()
+    else:
+        A, B = _f32c(A), _f32c(B)
     squeeze = A.dim() == 2
     if squeeze:
         A = A.unsqueeze(0)
         B = B.unsqueeze(0)
-    batch, N, K = A.shape
+    batch, N, KA = A.shape
     M = B.shape[1]
-    if B.shape[0] != batch or B.shape[2] != K:
+    if B.shape[0] != batch or B.shape[2] != KA:
         raise ValueError(f"gemm_nt: incompatible shapes {tuple(A.shape)} x {tuple(B.shape)}")
     if out is None:
         out = torch.empty(batch, N, M, dtype=torch.float32, device=A.device)
-    fn = lib.drg_gemm_nt_3xtf32 if (split3 and K % 3 == 0) else lib.drg_gemm_nt_tf32
-    check(fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), batch, N, M, K, float(alpha), _stream()))
+    if split3:
+        kc = (KA - SPLIT_TAIL) // 2
+        K = kc if K is None else int(K)
+        if split_pitch(K) != KA:
+            raise ValueError(f"gemm_nt: split operands of width {KA} do not belong to K = {K}")
+        check(lib.drg_gemm_nt_split16(A.data_ptr(), B.data_ptr(), out.data_ptr(), batch, N, M, K, float(alpha), _stream()))
+    else:
+        check(lib.drg_gemm_nt_tf32(A.data_ptr(), B.data_ptr(), out.data_ptr(), batch, N, M, KA, float(alpha), _stream()))
     return out.squeeze(0) if squeeze else out
 
 
@@ -183,9 +208,11 @@ class LazyPositionCode:
 
 @_on_device
 def prep_operand(x, scale=1.0, split=True, pattern=0, pe=None, pe_type=None, want_embedded=False):
-    """Positional embedding + scaling + hi/lo split of a [..., K] feature tensor (drg_prep_operand).
+    """Positional embedding + scaling + (split=True) the 16-bit hi/lo split of a [..., K] feature tensor (drg_prep_operand).
     pe: the position code tensor, or a LazyPositionCode (then the code is computed inside the kernel from the points).
-    Returns out ([..., 3K] if split else [..., K]) and, if want_embedded, the embedded features."""
+    Returns out (split: torch.int16 [..., split_pitch(K)] holding the fp16 bit patterns of the row-scaled values, [lo | hi | tail]
+    for pattern 0 and [hi | lo | tail] for pattern 1, see include/diffreg_b200.h; else fp32 [..., K]) and, if want_embedded, the
+    embedded features."""
     lazy = isinstance(pe, LazyPositionCode)
     _require_cuda(x, None if lazy else pe)
     lib = load_library()
@@ -206,7 +233,10 @@ def prep_operand(x, scale=1.0, split=True, pattern=0, pe=None, pe_type=None, wan
         want = (*x.shape, 2) if code == 1 else tuple(x.shape)
         if tuple(pe.shape) != want:
             raise ValueError(f"prep_operand: position code shape {tuple(pe.shape)} != {want}")
-    out = torch.empty(*x.shape[:-1], 3 * K if split else K, dtype=torch.float32, device=x.device)
+    if split:
+        out = torch.empty(*x.shape[:-1], split_pitch(K), dtype=torch.int16, device=x.device)
+    else:
+        out = torch.empty(*x.shape[:-1], K, dtype=torch.float32, device=x.device)
     emb = torch.empty_like(x) if want_embedded else None
     if lazy:
         import ctypes
@@ -486,13 +516,16 @@ def sinkhorn_soft_procrustes(scores, alpha, iters, src_mask, tgt_mask, src_pcd, 
     return out
 
 
+_split_out_cache = {}
+
+
 @_on_device
 def project_pair_split(src_feats, tgt_feats, w_operand, out_dim, scale, want_plain=False):
     """Both projections of Matching.forward and the operand preparation of the similarity GEMM in two launches:
-    drg_prep_operand_pair (hi/lo split of src | tgt features) + drg_project_split (tensor-core GEMM against the prepared
-    weight, epilogue writes scale * (x W^T) already split: src rows as the left operand, tgt rows as the right one).
-    src_feats [B,N,C], tgt_feats [B,M,C], w_operand = prep_operand(W, split=True, pattern=1) [C_out, 3C].
-    Returns (src_operand [B,N,3*C_out], tgt_operand [B,M,3*C_out], plain [B*(N+M), C_out] or None)."""
+    drg_prep_operand_pair (16-bit hi/lo split of src | tgt features) + drg_project_split16 (tensor-core GEMM against the
+    prepared weight, epilogue writes scale * (x W^T) already split: src rows as the left operand, tgt rows as the right one).
+    src_feats [B,N,C], tgt_feats [B,M,C], w_operand = prep_operand(W, split=True, pattern=1) [C_out, split_pitch(C)].
+    Returns (src_operand [B,N,split_pitch(C_out)], tgt_operand [B,M,split_pitch(C_out)] (int16), plain [B*(N+M), C_out] or None)."""
     _require_cuda(src_feats, tgt_feats, w_operand)
     lib = load_library()
     src_feats = _f32c(src_feats)
@@ -501,10 +534,14 @@ def project_pair_split(src_feats, tgt_feats, w_operand, out_dim, scale, want_pla
     M = tgt_feats.shape[1]
     dev = src_feats.device
     rows_a, rows_b = B * N, B * M
-    a3 = torch.empty(rows_a + rows_b, 3 * C, dtype=torch.float32, device=dev)
-    check(lib.drg_prep_operand_pair(src_feats.data_ptr(), rows_a, 0, tgt_feats.data_ptr(), rows_b, 0, C, 1.0, 1, a3.data_ptr(), _stream()))
-    split = torch.empty(rows_a + rows_b, 3 * out_dim, dtype=torch.float32, device=dev)
+    a16 = torch.empty(rows_a + rows_b, split_pitch(C), dtype=torch.int16, device=dev)
+    check(lib.drg_prep_operand_pair(src_feats.data_ptr(), rows_a, 0, tgt_feats.data_ptr(), rows_b, 0, C, 1.0, 1, a16.data_ptr(), _stream()))
+    kc_out, pitch_out = split_cols(out_dim), split_pitch(out_dim)
+    if kc_out == out_dim:
+        split = torch.empty(rows_a + rows_b, pitch_out, dtype=torch.int16, device=dev)
+    else:
+        split = torch.zeros(rows_a + rows_b, pitch_out, dtype=torch.int16, device=dev)   # the epilogue leaves the padding columns alone
     plain = torch.empty(rows_a + rows_b, out_dim, dtype=torch.float32, device=dev) if want_plain else None
-    check(lib.drg_project_split3(a3.data_ptr(), w_operand.data_ptr(), rows_a + rows_b, rows_a, out_dim, 3 * C, float(scale), _ptr(plain),
-                                 split.data_ptr(), _stream()))
-    return split[:rows_a].view(B, N, 3 * out_dim), split[rows_a:].view(B, M, 3 * out_dim), plain
+    check(lib.drg_project_split16(a16.data_ptr(), w_operand.data_ptr(), rows_a + rows_b, rows_a, out_dim, C, float(scale), _ptr(plain),
+                                  split.data_ptr(), _stream()))
+    return split[:rows_a].view(B, N, pitch_out), split[rows_a:].view(B, M, pitch_out), plain

@@ -178,31 +178,35 @@ int drg_dual_softmax(const float* sim, const uint8_t* src_mask, const uint8_t* t
  *   replaces torch.einsum("bsc,btc->bst", src, tgt)   Diff-Reg-4dmatch/models/matching.py:149,161
  *            (= Diff-Reg-3dmatch/models/matching.py:195,207; Diff-Reg-2d3d/experiments/<exp>/matching.py:110,122)
  *   and, with B = the weight [C_out, C_in], the nn.Linear projections  matching.py:127-128.
- *   Arithmetic: tcgen05.mma kind::tf32 with fp32 accumulation.  Feed operands produced by
- *   drg_prep_operand(split=1) (K -> 3K) for an fp32-accurate ("3xTF32") product.
+ *   Arithmetic: tcgen05.mma kind::tf32 with fp32 accumulation (10 mantissa bits of each operand are used).
  *   Requires K % 4 == 0 and 16-byte aligned A, B.  No workspace.
  * ------------------------------------------------------------------------------------ */
 int drg_gemm_nt_tf32(const float* A, const float* B, float* C, int batch, int N, int M, int K, float alpha, void* stream);
 
-/* The same product for operands in the 3xTF32 layout of drg_prep_operand(split = 1): A' = [A_lo | A_hi | A_hi] (pattern 0),
- *   B' = [B_hi | B_lo | B_hi] (pattern 1), K3 = 3 * K.  The kernel fetches the four distinct tiles of a k-chunk once and
- *   issues lo.hi + hi.lo + hi.hi from them (one third less operand traffic than drg_gemm_nt_tf32 on the same arrays; equal
- *   up to the order of the fp32 accumulation).  Falls back to the generic kernel when K is not a multiple of 32.
- *   drg_project_split3 is drg_project_split for operands in that layout. */
-int drg_gemm_nt_3xtf32(const float* A, const float* B, float* C, int batch, int N, int M, int K3, float alpha, void* stream);
-int drg_project_split3(const float* A, const float* W, int rows, int rows_left, int C_out, int K3, float scale, float* plain_out,
-                       float* split_out, void* stream);
+/* The fp32-accurate product (what the reference's einsum computes with torch's allow_tf32 = False) from 16-bit SPLIT operands.
+ *   A split operand of a [rows, K] matrix is a 16-bit array [rows, 2 kc + 8], kc = K rounded up to 64:
+ *     every row is scaled by a power of two 2^e that puts its largest magnitude into [2^14, 2^15) (fp16's range);
+ *     x 2^e = hi + lo with hi = fp16(x 2^e) (11 significant bits) and lo = fp16(x 2^e - hi);
+ *     the row holds [lo | hi | tail] (left operand, pattern 0) or [hi | lo | tail] (right operand, pattern 1): two segments of
+ *     kc columns (padding zero) and a tail of four floats (2^-e, Euclidean norm of the row, 0, 0).
+ *   The kernel accumulates lo.hi + hi.lo + hi.hi with tcgen05.mma kind::f16 in fp32 (dropped: lo.lo ~ 2^-22 relative) and
+ *   multiplies 2^-e of the row and of the column back in its epilogue (exact).  drg_prep_operand(split = 1) and the split
+ *   epilogue below produce the operands.  K here is the column count of the ORIGINAL operand.  A16 [batch, N, 2 kc + 8],
+ *   B16 [batch, M, 2 kc + 8].  (fp16 x bf16 products are not available on the tensor core: kind::f16 takes one format.) */
+int drg_gemm_nt_split16(const void* A16, const void* B16, float* C, int batch, int N, int M, int K, float alpha, void* stream);
 
 /* Projection with the operand preparation of the similarity GEMM fused into its epilogue:
- *   split_out[rows, 3*C_out] = split(scale * A . W^T), rows < rows_left as the left operand [lo|hi|hi], the others as the
- *   right operand [hi|lo|hi]; plain_out (optional) [rows, C_out] = A . W^T (what the reference stores in data[...]).
+ *   split_out16[rows, 2 * kc_out + 8] (16-bit split operand, kc_out = C_out rounded up to 64; the caller zeroes padding columns
+ *   once) = split(scale * A . W^T): rows < rows_left as the left operand [lo | hi | tail], the others as the right operand
+ *   [hi | lo | tail]; an output row's scale comes from the bound |y_ij| <= ||x_i|| max_j ||W_j|| (the norms travel in the
+ *   operands' row tails); plain_out (optional) [rows, C_out] fp32 = A . W^T (what the reference stores in data[...]).
  *   replaces src_proj on both feature sets + the 1/sqrt(C) scaling  Diff-Reg-4dmatch/models/matching.py:127-128,144-145
- *   A [rows, K], W [C_out, K] (both already split with drg_prep_operand / drg_prep_operand_pair when K = 3*C_in). */
-int drg_project_split(const float* A, const float* W, int rows, int rows_left, int C_out, int K, float scale, float* plain_out,
-                      float* split_out, void* stream);
+ *   A16 [rows, 2 kc + 8], W16 [C_out, 2 kc + 8]: split operands of the features (pattern 0) and of the weight (pattern 1). */
+int drg_project_split16(const void* A16, const void* W16, int rows, int rows_left, int C_out, int K, float scale, float* plain_out,
+                        void* split_out16, void* stream);
 /* drg_prep_operand over two source tensors in one launch: out rows [0, rows_a) from in_a (pattern_a), then rows_b rows from in_b. */
 int drg_prep_operand_pair(const float* in_a, long long rows_a, int pattern_a, const float* in_b, long long rows_b, int pattern_b,
-                          int K, float scale, int split, float* out, void* stream);
+                          int K, float scale, int split, void* out, void* stream);
 
 /* Volumetric position code from point coordinates (next-row widening)
  *   replaces VolumetricPositionEncoding.forward / voxelize   Diff-Reg-4dmatch/models/position_encoding.py:16-24,49-87
@@ -217,9 +221,10 @@ int drg_position_code(const float* xyz, const float* div_term, long long points,
  *   and       feat / feat.shape[-1] ** .5     Diff-Reg-4dmatch/models/matching.py:144-145
  *   in [rows,K]; pe: rotary [rows,K,2] (cos,sin) for pe_type 1, additive [rows,K] for pe_type 2, NULL for 0;
  *   embedded (optional) [rows,K] receives the features after the embedding and before scaling (data["src_feats"]);
- *   out: split=0 -> [rows,K] = scale*x;  split=1 -> [rows,3K] = [lo|hi|hi] (pattern 0) or [hi|lo|hi] (pattern 1). */
+ *   out: split=0 -> fp32 [rows,K] = scale*x;  split=1 -> the 16-bit split operand [rows, 2*kc + 8] of scale*x (pattern 0:
+ *   [lo | hi | tail], pattern 1: [hi | lo | tail]; see drg_gemm_nt_split16). */
 int drg_prep_operand(const float* in, const float* pe, int pe_type, long long rows, int K, float scale, int split, int pattern,
-                     float* embedded, float* out, void* stream);
+                     float* embedded, void* out, void* stream);
 
 /* drg_prep_operand with the position code computed inside the kernel from the point coordinates (SURVEY.md 8f rank 1:
  *   VolumetricPositionEncoding.forward fused into the GEMM operand staging): xyz [rows,3], div_term [K/6] and origin3 (HOST
@@ -228,7 +233,7 @@ int drg_prep_operand(const float* in, const float* pe, int pe_type, long long ro
  *   replaces Diff-Reg-4dmatch/models/position_encoding.py:49-87 + :26-46 as called at models/transformer.py:165-166 and
  *   models/matching.py:135-137 */
 int drg_prep_operand_xyz(const float* in, const float* xyz, const float* div_term, const float* origin3, float voxel_size,
-                         int pe_type, long long rows, int K, float scale, int split, int pattern, float* embedded, float* out,
+                         int pe_type, long long rows, int K, float scale, int split, int pattern, float* embedded, void* out,
                          void* stream);
 
 /* ------------------------------------------------------------------------------------

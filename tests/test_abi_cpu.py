@@ -21,7 +21,7 @@ def test_header_declares_the_path():
     for needed in ("drg_sinkhorn", "drg_dual_softmax", "drg_gemm_nt_tf32", "drg_prep_operand", "drg_match_count", "drg_match_write",
                    "drg_soft_procrustes", "drg_weighted_procrustes", "drg_sinkhorn_shard_local", "drg_sinkhorn_shard_update",
                    "drg_sinkhorn_shard_local_exchange", "drg_sinkhorn_shard_iterate", "drg_p2p_handle_bytes", "drg_p2p_create", "drg_p2p_connect", "drg_p2p_status",
-                   "drg_p2p_destroy", "drg_position_code", "drg_gemm_nt_3xtf32", "drg_project_split3"):
+                   "drg_p2p_destroy", "drg_position_code", "drg_gemm_nt_split16", "drg_project_split16", "drg_prep_operand_xyz", "drg_topk_match_count"):
         assert needed in names
 
 

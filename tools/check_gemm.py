@@ -22,7 +22,7 @@ for (b, n, m, k) in shapes:
     # 3xTF32
     A3 = ops.prep_operand(A, 1.0, True, 0)
     B3 = ops.prep_operand(B, 1.0, True, 1)
-    C3 = ops.gemm_nt(A3, B3, alpha=0.5)
+    C3 = ops.gemm_nt(A3, B3, alpha=0.5, split3=True, K=k)
     torch.cuda.synchronize()
     err3 = (C3.double() - ref).abs().max().item()
     ref32 = 0.5 * torch.einsum("bnk,bmk->bnm", A, B)

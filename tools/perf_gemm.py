@@ -9,13 +9,13 @@ A3 = ops.prep_operand(A, 1.0 / 16, True, 0); B3 = ops.prep_operand(B, 1.0 / 16, 
 out = torch.empty(1, n, n, device="cuda")
 for split3 in (False, True):
     for _ in range(3):
-        ops.gemm_nt(A3, B3, out=out, split3=split3)
+        ops.gemm_nt(A3, B3, out=out, split3=True) if split3 else ops.gemm_nt(A / 16, B / 16, out=out)
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20):
-        ops.gemm_nt(A3, B3, out=out, split3=split3)
+        ops.gemm_nt(A3, B3, out=out, split3=True) if split3 else ops.gemm_nt(A / 16, B / 16, out=out)
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / 20
     print(json.dumps({"split3": split3, "us": round(us, 1),
-                      "tf32_TFLOPs": round(2 * 3 * k * n * n / us / 1e6, 1)}), flush=True)
+                      "useful_TFLOPs": round(2 * k * n * n / us / 1e6, 1)}), flush=True)
