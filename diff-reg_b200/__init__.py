@@ -7,6 +7,7 @@ Public surface (mirrors the reference):
     Matching2D3D                                             (2D-3D flavour head)
     SoftProcrustesLayer                                      (procrustes.py)
     VolumetricPositionEncoding                               (position_encoding.py; next-row widening)
+    GeometryAttentionLayer, RepositioningTransformer         (transformer.py; the denoising transformer)
     DenoisingSampler                                         (fused per-step driver)
     HostStepPipeline                                         (host buffers in / results out, copies overlapped, graph replay)
     RowShardedSinkhorn, shard_rows, shard_units              (multi-GPU paths, distributed.py)
@@ -33,6 +34,9 @@ def __getattr__(name):
     if name == "VolumetricPositionEncoding":
         from . import position_encoding
         return position_encoding.VolumetricPositionEncoding
+    if name in ("GeometryAttentionLayer", "RepositioningTransformer"):
+        from . import transformer
+        return getattr(transformer, name)
     if name == "HostStepPipeline":
         from . import hostpipe
         return hostpipe.HostStepPipeline

@@ -86,6 +86,13 @@ def _declare(lib):
     lib.drg_project_split16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
     lib.drg_prep_operand.restype = c_int
     lib.drg_prep_operand.argtypes = [c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.drg_prep_operand_ext.restype = c_int
+    lib.drg_prep_operand_ext.argtypes = [c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                         c_void_p, c_void_p]
+    lib.drg_attn_softmax.restype = c_int
+    lib.drg_attn_softmax.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
+    lib.drg_layernorm.restype = c_int
+    lib.drg_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p, c_void_p]
     lib.drg_prep_operand_xyz.restype = c_int
     lib.drg_prep_operand_xyz.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), c_float, c_int, c_ll, c_int, c_float,
                                          c_int, c_int, c_void_p, c_void_p, c_void_p]

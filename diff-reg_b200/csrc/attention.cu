@@ -1,0 +1,165 @@
+// Elementwise / row kernels of the geometry attention layer (the denoising transformer's building block):
+//   masked, scaled row softmax of the attention logits, written straight as the split operand of the P.V GEMM
+//     replaces   a.masked_fill_(q_mask & ~kv_mask, -inf); a = a / sqrt(d); a = softmax(a, dim=2)
+//                Diff-Reg-4dmatch/models/transformer.py:80-84
+//   LayerNorm (+ optional residual)
+//     replaces   self.norm1(message) / x + self.norm2(message)          transformer.py:88,92-94
+// The matrix products of the layer (q / k / v / merge / MLP projections, Q.K^T, P.V) run on the tcgen05 GEMM of gemm.cu
+// with the fp16 split operands of features.cu; nothing here needs the tensor cores.  sm_100a.
+#include "common.cuh"
+
+namespace drg {
+
+constexpr int ATT_THREADS = 256;
+
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < ATT_THREADS / 32; ++w) r = fmaxf(r, red[w]);
+  return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < ATT_THREADS / 32; ++w) r += red[w];   // fixed order: deterministic
+  return r;
+}
+
+// One CTA per row (b, h, l) of the logits [B*H, L, S].  The logit of a VALID query against an INVALID key is -inf (the
+// reference's mask expression q_mask * ~kv_mask: rows of invalid queries are left alone), then scaled by 1 / sqrt(d), then
+// softmax over the keys.  A valid query with no valid key yields NaN, as in the reference.
+//   P   (optional) fp32 probabilities [B*H, L, S] (may alias the logits)
+//   P16 (optional) the same row as the LEFT split operand of the P.V GEMM: [lo | hi | tail], row pitch 2 kc + 8 (features.cu)
+__global__ void __launch_bounds__(ATT_THREADS) attn_softmax_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ q_mask,
+                                                                   const uint8_t* __restrict__ kv_mask, int B, int H, int L, int S,
+                                                                   float scale, float* P, unsigned short* __restrict__ P16) {
+  __shared__ float red[ATT_THREADS / 32];
+  const long long rows = (long long)B * H * L;
+  const int kc = split16_kc(S), pitch = split16_pitch(S);
+  const float scale2 = scale * LOG2E;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const long long bh = row / L;
+    const int l = (int)(row - bh * L);
+    const int b = (int)(bh / H);
+    const float* a = logits + row * S;
+    const bool mask_keys = kv_mask != nullptr && (q_mask == nullptr || q_mask[(size_t)b * L + l]);
+    const uint8_t* km = kv_mask ? kv_mask + (size_t)b * S : nullptr;
+    // pass 1: maximum of the scaled, masked logits (log2 domain)
+    float m = -INFINITY;
+    for (int s = threadIdx.x; s < S; s += ATT_THREADS) {
+      float x = a[s];
+      if (mask_keys && !km[s]) x = -INFINITY;
+      m = fmaxf(m, x * scale2);
+    }
+    m = block_reduce_max(m, red);
+    // pass 2: sum of the exponentials
+    float sum = 0.f;
+    for (int s = threadIdx.x; s < S; s += ATT_THREADS) {
+      float x = a[s];
+      if (mask_keys && !km[s]) x = -INFINITY;
+      sum += ex2(x * scale2 - m);            // all keys masked: -inf - -inf = NaN, like the reference
+    }
+    sum = block_reduce_sum(sum, red);
+    const float inv_sum = 1.f / sum;
+    // the row maximum of P is 1 / sum: the split operand's power-of-two scale puts it into [2^14, 2^15)
+    int e = 0;
+    if (inv_sum > 0.f && inv_sum <= 3.0e38f) e = min(max(14 - ilogbf(inv_sum), -126), 126);
+    const float sc = __int_as_float((e + 127) << 23);
+    unsigned short* o = P16 ? P16 + row * pitch : nullptr;
+    float ss = 0.f;
+    for (int s = threadIdx.x; s < kc; s += ATT_THREADS) {
+      float pr = 0.f;
+      if (s < S) {
+        float x = a[s];
+        if (mask_keys && !km[s]) x = -INFINITY;
+        pr = ex2(x * scale2 - m) * inv_sum;
+        if (P) P[row * S + s] = pr;
+      }
+      if (o) {
+        const float y = pr * sc;
+        ss = fmaf(y, y, ss);
+        unsigned short h, lo;
+        asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(y));
+        float hf;
+        asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
+        asm("cvt.rn.f16.f32 %0, %1;" : "=h"(lo) : "f"(y - hf));
+        o[s] = lo;          // pattern 0 (left operand): [lo | hi]
+        o[kc + s] = h;
+      }
+    }
+    if (o) {
+      ss = block_reduce_sum(ss, red);
+      if (threadIdx.x == 0) {
+        const float inv = __int_as_float((127 - e) << 23);
+        *reinterpret_cast<float4*>(o + 2 * kc) = make_float4(inv, sqrtf(ss) * inv, 0.f, 0.f);
+      }
+    }
+    __syncthreads();   // `red` is reused by the next row
+  }
+}
+
+// LayerNorm over the last dimension, one warp per row: y = (x - mean) / sqrt(var + eps) * w + b (biased variance, two passes
+// like torch), out = residual + y when a residual is given.
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, const float* __restrict__ residual,
+                                                        long long rows, int C, float eps, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float* x = in + row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += x[c];
+    const float mean = warp_sum(s) / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = x[c] - mean;
+      v = fmaf(d, d, v);
+    }
+    const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+    for (int c = lane; c < C; c += 32) {
+      float y = (x[c] - mean) * rstd;
+      if (w) y *= w[c];
+      if (bias) y += bias[c];
+      if (residual) y += residual[row * C + c];
+      out[row * C + c] = y;
+    }
+  }
+}
+
+}  // namespace drg
+
+using namespace drg;
+
+extern "C" int drg_attn_softmax(const float* logits, const uint8_t* q_mask, const uint8_t* kv_mask, int B, int H, int L, int S,
+                                float scale, float* P, void* P16, void* stream) {
+  DRG_CHECK_ARG(logits != nullptr && (P != nullptr || P16 != nullptr), "logits and at least one output must be non-null");
+  DRG_CHECK_ARG(B >= 1 && H >= 1 && L >= 1 && S >= 1, "B, H, L, S must be >= 1");
+  DRG_CHECK_ARG(P16 == nullptr || (((uintptr_t)P16) & 15u) == 0, "P16 must be 16-byte aligned");
+  const long long rows = (long long)B * H * L;
+  const int grid = (int)(rows < (long long)NUM_SMS * 8 ? rows : (long long)NUM_SMS * 8);
+  attn_softmax_kernel<<<grid, ATT_THREADS, 0, (cudaStream_t)stream>>>(logits, q_mask, kv_mask, B, H, L, S, scale, P,
+                                                                      reinterpret_cast<unsigned short*>(P16));
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+extern "C" int drg_layernorm(const float* in, const float* weight, const float* bias, const float* residual, long long rows, int C,
+                             float eps, float* out, void* stream) {
+  DRG_CHECK_ARG(in != nullptr && out != nullptr, "in / out must be non-null");
+  DRG_CHECK_ARG(rows >= 1 && C >= 1, "rows and C must be >= 1");
+  long long blocks = (rows * 32 + 255) / 256;
+  if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
+  layernorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, weight, bias, residual, rows, C, eps, out);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}

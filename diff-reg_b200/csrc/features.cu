@@ -37,6 +37,9 @@ struct PrepParams {
   int split;         // 1: 16-bit split layout (row-scaled fp16 hi + fp16 lo), 0: plain scaled copy
   int pattern;       // 0: [lo | hi] (left operand)   1: [hi | lo] (right operand)
   float scale;
+  int relu;          // 1: max(x, 0) before the scaling (the ReLU between the two linears of the attention layer's MLP)
+  int heads, seq;    // heads > 1: the input rows are (b, l, h) -- [B, seq, heads, K] -- and the output rows (b, h, l): the per-head
+                     //   operands of the attention GEMMs leave the staging kernel already head-major
 };
 
 // x' = x * 2^e (the row's power-of-two scale) as hi + lo, both fp16: hi = fp16(x'), lo = fp16(x' - hi).  With the row maximum
@@ -113,11 +116,27 @@ __device__ __forceinline__ float4 prep_load_quad(const PrepParams& p, long long 
     x = make_float4(xv[0], xv[1], xv[2], xv[3]);
   }
   if (store_embedded && p.embedded) *reinterpret_cast<float4*>(p.embedded + row * p.K + k) = x;
+  if (p.relu) {
+    x.x = fmaxf(x.x, 0.f);
+    x.y = fmaxf(x.y, 0.f);
+    x.z = fmaxf(x.z, 0.f);
+    x.w = fmaxf(x.w, 0.f);
+  }
   x.x *= p.scale;
   x.y *= p.scale;
   x.z *= p.scale;
   x.w *= p.scale;
   return x;
+}
+
+// input row (b, l, h) -> output row (b, h, l) when the rows are per-head slices of [B, seq, heads, K]
+__device__ __forceinline__ long long prep_out_row(const PrepParams& p, long long row) {
+  if (p.heads <= 1) return row;
+  const long long bl = row / p.heads;
+  const int h = (int)(row - bl * p.heads);
+  const long long b = bl / p.seq;
+  const long long l = bl - b * p.seq;
+  return (b * p.heads + h) * p.seq + l;
 }
 
 // plain scaled copy (split == 0): one quad per thread
@@ -129,7 +148,7 @@ __global__ void __launch_bounds__(256) prep_operand_kernel(const PrepParams p) {
     const long long row = idx / K4;
     const int k = (int)(idx - row * K4) << 2;
     const float4 x = prep_load_quad<PEK>(p, row, k, true);
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.K + k) = x;
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + prep_out_row(p, row) * p.K + k) = x;
   }
 }
 
@@ -171,7 +190,7 @@ __global__ void __launch_bounds__(256) prep_split_kernel(const PrepParams p) {
     int e = 0;
     if (amax > 0.f && !weird) e = min(max(14 - ilogbf(amax), -126), 126);   // amax * 2^e in [2^14, 2^15)
     const float sc = __int_as_float((e + 127) << 23), inv = __int_as_float((127 - e) << 23);
-    unsigned short* o = reinterpret_cast<unsigned short*>(p.out) + row * pitch;
+    unsigned short* o = reinterpret_cast<unsigned short*>(p.out) + prep_out_row(p, row) * pitch;
     const int pat = (p.in2 != nullptr && row >= p.rows1) ? p.pattern2 : p.pattern;
     float ss = 0.f;
     auto emit = [&](int q, float4 x) {   // quad q of the padded row; x is ignored in the padding
@@ -215,7 +234,8 @@ using namespace drg;
 
 static int prep_run(const float* in, const float* in2, long long rows1, const float* pe, int pe_type, long long rows, int K,
                     float scale, int split, int pattern, int pattern2, float* embedded, void* out, void* stream,
-                    const float* xyz = nullptr, const float* div_term = nullptr, const float* origin3 = nullptr, float voxel = 1.f) {
+                    const float* xyz = nullptr, const float* div_term = nullptr, const float* origin3 = nullptr, float voxel = 1.f,
+                    int relu = 0, int heads = 1, int seq = 1) {
   DRG_CHECK_ARG(in && out, "in/out must be non-null");
   DRG_CHECK_ARG(rows >= 1 && K >= 4, "rows >= 1 and K >= 4 required");
   DRG_CHECK_ARG(pe_type >= 0 && pe_type <= 4, "pe_type must be 0 (none), 1 (rotary), 2 (sinusoidal), 3 / 4 (the same from xyz)");
@@ -249,6 +269,9 @@ static int prep_run(const float* in, const float* in2, long long rows1, const fl
   p.split = split;
   p.pattern = pattern;
   p.scale = scale;
+  p.relu = relu;
+  p.heads = heads;
+  p.seq = seq;
   const long long total = split ? rows * 32 : rows * (K / 4);   // split: one warp per row
   long long blocks = (total + 255) / 256;
   if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
@@ -273,6 +296,14 @@ static int prep_run(const float* in, const float* in2, long long rows1, const fl
 extern "C" int drg_prep_operand(const float* in, const float* pe, int pe_type, long long rows, int K, float scale, int split,
                                 int pattern, float* embedded, void* out, void* stream) {
   return prep_run(in, nullptr, rows, pe, pe_type, rows, K, scale, split, pattern, pattern, embedded, out, stream);
+}
+
+extern "C" int drg_prep_operand_ext(const float* in, const float* pe, int pe_type, long long rows, int K, float scale, int split,
+                                    int pattern, int relu, int heads, int seq, float* embedded, void* out, void* stream) {
+  DRG_CHECK_ARG(heads >= 1 && seq >= 1, "heads and seq must be >= 1");
+  DRG_CHECK_ARG(heads == 1 || rows % ((long long)heads * seq) == 0, "rows must be a multiple of heads * seq");
+  return prep_run(in, nullptr, rows, pe, pe_type, rows, K, scale, split, pattern, pattern, embedded, out, stream, nullptr, nullptr,
+                  nullptr, 1.f, relu, heads, seq);
 }
 
 extern "C" int drg_prep_operand_xyz(const float* in, const float* xyz, const float* div_term, const float* origin3, float voxel_size,

@@ -251,6 +251,77 @@ def prep_operand(x, scale=1.0, split=True, pattern=0, pe=None, pe_type=None, wan
 
 
 @_on_device
+def prep_heads(x, heads, pattern, pe=None, pe_type=None, scale=1.0):
+    """Per-head split operands of the attention GEMMs: x [B, L, C] (C = heads * d) -> torch.int16 [B * heads, L, split_pitch(d)],
+    head-major, with the rotary / additive position code (pe [B, L, C, 2] / [B, L, C]) applied on the way (drg_prep_operand_ext;
+    Diff-Reg-4dmatch/models/transformer.py:60-79)."""
+    _require_cuda(x, pe)
+    lib = load_library()
+    x = _f32c(x)
+    B, L, C = x.shape
+    if C % heads or (C // heads) % 4:
+        raise ValueError(f"prep_heads: {C} channels do not split into {heads} heads of a multiple of 4 channels")
+    d = C // heads
+    code = 0
+    if pe is not None:
+        code = {"rotary": 1, "sinusoidal": 2}[pe_type]
+        pe = _f32c(pe)
+        want = (B, L, C, 2) if code == 1 else (B, L, C)
+        if tuple(pe.shape) != want:
+            raise ValueError(f"prep_heads: position code shape {tuple(pe.shape)} != {want}")
+    out = torch.empty(B * heads, L, split_pitch(d), dtype=torch.int16, device=x.device)
+    check(lib.drg_prep_operand_ext(x.data_ptr(), _ptr(pe), code, B * L * heads, d, float(scale), 1, int(pattern), 0, int(heads), int(L),
+                                   None, out.data_ptr(), _stream()))
+    return out
+
+
+@_on_device
+def prep_relu(x, pattern=0):
+    """Split operand of relu(x) (the nn.ReLU between the MLP's two linears, transformer.py:33-37)."""
+    _require_cuda(x)
+    lib = load_library()
+    x = _f32c(x)
+    K = x.shape[-1]
+    out = torch.empty(*x.shape[:-1], split_pitch(K), dtype=torch.int16, device=x.device)
+    check(lib.drg_prep_operand_ext(x.data_ptr(), None, 0, x.numel() // K, K, 1.0, 1, int(pattern), 1, 1, 1, None, out.data_ptr(), _stream()))
+    return out
+
+
+@_on_device
+def attn_softmax(logits, heads, q_mask, kv_mask, scale, want_operand=True, want_probs=False):
+    """Masked, scaled softmax over the keys of logits [B * heads, L, S] (drg_attn_softmax; transformer.py:80-84).
+    Returns the probabilities as the left split operand of the P.V GEMM (torch.int16 [B * heads, L, split_pitch(S)]) and / or fp32."""
+    _require_cuda(logits, q_mask, kv_mask)
+    lib = load_library()
+    logits = _f32c(logits)
+    BH, L, S = logits.shape
+    B = BH // heads
+    qm = _as_mask(q_mask) if q_mask is not None and kv_mask is not None else None
+    km = _as_mask(kv_mask) if kv_mask is not None else None
+    P = torch.empty_like(logits) if want_probs else None
+    P16 = torch.empty(BH, L, split_pitch(S), dtype=torch.int16, device=logits.device) if want_operand else None
+    check(lib.drg_attn_softmax(logits.data_ptr(), _ptr(qm), _ptr(km), B, heads, L, S, float(scale), _ptr(P), _ptr(P16), _stream()))
+    if want_operand and want_probs:
+        return P16, P
+    return P16 if want_operand else P
+
+
+@_on_device
+def layernorm(x, weight, bias, eps=1e-5, residual=None):
+    """[residual +] LayerNorm(x) over the last dimension (drg_layernorm; transformer.py:88,92-94)."""
+    _require_cuda(x, weight, bias, residual)
+    lib = load_library()
+    x = _f32c(x)
+    C = x.shape[-1]
+    out = torch.empty_like(x)
+    w = _f32c(weight) if weight is not None else None
+    b = _f32c(bias) if bias is not None else None
+    r = _f32c(residual) if residual is not None else None
+    check(lib.drg_layernorm(x.data_ptr(), _ptr(w), _ptr(b), _ptr(r), x.numel() // C, C, float(eps), out.data_ptr(), _stream()))
+    return out
+
+
+@_on_device
 def _match(x, mode, mutual, threshold, largest, want_mask, capacity=None):
     """capacity=None: read the match count on the host (as torch.nonzero() does) and return exact-size outputs.
     capacity=int: sync-free; returns (index [capacity,3], vals [capacity], mask, count) with the count on the device."""

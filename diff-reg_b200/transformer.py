@@ -1,0 +1,221 @@
+"""Drop-in for the reference's ``models/transformer.py`` (the denoising transformer --
+the other half of every sampler step).
+
+``GeometryAttentionLayer(config)`` and ``RepositioningTransformer(config)`` keep the reference's constructor keys
+(``feature_dim, n_head, pe_type, layer_types, positioning_type, entangled, vol_bnds, voxel_size, feature_matching,
+procrustes``), argument order, return tuples and ``state_dict`` keys (``layers.<i>.q_proj.weight`` ..., positioning layers
+``layers.<i>.0.src_proj.weight``, ``layers.<i>.0.bin_score``), so a reference checkpoint loads strictly
+(Diff-Reg-4dmatch/models/transformer.py:13-96, 103-233).  Shadow the reference module with
+
+    # models/transformer.py
+    from diffreg_b200.transformer import GeometryAttentionLayer, RepositioningTransformer      # noqa: F401
+
+Every matrix product of a layer -- the q / k / v / merge / MLP projections, Q.K^T per head and P.V per head -- runs on the
+tcgen05 GEMM with fp16 split operands (fp32-accurate, like the reference's einsum / nn.Linear with TF32 off); the rotary code
+and the head split are applied in the operand staging, the masked softmax writes the P.V operand directly, LayerNorm and the
+residual are one kernel each.  The attention matrix [B * heads, L, S] is materialised in HBM (a first, correct version: the
+tensor-core flash kernel that keeps it on chip is the next step).  CUDA tensors only; forward-only
+(training keeps the reference module); ``positioning_type`` 'procrustes' only on the positioning layers ('oracle' / 'randSO3'
+need ground truth / host random numbers and stay with the reference)."""
+import copy
+
+import torch
+from torch import nn
+
+from . import ops
+from .matching import Matching, _no_grad_inputs
+from .position_encoding import VolumetricPositionEncoding as VolPE
+from .procrustes import SoftProcrustesLayer
+
+
+class _Cfg(dict):
+    """The reference indexes its config like a dict and VolPE reads attributes: serve both."""
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+def _cfg(config):
+    return config if not isinstance(config, dict) or isinstance(config, _Cfg) else _Cfg(config)
+
+
+class GeometryAttentionLayer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        d_model = config['feature_dim']
+        nhead = config['n_head']
+        self.dim = d_model // nhead
+        self.nhead = nhead
+        self.pe_type = config['pe_type']
+        if d_model % nhead or self.dim % 4:
+            raise ValueError("GeometryAttentionLayer: feature_dim / n_head must be a multiple of 4 (operand rows of the head GEMMs)")
+        self.q_proj = nn.Linear(d_model, d_model, bias=False)
+        self.k_proj = nn.Linear(d_model, d_model, bias=False)
+        self.v_proj = nn.Linear(d_model, d_model, bias=False)
+        self.merge = nn.Linear(d_model, d_model, bias=False)
+        self.mlp = nn.Sequential(
+            nn.Linear(d_model * 2, d_model * 2, bias=False),
+            nn.ReLU(True),
+            nn.Linear(d_model * 2, d_model, bias=False),
+        )
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self._w_cache = {}
+
+    # ---- weights as right-hand split operands, re-staged when a weight changes ----
+    def _w(self, name, lin):
+        w = lin.weight
+        key = (w.data_ptr(), w._version, w.device)
+        hit = self._w_cache.get(name)
+        if hit is None or hit[0] != key:
+            hit = (key, ops.prep_operand(w.detach(), 1.0, True, 1))
+            self._w_cache[name] = hit
+        return hit[1]
+
+    def _linear(self, name, lin, a16, rows):
+        """a16: left split operand [rows, split_pitch(K)] -> fp32 [rows, C_out]."""
+        return ops.gemm_nt(a16.reshape(rows, a16.shape[-1]), self._w(name, lin), split3=True, K=lin.weight.shape[1])
+
+    def forward(self, x, source, x_pe, source_pe, x_mask=None, source_mask=None):
+        _no_grad_inputs(x, source, x_pe, source_pe, module=self)
+        with torch.no_grad():
+            return self._forward(x, source, x_pe, source_pe, x_mask, source_mask)
+
+    def _forward(self, x, source, x_pe, source_pe, x_mask, source_mask):
+        if self.pe_type not in ("sinusoidal", "rotary"):
+            raise KeyError()
+        bs, L, C = x.shape
+        S = source.shape[1]
+        H, d = self.nhead, self.dim
+        same = source is x
+        rotary = self.pe_type == "rotary"
+        # ---- projections (transformer.py:52-66).  sinusoidal: w(x + p); rotary: R(w x)
+        add_q = x_pe if (not rotary and x_pe is not None) else None
+        add_k = source_pe if (not rotary and x_pe is not None) else None      # (the reference tests qp only)
+        xq = ops.prep_operand(x, 1.0, True, 0, pe=add_q, pe_type="sinusoidal" if add_q is not None else None)
+        if same and add_k is add_q:
+            xk = xq
+        else:
+            xk = ops.prep_operand(source, 1.0, True, 0, pe=add_k, pe_type="sinusoidal" if add_k is not None else None)
+        xv = xk if add_k is None else ops.prep_operand(source, 1.0, True, 0)
+        qw = self._linear("q", self.q_proj, xq, bs * L).view(bs, L, C)
+        kw = self._linear("k", self.k_proj, xk, bs * S).view(bs, S, C)
+        vw = self._linear("v", self.v_proj, xv, bs * S).view(bs, S, C)
+        # ---- per-head operands; the rotary code is applied in the staging (transformer.py:68-77)
+        rq = x_pe if (rotary and x_pe is not None) else None
+        rk = source_pe if (rotary and x_pe is not None) else None
+        q16 = ops.prep_heads(qw, H, 0, pe=rq, pe_type="rotary" if rq is not None else None)          # [bs*H, L, .]
+        k16 = ops.prep_heads(kw, H, 1, pe=rk, pe_type="rotary" if rk is not None else None)          # [bs*H, S, .]
+        # ---- attention (transformer.py:79-85): logits, masked scaled softmax, P.V
+        logits = ops.gemm_nt(q16, k16, split3=True, K=d)                                            # [bs*H, L, S]
+        p16 = ops.attn_softmax(logits, H, x_mask if source_mask is not None else None, source_mask, 1.0 / d ** 0.5)
+        vt = vw.view(bs, S, H, d).permute(0, 2, 3, 1).contiguous().view(bs * H, d, S)               # V^T per head, K-major over the keys
+        if S % 4:                                   # operand rows are staged 16 bytes at a time; same padded segment width
+            vt = torch.nn.functional.pad(vt, (0, 4 - S % 4))
+        vt16 = ops.prep_operand(vt, 1.0, True, 1)
+        o = ops.gemm_nt(p16, vt16, split3=True, K=S)                                                # [bs*H, L, d]
+        o = o.view(bs, H, L, d).permute(0, 2, 1, 3).contiguous().view(bs * L, C)
+        # ---- merge, norm, MLP, norm, residual (transformer.py:87-94)
+        message = self._linear("merge", self.merge, ops.prep_operand(o, 1.0, True, 0), bs * L)
+        message = ops.layernorm(message, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        cat = torch.cat([x.reshape(bs * L, C).float(), message], dim=1)
+        hmid = self._linear("mlp0", self.mlp[0], ops.prep_operand(cat, 1.0, True, 0), bs * L)
+        message = self._linear("mlp2", self.mlp[2], ops.prep_relu(hmid, 0), bs * L)
+        e = ops.layernorm(message, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=x.reshape(bs * L, C))
+        return e.view(bs, L, C)
+
+
+class RepositioningTransformer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        config = _cfg(config)
+        self.d_model = config['feature_dim']
+        self.nhead = config['n_head']
+        self.layer_types = config['layer_types']
+        self.positioning_type = config['positioning_type']
+        self.pe_type = config['pe_type']
+        self.entangled = config['entangled']
+        self.positional_encoding = VolPE(config)
+        encoder_layer = GeometryAttentionLayer(config)
+        self.layers = nn.ModuleList()
+        for l_type in self.layer_types:
+            if l_type in ['self', 'cross']:
+                self.layers.append(copy.deepcopy(encoder_layer))
+            elif l_type == "positioning":
+                if self.positioning_type == 'procrustes':
+                    positioning_layer = nn.ModuleList()
+                    positioning_layer.append(Matching(config['feature_matching']))
+                    positioning_layer.append(SoftProcrustesLayer(_cfg(config['procrustes'])))
+                    self.layers.append(positioning_layer)
+                elif self.positioning_type in ['oracle', 'randSO3']:
+                    self.layers.append(None)
+                else:
+                    raise KeyError(self.positioning_type + " undefined positional encoding type")
+            else:
+                raise KeyError()
+        self._reset_parameters()
+
+    def forward(self, src_feat, tgt_feat, s_pcd, t_pcd, src_mask, tgt_mask, data, T=None, timers=None):
+        _no_grad_inputs(src_feat, tgt_feat, s_pcd, t_pcd, module=self)
+        with torch.no_grad():
+            return self._forward(src_feat, tgt_feat, s_pcd, t_pcd, src_mask, tgt_mask, data, T, timers)
+
+    def _forward(self, src_feat, tgt_feat, s_pcd, t_pcd, src_mask, tgt_mask, data, T, timers):
+        self.timers = timers
+        assert self.d_model == src_feat.size(2), "the feature number of src and transformer must be equal"
+        if T is not None:
+            R, t = T
+            src_pcd_wrapped = (torch.matmul(R, s_pcd.transpose(1, 2)) + t).transpose(1, 2)
+            tgt_pcd_wrapped = t_pcd
+        else:
+            src_pcd_wrapped = s_pcd
+            tgt_pcd_wrapped = t_pcd
+        src_pe = self.positional_encoding(src_pcd_wrapped)
+        tgt_pe = self.positional_encoding(tgt_pcd_wrapped)
+        data.update({"position_layers": {}})
+        position_layer = 0
+        if not self.entangled:
+            for layer, name in zip(self.layers, self.layer_types):
+                if name == 'self':
+                    src_feat = layer(src_feat, src_feat, src_pe, src_pe, src_mask, src_mask)
+                    tgt_feat = layer(tgt_feat, tgt_feat, tgt_pe, tgt_pe, tgt_mask, tgt_mask)
+                elif name == 'cross':
+                    src_feat = layer(src_feat, tgt_feat, src_pe, tgt_pe, src_mask, tgt_mask)
+                    tgt_feat = layer(tgt_feat, src_feat, tgt_pe, src_pe, tgt_mask, src_mask)
+                elif name == 'positioning':
+                    if self.positioning_type != 'procrustes':
+                        raise NotImplementedError("diffreg_b200.RepositioningTransformer: positioning_type "
+                                                  f"{self.positioning_type!r} stays with the reference module")
+                    conf_matrix, match_pred = layer[0](src_feat, tgt_feat, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type=self.pe_type)
+                    position_layer += 1
+                    data["position_layers"][position_layer] = {"conf_matrix": conf_matrix, "match_pred": match_pred}
+                    R, t, R_forwd, t_forwd, condition, solution_mask = layer[1](conf_matrix, s_pcd, t_pcd, src_mask, tgt_mask)
+                    data["position_layers"][position_layer].update({
+                        "R_s2t_pred": R, "t_s2t_pred": t, "solution_mask": solution_mask, "condition": condition})
+                    src_pcd_wrapped = (torch.matmul(R_forwd, s_pcd.transpose(1, 2)) + t_forwd).transpose(1, 2)
+                    tgt_pcd_wrapped = t_pcd
+                    src_pe = self.positional_encoding(src_pcd_wrapped)
+                    tgt_pe = self.positional_encoding(tgt_pcd_wrapped)
+                else:
+                    raise KeyError
+            return src_feat, tgt_feat, src_pe, tgt_pe
+        # position and feature entangled: the code is added / rotated into the features once, the layers see no code
+        src_feat = VolPE.embed_pos(self.pe_type, src_feat, src_pe)
+        tgt_feat = VolPE.embed_pos(self.pe_type, tgt_feat, tgt_pe)
+        for layer, name in zip(self.layers, self.layer_types):
+            if name == 'self':
+                src_feat = layer(src_feat, src_feat, None, None, src_mask, src_mask)
+                tgt_feat = layer(tgt_feat, tgt_feat, None, None, tgt_mask, tgt_mask)
+            elif name == 'cross':
+                src_feat = layer(src_feat, tgt_feat, None, None, src_mask, tgt_mask)
+                tgt_feat = layer(tgt_feat, src_feat, None, None, tgt_mask, src_mask)
+            elif name == 'positioning':
+                pass
+        return src_feat, tgt_feat, src_pe, tgt_pe
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)

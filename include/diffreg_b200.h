@@ -236,6 +236,32 @@ int drg_prep_operand_xyz(const float* in, const float* xyz, const float* div_ter
                          int pe_type, long long rows, int K, float scale, int split, int pattern, float* embedded, void* out,
                          void* stream);
 
+/* drg_prep_operand with two more staging options (the attention layer of the denoising transformer):
+ *   relu  = 1: max(x, 0) before the scaling -- the nn.ReLU between the two linears of the layer's MLP
+ *              Diff-Reg-4dmatch/models/transformer.py:33-37
+ *   heads > 1: `in` is [B, seq, heads, K] (rows = B * seq * heads, one row per (b, l, h) head slice; a rotary / additive code
+ *              tensor is indexed the same way) and the output rows are head-major (b, h, l): the per-head operands of
+ *              torch.einsum("nlhd,nshd->nlsh", qw, kw)   transformer.py:79   leave the staging kernel as [B * heads, seq, .] */
+int drg_prep_operand_ext(const float* in, const float* pe, int pe_type, long long rows, int K, float scale, int split, int pattern,
+                         int relu, int heads, int seq, float* embedded, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Geometry attention layer (denoising transformer): the row kernels between its GEMMs
+ *   drg_attn_softmax   logits [B*H, L, S] (the batched Q.K^T of drg_gemm_nt_split16) -> attention probabilities:
+ *                      a.masked_fill_(q_mask[:, :, None, None] * (~kv_mask[:, None, :, None]), -inf); a = a / sqrt(d);
+ *                      a = softmax(a, dim=2)             Diff-Reg-4dmatch/models/transformer.py:80-84
+ *                      (keys are masked for VALID queries only, as the reference's expression does; a valid query without a
+ *                      valid key yields NaN, as there).  q_mask [B, L], kv_mask [B, S] bool or NULL; scale = 1 / sqrt(d).
+ *                      P (optional) [B*H, L, S] fp32, may alias logits; P16 (optional) the same rows as the LEFT split
+ *                      operand [B*H, L, 2 kc(S) + 8] of the P.V product (drg_gemm_nt_split16).
+ *   drg_layernorm      out = [residual +] LayerNorm(in) over the last dimension C, affine (weight / bias may be NULL)
+ *                      replaces self.norm1(message), x + self.norm2(message)     transformer.py:88,92-94
+ * ------------------------------------------------------------------------------------ */
+int drg_attn_softmax(const float* logits, const uint8_t* q_mask, const uint8_t* kv_mask, int B, int H, int L, int S, float scale,
+                     float* P, void* P16, void* stream);
+int drg_layernorm(const float* in, const float* weight, const float* bias, const float* residual, long long rows, int C, float eps,
+                  float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Correspondence extraction
  *   mode 0: Matching.get_match(conf, thr, mutual)       Diff-Reg-4dmatch/models/matching.py:71-88 (= get_topk_match :90-107)

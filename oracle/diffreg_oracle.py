@@ -461,6 +461,69 @@ def sampler(flavour, p: MatchingParams, src_feats, tgt_feats, s_pcd, t_pcd, src_
 # --------------------------------------------------------------------------------------
 # synthetic inputs shared by tests, smoke() and bench.py
 # --------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------------------------
+# Denoising transformer: one geometry attention layer and the self / cross stack
+# ---------------------------------------------------------------------------------------------------------------
+def geometry_attention_layer(w, x, source, x_pe, source_pe, x_mask, source_mask, pe_type, nhead, eps=1e-5):
+    """``GeometryAttentionLayer.forward`` 4d/models/transformer.py:43-96.  `w`: dict with the module's state_dict keys
+    (q_proj.weight, k_proj.weight, v_proj.weight, merge.weight, mlp.0.weight, mlp.2.weight, norm1.weight/bias,
+    norm2.weight/bias).  Computed in the dtype of x (fp32 like the reference, or fp64 for an error yardstick)."""
+    dt = x.dtype
+    g = lambda k: w[k].to(dt)
+    bs = x.shape[0]
+    q, k, v = x, source, source
+    if pe_type == "sinusoidal":
+        if x_pe is not None:                      # :52-55
+            q = q + x_pe
+            k = k + source_pe
+        qw, kw, vw = q @ g("q_proj.weight").t(), k @ g("k_proj.weight").t(), v @ g("v_proj.weight").t()
+    elif pe_type == "rotary":
+        qw, kw, vw = q @ g("q_proj.weight").t(), k @ g("k_proj.weight").t(), v @ g("v_proj.weight").t()
+        if x_pe is not None:                      # :66-70
+            qw = embed_rotary(qw, x_pe[..., 0].to(dt), x_pe[..., 1].to(dt))
+            kw = embed_rotary(kw, source_pe[..., 0].to(dt), source_pe[..., 1].to(dt))
+    else:
+        raise KeyError()
+    dim = qw.shape[-1] // nhead
+    qw = qw.view(bs, -1, nhead, dim)
+    kw = kw.view(bs, -1, nhead, dim)
+    vw = vw.view(bs, -1, nhead, dim)
+    a = torch.einsum("nlhd,nshd->nlsh", qw, kw)   # :79
+    if source_mask is not None:                   # :80-81: keys are masked for VALID queries only
+        a = a.masked_fill(x_mask[:, :, None, None] * (~source_mask[:, None, :, None]), float("-inf"))
+    a = a / qw.size(3) ** 0.5
+    a = torch.softmax(a, dim=2)
+    o = torch.einsum("nlsh,nshd->nlhd", a, vw).contiguous()
+    message = o.view(bs, -1, nhead * dim) @ g("merge.weight").t()
+    message = torch.nn.functional.layer_norm(message, (message.shape[-1],), g("norm1.weight"), g("norm1.bias"), eps)
+    h = torch.cat([x, message], dim=2) @ g("mlp.0.weight").t()
+    message = torch.relu(h) @ g("mlp.2.weight").t()
+    message = torch.nn.functional.layer_norm(message, (message.shape[-1],), g("norm2.weight"), g("norm2.bias"), eps)
+    return x + message
+
+
+def attention_stack(layer_weights, layer_types, src_feat, tgt_feat, src_pe, tgt_pe, src_mask, tgt_mask, pe_type, nhead,
+                    entangled=False):
+    """The self / cross layers of ``RepositioningTransformer.forward`` 4d/models/transformer.py:169-233 (no positioning
+    layer: the denoising transformer of pipeline.py:84-85 has none).  `layer_weights[i]` is the state dict of layer i."""
+    if entangled:                                 # :217-219
+        src_feat = embed_pos(pe_type, src_feat, src_pe)
+        tgt_feat = embed_pos(pe_type, tgt_feat, tgt_pe)
+        sp = tp = None
+    else:
+        sp, tp = src_pe, tgt_pe
+    for w, name in zip(layer_weights, layer_types):
+        if name == "self":
+            src_feat = geometry_attention_layer(w, src_feat, src_feat, sp, sp, src_mask, src_mask, pe_type, nhead)
+            tgt_feat = geometry_attention_layer(w, tgt_feat, tgt_feat, tp, tp, tgt_mask, tgt_mask, pe_type, nhead)
+        elif name == "cross":
+            src_feat = geometry_attention_layer(w, src_feat, tgt_feat, sp, tp, src_mask, tgt_mask, pe_type, nhead)
+            tgt_feat = geometry_attention_layer(w, tgt_feat, src_feat, tp, sp, tgt_mask, src_mask, pe_type, nhead)
+        else:
+            raise KeyError(name)
+    return src_feat, tgt_feat
+
+
 def random_rotation(gen):
     q = torch.randn(4, generator=gen)
     q = q / q.norm()

@@ -104,6 +104,39 @@ def test_position_encoding_interface_matches_the_reference():
         ref_loader.unload()
 
 
+@needs_ref
+def test_transformer_interface_and_state_dict_match_the_reference():
+    """GeometryAttentionLayer / RepositioningTransformer take the reference's config keys and arguments
+    and hold the reference's parameters under the reference's names (a reference checkpoint loads strictly, and back)."""
+    ref = ref_loader.load_flavour("4d")
+    try:
+        from diffreg_b200 import transformer as OT
+        RT = ref.transformer
+        for cls in ("GeometryAttentionLayer", "RepositioningTransformer"):
+            for name in ("__init__", "forward"):
+                _assert_prefix(getattr(getattr(RT, cls), name), getattr(getattr(OT, cls), name), f"{cls}.{name}")
+
+        class Cfg(dict):
+            __getattr__ = dict.__getitem__
+        lc = Cfg(feature_dim=48, n_head=4, pe_type="rotary")
+        rsd, osd = RT.GeometryAttentionLayer(lc).state_dict(), OT.GeometryAttentionLayer(lc).state_dict()
+        assert list(rsd.keys()) == list(osd.keys())
+        assert all(rsd[k].shape == osd[k].shape and rsd[k].dtype == osd[k].dtype for k in rsd)
+        tc = Cfg(feature_dim=48, n_head=4, layer_types=["self", "cross", "positioning", "self", "cross"], positioning_type="procrustes",
+                 pe_type="rotary", entangled=False, vol_bnds=[[-3.6, -2.4, 1.14], [1.093, 0.78, 2.92]], voxel_size=0.04,
+                 feature_matching=_cfg(48), procrustes=Cfg(max_condition_num=40, sample_rate=1.0))
+        rn, on = RT.RepositioningTransformer(tc), OT.RepositioningTransformer(tc)
+        rsd, osd = rn.state_dict(), on.state_dict()
+        assert list(rsd.keys()) == list(osd.keys())
+        assert all(rsd[k].shape == osd[k].shape and rsd[k].dtype == osd[k].dtype for k in rsd)
+        on.load_state_dict(rsd, strict=True)
+        rn.load_state_dict(osd, strict=True)
+        for attr in ("d_model", "nhead", "layer_types", "positioning_type", "pe_type", "entangled", "positional_encoding", "layers"):
+            assert hasattr(on, attr), attr
+    finally:
+        ref_loader.unload()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def test_autograd_tracked_calls_raise_instead_of_detaching():
     """Every public entry point of the modules; CPU tensors are enough (the check precedes any device work)."""
@@ -165,6 +198,7 @@ SHIMS = {
     "Diff-Reg-4dmatch/models/matching.py": ["Matching", "log_optimal_transport"],
     "Diff-Reg-4dmatch/models/procrustes.py": ["SoftProcrustesLayer"],
     "Diff-Reg-4dmatch/models/position_encoding.py": ["VolumetricPositionEncoding"],
+    "Diff-Reg-4dmatch/models/transformer.py": ["GeometryAttentionLayer", "RepositioningTransformer"],
     "Diff-Reg-3dmatch/models/matching.py": ["Matching", "log_optimal_transport", "mutual_topk_select"],
     "Diff-Reg-3dmatch/models/procrustes.py": ["SoftProcrustesLayer"],
     "Diff-Reg-2d3d/experiments/matching.py": ["Matching", "log_optimal_transport"],

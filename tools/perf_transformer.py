@@ -1,0 +1,53 @@
+"""Timing of the denoising transformer drop-in (six self / cross layers) at the bench shape, with the reference module on the
+same GPU as the yardstick when oracle/_ref is present (tuning tool; CUDA events, median of repetitions)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import diffreg_b200
+from oracle import ref_loader
+
+
+class Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+bnds = [[-3.6, -2.4, 1.14], [1.093, 0.78, 2.92]]
+cfg = Cfg(feature_dim=C, n_head=4, layer_types=['self', 'cross'] * 3, positioning_type="procrustes", pe_type="rotary", entangled=False,
+          vol_bnds=bnds, voxel_size=0.04)
+g = torch.Generator().manual_seed(1)
+lo, hi = torch.tensor(bnds[0]), torch.tensor(bnds[1])
+s_pcd = (lo + (hi - lo) * torch.rand(1, n, 3, generator=g)).cuda()
+t_pcd = (lo + (hi - lo) * torch.rand(1, n, 3, generator=g)).cuda()
+sf, tf = torch.randn(1, n, C, generator=g).cuda(), torch.randn(1, n, C, generator=g).cuda()
+sm = torch.ones(1, n, dtype=torch.bool).cuda()
+
+
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+onet = diffreg_b200.RepositioningTransformer(cfg).cuda().eval()
+out = {"n": n, "C": C, "layers": 6}
+if ref_loader.available():
+    ref = ref_loader.load_flavour("4d")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rnet = ref.transformer.RepositioningTransformer(cfg).cuda().eval()
+    onet.load_state_dict(rnet.state_dict(), strict=True)
+    with torch.no_grad():
+        r = rnet(sf, tf, s_pcd, t_pcd, sm, sm, {})
+        o = onet(sf, tf, s_pcd, t_pcd, sm, sm, {})
+        out["max_abs_diff_vs_reference"] = max((o[0] - r[0]).abs().max().item(), (o[1] - r[1]).abs().max().item())
+        out["reference_module_ms"] = timed(lambda: rnet(sf, tf, s_pcd, t_pcd, sm, sm, {}))
+c0 = diffreg_b200.launch_count()
+onet(sf, tf, s_pcd, t_pcd, sm, sm, {})
+out["launches"] = diffreg_b200.launch_count() - c0
+out["dropin_ms"] = timed(lambda: onet(sf, tf, s_pcd, t_pcd, sm, sm, {}))
+print(json.dumps(out), flush=True)
