@@ -550,6 +550,121 @@ __global__ void __launch_bounds__(SKH_THREADS, 1) skh_iter2_kernel(const SkhPara
   for (int j = M + 1 + tid; j < Mv; j += SKH_THREADS) v2_s[j] = -INFINITY;
   __syncthreads();
 
+  if constexpr (R == 1) {
+    // ---- wide rows (8192 < M <= 16384: one row per stage, two stages).  The software-pipelined loop below keeps TWO rows
+    //      resident (row partial of s + 1, column pass of s), i.e. the whole ring, so every row's load started only after
+    //      the row before it had been consumed: DRAM latency exposed once per row (measured 9 k cycles per row against the
+    //      3 k its 64 KB need at the SM's share of HBM).  Here a thread pulls its KQ quads of the row into registers once
+    //      and runs BOTH directions from them (as the persistent kernel does): the stage is free after the first barrier
+    //      and is re-armed right there, so two rows are always in flight.  Two block barriers per row (maximum, sum); the
+    //      arithmetic is the exact log-domain pass of the loop below.
+    float cm[KQ * 4], cs[KQ * 4];
+#pragma unroll
+    for (int e = 0; e < KQ * 4; ++e) {
+      cm[e] = NEG_BIG;
+      cs[e] = 0.f;
+    }
+    LseAcc uacc = lse_empty();  // thread 0: running LSE of the u_i of this CTA's rows (dustbin column)
+    float* rmax_s = reinterpret_cast<float*>(rowpart);  // [SKH_WARPS]
+    float* rsum_s = rmax_s + SKH_WARPS;                 // [SKH_WARPS]
+    const float dust2 = v2_s[M];
+    for (int s = s_begin; s < s_end; ++s) {
+      const int it = s - s_begin;
+      const int st = it % nstage;
+      mbar_wait(&full[st], (uint32_t)((it / nstage) & 1));
+      const float* row = stage0 + (size_t)st * stage_floats;
+      const int i = s;
+      const bool row_live = !(p.apply_mask && !p.dual && !p.src_mask[(size_t)b * N + i]);
+      float4 z[KQ];
+      float m = NEG_BIG;
+#pragma unroll
+      for (int k = 0; k < KQ; ++k) {
+        const int c = 4 * (tid + SKH_THREADS * k);
+        if (FULL || c < M) {
+          z[k] = *reinterpret_cast<const float4*>(row + c);
+          const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+          m = fmaxf(m, fmaxf(fmaxf(fmaf(z[k].x, zs, vv.x), fmaf(z[k].y, zs, vv.y)), fmaxf(fmaf(z[k].z, zs, vv.z), fmaf(z[k].w, zs, vv.w))));
+        } else {
+          z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      m = warp_max(m);
+      if (lane == 0) rmax_s[warp] = m;
+      __syncthreads();  // every thread holds its part of the row: the stage is free
+      if (tid == 0 && s + nstage < s_end) issue_slab(s + nstage, st);
+      float mrow = NEG_BIG;
+#pragma unroll
+      for (int w = 0; w < SKH_WARPS; w += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(rmax_s + w);
+        mrow = fmaxf(mrow, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+      }
+      if (!p.dual) mrow = fmaxf(mrow, dust2);  // the dustbin column entry (alpha + v_M) is always finite
+      float sum = 0.f;
+      if (row_live) {
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (tid + SKH_THREADS * k);
+          if (FULL || c < M) {
+            const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+            sum += (ex2(fmaf(z[k].x, zs, vv.x) - mrow) + ex2(fmaf(z[k].y, zs, vv.y) - mrow)) +
+                   (ex2(fmaf(z[k].z, zs, vv.z) - mrow) + ex2(fmaf(z[k].w, zs, vv.w) - mrow));
+          }
+        }
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) rsum_s[warp] = sum;
+      __syncthreads();
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < SKH_WARPS; w += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(rsum_s + w);
+        tot += (q.x + q.y) + (q.z + q.w);
+      }
+      float ui, u2;
+      const bool src_ok = (!p.apply_mask && !p.dual) || p.src_mask[(size_t)b * N + i];
+      if (!p.dual) {
+        const float rowlse2 = mrow + lg2(tot + ex2(dust2 - mrow));  // a padded row (fused mask) holds its dustbin entry only
+        ui = bc.norm - rowlse2 * LN2;
+        u2 = src_ok ? (ui - shift) * LOG2E : -INFINITY;  // column pass sees (S - shift) + u
+      } else {
+        ui = -(mrow + lg2(tot)) * LN2;  // -(row log-sum-exp), natural log
+        u2 = src_ok ? 0.f : -INFINITY;
+      }
+      if (tid == 0) {
+        p.u[(size_t)b * p.ldu + i] = ui;
+        if (!p.dual) lse_add_value(uacc, ui * LOG2E);
+      }
+#pragma unroll
+      for (int k = 0; k < KQ; ++k) {
+        const int c = 4 * (tid + SKH_THREADS * k);
+        if (FULL || c < M) {
+          const float y[4] = {fmaf(z[k].x, zs, u2), fmaf(z[k].y, zs, u2), fmaf(z[k].z, zs, u2), fmaf(z[k].w, zs, u2)};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float& am = cm[4 * k + e];
+            float& as = cs[4 * k + e];
+            if (y[e] > am + 32.f) {  // lazy re-reference: rare after the first rows
+              as *= ex2(am - y[e]);
+              am = y[e];
+            }
+            as += ex2(y[e] - am);
+          }
+        }
+      }
+    }
+    float2* cp = p.colpart + ((size_t)b * G + g) * M;
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+      const int c = 4 * (tid + SKH_THREADS * k);
+      if (FULL || c < M) {
+        *reinterpret_cast<float4*>(cp + c) = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
+        *reinterpret_cast<float4*>(cp + c + 2) = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
+      }
+    }
+    if (!p.dual && tid == 0) p.upart[(size_t)b * G + g] = make_float2(uacc.m, uacc.s);
+    return;
+  }
+
   // ---- this warp's row segment
   const int wr = warp / SEG, wseg = warp % SEG;
   const int seg_len = FULL ? NCH * 128 : ((((M + SEG - 1) / SEG) + 127) & ~127);

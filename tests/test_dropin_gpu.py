@@ -4,8 +4,8 @@ produces over its own matching / procrustes modules.
 
 The reference sources come from /root/reference when present, else from the copy under oracle/_ref (oracle/make_ref.py;
 it travels to the GPU box).  Both runs happen here on the GPU: run A imports the pure reference tree, run B an overlay
-directory = the same tree with models/matching.py and models/procrustes.py (and, in one variant, position_encoding.py)
-replaced by the shims.  The sampler loop is the one of 4d/models/pipeline.py:171-190 written out call by call (it lives in
+directory = the same tree with models/matching.py and models/procrustes.py (and, in further variants, position_encoding.py
+and transformer.py -- then the whole coarse stage and every sampler step run on this library's kernels) replaced by the shims.  The sampler loop is the one of 4d/models/pipeline.py:171-190 written out call by call (it lives in
 the middle of Pipeline.forward, behind the KPConv backbone); everything it calls -- Pipeline.get_warped_from_noising_matching,
 Pipeline.predict_noise_from_start, RepositioningTransformer.forward, Matching.forward, SoftProcrustesLayer.forward -- is the
 reference's or the shim's, never DenoisingSampler.
@@ -65,6 +65,8 @@ def _overlay(tmp_path, shim_pe):
                     ignore=shutil.ignore_patterns("*.pth", "*.ply", "*.npz", "__pycache__", "data", "snapshot", "cpp_wrappers"))
     shim = os.path.join(ROOT, "shims", "Diff-Reg-4dmatch", "models")
     names = ["matching.py", "procrustes.py"] + (["position_encoding.py"] if shim_pe else [])
+    if shim_pe == "all":                      # ... and the transformer itself
+        names.append("transformer.py")
     for n in names:
         shutil.copyfile(os.path.join(shim, n), os.path.join(dst, "models", n))
     return dst
@@ -145,7 +147,7 @@ def _run(ns, obj, pb, steps=3):
     return {k: v.detach().cpu() for k, v in out.items()}
 
 
-@pytest.mark.parametrize("shim_pe", [False, True])
+@pytest.mark.parametrize("shim_pe", [False, True, "all"])
 def test_reference_pipeline_code_runs_over_the_shims(tmp_path, shim_pe):
     import diffreg_b200
     N, M = 120, 104
@@ -158,7 +160,10 @@ def test_reference_pipeline_code_runs_over_the_shims(tmp_path, shim_pe):
         before = diffreg_b200.launch_count()
         ns_b = _import_tree(_overlay(tmp_path, shim_pe))
         assert ns_b.matching.Matching is diffreg_b200.Matching
-        assert ns_b.transformer.Matching is diffreg_b200.Matching            # transformer.py:7 picked the shim up
+        if shim_pe == "all":
+            assert ns_b.transformer.RepositioningTransformer is diffreg_b200.RepositioningTransformer
+        else:
+            assert ns_b.transformer.Matching is diffreg_b200.Matching        # transformer.py:7 picked the shim up
         assert ns_b.pipeline.log_optimal_transport is diffreg_b200.log_optimal_transport
         obj_b, _ = _build(ns_b, weights)
         got = _run(ns_b, obj_b, pb)
