@@ -556,51 +556,154 @@ __global__ void __launch_bounds__(SKH_THREADS, 1) skh_iter2_kernel(const SkhPara
     //      the row before it had been consumed: DRAM latency exposed once per row (measured 9 k cycles per row against the
     //      3 k its 64 KB need at the SM's share of HBM).  Here a thread pulls its KQ quads of the row into registers once
     //      and runs BOTH directions from them (as the persistent kernel does): the stage is free after the first barrier
-    //      and is re-armed right there, so two rows are always in flight.  Two block barriers per row (maximum, sum); the
-    //      arithmetic is the exact log-domain pass of the loop below.
-    float cm[KQ * 4], cs[KQ * 4];
+    //      and is re-armed right there, so two rows are always in flight.
+    //      Sinkhorn rows take the SCALED form of the persistent kernel: e_ij = 2^(x_ij + v_j - ref_i) is computed once and
+    //      serves the row sum and, divided by it, the column sums (one MUFU per element, one barrier per row).  ref_i comes
+    //      from the row potential of the previous iteration (u in HBM; 0 before the first: any finite reference is exact as
+    //      long as nothing overflows) and every row CHECKS its sum: outside [2^-60, 2^60] (or NaN) the row is redone from
+    //      shared memory with its exact maximum -- no global "the potentials moved little" condition is needed.  Column
+    //      sums are carried against the uniform reference 2^(norm2 - shift2 - v2_j) (row-normalised entries are <= 1, so
+    //      nothing overflows), which is what the (max, sum) pairs handed to the column merge hold.  Dual-softmax rows keep
+    //      the exact two-reduction log-domain pass.
+    float cs[KQ * 4];
 #pragma unroll
-    for (int e = 0; e < KQ * 4; ++e) {
-      cm[e] = NEG_BIG;
-      cs[e] = 0.f;
+    for (int e = 0; e < KQ * 4; ++e) cs[e] = 0.f;
+    float cm[KQ * 4];           // dual mode only: online column maxima
+    if (p.dual) {
+#pragma unroll
+      for (int e = 0; e < KQ * 4; ++e) cm[e] = NEG_BIG;
     }
     LseAcc uacc = lse_empty();  // thread 0: running LSE of the u_i of this CTA's rows (dustbin column)
     float* rmax_s = reinterpret_cast<float*>(rowpart);  // [SKH_WARPS]
     float* rsum_s = rmax_s + SKH_WARPS;                 // [SKH_WARPS]
+    float* rsum2_s = rsum_s + SKH_WARPS;                // [SKH_WARPS] (second buffer: consecutive rows alternate)
     const float dust2 = v2_s[M];
+    const float norm2 = bc.norm * LOG2E, shift2 = shift * LOG2E;
+    auto block_sum16 = [&](const float* buf) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < SKH_WARPS; w += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(buf + w);
+        t += (q.x + q.y) + (q.z + q.w);
+      }
+      return t;
+    };
     for (int s = s_begin; s < s_end; ++s) {
       const int it = s - s_begin;
       const int st = it % nstage;
-      mbar_wait(&full[st], (uint32_t)((it / nstage) & 1));
-      const float* row = stage0 + (size_t)st * stage_floats;
       const int i = s;
       const bool row_live = !(p.apply_mask && !p.dual && !p.src_mask[(size_t)b * N + i]);
+      const bool src_ok = (!p.apply_mask && !p.dual) || p.src_mask[(size_t)b * N + i];
+      float mh = 0.f;
+      if (!p.dual) mh = (bc.norm - __ldcg(p.u + (size_t)b * p.ldu + i)) * LOG2E;  // row reference: last iteration's row log-sum-exp
+      mbar_wait(&full[st], (uint32_t)((it / nstage) & 1));
+      const float* row = stage0 + (size_t)st * stage_floats;
       float4 z[KQ];
-      float m = NEG_BIG;
+      float ui, u2;
+      if (!p.dual) {
+        float* rs_buf = (it & 1) ? rsum2_s : rsum_s;
+        float rs = 0.f;
 #pragma unroll
-      for (int k = 0; k < KQ; ++k) {
-        const int c = 4 * (tid + SKH_THREADS * k);
-        if (FULL || c < M) {
-          z[k] = *reinterpret_cast<const float4*>(row + c);
-          const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
-          m = fmaxf(m, fmaxf(fmaxf(fmaf(z[k].x, zs, vv.x), fmaf(z[k].y, zs, vv.y)), fmaxf(fmaf(z[k].z, zs, vv.z), fmaf(z[k].w, zs, vv.w))));
-        } else {
-          z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (tid + SKH_THREADS * k);
+          if ((FULL || c < M) && row_live) {
+            const float4 zz = *reinterpret_cast<const float4*>(row + c);
+            const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+            float4 e;
+            e.x = ex2(fmaf(zz.x, zs, vv.x) - mh);
+            e.y = ex2(fmaf(zz.y, zs, vv.y) - mh);
+            e.z = ex2(fmaf(zz.z, zs, vv.z) - mh);
+            e.w = ex2(fmaf(zz.w, zs, vv.w) - mh);
+            z[k] = e;
+            rs += (e.x + e.y) + (e.z + e.w);
+          } else {
+            z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-      }
-      m = warp_max(m);
-      if (lane == 0) rmax_s[warp] = m;
-      __syncthreads();  // every thread holds its part of the row: the stage is free
-      if (tid == 0 && s + nstage < s_end) issue_slab(s + nstage, st);
-      float mrow = NEG_BIG;
+        rs = warp_sum(rs);
+        if (lane == 0) rs_buf[warp] = rs;
+        __syncthreads();  // every thread holds its part of the row
+        float tot = block_sum16(rs_buf);
+        const float edust = ex2(dust2 - mh);
+        const bool healthy = !row_live || (tot + edust > 8.6736174e-19f && tot + edust < 1.1529215e18f);  // uniform over the CTA
+        if (!healthy) {
+          // rare (a reference far from the row's scale): exact row maximum from the row still in shared memory
+          float m = NEG_BIG;
 #pragma unroll
-      for (int w = 0; w < SKH_WARPS; w += 4) {
-        const float4 q = *reinterpret_cast<const float4*>(rmax_s + w);
-        mrow = fmaxf(mrow, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
-      }
-      if (!p.dual) mrow = fmaxf(mrow, dust2);  // the dustbin column entry (alpha + v_M) is always finite
-      float sum = 0.f;
-      if (row_live) {
+          for (int k = 0; k < KQ; ++k) {
+            const int c = 4 * (tid + SKH_THREADS * k);
+            if (FULL || c < M) {
+              const float4 zz = *reinterpret_cast<const float4*>(row + c);
+              const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+              m = fmaxf(m, fmaxf(fmaxf(fmaf(zz.x, zs, vv.x), fmaf(zz.y, zs, vv.y)), fmaxf(fmaf(zz.z, zs, vv.z), fmaf(zz.w, zs, vv.w))));
+            }
+          }
+          m = warp_max(m);
+          if (lane == 0) rmax_s[warp] = m;
+          __syncthreads();
+          float mrow = dust2;
+#pragma unroll
+          for (int w = 0; w < SKH_WARPS; ++w) mrow = fmaxf(mrow, rmax_s[w]);
+          mh = mrow;
+          rs = 0.f;
+#pragma unroll
+          for (int k = 0; k < KQ; ++k) {
+            const int c = 4 * (tid + SKH_THREADS * k);
+            if (FULL || c < M) {
+              const float4 zz = *reinterpret_cast<const float4*>(row + c);
+              const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+              float4 e;
+              e.x = ex2(fmaf(zz.x, zs, vv.x) - mh);
+              e.y = ex2(fmaf(zz.y, zs, vv.y) - mh);
+              e.z = ex2(fmaf(zz.z, zs, vv.z) - mh);
+              e.w = ex2(fmaf(zz.w, zs, vv.w) - mh);
+              z[k] = e;
+              rs += (e.x + e.y) + (e.z + e.w);
+            }
+          }
+          rs = warp_sum(rs);
+          __syncthreads();          // rmax_s / the other sum buffer have been read
+          float* rs_buf2 = (it & 1) ? rsum_s : rsum2_s;
+          if (lane == 0) rs_buf2[warp] = rs;
+          __syncthreads();
+          tot = block_sum16(rs_buf2);
+          __syncthreads();          // ... before the next row writes that buffer
+        }
+        if (tid == 0 && s + nstage < s_end) issue_slab(s + nstage, st);  // the stage is free: re-arm it
+        const float srow = tot + ex2(dust2 - mh);       // + the dustbin column entry (alpha + v_M)
+        const float rowlse2 = row_live ? mh + lg2(srow) : dust2;  // a padded row (fused mask) holds its dustbin entry only
+        ui = bc.norm - rowlse2 * LN2;
+        u2 = src_ok ? (ui - shift) * LOG2E : -INFINITY;
+        const float w = (row_live && src_ok) ? 1.f / srow : 0.f;
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          cs[4 * k + 0] = fmaf(z[k].x, w, cs[4 * k + 0]);
+          cs[4 * k + 1] = fmaf(z[k].y, w, cs[4 * k + 1]);
+          cs[4 * k + 2] = fmaf(z[k].z, w, cs[4 * k + 2]);
+          cs[4 * k + 3] = fmaf(z[k].w, w, cs[4 * k + 3]);
+        }
+      } else {
+        // dual softmax: exact log-domain pass (row maximum, sum, online column maxima)
+        float m = NEG_BIG;
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (tid + SKH_THREADS * k);
+          if (FULL || c < M) {
+            z[k] = *reinterpret_cast<const float4*>(row + c);
+            const float4 vv = *reinterpret_cast<const float4*>(v2_s + c);
+            m = fmaxf(m, fmaxf(fmaxf(fmaf(z[k].x, zs, vv.x), fmaf(z[k].y, zs, vv.y)), fmaxf(fmaf(z[k].z, zs, vv.z), fmaf(z[k].w, zs, vv.w))));
+          } else {
+            z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        m = warp_max(m);
+        if (lane == 0) rmax_s[warp] = m;
+        __syncthreads();  // every thread holds its part of the row: the stage is free
+        if (tid == 0 && s + nstage < s_end) issue_slab(s + nstage, st);
+        float mrow = NEG_BIG;
+#pragma unroll
+        for (int w = 0; w < SKH_WARPS; ++w) mrow = fmaxf(mrow, rmax_s[w]);
+        float sum = 0.f;
 #pragma unroll
         for (int k = 0; k < KQ; ++k) {
           const int c = 4 * (tid + SKH_THREADS * k);
@@ -610,46 +713,33 @@ __global__ void __launch_bounds__(SKH_THREADS, 1) skh_iter2_kernel(const SkhPara
                    (ex2(fmaf(z[k].z, zs, vv.z) - mrow) + ex2(fmaf(z[k].w, zs, vv.w) - mrow));
           }
         }
-      }
-      sum = warp_sum(sum);
-      if (lane == 0) rsum_s[warp] = sum;
-      __syncthreads();
-      float tot = 0.f;
-#pragma unroll
-      for (int w = 0; w < SKH_WARPS; w += 4) {
-        const float4 q = *reinterpret_cast<const float4*>(rsum_s + w);
-        tot += (q.x + q.y) + (q.z + q.w);
-      }
-      float ui, u2;
-      const bool src_ok = (!p.apply_mask && !p.dual) || p.src_mask[(size_t)b * N + i];
-      if (!p.dual) {
-        const float rowlse2 = mrow + lg2(tot + ex2(dust2 - mrow));  // a padded row (fused mask) holds its dustbin entry only
-        ui = bc.norm - rowlse2 * LN2;
-        u2 = src_ok ? (ui - shift) * LOG2E : -INFINITY;  // column pass sees (S - shift) + u
-      } else {
+        sum = warp_sum(sum);
+        if (lane == 0) rsum_s[warp] = sum;
+        __syncthreads();
+        const float tot = block_sum16(rsum_s);
         ui = -(mrow + lg2(tot)) * LN2;  // -(row log-sum-exp), natural log
         u2 = src_ok ? 0.f : -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          const int c = 4 * (tid + SKH_THREADS * k);
+          if (FULL || c < M) {
+            const float y[4] = {fmaf(z[k].x, zs, u2), fmaf(z[k].y, zs, u2), fmaf(z[k].z, zs, u2), fmaf(z[k].w, zs, u2)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float& am = cm[4 * k + e];
+              float& as = cs[4 * k + e];
+              if (y[e] > am + 32.f) {  // lazy re-reference: rare after the first rows
+                as *= ex2(am - y[e]);
+                am = y[e];
+              }
+              as += ex2(y[e] - am);
+            }
+          }
+        }
       }
       if (tid == 0) {
         p.u[(size_t)b * p.ldu + i] = ui;
         if (!p.dual) lse_add_value(uacc, ui * LOG2E);
-      }
-#pragma unroll
-      for (int k = 0; k < KQ; ++k) {
-        const int c = 4 * (tid + SKH_THREADS * k);
-        if (FULL || c < M) {
-          const float y[4] = {fmaf(z[k].x, zs, u2), fmaf(z[k].y, zs, u2), fmaf(z[k].z, zs, u2), fmaf(z[k].w, zs, u2)};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float& am = cm[4 * k + e];
-            float& as = cs[4 * k + e];
-            if (y[e] > am + 32.f) {  // lazy re-reference: rare after the first rows
-              as *= ex2(am - y[e]);
-              am = y[e];
-            }
-            as += ex2(y[e] - am);
-          }
-        }
       }
     }
     float2* cp = p.colpart + ((size_t)b * G + g) * M;
@@ -657,8 +747,20 @@ __global__ void __launch_bounds__(SKH_THREADS, 1) skh_iter2_kernel(const SkhPara
     for (int k = 0; k < KQ; ++k) {
       const int c = 4 * (tid + SKH_THREADS * k);
       if (FULL || c < M) {
-        *reinterpret_cast<float4*>(cp + c) = make_float4(cm[4 * k], cs[4 * k], cm[4 * k + 1], cs[4 * k + 1]);
-        *reinterpret_cast<float4*>(cp + c + 2) = make_float4(cm[4 * k + 2], cs[4 * k + 2], cm[4 * k + 3], cs[4 * k + 3]);
+        float ref[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (p.dual) {
+            ref[e] = cm[4 * k + e];
+          } else {  // sum_i 2^(x_ij + u_i log2e) = 2^(norm2 - shift2 - v2_j) * sum_i e_ij / srow_i
+            const float v2j = v2_s[c + e];
+            const bool okc = v2j > -INFINITY;
+            ref[e] = okc ? (norm2 - v2j - shift2) : NEG_BIG;
+            if (!okc) cs[4 * k + e] = 0.f;
+          }
+        }
+        *reinterpret_cast<float4*>(cp + c) = make_float4(ref[0], cs[4 * k], ref[1], cs[4 * k + 1]);
+        *reinterpret_cast<float4*>(cp + c + 2) = make_float4(ref[2], cs[4 * k + 2], ref[3], cs[4 * k + 3]);
       }
     }
     if (!p.dual && tid == 0) p.upart[(size_t)b * G + g] = make_float2(uacc.m, uacc.s);
