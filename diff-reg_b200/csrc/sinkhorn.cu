@@ -1816,9 +1816,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
     float* conf_b = f.conf ? f.conf + (size_t)b * N * M : nullptr;
     const float* noise_b = f.noise ? f.noise + (size_t)b * N * M : nullptr;
     const unsigned long long quad_base = ((unsigned long long)b * N * M) >> 2;   // Philox counter = global quad index
-    auto body = [&](auto masked_c, auto ddim_c) {
+    // NOISE: 0 none, 1 caller tensor, 2 in-kernel Philox.  The slab's RR x KQ quads are straight-line code (the compiler
+    // interleaves their Philox / exp chains -- the phase is latency-bound on 16 warps per SM); the arg-max bookkeeping of
+    // the rare quads that hold an entry above the floor is deferred to after the slab (a flag bit per quad, the few
+    // confidences recomputed from the slab still in shared memory), so no data-dependent branch splits the hot code.
+    auto body = [&](auto masked_c, auto ddim_c, auto noise_c) {
       constexpr bool MASKED = decltype(masked_c)::value;
       constexpr bool DDIM = decltype(ddim_c)::value;
+      constexpr int NOISE = decltype(noise_c)::value;
       for (int s = rg; s < ns; s += P2_GROUPS) {
         const int q0 = NWf * s;
         const int stg_z = q0 % Df;
@@ -1830,58 +1835,83 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
           mbar_wait(&full[stg_x], (base_parity(stg_x) + (uint32_t)((q0 + 1) / Df)) & 1u);
           slab_x = ring + (size_t)stg_x * stage_floats;
         }
+        unsigned int hot = 0u;   // bit r * KQ + k: that quad holds an entry above the floor
+        float ui_r[RR];
+        bool ok_r[RR];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+          const int i = min(row0 + s * RR + r, row1 - 1);   // (rows past the CTA's range: clamped, nothing is stored for them)
+          ui_r[r] = __ldcg(u_b + i);
+          ok_r[r] = !MASKED || smask[i];
+        }
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
           const int i = row0 + s * RR + r;
-          if (i < row1) {   // rows past the CTA's range were not copied
+          const bool row_in = i < row1;   // rows past the CTA's range were not copied
+          const size_t row_off = (size_t)min(i, row1 - 1) * M + 4 * ct;
+#pragma unroll
+          for (int k = 0; k < KQ; ++k) {
+            const int c = 4 * (ct + P2_TPR * k);
+            if (FULL || c < M) {
+              const float4 z4 = *reinterpret_cast<const float4*>(slab_z + (size_t)r * M + c);
+              float nz[4] = {0.f, 0.f, 0.f, 0.f};
+              float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (DDIM) {
+                t4 = *reinterpret_cast<const float4*>(slab_x + (size_t)r * M + c);
+                if (NOISE == 1) {
+                  const float4 n4 = ldg_stream4(noise_b + row_off + 4 * P2_TPR * k);
+                  nz[0] = n4.x; nz[1] = n4.y; nz[2] = n4.z; nz[3] = n4.w;
+                } else if (NOISE == 2) {
+                  const unsigned long long quad = quad_base + ((row_off + 4 * P2_TPR * k) >> 2);
+                  const float4 n4 = philox_normal4_rk((unsigned int)quad, (unsigned int)(quad >> 32), off_lo, off_hi, f.rk);
+                  nz[0] = n4.x; nz[1] = n4.y; nz[2] = n4.z; nz[3] = n4.w;
+                }
+              }
+              const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+              const float xt[4] = {t4.x, t4.y, t4.z, t4.w};
+              float cf[4], o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const bool ok = !MASKED || (ok_r[r] && ((tmbits >> (4 * k + e)) & 1u));
+                const float zz = ok ? (z[e] - shift) : -INFINITY;
+                const float la = ((zz + ui_r[r]) + vj[k][e]) - bc.norm;  // same association as matching.py:34-36
+                cf[e] = ex2(la * LOG2E);
+                if (DDIM) o[e] = ok ? fmaf(f.k_x0, cf[e], fmaf(f.k_xt, xt[e] - xt_shift, f.sigma * nz[e])) : -INFINITY;
+                else o[e] = cf[e];
+              }
+              if (row_in) {
+                *reinterpret_cast<float4*>(out_b + row_off + 4 * P2_TPR * k) = make_float4(o[0], o[1], o[2], o[3]);
+                if (DDIM && conf_b) *reinterpret_cast<float4*>(conf_b + row_off + 4 * P2_TPR * k) = make_float4(cf[0], cf[1], cf[2], cf[3]);
+              }
+              if (row_in && fmaxf(fmaxf(cf[0], cf[1]), fmaxf(cf[2], cf[3])) > floor_v) hot |= 1u << (r * KQ + k);
+            }
+          }
+        }
+        // arg-max keys: only entries above the floor (a row of the plan sums to <= 1: a handful per row) -- straight to the
+        // packed 64-bit keys with atomicMax (largest value, then lowest index); the confidences are recomputed exactly
+        if (track && hot) {
+#pragma unroll 1
+          while (hot) {
+            const int bit = __ffs(hot) - 1;
+            hot &= hot - 1u;
+            const int r = bit / KQ, k = bit - r * KQ;
+            const int i = row0 + s * RR + r;
+            const int c = 4 * (ct + P2_TPR * k);
+            const float4 z4 = *reinterpret_cast<const float4*>(slab_z + (size_t)r * M + c);
+            const float z[4] = {z4.x, z4.y, z4.z, z4.w};
             const float ui = __ldcg(u_b + i);
             const bool row_ok = !MASKED || smask[i];
-            const size_t row_off = (size_t)i * M + 4 * ct;
-            float* out_r = out_b + row_off;
+            const float4 vq = __ldcg(reinterpret_cast<const float4*>(v_b + c));
+            const float vv[4] = {vq.x, vq.y, vq.z, vq.w};
 #pragma unroll
-            for (int k = 0; k < KQ; ++k) {
-              const int c = 4 * (ct + P2_TPR * k);
-              if (FULL || c < M) {
-                const float4 z4 = *reinterpret_cast<const float4*>(slab_z + (size_t)r * M + c);
-                float nz[4] = {0.f, 0.f, 0.f, 0.f};
-                float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (DDIM) {
-                  t4 = *reinterpret_cast<const float4*>(slab_x + (size_t)r * M + c);
-                  if (noise_b) {
-                    const float4 n4 = ldg_stream4(noise_b + row_off + 4 * P2_TPR * k);
-                    nz[0] = n4.x; nz[1] = n4.y; nz[2] = n4.z; nz[3] = n4.w;
-                  } else if (f.gen_noise) {
-                    const unsigned long long quad = quad_base + ((row_off + 4 * P2_TPR * k) >> 2);
-                    const float4 n4 = philox_normal4_rk((unsigned int)quad, (unsigned int)(quad >> 32), off_lo, off_hi, f.rk);
-                    nz[0] = n4.x; nz[1] = n4.y; nz[2] = n4.z; nz[3] = n4.w;
-                  }
-                }
-                const float z[4] = {z4.x, z4.y, z4.z, z4.w};
-                const float xt[4] = {t4.x, t4.y, t4.z, t4.w};
-                float cf[4], o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const bool ok = !MASKED || (row_ok && ((tmbits >> (4 * k + e)) & 1u));
-                  const float zz = ok ? (z[e] - shift) : -INFINITY;
-                  const float la = ((zz + ui) + vj[k][e]) - bc.norm;  // same association as matching.py:34-36
-                  cf[e] = ex2(la * LOG2E);
-                  if (DDIM) o[e] = ok ? fmaf(f.k_x0, cf[e], fmaf(f.k_xt, xt[e] - xt_shift, f.sigma * nz[e])) : -INFINITY;
-                  else o[e] = cf[e];
-                }
-                *reinterpret_cast<float4*>(out_r + 4 * P2_TPR * k) = make_float4(o[0], o[1], o[2], o[3]);
-                if (DDIM && conf_b) *reinterpret_cast<float4*>(conf_b + row_off + 4 * P2_TPR * k) = make_float4(cf[0], cf[1], cf[2], cf[3]);
-                // arg-max keys: only entries above the floor (a row of the plan sums to <= 1: a handful per row) -- straight
-                // to the packed 64-bit keys with atomicMax (largest value, then lowest index)
-                if (track && fmaxf(fmaxf(cf[0], cf[1]), fmaxf(cf[2], cf[3])) > floor_v) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    if (cf[e] > floor_v) {
-                      const unsigned long long hi = (unsigned long long)float_to_ordered(cf[e]) << 32;
-                      atomicMax(&f.rowbest[(size_t)b * N + i], hi | (unsigned long long)(0xFFFFFFFFu - (unsigned int)(c + e)));
-                      atomicMax(&f.colbest[(size_t)b * M + c + e], hi | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i));
-                    }
-                  }
-                }
+            for (int e = 0; e < 4; ++e) {
+              const bool ok = !MASKED || (row_ok && p.tgt_mask[(size_t)b * M + c + e]);
+              const float zz = ok ? (z[e] - shift) : -INFINITY;
+              const float cfe = ex2((((zz + ui) + vv[e]) - bc.norm) * LOG2E);
+              if (cfe > floor_v) {
+                const unsigned long long hi = (unsigned long long)float_to_ordered(cfe) << 32;
+                atomicMax(&f.rowbest[(size_t)b * N + i], hi | (unsigned long long)(0xFFFFFFFFu - (unsigned int)(c + e)));
+                atomicMax(&f.colbest[(size_t)b * M + c + e], hi | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i));
               }
             }
           }
@@ -1896,12 +1926,22 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
         }
       }
     };
+    using T_ = std::true_type;
+    using F_ = std::false_type;
+    using N0 = std::integral_constant<int, 0>;
+    using N1 = std::integral_constant<int, 1>;
+    using N2 = std::integral_constant<int, 2>;
+    const int noise_mode = !f_ddim ? 0 : noise_b ? 1 : f.gen_noise ? 2 : 0;
     if (masked) {
-      if (f_ddim) body(std::true_type{}, std::true_type{});
-      else body(std::true_type{}, std::false_type{});
+      if (!f_ddim) body(T_{}, F_{}, N0{});
+      else if (noise_mode == 2) body(T_{}, T_{}, N2{});
+      else if (noise_mode == 1) body(T_{}, T_{}, N1{});
+      else body(T_{}, T_{}, N0{});
     } else {
-      if (f_ddim) body(std::false_type{}, std::true_type{});
-      else body(std::false_type{}, std::false_type{});
+      if (!f_ddim) body(F_{}, F_{}, N0{});
+      else if (noise_mode == 2) body(F_{}, T_{}, N2{});
+      else if (noise_mode == 1) body(F_{}, T_{}, N1{});
+      else body(F_{}, T_{}, N0{});
     }
     if (tid == 0) DRG_STAMP(751);
   }
