@@ -16,9 +16,10 @@ Each GPU runs its own independent sample (weak scaling, no collective on the dat
 Printed JSON line (rank 0): value = steps/s with inputs resident in HBM (CUDA-graph replay of the 20 step
 graphs); e2e = the same step driven through the public modules with HOST (pinned) inputs copied in and the
 step's results (pose, match count, matches) copied out every step; roofline = the dominant kernel (the persistent
-Sinkhorn) timed with CUDA events inside an eager pass over the same steps; cpu_baseline = the reference on the host;
+Sinkhorn launch that carries the whole log_optimal_transport + DDIM call) timed with CUDA events inside an eager pass over the
+same steps; cpu_baseline = the reference on the host;
 rowshard = BASELINE.json configs[4] (N=M=16384, 100 iterations; rows sharded over the N ranks); other_configs =
-configs[0], [1], [3] timed once each (N=1 only).  `config` is identical in both arms; how a run was timed is in `run_info`.
+configs[0], [1], [3] timed once each and one forward of the denoising transformer drop-in (N=1 only).  `config` is identical in both arms; how a run was timed is in `run_info`.
 """
 import argparse
 import json
@@ -393,17 +394,19 @@ def run_ours(args):
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
 
     def e2e_run(first, count):
-        # the host runs one step ahead: step i + 1 is enqueued (and step i + 2's input copy behind it) before step i's
-        # results are awaited, so the GPU never idles while the host wakes up and reads a result
+        # the host runs two steps ahead: steps i + 1 and i + 2 (each behind its own input copy) are enqueued before step i's
+        # results are awaited, so the GPU does not idle while the host wakes up and reads a result -- or misses a beat
         end = first + count
         pipe.prefetch(first)
         pipe.launch(first)
-        pipe.prefetch(first + 1)
+        if first + 1 < end:
+            pipe.prefetch(first + 1)
+            pipe.launch(first + 1)
         last = None
         for i in range(first, end):
-            if i + 1 < end:
-                pipe.launch(i + 1)
-                pipe.prefetch(i + 2)
+            if i + 2 < end:
+                pipe.prefetch(i + 2)      # waits (on the device) for step i, the last reader of that input set
+                pipe.launch(i + 2)
             last = int(pipe.finish(i)["count"][0])
         return last
 
@@ -412,9 +415,28 @@ def run_ours(args):
         for k_ in st_:
             st_[k_].copy_(host[k_])
     pipe.reset(d["x_T"])
-    w2 = max(args.warmup, 3)
+    # untimed warm-up of the host-driven loop: the first ~50 ms of stepping from host buffers run measurably slower than the
+    # steady state (measured: 40-step repetitions of 20.9, 16.5, 14.9, 13.6, 13.6 ms -- pinned-buffer / link / host-thread
+    # warm-up, not GPU clocks), so the loop runs for a few repetitions' worth of steps before anything is timed
+    w2 = max(args.warmup, 3, 4 * args.steps)
+    w2 += w2 % 2            # (keep the step parity of the timed repetitions)
     e2e_run(0, w2)
     torch.cuda.synchronize()
+    # ... and, in the first process on a fresh box, the ramp lasts longer than that (measured: 20-step repetitions of 10.9 ms
+    # falling to 8.4 ms over 0.3 s and still falling, against a steady 6.9 ms in the next process on the same box -- the
+    # host <-> device link coming out of its idle state): keep stepping, untimed, until two consecutive repetitions agree to
+    # 2 %, for at most ~3 s
+    prev, spent = None, 0.0
+    while spent < 3.0:
+        t0 = time.perf_counter()
+        e2e_run(w2, args.steps + args.steps % 2)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        spent += dt
+        w2 += args.steps + args.steps % 2
+        if prev is not None and abs(dt - prev) <= 0.02 * prev:
+            break
+        prev = dt
     # K steps per repetition, E2E_REPS repetitions, the MEDIAN is reported (K = 20 steps are ~7 ms of wall clock: one host
     # hiccup would move a single measurement by percent); every repetition is bracketed like the timed region above
     e2e_reps = []
@@ -546,7 +568,7 @@ def run_ours(args):
                              "precision": args.precision, "noise": "in-kernel Philox4x32-7"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "h2d_copies_per_step": 1, "repetitions_s": [round(x, 6) for x in e2e_reps], "statistic": "median of repetitions",
-                        "host_runs_ahead_steps": 1},
+                        "host_runs_ahead_steps": 2},
                 "gpu_launches": int(e2e_launches * world), "launches_per_step": int(launches_per_step),
                 "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "kernel_ms_per_step": kernel_ms,
                 "rowshard": rowshard, "other_configs": other}
@@ -555,7 +577,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-E2E_REPS = 5
+E2E_REPS = 7
 
 
 def _event_ms(torch, fn, reps, dist=None, dev=None):
@@ -687,6 +709,34 @@ def bench_other_configs(torch, dev):
     out["config3"] = {"workload": "configs[3]: 2D-3D flavour N=4800 x M=2048, d=256, arbitrary masks, 10 sampler steps + final Sinkhorn + "
                                   "mutual_topk_select(k=1, mutual=False), eager launches",
                       "ms_per_sample": ms, "steps_per_s": 1e3 * 10 / ms}
+    del dd, pb, x_T
+    # widening: the denoising transformer of pipeline.py:84-85 -- six self / cross geometry attention layers at
+    # the real 4DMatch width C = 528 (4 heads of 132), rotary code, N = M = 4096 points.  Not part of the metric's step (the
+    # headline holds the features fixed); reported so that the cost of the other half of a full reverse step is known.
+    try:
+        class _Cfg(dict):
+            __getattr__ = dict.__getitem__
+        bnds = [[-3.6, -2.4, 1.14], [1.093, 0.78, 2.92]]
+        tcfg = _Cfg(feature_dim=528, n_head=4, layer_types=["self", "cross"] * 3, positioning_type="procrustes", pe_type="rotary",
+                    entangled=False, vol_bnds=bnds, voxel_size=0.04)
+        g = torch.Generator().manual_seed(5000)
+        lo, hi = torch.tensor(bnds[0]), torch.tensor(bnds[1])
+        sp = (lo + (hi - lo) * torch.rand(1, N_PTS, 3, generator=g)).to(dev)
+        tp = (lo + (hi - lo) * torch.rand(1, N_PTS, 3, generator=g)).to(dev)
+        sf, tf = torch.randn(1, N_PTS, 528, generator=g).to(dev), torch.randn(1, N_PTS, 528, generator=g).to(dev)
+        mk = torch.ones(1, N_PTS, dtype=torch.bool, device=dev)
+        net = diffreg_b200.RepositioningTransformer(tcfg).to(dev).eval()
+        fnt = lambda: net(sf, tf, sp, tp, mk, mk, {})
+        fnt()
+        c0 = diffreg_b200.launch_count()
+        fnt()
+        launches = diffreg_b200.launch_count() - c0
+        ms = _event_ms(torch, fnt, 3)
+        out["denoising_transformer"] = {"workload": "SURVEY 8f rank 2 (not in the metric): RepositioningTransformer, 6 self / cross geometry "
+                                                    "attention layers, C=528, 4 heads, rotary code, N=M=4096, one forward (both directions of every layer)",
+                                        "ms_per_forward": ms, "kernel_launches": int(launches)}
+    except Exception as e:  # noqa: BLE001 -- an extra line, never the reason a bench run fails
+        out["denoising_transformer"] = {"error": str(e)[:200]}
     return out
 
 

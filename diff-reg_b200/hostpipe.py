@@ -15,10 +15,12 @@ into pinned host buffers before `finish` returns.
     for i in range(steps):
         pipe.launch(i)                         # graph replay + result copies on the compute stream
         pipe.prefetch(i + 1)                   # one H2D copy, overlaps step i (staging(i + 1) filled by the caller)
-        out = pipe.finish(i)                   # waits for step i only; pinned host tensors, valid until launch(i + 2)
+        out = pipe.finish(i)                   # waits for step i only; pinned host tensors, valid until launch(i + 3)
 
-launch(i + 1) may be issued before finish(i) (the two input sets, state buffers and result buffers are double-buffered
-for exactly that): the host then runs one step ahead and the GPU never waits for the host's wake-up after a result.
+launch(i + 1) and launch(i + 2) may be issued before finish(i): the input sets and state buffers are double-buffered
+(prefetch(i + 2) waits on the device for step i, the last reader of its set) and the result buffers are three deep, so
+the host can run up to TWO steps ahead and a host hiccup of a whole step time does not idle the GPU.  Order per step:
+prefetch(j) before launch(j).
 
 The step index selects the DDIM time pair (i mod sampler.steps); consecutive steps alternate between the two
 input sets and between the two state buffers, which is why sampler.steps must be even when graphs are used.
@@ -70,7 +72,7 @@ class HostStepPipeline:
                           "condition": torch.empty(1, dtype=torch.float64).pin_memory(),
                           "count": torch.empty(1, dtype=torch.int32).pin_memory(),
                           "index": torch.empty(cap, 3, dtype=torch.int64).pin_memory(),
-                          "mconf": torch.empty(cap).pin_memory()} for _ in range(2)]
+                          "mconf": torch.empty(cap).pin_memory()} for _ in range(3)]
         self.h2d_bytes = self.packed_bytes        # what one prefetch moves (the six tensors + < 1.5 KB of alignment padding)
         self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.host_out[0].values())
         self.compute = torch.cuda.Stream(device=self.dev)
@@ -78,7 +80,7 @@ class HostStepPipeline:
         self.out = torch.cuda.Stream(device=self.dev) if results_stream else self.compute   # device -> host (results)
         self.ev_in = [torch.cuda.Event(), torch.cuda.Event()]
         self.ev_free = [torch.cuda.Event(), torch.cuda.Event()]
-        self.ev_out = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ev_out = [torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()]
         self.graphs = None
         self.aux = [None] * sampler.steps
         if use_graphs:
@@ -157,22 +159,22 @@ class HostStepPipeline:
         with torch.cuda.stream(self.out):
             self.out.wait_event(self.ev_free[i % 2])
             index, mconf, _, count = aux["match"]
-            ho = self.host_out[i % 2]
+            ho = self.host_out[i % 3]
             ho["R"].copy_(aux["pose"]["R_forwd"], non_blocking=True)
             ho["t"].copy_(aux["pose"]["t_forwd"], non_blocking=True)
             ho["condition"].copy_(aux["pose"]["condition"], non_blocking=True)
             ho["count"].copy_(count, non_blocking=True)
             ho["index"].copy_(index, non_blocking=True)
             ho["mconf"].copy_(mconf, non_blocking=True)
-            self.ev_out[i % 2].record(self.out)
+            self.ev_out[i % 3].record(self.out)
             if self.graphs is None:
                 for t_ in (aux["pose"]["R_forwd"], aux["pose"]["t_forwd"], aux["pose"]["condition"], count, index, mconf):
                     t_.record_stream(self.out)
 
     def finish(self, i):
-        """Wait for step i's results; returns a dict of pinned host tensors (valid until launch(i + 2))."""
-        self.ev_out[i % 2].synchronize()
-        return self.host_out[i % 2]
+        """Wait for step i's results; returns a dict of pinned host tensors (valid until launch(i + 3))."""
+        self.ev_out[i % 3].synchronize()
+        return self.host_out[i % 3]
 
     def state(self, i):
         """The device state x after step i-1 (input of step i)."""

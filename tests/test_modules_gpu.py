@@ -329,6 +329,21 @@ def test_host_step_pipeline_matches_direct_steps():
         assert torch.equal(out["R"], R) and torch.equal(out["t"], t)
         assert torch.equal(out["index"][:n], idx) and torch.equal(out["mconf"][:n], mconf)
     assert torch.equal(pipe.state(STEPS), x_direct)
+    # the host two steps ahead (what bench.py's e2e loop does): prefetch(j) + launch(j) for j = i + 2 before finish(i)
+    pipe.counter.zero_()
+    pipe.reset(x_T)
+    for j in range(2):
+        pipe.prefetch(j)
+        pipe.launch(j)
+    for i in range(STEPS):
+        if i + 2 < STEPS:
+            pipe.prefetch(i + 2)
+            pipe.launch(i + 2)
+        out = pipe.finish(i)
+        R, t, n, idx, mconf = want[i]
+        assert int(out["count"][0]) == n and torch.equal(out["R"], R) and torch.equal(out["t"], t)
+        assert torch.equal(out["index"][:n], idx) and torch.equal(out["mconf"][:n], mconf)
+    assert torch.equal(pipe.state(STEPS), x_direct)
     payload = sum(v.numel() * v.element_size() for v in pinned.values())
     assert payload <= pipe.h2d_bytes < payload + 6 * 256               # the six tensors + alignment padding, one copy
 
