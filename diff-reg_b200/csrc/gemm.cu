@@ -11,7 +11,7 @@
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8),
 //               four per k-step, accumulating in TMEM; tcgen05.commit releases the smem stage and,
 //               after the last k-step, publishes the accumulator to the epilogue
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), scale, swizzled st.shared,
+//   warps 2..9  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), scale, swizzled st.shared,
 //               TMA tensor store of 32 x 32 boxes (clipped at the matrix edge by the TMA unit)
 // Two TMEM accumulator stages (2 x BN columns) let the MMA of tile t+1 overlap the epilogue of t.
 //
@@ -33,7 +33,8 @@ namespace drg {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 32;  // fp32 elements per k-step: 128 bytes = one swizzle-atom row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quadrant (they split the tile's 32-column chunks)
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 4;  // 16 KB
 constexpr int GEMM_OUT_BOX_BYTES = 32 * 32 * 4;            // one epilogue box: 32 rows x 32 columns
 constexpr int GEMM_MAX_STAGES = 8;
@@ -51,6 +52,23 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* 
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the same load delivered to the same shared-memory offset of every CTA of the cluster named in cta_mask (and signalling the
+// mbarrier at the same offset in each of them)
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;"
+      :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 template <int N>
 __device__ __forceinline__ void bulk_wait_group_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -99,6 +117,12 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // arrive on an mbarrier once all tcgen05.mma issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same arrival on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 // 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = lane = accumulator row)
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -190,7 +214,13 @@ struct GemmShape {
 // kc 16-bit columns.  A stage holds the four tiles A_lo, A_hi, B_hi, B_lo of one 64-column k-step (128-byte rows, the same
 // tile geometry and swizzle as the fp32 mode) and the MMA warp issues lo.hi, hi.lo, hi.hi (kind::f16, K = 16, four each
 // per k-step) from them.
-template <int BN, bool SPLIT3>
+// MC (launched as clusters of two CTAs): the two CTAs of a cluster work on the two 128-row tiles (2p, 2p + 1) of the SAME
+// column block, so they need the same B tile: each loads half of its rows and multicasts them into both CTAs' shared memory
+// (cp.async.bulk.tensor ... .multicast::cluster).  A third less operand traffic from L2 per tile -- the kernel runs at the
+// L2 -> SM rate (ncu: 244 MB over the crossbar in 38 us = 6.3 TB/s against ~8-9.6 TB/s for a pure L2 stream,
+// profiles/r1_stream_l2_microbench.log, while also writing the output).  A stage is refilled by BOTH CTAs, so it is free only
+// when both have consumed it: the MMA warp's tcgen05.commit arrives on the stage's "empty" barrier of both CTAs (count 2).
+template <int BN, bool SPLIT3, bool MC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS,
@@ -216,7 +246,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint8_t* sB = sA + (size_t)nstage * A_STAGE_BYTES;
   uint8_t* sOut = sB + (size_t)nstage * B_STAGE_BYTES;  // [4 warps][2][4 KB]
 
-  const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM;
+  // MC: the units below are PAIRS of vertically adjacent tiles (the host guarantees an even number of row blocks); this CTA
+  // takes row block 2 * mb + rank of a pair
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
+  const int first_unit = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tiles_m = MC ? ((s.N + GEMM_BM - 1) / GEMM_BM) / 2 : (s.N + GEMM_BM - 1) / GEMM_BM;
   const int tiles_n = (s.M + BN - 1) / BN;
   const int tiles = s.batch * tiles_m * tiles_n;
   constexpr int KSTEP = SPLIT3 ? 64 : GEMM_BK;   // operand columns per k-step: 128 bytes either way
@@ -232,27 +267,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     mb = rem / tiles_n;
     const int nb = rem - mb * tiles_n;
     n0 = nb * BN + ((narrow && ((unit - s.wide_tiles) & 1)) ? BN / 2 : 0);
+    if (MC) mb = 2 * mb + (int)crank;
   };
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    if (s.wide_tiles < tiles) prefetch_tmap(&tmBh);
+    if (MC || s.wide_tiles < tiles) prefetch_tmap(&tmBh);
     if (!s.direct_store) prefetch_tmap(&tmC);
     if (s.split_tma) prefetch_tmap(&tmS);
     for (int i = 0; i < nstage; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], MC ? 2 : 1);   // MC: released by the MMA warps of both CTAs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[i], GEMM_EPI_WARPS);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_slot);
   tcgen05_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();   // the peer's barriers are initialised before anything of ours can reach them
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -261,7 +298,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      for (int unit = first_unit; unit < units; unit += unit_stride) {
         int b, mb, n0;
         bool narrow;
         decode(unit, b, mb, n0, narrow);
@@ -273,10 +310,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           uint8_t* a_dst = sA + (size_t)stage * A_STAGE_BYTES;
           uint8_t* b_dst = sB + (size_t)stage * B_STAGE_BYTES;
           tma_load_3d(a_dst, &tmA, k * KSTEP, mb * GEMM_BM, b, &full_bar[stage]);   // SPLIT3: A_lo
-          tma_load_3d(b_dst, tb, k * KSTEP, n0, b, &full_bar[stage]);               // SPLIT3: B_hi
-          if (SPLIT3) {
-            tma_load_3d(a_dst + GEMM_A_STAGE_BYTES, &tmA, s.kc + k * KSTEP, mb * GEMM_BM, b, &full_bar[stage]);  // A_hi
-            tma_load_3d(b_dst + B_TILE_BYTES, tb, s.kc + k * KSTEP, n0, b, &full_bar[stage]);                    // B_lo
+          if (SPLIT3) tma_load_3d(a_dst + GEMM_A_STAGE_BYTES, &tmA, s.kc + k * KSTEP, mb * GEMM_BM, b, &full_bar[stage]);  // A_hi
+          if (MC && !narrow) {
+            // this CTA's half of the B tile's rows, into both CTAs (tmBh boxes are BN / 2 rows high)
+            const int r0 = n0 + (int)crank * (BN / 2);
+            uint8_t* dst = b_dst + (size_t)crank * (B_TILE_BYTES / 2);
+            tma_load_3d_mc(dst, &tmBh, k * KSTEP, r0, b, &full_bar[stage], (uint16_t)3);                               // B_hi
+            if (SPLIT3) tma_load_3d_mc(dst + B_TILE_BYTES, &tmBh, s.kc + k * KSTEP, r0, b, &full_bar[stage], (uint16_t)3);  // B_lo
+          } else {
+            tma_load_3d(b_dst, tb, k * KSTEP, n0, b, &full_bar[stage]);               // SPLIT3: B_hi
+            if (SPLIT3) tma_load_3d(b_dst + B_TILE_BYTES, tb, s.kc + k * KSTEP, n0, b, &full_bar[stage]);  // B_lo
           }
           if (++stage == nstage) {
             stage = 0;
@@ -296,7 +339,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      for (int unit = first_unit; unit < units; unit += unit_stride) {
         const int nw = unit >= s.wide_tiles ? 1 : 0;
         const uint32_t idesc = nw ? idesc_half : idesc_wide;
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
@@ -325,7 +368,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               umma_tf32(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (uint32_t)((k | kk) != 0));
             }
           }
-          umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs have read it
+          if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // ... in both CTAs: either may refill (its half of) the stage
+          else umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs have read it
           if (++stage == nstage) {
             stage = 0;
             phase ^= 1u;
@@ -337,12 +381,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read: lanes 32q .. 32q+31
-    uint8_t* stg = sOut + (size_t)q * 2 * GEMM_OUT_BOX_BYTES;
+    // ===================== epilogue (warps 2..9) =====================
+    // Eight warps: a warp may read the TMEM lane quadrant (warp % 4) only, so two warps share a quadrant and take alternate
+    // 32-column chunks of the tile.  With four warps a 128 x 256 tile was 8 boxes per warp at ~2.5 k cycles each (tcgen05.ld,
+    // scale, st.shared, proxy fence, TMA store, wait for the staging buffer): 20 k cycles per tile against 11 k for the tile's
+    // main loop -- the epilogue, not the operand traffic, set the pace (ncu: tensor pipe 31 % of elapsed, L2 -> SM at half the
+    // fabric rate, the single-pass tf32 kernel with half the MMAs exactly as slow).
+    const int ew = warp - 2;
+    const int q = warp & 3;   // TMEM lane quadrant this warp may read: lanes 32q .. 32q+31
+    const int half = ew >> 2; // which of the quadrant's two warps
+    uint8_t* stg = sOut + (size_t)ew * GEMM_OUT_BOX_BYTES;   // one 4 KB staging box per warp
     int as = 0;
     uint32_t aphase = 0;
-    int buf = 0;
     // SPLIT3: the operands' row tails.  op_pitch in 16-bit units; tail floats: [0] = 1 / row scale, [1] = row norm
     const int op_pitch = 2 * s.kc + 8;
     auto tail_of = [&](const unsigned short* op, size_t row) { return reinterpret_cast<const float*>(op + row * op_pitch + 2 * s.kc); };
@@ -351,7 +401,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       for (int j = lane; j < s.M; j += 32) wmax = fmaxf(wmax, tail_of(s.B16, (size_t)j)[1]);
       wmax = warp_max(wmax);
     }
-    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    for (int unit = first_unit; unit < units; unit += unit_stride) {
       int b, mb, n0;
       bool narrow;
       decode(unit, b, mb, n0, narrow);
@@ -375,7 +425,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_wait(&tmem_full_bar[as], aphase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = half; c < nchunks; c += 2) {
         const int col0 = n0 + c * 32;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
@@ -407,7 +457,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           // row-major) are staged in this warp's two buffers and leave as two TMA tensor stores into the split operand
           const float sc = s.alpha * s.split_scale * sc_out;
           uint8_t* hi_box = stg;
-          uint8_t* lo_box = stg + GEMM_OUT_BOX_BYTES;
+          uint8_t* lo_box = stg + GEMM_OUT_BOX_BYTES / 2;   // (16-bit boxes are 2 KB each)
           if (lane == 0) bulk_wait_group_read<0>();  // the previous chunk's stores have finished reading both buffers
           __syncwarp();
 #pragma unroll
@@ -449,10 +499,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
           if (s.C == nullptr) continue;
         }
-        uint8_t* box = stg + (size_t)buf * GEMM_OUT_BOX_BYTES;
+        uint8_t* box = stg;
         if (!s.direct_store) {
-          // the TMA store issued two boxes ago from this buffer must have finished READING it
-          if (lane == 0) bulk_wait_group_read<1>();
+          // the TMA store of this warp's previous box must have finished READING the buffer (it was issued before the
+          // tcgen05.ld and the scaling of this box: the wait is short)
+          if (lane == 0) bulk_wait_group_read<0>();
           __syncwarp();
         }
         // 128B-swizzled staging: row = lane, 16-byte chunk j lands at chunk j ^ (lane & 7)
@@ -486,7 +537,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
           __syncwarp();
         }
-        buf ^= 1;
       }
       // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
       tcgen05_fence_before();
@@ -500,6 +550,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   tcgen05_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   tcgen05_fence_after();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
@@ -549,7 +600,7 @@ template <int BN, bool SPLIT3>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tS,
                        const CUtensorMap& tBh, GemmShape s, cudaStream_t st) {
   constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (GEMM_A_STAGE_BYTES + BN * GEMM_BK * 4);
-  const size_t out_bytes = 4 * 2 * GEMM_OUT_BOX_BYTES;
+  const size_t out_bytes = (size_t)GEMM_EPI_WARPS * GEMM_OUT_BOX_BYTES;
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - out_bytes - 256 /*static*/;
   int nstage = (int)(budget / STAGE_BYTES);
   if (nstage > GEMM_MAX_STAGES) nstage = GEMM_MAX_STAGES;
@@ -558,8 +609,39 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   if (nstage < 2) nstage = 2;
   s.nstage = nstage;
   const size_t smem = 1024 + (size_t)nstage * STAGE_BYTES + out_bytes;
-  DRG_CUDA((cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM, tiles_n = (s.M + BN - 1) / BN;
+  // Two-CTA clusters sharing the B tile (kernel template MC): split operands, wide tiles, an even number of row blocks, a
+  // B operand worth sharing (a weight of a few hundred rows is not) and no split epilogue.
+  const bool mc = SPLIT3 && BN >= 128 && tiles_m >= 2 && (tiles_m % 2) == 0 && s.split_out == nullptr && s.M >= 2 * BN;
+  if (mc) {
+    if constexpr (SPLIT3 && BN >= 128) {
+      DRG_CUDA((cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+      const long long pairs = (long long)s.batch * (tiles_m / 2) * tiles_n;
+      const int nclusters = (int)(pairs < NUM_SMS / 2 ? pairs : NUM_SMS / 2);
+      const int rem = (int)(pairs % nclusters);
+      s.wide_tiles = (int)pairs;   // (counted in pairs of tiles in this mode)
+      if (pairs > nclusters && rem > 0 && 2 * rem <= nclusters) s.wide_tiles = (int)pairs - rem;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * nclusters);
+      cfg.blockDim = dim3(GEMM_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      {
+        ProfScope prof_scope(PROF_GEMM, st);
+        DRG_CUDA((cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, SPLIT3, true>, tA, tB, tC, tS, tBh, s)));
+      }
+      DRG_LAUNCH_CHECK();
+      return DRG_OK;
+    }
+  }
+  DRG_CUDA((cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   const long long tiles = (long long)s.batch * tiles_m * tiles_n;
   const int grid = (int)(tiles < NUM_SMS ? tiles : NUM_SMS);
   // Tail balancing: with `rem` tiles left for the last, partial wave of the persistent grid, the wave costs a full tile
@@ -570,7 +652,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   if (BN >= 128 && tiles > grid && rem > 0 && 2 * rem <= grid) s.wide_tiles = (int)tiles - rem;
   {
     ProfScope prof_scope(PROF_GEMM, st);
-    gemm_tf32_kernel<BN, SPLIT3><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tS, tBh, s);
+    gemm_tf32_kernel<BN, SPLIT3, false><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tS, tBh, s);
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
