@@ -19,6 +19,7 @@ ap.add_argument("--size", type=int, default=16384)
 ap.add_argument("--iters", type=int, default=100)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+ap.add_argument("--profile", action="store_true", help="rank 0 also prints the average device time of every kernel of one call (CUPTI)")
 args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -53,6 +54,21 @@ for _ in range(args.reps):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     times.append(float(t.item()))
 ms = sorted(times)[len(times) // 2]
+if args.profile:
+    from collections import defaultdict
+    from torch.profiler import profile, ProfilerActivity
+    dist.barrier(); torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        op(scores, alpha, args.iters, src_mask, tgt_mask, out_mode="conf")
+        torch.cuda.synchronize()
+    if rank == 0:
+        tot, cnt = defaultdict(float), defaultdict(int)
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                nm = ev.name.split("(")[0][:60]
+                tot[nm] += ev.device_time; cnt[nm] += 1
+        for nm in sorted(tot, key=lambda k: -tot[k]):
+            print(f"[profile] {tot[nm]:10.1f} us  {cnt[nm]:5d} launches  {tot[nm] / cnt[nm]:8.1f} us each  {nm}", file=sys.stderr, flush=True)
 # the two exchange paths must agree (same arithmetic up to the order of the P-way combine)
 other = D.RowShardedSinkhorn(exchange="nccl" if args.exchange == "p2p" else "p2p")
 ref = other(scores, alpha, min(args.iters, 10), src_mask, tgt_mask, out_mode="conf")
