@@ -60,6 +60,23 @@ __device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* tm,
       :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(cta_mask)
       : "memory");
 }
+// cta_group::2 form: the load lands in THIS CTA's shared memory and signals the mbarrier `bar_cluster_addr`, a shared::cluster
+// address that may name the peer CTA's barrier (the pair's MMA issuer waits on one barrier for both CTAs' tiles)
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster_addr)
+      : "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -117,6 +134,33 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // arrive on an mbarrier once all tcgen05.mma issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem of both CTAs] (+)= A . B^T as ONE 256 x N MMA of a CTA pair: each CTA holds 128 rows of A and N / 2 rows of B at the
+// same shared-memory offsets, each CTA's TMEM receives its 128 rows of D.  Issued by one thread of the pair's leader CTA.
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of the pair's MMAs, arriving on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot_in_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 // the same arrival on the mbarrier at this offset in every CTA of cta_mask
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
@@ -191,7 +235,7 @@ struct GemmShape {
   float alpha;
   int nstage;
   int split_tma;     // 1: the split epilogue stages hi / lo boxes in shared memory and writes them with TMA stores (tmS)
-  int direct_store;  // 1: C row pitch not TMA-storable (M % 4 != 0) -> coalesced st.global from the staging tile
+  int direct_store;  // 1: C rows not 16-byte aligned (M % 4 != 0) -> scalar st.global from the staging tile; 0: st.global.v4
   int kc;            // SPLIT kernels: 16-bit columns of ONE operand segment (the operand rows are [seg0 | seg1 | tail], pitch
                      //   2 * kc + 8; kc = K rounded up to 64, the padding holds zeros), a multiple of 64 = one 128-byte k-step
   const unsigned short* A16;  // SPLIT kernels: the operands themselves, for the row tails (1 / scale, norm) the epilogue reads
@@ -220,12 +264,19 @@ struct GemmShape {
 // L2 -> SM rate (ncu: 244 MB over the crossbar in 38 us = 6.3 TB/s against ~8-9.6 TB/s for a pure L2 stream,
 // profiles/r1_stream_l2_microbench.log, while also writing the output).  A stage is refilled by BOTH CTAs, so it is free only
 // when both have consumed it: the MMA warp's tcgen05.commit arrives on the stage's "empty" barrier of both CTAs (count 2).
-template <int BN, bool SPLIT3, bool MC>
+// MODE 2 (PAIR, clusters of two CTAs as well): the pair runs ONE tcgen05.mma.cta_group::2 of 256 x BN per step -- each CTA holds
+// its 128 rows of A and only HALF of the B tile's rows (the tensor core reads the other half out of the peer's shared memory), so
+// a CTA takes in 64 KB instead of 96 KB per k-step and three stages fit instead of two.  The leader CTA's MMA warp issues for
+// the pair; both CTAs' TMA loads signal the leader's "full" barrier; its commits arrive on both CTAs' "empty" / "accumulator
+// full" barriers, and both CTAs' epilogue warps arrive on the leader's "accumulator empty" barrier.
+template <int BN, bool SPLIT3, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS,
-                     const __grid_constant__ CUtensorMap tmBh, const GemmShape s) {
-  constexpr int B_TILE_BYTES = BN * GEMM_BK * 4;
+                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBq, const GemmShape s) {
+  constexpr bool MC = MODE == 1, PAIR = MODE == 2, CL = MODE != 0;
+  static_assert(!PAIR || (SPLIT3 && BN == 256), "pair mode: split operands, 256-wide tiles");
+  constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 4;   // PAIR: this CTA's half of the tile's rows
   constexpr int A_STAGE_BYTES = (SPLIT3 ? 2 : 1) * GEMM_A_STAGE_BYTES;
   constexpr int B_STAGE_BYTES = (SPLIT3 ? 2 : 1) * B_TILE_BYTES;
   constexpr int TMEM_COLS = 2 * BN;  // 128, 256 or 512: a power of two >= 32
@@ -248,10 +299,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   // MC: the units below are PAIRS of vertically adjacent tiles (the host guarantees an even number of row blocks); this CTA
   // takes row block 2 * mb + rank of a pair
-  const uint32_t crank = MC ? cluster_ctarank() : 0u;
-  const int first_unit = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_stride = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int tiles_m = MC ? ((s.N + GEMM_BM - 1) / GEMM_BM) / 2 : (s.N + GEMM_BM - 1) / GEMM_BM;
+  const uint32_t crank = CL ? cluster_ctarank() : 0u;
+  const int first_unit = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tiles_m = CL ? ((s.N + GEMM_BM - 1) / GEMM_BM) / 2 : (s.N + GEMM_BM - 1) / GEMM_BM;
   const int tiles_n = (s.M + BN - 1) / BN;
   const int tiles = s.batch * tiles_m * tiles_n;
   constexpr int KSTEP = SPLIT3 ? 64 : GEMM_BK;   // operand columns per k-step: 128 bytes either way
@@ -267,29 +318,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     mb = rem / tiles_n;
     const int nb = rem - mb * tiles_n;
     n0 = nb * BN + ((narrow && ((unit - s.wide_tiles) & 1)) ? BN / 2 : 0);
-    if (MC) mb = 2 * mb + (int)crank;
+    if (CL) mb = 2 * mb + (int)crank;
   };
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    if (MC || s.wide_tiles < tiles) prefetch_tmap(&tmBh);
-    if (!s.direct_store) prefetch_tmap(&tmC);
+    if (CL || s.wide_tiles < tiles) prefetch_tmap(&tmBh);
+    if (PAIR && s.wide_tiles < tiles) prefetch_tmap(&tmBq);
     if (s.split_tma) prefetch_tmap(&tmS);
     for (int i = 0; i < nstage; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], MC ? 2 : 1);   // MC: released by the MMA warps of both CTAs
+      mbar_init(&empty_bar[i], MC ? 2 : 1);   // MC: released by the MMA warps of both CTAs (PAIR: one commit of the leader, multicast)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], GEMM_EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[i], PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);  // one arrival per epilogue warp (PAIR: of both CTAs, on the leader's)
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_slot);
+  if (PAIR) {
+    __syncthreads();
+    cluster_sync_all();           // both CTAs are resident and their barriers initialised before the pair allocates TMEM together
+    if (warp == 1) tmem_alloc_2sm<TMEM_COLS>(&tmem_base_slot);
+  } else if (warp == 1) {
+    tmem_alloc<TMEM_COLS>(&tmem_base_slot);
+  }
   tcgen05_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();   // the peer's barriers are initialised before anything of ours can reach them
+  if (CL) cluster_sync_all();   // the peer's barriers are initialised before anything of ours can reach them
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -306,9 +363,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const uint32_t bytes = (uint32_t)(A_STAGE_BYTES + (narrow ? B_STAGE_BYTES / 2 : B_STAGE_BYTES));
         for (int k = 0; k < kblocks; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], bytes);
           uint8_t* a_dst = sA + (size_t)stage * A_STAGE_BYTES;
           uint8_t* b_dst = sB + (size_t)stage * B_STAGE_BYTES;
+          if (PAIR) {
+            // both CTAs' tiles are accounted on the LEADER's barrier (the leader expects the bytes of both)
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * bytes);
+            const uint32_t lbar = map_to_cta(&full_bar[stage], 0u);
+            const int rows_b = narrow ? BN / 4 : BN / 2;          // this CTA's half of the (narrow: half-width) B tile
+            const CUtensorMap* tbp = narrow ? &tmBq : &tmBh;
+            const int r0 = n0 + (int)crank * rows_b;
+            tma_load_3d_2sm(a_dst, &tmA, k * KSTEP, mb * GEMM_BM, b, lbar);                                   // A_lo
+            tma_load_3d_2sm(a_dst + GEMM_A_STAGE_BYTES, &tmA, s.kc + k * KSTEP, mb * GEMM_BM, b, lbar);       // A_hi
+            tma_load_3d_2sm(b_dst, tbp, k * KSTEP, r0, b, lbar);                                             // B_hi (half)
+            tma_load_3d_2sm(b_dst + B_TILE_BYTES, tbp, s.kc + k * KSTEP, r0, b, lbar);                       // B_lo (half)
+            if (++stage == nstage) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
           tma_load_3d(a_dst, &tmA, k * KSTEP, mb * GEMM_BM, b, &full_bar[stage]);   // SPLIT3: A_lo
           if (SPLIT3) tma_load_3d(a_dst + GEMM_A_STAGE_BYTES, &tmA, s.kc + k * KSTEP, mb * GEMM_BM, b, &full_bar[stage]);  // A_hi
           if (MC && !narrow) {
@@ -329,12 +403,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (PAIR: the leader CTA's, for both) =====================
+    if (lane == 0 && !(PAIR && crank != 0)) {
       constexpr uint32_t idesc_wide = make_idesc_tf32(GEMM_BM, BN);
       constexpr uint32_t idesc_half = make_idesc_tf32(GEMM_BM, BN / 2);
       // 16-bit split mode: fp16 x fp16 for all three terms
-      constexpr uint32_t id16[2] = {make_idesc_f16(GEMM_BM, BN, FMT_F16, FMT_F16), make_idesc_f16(GEMM_BM, BN / 2, FMT_F16, FMT_F16)};
+      constexpr uint32_t id16[2] = {make_idesc_f16(PAIR ? 2 * GEMM_BM : GEMM_BM, BN, FMT_F16, FMT_F16),
+                                    make_idesc_f16(PAIR ? 2 * GEMM_BM : GEMM_BM, BN / 2, FMT_F16, FMT_F16)};
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -357,9 +432,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {     // 4 x 16 columns; +32 bytes along K inside the swizzle atom = +2 in (addr >> 4)
               const uint64_t o = (uint64_t)(2 * kk);
-              umma_f16(d_tmem, a_desc + o, b_desc + o, id16[nw], (uint32_t)((k | kk) != 0));  // lo . hi
-              umma_f16(d_tmem, ah_desc + o, bl_desc + o, id16[nw], 1u);                        // hi . lo
-              umma_f16(d_tmem, ah_desc + o, b_desc + o, id16[nw], 1u);                         // hi . hi
+              if (PAIR) {
+                umma_f16_2sm(d_tmem, a_desc + o, b_desc + o, id16[nw], (uint32_t)((k | kk) != 0));  // lo . hi
+                umma_f16_2sm(d_tmem, ah_desc + o, bl_desc + o, id16[nw], 1u);                        // hi . lo
+                umma_f16_2sm(d_tmem, ah_desc + o, b_desc + o, id16[nw], 1u);                         // hi . hi
+              } else {
+                umma_f16(d_tmem, a_desc + o, b_desc + o, id16[nw], (uint32_t)((k | kk) != 0));  // lo . hi
+                umma_f16(d_tmem, ah_desc + o, bl_desc + o, id16[nw], 1u);                        // hi . lo
+                umma_f16(d_tmem, ah_desc + o, b_desc + o, id16[nw], 1u);                         // hi . hi
+              }
             }
           } else {
 #pragma unroll
@@ -368,14 +449,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               umma_tf32(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (uint32_t)((k | kk) != 0));
             }
           }
-          if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // ... in both CTAs: either may refill (its half of) the stage
+          if (PAIR) umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)3);   // both CTAs' producers may refill their halves
+          else if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // ... in both CTAs: either may refill (its half of) the stage
           else umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs have read it
           if (++stage == nstage) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tmem_full_bar[as]);  // accumulator complete
+        if (PAIR) umma_commit_2sm_mc(&tmem_full_bar[as], (uint16_t)3);  // accumulator complete, in both CTAs
+        else umma_commit(&tmem_full_bar[as]);  // accumulator complete
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
@@ -383,10 +466,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   } else {
     // ===================== epilogue (warps 2..9) =====================
     // Eight warps: a warp may read the TMEM lane quadrant (warp % 4) only, so two warps share a quadrant and take alternate
-    // 32-column chunks of the tile.  With four warps a 128 x 256 tile was 8 boxes per warp at ~2.5 k cycles each (tcgen05.ld,
-    // scale, st.shared, proxy fence, TMA store, wait for the staging buffer): 20 k cycles per tile against 11 k for the tile's
-    // main loop -- the epilogue, not the operand traffic, set the pace (ncu: tensor pipe 31 % of elapsed, L2 -> SM at half the
-    // fabric rate, the single-pass tf32 kernel with half the MMAs exactly as slow).
+    // 32-column chunks of the tile (measured: no faster than four warps on the 4096^2 GEMM -- the epilogue does not set the pace
+    // there -- but 10 % on the one-tile-per-CTA projection GEMM).
     const int ew = warp - 2;
     const int q = warp & 3;   // TMEM lane quadrant this warp may read: lanes 32q .. 32q+31
     const int half = ew >> 2; // which of the quadrant's two warps
@@ -499,14 +580,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
           if (s.C == nullptr) continue;
         }
+        // The box goes through this warp's swizzled staging buffer (row = lane, 16-byte chunk j at chunk j ^ (lane & 7)) and
+        // leaves with plain vector stores: four rows x 128 contiguous bytes per instruction.  (Round 1 / early round 2 used TMA
+        // tensor stores of 32 x 32 boxes here; measured, they drain at ~7.5 B/clk/SM -- 17 cycles per 128-byte box row -- which
+        // made the OUTPUT path, not the operands or the MMAs, the bound of the 4096^2 GEMM: 1.8 TB/s for the 64 MB result,
+        // where the Sinkhorn's final pass writes the same matrix with st.global.v4 at 5.6 TB/s.)
         uint8_t* box = stg;
-        if (!s.direct_store) {
-          // the TMA store of this warp's previous box must have finished READING the buffer (it was issued before the
-          // tcgen05.ld and the scaling of this box: the wait is short)
-          if (lane == 0) bulk_wait_group_read<0>();
-          __syncwarp();
-        }
-        // 128B-swizzled staging: row = lane, 16-byte chunk j lands at chunk j ^ (lane & 7)
+        __syncwarp();   // the previous box has been read out of the buffer by every lane
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o;
@@ -516,18 +596,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           o.w = __uint_as_float(r[4 * j + 3]) * s.alpha;
           *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
         }
+        __syncwarp();
+        float* Cb = s.C + (size_t)b * s.N * s.M;
         if (!s.direct_store) {
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&tmC, box, col0, row0, b);
-            bulk_commit_group();
+          // 16-byte aligned rows (M % 4 == 0): lanes 8 i .. 8 i + 7 write the eight 16-byte chunks of one row
+          const int chunk = lane & 7;
+          const int col = col0 + 4 * chunk;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3);
+            const int row = row0 + rr;
+            const float4 v = *reinterpret_cast<const float4*>(box + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+            if (row < s.N && col < s.M) *reinterpret_cast<float4*>(Cb + (size_t)row * s.M + col) = v;
           }
         } else {
-          __syncwarp();
           // coalesced scalar stores: lane = column, loop over the 32 rows of the box
           const int col = col0 + lane;
-          float* Cb = s.C + (size_t)b * s.N * s.M;
           for (int rr = 0; rr < 32; ++rr) {
             const int row = row0 + rr;
             if (row < s.N && col < s.M) {
@@ -535,24 +619,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               Cb[(size_t)row * s.M + col] = val;
             }
           }
-          __syncwarp();
         }
       }
       // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(map_to_cta(&tmem_empty_bar[as], 0u));   // the pair's MMA issuer lives in the leader CTA
+        else mbar_arrive(&tmem_empty_bar[as]);
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
-    if ((!s.direct_store || s.split_tma) && lane == 0) bulk_wait_group<0>();  // smem must outlive the last stores
+    if (s.split_tma && lane == 0) bulk_wait_group<0>();  // smem must outlive the last TMA stores (split epilogue)
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  if (CL) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   tcgen05_fence_after();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
 }
 
 // ---- host side --------------------------------------------------------------------------
@@ -596,52 +685,62 @@ static bool make_tmap(CUtensorMap* tm, const void* ptr, int batch, int rows, int
   return true;
 }
 
+template <int BN, bool SPLIT3, int MODE>
+static int launch_cluster(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tS,
+                          const CUtensorMap& tBh, const CUtensorMap& tBq, GemmShape s, size_t smem, cudaStream_t st) {
+  const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM, tiles_n = (s.M + BN - 1) / BN;
+  DRG_CUDA((cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT3, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+  const long long pairs = (long long)s.batch * (tiles_m / 2) * tiles_n;
+  const int nclusters = (int)(pairs < NUM_SMS / 2 ? pairs : NUM_SMS / 2);
+  const int rem = (int)(pairs % nclusters);
+  s.wide_tiles = (int)pairs;   // (counted in pairs of tiles in the cluster modes)
+  if (pairs > nclusters && rem > 0 && 2 * rem <= nclusters) s.wide_tiles = (int)pairs - rem;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * nclusters);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  {
+    ProfScope prof_scope(PROF_GEMM, st);
+    DRG_CUDA((cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, SPLIT3, MODE>, tA, tB, tC, tS, tBh, tBq, s)));
+  }
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
 template <int BN, bool SPLIT3>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tS,
-                       const CUtensorMap& tBh, GemmShape s, cudaStream_t st) {
-  constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (GEMM_A_STAGE_BYTES + BN * GEMM_BK * 4);
+                       const CUtensorMap& tBh, const CUtensorMap& tBq, GemmShape s, cudaStream_t st) {
+  const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM, tiles_n = (s.M + BN - 1) / BN;
+  // Two-CTA clusters (kernel template MODE 1 / 2): split operands, wide tiles, an even number of row blocks, a B operand worth
+  // sharing (a weight of a few hundred rows is not) and no split epilogue.  256-wide tiles: the pair runs cta_group::2 MMAs
+  // (half of the B tile per CTA); 128-wide: each CTA loads half of the B tile and multicasts it.
+  const bool cluster_ok = SPLIT3 && BN >= 128 && tiles_m >= 2 && (tiles_m % 2) == 0 && s.split_out == nullptr && s.M >= 2 * BN;
+  const bool pair = cluster_ok && BN == 256;
+  const int stage_bytes = (SPLIT3 ? 2 : 1) * (GEMM_A_STAGE_BYTES + (pair ? BN / 2 : BN) * GEMM_BK * 4);
   const size_t out_bytes = (size_t)GEMM_EPI_WARPS * GEMM_OUT_BOX_BYTES;
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - out_bytes - 256 /*static*/;
-  int nstage = (int)(budget / STAGE_BYTES);
+  int nstage = (int)(budget / stage_bytes);
   if (nstage > GEMM_MAX_STAGES) nstage = GEMM_MAX_STAGES;
   const int kblocks = SPLIT3 ? s.kc / 64 : (s.K + GEMM_BK - 1) / GEMM_BK;
   if (nstage > 2 * kblocks) nstage = 2 * kblocks;  // no point in more stages than two tiles of k-steps
   if (nstage < 2) nstage = 2;
   s.nstage = nstage;
-  const size_t smem = 1024 + (size_t)nstage * STAGE_BYTES + out_bytes;
-  const int tiles_m = (s.N + GEMM_BM - 1) / GEMM_BM, tiles_n = (s.M + BN - 1) / BN;
-  // Two-CTA clusters sharing the B tile (kernel template MC): split operands, wide tiles, an even number of row blocks, a
-  // B operand worth sharing (a weight of a few hundred rows is not) and no split epilogue.
-  const bool mc = SPLIT3 && BN >= 128 && tiles_m >= 2 && (tiles_m % 2) == 0 && s.split_out == nullptr && s.M >= 2 * BN;
-  if (mc) {
-    if constexpr (SPLIT3 && BN >= 128) {
-      DRG_CUDA((cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-      const long long pairs = (long long)s.batch * (tiles_m / 2) * tiles_n;
-      const int nclusters = (int)(pairs < NUM_SMS / 2 ? pairs : NUM_SMS / 2);
-      const int rem = (int)(pairs % nclusters);
-      s.wide_tiles = (int)pairs;   // (counted in pairs of tiles in this mode)
-      if (pairs > nclusters && rem > 0 && 2 * rem <= nclusters) s.wide_tiles = (int)pairs - rem;
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(2 * nclusters);
-      cfg.blockDim = dim3(GEMM_THREADS);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      {
-        ProfScope prof_scope(PROF_GEMM, st);
-        DRG_CUDA((cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, SPLIT3, true>, tA, tB, tC, tS, tBh, s)));
-      }
-      DRG_LAUNCH_CHECK();
-      return DRG_OK;
-    }
+  const size_t smem = 1024 + (size_t)nstage * stage_bytes + out_bytes;
+  if constexpr (SPLIT3 && BN == 256) {
+    if (pair) return launch_cluster<BN, SPLIT3, 2>(tA, tB, tC, tS, tBh, tBq, s, smem, st);
   }
-  DRG_CUDA((cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+  if constexpr (SPLIT3 && BN == 128) {
+    if (cluster_ok) return launch_cluster<BN, SPLIT3, 1>(tA, tB, tC, tS, tBh, tBq, s, smem, st);
+  }
+  DRG_CUDA((cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   const long long tiles = (long long)s.batch * tiles_m * tiles_n;
   const int grid = (int)(tiles < NUM_SMS ? tiles : NUM_SMS);
   // Tail balancing: with `rem` tiles left for the last, partial wave of the persistent grid, the wave costs a full tile
@@ -652,7 +751,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   if (BN >= 128 && tiles > grid && rem > 0 && 2 * rem <= grid) s.wide_tiles = (int)tiles - rem;
   {
     ProfScope prof_scope(PROF_GEMM, st);
-    gemm_tf32_kernel<BN, SPLIT3, false><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tS, tBh, s);
+    gemm_tf32_kernel<BN, SPLIT3, 0><<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tS, tBh, tBq, s);
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
@@ -721,14 +820,16 @@ static int gemm_run(const void* A, const void* B, float* C, int batch, int N, in
   s.B16 = split16 ? reinterpret_cast<const unsigned short*>(B) : nullptr;
   // split epilogue through TMA stores when only the split operand is wanted and the left / right boundary is box-aligned
   s.split_tma = (split_out != nullptr && C == nullptr && (split_rows0 % 32) == 0) ? 1 : 0;
-  CUtensorMap tA, tB, tC, tS, tBh;
+  CUtensorMap tA, tB, tC, tS, tBh, tBq;
   const int eb = split16 ? 2 : 4, kcols = split16 ? 2 * kc + 8 : K, kbox = split16 ? 64 : GEMM_BK;   // (+8: the row tail)
   if (!make_tmap(&tA, A, batch, N, kcols, GEMM_BM, kbox, eb)) return DRG_ERR_CUDA;
   if (!make_tmap(&tB, B, batch, M, kcols, BN, kbox, eb)) return DRG_ERR_CUDA;
   if (BN >= 128) {
-    if (!make_tmap(&tBh, B, batch, M, kcols, BN / 2, kbox, eb)) return DRG_ERR_CUDA;   // half-width units of the tail wave
+    if (!make_tmap(&tBh, B, batch, M, kcols, BN / 2, kbox, eb)) return DRG_ERR_CUDA;   // half-width units of the tail wave / half tiles of a pair
+    if (!make_tmap(&tBq, B, batch, M, kcols, BN / 4, kbox, eb)) return DRG_ERR_CUDA;   // a pair's halves of half-width units
   } else {
     tBh = tB;
+    tBq = tB;
   }
   if (!s.direct_store) {
     if (!make_tmap(&tC, C, batch, N, M, 32, 32)) return DRG_ERR_CUDA;
@@ -742,15 +843,15 @@ static int gemm_run(const void* A, const void* B, float* C, int batch, int N, in
   }
   if (split16) {
     switch (BN) {
-      case 256: return launch_gemm<256, true>(tA, tB, tC, tS, tBh, s, st);
-      case 128: return launch_gemm<128, true>(tA, tB, tC, tS, tBh, s, st);
-      default: return launch_gemm<64, true>(tA, tB, tC, tS, tBh, s, st);
+      case 256: return launch_gemm<256, true>(tA, tB, tC, tS, tBh, tBq, s, st);
+      case 128: return launch_gemm<128, true>(tA, tB, tC, tS, tBh, tBq, s, st);
+      default: return launch_gemm<64, true>(tA, tB, tC, tS, tBh, tBq, s, st);
     }
   }
   switch (BN) {
-    case 256: return launch_gemm<256, false>(tA, tB, tC, tS, tBh, s, st);
-    case 128: return launch_gemm<128, false>(tA, tB, tC, tS, tBh, s, st);
-    default: return launch_gemm<64, false>(tA, tB, tC, tS, tBh, s, st);
+    case 256: return launch_gemm<256, false>(tA, tB, tC, tS, tBh, tBq, s, st);
+    case 128: return launch_gemm<128, false>(tA, tB, tC, tS, tBh, tBq, s, st);
+    default: return launch_gemm<64, false>(tA, tB, tC, tS, tBh, tBq, s, st);
   }
 }
 
