@@ -1662,9 +1662,11 @@ __global__ void __launch_bounds__(P2_THREADS, 1) skh_persist2_kernel(const SkhPa
         }
       }
       group_barrier(0);  // xcomb (aliased on the ring) has been read
-      if (tid == 0 && (it + 1 < iters || do_collect))
+      // (issued by thread 32, not thread 0: thread 0 carries the CTA's arrival at the grid barrier below, and six TMA issues
+      //  with their proxy fences would sit in front of it)
+      if (tid == 32 && (it + 1 < iters || do_collect))
         for (int s = 0; s < D && s < ns; ++s) issue_slab_to(((it + 1) * ns + s) % D, s);  // the scores do not change: prefetch across the barriers
-      if (tid == 0 && it + 1 == iters && do_final)
+      if (tid == 32 && it + 1 == iters && do_final)
         for (int q = 0; q < Df && q < NWf * ns; ++q) issue_final(q);   // neither do the final phase's inputs
     }
     if (tid == 0) {

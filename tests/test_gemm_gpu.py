@@ -147,3 +147,20 @@ def test_project_pair_split_matches_fp64():
         ref32 = ((xs @ W.t()) * scale) @ ((xt @ W.t()) * scale).transpose(1, 2)
         err32 = (ref32.double() - ref).abs().max().item()
         assert (sim.double() - ref).abs().max().item() <= max(8 * err32, 1e-6)
+
+
+@pytest.mark.parametrize("b,n,m,k", [(1, 512, 512, 64), (1, 256, 768, 200), (2, 384, 1100, 132), (1, 1000, 2052, 96), (1, 640, 640, 256),
+                                     (3, 256, 512, 72)])
+def test_split_gemm_cluster_modes(b, n, m, k):
+    """Shapes that take the two-CTA cluster paths (cta_group::2 pairs for 256-wide tiles, multicast B tiles for 128-wide ones:
+    an even number of 128-row blocks, M >= 2 tile widths), with ragged last row / column blocks, several batches and K that is not
+    a multiple of the 64-column k-step: same result as the fp64 product within the split GEMM's bound."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(1000 * n + m + k)
+    A = torch.randn(b, n, k, generator=g)
+    B = torch.randn(b, m, k, generator=g)
+    ref = torch.einsum("bnk,bmk->bnm", A.double(), B.double())
+    C = ops.gemm_nt(ops.prep_operand(A.cuda(), 1.0, True, 0), ops.prep_operand(B.cuda(), 1.0, True, 1), split3=True, K=k).cpu()
+    ref32 = torch.einsum("bnk,bmk->bnm", A, B)
+    err32 = (ref32.double() - ref).abs().max().item()
+    assert (C.double() - ref).abs().max().item() <= max(8 * err32, 1e-6)
