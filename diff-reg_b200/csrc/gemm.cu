@@ -707,9 +707,14 @@ static int launch_cluster(const CUtensorMap& tA, const CUtensorMap& tB, const CU
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  cudaError_t e;
   {
     ProfScope prof_scope(PROF_GEMM, st);
-    DRG_CUDA((cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, SPLIT3, MODE>, tA, tB, tC, tS, tBh, tBq, s)));
+    e = cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, SPLIT3, MODE>, tA, tB, tC, tS, tBh, tBq, s);
+  }
+  if (e != cudaSuccess) {   // a device / partition that cannot place two-CTA clusters: the caller falls back to single CTAs
+    (void)cudaGetLastError();
+    return -1;
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
@@ -735,10 +740,36 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   s.nstage = nstage;
   const size_t smem = 1024 + (size_t)nstage * stage_bytes + out_bytes;
   if constexpr (SPLIT3 && BN == 256) {
-    if (pair) return launch_cluster<BN, SPLIT3, 2>(tA, tB, tC, tS, tBh, tBq, s, smem, st);
+    if (pair) {
+      const int rc = launch_cluster<BN, SPLIT3, 2>(tA, tB, tC, tS, tBh, tBq, s, smem, st);
+      if (rc != -1) return rc;
+      // cluster launch refused: single-CTA kernel with its own (two-stage) geometry
+      GemmShape s1 = s;
+      const int sb1 = 2 * (GEMM_A_STAGE_BYTES + BN * GEMM_BK * 4);
+      int ns1 = (int)(budget / sb1);
+      if (ns1 > 2 * kblocks) ns1 = 2 * kblocks;
+      if (ns1 < 2) ns1 = 2;
+      s1.nstage = ns1;
+      const size_t smem1 = 1024 + (size_t)ns1 * sb1 + out_bytes;
+      DRG_CUDA((cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)));
+      const long long tiles1 = (long long)s.batch * tiles_m * tiles_n;
+      const int grid1 = (int)(tiles1 < NUM_SMS ? tiles1 : NUM_SMS);
+      const int rem1 = (int)(tiles1 % grid1);
+      s1.wide_tiles = (int)tiles1;
+      if (tiles1 > grid1 && rem1 > 0 && 2 * rem1 <= grid1) s1.wide_tiles = (int)tiles1 - rem1;
+      {
+        ProfScope prof_scope(PROF_GEMM, st);
+        gemm_tf32_kernel<BN, SPLIT3, 0><<<grid1, GEMM_THREADS, smem1, st>>>(tA, tB, tC, tS, tBh, tBq, s1);
+      }
+      DRG_LAUNCH_CHECK();
+      return DRG_OK;
+    }
   }
   if constexpr (SPLIT3 && BN == 128) {
-    if (cluster_ok) return launch_cluster<BN, SPLIT3, 1>(tA, tB, tC, tS, tBh, tBq, s, smem, st);
+    if (cluster_ok) {
+      const int rc = launch_cluster<BN, SPLIT3, 1>(tA, tB, tC, tS, tBh, tBq, s, smem, st);
+      if (rc != -1) return rc;   // (same stage geometry as the single-CTA kernel: fall through)
+    }
   }
   DRG_CUDA((cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   const long long tiles = (long long)s.batch * tiles_m * tiles_n;
