@@ -8,6 +8,7 @@ Public surface (mirrors the reference):
     SoftProcrustesLayer                                      (procrustes.py)
     VolumetricPositionEncoding                               (position_encoding.py; next-row widening)
     GeometryAttentionLayer, RepositioningTransformer         (transformer.py; the denoising transformer)
+    CrossModalFusionModule                                   (fusion.py; the 2D-3D flavour's fusion / denoising transformer)
     DenoisingSampler                                         (fused per-step driver)
     HostStepPipeline                                         (host buffers in / results out, copies overlapped, graph replay)
     RowShardedSinkhorn, shard_rows, shard_units              (multi-GPU paths, distributed.py)
@@ -37,6 +38,9 @@ def __getattr__(name):
     if name in ("GeometryAttentionLayer", "RepositioningTransformer"):
         from . import transformer
         return getattr(transformer, name)
+    if name == "CrossModalFusionModule":
+        from . import fusion
+        return fusion.CrossModalFusionModule
     if name == "HostStepPipeline":
         from . import hostpipe
         return hostpipe.HostStepPipeline

@@ -204,30 +204,62 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_softmax_vec_kernel(const flo
 }
 
 // LayerNorm over the last dimension, one warp per row: y = (x - mean) / sqrt(var + eps) * w + b (biased variance, two passes
-// like torch), out = residual + y when a residual is given.
+// like torch).  With a residual: out = residual + LayerNorm(in) (pre_add == 0: the geometry attention layer's x + norm2(message))
+// or out = LayerNorm(in + residual) (pre_add == 1: the post-norm of vision3d's attention / feed-forward blocks).
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                         const float* __restrict__ bias, const float* __restrict__ residual,
-                                                        long long rows, int C, float eps, float* __restrict__ out) {
+                                                        long long rows, int C, float eps, int pre_add, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool pre = pre_add && residual != nullptr;
   for (long long row = warp0; row < rows; row += nwarps) {
     const float* x = in + row * C;
+    const float* r = residual ? residual + row * C : nullptr;
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += x[c];
+    for (int c = lane; c < C; c += 32) s += pre ? x[c] + r[c] : x[c];
     const float mean = warp_sum(s) / (float)C;
     float v = 0.f;
     for (int c = lane; c < C; c += 32) {
-      const float d = x[c] - mean;
+      const float d = (pre ? x[c] + r[c] : x[c]) - mean;
       v = fmaf(d, d, v);
     }
     const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
     for (int c = lane; c < C; c += 32) {
-      float y = (x[c] - mean) * rstd;
+      float y = ((pre ? x[c] + r[c] : x[c]) - mean) * rstd;
       if (w) y *= w[c];
       if (bias) y += bias[c];
-      if (residual) y += residual[row * C + c];
+      if (r && !pre) y += r[c];
       out[row * C + c] = y;
     }
+  }
+}
+
+// Fourier embedding of coordinates (vision3d FourierEmbedding with use_input: the 2D-3D fusion module's positional term):
+//   out[row] = [x (n) | for l < L: sin(f_l x) (n), cos(f_l x) (n)],  f_l = 2^(k0 + l) [* pi]
+//   replaces FourierEmbedding.forward   Diff-Reg-2d3d/vision3d/layers/embedding.py:75-99; `center` (optional, [n]) is subtracted
+//   first (CrossModalFusionModule.create_3d_embedding: points - points.mean(dim=1), fusion_module.py:57)
+__global__ void __launch_bounds__(256) fourier_embed_kernel(const float* __restrict__ x, const float* __restrict__ center, long long rows,
+                                                            int n, int L, float k0, int use_pi, int use_input, float* __restrict__ out) {
+  const int width = (use_input ? n : 0) + 2 * L * n;
+  const long long total = rows * width;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / width;
+    int c = (int)(idx - row * width);
+    float val;
+    if (use_input && c < n) {
+      val = x[row * n + c] - (center ? center[c] : 0.f);
+    } else {
+      if (use_input) c -= n;
+      const int l = c / (2 * n);
+      const int r = c - l * 2 * n;
+      const int comp = r < n ? r : r - n;
+      const float e = k0 + (float)l;               // integer exponents (every shipped use): an exact power of two, as
+      float f = e == rintf(e) ? ldexpf(1.f, (int)e) : exp2f(e);   // 2.0 ** arange is in fp32; exp2f alone is only good to 2 ulp
+      if (use_pi) f *= 3.14159265358979323846f;
+      const float th = f * (x[row * n + comp] - (center ? center[comp] : 0.f));
+      val = r < n ? sinf(th) : cosf(th);
+    }
+    out[idx] = val;
   }
 }
 
@@ -254,13 +286,25 @@ extern "C" int drg_attn_softmax(const float* logits, const uint8_t* q_mask, cons
   return DRG_OK;
 }
 
-extern "C" int drg_layernorm(const float* in, const float* weight, const float* bias, const float* residual, long long rows, int C,
-                             float eps, float* out, void* stream) {
+extern "C" int drg_layernorm(const float* in, const float* weight, const float* bias, const float* residual, int pre_add, long long rows,
+                             int C, float eps, float* out, void* stream) {
   DRG_CHECK_ARG(in != nullptr && out != nullptr, "in / out must be non-null");
   DRG_CHECK_ARG(rows >= 1 && C >= 1, "rows and C must be >= 1");
   long long blocks = (rows * 32 + 255) / 256;
   if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
-  layernorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, weight, bias, residual, rows, C, eps, out);
+  layernorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, weight, bias, residual, rows, C, eps, pre_add, out);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+extern "C" int drg_fourier_embed(const float* x, const float* center, long long rows, int n, int length, float k0, int use_pi,
+                                 int use_input, float* out, void* stream) {
+  DRG_CHECK_ARG(x != nullptr && out != nullptr, "x / out must be non-null");
+  DRG_CHECK_ARG(rows >= 1 && n >= 1 && length >= 1, "rows, n, length must be >= 1");
+  const long long total = rows * ((use_input ? n : 0) + 2ll * length * n);
+  long long blocks = (total + 255) / 256;
+  if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
+  fourier_embed_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, center, rows, n, length, k0, use_pi, use_input, out);
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }

@@ -244,6 +244,7 @@ struct GemmShape {
                      //   last, partial wave -- are processed as twice as many HALF-width tiles so that one round of the
                      //   persistent grid finishes them in half a tile time (wide_tiles == tiles: no split)
   float* C;          // may be NULL when only the split output is wanted
+  const float* bias; // optional [M]: C[., j] += bias[j] (the bias of an nn.Linear whose weight is the right operand)
   // optional fused operand preparation of the NEXT GEMM (projection -> similarity): split_out [N, 2 * split_kc + 8] (16-bit)
   // receives scale*alpha*acc as a split operand: [lo | hi | tail] for rows < split_rows0 (left operand), [hi | lo | tail] for the
   // others (right operand); columns [M, split_kc) of each segment are the caller's zero padding.  The row scale of an output
@@ -606,8 +607,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + (lane >> 3);
             const int row = row0 + rr;
-            const float4 v = *reinterpret_cast<const float4*>(box + rr * 128 + ((chunk ^ (rr & 7)) << 4));
-            if (row < s.N && col < s.M) *reinterpret_cast<float4*>(Cb + (size_t)row * s.M + col) = v;
+            float4 v = *reinterpret_cast<const float4*>(box + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+            if (row < s.N && col < s.M) {
+              if (s.bias) {
+                const float4 bq = *reinterpret_cast<const float4*>(s.bias + col);
+                v.x += bq.x; v.y += bq.y; v.z += bq.z; v.w += bq.w;
+              }
+              *reinterpret_cast<float4*>(Cb + (size_t)row * s.M + col) = v;
+            }
           }
         } else {
           // coalesced scalar stores: lane = column, loop over the 32 rows of the box
@@ -616,7 +623,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const int row = row0 + rr;
             if (row < s.N && col < s.M) {
               const float val = *reinterpret_cast<const float*>(box + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
-              Cb[(size_t)row * s.M + col] = val;
+              Cb[(size_t)row * s.M + col] = s.bias ? val + s.bias[col] : val;
             }
           }
         }
@@ -796,7 +803,7 @@ using namespace drg;
 // (split16 == true; drg_prep_operand(split = 1) / the split epilogue write them).  split_out (optional, batch == 1): the 16-bit
 // split operand [N, 2 * split_kc] of the next GEMM, split_kc = M rounded up to 64 (its padding columns must be zero already).
 static int gemm_run(const void* A, const void* B, float* C, int batch, int N, int M, int K, float alpha, unsigned short* split_out,
-                    int split_rows0, float split_scale, void* stream, bool split16 = false) {
+                    int split_rows0, float split_scale, void* stream, bool split16 = false, const float* bias = nullptr) {
   DRG_CHECK_ARG(A && B && (C || split_out), "A/B and an output must be non-null");
   DRG_CHECK_ARG(batch >= 1 && N >= 1 && M >= 1 && K >= 1, "batch, N, M, K must be >= 1");
   if ((!split16 && K % 4 != 0) || ((uintptr_t)A & 15u) || ((uintptr_t)B & 15u)) {
@@ -841,6 +848,7 @@ static int gemm_run(const void* A, const void* B, float* C, int batch, int N, in
   s.batch = batch;
   s.alpha = alpha;
   s.C = C;
+  s.bias = bias;
   s.split_out = split_out;
   s.split_kc = (M + 63) & ~63;
   s.split_rows0 = split_rows0;
@@ -898,6 +906,14 @@ extern "C" int drg_gemm_nt_split16(const void* A16, const void* B16, float* C, i
                                    void* stream) {
   DRG_CHECK_ARG(C != nullptr, "C is null");
   return gemm_run(A16, B16, C, batch, N, M, K, alpha, nullptr, 0, 1.f, stream, true);
+}
+
+// the same with a bias row added to every output row: C = alpha * A . B^T + bias (an nn.Linear with bias, B = its weight)
+extern "C" int drg_gemm_nt_split16_bias(const void* A16, const void* B16, const float* bias, float* C, int batch, int N, int M, int K,
+                                        float alpha, void* stream) {
+  DRG_CHECK_ARG(C != nullptr, "C is null");
+  DRG_CHECK_ARG(bias == nullptr || (((uintptr_t)bias) & 15u) == 0, "bias must be 16-byte aligned");
+  return gemm_run(A16, B16, C, batch, N, M, K, alpha, nullptr, 0, 1.f, stream, true, bias);
 }
 
 extern "C" int drg_project_split16(const void* A16, const void* W16, int rows, int rows_left, int C_out, int K, float scale,

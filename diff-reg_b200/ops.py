@@ -156,7 +156,7 @@ def split_pitch(K):
 
 
 @_on_device
-def gemm_nt(A, B, alpha=1.0, out=None, split3=False, K=None):
+def gemm_nt(A, B, alpha=1.0, out=None, split3=False, K=None, bias=None):
     """C[b] = alpha * A[b] @ B[b]^T on the tensor cores.  A [batch,N,K] or [N,K]; B likewise.
     split3=False: fp32 operands, one tcgen05 kind::tf32 pass (drg_gemm_nt_tf32; 10 mantissa bits of the operands).
     split3=True: A, B are the 16-bit split operands of prep_operand(split=True) (patterns 0 / 1, torch.int16 [.., split_pitch(K)]);
@@ -186,8 +186,17 @@ def gemm_nt(A, B, alpha=1.0, out=None, split3=False, K=None):
         K = kc if K is None else int(K)
         if split_pitch(K) != KA:
             raise ValueError(f"gemm_nt: split operands of width {KA} do not belong to K = {K}")
-        check(lib.drg_gemm_nt_split16(A.data_ptr(), B.data_ptr(), out.data_ptr(), batch, N, M, K, float(alpha), _stream()))
+        if bias is not None:
+            bias = _f32c(bias)
+            if bias.numel() != M:
+                raise ValueError(f"gemm_nt: bias of {bias.numel()} entries for {M} output columns")
+            check(lib.drg_gemm_nt_split16_bias(A.data_ptr(), B.data_ptr(), bias.data_ptr(), out.data_ptr(), batch, N, M, K, float(alpha),
+                                               _stream()))
+        else:
+            check(lib.drg_gemm_nt_split16(A.data_ptr(), B.data_ptr(), out.data_ptr(), batch, N, M, K, float(alpha), _stream()))
     else:
+        if bias is not None:
+            raise ValueError("gemm_nt: bias needs the split operands (split3=True)")
         check(lib.drg_gemm_nt_tf32(A.data_ptr(), B.data_ptr(), out.data_ptr(), batch, N, M, KA, float(alpha), _stream()))
     return out.squeeze(0) if squeeze else out
 
@@ -307,8 +316,9 @@ def attn_softmax(logits, heads, q_mask, kv_mask, scale, want_operand=True, want_
 
 
 @_on_device
-def layernorm(x, weight, bias, eps=1e-5, residual=None):
-    """[residual +] LayerNorm(x) over the last dimension (drg_layernorm; transformer.py:88,92-94)."""
+def layernorm(x, weight, bias, eps=1e-5, residual=None, pre_add=False):
+    """residual + LayerNorm(x) (pre_add=False; 4d transformer.py:88,92-94) or LayerNorm(x + residual) (pre_add=True; vision3d
+    transformer.py:214,236) over the last dimension (drg_layernorm)."""
     _require_cuda(x, weight, bias, residual)
     lib = load_library()
     x = _f32c(x)
@@ -317,7 +327,24 @@ def layernorm(x, weight, bias, eps=1e-5, residual=None):
     w = _f32c(weight) if weight is not None else None
     b = _f32c(bias) if bias is not None else None
     r = _f32c(residual) if residual is not None else None
-    check(lib.drg_layernorm(x.data_ptr(), _ptr(w), _ptr(b), _ptr(r), x.numel() // C, C, float(eps), out.data_ptr(), _stream()))
+    check(lib.drg_layernorm(x.data_ptr(), _ptr(w), _ptr(b), _ptr(r), int(bool(pre_add)), x.numel() // C, C, float(eps), out.data_ptr(),
+                            _stream()))
+    return out
+
+
+@_on_device
+def fourier_embed(x, length, k0=0.0, use_pi=True, use_input=False, center=None):
+    """vision3d FourierEmbedding.forward of (x - center): x [..., n] -> [..., n * (2 * length + use_input)] (drg_fourier_embed)."""
+    _require_cuda(x, center)
+    lib = load_library()
+    x = _f32c(x)
+    n = x.shape[-1]
+    c = _f32c(center).reshape(-1) if center is not None else None
+    if c is not None and c.numel() != n:
+        raise ValueError("fourier_embed: center must hold one value per coordinate")
+    out = torch.empty(*x.shape[:-1], n * (2 * int(length) + int(bool(use_input))), dtype=torch.float32, device=x.device)
+    check(lib.drg_fourier_embed(x.data_ptr(), _ptr(c), x.numel() // n, n, int(length), float(k0), int(bool(use_pi)), int(bool(use_input)),
+                                out.data_ptr(), _stream()))
     return out
 
 

@@ -254,13 +254,24 @@ int drg_prep_operand_ext(const float* in, const float* pe, int pe_type, long lon
  *                      valid key yields NaN, as there).  q_mask [B, L], kv_mask [B, S] bool or NULL; scale = 1 / sqrt(d).
  *                      P (optional) [B*H, L, S] fp32, may alias logits; P16 (optional) the same rows as the LEFT split
  *                      operand [B*H, L, 2 kc(S) + 8] of the P.V product (drg_gemm_nt_split16).
- *   drg_layernorm      out = [residual +] LayerNorm(in) over the last dimension C, affine (weight / bias may be NULL)
+ *   drg_layernorm      out = [residual +] LayerNorm(in) over the last dimension C, affine (weight / bias may be NULL); pre_add = 0
  *                      replaces self.norm1(message), x + self.norm2(message)     transformer.py:88,92-94
  * ------------------------------------------------------------------------------------ */
 int drg_attn_softmax(const float* logits, const uint8_t* q_mask, const uint8_t* kv_mask, int B, int H, int L, int S, float scale,
                      float* P, void* P16, void* stream);
-int drg_layernorm(const float* in, const float* weight, const float* bias, const float* residual, long long rows, int C, float eps,
-                  float* out, void* stream);
+int drg_layernorm(const float* in, const float* weight, const float* bias, const float* residual, int pre_add, long long rows, int C,
+                  float eps, float* out, void* stream);
+/* 2D-3D flavour of the same row (CrossModalFusionModule, Diff-Reg-2d3d/experiments/<exp>/fusion_module.py:10-107, built from
+ * vision3d's TransformerLayer, Diff-Reg-2d3d/vision3d/layers/transformer.py:8-301):
+ *   drg_layernorm with pre_add = 1   out = LayerNorm(in + residual)            transformer.py:214,236 (post-norm blocks)
+ *   drg_gemm_nt_split16_bias         C = alpha * A . B^T + bias[M]             the nn.Linear layers with bias of that module
+ *   drg_fourier_embed                [x | sin(2^l x), cos(2^l x), l < L] of (x - center)
+ *                                    replaces FourierEmbedding.forward  vision3d/layers/embedding.py:75-99 and the centring of
+ *                                    create_3d_embedding  fusion_module.py:56-60; out [rows, n * (2 L + use_input)]          */
+int drg_gemm_nt_split16_bias(const void* A16, const void* B16, const float* bias, float* C, int batch, int N, int M, int K, float alpha,
+                             void* stream);
+int drg_fourier_embed(const float* x, const float* center, long long rows, int n, int length, float k0, int use_pi, int use_input,
+                      float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Correspondence extraction

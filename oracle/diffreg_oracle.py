@@ -524,6 +524,70 @@ def attention_stack(layer_weights, layer_types, src_feat, tgt_feat, src_pe, tgt_
     return src_feat, tgt_feat
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# 2D-3D flavour of the same row: CrossModalFusionModule (vision3d TransformerLayer blocks + Fourier embedding)
+# ---------------------------------------------------------------------------------------------------------------
+def fourier_embedding(x, length, k0=0.0, use_pi=True, use_input=False):
+    """``FourierEmbedding.forward`` 2d3d/vision3d/layers/embedding.py:75-99: [x | sin(f_0 x), cos(f_0 x), sin(f_1 x) ...] with
+    f_l = 2^(k0 + l) [* pi]; each (sin | cos) block is as wide as x."""
+    n = x.shape[-1]
+    f = (2.0 ** torch.arange(k0, k0 + length).float()).to(x.dtype).view(1, -1, 1)
+    if use_pi:
+        f = f * math.pi
+    th = f * x.reshape(-1, 1, n)
+    emb = torch.cat([torch.sin(th), torch.cos(th)], dim=-1).view(*x.shape[:-1], 2 * length * n)
+    return torch.cat([x, emb], dim=-1) if use_input else emb
+
+
+def vision3d_transformer_layer(w, q_tokens, k_tokens, v_tokens, k_masks, nhead, eps=1e-5):
+    """``TransformerLayer.forward`` 2d3d/vision3d/layers/transformer.py:8-301 as the fusion module calls it (tokens and key masks
+    only; k_masks True = key ignored, :76,:131).  `w`: the layer's state_dict (attention.attention.{q,k,v}_token_layer.*,
+    attention.linear.*, attention.norm.*, output.expand.*, output.squeeze.*, output.norm.*).  Returns (tokens, scores)."""
+    dt = q_tokens.dtype
+    lin = lambda name, x: x @ w[name + ".weight"].to(dt).t() + w[name + ".bias"].to(dt)
+    B, N, C = q_tokens.shape
+    M = k_tokens.shape[1]
+    d = C // nhead
+    q = lin("attention.attention.q_token_layer", q_tokens).view(B, N, nhead, d).permute(0, 2, 1, 3)
+    k = lin("attention.attention.k_token_layer", k_tokens).view(B, M, nhead, d).permute(0, 2, 1, 3)
+    v = lin("attention.attention.v_token_layer", v_tokens).view(B, M, nhead, d).permute(0, 2, 1, 3)
+    a = torch.einsum("bhnc,bhmc->bhnm", q, k) / d ** 0.5                                   # :127-128
+    if k_masks is not None:
+        a = a.masked_fill(k_masks[:, None, None, :], float("-inf"))                        # :133-134
+    a = torch.softmax(a, dim=-1)
+    hidden = torch.matmul(a, v).permute(0, 2, 1, 3).reshape(B, N, C)                       # :154-156
+    hidden = lin("attention.linear", hidden)
+    ln = lambda name, x: torch.nn.functional.layer_norm(x, (C,), w[name + ".weight"].to(dt), w[name + ".bias"].to(dt), eps)
+    tokens = ln("attention.norm", hidden + q_tokens)                                       # :214
+    hidden = lin("output.squeeze", torch.relu(lin("output.expand", tokens)))               # :232-234
+    return ln("output.norm", tokens + hidden), a                                           # :236
+
+
+def cross_modal_fusion(w, blocks, nhead, img_feats, img_feats_dino, img_pixels, pcd_feats, pcd_points, img_masks=None,
+                       pcd_masks=None, use_embedding=True, embedding_dim=10):
+    """``CrossModalFusionModule.forward`` 2d3d/experiments/<exp>/fusion_module.py:61-107.  `w`: the module's state_dict."""
+    dt = img_feats.dtype
+    lin = lambda name, x: x @ w[name + ".weight"].to(dt).t() + w[name + ".bias"].to(dt)
+    img = torch.relu(torch.cat([lin("img_in_proj", img_feats), lin("img_in_proj_dino", img_feats_dino)], dim=-1))   # :83
+    img = lin("img_in_proj_all", img)
+    pcd = lin("pcd_in_proj", pcd_feats)
+    if use_embedding:
+        img = img + lin("img_emb_proj", fourier_embedding(img_pixels, embedding_dim, use_pi=False, use_input=True))   # :51-54
+        pts = pcd_points - pcd_points.mean(dim=1)                                                                      # :57
+        pcd = pcd + lin("pcd_emb_proj", fourier_embedding(pts, embedding_dim, use_pi=False, use_input=True))
+    for i, block in enumerate(blocks):
+        lw = {k[len(f"transformer.{i}."):]: v for k, v in w.items() if k.startswith(f"transformer.{i}.")}
+        if block == "self":                                                                                            # :95-101
+            img = vision3d_transformer_layer(lw, img, img, img, img_masks, nhead)[0]
+            pcd = vision3d_transformer_layer(lw, pcd, pcd, pcd, pcd_masks, nhead)[0]
+        elif block == "cross":
+            img = vision3d_transformer_layer(lw, img, pcd, pcd, pcd_masks, nhead)[0]
+            pcd = vision3d_transformer_layer(lw, pcd, img, img, img_masks, nhead)[0]
+        else:
+            raise KeyError(block)
+    return lin("out_proj", img), lin("out_proj", pcd)
+
+
 def random_rotation(gen):
     q = torch.randn(4, generator=gen)
     q = q / q.norm()

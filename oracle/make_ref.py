@@ -41,7 +41,12 @@ FILES = [
     EXP_2D3D + "/procrustes.py",
     EXP_2D3D + "/position_encoding.py",
     "Diff-Reg-2d3d/vision3d/ops/mutual_topk_select.py",
-]
+    # the 2D-3D fusion module and the pure-torch vision3d layer files it imports
+    EXP_2D3D + "/fusion_module.py",
+    "Diff-Reg-2d3d/vision3d/layers/transformer.py",
+    "Diff-Reg-2d3d/vision3d/layers/embedding.py",
+] + ["Diff-Reg-2d3d/vision3d/layers/basic_layers/" + f for f in
+     ("__init__.py", "builder.py", "depthwise_conv.py", "monte_carlo_dropout.py", "norm.py", "separable_conv.py", "utils.py")]
 
 
 def make_ref(verbose=True):

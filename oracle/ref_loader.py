@@ -81,6 +81,39 @@ def load_flavour(name):
     return ns
 
 
+def load_fusion():
+    """The 2D-3D fusion module and the two vision3d layer files it is built from (transformer.py, embedding.py), unmodified.
+    `vision3d/layers/__init__.py` imports the whole layer zoo (and with it the compiled `vision3d.ext`, absent here), so the
+    packages `vision3d` / `vision3d.layers` are registered as empty namespaces and only the needed files are imported into
+    them.  Returns ns.fusion (CrossModalFusionModule), ns.transformer (TransformerLayer ...), ns.embedding (FourierEmbedding)."""
+    root, _ = reference_root()
+    if root is None or not os.path.exists(os.path.join(root, "Diff-Reg-2d3d", "vision3d", "layers", "transformer.py")):
+        raise RuntimeError("reference sources of the 2D-3D fusion module not found")
+    _purge(_PREFIXES + ["fusion_module"])
+    base = os.path.join(root, "Diff-Reg-2d3d")
+    v3d = types.ModuleType("vision3d")
+    v3d.__path__ = [os.path.join(base, "vision3d")]
+    lay = types.ModuleType("vision3d.layers")
+    lay.__path__ = [os.path.join(base, "vision3d", "layers")]
+    sys.modules["vision3d"] = v3d
+    sys.modules["vision3d.layers"] = lay
+    v3d.layers = lay
+    ns = SimpleNamespace(root=root)
+    ns.transformer = importlib.import_module("vision3d.layers.transformer")
+    ns.embedding = importlib.import_module("vision3d.layers.embedding")
+    lay.TransformerLayer = ns.transformer.TransformerLayer
+    lay.FourierEmbedding = ns.embedding.FourierEmbedding
+    spec = importlib.util.spec_from_file_location("fusion_module", os.path.join(base, "experiments", EXP_2D3D.split("/")[-1], "fusion_module.py"))
+    ns.fusion = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ns.fusion)
+    return ns
+
+
+def fusion_available():
+    root, _ = reference_root()
+    return root is not None and os.path.exists(os.path.join(root, "Diff-Reg-2d3d", "vision3d", "layers", "basic_layers", "builder.py"))
+
+
 def unload():
     root, _ = reference_root()
     _purge(_PREFIXES)

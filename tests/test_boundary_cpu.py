@@ -104,6 +104,45 @@ def test_position_encoding_interface_matches_the_reference():
         ref_loader.unload()
 
 
+@pytest.mark.skipif(not ref_loader.fusion_available(), reason="reference sources of the 2D-3D fusion module not present")
+def test_fusion_module_interface_and_state_dict_match_the_reference():
+    """2D-3D flavour of 8f rank 2: CrossModalFusionModule / TransformerLayer / FourierEmbedding behind the reference's constructor
+    and forward signatures, parameters under the reference's names (a reference checkpoint loads strictly, and back)."""
+    ref = ref_loader.load_fusion()
+    try:
+        from diffreg_b200 import fusion as OF
+        pairs = [(ref.fusion.CrossModalFusionModule, OF.CrossModalFusionModule), (ref.transformer.TransformerLayer, OF.TransformerLayer),
+                 (ref.transformer.AttentionLayer, OF.AttentionLayer), (ref.transformer.AttentionOutput, OF.AttentionOutput),
+                 (ref.transformer.MultiHeadAttention, OF.MultiHeadAttention), (ref.embedding.FourierEmbedding, OF.FourierEmbedding)]
+        for rc, oc in pairs:
+            _assert_prefix(rc.__init__, oc.__init__, rc.__name__ + ".__init__")
+        for rc, oc in pairs[:2] + pairs[-1:]:
+            _assert_prefix(rc.forward, oc.forward, rc.__name__ + ".forward")
+        for name in ("create_2d_embedding", "create_3d_embedding"):
+            _assert_prefix(getattr(pairs[0][0], name), getattr(pairs[0][1], name), name)
+        blocks = ["self", "cross", "self", "cross", "self", "cross"]
+        for use_emb in (True, False):
+            rn = ref.fusion.CrossModalFusionModule(512, 512, 256, 256, 4, blocks, use_embedding=use_emb)   # config.py:135-141
+            on = OF.CrossModalFusionModule(512, 512, 256, 256, 4, blocks, use_embedding=use_emb)
+            rsd, osd = rn.state_dict(), on.state_dict()
+            assert list(rsd.keys()) == list(osd.keys())
+            assert all(rsd[k].shape == osd[k].shape and rsd[k].dtype == osd[k].dtype for k in rsd)
+            on.load_state_dict(rsd, strict=True)
+            rn.load_state_dict(osd, strict=True)
+        # what the fusion module never uses stays with the reference module: refused, not computed differently
+        with pytest.raises(NotImplementedError):
+            OF.TransformerLayer(64, 4, dropout=0.1)
+        with pytest.raises(NotImplementedError):
+            OF.TransformerLayer(64, 4, act_cfg="GELU")
+        with pytest.raises(NotImplementedError):
+            OF.TransformerLayer(64, 4, qk_embed_proj=True)
+        x = torch.randn(1, 5, 64, requires_grad=True)
+        with pytest.raises(RuntimeError, match="forward-only"):
+            OF.TransformerLayer(64, 4)(x, x, x)
+    finally:
+        ref_loader.unload()
+
+
 @needs_ref
 def test_transformer_interface_and_state_dict_match_the_reference():
     """GeometryAttentionLayer / RepositioningTransformer take the reference's config keys and arguments
@@ -203,6 +242,7 @@ SHIMS = {
     "Diff-Reg-3dmatch/models/procrustes.py": ["SoftProcrustesLayer"],
     "Diff-Reg-2d3d/experiments/matching.py": ["Matching", "log_optimal_transport"],
     "Diff-Reg-2d3d/experiments/procrustes.py": ["SoftProcrustesLayer"],
+    "Diff-Reg-2d3d/experiments/fusion_module.py": ["CrossModalFusionModule"],
 }
 
 

@@ -1,0 +1,46 @@
+"""Timing of the 2D-3D fusion / denoising transformer drop-in (CrossModalFusionModule, six blocks, 512 -> 256, 4 heads) at BASELINE
+configs[3]'s token counts (2048 image patches x 4800 points), with the reference module on the same GPU as the yardstick when
+oracle/_ref is present (tuning tool; CUDA events, median of repetitions)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import diffreg_b200
+from oracle import ref_loader
+
+n_img = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+n_pcd = int(sys.argv[2]) if len(sys.argv) > 2 else 4800
+blocks = ["self", "cross"] * 3
+g = torch.Generator().manual_seed(1)
+img, dino = torch.randn(1, n_img, 512, generator=g).cuda(), torch.randn(1, n_img, 1024, generator=g).cuda()
+pcd = torch.randn(1, n_pcd, 512, generator=g).cuda()
+pix = (torch.rand(1, n_img, 2, generator=g) * 2.0 - 1.0).cuda()
+pts = (torch.randn(1, n_pcd, 3, generator=g) * 0.8 + torch.tensor([0.3, -0.2, 2.0])).cuda()
+
+
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+onet = diffreg_b200.CrossModalFusionModule(512, 512, 256, 256, 4, blocks).cuda().eval()
+out = {"n_img": n_img, "n_pcd": n_pcd, "blocks": 6}
+if ref_loader.fusion_available():
+    ref = ref_loader.load_fusion()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rnet = ref.fusion.CrossModalFusionModule(512, 512, 256, 256, 4, blocks).cuda().eval()
+    onet.load_state_dict(rnet.state_dict(), strict=True)
+    with torch.no_grad():
+        r = rnet(img, dino, pix, pcd, pts)
+        o = onet(img, dino, pix, pcd, pts)
+        out["max_abs_diff_vs_reference"] = max((o[0] - r[0]).abs().max().item(), (o[1] - r[1]).abs().max().item())
+        out["reference_module_ms"] = timed(lambda: rnet(img, dino, pix, pcd, pts))
+c0 = diffreg_b200.launch_count()
+onet(img, dino, pix, pcd, pts)
+out["launches"] = diffreg_b200.launch_count() - c0
+out["dropin_ms"] = timed(lambda: onet(img, dino, pix, pcd, pts))
+print(json.dumps(out), flush=True)
