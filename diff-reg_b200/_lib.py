@@ -95,6 +95,9 @@ def _declare(lib):
     lib.drg_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_void_p, c_void_p]
     lib.drg_gemm_nt_split16_bias.restype = c_int
     lib.drg_gemm_nt_split16_bias.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
+    lib.drg_attention_split16.restype = c_int
+    lib.drg_attention_split16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                          c_void_p, c_void_p]
     lib.drg_fourier_embed.restype = c_int
     lib.drg_fourier_embed.argtypes = [c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p]
     lib.drg_prep_operand_xyz.restype = c_int

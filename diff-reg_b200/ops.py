@@ -315,6 +315,32 @@ def attn_softmax(logits, heads, q_mask, kv_mask, scale, want_operand=True, want_
     return P16 if want_operand else P
 
 
+FLASH_MAX_HEAD = 176     # widest head drg_attention_split16 takes (shared memory: Q, K, V^T and P tiles of one CTA)
+
+
+@_on_device
+def attention(q16, k16, v, heads, q_mask, kv_mask, scale, d):
+    """softmax(Q K^T * scale + mask) V per head in one kernel (drg_attention_split16).  q16 [B*H, L, split_pitch(d)] / k16
+    [B*H, S, split_pitch(d)]: the per-head split operands of prep_heads (patterns 0 / 1); v [B, S, H*d] fp32; masks [B, L] /
+    [B, S] bool (True = valid) or None, keys masked for valid queries only.  Returns [B, L, H*d] fp32."""
+    _require_cuda(q16, k16, v, q_mask, kv_mask)
+    lib = load_library()
+    BH, L, _ = q16.shape
+    S = k16.shape[1]
+    B = BH // heads
+    v = _f32c(v)
+    vt = v.view(B, S, heads, d).permute(0, 2, 3, 1).contiguous().view(BH, d, S)      # V^T per head, the keys along the row
+    if S % 4:                                   # operand rows are staged 16 bytes at a time
+        vt = torch.nn.functional.pad(vt, (0, 4 - S % 4))
+    vt16 = prep_operand(vt, 1.0, True, 1)
+    qm = _as_mask(q_mask, B, L, q16.device) if q_mask is not None else None
+    km = _as_mask(kv_mask, B, S, q16.device) if kv_mask is not None else None
+    out = torch.empty(B, L, heads * d, dtype=torch.float32, device=q16.device)
+    check(lib.drg_attention_split16(q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), _ptr(qm), _ptr(km), B, heads, L, S, int(d),
+                                    float(scale), out.data_ptr(), _stream()))
+    return out
+
+
 @_on_device
 def layernorm(x, weight, bias, eps=1e-5, residual=None, pre_add=False):
     """residual + LayerNorm(x) (pre_add=False; 4d transformer.py:88,92-94) or LayerNorm(x + residual) (pre_add=True; vision3d

@@ -270,6 +270,18 @@ int drg_layernorm(const float* in, const float* weight, const float* bias, const
  *                                    create_3d_embedding  fusion_module.py:56-60; out [rows, n * (2 L + use_input)]          */
 int drg_gemm_nt_split16_bias(const void* A16, const void* B16, const float* bias, float* C, int batch, int N, int M, int K, float alpha,
                              void* stream);
+/* Fused attention: out[b, l, h, :] = softmax_s(Q[b,h,l,:] . K[b,h,s,:] * scale + mask) . V[b,h,s,:] in ONE kernel -- logits in
+ * TMEM, probabilities split to fp16 hi / lo on the fly, O accumulated in TMEM; the [L, S] attention matrix never reaches HBM.
+ *   replaces einsum / masked_fill / softmax / einsum   Diff-Reg-4dmatch/models/transformer.py:79-85 and
+ *            einsum / masked_fill / softmax / matmul   Diff-Reg-2d3d/vision3d/layers/transformer.py:127-154
+ *   Q16 [B*H, L, 2 kc(d) + 8]   LEFT split operand per head  (drg_prep_operand_ext, pattern 0, head-major)
+ *   K16 [B*H, S, 2 kc(d) + 8]   RIGHT split operand per head (pattern 1)
+ *   Vt16 [B*H, d, 2 kc(S) + 8]  RIGHT split operand of V^T per head (keys along the row)
+ *   q_mask [B, L] / kv_mask [B, S] bool or NULL, 1 = valid: the keys with kv_mask == 0 are masked for the queries with
+ *   q_mask != 0 (all queries when q_mask is NULL) -- the reference's expression; a valid query without a valid key yields NaN.
+ *   out [B, L, H * d] fp32.  d % 4 == 0, d <= 176 (DRG_ERR_UNSUPPORTED otherwise: the caller keeps the three-kernel path). */
+int drg_attention_split16(const void* Q16, const void* K16, const void* Vt16, const uint8_t* q_mask, const uint8_t* kv_mask, int B,
+                          int H, int L, int S, int d, float scale, float* out, void* stream);
 int drg_fourier_embed(const float* x, const float* center, long long rows, int n, int length, float k0, int use_pi, int use_input,
                       float* out, void* stream);
 
