@@ -95,6 +95,8 @@ def _declare(lib):
     lib.drg_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_void_p, c_void_p]
     lib.drg_gemm_nt_split16_bias.restype = c_int
     lib.drg_gemm_nt_split16_bias.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
+    lib.drg_prep_vt_split16.restype = c_int
+    lib.drg_prep_vt_split16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.drg_attention_split16.restype = c_int
     lib.drg_attention_split16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                           c_void_p, c_void_p]

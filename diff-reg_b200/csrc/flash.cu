@@ -12,13 +12,16 @@
 // V'^T = [V_hi | V_lo | tail] per head with the KEYS along the row -- and the probabilities are split into fp16 hi / lo halves
 // on the fly.  S = Q_lo.K_hi + Q_hi.K_lo + Q_hi.K_hi, O += P_lo.V_hi + P_hi.V_lo + P_hi.V_hi, fp32 accumulation in TMEM.
 //
-// One CTA = 128 queries of one (batch, head); keys in tiles of 64.  160 threads:
-//   warp 4 (one elected lane)  TMA producer and MMA issuer: Q once; per key tile the K tile -> S = Q.K^T into one of TWO TMEM
-//                              accumulators (S of tile t+1 is computed while the softmax warps work on tile t), the V^T tile,
-//                              and -- once the softmax warps have published P -- O += P.V (O lives in TMEM for the whole pass)
-//   warps 0..3                 softmax: thread = query row = TMEM lane.  tcgen05.ld of the row's 64 logits, row / column scales of
-//                              the split operands, masks, running maximum, exp2, row sum, fp16 hi / lo split of P written as the
-//                              128-byte-swizzled K-major A operand of the P.V product
+// One CTA = 128 queries of one (batch, head); keys in tiles of 64.  320 threads:
+//   warp 5 (one elected lane)  TMA producer: Q once, then the K tiles (one tile ahead) and V^T tiles through two rings of shared-memory
+//                              stages (two stages each where they fit: every head width but the 132 of 4DMatch, whose Q tile
+//                              alone is 96 KB), freed by the tensor core's commits
+//   warp 4 (one elected lane)  MMA issuer: S = Q.K^T of tile t+1 into one of TWO TMEM accumulators while the softmax warps work on
+//                              tile t, then -- once they have published P -- O += P.V of tile t (O lives in TMEM for the whole pass)
+//   warps 0..3, 6..9           softmax: two threads per query row (= TMEM lane), 32 of the tile's 64 logits each.  tcgen05.ld, row /
+//                              column scales of the split operands, masks, running maximum (the halves exchange theirs through
+//                              shared memory), exp2, row sum, fp16 hi / lo split of P written as the 128-byte-swizzled K-major
+//                              A operand of the P.V product
 // Online softmax with a LAZY reference: P = 2^(s - m_ref + 6) with m_ref only moved (and O, l rescaled through tcgen05.ld / st)
 // when the tile's maximum exceeds it by more than 8 (log2 units), so P <= 2^14 stays inside fp16 and the rescale of the
 // accumulator is rare after the first tiles.  The 2^6 and the stale reference cancel in O / l.
@@ -28,7 +31,7 @@ namespace drg {
 
 constexpr int FA_BM = 128;        // queries per CTA (TMEM lanes)
 constexpr int FA_BN = 64;         // keys per tile = one 128-byte swizzle-atom row of 16-bit P
-constexpr int FA_THREADS = 160;
+constexpr int FA_THREADS = 320;    // 8 softmax warps + the MMA issuer (warp 4) + the TMA producer (warp 5)
 constexpr float FA_TAU = 8.f;     // move the reference when a tile's maximum exceeds it by more than this (log2 units)
 constexpr float FA_PSHIFT = 6.f;  // P is carried as 2^6 * exp(.): hi / lo halves of the small entries stay normal fp16 numbers
 constexpr int FA_Q_CHUNK = FA_BM * 128;   // bytes of one 64-column chunk of the Q tile
@@ -41,11 +44,16 @@ struct FlashShape {
   int B, H, L, S, d;
   int kc;        // 16-bit columns of one segment of the Q / K operand rows (d rounded up to 64)
   int kcS;       // ... of the V^T operand rows (S rounded up to 64)
+  int nfull, npiece;  // a Q / K operand segment in shared memory: nfull 64-column chunks (128-byte swizzle) + npiece 16-column
+                      // pieces (32-byte swizzle) -- d rounded up to 16, not to 64: the 132-wide heads of 4DMatch take 9 k-steps
+                      // per product term instead of 12 and 72 + 36 KB for the Q / K tiles instead of 96 + 48
+  int KS, VS;    // shared-memory stages of the K / V^T tile rings (1 or 2)
   int ND;        // d rounded up to 16: N of the P.V MMA (rows of the V^T tile; rows >= d are TMA zero fill)
   float scale2;  // softmax scale * log2(e)
   const unsigned short *Q16, *K16, *V16;
   const uint8_t *q_mask, *kv_mask;
   float* out;    // [B, L, H * d]
+  long long* tl; // tuning stamps of CTA (0, 0): 16 per key tile for the first 64 tiles, or NULL
 };
 
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -63,50 +71,105 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// K-major operand tile whose rows are 32 bytes (16 fp16) wide, 32-byte swizzle: groups of 8 rows (256 bytes) 256 B apart
+__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(256u >> 4) << 32;   // stride byte offset
+  d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
+  d |= (uint64_t)6 << 61;             // SWIZZLE_32B
+  return d;
+}
+// The MMA warp runs its loop with all 32 lanes converged and ELECTS one lane per instruction: descriptors, addresses and loop
+// counters stay warp-uniform (uniform registers), so a tcgen05.mma costs a handful of issue slots.  Under `if (lane == 0)` the
+// compiler cannot prove uniformity and wraps every UTCHMMA in an elect / branch loop: ~75 cycles per MMA measured
+// (tools/fa_timeline.py), more than the 32 cycles a 128 x 64 x 16 MMA occupies the tensor pipe.
+__device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float fa_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void softmax_warps_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void softmax_warps_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// (x0, x1) = hi + lo, both fp16 pairs: one packed conversion per pair (F2FP) instead of two scalar ones on the XU pipe
+__device__ __forceinline__ void split16x2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
+  uint32_t h;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));      // low half = x0
+  float h0, h1;
+  asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}" : "=f"(h0), "=f"(h1) : "r"(h));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(x1 - h1), "f"(x0 - h0));
+  hi2 = h;
+}
 
 template <int TMEM_COLS>
 __global__ void __launch_bounds__(FA_THREADS, 1)
     flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                      const __grid_constant__ CUtensorMap tmV, const FlashShape s) {
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQp,
+                      const __grid_constant__ CUtensorMap tmKp, const FlashShape s) {
   extern __shared__ uint8_t smem_dyn[];
-  __shared__ __align__(8) uint64_t bar_q, bar_k, bar_v, bar_p, bar_pv;
-  __shared__ __align__(8) uint64_t bar_s[2];
+  __shared__ __align__(8) uint64_t bar_q, bar_p, bar_pv;
+  __shared__ __align__(8) uint64_t bar_s[2], bar_kfull[2], bar_kfree[2], bar_vfull[2], bar_vfree[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float colinfo[2][3][FA_BN];   // per tile parity: 1 / scale of the key rows, bias (0 / -inf) without and with the key mask
+  __shared__ float rowmax[2][2][FA_BM];    // per tile parity: the two column halves' row maxima
+  __shared__ float rowsum[2][FA_BM];       // the two halves' row sums (epilogue)
   __shared__ float vscale[256];            // 1 / scale of the V^T rows (= output channels)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y, b = bh / s.H, h = bh - b * s.H;
   const int q0 = blockIdx.x * FA_BM;
-  const int nq = 2 * s.kc / 64;            // 64-column chunks of a Q / K operand row (both segments)
-  const int nh = s.kc / 64;                // ... of one segment
+  const int nfull = s.nfull, npiece = s.npiece;
+  const uint32_t q_seg = (uint32_t)(nfull * FA_Q_CHUNK + npiece * (FA_Q_CHUNK / 4));   // bytes of one segment (lo or hi) of the Q tile
+  const uint32_t k_seg = (uint32_t)(nfull * FA_K_CHUNK + npiece * (FA_K_CHUNK / 4));
   const int T = (s.S + FA_BN - 1) / FA_BN;
 
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* aligned = smem_dyn + (base - smem_u32(smem_dyn));
   uint8_t* sQ = aligned;
-  uint8_t* sK = sQ + (size_t)nq * FA_Q_CHUNK;
-  uint8_t* sV = sK + (size_t)nq * FA_K_CHUNK;
-  uint8_t* sP = sV + (size_t)2 * s.ND * 128;   // [hi | lo]
+  uint8_t* sK = sQ + (size_t)2 * q_seg;
+  const uint32_t k_bytes = 2u * k_seg;                  // one K tile stage
+  const uint32_t v_bytes = (uint32_t)s.ND * 128u;       // one half (hi or lo) of a V^T tile stage
+  uint8_t* sV = sK + (size_t)s.KS * k_bytes;
+  uint8_t* sP = sV + (size_t)s.VS * 2 * v_bytes;   // [hi | lo]
 
   if (tid == 0) {
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
+    if (npiece) {
+      prefetch_tmap(&tmQp);
+      prefetch_tmap(&tmKp);
+    }
     mbar_init(&bar_q, 1);
-    mbar_init(&bar_k, 1);
-    mbar_init(&bar_v, 1);
-    mbar_init(&bar_p, FA_BM);
+    mbar_init(&bar_p, 2 * FA_BM);
     mbar_init(&bar_pv, 1);
-    mbar_init(&bar_s[0], 1);
-    mbar_init(&bar_s[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_kfull[i], 1);
+      mbar_init(&bar_kfree[i], 1);
+      mbar_init(&bar_vfull[i], 1);
+      mbar_init(&bar_vfree[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 4) tmem_alloc<TMEM_COLS>(&tmem_base_slot);
@@ -118,174 +181,224 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp == 4) {
+  if (warp == 5) {
     if (lane == 0) {
-      // ===================== TMA producer + MMA issuer =====================
-      const uint32_t idesc_s = make_idesc_f16(FA_BM, FA_BN, FMT_F16, FMT_F16);
-      const uint32_t idesc_o = make_idesc_f16(FA_BM, s.ND, FMT_F16, FMT_F16);
-      const uint32_t v_bytes = (uint32_t)s.ND * 128u;
+      // ===================== TMA producer =====================
       auto load_k = [&](int t) {
-        mbar_arrive_expect_tx(&bar_k, (uint32_t)nq * FA_K_CHUNK);
-        for (int c = 0; c < nq; ++c) tma_load_3d(sK + (size_t)c * FA_K_CHUNK, &tmK, c * 64, t * FA_BN, bh, &bar_k);
+        const int st = t % s.KS;
+        mbar_wait(&bar_kfree[st], (uint32_t)(((t / s.KS) & 1) ^ 1));   // S of tile t - KS has read the stage (first pass: free)
+        mbar_arrive_expect_tx(&bar_kfull[st], k_bytes);
+        uint8_t* dst = sK + (size_t)st * k_bytes;
+        for (int seg = 0; seg < 2; ++seg) {
+          uint8_t* sd = dst + (size_t)seg * k_seg;
+          for (int c = 0; c < nfull; ++c) tma_load_3d(sd + (size_t)c * FA_K_CHUNK, &tmK, seg * s.kc + c * 64, t * FA_BN, bh, &bar_kfull[st]);
+          for (int c = 0; c < npiece; ++c)
+            tma_load_3d(sd + (size_t)nfull * FA_K_CHUNK + (size_t)c * (FA_K_CHUNK / 4), &tmKp, seg * s.kc + nfull * 64 + c * 16, t * FA_BN, bh,
+                        &bar_kfull[st]);
+        }
       };
       auto load_v = [&](int t) {
-        mbar_arrive_expect_tx(&bar_v, 2u * v_bytes);
-        tma_load_3d(sV, &tmV, t * FA_BN, 0, bh, &bar_v);                     // V_hi: keys of this tile along the row
-        tma_load_3d(sV + v_bytes, &tmV, s.kcS + t * FA_BN, 0, bh, &bar_v);   // V_lo
+        const int st = t % s.VS;
+        mbar_wait(&bar_vfree[st], (uint32_t)(((t / s.VS) & 1) ^ 1));   // P.V of tile t - VS has read the stage
+        mbar_arrive_expect_tx(&bar_vfull[st], 2u * v_bytes);
+        uint8_t* dst = sV + (size_t)st * 2 * v_bytes;
+        tma_load_3d(dst, &tmV, t * FA_BN, 0, bh, &bar_vfull[st]);                     // V_hi: keys of this tile along the row
+        tma_load_3d(dst + v_bytes, &tmV, s.kcS + t * FA_BN, 0, bh, &bar_vfull[st]);   // V_lo
       };
+      mbar_arrive_expect_tx(&bar_q, 2u * q_seg);
+      for (int seg = 0; seg < 2; ++seg) {
+        uint8_t* sd = sQ + (size_t)seg * q_seg;
+        for (int c = 0; c < nfull; ++c) tma_load_3d(sd + (size_t)c * FA_Q_CHUNK, &tmQ, seg * s.kc + c * 64, q0, bh, &bar_q);
+        for (int c = 0; c < npiece; ++c)
+          tma_load_3d(sd + (size_t)nfull * FA_Q_CHUNK + (size_t)c * (FA_Q_CHUNK / 4), &tmQp, seg * s.kc + nfull * 64 + c * 16, q0, bh, &bar_q);
+      }
+      load_k(0);
+      for (int t = 0; t < T; ++t) {     // K runs one tile ahead of V: S(t+1) is issued before P.V(t), so its stage frees first
+        if (t + 1 < T) load_k(t + 1);
+        load_v(t);
+      }
+    }
+  } else if (warp == 4) {
+    {
+      // ===================== MMA issuer: the whole warp, converged; one elected lane per instruction =====================
+      // (a spin loop leaves the lanes formally diverged: reconverge, or everything after it is compiled for a diverged warp)
+      auto wwait = [&](uint64_t* bar, uint32_t parity) {
+        mbar_wait(bar, parity);
+        __syncwarp();
+      };
+      const uint32_t idesc_s = make_idesc_f16(FA_BM, FA_BN, FMT_F16, FMT_F16);
+      const uint32_t idesc_o = make_idesc_f16(FA_BM, s.ND, FMT_F16, FMT_F16);
+      const uint64_t q128 = make_smem_desc_sw128(smem_u32(sQ)), q32 = make_smem_desc_sw32(smem_u32(sQ));
+      const uint64_t k128 = make_smem_desc_sw128(smem_u32(sK)), k32 = make_smem_desc_sw32(smem_u32(sK));
       auto issue_s = [&](int t) {
+        const int st = t % s.KS;
+        wwait(&bar_kfull[st], (uint32_t)((t / s.KS) & 1));
+        tcgen05_fence_after();
+        if (s.tl && blockIdx.x == 0 && blockIdx.y == 0 && t >= 1 && t <= 64 && lane == 0) s.tl[(t - 1) * 16 + 13] = clock64();
+        __syncwarp();
         const uint32_t d_tmem = tmem_base + (uint32_t)((t & 1) * FA_BN);
         uint32_t acc = 0u;
-        // the small terms first (the accumulator is rounded at every step): chunk c of Q' against chunk c of K' is Q_lo.K_hi
-        // for the first segment and Q_hi.K_lo for the second; then Q_hi.K_hi
-        for (int c = 0; c < nq; ++c) {
-          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sQ + (size_t)c * FA_Q_CHUNK));
-          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sK + (size_t)c * FA_K_CHUNK));
+        // Descriptors are base + constant offsets in 16-byte units (the start-address field is the low word: plain 64-bit
+        // adds, all warp-uniform).  The small terms first (the accumulator is rounded at every step): Q' = [lo | hi],
+        // K' = [hi | lo], so segment 0 x segment 0 is Q_lo.K_hi and segment 1 x segment 1 is Q_hi.K_lo; then Q_hi.K_hi
+        const uint64_t kofs = (uint64_t)(((uint32_t)st * k_bytes) >> 4);
+        auto term = [&](uint32_t qs, uint32_t ks) {
+          const uint64_t qo = (uint64_t)((qs * q_seg) >> 4), ko = kofs + (uint64_t)((ks * k_seg) >> 4);
+          for (int c = 0; c < nfull; ++c) {
+            const uint64_t a_desc = q128 + qo + (uint64_t)(c * (FA_Q_CHUNK >> 4)), b_desc = k128 + ko + (uint64_t)(c * (FA_K_CHUNK >> 4));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            umma_f16(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc_s, acc);
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_f16_elect(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc_s, acc);
+              acc = 1u;
+            }
+          }
+          for (int c = 0; c < npiece; ++c) {     // 16-column pieces: one K = 16 step each, rows of 32 bytes
+            umma_f16_elect(d_tmem, q32 + qo + (uint64_t)(nfull * (FA_Q_CHUNK >> 4) + c * (FA_Q_CHUNK >> 6)),
+                           k32 + ko + (uint64_t)(nfull * (FA_K_CHUNK >> 4) + c * (FA_K_CHUNK >> 6)), idesc_s, acc);
             acc = 1u;
           }
-        }
-        for (int c = 0; c < nh; ++c) {
-          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sQ + (size_t)(nh + c) * FA_Q_CHUNK));
-          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sK + (size_t)c * FA_K_CHUNK));
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc_s, 1u);
-        }
-        umma_commit(&bar_s[t & 1]);
+        };
+        term(0, 0);
+        term(1, 1);
+        term(1, 0);
+        if (s.tl && blockIdx.x == 0 && blockIdx.y == 0 && t >= 1 && t <= 64 && lane == 0) s.tl[(t - 1) * 16 + 14] = clock64();
+        __syncwarp();
+        umma_commit_elect(&bar_kfree[st]);      // the K stage may be refilled ...
+        umma_commit_elect(&bar_s[t & 1]);       // ... and the logits are ready
       };
-      mbar_arrive_expect_tx(&bar_q, (uint32_t)nq * FA_Q_CHUNK);
-      for (int c = 0; c < nq; ++c) tma_load_3d(sQ + (size_t)c * FA_Q_CHUNK, &tmQ, c * 64, q0, bh, &bar_q);
-      load_k(0);
-      load_v(0);
-      mbar_wait(&bar_q, 0u);
-      mbar_wait(&bar_k, 0u);
-      tcgen05_fence_after();
+      wwait(&bar_q, 0u);
       issue_s(0);
       const uint64_t ph_desc = make_smem_desc_sw128(smem_u32(sP));
       const uint64_t pl_desc = make_smem_desc_sw128(smem_u32(sP + FA_P_BYTES));
-      const uint64_t vh_desc = make_smem_desc_sw128(smem_u32(sV));
-      const uint64_t vl_desc = make_smem_desc_sw128(smem_u32(sV + v_bytes));
       const uint32_t o_tmem = tmem_base + FA_O_COL;
       for (int t = 0; t < T; ++t) {
-        mbar_wait(&bar_s[t & 1], (uint32_t)((t >> 1) & 1));   // S(t) complete: the K tile may be replaced
-        if (t + 1 < T) {
-          load_k(t + 1);
-          mbar_wait(&bar_k, (uint32_t)((t + 1) & 1));
-          tcgen05_fence_after();
-          issue_s(t + 1);            // into the other accumulator, whose tile t - 1 the softmax warps have consumed (bar_p of t - 1)
-        }
-        mbar_wait(&bar_v, (uint32_t)(t & 1));
-        mbar_wait(&bar_p, (uint32_t)(t & 1));
+        // S(t+1) into the other accumulator, whose tile t - 1 the softmax warps have consumed (bar_p of t - 1, waited below)
+        const bool rec = s.tl && blockIdx.x == 0 && blockIdx.y == 0 && t < 64 && lane == 0;
+        if (rec) s.tl[t * 16 + 0] = clock64();
+        __syncwarp();
+        if (t + 1 < T) issue_s(t + 1);
+        if (rec) s.tl[t * 16 + 1] = clock64();
+        __syncwarp();
+        const int vs = t % s.VS;
+        wwait(&bar_vfull[vs], (uint32_t)((t / s.VS) & 1));
+        wwait(&bar_p, (uint32_t)(t & 1));
         tcgen05_fence_after();
+        if (rec) s.tl[t * 16 + 2] = clock64();
+        __syncwarp();
+        const uint64_t vh_desc = make_smem_desc_sw128(smem_u32(sV + (size_t)vs * 2 * v_bytes));
+        const uint64_t vl_desc = make_smem_desc_sw128(smem_u32(sV + (size_t)vs * 2 * v_bytes + v_bytes));
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t o = (uint64_t)(2 * kk);
-          umma_f16(o_tmem, pl_desc + o, vh_desc + o, idesc_o, (uint32_t)((t | kk) != 0));   // P_lo . V_hi
-          umma_f16(o_tmem, ph_desc + o, vl_desc + o, idesc_o, 1u);                          // P_hi . V_lo
-          umma_f16(o_tmem, ph_desc + o, vh_desc + o, idesc_o, 1u);                          // P_hi . V_hi
+          umma_f16_elect(o_tmem, pl_desc + o, vh_desc + o, idesc_o, (uint32_t)((t | kk) != 0));   // P_lo . V_hi
+          umma_f16_elect(o_tmem, ph_desc + o, vl_desc + o, idesc_o, 1u);                          // P_hi . V_lo
+          umma_f16_elect(o_tmem, ph_desc + o, vh_desc + o, idesc_o, 1u);                          // P_hi . V_hi
         }
-        umma_commit(&bar_pv);
-        if (t + 1 < T) {
-          mbar_wait(&bar_pv, (uint32_t)(t & 1));   // the V tile (and P) have been read
-          load_v(t + 1);
-        }
+        umma_commit_elect(&bar_vfree[vs]);
+        umma_commit_elect(&bar_pv);             // P may be overwritten, O holds tile t
+        if (rec) s.tl[t * 16 + 3] = clock64();
+        __syncwarp();
       }
     }
   } else {
-    // ===================== softmax warps: thread = query row =====================
-    const int row = tid, q = q0 + row;
+    // ===================== softmax warps: two threads per query row (= TMEM lane), 32 of the tile's 64 keys each =====================
+    // warps w and w + 4 share TMEM lane quadrant w & 3 (a warp may only read lanes 32 (w % 4) ...) and take the two column halves
+    const int quad = warp & 3, half = warp >= 6 ? 1 : 0;   // warps 0..3: quadrants 0..3, first half; warps 6..9: quadrants 2, 3, 0, 1, second half
+    const int stid = (half * 4 + quad) * 32 + lane;        // 0..255
+    const int row = quad * 32 + lane, q = q0 + row;
     const bool row_ok = q < s.L;
-    const float iq = row_ok ? reinterpret_cast<const float*>(s.Q16 + ((size_t)bh * s.L + q) * pitch_d + 2 * s.kc)[0] * s.scale2 : 0.f;
+    const float iq = row_ok ? reinterpret_cast<const float*>(s.Q16 + ((size_t)bh * s.L + q) * pitch_d + 2 * s.kc)[0] * s.scale2 : 1.f;
     // keys are masked for valid queries only (transformer.py:80-81); no query mask = every query valid (vision3d's k_masks)
     const bool use_mask = s.kv_mask != nullptr && (s.q_mask == nullptr || (row_ok && s.q_mask[(size_t)b * s.L + q] != 0));
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float NEG_INF = __int_as_float(0xff800000);
-    float m_ref = NEG_INF, l = 0.f;
+    float m_ref = NEG_INF, l = 0.f;                        // l: this thread's half of the row sum (both halves share m_ref)
     uint8_t* p_row = sP + (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128;
+    // this thread's 16-column chunks of the O accumulator (rescale, epilogue)
+    const int n16 = s.ND / 16, c16_lo = half ? (n16 + 1) / 2 : 0, c16_hi = half ? n16 : (n16 + 1) / 2;
     // the key rows' scales and mask bytes of tile t are fetched one tile ahead (scattered 4-byte loads: their latency stays off
-    // the per-tile critical path)
+    // the per-tile critical path) and published by the per-tile barrier of the tile before
     float n_ik = 0.f;
     bool n_ok = false, n_kv = false;
     auto fetch_cols = [&](int t) {
-      if (tid < FA_BN && t < T) {
-        const int j = t * FA_BN + tid;
+      if (stid < FA_BN && t < T) {
+        const int j = t * FA_BN + stid;
         n_ok = j < s.S;
         n_ik = n_ok ? reinterpret_cast<const float*>(s.K16 + ((size_t)bh * s.S + j) * pitch_d + 2 * s.kc)[0] : 0.f;
         n_kv = n_ok && (s.kv_mask == nullptr || s.kv_mask[(size_t)b * s.S + j] != 0);
       }
     };
+    auto publish_cols = [&](int t) {
+      if (stid < FA_BN && t < T) {
+        colinfo[t & 1][0][stid] = n_ik;
+        colinfo[t & 1][1][stid] = n_ok ? 0.f : NEG_INF;
+        colinfo[t & 1][2][stid] = n_kv ? 0.f : NEG_INF;
+      }
+    };
     fetch_cols(0);
+    publish_cols(0);
+    fetch_cols(1);
+    softmax_warps_sync();
     for (int t = 0; t < T; ++t) {
       const int par = t & 1;
-      if (tid < FA_BN) {
-        colinfo[par][0][tid] = n_ik;
-        colinfo[par][1][tid] = n_ok ? 0.f : NEG_INF;
-        colinfo[par][2][tid] = n_kv ? 0.f : NEG_INF;
-      }
-      fetch_cols(t + 1);
-      softmax_warps_sync();
-      const float4* ik4 = reinterpret_cast<const float4*>(colinfo[par][0]);
-      const float4* kb4 = reinterpret_cast<const float4*>(use_mask ? colinfo[par][2] : colinfo[par][1]);
+      publish_cols(t + 1);      // (nobody reads that buffer any more: tile t - 1's logits were scaled before its barrier)
+      fetch_cols(t + 2);
+      const float4* ik4 = reinterpret_cast<const float4*>(colinfo[par][0] + half * 32);
+      const float4* kb4 = reinterpret_cast<const float4*>((use_mask ? colinfo[par][2] : colinfo[par][1]) + half * 32);
+      const bool rec = s.tl && blockIdx.x == 0 && blockIdx.y == 0 && t < 64 && stid == 0;
+      if (rec) s.tl[t * 16 + 4] = clock64();
       mbar_wait(&bar_s[par], (uint32_t)((t >> 1) & 1));
       tcgen05_fence_after();
-      uint32_t a0[32], a1[32];
-      tmem_ld_32x32b_x32(lane_addr + (uint32_t)(par * FA_BN), a0);
-      tmem_ld_32x32b_x32(lane_addr + (uint32_t)(par * FA_BN + 32), a1);
+      if (rec) s.tl[t * 16 + 5] = clock64();
+      uint32_t a0[32];
+      tmem_ld_32x32b_x32(lane_addr + (uint32_t)(par * FA_BN + half * 32), a0);
       tmem_wait_ld();
-      float m_tile = NEG_INF;
+      if (rec) s.tl[t * 16 + 6] = clock64();
+      // x_j = acc_j / scale(key j) (+ -inf where masked); the logit is iq x_j with iq > 0 the row's factor: the maximum is taken
+      // over x and the factor rides in the exponent's FFMA
+      float m_half = NEG_INF;
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 i0 = ik4[j4], b0 = kb4[j4], i1 = ik4[8 + j4], b1 = kb4[8 + j4];
-        const float v0 = fmaf(__uint_as_float(a0[4 * j4]), iq * i0.x, b0.x), v1 = fmaf(__uint_as_float(a0[4 * j4 + 1]), iq * i0.y, b0.y);
-        const float v2 = fmaf(__uint_as_float(a0[4 * j4 + 2]), iq * i0.z, b0.z), v3 = fmaf(__uint_as_float(a0[4 * j4 + 3]), iq * i0.w, b0.w);
-        const float w0 = fmaf(__uint_as_float(a1[4 * j4]), iq * i1.x, b1.x), w1 = fmaf(__uint_as_float(a1[4 * j4 + 1]), iq * i1.y, b1.y);
-        const float w2 = fmaf(__uint_as_float(a1[4 * j4 + 2]), iq * i1.z, b1.z), w3 = fmaf(__uint_as_float(a1[4 * j4 + 3]), iq * i1.w, b1.w);
+        const float4 i0 = ik4[j4], b0 = kb4[j4];
+        const float v0 = fmaf(__uint_as_float(a0[4 * j4]), i0.x, b0.x), v1 = fmaf(__uint_as_float(a0[4 * j4 + 1]), i0.y, b0.y);
+        const float v2 = fmaf(__uint_as_float(a0[4 * j4 + 2]), i0.z, b0.z), v3 = fmaf(__uint_as_float(a0[4 * j4 + 3]), i0.w, b0.w);
         a0[4 * j4] = __float_as_uint(v0); a0[4 * j4 + 1] = __float_as_uint(v1); a0[4 * j4 + 2] = __float_as_uint(v2); a0[4 * j4 + 3] = __float_as_uint(v3);
-        a1[4 * j4] = __float_as_uint(w0); a1[4 * j4 + 1] = __float_as_uint(w1); a1[4 * j4 + 2] = __float_as_uint(w2); a1[4 * j4 + 3] = __float_as_uint(w3);
-        m_tile = fmaxf(m_tile, fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(w0, w1), fmaxf(w2, w3))));
+        m_half = fmaxf(m_half, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
       }
-      const bool need = m_tile > m_ref + FA_TAU;       // (m_ref = -inf: any finite maximum moves it)
+      m_half *= iq;
+      rowmax[par][half][row] = m_half;
+      if (rec) s.tl[t * 16 + 7] = clock64();
+      softmax_warps_sync();     // the other half's maximum; next tile's column info
+      if (rec) s.tl[t * 16 + 8] = clock64();
+      const float m_tile = fmaxf(m_half, rowmax[par][half ^ 1][row]);
+      const bool need = m_tile > m_ref + FA_TAU;       // (m_ref = -inf: any finite maximum moves it); identical in both halves
       const float m_new = need ? m_tile : m_ref;
       const float m_use = m_new == NEG_INF ? 0.f : m_new;   // nothing but masked keys so far: P = 2^(-inf) = 0, not NaN
       const float off = FA_PSHIFT - m_use;
-      // P of this tile, split into fp16 halves: a0 <- packed hi pairs / lo pairs (16 words each), likewise a1
+      // P of this half of the tile, split into fp16 halves, two entries per conversion
       float lsum = 0.f;
-      uint32_t hi[32], lo[32];
+      uint32_t hi[16], lo[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        unsigned short h0, l0, h1, l1;
-        const float p0 = fa_ex2(__uint_as_float(a0[2 * j]) + off), p1 = fa_ex2(__uint_as_float(a0[2 * j + 1]) + off);
+        const float p0 = fa_ex2(fmaf(__uint_as_float(a0[2 * j]), iq, off)), p1 = fa_ex2(fmaf(__uint_as_float(a0[2 * j + 1]), iq, off));
         lsum += p0 + p1;
-        split16(p0, h0, l0);
-        split16(p1, h1, l1);
-        hi[j] = pack16(h0, h1);
-        lo[j] = pack16(l0, l1);
+        split16x2(p0, p1, hi[j], lo[j]);
       }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        unsigned short h0, l0, h1, l1;
-        const float p0 = fa_ex2(__uint_as_float(a1[2 * j]) + off), p1 = fa_ex2(__uint_as_float(a1[2 * j + 1]) + off);
-        lsum += p0 + p1;
-        split16(p0, h0, l0);
-        split16(p1, h1, l1);
-        hi[16 + j] = pack16(h0, h1);
-        lo[16 + j] = pack16(l0, l1);
-      }
+      if (rec) s.tl[t * 16 + 9] = clock64();
       if (t > 0) {
         mbar_wait(&bar_pv, (uint32_t)((t - 1) & 1));   // P.V of the previous tile has read P and updated O
         tcgen05_fence_after();
+        if (rec) s.tl[t * 16 + 10] = clock64();
         if (__any_sync(0xffffffffu, need)) {
           const float f = need ? fa_ex2(m_ref - m_new) : 1.f;   // (m_ref = -inf: O and l are zero, f = 0)
           l *= f;
-          for (int c0 = 0; c0 < s.ND; c0 += 16) {
+          for (int c = c16_lo; c < c16_hi; ++c) {
             uint32_t r[16];
-            tmem_ld_32x32b_x16(lane_addr + FA_O_COL + (uint32_t)c0, r);
+            tmem_ld_32x32b_x16(lane_addr + FA_O_COL + (uint32_t)(c * 16), r);
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * f);
-            tmem_st_32x32b_x16(lane_addr + FA_O_COL + (uint32_t)c0, r);
+            tmem_st_32x32b_x16(lane_addr + FA_O_COL + (uint32_t)(c * 16), r);
           }
           tmem_wait_st();
         }
@@ -294,21 +407,27 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       l += lsum;
       // the A operand of P.V: K-major rows of 64 fp16 = 128 bytes, 16-byte chunk c of row r at chunk position c ^ (r & 7)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int pos = (c ^ (row & 7)) << 4;
+      for (int c = 0; c < 4; ++c) {
+        const int pos = ((4 * half + c) ^ (row & 7)) << 4;
         *reinterpret_cast<uint4*>(p_row + pos) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
         *reinterpret_cast<uint4*>(p_row + FA_P_BYTES + pos) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
       }
+      if (rec) s.tl[t * 16 + 11] = clock64();
       fence_proxy_async();
       tcgen05_fence_before();
       mbar_arrive(&bar_p);
+      if (rec) s.tl[t * 16 + 12] = clock64();
     }
     // ---- epilogue: O / l, the V^T rows' scales undone, [B, L, H * d] ----
+    rowsum[half][row] = l;
+    softmax_warps_sync();
+    const float l_row = l + rowsum[half ^ 1][row];
     mbar_wait(&bar_pv, (uint32_t)((T - 1) & 1));
     tcgen05_fence_after();
-    const float inv_l = 1.f / l;     // l = 0 (a valid query without a valid key): 0 * inf = NaN, as softmax of all -inf is
+    const float inv_l = 1.f / l_row;     // l = 0 (a valid query without a valid key): 0 * inf = NaN, as softmax of all -inf is
     float* orow = s.out + (((size_t)b * s.L + (row_ok ? q : 0)) * s.H + h) * s.d;
-    for (int c0 = 0; c0 < s.ND; c0 += 16) {
+    for (int c = c16_lo; c < c16_hi; ++c) {
+      const int c0 = c * 16;
       uint32_t r[16];
       tmem_ld_32x32b_x16(lane_addr + FA_O_COL + (uint32_t)c0, r);
       tmem_wait_ld();
@@ -326,6 +445,78 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// The V operand of the fused attention: V [B, S, H * d] fp32 -> per head the RIGHT split operand of V^T, [B * H, d, 2 kc(S) + 8]
+// = [hi | lo | tail] with the KEYS along the row (what four launches -- permute, contiguous, pad, drg_prep_operand -- produced).
+// Two kernels: the channels' maxima over the keys (row scale 2^e: maximum into [2^14, 2^15), the rule of features.cu) with
+// atomicMax on the bit patterns of |x|, then 64-key x 32-channel tiles transposed through shared memory, split and written
+// key-contiguous.  The tail holds 1 / scale only (nothing reads a norm of V^T rows).
+__global__ void __launch_bounds__(256) vt_colmax_kernel(const float* __restrict__ V, int H, int S, int d, unsigned int* __restrict__ cmax) {
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int C = H * d;
+  const float* vb = V + (size_t)b * S * C + (size_t)h * d;
+  const int j0 = blockIdx.x * 128, j1 = min(j0 + 128, S);
+  // thread = (channel quad, key phase): d / 4 quads side by side, 16-byte loads
+  const int nquad = d >> 2, per = 256 / nquad > 0 ? 256 / nquad : 1;
+  const int qd = threadIdx.x % nquad, ph = threadIdx.x / nquad;
+  __shared__ unsigned int smax[1024];
+  for (int i = threadIdx.x; i < d; i += 256) smax[i] = 0u;
+  __syncthreads();
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = j0 + ph; j < (ph < per ? j1 : 0); j += per) {
+    const float4 x = *reinterpret_cast<const float4*>(vb + (size_t)j * C + 4 * qd);
+    m.x = fmaxf(m.x, fabsf(x.x)); m.y = fmaxf(m.y, fabsf(x.y)); m.z = fmaxf(m.z, fabsf(x.z)); m.w = fmaxf(m.w, fabsf(x.w));
+    if (!(fabsf(x.x) <= 3.0e38f)) m.x = __int_as_float(0x7f800000);   // Inf / NaN: no scaling for that channel
+    if (!(fabsf(x.y) <= 3.0e38f)) m.y = __int_as_float(0x7f800000);
+    if (!(fabsf(x.z) <= 3.0e38f)) m.z = __int_as_float(0x7f800000);
+    if (!(fabsf(x.w) <= 3.0e38f)) m.w = __int_as_float(0x7f800000);
+  }
+  // non-negative floats order like their bit patterns: the CTA's maxima in shared memory, then one global atomic per channel
+  atomicMax(&smax[4 * qd], __float_as_uint(m.x));
+  atomicMax(&smax[4 * qd + 1], __float_as_uint(m.y));
+  atomicMax(&smax[4 * qd + 2], __float_as_uint(m.z));
+  atomicMax(&smax[4 * qd + 3], __float_as_uint(m.w));
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += 256) atomicMax(cmax + (size_t)bh * d + i, smax[i]);
+}
+
+__global__ void __launch_bounds__(256) vt_split_kernel(const float* __restrict__ V, const unsigned int* __restrict__ cmax, int H, int S, int d,
+                                                      unsigned short* __restrict__ out) {
+  __shared__ float tile[64][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int bh = blockIdx.z, b = bh / H, h = bh - b * H, c0 = blockIdx.y * 32, j0 = blockIdx.x * 64;
+  const int C = H * d, kcS = split16_kc(S);
+  const size_t pitch = (size_t)2 * kcS + 8;
+  const float* vb = V + (size_t)b * S * C + (size_t)h * d;
+  const int c = c0 + tx;
+  float sc = 1.f;
+  if (c < d) {
+    const float amax = __uint_as_float(cmax[(size_t)bh * d + c]);
+    int e = 0;
+    if (amax > 0.f && amax <= 3.0e38f) e = min(max(14 - ilogbf(amax), -126), 126);
+    sc = __int_as_float((e + 127) << 23);
+    if (j0 == 0 && ty == 0)
+      *reinterpret_cast<float4*>(out + ((size_t)bh * d + c) * pitch + 2 * kcS) = make_float4(__int_as_float((127 - e) << 23), 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int key = j0 + ty + 8 * i;
+    tile[ty + 8 * i][tx] = (key < S && c < d) ? vb[(size_t)key * C + c] * sc : 0.f;   // (keys S .. kc(S): the segment's zero padding)
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = ty + 8 * i;                  // 32 channels x 64 keys: lane = key pair
+    if (c0 + ch < d) {
+      unsigned short h0, l0, h1, l1;
+      split16(tile[2 * tx][ch], h0, l0);
+      split16(tile[2 * tx + 1][ch], h1, l1);
+      unsigned short* o = out + ((size_t)bh * d + c0 + ch) * pitch + j0 + 2 * tx;
+      *reinterpret_cast<uint32_t*>(o) = pack16(h0, h1);          // [hi | lo]: the right operand's pattern
+      *reinterpret_cast<uint32_t*>(o + kcS) = pack16(l0, l1);
+    }
+  }
 }
 
 }  // namespace drg
@@ -352,13 +543,35 @@ extern "C" int drg_attention_split16(const void* Q16, const void* K16, const voi
   s.q_mask = q_mask;
   s.kv_mask = kv_mask;
   s.out = out;
-  const int BH = B * H, nq = 2 * s.kc / 64;
-  CUtensorMap tQ, tK, tV;
+  s.tl = g_tuning_stamps;   // tuning hook (drg_tuning_set_stamp_buffer; tools/fa_timeline.py): NULL unless a tool set it
+  const int BH = B * H;
+  const int kc16 = (d + 15) & ~15;
+  s.nfull = kc16 / 64;
+  s.npiece = (kc16 % 64) / 16;
+  CUtensorMap tQ, tK, tV, tQp, tKp;
   if (!make_tmap(&tQ, Q16, BH, L, 2 * s.kc + 8, FA_BM, 64, 2)) return DRG_ERR_CUDA;
   if (!make_tmap(&tK, K16, BH, S, 2 * s.kc + 8, FA_BN, 64, 2)) return DRG_ERR_CUDA;
   if (!make_tmap(&tV, Vt16, BH, d, 2 * s.kcS + 8, s.ND, 64, 2)) return DRG_ERR_CUDA;
-  const size_t smem = 1024 + (size_t)nq * (FA_Q_CHUNK + FA_K_CHUNK) + (size_t)2 * s.ND * 128 + 2 * FA_P_BYTES;
-  if (smem + 3072 > 227 * 1024) {   // (+ the kernel's static shared memory)
+  if (s.npiece) {
+    if (!make_tmap(&tQp, Q16, BH, L, 2 * s.kc + 8, FA_BM, 16, 2, true, true)) return DRG_ERR_CUDA;
+    if (!make_tmap(&tKp, K16, BH, S, 2 * s.kc + 8, FA_BN, 16, 2, true, true)) return DRG_ERR_CUDA;
+  } else {
+    tQp = tQ;
+    tKp = tK;
+  }
+  const size_t budget = 227 * 1024 - 6144;     // (the kernel's static shared memory)
+  const size_t k_stage = (size_t)2 * (s.nfull * FA_K_CHUNK + s.npiece * (FA_K_CHUNK / 4)), v_stage = (size_t)2 * s.ND * 128;
+  size_t smem = 1024 + (size_t)2 * (s.nfull * FA_Q_CHUNK + s.npiece * (FA_Q_CHUNK / 4)) + k_stage + v_stage + 2 * FA_P_BYTES;
+  s.KS = s.VS = 1;
+  if (smem + k_stage <= budget) {
+    s.KS = 2;
+    smem += k_stage;
+  }
+  if (smem + v_stage <= budget) {
+    s.VS = 2;
+    smem += v_stage;
+  }
+  if (smem > budget) {
     set_error("attention: %zu bytes of shared memory for head width %d", smem, d);
     return DRG_ERR_UNSUPPORTED;
   }
@@ -370,11 +583,27 @@ extern "C" int drg_attention_split16(const void* Q16, const void* K16, const voi
   }
   if (FA_O_COL + s.ND <= 256) {
     DRG_CUDA((cudaFuncSetAttribute(flash_attn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-    flash_attn_kernel<256><<<grid, FA_THREADS, smem, st>>>(tQ, tK, tV, s);
+    flash_attn_kernel<256><<<grid, FA_THREADS, smem, st>>>(tQ, tK, tV, tQp, tKp, s);
   } else {
     DRG_CUDA((cudaFuncSetAttribute(flash_attn_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-    flash_attn_kernel<512><<<grid, FA_THREADS, smem, st>>>(tQ, tK, tV, s);
+    flash_attn_kernel<512><<<grid, FA_THREADS, smem, st>>>(tQ, tK, tV, tQp, tKp, s);
   }
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+extern "C" int drg_prep_vt_split16(const float* V, int B, int H, int S, int d, void* Vt16, void* workspace, void* stream) {
+  DRG_CHECK_ARG(V && Vt16 && workspace, "V / Vt16 / workspace must be non-null");
+  DRG_CHECK_ARG(B >= 1 && H >= 1 && S >= 1 && d >= 4 && d % 4 == 0 && B * H <= 65535, "B, H, S >= 1, d a multiple of 4, B * H <= 65535");
+  DRG_CHECK_ARG(((((uintptr_t)Vt16) | ((uintptr_t)V)) & 15u) == 0 && d <= 1024, "V / Vt16 must be 16-byte aligned, d <= 1024");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* cmax = reinterpret_cast<unsigned int*>(workspace);     // [B * H, d]
+  DRG_CUDA(cudaMemsetAsync(cmax, 0, (size_t)B * H * d * sizeof(unsigned int), st));
+  vt_colmax_kernel<<<dim3((unsigned)((S + 127) / 128), (unsigned)(B * H)), 256, 0, st>>>(V, H, S, d, cmax);
+  DRG_LAUNCH_CHECK();
+  const int kcS = split16_kc(S);
+  vt_split_kernel<<<dim3((unsigned)(kcS / 64), (unsigned)((d + 31) / 32), (unsigned)(B * H)), 256, 0, st>>>(
+      V, cmax, H, S, d, reinterpret_cast<unsigned short*>(Vt16));
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }

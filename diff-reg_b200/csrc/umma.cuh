@@ -217,7 +217,7 @@ static PFN_encodeTiled get_encode_fn() {
 // elem_bytes 4: fp32, 128-byte swizzle (operands, fp32 output boxes); 2: 16-bit (the type tag is irrelevant to a copy; fp16 and
 // bf16 segments share one map), 128-byte swizzle when `swizzle`, plain rows otherwise (the split epilogue's store boxes)
 static bool make_tmap(CUtensorMap* tm, const void* ptr, int batch, int rows, int cols, int box_rows, int box_cols, int elem_bytes = 4,
-                      bool swizzle = true) {
+                      bool swizzle = true, bool swizzle32 = false) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -228,7 +228,7 @@ static bool make_tmap(CUtensorMap* tm, const void* ptr, int batch, int rows, int
   cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = enc(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(ptr), dims,
-                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? (swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B) : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d] box [%d,%d]", (int)r, batch, rows, cols, box_rows, box_cols);

@@ -104,8 +104,10 @@ class MultiHeadAttention(nn.Module):
         v = _linear(self._cache, self.v_token_layer, v_tokens)
         q16 = ops.prep_heads(q, H, 0)
         k16 = ops.prep_heads(k, H, 1)
-        logits = ops.gemm_nt(q16, k16, split3=True, K=d)                               # [B*H, N, M]
         keep = None if k_masks is None else ~k_masks                                   # k_masks: True = ignored (transformer.py:76)
+        if not want_scores and d <= ops.FLASH_MAX_HEAD:                                # one fused kernel; the scores never reach HBM
+            return ops.attention(q16, k16, v, H, None, keep, 1.0 / d ** 0.5, d), None
+        logits = ops.gemm_nt(q16, k16, split3=True, K=d)                               # [B*H, N, M]
         res = ops.attn_softmax(logits, H, None, keep, 1.0 / d ** 0.5, want_operand=True, want_probs=want_scores)
         p16, scores = res if want_scores else (res, None)
         vt = v.view(B, M, H, d).permute(0, 2, 3, 1).contiguous().view(B * H, d, M)

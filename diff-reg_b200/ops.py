@@ -329,10 +329,9 @@ def attention(q16, k16, v, heads, q_mask, kv_mask, scale, d):
     S = k16.shape[1]
     B = BH // heads
     v = _f32c(v)
-    vt = v.view(B, S, heads, d).permute(0, 2, 3, 1).contiguous().view(BH, d, S)      # V^T per head, the keys along the row
-    if S % 4:                                   # operand rows are staged 16 bytes at a time
-        vt = torch.nn.functional.pad(vt, (0, 4 - S % 4))
-    vt16 = prep_operand(vt, 1.0, True, 1)
+    vt16 = torch.empty(BH, d, split_pitch(S), dtype=torch.int16, device=q16.device)  # V^T per head, the keys along the row
+    ws = workspace(BH * d * 4, q16.device, tag="attention_vmax")
+    check(lib.drg_prep_vt_split16(v.data_ptr(), B, heads, S, int(d), vt16.data_ptr(), ws.data_ptr(), _stream()))
     qm = _as_mask(q_mask, B, L, q16.device) if q_mask is not None else None
     km = _as_mask(kv_mask, B, S, q16.device) if kv_mask is not None else None
     out = torch.empty(B, L, heads * d, dtype=torch.float32, device=q16.device)

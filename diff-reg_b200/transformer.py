@@ -108,15 +108,20 @@ class GeometryAttentionLayer(nn.Module):
         rk = source_pe if (rotary and x_pe is not None) else None
         q16 = ops.prep_heads(qw, H, 0, pe=rq, pe_type="rotary" if rq is not None else None)          # [bs*H, L, .]
         k16 = ops.prep_heads(kw, H, 1, pe=rk, pe_type="rotary" if rk is not None else None)          # [bs*H, S, .]
-        # ---- attention (transformer.py:79-85): logits, masked scaled softmax, P.V
-        logits = ops.gemm_nt(q16, k16, split3=True, K=d)                                            # [bs*H, L, S]
-        p16 = ops.attn_softmax(logits, H, x_mask if source_mask is not None else None, source_mask, 1.0 / d ** 0.5)
-        vt = vw.view(bs, S, H, d).permute(0, 2, 3, 1).contiguous().view(bs * H, d, S)               # V^T per head, K-major over the keys
-        if S % 4:                                   # operand rows are staged 16 bytes at a time; same padded segment width
-            vt = torch.nn.functional.pad(vt, (0, 4 - S % 4))
-        vt16 = ops.prep_operand(vt, 1.0, True, 1)
-        o = ops.gemm_nt(p16, vt16, split3=True, K=S)                                                # [bs*H, L, d]
-        o = o.view(bs, H, L, d).permute(0, 2, 1, 3).contiguous().view(bs * L, C)
+        # ---- attention (transformer.py:79-85): one fused kernel (logits in TMEM, online softmax, P.V accumulated in TMEM); heads
+        # wider than it can hold take the three-kernel path (Q.K^T GEMM, masked scaled softmax, P.V GEMM through HBM)
+        if d <= ops.FLASH_MAX_HEAD:
+            o = ops.attention(q16, k16, vw, H, x_mask if source_mask is not None else None, source_mask, 1.0 / d ** 0.5, d)
+            o = o.view(bs * L, C)
+        else:
+            logits = ops.gemm_nt(q16, k16, split3=True, K=d)                                            # [bs*H, L, S]
+            p16 = ops.attn_softmax(logits, H, x_mask if source_mask is not None else None, source_mask, 1.0 / d ** 0.5)
+            vt = vw.view(bs, S, H, d).permute(0, 2, 3, 1).contiguous().view(bs * H, d, S)               # V^T per head, K-major over the keys
+            if S % 4:                                   # operand rows are staged 16 bytes at a time; same padded segment width
+                vt = torch.nn.functional.pad(vt, (0, 4 - S % 4))
+            vt16 = ops.prep_operand(vt, 1.0, True, 1)
+            o = ops.gemm_nt(p16, vt16, split3=True, K=S)                                                # [bs*H, L, d]
+            o = o.view(bs, H, L, d).permute(0, 2, 1, 3).contiguous().view(bs * L, C)
         # ---- merge, norm, MLP, norm, residual (transformer.py:87-94)
         message = self._linear("merge", self.merge, ops.prep_operand(o, 1.0, True, 0), bs * L)
         message = ops.layernorm(message, self.norm1.weight, self.norm1.bias, self.norm1.eps)

@@ -280,6 +280,9 @@ int drg_gemm_nt_split16_bias(const void* A16, const void* B16, const float* bias
  *   q_mask [B, L] / kv_mask [B, S] bool or NULL, 1 = valid: the keys with kv_mask == 0 are masked for the queries with
  *   q_mask != 0 (all queries when q_mask is NULL) -- the reference's expression; a valid query without a valid key yields NaN.
  *   out [B, L, H * d] fp32.  d % 4 == 0, d <= 176 (DRG_ERR_UNSUPPORTED otherwise: the caller keeps the three-kernel path). */
+/*   drg_prep_vt_split16: V [B, S, H * d] fp32 -> Vt16 as above (per head V^T, the keys along the row; the tail holds 1 / scale
+ *   only).  workspace: B * H * d * 4 bytes (the channels' maxima). */
+int drg_prep_vt_split16(const float* V, int B, int H, int S, int d, void* Vt16, void* workspace, void* stream);
 int drg_attention_split16(const void* Q16, const void* K16, const void* Vt16, const uint8_t* q_mask, const uint8_t* kv_mask, int B,
                           int H, int L, int S, int d, float scale, float* out, void* stream);
 int drg_fourier_embed(const float* x, const float* center, long long rows, int n, int length, float k0, int use_pi, int use_input,

@@ -31,6 +31,15 @@ for (H, L, S, d) in ((4, 4096, 4096, 132), (4, 4096, 4096, 64), (4, 2048, 4800, 
     fused = lambda: ops.attention(q16, k16, v, H, None, None, scale, d)
     a, b = fused(), three().view(1, H, L, d).permute(0, 2, 1, 3).reshape(1, L, H * d)
     flops = 2 * 2.0 * H * L * S * d
-    tf, t3 = timed(fused), timed(three)
+    def graphed(fn):          # GPU time without the eager launch gaps: one CUDA-graph replay of the same launches
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            fn(); fn()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, stream=st):
+                fn()
+        torch.cuda.synchronize()
+        return timed(g_.replay)
+    tf, t3 = graphed(fused), graphed(three)
     print(json.dumps({"H": H, "L": L, "S": S, "d": d, "fused_us": round(tf, 1), "three_kernel_us": round(t3, 1),
                       "useful_TFLOPs": round(flops / tf / 1e6, 1), "max_abs_diff": (a - b).abs().max().item()}), flush=True)
