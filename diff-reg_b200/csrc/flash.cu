@@ -13,15 +13,19 @@
 // on the fly.  S = Q_lo.K_hi + Q_hi.K_lo + Q_hi.K_hi, O += P_lo.V_hi + P_hi.V_lo + P_hi.V_hi, fp32 accumulation in TMEM.
 //
 // One CTA = 128 queries of one (batch, head); keys in tiles of 64.  320 threads:
-//   warp 5 (one elected lane)  TMA producer: Q once, then the K tiles (one tile ahead) and V^T tiles through two rings of shared-memory
-//                              stages (two stages each where they fit: every head width but the 132 of 4DMatch, whose Q tile
-//                              alone is 96 KB), freed by the tensor core's commits
-//   warp 4 (one elected lane)  MMA issuer: S = Q.K^T of tile t+1 into one of TWO TMEM accumulators while the softmax warps work on
-//                              tile t, then -- once they have published P -- O += P.V of tile t (O lives in TMEM for the whole pass)
-//   warps 0..3, 6..9           softmax: two threads per query row (= TMEM lane), 32 of the tile's 64 logits each.  tcgen05.ld, row /
-//                              column scales of the split operands, masks, running maximum (the halves exchange theirs through
-//                              shared memory), exp2, row sum, fp16 hi / lo split of P written as the 128-byte-swizzled K-major
-//                              A operand of the P.V product
+//   warp 5   TMA producer (lane 0): Q once, then the K tiles (one tile ahead) and V^T tiles through two rings of shared-memory
+//            stages (K double-buffered at every supported head width, V^T where it fits), freed by the tensor core's commits;
+//            all lanes: the key tiles' column info (operand row scales, mask bytes) through a ring of four slots
+//   warp 4   MMA issuer, the whole warp converged with one ELECTED lane per instruction: S = Q.K^T of tile t+1 into one of TWO
+//            TMEM accumulators while the softmax warps work on tile t, then -- once they have published P -- O += P.V of tile t
+//            (O lives in TMEM for the whole pass).  Straight-line issue code (the kernel is templated on the operand chunk
+//            counts): a 128 x 64 x 16 MMA occupies the pipe for 32 cycles, a loop with run-time bounds needs ~90 per MMA.
+//   warps 0..3, 6..9   softmax: two threads per query row (= TMEM lane), 32 of the tile's 64 logits each.  tcgen05.ld, row /
+//            column scales of the split operands, masks, running maximum (the halves exchange theirs through shared memory),
+//            exp2, row sum, fp16 hi / lo split of P (packed conversions) written as the 128-byte-swizzled K-major A operand
+//            of the P.V product
+// Head widths that are not multiples of 64 keep their Q / K tiles as 64-column chunks (128-byte swizzle) plus 16-column pieces
+// (32-byte swizzle): the 132-wide heads of 4DMatch take 27 instead of 36 k-steps per S tile and 72 + 36 KB instead of 96 + 48.
 // Online softmax with a LAZY reference: P = 2^(s - m_ref + 6) with m_ref only moved (and O, l rescaled through tcgen05.ld / st)
 // when the tile's maximum exceeds it by more than 8 (log2 units), so P <= 2^14 stays inside fp16 and the rescale of the
 // accumulator is rare after the first tiles.  The 2^6 and the stale reference cancel in O / l.
@@ -31,7 +35,9 @@ namespace drg {
 
 constexpr int FA_BM = 128;        // queries per CTA (TMEM lanes)
 constexpr int FA_BN = 64;         // keys per tile = one 128-byte swizzle-atom row of 16-bit P
-constexpr int FA_THREADS = 320;    // 8 softmax warps + the MMA issuer (warp 4) + the TMA producer (warp 5)
+constexpr int FA_PARTS = 2;         // softmax threads per query row (measured: 4 -- sixteen softmax warps -- is slower, 122 vs 112 us)
+constexpr int FA_CP = 64 / FA_PARTS;   // columns of a key tile per softmax thread
+constexpr int FA_THREADS = 32 * (4 * FA_PARTS + 2);   // 4 FA_PARTS softmax warps + the MMA issuer (warp 4) + the TMA producer (warp 5)
 constexpr float FA_TAU = 8.f;     // move the reference when a tile's maximum exceeds it by more than this (log2 units)
 constexpr float FA_PSHIFT = 6.f;  // P is carried as 2^6 * exp(.): hi / lo halves of the small entries stay normal fp16 numbers
 constexpr int FA_Q_CHUNK = FA_BM * 128;   // bytes of one 64-column chunk of the Q tile
@@ -110,7 +116,7 @@ __device__ __forceinline__ float fa_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void softmax_warps_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void softmax_warps_sync() { asm volatile("bar.sync 1, %0;" ::"n"(128 * FA_PARTS) : "memory"); }
 // (x0, x1) = hi + lo, both fp16 pairs: one packed conversion per pair (F2FP) instead of two scalar ones on the XU pipe
 __device__ __forceinline__ void split16x2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
   uint32_t h;
@@ -121,7 +127,24 @@ __device__ __forceinline__ void split16x2(float x0, float x1, uint32_t& hi2, uin
   hi2 = h;
 }
 
-template <int TMEM_COLS>
+// Tuning stamps (tools/fa_timeline.py) are compiled in only with -DDRG_FA_TIMELINE: even predicated off, their stores sit in the
+// softmax warps' instruction stream
+#ifdef DRG_FA_TIMELINE
+#define FA_STAMP(k)                                                                                  \
+  do {                                                                                               \
+    if (s.tl && blockIdx.x == 0 && blockIdx.y == 0 && t < 64 && stid == 0) s.tl[t * 16 + (k)] = clock64(); \
+  } while (0)
+#define FA_STAMP_MMA(tt, k)                                                                                  \
+  do {                                                                                                       \
+    if (s.tl && blockIdx.x == 0 && blockIdx.y == 0 && (tt) >= 0 && (tt) < 64 && lane == 0) s.tl[(tt) * 16 + (k)] = clock64(); \
+    __syncwarp();                                                                                            \
+  } while (0)
+#else
+#define FA_STAMP(k) do { } while (0)
+#define FA_STAMP_MMA(tt, k) do { } while (0)
+#endif
+
+template <int NFULL, int NPIECE>
 __global__ void __launch_bounds__(FA_THREADS, 1)
     flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQp,
@@ -130,15 +153,19 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   __shared__ __align__(8) uint64_t bar_q, bar_p, bar_pv;
   __shared__ __align__(8) uint64_t bar_s[2], bar_kfull[2], bar_kfree[2], bar_vfull[2], bar_vfree[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float colinfo[2][3][FA_BN];   // per tile parity: 1 / scale of the key rows, bias (0 / -inf) without and with the key mask
-  __shared__ float rowmax[2][2][FA_BM];    // per tile parity: the two column halves' row maxima
-  __shared__ float rowsum[2][FA_BM];       // the two halves' row sums (epilogue)
+  __shared__ __align__(8) uint64_t bar_ci[4];
+  __shared__ __align__(16) float colinfo[4][3][FA_BN];   // per tile parity: 1 / scale of the key rows, bias (0 / -inf) without and with the key mask
+  __shared__ float rowmax[2][FA_PARTS][FA_BM];   // per tile parity: the column parts' row maxima
+  __shared__ float rowsum[FA_PARTS][FA_BM];      // the parts' row sums (epilogue)
   __shared__ float vscale[256];            // 1 / scale of the V^T rows (= output channels)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y, b = bh / s.H, h = bh - b * s.H;
   const int q0 = blockIdx.x * FA_BM;
-  const int nfull = s.nfull, npiece = s.npiece;
+  // NFULL 64-column chunks + NPIECE 16-column pieces per operand segment: compile-time, so that the MMA warp's issue loops are
+  // straight-line code (a loop with run-time bounds costs ~90 cycles per MMA in that single warp, unrolled code ~40)
+  constexpr int nfull = NFULL, npiece = NPIECE;
+  constexpr int TMEM_COLS = (FA_S_COLS + 16 * (4 * NFULL + NPIECE)) <= 256 ? 256 : 512;   // S x 2 + O (ND = 16 (4 NFULL + NPIECE) columns)
   const uint32_t q_seg = (uint32_t)(nfull * FA_Q_CHUNK + npiece * (FA_Q_CHUNK / 4));   // bytes of one segment (lo or hi) of the Q tile
   const uint32_t k_seg = (uint32_t)(nfull * FA_K_CHUNK + npiece * (FA_K_CHUNK / 4));
   const int T = (s.S + FA_BN - 1) / FA_BN;
@@ -161,8 +188,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       prefetch_tmap(&tmKp);
     }
     mbar_init(&bar_q, 1);
-    mbar_init(&bar_p, 2 * FA_BM);
+    mbar_init(&bar_p, FA_PARTS * FA_BM);
     mbar_init(&bar_pv, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_ci[i], 32);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_s[i], 1);
       mbar_init(&bar_kfull[i], 1);
@@ -182,8 +210,36 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 5) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    {
+      // ===================== TMA producer (lane 0) + the key tiles' column info (all lanes) =====================
+      // Column info of a key tile = the K operand rows' 1 / scale and the mask bytes: scattered 4- / 1-byte global loads.  In the
+      // softmax warps such a load stalled its warp for ~500 cycles per tile at ISSUE, however far ahead it was requested
+      // (tools/fa_timeline.py; 117.7 -> 103.3 us without them), so this warp -- which runs ahead of everybody anyway -- fetches
+      // them one tile ahead into registers and publishes them through a ring of four shared-memory slots (bar_ci).  A slot's
+      // previous user, tile t - 4, is done: K(t)'s stage is only free once S(t - KS) has completed, which the MMA warp issued
+      // after the softmax warps had published P(t - KS - 1).
+      const float NEG_INF = __int_as_float(0xff800000);
+      float c_ik[2] = {0.f, 0.f};
+      bool c_ok[2] = {false, false}, c_kv[2] = {false, false};
+      auto fetch_cols = [&](int t) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int j = t * FA_BN + lane + 32 * i;
+          c_ok[i] = t < T && j < s.S;
+          c_ik[i] = c_ok[i] ? reinterpret_cast<const float*>(s.K16 + ((size_t)bh * s.S + j) * pitch_d + 2 * s.kc)[0] : 0.f;
+          c_kv[i] = c_ok[i] && (s.kv_mask == nullptr || s.kv_mask[(size_t)b * s.S + j] != 0);
+        }
+      };
+      auto publish_cols = [&](int t) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          colinfo[t & 3][0][lane + 32 * i] = c_ik[i];
+          colinfo[t & 3][1][lane + 32 * i] = c_ok[i] ? 0.f : NEG_INF;
+          colinfo[t & 3][2][lane + 32 * i] = c_kv[i] ? 0.f : NEG_INF;
+        }
+        mbar_arrive(&bar_ci[t & 3]);     // (release; 32 arrivals complete the phase)
+      };
+      fetch_cols(0);
       auto load_k = [&](int t) {
         const int st = t % s.KS;
         mbar_wait(&bar_kfree[st], (uint32_t)(((t / s.KS) & 1) ^ 1));   // S of tile t - KS has read the stage (first pass: free)
@@ -205,17 +261,28 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         tma_load_3d(dst, &tmV, t * FA_BN, 0, bh, &bar_vfull[st]);                     // V_hi: keys of this tile along the row
         tma_load_3d(dst + v_bytes, &tmV, s.kcS + t * FA_BN, 0, bh, &bar_vfull[st]);   // V_lo
       };
-      mbar_arrive_expect_tx(&bar_q, 2u * q_seg);
-      for (int seg = 0; seg < 2; ++seg) {
-        uint8_t* sd = sQ + (size_t)seg * q_seg;
-        for (int c = 0; c < nfull; ++c) tma_load_3d(sd + (size_t)c * FA_Q_CHUNK, &tmQ, seg * s.kc + c * 64, q0, bh, &bar_q);
-        for (int c = 0; c < npiece; ++c)
-          tma_load_3d(sd + (size_t)nfull * FA_Q_CHUNK + (size_t)c * (FA_Q_CHUNK / 4), &tmQp, seg * s.kc + nfull * 64 + c * 16, q0, bh, &bar_q);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bar_q, 2u * q_seg);
+        for (int seg = 0; seg < 2; ++seg) {
+          uint8_t* sd = sQ + (size_t)seg * q_seg;
+          for (int c = 0; c < nfull; ++c) tma_load_3d(sd + (size_t)c * FA_Q_CHUNK, &tmQ, seg * s.kc + c * 64, q0, bh, &bar_q);
+          for (int c = 0; c < npiece; ++c)
+            tma_load_3d(sd + (size_t)nfull * FA_Q_CHUNK + (size_t)c * (FA_Q_CHUNK / 4), &tmQp, seg * s.kc + nfull * 64 + c * 16, q0, bh, &bar_q);
+        }
+        load_k(0);
       }
-      load_k(0);
+      __syncwarp();
+      publish_cols(0);
+      fetch_cols(1);
       for (int t = 0; t < T; ++t) {     // K runs one tile ahead of V: S(t+1) is issued before P.V(t), so its stage frees first
-        if (t + 1 < T) load_k(t + 1);
-        load_v(t);
+        if (t + 1 < T) {
+          if (lane == 0) load_k(t + 1);
+          __syncwarp();
+          publish_cols(t + 1);
+          fetch_cols(t + 2);
+        }
+        if (lane == 0) load_v(t);
+        __syncwarp();
       }
     }
   } else if (warp == 4) {
@@ -234,8 +301,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         const int st = t % s.KS;
         wwait(&bar_kfull[st], (uint32_t)((t / s.KS) & 1));
         tcgen05_fence_after();
-        if (s.tl && blockIdx.x == 0 && blockIdx.y == 0 && t >= 1 && t <= 64 && lane == 0) s.tl[(t - 1) * 16 + 13] = clock64();
-        __syncwarp();
+        FA_STAMP_MMA(t - 1, 13);
         const uint32_t d_tmem = tmem_base + (uint32_t)((t & 1) * FA_BN);
         uint32_t acc = 0u;
         // Descriptors are base + constant offsets in 16-byte units (the start-address field is the low word: plain 64-bit
@@ -244,6 +310,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         const uint64_t kofs = (uint64_t)(((uint32_t)st * k_bytes) >> 4);
         auto term = [&](uint32_t qs, uint32_t ks) {
           const uint64_t qo = (uint64_t)((qs * q_seg) >> 4), ko = kofs + (uint64_t)((ks * k_seg) >> 4);
+#pragma unroll
           for (int c = 0; c < nfull; ++c) {
             const uint64_t a_desc = q128 + qo + (uint64_t)(c * (FA_Q_CHUNK >> 4)), b_desc = k128 + ko + (uint64_t)(c * (FA_K_CHUNK >> 4));
 #pragma unroll
@@ -252,6 +319,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
               acc = 1u;
             }
           }
+#pragma unroll
           for (int c = 0; c < npiece; ++c) {     // 16-column pieces: one K = 16 step each, rows of 32 bytes
             umma_f16_elect(d_tmem, q32 + qo + (uint64_t)(nfull * (FA_Q_CHUNK >> 4) + c * (FA_Q_CHUNK >> 6)),
                            k32 + ko + (uint64_t)(nfull * (FA_K_CHUNK >> 4) + c * (FA_K_CHUNK >> 6)), idesc_s, acc);
@@ -261,8 +329,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         term(0, 0);
         term(1, 1);
         term(1, 0);
-        if (s.tl && blockIdx.x == 0 && blockIdx.y == 0 && t >= 1 && t <= 64 && lane == 0) s.tl[(t - 1) * 16 + 14] = clock64();
-        __syncwarp();
+        FA_STAMP_MMA(t - 1, 14);
         umma_commit_elect(&bar_kfree[st]);      // the K stage may be refilled ...
         umma_commit_elect(&bar_s[t & 1]);       // ... and the logits are ready
       };
@@ -273,18 +340,14 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       const uint32_t o_tmem = tmem_base + FA_O_COL;
       for (int t = 0; t < T; ++t) {
         // S(t+1) into the other accumulator, whose tile t - 1 the softmax warps have consumed (bar_p of t - 1, waited below)
-        const bool rec = s.tl && blockIdx.x == 0 && blockIdx.y == 0 && t < 64 && lane == 0;
-        if (rec) s.tl[t * 16 + 0] = clock64();
-        __syncwarp();
+        FA_STAMP_MMA(t, 0);
         if (t + 1 < T) issue_s(t + 1);
-        if (rec) s.tl[t * 16 + 1] = clock64();
-        __syncwarp();
+        FA_STAMP_MMA(t, 1);
         const int vs = t % s.VS;
         wwait(&bar_vfull[vs], (uint32_t)((t / s.VS) & 1));
         wwait(&bar_p, (uint32_t)(t & 1));
         tcgen05_fence_after();
-        if (rec) s.tl[t * 16 + 2] = clock64();
-        __syncwarp();
+        FA_STAMP_MMA(t, 2);
         const uint64_t vh_desc = make_smem_desc_sw128(smem_u32(sV + (size_t)vs * 2 * v_bytes));
         const uint64_t vl_desc = make_smem_desc_sw128(smem_u32(sV + (size_t)vs * 2 * v_bytes + v_bytes));
 #pragma unroll
@@ -296,15 +359,16 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         }
         umma_commit_elect(&bar_vfree[vs]);
         umma_commit_elect(&bar_pv);             // P may be overwritten, O holds tile t
-        if (rec) s.tl[t * 16 + 3] = clock64();
-        __syncwarp();
+        FA_STAMP_MMA(t, 3);
       }
     }
   } else {
-    // ===================== softmax warps: two threads per query row (= TMEM lane), 32 of the tile's 64 keys each =====================
-    // warps w and w + 4 share TMEM lane quadrant w & 3 (a warp may only read lanes 32 (w % 4) ...) and take the two column halves
-    const int quad = warp & 3, half = warp >= 6 ? 1 : 0;   // warps 0..3: quadrants 0..3, first half; warps 6..9: quadrants 2, 3, 0, 1, second half
-    const int stid = (half * 4 + quad) * 32 + lane;        // 0..255
+    // ===================== softmax warps: FA_PARTS threads per query row (= TMEM lane), 64 / FA_PARTS of the tile's 64 keys each =====================
+    // The chain wait-S / tcgen05.ld / scale / max / exp2 / split / store / arrive of a tile is latency bound (measured with two
+    // threads per row: 2500 cycles per tile at 35 % issue utilisation), so it is spread over sixteen warps.  A warp may only read
+    // TMEM lanes 32 (w % 4) ...: the four warps of a lane quadrant take the four 16-column parts of the tile.
+    const int quad = warp & 3, part = warp < 4 ? 0 : 1 + (warp - 6) / 4;   // warps 0..3, 6..9 (, 10..13, 14..17)
+    [[maybe_unused]] const int stid = (part * 4 + quad) * 32 + lane;        // 0..511
     const int row = quad * 32 + lane, q = q0 + row;
     const bool row_ok = q < s.L;
     const float iq = row_ok ? reinterpret_cast<const float*>(s.Q16 + ((size_t)bh * s.L + q) * pitch_d + 2 * s.kc)[0] * s.scale2 : 1.f;
@@ -312,83 +376,63 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     const bool use_mask = s.kv_mask != nullptr && (s.q_mask == nullptr || (row_ok && s.q_mask[(size_t)b * s.L + q] != 0));
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float NEG_INF = __int_as_float(0xff800000);
-    float m_ref = NEG_INF, l = 0.f;                        // l: this thread's half of the row sum (both halves share m_ref)
+    float m_ref = NEG_INF, l = 0.f;                        // l: this thread's part of the row sum (the parts share m_ref)
     uint8_t* p_row = sP + (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128;
     // this thread's 16-column chunks of the O accumulator (rescale, epilogue)
-    const int n16 = s.ND / 16, c16_lo = half ? (n16 + 1) / 2 : 0, c16_hi = half ? n16 : (n16 + 1) / 2;
-    // the key rows' scales and mask bytes of tile t are fetched one tile ahead (scattered 4-byte loads: their latency stays off
-    // the per-tile critical path) and published by the per-tile barrier of the tile before
-    float n_ik = 0.f;
-    bool n_ok = false, n_kv = false;
-    auto fetch_cols = [&](int t) {
-      if (stid < FA_BN && t < T) {
-        const int j = t * FA_BN + stid;
-        n_ok = j < s.S;
-        n_ik = n_ok ? reinterpret_cast<const float*>(s.K16 + ((size_t)bh * s.S + j) * pitch_d + 2 * s.kc)[0] : 0.f;
-        n_kv = n_ok && (s.kv_mask == nullptr || s.kv_mask[(size_t)b * s.S + j] != 0);
-      }
-    };
-    auto publish_cols = [&](int t) {
-      if (stid < FA_BN && t < T) {
-        colinfo[t & 1][0][stid] = n_ik;
-        colinfo[t & 1][1][stid] = n_ok ? 0.f : NEG_INF;
-        colinfo[t & 1][2][stid] = n_kv ? 0.f : NEG_INF;
-      }
-    };
-    fetch_cols(0);
-    publish_cols(0);
-    fetch_cols(1);
-    softmax_warps_sync();
+    const int n16 = s.ND / 16, c16_lo = (part * n16) / FA_PARTS, c16_hi = ((part + 1) * n16) / FA_PARTS;
     for (int t = 0; t < T; ++t) {
       const int par = t & 1;
-      publish_cols(t + 1);      // (nobody reads that buffer any more: tile t - 1's logits were scaled before its barrier)
-      fetch_cols(t + 2);
-      const float4* ik4 = reinterpret_cast<const float4*>(colinfo[par][0] + half * 32);
-      const float4* kb4 = reinterpret_cast<const float4*>((use_mask ? colinfo[par][2] : colinfo[par][1]) + half * 32);
-      const bool rec = s.tl && blockIdx.x == 0 && blockIdx.y == 0 && t < 64 && stid == 0;
-      if (rec) s.tl[t * 16 + 4] = clock64();
+      FA_STAMP(15);
+      const float4* ik4 = reinterpret_cast<const float4*>(colinfo[t & 3][0] + part * FA_CP);
+      const float4* kb4 = reinterpret_cast<const float4*>((use_mask ? colinfo[t & 3][2] : colinfo[t & 3][1]) + part * FA_CP);
+      mbar_wait(&bar_ci[t & 3], (uint32_t)((t >> 2) & 1));     // the tile's column info (producer warp)
+      FA_STAMP(4);
       mbar_wait(&bar_s[par], (uint32_t)((t >> 1) & 1));
       tcgen05_fence_after();
-      if (rec) s.tl[t * 16 + 5] = clock64();
-      uint32_t a0[32];
-      tmem_ld_32x32b_x32(lane_addr + (uint32_t)(par * FA_BN + half * 32), a0);
+      FA_STAMP(5);
+      uint32_t a0[FA_CP];
+#pragma unroll
+      for (int c = 0; c < FA_CP / 16; ++c)
+        tmem_ld_32x32b_x16(lane_addr + (uint32_t)(par * FA_BN + part * FA_CP + 16 * c), *reinterpret_cast<uint32_t(*)[16]>(a0 + 16 * c));
       tmem_wait_ld();
-      if (rec) s.tl[t * 16 + 6] = clock64();
+      FA_STAMP(6);
       // x_j = acc_j / scale(key j) (+ -inf where masked); the logit is iq x_j with iq > 0 the row's factor: the maximum is taken
       // over x and the factor rides in the exponent's FFMA
-      float m_half = NEG_INF;
+      float m_part = NEG_INF;
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
+      for (int j4 = 0; j4 < FA_CP / 4; ++j4) {
         const float4 i0 = ik4[j4], b0 = kb4[j4];
         const float v0 = fmaf(__uint_as_float(a0[4 * j4]), i0.x, b0.x), v1 = fmaf(__uint_as_float(a0[4 * j4 + 1]), i0.y, b0.y);
         const float v2 = fmaf(__uint_as_float(a0[4 * j4 + 2]), i0.z, b0.z), v3 = fmaf(__uint_as_float(a0[4 * j4 + 3]), i0.w, b0.w);
         a0[4 * j4] = __float_as_uint(v0); a0[4 * j4 + 1] = __float_as_uint(v1); a0[4 * j4 + 2] = __float_as_uint(v2); a0[4 * j4 + 3] = __float_as_uint(v3);
-        m_half = fmaxf(m_half, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
+        m_part = fmaxf(m_part, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
       }
-      m_half *= iq;
-      rowmax[par][half][row] = m_half;
-      if (rec) s.tl[t * 16 + 7] = clock64();
-      softmax_warps_sync();     // the other half's maximum; next tile's column info
-      if (rec) s.tl[t * 16 + 8] = clock64();
-      const float m_tile = fmaxf(m_half, rowmax[par][half ^ 1][row]);
-      const bool need = m_tile > m_ref + FA_TAU;       // (m_ref = -inf: any finite maximum moves it); identical in both halves
+      m_part *= iq;
+      rowmax[par][part][row] = m_part;
+      FA_STAMP(7);
+      softmax_warps_sync();     // the other parts' maxima
+      FA_STAMP(8);
+      float m_tile = rowmax[par][0][row];
+#pragma unroll
+      for (int pp = 1; pp < FA_PARTS; ++pp) m_tile = fmaxf(m_tile, rowmax[par][pp][row]);
+      const bool need = m_tile > m_ref + FA_TAU;       // (m_ref = -inf: any finite maximum moves it); identical in all parts
       const float m_new = need ? m_tile : m_ref;
       const float m_use = m_new == NEG_INF ? 0.f : m_new;   // nothing but masked keys so far: P = 2^(-inf) = 0, not NaN
       const float off = FA_PSHIFT - m_use;
-      // P of this half of the tile, split into fp16 halves, two entries per conversion
+      // P of this part of the tile, split into fp16 halves, two entries per conversion
       float lsum = 0.f;
-      uint32_t hi[16], lo[16];
+      uint32_t hi[FA_CP / 2], lo[FA_CP / 2];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < FA_CP / 2; ++j) {
         const float p0 = fa_ex2(fmaf(__uint_as_float(a0[2 * j]), iq, off)), p1 = fa_ex2(fmaf(__uint_as_float(a0[2 * j + 1]), iq, off));
         lsum += p0 + p1;
         split16x2(p0, p1, hi[j], lo[j]);
       }
-      if (rec) s.tl[t * 16 + 9] = clock64();
+      FA_STAMP(9);
       if (t > 0) {
         mbar_wait(&bar_pv, (uint32_t)((t - 1) & 1));   // P.V of the previous tile has read P and updated O
         tcgen05_fence_after();
-        if (rec) s.tl[t * 16 + 10] = clock64();
+        FA_STAMP(10);
         if (__any_sync(0xffffffffu, need)) {
           const float f = need ? fa_ex2(m_ref - m_new) : 1.f;   // (m_ref = -inf: O and l are zero, f = 0)
           l *= f;
@@ -407,21 +451,23 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       l += lsum;
       // the A operand of P.V: K-major rows of 64 fp16 = 128 bytes, 16-byte chunk c of row r at chunk position c ^ (r & 7)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int pos = ((4 * half + c) ^ (row & 7)) << 4;
+      for (int c = 0; c < FA_CP / 8; ++c) {
+        const int pos = (((FA_CP / 8) * part + c) ^ (row & 7)) << 4;
         *reinterpret_cast<uint4*>(p_row + pos) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
         *reinterpret_cast<uint4*>(p_row + FA_P_BYTES + pos) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
       }
-      if (rec) s.tl[t * 16 + 11] = clock64();
+      FA_STAMP(11);
       fence_proxy_async();
       tcgen05_fence_before();
       mbar_arrive(&bar_p);
-      if (rec) s.tl[t * 16 + 12] = clock64();
+      FA_STAMP(12);
     }
     // ---- epilogue: O / l, the V^T rows' scales undone, [B, L, H * d] ----
-    rowsum[half][row] = l;
+    rowsum[part][row] = l;
     softmax_warps_sync();
-    const float l_row = l + rowsum[half ^ 1][row];
+    float l_row = rowsum[0][row];
+#pragma unroll
+    for (int pp = 1; pp < FA_PARTS; ++pp) l_row += rowsum[pp][row];
     mbar_wait(&bar_pv, (uint32_t)((T - 1) & 1));
     tcgen05_fence_after();
     const float inv_l = 1.f / l_row;     // l = 0 (a valid query without a valid key): 0 * inf = NaN, as softmax of all -inf is
@@ -559,7 +605,7 @@ extern "C" int drg_attention_split16(const void* Q16, const void* K16, const voi
     tQp = tQ;
     tKp = tK;
   }
-  const size_t budget = 227 * 1024 - 6144;     // (the kernel's static shared memory)
+  const size_t budget = 227 * 1024 - 9216;     // (the kernel's static shared memory)
   const size_t k_stage = (size_t)2 * (s.nfull * FA_K_CHUNK + s.npiece * (FA_K_CHUNK / 4)), v_stage = (size_t)2 * s.ND * 128;
   size_t smem = 1024 + (size_t)2 * (s.nfull * FA_Q_CHUNK + s.npiece * (FA_Q_CHUNK / 4)) + k_stage + v_stage + 2 * FA_P_BYTES;
   s.KS = s.VS = 1;
@@ -581,12 +627,19 @@ extern "C" int drg_attention_split16(const void* Q16, const void* K16, const voi
     set_error("attention: batch * heads = %d exceeds the grid", BH);
     return DRG_ERR_UNSUPPORTED;
   }
-  if (FA_O_COL + s.ND <= 256) {
-    DRG_CUDA((cudaFuncSetAttribute(flash_attn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-    flash_attn_kernel<256><<<grid, FA_THREADS, smem, st>>>(tQ, tK, tV, tQp, tKp, s);
-  } else {
-    DRG_CUDA((cudaFuncSetAttribute(flash_attn_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-    flash_attn_kernel<512><<<grid, FA_THREADS, smem, st>>>(tQ, tK, tV, tQp, tKp, s);
+  bool launched = false;
+#define FA_CASE(NF, NP)                                                                                                   \
+  if (s.nfull == NF && s.npiece == NP) {                                                                                  \
+    DRG_CUDA((cudaFuncSetAttribute(flash_attn_kernel<NF, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))); \
+    flash_attn_kernel<NF, NP><<<grid, FA_THREADS, smem, st>>>(tQ, tK, tV, tQp, tKp, s);                                  \
+    launched = true;                                                                                                      \
+  }
+  FA_CASE(0, 1) FA_CASE(0, 2) FA_CASE(0, 3) FA_CASE(1, 0) FA_CASE(1, 1) FA_CASE(1, 2) FA_CASE(1, 3)
+  FA_CASE(2, 0) FA_CASE(2, 1) FA_CASE(2, 2) FA_CASE(2, 3)
+#undef FA_CASE
+  if (!launched) {
+    set_error("attention: no kernel for head width %d", d);
+    return DRG_ERR_UNSUPPORTED;
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;

@@ -18,7 +18,10 @@ ops.attention(q16, k16, v, H, None, None, 1.0 / math.sqrt(d), d)
 torch.cuda.synchronize()
 t = tl.cpu().view(64, 16)
 names = ["mma:iter start", "mma:S(t+1) issued", "mma:p(t) seen", "mma:PV issued", "sm:tile start", "sm:S ready", "sm:ld done", "sm:max written",
-         "sm:barrier passed", "sm:exp done", "sm:pv(t-1) seen", "sm:P stored", "sm:arrived", "mma:kfull seen", "mma:S mmas issued"]
+         "sm:barrier passed", "sm:exp done", "sm:pv(t-1) seen", "sm:P stored", "sm:arrived", "mma:kfull seen", "mma:S mmas issued", "sm:loop top"]
 base = int(t[8, 4])
-for tt in range(8, 13):
-    print("tile", tt, " ".join(f"{names[i]}={int(t[tt, i]) - base}" for i in range(15)))
+for tt in range(10, 13):
+    print("tile", tt, " ".join(f"{names[i]}={int(t[tt, i]) - base}" for i in range(16)))
+
+ts = t[:, 4] - t[0, 4]
+print("softmax tile starts (cycles since tile 0):", [int(x) for x in ts[:min(64, (S + 63) // 64)].tolist()])
