@@ -20,6 +20,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .graphs import ForwardGraphCache
 from .matching import _no_grad_inputs
 
 
@@ -203,6 +204,8 @@ class CrossModalFusionModule(nn.Module):
             layers.append(TransformerLayer(hidden_dim, num_heads, dropout=dropout, act_cfg=activation_fn))
         self.transformer = nn.ModuleList(layers)
         self._cache = _WeightCache()
+        self.graph_replay = True          # (set False to run every call eagerly)
+        self._graphs = ForwardGraphCache()
 
     def _padded_linear(self, lin, x):
         """A linear whose input width is not a multiple of 4 (the 42 / 63 wide Fourier embeddings): zero columns are appended to
@@ -238,18 +241,24 @@ class CrossModalFusionModule(nn.Module):
     def forward(self, img_feats, img_feats_dino, img_pixels, pcd_feats, pcd_points, img_masks=None, pcd_masks=None):
         _no_grad_inputs(img_feats, img_feats_dino, img_pixels, pcd_feats, pcd_points, module=self)
         with torch.no_grad():
-            a = _linear(self._cache, self.img_in_proj, img_feats)
-            b = _linear(self._cache, self.img_in_proj_dino, img_feats_dino)
-            img_tokens = _linear(self._cache, self.img_in_proj_all, torch.cat([a, b], dim=-1), relu=True)   # relu(cat(...)) in the staging
-            pcd_tokens = _linear(self._cache, self.pcd_in_proj, pcd_feats)
-            if self.use_embedding:
-                img_tokens = img_tokens + self.create_2d_embedding(img_pixels)
-                pcd_tokens = pcd_tokens + self.create_3d_embedding(pcd_points)
-            for i, block in enumerate(self.blocks):
-                if block == "self":
-                    img_tokens = self.transformer[i](img_tokens, img_tokens, img_tokens, k_masks=img_masks)
-                    pcd_tokens = self.transformer[i](pcd_tokens, pcd_tokens, pcd_tokens, k_masks=pcd_masks)
-                else:
-                    img_tokens = self.transformer[i](img_tokens, pcd_tokens, pcd_tokens, k_masks=pcd_masks)
-                    pcd_tokens = self.transformer[i](pcd_tokens, img_tokens, img_tokens, k_masks=img_masks)
-            return _linear(self._cache, self.out_proj, img_tokens), _linear(self._cache, self.out_proj, pcd_tokens)
+            if self.graph_replay and img_feats.is_cuda:      # one CUDA-graph replay per call once a signature was seen twice
+                return self._graphs.run(self, self._forward, (img_feats, img_feats_dino, img_pixels, pcd_feats, pcd_points, img_masks,
+                                                              pcd_masks))
+            return self._forward(img_feats, img_feats_dino, img_pixels, pcd_feats, pcd_points, img_masks, pcd_masks)
+
+    def _forward(self, img_feats, img_feats_dino, img_pixels, pcd_feats, pcd_points, img_masks, pcd_masks):
+        a = _linear(self._cache, self.img_in_proj, img_feats)
+        b = _linear(self._cache, self.img_in_proj_dino, img_feats_dino)
+        img_tokens = _linear(self._cache, self.img_in_proj_all, torch.cat([a, b], dim=-1), relu=True)   # relu(cat(...)) in the staging
+        pcd_tokens = _linear(self._cache, self.pcd_in_proj, pcd_feats)
+        if self.use_embedding:
+            img_tokens = img_tokens + self.create_2d_embedding(img_pixels)
+            pcd_tokens = pcd_tokens + self.create_3d_embedding(pcd_points)
+        for i, block in enumerate(self.blocks):
+            if block == "self":
+                img_tokens = self.transformer[i](img_tokens, img_tokens, img_tokens, k_masks=img_masks)
+                pcd_tokens = self.transformer[i](pcd_tokens, pcd_tokens, pcd_tokens, k_masks=pcd_masks)
+            else:
+                img_tokens = self.transformer[i](img_tokens, pcd_tokens, pcd_tokens, k_masks=pcd_masks)
+                pcd_tokens = self.transformer[i](pcd_tokens, img_tokens, img_tokens, k_masks=img_masks)
+        return _linear(self._cache, self.out_proj, img_tokens), _linear(self._cache, self.out_proj, pcd_tokens)

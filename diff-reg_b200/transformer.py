@@ -23,6 +23,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .graphs import ForwardGraphCache
 from .matching import Matching, _no_grad_inputs
 from .position_encoding import VolumetricPositionEncoding as VolPE
 from .procrustes import SoftProcrustesLayer
@@ -161,10 +162,23 @@ class RepositioningTransformer(nn.Module):
             else:
                 raise KeyError()
         self._reset_parameters()
+        self.graph_replay = True          # (set False to run every call eagerly)
+        self._graphs = ForwardGraphCache()
 
     def forward(self, src_feat, tgt_feat, s_pcd, t_pcd, src_mask, tgt_mask, data, T=None, timers=None):
         _no_grad_inputs(src_feat, tgt_feat, s_pcd, t_pcd, module=self)
         with torch.no_grad():
+            # the denoising transformer (self / cross layers only, no host synchronisation inside): one CUDA-graph replay per call
+            # once a signature has been seen twice (graphs.py); stacks with positioning layers run eagerly
+            if self.graph_replay and "positioning" not in self.layer_types and timers is None and src_feat.is_cuda:
+                R, t = T if T is not None else (None, None)
+
+                def fn(sf, tf, sp, tp, sm, tm, R_, t_):
+                    return self._forward(sf, tf, sp, tp, sm, tm, {}, None if R_ is None else (R_, t_), None)
+                out = self._graphs.run(self, fn, (src_feat, tgt_feat, s_pcd, t_pcd, src_mask, tgt_mask, R, t))
+                self.timers = timers
+                data.update({"position_layers": {}})
+                return out
             return self._forward(src_feat, tgt_feat, s_pcd, t_pcd, src_mask, tgt_mask, data, T, timers)
 
     def _forward(self, src_feat, tgt_feat, s_pcd, t_pcd, src_mask, tgt_mask, data, T, timers):

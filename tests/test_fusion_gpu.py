@@ -168,3 +168,29 @@ def test_fusion_module_against_the_reference_module_on_the_gpu():
         assert (oi - ri).abs().max().item() <= TOL and (op - rp).abs().max().item() <= TOL
     finally:
         ref_loader.unload()
+
+
+def test_fusion_module_graph_replay_matches_eager():
+    """Calls 2+ with the same argument shapes replay the forward as one CUDA graph (graphs.py): same kernels, same results as the
+    eager forward on fresh inputs; a changed weight invalidates the graph."""
+    import diffreg_b200
+    g = torch.Generator().manual_seed(71)
+    blocks = ["self", "cross"]
+    net = diffreg_b200.CrossModalFusionModule(64, 64, 24, 32, 4, blocks).cuda().eval()
+    _randomise(net, g)
+
+    def inputs():
+        return (torch.randn(1, 70, 64, generator=g).cuda(), torch.randn(1, 70, 128, generator=g).cuda(),
+                (torch.rand(1, 70, 2, generator=g) * 2 - 1).cuda(), torch.randn(1, 90, 64, generator=g).cuda(),
+                torch.randn(1, 90, 3, generator=g).cuda())
+    for call in range(4):
+        x = inputs()
+        if call == 3:
+            with torch.no_grad():
+                net.out_proj.weight.mul_(1.5)       # parameter state is part of the graph's signature
+        net.graph_replay = True
+        a = net(*x)
+        net.graph_replay = False
+        b = net(*x)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), call
+    assert net._graphs.replays == 2                 # call 0 eager, 1 captures + replays, 2 replays; call 3: new signature, eager

@@ -195,3 +195,31 @@ def test_denoising_transformer_against_the_reference_module_at_528():
         assert (os_ - rs).abs().max().item() <= TOL and (ot - rt).abs().max().item() <= TOL
     finally:
         ref_loader.unload()
+
+
+def test_denoising_transformer_graph_replay_matches_eager():
+    """The self / cross stack replays as one CUDA graph from the second call with the same shapes on (graphs.py): identical
+    results on fresh inputs; stacks with positioning layers never take that path."""
+    import diffreg_b200
+    g = torch.Generator().manual_seed(51)
+    torch.manual_seed(51)
+    B, N, M, C, H = 1, 150, 170, 48, 4
+    bnds = [[-3.6, -2.4, 1.14], [1.093, 0.78, 2.92]]
+    cfg = Cfg(feature_dim=C, n_head=H, layer_types=['self', 'cross'], positioning_type="procrustes", pe_type="rotary", entangled=False,
+              vol_bnds=bnds, voxel_size=0.04)
+    net = diffreg_b200.RepositioningTransformer(cfg).cuda().eval()
+    lo, hi = torch.tensor(bnds[0]), torch.tensor(bnds[1])
+    sm, tm = torch.ones(B, N, dtype=torch.bool).cuda(), torch.ones(B, M, dtype=torch.bool).cuda()
+    sm[:, N - 7:] = False
+    for call in range(3):
+        s_pcd = (lo + (hi - lo) * torch.rand(B, N, 3, generator=g)).cuda()
+        t_pcd = (lo + (hi - lo) * torch.rand(B, M, 3, generator=g)).cuda()
+        sf, tf = torch.randn(B, N, C, generator=g).cuda(), torch.randn(B, M, C, generator=g).cuda()
+        net.graph_replay = True
+        d1 = {}
+        a = net(sf, tf, s_pcd, t_pcd, sm, tm, d1)
+        net.graph_replay = False
+        b = net(sf, tf, s_pcd, t_pcd, sm, tm, {})
+        assert d1["position_layers"] == {}
+        assert all(torch.equal(x, y) for x, y in zip(a, b)), call
+    assert net._graphs.replays == 2

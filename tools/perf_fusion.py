@@ -39,8 +39,22 @@ if ref_loader.fusion_available():
         o = onet(img, dino, pix, pcd, pts)
         out["max_abs_diff_vs_reference"] = max((o[0] - r[0]).abs().max().item(), (o[1] - r[1]).abs().max().item())
         out["reference_module_ms"] = timed(lambda: rnet(img, dino, pix, pcd, pts))
+onet.graph_replay = False
 c0 = diffreg_b200.launch_count()
 onet(img, dino, pix, pcd, pts)
 out["launches"] = diffreg_b200.launch_count() - c0
-out["dropin_ms"] = timed(lambda: onet(img, dino, pix, pcd, pts))
+onet.graph_replay = False
+out["dropin_eager_ms"] = timed(lambda: onet(img, dino, pix, pcd, pts))
+onet.graph_replay = True
+out["dropin_ms"] = timed(lambda: onet(img, dino, pix, pcd, pts))      # as called by the sampler: one CUDA-graph replay per call from the 2nd call on
+# the same forward captured by hand, without the copies in / clones out of the module's own replay path
+onet.graph_replay = False
+st = torch.cuda.Stream()
+with torch.cuda.stream(st):
+    onet(img, dino, pix, pcd, pts); onet(img, dino, pix, pcd, pts)
+    g_ = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_, stream=st):
+        onet(img, dino, pix, pcd, pts)
+torch.cuda.synchronize()
+out["dropin_graph_replay_ms"] = timed(g_.replay)
 print(json.dumps(out), flush=True)
