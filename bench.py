@@ -19,7 +19,7 @@ step's results (pose, match count, matches) copied out every step; roofline = th
 Sinkhorn launch that carries the whole log_optimal_transport + DDIM call) timed with CUDA events inside an eager pass over the
 same steps; cpu_baseline = the reference on the host;
 rowshard = BASELINE.json configs[4] (N=M=16384, 100 iterations; rows sharded over the N ranks); other_configs =
-configs[0], [1], [3] timed once each and one forward of the denoising transformer drop-in (N=1 only).  `config` is identical in both arms; how a run was timed is in `run_info`.
+configs[0], [1], [3] timed once each and one forward of each denoising-transformer drop-in (4DMatch stack, 2D-3D fusion module; N=1 only).  `config` is identical in both arms; how a run was timed is in `run_info`.
 """
 import argparse
 import json
@@ -727,16 +727,45 @@ def bench_other_configs(torch, dev):
         mk = torch.ones(1, N_PTS, dtype=torch.bool, device=dev)
         net = diffreg_b200.RepositioningTransformer(tcfg).to(dev).eval()
         fnt = lambda: net(sf, tf, sp, tp, mk, mk, {})
+        net.graph_replay = False
         fnt()
         c0 = diffreg_b200.launch_count()
         fnt()
         launches = diffreg_b200.launch_count() - c0
+        ms_eager = _event_ms(torch, fnt, 3)
+        net.graph_replay = True          # the module's own path: one CUDA-graph replay per call from the second call on
+        fnt()
+        fnt()
         ms = _event_ms(torch, fnt, 3)
         out["denoising_transformer"] = {"workload": "SURVEY 8f rank 2 (not in the metric): RepositioningTransformer, 6 self / cross geometry "
                                                     "attention layers, C=528, 4 heads, rotary code, N=M=4096, one forward (both directions of every layer)",
-                                        "ms_per_forward": ms, "kernel_launches": int(launches)}
+                                        "ms_per_forward": ms, "ms_per_forward_eager": ms_eager, "kernel_launches": int(launches)}
     except Exception as e:  # noqa: BLE001 -- an extra line, never the reason a bench run fails
         out["denoising_transformer"] = {"error": str(e)[:200]}
+    # ... and its 2D-3D counterpart (fusion_module.py:61-107): six blocks, 512 -> 256, 4 heads of 64, Fourier embedding, 2048 image
+    # patches x 4800 points (configs[3]'s token counts)
+    try:
+        g = torch.Generator().manual_seed(5001)
+        fnet = diffreg_b200.CrossModalFusionModule(512, 512, 256, 256, 4, ["self", "cross"] * 3).to(dev).eval()
+        fin = (torch.randn(1, 2048, 512, generator=g).to(dev), torch.randn(1, 2048, 1024, generator=g).to(dev),
+               (torch.rand(1, 2048, 2, generator=g) * 2.0 - 1.0).to(dev), torch.randn(1, 4800, 512, generator=g).to(dev),
+               (torch.randn(1, 4800, 3, generator=g) * 0.8).to(dev))
+        fnf = lambda: fnet(*fin)
+        fnet.graph_replay = False
+        fnf()
+        c0 = diffreg_b200.launch_count()
+        fnf()
+        launches = diffreg_b200.launch_count() - c0
+        ms_eager = _event_ms(torch, fnf, 3)
+        fnet.graph_replay = True
+        fnf()
+        fnf()
+        ms = _event_ms(torch, fnf, 3)
+        out["fusion_module_2d3d"] = {"workload": "SURVEY 8f rank 2 (not in the metric): CrossModalFusionModule, 6 self / cross blocks, 512 -> 256, "
+                                                 "4 heads, Fourier embedding, 2048 image patches x 4800 points, one forward",
+                                     "ms_per_forward": ms, "ms_per_forward_eager": ms_eager, "kernel_launches": int(launches)}
+    except Exception as e:  # noqa: BLE001
+        out["fusion_module_2d3d"] = {"error": str(e)[:200]}
     return out
 
 
