@@ -39,6 +39,7 @@ constexpr int FA_PARTS = 2;         // softmax threads per query row (measured: 
 constexpr int FA_CP = 64 / FA_PARTS;   // columns of a key tile per softmax thread
 constexpr int FA_THREADS = 32 * (4 * FA_PARTS + 2);   // 4 FA_PARTS softmax warps + the MMA issuer (warp 4) + the TMA producer (warp 5)
 constexpr float FA_TAU = 8.f;     // move the reference when a tile's maximum exceeds it by more than this (log2 units)
+constexpr int FA_CH = 8;           // key tiles per accumulation chunk of O (see the drain in the softmax warps)
 constexpr float FA_PSHIFT = 6.f;  // P is carried as 2^6 * exp(.): hi / lo halves of the small entries stay normal fp16 numbers
 constexpr int FA_Q_CHUNK = FA_BM * 128;   // bytes of one 64-column chunk of the Q tile
 constexpr int FA_K_CHUNK = FA_BN * 128;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   // NFULL 64-column chunks + NPIECE 16-column pieces per operand segment: compile-time, so that the MMA warp's issue loops are
   // straight-line code (a loop with run-time bounds costs ~90 cycles per MMA in that single warp, unrolled code ~40)
   constexpr int nfull = NFULL, npiece = NPIECE;
-  constexpr int TMEM_COLS = (FA_S_COLS + 16 * (4 * NFULL + NPIECE)) <= 256 ? 256 : 512;   // S x 2 + O (ND = 16 (4 NFULL + NPIECE) columns)
+  constexpr int TMEM_COLS = (FA_S_COLS + 2 * 16 * (4 * NFULL + NPIECE)) <= 256 ? 256 : 512;   // S x 2 + O chunk + O total (ND = 16 (4 NFULL + NPIECE) columns each)
   const uint32_t q_seg = (uint32_t)(nfull * FA_Q_CHUNK + npiece * (FA_Q_CHUNK / 4));   // bytes of one segment (lo or hi) of the Q tile
   const uint32_t k_seg = (uint32_t)(nfull * FA_K_CHUNK + npiece * (FA_K_CHUNK / 4));
   const int T = (s.S + FA_BN - 1) / FA_BN;
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t o = (uint64_t)(2 * kk);
-          umma_f16_elect(o_tmem, pl_desc + o, vh_desc + o, idesc_o, (uint32_t)((t | kk) != 0));   // P_lo . V_hi
+          umma_f16_elect(o_tmem, pl_desc + o, vh_desc + o, idesc_o, (uint32_t)(((t % FA_CH) | kk) != 0));   // P_lo . V_hi (a new chunk of FA_CH tiles starts from zero)
           umma_f16_elect(o_tmem, ph_desc + o, vl_desc + o, idesc_o, 1u);                          // P_hi . V_lo
           umma_f16_elect(o_tmem, ph_desc + o, vh_desc + o, idesc_o, 1u);                          // P_hi . V_hi
         }
@@ -433,16 +434,36 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         mbar_wait(&bar_pv, (uint32_t)((t - 1) & 1));   // P.V of the previous tile has read P and updated O
         tcgen05_fence_after();
         FA_STAMP(10);
-        if (__any_sync(0xffffffffu, need)) {
+        // The tensor core's fp32 accumulator TRUNCATES at every step: over thousands of keys (hundreds of MMAs into one accumulator)
+        // that bias reaches ~2^-17 relative.  O is therefore accumulated in chunks of FA_CH key tiles (96 MMAs) and the chunks are
+        // summed here with round-to-nearest adds into a second TMEM region (O total, columns FA_O_COL + ND ...).
+        const bool drain = (t % FA_CH) == 0;          // O chunk is complete: P.V of this tile starts the next one from zero
+        const bool has_total = t > FA_CH;             // (the first drain, at t == FA_CH, initialises O total)
+        const bool any_need = __any_sync(0xffffffffu, need);
+        if (any_need || drain) {
           const float f = need ? fa_ex2(m_ref - m_new) : 1.f;   // (m_ref = -inf: O and l are zero, f = 0)
           l *= f;
           for (int c = c16_lo; c < c16_hi; ++c) {
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(lane_addr + FA_O_COL + (uint32_t)(c * 16), r);
+            uint32_t r[16], tt[16];
+            const uint32_t col = FA_O_COL + (uint32_t)(c * 16);
+            tmem_ld_32x32b_x16(lane_addr + col, r);
+            if (has_total) tmem_ld_32x32b_x16(lane_addr + col + (uint32_t)s.ND, tt);
             tmem_wait_ld();
+            if (drain) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * f);
-            tmem_st_32x32b_x16(lane_addr + FA_O_COL + (uint32_t)(c * 16), r);
+              for (int j = 0; j < 16; ++j)
+                tt[j] = __float_as_uint(has_total ? fmaf(__uint_as_float(tt[j]), f, __uint_as_float(r[j]) * f) : __uint_as_float(r[j]) * f);
+              tmem_st_32x32b_x16(lane_addr + col + (uint32_t)s.ND, tt);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * f);
+              tmem_st_32x32b_x16(lane_addr + col, r);
+              if (has_total) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) tt[j] = __float_as_uint(__uint_as_float(tt[j]) * f);
+                tmem_st_32x32b_x16(lane_addr + col + (uint32_t)s.ND, tt);
+              }
+            }
           }
           tmem_wait_st();
         }
@@ -476,6 +497,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       const int c0 = c * 16;
       uint32_t r[16];
       tmem_ld_32x32b_x16(lane_addr + FA_O_COL + (uint32_t)c0, r);
+      if (T > FA_CH) {                 // the chunks drained so far
+        uint32_t tt[16];
+        tmem_ld_32x32b_x16(lane_addr + FA_O_COL + (uint32_t)(s.ND + c0), tt);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(tt[j]));
+      }
       tmem_wait_ld();
       if (row_ok) {
 #pragma unroll
