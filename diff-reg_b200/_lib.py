@@ -95,6 +95,11 @@ def _declare(lib):
     lib.drg_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_void_p, c_void_p]
     lib.drg_gemm_nt_split16_bias.restype = c_int
     lib.drg_gemm_nt_split16_bias.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
+    lib.drg_sinkhorn_backward_workspace_bytes.restype = ctypes.c_size_t
+    lib.drg_sinkhorn_backward_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.drg_sinkhorn_backward.restype = c_int
+    lib.drg_sinkhorn_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_void_p]
     lib.drg_prep_vt_split16.restype = c_int
     lib.drg_prep_vt_split16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.drg_attention_split16.restype = c_int

@@ -34,12 +34,36 @@ def _no_grad_inputs(*tensors, module=None):
         raise DiffRegLibraryError(_FORWARD_ONLY)
 
 
+class _LogOptimalTransportFn(torch.autograd.Function):
+    """log_optimal_transport with a CUDA backward: forward = the Sinkhorn kernels, backward =
+    drg_sinkhorn_backward (2 I + 1 passes over the scores instead of the ~60 torch's autograd makes through the unrolled
+    logsumexp recursion of matching.py:30-32)."""
+
+    @staticmethod
+    def forward(ctx, scores, alpha, iters, src_mask, tgt_mask):
+        out = ops.sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full")
+        ctx.save_for_backward(scores, alpha, src_mask, tgt_mask)
+        ctx.iters = int(iters)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        scores, alpha, src_mask, tgt_mask = ctx.saved_tensors
+        gs, ga = ops.sinkhorn_backward(scores, alpha, ctx.iters, src_mask, tgt_mask, grad_out.contiguous())
+        return (gs.to(scores.dtype) if ctx.needs_input_grad[0] else None,
+                ga.to(alpha.dtype).reshape(alpha.shape) if ctx.needs_input_grad[1] else None, None, None, None)
+
+
 def log_optimal_transport(scores, alpha, iters, src_mask, tgt_mask):
     """[B,N,M] scores -> [B,N+1,M+1] log-assignment (Z + u + v - norm).
 
     Computed in fp32; an fp64 `scores` (the reference's fp64 sampler state) gives an
-    fp64 result holding the fp32-accurate values."""
-    _no_grad_inputs(scores, alpha)
+    fp64 result holding the fp32-accurate values.  Differentiable with respect to `scores` and `alpha` (fp32, CUDA): when
+    autograd is recording and either requires grad, the result carries a CUDA backward (_LogOptimalTransportFn)."""
+    if torch.is_grad_enabled() and (scores.requires_grad or (torch.is_tensor(alpha) and alpha.requires_grad)):
+        if scores.dtype != torch.float32:
+            raise DiffRegLibraryError("log_optimal_transport: the differentiable path takes fp32 scores")
+        return _LogOptimalTransportFn.apply(scores, alpha, iters, src_mask, tgt_mask)
     with torch.no_grad():
         out = ops.sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full")
         return out.to(scores.dtype) if scores.dtype == torch.float64 else out
@@ -174,8 +198,48 @@ class Matching(nn.Module):
             return ops.dual_softmax(sim, src_mask, tgt_mask, self.temperature)
         return ops.sinkhorn(sim, self.bin_score, self.skh_iters, src_mask, tgt_mask, out_mode="conf", apply_mask=True)
 
+    def _records_grad(self, *tensors):
+        return torch.is_grad_enabled() and (any(torch.is_tensor(t) and t.requires_grad for t in tensors) or
+                                            (self.training and any(q.requires_grad for q in self.parameters())))
+
+    def _forward_train(self, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type):
+        """Training forward of the Sinkhorn branch with autograd recording (matching.py:118-173).  The
+        projections, the position code and the similarity contraction are torch ops (library GEMMs and elementwise kernels,
+        differentiable as they stand); the Sinkhorn -- where autograd would make ~60 passes over the N x M matrix forward and
+        backward -- runs on this library's kernels in both directions (_LogOptimalTransportFn)."""
+        fs = torch.nn.functional.linear(src_feats, self.src_proj.weight)
+        ft = torch.nn.functional.linear(tgt_feats, self.src_proj.weight)            # the same weight on both sides (:127-128)
+        data.update({"src_feats_nopos": fs, "tgt_feats_nopos": ft})
+        if not self.entangled and src_pe is not None:                              # :135-137
+            def embed(x, pe):
+                if pe_type == "rotary":
+                    x2 = torch.stack([-x[..., 1::2], x[..., ::2]], dim=-1).reshape_as(x)
+                    return x * pe[..., 0] + x2 * pe[..., 1]
+                if pe_type == "sinusoidal":
+                    return x + pe
+                raise KeyError(pe_type)
+            fs, ft = embed(fs, src_pe), embed(ft, tgt_pe)
+        data.update({"src_feats": fs, "tgt_feats": ft})
+        scale = fs.shape[-1] ** .5
+        sim = torch.einsum("bsc,btc->bst", fs / scale, ft / scale)                   # :144-145, :161
+        if src_mask is not None:
+            sim = sim.masked_fill(~(src_mask[..., None] * tgt_mask[:, None]).bool(), float("-inf"))   # :163-165
+        else:
+            src_mask = torch.ones(sim.shape[:2], dtype=torch.bool, device=sim.device)
+            tgt_mask = torch.ones(sim.shape[0], sim.shape[2], dtype=torch.bool, device=sim.device)
+        log_assign = log_optimal_transport(sim, self.bin_score, self.skh_iters, src_mask, tgt_mask)
+        conf_matrix = log_assign.exp()[:, :-1, :-1].contiguous()                   # :169-170
+        with torch.no_grad():
+            coarse_match, _, _ = ops.get_match(conf_matrix.detach(), self.confidence_threshold, True, want_mask=False)
+        return conf_matrix, coarse_match
+
     def forward(self, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type="rotary"):
-        """-> (conf_matrix [B,N,M], coarse_match [K,3] int64); writes the four feature tensors into `data`."""
+        """-> (conf_matrix [B,N,M], coarse_match [K,3] int64); writes the four feature tensors into `data`.  When autograd is
+        recording (training mode / inputs that require grad) the Sinkhorn branch returns a differentiable conf_matrix
+        (_forward_train); the dual-softmax branch, forward1 and the 2D-3D head stay forward-only and raise."""
+        if self.match_type == "sinkhorn" and type(self) is Matching and src_feats.is_cuda and \
+                self._records_grad(src_feats, tgt_feats, src_pe, tgt_pe):
+            return self._forward_train(src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type)
         _no_grad_inputs(src_feats, tgt_feats, src_pe, tgt_pe, module=self)
         with torch.no_grad():
             sim = self.similarity(src_feats, tgt_feats, src_pe, tgt_pe, pe_type, data)

@@ -124,6 +124,37 @@ def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", appl
 
 
 @_on_device
+def sinkhorn_backward(scores, alpha, iters, src_mask, tgt_mask, grad_out):
+    """(dL/d scores [B,N,M], dL/d alpha 0-dim) of log_optimal_transport given dL/d out [B,N+1,M+1] (drg_sinkhorn_backward).
+    The potentials after every iteration are recovered by re-running the forward with iters = 1..I (potentials only: the
+    forward keeps just the final pair)."""
+    _require_cuda(scores, alpha, src_mask, tgt_mask, grad_out)
+    lib = load_library()
+    scores = _f32c(scores.detach())
+    B, N, M = scores.shape
+    dev = scores.device
+    sm, tm = _as_mask(src_mask, B, N, dev), _as_mask(tgt_mask, B, M, dev)
+    a = _f32c(alpha.detach().reshape(()))
+    G = _f32c(grad_out)
+    if tuple(G.shape) != (B, N + 1, M + 1):
+        raise ValueError(f"sinkhorn_backward: grad_out of shape {tuple(G.shape)} for scores {tuple(scores.shape)}")
+    iters = int(iters)
+    u_all = torch.empty(iters, B, N + 1, dtype=torch.float32, device=dev)
+    v_all = torch.empty(iters, B, M + 1, dtype=torch.float32, device=dev)
+    for t in range(1, iters + 1):
+        _, u, v = sinkhorn(scores, a, t, sm, tm, out_mode="none", return_potentials=True)
+        u_all[t - 1].copy_(u)
+        v_all[t - 1].copy_(v)
+    gs = torch.empty(B, N, M, dtype=torch.float32, device=dev)
+    ga = torch.empty(B, dtype=torch.float32, device=dev)
+    nbytes = lib.drg_sinkhorn_backward_workspace_bytes(B, N, M, iters)
+    ws = workspace(nbytes, dev, "sinkhorn_backward")
+    check(lib.drg_sinkhorn_backward(scores.data_ptr(), a.data_ptr(), sm.data_ptr(), tm.data_ptr(), B, N, M, iters, u_all.data_ptr(),
+                                    v_all.data_ptr(), G.data_ptr(), gs.data_ptr(), ga.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return gs, ga.sum()
+
+
+@_on_device
 def dual_softmax(sim, src_mask, tgt_mask, temperature):
     """conf = softmax over src (masked) * softmax over tgt (masked) of sim / temperature."""
     _require_cuda(sim, src_mask, tgt_mask)

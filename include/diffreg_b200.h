@@ -123,6 +123,17 @@ typedef struct drg_sinkhorn_args {
 size_t drg_sinkhorn_workspace_bytes(int B, int N, int M);
 int drg_sinkhorn(const drg_sinkhorn_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward pass of the log-domain Sinkhorn (the training path): what torch's autograd computes for
+ *   loss.backward() through log_optimal_transport   Diff-Reg-4dmatch/models/matching.py:6-38 (called at :167)
+ * as 2 * iters "weighted exp" mat-vec passes over the scores and one final pass (2 iters + 1 reads, 1 write; deterministic).
+ *   scores [B,N,M] as the forward saw them (-inf at masked entries), alpha device scalar, masks [B,N] / [B,M] bool (counts only),
+ *   u_all [iters,B,N+1] / v_all [iters,B,M+1]: the potentials after each iteration t = 1..iters (drg_sinkhorn with iters = t,
+ *   DRG_OUT_NONE), grad_out [B,N+1,M+1] = dL/d out  ->  grad_scores [B,N,M], grad_alpha [B] (per batch element; sum them). */
+size_t drg_sinkhorn_backward_workspace_bytes(int B, int N, int M, int iters);
+int drg_sinkhorn_backward(const float* scores, const float* alpha, const uint8_t* src_mask, const uint8_t* tgt_mask, int B, int N, int M,
+                          int iters, const float* u_all, const float* v_all, const float* grad_out, float* grad_scores,
+                          float* grad_alpha, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Row-sharded Sinkhorn: ONE matrix whose rows are spread over several GPUs (BASELINE.json configs[4]).
  *   The reference has no counterpart (its matrix always lives on one GPU); the arithmetic is

@@ -94,6 +94,43 @@ def sinkhorn_potentials(scores, alpha, iters, src_mask, tgt_mask):
     return u, v, norm
 
 
+def log_optimal_transport_backward(scores, alpha, iters, src_mask, tgt_mask, grad_out):
+    """(dL/d scores, dL/d alpha) of ``log_optimal_transport`` for a given dL/d out -- what torch's autograd returns for
+    ``loss.backward()`` through 4d/models/matching.py:6-38, written out so that the CUDA backward can be
+    checked in fp64 without autograd.  With Pc_t = exp(Z + u_t + v_t - log_nu) (column softmax of the v_t step) and
+    Pr_t = exp(Z + v_{t-1} + u_t - log_mu) (row softmax of the u_t step):
+        gv = colsum(G); gu = rowsum(G)
+        for t = I..1:  gZ -= gv Pc_t;  gu -= sum_j gv Pc_t;   gZ -= gu Pr_t;  gv = -sum_i gu Pr_t;  gu = 0
+    Checked against the autograd of the unmodified reference (tests/test_oracle_golden.py, golden ``lotb_*``)."""
+    B, N, M = scores.shape
+    dt = scores.dtype
+    n_src = src_mask.sum(dim=1, keepdim=True)
+    n_tgt = tgt_mask.sum(dim=1, keepdim=True)
+    Z = torch.cat((torch.cat((scores, alpha.expand(B, N, 1)), dim=2), alpha.expand(B, 1, M + 1)), dim=1)
+    norm = -(n_src + n_tgt).log().to(dt)
+    log_mu = torch.cat((norm.expand(B, N), n_tgt.log().to(dt) + norm), dim=1)
+    log_nu = torch.cat((norm.expand(B, M), n_src.log().to(dt) + norm), dim=1)
+    us, vs = [], [torch.zeros_like(log_nu)]
+    u, v = torch.zeros_like(log_mu), vs[0]
+    for _ in range(int(iters)):
+        u = log_mu - torch.logsumexp(Z + v[:, None, :], dim=2)
+        v = log_nu - torch.logsumexp(Z + u[:, :, None], dim=1)
+        us.append(u)
+        vs.append(v)
+    gZ = grad_out.clone()
+    gu, gv = grad_out.sum(dim=2), grad_out.sum(dim=1)
+    for t in range(int(iters), 0, -1):
+        u_t, v_t, v_p = us[t - 1], vs[t], vs[t - 1]
+        Pc = torch.exp(Z + u_t[:, :, None] + v_t[:, None, :] - log_nu[:, None, :])
+        gZ = gZ - gv[:, None, :] * Pc
+        gu = gu - (gv[:, None, :] * Pc).sum(dim=2)
+        Pr = torch.exp(Z + v_p[:, None, :] + u_t[:, :, None] - log_mu[:, :, None])
+        gZ = gZ - gu[:, :, None] * Pr
+        gv = -(gu[:, :, None] * Pr).sum(dim=1)
+        gu = torch.zeros_like(gu)
+    return gZ[:, :N, :M], gZ[:, N, :].sum() + gZ[:, :N, M].sum()
+
+
 def pair_mask(src_mask, tgt_mask):
     """[B,N,M] validity mask, as built at 4d/models/matching.py:163-165."""
     return (src_mask[..., None] * tgt_mask[:, None]).bool()

@@ -1,0 +1,89 @@
+"""Training path: the CUDA backward of log_optimal_transport (drg_sinkhorn_backward) and the differentiable
+Sinkhorn branch of Matching.forward, through the C ABI, against the reference's autograd (golden gradients, tests/golden/lotb_*.npz,
+made by make_golden_lotb.py from the unmodified reference) and against the oracle's written-out backward in fp64.
+Tolerance: 2e-5 relative to the largest gradient entry (fp32 exps of sums of three potentials)."""
+import pytest
+import torch
+
+from oracle import diffreg_oracle as O
+from helpers import load, names
+
+pytestmark = pytest.mark.gpu
+REL = 2e-5
+
+
+@pytest.mark.parametrize("name", [n for n in names("lotb_") if "matching" not in n])
+def test_sinkhorn_backward_against_the_reference_autograd(name):
+    import diffreg_b200
+    g = load(name)
+    scores = g["scores"].cuda().requires_grad_()
+    alpha = torch.tensor(float(g["alpha"]), device="cuda", requires_grad=True)
+    out = diffreg_b200.log_optimal_transport(scores, alpha, int(g["iters"]), g["src_mask"].cuda(), g["tgt_mask"].cuda())
+    assert out.requires_grad
+    fin_o = torch.isfinite(g["out"])
+    assert (out.detach().cpu()[fin_o] - g["out"][fin_o]).abs().max().item() <= 1e-4
+    (out * g["grad_out"].cuda()).sum().backward()
+    fin = torch.isfinite(g["scores"])
+    scale = g["grad_scores"][fin].abs().max().item()
+    assert (scores.grad.cpu()[fin] - g["grad_scores"][fin]).abs().max().item() <= REL * scale
+    assert abs(alpha.grad.item() - float(g["grad_alpha"])) <= 1e-4 * max(1.0, abs(float(g["grad_alpha"])))
+
+
+@pytest.mark.parametrize("B,N,M,iters", [(1, 700, 900, 3), (3, 257, 130, 3), (1, 64, 1500, 2), (2, 100, 100, 7)])
+def test_sinkhorn_backward_against_the_oracle_in_fp64(B, N, M, iters):
+    from diffreg_b200 import ops
+    g = torch.Generator().manual_seed(N + M + iters)
+    scores = torch.randn(B, N, M, generator=g) * 3.0
+    sm, tm = torch.rand(B, N, generator=g) > 0.1, torch.rand(B, M, generator=g) > 0.1
+    scores = scores.masked_fill(~(sm[..., None] * tm[:, None]).bool(), float("-inf"))
+    alpha = torch.tensor(0.7)
+    G = torch.randn(B, N + 1, M + 1, generator=g)
+    gs64, ga64 = O.log_optimal_transport_backward(scores.double(), alpha.double(), iters, sm, tm, G.double())
+    gs, ga = ops.sinkhorn_backward(scores.cuda(), alpha.cuda(), iters, sm.cuda(), tm.cuda(), G.cuda())
+    fin = torch.isfinite(scores)
+    scale = gs64[fin].abs().max().item()
+    assert (gs.cpu().double()[fin] - gs64[fin]).abs().max().item() <= REL * scale
+    assert abs(ga.item() - ga64.item()) <= 1e-4 * max(1.0, abs(ga64.item()))
+
+
+def test_sinkhorn_backward_is_deterministic():
+    from diffreg_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    scores, G = torch.randn(1, 300, 400, generator=g).cuda(), torch.randn(1, 301, 401, generator=g).cuda()
+    ones = lambda n: torch.ones(1, n, dtype=torch.bool, device="cuda")
+    a = ops.sinkhorn_backward(scores, torch.tensor(1.0).cuda(), 3, ones(300), ones(400), G)
+    b = ops.sinkhorn_backward(scores, torch.tensor(1.0).cuda(), 3, ones(300), ones(400), G)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("name", names("lotb_matching_"))
+def test_matching_forward_in_training_mode_against_the_reference_autograd(name):
+    """Matching.forward with autograd recording (module in train(), features that require grad): conf_matrix and the gradients of
+    the features, the projection weight and bin_score against the reference module's."""
+    import diffreg_b200
+    g = load(name)
+    C = g["src_feats"].shape[-1]
+    cfg = dict(match_type="sinkhorn", confidence_threshold=0.2, feature_dim=C, entangled=bool(int(g["entangled"])), dsmax_temperature=0.1,
+               skh_init_bin_score=1.0, skh_iters=3, skh_prefilter=False)
+    head = diffreg_b200.Matching(cfg).cuda().train()
+    with torch.no_grad():
+        head.src_proj.weight.copy_(g["weight"].cuda())
+        head.bin_score.copy_(torch.tensor(float(g["bin_score"])))
+    src, tgt = g["src_feats"].cuda().requires_grad_(), g["tgt_feats"].cuda().requires_grad_()
+    spe = g["src_pe"].cuda() if "src_pe" in g else None
+    tpe = g["tgt_pe"].cuda() if "tgt_pe" in g else None
+    data = {}
+    conf, match = head(src, tgt, spe, tpe, g["src_mask"].cuda(), g["tgt_mask"].cuda(), data, pe_type="rotary")
+    assert conf.requires_grad and set(data) == {"src_feats_nopos", "tgt_feats_nopos", "src_feats", "tgt_feats"}
+    assert (conf.detach().cpu() - g["conf"]).abs().max().item() <= 1e-5
+    assert torch.equal(match.cpu(), g["match"])
+    (conf * g["W"].cuda()).sum().backward()
+    for got, key in ((src.grad, "grad_src"), (tgt.grad, "grad_tgt"), (head.src_proj.weight.grad, "grad_weight")):
+        want = g[key]
+        assert (got.cpu() - want).abs().max().item() <= 1e-4 * max(1e-3, want.abs().max().item()), key
+    assert abs(head.bin_score.grad.item() - float(g["grad_bin_score"])) <= 1e-4 * max(1.0, abs(float(g["grad_bin_score"])))
+    # eval mode + no_grad: the forward-only kernels, same confidences
+    head.eval()
+    with torch.no_grad():
+        conf2, _ = head(src.detach(), tgt.detach(), spe, tpe, g["src_mask"].cuda(), g["tgt_mask"].cuda(), {}, pe_type="rotary")
+    assert (conf2 - conf.detach()).abs().max().item() <= 1e-5
