@@ -41,15 +41,16 @@ class _LogOptimalTransportFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, scores, alpha, iters, src_mask, tgt_mask):
-        out = ops.sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full")
-        ctx.save_for_backward(scores, alpha, src_mask, tgt_mask)
+        u_all, v_all, out = ops.sinkhorn_potentials_per_iteration(scores.detach(), alpha.detach().reshape(()).float(), iters, src_mask,
+                                                                  tgt_mask, want_out=True)
+        ctx.save_for_backward(scores, alpha, src_mask, tgt_mask, u_all, v_all)     # the potentials after every iteration: O(I (N + M))
         ctx.iters = int(iters)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        scores, alpha, src_mask, tgt_mask = ctx.saved_tensors
-        gs, ga = ops.sinkhorn_backward(scores, alpha, ctx.iters, src_mask, tgt_mask, grad_out.contiguous())
+        scores, alpha, src_mask, tgt_mask, u_all, v_all = ctx.saved_tensors
+        gs, ga = ops.sinkhorn_backward(scores, alpha, ctx.iters, src_mask, tgt_mask, grad_out.contiguous(), potentials=(u_all, v_all))
         return (gs.to(scores.dtype) if ctx.needs_input_grad[0] else None,
                 ga.to(alpha.dtype).reshape(alpha.shape) if ctx.needs_input_grad[1] else None, None, None, None)
 

@@ -124,10 +124,29 @@ def sinkhorn(scores, alpha, iters, src_mask, tgt_mask, out_mode="log_full", appl
 
 
 @_on_device
-def sinkhorn_backward(scores, alpha, iters, src_mask, tgt_mask, grad_out):
+def sinkhorn_potentials_per_iteration(scores, alpha, iters, src_mask, tgt_mask, want_out=False):
+    """u_t [I,B,N+1], v_t [I,B,M+1] for t = 1..I (what the backward needs), by running the forward with iters = 1..I -- the
+    persistent kernel keeps only the final pair.  want_out: also the log-assignment of the last run ([B,N+1,M+1])."""
+    B, N, M = scores.shape
+    dev = scores.device
+    iters = int(iters)
+    u_all = torch.empty(iters, B, N + 1, dtype=torch.float32, device=dev)
+    v_all = torch.empty(iters, B, M + 1, dtype=torch.float32, device=dev)
+    out = None
+    for t in range(1, iters + 1):
+        last = want_out and t == iters
+        res = sinkhorn(scores, alpha, t, src_mask, tgt_mask, out_mode="log_full" if last else "none", return_potentials=True)
+        if last:
+            out = res[0]
+        u_all[t - 1].copy_(res[1])
+        v_all[t - 1].copy_(res[2])
+    return (u_all, v_all, out) if want_out else (u_all, v_all)
+
+
+@_on_device
+def sinkhorn_backward(scores, alpha, iters, src_mask, tgt_mask, grad_out, potentials=None):
     """(dL/d scores [B,N,M], dL/d alpha 0-dim) of log_optimal_transport given dL/d out [B,N+1,M+1] (drg_sinkhorn_backward).
-    The potentials after every iteration are recovered by re-running the forward with iters = 1..I (potentials only: the
-    forward keeps just the final pair)."""
+    potentials: (u_all, v_all) of sinkhorn_potentials_per_iteration when the forward kept them, else they are recomputed."""
     _require_cuda(scores, alpha, src_mask, tgt_mask, grad_out)
     lib = load_library()
     scores = _f32c(scores.detach())
@@ -139,12 +158,7 @@ def sinkhorn_backward(scores, alpha, iters, src_mask, tgt_mask, grad_out):
     if tuple(G.shape) != (B, N + 1, M + 1):
         raise ValueError(f"sinkhorn_backward: grad_out of shape {tuple(G.shape)} for scores {tuple(scores.shape)}")
     iters = int(iters)
-    u_all = torch.empty(iters, B, N + 1, dtype=torch.float32, device=dev)
-    v_all = torch.empty(iters, B, M + 1, dtype=torch.float32, device=dev)
-    for t in range(1, iters + 1):
-        _, u, v = sinkhorn(scores, a, t, sm, tm, out_mode="none", return_potentials=True)
-        u_all[t - 1].copy_(u)
-        v_all[t - 1].copy_(v)
+    u_all, v_all = potentials if potentials is not None else sinkhorn_potentials_per_iteration(scores, a, iters, sm, tm)
     gs = torch.empty(B, N, M, dtype=torch.float32, device=dev)
     ga = torch.empty(B, dtype=torch.float32, device=dev)
     nbytes = lib.drg_sinkhorn_backward_workspace_bytes(B, N, M, iters)
