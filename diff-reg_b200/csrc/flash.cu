@@ -60,6 +60,10 @@ struct FlashShape {
   const unsigned short *Q16, *K16, *V16;
   const uint8_t *q_mask, *kv_mask;
   float* out;    // [B, L, H * d]
+  int nsplit;    // the keys are split over nsplit CTAs per (query tile, head) (grid.z); > 1: partial results go to `part` / `part_ml`
+  int tiles_per_split;
+  float* part;   // [nsplit, B, L, H * d] un-normalised partial outputs (relative to the split's own reference)
+  float2* part_ml;  // [nsplit, B * H, L] (reference m in log2 units, row sum l)
   long long* tl; // tuning stamps of CTA (0, 0): 16 per key tile for the first 64 tiles, or NULL
 };
 
@@ -169,7 +173,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   constexpr int TMEM_COLS = (FA_S_COLS + 2 * 16 * (4 * NFULL + NPIECE)) <= 256 ? 256 : 512;   // S x 2 + O chunk + O total (ND = 16 (4 NFULL + NPIECE) columns each)
   const uint32_t q_seg = (uint32_t)(nfull * FA_Q_CHUNK + npiece * (FA_Q_CHUNK / 4));   // bytes of one segment (lo or hi) of the Q tile
   const uint32_t k_seg = (uint32_t)(nfull * FA_K_CHUNK + npiece * (FA_K_CHUNK / 4));
-  const int T = (s.S + FA_BN - 1) / FA_BN;
+  // this CTA's key tiles: [tile0, tile0 + T) of the (S + 63) / 64 tiles (all of them unless the keys are split over grid.z)
+  const int tile0 = (int)blockIdx.z * s.tiles_per_split;
+  const int T = min(s.tiles_per_split, (s.S + FA_BN - 1) / FA_BN - tile0);
 
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* aligned = smem_dyn + (base - smem_u32(smem_dyn));
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       auto fetch_cols = [&](int t) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const int j = t * FA_BN + lane + 32 * i;
+          const int j = (tile0 + t) * FA_BN + lane + 32 * i;
           c_ok[i] = t < T && j < s.S;
           c_ik[i] = c_ok[i] ? reinterpret_cast<const float*>(s.K16 + ((size_t)bh * s.S + j) * pitch_d + 2 * s.kc)[0] : 0.f;
           c_kv[i] = c_ok[i] && (s.kv_mask == nullptr || s.kv_mask[(size_t)b * s.S + j] != 0);
@@ -248,9 +254,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         uint8_t* dst = sK + (size_t)st * k_bytes;
         for (int seg = 0; seg < 2; ++seg) {
           uint8_t* sd = dst + (size_t)seg * k_seg;
-          for (int c = 0; c < nfull; ++c) tma_load_3d(sd + (size_t)c * FA_K_CHUNK, &tmK, seg * s.kc + c * 64, t * FA_BN, bh, &bar_kfull[st]);
+          for (int c = 0; c < nfull; ++c) tma_load_3d(sd + (size_t)c * FA_K_CHUNK, &tmK, seg * s.kc + c * 64, (tile0 + t) * FA_BN, bh, &bar_kfull[st]);
           for (int c = 0; c < npiece; ++c)
-            tma_load_3d(sd + (size_t)nfull * FA_K_CHUNK + (size_t)c * (FA_K_CHUNK / 4), &tmKp, seg * s.kc + nfull * 64 + c * 16, t * FA_BN, bh,
+            tma_load_3d(sd + (size_t)nfull * FA_K_CHUNK + (size_t)c * (FA_K_CHUNK / 4), &tmKp, seg * s.kc + nfull * 64 + c * 16, (tile0 + t) * FA_BN, bh,
                         &bar_kfull[st]);
         }
       };
@@ -259,8 +265,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         mbar_wait(&bar_vfree[st], (uint32_t)(((t / s.VS) & 1) ^ 1));   // P.V of tile t - VS has read the stage
         mbar_arrive_expect_tx(&bar_vfull[st], 2u * v_bytes);
         uint8_t* dst = sV + (size_t)st * 2 * v_bytes;
-        tma_load_3d(dst, &tmV, t * FA_BN, 0, bh, &bar_vfull[st]);                     // V_hi: keys of this tile along the row
-        tma_load_3d(dst + v_bytes, &tmV, s.kcS + t * FA_BN, 0, bh, &bar_vfull[st]);   // V_lo
+        tma_load_3d(dst, &tmV, (tile0 + t) * FA_BN, 0, bh, &bar_vfull[st]);                     // V_hi: keys of this tile along the row
+        tma_load_3d(dst + v_bytes, &tmV, s.kcS + (tile0 + t) * FA_BN, 0, bh, &bar_vfull[st]);   // V_lo
       };
       if (lane == 0) {
         mbar_arrive_expect_tx(&bar_q, 2u * q_seg);
@@ -491,8 +497,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     for (int pp = 1; pp < FA_PARTS; ++pp) l_row += rowsum[pp][row];
     mbar_wait(&bar_pv, (uint32_t)((T - 1) & 1));
     tcgen05_fence_after();
-    const float inv_l = 1.f / l_row;     // l = 0 (a valid query without a valid key): 0 * inf = NaN, as softmax of all -inf is
-    float* orow = s.out + (((size_t)b * s.L + (row_ok ? q : 0)) * s.H + h) * s.d;
+    // one CTA per (query tile, head): O / l.  Keys split over grid.z: the un-normalised O with (m_ref, l) for attn_combine_kernel
+    const bool split = s.nsplit > 1;
+    const float inv_l = split ? 1.f : 1.f / l_row;   // l = 0 (a valid query without a valid key): 0 * inf = NaN, as softmax of all -inf is
+    float* orow = (split ? s.part + (size_t)blockIdx.z * s.B * s.L * s.H * s.d : s.out) + (((size_t)b * s.L + (row_ok ? q : 0)) * s.H + h) * s.d;
+    if (split && part == 0 && row_ok) s.part_ml[((size_t)blockIdx.z * s.B * s.H + bh) * s.L + q] = make_float2(m_ref, l_row);
     for (int c = c16_lo; c < c16_hi; ++c) {
       const int c0 = c * 16;
       uint32_t r[16];
@@ -519,6 +528,36 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// Keys split over nsplit CTAs: out = sum_z 2^(m_z - m*) O_z / sum_z 2^(m_z - m*) l_z with m* = max_z m_z (each split's O_z and l_z are
+// relative to its own reference m_z).  One thread per four output channels.
+__global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restrict__ part, const float2* __restrict__ part_ml, int nsplit,
+                                                          int B, int H, int L, int d, float* __restrict__ out) {
+  const int d4 = d >> 2;
+  const size_t total = (size_t)B * L * H * d4;
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % d4);
+  const size_t r = idx / d4;             // (b * L + l) * H + h
+  const int h = (int)(r % H);
+  const size_t bl = r / H;
+  const int l = (int)(bl % L), b = (int)(bl / L);
+  const size_t slab = (size_t)B * L * H * d, mlslab = (size_t)B * H * L;
+  const size_t mlo = ((size_t)b * H + h) * L + l;
+  float m_star = __int_as_float(0xff800000);
+  for (int z = 0; z < nsplit; ++z) m_star = fmaxf(m_star, part_ml[z * mlslab + mlo].x);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float lsum = 0.f;
+  for (int z = 0; z < nsplit; ++z) {
+    const float2 ml = part_ml[z * mlslab + mlo];
+    const float w = ml.x == m_star ? 1.f : exp2f(ml.x - m_star);     // (all splits masked: m* = -inf, w = 1, l = 0 -> NaN below)
+    const float4 o = *reinterpret_cast<const float4*>(part + z * slab + r * d + 4 * c4);
+    acc.x = fmaf(w, o.x, acc.x); acc.y = fmaf(w, o.y, acc.y); acc.z = fmaf(w, o.z, acc.z); acc.w = fmaf(w, o.w, acc.w);
+    lsum = fmaf(w, ml.y, lsum);
+  }
+  const float inv = 1.f / lsum;
+  *reinterpret_cast<float4*>(out + r * d + 4 * c4) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
 }
 
 // The V operand of the fused attention: V [B, S, H * d] fp32 -> per head the RIGHT split operand of V^T, [B * H, d, 2 kc(S) + 8]
@@ -597,9 +636,37 @@ __global__ void __launch_bounds__(256) vt_split_kernel(const float* __restrict__
 
 using namespace drg;
 
+// How many CTAs share the keys of one (query tile, head): with `units` such pairs of T key tiles each on NUM_SMS SMs (one CTA per
+// SM), n splits cost ceil(units n / NUM_SMS) rounds of ceil(T / n) tiles + ~3 tiles' worth of prologue / epilogue per CTA
+// (+ the combine pass).  4 heads x 4096 queries: 128 units -> 1; the 2D-3D flavour's 2048 / 4800 tokens (64 / 152 units) -> 2 .. 4.
+constexpr int FA_MAX_SPLIT = 8;
+static int fa_choose_nsplit(long long units, int T) {
+  int best_n = 1;
+  long long best = -1;
+  for (int n : {1, 2, 3, 4, 6, 8}) {
+    const int per = (T + n - 1) / n;
+    if (n > 1 && per < 4) break;
+    const long long rounds = (units * n + NUM_SMS - 1) / NUM_SMS;
+    const long long cost = rounds * (per + 3) + (n > 1 ? 2 : 0);
+    if (best < 0 || cost < best) {
+      best = cost;
+      best_n = n;
+    }
+  }
+  return best_n;
+}
+
+extern "C" size_t drg_attention_workspace_bytes(int B, int H, int L, int S, int d) {
+  (void)S;
+  if (B < 1 || H < 1 || L < 1 || d < 1) return 0;
+  return align_up((size_t)FA_MAX_SPLIT * ((size_t)B * L * H * d * sizeof(float) + (size_t)B * H * L * sizeof(float2)), 256);
+}
+
 extern "C" int drg_attention_split16(const void* Q16, const void* K16, const void* Vt16, const uint8_t* q_mask, const uint8_t* kv_mask,
-                                     int B, int H, int L, int S, int d, float scale, float* out, void* stream) {
+                                     int B, int H, int L, int S, int d, float scale, float* out, int nsplit, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
   DRG_CHECK_ARG(Q16 && K16 && Vt16 && out, "Q16 / K16 / Vt16 / out must be non-null");
+  DRG_CHECK_ARG(nsplit >= 0 && nsplit <= FA_MAX_SPLIT, "nsplit must be 0 (choose) .. 8");
   DRG_CHECK_ARG(B >= 1 && H >= 1 && L >= 1 && S >= 1 && d >= 1, "B, H, L, S, d must be >= 1");
   if (d % 4 != 0 || d > 176 || (((uintptr_t)Q16 | (uintptr_t)K16 | (uintptr_t)Vt16 | (uintptr_t)out) & 15u)) {
     set_error("attention: head width must be a multiple of 4 and <= 176 (got %d), buffers 16-byte aligned", d);
@@ -650,7 +717,19 @@ extern "C" int drg_attention_split16(const void* Q16, const void* K16, const voi
     return DRG_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const dim3 grid((unsigned)((L + FA_BM - 1) / FA_BM), (unsigned)BH);
+  const int qtiles = (L + FA_BM - 1) / FA_BM, T = (S + FA_BN - 1) / FA_BN;
+  if (nsplit == 0) nsplit = workspace ? fa_choose_nsplit((long long)qtiles * BH, T) : 1;
+  if (nsplit > T) nsplit = T;
+  s.tiles_per_split = (T + nsplit - 1) / nsplit;
+  nsplit = (T + s.tiles_per_split - 1) / s.tiles_per_split;        // (no empty split)
+  s.nsplit = nsplit;
+  if (nsplit > 1) {
+    DRG_CHECK_ARG(workspace != nullptr && workspace_bytes >= drg_attention_workspace_bytes(B, H, L, S, d) && (((uintptr_t)workspace) & 15u) == 0,
+                  "split keys need the workspace of drg_attention_workspace_bytes (16-byte aligned)");
+    s.part = reinterpret_cast<float*>(workspace);
+    s.part_ml = reinterpret_cast<float2*>(s.part + (size_t)nsplit * B * L * H * d);
+  }
+  const dim3 grid((unsigned)qtiles, (unsigned)BH, (unsigned)nsplit);
   if (BH > 65535) {
     set_error("attention: batch * heads = %d exceeds the grid", BH);
     return DRG_ERR_UNSUPPORTED;
@@ -668,6 +747,11 @@ extern "C" int drg_attention_split16(const void* Q16, const void* K16, const voi
   if (!launched) {
     set_error("attention: no kernel for head width %d", d);
     return DRG_ERR_UNSUPPORTED;
+  }
+  if (nsplit > 1) {
+    DRG_LAUNCH_CHECK();
+    const size_t total = (size_t)B * L * H * (d / 4);
+    attn_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s.part, s.part_ml, nsplit, B, H, L, d, out);
   }
   DRG_LAUNCH_CHECK();
   return DRG_OK;

@@ -364,10 +364,11 @@ FLASH_MAX_HEAD = 176     # widest head drg_attention_split16 takes (shared memor
 
 
 @_on_device
-def attention(q16, k16, v, heads, q_mask, kv_mask, scale, d):
+def attention(q16, k16, v, heads, q_mask, kv_mask, scale, d, nsplit=0):
     """softmax(Q K^T * scale + mask) V per head in one kernel (drg_attention_split16).  q16 [B*H, L, split_pitch(d)] / k16
     [B*H, S, split_pitch(d)]: the per-head split operands of prep_heads (patterns 0 / 1); v [B, S, H*d] fp32; masks [B, L] /
-    [B, S] bool (True = valid) or None, keys masked for valid queries only.  Returns [B, L, H*d] fp32."""
+    [B, S] bool (True = valid) or None, keys masked for valid queries only.  nsplit: CTAs sharing the keys of one (query tile,
+    head) -- 0 = chosen by the library (small grids are split), 1 = never.  Returns [B, L, H*d] fp32."""
     _require_cuda(q16, k16, v, q_mask, kv_mask)
     lib = load_library()
     BH, L, _ = q16.shape
@@ -380,8 +381,9 @@ def attention(q16, k16, v, heads, q_mask, kv_mask, scale, d):
     qm = _as_mask(q_mask, B, L, q16.device) if q_mask is not None else None
     km = _as_mask(kv_mask, B, S, q16.device) if kv_mask is not None else None
     out = torch.empty(B, L, heads * d, dtype=torch.float32, device=q16.device)
+    wsa = workspace(lib.drg_attention_workspace_bytes(B, heads, L, S, int(d)), q16.device, tag="attention_split") if nsplit != 1 else None
     check(lib.drg_attention_split16(q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), _ptr(qm), _ptr(km), B, heads, L, S, int(d),
-                                    float(scale), out.data_ptr(), _stream()))
+                                    float(scale), out.data_ptr(), int(nsplit), _ptr(wsa), wsa.numel() if wsa is not None else 0, _stream()))
     return out
 
 

@@ -294,8 +294,13 @@ int drg_gemm_nt_split16_bias(const void* A16, const void* B16, const float* bias
 /*   drg_prep_vt_split16: V [B, S, H * d] fp32 -> Vt16 as above (per head V^T, the keys along the row; the tail holds 1 / scale
  *   only).  workspace: B * H * d * 4 bytes (the channels' maxima). */
 int drg_prep_vt_split16(const float* V, int B, int H, int S, int d, void* Vt16, void* workspace, void* stream);
+/*   nsplit: the keys of one (query tile, head) are shared by nsplit CTAs whose partial results a second kernel combines (small
+ *   grids: 2048 queries x 4 heads are 64 CTAs for 148 SMs); 0 = chosen by the library, 1 = never split.  workspace (may be NULL
+ *   with nsplit <= 1): drg_attention_workspace_bytes(B, H, L, S, d) bytes. */
+size_t drg_attention_workspace_bytes(int B, int H, int L, int S, int d);
 int drg_attention_split16(const void* Q16, const void* K16, const void* Vt16, const uint8_t* q_mask, const uint8_t* kv_mask, int B,
-                          int H, int L, int S, int d, float scale, float* out, void* stream);
+                          int H, int L, int S, int d, float scale, float* out, int nsplit, void* workspace, size_t workspace_bytes,
+                          void* stream);
 int drg_fourier_embed(const float* x, const float* center, long long rows, int n, int length, float k0, int use_pi, int use_input,
                       float* out, void* stream);
 

@@ -23,13 +23,13 @@ def _ref64(q, k, v, H, qm, km, scale):
     return torch.einsum("nlsh,nshd->nlhd", a, vh).reshape(B, L, C)
 
 
-def _run(q, k, v, H, qm, km, scale):
+def _run(q, k, v, H, qm, km, scale, nsplit=0):
     from diffreg_b200 import ops
     d = q.shape[-1] // H
     c = lambda t: None if t is None else t.cuda()
     q16 = ops.prep_heads(q.cuda(), H, 0)
     k16 = ops.prep_heads(k.cuda(), H, 1)
-    out = ops.attention(q16, k16, v.cuda(), H, c(qm), c(km), scale, d)
+    out = ops.attention(q16, k16, v.cuda(), H, c(qm), c(km), scale, d, nsplit=nsplit)
     torch.cuda.synchronize()
     return out.cpu()
 
@@ -135,3 +135,24 @@ def test_attention_long_rows_accumulate_in_chunks():
     out = _run(q, k, v, H, None, None, scale)
     err = (out.double() - ref).abs().max().item()
     assert err <= 1e-5, err                                    # measured 6.9e-6 on values ~1.5 (one chunk = 96 truncating MMAs); unchunked ~5e-5
+
+
+@pytest.mark.parametrize("nsplit", [1, 2, 3, 8])
+def test_attention_with_the_keys_split_over_several_ctas(nsplit):
+    """Small grids share the keys of a (query tile, head) among several CTAs (grid.z) and combine the partial results: same
+    result whatever the split, masks and NaN rows included."""
+    g = torch.Generator().manual_seed(9)
+    B, H, L, S, d = 2, 2, 200, 1500, 64
+    q, k, v = torch.randn(B, L, H * d, generator=g), torch.randn(B, S, H * d, generator=g) * 1.5, torch.randn(B, S, H * d, generator=g)
+    qm, km = torch.rand(B, L, generator=g) > 0.2, torch.rand(B, S, generator=g) > 0.2
+    km[1, :1100] = False                     # batch 1: the first splits see masked keys only
+    scale = 1.0 / math.sqrt(d)
+    ref = _ref64(q, k, v, H, qm, km, scale)
+    out = _run(q, k, v, H, qm, km, scale, nsplit=nsplit)
+    assert torch.equal(torch.isnan(out), torch.isnan(ref))
+    ok = ~torch.isnan(ref)
+    assert (out.double()[ok] - ref[ok]).abs().max().item() <= 2e-5
+    km[0] = False                            # batch 0: no valid key at all -> NaN for its valid queries in every split
+    ref = _ref64(q, k, v, H, qm, km, scale)
+    out = _run(q, k, v, H, qm, km, scale, nsplit=nsplit)
+    assert torch.equal(torch.isnan(out), torch.isnan(ref))
