@@ -84,7 +84,23 @@ __global__ void __launch_bounds__(256) lotb_row_kernel(const LotbParams p, int t
   const float* gv = lotb_gv(p, t, b);
   const float* Gr = p.G + ((size_t)b * (p.N + 1) + i) * (p.M + 1);
   float acc = 0.f, base = 0.f;
-  for (int j = lane; j <= p.M; j += 32) {
+  int j_begin = 0;
+  if (i < p.N && (p.M & 3) == 0 && ((uintptr_t)p.scores & 15u) == 0) {
+    // interior columns four at a time (the score row is 16-byte aligned); log_nu = norm there
+    const float4* zr = reinterpret_cast<const float4*>(p.scores + ((size_t)b * p.N + i) * p.M);
+    const float c0 = ui - p.consts[4 * b];
+    for (int q = lane; q < (p.M >> 2); q += 32) {
+      const float4 z = zr[q];
+      const int j = q << 2;
+      acc = fmaf(gv[j], expf(z.x + c0 + vt[j]), acc);
+      acc = fmaf(gv[j + 1], expf(z.y + c0 + vt[j + 1]), acc);
+      acc = fmaf(gv[j + 2], expf(z.z + c0 + vt[j + 2]), acc);
+      acc = fmaf(gv[j + 3], expf(z.w + c0 + vt[j + 3]), acc);
+      if (with_G) base += (Gr[j] + Gr[j + 1]) + (Gr[j + 2] + Gr[j + 3]);
+    }
+    j_begin = p.M;      // the dustbin column below
+  }
+  for (int j = j_begin + lane; j <= p.M; j += 32) {
     const float z = lotb_z(p, b, i, j, alpha);
     acc = fmaf(gv[j], expf(z + ui + (vt[j] - lotb_log_nu(p, b, j))), acc);
     if (with_G) base += Gr[j];
@@ -108,7 +124,19 @@ __global__ void __launch_bounds__(256) lotb_col_kernel(const LotbParams p, int t
     const float* ut = lotb_u(p, t, b);
     const float* gu = lotb_gu(p, t, b);
     const float vp = t > 1 ? lotb_v(p, t - 1, b)[j] : 0.f;
-    for (int i = i0; i < i1; ++i)
+    int i = i0;
+    if (j < p.M) {
+      const float nrm = p.consts[4 * b];
+      const float* zc = p.scores + (size_t)b * p.N * p.M + j;
+      for (; i + 4 <= min(i1, p.N); i += 4) {          // four rows in flight (interior rows: log_mu = norm)
+        const float z0 = zc[(size_t)i * p.M], z1 = zc[(size_t)(i + 1) * p.M], z2 = zc[(size_t)(i + 2) * p.M], z3 = zc[(size_t)(i + 3) * p.M];
+        acc = fmaf(gu[i], expf(z0 + (ut[i] - nrm) + vp), acc);
+        acc = fmaf(gu[i + 1], expf(z1 + (ut[i + 1] - nrm) + vp), acc);
+        acc = fmaf(gu[i + 2], expf(z2 + (ut[i + 2] - nrm) + vp), acc);
+        acc = fmaf(gu[i + 3], expf(z3 + (ut[i + 3] - nrm) + vp), acc);
+      }
+    }
+    for (; i < i1; ++i)
       acc = fmaf(gu[i], expf(lotb_z(p, b, i, j, alpha) + (ut[i] - lotb_log_mu(p, b, i)) + vp), acc);
   }
   p.colpart[((size_t)b * p.nslab + blockIdx.y) * (p.M + 1) + j] = acc;
