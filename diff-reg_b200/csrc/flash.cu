@@ -656,10 +656,20 @@ static int fa_choose_nsplit(long long units, int T) {
   return best_n;
 }
 
-extern "C" size_t drg_attention_workspace_bytes(int B, int H, int L, int S, int d) {
-  (void)S;
-  if (B < 1 || H < 1 || L < 1 || d < 1) return 0;
-  return align_up((size_t)FA_MAX_SPLIT * ((size_t)B * L * H * d * sizeof(float) + (size_t)B * H * L * sizeof(float2)), 256);
+// the split count drg_attention_split16 uses for nsplit = 0 (chosen) or a requested nsplit (clipped to the number of key tiles)
+static int fa_effective_nsplit(int B, int H, int L, int S, int nsplit) {
+  const int qtiles = (L + FA_BM - 1) / FA_BM, T = (S + FA_BN - 1) / FA_BN;
+  if (nsplit == 0) nsplit = fa_choose_nsplit((long long)qtiles * B * H, T);
+  if (nsplit > T) nsplit = T;
+  const int per = (T + nsplit - 1) / nsplit;
+  return (T + per - 1) / per;        // (no empty split)
+}
+
+extern "C" size_t drg_attention_workspace_bytes(int B, int H, int L, int S, int d, int nsplit) {
+  if (B < 1 || H < 1 || L < 1 || S < 1 || d < 1 || nsplit < 0 || nsplit > FA_MAX_SPLIT) return 0;
+  const int n = fa_effective_nsplit(B, H, L, S, nsplit);
+  if (n <= 1) return 0;
+  return align_up((size_t)n * ((size_t)B * L * H * d * sizeof(float) + (size_t)B * H * L * sizeof(float2)), 256);
 }
 
 extern "C" int drg_attention_split16(const void* Q16, const void* K16, const void* Vt16, const uint8_t* q_mask, const uint8_t* kv_mask,
@@ -718,13 +728,13 @@ extern "C" int drg_attention_split16(const void* Q16, const void* K16, const voi
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int qtiles = (L + FA_BM - 1) / FA_BM, T = (S + FA_BN - 1) / FA_BN;
-  if (nsplit == 0) nsplit = workspace ? fa_choose_nsplit((long long)qtiles * BH, T) : 1;
-  if (nsplit > T) nsplit = T;
+  const int requested = nsplit;
+  nsplit = fa_effective_nsplit(B, H, L, S, requested);
   s.tiles_per_split = (T + nsplit - 1) / nsplit;
-  nsplit = (T + s.tiles_per_split - 1) / s.tiles_per_split;        // (no empty split)
   s.nsplit = nsplit;
   if (nsplit > 1) {
-    DRG_CHECK_ARG(workspace != nullptr && workspace_bytes >= drg_attention_workspace_bytes(B, H, L, S, d) && (((uintptr_t)workspace) & 15u) == 0,
+    DRG_CHECK_ARG(workspace != nullptr && workspace_bytes >= drg_attention_workspace_bytes(B, H, L, S, d, requested) &&
+                      (((uintptr_t)workspace) & 15u) == 0,
                   "split keys need the workspace of drg_attention_workspace_bytes (16-byte aligned)");
     s.part = reinterpret_cast<float*>(workspace);
     s.part_ml = reinterpret_cast<float2*>(s.part + (size_t)nsplit * B * L * H * d);

@@ -213,6 +213,114 @@ __global__ void __launch_bounds__(256) lotb_alpha_kernel(const LotbParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Backward of the dual-softmax branch (matching.py:147-157): conf = A * B, A = softmax over the SRC axis of sim / T with the invalid
+// src rows at -inf, B = softmax over the TGT axis with the invalid tgt columns at -inf.  With P = A B, c_j = sum_i G_ij P_ij and
+// r_i = sum_j G_ij P_ij:   dL/d sim_ij = (2 P_ij G_ij - A_ij c_j - B_ij r_i) / T.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct DsbParams {
+  const float* sim;       // [B, N, M]
+  const uint8_t* src_mask;
+  const uint8_t* tgt_mask;
+  const float* G;         // [B, N, M]
+  float* rstat;           // [B, N, 2] (max, sum) of the rows over the valid tgt columns
+  float* cstat;           // [B, M, 2] (max, sum) of the columns over the valid src rows
+  float* r;               // [B, N]
+  float* c;               // [B, M]
+  float* colpart;         // [B, nslab, M, 2]
+  float* gsim;            // [B, N, M]
+  int B, N, M, nslab;
+  float inv_T;
+};
+__device__ __forceinline__ void dsb_merge(float& m, float& sum, float m2, float s2) {
+  const float mn = fmaxf(m, m2);
+  if (mn == __int_as_float(0xff800000)) return;       // both empty
+  sum = sum * expf(m - mn) + s2 * expf(m2 - mn);
+  m = mn;
+}
+// A_ij, B_ij from the statistics
+__device__ __forceinline__ void dsb_ab(const DsbParams& p, int b, int i, int j, float x, bool sv, bool tv, float& A, float& Bv) {
+  const float2 cs = reinterpret_cast<const float2*>(p.cstat)[(size_t)b * p.M + j];
+  const float2 rs = reinterpret_cast<const float2*>(p.rstat)[(size_t)b * p.N + i];
+  A = sv ? expf(x - cs.x) / cs.y : 0.f;
+  Bv = tv ? expf(x - rs.x) / rs.y : 0.f;
+}
+// mode 0: row statistics; mode 1: r_i = sum_j G P.  One warp per row.
+__global__ void __launch_bounds__(256) dsb_row_kernel(const DsbParams p, int mode) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= p.N) return;
+  const float* xr = p.sim + ((size_t)b * p.N + i) * p.M;
+  const uint8_t* tm = p.tgt_mask + (size_t)b * p.M;
+  if (mode == 0) {
+    float m = __int_as_float(0xff800000), sum = 0.f;
+    for (int j = lane; j < p.M; j += 32)
+      if (tm[j]) dsb_merge(m, sum, xr[j] * p.inv_T, 1.f);
+    for (int o = 16; o > 0; o >>= 1) dsb_merge(m, sum, __shfl_xor_sync(0xffffffffu, m, o), __shfl_xor_sync(0xffffffffu, sum, o));
+    if (lane == 0) reinterpret_cast<float2*>(p.rstat)[(size_t)b * p.N + i] = make_float2(m, sum);
+    return;
+  }
+  const bool sv = p.src_mask[(size_t)b * p.N + i] != 0;
+  const float* gr = p.G + ((size_t)b * p.N + i) * p.M;
+  float acc = 0.f;
+  for (int j = lane; j < p.M; j += 32) {
+    float A, Bv;
+    dsb_ab(p, b, i, j, xr[j] * p.inv_T, sv, tm[j] != 0, A, Bv);
+    acc = fmaf(gr[j], A * Bv, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) p.r[(size_t)b * p.N + i] = acc;
+}
+// mode 0: column statistics; mode 1: c_j = sum_i G P.  One thread per column over a slab of rows, then a fixed-order reduce.
+__global__ void __launch_bounds__(256) dsb_col_kernel(const DsbParams p, int mode) {
+  const int b = blockIdx.z, j = blockIdx.x * 256 + threadIdx.x;
+  const int i0 = blockIdx.y * LOTB_SLAB, i1 = min(i0 + LOTB_SLAB, p.N);
+  if (j >= p.M) return;
+  const uint8_t* sm = p.src_mask + (size_t)b * p.N;
+  float2* out = reinterpret_cast<float2*>(p.colpart) + ((size_t)b * p.nslab + blockIdx.y) * p.M + j;
+  if (mode == 0) {
+    float m = __int_as_float(0xff800000), sum = 0.f;
+    for (int i = i0; i < i1; ++i)
+      if (sm[i]) dsb_merge(m, sum, p.sim[((size_t)b * p.N + i) * p.M + j] * p.inv_T, 1.f);
+    *out = make_float2(m, sum);
+    return;
+  }
+  const bool tv = p.tgt_mask[(size_t)b * p.M + j] != 0;
+  float acc = 0.f;
+  for (int i = i0; i < i1; ++i) {
+    float A, Bv;
+    dsb_ab(p, b, i, j, p.sim[((size_t)b * p.N + i) * p.M + j] * p.inv_T, sm[i] != 0, tv, A, Bv);
+    acc = fmaf(p.G[((size_t)b * p.N + i) * p.M + j], A * Bv, acc);
+  }
+  *out = make_float2(acc, 0.f);
+}
+__global__ void __launch_bounds__(256) dsb_colreduce_kernel(const DsbParams p, int mode) {
+  const int b = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= p.M) return;
+  const float2* part = reinterpret_cast<const float2*>(p.colpart) + (size_t)b * p.nslab * p.M + j;
+  if (mode == 0) {
+    float m = __int_as_float(0xff800000), sum = 0.f;
+    for (int s2 = 0; s2 < p.nslab; ++s2) dsb_merge(m, sum, part[(size_t)s2 * p.M].x, part[(size_t)s2 * p.M].y);
+    reinterpret_cast<float2*>(p.cstat)[(size_t)b * p.M + j] = make_float2(m, sum);
+  } else {
+    float acc = 0.f;
+    for (int s2 = 0; s2 < p.nslab; ++s2) acc += part[(size_t)s2 * p.M].x;
+    p.c[(size_t)b * p.M + j] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) dsb_final_kernel(const DsbParams p) {
+  const int b = blockIdx.z, j = blockIdx.x * 256 + threadIdx.x;
+  const int i0 = blockIdx.y * LOTB_SLAB, i1 = min(i0 + LOTB_SLAB, p.N);
+  if (j >= p.M) return;
+  const bool tv = p.tgt_mask[(size_t)b * p.M + j] != 0;
+  const float cj = p.c[(size_t)b * p.M + j];
+  for (int i = i0; i < i1; ++i) {
+    const size_t e = ((size_t)b * p.N + i) * p.M + j;
+    float A, Bv;
+    dsb_ab(p, b, i, j, p.sim[e] * p.inv_T, p.src_mask[(size_t)b * p.N + i] != 0, tv, A, Bv);
+    p.gsim[e] = (2.f * A * Bv * p.G[e] - A * cj - Bv * p.r[(size_t)b * p.N + i]) * p.inv_T;
+  }
+}
+
 }  // namespace drg
 
 using namespace drg;
@@ -274,6 +382,45 @@ extern "C" int drg_sinkhorn_backward(const float* scores, const float* alpha, co
   }
   DRG_LAUNCH_CHECK();
   lotb_alpha_kernel<<<B, 256, 0, st>>>(p);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}
+
+extern "C" size_t drg_dual_softmax_backward_workspace_bytes(int B, int N, int M) {
+  if (B < 1 || N < 1 || M < 1) return 0;
+  const size_t nslab = (size_t)(N + LOTB_SLAB - 1) / LOTB_SLAB;
+  return align_up(((size_t)B * N * 3 + (size_t)B * M * 3 + (size_t)B * nslab * M * 2) * sizeof(float), 256);
+}
+
+extern "C" int drg_dual_softmax_backward(const float* sim, const uint8_t* src_mask, const uint8_t* tgt_mask, int B, int N, int M,
+                                         float temperature, const float* grad_conf, float* grad_sim, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  DRG_CHECK_ARG(sim && src_mask && tgt_mask && grad_conf && grad_sim && workspace, "all pointers must be non-null");
+  DRG_CHECK_ARG(B >= 1 && N >= 1 && M >= 1 && B <= 65535 && temperature > 0.f, "B, N, M >= 1, temperature > 0");
+  DRG_CHECK_ARG(workspace_bytes >= drg_dual_softmax_backward_workspace_bytes(B, N, M), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  DsbParams p{};
+  p.sim = sim; p.src_mask = src_mask; p.tgt_mask = tgt_mask; p.G = grad_conf; p.gsim = grad_sim;
+  p.B = B; p.N = N; p.M = M;
+  p.nslab = (N + LOTB_SLAB - 1) / LOTB_SLAB;
+  p.inv_T = 1.f / temperature;
+  float* w = reinterpret_cast<float*>(workspace);
+  p.rstat = w;
+  p.cstat = p.rstat + (size_t)2 * B * N;
+  p.r = p.cstat + (size_t)2 * B * M;
+  p.c = p.r + (size_t)B * N;
+  p.colpart = p.c + (size_t)B * M;
+  const dim3 grow((unsigned)((N + 7) / 8), (unsigned)B), gcol((unsigned)((M + 255) / 256), (unsigned)p.nslab, (unsigned)B),
+      gred((unsigned)((M + 255) / 256), (unsigned)B);
+  for (int mode = 0; mode < 2; ++mode) {     // statistics, then the weighted sums that need them
+    dsb_row_kernel<<<grow, 256, 0, st>>>(p, mode);
+    DRG_LAUNCH_CHECK();
+    dsb_col_kernel<<<gcol, 256, 0, st>>>(p, mode);
+    DRG_LAUNCH_CHECK();
+    dsb_colreduce_kernel<<<gred, 256, 0, st>>>(p, mode);
+    DRG_LAUNCH_CHECK();
+  }
+  dsb_final_kernel<<<gcol, 256, 0, st>>>(p);
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }

@@ -55,6 +55,21 @@ class _LogOptimalTransportFn(torch.autograd.Function):
                 ga.to(alpha.dtype).reshape(alpha.shape) if ctx.needs_input_grad[1] else None, None, None, None)
 
 
+class _DualSoftmaxFn(torch.autograd.Function):
+    """The dual-softmax confidence (matching.py:147-157) with a CUDA backward (drg_dual_softmax_backward)."""
+
+    @staticmethod
+    def forward(ctx, sim, src_mask, tgt_mask, temperature):
+        ctx.save_for_backward(sim, src_mask, tgt_mask)
+        ctx.temperature = float(temperature)
+        return ops.dual_softmax(sim, src_mask, tgt_mask, temperature)
+
+    @staticmethod
+    def backward(ctx, grad_conf):
+        sim, src_mask, tgt_mask = ctx.saved_tensors
+        return ops.dual_softmax_backward(sim, src_mask, tgt_mask, ctx.temperature, grad_conf.contiguous()), None, None, None
+
+
 def log_optimal_transport(scores, alpha, iters, src_mask, tgt_mask):
     """[B,N,M] scores -> [B,N+1,M+1] log-assignment (Z + u + v - norm).
 
@@ -203,8 +218,8 @@ class Matching(nn.Module):
         return torch.is_grad_enabled() and (any(torch.is_tensor(t) and t.requires_grad for t in tensors) or
                                             (self.training and any(q.requires_grad for q in self.parameters())))
 
-    def _forward_train(self, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type):
-        """Training forward of the Sinkhorn branch with autograd recording (matching.py:118-173).  The
+    def _conf_train(self, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type):
+        """conf_matrix of either branch with autograd recording (matching.py:118-173).  The
         projections, the position code and the similarity contraction are torch ops (library GEMMs and elementwise kernels,
         differentiable as they stand); the Sinkhorn -- where autograd would make ~60 passes over the N x M matrix forward and
         backward -- runs on this library's kernels in both directions (_LogOptimalTransportFn)."""
@@ -223,24 +238,28 @@ class Matching(nn.Module):
         data.update({"src_feats": fs, "tgt_feats": ft})
         scale = fs.shape[-1] ** .5
         sim = torch.einsum("bsc,btc->bst", fs / scale, ft / scale)                   # :144-145, :161
+        if self.match_type == "dual_softmax":                                      # :147-157 (temperature and masks inside the kernels)
+            if src_mask is None:
+                src_mask = torch.ones(sim.shape[:2], dtype=torch.bool, device=sim.device)
+                tgt_mask = torch.ones(sim.shape[0], sim.shape[2], dtype=torch.bool, device=sim.device)
+            return _DualSoftmaxFn.apply(sim, src_mask, tgt_mask, self.temperature)
         if src_mask is not None:
             sim = sim.masked_fill(~(src_mask[..., None] * tgt_mask[:, None]).bool(), float("-inf"))   # :163-165
         else:
             src_mask = torch.ones(sim.shape[:2], dtype=torch.bool, device=sim.device)
             tgt_mask = torch.ones(sim.shape[0], sim.shape[2], dtype=torch.bool, device=sim.device)
         log_assign = log_optimal_transport(sim, self.bin_score, self.skh_iters, src_mask, tgt_mask)
-        conf_matrix = log_assign.exp()[:, :-1, :-1].contiguous()                   # :169-170
-        with torch.no_grad():
-            coarse_match, _, _ = ops.get_match(conf_matrix.detach(), self.confidence_threshold, True, want_mask=False)
-        return conf_matrix, coarse_match
+        return log_assign.exp()[:, :-1, :-1].contiguous()                          # :169-170
 
     def forward(self, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type="rotary"):
         """-> (conf_matrix [B,N,M], coarse_match [K,3] int64); writes the four feature tensors into `data`.  When autograd is
         recording (training mode / inputs that require grad) the Sinkhorn branch returns a differentiable conf_matrix
-        (_forward_train); the dual-softmax branch, forward1 and the 2D-3D head stay forward-only and raise."""
-        if self.match_type == "sinkhorn" and type(self) is Matching and src_feats.is_cuda and \
-                self._records_grad(src_feats, tgt_feats, src_pe, tgt_pe):
-            return self._forward_train(src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type)
+        (_conf_train: both branches; likewise forward1 and the 2D-3D head's Sinkhorn branch)."""
+        if src_feats.is_cuda and self._records_grad(src_feats, tgt_feats, src_pe, tgt_pe):
+            conf_matrix = self._conf_train(src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type)
+            with torch.no_grad():
+                coarse_match, _, _ = ops.get_match(conf_matrix.detach(), self.confidence_threshold, True, want_mask=False)
+            return conf_matrix, coarse_match
         _no_grad_inputs(src_feats, tgt_feats, src_pe, tgt_pe, module=self)
         with torch.no_grad():
             sim = self.similarity(src_feats, tgt_feats, src_pe, tgt_pe, pe_type, data)
@@ -250,6 +269,12 @@ class Matching(nn.Module):
 
     def forward1(self, src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type="rotary", mutual=False):
         """3DMatch variant (3d matching.py:221-283): top-1 row/column matches as [K,3] with a zero batch column."""
+        if src_feats.is_cuda and self._records_grad(src_feats, tgt_feats, src_pe, tgt_pe):
+            conf_matrix = self._conf_train(src_feats, tgt_feats, src_pe, tgt_pe, src_mask, tgt_mask, data, pe_type)
+            with torch.no_grad():
+                r, c, _ = ops.top1_select(conf_matrix.detach().squeeze(0), True, None, mutual)
+                coarse_match = torch.cat([torch.zeros_like(r).unsqueeze(-1), r.unsqueeze(-1), c.unsqueeze(-1)], dim=-1)
+            return conf_matrix, coarse_match
         _no_grad_inputs(src_feats, tgt_feats, src_pe, tgt_pe, module=self)
         with torch.no_grad():
             sim = self.similarity(src_feats, tgt_feats, src_pe, tgt_pe, pe_type, data)
@@ -267,7 +292,13 @@ class Matching2D3D(Matching):
         self.mutual = mutual
 
     def forward(self, src_feats, tgt_feats, src_mask, tgt_mask, mutual=True):
-        """-> (conf_matrix [1,N,M], src_indices [K], tgt_indices [K], weights [K])"""
+        """-> (conf_matrix [1,N,M], src_indices [K], tgt_indices [K], weights [K]); differentiable (conf_matrix and the gathered
+        weights, as in the reference: matching.py:122-136) when autograd is recording and match_type is sinkhorn."""
+        if self.match_type == "sinkhorn" and src_feats.is_cuda and self._records_grad(src_feats, tgt_feats):
+            conf_matrix = self._conf_train(src_feats, tgt_feats, None, None, src_mask, tgt_mask, {}, None)
+            with torch.no_grad():
+                src_indices, tgt_indices, _ = ops.top1_select(conf_matrix.detach().squeeze(0), True, None, mutual)
+            return conf_matrix, src_indices, tgt_indices, conf_matrix[0][src_indices, tgt_indices]
         _no_grad_inputs(src_feats, tgt_feats, module=self)
         with torch.no_grad():
             sim = self.similarity(src_feats, tgt_feats)

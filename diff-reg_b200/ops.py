@@ -360,6 +360,22 @@ def attn_softmax(logits, heads, q_mask, kv_mask, scale, want_operand=True, want_
     return P16 if want_operand else P
 
 
+@_on_device
+def dual_softmax_backward(sim, src_mask, tgt_mask, temperature, grad_conf):
+    """dL/d sim [B,N,M] of dual_softmax given dL/d conf (drg_dual_softmax_backward)."""
+    _require_cuda(sim, src_mask, tgt_mask, grad_conf)
+    lib = load_library()
+    sim = _f32c(sim.detach())
+    B, N, M = sim.shape
+    sm, tm = _as_mask(src_mask, B, N, sim.device), _as_mask(tgt_mask, B, M, sim.device)
+    G = _f32c(grad_conf)
+    out = torch.empty_like(sim)
+    ws = workspace(lib.drg_dual_softmax_backward_workspace_bytes(B, N, M), sim.device, "dual_softmax_backward")
+    check(lib.drg_dual_softmax_backward(sim.data_ptr(), sm.data_ptr(), tm.data_ptr(), B, N, M, float(temperature), G.data_ptr(),
+                                        out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
 FLASH_MAX_HEAD = 176     # widest head drg_attention_split16 takes (shared memory: Q, K, V^T and P tiles of one CTA)
 
 
@@ -381,7 +397,8 @@ def attention(q16, k16, v, heads, q_mask, kv_mask, scale, d, nsplit=0):
     qm = _as_mask(q_mask, B, L, q16.device) if q_mask is not None else None
     km = _as_mask(kv_mask, B, S, q16.device) if kv_mask is not None else None
     out = torch.empty(B, L, heads * d, dtype=torch.float32, device=q16.device)
-    wsa = workspace(lib.drg_attention_workspace_bytes(B, heads, L, S, int(d)), q16.device, tag="attention_split") if nsplit != 1 else None
+    nws = lib.drg_attention_workspace_bytes(B, heads, L, S, int(d), int(nsplit))      # 0: this call keeps one CTA per (query tile, head)
+    wsa = workspace(nws, q16.device, tag="attention_split") if nws else None
     check(lib.drg_attention_split16(q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), _ptr(qm), _ptr(km), B, heads, L, S, int(d),
                                     float(scale), out.data_ptr(), int(nsplit), _ptr(wsa), wsa.numel() if wsa is not None else 0, _stream()))
     return out

@@ -134,6 +134,12 @@ int drg_sinkhorn_backward(const float* scores, const float* alpha, const uint8_t
                           int iters, const float* u_all, const float* v_all, const float* grad_out, float* grad_scores,
                           float* grad_alpha, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ... and of the dual-softmax branch (matching.py:147-157): grad_sim [B,N,M] from grad_conf [B,N,M]; sim is the undivided
+ * similarity (the temperature is applied inside, as in drg_dual_softmax). */
+size_t drg_dual_softmax_backward_workspace_bytes(int B, int N, int M);
+int drg_dual_softmax_backward(const float* sim, const uint8_t* src_mask, const uint8_t* tgt_mask, int B, int N, int M, float temperature,
+                              const float* grad_conf, float* grad_sim, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Row-sharded Sinkhorn: ONE matrix whose rows are spread over several GPUs (BASELINE.json configs[4]).
  *   The reference has no counterpart (its matrix always lives on one GPU); the arithmetic is
@@ -295,9 +301,9 @@ int drg_gemm_nt_split16_bias(const void* A16, const void* B16, const float* bias
  *   only).  workspace: B * H * d * 4 bytes (the channels' maxima). */
 int drg_prep_vt_split16(const float* V, int B, int H, int S, int d, void* Vt16, void* workspace, void* stream);
 /*   nsplit: the keys of one (query tile, head) are shared by nsplit CTAs whose partial results a second kernel combines (small
- *   grids: 2048 queries x 4 heads are 64 CTAs for 148 SMs); 0 = chosen by the library, 1 = never split.  workspace (may be NULL
- *   with nsplit <= 1): drg_attention_workspace_bytes(B, H, L, S, d) bytes. */
-size_t drg_attention_workspace_bytes(int B, int H, int L, int S, int d);
+ *   grids: 2048 queries x 4 heads are 64 CTAs for 148 SMs); 0 = chosen by the library, 1 = never split.  workspace:
+ *   drg_attention_workspace_bytes(B, H, L, S, d, nsplit) bytes for the same nsplit (0 when the call will not split: NULL is fine). */
+size_t drg_attention_workspace_bytes(int B, int H, int L, int S, int d, int nsplit);
 int drg_attention_split16(const void* Q16, const void* K16, const void* Vt16, const uint8_t* q_mask, const uint8_t* kv_mask, int B,
                           int H, int L, int S, int d, float scale, float* out, int nsplit, void* workspace, size_t workspace_bytes,
                           void* stream);

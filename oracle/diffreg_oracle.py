@@ -131,6 +131,19 @@ def log_optimal_transport_backward(scores, alpha, iters, src_mask, tgt_mask, gra
     return gZ[:, :N, :M], gZ[:, N, :].sum() + gZ[:, :N, M].sum()
 
 
+def dual_softmax_backward(sim, src_mask, tgt_mask, temperature, grad_conf):
+    """dL/d sim of the dual-softmax confidence (4d/models/matching.py:147-157) for a given dL/d conf: with A = softmax over the src
+    axis (invalid src rows at -inf), B = softmax over the tgt axis (invalid tgt columns at -inf), P = A B, c_j = sum_i G P,
+    r_i = sum_j G P:  (2 P G - A c_j - B r_i) / T.  Checked against the reference's autograd (golden ``lotb_matching_train_dual*``)."""
+    s1 = (sim / temperature).masked_fill(~src_mask[:, :, None], float("-inf"))
+    s2 = (sim / temperature).masked_fill(~tgt_mask[:, None, :], float("-inf"))
+    A, Bm = torch.softmax(s1, dim=1), torch.softmax(s2, dim=2)
+    P = A * Bm
+    c = (grad_conf * P).sum(dim=1, keepdim=True)
+    r = (grad_conf * P).sum(dim=2, keepdim=True)
+    return (2.0 * P * grad_conf - A * c - Bm * r) / temperature
+
+
 def pair_mask(src_mask, tgt_mask):
     """[B,N,M] validity mask, as built at 4d/models/matching.py:163-165."""
     return (src_mask[..., None] * tgt_mask[:, None]).bool()

@@ -38,10 +38,10 @@ def run_lot(tag, B, N, M, iters, kind, seed):
                    grad_scores=scores.grad, grad_alpha=alpha.grad))
 
 
-def run_matching(tag, B, N, M, C, entangled, seed):
+def run_matching(tag, B, N, M, C, entangled, seed, match_type="sinkhorn"):
     g = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
-    cfg = dict(match_type="sinkhorn", confidence_threshold=0.2, feature_dim=C, entangled=entangled, dsmax_temperature=0.1,
+    cfg = dict(match_type=match_type, confidence_threshold=0.2, feature_dim=C, entangled=entangled, dsmax_temperature=0.1,
                skh_init_bin_score=1.0, skh_iters=3, skh_prefilter=False)
     head = ref.matching.Matching(cfg).train()
     src = torch.randn(B, N, C, generator=g).requires_grad_()
@@ -57,9 +57,11 @@ def run_matching(tag, B, N, M, C, entangled, seed):
     conf, match = head(src, tgt, pe.get("src_pe"), pe.get("tgt_pe"), sm, tm, {}, pe_type="rotary")
     W = torch.rand(conf.shape, generator=g)
     (conf * W).sum().backward()
-    rec = dict(src_feats=src.detach(), tgt_feats=tgt.detach(), src_mask=sm, tgt_mask=tm, entangled=int(entangled), W=W,
+    rec = dict(src_feats=src.detach(), tgt_feats=tgt.detach(), src_mask=sm, tgt_mask=tm, entangled=int(entangled), W=W, match_type=match_type,
                conf=conf.detach(), match=match, grad_src=src.grad, grad_tgt=tgt.grad, grad_weight=head.src_proj.weight.grad,
-               grad_bin_score=head.bin_score.grad, weight=head.src_proj.weight.detach(), bin_score=head.bin_score.detach())
+               weight=head.src_proj.weight.detach())
+    if match_type == "sinkhorn":
+        rec.update(grad_bin_score=head.bin_score.grad, bin_score=head.bin_score.detach())
     rec.update(pe)
     save(tag, rec)
 
@@ -70,3 +72,36 @@ run_lot("lotb_arbitrary_i5", 1, 37, 52, 5, "arbitrary", 83)
 run_lot("lotb_wide_i1", 1, 9, 300, 1, "prefix", 84)
 run_matching("lotb_matching_train_entangled", 2, 30, 26, 32, True, 85)
 run_matching("lotb_matching_train_rotary", 1, 28, 35, 24, False, 86)
+run_matching("lotb_matching_train_dualsoftmax", 2, 27, 33, 32, True, 87, match_type="dual_softmax")
+
+
+class cpu_cuda:
+    def __enter__(self):
+        self._orig = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda = self._orig
+
+
+def run_matching_2d3d(tag, N, M, C, seed):
+    """The 2D-3D head in training mode (experiments/<exp>/matching.py:91-147): conf_matrix and the gathered weights carry gradients."""
+    r2 = ref_loader.load_flavour("2d3d")
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    cfg = dict(match_type="sinkhorn", confidence_threshold=0.2, feature_dim=C, entangled=True, dsmax_temperature=0.1,
+               skh_init_bin_score=1.0, skh_iters=3, skh_prefilter=False)
+    head = r2.matching.Matching(cfg).train()
+    src = torch.randn(1, N, C, generator=g).requires_grad_()
+    tgt = torch.randn(1, M, C, generator=g).requires_grad_()
+    sm, tm = torch.rand(1, N, generator=g) > 0.1, torch.rand(1, M, generator=g) > 0.1
+    with cpu_cuda():
+        conf, si, ti, w = head(src, tgt, sm, tm, True)
+    W = torch.rand(conf.shape, generator=g)
+    ((conf * W).sum() + (w * torch.arange(1, w.numel() + 1)).sum()).backward()
+    save(tag, dict(src_feats=src.detach(), tgt_feats=tgt.detach(), src_mask=sm, tgt_mask=tm, W=W, conf=conf.detach(), src_indices=si,
+                   tgt_indices=ti, weights=w.detach(), grad_src=src.grad, grad_tgt=tgt.grad, grad_weight=head.src_proj.weight.grad,
+                   grad_bin_score=head.bin_score.grad, weight=head.src_proj.weight.detach(), bin_score=head.bin_score.detach()))
+
+
+run_matching_2d3d("lotb_matching2d3d_train", 31, 26, 32, 88)

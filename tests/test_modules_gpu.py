@@ -146,20 +146,19 @@ def test_forward_only_guard():
     conf = torch.rand(1, 8, 8, device=DEV, requires_grad=True)
     pts = torch.randn(1, 8, 3, device=DEV)
     assert m(x, y, None, None, ones, ones, {})[0].requires_grad          # the Sinkhorn branch is differentiable (8f rank 3)
-    with pytest.raises(Err, match="forward-only"):
-        m.forward1(x, y, None, None, ones, ones, {})
-    with pytest.raises(Err, match="forward-only"):
-        m2(x, y, ones, ones)
+    assert m.forward1(x, y, None, None, ones, ones, {})[0].requires_grad
+    conf2, si, ti, w2 = m2(x, y, ones, ones)
+    assert conf2.requires_grad and w2.requires_grad and torch.equal(w2.detach(), conf2.detach()[0][si, ti])
     with pytest.raises(Err, match="forward-only"):
         proc(conf, pts, pts, ones, ones)
     with pytest.raises(Err, match="forward-only"):
         SoftProcrustesLayer.batch_weighted_procrustes(pts, pts, torch.rand(1, 8, 1, device=DEV, requires_grad=True))
-    # log_optimal_transport and the Sinkhorn branch of Matching.forward are differentiable (tests/test_backward_gpu.py); the
-    # dual-softmax branch in training mode still raises
+    # log_optimal_transport and both branches of Matching.forward are differentiable (tests/test_backward_gpu.py)
     assert diffreg_b200.log_optimal_transport(torch.randn(1, 4, 4, device=DEV, requires_grad=True), torch.tensor(1.0, device=DEV), 3,
                                               ones[:, :4], ones[:, :4]).requires_grad
+    assert diffreg_b200.Matching(_cfg(32, "dual_softmax")).to(DEV)(x.detach(), y, None, None, ones, ones, {})[0].requires_grad
     with pytest.raises(Err, match="forward-only"):
-        diffreg_b200.Matching(_cfg(32, "dual_softmax")).to(DEV)(x.detach(), y, None, None, ones, ones, {})   # training mode, trainable weights
+        diffreg_b200.Matching.get_match(conf, 0.2)          # the reference's mconf = conf[index] is differentiable: not built
     # the same calls under no_grad (how the reference's testers call) run
     with torch.no_grad():
         c1, _ = m(x, y, None, None, ones, ones, {})
