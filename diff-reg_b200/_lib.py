@@ -105,6 +105,9 @@ def _declare(lib):
     lib.drg_dual_softmax_backward.restype = c_int
     lib.drg_dual_softmax_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                               ctypes.c_size_t, c_void_p]
+    lib.drg_weighted_procrustes_backward.restype = c_int
+    lib.drg_weighted_procrustes_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                                     c_void_p, c_void_p]
     lib.drg_prep_vt_split16.restype = c_int
     lib.drg_prep_vt_split16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.drg_attention_split16.restype = c_int

@@ -556,6 +556,22 @@ def weighted_procrustes(X, Y, w, eps=1e-4):
 
 
 @_on_device
+def weighted_procrustes_backward(X, Y, w, R, grad_R, grad_t, eps=1e-4):
+    """dL/d w [B,K,1] of weighted_procrustes given dL/d R [B,3,3] and dL/d t [B,3,1] (drg_weighted_procrustes_backward)."""
+    _require_cuda(X, Y, w, R, grad_R, grad_t)
+    lib = load_library()
+    X, Y, R = _f32c(X), _f32c(Y), _f32c(R)
+    B, K, _ = X.shape
+    wf = _f32c(w).reshape(B, K)
+    gR = _f32c(grad_R) if grad_R is not None else torch.zeros(B, 3, 3, dtype=torch.float32, device=X.device)
+    gt = _f32c(grad_t) if grad_t is not None else torch.zeros(B, 3, 1, dtype=torch.float32, device=X.device)
+    gw = torch.empty(B, K, dtype=torch.float32, device=X.device)
+    check(lib.drg_weighted_procrustes_backward(X.data_ptr(), Y.data_ptr(), wf.data_ptr(), R.data_ptr(), gR.data_ptr(), gt.data_ptr(), B, K,
+                                               float(eps), gw.data_ptr(), _stream()))
+    return gw.view(w.shape)
+
+
+@_on_device
 def sigmoid(x):
     _require_cuda(x)
     x = _f32c(x)

@@ -399,6 +399,11 @@ int drg_sinkhorn_soft_procrustes(const drg_sinkhorn_args* s, const drg_procruste
 int drg_weighted_procrustes(const float* X, const float* Y, const float* w, int B, int K, float eps, float* R, float* t,
                             double* condition, void* stream);
 
+/* ... and its backward pass with respect to the weights (the reference's motion loss differentiates R, t through the host SVD,
+ * Diff-Reg-4dmatch/models/loss.py:110-131): grad_R [B,3,3], grad_t [B,3,1] -> grad_w [B,K]; R = the forward's result. */
+int drg_weighted_procrustes_backward(const float* X, const float* Y, const float* w, const float* R, const float* grad_R,
+                                     const float* grad_t, int B, int K, float eps, float* grad_w, void* stream);
+
 /* Elementwise tail / head of the samplers.
  *   drg_sigmoid:   conf_matrix_pred = sigmoid(x)        Diff-Reg-4dmatch/models/pipeline.py:192
  *   drg_min_value: x.min() of the 3DMatch sampler       Diff-Reg-3dmatch/models/pipeline.py:239,264

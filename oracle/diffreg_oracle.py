@@ -352,6 +352,37 @@ def batch_weighted_procrustes(X, Y, w, eps=1e-4):
     return R, t, cond                                                   # cond stays on the CPU, as in the reference
 
 
+def weighted_procrustes_backward(X, Y, w, R, grad_R, grad_t, eps=1e-4):
+    """dL/d w [B,K,1] of ``batch_weighted_procrustes`` for given dL/d R, dL/d t -- what torch's autograd returns through
+    4d/models/procrustes.py:18-44 (incl. its host SVD), written without an SVD: H = R^T M is symmetric and a perturbation dM turns
+    R by R [omega]x with (tr(H) I - H) omega = vee(R^T dM - dM^T R).  Checked against the reference's autograd (golden ``procrb_*``)."""
+    def vee(A):
+        return torch.stack([A[..., 2, 1], A[..., 0, 2], A[..., 1, 0]], -1)
+
+    def hat(e):
+        z = torch.zeros_like(e[..., 0])
+        return torch.stack([torch.stack([z, -e[..., 2], e[..., 1]], -1), torch.stack([e[..., 2], z, -e[..., 0]], -1),
+                            torch.stack([-e[..., 1], e[..., 0], z], -1)], -2)
+    W1 = w.abs().sum(1, keepdim=True)
+    wt = w / (W1 + eps)
+    sw = wt.sum(1, keepdim=True)
+    muX, muY = (wt * X).sum(1, keepdim=True), (wt * Y).sum(1, keepdim=True)
+    Xc, Yc = X - muX, Y - muY
+    M = Yc.transpose(1, 2) @ (wt * Xc)
+    gRp = grad_R - grad_t @ muX
+    gmuY = grad_t.transpose(1, 2)
+    gmuX = -(R.transpose(1, 2) @ grad_t).transpose(1, 2)
+    H = R.transpose(1, 2) @ M
+    Kmat = torch.diag_embed(H.diagonal(dim1=1, dim2=2).sum(-1, keepdim=True).expand(-1, 3)) - H
+    C = R.transpose(1, 2) @ gRp
+    e = torch.linalg.solve(Kmat, vee(0.5 * (C - C.transpose(1, 2))).unsqueeze(-1)).squeeze(-1)
+    gM = 2.0 * R @ hat(e)
+    gmuX = gmuX - (gM.transpose(1, 2) @ ((1 - sw) * muY).transpose(1, 2)).transpose(1, 2)
+    gmuY = gmuY - (gM @ ((1 - sw) * muX).transpose(1, 2)).transpose(1, 2)
+    gwt = ((Yc @ gM) * Xc).sum(-1, keepdim=True) + (X * gmuX).sum(-1, keepdim=True) + (Y * gmuY).sum(-1, keepdim=True)
+    return gwt / (W1 + eps) - torch.sign(w) * (gwt * w).sum(1, keepdim=True) / (W1 + eps) ** 2
+
+
 def soft_procrustes(conf, src_pcd, tgt_pcd, src_mask, tgt_mask, sample_rate=1.0,
                     max_condition_num=40.0, padded_lengths=False):
     """``SoftProcrustesLayer.forward``, 4d/models/procrustes.py:48-93.

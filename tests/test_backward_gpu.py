@@ -126,3 +126,57 @@ def test_matching_forward_in_training_mode_against_the_reference_autograd(name):
     with torch.no_grad():
         conf2, _ = head(src.detach(), tgt.detach(), spe, tpe, g["src_mask"].cuda(), g["tgt_mask"].cuda(), {}, pe_type="rotary")
     assert (conf2 - conf.detach()).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("name", names("procrb_kabsch_"))
+def test_weighted_procrustes_backward_against_the_reference_autograd(name):
+    from diffreg_b200.procrustes import SoftProcrustesLayer
+    g = load(name)
+    w = g["w"].cuda().requires_grad_()
+    R, t, cond = SoftProcrustesLayer.batch_weighted_procrustes(g["X"].cuda(), g["Y"].cuda(), w)
+    assert R.requires_grad and t.requires_grad and not cond.requires_grad
+    assert (R.detach().cpu() - g["R"]).abs().max().item() <= 1e-5 and (t.detach().cpu() - g["t"]).abs().max().item() <= 1e-5
+    ((R * g["grad_R"].cuda()).sum() + (t * g["grad_t"].cuda()).sum()).backward()
+    want = g["grad_w"]
+    assert (w.grad.cpu() - want).abs().max().item() <= 5e-5 * want.abs().max().item()
+    # deterministic
+    w2 = g["w"].cuda().requires_grad_()
+    R2, t2, _ = SoftProcrustesLayer.batch_weighted_procrustes(g["X"].cuda(), g["Y"].cuda(), w2)
+    ((R2 * g["grad_R"].cuda()).sum() + (t2 * g["grad_t"].cuda()).sum()).backward()
+    assert torch.equal(w.grad, w2.grad)
+
+
+def test_weighted_procrustes_backward_against_the_oracle_in_fp64():
+    from diffreg_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    B, K = 4, 4096
+    X = torch.randn(B, K, 3, generator=g)
+    Y = torch.stack([(O.random_rotation(g) @ X[b].t()).t() for b in range(B)]) + 0.05 * torch.randn(B, K, 3, generator=g) + 1.5
+    w = torch.rand(B, K, 1, generator=g)
+    gR, gt = torch.randn(B, 3, 3, generator=g), torch.randn(B, 3, 1, generator=g)
+    R, t, _ = ops.weighted_procrustes(X.cuda(), Y.cuda(), w.cuda())
+    R32, _, _ = O.batch_weighted_procrustes(X, Y, w)                      # (the reference's solve returns fp32: quirk Q5)
+    assert (R.cpu() - R32).abs().max().item() <= 1e-5
+    want = O.weighted_procrustes_backward(X.double(), Y.double(), w.double(), R32.double(), gR.double(), gt.double())
+    got = ops.weighted_procrustes_backward(X.cuda(), Y.cuda(), w.cuda(), R, gR.cuda(), gt.cuda()).cpu().double()
+    assert (got - want).abs().max().item() <= 5e-5 * want.abs().max().item()
+
+
+def test_soft_procrustes_layer_in_training_mode_against_the_reference_autograd():
+    """SoftProcrustesLayer.forward with a tracked confidence matrix: pose and dL/d conf (non-zero at the selected entries only)."""
+    from types import SimpleNamespace
+    import diffreg_b200
+    g = load("procrb_layer")
+    layer = diffreg_b200.SoftProcrustesLayer(SimpleNamespace(sample_rate=float(g["sample_rate"]), max_condition_num=float(g["max_condition_num"])))
+    conf = g["conf"].cuda().requires_grad_()
+    R, t, Rf, tf, cond, mask = layer(conf, g["src_pcd"].cuda(), g["tgt_pcd"].cuda(), g["src_mask"].cuda(), g["tgt_mask"].cuda())
+    assert (R.detach().cpu() - g["R"]).abs().max().item() <= 1e-5 and (t.detach().cpu() - g["t"]).abs().max().item() <= 1e-5
+    assert bool(mask.all())
+    ((Rf * g["grad_R"].cuda()).sum() + (tf * g["grad_t"].cuda()).sum()).backward()
+    want = g["grad_conf"]
+    assert torch.equal(conf.grad.cpu() != 0, want != 0)
+    assert (conf.grad.cpu() - want).abs().max().item() <= 5e-5 * want.abs().max().item()
+    # the forward-only call gives the same pose
+    with torch.no_grad():
+        R0 = layer(conf.detach(), g["src_pcd"].cuda(), g["tgt_pcd"].cuda(), g["src_mask"].cuda(), g["tgt_mask"].cuda())[0]
+    assert (R0 - R.detach()).abs().max().item() <= 1e-5

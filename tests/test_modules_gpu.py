@@ -149,10 +149,11 @@ def test_forward_only_guard():
     assert m.forward1(x, y, None, None, ones, ones, {})[0].requires_grad
     conf2, si, ti, w2 = m2(x, y, ones, ones)
     assert conf2.requires_grad and w2.requires_grad and torch.equal(w2.detach(), conf2.detach()[0][si, ti])
+    # SoftProcrustes is differentiable in the confidences / weights (tests/test_backward_gpu.py); tracked POINTS raise
+    assert proc(conf, pts, pts, ones, ones)[0].requires_grad
+    assert SoftProcrustesLayer.batch_weighted_procrustes(pts, pts, torch.rand(1, 8, 1, device=DEV, requires_grad=True))[0].requires_grad
     with pytest.raises(Err, match="forward-only"):
-        proc(conf, pts, pts, ones, ones)
-    with pytest.raises(Err, match="forward-only"):
-        SoftProcrustesLayer.batch_weighted_procrustes(pts, pts, torch.rand(1, 8, 1, device=DEV, requires_grad=True))
+        proc(conf.detach(), pts.clone().requires_grad_(), pts, ones, ones)
     # log_optimal_transport and both branches of Matching.forward are differentiable (tests/test_backward_gpu.py)
     assert diffreg_b200.log_optimal_transport(torch.randn(1, 4, 4, device=DEV, requires_grad=True), torch.tensor(1.0, device=DEV), 3,
                                               ones[:, :4], ones[:, :4]).requires_grad
