@@ -180,3 +180,42 @@ def test_soft_procrustes_layer_in_training_mode_against_the_reference_autograd()
     with torch.no_grad():
         R0 = layer(conf.detach(), g["src_pcd"].cuda(), g["tgt_pcd"].cuda(), g["src_mask"].cuda(), g["tgt_mask"].cuda())[0]
     assert (R0 - R.detach()).abs().max().item() <= 1e-5
+
+
+def test_training_step_through_matching_and_pose_against_the_reference_modules():
+    """Matching.forward -> conf -> SoftProcrustesLayer -> a loss on conf, R, t -> backward, with the reference's own modules on the
+    same GPU as the yardstick (same weights): gradients of the features, the projection weight and bin_score."""
+    from types import SimpleNamespace
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference sources not present (/root/reference or oracle/_ref)")
+    import diffreg_b200
+    ref = ref_loader.load_flavour("4d")
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        n, C = 320, 64
+        pb = O.make_problem(11, 1, n, n - 40, C, prefix_valid=[(300, 260)])
+        cfg = dict(match_type="sinkhorn", confidence_threshold=0.2, feature_dim=C, entangled=True, dsmax_temperature=0.1,
+                   skh_init_bin_score=1.0, skh_iters=3, skh_prefilter=False)
+        pcfg = SimpleNamespace(sample_rate=1.0, max_condition_num=1e9)
+        t = {k: pb[k].cuda() for k in ("src_feats", "tgt_feats", "s_pcd", "t_pcd", "src_mask", "tgt_mask")}
+        g = torch.Generator().manual_seed(1)
+        Wc = torch.rand(1, n, n - 40, generator=g).cuda()
+        gR, gt = torch.randn(1, 3, 3, generator=g).cuda(), torch.randn(1, 3, 1, generator=g).cuda()
+
+        def step(head, proc):
+            src, tgt = t["src_feats"].clone().requires_grad_(), t["tgt_feats"].clone().requires_grad_()
+            conf, _ = head(src, tgt, None, None, t["src_mask"], t["tgt_mask"], {})
+            R, tt, _, _, _, _ = proc(conf, t["s_pcd"], t["t_pcd"], t["src_mask"], t["tgt_mask"])
+            ((conf * Wc).sum() + (R * gR).sum() + (tt * gt).sum()).backward()
+            return src.grad, tgt.grad, head.src_proj.weight.grad, head.bin_score.grad
+        head = diffreg_b200.Matching(cfg).cuda().train()
+        rhead = ref.matching.Matching(cfg).cuda().train()
+        rhead.load_state_dict(head.state_dict())
+        a = step(head, diffreg_b200.SoftProcrustesLayer(pcfg))
+        b = step(rhead, ref.procrustes.SoftProcrustesLayer(pcfg))
+        for x, y in zip(a[:3], b[:3]):
+            assert (x - y).abs().max().item() <= 1e-4 * y.abs().max().item()
+        assert abs(a[3].item() - b[3].item()) <= 1e-4 * max(1.0, abs(b[3].item()))
+    finally:
+        ref_loader.unload()
