@@ -742,6 +742,30 @@ def bench_other_configs(torch, dev):
                                         "ms_per_forward": ms, "ms_per_forward_eager": ms_eager, "kernel_launches": int(launches)}
     except Exception as e:  # noqa: BLE001 -- an extra line, never the reason a bench run fails
         out["denoising_transformer"] = {"error": str(e)[:200]}
+    # widening: one training step of the two modules on the path -- Matching.forward -> conf -> SoftProcrustesLayer ->
+    # a loss on conf, R, t -> backward (CUDA backward kernels of the Sinkhorn and the Kabsch solve) -- at the headline shape
+    try:
+        pbt = make_batch(5002, 1, N_PTS, N_PTS, FEAT_DIM)
+        tcfg2 = dict(match_type="sinkhorn", confidence_threshold=0.2, feature_dim=256, entangled=True, dsmax_temperature=0.1,
+                     skh_init_bin_score=1.0, skh_iters=3, skh_prefilter=False)
+        thead = diffreg_b200.Matching(tcfg2).to(dev).train()
+        tproc = diffreg_b200.SoftProcrustesLayer(SimpleNamespace(sample_rate=1.0, max_condition_num=1e9))
+        tt = {k: pbt[k].to(dev) for k in ("src_feats", "tgt_feats", "s_pcd", "t_pcd", "src_mask", "tgt_mask")}
+        Wc = torch.rand(1, N_PTS, N_PTS, device=dev)
+
+        def train_step():
+            src, tgt = tt["src_feats"].clone().requires_grad_(), tt["tgt_feats"].clone().requires_grad_()
+            thead.zero_grad(set_to_none=True)
+            conf, _ = thead(src, tgt, None, None, tt["src_mask"], tt["tgt_mask"], {})
+            R, t_, _, _, _, _ = tproc(conf, tt["s_pcd"], tt["t_pcd"], tt["src_mask"], tt["tgt_mask"])
+            ((conf * Wc).sum() + R.sum() + t_.sum()).backward()
+        train_step()
+        out["training_step"] = {"workload": "SURVEY 8f rank 3 (not in the metric): Matching.forward -> SoftProcrustesLayer -> loss -> backward, "
+                                            "N=M=4096, d=256, 3 Sinkhorn iterations (forward + backward)",
+                                "ms_per_step": _event_ms(torch, train_step, 3)}
+        del pbt, tt, Wc
+    except Exception as e:  # noqa: BLE001
+        out["training_step"] = {"error": str(e)[:200]}
     # ... and its 2D-3D counterpart (fusion_module.py:61-107): six blocks, 512 -> 256, 4 heads of 64, Fourier embedding, 2048 image
     # patches x 4800 points (configs[3]'s token counts)
     try:
