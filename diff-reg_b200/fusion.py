@@ -51,11 +51,12 @@ class _WeightCache:
         return hit[1]
 
 
-def _linear(cache, lin, x, relu=False):
-    """nn.Linear (with bias) of x [..., K] -> [..., C_out] through the split GEMM; relu: applied to x in the staging."""
+def _linear(cache, lin, x, relu=False, staged=None):
+    """nn.Linear (with bias) of x [..., K] -> [..., C_out] through the split GEMM; relu: applied to x in the staging; staged: the
+    left split operand of x when the caller has it already (q / k / v of a self-attention block share one staging)."""
     K = x.shape[-1]
     rows = x.numel() // K
-    a16 = ops.prep_relu(x, 0) if relu else ops.prep_operand(x, 1.0, True, 0)
+    a16 = staged if staged is not None else (ops.prep_relu(x, 0) if relu else ops.prep_operand(x, 1.0, True, 0))
     out = ops.gemm_nt(a16.reshape(rows, a16.shape[-1]), cache.get(lin), split3=True, K=K, bias=lin.bias)
     return out.view(*x.shape[:-1], lin.weight.shape[0])
 
@@ -100,9 +101,13 @@ class MultiHeadAttention(nn.Module):
         B, N, C = q_tokens.shape
         M = k_tokens.shape[1]
         H, d = self.num_heads, self.d_model_per_head
-        q = _linear(self._cache, self.q_token_layer, q_tokens)
-        k = _linear(self._cache, self.k_token_layer, k_tokens)
-        v = _linear(self._cache, self.v_token_layer, v_tokens)
+        # one staging per distinct input: self blocks pass the same tensor three times, cross blocks the same keys and values
+        sq = ops.prep_operand(q_tokens, 1.0, True, 0)
+        sk = sq if k_tokens is q_tokens else ops.prep_operand(k_tokens, 1.0, True, 0)
+        sv = sk if v_tokens is k_tokens else (sq if v_tokens is q_tokens else ops.prep_operand(v_tokens, 1.0, True, 0))
+        q = _linear(self._cache, self.q_token_layer, q_tokens, staged=sq)
+        k = _linear(self._cache, self.k_token_layer, k_tokens, staged=sk)
+        v = _linear(self._cache, self.v_token_layer, v_tokens, staged=sv)
         q16 = ops.prep_heads(q, H, 0)
         k16 = ops.prep_heads(k, H, 1)
         keep = None if k_masks is None else ~k_masks                                   # k_masks: True = ignored (transformer.py:76)
