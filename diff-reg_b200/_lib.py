@@ -92,7 +92,7 @@ def _declare(lib):
     lib.drg_attn_softmax.restype = c_int
     lib.drg_attn_softmax.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
     lib.drg_layernorm.restype = c_int
-    lib.drg_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_void_p, c_void_p]
+    lib.drg_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_void_p, c_void_p, c_void_p]
     lib.drg_gemm_nt_split16_bias.restype = c_int
     lib.drg_gemm_nt_split16_bias.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
     lib.drg_sinkhorn_backward_workspace_bytes.restype = ctypes.c_size_t

@@ -206,12 +206,31 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_softmax_vec_kernel(const flo
 // LayerNorm over the last dimension, one warp per row: y = (x - mean) / sqrt(var + eps) * w + b (biased variance, two passes
 // like torch).  With a residual: out = residual + LayerNorm(in) (pre_add == 0: the geometry attention layer's x + norm2(message))
 // or out = LayerNorm(in + residual) (pre_add == 1: the post-norm of vision3d's attention / feed-forward blocks).
+// split16 (optional): the same rows as the LEFT split operand of the next linear ([lo | hi | tail], features.cu's format: row scale
+// 2^e with the maximum in [2^14, 2^15), fp16 hi / lo halves, zero padding up to whole 64-column k-steps, tail = 1 / scale and the
+// row norm), so that the consumer needs no staging launch.  The row stays in registers between the maximum and the conversion
+// (C <= 32 * LN_MAXV).
+constexpr int LN_MAXV = 36;   // rows of up to 1152 columns (kc(C) <= 32 * LN_MAXV)
+// x = hi + lo, both fp16 (x is already row-scaled into fp16's range): hi = fp16(x), lo = fp16(x - hi)   (as features.cu)
+__device__ __forceinline__ void ln_split16(float x, unsigned short& hi_bits, unsigned short& lo_bits) {
+  unsigned short h;
+  asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  float hf;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
+  unsigned short l;
+  asm("cvt.rn.f16.f32 %0, %1;" : "=h"(l) : "f"(x - hf));
+  hi_bits = h;
+  lo_bits = l;
+}
+template <int NV>      // NV == 0: no split output; else ceil(kc(C) / 32) <= NV values of a row per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                         const float* __restrict__ bias, const float* __restrict__ residual,
-                                                        long long rows, int C, float eps, int pre_add, float* __restrict__ out) {
+                                                        long long rows, int C, float eps, int pre_add, float* __restrict__ out,
+                                                        unsigned short* __restrict__ split_out) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const bool pre = pre_add && residual != nullptr;
+  const int Kp = split16_kc(C), pitch = split16_pitch(C);
   for (long long row = warp0; row < rows; row += nwarps) {
     const float* x = in + row * C;
     const float* r = residual ? residual + row * C : nullptr;
@@ -224,12 +243,60 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       v = fmaf(d, d, v);
     }
     const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
-    for (int c = lane; c < C; c += 32) {
-      float y = ((pre ? x[c] + r[c] : x[c]) - mean) * rstd;
-      if (w) y *= w[c];
-      if (bias) y += bias[c];
-      if (r && !pre) y += r[c];
-      out[row * C + c] = y;
+    constexpr bool SPLIT = NV > 0;
+    float yv[SPLIT ? NV : 1];
+    float amax = 0.f;
+    bool weird = false;
+    if (!SPLIT) {
+      for (int c = lane; c < C; c += 32) {
+        float y = ((pre ? x[c] + r[c] : x[c]) - mean) * rstd;
+        if (w) y *= w[c];
+        if (bias) y += bias[c];
+        if (r && !pre) y += r[c];
+        out[row * C + c] = y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < (SPLIT ? NV : 1); ++k) {
+        const int c = lane + 32 * k;
+        yv[k] = 0.f;
+        if (c < C) {
+          float y = ((pre ? x[c] + r[c] : x[c]) - mean) * rstd;
+          if (w) y *= w[c];
+          if (bias) y += bias[c];
+          if (r && !pre) y += r[c];
+          out[row * C + c] = y;
+          yv[k] = y;
+          const float m = fabsf(y);
+          weird |= !(m <= 3.0e38f);
+          amax = fmaxf(amax, m);
+        }
+      }
+    }
+    if (SPLIT) {
+      amax = warp_max(amax);
+      weird = __any_sync(0xffffffffu, weird);
+      int e = 0;
+      if (amax > 0.f && !weird) e = min(max(14 - ilogbf(amax), -126), 126);
+      const float sc = __int_as_float((e + 127) << 23), inv = __int_as_float((127 - e) << 23);
+      unsigned short* o = split_out + row * pitch;
+      float ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < (SPLIT ? NV : 1); ++k) {
+        const int c = lane + 32 * k;
+        if (c < Kp) {
+          unsigned short hb = 0, lb = 0;
+          if (c < C) {
+            const float ys = yv[k] * sc;
+            ss = fmaf(ys, ys, ss);
+            ln_split16(ys, hb, lb);
+          }
+          o[c] = lb;             // pattern 0: [lo | hi | tail]
+          o[Kp + c] = hb;
+        }
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) *reinterpret_cast<float4*>(o + 2 * Kp) = make_float4(inv, sqrtf(ss) * inv, 0.f, 0.f);
     }
   }
 }
@@ -287,12 +354,24 @@ extern "C" int drg_attn_softmax(const float* logits, const uint8_t* q_mask, cons
 }
 
 extern "C" int drg_layernorm(const float* in, const float* weight, const float* bias, const float* residual, int pre_add, long long rows,
-                             int C, float eps, float* out, void* stream) {
+                             int C, float eps, float* out, void* split16_out, void* stream) {
   DRG_CHECK_ARG(in != nullptr && out != nullptr, "in / out must be non-null");
   DRG_CHECK_ARG(rows >= 1 && C >= 1, "rows and C must be >= 1");
   long long blocks = (rows * 32 + 255) / 256;
   if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
-  layernorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, weight, bias, residual, rows, C, eps, pre_add, out);
+  if (split16_out) {
+    if (split16_kc(C) > 32 * LN_MAXV || (((uintptr_t)split16_out) & 15u)) {
+      set_error("layernorm: the split output takes rows of up to %d columns (got %d), 16-byte aligned", 32 * LN_MAXV, C);
+      return DRG_ERR_UNSUPPORTED;
+    }
+    unsigned short* so = reinterpret_cast<unsigned short*>(split16_out);
+    const int nv = (split16_kc(C) + 31) / 32;
+    if (nv <= 8) layernorm_kernel<8><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, weight, bias, residual, rows, C, eps, pre_add, out, so);
+    else if (nv <= 18) layernorm_kernel<18><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, weight, bias, residual, rows, C, eps, pre_add, out, so);
+    else layernorm_kernel<LN_MAXV><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, weight, bias, residual, rows, C, eps, pre_add, out, so);
+  } else {
+    layernorm_kernel<0><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, weight, bias, residual, rows, C, eps, pre_add, out, nullptr);
+  }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }

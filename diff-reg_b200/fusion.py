@@ -139,7 +139,7 @@ class AttentionLayer(nn.Module):
     def forward(self, q_tokens, k_tokens, v_tokens, want_scores=False, **kw):
         hidden, scores = self.attention(q_tokens, k_tokens, v_tokens, want_scores=want_scores, **kw)
         hidden = _linear(self._cache, self.linear, hidden)
-        out = ops.layernorm(hidden, self.norm.weight, self.norm.bias, self.norm.eps, residual=q_tokens, pre_add=True)
+        out = ops.layernorm(hidden, self.norm.weight, self.norm.bias, self.norm.eps, residual=q_tokens, pre_add=True, stage=True)
         return out, scores
 
 
@@ -159,7 +159,7 @@ class AttentionOutput(nn.Module):
     def forward(self, input_tokens):
         hidden = _linear(self._cache, self.expand, input_tokens)
         hidden = _linear(self._cache, self.squeeze, hidden, relu=True)
-        return ops.layernorm(hidden, self.norm.weight, self.norm.bias, self.norm.eps, residual=input_tokens, pre_add=True)
+        return ops.layernorm(hidden, self.norm.weight, self.norm.bias, self.norm.eps, residual=input_tokens, pre_add=True, stage=True)
 
 
 class TransformerLayer(nn.Module):

@@ -269,6 +269,10 @@ def prep_operand(x, scale=1.0, split=True, pattern=0, pe=None, pe_type=None, wan
     embedded features."""
     lazy = isinstance(pe, LazyPositionCode)
     _require_cuda(x, None if lazy else pe)
+    if split and pattern == 0 and pe is None and scale == 1.0 and not want_embedded:
+        staged = getattr(x, "_drg_a16", None)          # written by the kernel that produced x (layernorm(stage=True))
+        if staged is not None and staged.shape[:-1] == x.shape[:-1]:
+            return staged
     lib = load_library()
     x = _f32c(x)
     K = x.shape[-1]
@@ -405,7 +409,7 @@ def attention(q16, k16, v, heads, q_mask, kv_mask, scale, d, nsplit=0):
 
 
 @_on_device
-def layernorm(x, weight, bias, eps=1e-5, residual=None, pre_add=False):
+def layernorm(x, weight, bias, eps=1e-5, residual=None, pre_add=False, stage=False):
     """residual + LayerNorm(x) (pre_add=False; 4d transformer.py:88,92-94) or LayerNorm(x + residual) (pre_add=True; vision3d
     transformer.py:214,236) over the last dimension (drg_layernorm)."""
     _require_cuda(x, weight, bias, residual)
@@ -416,8 +420,13 @@ def layernorm(x, weight, bias, eps=1e-5, residual=None, pre_add=False):
     w = _f32c(weight) if weight is not None else None
     b = _f32c(bias) if bias is not None else None
     r = _f32c(residual) if residual is not None else None
+    # stage: the kernel also writes the result as the LEFT split operand of the next linear; it rides on the returned tensor and
+    # prep_operand() hands it out instead of launching a staging kernel
+    a16 = torch.empty(*x.shape[:-1], split_pitch(C), dtype=torch.int16, device=x.device) if (stage and C % 4 == 0 and C <= 1152) else None
     check(lib.drg_layernorm(x.data_ptr(), _ptr(w), _ptr(b), _ptr(r), int(bool(pre_add)), x.numel() // C, C, float(eps), out.data_ptr(),
-                            _stream()))
+                            _ptr(a16), _stream()))
+    if a16 is not None:
+        out._drg_a16 = a16
     return out
 
 

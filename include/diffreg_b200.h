@@ -277,7 +277,8 @@ int drg_prep_operand_ext(const float* in, const float* pe, int pe_type, long lon
 int drg_attn_softmax(const float* logits, const uint8_t* q_mask, const uint8_t* kv_mask, int B, int H, int L, int S, float scale,
                      float* P, void* P16, void* stream);
 int drg_layernorm(const float* in, const float* weight, const float* bias, const float* residual, int pre_add, long long rows, int C,
-                  float eps, float* out, void* stream);
+                  float eps, float* out, void* split16_out /* optional [rows, 2 kc(C) + 8]: out also as the LEFT split operand */,
+                  void* stream);
 /* 2D-3D flavour of the same row (CrossModalFusionModule, Diff-Reg-2d3d/experiments/<exp>/fusion_module.py:10-107, built from
  * vision3d's TransformerLayer, Diff-Reg-2d3d/vision3d/layers/transformer.py:8-301):
  *   drg_layernorm with pre_add = 1   out = LayerNorm(in + residual)            transformer.py:214,236 (post-norm blocks)

@@ -223,3 +223,25 @@ def test_denoising_transformer_graph_replay_matches_eager():
         assert d1["position_layers"] == {}
         assert all(torch.equal(x, y) for x, y in zip(a, b)), call
     assert net._graphs.replays == 2
+
+
+def test_layernorm_stages_the_next_linear_operand():
+    """layernorm(stage=True) also writes its result as the left split operand; prep_operand hands that out instead of staging again,
+    and it is bit-identical to a separate staging of the fp32 result."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(6)
+    for C in (24, 256, 528):
+        x, r = torch.randn(2, 37, C, generator=g).cuda() * 3.0, torch.randn(2, 37, C, generator=g).cuda()
+        w, b = torch.randn(C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
+        for pre in (False, True):
+            out = ops.layernorm(x, w, b, 1e-5, residual=r, pre_add=pre, stage=True)
+            plain = ops.layernorm(x, w, b, 1e-5, residual=r, pre_add=pre)
+            assert (out - plain).abs().max().item() <= 2e-6            # (the two instantiations may contract y * w + b differently)
+            fused = ops.prep_operand(out, 1.0, True, 0)
+            assert fused is out._drg_a16
+            again = ops.prep_operand(out.clone(), 1.0, True, 0)          # a separate staging of the same fp32 values
+            kc = ops.split_cols(C)
+            assert torch.equal(fused[..., :2 * kc + 2], again[..., :2 * kc + 2])     # hi / lo halves, padding and 1 / scale: bit for bit
+            nf = fused[..., 2 * kc:].contiguous().view(torch.float32)[..., 1]
+            na = again[..., 2 * kc:].contiguous().view(torch.float32)[..., 1]
+            assert (nf - na).abs().max().item() <= 1e-5 * na.abs().max().item()      # the row norm: another summation order
