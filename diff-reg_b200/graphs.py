@@ -39,6 +39,10 @@ class ForwardGraphCache:
         """fn(*tensors) -> tuple of tensors.  `tensors`: CUDA tensors or None."""
         if not self.enabled or torch.cuda.is_current_stream_capturing():     # (inside somebody else's capture: just launch)
             return fn(*tensors)
+        cur = torch.cuda.current_device()
+        if any(t is not None and (not t.is_cuda or t.device.index != cur) for t in tensors):
+            return fn(*tensors)                 # tensors of another device than the current one: the ops switch devices per call
+
         key = self._signature(module, tensors)
         entry = self._entries.get(key)
         if entry is None:
