@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (PAIR: the leader CTA's, for both) =====================
-    if (lane == 0 && !(PAIR && crank != 0)) {
+    // the whole warp runs the loop, converged; one ELECTED lane per instruction (umma.cuh)
+    if (!(PAIR && crank != 0)) {
       constexpr uint32_t idesc_wide = make_idesc_tf32(GEMM_BM, BN);
       constexpr uint32_t idesc_half = make_idesc_tf32(GEMM_BM, BN / 2);
       // 16-bit split mode: fp16 x fp16 for all three terms
@@ -226,10 +227,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int nw = unit >= s.wide_tiles ? 1 : 0;
         const uint32_t idesc = nw ? idesc_half : idesc_wide;
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
+        __syncwarp();
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int k = 0; k < kblocks; ++k) {
           mbar_wait(&full_bar[stage], phase);
+          __syncwarp();
           tcgen05_fence_after();
           const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + (size_t)stage * A_STAGE_BYTES));
           const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sB + (size_t)stage * B_STAGE_BYTES));
@@ -241,32 +244,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             for (int kk = 0; kk < 4; ++kk) {     // 4 x 16 columns; +32 bytes along K inside the swizzle atom = +2 in (addr >> 4)
               const uint64_t o = (uint64_t)(2 * kk);
               if (PAIR) {
-                umma_f16_2sm(d_tmem, a_desc + o, b_desc + o, id16[nw], (uint32_t)((k | kk) != 0));  // lo . hi
-                umma_f16_2sm(d_tmem, ah_desc + o, bl_desc + o, id16[nw], 1u);                        // hi . lo
-                umma_f16_2sm(d_tmem, ah_desc + o, b_desc + o, id16[nw], 1u);                         // hi . hi
+                umma_f16_2sm_e(d_tmem, a_desc + o, b_desc + o, id16[nw], (uint32_t)((k | kk) != 0));  // lo . hi
+                umma_f16_2sm_e(d_tmem, ah_desc + o, bl_desc + o, id16[nw], 1u);                        // hi . lo
+                umma_f16_2sm_e(d_tmem, ah_desc + o, b_desc + o, id16[nw], 1u);                         // hi . hi
               } else {
-                umma_f16(d_tmem, a_desc + o, b_desc + o, id16[nw], (uint32_t)((k | kk) != 0));  // lo . hi
-                umma_f16(d_tmem, ah_desc + o, bl_desc + o, id16[nw], 1u);                        // hi . lo
-                umma_f16(d_tmem, ah_desc + o, b_desc + o, id16[nw], 1u);                         // hi . hi
+                umma_f16_e(d_tmem, a_desc + o, b_desc + o, id16[nw], (uint32_t)((k | kk) != 0));  // lo . hi
+                umma_f16_e(d_tmem, ah_desc + o, bl_desc + o, id16[nw], 1u);                        // hi . lo
+                umma_f16_e(d_tmem, ah_desc + o, b_desc + o, id16[nw], 1u);                         // hi . hi
               }
             }
           } else {
 #pragma unroll
             for (int kk = 0; kk < GEMM_BK / 8; ++kk) {
               // advance 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-              umma_tf32(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (uint32_t)((k | kk) != 0));
+              umma_tf32_e(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (uint32_t)((k | kk) != 0));
             }
           }
-          if (PAIR) umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)3);   // both CTAs' producers may refill their halves
-          else if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // ... in both CTAs: either may refill (its half of) the stage
-          else umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs have read it
+          if (PAIR) umma_commit_2sm_mc_e(&empty_bar[stage], (uint16_t)3);   // both CTAs' producers may refill their halves
+          else if (MC) umma_commit_mc_e(&empty_bar[stage], (uint16_t)3);   // ... in both CTAs: either may refill (its half of) the stage
+          else umma_commit_e(&empty_bar[stage]);  // smem stage reusable once these MMAs have read it
           if (++stage == nstage) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        if (PAIR) umma_commit_2sm_mc(&tmem_full_bar[as], (uint16_t)3);  // accumulator complete, in both CTAs
-        else umma_commit(&tmem_full_bar[as]);  // accumulator complete
+        if (PAIR) umma_commit_2sm_mc_e(&tmem_full_bar[as], (uint16_t)3);  // accumulator complete, in both CTAs
+        else umma_commit_e(&tmem_full_bar[as]);  // accumulator complete
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
