@@ -90,14 +90,21 @@ def mutual_topk_select(score_mat, k, largest=True, threshold=None, mutual=True, 
     -> (row_indices [K], col_indices [K], scores [K]) in row-major order, or the [N,M] bool matrix if not reduce_result.
     k = 1 (the sampler's final selection: 3d pipeline.py:275-277, 2d3d model.py:692-694, matching.py:134-136) runs the
     single-pass arg-max kernels; k > 1 (k <= 8) the general top-k kernels."""
-    _no_grad_inputs(score_mat)          # the reference's gathered scores are differentiable
+    # the reference's gathered scores are differentiable: with a tracked score_mat the selection runs on the detached matrix and
+    # the scores are gathered from the tracked one
+    tracked = torch.is_grad_enabled() and score_mat.requires_grad and score_mat.is_cuda
+    if not tracked:
+        _no_grad_inputs(score_mat)
     with torch.no_grad():
+        sm = score_mat.detach()
         if k == 1 and reduce_result:
-            return ops.top1_select(score_mat, largest, threshold, mutual)
-        index, vals, mask = ops.topk_select(score_mat.unsqueeze(0), k, largest, threshold, mutual, want_mask=not reduce_result)
-        if reduce_result:
-            return index[:, 1].contiguous(), index[:, 2].contiguous(), vals
-        return mask.squeeze(0)
+            rows, cols, vals = ops.top1_select(sm, largest, threshold, mutual)
+        else:
+            index, vals, mask = ops.topk_select(sm.unsqueeze(0), k, largest, threshold, mutual, want_mask=not reduce_result)
+            if not reduce_result:
+                return mask.squeeze(0)
+            rows, cols = index[:, 1].contiguous(), index[:, 2].contiguous()
+    return rows, cols, (score_mat[rows, cols] if tracked else vals)
 
 
 def batch_mutual_topk_select(score_mat, k, row_masks=None, col_masks=None, largest=True, threshold=None, mutual=True,
@@ -142,11 +149,15 @@ class Matching(nn.Module):
     # ---- correspondence extraction (static, like the reference) ----
     @staticmethod
     def get_match(conf_matrix, thr=0.0, mutual=True):
-        """(index [K,3], mconf [K], mask): the reference's mconf = conf[index] is differentiable, so a tracked
-        conf_matrix raises here too."""
-        _no_grad_inputs(conf_matrix)
+        """(index [K,3], mconf [K], mask).  With a tracked conf_matrix the gathered mconf = conf[index] is differentiable, as
+        the reference's is (matching.py:86-87): the selection runs on the detached matrix, the gather on the tracked one."""
+        tracked = torch.is_grad_enabled() and conf_matrix.requires_grad and conf_matrix.is_cuda
+        if not tracked:
+            _no_grad_inputs(conf_matrix)
         with torch.no_grad():
-            index, mconf, mask = ops.get_match(conf_matrix, thr, mutual, want_mask=True)
+            index, mconf, mask = ops.get_match(conf_matrix.detach(), thr, mutual, want_mask=True)
+        if tracked:
+            mconf = conf_matrix[index[:, 0], index[:, 1], index[:, 2]]
         return index, mconf, mask
 
     @staticmethod

@@ -158,8 +158,10 @@ def test_forward_only_guard():
     assert diffreg_b200.log_optimal_transport(torch.randn(1, 4, 4, device=DEV, requires_grad=True), torch.tensor(1.0, device=DEV), 3,
                                               ones[:, :4], ones[:, :4]).requires_grad
     assert diffreg_b200.Matching(_cfg(32, "dual_softmax")).to(DEV)(x.detach(), y, None, None, ones, ones, {})[0].requires_grad
-    with pytest.raises(Err, match="forward-only"):
-        diffreg_b200.Matching.get_match(conf, 0.2)          # the reference's mconf = conf[index] is differentiable: not built
+    idx, mconf, _ = diffreg_b200.Matching.get_match(conf, 0.2)          # mconf = conf[index] is differentiable, as the reference's
+    assert mconf.requires_grad and torch.equal(mconf.detach(), conf.detach()[idx[:, 0], idx[:, 1], idx[:, 2]])
+    r_, c_, w_ = diffreg_b200.mutual_topk_select(conf[0], 1)
+    assert w_.requires_grad and torch.equal(w_.detach(), conf.detach()[0][r_, c_])
     # the same calls under no_grad (how the reference's testers call) run
     with torch.no_grad():
         c1, _ = m(x, y, None, None, ones, ones, {})
