@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   __shared__ __align__(8) uint64_t bar_s[2], bar_kfull[2], bar_kfree[2], bar_vfull[2], bar_vfree[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(8) uint64_t bar_ci[4];
-  __shared__ __align__(16) float colinfo[4][3][FA_BN];   // per tile parity: 1 / scale of the key rows, bias (0 / -inf) without and with the key mask
+  __shared__ __align__(16) float colinfo[4][3][FA_BN];   // ring of four key tiles: 1 / scale of the key rows, bias (0 / -inf) without and with the key mask
   __shared__ float rowmax[2][FA_PARTS][FA_BM];   // per tile parity: the column parts' row maxima
   __shared__ float rowsum[FA_PARTS][FA_BM];      // the parts' row sums (epilogue)
   __shared__ float vscale[256];            // 1 / scale of the V^T rows (= output channels)
