@@ -195,21 +195,29 @@ __global__ void __launch_bounds__(256) lotb_final_kernel(const LotbParams p) {
   }
 }
 
-// dL/d alpha of one batch element: dL/dZ summed over the dustbin row and column (fixed order)
-__global__ void __launch_bounds__(256) lotb_alpha_kernel(const LotbParams p) {
+// dL/d alpha of one batch element: dL/dZ summed over the dustbin row and column -- one entry per thread, block sums into
+// alphapart[b][block], then a fixed-order sum (a single CTA per batch element needed 72 us for the 8193 entries of a 4096^2 problem)
+__global__ void __launch_bounds__(256) lotb_alpha_kernel(const LotbParams p, float* __restrict__ alphapart) {
   __shared__ float red[8];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y, e = blockIdx.x * 256 + threadIdx.x;
   const float alpha = *p.alpha;
   float acc = 0.f;
-  for (int j = threadIdx.x; j <= p.M; j += 256) acc += lotb_gz(p, b, p.N, j, alpha);
-  for (int i = threadIdx.x; i < p.N; i += 256) acc += lotb_gz(p, b, i, p.M, alpha);
+  if (e <= p.M) acc = lotb_gz(p, b, p.N, e, alpha);                    // the dustbin row (incl. the corner)
+  else if (e <= p.M + p.N) acc = lotb_gz(p, b, e - p.M - 1, p.M, alpha);  // the dustbin column
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += red[w];
-    p.galpha[b] = s;
+    alphapart[(size_t)b * gridDim.x + blockIdx.x] = s;
+  }
+}
+__global__ void lotb_alpha_reduce_kernel(const float* __restrict__ alphapart, int nblk, float* __restrict__ galpha) {
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < nblk; ++k) s += alphapart[(size_t)blockIdx.x * nblk + k];
+    galpha[blockIdx.x] = s;
   }
 }
 
@@ -329,7 +337,8 @@ static int lotb_nslab(int N) { return (N + 1 + LOTB_SLAB - 1) / LOTB_SLAB; }
 
 extern "C" size_t drg_sinkhorn_backward_workspace_bytes(int B, int N, int M, int iters) {
   if (B < 1 || N < 1 || M < 1 || iters < 1) return 0;
-  const size_t f = (size_t)4 * B + (size_t)iters * B * (N + 1) + (size_t)iters * B * (M + 1) + (size_t)B * lotb_nslab(N) * (M + 1);
+  const size_t f = (size_t)4 * B + (size_t)iters * B * (N + 1) + (size_t)iters * B * (M + 1) + (size_t)B * lotb_nslab(N) * (M + 1) +
+                   (size_t)B * ((N + M + 1 + 255) / 256);
   return align_up(f * sizeof(float), 256);
 }
 
@@ -381,7 +390,11 @@ extern "C" int drg_sinkhorn_backward(const float* scores, const float* alpha, co
     default: lotb_final_kernel<0><<<gfin, 256, 0, st>>>(p); break;
   }
   DRG_LAUNCH_CHECK();
-  lotb_alpha_kernel<<<B, 256, 0, st>>>(p);
+  const int nblk = (N + M + 1 + 255) / 256;
+  float* alphapart = p.colpart + (size_t)B * p.nslab * (M + 1);
+  lotb_alpha_kernel<<<dim3((unsigned)nblk, (unsigned)B), 256, 0, st>>>(p, alphapart);
+  DRG_LAUNCH_CHECK();
+  lotb_alpha_reduce_kernel<<<B, 32, 0, st>>>(alphapart, nblk, p.galpha);
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }
