@@ -11,6 +11,7 @@ Public surface (mirrors the reference):
     CrossModalFusionModule                                   (fusion.py; the 2D-3D flavour's fusion / denoising transformer)
     DenoisingSampler                                         (fused per-step driver)
     HostStepPipeline                                         (host buffers in / results out, copies overlapped, graph replay)
+    ransac_pose_estimation, ransac_regist_coarse             (registration.py; correspondence RANSAC)
     RowShardedSinkhorn, shard_rows, shard_units              (multi-GPU paths, distributed.py)
 Everything computes through libdiffreg_b200.so (C ABI, include/diffreg_b200.h).  There is
 no CPU or eager-PyTorch fallback: a missing library or a non-CUDA tensor raises.
@@ -41,6 +42,9 @@ def __getattr__(name):
     if name == "CrossModalFusionModule":
         from . import fusion
         return fusion.CrossModalFusionModule
+    if name in ("ransac_pose_estimation", "ransac_regist_coarse"):
+        from . import registration
+        return getattr(registration, name)
     if name == "HostStepPipeline":
         from . import hostpipe
         return hostpipe.HostStepPipeline

@@ -1,0 +1,316 @@
+// Correspondence RANSAC on the device: the consumer of get_match's correspondences in the
+// 3DMatch / 4DMatch evaluation,
+//   Diff-Reg-4dmatch/models/loss.py:13-24   ransac_pose_estimation -> open3d registration_ransac_based_on_correspondence
+//   Diff-Reg-4dmatch/models/loss.py:366-398 MatchMotionLoss.ransac_regist_coarse (per batch element, < 3 matches -> identity)
+// Open3D (pinned 0.13.0 in eccv24_4d_env.yml, absent from this image) runs max_iteration = 50000 trials one after the
+// other on the host: draw ransac_n correspondences (with replacement), fit a rigid transform to them
+// (TransformationEstimationPointToPoint(False): Umeyama without scale), count the correspondences within
+// max_correspondence_distance of their partner under that transform (fitness = inliers / C, inlier_rmse), keep the trial
+// with the higher fitness, the lower rmse on equal fitness.  Here every trial is one THREAD: the trials are independent, the
+// correspondences are staged once per CTA in shared memory (every thread of a warp reads the same correspondence: a
+// broadcast), and the best trial is a fixed-order reduction -- the result is a function of (inputs, seed) only.
+// The draws come from a counter-based generator (splitmix64 of (seed, batch element, trial, draw)), so the oracle draws the
+// same samples; Open3D seeds a Mersenne twister from random_device, so no run of the reference is reproducible either
+// (its tester repeats the evaluation "to combat ransac nondeterministic", Diff-Reg-3dmatch/lib/tester.py:25).
+#include "common.cuh"
+
+namespace drg {
+namespace {
+
+constexpr int RS_THREADS = 128;   // trials per CTA
+constexpr int RS_TILE = 1024;     // correspondences staged per shared-memory tile (24 KB)
+constexpr int RS_MAX_N = 8;       // ransac_n <= 8
+
+__host__ __device__ inline unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// draw j of trial h of batch element b: uniform in [0, C) (multiply-shift of the generator's high 32 bits)
+__device__ __forceinline__ int draw_index(unsigned long long seed, int b, int h, int j, int C) {
+  const unsigned long long ctr = ((unsigned long long)(unsigned)b << 40) ^ ((unsigned long long)(unsigned)h << 4) ^ (unsigned long long)j;
+  const unsigned long long r = splitmix64(seed ^ splitmix64(ctr));
+  return (int)(((r >> 32) * (unsigned long long)C) >> 32);
+}
+
+// Eigenvectors of a symmetric 3x3 matrix (cyclic Jacobi, fp64), eigenvalues descending.
+__device__ void eig3_sym(double A[3][3], double V[3][3], double lam[3]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    const double dg = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+    if (off <= 1e-32 * dg || off == 0.0) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;
+        const double d = A[q][q] - A[p][p];
+        const double t = (d >= 0.0 ? 2.0 : -2.0) * apq / (fabs(d) + sqrt(d * d + 4.0 * apq * apq));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        const int r = 3 - p - q;  // the third index
+        const double arp = A[r][p], arq = A[r][q];
+        A[p][p] -= t * apq;
+        A[q][q] += t * apq;
+        A[p][q] = A[q][p] = 0.0;
+        A[r][p] = A[p][r] = c * arp - s * arq;
+        A[r][q] = A[q][r] = s * arp + c * arq;
+        for (int i = 0; i < 3; ++i) {
+          const double vp = V[i][p], vq = V[i][q];
+          V[i][p] = c * vp - s * vq;
+          V[i][q] = s * vp + c * vq;
+        }
+      }
+  }
+  for (int j = 0; j < 3; ++j) lam[j] = A[j][j];
+  for (int a = 0; a < 2; ++a)
+    for (int b = a + 1; b < 3; ++b)
+      if (lam[b] > lam[a]) {
+        double tmp = lam[a]; lam[a] = lam[b]; lam[b] = tmp;
+        for (int i = 0; i < 3; ++i) { tmp = V[i][a]; V[i][a] = V[i][b]; V[i][b] = tmp; }
+      }
+}
+
+// Rigid fit y ~ R x + t to n point pairs (Kabsch / Umeyama without scale).  With H = sum (y - my)(x - mx)^T = U S V^T the
+// answer U diag(1, 1, det U det V) V^T equals u0 v0^T + u1 v1^T + (u0 x u1)(v0 x v1)^T whatever the sign of the third pair,
+// so only the two leading singular pairs are needed -- three points always give a rank-2 H.  false: the sample is
+// degenerate (coincident or collinear points: second singular value below 1e-7 of the first).
+__device__ bool rigid_fit(const float* xs, const float* ys, int n, float R[9], float t[3]) {
+  double mx[3] = {0, 0, 0}, my[3] = {0, 0, 0};
+  for (int k = 0; k < n; ++k)
+    for (int a = 0; a < 3; ++a) {
+      mx[a] += (double)xs[k * 3 + a];
+      my[a] += (double)ys[k * 3 + a];
+    }
+  const double inv = 1.0 / (double)n;
+  for (int a = 0; a < 3; ++a) { mx[a] *= inv; my[a] *= inv; }
+  double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int k = 0; k < n; ++k)
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) H[a][c] += ((double)ys[k * 3 + a] - my[a]) * ((double)xs[k * 3 + c] - mx[c]);
+  double A[3][3], V[3][3], lam[3];
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) A[a][c] = H[0][a] * H[0][c] + H[1][a] * H[1][c] + H[2][a] * H[2][c];  // H^T H
+  eig3_sym(A, V, lam);
+  if (!(lam[0] > 0.0) || !(lam[1] > 1e-14 * lam[0])) return false;
+  double u0[3], u1[3];
+  for (int a = 0; a < 3; ++a) {
+    u0[a] = H[a][0] * V[0][0] + H[a][1] * V[1][0] + H[a][2] * V[2][0];
+    u1[a] = H[a][0] * V[0][1] + H[a][1] * V[1][1] + H[a][2] * V[2][1];
+  }
+  double n0 = 1.0 / sqrt(u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
+  for (int a = 0; a < 3; ++a) u0[a] *= n0;
+  const double dot = u0[0] * u1[0] + u0[1] * u1[1] + u0[2] * u1[2];
+  for (int a = 0; a < 3; ++a) u1[a] -= dot * u0[a];
+  const double n1 = 1.0 / sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+  for (int a = 0; a < 3; ++a) u1[a] *= n1;
+  const double u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+  const double v2[3] = {V[1][0] * V[2][1] - V[2][0] * V[1][1], V[2][0] * V[0][1] - V[0][0] * V[2][1],
+                        V[0][0] * V[1][1] - V[1][0] * V[0][1]};
+  double Rd[3][3];
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) Rd[a][c] = u0[a] * V[c][0] + u1[a] * V[c][1] + u2[a] * v2[c];
+  for (int a = 0; a < 3; ++a) {
+    t[a] = (float)(my[a] - (Rd[a][0] * mx[0] + Rd[a][1] * mx[1] + Rd[a][2] * mx[2]));
+    for (int c = 0; c < 3; ++c) R[a * 3 + c] = (float)Rd[a][c];
+  }
+  return true;
+}
+
+struct RansacParams {
+  const float* src;          // [B, N, 3]
+  const float* tgt;          // [B, M, 3]
+  const long long* match;    // [C_total, 3] rows (b, i, j), grouped by b
+  const int* offsets;        // [B + 1] first row of every batch element
+  int B, N, M, n, T;
+  float thr2;
+  unsigned long long seed;
+  unsigned long long* cta_best;  // [B, ctas] packed (count, ~err bits) of the CTA's best trial
+  int* cta_best_h;               // [B, ctas]
+  int* hyp_count;                // optional [B, T]
+  float* hyp_err2;               // optional [B, T]
+  float* pose;                   // [B, 4, 4]
+  float* fitness;                // [B]
+  float* rmse;                   // [B]
+  int* best;                     // [B] winning trial (-1: fewer than 3 correspondences or no valid trial)
+  int* inliers;                  // [B]
+};
+
+__device__ __forceinline__ bool fit_trial(const RansacParams& p, int b, int h, int c0, int C, float R[9], float t[3]) {
+  float xs[RS_MAX_N * 3], ys[RS_MAX_N * 3];
+  for (int j = 0; j < p.n; ++j) {
+    const long long* row = p.match + (long long)(c0 + draw_index(p.seed, b, h, j, C)) * 3;
+    const float* s = p.src + ((long long)b * p.N + row[1]) * 3;
+    const float* g = p.tgt + ((long long)b * p.M + row[2]) * 3;
+    for (int a = 0; a < 3; ++a) { xs[j * 3 + a] = s[a]; ys[j * 3 + a] = g[a]; }
+  }
+  return rigid_fit(xs, ys, p.n, R, t);
+}
+
+// (count, err2) -> 64-bit key, larger is better: more inliers first, then the smaller squared-error sum (at equal count
+// the rmse order is the err2 order); err2 >= 0 so its float bits are monotone.
+__device__ __forceinline__ unsigned long long trial_key(int count, float err2) {
+  return ((unsigned long long)(unsigned)count << 32) | (unsigned long long)(0xFFFFFFFFu - __float_as_uint(err2));
+}
+
+// grid (ctas, B), RS_THREADS threads: thread = trial.  Correspondences pass through shared memory in tiles.
+__global__ void __launch_bounds__(RS_THREADS) ransac_trials_kernel(RansacParams p) {
+  __shared__ float sm[RS_TILE * 6];
+  __shared__ unsigned long long wkey[RS_THREADS / 32];
+  __shared__ int wh[RS_THREADS / 32];
+  const int b = blockIdx.y;
+  const int c0 = p.offsets[b], C = p.offsets[b + 1] - c0;
+  const int h = blockIdx.x * RS_THREADS + threadIdx.x;
+  float R[9], t[3];
+  bool valid = false;
+  if (C >= 3 && h < p.T) valid = fit_trial(p, b, h, c0, C, R, t);
+  int count = 0;
+  float err2 = 0.f;
+  for (int base = 0; base < C; base += RS_TILE) {
+    const int len = min(RS_TILE, C - base);
+    __syncthreads();
+    for (int k = threadIdx.x; k < len; k += RS_THREADS) {
+      const long long* row = p.match + (long long)(c0 + base + k) * 3;
+      const float* s = p.src + ((long long)b * p.N + row[1]) * 3;
+      const float* g = p.tgt + ((long long)b * p.M + row[2]) * 3;
+      sm[k * 6 + 0] = s[0]; sm[k * 6 + 1] = s[1]; sm[k * 6 + 2] = s[2];
+      sm[k * 6 + 3] = g[0]; sm[k * 6 + 4] = g[1]; sm[k * 6 + 5] = g[2];
+    }
+    __syncthreads();
+    if (valid) {
+#pragma unroll 4
+      for (int k = 0; k < len; ++k) {
+        const float2 a0 = *reinterpret_cast<const float2*>(&sm[k * 6]);
+        const float2 a1 = *reinterpret_cast<const float2*>(&sm[k * 6 + 2]);
+        const float2 a2 = *reinterpret_cast<const float2*>(&sm[k * 6 + 4]);
+        const float x = a0.x, y = a0.y, z = a1.x;
+        const float dx = fmaf(R[0], x, fmaf(R[1], y, fmaf(R[2], z, t[0]))) - a1.y;
+        const float dy = fmaf(R[3], x, fmaf(R[4], y, fmaf(R[5], z, t[1]))) - a2.x;
+        const float dz = fmaf(R[6], x, fmaf(R[7], y, fmaf(R[8], z, t[2]))) - a2.y;
+        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        if (d2 < p.thr2) {  // open3d: dis < max_correspondence_distance
+          ++count;
+          err2 += d2;
+        }
+      }
+    }
+  }
+  if (h < p.T && p.hyp_count) {
+    p.hyp_count[(long long)b * p.T + h] = valid ? count : -1;
+    p.hyp_err2[(long long)b * p.T + h] = err2;
+  }
+  // best trial of the CTA: larger key, then the lower trial number (the sequential loop keeps the first of equals)
+  unsigned long long key = (valid && count > 0) ? trial_key(count, err2) : 0ull;
+  int bh = h;
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long k2 = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+    const int h2 = __shfl_xor_sync(0xFFFFFFFFu, bh, o);
+    if (k2 > key || (k2 == key && h2 < bh)) { key = k2; bh = h2; }
+  }
+  if ((threadIdx.x & 31) == 0) { wkey[threadIdx.x >> 5] = key; wh[threadIdx.x >> 5] = bh; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < RS_THREADS / 32; ++w)
+      if (wkey[w] > key || (wkey[w] == key && wh[w] < bh)) { key = wkey[w]; bh = wh[w]; }
+    p.cta_best[(long long)b * gridDim.x + blockIdx.x] = key;
+    p.cta_best_h[(long long)b * gridDim.x + blockIdx.x] = bh;
+  }
+}
+
+// grid B, 256 threads: best CTA entry, then the winning trial's fit once more (same code, same bits) -> pose.
+__global__ void __launch_bounds__(256) ransac_finish_kernel(RansacParams p, int ctas) {
+  __shared__ unsigned long long skey[256];
+  __shared__ int sh[256];
+  const int b = blockIdx.x;
+  unsigned long long key = 0ull;
+  int bh = 0x7FFFFFFF;
+  for (int k = threadIdx.x; k < ctas; k += 256) {
+    const unsigned long long k2 = p.cta_best[(long long)b * ctas + k];
+    const int h2 = p.cta_best_h[(long long)b * ctas + k];
+    if (k2 > key || (k2 == key && h2 < bh)) { key = k2; bh = h2; }
+  }
+  skey[threadIdx.x] = key;
+  sh[threadIdx.x] = bh;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const unsigned long long k2 = skey[threadIdx.x + o];
+      const int h2 = sh[threadIdx.x + o];
+      if (k2 > skey[threadIdx.x] || (k2 == skey[threadIdx.x] && h2 < sh[threadIdx.x])) { skey[threadIdx.x] = k2; sh[threadIdx.x] = h2; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  key = skey[0];
+  bh = sh[0];
+  const int c0 = p.offsets[b], C = p.offsets[b + 1] - c0;
+  float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
+  const int count = (int)(key >> 32);
+  const bool found = C >= 3 && count > 0 && fit_trial(p, b, bh, c0, C, R, t);
+  if (!found) {  // loss.py:384-387: identity; open3d returns the identity with fitness 0 when no trial had an inlier
+    const float I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int k = 0; k < 9; ++k) R[k] = I9[k];
+    t[0] = t[1] = t[2] = 0.f;
+  }
+  float* P = p.pose + (long long)b * 16;
+  for (int a = 0; a < 3; ++a) {
+    for (int c = 0; c < 3; ++c) P[a * 4 + c] = R[a * 3 + c];
+    P[a * 4 + 3] = t[a];
+  }
+  P[12] = P[13] = P[14] = 0.f;
+  P[15] = 1.f;
+  const float err2 = __uint_as_float(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+  p.fitness[b] = found ? (float)count / (float)C : 0.f;
+  p.rmse[b] = found ? sqrtf(err2 / (float)count) : 0.f;
+  p.best[b] = found ? bh : -1;
+  p.inliers[b] = found ? count : 0;
+}
+
+inline int ransac_ctas(int T) { return (T + RS_THREADS - 1) / RS_THREADS; }
+
+}  // namespace
+}  // namespace drg
+
+using namespace drg;
+
+extern "C" size_t drg_ransac_workspace_bytes(int B, int max_iteration) {
+  if (B < 1 || max_iteration < 1) return 0;
+  const size_t ctas = (size_t)ransac_ctas(max_iteration);
+  return align_up((size_t)B * ctas * sizeof(unsigned long long), 256) + align_up((size_t)B * ctas * sizeof(int), 256);
+}
+
+extern "C" int drg_ransac_correspondence(const float* src, const float* tgt, int B, int N, int M, const long long* match,
+                                         const int* offsets, float max_correspondence_distance, int ransac_n, int max_iteration,
+                                         unsigned long long seed, float* pose, float* fitness, float* inlier_rmse, int* best_trial,
+                                         int* inlier_count, int* trial_count, float* trial_err2, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  DRG_CHECK_ARG(src && tgt && offsets && pose && fitness && inlier_rmse && best_trial && inlier_count && workspace,
+                "src/tgt/offsets/outputs/workspace must be non-null");
+  DRG_CHECK_ARG(B >= 1 && N >= 1 && M >= 1, "B, N, M must be >= 1");
+  DRG_CHECK_ARG(B <= 65535, "B must be <= 65535");
+  DRG_CHECK_ARG(ransac_n >= 3 && ransac_n <= RS_MAX_N, "ransac_n must be in [3, 8]");
+  DRG_CHECK_ARG(max_iteration >= 1 && max_iteration <= (1 << 27), "max_iteration must be in [1, 2^27]");
+  DRG_CHECK_ARG(max_correspondence_distance > 0.f, "max_correspondence_distance must be > 0");
+  DRG_CHECK_ARG((trial_count == nullptr) == (trial_err2 == nullptr), "trial_count and trial_err2 go together");
+  if (workspace_bytes < drg_ransac_workspace_bytes(B, max_iteration)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, drg_ransac_workspace_bytes(B, max_iteration));
+    return DRG_ERR_WORKSPACE;
+  }
+  const int ctas = ransac_ctas(max_iteration);
+  RansacParams p;
+  p.src = src; p.tgt = tgt; p.match = match; p.offsets = offsets;
+  p.B = B; p.N = N; p.M = M; p.n = ransac_n; p.T = max_iteration;
+  p.thr2 = max_correspondence_distance * max_correspondence_distance;
+  p.seed = seed;
+  p.cta_best = (unsigned long long*)workspace;
+  p.cta_best_h = (int*)((char*)workspace + align_up((size_t)B * ctas * sizeof(unsigned long long), 256));
+  p.hyp_count = trial_count; p.hyp_err2 = trial_err2;
+  p.pose = pose; p.fitness = fitness; p.rmse = inlier_rmse; p.best = best_trial; p.inliers = inlier_count;
+  cudaStream_t st = (cudaStream_t)stream;
+  ransac_trials_kernel<<<dim3(ctas, B), RS_THREADS, 0, st>>>(p);
+  DRG_LAUNCH_CHECK();
+  ransac_finish_kernel<<<B, 256, 0, st>>>(p, ctas);
+  DRG_LAUNCH_CHECK();
+  return DRG_OK;
+}

@@ -709,3 +709,103 @@ def make_problem(seed, B, N, M, C=256, prefix_valid=None, arbitrary_invalid=0.0)
         tgt_mask &= torch.rand(B, M, generator=g) >= arbitrary_invalid
     return dict(src_feats=src_feats, tgt_feats=tgt_feats, W=W, s_pcd=s_pcd, t_pcd=t_pcd,
                 src_mask=src_mask, tgt_mask=tgt_mask)
+
+
+# --------------------------------------------------------------------------------------
+# Correspondence RANSAC (SURVEY.md 8f rank 4).  PARITY UNPINNED: the algorithm lives in open3d (pinned 0.13.0 in
+# Diff-Reg-4dmatch/eccv24_4d_env.yml, absent from this image and not importable here), called at
+# Diff-Reg-4dmatch/models/loss.py:13-24 (ransac_pose_estimation) from loss.py:366-398 (ransac_regist_coarse).  This is
+# a restatement of open3d's published registration_ransac_based_on_correspondence (trial = draw ransac_n correspondences
+# with replacement, Umeyama-without-scale fit, inliers = correspondences closer than the threshold under the fit, best =
+# more inliers, then lower rmse) with the CUDA path's counter-based draws, so that both evaluate the SAME trials; open3d
+# itself seeds from random_device and is not reproducible run to run.  No golden vectors exist for it.
+# --------------------------------------------------------------------------------------
+def _splitmix64(x):
+    import numpy as np
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def ransac_draws(seed, b, trials, ransac_n, num_corr):
+    """[trials, ransac_n] correspondence numbers of batch element b (the generator of csrc/ransac.cu: draw_index)."""
+    import numpy as np
+    h = np.arange(trials, dtype=np.uint64)[:, None]
+    j = np.arange(ransac_n, dtype=np.uint64)[None, :]
+    ctr = (np.uint64(b) << np.uint64(40)) ^ (h << np.uint64(4)) ^ j
+    r = _splitmix64(np.uint64(seed) ^ _splitmix64(ctr))
+    return (((r >> np.uint64(32)) * np.uint64(num_corr)) >> np.uint64(32)).astype(np.int64)
+
+
+def rigid_fit(xs, ys):
+    """Kabsch / Umeyama without scale on [T,n,3] fp32 point pairs in fp64 (numpy SVD, det fix on the last singular pair)
+    -> R [T,3,3] fp32, t [T,3] fp32, valid [T] (second singular value above 1e-7 of the first)."""
+    import numpy as np
+    xs = xs.astype(np.float64)
+    ys = ys.astype(np.float64)
+    mx, my = xs.mean(1), ys.mean(1)
+    H = np.einsum("tka,tkc->tac", ys - my[:, None], xs - mx[:, None])
+    U, s, Vt = np.linalg.svd(H)
+    valid = (s[:, 0] > 0) & (s[:, 1] > 1e-7 * s[:, 0])
+    d = np.sign(np.linalg.det(U) * np.linalg.det(Vt))
+    D = np.tile(np.eye(3), (len(H), 1, 1))
+    D[:, 2, 2] = d
+    R = U @ D @ Vt
+    t = my - np.einsum("tac,tc->ta", R, mx)
+    return R.astype(np.float32), t.astype(np.float32), valid
+
+
+def ransac_correspondence(src_pcd, tgt_pcd, match_pred, distance_threshold=0.05, ransac_n=3, max_iteration=50000, seed=0,
+                          chunk=2048):
+    """numpy restatement; src_pcd [B,N,3], tgt_pcd [B,M,3], match_pred [C,3] (b, i, j) grouped by b.
+    -> dict of numpy arrays: pose [B,4,4], fitness, inlier_rmse, best_trial, inlier_count, trial_count [B,T], trial_err2 [B,T]."""
+    import numpy as np
+    src = np.asarray(src_pcd, dtype=np.float32)
+    tgt = np.asarray(tgt_pcd, dtype=np.float32)
+    match = np.asarray(match_pred, dtype=np.int64).reshape(-1, 3)
+    B, T = src.shape[0], int(max_iteration)
+    thr2 = np.float32(distance_threshold) * np.float32(distance_threshold)
+    out = {"pose": np.tile(np.eye(4, dtype=np.float32), (B, 1, 1)), "fitness": np.zeros(B, np.float32),
+           "inlier_rmse": np.zeros(B, np.float32), "best_trial": np.full(B, -1, np.int32), "inlier_count": np.zeros(B, np.int32),
+           "trial_count": np.zeros((B, T), np.int32), "trial_err2": np.zeros((B, T), np.float32)}
+    for b in range(B):
+        rows = match[match[:, 0] == b]
+        C = len(rows)
+        if C < 3:  # loss.py:384-387
+            continue
+        S, G = src[b][rows[:, 1]], tgt[b][rows[:, 2]]
+        pick = ransac_draws(seed, b, T, ransac_n, C)
+        R, t, valid = rigid_fit(S[pick], G[pick])
+        cnt = np.zeros(T, np.int32)
+        err = np.zeros(T, np.float32)
+        for a in range(0, T, chunk):
+            P = np.einsum("tac,kc->tka", R[a:a + chunk], S) + t[a:a + chunk, None, :]
+            d2 = ((P - G[None]) ** 2).sum(-1).astype(np.float32)
+            inl = d2 < thr2
+            cnt[a:a + chunk] = inl.sum(1)
+            err[a:a + chunk] = np.where(inl, d2, np.float32(0)).sum(1, dtype=np.float32)
+        cnt = np.where(valid, cnt, -1).astype(np.int32)
+        err = np.where(valid, err, np.float32(0)).astype(np.float32)
+        out["trial_count"][b], out["trial_err2"][b] = cnt, err
+        best = ransac_best_trial(cnt, err)
+        if best < 0:
+            continue
+        out["best_trial"][b], out["inlier_count"][b] = best, cnt[best]
+        out["fitness"][b] = np.float32(cnt[best]) / np.float32(C)
+        out["inlier_rmse"][b] = np.sqrt(err[best] / np.float32(cnt[best]))
+        out["pose"][b, :3, :3], out["pose"][b, :3, 3] = R[best], t[best]
+    return out
+
+
+def ransac_best_trial(trial_count, trial_err2):
+    """open3d's sequential 'is better' scan as one arg-max: most inliers, then the smaller error sum, then the first trial."""
+    import numpy as np
+    cnt = np.asarray(trial_count)
+    if not (cnt > 0).any():
+        return -1
+    top = cnt.max()
+    cand = np.flatnonzero(cnt == top)
+    e = np.asarray(trial_err2)[cand]
+    return int(cand[np.flatnonzero(e == e.min())[0]])
