@@ -108,7 +108,7 @@ def _declare(lib):
     lib.drg_ransac_workspace_bytes.restype = c_size_t
     lib.drg_ransac_workspace_bytes.argtypes = [c_int, c_int]
     lib.drg_ransac_correspondence.restype = c_int
-    lib.drg_ransac_correspondence.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_int,
+    lib.drg_ransac_correspondence.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_longlong, c_void_p, c_float, c_int, c_int,
                                               ctypes.c_ulonglong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_size_t, c_void_p]
     lib.drg_weighted_procrustes_backward.restype = c_int

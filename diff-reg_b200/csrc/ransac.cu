@@ -42,13 +42,18 @@ __device__ void eig3_sym(double A[3][3], double V[3][3], double lam[3]) {
     const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
     const double dg = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
     if (off <= 1e-32 * dg || off == 0.0) break;
+#pragma unroll
     for (int p = 0; p < 2; ++p)
+#pragma unroll
       for (int q = p + 1; q < 3; ++q) {
         const double apq = A[p][q];
         if (apq == 0.0) continue;
         const double d = A[q][q] - A[p][p];
-        const double t = (d >= 0.0 ? 2.0 : -2.0) * apq / (fabs(d) + sqrt(d * d + 4.0 * apq * apq));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        // fp64 sqrt and division are long software sequences and 50 000 threads run ~15 rotations each: one rsqrt for the
+        // root (x rsqrt(x), x > 0 here), one reciprocal, one rsqrt for the cosine
+        const double rad = d * d + 4.0 * apq * apq;
+        const double t = (d >= 0.0 ? 2.0 : -2.0) * apq * __drcp_rn(fabs(d) + rad * rsqrt(rad));
+        const double c = rsqrt(1.0 + t * t), s = c * t;
         const int r = 3 - p - q;  // the third index
         const double arp = A[r][p], arq = A[r][q];
         A[p][p] -= t * apq;
@@ -64,7 +69,9 @@ __device__ void eig3_sym(double A[3][3], double V[3][3], double lam[3]) {
       }
   }
   for (int j = 0; j < 3; ++j) lam[j] = A[j][j];
+#pragma unroll
   for (int a = 0; a < 2; ++a)
+#pragma unroll
     for (int b = a + 1; b < 3; ++b)
       if (lam[b] > lam[a]) {
         double tmp = lam[a]; lam[a] = lam[b]; lam[b] = tmp;
@@ -76,9 +83,14 @@ __device__ void eig3_sym(double A[3][3], double V[3][3], double lam[3]) {
 // answer U diag(1, 1, det U det V) V^T equals u0 v0^T + u1 v1^T + (u0 x u1)(v0 x v1)^T whatever the sign of the third pair,
 // so only the two leading singular pairs are needed -- three points always give a rank-2 H.  false: the sample is
 // degenerate (coincident or collinear points: second singular value below 1e-7 of the first).
-__device__ bool rigid_fit(const float* xs, const float* ys, int n, float R[9], float t[3]) {
+// NS: ransac_n at compile time (sample arrays in registers), 0 = run time.
+template <int NS>
+__device__ __forceinline__ bool rigid_fit(const float* xs, const float* ys, int n_rt, float R[9], float t[3]) {
+  const int n = NS ? NS : n_rt;
   double mx[3] = {0, 0, 0}, my[3] = {0, 0, 0};
+#pragma unroll
   for (int k = 0; k < n; ++k)
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
       mx[a] += (double)xs[k * 3 + a];
       my[a] += (double)ys[k * 3 + a];
@@ -86,8 +98,11 @@ __device__ bool rigid_fit(const float* xs, const float* ys, int n, float R[9], f
   const double inv = 1.0 / (double)n;
   for (int a = 0; a < 3; ++a) { mx[a] *= inv; my[a] *= inv; }
   double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
   for (int k = 0; k < n; ++k)
+#pragma unroll
     for (int a = 0; a < 3; ++a)
+#pragma unroll
       for (int c = 0; c < 3; ++c) H[a][c] += ((double)ys[k * 3 + a] - my[a]) * ((double)xs[k * 3 + c] - mx[c]);
   double A[3][3], V[3][3], lam[3];
   for (int a = 0; a < 3; ++a)
@@ -99,11 +114,11 @@ __device__ bool rigid_fit(const float* xs, const float* ys, int n, float R[9], f
     u0[a] = H[a][0] * V[0][0] + H[a][1] * V[1][0] + H[a][2] * V[2][0];
     u1[a] = H[a][0] * V[0][1] + H[a][1] * V[1][1] + H[a][2] * V[2][1];
   }
-  double n0 = 1.0 / sqrt(u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
+  const double n0 = rsqrt(u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
   for (int a = 0; a < 3; ++a) u0[a] *= n0;
   const double dot = u0[0] * u1[0] + u0[1] * u1[1] + u0[2] * u1[2];
   for (int a = 0; a < 3; ++a) u1[a] -= dot * u0[a];
-  const double n1 = 1.0 / sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+  const double n1 = rsqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
   for (int a = 0; a < 3; ++a) u1[a] *= n1;
   const double u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
   const double v2[3] = {V[1][0] * V[2][1] - V[2][0] * V[1][1], V[2][0] * V[0][1] - V[0][0] * V[2][1],
@@ -122,12 +137,14 @@ struct RansacParams {
   const float* src;          // [B, N, 3]
   const float* tgt;          // [B, M, 3]
   const long long* match;    // [C_total, 3] rows (b, i, j), grouped by b
-  const int* offsets;        // [B + 1] first row of every batch element
+  const int* offsets;        // [B + 1] first row of every batch element (in the workspace: written by ransac_prep_kernel)
+  unsigned int* tickets;     // [B] CTAs of the batch element that have finished (zeroed by ransac_prep_kernel)
   int B, N, M, n, T;
   float thr2;
   unsigned long long seed;
   unsigned long long* cta_best;  // [B, ctas] packed (count, ~err bits) of the CTA's best trial
   int* cta_best_h;               // [B, ctas]
+  float* cta_pose;               // [B, ctas, 12] R (row-major) and t of that trial
   int* hyp_count;                // optional [B, T]
   float* hyp_err2;               // optional [B, T]
   float* pose;                   // [B, 4, 4]
@@ -137,15 +154,19 @@ struct RansacParams {
   int* inliers;                  // [B]
 };
 
+template <int NS>
 __device__ __forceinline__ bool fit_trial(const RansacParams& p, int b, int h, int c0, int C, float R[9], float t[3]) {
-  float xs[RS_MAX_N * 3], ys[RS_MAX_N * 3];
-  for (int j = 0; j < p.n; ++j) {
+  float xs[(NS ? NS : RS_MAX_N) * 3], ys[(NS ? NS : RS_MAX_N) * 3];
+  const int n = NS ? NS : p.n;
+#pragma unroll
+  for (int j = 0; j < n; ++j) {
     const long long* row = p.match + (long long)(c0 + draw_index(p.seed, b, h, j, C)) * 3;
     const float* s = p.src + ((long long)b * p.N + row[1]) * 3;
     const float* g = p.tgt + ((long long)b * p.M + row[2]) * 3;
+#pragma unroll
     for (int a = 0; a < 3; ++a) { xs[j * 3 + a] = s[a]; ys[j * 3 + a] = g[a]; }
   }
-  return rigid_fit(xs, ys, p.n, R, t);
+  return rigid_fit<NS>(xs, ys, p.n, R, t);
 }
 
 // (count, err2) -> 64-bit key, larger is better: more inliers first, then the smaller squared-error sum (at equal count
@@ -154,7 +175,9 @@ __device__ __forceinline__ unsigned long long trial_key(int count, float err2) {
   return ((unsigned long long)(unsigned)count << 32) | (unsigned long long)(0xFFFFFFFFu - __float_as_uint(err2));
 }
 
-// grid (ctas, B), RS_THREADS threads: thread = trial.  Correspondences pass through shared memory in tiles.
+// grid (ctas, B), RS_THREADS threads: thread = trial.  Correspondences pass through shared memory in tiles.  The last CTA
+// of a batch element to finish reduces the CTA bests and writes the pose.
+template <int NS>
 __global__ void __launch_bounds__(RS_THREADS) ransac_trials_kernel(RansacParams p) {
   __shared__ float sm[RS_TILE * 6];
   __shared__ unsigned long long wkey[RS_THREADS / 32];
@@ -164,7 +187,7 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_trials_kernel(RansacParams 
   const int h = blockIdx.x * RS_THREADS + threadIdx.x;
   float R[9], t[3];
   bool valid = false;
-  if (C >= 3 && h < p.T) valid = fit_trial(p, b, h, c0, C, R, t);
+  if (C >= 3 && h < p.T) valid = fit_trial<NS>(p, b, h, c0, C, R, t);
   int count = 0;
   float err2 = 0.f;
   for (int base = 0; base < C; base += RS_TILE) {
@@ -210,45 +233,61 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_trials_kernel(RansacParams 
   }
   if ((threadIdx.x & 31) == 0) { wkey[threadIdx.x >> 5] = key; wh[threadIdx.x >> 5] = bh; }
   __syncthreads();
+  __shared__ bool last;
+  __shared__ int cta_h;
   if (threadIdx.x == 0) {
     for (int w = 1; w < RS_THREADS / 32; ++w)
       if (wkey[w] > key || (wkey[w] == key && wh[w] < bh)) { key = wkey[w]; bh = wh[w]; }
     p.cta_best[(long long)b * gridDim.x + blockIdx.x] = key;
     p.cta_best_h[(long long)b * gridDim.x + blockIdx.x] = bh;
+    cta_h = key ? bh : -1;
   }
-}
-
-// grid B, 256 threads: best CTA entry, then the winning trial's fit once more (same code, same bits) -> pose.
-__global__ void __launch_bounds__(256) ransac_finish_kernel(RansacParams p, int ctas) {
-  __shared__ unsigned long long skey[256];
-  __shared__ int sh[256];
-  const int b = blockIdx.x;
-  unsigned long long key = 0ull;
-  int bh = 0x7FFFFFFF;
-  for (int k = threadIdx.x; k < ctas; k += 256) {
-    const unsigned long long k2 = p.cta_best[(long long)b * ctas + k];
-    const int h2 = p.cta_best_h[(long long)b * ctas + k];
+  __syncthreads();
+  if (h == cta_h) {  // the CTA's best trial leaves its fit: the finisher copies it (a single-thread fp64 refit took 10 us)
+    float* q = p.cta_pose + ((long long)b * gridDim.x + blockIdx.x) * 12;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) q[k] = R[k];
+    q[9] = t[0]; q[10] = t[1]; q[11] = t[2];
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(&p.tickets[b], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  // The last CTA of the batch element to finish picks the best CTA record (fixed order: the result does not depend on which
+  // CTA is last) and publishes its pose.
+  __threadfence();
+  const int ctas = gridDim.x;
+  key = 0ull;
+  bh = 0x7FFFFFFF;
+  for (int k = threadIdx.x; k < ctas; k += RS_THREADS) {
+    const unsigned long long k2 = __ldcg(&p.cta_best[(long long)b * ctas + k]);
+    const int h2 = __ldcg(&p.cta_best_h[(long long)b * ctas + k]);
     if (k2 > key || (k2 == key && h2 < bh)) { key = k2; bh = h2; }
   }
-  skey[threadIdx.x] = key;
-  sh[threadIdx.x] = bh;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      const unsigned long long k2 = skey[threadIdx.x + o];
-      const int h2 = sh[threadIdx.x + o];
-      if (k2 > skey[threadIdx.x] || (k2 == skey[threadIdx.x] && h2 < sh[threadIdx.x])) { skey[threadIdx.x] = k2; sh[threadIdx.x] = h2; }
-    }
-    __syncthreads();
+  // a trial belongs to exactly one CTA (h / RS_THREADS), so (key, h) carries the record number along
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long k2 = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+    const int h2 = __shfl_xor_sync(0xFFFFFFFFu, bh, o);
+    if (k2 > key || (k2 == key && h2 < bh)) { key = k2; bh = h2; }
   }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { wkey[threadIdx.x >> 5] = key; wh[threadIdx.x >> 5] = bh; }
+  __syncthreads();
   if (threadIdx.x != 0) return;
-  key = skey[0];
-  bh = sh[0];
-  const int c0 = p.offsets[b], C = p.offsets[b + 1] - c0;
-  float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
-  const int count = (int)(key >> 32);
-  const bool found = C >= 3 && count > 0 && fit_trial(p, b, bh, c0, C, R, t);
-  if (!found) {  // loss.py:384-387: identity; open3d returns the identity with fitness 0 when no trial had an inlier
+  for (int w = 1; w < RS_THREADS / 32; ++w)
+    if (wkey[w] > key || (wkey[w] == key && wh[w] < bh)) { key = wkey[w]; bh = wh[w]; }
+  p.tickets[b] = 0u;
+  const int cbest = (int)(key >> 32);
+  const bool found = C >= 3 && cbest > 0;
+  if (found) {
+    const float* q = p.cta_pose + ((long long)b * ctas + bh / RS_THREADS) * 12;
+    for (int k = 0; k < 9; ++k) R[k] = __ldcg(q + k);
+    for (int k = 0; k < 3; ++k) t[k] = __ldcg(q + 9 + k);
+  } else {  // loss.py:384-387: identity; open3d returns the identity with fitness 0 when no trial had an inlier
     const float I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     for (int k = 0; k < 9; ++k) R[k] = I9[k];
     t[0] = t[1] = t[2] = 0.f;
@@ -260,11 +299,30 @@ __global__ void __launch_bounds__(256) ransac_finish_kernel(RansacParams p, int 
   }
   P[12] = P[13] = P[14] = 0.f;
   P[15] = 1.f;
-  const float err2 = __uint_as_float(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
-  p.fitness[b] = found ? (float)count / (float)C : 0.f;
-  p.rmse[b] = found ? sqrtf(err2 / (float)count) : 0.f;
+  const float ebest = __uint_as_float(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+  p.fitness[b] = found ? (float)cbest / (float)C : 0.f;
+  p.rmse[b] = found ? sqrtf(ebest / (float)cbest) : 0.f;
   p.best[b] = found ? bh : -1;
-  p.inliers[b] = found ? count : 0;
+  p.inliers[b] = found ? cbest : 0;
+}
+
+// one CTA: first row of every batch element in the (b, i, j) list (rows grouped by ascending b) by binary search -- or a copy
+// of the caller's offsets -- and the tickets cleared.
+__global__ void ransac_prep_kernel(const long long* match, long long rows, const int* offsets_in, int B, int* offsets,
+                                   unsigned int* tickets) {
+  for (int b = threadIdx.x; b <= B; b += blockDim.x) {
+    if (offsets_in) {
+      offsets[b] = offsets_in[b];
+    } else {
+      long long lo = 0, hi = rows;  // first row with batch number >= b
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (match[mid * 3] < (long long)b) lo = mid + 1; else hi = mid;
+      }
+      offsets[b] = (int)lo;
+    }
+    if (b < B) tickets[b] = 0u;
+  }
 }
 
 inline int ransac_ctas(int T) { return (T + RS_THREADS - 1) / RS_THREADS; }
@@ -277,18 +335,21 @@ using namespace drg;
 extern "C" size_t drg_ransac_workspace_bytes(int B, int max_iteration) {
   if (B < 1 || max_iteration < 1) return 0;
   const size_t ctas = (size_t)ransac_ctas(max_iteration);
-  return align_up((size_t)B * ctas * sizeof(unsigned long long), 256) + align_up((size_t)B * ctas * sizeof(int), 256);
+  return align_up((size_t)B * ctas * sizeof(unsigned long long), 256) + align_up((size_t)B * ctas * sizeof(int), 256) +
+         align_up((size_t)B * ctas * 12 * sizeof(float), 256) + align_up((size_t)(B + 1) * sizeof(int), 256) +
+         align_up((size_t)B * sizeof(unsigned int), 256);
 }
 
 extern "C" int drg_ransac_correspondence(const float* src, const float* tgt, int B, int N, int M, const long long* match,
-                                         const int* offsets, float max_correspondence_distance, int ransac_n, int max_iteration,
-                                         unsigned long long seed, float* pose, float* fitness, float* inlier_rmse, int* best_trial,
-                                         int* inlier_count, int* trial_count, float* trial_err2, void* workspace,
-                                         size_t workspace_bytes, void* stream) {
-  DRG_CHECK_ARG(src && tgt && offsets && pose && fitness && inlier_rmse && best_trial && inlier_count && workspace,
-                "src/tgt/offsets/outputs/workspace must be non-null");
+                                         long long num_match, const int* offsets, float max_correspondence_distance, int ransac_n,
+                                         int max_iteration, unsigned long long seed, float* pose, float* fitness,
+                                         float* inlier_rmse, int* best_trial, int* inlier_count, int* trial_count,
+                                         float* trial_err2, void* workspace, size_t workspace_bytes, void* stream) {
+  DRG_CHECK_ARG(src && tgt && pose && fitness && inlier_rmse && best_trial && inlier_count && workspace,
+                "src/tgt/outputs/workspace must be non-null");
   DRG_CHECK_ARG(B >= 1 && N >= 1 && M >= 1, "B, N, M must be >= 1");
   DRG_CHECK_ARG(B <= 65535, "B must be <= 65535");
+  DRG_CHECK_ARG(num_match >= 0 && num_match < (1ll << 31) && (match || num_match == 0), "match must hold num_match (< 2^31) rows");
   DRG_CHECK_ARG(ransac_n >= 3 && ransac_n <= RS_MAX_N, "ransac_n must be in [3, 8]");
   DRG_CHECK_ARG(max_iteration >= 1 && max_iteration <= (1 << 27), "max_iteration must be in [1, 2^27]");
   DRG_CHECK_ARG(max_correspondence_distance > 0.f, "max_correspondence_distance must be > 0");
@@ -298,19 +359,32 @@ extern "C" int drg_ransac_correspondence(const float* src, const float* tgt, int
     return DRG_ERR_WORKSPACE;
   }
   const int ctas = ransac_ctas(max_iteration);
+  char* w = (char*)workspace;
   RansacParams p;
-  p.src = src; p.tgt = tgt; p.match = match; p.offsets = offsets;
+  p.cta_best = (unsigned long long*)w;
+  w += align_up((size_t)B * ctas * sizeof(unsigned long long), 256);
+  p.cta_best_h = (int*)w;
+  w += align_up((size_t)B * ctas * sizeof(int), 256);
+  p.cta_pose = (float*)w;
+  w += align_up((size_t)B * ctas * 12 * sizeof(float), 256);
+  int* offs = (int*)w;
+  w += align_up((size_t)(B + 1) * sizeof(int), 256);
+  p.tickets = (unsigned int*)w;
+  p.src = src; p.tgt = tgt; p.match = match; p.offsets = offs;
   p.B = B; p.N = N; p.M = M; p.n = ransac_n; p.T = max_iteration;
   p.thr2 = max_correspondence_distance * max_correspondence_distance;
   p.seed = seed;
-  p.cta_best = (unsigned long long*)workspace;
-  p.cta_best_h = (int*)((char*)workspace + align_up((size_t)B * ctas * sizeof(unsigned long long), 256));
   p.hyp_count = trial_count; p.hyp_err2 = trial_err2;
   p.pose = pose; p.fitness = fitness; p.rmse = inlier_rmse; p.best = best_trial; p.inliers = inlier_count;
   cudaStream_t st = (cudaStream_t)stream;
-  ransac_trials_kernel<<<dim3(ctas, B), RS_THREADS, 0, st>>>(p);
+  ransac_prep_kernel<<<1, 256, 0, st>>>(match, num_match, offsets, B, offs, p.tickets);
   DRG_LAUNCH_CHECK();
-  ransac_finish_kernel<<<B, 256, 0, st>>>(p, ctas);
+  if (ransac_n == 3)
+    ransac_trials_kernel<3><<<dim3(ctas, B), RS_THREADS, 0, st>>>(p);
+  else if (ransac_n == 4)
+    ransac_trials_kernel<4><<<dim3(ctas, B), RS_THREADS, 0, st>>>(p);
+  else
+    ransac_trials_kernel<0><<<dim3(ctas, B), RS_THREADS, 0, st>>>(p);
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }

@@ -587,7 +587,7 @@ def ransac_correspondence(src_pcd, tgt_pcd, match_pred, distance_threshold=0.05,
 
     src_pcd [B,N,3], tgt_pcd [B,M,3], match_pred [C,3] int64 rows (b, i, j) grouped by b (get_match's output)
     -> dict(pose [B,4,4], fitness [B], inlier_rmse [B], best_trial [B] int32, inlier_count [B] int32
-            [, trial_count [B,T] int32, trial_err2 [B,T]]); nothing synchronises with the host."""
+            [, trial_count [B,T] int32, trial_err2 [B,T]]); two launches, nothing synchronises with the host."""
     _require_cuda(src_pcd, tgt_pcd, match_pred)
     lib = load_library()
     src, tgt = _f32c(src_pcd), _f32c(tgt_pcd)
@@ -596,12 +596,11 @@ def ransac_correspondence(src_pcd, tgt_pcd, match_pred, distance_threshold=0.05,
     B, N, M = src.shape[0], src.shape[1], tgt.shape[1]
     dev = src.device
     match = match_pred.to(torch.int64).contiguous().view(-1, 3)
-    bounds = torch.arange(B + 1, device=dev, dtype=torch.int64)
-    offsets = torch.searchsorted(match[:, 0].contiguous(), bounds).to(torch.int32)
     T = int(max_iteration)
-    out = {"pose": torch.empty(B, 4, 4, dtype=torch.float32, device=dev), "fitness": torch.empty(B, dtype=torch.float32, device=dev),
-           "inlier_rmse": torch.empty(B, dtype=torch.float32, device=dev), "best_trial": torch.empty(B, dtype=torch.int32, device=dev),
-           "inlier_count": torch.empty(B, dtype=torch.int32, device=dev)}
+    fl = torch.empty(B * 18, dtype=torch.float32, device=dev)  # pose | fitness | rmse
+    it = torch.empty(2, B, dtype=torch.int32, device=dev)
+    out = {"pose": fl[:B * 16].view(B, 4, 4), "fitness": fl[B * 16:B * 17], "inlier_rmse": fl[B * 17:], "best_trial": it[0],
+           "inlier_count": it[1]}
     tc = te = None
     if want_trials:
         tc = out["trial_count"] = torch.empty(B, T, dtype=torch.int32, device=dev)
@@ -609,7 +608,7 @@ def ransac_correspondence(src_pcd, tgt_pcd, match_pred, distance_threshold=0.05,
     nbytes = lib.drg_ransac_workspace_bytes(B, T)
     ws = workspace(nbytes, dev, "ransac")
     check(lib.drg_ransac_correspondence(src.data_ptr(), tgt.data_ptr(), B, N, M, match.data_ptr() if match.numel() else None,
-                                        offsets.data_ptr(), float(distance_threshold), int(ransac_n), T, int(seed) & (2 ** 64 - 1),
+                                        match.shape[0], None, float(distance_threshold), int(ransac_n), T, int(seed) & (2 ** 64 - 1),
                                         out["pose"].data_ptr(), out["fitness"].data_ptr(), out["inlier_rmse"].data_ptr(),
                                         out["best_trial"].data_ptr(), out["inlier_count"].data_ptr(),
                                         tc.data_ptr() if tc is not None else None, te.data_ptr() if te is not None else None,

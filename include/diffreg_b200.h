@@ -410,7 +410,8 @@ int drg_weighted_procrustes_backward(const float* X, const float* Y, const float
  *            (open3d 0.13 registration_ransac_based_on_correspondence, TransformationEstimationPointToPoint(False),
  *             RANSACConvergenceCriteria(50000, ...)) inside MatchMotionLoss.ransac_regist_coarse   loss.py:366-398
  *   src [B,N,3], tgt [B,M,3]; match [C,3] int64 rows (b, i, j) grouped by b -- get_match's match_pred as it stands;
- *   offsets [B+1] int32 DEVICE: first row of every batch element (fewer than 3 rows -> identity, loss.py:384-387).
+ *   num_match = C; offsets [B+1] int32 DEVICE: first row of every batch element, or NULL: found on the device by binary
+ *   search on the batch column (rows grouped by ascending b).  Fewer than 3 rows -> identity (loss.py:384-387).
  *   Every one of the max_iteration trials runs (one thread each): ransac_n draws with replacement from a counter-based
  *   generator (seed, b, trial, draw), rigid fit, inlier count with |R s + t - g| < max_correspondence_distance; the best trial
  *   is the one with the most inliers, then the smaller rmse, then the lower trial number.
@@ -418,9 +419,9 @@ int drg_weighted_procrustes_backward(const float* X, const float* Y, const float
  *      inlier_count [B]; optional per-trial records trial_count [B,max_iteration] (-1: degenerate sample) and
  *      trial_err2 [B,max_iteration] (both or neither). */
 size_t drg_ransac_workspace_bytes(int B, int max_iteration);
-int drg_ransac_correspondence(const float* src, const float* tgt, int B, int N, int M, const long long* match, const int* offsets,
-                              float max_correspondence_distance, int ransac_n, int max_iteration, unsigned long long seed,
-                              float* pose, float* fitness, float* inlier_rmse, int* best_trial, int* inlier_count,
+int drg_ransac_correspondence(const float* src, const float* tgt, int B, int N, int M, const long long* match, long long num_match,
+                              const int* offsets, float max_correspondence_distance, int ransac_n, int max_iteration,
+                              unsigned long long seed, float* pose, float* fitness, float* inlier_rmse, int* best_trial, int* inlier_count,
                               int* trial_count, float* trial_err2, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Elementwise tail / head of the samplers.

@@ -120,3 +120,31 @@ def test_argument_errors():
         ops.ransac_correspondence(src.cuda(), tgt.cuda(), match.cuda(), 0.0, 3, 64)
     with pytest.raises(Exception):
         ops.ransac_correspondence(src, tgt, match)
+
+
+def test_explicit_offsets_through_the_c_abi():
+    """The C ABI takes the batch offsets from the caller as well (the wrapper lets the library find them): same result."""
+    from diffreg_b200 import ops
+    from diffreg_b200._lib import check, load_library
+    src, tgt, match, _, _ = _problem(21, 3, 500, 500, [120, 0, 300], 0.5)
+    src, tgt, match = src.cuda(), tgt.cuda(), match.cuda()
+    want = ops.ransac_correspondence(src, tgt, match, 0.05, 3, 2048, seed=9)
+    lib = load_library()
+    offsets = torch.tensor([0, 120, 120, 420], dtype=torch.int32, device="cuda")
+    pose = torch.empty(3, 4, 4, device="cuda")
+    fit, rmse = torch.empty(3, device="cuda"), torch.empty(3, device="cuda")
+    best, cnt = torch.empty(3, dtype=torch.int32, device="cuda"), torch.empty(3, dtype=torch.int32, device="cuda")
+    nbytes = lib.drg_ransac_workspace_bytes(3, 2048)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    args = [src.data_ptr(), tgt.data_ptr(), 3, 500, 500, match.data_ptr(), match.shape[0], offsets.data_ptr(), 0.05, 3, 2048, 9,
+            pose.data_ptr(), fit.data_ptr(), rmse.data_ptr(), best.data_ptr(), cnt.data_ptr(), None, None, ws.data_ptr(), nbytes,
+            torch.cuda.current_stream().cuda_stream]
+    check(lib.drg_ransac_correspondence(*args))
+    check(lib.drg_ransac_correspondence(*args))  # the tickets reset themselves: a second call on the same workspace
+    torch.cuda.synchronize()
+    assert torch.equal(pose, want["pose"]) and torch.equal(best, want["best_trial"]) and torch.equal(cnt, want["inlier_count"])
+    assert torch.equal(fit, want["fitness"]) and torch.equal(rmse, want["inlier_rmse"])
+    assert best.cpu().tolist()[1] == -1
+    args[-2] = nbytes - 1
+    with pytest.raises(Exception):
+        check(lib.drg_ransac_correspondence(*args))
