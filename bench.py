@@ -19,7 +19,7 @@ step's results (pose, match count, matches) copied out every step; roofline = th
 Sinkhorn launch that carries the whole log_optimal_transport + DDIM call) timed with CUDA events inside an eager pass over the
 same steps; cpu_baseline = the reference on the host;
 rowshard = BASELINE.json configs[4] (N=M=16384, 100 iterations; rows sharded over the N ranks); other_configs =
-configs[0], [1], [3] timed once each and one forward of each denoising-transformer drop-in (4DMatch stack, 2D-3D fusion module; N=1 only).  `config` is identical in both arms; how a run was timed is in `run_info`.
+configs[0], [1], [3] timed once each, one forward of each denoising-transformer drop-in (4DMatch stack, 2D-3D fusion module), a training step and the correspondence RANSAC (N=1 only).  `config` is identical in both arms; how a run was timed is in `run_info`.
 """
 import argparse
 import json
@@ -792,6 +792,24 @@ def bench_other_configs(torch, dev):
                                      "ms_per_forward": ms, "ms_per_forward_eager": ms_eager, "kernel_launches": int(launches)}
     except Exception as e:  # noqa: BLE001
         out["fusion_module_2d3d"] = {"error": str(e)[:200]}
+    # widening: the correspondence RANSAC of the 3DMatch / 4DMatch evaluation (loss.py:13-24: open3d on the
+    # host in the reference), 50 000 trials over 2000 correspondences of one pair
+    try:
+        from diffreg_b200 import ops as _ops
+        g = torch.Generator().manual_seed(5003)
+        rs = (torch.rand(1, N_PTS, 3, generator=g) * 2 - 1).to(dev)
+        rt = (torch.rand(1, N_PTS, 3, generator=g) * 2 - 1).to(dev)
+        ri, rj = torch.randperm(N_PTS, generator=g)[:2000], torch.randperm(N_PTS, generator=g)[:2000]
+        rt[0, rj[:500]] = rs[0, ri[:500]] + 0.25
+        rm = torch.stack([torch.zeros(2000, dtype=torch.int64), ri, rj], 1).to(dev)
+        fnr = lambda: _ops.ransac_correspondence(rs, rt, rm, 0.05, 3, 50000, seed=1)
+        for _ in range(3):
+            res = fnr()
+        out["ransac"] = {"workload": "SURVEY 8f rank 4 (not in the metric): correspondence RANSAC, 50000 trials x 2000 correspondences, "
+                                     "ransac_n=3, threshold 0.05 (25 % inliers planted)",
+                         "ms_per_call": _event_ms(torch, fnr, 7), "fitness": float(res["fitness"][0])}
+    except Exception as e:  # noqa: BLE001
+        out["ransac"] = {"error": str(e)[:200]}
     return out
 
 
