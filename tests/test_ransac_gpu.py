@@ -148,3 +148,39 @@ def test_explicit_offsets_through_the_c_abi():
     args[-2] = nbytes - 1
     with pytest.raises(Exception):
         check(lib.drg_ransac_correspondence(*args))
+
+
+def test_matching_head_to_ransac_pose():
+    """The consumer chain of the evaluation (Diff-Reg-3dmatch/lib/tester.py:79-85): Matching.forward -> match_pred ->
+    ransac_regist_coarse, all on the device.  Features of corresponding points agree up to noise, a third of the target
+    points have no partner: the RANSAC pose is the planted motion to the point noise."""
+    import diffreg_b200
+    from diffreg_b200 import registration
+    B, N, M, C = 2, 1024, 1100, 64
+    g = torch.Generator().manual_seed(77)
+    src_feats = torch.randn(B, N, C, generator=g)
+    s_pcd = torch.rand(B, N, 3, generator=g) * 2 - 1
+    tgt_feats = torch.randn(B, M, C, generator=g)
+    t_pcd = torch.rand(B, M, 3, generator=g) * 2 - 1
+    Rs, ts = [], []
+    for b in range(B):
+        R, t = orc.random_rotation(g).float(), torch.rand(3, generator=g) - 0.5
+        part = torch.randperm(N, generator=g)[: (2 * M) // 3]          # distinct partners for two thirds of the target points
+        where = torch.randperm(M, generator=g)[: (2 * M) // 3]
+        tgt_feats[b, where] = src_feats[b, part] + 0.2 * torch.randn(len(part), C, generator=g)
+        t_pcd[b, where] = s_pcd[b, part] @ R.T + t + 0.004 * torch.randn(len(part), 3, generator=g)
+        Rs.append(R)
+        ts.append(t)
+    cfg = dict(match_type="sinkhorn", confidence_threshold=0.2, feature_dim=C, entangled=True, dsmax_temperature=0.1,
+               skh_init_bin_score=1.0, skh_iters=3, skh_prefilter=False)
+    head = diffreg_b200.Matching(cfg).cuda().eval()
+    with torch.no_grad():
+        head.src_proj.weight.copy_(torch.eye(C))                        # identity projection: the similarity is the features' own
+    src_mask, tgt_mask = torch.ones(B, N, dtype=torch.bool).cuda(), torch.ones(B, M, dtype=torch.bool).cuda()
+    # the head divides both sides by sqrt(C) (matching.py:141): a scale of 3.5 puts partners at a similarity of ~12, strangers at ~N(0, 1.5)
+    conf, match_pred = head(3.5 * src_feats.cuda(), 3.5 * tgt_feats.cuda(), None, None, src_mask, tgt_mask, {})
+    assert match_pred.shape[1] == 3 and match_pred.shape[0] > 200
+    rot, trn = registration.ransac_regist_coarse(s_pcd.cuda(), t_pcd.cuda(), src_mask, tgt_mask, match_pred, seed=3)
+    for b in range(B):
+        assert rot_angle(rot[b].cpu(), Rs[b]).item() < 0.02
+        assert (trn[b, :, 0].cpu() - ts[b]).abs().max().item() < 0.02
