@@ -17,7 +17,8 @@
 namespace drg {
 namespace {
 
-constexpr int RS_THREADS = 128;   // trials per CTA
+constexpr int RS_MIN_THREADS = 64;   // trials per CTA: chosen per call (ransac_block) so that the CTAs fill the SMs evenly
+constexpr int RS_MAX_THREADS = 384;
 constexpr int RS_TILE = 1024;     // correspondences staged per shared-memory tile (24 KB)
 constexpr int RS_MAX_N = 8;       // ransac_n <= 8
 
@@ -83,9 +84,83 @@ __device__ void eig3_sym(double A[3][3], double V[3][3], double lam[3]) {
 // answer U diag(1, 1, det U det V) V^T equals u0 v0^T + u1 v1^T + (u0 x u1)(v0 x v1)^T whatever the sign of the third pair,
 // so only the two leading singular pairs are needed -- three points always give a rank-2 H.  false: the sample is
 // degenerate (coincident or collinear points: second singular value below 1e-7 of the first).
+// Three pairs: closed form.  Both centred triangles lie in planes; with right-handed orthonormal frames (e1, e2, ne) of the source
+// plane and (f1, f2, nf) of the target plane H = F h E^T with the 2 x 2 matrix h = sum beta_k alpha_k^T of the in-plane
+// coordinates, so the two leading singular pairs of H are those of h and  U diag(1, 1, det U det V) V^T = F q E^T + det(q) nf ne^T
+// with q the orthogonal polar factor of h: the rotation (c, -s; s, c), (c, s) ~ (h00 + h11, h10 - h01), when det h > 0, the
+// reflection (a, b; b, -a), (a, b) ~ (h00 - h11, h01 + h10), when det h < 0.  No iteration, five rsqrt.
+__device__ __forceinline__ bool rigid_fit3(const float* xs, const float* ys, float R[9], float t[3]) {
+  double x[3][3], y[3][3], mx[3], my[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { x[k][a] = (double)xs[k * 3 + a]; y[k][a] = (double)ys[k * 3 + a]; }
+    mx[a] = (x[0][a] + x[1][a] + x[2][a]) * (1.0 / 3.0);
+    my[a] = (y[0][a] + y[1][a] + y[2][a]) * (1.0 / 3.0);
+  }
+  double fr[2][3][3];  // [source | target][e1, e2, n][xyz]
+  bool ok = true;
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    const double(*p)[3] = w ? y : x;
+    const double d1[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]};
+    const double d2[3] = {p[2][0] - p[0][0], p[2][1] - p[0][1], p[2][2] - p[0][2]};
+    const double n[3] = {d1[1] * d2[2] - d1[2] * d2[1], d1[2] * d2[0] - d1[0] * d2[2], d1[0] * d2[1] - d1[1] * d2[0]};
+    const double l1 = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2], ln = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    ok = ok && l1 > 0.0 && ln > 0.0;
+    const double i1 = rsqrt(l1), in = rsqrt(ln);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { fr[w][0][a] = d1[a] * i1; fr[w][2][a] = n[a] * in; }
+    fr[w][1][0] = fr[w][2][1] * fr[w][0][2] - fr[w][2][2] * fr[w][0][1];  // e2 = n x e1
+    fr[w][1][1] = fr[w][2][2] * fr[w][0][0] - fr[w][2][0] * fr[w][0][2];
+    fr[w][1][2] = fr[w][2][0] * fr[w][0][1] - fr[w][2][1] * fr[w][0][0];
+  }
+  if (!ok) return false;
+  double h[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double al[2], be[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      al[i] = fr[0][i][0] * (x[k][0] - mx[0]) + fr[0][i][1] * (x[k][1] - mx[1]) + fr[0][i][2] * (x[k][2] - mx[2]);
+      be[i] = fr[1][i][0] * (y[k][0] - my[0]) + fr[1][i][1] * (y[k][1] - my[1]) + fr[1][i][2] * (y[k][2] - my[2]);
+    }
+    h[0][0] += be[0] * al[0]; h[0][1] += be[0] * al[1];
+    h[1][0] += be[1] * al[0]; h[1][1] += be[1] * al[1];
+  }
+  const double det = h[0][0] * h[1][1] - h[0][1] * h[1][0];
+  const double fro = h[0][0] * h[0][0] + h[0][1] * h[0][1] + h[1][0] * h[1][0] + h[1][1] * h[1][1];
+  if (!(fabs(det) > 1e-7 * fro)) return false;  // second singular value below ~1e-7 of the first
+  double q[2][2], dq;
+  if (det > 0.0) {
+    const double c = h[0][0] + h[1][1], sn = h[1][0] - h[0][1], r = rsqrt(c * c + sn * sn);
+    q[0][0] = c * r; q[0][1] = -sn * r; q[1][0] = sn * r; q[1][1] = c * r;
+    dq = 1.0;
+  } else {
+    const double a = h[0][0] - h[1][1], b = h[0][1] + h[1][0], r = rsqrt(a * a + b * b);
+    q[0][0] = a * r; q[0][1] = b * r; q[1][0] = b * r; q[1][1] = -a * r;
+    dq = -1.0;
+  }
+  double Rd[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      Rd[a][c] = fr[1][0][a] * (q[0][0] * fr[0][0][c] + q[0][1] * fr[0][1][c]) + fr[1][1][a] * (q[1][0] * fr[0][0][c] + q[1][1] * fr[0][1][c]) +
+                 dq * fr[1][2][a] * fr[0][2][c];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    t[a] = (float)(my[a] - (Rd[a][0] * mx[0] + Rd[a][1] * mx[1] + Rd[a][2] * mx[2]));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) R[a * 3 + c] = (float)Rd[a][c];
+  }
+  return true;
+}
+
 // NS: ransac_n at compile time (sample arrays in registers), 0 = run time.
 template <int NS>
 __device__ __forceinline__ bool rigid_fit(const float* xs, const float* ys, int n_rt, float R[9], float t[3]) {
+  if (NS == 3) return rigid_fit3(xs, ys, R, t);
   const int n = NS ? NS : n_rt;
   double mx[3] = {0, 0, 0}, my[3] = {0, 0, 0};
 #pragma unroll
@@ -175,16 +250,19 @@ __device__ __forceinline__ unsigned long long trial_key(int count, float err2) {
   return ((unsigned long long)(unsigned)count << 32) | (unsigned long long)(0xFFFFFFFFu - __float_as_uint(err2));
 }
 
-// grid (ctas, B), RS_THREADS threads: thread = trial.  Correspondences pass through shared memory in tiles.  The last CTA
+// grid (ctas, B), blockDim.x (a multiple of 32, <= RS_MAX_THREADS) threads: thread = trial.  Correspondences pass through shared memory in tiles.  The last CTA
 // of a batch element to finish reduces the CTA bests and writes the pose.
-template <int NS>
-__global__ void __launch_bounds__(RS_THREADS) ransac_trials_kernel(RansacParams p) {
+// MAXT: the launch bound (ptxas allocates 96 registers under a bound of 128 and 80, with a slower inner loop, under 384: the
+// multi-wave launches keep the small bound).
+template <int NS, int MAXT>
+__global__ void __launch_bounds__(MAXT) ransac_trials_kernel(RansacParams p) {
   __shared__ float sm[RS_TILE * 6];
-  __shared__ unsigned long long wkey[RS_THREADS / 32];
-  __shared__ int wh[RS_THREADS / 32];
+  __shared__ unsigned long long wkey[RS_MAX_THREADS / 32];
+  __shared__ int wh[RS_MAX_THREADS / 32];
+  const int nthr = blockDim.x, nwarp = nthr >> 5;
   const int b = blockIdx.y;
   const int c0 = p.offsets[b], C = p.offsets[b + 1] - c0;
-  const int h = blockIdx.x * RS_THREADS + threadIdx.x;
+  const int h = blockIdx.x * nthr + threadIdx.x;
   float R[9], t[3];
   bool valid = false;
   if (C >= 3 && h < p.T) valid = fit_trial<NS>(p, b, h, c0, C, R, t);
@@ -193,7 +271,7 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_trials_kernel(RansacParams 
   for (int base = 0; base < C; base += RS_TILE) {
     const int len = min(RS_TILE, C - base);
     __syncthreads();
-    for (int k = threadIdx.x; k < len; k += RS_THREADS) {
+    for (int k = threadIdx.x; k < len; k += nthr) {
       const long long* row = p.match + (long long)(c0 + base + k) * 3;
       const float* s = p.src + ((long long)b * p.N + row[1]) * 3;
       const float* g = p.tgt + ((long long)b * p.M + row[2]) * 3;
@@ -236,7 +314,7 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_trials_kernel(RansacParams 
   __shared__ bool last;
   __shared__ int cta_h;
   if (threadIdx.x == 0) {
-    for (int w = 1; w < RS_THREADS / 32; ++w)
+    for (int w = 1; w < nwarp; ++w)
       if (wkey[w] > key || (wkey[w] == key && wh[w] < bh)) { key = wkey[w]; bh = wh[w]; }
     p.cta_best[(long long)b * gridDim.x + blockIdx.x] = key;
     p.cta_best_h[(long long)b * gridDim.x + blockIdx.x] = bh;
@@ -263,12 +341,12 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_trials_kernel(RansacParams 
   const int ctas = gridDim.x;
   key = 0ull;
   bh = 0x7FFFFFFF;
-  for (int k = threadIdx.x; k < ctas; k += RS_THREADS) {
+  for (int k = threadIdx.x; k < ctas; k += nthr) {
     const unsigned long long k2 = __ldcg(&p.cta_best[(long long)b * ctas + k]);
     const int h2 = __ldcg(&p.cta_best_h[(long long)b * ctas + k]);
     if (k2 > key || (k2 == key && h2 < bh)) { key = k2; bh = h2; }
   }
-  // a trial belongs to exactly one CTA (h / RS_THREADS), so (key, h) carries the record number along
+  // a trial belongs to exactly one CTA (h / blockDim.x), so (key, h) carries the record number along
   for (int o = 16; o > 0; o >>= 1) {
     const unsigned long long k2 = __shfl_xor_sync(0xFFFFFFFFu, key, o);
     const int h2 = __shfl_xor_sync(0xFFFFFFFFu, bh, o);
@@ -278,13 +356,13 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_trials_kernel(RansacParams 
   if ((threadIdx.x & 31) == 0) { wkey[threadIdx.x >> 5] = key; wh[threadIdx.x >> 5] = bh; }
   __syncthreads();
   if (threadIdx.x != 0) return;
-  for (int w = 1; w < RS_THREADS / 32; ++w)
+  for (int w = 1; w < nwarp; ++w)
     if (wkey[w] > key || (wkey[w] == key && wh[w] < bh)) { key = wkey[w]; bh = wh[w]; }
   p.tickets[b] = 0u;
   const int cbest = (int)(key >> 32);
   const bool found = C >= 3 && cbest > 0;
   if (found) {
-    const float* q = p.cta_pose + ((long long)b * ctas + bh / RS_THREADS) * 12;
+    const float* q = p.cta_pose + ((long long)b * ctas + bh / nthr) * 12;
     for (int k = 0; k < 9; ++k) R[k] = __ldcg(q + k);
     for (int k = 0; k < 3; ++k) t[k] = __ldcg(q + 9 + k);
   } else {  // loss.py:384-387: identity; open3d returns the identity with fitness 0 when no trial had an inlier
@@ -325,7 +403,33 @@ __global__ void ransac_prep_kernel(const long long* match, long long rows, const
   }
 }
 
-inline int ransac_ctas(int T) { return (T + RS_THREADS - 1) / RS_THREADS; }
+// upper bound of the CTAs per batch element (workspace layout)
+inline int ransac_ctas(int T) { return (T + RS_MIN_THREADS - 1) / RS_MIN_THREADS; }
+// Threads per CTA.  The kernel is issue-bound and one trial is one thread, so what matters is that every SM gets the same
+// number of warps: 50 000 trials in CTAs of 128 are 391 CTAs = 2 or 3 per SM (measured: SMs active 73 % of the kernel's
+// duration), in CTAs of 352 they are 143 CTAs = one per SM.  Pick the size with the best (wave fill) x (lane fill).
+inline int ransac_block(int T, int B, int regs_per_thread) {
+  int best = 128;
+  double best_eff = -1.0;
+  // several waves of CTAs: the block scheduler evens the SMs out by itself and small CTAs leave the shorter tail (measured
+  // with 8 x 50 000 trials: 0.70 ms in CTAs of 128, 0.80 ms with the size this search picks)
+  if ((long long)((T + 127) / 128) * B > (long long)NUM_SMS * (65536 / (regs_per_thread * 128))) return 128;
+  for (int tpb = RS_MIN_THREADS; tpb <= RS_MAX_THREADS; tpb += 32) {
+    const long long ctas = (long long)((T + tpb - 1) / tpb) * B;
+    int resident = 65536 / (regs_per_thread * tpb);
+    if (resident > 8) resident = 8;   // 24.6 KB of static shared memory per CTA
+    if (resident < 1) continue;
+    const double waves = (double)ctas / (double)(NUM_SMS * resident);
+    double full = waves;
+    if (full != (double)(long long)full) full = (double)((long long)full + 1);
+    const double eff = waves / full * (double)T / (double)(((T + tpb - 1) / tpb) * (long long)tpb);
+    if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && tpb > best)) {  // ties: the larger CTA stages the list fewer times
+      best_eff = eff > best_eff ? eff : best_eff;
+      best = tpb;
+    }
+  }
+  return best;
+}
 
 }  // namespace
 }  // namespace drg
@@ -379,12 +483,23 @@ extern "C" int drg_ransac_correspondence(const float* src, const float* tgt, int
   cudaStream_t st = (cudaStream_t)stream;
   ransac_prep_kernel<<<1, 256, 0, st>>>(match, num_match, offsets, B, offs, p.tickets);
   DRG_LAUNCH_CHECK();
-  if (ransac_n == 3)
-    ransac_trials_kernel<3><<<dim3(ctas, B), RS_THREADS, 0, st>>>(p);
-  else if (ransac_n == 4)
-    ransac_trials_kernel<4><<<dim3(ctas, B), RS_THREADS, 0, st>>>(p);
-  else
-    ransac_trials_kernel<0><<<dim3(ctas, B), RS_THREADS, 0, st>>>(p);
+  const int tpb = ransac_block(max_iteration, B, 96);
+  const dim3 grid((max_iteration + tpb - 1) / tpb, B);
+  if (tpb <= 128) {
+    if (ransac_n == 3)
+      ransac_trials_kernel<3, 128><<<grid, tpb, 0, st>>>(p);
+    else if (ransac_n == 4)
+      ransac_trials_kernel<4, 128><<<grid, tpb, 0, st>>>(p);
+    else
+      ransac_trials_kernel<0, 128><<<grid, tpb, 0, st>>>(p);
+  } else {
+    if (ransac_n == 3)
+      ransac_trials_kernel<3, RS_MAX_THREADS><<<grid, tpb, 0, st>>>(p);
+    else if (ransac_n == 4)
+      ransac_trials_kernel<4, RS_MAX_THREADS><<<grid, tpb, 0, st>>>(p);
+    else
+      ransac_trials_kernel<0, RS_MAX_THREADS><<<grid, tpb, 0, st>>>(p);
+  }
   DRG_LAUNCH_CHECK();
   return DRG_OK;
 }
