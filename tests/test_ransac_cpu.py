@@ -53,3 +53,31 @@ def test_selection_rule_and_planted_pose():
     assert out["inlier_count"][0] >= 20 and abs(out["fitness"][0] - out["inlier_count"][0] / 40) < 1e-6
     assert np.abs(out["pose"][0, :3, :3] - R).max() < 1e-4 and np.abs(out["pose"][0, :3, 3] - t).max() < 1e-4
     assert (out["pose"][1] == np.eye(4)).all() and out["best_trial"][1] == -1  # two matches: identity (loss.py:384-387)
+
+
+def test_reference_signatures_of_the_ransac_entry_points():
+    """registration.ransac_pose_estimation / ransac_regist_coarse accept every call the reference's functions accept
+    (Diff-Reg-4dmatch/models/loss.py:13, 366): same leading parameter names, order and defaults.  loss.py imports open3d and
+    cannot be imported here, so its signatures are read from the source with ast; skipped when the reference is absent."""
+    import ast
+    import inspect
+    import os
+
+    import pytest
+    path = "/root/reference/Diff-Reg-4dmatch/models/loss.py"
+    if not os.path.exists(path):
+        pytest.skip("reference sources not present")
+    from diffreg_b200 import registration
+    tree = ast.parse(open(path).read())
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in ("ransac_pose_estimation", "ransac_regist_coarse"):
+            names = [a.arg for a in node.args.args]
+            defaults = [ast.literal_eval(d) for d in node.args.defaults]
+            found[node.name] = (names, dict(zip(names[len(names) - len(defaults):], defaults)))
+    assert set(found) == {"ransac_pose_estimation", "ransac_regist_coarse"}
+    for name, (names, defaults) in found.items():
+        ours = inspect.signature(getattr(registration, name)).parameters
+        assert list(ours)[:len(names)] == names, (name, list(ours), names)
+        for k, v in defaults.items():
+            assert ours[k].default == v, (name, k)
