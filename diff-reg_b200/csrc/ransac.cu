@@ -229,6 +229,10 @@ struct RansacParams {
   int* inliers;                  // [B]
 };
 
+// a point number outside [0, n) in the match list (the reference would raise an IndexError on the host; a launch cannot) is
+// clamped so that no read leaves the point clouds
+__device__ __forceinline__ long long clamp_index(long long i, int n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); }
+
 template <int NS>
 __device__ __forceinline__ bool fit_trial(const RansacParams& p, int b, int h, int c0, int C, float R[9], float t[3]) {
   float xs[(NS ? NS : RS_MAX_N) * 3], ys[(NS ? NS : RS_MAX_N) * 3];
@@ -236,8 +240,8 @@ __device__ __forceinline__ bool fit_trial(const RansacParams& p, int b, int h, i
 #pragma unroll
   for (int j = 0; j < n; ++j) {
     const long long* row = p.match + (long long)(c0 + draw_index(p.seed, b, h, j, C)) * 3;
-    const float* s = p.src + ((long long)b * p.N + row[1]) * 3;
-    const float* g = p.tgt + ((long long)b * p.M + row[2]) * 3;
+    const float* s = p.src + ((long long)b * p.N + clamp_index(row[1], p.N)) * 3;
+    const float* g = p.tgt + ((long long)b * p.M + clamp_index(row[2], p.M)) * 3;
 #pragma unroll
     for (int a = 0; a < 3; ++a) { xs[j * 3 + a] = s[a]; ys[j * 3 + a] = g[a]; }
   }
@@ -273,8 +277,8 @@ __global__ void __launch_bounds__(MAXT) ransac_trials_kernel(RansacParams p) {
     __syncthreads();
     for (int k = threadIdx.x; k < len; k += nthr) {
       const long long* row = p.match + (long long)(c0 + base + k) * 3;
-      const float* s = p.src + ((long long)b * p.N + row[1]) * 3;
-      const float* g = p.tgt + ((long long)b * p.M + row[2]) * 3;
+      const float* s = p.src + ((long long)b * p.N + clamp_index(row[1], p.N)) * 3;
+      const float* g = p.tgt + ((long long)b * p.M + clamp_index(row[2], p.M)) * 3;
       sm[k * 6 + 0] = s[0]; sm[k * 6 + 1] = s[1]; sm[k * 6 + 2] = s[2];
       sm[k * 6 + 3] = g[0]; sm[k * 6 + 4] = g[1]; sm[k * 6 + 5] = g[2];
     }

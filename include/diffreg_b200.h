@@ -412,6 +412,7 @@ int drg_weighted_procrustes_backward(const float* X, const float* Y, const float
  *   src [B,N,3], tgt [B,M,3]; match [C,3] int64 rows (b, i, j) grouped by b -- get_match's match_pred as it stands;
  *   num_match = C; offsets [B+1] int32 DEVICE: first row of every batch element, or NULL: found on the device by binary
  *   search on the batch column (rows grouped by ascending b).  Fewer than 3 rows -> identity (loss.py:384-387).
+ *   Point numbers outside [0, N) / [0, M) are clamped (the reference raises an IndexError on the host).
  *   Every one of the max_iteration trials runs (one thread each): ransac_n draws with replacement from a counter-based
  *   generator (seed, b, trial, draw), rigid fit, inlier count with |R s + t - g| < max_correspondence_distance; the best trial
  *   is the one with the most inliers, then the smaller rmse, then the lower trial number.

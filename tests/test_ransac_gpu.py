@@ -184,3 +184,16 @@ def test_matching_head_to_ransac_pose():
     for b in range(B):
         assert rot_angle(rot[b].cpu(), Rs[b]).item() < 0.02
         assert (trn[b, :, 0].cpu() - ts[b]).abs().max().item() < 0.02
+
+
+def test_out_of_range_point_numbers_do_not_read_outside_the_clouds():
+    """A match row pointing outside the point clouds (an IndexError on the host in the reference) is clamped on the device: the
+    call completes and the valid correspondences still decide the pose (run under compute-sanitizer memcheck: 0 errors)."""
+    from diffreg_b200 import ops
+    src, tgt, match, Rgt, _ = _problem(31, 1, 200, 220, [100], 0.8, noise=0.0)
+    bad = match.clone()
+    bad[3, 1], bad[5, 2], bad[7, 1] = 10 ** 9, -4, 200
+    out = ops.ransac_correspondence(src.cuda(), tgt.cuda(), bad.cuda(), 0.05, 3, 2048, seed=2)
+    torch.cuda.synchronize()
+    assert int(out["inlier_count"][0]) >= 75
+    assert rot_angle(out["pose"][0, :3, :3].cpu(), Rgt[0]).item() < 1e-4
