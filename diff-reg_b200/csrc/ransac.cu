@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(MAXT) ransac_trials_kernel(RansacParams p) {
   if (C >= 3 && h < p.T) valid = fit_trial<NS>(p, b, h, c0, C, R, t);
   int count = 0;
   float err2 = 0.f;
+  const float thr2 = p.thr2;
   for (int base = 0; base < C; base += RS_TILE) {
     const int len = min(RS_TILE, C - base);
     __syncthreads();
@@ -294,10 +295,9 @@ __global__ void __launch_bounds__(MAXT) ransac_trials_kernel(RansacParams p) {
         const float dy = fmaf(R[3], x, fmaf(R[4], y, fmaf(R[5], z, t[1]))) - a2.x;
         const float dz = fmaf(R[6], x, fmaf(R[7], y, fmaf(R[8], z, t[2]))) - a2.y;
         const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        if (d2 < p.thr2) {  // open3d: dis < max_correspondence_distance
-          ++count;
-          err2 += d2;
-        }
+        // open3d: dis < max_correspondence_distance.  Predicated adds written out: the compiler's own choice for the count was an
+        // add plus a predicated IMAD.MOV, which sits on the FMA pipe -- the pipe this loop is bound by.
+        asm("{\n\t.reg .pred q;\n\tsetp.lt.f32 q, %2, %3;\n\t@q add.s32 %0, %0, 1;\n\t@q add.f32 %1, %1, %2;\n\t}" : "+r"(count), "+f"(err2) : "f"(d2), "f"(thr2));
       }
     }
   }
